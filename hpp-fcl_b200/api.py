@@ -1,0 +1,392 @@
+"""Host-side mirror of the hpp-fcl query interface for the accelerated path.
+
+Same names, argument meaning and error behaviour as the reference's Python /
+C++ surface for this path (python/collision.cc, python/distance.cc;
+include/hpp/fcl/{collision,distance,collision_data}.h):
+
+    collide(o1, tf1, o2, tf2, request, result) -> number of contacts
+    distance(o1, tf1, o2, tf2, request, result) -> min distance
+    ComputeCollision / ComputeDistance functors (collision.h:79-117)
+    BatchQuery: the batched form (many (o1,tf1,o2,tf2) tuples, one launch)
+
+Every call runs on the GPU through the C-ABI (engine.Engine); there is no CPU
+path.  Single-pair calls are batches of one.
+"""
+import numpy as np
+
+from . import _pod as P
+from .engine import Engine
+
+_NAN3 = np.full(3, np.nan)
+
+
+# ---------------------------------------------------------------- geometry ---
+class Transform3f:
+    """math/transform.h:56-216 (rotation matrix + translation)."""
+
+    def __init__(self, R=None, T=None):
+        self.R = np.eye(3) if R is None else np.asarray(R, dtype=np.float64).reshape(3, 3)
+        self.T = np.zeros(3) if T is None else np.asarray(T, dtype=np.float64).reshape(3)
+
+    @staticmethod
+    def from_quat(w, x, y, z, T=None):
+        from .workloads import quat_to_rot
+        return Transform3f(quat_to_rot(w, x, y, z), T)
+
+    def transform(self, v):
+        return self.R @ np.asarray(v, dtype=np.float64) + self.T
+
+    def __mul__(self, o):  # transform.h:186-188
+        return Transform3f(self.R @ o.R, self.R @ o.T + self.T)
+
+    def getRotation(self):
+        return self.R
+
+    def getTranslation(self):
+        return self.T
+
+    def setTranslation(self, T):
+        self.T = np.asarray(T, dtype=np.float64).reshape(3)
+
+    def pod(self):
+        return P.make_transforms(self.R[None], self.T[None])
+
+
+class CollisionGeometry:
+    node_type = None
+
+    def __init__(self):
+        self._ssr = 0.0
+
+    def setSweptSphereRadius(self, r):  # geometric_shapes.h:77-85
+        if r < 0:
+            raise ValueError("Swept-sphere radius must be positive.")
+        self._ssr = float(r)
+
+    def getSweptSphereRadius(self):
+        return self._ssr
+
+    def getNodeType(self):
+        return self.node_type
+
+    def _params(self):
+        return (0.0, 0.0, 0.0)
+
+    def _points(self):
+        return None
+
+
+class Box(CollisionGeometry):
+    node_type = P.GEOM_BOX
+
+    def __init__(self, x, y=None, z=None):  # full side lengths; halfSide = side / 2 (geometric_shapes.h:164-187)
+        super().__init__()
+        side = np.asarray(x if y is None else (x, y, z), dtype=np.float64)
+        self.halfSide = side / 2
+
+    def _params(self):
+        return tuple(self.halfSide)
+
+
+class Sphere(CollisionGeometry):
+    node_type = P.GEOM_SPHERE
+
+    def __init__(self, radius):
+        super().__init__()
+        self.radius = float(radius)
+
+    def _params(self):
+        return (self.radius, 0.0, 0.0)
+
+
+class Ellipsoid(CollisionGeometry):
+    node_type = P.GEOM_ELLIPSOID
+
+    def __init__(self, rx, ry=None, rz=None):
+        super().__init__()
+        self.radii = np.asarray(rx if ry is None else (rx, ry, rz), dtype=np.float64)
+
+    def _params(self):
+        return tuple(self.radii)
+
+
+class _RadiusLength(CollisionGeometry):
+    def __init__(self, radius, lz):  # halfLength = lz / 2 (geometric_shapes.h:386-400)
+        super().__init__()
+        self.radius = float(radius)
+        self.halfLength = float(lz) / 2
+
+    def _params(self):
+        return (self.radius, self.halfLength, 0.0)
+
+
+class Capsule(_RadiusLength):
+    node_type = P.GEOM_CAPSULE
+
+
+class Cone(_RadiusLength):
+    node_type = P.GEOM_CONE
+
+
+class Cylinder(_RadiusLength):
+    node_type = P.GEOM_CYLINDER
+
+
+class Convex(CollisionGeometry):
+    """ConvexBase / Convex<Triangle> (geometric_shapes.h:638-872, shape/convex.h)."""
+    node_type = P.GEOM_CONVEX
+
+    def __init__(self, points, triangles=None):
+        super().__init__()
+        self.points = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        self.num_points = self.points.shape[0]
+        self.triangles = None if triangles is None else np.ascontiguousarray(triangles, dtype=np.uint32)
+
+    def _points(self):
+        return self.points
+
+
+class TriangleP(CollisionGeometry):
+    node_type = P.GEOM_TRIANGLE
+
+    def __init__(self, a, b, c):
+        super().__init__()
+        self.a, self.b, self.c = [np.asarray(v, dtype=np.float64).reshape(3) for v in (a, b, c)]
+
+    def _points(self):
+        return np.stack([self.a, self.b, self.c])
+
+
+# ---------------------------------------------------------- requests/results --
+class _QueryRequest:
+    _pod_cls = None
+
+    def __init__(self, **kw):
+        self._pod = self._pod_cls(**kw)
+
+    def __getattr__(self, k):
+        pod = object.__getattribute__(self, "_pod")
+        if hasattr(pod.q, k):
+            return getattr(pod.q, k)
+        return getattr(pod, k)
+
+    def __setattr__(self, k, v):
+        if k == "_pod":
+            object.__setattr__(self, k, v)
+        elif hasattr(self._pod.q, k):
+            setattr(self._pod.q, k, v)
+        elif hasattr(self._pod, k):
+            setattr(self._pod, k, v)
+        else:
+            raise AttributeError(k)
+
+
+class CollisionRequest(_QueryRequest):  # collision_data.h:312-383
+    _pod_cls = P.CollisionRequestPOD
+
+
+class DistanceRequest(_QueryRequest):  # collision_data.h:987-1050
+    _pod_cls = P.DistanceRequestPOD
+
+
+class Contact:  # collision_data.h:59-166
+    NONE = -1
+
+    def __init__(self, o1, o2, rec):
+        self.o1, self.o2 = o1, o2
+        self.b1, self.b2 = int(rec["b1"]), int(rec["b2"])
+        self.normal = rec["normal"].copy()
+        self.nearest_points = [rec["p1"].copy(), rec["p2"].copy()]
+        self.pos = rec["pos"].copy()
+        self.penetration_depth = float(rec["distance"])
+
+
+class CollisionResult:  # collision_data.h:391-509
+    def __init__(self):
+        self.clear()
+
+    def clear(self):
+        self.contacts = []
+        self.distance_lower_bound = P.DBL_MAX
+        self.normal = _NAN3.copy()
+        self.nearest_points = [_NAN3.copy(), _NAN3.copy()]
+        self.cached_gjk_guess = np.array([1.0, 0.0, 0.0])
+        self.cached_support_func_guess = np.zeros(2, dtype=np.int32)
+
+    def numContacts(self):
+        return len(self.contacts)
+
+    def isCollision(self):
+        return len(self.contacts) > 0
+
+    def getContact(self, i):
+        if i >= len(self.contacts):
+            raise IndexError("The index is out of range.")
+        return self.contacts[i]
+
+
+class DistanceResult:  # collision_data.h:1053-1174
+    NONE = -1
+
+    def __init__(self):
+        self.clear()
+
+    def clear(self):
+        self.min_distance = P.DBL_MAX
+        self.nearest_points = [_NAN3.copy(), _NAN3.copy()]
+        self.normal = _NAN3.copy()
+        self.o1 = self.o2 = None
+        self.b1 = self.b2 = -1
+        self.cached_gjk_guess = np.array([1.0, 0.0, 0.0])
+        self.cached_support_func_guess = np.zeros(2, dtype=np.int32)
+
+
+# ----------------------------------------------------------------- engine ----
+_DEFAULT = {}
+
+
+def default_engine(device=0):
+    if device not in _DEFAULT:
+        _DEFAULT[device] = _Scene(Engine(device))
+    return _DEFAULT[device]
+
+
+class _Scene:
+    """Geometry handle cache keyed by object identity (the arena of SURVEY 8b)."""
+
+    def __init__(self, engine):
+        self.engine = engine
+        self._handles = {}
+        self._dirty = False
+
+    def handle(self, geom):
+        key = id(geom)
+        ent = self._handles.get(key)
+        sig = (geom.node_type, geom._params(), geom.getSweptSphereRadius())
+        if ent is not None and ent[1] == sig and ent[2] is geom:
+            return ent[0]
+        data = 0
+        pts = geom._points()
+        if pts is not None:
+            data = self.engine.register_convex(pts)
+        rec = P.make_shapes([geom.node_type], [geom._params()], ssr=geom.getSweptSphereRadius(), data=data)
+        h = int(self.engine.register_shapes(rec)[0])
+        self._handles[key] = (h, sig, geom)
+        self._dirty = True
+        return h
+
+    def commit(self):
+        if self._dirty:
+            self.engine.commit()
+            self._dirty = False
+
+
+def _tf_array(tfs):
+    if isinstance(tfs, np.ndarray) and tfs.dtype == P.transform_dtype:
+        return tfs
+    if isinstance(tfs, Transform3f):
+        tfs = [tfs]
+    R = np.stack([t.R for t in tfs])
+    T = np.stack([t.T for t in tfs])
+    return P.make_transforms(R, T)
+
+
+class BatchQuery:
+    """Batched collide()/distance(): the seam a broadphase CollisionCallBackCollect
+    (broadphase/default_broadphase_callbacks.h:224-252) feeds."""
+
+    def __init__(self, device=0):
+        self.scene = default_engine(device)
+
+    def handles(self, geoms):
+        return np.array([self.scene.handle(g) for g in geoms], dtype=np.uint32)
+
+    def distance(self, geoms1, tfs1, geoms2, tfs2, request=None):
+        request = request or DistanceRequest()
+        h1, h2 = self.handles(geoms1), self.handles(geoms2)
+        self.scene.commit()
+        return self.scene.engine.batch_distance(h1, _tf_array(tfs1), h2, _tf_array(tfs2), request._pod)
+
+    def collide(self, geoms1, tfs1, geoms2, tfs2, request=None):
+        request = request or CollisionRequest()
+        if request.num_max_contacts == 0:  # collision.cpp:82-85
+            raise ValueError("Invalid number of max contacts (current value is 0).")
+        h1, h2 = self.handles(geoms1), self.handles(geoms2)
+        self.scene.commit()
+        return self.scene.engine.batch_collide(h1, _tf_array(tfs1), h2, _tf_array(tfs2), request._pod)
+
+
+def _unsupported(o1, o2, what):
+    raise ValueError("%s function between node type %s and node type %s is not yet supported."
+                     % (what, o1.node_type, o2.node_type))
+
+
+def collide(o1, tf1, o2, tf2, request, result, device=0):
+    """collide() of src/collision.cpp:69-130. Results accumulate: callers clear()."""
+    if request.security_margin == -np.inf:  # :73-76
+        result.clear()
+        return 0
+    if request.num_max_contacts == 0:
+        raise ValueError("Invalid number of max contacts (current value is 0).")
+    if result.isCollision() and request.num_max_contacts <= result.numContacts():  # isSatisfied
+        return result.numContacts()
+    bq = BatchQuery(device)
+    scene = bq.scene
+    h1, h2 = scene.handle(o1), scene.handle(o2)
+    scene.commit()
+    out, gg, gh = scene.engine.batch_collide([h1], _tf_array(tf1), [h2], _tf_array(tf2), request._pod,
+                                             want_guess=True)
+    rec = out[0]
+    if P.status_path(rec["status"]) == P.PATH_UNSUPPORTED:
+        _unsupported(o1, o2, "Collision")
+    if rec["distance_lower_bound"] < result.distance_lower_bound:
+        result.distance_lower_bound = float(rec["distance_lower_bound"])
+        result.nearest_points = [rec["p1"].copy(), rec["p2"].copy()]
+        result.normal = rec["normal"].copy()
+    if rec["num_contacts"]:
+        result.contacts.append(Contact(o1, o2, rec))
+    result.cached_gjk_guess = gg[0]
+    result.cached_support_func_guess = gh[0]
+    return result.numContacts() if rec["num_contacts"] else 0
+
+
+def distance(o1, tf1, o2, tf2, request, result, device=0):
+    """distance() of src/distance.cpp:60-109."""
+    if result.min_distance <= 0:  # DistanceRequest::isSatisfied
+        return result.min_distance
+    bq = BatchQuery(device)
+    scene = bq.scene
+    h1, h2 = scene.handle(o1), scene.handle(o2)
+    scene.commit()
+    out, gg, gh = scene.engine.batch_distance([h1], _tf_array(tf1), [h2], _tf_array(tf2), request._pod,
+                                              want_guess=True)
+    rec = out[0]
+    if P.status_path(rec["status"]) == P.PATH_UNSUPPORTED:
+        _unsupported(o1, o2, "Distance")
+    d = float(rec["min_distance"])
+    closed = P.status_path(rec["status"]) == P.PATH_CLOSED_FORM
+    if closed or result.min_distance > d:
+        result.min_distance = d
+        result.o1, result.o2 = o1, o2
+        result.b1, result.b2 = int(rec["b1"]), int(rec["b2"])
+        result.nearest_points = [rec["p1"].copy(), rec["p2"].copy()]
+        result.normal = rec["normal"].copy()
+    result.cached_gjk_guess = gg[0]
+    result.cached_support_func_guess = gh[0]
+    return d
+
+
+class ComputeCollision:  # collision.h:79-117
+    def __init__(self, o1, o2):
+        self.o1, self.o2 = o1, o2
+
+    def __call__(self, tf1, tf2, request, result):
+        return collide(self.o1, tf1, self.o2, tf2, request, result)
+
+
+class ComputeDistance:  # distance.h:74-112
+    def __init__(self, o1, o2):
+        self.o1, self.o2 = o1, o2
+
+    def __call__(self, tf1, tf2, request, result):
+        return distance(self.o1, tf1, self.o2, tf2, request, result)

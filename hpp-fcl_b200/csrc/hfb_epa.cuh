@@ -1,0 +1,418 @@
+// EPA for one shape pair on an index-based polytope that lives in a per-pair
+// workspace (shared memory for the lane-group kernels).
+//
+// Replaces GJK::encloseOrigin (src/narrowphase/gjk.cpp:437-492) and
+// EPA::{reset,newFace,findClosestFace,evaluate,expand,getWitnessPointsAndNormal}
+// (:1012-1466).
+//
+// Design differences from the reference (same arithmetic and same outcomes):
+//  * faces are slots addressed by u8 ids, not a std::vector of pointer-linked
+//    nodes (gjk.h:261-308).  The reference's `hull` list is newest-first and
+//    findClosestFace keeps the first strict minimum, so "list order" is carried
+//    by a per-face append sequence number: the closest face is the argmin of d^2
+//    with ties broken towards the LARGEST sequence number.  That makes the scan a
+//    lane-parallel reduction.
+//  * `stock` is a LIFO of free slots (slot identity has no numerical meaning;
+//    only the count matters for OutOfFaces).
+//  * the recursive expand (:1361-1449) and encloseOrigin run on explicit stacks.
+#pragma once
+#include "hfb_gjk.cuh"
+
+namespace hfb {
+
+#define HFB_EPA_CAP_IT 64
+#define HFB_EPA_MAXV (HFB_EPA_CAP_IT + 4)
+#define HFB_EPA_MAXF (2 * HFB_EPA_CAP_IT + 4)
+#define HFB_EPA_NONE 0xff
+
+struct EpaWs {
+  double vw0[HFB_EPA_MAXV * 3];
+  double vw1[HFB_EPA_MAXV * 3];
+  double fn[HFB_EPA_MAXF * 3];
+  double fd[HFB_EPA_MAXF];
+  uint16_t fseq[HFB_EPA_MAXF];
+  uint8_t fvid[HFB_EPA_MAXF * 3];
+  uint8_t fadj[HFB_EPA_MAXF * 3];
+  uint8_t fedge[HFB_EPA_MAXF * 3];
+  uint8_t fpass[HFB_EPA_MAXF];
+  uint8_t fflag[HFB_EPA_MAXF];  // bit0: in hull, bit1: ignore
+  uint8_t stock[HFB_EPA_MAXF];
+  uint8_t stk_f[HFB_EPA_MAXF + 4];
+  uint8_t stk_s[HFB_EPA_MAXF + 4];  // e | stage << 2
+};
+
+struct EpaParams {
+  double tolerance;
+  unsigned max_iterations;
+};
+
+struct EpaState {
+  int status;       // EPA::Status value
+  v3 normal;
+  double depth;
+  int rank;         // result.rank (3, or 1 on FallBack)
+  SV r0, r1, r2;    // result.vertex[0..2]
+  int hint0, hint1;
+  unsigned iterations;
+  // bookkeeping
+  int num_vertices, hull_count, stock_top, seq;
+  unsigned nfaces_cap, nverts_cap;
+};
+
+HFB_HD v3 ws_vw(const EpaWs* ws, int i) {
+  return mk(ws->vw0[3 * i] - ws->vw1[3 * i], ws->vw0[3 * i + 1] - ws->vw1[3 * i + 1],
+            ws->vw0[3 * i + 2] - ws->vw1[3 * i + 2]);
+}
+HFB_HD SV ws_sv(const EpaWs* ws, int i) {
+  SV s;
+  s.w0 = mk(ws->vw0[3 * i], ws->vw0[3 * i + 1], ws->vw0[3 * i + 2]);
+  s.w1 = mk(ws->vw1[3 * i], ws->vw1[3 * i + 1], ws->vw1[3 * i + 2]);
+  s.w = s.w0 - s.w1;
+  return s;
+}
+HFB_HD void ws_put_v(EpaWs* ws, int i, const SV& s) {
+  ws->vw0[3 * i] = s.w0.x;
+  ws->vw0[3 * i + 1] = s.w0.y;
+  ws->vw0[3 * i + 2] = s.w0.z;
+  ws->vw1[3 * i] = s.w1.x;
+  ws->vw1[3 * i + 1] = s.w1.y;
+  ws->vw1[3 * i + 2] = s.w1.z;
+}
+HFB_HD v3 ws_fn(const EpaWs* ws, int f) { return mk(ws->fn[3 * f], ws->fn[3 * f + 1], ws->fn[3 * f + 2]); }
+
+HFB_HD void epa_bind(EpaWs* ws, int fa, int ea, int fb, int eb) {  // gjk.h:312-320
+  ws->fedge[3 * fa + ea] = (uint8_t)eb;
+  ws->fadj[3 * fa + ea] = (uint8_t)fb;
+  ws->fedge[3 * fb + eb] = (uint8_t)ea;
+  ws->fadj[3 * fb + eb] = (uint8_t)fa;
+}
+HFB_HD void epa_hull_remove(EpaWs* ws, EpaState& E, int f) {  // hull.remove + stock.append
+  ws->fflag[f] = 0;
+  E.hull_count -= 1;
+  ws->stock[E.stock_top++] = (uint8_t)f;
+}
+
+// EPA::newFace (:1068-1138). returns slot id or HFB_EPA_NONE
+HFB_HD int epa_new_face(EpaWs* ws, EpaState& E, double tol, int ia, int ib, int ic, bool force) {
+  if (E.stock_top > 0) {
+    const int f = ws->stock[--E.stock_top];
+    E.hull_count += 1;
+    ws->fflag[f] = 1;
+    ws->fseq[f] = (uint16_t)(E.seq++);
+    ws->fpass[f] = 0;
+    ws->fvid[3 * f] = (uint8_t)ia;
+    ws->fvid[3 * f + 1] = (uint8_t)ib;
+    ws->fvid[3 * f + 2] = (uint8_t)ic;
+    const v3 a = ws_vw(ws, ia), b = ws_vw(ws, ib), c = ws_vw(ws, ic);
+    v3 n = cross(b - a, c - a);
+    if (nrm(n) > DBL_EPSILON) {
+      n = unit(n);
+      ws->fn[3 * f] = n.x;
+      ws->fn[3 * f + 1] = n.y;
+      ws->fn[3 * f + 2] = n.z;
+      const double a_dot_nab = dot(a, cross(b - a, n));
+      const double b_dot_nbc = dot(b, cross(c - b, n));
+      const double c_dot_nca = dot(c, cross(a - c, n));
+      double d;
+      if (a_dot_nab >= -tol && b_dot_nbc >= -tol && c_dot_nca >= -tol) {
+        d = dot(a, n);
+      } else {
+        d = DBL_MAX;
+        ws->fflag[f] = 3;  // in hull + ignore
+      }
+      ws->fd[f] = d;
+      if (d >= -tol || force) return f;
+      E.status = HFB_EPA_NON_CONVEX;
+    } else {
+      E.status = HFB_EPA_DEGENERATED;
+    }
+    epa_hull_remove(ws, E, f);
+    return HFB_EPA_NONE;
+  }
+  E.status = HFB_EPA_OUT_OF_FACES;
+  return HFB_EPA_NONE;
+}
+
+// EPA::findClosestFace (:1141-1154): argmin d^2 over non-ignored hull faces,
+// ties -> newest (largest seq); all ignored -> hull.root (newest face).
+template <int G>
+HFB_HD int epa_find_closest(const EpaWs* ws, const EpaState& E) {
+  double best = DBL_MAX;
+  int bseq = -1, bidx = HFB_EPA_NONE;
+  int rseq = -1, ridx = HFB_EPA_NONE;  // newest face in the hull
+  for (int f = Coop<G>::lane(); f < (int)E.nfaces_cap; f += G) {
+    const int fl = ws->fflag[f];
+    if (!(fl & 1)) continue;
+    const int sq = ws->fseq[f];
+    if (sq > rseq) {
+      rseq = sq;
+      ridx = f;
+    }
+    if (fl & 2) continue;
+    const double sqd = ws->fd[f] * ws->fd[f];
+    if (sqd < best || (sqd == best && sq > bseq && bidx != HFB_EPA_NONE)) {
+      best = sqd;
+      bseq = sq;
+      bidx = f;
+    }
+  }
+#if defined(__CUDA_ARCH__)
+  if (G > 1) {
+    const unsigned m = Coop<G>::mask();
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+      const double ob = __shfl_xor_sync(m, best, off);
+      const int os = __shfl_xor_sync(m, bseq, off);
+      const int oi = __shfl_xor_sync(m, bidx, off);
+      const int ors = __shfl_xor_sync(m, rseq, off);
+      const int ori = __shfl_xor_sync(m, ridx, off);
+      // candidate validity first (a lane with no candidate has bidx == NONE)
+      const bool mine = bidx != HFB_EPA_NONE, theirs = oi != HFB_EPA_NONE;
+      if (theirs && (!mine || ob < best || (ob == best && os > bseq))) {
+        best = ob;
+        bseq = os;
+        bidx = oi;
+      }
+      if (ors > rseq) {
+        rseq = ors;
+        ridx = ori;
+      }
+    }
+  }
+#endif
+  return bidx != HFB_EPA_NONE ? bidx : ridx;
+}
+
+// EPA::expand (:1361-1449), iterative.  Returns `valid`.
+HFB_HD bool epa_expand(EpaWs* ws, EpaState& E, double tol, int pass, v3 ww, int id_w, int f0, int e0,
+                       int& hz_first, int& hz_cur, int& hz_num) {
+  const double dummy_precision = 3 * sqrt(DBL_EPSILON);
+  int sp = 0;
+  ws->stk_f[0] = (uint8_t)f0;
+  ws->stk_s[0] = (uint8_t)e0;
+  bool ret = false;
+  while (sp >= 0) {
+    const int f = ws->stk_f[sp];
+    const int e = ws->stk_s[sp] & 3;
+    const int stage = ws->stk_s[sp] >> 2;
+    const int e1 = e == 2 ? 0 : e + 1;
+    const int e2 = e == 0 ? 2 : e - 1;
+    if (stage == 0) {
+      if (ws->fpass[f] == pass) {
+        E.status = HFB_EPA_INVALID_HULL;
+        return false;
+      }
+      const v3 vf = ws_vw(ws, ws->fvid[3 * f + e]);
+      if (dot(ws_fn(ws, f), ww - vf) < dummy_precision) {
+        // case 1: support point "below" f -> new face on edge e of f
+        const int nf = epa_new_face(ws, E, tol, ws->fvid[3 * f + e1], ws->fvid[3 * f + e], id_w, false);
+        if (nf == HFB_EPA_NONE) return false;
+        epa_bind(ws, nf, 0, f, e);
+        if (hz_cur != HFB_EPA_NONE) epa_bind(ws, nf, 2, hz_cur, 1);
+        else hz_first = nf;
+        hz_cur = nf;
+        ++hz_num;
+        ret = true;
+        --sp;
+        continue;
+      }
+      // case 2: "above" f -> recurse on the two other edges
+      ws->fpass[f] = (uint8_t)pass;
+      ws->stk_s[sp] = (uint8_t)(e | (1 << 2));
+      ++sp;
+      ws->stk_f[sp] = ws->fadj[3 * f + e1];
+      ws->stk_s[sp] = ws->fedge[3 * f + e1];
+      continue;
+    }
+    if (!ret) return false;  // a failed sub-expand fails every caller (&& short-circuit)
+    if (stage == 1) {
+      ws->stk_s[sp] = (uint8_t)(e | (2 << 2));
+      ++sp;
+      ws->stk_f[sp] = ws->fadj[3 * f + e2];
+      ws->stk_s[sp] = ws->fedge[3 * f + e2];
+      continue;
+    }
+    // stage 2: both sub-expands succeeded
+    epa_hull_remove(ws, E, f);
+    ret = true;
+    --sp;
+  }
+  return ret;
+}
+
+// GJK::encloseOrigin (:437-492), iterative depth-first search.
+template <int G, int CAPS>
+HFB_HD bool gjk_enclose_origin(const ShapeD& sa, const ShapeD& sb, const MinkD& md, GjkState& g) {
+  const int base = g.rank;
+  int cnt1 = 0, cnt2 = 0, cnt3 = 0;
+  int h0 = 0, h1 = 0;  // fresh zero hint per call in the reference; unused by the exhaustive argmax
+  for (;;) {
+    const int r = g.rank;
+    if (r == 4) {
+      if (fabs(triple(g.s0.w - g.s3.w, g.s1.w - g.s3.w, g.s2.w - g.s3.w)) > 0) return true;
+      if (base == 4) return false;
+      g.rank = 3;  // removeVertex, back in the rank-3 frame
+      continue;
+    }
+    const int c = r == 1 ? cnt1 : (r == 2 ? cnt2 : cnt3);
+    const int ncand = r == 3 ? 2 : 6;
+    if (c >= ncand) {
+      if (r == base) return false;
+      if (r == 2) cnt2 = 0; else if (r == 3) cnt3 = 0;
+      g.rank = r - 1;  // removeVertex in the parent frame
+      continue;
+    }
+    if (r == 1) cnt1 = c + 1; else if (r == 2) cnt2 = c + 1; else cnt3 = c + 1;
+    v3 dir;
+    if (r == 1) {
+      // both tries of axis i query +e_i (axis[i] = -1; appendVertex(-axis), :447-448)
+      const int i = c >> 1;
+      if (c & 1) dir = -mk(i == 0 ? -1.0 : 0.0, i == 1 ? -1.0 : 0.0, i == 2 ? -1.0 : 0.0);
+      else dir = mk(i == 0 ? 1.0 : 0.0, i == 1 ? 1.0 : 0.0, i == 2 ? 1.0 : 0.0);
+    } else if (r == 2) {
+      const int i = c >> 1;
+      const v3 d = g.s1.w - g.s0.w;
+      const v3 axis = mk(i == 0 ? 1.0 : 0.0, i == 1 ? 1.0 : 0.0, i == 2 ? 1.0 : 0.0);
+      const v3 p = cross(d, axis);
+      if (is_zero(p, HFB_DUMMY_PRECISION)) continue;
+      dir = (c & 1) ? -p : p;
+    } else {
+      const v3 axis = cross(g.s1.w - g.s0.w, g.s2.w - g.s0.w);
+      if (is_zero(axis, HFB_DUMMY_PRECISION)) continue;
+      dir = (c & 1) ? -axis : axis;
+    }
+    const SV nv = gjk_support<G, CAPS>(sa, sb, md, dir, h0, h1);
+    put(g, r, nv);
+    g.rank = r + 1;
+  }
+}
+
+// EPA::evaluate (:1156-1316)
+template <int G, int CAPS>
+HFB_HD void epa_evaluate(const ShapeD& sa, const ShapeD& sb, const MinkD& md, const EpaParams& P,
+                         GjkState& g, EpaWs* ws, EpaState& E) {
+  const double tol = P.tolerance;
+  E.hint0 = g.hint0;
+  E.hint1 = g.hint1;
+  E.iterations = 0;
+  E.depth = 0;
+  E.normal = mk(0, 0, 0);
+  E.nverts_cap = P.max_iterations + 4;
+  E.nfaces_cap = 2 * P.max_iterations + 4;
+
+  const bool enclosed = gjk_enclose_origin<G, CAPS>(sa, sb, md, g);
+  if (g.rank > 1 && enclosed) {
+    // reset (:1014-1037): all faces in stock, first allocation = slot 0
+    E.hull_count = 0;
+    E.seq = 0;
+    E.stock_top = (int)E.nfaces_cap;
+    for (int k = 0; k < (int)E.nfaces_cap; ++k) {
+      ws->stock[k] = (uint8_t)(E.nfaces_cap - 1 - k);
+      ws->fflag[k] = 0;
+    }
+    E.status = HFB_EPA_VALID;
+    E.num_vertices = 0;
+    // outward orientation (:1178-1184)
+    if (dot(g.s0.w - g.s3.w, cross(g.s1.w - g.s3.w, g.s2.w - g.s3.w)) < 0) {
+      const SV tmp = g.s0;
+      g.s0 = g.s1;
+      g.s1 = tmp;
+    }
+    ws_put_v(ws, 0, g.s0);
+    ws_put_v(ws, 1, g.s1);
+    ws_put_v(ws, 2, g.s2);
+    ws_put_v(ws, 3, g.s3);
+    E.num_vertices = 4;
+    const int t0 = epa_new_face(ws, E, tol, 0, 1, 2, true);
+    const int t1 = epa_new_face(ws, E, tol, 1, 0, 3, true);
+    const int t2 = epa_new_face(ws, E, tol, 2, 1, 3, true);
+    const int t3 = epa_new_face(ws, E, tol, 0, 2, 3, true);
+    if (E.hull_count == 4) {
+      epa_bind(ws, t0, 0, t1, 0);
+      epa_bind(ws, t0, 1, t2, 0);
+      epa_bind(ws, t0, 2, t3, 0);
+      epa_bind(ws, t1, 1, t3, 2);
+      epa_bind(ws, t1, 2, t2, 1);
+      epa_bind(ws, t2, 2, t3, 1);
+
+      int closest = epa_find_closest<G>(ws, E);
+      // `outer` is a COPY of the last good closest face (:1208,1284)
+      v3 outer_n = ws_fn(ws, closest);
+      double outer_d = ws->fd[closest];
+      int ov0 = ws->fvid[3 * closest], ov1 = ws->fvid[3 * closest + 1], ov2 = ws->fvid[3 * closest + 2];
+
+      E.status = HFB_EPA_VALID;
+      unsigned it = 0;
+      int pass = 0;
+      for (; it < P.max_iterations; ++it) {
+        if (E.num_vertices >= (int)E.nverts_cap) {
+          E.status = HFB_EPA_OUT_OF_VERTICES;
+          break;
+        }
+        int hz_first = HFB_EPA_NONE, hz_cur = HFB_EPA_NONE, hz_num = 0;
+        const int id_w = E.num_vertices++;
+        ws->fpass[closest] = (uint8_t)(++pass);
+        const v3 cn = ws_fn(ws, closest);
+        const SV w = gjk_support<G, CAPS>(sa, sb, md, cn, E.hint0, E.hint1);
+        ws_put_v(ws, id_w, w);
+
+        const v3 vf1 = ws_vw(ws, ws->fvid[3 * closest]);
+        const v3 vf2 = ws_vw(ws, ws->fvid[3 * closest + 1]);
+        const v3 vf3 = ws_vw(ws, ws->fvid[3 * closest + 2]);
+        const double fdist = dot(cn, w.w - vf1);
+        const double wnorm = nrm(w.w);
+        if (fdist <= tol + tol * wnorm) {
+          E.status = HFB_EPA_ACCURACY_REACHED;
+          break;
+        }
+        if (nrm(w.w - vf1) <= tol + tol * wnorm || nrm(w.w - vf2) <= tol + tol * wnorm ||
+            nrm(w.w - vf3) <= tol + tol * wnorm) {
+          E.status = HFB_EPA_ACCURACY_REACHED;
+          break;
+        }
+        bool valid = true;
+        for (int j = 0; (j < 3) && valid; ++j)
+          valid = valid && epa_expand(ws, E, tol, pass, w.w, id_w, ws->fadj[3 * closest + j],
+                                      ws->fedge[3 * closest + j], hz_first, hz_cur, hz_num);
+        if (!valid || hz_num < 3) break;
+        epa_bind(ws, hz_first, 2, hz_cur, 1);
+        epa_hull_remove(ws, E, closest);
+        closest = epa_find_closest<G>(ws, E);
+        outer_n = ws_fn(ws, closest);
+        outer_d = ws->fd[closest];
+        ov0 = ws->fvid[3 * closest];
+        ov1 = ws->fvid[3 * closest + 1];
+        ov2 = ws->fvid[3 * closest + 2];
+      }
+      E.iterations = it;
+      if (!(it < P.max_iterations)) E.status = HFB_EPA_FAILED;
+      E.normal = outer_n;
+      E.depth = outer_d + (md.ssr0 + md.ssr1);
+      E.rank = 3;
+      E.r0 = ws_sv(ws, ov0);
+      E.r1 = ws_sv(ws, ov1);
+      E.r2 = ws_sv(ws, ov2);
+      return;
+    }
+  }
+  // FallBack (:1299-1315); the solver maps it to EPAFailedExtract... (narrowphase.h:574-582)
+  E.status = HFB_EPA_FALLBACK;
+  E.depth = 0;
+  E.rank = 1;
+  E.r0 = g.s0;
+}
+
+// EPA::getWitnessPointsAndNormal (:1451-1466)
+HFB_HD void epa_witness(const EpaState& E, const MinkD& md, v3& w0, v3& w1, v3& normal) {
+  SV dummy = E.r0;
+  closest_points(E.r0, E.r1, E.r2, dummy, E.rank, w0, w1);
+  if (nrm(w0 - w1) > HFB_DUMMY_PRECISION) {
+    if (E.depth >= 0) normal = unit(w0 - w1);
+    else normal = unit(w1 - w0);
+  } else {
+    normal = E.normal;
+  }
+  inflate(md, normal, w0, w1);
+}
+
+}  // namespace hfb

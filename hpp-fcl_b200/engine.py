@@ -1,0 +1,194 @@
+"""ctypes binding of the C-ABI (include/hppfcl_b200.h) -- the drop-in boundary.
+
+`Engine` owns one hfb_ctx (one CUDA device).  Everything that computes goes
+through libhppfcl_b200.so; there is no Python or CPU fallback: a missing library
+or a missing GPU raises EngineError.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _pod as P
+from .build import library_path
+
+_LIB = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+_ERR = {1: "invalid argument", 2: "no CUDA device", 3: "CUDA error", 4: "unsupported pair",
+        5: "out of memory"}
+
+
+def load_library(path=None):
+    """dlopen the in-tree extension. Works without a GPU (symbols only)."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    path = path or library_path()
+    if not os.path.exists(path):
+        raise EngineError("CUDA extension %s is not built (run __graft_entry__.build())" % path)
+    L = C.CDLL(path)
+    vp, sz, u32 = C.c_void_p, C.c_size_t, C.c_uint32
+    L.hfb_ctx_create.argtypes = [C.c_int, C.POINTER(vp)]
+    L.hfb_ctx_destroy.argtypes = [vp]
+    L.hfb_last_error.argtypes = [vp]
+    L.hfb_last_error.restype = C.c_char_p
+    L.hfb_version.restype = C.c_char_p
+    L.hfb_default_distance_request.argtypes = [vp]
+    L.hfb_default_collision_request.argtypes = [vp]
+    L.hfb_geom_register_shapes.argtypes = [vp, vp, sz, vp]
+    L.hfb_geom_register_convex.argtypes = [vp, vp, u32, vp]
+    L.hfb_geom_register_bvh_obbrss.argtypes = [vp, vp, u32, vp, u32, vp, u32, vp]
+    L.hfb_geom_commit.argtypes = [vp]
+    L.hfb_geom_device_arena.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
+    L.hfb_geom_num_shapes.argtypes = [vp]
+    L.hfb_geom_num_shapes.restype = sz
+    for name in ("hfb_batch_distance", "hfb_batch_collide"):
+        getattr(L, name).argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
+        getattr(L, name + "_device").argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.hfb_batch_convex_support.argtypes = [vp, sz, vp, vp, vp, vp]
+    L.hfb_batch_convex_support_device.argtypes = [vp, sz, vp, vp, vp, vp, vp]
+    L.hfb_get_stats.argtypes = [vp, vp]
+    if path == library_path():
+        _LIB = L
+    return L
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Engine:
+    """One device context + geometry arena (ctx_create / geom_register_* / batch_*)."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = C.c_void_p()
+        rc = self.L.hfb_ctx_create(int(device), C.byref(h))
+        if rc != 0:
+            raise EngineError("hfb_ctx_create(device=%d) failed: %s (no CPU fallback exists)"
+                              % (device, _ERR.get(rc, rc)))
+        self.h = h
+        self.device = device
+
+    # -- lifetime ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hfb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            msg = self.L.hfb_last_error(self.h)
+            raise EngineError("%s: %s" % (_ERR.get(rc, rc), msg.decode() if msg else ""))
+
+    # -- geometry ---------------------------------------------------------
+    def register_convex(self, points):
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        cid = C.c_uint32()
+        self._check(self.L.hfb_geom_register_convex(self.h, _ptr(pts), pts.shape[0], C.byref(cid)))
+        return cid.value
+
+    def register_shapes(self, shapes):
+        shapes = np.ascontiguousarray(shapes, dtype=P.shape_dtype)
+        handles = np.zeros(shapes.shape[0], dtype=np.uint32)
+        self._check(self.L.hfb_geom_register_shapes(self.h, _ptr(shapes), shapes.shape[0], _ptr(handles)))
+        return handles
+
+    def register_bvh_obbrss(self, nodes, vertices, triangles):
+        nodes = np.ascontiguousarray(nodes, dtype=P.bvh_node_dtype)
+        v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+        t = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
+        h = C.c_uint32()
+        self._check(self.L.hfb_geom_register_bvh_obbrss(self.h, _ptr(nodes), nodes.shape[0], _ptr(v),
+                                                        v.shape[0], _ptr(t), t.shape[0], C.byref(h)))
+        return h.value
+
+    def commit(self):
+        self._check(self.L.hfb_geom_commit(self.h))
+
+    def device_arena(self):
+        base = C.c_void_p()
+        n = C.c_size_t()
+        self._check(self.L.hfb_geom_device_arena(self.h, C.byref(base), C.byref(n)))
+        return base.value, n.value
+
+    # -- host-buffer queries (H2D + kernels + D2H inside the call) ----------
+    def _host_call(self, fn, out_dtype, h1, tf1, h2, tf2, req, want_guess, out=None):
+        h1 = np.ascontiguousarray(h1, dtype=np.uint32)
+        h2 = np.ascontiguousarray(h2, dtype=np.uint32)
+        tf1 = np.ascontiguousarray(tf1, dtype=P.transform_dtype)
+        tf2 = np.ascontiguousarray(tf2, dtype=P.transform_dtype)
+        n = h1.shape[0]
+        if not (h2.shape[0] == n and tf1.shape[0] == n and tf2.shape[0] == n):
+            raise ValueError("batch arrays must have equal length")
+        if out is None:
+            out = np.empty(n, dtype=out_dtype)
+        g = None
+        gg = gh = None
+        if want_guess:
+            gg = np.zeros((n, 3), dtype=np.float64)
+            gh = np.zeros((n, 2), dtype=np.int32)
+            g = P.GuessOut(_ptr(gg), _ptr(gh))
+        self._check(fn(self.h, n, _ptr(h1), _ptr(tf1), _ptr(h2), _ptr(tf2), C.byref(req), _ptr(out),
+                       C.byref(g) if g is not None else None))
+        if want_guess:
+            return out, gg, gh
+        return out
+
+    def batch_distance(self, h1, tf1, h2, tf2, req=None, want_guess=False, out=None):
+        req = req or P.DistanceRequestPOD()
+        return self._host_call(self.L.hfb_batch_distance, P.distance_result_dtype, h1, tf1, h2, tf2,
+                               req, want_guess, out)
+
+    def batch_collide(self, h1, tf1, h2, tf2, req=None, want_guess=False, out=None):
+        req = req or P.CollisionRequestPOD()
+        return self._host_call(self.L.hfb_batch_collide, P.contact_dtype, h1, tf1, h2, tf2, req,
+                               want_guess, out)
+
+    def batch_convex_support(self, convex_ids, dirs):
+        ids = np.ascontiguousarray(convex_ids, dtype=np.uint32)
+        d = np.ascontiguousarray(dirs, dtype=np.float64).reshape(-1, 3)
+        idx = np.zeros(ids.shape[0], dtype=np.int32)
+        sup = np.zeros((ids.shape[0], 3), dtype=np.float64)
+        self._check(self.L.hfb_batch_convex_support(self.h, ids.shape[0], _ptr(ids), _ptr(d), _ptr(idx),
+                                                    _ptr(sup)))
+        return idx, sup
+
+    # -- device-buffer queries (raw device pointers, async on `stream`) ------
+    def batch_distance_device(self, n, d_h1, d_tf1, d_h2, d_tf2, d_out, req=None, stream=0, d_guess=None):
+        req = req or P.DistanceRequestPOD()
+        self._check(self.L.hfb_batch_distance_device(self.h, n, _ptr(d_h1), _ptr(d_tf1), _ptr(d_h2),
+                                                     _ptr(d_tf2), C.byref(req), _ptr(d_out),
+                                                     C.byref(d_guess) if d_guess is not None else None,
+                                                     _ptr(stream)))
+
+    def batch_collide_device(self, n, d_h1, d_tf1, d_h2, d_tf2, d_out, req=None, stream=0, d_guess=None):
+        req = req or P.CollisionRequestPOD()
+        self._check(self.L.hfb_batch_collide_device(self.h, n, _ptr(d_h1), _ptr(d_tf1), _ptr(d_h2),
+                                                    _ptr(d_tf2), C.byref(req), _ptr(d_out),
+                                                    C.byref(d_guess) if d_guess is not None else None,
+                                                    _ptr(stream)))
+
+    def batch_convex_support_device(self, n, d_ids, d_dirs, d_idx, d_sup, stream=0):
+        self._check(self.L.hfb_batch_convex_support_device(self.h, n, _ptr(d_ids), _ptr(d_dirs),
+                                                           _ptr(d_idx), _ptr(d_sup), _ptr(stream)))
+
+    def stats(self):
+        s = P.Stats()
+        self._check(self.L.hfb_get_stats(self.h, C.byref(s)))
+        return {f[0]: getattr(s, f[0]) for f in P.Stats._fields_}

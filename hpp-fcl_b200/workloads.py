@@ -1,0 +1,133 @@
+"""Seeded synthetic workloads for the BASELINE.json configs.
+
+Pure numpy/scipy generators; they produce POD arrays (see _pod.py) that are fed
+identically to the CUDA engine, to the oracle and to the CPU emulation harness.
+Generators mirror the reference's test helpers:
+  generateRandomTransforms  test/utility.cpp:198-247
+  constructPolytopeFromEllipsoid / random hulls  test/utility.cpp:501-557
+"""
+import numpy as np
+
+from . import _pod as P
+
+
+def random_rotations(rng, n):
+    """Uniform unit quaternions -> rotation matrices (n,3,3) (math/transform.h:228-250)."""
+    u1, u2, u3 = rng.random(n), rng.random(n), rng.random(n)
+    m1, m2 = np.sqrt(1.0 - u1), np.sqrt(u1)
+    w, x = m1 * np.sin(2 * np.pi * u2), m1 * np.cos(2 * np.pi * u2)
+    y, z = m2 * np.sin(2 * np.pi * u3), m2 * np.cos(2 * np.pi * u3)
+    return quat_to_rot(w, x, y, z)
+
+
+def quat_to_rot(w, x, y, z):
+    w, x, y, z = [np.asarray(a, dtype=np.float64) for a in (w, x, y, z)]
+    R = np.empty(w.shape + (3, 3))
+    R[..., 0, 0] = 1 - 2 * (y * y + z * z)
+    R[..., 0, 1] = 2 * (x * y - z * w)
+    R[..., 0, 2] = 2 * (x * z + y * w)
+    R[..., 1, 0] = 2 * (x * y + z * w)
+    R[..., 1, 1] = 1 - 2 * (x * x + z * z)
+    R[..., 1, 2] = 2 * (y * z - x * w)
+    R[..., 2, 0] = 2 * (x * z - y * w)
+    R[..., 2, 1] = 2 * (y * z + x * w)
+    R[..., 2, 2] = 1 - 2 * (x * x + y * y)
+    return R
+
+
+def random_transforms(rng, n, lo, hi):
+    lo = np.asarray(lo, dtype=np.float64)
+    hi = np.asarray(hi, dtype=np.float64)
+    T = lo + (hi - lo) * rng.random((n, 3))
+    return P.make_transforms(random_rotations(rng, n), T)
+
+
+def identity_transforms(n, T=None):
+    R = np.broadcast_to(np.eye(3), (n, 3, 3))
+    return P.make_transforms(R, np.zeros((n, 3)) if T is None else T)
+
+
+def random_primitive_shapes(rng, n, types):
+    """n shape records with type drawn uniformly from `types`; sizes as in
+    test/normal_and_nearest_points.cpp:283-… (U[0.05,1] radii / half sides)."""
+    types = np.asarray(types, dtype=np.uint32)
+    t = types[rng.integers(0, len(types), n)]
+    p = 0.05 + 0.95 * rng.random((n, 3))
+    out = P.make_shapes(t, p)
+    # capsule/cylinder/cone: p[0] = radius, p[1] = halfLength in [0.075, 0.5]
+    lz = 0.15 + 0.85 * rng.random(n)
+    m = (t == P.GEOM_CAPSULE) | (t == P.GEOM_CYLINDER) | (t == P.GEOM_CONE)
+    out["p"][m, 1] = lz[m] / 2
+    out["p"][m, 2] = 0.0
+    ms = t == P.GEOM_SPHERE
+    out["p"][ms, 1:] = 0.0
+    return out
+
+
+def config2_mixed_primitives(n_pairs, seed=0xFC1 + 2, pool=65536,
+                             types=(P.GEOM_SPHERE, P.GEOM_CAPSULE, P.GEOM_BOX, P.GEOM_CYLINDER)):
+    """BASELINE config 2: mixed primitive pairs (sphere/capsule/box/cylinder), random poses;
+    relative translation U[-3,3]^2 x U[0,3] as test/accelerated_gjk.cpp:122."""
+    rng = np.random.default_rng(seed)
+    shapes = random_primitive_shapes(rng, pool, types)
+    h1 = rng.integers(0, pool, n_pairs).astype(np.uint32)
+    h2 = rng.integers(0, pool, n_pairs).astype(np.uint32)
+    tf1 = random_transforms(rng, n_pairs, (0, 0, 0), (0, 0, 0))
+    tf2 = random_transforms(rng, n_pairs, (-3, -3, 0), (3, 3, 3))
+    # move the whole scene so poses are not origin-centred
+    off = -5 + 10 * rng.random((n_pairs, 3))
+    tf1["T"] += off
+    tf2["T"] += off
+    return dict(shapes=shapes, h1=h1, tf1=tf1, h2=h2, tf2=tf2)
+
+
+def ellipsoid_hull(rng, nv=64, radii=None):
+    """nv points on a random ellipsoid (all are hull vertices) + triangulated hull faces."""
+    from scipy.spatial import ConvexHull
+    if radii is None:
+        radii = 0.05 + 0.95 * rng.random(3)
+    while True:
+        v = rng.normal(size=(nv, 3))
+        v /= np.linalg.norm(v, axis=1, keepdims=True)
+        pts = v * radii
+        hull = ConvexHull(pts)
+        if len(hull.vertices) == nv:
+            break
+    tris = hull.simplices.astype(np.uint32)
+    # orient faces outward (fillNeighbors only needs adjacency, convex.hxx:231-280)
+    c = pts.mean(axis=0)
+    a, b, cc = pts[tris[:, 0]], pts[tris[:, 1]], pts[tris[:, 2]]
+    flip = np.einsum("ij,ij->i", np.cross(b - a, cc - a), a - c) < 0
+    tris[flip] = tris[flip][:, [0, 2, 1]]
+    return pts, tris
+
+
+def config3_convex_pairs(n_pairs, seed=0xFC1 + 3, pool=1024, nv=64):
+    """BASELINE config 3: ConvexBase(nv) x ConvexBase(nv); ~half of the pairs overlap."""
+    rng = np.random.default_rng(seed)
+    hulls = [ellipsoid_hull(rng, nv) for _ in range(pool)]
+    h1 = rng.integers(0, pool, n_pairs).astype(np.uint32)
+    h2 = rng.integers(0, pool, n_pairs).astype(np.uint32)
+    tf1 = random_transforms(rng, n_pairs, (0, 0, 0), (0, 0, 0))
+    tf2 = random_transforms(rng, n_pairs, (-1.0, -1.0, -1.0), (1.0, 1.0, 1.0))
+    off = -5 + 10 * rng.random((n_pairs, 3))
+    tf1["T"] += off
+    tf2["T"] += off
+    return dict(hulls=hulls, h1=h1, tf1=tf1, h2=h2, tf2=tf2)
+
+
+def icosahedron_from_ellipsoid(radii):
+    """constructPolytopeFromEllipsoid (test/utility.cpp:486-557): 12 vertices, 20 faces.
+    toEllipsoid: point /= ||point||, then scaled per axis by the radii."""
+    phi = (1 + np.sqrt(5)) / 2
+    pts = np.array([
+        [-1, phi, 0], [1, phi, 0], [-1, -phi, 0], [1, -phi, 0],
+        [0, -1, phi], [0, 1, phi], [0, -1, -phi], [0, 1, -phi],
+        [phi, 0, -1], [phi, 0, 1], [-phi, 0, -1], [-phi, 0, 1]], dtype=np.float64)
+    pts /= np.linalg.norm(pts, axis=1, keepdims=True)
+    pts *= np.asarray(radii, dtype=np.float64)
+    tris = np.array([
+        [0, 11, 5], [0, 5, 1], [0, 1, 7], [0, 7, 10], [0, 10, 11], [1, 5, 9], [5, 11, 4],
+        [11, 10, 2], [10, 7, 6], [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8],
+        [3, 8, 9], [4, 9, 5], [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=np.uint32)
+    return pts, tris

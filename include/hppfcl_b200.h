@@ -1,0 +1,301 @@
+/*
+ * hppfcl_b200.h -- C-ABI of the B200-native batched narrow-phase engine.
+ *
+ * This is the drop-in boundary for the hot path of hpp-fcl
+ * (collide()/distance() -> ShapeShapeDistance -> GJKSolver::shapeDistance ->
+ * GJK::evaluate / EPA::evaluate, plus OBBRSS BVH traversal).  The reference has
+ * no FFI of its own; its de-facto operator interface is the function-pointer
+ * matrix and the two free functions:
+ *
+ *   CollisionFunc   include/hpp/fcl/collision_func_matrix.h:61-67
+ *   DistanceFunc    include/hpp/fcl/distance_func_matrix.h:59-65
+ *   collide(o1,tf1,o2,tf2,CollisionRequest,CollisionResult&)  include/hpp/fcl/collision.h:65-70
+ *   distance(o1,tf1,o2,tf2,DistanceRequest,DistanceResult&)   include/hpp/fcl/distance.h:60-65
+ *
+ * Every entry point below is the batched form of one of those calls: plain
+ * pointers and sizes, no C++ / torch types, int error codes (0 = ok), no
+ * exceptions across the boundary.  Geometry (the reference's caller-owned
+ * `const CollisionGeometry*`) is registered once into a device-resident arena
+ * and referred to by a 32-bit handle; per pair the caller passes two handles
+ * and two Transform3f-compatible poses.
+ *
+ * All floating point is IEEE binary64 (FCL_REAL = double,
+ * include/hpp/fcl/data_types.h:66-71).
+ */
+#ifndef HPPFCL_B200_H
+#define HPPFCL_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- node types: numeric values mirror hpp::fcl::NODE_TYPE
+ *      (include/hpp/fcl/collision_object.h:65-89) ------------------------- */
+enum {
+  HFB_BV_OBBRSS = 5,
+  HFB_GEOM_BOX = 9,
+  HFB_GEOM_SPHERE = 10,
+  HFB_GEOM_CAPSULE = 11,
+  HFB_GEOM_CONE = 12,
+  HFB_GEOM_CYLINDER = 13,
+  HFB_GEOM_CONVEX = 14,
+  HFB_GEOM_PLANE = 15,     /* not supported by the batch path (yet) */
+  HFB_GEOM_HALFSPACE = 16, /* not supported by the batch path (yet) */
+  HFB_GEOM_TRIANGLE = 17,
+  HFB_GEOM_ELLIPSOID = 19
+};
+
+/* ---- enums of include/hpp/fcl/data_types.h:85-98 ----------------------- */
+enum { HFB_GUESS_DEFAULT = 0, HFB_GUESS_CACHED = 1, HFB_GUESS_BOUNDING_VOLUME = 2 };
+enum { HFB_GJK_DEFAULT = 0, HFB_GJK_POLYAK = 1, HFB_GJK_NESTEROV = 2 };
+enum { HFB_CRIT_DEFAULT = 0, HFB_CRIT_DUALITY_GAP = 1, HFB_CRIT_HYBRID = 2 };
+enum { HFB_CRIT_RELATIVE = 0, HFB_CRIT_ABSOLUTE = 1 };
+
+/* ---- GJK::Status (include/hpp/fcl/narrowphase/gjk.h:95-102) ------------ */
+enum {
+  HFB_GJK_DID_NOT_RUN = 0,
+  HFB_GJK_FAILED = 1,
+  HFB_GJK_NO_COLLISION_EARLY_STOPPED = 2,
+  HFB_GJK_NO_COLLISION = 3,
+  HFB_GJK_COLLISION_WITH_PENETRATION = 4,
+  HFB_GJK_COLLISION = 5
+};
+/* ---- EPA::Status (gjk.h:330-341), stored as (value & 0xff) ------------- */
+enum {
+  HFB_EPA_DID_NOT_RUN = 0xff, /* -1 */
+  HFB_EPA_FAILED = 0,
+  HFB_EPA_VALID = 1,
+  HFB_EPA_ACCURACY_REACHED = 3,
+  HFB_EPA_DEGENERATED = 2,
+  HFB_EPA_NON_CONVEX = 4,
+  HFB_EPA_INVALID_HULL = 6,
+  HFB_EPA_OUT_OF_FACES = 8,
+  HFB_EPA_OUT_OF_VERTICES = 10,
+  HFB_EPA_FALLBACK = 12
+};
+
+/* status word layout of hfb_distance_result.status / hfb_contact.status */
+#define HFB_STATUS_GJK(s) ((s) & 0xffu)
+#define HFB_STATUS_EPA(s) (((s) >> 8) & 0xffu)
+#define HFB_STATUS_PATH(s) (((s) >> 16) & 0xffu)
+enum { HFB_PATH_GJK = 0, HFB_PATH_CLOSED_FORM = 1, HFB_PATH_BVH = 2, HFB_PATH_UNSUPPORTED = 0xee };
+
+/* error codes */
+enum {
+  HFB_OK = 0,
+  HFB_ERR_INVALID_ARGUMENT = 1, /* std::invalid_argument in the reference */
+  HFB_ERR_NO_DEVICE = 2,        /* no CUDA device / extension unusable   */
+  HFB_ERR_CUDA = 3,
+  HFB_ERR_UNSUPPORTED_PAIR = 4, /* collision.cpp:110-117 "not yet supported" */
+  HFB_ERR_OUT_OF_MEMORY = 5
+};
+
+/* ---- Transform3f (include/hpp/fcl/math/transform.h:56-216): R then T.
+ *      R is COLUMN-major, exactly Eigen's Matrix3d storage, so a binding can
+ *      memcpy tf.getRotation().data() and tf.getTranslation().data(). 96 B. */
+typedef struct hfb_transform {
+  double R[9];
+  double T[3];
+} hfb_transform;
+
+/* ---- one shape record (40 B), the flattened ShapeBase subclass
+ *      (include/hpp/fcl/shape/geometric_shapes.h:164-634):
+ *        BOX        p = halfSide
+ *        SPHERE     p[0] = radius
+ *        CAPSULE    p[0] = radius, p[1] = halfLength
+ *        CONE       p[0] = radius, p[1] = halfLength
+ *        CYLINDER   p[0] = radius, p[1] = halfLength
+ *        ELLIPSOID  p = radii
+ *        CONVEX     data = convex id (see hfb_geom_register_convex)
+ *        TRIANGLE   data = convex id of a 3-point vertex set (a,b,c)
+ *      ssr = ShapeBase::getSweptSphereRadius()                             */
+typedef struct hfb_shape {
+  uint32_t type;
+  uint32_t data;
+  double p[3];
+  double ssr;
+} hfb_shape;
+
+/* ---- QueryRequest (include/hpp/fcl/collision_data.h:171-274) ----------- */
+typedef struct hfb_query_request {
+  int32_t gjk_initial_guess;              /* HFB_GUESS_*            default DEFAULT */
+  int32_t gjk_variant;                    /* HFB_GJK_*              default DEFAULT */
+  int32_t gjk_convergence_criterion;      /* HFB_CRIT_*             default DEFAULT */
+  int32_t gjk_convergence_criterion_type; /* HFB_CRIT_RELATIVE/ABS  default RELATIVE */
+  uint32_t gjk_max_iterations;            /* 128 */
+  uint32_t epa_max_iterations;            /* 64  */
+  double gjk_tolerance;                   /* 1e-6 */
+  double epa_tolerance;                   /* 1e-6 */
+  double collision_distance_threshold;    /* 1e-12 (Eigen dummy_precision) */
+  /* optional per-pair warm start (QueryRequest::cached_gjk_guess /
+   * cached_support_func_guess, collision_data.h:180-184); NULL => (1,0,0),(0,0).
+   * Host pointers for the host entry points, device pointers for *_device. */
+  const double* cached_gjk_guess;           /* n x 3 */
+  const int32_t* cached_support_func_guess; /* n x 2 */
+} hfb_query_request;
+
+/* ---- DistanceRequest (collision_data.h:987-1050) ----------------------- */
+typedef struct hfb_distance_request {
+  hfb_query_request q;
+  int32_t enable_signed_distance; /* default 1 */
+  int32_t _pad;
+  double rel_err; /* BVH traversal only */
+  double abs_err; /* BVH traversal only */
+} hfb_distance_request;
+
+/* ---- CollisionRequest (collision_data.h:312-383) ----------------------- */
+typedef struct hfb_collision_request {
+  hfb_query_request q;
+  uint32_t num_max_contacts; /* default 1 (the batch path returns <= 1 per pair) */
+  int32_t enable_contact;    /* default 1 */
+  double security_margin;    /* default 0 */
+  double break_distance;     /* default 1e-3 */
+  double distance_upper_bound; /* default +DBL_MAX */
+} hfb_collision_request;
+
+/* ---- DistanceResult (collision_data.h:1053-1096) as a flat 104 B record:
+ *      min_distance, nearest_points[2], normal, b1, b2 (+ status, iterations,
+ *      and the warm-start outputs QueryResult::cached_* when requested).   */
+typedef struct hfb_distance_result {
+  double min_distance;
+  double p1[3];
+  double p2[3];
+  double normal[3];
+  int32_t b1, b2;      /* -1 (NONE) for primitives, triangle id for meshes */
+  uint32_t status;     /* HFB_STATUS_* */
+  uint32_t iterations; /* gjk | epa << 16 */
+} hfb_distance_result;
+
+/* ---- one collide() outcome: CollisionResult with <= 1 Contact
+ *      (collision_data.h:59-166, 391-509).  distance = signed distance
+ *      (= Contact::penetration_depth), distance_lower_bound as the reference
+ *      sets it in updateDistanceLowerBoundFromLeaf (:1186-1197). 136 B.    */
+typedef struct hfb_contact {
+  double distance;
+  double p1[3];
+  double p2[3];
+  double normal[3];
+  double pos[3];
+  double distance_lower_bound;
+  int32_t b1, b2;
+  uint32_t status;
+  uint32_t num_contacts; /* 0 or 1: the collide() return value */
+  uint32_t iterations;
+  uint32_t _pad;
+} hfb_contact;
+
+/* optional warm-start outputs (QueryResult::cached_gjk_guess,
+ * cached_support_func_guess; collision.cpp:125-127) */
+typedef struct hfb_guess_out {
+  double* cached_gjk_guess;           /* n x 3 or NULL */
+  int32_t* cached_support_func_guess; /* n x 2 or NULL */
+} hfb_guess_out;
+
+typedef struct hfb_ctx hfb_ctx;
+
+/* ---- lifetime ---------------------------------------------------------- */
+/* Creates a context bound to CUDA device `device`. Fails with
+ * HFB_ERR_NO_DEVICE when there is no usable GPU: there is no CPU fallback. */
+int hfb_ctx_create(int device, hfb_ctx** out);
+void hfb_ctx_destroy(hfb_ctx* ctx);
+const char* hfb_last_error(const hfb_ctx* ctx);
+/* library self-description; callable without a GPU */
+const char* hfb_version(void);
+void hfb_default_distance_request(hfb_distance_request* r);
+void hfb_default_collision_request(hfb_collision_request* r);
+
+/* ---- geometry arena (replaces caller-owned `const CollisionGeometry*`) -- */
+/* Registers `n` primitive shape records; handles_out[i] is the handle of
+ * shapes[i]. CONVEX/TRIANGLE records must carry a convex id from
+ * hfb_geom_register_convex. */
+int hfb_geom_register_shapes(hfb_ctx* ctx, const hfb_shape* shapes, size_t n,
+                             uint32_t* handles_out);
+/* Registers the vertex set of a ConvexBase (geometric_shapes.h:638-872):
+ * `points` = num_points x 3 doubles. Returns the convex id in *convex_id. */
+int hfb_geom_register_convex(hfb_ctx* ctx, const double* points,
+                             uint32_t num_points, uint32_t* convex_id);
+/* Registers a BVHModel<OBBRSS> (include/hpp/fcl/BVH/BVH_model.h:315-496,
+ * BV/BV_node.h:52-148, BV/OBBRSS.h) built on the host: `nodes` = num_nodes
+ * records of hfb_bvh_node, vertices num_vertices x 3, triangles num_tris x 3. */
+typedef struct hfb_bvh_node {
+  int32_t first_child;      /* <0: leaf, primitive id = -(first_child+1) */
+  uint32_t first_primitive;
+  uint32_t num_primitives;
+  uint32_t _pad;
+  double obb_axes[9];   /* OBB::axes, column-major */
+  double obb_To[3];     /* OBB::To     */
+  double obb_extent[3]; /* OBB::extent */
+  double rss_axes[9];   /* RSS::axes, column-major */
+  double rss_Tr[3];     /* RSS::Tr     */
+  double rss_length[2]; /* RSS::length */
+  double rss_radius;    /* RSS::radius */
+} hfb_bvh_node;
+int hfb_geom_register_bvh_obbrss(hfb_ctx* ctx, const hfb_bvh_node* nodes,
+                                 uint32_t num_nodes, const double* vertices,
+                                 uint32_t num_vertices, const uint32_t* triangles,
+                                 uint32_t num_triangles, uint32_t* handle_out);
+/* Uploads everything registered so far to the device. Must be called before
+ * the first query and after any further registration. */
+int hfb_geom_commit(hfb_ctx* ctx);
+/* Device pointers of the committed arena (for NCCL broadcast by the host
+ * layer): shape table, point pool, convex descriptors. */
+int hfb_geom_device_arena(hfb_ctx* ctx, void** base, size_t* bytes);
+size_t hfb_geom_num_shapes(const hfb_ctx* ctx);
+
+/* ---- batched distance(): n independent (o1,tf1,o2,tf2) queries --------- */
+/* HOST buffers in/out; blocking.  Mirrors distance() of src/distance.cpp:60-109
+ * applied to each pair with a fresh DistanceResult. */
+int hfb_batch_distance(hfb_ctx* ctx, size_t n, const uint32_t* h1,
+                       const hfb_transform* tf1, const uint32_t* h2,
+                       const hfb_transform* tf2, const hfb_distance_request* req,
+                       hfb_distance_result* out, const hfb_guess_out* guess_out);
+/* DEVICE buffers in/out; asynchronous on `cuda_stream` (a cudaStream_t). */
+int hfb_batch_distance_device(hfb_ctx* ctx, size_t n, const uint32_t* d_h1,
+                              const hfb_transform* d_tf1, const uint32_t* d_h2,
+                              const hfb_transform* d_tf2,
+                              const hfb_distance_request* req,
+                              hfb_distance_result* d_out,
+                              const hfb_guess_out* d_guess_out, void* cuda_stream);
+
+/* ---- batched collide(): mirrors collide() of src/collision.cpp:69-130 --- */
+int hfb_batch_collide(hfb_ctx* ctx, size_t n, const uint32_t* h1,
+                      const hfb_transform* tf1, const uint32_t* h2,
+                      const hfb_transform* tf2, const hfb_collision_request* req,
+                      hfb_contact* out, const hfb_guess_out* guess_out);
+int hfb_batch_collide_device(hfb_ctx* ctx, size_t n, const uint32_t* d_h1,
+                             const hfb_transform* d_tf1, const uint32_t* d_h2,
+                             const hfb_transform* d_tf2,
+                             const hfb_collision_request* req, hfb_contact* d_out,
+                             const hfb_guess_out* d_guess_out, void* cuda_stream);
+
+/* ---- batched ConvexBase support function (the convex-support kernel):
+ *      for each query i: argmax_v <dir_i, v> over the vertices of convex
+ *      convex_ids[i]  (getShapeSupportLinear, support_functions.cpp:401-421;
+ *      strict '>' => lowest index on ties).  index_out[i] = vertex index,
+ *      support_out[i] = the vertex. */
+int hfb_batch_convex_support(hfb_ctx* ctx, size_t n, const uint32_t* convex_ids,
+                             const double* dirs, int32_t* index_out,
+                             double* support_out);
+int hfb_batch_convex_support_device(hfb_ctx* ctx, size_t n,
+                                    const uint32_t* d_convex_ids,
+                                    const double* d_dirs, int32_t* d_index_out,
+                                    double* d_support_out, void* cuda_stream);
+
+/* ---- counters (mirror enable_statistics num_bv_tests / num_leaf_tests,
+ *      traversal_node_bvh_shape.h:91-93) and launch accounting ------------ */
+typedef struct hfb_stats {
+  uint64_t kernel_launches; /* kernels launched by this ctx since creation */
+  uint64_t pairs_processed;
+  uint64_t epa_pairs;       /* pairs that went through the EPA kernel */
+  uint64_t bv_tests;
+  uint64_t leaf_tests;
+} hfb_stats;
+int hfb_get_stats(hfb_ctx* ctx, hfb_stats* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPPFCL_B200_H */

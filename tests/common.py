@@ -1,0 +1,175 @@
+"""Shared test helpers: the same geometry registered in the oracle (CPU
+restatement of the reference), the CPU emulation of the device code (tests/emu)
+and -- on a GPU box -- the CUDA engine; plus the parity comparison."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import hppfcl_b200 as hf  # noqa: E402
+from hppfcl_b200 import _pod as P  # noqa: E402
+from oracle import oracle_lib  # noqa: E402
+
+EMU_DIR = os.path.join(ROOT, "tests", "emu")
+_EMU = None
+
+
+def emu_lib():
+    global _EMU
+    if _EMU is None:
+        so = os.path.join(EMU_DIR, "libemu.so")
+        src = os.path.join(EMU_DIR, "emu.cpp")
+        csrc = os.path.join(ROOT, "hpp-fcl_b200", "csrc")
+        deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off",
+                                   "-march=x86-64-v2", "-Wno-unknown-pragmas", "-shared", "-o", so, src])
+        L = C.CDLL(so)
+        L.emu_create.restype = C.c_void_p
+        L.emu_destroy.argtypes = [C.c_void_p]
+        L.emu_register_convex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
+        L.emu_register_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.emu_register_shapes.restype = C.c_int64
+        for name in ("emu_batch_distance", "emu_batch_collide"):
+            getattr(L, name).argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 7
+        L.emu_batch_convex_support.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 4
+        _EMU = L
+    return _EMU
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class EmuScene:
+    def __init__(self):
+        self.L = emu_lib()
+        self.h = C.c_void_p(self.L.emu_create())
+
+    def __del__(self):
+        try:
+            self.L.emu_destroy(self.h)
+        except Exception:
+            pass
+
+    def register_convex(self, points):
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        return self.L.emu_register_convex(self.h, _ptr(pts), pts.shape[0])
+
+    def register_shapes(self, shapes):
+        shapes = np.ascontiguousarray(shapes, dtype=P.shape_dtype)
+        first = self.L.emu_register_shapes(self.h, _ptr(shapes), shapes.shape[0])
+        assert first >= 0
+        return np.arange(first, first + shapes.shape[0], dtype=np.uint32)
+
+    def commit(self):
+        pass
+
+    def _run(self, fn, dtype, h1, tf1, h2, tf2, req, want_guess):
+        h1 = np.ascontiguousarray(h1, dtype=np.uint32)
+        h2 = np.ascontiguousarray(h2, dtype=np.uint32)
+        tf1 = np.ascontiguousarray(tf1, dtype=P.transform_dtype)
+        tf2 = np.ascontiguousarray(tf2, dtype=P.transform_dtype)
+        n = h1.shape[0]
+        out = np.zeros(n, dtype=dtype)
+        g = gg = gh = None
+        if want_guess:
+            gg = np.zeros((n, 3))
+            gh = np.zeros((n, 2), dtype=np.int32)
+            g = P.GuessOut(_ptr(gg), _ptr(gh))
+        rc = fn(self.h, n, _ptr(h1), _ptr(tf1), _ptr(h2), _ptr(tf2), C.byref(req), _ptr(out),
+                C.byref(g) if g is not None else None)
+        if rc != 0:
+            raise ValueError("emu error %d" % rc)
+        return (out, gg, gh) if want_guess else out
+
+    def batch_distance(self, h1, tf1, h2, tf2, req=None, want_guess=False):
+        return self._run(self.L.emu_batch_distance, P.distance_result_dtype, h1, tf1, h2, tf2,
+                         req or P.DistanceRequestPOD(), want_guess)
+
+    def batch_collide(self, h1, tf1, h2, tf2, req=None, want_guess=False):
+        return self._run(self.L.emu_batch_collide, P.contact_dtype, h1, tf1, h2, tf2,
+                         req or P.CollisionRequestPOD(), want_guess)
+
+    def batch_convex_support(self, ids, dirs):
+        ids = np.ascontiguousarray(ids, dtype=np.uint32)
+        d = np.ascontiguousarray(dirs, dtype=np.float64).reshape(-1, 3)
+        idx = np.zeros(ids.shape[0], dtype=np.int32)
+        sup = np.zeros((ids.shape[0], 3))
+        rc = self.L.emu_batch_convex_support(self.h, ids.shape[0], _ptr(ids), _ptr(d), _ptr(idx), _ptr(sup))
+        assert rc == 0
+        return idx, sup
+
+
+class MultiScene:
+    """Registers identical geometry in every backend given."""
+
+    def __init__(self, backends):
+        self.b = backends  # dict name -> scene object
+
+    def register_convex(self, points, tris=None):
+        ids = set()
+        for name, s in self.b.items():
+            if name == "oracle":
+                ids.add(int(s.register_convex(points, tris)))
+            else:
+                ids.add(int(s.register_convex(points)))
+        assert len(ids) == 1
+        return ids.pop()
+
+    def register_shapes(self, shapes):
+        hs = [s.register_shapes(shapes) for s in self.b.values()]
+        for h in hs[1:]:
+            assert np.array_equal(h, hs[0])
+        return hs[0]
+
+    def commit(self):
+        for name, s in self.b.items():
+            if hasattr(s, "commit"):
+                s.commit()
+
+
+def make_scenes(gpu=False, emu=True):
+    b = {"oracle": oracle_lib.OracleScene(P)}
+    if emu:
+        b["emu"] = EmuScene()
+    if gpu:
+        b["gpu"] = hf.Engine(0)
+    return MultiScene(b)
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+def compare_distance(ref, got, rtol=1e-6, exact=True, what=""):
+    """north_star bar: status/flags/indices bit-exact; distances, points, normals within
+    1e-6 relative.  With exact=True additionally require bitwise-identical doubles
+    (oracle and device code execute the same IEEE operation sequence)."""
+    assert ref.shape == got.shape
+    assert np.array_equal(ref["status"], got["status"]), "%s: status words differ at %s" % (
+        what, np.nonzero(ref["status"] != got["status"])[0][:10])
+    assert np.array_equal(ref["iterations"], got["iterations"]), "%s: iteration counts differ" % what
+    assert np.array_equal(ref["b1"], got["b1"]) and np.array_equal(ref["b2"], got["b2"])
+    dname = "min_distance" if "min_distance" in ref.dtype.names else "distance"
+    for f in (dname, "p1", "p2", "normal") + (("pos", "distance_lower_bound") if "pos" in ref.dtype.names else ()):
+        a, b = ref[f], got[f]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), "%s: NaN pattern differs in %s" % (what, f)
+        if exact:
+            bad = _bits(a) != _bits(b)
+            bad &= ~(np.isnan(a) & np.isnan(b))
+            bad &= ~((a == 0) & (b == 0))
+            assert not bad.any(), "%s: %s not bit-identical at rows %s (max abs diff %g)" % (
+                what, f, np.unique(np.nonzero(bad)[0])[:10], np.nanmax(np.abs(a - b)))
+        else:
+            m = ~np.isnan(a)
+            scale = np.maximum(1.0, np.abs(a[m]))
+            assert np.all(np.abs(a[m] - b[m]) <= rtol * scale), "%s: %s exceeds rtol" % (what, f)
+    if "num_contacts" in ref.dtype.names:
+        assert np.array_equal(ref["num_contacts"], got["num_contacts"]), "%s: collide flags differ" % what

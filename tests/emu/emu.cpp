@@ -1,0 +1,153 @@
+// TEST HARNESS ONLY -- not part of the product and never loaded by it.
+//
+// Compiles the per-pair DEVICE code of hpp-fcl_b200/csrc/*.cuh with g++ (G = 1
+// lane per pair, HFB_HD expands to `inline`) so that the exact arithmetic the
+// CUDA kernels execute can be checked against the oracle in the CPU-only
+// container (`-m "not gpu"` tests).  The product library has no such path: its
+// entry points fail with HFB_ERR_NO_DEVICE when there is no GPU.
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+
+#include "../../hpp-fcl_b200/csrc/hfb_arena.cuh"
+#include "../../hpp-fcl_b200/csrc/hfb_request.cuh"
+
+using namespace hfb;
+
+namespace {
+struct Emu {
+  HostArena arena;
+};
+constexpr int CAPS_ALL = CAP_PRIM | CAP_CONVEX | CAP_TRI;
+
+inline PairIn load_pair(const ArenaView& A, size_t i, const uint32_t* h1, const hfb_transform* tf1,
+                        const uint32_t* h2, const hfb_transform* tf2, const hfb_query_request& q) {
+  PairIn in;
+  in.s1 = load_shape<CAPS_ALL>(A, h1[i]);
+  in.s2 = load_shape<CAPS_ALL>(A, h2[i]);
+  in.tf1 = load_xf(tf1[i].R);
+  in.tf2 = load_xf(tf2[i].R);
+  in.cached_guess = mk(1, 0, 0);
+  in.hint0 = in.hint1 = 0;
+  if (q.gjk_initial_guess == HFB_GUESS_CACHED) {
+    if (q.cached_gjk_guess) in.cached_guess = mk(q.cached_gjk_guess[3 * i], q.cached_gjk_guess[3 * i + 1], q.cached_gjk_guess[3 * i + 2]);
+    if (q.cached_support_func_guess) {
+      in.hint0 = q.cached_support_func_guess[2 * i];
+      in.hint1 = q.cached_support_func_guess[2 * i + 1];
+    }
+  }
+  return in;
+}
+
+inline void run_pair(const PairIn& in, const SolverP& P, EpaWs* ws, PairOut& o) {
+  GjkState g;
+  std::memset(&g, 0, sizeof(g));
+  if (pair_phase1<1, CAPS_ALL>(in, P, o, g)) pair_phase2<1, CAPS_ALL>(in, P, g, ws, o);
+}
+
+inline void put_guess(const hfb_guess_out* go, size_t i, const PairOut& o) {
+  if (!go) return;
+  if (go->cached_gjk_guess) {
+    go->cached_gjk_guess[3 * i] = o.cached_guess.x;
+    go->cached_gjk_guess[3 * i + 1] = o.cached_guess.y;
+    go->cached_gjk_guess[3 * i + 2] = o.cached_guess.z;
+  }
+  if (go->cached_support_func_guess) {
+    go->cached_support_func_guess[2 * i] = o.hint0;
+    go->cached_support_func_guess[2 * i + 1] = o.hint1;
+  }
+}
+}  // namespace
+
+extern "C" {
+
+void* emu_create() { return new Emu(); }
+void emu_destroy(void* e) { delete static_cast<Emu*>(e); }
+
+int emu_register_convex(void* e, const double* pts, uint32_t n) {
+  return (int)static_cast<Emu*>(e)->arena.add_convex(pts, n);
+}
+int64_t emu_register_shapes(void* e, const hfb_shape* shapes, size_t n) {
+  Emu* E = static_cast<Emu*>(e);
+  int64_t first = (int64_t)E->arena.shapes.size();
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t h;
+    if (!E->arena.add_shape(shapes[i], &h)) return -1;
+  }
+  return first;
+}
+
+int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transform* tf1,
+                       const uint32_t* h2, const hfb_transform* tf2, const hfb_distance_request* req,
+                       hfb_distance_result* out, const hfb_guess_out* go) {
+  Emu* E = static_cast<Emu*>(e);
+  if (int rc = validate_query(req->q)) return rc;
+  const SolverP P = solver_from_distance_request(*req);
+  const ArenaView A = E->arena.view();
+  std::unique_ptr<EpaWs> ws(new EpaWs());
+  for (size_t i = 0; i < n; ++i) {
+    if (h1[i] >= A.nshapes || h2[i] >= A.nshapes) return HFB_ERR_INVALID_ARGUMENT;
+    const PairIn in = load_pair(A, i, h1, tf1, h2, tf2, req->q);
+    PairOut o;
+    run_pair(in, P, ws.get(), o);
+    write_distance(o, &out[i]);
+    put_guess(go, i, o);
+  }
+  return HFB_OK;
+}
+
+int emu_batch_collide(void* e, size_t n, const uint32_t* h1, const hfb_transform* tf1,
+                      const uint32_t* h2, const hfb_transform* tf2, const hfb_collision_request* req,
+                      hfb_contact* out, const hfb_guess_out* go) {
+  Emu* E = static_cast<Emu*>(e);
+  if (int rc = validate_query(req->q)) return rc;
+  const bool minus_inf = req->security_margin == -INFINITY;
+  if (!minus_inf && req->num_max_contacts == 0) return HFB_ERR_INVALID_ARGUMENT;
+  const SolverP P = solver_from_collision_request(*req);
+  CollideP C;
+  C.security_margin = req->security_margin;
+  C.collision_distance_threshold = req->q.collision_distance_threshold;
+  const ArenaView A = E->arena.view();
+  std::unique_ptr<EpaWs> ws(new EpaWs());
+  for (size_t i = 0; i < n; ++i) {
+    if (h1[i] >= A.nshapes || h2[i] >= A.nshapes) return HFB_ERR_INVALID_ARGUMENT;
+    PairOut o;
+    if (minus_inf) {  // collision.cpp:73-76: result.clear(); return
+      o.status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
+      o.iterations = 0;
+      write_contact(o, C, &out[i]);
+      out[i].status = 0;
+      continue;
+    }
+    const PairIn in = load_pair(A, i, h1, tf1, h2, tf2, req->q);
+    run_pair(in, P, ws.get(), o);
+    write_contact(o, C, &out[i]);
+    put_guess(go, i, o);
+  }
+  return HFB_OK;
+}
+
+int emu_batch_convex_support(void* e, size_t n, const uint32_t* ids, const double* dirs, int32_t* idx,
+                             double* sup) {
+  Emu* E = static_cast<Emu*>(e);
+  const ArenaView A = E->arena.view();
+  for (size_t i = 0; i < n; ++i) {
+    if (ids[i] >= A.ncvx) return HFB_ERR_INVALID_ARGUMENT;
+    ShapeD s;
+    const ConvexDesc& d = A.cvx[ids[i]];
+    s.type = HFB_GEOM_CONVEX;
+    s.cx = A.pool + d.off;
+    s.cy = s.cx + d.vpad;
+    s.cz = s.cy + d.vpad;
+    s.nv = (int)d.nv;
+    int hint = 0;
+    const v3 r = shape_support<1, CAP_CONVEX>(s, mk(dirs[3 * i], dirs[3 * i + 1], dirs[3 * i + 2]), hint);
+    idx[i] = hint;
+    sup[3 * i] = r.x;
+    sup[3 * i + 1] = r.y;
+    sup[3 * i + 2] = r.z;
+  }
+  return HFB_OK;
+}
+
+}  // extern "C"
