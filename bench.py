@@ -1,0 +1,301 @@
+#!/usr/bin/env python
+"""bench.py -- shape-pair distance queries/sec on a 1M-pair batch (BASELINE.json).
+
+  python bench.py --gpus N --steps K --warmup W            (our arm; torchrun for N>1)
+  python bench.py --impl reference --gpus N --steps K ...   (CPU reference arm)
+
+One "step" = one pass of the hot path (distance(): closed form / GJK / EPA + witness
+points) over one batch of synthetic pairs.  Workload at every N: BASELINE config 2,
+`--pairs` (default 1M) mixed primitive pairs PER GPU (weak scaling), distinct
+seeds per rank.  `value` = pairs/s with inputs resident in HBM; `e2e` = the same
+through the host C-ABI call (hfb_batch_distance) with pinned HOST buffers, H2D and
+D2H inside the timed region.  For N>1 geometry is broadcast once over NCCL and the
+per-rank result buffers are all-gathered inside the timed step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "shape_pair_distance_queries_per_sec"
+UNIT = "pairs/s"
+# algorithmic bytes per pair of the phase-1 kernel (DESIGN.md "roofline"):
+#   2 handles (8) + 2 poses (192) + 2 shape records (80) + 1 result record (96)
+BYTES_PER_PAIR = 8 + 192 + 80 + 96
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=1_000_000)
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3"])
+    ap.add_argument("--variant", type=int, default=0, help="0 DefaultGJK, 2 NesterovAcceleration")
+    ap.add_argument("--cpu-sample", type=int, default=400_000)
+    return ap.parse_args()
+
+
+def env_rank():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.stop_flag = threading.Event()
+        self.rows = []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True,
+                                     timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        self.stop_flag.set()
+        self.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 3 + k and r[3 + k] == "Active" for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+def make_workload(args, rank):
+    from hppfcl_b200 import workloads as W
+    if args.workload == "config2":
+        w = W.config2_mixed_primitives(args.pairs, seed=0xFC1 + 2 + 1000 * rank)
+        name = "config2: %d mixed primitive pairs (sphere/capsule/box/cylinder), GJK distance + witness points" % args.pairs
+    else:
+        w = W.config3_convex_pairs(args.pairs, seed=0xFC1 + 3 + 1000 * rank)
+        name = "config3: %d ConvexBase(64) x ConvexBase(64) pairs, distance + EPA" % args.pairs
+    return w, name
+
+
+def register(eng_or_orc, w, args, oracle=False):
+    from hppfcl_b200 import _pod as P
+    if args.workload == "config2":
+        return eng_or_orc.register_shapes(w["shapes"])
+    cids = []
+    for pts, tris in w["hulls"]:
+        cids.append(eng_or_orc.register_convex(pts, tris) if oracle else eng_or_orc.register_convex(pts))
+    return eng_or_orc.register_shapes(P.make_shapes([P.GEOM_CONVEX] * len(cids), np.zeros((len(cids), 3)), data=cids))
+
+
+def cpu_reference_rate(args, w, n_sample, threads=0):
+    """The reference's CPU path (oracle restatement: the reference itself needs Eigen+Boost and
+    cannot be built in this image) on a bounded sample of the same workload."""
+    from hppfcl_b200 import _pod as P
+    from oracle import oracle_lib
+    orc = oracle_lib.OracleScene(P)
+    hs = register(orc, w, args, oracle=True)
+    n = min(n_sample, len(w["h1"]))
+    h1, h2 = hs[w["h1"][:n] % len(hs)], hs[w["h2"][:n] % len(hs)]
+    req = P.DistanceRequestPOD(gjk_variant=args.variant)
+    cores = oracle_lib.lib().oracle_max_threads() if threads == 0 else threads
+    orc.batch_distance(h1[:20000], w["tf1"][:20000], h2[:20000], w["tf2"][:20000], req, nthreads=threads)
+    t0 = time.perf_counter()
+    orc.batch_distance(h1, w["tf1"][:n], h2, w["tf2"][:n], req, nthreads=threads)
+    dt = time.perf_counter() - t0
+    return n / dt, cores, n
+
+
+def run_reference(args):
+    rank, local, world = env_rank()
+    if rank != 0:
+        return
+    w, name = make_workload(args, 0)
+    rates = []
+    n = args.cpu_sample
+    cores = 1
+    for it in range(args.warmup + args.steps):
+        r, cores, n = cpu_reference_rate(args, w, args.cpu_sample)
+        if it >= args.warmup:
+            rates.append(r)
+    v = float(np.mean(rates))
+    # whole-job figure under weak scaling: the CPU box is one host regardless of N
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "impl": "reference", "config": {"workload": name, "sample_pairs_per_step": n},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "%d pairs of the same seeded workload per step, OpenMP static over pairs" % n},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import hppfcl_b200 as hf
+    from hppfcl_b200 import _pod as P
+
+    rank, local, world = env_rank()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    hf.build_extension()
+    w, name = make_workload(args, rank)
+    n = args.pairs
+
+    # ---- geometry: rank 0's arena is broadcast once over NCCL, every rank registers it ------
+    if world > 1 and args.workload == "config2":
+        g = torch.from_numpy(w["shapes"].view(np.uint8).copy()).cuda()
+        dist.broadcast(g, 0)
+        w["shapes"] = g.cpu().numpy().view(P.shape_dtype)
+    eng = hf.Engine(local)
+    hs = register(eng, w, args)
+    eng.commit()
+    h1 = hs[w["h1"] % len(hs)].astype(np.uint32)
+    h2 = hs[w["h2"] % len(hs)].astype(np.uint32)
+    req = P.DistanceRequestPOD(gjk_variant=args.variant)
+
+    def dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
+
+    d_h1, d_h2, d_tf1, d_tf2 = dev(h1), dev(h2), dev(w["tf1"]), dev(w["tf2"])
+    out_bytes = n * P.distance_result_dtype.itemsize
+    d_out = torch.empty(out_bytes, dtype=torch.uint8, device="cuda")
+    d_all = torch.empty(out_bytes * world, dtype=torch.uint8, device="cuda") if world > 1 else None
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        eng.batch_distance_device(n, d_h1.data_ptr(), d_tf1.data_ptr(), d_h2.data_ptr(), d_tf2.data_ptr(),
+                                  d_out.data_ptr(), req, stream=stream)
+        if world > 1:
+            dist.all_gather_into_tensor(d_all, d_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    st0 = eng.stats()
+    eng.set_profiling(True)
+    eng.kernel_times(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    kt = eng.kernel_times(reset=True)
+    eng.set_profiling(False)
+    st1 = eng.stats()
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * n * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host C-ABI call with pinned host buffers, H2D + D2H inside --------------------
+    def pinned(a):
+        t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
+        return t, t.numpy().view(a.dtype).reshape(a.shape)
+
+    keep = []
+    ph = []
+    for a in (h1, w["tf1"], h2, w["tf2"]):
+        t, v = pinned(a)
+        keep.append(t)
+        ph.append(v)
+    t_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
+    host_out = t_out.numpy().view(P.distance_result_dtype)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        eng.batch_distance(ph[0], ph[1], ph[2], ph[3], req, out=host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.batch_distance(ph[0], ph[1], ph[2], ph[3], req, out=host_out)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+    e2e_value = world * n * e2e_steps / dt
+    clocks = sampler.summary()
+    checksum = float(np.nansum(host_out["min_distance"][:: max(1, n // 4096)]))
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+        pairs_ms = kt["pairs_ms"] / max(1, kt["pairs_launches"])
+        achieved = BYTES_PER_PAIR * n / (pairs_ms * 1e-3) / 1e9 if pairs_ms > 0 else None
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": name, "pairs_per_gpu": n, "gjk_variant": args.variant,
+                       "l2": "inputs+outputs per step (%d MB) exceed the 126 MB L2; no explicit flush"
+                             % ((n * (BYTES_PER_PAIR - 80)) >> 20),
+                       "parallelism": "pairs sharded over %d rank(s); geometry broadcast once; results all-gathered per step" % world},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 200),
+                    "d2h_bytes_per_step": int(out_bytes), "steps": e2e_steps, "checksum": checksum},
+            "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "k_pairs<1,CAP_PRIM,0> (phase 1: closed form / GJK / witness)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "bytes_per_pair": BYTES_PER_PAIR, "kernel_ms": pairs_ms, "peak_source": peak_src},
+            "kernels": {"pairs_ms_per_step": kt["pairs_ms"] / args.steps, "epa_ms_per_step": kt["epa_ms"] / args.steps,
+                        "epa_pairs_per_step": (st1["epa_pairs"] - st0["epa_pairs"]) / max(1, args.steps)},
+        }
+        if world == 1:
+            v, cores, ns = cpu_reference_rate(args, w, args.cpu_sample)
+            v1, _, ns1 = cpu_reference_rate(args, w, min(args.cpu_sample, 100_000), threads=1)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "%d pairs of the same workload, oracle (CPU restatement of hpp-fcl), OpenMP over pairs" % ns,
+                                    "single_thread_value": v1}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -141,6 +141,11 @@ class Stats(C.Structure):
                 ("epa_pairs", C.c_uint64), ("bv_tests", C.c_uint64), ("leaf_tests", C.c_uint64)]
 
 
+class KernelTimes(C.Structure):
+    _fields_ = [("pairs_ms", C.c_double), ("epa_ms", C.c_double), ("other_ms", C.c_double),
+                ("pairs_launches", C.c_uint64), ("epa_launches", C.c_uint64), ("other_launches", C.c_uint64)]
+
+
 def status_gjk(s):
     return np.asarray(s) & 0xFF
 

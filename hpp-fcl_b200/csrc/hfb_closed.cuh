@@ -220,7 +220,7 @@ HFB_HD Wit capsule_capsule(const ShapeD& s1, const xf& tf1, const ShapeD& s2, co
     w1 = clamped_linear(p1, -c, a, d1);
     w2 = p2;
   } else {
-    const double denom = fmax(a * e - b * b, 0);
+    const double denom = fmax(a * e - b * b, 0.0);
     double s, t;
     if (denom > EPS) {
       const double num = b * f - c * e;

@@ -1,0 +1,846 @@
+// CUDA kernels (sm_100a) and the C-ABI of include/hppfcl_b200.h.
+//
+// Kernel inventory
+//   k_pairs<G,CAPS,MODE>   phase 1: one lane-group of G threads per shape pair:
+//                          closed form or GJK (+ witness extraction); pairs that
+//                          need EPA are compacted into a device queue.
+//   k_epa<G,CAPS,MODE>     phase 2: persistent kernel over the EPA queue, one warp
+//                          per pair, polytope in per-warp shared memory.
+//   k_classify             splits a batch into primitive-only pairs (thread per
+//                          pair) and pairs touching ConvexBase/TriangleP (warp per
+//                          pair) when the arena holds both.
+//   k_convex_support       batched ConvexBase support argmax (warp per query,
+//                          coalesced streaming of the vertex block: HBM-bound).
+// MODE 0 = distance() epilogue, MODE 1 = collide() epilogue.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "hfb_arena.cuh"
+#include "hfb_request.cuh"
+
+using namespace hfb;
+
+#define CAPS_ALL (CAP_PRIM | CAP_CONVEX | CAP_TRI)
+#ifndef HFB_GC
+#define HFB_GC 32  // lanes per pair for pairs touching ConvexBase / TriangleP
+#endif
+#ifndef HFB_GE
+#define HFB_GE 32  // lanes per pair in the EPA kernel
+#endif
+
+// ---------------------------------------------------------------- EPA queue --
+struct EpaItem {
+  uint32_t pair;
+  int32_t rank;
+  int32_t hint0, hint1;
+  uint32_t gjk_iterations;
+  uint32_t _pad;
+  double w0[12];
+  double w1[12];
+};
+
+struct BatchArgs {
+  ArenaView A;
+  const uint32_t* h1;
+  const hfb_transform* tf1;
+  const uint32_t* h2;
+  const hfb_transform* tf2;
+  const double* guess_in;     // n x 3 or null
+  const int32_t* hint_in;     // n x 2 or null
+  double* guess_out;          // n x 3 or null
+  int32_t* hint_out;          // n x 2 or null
+  void* out;                  // hfb_distance_result* or hfb_contact*
+  EpaItem* queue;
+  unsigned* queue_count;      // [0] = items pushed this batch, [1] = running total
+  const uint32_t* index_list; // optional indirection (class lists)
+  const unsigned* index_count;
+  SolverP P;
+  CollideP C;
+  unsigned n;
+};
+
+template <int CAPS>
+__device__ __forceinline__ PairIn load_pair_in(const BatchArgs& a, unsigned i) {
+  PairIn in;
+  in.s1 = load_shape<CAPS>(a.A, a.h1[i]);
+  in.s2 = load_shape<CAPS>(a.A, a.h2[i]);
+  in.tf1 = load_xf(a.tf1[i].R);
+  in.tf2 = load_xf(a.tf2[i].R);
+  in.cached_guess = mk(1, 0, 0);
+  in.hint0 = in.hint1 = 0;
+  if (a.P.initial_guess == HFB_GUESS_CACHED) {
+    if (a.guess_in) in.cached_guess = mk(a.guess_in[3 * i], a.guess_in[3 * i + 1], a.guess_in[3 * i + 2]);
+    if (a.hint_in) {
+      in.hint0 = a.hint_in[2 * i];
+      in.hint1 = a.hint_in[2 * i + 1];
+    }
+  }
+  return in;
+}
+
+template <int MODE>
+__device__ __forceinline__ void store_result(const BatchArgs& a, unsigned i, const PairOut& o) {
+  if (MODE == 0) write_distance(o, reinterpret_cast<hfb_distance_result*>(a.out) + i);
+  else write_contact(o, a.C, reinterpret_cast<hfb_contact*>(a.out) + i);
+  if (a.guess_out) {
+    a.guess_out[3 * i] = o.cached_guess.x;
+    a.guess_out[3 * i + 1] = o.cached_guess.y;
+    a.guess_out[3 * i + 2] = o.cached_guess.z;
+  }
+  if (a.hint_out) {
+    a.hint_out[2 * i] = o.hint0;
+    a.hint_out[2 * i + 1] = o.hint1;
+  }
+}
+
+__device__ __forceinline__ void st3(double* p, v3 v) {
+  p[0] = v.x;
+  p[1] = v.y;
+  p[2] = v.z;
+}
+__device__ __forceinline__ v3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
+
+// ------------------------------------------------------------------ phase 1 --
+template <int G, int CAPS, int MODE>
+__global__ void __launch_bounds__(128) k_pairs(const BatchArgs a) {
+  const unsigned ngroups = (gridDim.x * blockDim.x) / G;
+  const unsigned gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const unsigned total = a.index_list ? *a.index_count : a.n;
+  for (unsigned k = gid; k < total; k += ngroups) {
+    const unsigned i = a.index_list ? a.index_list[k] : k;
+    const PairIn in = load_pair_in<CAPS>(a, i);
+    PairOut o;
+    GjkState g;
+    const bool need_epa = pair_phase1<G, CAPS>(in, a.P, o, g);
+    if (Coop<G>::lane() == 0) {
+      if (need_epa) {
+        const unsigned slot = atomicAdd(a.queue_count, 1u);
+        atomicAdd(a.queue_count + 1, 1u);
+        EpaItem* it = a.queue + slot;
+        it->pair = i;
+        it->rank = g.rank;
+        it->hint0 = g.hint0;
+        it->hint1 = g.hint1;
+        it->gjk_iterations = g.iterations;
+        st3(it->w0 + 0, g.s0.w0);
+        st3(it->w1 + 0, g.s0.w1);
+        st3(it->w0 + 3, g.s1.w0);
+        st3(it->w1 + 3, g.s1.w1);
+        st3(it->w0 + 6, g.s2.w0);
+        st3(it->w1 + 6, g.s2.w1);
+        st3(it->w0 + 9, g.s3.w0);
+        st3(it->w1 + 9, g.s3.w1);
+      } else {
+        store_result<MODE>(a, i, o);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------ phase 2 --
+template <int G, int CAPS, int MODE>
+__global__ void __launch_bounds__(128) k_epa(const BatchArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  const unsigned lg = threadIdx.x / G;  // group within block
+  EpaWs* ws = reinterpret_cast<EpaWs*>(smem) + lg;
+  const unsigned ngroups = (gridDim.x * blockDim.x) / G;
+  const unsigned gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
+  const unsigned total = *a.queue_count;
+  for (unsigned k = gid; k < total; k += ngroups) {
+    const EpaItem* it = a.queue + k;
+    const unsigned i = it->pair;
+    const PairIn in = load_pair_in<CAPS>(a, i);
+    GjkState g;
+    g.rank = it->rank;
+    g.hint0 = it->hint0;
+    g.hint1 = it->hint1;
+    g.iterations = it->gjk_iterations;
+    g.status = HFB_GJK_COLLISION;
+    g.distance = 0;
+    g.ray = mk(0, 0, 0);
+    g.s0.w0 = ld3(it->w0 + 0);
+    g.s0.w1 = ld3(it->w1 + 0);
+    g.s1.w0 = ld3(it->w0 + 3);
+    g.s1.w1 = ld3(it->w1 + 3);
+    g.s2.w0 = ld3(it->w0 + 6);
+    g.s2.w1 = ld3(it->w1 + 6);
+    g.s3.w0 = ld3(it->w0 + 9);
+    g.s3.w1 = ld3(it->w1 + 9);
+    g.s0.w = g.s0.w0 - g.s0.w1;
+    g.s1.w = g.s1.w0 - g.s1.w1;
+    g.s2.w = g.s2.w0 - g.s2.w1;
+    g.s3.w = g.s3.w0 - g.s3.w1;
+    PairOut o;
+    o.cached_guess = mk(1, 0, 0);
+    o.hint0 = o.hint1 = 0;
+    Coop<G>::sync();
+    pair_phase2<G, CAPS>(in, a.P, g, ws, o);
+    if (Coop<G>::lane() == 0) store_result<MODE>(a, i, o);
+    Coop<G>::sync();
+  }
+}
+
+// ---------------------------------------------------------------- classify ---
+// list 0: both shapes primitive; list 1: anything touching CONVEX / TRIANGLE
+__global__ void k_classify(const hfb_shape* shapes, const uint32_t* h1, const uint32_t* h2, unsigned n,
+                           uint32_t* list0, uint32_t* list1, unsigned* counts) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = i < n;
+  int cls = 0;
+  if (valid) {
+    const uint32_t t1 = shapes[h1[i]].type, t2 = shapes[h2[i]].type;
+    const bool c1 = t1 == HFB_GEOM_CONVEX || t1 == HFB_GEOM_TRIANGLE;
+    const bool c2 = t2 == HFB_GEOM_CONVEX || t2 == HFB_GEOM_TRIANGLE;
+    cls = (c1 || c2) ? 1 : 0;
+  }
+  // warp-aggregated append
+  const unsigned m0 = __ballot_sync(0xffffffffu, valid && cls == 0);
+  const unsigned m1 = __ballot_sync(0xffffffffu, valid && cls == 1);
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned b0 = 0, b1 = 0;
+  if (lane == 0) {
+    if (m0) b0 = atomicAdd(counts + 0, __popc(m0));
+    if (m1) b1 = atomicAdd(counts + 1, __popc(m1));
+  }
+  b0 = __shfl_sync(0xffffffffu, b0, 0);
+  b1 = __shfl_sync(0xffffffffu, b1, 0);
+  if (valid) {
+    const unsigned lt = (1u << lane) - 1u;
+    if (cls == 0) list0[b0 + __popc(m0 & lt)] = i;
+    else list1[b1 + __popc(m1 & lt)] = i;
+  }
+}
+
+// ----------------------------------------------------- convex support kernel --
+// One warp per query: streams the SoA vertex block (coalesced 256-B rows) and
+// reduces with shuffles.  Algorithmic traffic per query: 24*nv + 24 + 28 bytes.
+__global__ void __launch_bounds__(256) k_convex_support(const ConvexDesc* cvx, const double* pool,
+                                                        const uint32_t* ids, const double* dirs,
+                                                        int32_t* idx_out, double* sup_out, unsigned n) {
+  const unsigned warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const unsigned nwarps = (gridDim.x * blockDim.x) >> 5;
+  const unsigned lane = threadIdx.x & 31u;
+  for (unsigned q = warp; q < n; q += nwarps) {
+    const ConvexDesc d = cvx[ids[q]];
+    const double* x = pool + d.off;
+    const double* y = x + d.vpad;
+    const double* z = y + d.vpad;
+    const double dx = dirs[3 * q], dy = dirs[3 * q + 1], dz = dirs[3 * q + 2];
+    double best = -DBL_MAX;
+    int bi = 0x7fffffff;
+    bool first = true;
+    for (unsigned i = lane; i < d.nv; i += 32) {
+      const double v = (x[i] * dx + y[i] * dy) + z[i] * dz;
+      if (first || v > best) {
+        best = v;
+        bi = (int)i;
+        first = false;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+      if (ov > best || (ov == best && oi < bi)) {
+        best = ov;
+        bi = oi;
+      }
+    }
+    if (lane == 0) {
+      idx_out[q] = bi;
+      sup_out[3 * q] = x[bi];
+      sup_out[3 * q + 1] = y[bi];
+      sup_out[3 * q + 2] = z[bi];
+    }
+  }
+}
+
+// ===================================================================== host ===
+namespace {
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+constexpr int kSlots = 3;
+constexpr size_t kChunk = 1u << 17;  // pairs per pipelined chunk of the host entry points
+
+struct Slot {
+  cudaStream_t stream = nullptr;
+  DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists;
+};
+
+}  // namespace
+
+struct hfb_ctx {
+  int device = 0;
+  int num_sms = 0;
+  HostArena arena;
+  bool committed = false;
+  DevBuf d_arena;
+  ArenaView dview{};
+  Slot slots[kSlots];
+  Slot dev_slot;  // resources of the *_device entry points (caller's stream)
+  DevBuf sup_ids, sup_dirs, sup_idx, sup_out;
+  hfb_stats stats{};
+  bool profiling = false;
+  struct Ev { cudaEvent_t a, b; int kind; };
+  std::vector<Ev> events;
+  hfb_kernel_times ktimes{};
+  std::string err;
+  std::mutex mu;
+};
+
+namespace {
+
+int fail(hfb_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+int cuda_fail(hfb_ctx* c, cudaError_t e, const char* where) {
+  return fail(c, e == cudaErrorMemoryAllocation ? HFB_ERR_OUT_OF_MEMORY : HFB_ERR_CUDA,
+              std::string(where) + ": " + cudaGetErrorString(e));
+}
+#define CK(call)                                                       \
+  do {                                                                 \
+    cudaError_t _e = (call);                                           \
+    if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call);           \
+  } while (0)
+
+// kernel timing hooks: kind 0 = pairs, 1 = epa, 2 = other
+struct KTimer {
+  hfb_ctx* c;
+  cudaStream_t s;
+  hfb_ctx::Ev ev{};
+  bool on;
+  KTimer(hfb_ctx* c_, cudaStream_t s_, int kind) : c(c_), s(s_), on(c_->profiling) {
+    if (!on) return;
+    ev.kind = kind;
+    cudaEventCreate(&ev.a);
+    cudaEventCreate(&ev.b);
+    cudaEventRecord(ev.a, s);
+  }
+  ~KTimer() {
+    if (!on) return;
+    cudaEventRecord(ev.b, s);
+    c->events.push_back(ev);
+  }
+};
+
+template <int G, int CAPS, int MODE>
+int launch_pairs(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s) {
+  if (work == 0) return HFB_OK;
+  const int threads = 128;
+  const unsigned groups_per_block = threads / G;
+  unsigned blocks = (work + groups_per_block - 1) / groups_per_block;
+  const unsigned cap = (unsigned)ctx->num_sms * 32u;  // grid-stride beyond this
+  if (blocks > cap) blocks = cap;
+  {
+    KTimer kt(ctx, s, 0);
+    k_pairs<G, CAPS, MODE><<<blocks, threads, 0, s>>>(a);
+  }
+  ctx->stats.kernel_launches++;
+  CK(cudaGetLastError());
+  return HFB_OK;
+}
+
+template <int G, int CAPS, int MODE>
+int launch_epa(hfb_ctx* ctx, const BatchArgs& a, cudaStream_t s) {
+  const int threads = 128;
+  const size_t smem = (threads / G) * sizeof(EpaWs);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CK(cudaFuncSetAttribute(k_epa<G, CAPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  int per_sm = 0;
+  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epa<G, CAPS, MODE>, threads, smem));
+  if (per_sm < 1) per_sm = 1;
+  {
+    KTimer kt(ctx, s, 1);
+    k_epa<G, CAPS, MODE><<<ctx->num_sms * per_sm, threads, smem, s>>>(a);
+  }
+  ctx->stats.kernel_launches++;
+  CK(cudaGetLastError());
+  return HFB_OK;
+}
+
+// runs one (sub)batch whose inputs/outputs are already device-resident
+template <int MODE>
+int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
+  const unsigned n = a.n;
+  if (n == 0) return HFB_OK;
+  CK(sl.queue.reserve((size_t)n * sizeof(EpaItem)));
+  if (!sl.counters.p) {
+    CK(sl.counters.reserve(8 * sizeof(unsigned)));
+    CK(cudaMemsetAsync(sl.counters.p, 0, 8 * sizeof(unsigned), s));
+  }
+  a.queue = static_cast<EpaItem*>(sl.queue.p);
+  unsigned* cnt = static_cast<unsigned*>(sl.counters.p);
+  a.queue_count = cnt;  // [0] batch queue count, [1] running total, [2..3] class counts
+  a.A = ctx->dview;
+  a.index_list = nullptr;
+  a.index_count = nullptr;
+  CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned), s));
+  const bool mixed = ctx->arena.has_convex || ctx->arena.has_tri;
+  int rc;
+  if (!mixed) {
+    if ((rc = launch_pairs<1, CAP_PRIM, MODE>(ctx, a, n, s))) return rc;
+    if (a.P.compute_penetration)
+      if ((rc = launch_epa<HFB_GE, CAP_PRIM, MODE>(ctx, a, s))) return rc;
+  } else {
+    CK(sl.lists.reserve((size_t)2 * n * sizeof(uint32_t)));
+    uint32_t* l0 = static_cast<uint32_t*>(sl.lists.p);
+    uint32_t* l1 = l0 + n;
+    CK(cudaMemsetAsync(cnt + 2, 0, 2 * sizeof(unsigned), s));
+    {
+      KTimer kt(ctx, s, 2);
+      k_classify<<<(n + 255) / 256, 256, 0, s>>>(ctx->dview.shapes, a.h1, a.h2, n, l0, l1, cnt + 2);
+    }
+    ctx->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    BatchArgs a0 = a, a1 = a;
+    a0.index_list = l0;
+    a0.index_count = cnt + 2;
+    a1.index_list = l1;
+    a1.index_count = cnt + 3;
+    if ((rc = launch_pairs<1, CAP_PRIM, MODE>(ctx, a0, n, s))) return rc;
+    if ((rc = launch_pairs<HFB_GC, CAPS_ALL, MODE>(ctx, a1, n, s))) return rc;
+    if (a.P.compute_penetration)
+      if ((rc = launch_epa<HFB_GE, CAPS_ALL, MODE>(ctx, a, s))) return rc;
+  }
+  ctx->stats.pairs_processed += n;
+  return HFB_OK;
+}
+
+int check_ready(hfb_ctx* ctx) {
+  if (!ctx) return HFB_ERR_INVALID_ARGUMENT;
+  if (!ctx->committed) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "geometry not committed (hfb_geom_commit)");
+  return HFB_OK;
+}
+
+// host-side handle validation (the reference dereferences caller pointers; here a
+// bad handle is an invalid argument, never a device fault)
+int check_handles(hfb_ctx* ctx, const uint32_t* h, size_t n) {
+  const uint32_t ns = (uint32_t)ctx->arena.shapes.size();
+  for (size_t i = 0; i < n; ++i)
+    if (h[i] >= ns) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "shape handle out of range");
+  return HFB_OK;
+}
+
+template <int MODE, typename Req, typename OutT>
+int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
+               const hfb_transform* tf2, const Req* req, const SolverP& P, const CollideP& Cp, OutT* out,
+               const hfb_guess_out* go) {
+  int rc;
+  if ((rc = check_ready(ctx))) return rc;
+  if (n == 0) return HFB_OK;
+  if (!h1 || !h2 || !tf1 || !tf2 || !out) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "null buffer");
+  if ((rc = check_handles(ctx, h1, n)) || (rc = check_handles(ctx, h2, n))) return rc;
+  CK(cudaSetDevice(ctx->device));
+  const bool cached = req->q.gjk_initial_guess == HFB_GUESS_CACHED;
+  const double* gin = cached ? req->q.cached_gjk_guess : nullptr;
+  const int32_t* hin = cached ? req->q.cached_support_func_guess : nullptr;
+  size_t done = 0;
+  int si = 0;
+  while (done < n) {
+    const size_t m = (n - done < kChunk) ? (n - done) : kChunk;
+    Slot& sl = ctx->slots[si];
+    cudaStream_t s = sl.stream;
+    // the slot's previous chunk must have drained before its buffers are reused
+    CK(cudaStreamSynchronize(s));
+    CK(sl.h1.reserve(m * 4));
+    CK(sl.h2.reserve(m * 4));
+    CK(sl.tf1.reserve(m * sizeof(hfb_transform)));
+    CK(sl.tf2.reserve(m * sizeof(hfb_transform)));
+    CK(sl.out.reserve(m * sizeof(OutT)));
+    CK(cudaMemcpyAsync(sl.h1.p, h1 + done, m * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(sl.h2.p, h2 + done, m * 4, cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(sl.tf1.p, tf1 + done, m * sizeof(hfb_transform), cudaMemcpyHostToDevice, s));
+    CK(cudaMemcpyAsync(sl.tf2.p, tf2 + done, m * sizeof(hfb_transform), cudaMemcpyHostToDevice, s));
+    BatchArgs a{};
+    a.n = (unsigned)m;
+    a.h1 = static_cast<const uint32_t*>(sl.h1.p);
+    a.h2 = static_cast<const uint32_t*>(sl.h2.p);
+    a.tf1 = static_cast<const hfb_transform*>(sl.tf1.p);
+    a.tf2 = static_cast<const hfb_transform*>(sl.tf2.p);
+    a.out = sl.out.p;
+    a.P = P;
+    a.C = Cp;
+    if (gin) {
+      CK(sl.gin.reserve(m * 24));
+      CK(cudaMemcpyAsync(sl.gin.p, gin + 3 * done, m * 24, cudaMemcpyHostToDevice, s));
+      a.guess_in = static_cast<const double*>(sl.gin.p);
+    }
+    if (hin) {
+      CK(sl.hin.reserve(m * 8));
+      CK(cudaMemcpyAsync(sl.hin.p, hin + 2 * done, m * 8, cudaMemcpyHostToDevice, s));
+      a.hint_in = static_cast<const int32_t*>(sl.hin.p);
+    }
+    if (go && go->cached_gjk_guess) {
+      CK(sl.gout.reserve(m * 24));
+      a.guess_out = static_cast<double*>(sl.gout.p);
+    }
+    if (go && go->cached_support_func_guess) {
+      CK(sl.hout.reserve(m * 8));
+      a.hint_out = static_cast<int32_t*>(sl.hout.p);
+    }
+    if ((rc = run_device_batch<MODE>(ctx, sl, a, s))) return rc;
+    CK(cudaMemcpyAsync(out + done, sl.out.p, m * sizeof(OutT), cudaMemcpyDeviceToHost, s));
+    if (a.guess_out)
+      CK(cudaMemcpyAsync(go->cached_gjk_guess + 3 * done, a.guess_out, m * 24, cudaMemcpyDeviceToHost, s));
+    if (a.hint_out)
+      CK(cudaMemcpyAsync(go->cached_support_func_guess + 2 * done, a.hint_out, m * 8, cudaMemcpyDeviceToHost, s));
+    done += m;
+    si = (si + 1) % kSlots;
+  }
+  for (int k = 0; k < kSlots; ++k) CK(cudaStreamSynchronize(ctx->slots[k].stream));
+  return HFB_OK;
+}
+
+template <int MODE, typename Req>
+int device_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
+                 const hfb_transform* tf2, const Req* req, const SolverP& P, const CollideP& Cp, void* out,
+                 const hfb_guess_out* go, void* stream) {
+  int rc;
+  if ((rc = check_ready(ctx))) return rc;
+  if (n == 0) return HFB_OK;
+  if (n > 0xffffffffull) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "batch too large");
+  if (!h1 || !h2 || !tf1 || !tf2 || !out) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "null buffer");
+  CK(cudaSetDevice(ctx->device));
+  const bool cached = req->q.gjk_initial_guess == HFB_GUESS_CACHED;
+  BatchArgs a{};
+  a.n = (unsigned)n;
+  a.h1 = h1;
+  a.h2 = h2;
+  a.tf1 = tf1;
+  a.tf2 = tf2;
+  a.out = out;
+  a.P = P;
+  a.C = Cp;
+  a.guess_in = cached ? req->q.cached_gjk_guess : nullptr;
+  a.hint_in = cached ? req->q.cached_support_func_guess : nullptr;
+  a.guess_out = go ? go->cached_gjk_guess : nullptr;
+  a.hint_out = go ? go->cached_support_func_guess : nullptr;
+  return run_device_batch<MODE>(ctx, ctx->dev_slot, a, static_cast<cudaStream_t>(stream));
+}
+
+}  // namespace
+
+// ==================================================================== C-ABI ===
+extern "C" {
+
+const char* hfb_version(void) { return "hppfcl_b200 0.1 (sm_100a, fp64, fmad=false)"; }
+
+void hfb_default_distance_request(hfb_distance_request* r) {
+  std::memset(r, 0, sizeof(*r));
+  r->q.gjk_max_iterations = 128;
+  r->q.epa_max_iterations = 64;
+  r->q.gjk_tolerance = 1e-6;
+  r->q.epa_tolerance = 1e-6;
+  r->q.collision_distance_threshold = 1e-12;
+  r->enable_signed_distance = 1;
+}
+void hfb_default_collision_request(hfb_collision_request* r) {
+  std::memset(r, 0, sizeof(*r));
+  r->q.gjk_max_iterations = 128;
+  r->q.epa_max_iterations = 64;
+  r->q.gjk_tolerance = 1e-6;
+  r->q.epa_tolerance = 1e-6;
+  r->q.collision_distance_threshold = 1e-12;
+  r->num_max_contacts = 1;
+  r->enable_contact = 1;
+  r->security_margin = 0;
+  r->break_distance = 1e-3;
+  r->distance_upper_bound = DBL_MAX;
+}
+
+int hfb_ctx_create(int device, hfb_ctx** out) {
+  if (!out) return HFB_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count)
+    return HFB_ERR_NO_DEVICE;  // no CPU fallback by design
+  if (cudaSetDevice(device) != cudaSuccess) return HFB_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return HFB_ERR_NO_DEVICE;
+  hfb_ctx* c = new hfb_ctx();
+  c->device = device;
+  c->num_sms = prop.multiProcessorCount;
+  for (int k = 0; k < kSlots; ++k)
+    if (cudaStreamCreateWithFlags(&c->slots[k].stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete c;
+      return HFB_ERR_CUDA;
+    }
+  *out = c;
+  return HFB_OK;
+}
+
+void hfb_ctx_destroy(hfb_ctx* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  auto rel = [](Slot& s) {
+    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists};
+    for (DevBuf* b : bs) b->release();
+    if (s.stream) cudaStreamDestroy(s.stream);
+  };
+  for (int k = 0; k < kSlots; ++k) rel(c->slots[k]);
+  rel(c->dev_slot);
+  c->d_arena.release();
+  c->sup_ids.release();
+  c->sup_dirs.release();
+  c->sup_idx.release();
+  c->sup_out.release();
+  delete c;
+}
+
+const char* hfb_last_error(const hfb_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int hfb_geom_register_shapes(hfb_ctx* ctx, const hfb_shape* shapes, size_t n, uint32_t* handles_out) {
+  if (!ctx || (!shapes && n)) return HFB_ERR_INVALID_ARGUMENT;
+  for (size_t i = 0; i < n; ++i) {
+    uint32_t h;
+    if (!ctx->arena.add_shape(shapes[i], &h)) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "bad convex id in shape record");
+    if (handles_out) handles_out[i] = h;
+  }
+  ctx->committed = false;
+  return HFB_OK;
+}
+
+int hfb_geom_register_convex(hfb_ctx* ctx, const double* points, uint32_t num_points, uint32_t* convex_id) {
+  if (!ctx || !points || num_points == 0 || !convex_id) return HFB_ERR_INVALID_ARGUMENT;
+  *convex_id = ctx->arena.add_convex(points, num_points);
+  ctx->committed = false;
+  return HFB_OK;
+}
+
+int hfb_geom_register_bvh_obbrss(hfb_ctx* ctx, const hfb_bvh_node*, uint32_t, const double*, uint32_t,
+                                 const uint32_t*, uint32_t, uint32_t*) {
+  return fail(ctx, HFB_ERR_UNSUPPORTED_PAIR, "OBBRSS BVH traversal is not implemented in this build");
+}
+
+int hfb_geom_commit(hfb_ctx* ctx) {
+  if (!ctx) return HFB_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  const HostArena& A = ctx->arena;
+  auto up = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t bs = up(A.shapes.size() * sizeof(hfb_shape));
+  const size_t bc = up(A.cvx.size() * sizeof(ConvexDesc));
+  const size_t bp = up(A.pool.size() * sizeof(double));
+  CK(cudaDeviceSynchronize());
+  CK(ctx->d_arena.reserve(bs + bc + bp + 256));
+  unsigned char* base = static_cast<unsigned char*>(ctx->d_arena.p);
+  if (!A.shapes.empty()) CK(cudaMemcpy(base, A.shapes.data(), A.shapes.size() * sizeof(hfb_shape), cudaMemcpyHostToDevice));
+  if (!A.cvx.empty()) CK(cudaMemcpy(base + bs, A.cvx.data(), A.cvx.size() * sizeof(ConvexDesc), cudaMemcpyHostToDevice));
+  if (!A.pool.empty()) CK(cudaMemcpy(base + bs + bc, A.pool.data(), A.pool.size() * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->dview.shapes = reinterpret_cast<const hfb_shape*>(base);
+  ctx->dview.cvx = reinterpret_cast<const ConvexDesc*>(base + bs);
+  ctx->dview.pool = reinterpret_cast<const double*>(base + bs + bc);
+  ctx->dview.nshapes = (uint32_t)A.shapes.size();
+  ctx->dview.ncvx = (uint32_t)A.cvx.size();
+  ctx->committed = true;
+  return HFB_OK;
+}
+
+int hfb_geom_device_arena(hfb_ctx* ctx, void** base, size_t* bytes) {
+  int rc;
+  if ((rc = check_ready(ctx))) return rc;
+  if (base) *base = ctx->d_arena.p;
+  if (bytes) *bytes = ctx->d_arena.cap;
+  return HFB_OK;
+}
+
+size_t hfb_geom_num_shapes(const hfb_ctx* ctx) { return ctx ? ctx->arena.shapes.size() : 0; }
+
+int hfb_batch_distance(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1,
+                       const uint32_t* h2, const hfb_transform* tf2, const hfb_distance_request* req,
+                       hfb_distance_result* out, const hfb_guess_out* go) {
+  if (!ctx || !req) return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (int rc = validate_query(req->q)) return fail(ctx, rc, "invalid request");
+  return host_batch<0>(ctx, n, h1, tf1, h2, tf2, req, solver_from_distance_request(*req), CollideP{0, 0}, out, go);
+}
+
+int hfb_batch_distance_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1,
+                              const uint32_t* h2, const hfb_transform* tf2, const hfb_distance_request* req,
+                              hfb_distance_result* out, const hfb_guess_out* go, void* stream) {
+  if (!ctx || !req) return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (int rc = validate_query(req->q)) return fail(ctx, rc, "invalid request");
+  return device_batch<0>(ctx, n, h1, tf1, h2, tf2, req, solver_from_distance_request(*req), CollideP{0, 0}, out, go, stream);
+}
+
+static int collide_prelude(hfb_ctx* ctx, const hfb_collision_request* req, bool* minus_inf) {
+  if (int rc = validate_query(req->q)) return fail(ctx, rc, "invalid request");
+  *minus_inf = req->security_margin == -INFINITY;
+  if (!*minus_inf && req->num_max_contacts == 0)  // collision.cpp:82-85
+    return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "Invalid number of max contacts (current value is 0).");
+  return HFB_OK;
+}
+
+// collision.cpp:73-76: security_margin == -inf => result.clear(), no contact
+__global__ void k_clear_contacts(hfb_contact* out, unsigned n) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  PairOut o;
+  o.status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
+  o.iterations = 0;
+  CollideP C{0, 0};
+  write_contact(o, C, out + i);
+  out[i].status = 0;
+}
+
+int hfb_batch_collide(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1,
+                      const uint32_t* h2, const hfb_transform* tf2, const hfb_collision_request* req,
+                      hfb_contact* out, const hfb_guess_out* go) {
+  if (!ctx || !req) return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  bool minus_inf;
+  if (int rc = collide_prelude(ctx, req, &minus_inf)) return rc;
+  if (minus_inf) {
+    if (int rc = check_ready(ctx)) return rc;
+    if (n == 0) return HFB_OK;
+    Slot& sl = ctx->slots[0];
+    CK(sl.out.reserve(n * sizeof(hfb_contact)));
+    k_clear_contacts<<<(unsigned)((n + 255) / 256), 256, 0, sl.stream>>>(static_cast<hfb_contact*>(sl.out.p), (unsigned)n);
+    ctx->stats.kernel_launches++;
+    CK(cudaMemcpyAsync(out, sl.out.p, n * sizeof(hfb_contact), cudaMemcpyDeviceToHost, sl.stream));
+    CK(cudaStreamSynchronize(sl.stream));
+    return HFB_OK;
+  }
+  CollideP C{req->security_margin, req->q.collision_distance_threshold};
+  return host_batch<1>(ctx, n, h1, tf1, h2, tf2, req, solver_from_collision_request(*req), C, out, go);
+}
+
+int hfb_batch_collide_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1,
+                             const uint32_t* h2, const hfb_transform* tf2, const hfb_collision_request* req,
+                             hfb_contact* out, const hfb_guess_out* go, void* stream) {
+  if (!ctx || !req) return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  bool minus_inf;
+  if (int rc = collide_prelude(ctx, req, &minus_inf)) return rc;
+  if (minus_inf) {
+    if (int rc = check_ready(ctx)) return rc;
+    if (n == 0) return HFB_OK;
+    k_clear_contacts<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, (unsigned)n);
+    ctx->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    return HFB_OK;
+  }
+  CollideP C{req->security_margin, req->q.collision_distance_threshold};
+  return device_batch<1>(ctx, n, h1, tf1, h2, tf2, req, solver_from_collision_request(*req), C, out, go, stream);
+}
+
+int hfb_batch_convex_support_device(hfb_ctx* ctx, size_t n, const uint32_t* ids, const double* dirs,
+                                    int32_t* idx, double* sup, void* stream) {
+  int rc;
+  if ((rc = check_ready(ctx))) return rc;
+  if (n == 0) return HFB_OK;
+  CK(cudaSetDevice(ctx->device));
+  const int threads = 256;
+  unsigned blocks = (unsigned)((n + 7) / 8);
+  const unsigned cap = (unsigned)ctx->num_sms * 16u;
+  if (blocks > cap) blocks = cap;
+  {
+    KTimer kt(ctx, static_cast<cudaStream_t>(stream), 2);
+    k_convex_support<<<blocks, threads, 0, static_cast<cudaStream_t>(stream)>>>(ctx->dview.cvx, ctx->dview.pool, ids, dirs, idx, sup, (unsigned)n);
+  }
+  ctx->stats.kernel_launches++;
+  CK(cudaGetLastError());
+  return HFB_OK;
+}
+
+int hfb_batch_convex_support(hfb_ctx* ctx, size_t n, const uint32_t* ids, const double* dirs, int32_t* idx,
+                             double* sup) {
+  int rc;
+  if ((rc = check_ready(ctx))) return rc;
+  if (n == 0) return HFB_OK;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  for (size_t i = 0; i < n; ++i)
+    if (ids[i] >= ctx->arena.cvx.size()) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "convex id out of range");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->slots[0].stream;
+  CK(ctx->sup_ids.reserve(n * 4));
+  CK(ctx->sup_dirs.reserve(n * 24));
+  CK(ctx->sup_idx.reserve(n * 4));
+  CK(ctx->sup_out.reserve(n * 24));
+  CK(cudaMemcpyAsync(ctx->sup_ids.p, ids, n * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->sup_dirs.p, dirs, n * 24, cudaMemcpyHostToDevice, s));
+  if ((rc = hfb_batch_convex_support_device(ctx, n, static_cast<uint32_t*>(ctx->sup_ids.p),
+                                            static_cast<double*>(ctx->sup_dirs.p),
+                                            static_cast<int32_t*>(ctx->sup_idx.p),
+                                            static_cast<double*>(ctx->sup_out.p), s)))
+    return rc;
+  CK(cudaMemcpyAsync(idx, ctx->sup_idx.p, n * 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(sup, ctx->sup_out.p, n * 24, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return HFB_OK;
+}
+
+int hfb_set_profiling(hfb_ctx* ctx, int enable) {
+  if (!ctx) return HFB_ERR_INVALID_ARGUMENT;
+  ctx->profiling = enable != 0;
+  return HFB_OK;
+}
+
+int hfb_get_kernel_times(hfb_ctx* ctx, hfb_kernel_times* out, int reset) {
+  if (!ctx || !out) return HFB_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  for (auto& e : ctx->events) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e.a, e.b);
+    if (e.kind == 0) { ctx->ktimes.pairs_ms += ms; ctx->ktimes.pairs_launches++; }
+    else if (e.kind == 1) { ctx->ktimes.epa_ms += ms; ctx->ktimes.epa_launches++; }
+    else { ctx->ktimes.other_ms += ms; ctx->ktimes.other_launches++; }
+    cudaEventDestroy(e.a);
+    cudaEventDestroy(e.b);
+  }
+  ctx->events.clear();
+  *out = ctx->ktimes;
+  if (reset) ctx->ktimes = hfb_kernel_times{};
+  return HFB_OK;
+}
+
+int hfb_get_stats(hfb_ctx* ctx, hfb_stats* out) {
+  if (!ctx || !out) return HFB_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  uint64_t epa = 0;
+  auto add = [&](Slot& s) -> cudaError_t {
+    if (!s.counters.p) return cudaSuccess;
+    unsigned v[2] = {0, 0};
+    cudaError_t e = cudaMemcpy(v, s.counters.p, sizeof(v), cudaMemcpyDeviceToHost);
+    epa += v[1];
+    return e;
+  };
+  for (int k = 0; k < kSlots; ++k) CK(add(ctx->slots[k]));
+  CK(add(ctx->dev_slot));
+  ctx->stats.epa_pairs = epa;
+  *out = ctx->stats;
+  return HFB_OK;
+}
+
+}  // extern "C"

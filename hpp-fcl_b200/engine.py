@@ -53,6 +53,8 @@ def load_library(path=None):
     L.hfb_batch_convex_support.argtypes = [vp, sz, vp, vp, vp, vp]
     L.hfb_batch_convex_support_device.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.hfb_get_stats.argtypes = [vp, vp]
+    L.hfb_set_profiling.argtypes = [vp, C.c_int]
+    L.hfb_get_kernel_times.argtypes = [vp, vp, C.c_int]
     if path == library_path():
         _LIB = L
     return L
@@ -187,6 +189,14 @@ class Engine:
     def batch_convex_support_device(self, n, d_ids, d_dirs, d_idx, d_sup, stream=0):
         self._check(self.L.hfb_batch_convex_support_device(self.h, n, _ptr(d_ids), _ptr(d_dirs),
                                                            _ptr(d_idx), _ptr(d_sup), _ptr(stream)))
+
+    def set_profiling(self, on=True):
+        self._check(self.L.hfb_set_profiling(self.h, int(on)))
+
+    def kernel_times(self, reset=True):
+        t = P.KernelTimes()
+        self._check(self.L.hfb_get_kernel_times(self.h, C.byref(t), int(reset)))
+        return {f[0]: getattr(t, f[0]) for f in P.KernelTimes._fields_}
 
     def stats(self):
         s = P.Stats()

@@ -156,7 +156,7 @@ typedef struct hfb_collision_request {
   double distance_upper_bound; /* default +DBL_MAX */
 } hfb_collision_request;
 
-/* ---- DistanceResult (collision_data.h:1053-1096) as a flat 104 B record:
+/* ---- DistanceResult (collision_data.h:1053-1096) as a flat 96 B record:
  *      min_distance, nearest_points[2], normal, b1, b2 (+ status, iterations,
  *      and the warm-start outputs QueryResult::cached_* when requested).   */
 typedef struct hfb_distance_result {
@@ -294,6 +294,20 @@ typedef struct hfb_stats {
   uint64_t leaf_tests;
 } hfb_stats;
 int hfb_get_stats(hfb_ctx* ctx, hfb_stats* out);
+
+/* optional per-kernel device timing (CUDA events recorded on the launching stream
+ * around every kernel launch; the reference's counterpart is request.enable_timings
+ * -> result.timings, collision.cpp:196-201).  Off by default. */
+typedef struct hfb_kernel_times {
+  double pairs_ms;   /* sum over launches of the phase-1 kernels (k_pairs*) */
+  double epa_ms;     /* sum over launches of the EPA kernel */
+  double other_ms;   /* classify / support / clear */
+  uint64_t pairs_launches;
+  uint64_t epa_launches;
+  uint64_t other_launches;
+} hfb_kernel_times;
+int hfb_set_profiling(hfb_ctx* ctx, int enable);
+int hfb_get_kernel_times(hfb_ctx* ctx, hfb_kernel_times* out, int reset);
 
 #ifdef __cplusplus
 }

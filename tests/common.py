@@ -155,7 +155,8 @@ def compare_distance(ref, got, rtol=1e-6, exact=True, what=""):
     assert ref.shape == got.shape
     assert np.array_equal(ref["status"], got["status"]), "%s: status words differ at %s" % (
         what, np.nonzero(ref["status"] != got["status"])[0][:10])
-    assert np.array_equal(ref["iterations"], got["iterations"]), "%s: iteration counts differ" % what
+    if exact:
+        assert np.array_equal(ref["iterations"], got["iterations"]), "%s: iteration counts differ" % what
     assert np.array_equal(ref["b1"], got["b1"]) and np.array_equal(ref["b2"], got["b2"])
     dname = "min_distance" if "min_distance" in ref.dtype.names else "distance"
     for f in (dname, "p1", "p2", "normal") + (("pos", "distance_lower_bound") if "pos" in ref.dtype.names else ()):

@@ -1,0 +1,228 @@
+"""CPU-only parity: the per-pair DEVICE code (hpp-fcl_b200/csrc/*.cuh compiled with g++ by
+tests/emu, one lane per pair) against the oracle on seeded batches.  This is what lets the
+kernels' arithmetic be debugged without a GPU; the `-m gpu` tests repeat it on the real kernels.
+Bar: status words, iteration counts, collide flags, warm-start outputs and every double
+bit-identical.
+"""
+import numpy as np
+import pytest
+
+from tests.common import P, compare_distance, make_scenes
+from hppfcl_b200 import workloads as W
+
+ALL_PRIMS = (P.GEOM_SPHERE, P.GEOM_CAPSULE, P.GEOM_BOX, P.GEOM_CYLINDER, P.GEOM_CONE, P.GEOM_ELLIPSOID)
+
+
+@pytest.fixture(scope="module")
+def prim():
+    sc = make_scenes()
+    w = W.config2_mixed_primitives(30000, pool=4096, types=ALL_PRIMS)
+    sc.register_shapes(w["shapes"])
+    return sc, w
+
+
+@pytest.mark.parametrize("variant", [P.DefaultGJK, P.PolyakAcceleration, P.NesterovAcceleration])
+@pytest.mark.parametrize("crit,ctype", [(P.Default, P.Relative), (P.DualityGap, P.Relative),
+                                        (P.DualityGap, P.Absolute), (P.Hybrid, P.Relative), (P.Hybrid, P.Absolute)])
+def test_distance_all_variants_and_criteria(prim, variant, crit, ctype):
+    sc, w = prim
+    req = P.DistanceRequestPOD(gjk_variant=variant, gjk_convergence_criterion=crit,
+                               gjk_convergence_criterion_type=ctype)
+    ro = sc.b["oracle"].batch_distance(w["h1"], w["tf1"], w["h2"], w["tf2"], req, nthreads=0)
+    re = sc.b["emu"].batch_distance(w["h1"], w["tf1"], w["h2"], w["tf2"], req)
+    compare_distance(ro, re, what="distance")
+    assert (P.status_epa(ro["status"]) == P.EPA_AccuracyReached).sum() > 100
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(security_margin=0.05), dict(security_margin=-0.02),
+                                dict(enable_contact=0, distance_upper_bound=0.0),
+                                dict(enable_contact=0), dict(distance_upper_bound=0.3),
+                                dict(gjk_max_iterations=4), dict(epa_max_iterations=3),
+                                dict(gjk_tolerance=1e-3, epa_tolerance=1e-3)])
+def test_collide_request_fields(prim, kw):
+    sc, w = prim
+    req = P.CollisionRequestPOD(**kw)
+    ro, og, oh = sc.b["oracle"].batch_collide(w["h1"], w["tf1"], w["h2"], w["tf2"], req, want_guess=True, nthreads=0)
+    re, eg, eh = sc.b["emu"].batch_collide(w["h1"], w["tf1"], w["h2"], w["tf2"], req, want_guess=True)
+    compare_distance(ro, re, what="collide %s" % kw)
+    assert np.array_equal(og.view(np.uint64), eg.view(np.uint64)) and np.array_equal(oh, eh)
+
+
+def test_signed_distance_off(prim):
+    sc, w = prim
+    req = P.DistanceRequestPOD(enable_signed_distance=0)
+    ro = sc.b["oracle"].batch_distance(w["h1"], w["tf1"], w["h2"], w["tf2"], req, nthreads=0)
+    re = sc.b["emu"].batch_distance(w["h1"], w["tf1"], w["h2"], w["tf2"], req)
+    compare_distance(ro, re, what="unsigned distance")
+    col = P.status_gjk(ro["status"]) == P.GJK_Collision
+    assert col.sum() > 100 and np.all(np.isnan(ro["p1"][col]))  # narrowphase.h:638-656
+
+
+def test_initial_guess_modes(prim):
+    sc, w = prim
+    n = 8000
+    a = [w["h1"][:n], w["tf1"][:n], w["h2"][:n], w["tf2"][:n]]
+    ro, og, oh = sc.b["oracle"].batch_distance(*a, want_guess=True)
+    req = P.DistanceRequestPOD(gjk_initial_guess=P.CachedGuess)
+    req.q.cached_gjk_guess = og.ctypes.data
+    req.q.cached_support_func_guess = oh.ctypes.data
+    r2 = sc.b["oracle"].batch_distance(*a, req)
+    e2 = sc.b["emu"].batch_distance(*a, req)
+    compare_distance(r2, e2, what="cached guess")
+    # warm-started GJK needs no more iterations than the cold start on average (README claim)
+    g = P.status_path(ro["status"]) == P.PATH_GJK
+    assert (r2["iterations"][g] & 0xffff).mean() < (ro["iterations"][g] & 0xffff).mean()
+    req = P.DistanceRequestPOD(gjk_initial_guess=P.BoundingVolumeGuess)
+    compare_distance(sc.b["oracle"].batch_distance(*a, req), sc.b["emu"].batch_distance(*a, req), what="bv guess")
+
+
+def test_swept_sphere_radius(prim):
+    """test/swept_sphere_radius.cpp: inflating a shape by ssr shifts the distance by ssr."""
+    sc = make_scenes()
+    rng = np.random.default_rng(4)
+    base = W.random_primitive_shapes(rng, 64, ALL_PRIMS)
+    infl = base.copy()
+    infl["ssr"] = 0.07
+    hb, hi = sc.register_shapes(base), sc.register_shapes(infl)
+    n = 5000
+    i1, i2 = rng.integers(0, 64, n), rng.integers(0, 64, n)
+    t1 = W.identity_transforms(n)
+    t2 = W.random_transforms(rng, n, (2.5, -1, -1), (4, 1, 1))  # separated
+    ro = sc.b["oracle"].batch_distance(hi[i1], t1, hi[i2], t2, nthreads=0)
+    re = sc.b["emu"].batch_distance(hi[i1], t1, hi[i2], t2)
+    compare_distance(ro, re, what="ssr")
+    r0 = sc.b["oracle"].batch_distance(hb[i1], t1, hb[i2], t2, nthreads=0)
+    assert np.allclose(ro["min_distance"], r0["min_distance"] - 0.14, atol=2e-6)
+
+
+def test_triangles_and_unsupported():
+    sc = make_scenes()
+    rng = np.random.default_rng(8)
+    tris = []
+    for _ in range(32):
+        cid = sc.register_convex(rng.normal(size=(3, 3)) * 0.5, None)
+        tris.append(cid)
+    ht = sc.register_shapes(P.make_shapes([P.GEOM_TRIANGLE] * 32, np.zeros((32, 3)), data=tris))
+    hp = sc.register_shapes(W.random_primitive_shapes(rng, 64, ALL_PRIMS))
+    hx = sc.register_shapes(P.make_shapes([P.GEOM_PLANE, P.GEOM_HALFSPACE], np.zeros((2, 3))))
+    allh = np.concatenate([ht, hp])
+    n = 20000
+    h1, h2 = allh[rng.integers(0, len(allh), n)], allh[rng.integers(0, len(allh), n)]
+    t1 = W.random_transforms(rng, n, (0, 0, 0), (0, 0, 0))
+    t2 = W.random_transforms(rng, n, (-1.5, -1.5, -1.5), (1.5, 1.5, 1.5))
+    for req in (P.DistanceRequestPOD(), P.DistanceRequestPOD(gjk_variant=P.NesterovAcceleration)):
+        ro = sc.b["oracle"].batch_distance(h1, t1, h2, t2, req, nthreads=0)
+        re = sc.b["emu"].batch_distance(h1, t1, h2, t2, req)
+        compare_distance(ro, re, what="triangles")
+    rc = sc.b["oracle"].batch_collide(h1, t1, h2, t2, nthreads=0)
+    compare_distance(rc, sc.b["emu"].batch_collide(h1, t1, h2, t2), what="triangles collide")
+    assert rc["num_contacts"].sum() > 500
+    # plane / halfspace pairs are reported per pair as unsupported (collision.cpp:110-117)
+    h1[:10] = hx[0]
+    h2[10:20] = hx[1]
+    ro = sc.b["oracle"].batch_distance(h1[:40], t1[:40], h2[:40], t2[:40])
+    re = sc.b["emu"].batch_distance(h1[:40], t1[:40], h2[:40], t2[:40])
+    compare_distance(ro, re, what="unsupported")
+    assert np.all(P.status_path(ro["status"][:20]) == P.PATH_UNSUPPORTED)
+
+
+def _convex(faithful, n=20000, pool=48):
+    sc = make_scenes()
+    w = W.config3_convex_pairs(n, pool=pool, nv=64)
+    cids = [sc.register_convex(p, t if faithful else None) for p, t in w["hulls"]]
+    rng = np.random.default_rng(5)
+    small = [W.icosahedron_from_ellipsoid(0.1 + rng.random(3)) for _ in range(16)]
+    cids += [sc.register_convex(p, t) for p, t in small]
+    hc = sc.register_shapes(P.make_shapes([P.GEOM_CONVEX] * len(cids), np.zeros((len(cids), 3)), data=cids))
+    hp = sc.register_shapes(W.random_primitive_shapes(np.random.default_rng(3), 128, ALL_PRIMS))
+    return sc, w, hc, hp
+
+
+@pytest.mark.parametrize("variant", [P.DefaultGJK, P.NesterovAcceleration, P.PolyakAcceleration])
+def test_convex_linear_scan_bit_exact(variant):
+    """ConvexBase support = linear scan (support_functions.cpp:401-421): 12-vertex hulls use it in
+    the reference; the 64-vertex hulls are registered in the oracle without neighbours so that it
+    runs the same exhaustive argmax as the kernels."""
+    sc, w, hc, hp = _convex(False)
+    h1, h2 = hc[w["h1"] % len(hc)], hc[w["h2"] % len(hc)]
+    req = P.CollisionRequestPOD(gjk_variant=variant)
+    ro, og, oh = sc.b["oracle"].batch_collide(h1, w["tf1"], h2, w["tf2"], req, want_guess=True, nthreads=0)
+    re, eg, eh = sc.b["emu"].batch_collide(h1, w["tf1"], h2, w["tf2"], req, want_guess=True)
+    compare_distance(ro, re, what="convex")
+    assert np.array_equal(oh, eh) and np.array_equal(og.view(np.uint64), eg.view(np.uint64))
+    assert 0.3 < ro["num_contacts"].mean() < 0.7
+    rng = np.random.default_rng(1)
+    allh = np.concatenate([hc, hp])
+    n = len(h1)
+    h1, h2 = allh[rng.integers(0, len(allh), n)], allh[rng.integers(0, len(allh), n)]
+    dreq = P.DistanceRequestPOD(gjk_variant=variant)
+    compare_distance(sc.b["oracle"].batch_distance(h1, w["tf1"], h2, w["tf2"], dreq, nthreads=0),
+                     sc.b["emu"].batch_distance(h1, w["tf1"], h2, w["tf2"], dreq), what="convex/primitive")
+
+
+@pytest.mark.parametrize("variant", [P.DefaultGJK, P.NesterovAcceleration])
+def test_convex_vs_reference_hill_climb(variant):
+    """Against the reference's >32-vertex hill-climbing support (support_functions.cpp:324-397,
+    with visited flags, warm starts and hint carry-over): the exhaustive argmax can pick a
+    different vertex only when the maximum is tied to rounding, so flags/statuses are exact and
+    polytope-polytope distances, witness points and normals agree to ~1e-12."""
+    sc, w, hc, hp = _convex(True)
+    h1, h2 = hc[w["h1"] % len(hc)], hc[w["h2"] % len(hc)]
+    req = P.CollisionRequestPOD(gjk_variant=variant)
+    ro = sc.b["oracle"].batch_collide(h1, w["tf1"], h2, w["tf2"], req, nthreads=0)
+    re = sc.b["emu"].batch_collide(h1, w["tf1"], h2, w["tf2"], req)
+    compare_distance(ro, re, rtol=1e-9, exact=False, what="convex vs hill-climb")
+    # the hill-climb and the linear scan agree on every fresh query (no state carried over)
+    rng = np.random.default_rng(2)
+    ids = rng.integers(0, len(w["hulls"]), 50000).astype(np.uint32)
+    dirs = rng.normal(size=(50000, 3))
+    li, _ = sc.b["oracle"].batch_convex_support(ids, dirs)
+    assert np.array_equal(li, sc.b["oracle"].batch_convex_support(ids, dirs, log=True))
+    ei, es = sc.b["emu"].batch_convex_support(ids, dirs)
+    assert np.array_equal(li, ei)
+
+
+def test_convex_vs_curved_primitive_hill_climb_tolerance():
+    """64-vertex hull vs curved primitive against the hill-climbing oracle: near-tie support
+    choices change the GJK/EPA path, and on curved shapes two valid solutions of a tol=1e-6 solve
+    differ by ~tol in distance (and ~sqrt(tol) in witness points).  Bar kept: statuses and
+    collide flags exact away from |d| < tol, distances within 1e-6 absolute."""
+    sc, w, hc, hp = _convex(True, n=12000)
+    rng = np.random.default_rng(3)
+    n = len(w["h1"])
+    h1, h2 = hc[rng.integers(0, 48, n)], hp[rng.integers(0, len(hp), n)]
+    ro = sc.b["oracle"].batch_collide(h1, w["tf1"], h2, w["tf2"], nthreads=0)
+    re = sc.b["emu"].batch_collide(h1, w["tf1"], h2, w["tf2"])
+    m = np.abs(ro["distance"]) > 1e-5
+    assert np.array_equal(ro["num_contacts"][m], re["num_contacts"][m])
+    assert np.array_equal(P.status_gjk(ro["status"])[m], P.status_gjk(re["status"])[m])
+    ok = ~np.isnan(ro["p1"][:, 0]) & ~np.isnan(re["p1"][:, 0])
+    assert np.max(np.abs(ro["distance"][ok] - re["distance"][ok])) < 2e-6
+
+
+def test_edge_cases():
+    sc = make_scenes()
+    hs = sc.register_shapes(W.random_primitive_shapes(np.random.default_rng(0), 8, ALL_PRIMS))
+    e = sc.b["emu"]
+    t = W.identity_transforms(4)
+    # empty batch
+    assert e.batch_distance(hs[:0], t[:0], hs[:0], t[:0]).shape == (0,)
+    # identical poses (deep penetration, identity relative transform path, minkowski_difference.cpp:281)
+    r = sc.b["oracle"].batch_distance(hs[:4], t, hs[:4], t)
+    compare_distance(r, e.batch_distance(hs[:4], t, hs[:4], t), what="coincident")
+    assert np.all(r["min_distance"] < 0)
+    # num_max_contacts == 0 -> invalid argument; security_margin == -inf -> cleared result
+    with pytest.raises(ValueError):
+        e.batch_collide(hs[:4], t, hs[:4], t, P.CollisionRequestPOD(num_max_contacts=0))
+    with pytest.raises(ValueError):
+        sc.b["oracle"].batch_collide(hs[:4], t, hs[:4], t, P.CollisionRequestPOD(num_max_contacts=0))
+    req = P.CollisionRequestPOD(security_margin=-np.inf)
+    r = sc.b["oracle"].batch_collide(hs[:4], t, hs[:4], t, req)
+    g = e.batch_collide(hs[:4], t, hs[:4], t, req)
+    assert r["num_contacts"].sum() == 0 and g["num_contacts"].sum() == 0
+    assert np.all(np.isnan(g["p1"])) and np.all(g["distance_lower_bound"] == P.DBL_MAX)
+    # invalid tolerance (gjk.cpp:62) and oversize EPA budget
+    with pytest.raises(ValueError):
+        e.batch_distance(hs[:4], t, hs[:4], t, P.DistanceRequestPOD(gjk_tolerance=0.0))
+    with pytest.raises(ValueError):
+        e.batch_distance(hs[:4], t, hs[:4], t, P.DistanceRequestPOD(epa_max_iterations=1000))

@@ -1,0 +1,204 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the oracle on the
+same seeded inputs.  Bar (BASELINE.json north_star): collide flags, status words,
+iteration counts and indices bit-exact; distances / witness points / normals
+within 1e-6 relative -- and, because oracle and kernels execute the same IEEE
+operation sequence (no FMA), the doubles are in fact required to be bit-identical.
+"""
+import numpy as np
+import pytest
+
+from tests.common import P, compare_distance, hf, make_scenes
+from hppfcl_b200 import workloads as W
+
+pytestmark = pytest.mark.gpu
+
+ALL_PRIMS = (P.GEOM_SPHERE, P.GEOM_CAPSULE, P.GEOM_BOX, P.GEOM_CYLINDER, P.GEOM_CONE, P.GEOM_ELLIPSOID)
+
+
+@pytest.fixture(scope="module")
+def prim_scene():
+    sc = make_scenes(gpu=True, emu=False)
+    w = W.config2_mixed_primitives(200_000, pool=8192, types=ALL_PRIMS)
+    sc.register_shapes(w["shapes"])
+    sc.commit()
+    return sc, w
+
+
+@pytest.mark.parametrize("variant", [P.DefaultGJK, P.NesterovAcceleration, P.PolyakAcceleration])
+def test_distance_primitives_all_types(prim_scene, variant):
+    sc, w = prim_scene
+    req = P.DistanceRequestPOD(gjk_variant=variant)
+    ref = sc.b["oracle"].batch_distance(w["h1"], w["tf1"], w["h2"], w["tf2"], req, nthreads=0)
+    got = sc.b["gpu"].batch_distance(w["h1"], w["tf1"], w["h2"], w["tf2"], req)
+    compare_distance(ref, got, what="distance variant %d" % variant)
+    assert (ref["min_distance"] < 0).sum() > 100  # the penetrating (EPA) branch is exercised
+
+
+@pytest.mark.parametrize("margin", [0.0, 0.05, -0.02])
+def test_collide_primitives(prim_scene, margin):
+    sc, w = prim_scene
+    req = P.CollisionRequestPOD(security_margin=margin)
+    ref = sc.b["oracle"].batch_collide(w["h1"], w["tf1"], w["h2"], w["tf2"], req, nthreads=0)
+    got = sc.b["gpu"].batch_collide(w["h1"], w["tf1"], w["h2"], w["tf2"], req)
+    compare_distance(ref, got, what="collide margin %g" % margin)
+    assert ref["num_contacts"].sum() > 100
+
+
+def test_collide_no_contact_info_early_stop(prim_scene):
+    """enable_contact=False + distance_upper_bound=0: GJK early exit (gjk.cpp:288-293), NaN witness."""
+    sc, w = prim_scene
+    req = P.CollisionRequestPOD(enable_contact=0, distance_upper_bound=0.0)
+    ref = sc.b["oracle"].batch_collide(w["h1"], w["tf1"], w["h2"], w["tf2"], req, nthreads=0)
+    got = sc.b["gpu"].batch_collide(w["h1"], w["tf1"], w["h2"], w["tf2"], req)
+    compare_distance(ref, got, what="collide early-stop")
+    assert (P.status_gjk(ref["status"]) == P.GJK_NoCollisionEarlyStopped).sum() > 100
+
+
+def test_cached_guess_roundtrip(prim_scene):
+    sc, w = prim_scene
+    n = 20000
+    sl = slice(0, n)
+    a = [w["h1"][sl], w["tf1"][sl], w["h2"][sl], w["tf2"][sl]]
+    ref, rg, rh = sc.b["oracle"].batch_distance(*a, want_guess=True)
+    got, gg, gh = sc.b["gpu"].batch_distance(*a, want_guess=True)
+    compare_distance(ref, got, what="guess pass 1")
+    assert np.array_equal(rg.view(np.uint64), gg.view(np.uint64)) and np.array_equal(rh, gh)
+    req = P.DistanceRequestPOD(gjk_initial_guess=P.CachedGuess)
+    req.q.cached_gjk_guess = rg.ctypes.data
+    req.q.cached_support_func_guess = rh.ctypes.data
+    ref2 = sc.b["oracle"].batch_distance(*a, req)
+    got2 = sc.b["gpu"].batch_distance(*a, req)
+    compare_distance(ref2, got2, what="guess pass 2")
+
+
+def _convex_scene(faithful):
+    """faithful=True: the oracle uses the reference's neighbour hill-climb for hulls with more
+    than 32 vertices (support_functions.cpp:324-397); faithful=False: hulls are registered in the
+    oracle without neighbours, so it runs the linear scan (:401-421) the kernels implement."""
+    sc = make_scenes(gpu=True, emu=False)
+    w = W.config3_convex_pairs(60_000, pool=96, nv=64)
+    cids = [sc.register_convex(p, t if faithful else None) for p, t in w["hulls"]]
+    rng = np.random.default_rng(5)
+    small = [W.icosahedron_from_ellipsoid(0.1 + rng.random(3)) for _ in range(16)]
+    cids += [sc.register_convex(p, t) for p, t in small]
+    hc = sc.register_shapes(P.make_shapes([P.GEOM_CONVEX] * len(cids), np.zeros((len(cids), 3)), data=cids))
+    prims = W.random_primitive_shapes(np.random.default_rng(3), 256, ALL_PRIMS)
+    hp = sc.register_shapes(prims)
+    sc.commit()
+    return sc, w, hc, hp
+
+
+@pytest.fixture(scope="module")
+def convex_scene():
+    return _convex_scene(False)
+
+
+@pytest.fixture(scope="module")
+def convex_scene_faithful():
+    return _convex_scene(True)
+
+
+@pytest.mark.parametrize("variant", [P.DefaultGJK, P.NesterovAcceleration])
+def test_convex_convex(convex_scene, variant):
+    sc, w, hc, hp = convex_scene
+    h1, h2 = hc[w["h1"] % len(hc)], hc[w["h2"] % len(hc)]
+    req = P.CollisionRequestPOD(gjk_variant=variant)
+    ref = sc.b["oracle"].batch_collide(h1, w["tf1"], h2, w["tf2"], req, nthreads=0)
+    got = sc.b["gpu"].batch_collide(h1, w["tf1"], h2, w["tf2"], req)
+    compare_distance(ref, got, what="convex collide variant %d" % variant)
+    assert 0.2 < ref["num_contacts"].mean() < 0.8
+    dreq = P.DistanceRequestPOD(gjk_variant=variant)
+    ref, rg, rh = sc.b["oracle"].batch_distance(h1, w["tf1"], h2, w["tf2"], dreq, want_guess=True, nthreads=0)
+    got, gg, gh = sc.b["gpu"].batch_distance(h1, w["tf1"], h2, w["tf2"], dreq, want_guess=True)
+    compare_distance(ref, got, what="convex distance variant %d" % variant)
+    assert np.array_equal(rh, gh), "support hints (witness vertex indices) differ"
+
+
+@pytest.mark.parametrize("variant", [P.DefaultGJK, P.NesterovAcceleration])
+def test_convex_convex_vs_hill_climb_reference(convex_scene_faithful, variant):
+    """64-vertex hulls against the reference's hill-climbing support: the support vertex can
+    differ only when the maximum is tied to rounding (direction normal to a face/edge, i.e. at
+    GJK convergence), so collide flags and statuses are bit-exact and distances / witness
+    points / normals agree far inside the 1e-6 bar for polytope-polytope pairs."""
+    sc, w, hc, hp = convex_scene_faithful
+    h1, h2 = hc[w["h1"] % len(hc)], hc[w["h2"] % len(hc)]
+    req = P.CollisionRequestPOD(gjk_variant=variant)
+    ref = sc.b["oracle"].batch_collide(h1, w["tf1"], h2, w["tf2"], req, nthreads=0)
+    got = sc.b["gpu"].batch_collide(h1, w["tf1"], h2, w["tf2"], req)
+    compare_distance(ref, got, rtol=1e-9, exact=False, what="convex collide (hill-climb oracle)")
+
+
+def test_convex_vs_primitives_mixed(convex_scene):
+    sc, w, hc, hp = convex_scene
+    rng = np.random.default_rng(11)
+    n = 40000
+    allh = np.concatenate([hc, hp])
+    h1 = allh[rng.integers(0, len(allh), n)]
+    h2 = allh[rng.integers(0, len(allh), n)]
+    ref = sc.b["oracle"].batch_distance(h1, w["tf1"][:n], h2, w["tf2"][:n], nthreads=0)
+    got = sc.b["gpu"].batch_distance(h1, w["tf1"][:n], h2, w["tf2"][:n])
+    compare_distance(ref, got, what="mixed convex/primitive")
+
+
+def test_convex_support_kernel(convex_scene):
+    sc, w, hc, hp = convex_scene
+    rng = np.random.default_rng(2)
+    n = 50000
+    ids = rng.integers(0, len(w["hulls"]) + 16, n).astype(np.uint32)
+    dirs = rng.normal(size=(n, 3))
+    dirs[:100] = np.eye(3)[rng.integers(0, 3, 100)]  # axis-aligned directions (tie-prone)
+    ri, rs = sc.b["oracle"].batch_convex_support(ids, dirs)
+    gi, gs = sc.b["gpu"].batch_convex_support(ids, dirs)
+    assert np.array_equal(ri, gi)
+    assert np.array_equal(rs.view(np.uint64), gs.view(np.uint64))
+
+
+def test_errors_and_edge_cases(prim_scene):
+    sc, w = prim_scene
+    eng = sc.b["gpu"]
+    # empty batch
+    out = eng.batch_distance(w["h1"][:0], w["tf1"][:0], w["h2"][:0], w["tf2"][:0])
+    assert out.shape == (0,)
+    # num_max_contacts == 0 -> invalid argument (collision.cpp:82-85)
+    with pytest.raises(hf.EngineError):
+        eng.batch_collide(w["h1"][:4], w["tf1"][:4], w["h2"][:4], w["tf2"][:4], P.CollisionRequestPOD(num_max_contacts=0))
+    # bad handle
+    bad = w["h1"][:4].copy()
+    bad[1] = 0x7fffffff
+    with pytest.raises(hf.EngineError):
+        eng.batch_distance(bad, w["tf1"][:4], w["h2"][:4], w["tf2"][:4])
+    # security_margin = -inf -> cleared results, no contacts (collision.cpp:73-76)
+    got = eng.batch_collide(w["h1"][:64], w["tf1"][:64], w["h2"][:64], w["tf2"][:64],
+                            P.CollisionRequestPOD(security_margin=-np.inf))
+    assert got["num_contacts"].sum() == 0 and np.all(np.isnan(got["p1"]))
+    # single pair (n = 1)
+    ref = sc.b["oracle"].batch_distance(w["h1"][:1], w["tf1"][:1], w["h2"][:1], w["tf2"][:1])
+    got = eng.batch_distance(w["h1"][:1], w["tf1"][:1], w["h2"][:1], w["tf2"][:1])
+    compare_distance(ref, got, what="n=1")
+
+
+def test_full_size_properties():
+    """1M-pair batch (BASELINE config 2 size): size-independent properties instead of the oracle:
+    p2 = p1 + d*n, |n| = 1, swapping the operands mirrors the result
+    (test/normal_and_nearest_points.cpp:74-241)."""
+    eng = hf.Engine(0)
+    w = W.config2_mixed_primitives(1_000_000)
+    eng.register_shapes(w["shapes"])
+    eng.commit()
+    r = eng.batch_distance(w["h1"], w["tf1"], w["h2"], w["tf2"])
+    ok = ~np.isnan(r["p1"][:, 0])
+    assert ok.mean() > 0.999
+    d = r["min_distance"][ok, None]
+    assert np.allclose(r["p1"][ok] + d * r["normal"][ok], r["p2"][ok], atol=1e-6)
+    assert np.allclose(np.linalg.norm(r["normal"][ok], axis=1), 1.0, atol=1e-9)
+    # a 64k slice against the oracle (all host threads)
+    from oracle import oracle_lib
+    orc = oracle_lib.OracleScene(P)
+    orc.register_shapes(w["shapes"])
+    s = slice(500_000, 565_536)
+    ref = orc.batch_distance(w["h1"][s], w["tf1"][s], w["h2"][s], w["tf2"][s], nthreads=0)
+    compare_distance(ref, r[s], what="1M slice")
+    # reversed operands: same distance within GJK tolerance, flipped normal
+    r2 = eng.batch_distance(w["h2"][s], w["tf2"][s], w["h1"][s], w["tf1"][s])
+    m = ~np.isnan(ref["p1"][:, 0]) & ~np.isnan(r2["p1"][:, 0])
+    assert np.allclose(ref["min_distance"][m], r2["min_distance"][m], atol=5e-4)
