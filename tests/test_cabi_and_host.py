@@ -1,0 +1,138 @@
+"""CPU-only: the C-ABI library loads and exports every symbol include/*.h declares (no compute
+calls), refuses to create a context without a GPU (no CPU fallback), and the host-side logic
+(request PODs, sharding over ranks with gloo) behaves."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from tests.common import P, ROOT, hf, make_scenes
+from hppfcl_b200 import workloads as W
+
+
+def declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "hppfcl_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(hfb_[a-z_0-9]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol(built):
+    L = hf.load_library()
+    syms = declared_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(L, s), "missing export %s" % s
+    assert b"sm_100a" in L.hfb_version()
+
+
+def test_pod_layouts_match_header(built):
+    # sizes the header documents; the defaults filled by the library equal the Python defaults
+    L = hf.load_library()
+    for cls, fn in ((P.DistanceRequestPOD, L.hfb_default_distance_request),
+                    (P.CollisionRequestPOD, L.hfb_default_collision_request)):
+        a, b = cls(), cls()
+        C.memset(C.byref(b), 0xAB, C.sizeof(b))
+        fn(C.byref(b))
+        assert bytes(a) == bytes(b)
+    assert C.sizeof(P.QueryRequest) == 64
+
+
+def test_no_gpu_means_no_context(built):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(hf.EngineError) as e:
+        hf.Engine(0)
+    assert "no CUDA device" in str(e.value) and "no CPU fallback" in str(e.value)
+
+
+def test_product_does_not_import_oracle():
+    """the oracle is test infrastructure: nothing under hpp-fcl_b200/ may import, include, link or
+    dlopen anything from oracle/ (comments may mention it)"""
+    pkg = os.path.join(ROOT, "hpp-fcl_b200")
+    pat = re.compile(r"(import\s+oracle|from\s+oracle|oracle_lib|liboracle|#include\s*[\"<][^\n]*oracle|oracle/)")
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert not pat.search(txt), "%s references the oracle" % f
+
+
+def test_shard_bounds():
+    from hppfcl_b200.sharding import shard_bounds
+    for n in (0, 1, 7, 8, 1000001):
+        for world in (1, 2, 3, 8):
+            b, per = shard_bounds(n, world)
+            assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+            assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))
+            assert all(hi - lo <= per for lo, hi in b)
+
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, %(root)r)
+import numpy as np, torch, torch.distributed as dist
+import hppfcl_b200 as hf
+from hppfcl_b200 import _pod as P, workloads as W, sharding as S
+from oracle import oracle_lib
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+n = 5001
+w = W.config2_mixed_primitives(n, pool=256, seed=3)          # same seed on every rank: the batch
+rng = np.random.default_rng(1)
+pts = rng.normal(size=(12, 3))
+shapes, cvx = S.broadcast_geometry(w["shapes"] if rank == 0 else None, [pts] if rank == 0 else None)
+assert np.array_equal(shapes.view(np.uint8), w["shapes"].view(np.uint8)) and np.allclose(cvx[0], pts)
+orc = oracle_lib.OracleScene(P)   # stand-in for the per-rank engine in this CPU test
+orc.register_shapes(shapes)
+def compute(lo, hi):
+    return orc.batch_distance(w["h1"][lo:hi], w["tf1"][lo:hi], w["h2"][lo:hi], w["tf2"][lo:hi])
+full = S.sharded_batch(compute, n, P.distance_result_dtype)
+ref = orc.batch_distance(w["h1"], w["tf1"], w["h2"], w["tf2"])
+assert full.shape == ref.shape
+a, b = full.view(np.uint8).reshape(n, -1), ref.view(np.uint8).reshape(n, -1)
+nan = np.isnan(ref["p1"][:, 0])
+assert np.array_equal(a[~nan], b[~nan]) and np.array_equal(full["status"], ref["status"])
+dist.barrier()
+if rank == 0:
+    print("SHARD-OK", world)
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_sharding(tmp_path, built):
+    """world_size 2 over gloo: geometry broadcast, pair-range sharding, result all-gather."""
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29577", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-3000:]
+    assert "SHARD-OK 2" in res.stdout
+
+
+def test_api_objects_without_gpu():
+    """reference-shaped host objects (constructors, defaults) -- no compute"""
+    b = hf.Box(6, 10, 2)
+    assert np.allclose(b.halfSide, [3, 5, 1])                      # geometric_shapes.h:164-187
+    c = hf.Capsule(2., 4.)
+    assert c.radius == 2. and c.halfLength == 2.                   # :386-400
+    r = hf.CollisionRequest()
+    assert r.num_max_contacts == 1 and r.enable_contact == 1 and r.security_margin == 0 \
+        and r.break_distance == 1e-3 and r.gjk_max_iterations == 128 and r.epa_max_iterations == 64 \
+        and r.gjk_tolerance == 1e-6 and r.collision_distance_threshold == 1e-12   # collision_data.h:312-366
+    d = hf.DistanceRequest()
+    assert d.enable_signed_distance == 1 and d.rel_err == 0 and d.abs_err == 0       # :987-1030
+    res = hf.CollisionResult()
+    assert res.numContacts() == 0 and not res.isCollision() and res.distance_lower_bound == P.DBL_MAX
+    dr = hf.DistanceResult()
+    assert dr.min_distance == P.DBL_MAX and np.all(np.isnan(dr.normal)) and dr.b1 == -1
+    t = hf.Transform3f.from_quat(1, 0, 0, 0, (1, 2, 3))
+    assert np.allclose(t.transform([1, 1, 1]), [2, 3, 4])
+    with pytest.raises(ValueError):
+        hf.Sphere(1).setSweptSphereRadius(-1)

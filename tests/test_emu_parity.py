@@ -7,7 +7,7 @@ bit-identical.
 import numpy as np
 import pytest
 
-from tests.common import P, compare_distance, make_scenes
+from tests.common import P, compare_distance, compare_hill_climb, make_scenes
 from hppfcl_b200 import workloads as W
 
 ALL_PRIMS = (P.GEOM_SPHERE, P.GEOM_CAPSULE, P.GEOM_BOX, P.GEOM_CYLINDER, P.GEOM_CONE, P.GEOM_ELLIPSOID)
@@ -171,7 +171,7 @@ def test_convex_vs_reference_hill_climb(variant):
     req = P.CollisionRequestPOD(gjk_variant=variant)
     ro = sc.b["oracle"].batch_collide(h1, w["tf1"], h2, w["tf2"], req, nthreads=0)
     re = sc.b["emu"].batch_collide(h1, w["tf1"], h2, w["tf2"], req)
-    compare_distance(ro, re, rtol=1e-9, exact=False, what="convex vs hill-climb")
+    compare_hill_climb(ro, re)
     # the hill-climb and the linear scan agree on every fresh query (no state carried over)
     rng = np.random.default_rng(2)
     ids = rng.integers(0, len(w["hulls"]), 50000).astype(np.uint32)

@@ -7,7 +7,7 @@ operation sequence (no FMA), the doubles are in fact required to be bit-identica
 import numpy as np
 import pytest
 
-from tests.common import P, compare_distance, hf, make_scenes
+from tests.common import P, compare_distance, compare_hill_climb, hf, make_scenes
 from hppfcl_b200 import workloads as W
 
 pytestmark = pytest.mark.gpu
@@ -125,7 +125,7 @@ def test_convex_convex_vs_hill_climb_reference(convex_scene_faithful, variant):
     req = P.CollisionRequestPOD(gjk_variant=variant)
     ref = sc.b["oracle"].batch_collide(h1, w["tf1"], h2, w["tf2"], req, nthreads=0)
     got = sc.b["gpu"].batch_collide(h1, w["tf1"], h2, w["tf2"], req)
-    compare_distance(ref, got, rtol=1e-9, exact=False, what="convex collide (hill-climb oracle)")
+    compare_hill_climb(ref, got)
 
 
 def test_convex_vs_primitives_mixed(convex_scene):
