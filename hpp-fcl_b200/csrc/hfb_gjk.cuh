@@ -406,7 +406,7 @@ HFB_HD void pset(Param4& r, int i, double v) {
   else if (i == 2) r.p2 = v;
   else r.p3 = v;
 }
-HFB_HD Param4 proj_line_origin(v3 a, v3 b) {
+HFB_HD_NOINLINE Param4 proj_line_origin(v3 a, v3 b) {
   Param4 res;
   res.p0 = res.p1 = res.p2 = res.p3 = 0;
   res.sqr_distance = -1;
@@ -430,7 +430,7 @@ HFB_HD Param4 proj_line_origin(v3 a, v3 b) {
   }
   return res;
 }
-HFB_HD Param4 proj_triangle_origin(v3 a, v3 b, v3 c) {
+HFB_HD_NOINLINE Param4 proj_triangle_origin(v3 a, v3 b, v3 c) {
   Param4 res;
   res.p0 = res.p1 = res.p2 = res.p3 = 0;
   res.sqr_distance = -1;
@@ -471,7 +471,7 @@ HFB_HD Param4 proj_triangle_origin(v3 a, v3 b, v3 c) {
   }
   return res;
 }
-HFB_HD Param4 proj_tetra_origin(v3 a, v3 b, v3 c, v3 d) {
+HFB_HD_NOINLINE Param4 proj_tetra_origin(v3 a, v3 b, v3 c, v3 d) {
   Param4 res;
   res.p0 = res.p1 = res.p2 = res.p3 = 0;
   res.sqr_distance = -1;
@@ -519,7 +519,7 @@ HFB_HD Param4 proj_tetra_origin(v3 a, v3 b, v3 c, v3 d) {
 }
 
 // details::getClosestPoints (gjk.cpp:94-151) on a by-value simplex
-HFB_HD void closest_points(const SV& v0, const SV& v1, const SV& v2, const SV& v3_, int rank, v3& w0,
+HFB_HD_NOINLINE void closest_points(const SV& v0, const SV& v1, const SV& v2, const SV& v3_, int rank, v3& w0,
                            v3& w1) {
   if (rank == 1) {
     w0 = v0.w0;

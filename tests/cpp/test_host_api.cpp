@@ -1,0 +1,127 @@
+// C++ host-API test: the reference's own box_box_distance / capsule tests, written against
+// the hppfcl_b200 mirror of the hpp-fcl interface (compare test/box_box_distance.cpp:62-254,
+// test/capsule_capsule.cpp:218-356, test/collision.cpp error paths).  Runs on the GPU box.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+
+#include "../../hpp-fcl_b200/host/hppfcl_b200.hpp"
+
+using namespace hppfcl_b200;
+
+static int failures = 0;
+#define CHECK(c)                                                          \
+  do {                                                                    \
+    if (!(c)) { std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #c); ++failures; } \
+  } while (0)
+#define CHECK_CLOSE(a, b, pct) CHECK(std::fabs((a) - (b)) <= (pct) / 100.0 * std::fmin(std::fabs(a), std::fabs(b)))
+
+int main() {
+  {  // distance_box_box_1 (box_box_distance.cpp:62-101)
+    CollisionGeometryPtr_t s1(new Box(6, 10, 2));
+    CollisionGeometryPtr_t s2(new Box(2, 2, 2));
+    Transform3f tf1;
+    Transform3f tf2(Vec3f(25, 20, 5));
+    CollisionObject o1(s1, tf1);
+    CollisionObject o2(s2, tf2);
+    DistanceRequest distanceRequest(true, true, 0, 0);
+    DistanceResult distanceResult;
+    distance(&o1, &o2, distanceRequest, distanceResult);
+    double dx = 25 - 3 - 1, dy = 20 - 5 - 1, dz = 5 - 1 - 1;
+    const Vec3f& p1 = distanceResult.nearest_points[0];
+    const Vec3f& p2 = distanceResult.nearest_points[1];
+    CHECK_CLOSE(distanceResult.min_distance, std::sqrt(dx * dx + dy * dy + dz * dz), 1e-4);
+    CHECK_CLOSE(p1[0], 3, 1e-6); CHECK_CLOSE(p1[1], 5, 1e-6); CHECK_CLOSE(p1[2], 1, 1e-6);
+    CHECK_CLOSE(p2[0], 24, 1e-6); CHECK_CLOSE(p2[1], 19, 1e-6); CHECK_CLOSE(p2[2], 4, 1e-6);
+  }
+  {  // distance_box_box_2 (:103-142)
+    CollisionGeometryPtr_t s1(new Box(6, 10, 2));
+    CollisionGeometryPtr_t s2(new Box(2, 2, 2));
+    static double pi = M_PI;
+    Transform3f tf1;
+    Transform3f tf2(makeQuat(cos(pi / 8), sin(pi / 8) / sqrt(3), sin(pi / 8) / sqrt(3), sin(pi / 8) / sqrt(3)),
+                    Vec3f(0, 0, 10));
+    CollisionObject o1(s1, tf1), o2(s2, tf2);
+    DistanceRequest distanceRequest(true, true, 0, 0);
+    DistanceResult distanceResult;
+    distance(&o1, &o2, distanceRequest, distanceResult);
+    const Vec3f& p1 = distanceResult.nearest_points[0];
+    const Vec3f& p2 = distanceResult.nearest_points[1];
+    CHECK_CLOSE(distanceResult.min_distance, -1.62123444 + 10 - 1, 1e-4);
+    CHECK_CLOSE(p1[0], 0.60947571, 1e-4); CHECK_CLOSE(p1[1], 0.01175873, 1e-4); CHECK_CLOSE(p1[2], 1, 1e-6);
+    CHECK_CLOSE(p2[0], 0.60947571, 1e-4); CHECK_CLOSE(p2[1], 0.01175873, 1e-4);
+    CHECK_CLOSE(p2[2], -1.62123444 + 10, 1e-4);
+  }
+  {  // distance_box_box_4 (:218-254)
+    Box s1(1, 1, 1), s2(1, 1, 1);
+    DistanceRequest distanceRequest(true, true, 0, 0);
+    DistanceResult distanceResult;
+    Transform3f tf1(Vec3f(2, 0, 0)), tf2;
+    distance(&s1, tf1, &s2, tf2, distanceRequest, distanceResult);
+    CHECK_CLOSE(distanceResult.min_distance, 1., 1e-4);
+    tf1.setTranslation(Vec3f(1.01, 0, 0));
+    distanceResult.clear();
+    distance(&s1, tf1, &s2, tf2, distanceRequest, distanceResult);
+    CHECK_CLOSE(distanceResult.min_distance, 0.01, 2e-3);
+    tf1.setTranslation(Vec3f(0.99, 0, 0));
+    distanceResult.clear();
+    distance(&s1, tf1, &s2, tf2, distanceRequest, distanceResult);
+    CHECK_CLOSE(distanceResult.min_distance, -0.01, 2e-3);
+    tf1.setTranslation(Vec3f(0, 0, 0));
+    distanceResult.clear();
+    distance(&s1, tf1, &s2, tf2, distanceRequest, distanceResult);
+    CHECK_CLOSE(distanceResult.min_distance, -1., 2e-3);
+    // results accumulate: without clear() a satisfied request returns early (shape_shape_func.h:57)
+    tf1.setTranslation(Vec3f(5, 0, 0));
+    CHECK(distance(&s1, tf1, &s2, tf2, distanceRequest, distanceResult) < 0);
+  }
+  {  // distance_capsulecapsule_transformZ2 (capsule_capsule.cpp:322-356)
+    CollisionGeometryPtr_t s1(new Capsule(5, 10)), s2(new Capsule(5, 10));
+    Transform3f tf1;
+    Transform3f tf2(makeQuat(sqrt(2) / 2, 0, sqrt(2) / 2, 0), Vec3f(0, 0, 25.1));
+    CollisionObject o1(s1, tf1), o2(s2, tf2);
+    DistanceRequest distanceRequest(true);
+    DistanceResult distanceResult;
+    distance(&o1, &o2, distanceRequest, distanceResult);
+    CHECK_CLOSE(distanceResult.min_distance, 10.1, 1e-6);
+    CHECK_CLOSE(distanceResult.nearest_points[0][2], 10, 1e-4);
+    CHECK_CLOSE(distanceResult.nearest_points[1][2], 20.1, 1e-4);
+  }
+  {  // collide(): contact, security margin, functor, error paths (collision.cpp:69-130)
+    Sphere s(1.0);
+    CollisionRequest req;
+    CollisionResult res;
+    Transform3f a, b(Vec3f(1.5, 0, 0));
+    CHECK(collide(&s, a, &s, b, req, res) == 1);
+    CHECK(res.isCollision() && res.numContacts() == 1);
+    const Contact& c = res.getContact(0);
+    CHECK(std::fabs(c.penetration_depth + 0.5) < 1e-12 && std::fabs(c.normal[0] - 1) < 1e-12);
+    CHECK(std::fabs(c.pos[0] - 0.75) < 1e-12 && c.b1 == Contact::NONE && c.o1 == &s);
+    res.clear();
+    b.setTranslation(Vec3f(2.1, 0, 0));
+    CHECK(collide(&s, a, &s, b, req, res) == 0 && std::fabs(res.distance_lower_bound - 0.1) < 1e-9);
+    req.security_margin = 0.2;
+    res.clear();
+    CHECK(ComputeCollision(&s, &s)(a, b, req, res) == 1);
+    req.security_margin = -std::numeric_limits<double>::infinity();
+    CHECK(collide(&s, a, &s, b, req, res) == 0 && !res.isCollision());
+    req.security_margin = 0;
+    req.num_max_contacts = 0;
+    bool thrown = false;
+    try { res.clear(); collide(&s, a, &s, b, req, res); } catch (const std::invalid_argument&) { thrown = true; }
+    CHECK(thrown);
+    // convex vs box through the batched form
+    std::vector<Vec3f> pts;
+    for (int i = 0; i < 8; ++i) pts.push_back(Vec3f((i & 1) ? .5 : -.5, (i & 2) ? .5 : -.5, (i & 4) ? .5 : -.5));
+    ConvexBase cube(pts);
+    Box bx(1, 1, 1);
+    BatchNarrowPhase batch;
+    for (int k = 0; k < 100; ++k) batch.add(&cube, Transform3f(), &bx, Transform3f(Vec3f(0.5 + 0.01 * k, 0, 0)));
+    std::vector<hfb_distance_result> r = batch.distance(DistanceRequest());
+    for (int k = 0; k < 100; ++k) CHECK(std::fabs(r[k].min_distance - (-0.5 + 0.01 * k)) < 1e-6);
+    std::vector<hfb_contact> cc = batch.collide(CollisionRequest());
+    CHECK(cc[10].num_contacts == 1 && cc[90].num_contacts == 0);
+  }
+  std::printf(failures ? "HOST-API-FAILED %d\n" : "HOST-API-OK\n", failures);
+  return failures ? 1 : 0;
+}
