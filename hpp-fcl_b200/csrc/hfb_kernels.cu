@@ -6,15 +6,18 @@
 //                          need EPA are compacted into a device queue.
 //   k_epa<G,CAPS,MODE>     phase 2: persistent kernel over the EPA queue, one warp
 //                          per pair, polytope in per-warp shared memory.
-//   k_classify             splits a batch into primitive-only pairs (thread per
-//                          pair) and pairs touching ConvexBase/TriangleP (warp per
-//                          pair) when the arena holds both.
+//   k_bin_hist/scan/scatter  device-side counting sort of the batch by pair class
+//                          (closed-form combos | GJK-routed primitive combos |
+//                          touches ConvexBase/TriangleP) so that every warp of the
+//                          pair kernels runs one code path; k_pairs is instantiated
+//                          per class (PATHS) to keep each kernel's code small.
 //   k_convex_support       batched ConvexBase support argmax (warp per query,
 //                          coalesced streaming of the vertex block: HBM-bound).
 // MODE 0 = distance() epilogue, MODE 1 = collide() epilogue.
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -26,12 +29,19 @@
 using namespace hfb;
 
 #define CAPS_ALL (CAP_PRIM | CAP_CONVEX | CAP_TRI)
-#ifndef HFB_GC
-#define HFB_GC 32  // lanes per pair for pairs touching ConvexBase / TriangleP
-#endif
-#ifndef HFB_GE
-#define HFB_GE 32  // lanes per pair in the EPA kernel
-#endif
+// lanes per pair: pairs touching ConvexBase/TriangleP (GC) and the EPA kernel (GE).
+// Instantiated for 8 / 16 / 32; the defaults can be overridden per context with the
+// environment variables HFB_GC / HFB_GE (tuning knobs, see profiles/).
+#define HFB_GC_DEFAULT 8
+#define HFB_GE_DEFAULT 8
+
+// pair classes of the device-side counting sort (k_bin_*): bins [0,8) closed-form
+// combos, [8,45) GJK-routed primitive combos (+ bin 44: unknown node types, reported
+// as unsupported), bin 45: pairs touching ConvexBase / TriangleP
+#define HFB_NBINS 46
+#define HFB_BIN_GJK0 8
+#define HFB_BIN_UNKNOWN 44
+#define HFB_BIN_CONVEX 45
 
 // ---------------------------------------------------------------- EPA queue --
 struct EpaItem {
@@ -57,8 +67,9 @@ struct BatchArgs {
   void* out;                  // hfb_distance_result* or hfb_contact*
   EpaItem* queue;
   unsigned* queue_count;      // [0] = items pushed this batch, [1] = running total
-  const uint32_t* index_list; // optional indirection (class lists)
-  const unsigned* index_count;
+  const uint32_t* index_list; // optional indirection: pair ids sorted by class (k_bin_scatter)
+  const unsigned* range_lo;   // device pointers to the [lo, hi) slice of index_list to process
+  const unsigned* range_hi;
   SolverP P;
   CollideP C;
   unsigned n;
@@ -106,17 +117,18 @@ __device__ __forceinline__ void st3(double* p, v3 v) {
 __device__ __forceinline__ v3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
 
 // ------------------------------------------------------------------ phase 1 --
-template <int G, int CAPS, int MODE>
+template <int G, int CAPS, int MODE, int PATHS>
 __global__ void __launch_bounds__(128) k_pairs(const BatchArgs a) {
   const unsigned ngroups = (gridDim.x * blockDim.x) / G;
   const unsigned gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-  const unsigned total = a.index_list ? *a.index_count : a.n;
-  for (unsigned k = gid; k < total; k += ngroups) {
+  const unsigned lo = a.index_list ? *a.range_lo : 0u;
+  const unsigned hi = a.index_list ? *a.range_hi : a.n;
+  for (unsigned k = lo + gid; k < hi; k += ngroups) {
     const unsigned i = a.index_list ? a.index_list[k] : k;
     const PairIn in = load_pair_in<CAPS>(a, i);
     PairOut o;
     GjkState g;
-    const bool need_epa = pair_phase1<G, CAPS>(in, a.P, o, g);
+    const bool need_epa = pair_phase1<G, CAPS, PATHS>(in, a.P, o, g);
     if (Coop<G>::lane() == 0) {
       if (need_epa) {
         const unsigned slot = atomicAdd(a.queue_count, 1u);
@@ -144,7 +156,7 @@ __global__ void __launch_bounds__(128) k_pairs(const BatchArgs a) {
 
 // ------------------------------------------------------------------ phase 2 --
 template <int G, int CAPS, int MODE>
-__global__ void __launch_bounds__(128) k_epa(const BatchArgs a) {
+__global__ void __launch_bounds__(4 * G) k_epa(const BatchArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned lg = threadIdx.x / G;  // group within block
   EpaWs* ws = reinterpret_cast<EpaWs*>(smem) + lg;
@@ -185,35 +197,72 @@ __global__ void __launch_bounds__(128) k_epa(const BatchArgs a) {
   }
 }
 
-// ---------------------------------------------------------------- classify ---
-// list 0: both shapes primitive; list 1: anything touching CONVEX / TRIANGLE
-__global__ void k_classify(const hfb_shape* shapes, const uint32_t* h1, const uint32_t* h2, unsigned n,
-                           uint32_t* list0, uint32_t* list1, unsigned* counts) {
+// --------------------------------------------------- pair-class counting sort ---
+__device__ __forceinline__ int type_index(uint32_t t) {
+  switch (t) {
+    case HFB_GEOM_BOX: return 0;
+    case HFB_GEOM_SPHERE: return 1;
+    case HFB_GEOM_CAPSULE: return 2;
+    case HFB_GEOM_CONE: return 3;
+    case HFB_GEOM_CYLINDER: return 4;
+    case HFB_GEOM_ELLIPSOID: return 5;
+    case HFB_GEOM_CONVEX: return 6;
+    case HFB_GEOM_TRIANGLE: return 7;
+    default: return 8;
+  }
+}
+__device__ __forceinline__ int pair_bin(uint32_t t1, uint32_t t2) {
+  const int a = type_index(t1), b = type_index(t2);
+  if (a == 8 || b == 8) return HFB_BIN_UNKNOWN;
+  if (a >= 6 || b >= 6) return HFB_BIN_CONVEX;
+  if (is_closed_form((int)t1, (int)t2)) {  // same predicate the per-pair dispatch uses
+    if (a == 1 && b == 1) return 0;
+    if (a == 1 && b == 2) return 1;
+    if (a == 2 && b == 1) return 2;
+    if (a == 1 && b == 4) return 3;
+    if (a == 4 && b == 1) return 4;
+    if (a == 0 && b == 1) return 5;
+    if (a == 1 && b == 0) return 6;
+    return 7;  // capsule-capsule
+  }
+  return HFB_BIN_GJK0 + a * 6 + b;
+}
+
+__global__ void __launch_bounds__(256) k_bin_hist(const hfb_shape* shapes, const uint32_t* h1, const uint32_t* h2,
+                                                  unsigned n, unsigned* hist) {
+  __shared__ unsigned sh[HFB_NBINS];
+  if (threadIdx.x < HFB_NBINS) sh[threadIdx.x] = 0;
+  __syncthreads();
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    atomicAdd(&sh[pair_bin(shapes[h1[i]].type, shapes[h2[i]].type)], 1u);
+  __syncthreads();
+  if (threadIdx.x < HFB_NBINS && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+// offsets[b] = first slot of bin b (offsets[HFB_NBINS] = n); cursor = running write position
+__global__ void k_bin_scan(const unsigned* hist, unsigned* offsets, unsigned* cursor) {
+  if (threadIdx.x == 0) {
+    unsigned acc = 0;
+    for (int b = 0; b < HFB_NBINS; ++b) {
+      offsets[b] = acc;
+      cursor[b] = acc;
+      acc += hist[b];
+    }
+    offsets[HFB_NBINS] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) k_bin_scatter(const hfb_shape* shapes, const uint32_t* h1, const uint32_t* h2,
+                                                     unsigned n, unsigned* cursor, uint32_t* perm) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool valid = i < n;
-  int cls = 0;
-  if (valid) {
-    const uint32_t t1 = shapes[h1[i]].type, t2 = shapes[h2[i]].type;
-    const bool c1 = t1 == HFB_GEOM_CONVEX || t1 == HFB_GEOM_TRIANGLE;
-    const bool c2 = t2 == HFB_GEOM_CONVEX || t2 == HFB_GEOM_TRIANGLE;
-    cls = (c1 || c2) ? 1 : 0;
-  }
-  // warp-aggregated append
-  const unsigned m0 = __ballot_sync(0xffffffffu, valid && cls == 0);
-  const unsigned m1 = __ballot_sync(0xffffffffu, valid && cls == 1);
+  const bool valid = i < n;
+  const int key = valid ? pair_bin(shapes[h1[i]].type, shapes[h2[i]].type) : -1;
+  // warp-aggregated append per key
+  const unsigned peers = __match_any_sync(0xffffffffu, key);
   const unsigned lane = threadIdx.x & 31u;
-  unsigned b0 = 0, b1 = 0;
-  if (lane == 0) {
-    if (m0) b0 = atomicAdd(counts + 0, __popc(m0));
-    if (m1) b1 = atomicAdd(counts + 1, __popc(m1));
-  }
-  b0 = __shfl_sync(0xffffffffu, b0, 0);
-  b1 = __shfl_sync(0xffffffffu, b1, 0);
-  if (valid) {
-    const unsigned lt = (1u << lane) - 1u;
-    if (cls == 0) list0[b0 + __popc(m0 & lt)] = i;
-    else list1[b1 + __popc(m1 & lt)] = i;
-  }
+  const int leader = __ffs(peers) - 1;
+  unsigned base = 0;
+  if (valid && (int)lane == leader) base = atomicAdd(&cursor[key], __popc(peers));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (valid) perm[base + __popc(peers & ((1u << lane) - 1u))] = i;
 }
 
 // ----------------------------------------------------- convex support kernel --
@@ -304,6 +353,7 @@ struct hfb_ctx {
   Slot dev_slot;  // resources of the *_device entry points (caller's stream)
   DevBuf sup_ids, sup_dirs, sup_idx, sup_out;
   hfb_stats stats{};
+  int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT;
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int kind; };
   std::vector<Ev> events;
@@ -328,7 +378,7 @@ int cuda_fail(hfb_ctx* c, cudaError_t e, const char* where) {
     if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call);           \
   } while (0)
 
-// kernel timing hooks: kind 0 = pairs, 1 = epa, 2 = other
+// kernel timing hooks: kind 0 = GJK pairs, 1 = epa, 2 = other, 3 = closed-form pairs, 4 = convex pairs
 struct KTimer {
   hfb_ctx* c;
   cudaStream_t s;
@@ -348,7 +398,7 @@ struct KTimer {
   }
 };
 
-template <int G, int CAPS, int MODE>
+template <int G, int CAPS, int MODE, int PATHS>
 int launch_pairs(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s) {
   if (work == 0) return HFB_OK;
   const int threads = 128;
@@ -357,8 +407,8 @@ int launch_pairs(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s
   const unsigned cap = (unsigned)ctx->num_sms * 32u;  // grid-stride beyond this
   if (blocks > cap) blocks = cap;
   {
-    KTimer kt(ctx, s, 0);
-    k_pairs<G, CAPS, MODE><<<blocks, threads, 0, s>>>(a);
+    KTimer kt(ctx, s, (CAPS != CAP_PRIM) ? 4 : (PATHS == PATH_CLOSED ? 3 : 0));
+    k_pairs<G, CAPS, MODE, PATHS><<<blocks, threads, 0, s>>>(a);
   }
   ctx->stats.kernel_launches++;
   CK(cudaGetLastError());
@@ -367,16 +417,14 @@ int launch_pairs(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s
 
 template <int G, int CAPS, int MODE>
 int launch_epa(hfb_ctx* ctx, const BatchArgs& a, cudaStream_t s) {
-  const int threads = 128;
-  const size_t smem = (threads / G) * sizeof(EpaWs);
-  static bool attr_set = false;
-  if (!attr_set) {
+  const int threads = 4 * G;
+  const size_t smem = 4 * sizeof(EpaWs);
+  static int per_sm = 0;
+  if (per_sm == 0) {
     CK(cudaFuncSetAttribute(k_epa<G, CAPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epa<G, CAPS, MODE>, threads, smem));
+    if (per_sm < 1) per_sm = 1;
   }
-  int per_sm = 0;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epa<G, CAPS, MODE>, threads, smem));
-  if (per_sm < 1) per_sm = 1;
   {
     KTimer kt(ctx, s, 1);
     k_epa<G, CAPS, MODE><<<ctx->num_sms * per_sm, threads, smem, s>>>(a);
@@ -386,49 +434,76 @@ int launch_epa(hfb_ctx* ctx, const BatchArgs& a, cudaStream_t s) {
   return HFB_OK;
 }
 
-// runs one (sub)batch whose inputs/outputs are already device-resident
+template <int CAPS, int MODE>
+int launch_epa_g(hfb_ctx* ctx, const BatchArgs& a, cudaStream_t s) {
+  switch (ctx->ge) {
+    case 8: return launch_epa<8, CAPS, MODE>(ctx, a, s);
+    case 16: return launch_epa<16, CAPS, MODE>(ctx, a, s);
+    default: return launch_epa<32, CAPS, MODE>(ctx, a, s);
+  }
+}
+template <int MODE>
+int launch_pairs_convex(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s) {
+  switch (ctx->gc) {
+    case 8: return launch_pairs<8, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
+    case 16: return launch_pairs<16, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
+    default: return launch_pairs<32, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
+  }
+}
+
+// runs one (sub)batch whose inputs/outputs are already device-resident:
+//   counting sort of the pairs by class -> closed-form kernel, GJK kernel (thread per pair),
+//   convex/triangle kernel (lane group per pair) -> EPA kernel over the queue
 template <int MODE>
 int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   const unsigned n = a.n;
   if (n == 0) return HFB_OK;
   CK(sl.queue.reserve((size_t)n * sizeof(EpaItem)));
+  // counters: [0] EPA queue count, [1] running EPA total, [8..8+NBINS) hist, then offsets (NBINS+1), cursor (NBINS)
+  const size_t ncnt = 8 + 3 * (HFB_NBINS + 2);
   if (!sl.counters.p) {
-    CK(sl.counters.reserve(8 * sizeof(unsigned)));
-    CK(cudaMemsetAsync(sl.counters.p, 0, 8 * sizeof(unsigned), s));
+    CK(sl.counters.reserve(ncnt * sizeof(unsigned)));
+    CK(cudaMemsetAsync(sl.counters.p, 0, ncnt * sizeof(unsigned), s));
   }
+  CK(sl.lists.reserve((size_t)n * sizeof(uint32_t)));
   a.queue = static_cast<EpaItem*>(sl.queue.p);
   unsigned* cnt = static_cast<unsigned*>(sl.counters.p);
-  a.queue_count = cnt;  // [0] batch queue count, [1] running total, [2..3] class counts
+  unsigned* hist = cnt + 8;
+  unsigned* offsets = hist + HFB_NBINS + 1;
+  unsigned* cursor = offsets + HFB_NBINS + 2;
+  uint32_t* perm = static_cast<uint32_t*>(sl.lists.p);
+  a.queue_count = cnt;
   a.A = ctx->dview;
-  a.index_list = nullptr;
-  a.index_count = nullptr;
   CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned), s));
-  const bool mixed = ctx->arena.has_convex || ctx->arena.has_tri;
+  CK(cudaMemsetAsync(hist, 0, HFB_NBINS * sizeof(unsigned), s));
+  {
+    KTimer kt(ctx, s, 2);
+    unsigned hb = (n + 255) / 256;
+    if (hb > (unsigned)ctx->num_sms * 8u) hb = (unsigned)ctx->num_sms * 8u;
+    k_bin_hist<<<hb, 256, 0, s>>>(ctx->dview.shapes, a.h1, a.h2, n, hist);
+    k_bin_scan<<<1, 32, 0, s>>>(hist, offsets, cursor);
+    k_bin_scatter<<<(n + 255) / 256, 256, 0, s>>>(ctx->dview.shapes, a.h1, a.h2, n, cursor, perm);
+  }
+  ctx->stats.kernel_launches += 3;
+  CK(cudaGetLastError());
+  a.index_list = perm;
   int rc;
-  if (!mixed) {
-    if ((rc = launch_pairs<1, CAP_PRIM, MODE>(ctx, a, n, s))) return rc;
-    if (a.P.compute_penetration)
-      if ((rc = launch_epa<HFB_GE, CAP_PRIM, MODE>(ctx, a, s))) return rc;
-  } else {
-    CK(sl.lists.reserve((size_t)2 * n * sizeof(uint32_t)));
-    uint32_t* l0 = static_cast<uint32_t*>(sl.lists.p);
-    uint32_t* l1 = l0 + n;
-    CK(cudaMemsetAsync(cnt + 2, 0, 2 * sizeof(unsigned), s));
-    {
-      KTimer kt(ctx, s, 2);
-      k_classify<<<(n + 255) / 256, 256, 0, s>>>(ctx->dview.shapes, a.h1, a.h2, n, l0, l1, cnt + 2);
-    }
-    ctx->stats.kernel_launches++;
-    CK(cudaGetLastError());
-    BatchArgs a0 = a, a1 = a;
-    a0.index_list = l0;
-    a0.index_count = cnt + 2;
-    a1.index_list = l1;
-    a1.index_count = cnt + 3;
-    if ((rc = launch_pairs<1, CAP_PRIM, MODE>(ctx, a0, n, s))) return rc;
-    if ((rc = launch_pairs<HFB_GC, CAPS_ALL, MODE>(ctx, a1, n, s))) return rc;
-    if (a.P.compute_penetration)
-      if ((rc = launch_epa<HFB_GE, CAPS_ALL, MODE>(ctx, a, s))) return rc;
+  BatchArgs ac = a, ag = a, av = a;
+  ac.range_lo = offsets + 0;
+  ac.range_hi = offsets + HFB_BIN_GJK0;
+  ag.range_lo = offsets + HFB_BIN_GJK0;
+  ag.range_hi = offsets + HFB_BIN_CONVEX;
+  av.range_lo = offsets + HFB_BIN_CONVEX;
+  av.range_hi = offsets + HFB_NBINS;
+  if ((rc = launch_pairs<1, CAP_PRIM, MODE, PATH_CLOSED>(ctx, ac, n, s))) return rc;
+  if ((rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE>(ctx, ag, n, s))) return rc;
+  const bool mixed = ctx->arena.has_convex || ctx->arena.has_tri;
+  if (mixed)
+    if ((rc = launch_pairs_convex<MODE>(ctx, av, n, s))) return rc;
+  if (a.P.compute_penetration) {
+    if (mixed) rc = launch_epa_g<CAPS_ALL, MODE>(ctx, a, s);
+    else rc = launch_epa_g<CAP_PRIM, MODE>(ctx, a, s);
+    if (rc) return rc;
   }
   ctx->stats.pairs_processed += n;
   return HFB_OK;
@@ -588,6 +663,13 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   hfb_ctx* c = new hfb_ctx();
   c->device = device;
   c->num_sms = prop.multiProcessorCount;
+  auto env_g = [](const char* name, int dflt) {
+    const char* v = getenv(name);
+    const int g = v ? atoi(v) : dflt;
+    return (g == 8 || g == 16 || g == 32) ? g : dflt;
+  };
+  c->gc = env_g("HFB_GC", HFB_GC_DEFAULT);
+  c->ge = env_g("HFB_GE", HFB_GE_DEFAULT);
   for (int k = 0; k < kSlots; ++k)
     if (cudaStreamCreateWithFlags(&c->slots[k].stream, cudaStreamNonBlocking) != cudaSuccess) {
       delete c;
@@ -814,6 +896,8 @@ int hfb_get_kernel_times(hfb_ctx* ctx, hfb_kernel_times* out, int reset) {
     cudaEventElapsedTime(&ms, e.a, e.b);
     if (e.kind == 0) { ctx->ktimes.pairs_ms += ms; ctx->ktimes.pairs_launches++; }
     else if (e.kind == 1) { ctx->ktimes.epa_ms += ms; ctx->ktimes.epa_launches++; }
+    else if (e.kind == 3) { ctx->ktimes.closed_ms += ms; ctx->ktimes.closed_launches++; }
+    else if (e.kind == 4) { ctx->ktimes.convex_ms += ms; ctx->ktimes.convex_launches++; }
     else { ctx->ktimes.other_ms += ms; ctx->ktimes.other_launches++; }
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);

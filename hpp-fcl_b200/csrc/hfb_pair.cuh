@@ -125,9 +125,13 @@ HFB_HD void unswap(const GjkSetup& S, PairOut& o) {  // narrowphase.h:344-346
   }
 }
 
+// which code paths a kernel instantiation carries (the batch is binned by pair class first,
+// so each kernel only needs its own path: smaller code, no divergence between classes)
+enum { PATH_CLOSED = 1, PATH_GJKROUTE = 2, PATH_BOTH = 3 };
+
 // ---- phase 1 -----------------------------------------------------------------
 // returns true when EPA must still run (g holds GJK's final simplex).
-template <int G, int CAPS>
+template <int G, int CAPS, int PATHS = PATH_BOTH>
 HFB_HD bool pair_phase1(const PairIn& in, const SolverP& P, PairOut& o, GjkState& g) {
   const int t1 = in.s1.type, t2 = in.s2.type;
   o.cached_guess = (P.initial_guess == HFB_GUESS_CACHED) ? in.cached_guess : mk(1, 0, 0);
@@ -140,7 +144,7 @@ HFB_HD bool pair_phase1(const PairIn& in, const SolverP& P, PairOut& o, GjkState
     o.status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
     return false;
   }
-  if ((CAPS & CAP_PRIM) && is_closed_form(t1, t2)) {
+  if ((PATHS & PATH_CLOSED) && (CAPS & CAP_PRIM) && is_closed_form(t1, t2)) {
     Wit w;
     if (t1 == HFB_GEOM_SPHERE && t2 == HFB_GEOM_SPHERE) w = sphere_sphere(in.s1, in.tf1, in.s2, in.tf2);
     else if (t1 == HFB_GEOM_SPHERE && t2 == HFB_GEOM_CAPSULE) w = sphere_capsule(in.s1, in.tf1, in.s2, in.tf2);
@@ -162,6 +166,12 @@ HFB_HD bool pair_phase1(const PairIn& in, const SolverP& P, PairOut& o, GjkState
     return false;
   }
 
+  if (!(PATHS & PATH_GJKROUTE)) {  // mis-binned pair: cannot happen (k_bin_* and is_closed_form agree)
+    o.distance = DBL_MAX;
+    o.p1 = o.p2 = o.normal = nan3();
+    o.status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
+    return false;
+  }
   if ((CAPS & CAP_TRI) && t1 == HFB_GEOM_TRIANGLE && t2 == HFB_GEOM_TRIANGLE) {
     // triangle_triangle.cpp:47-104: world-frame triangles, GJK only
     ShapeD a = in.s1, b = in.s2;

@@ -320,23 +320,40 @@ class Context {
   ~Context() { hfb_ctx_destroy(ctx); }
   hfb_ctx* raw() { return ctx; }
   uint32_t handle(const CollisionGeometry* g) {
-    auto it = handles.find(g);
-    if (it != handles.end()) return it->second;
     hfb_shape rec;
     rec.type = (uint32_t)g->getNodeType();
     rec.data = 0;
     g->params(rec.p);
     const ShapeBase* sb = dynamic_cast<const ShapeBase*>(g);
     rec.ssr = sb ? sb->getSweptSphereRadius() : 0.0;
-    if (const std::vector<Vec3f>* v = g->vertices()) {
-      std::vector<double> flat(3 * v->size());
+    const std::vector<Vec3f>* verts = g->vertices();
+    // the cache is keyed by address, so an entry is only valid while the flattened record still
+    // matches (a freed geometry's address can be reused by a different shape)
+    auto it = handles.find(g);
+    if (it != handles.end()) {
+      const Entry& e = it->second;
+      bool same = e.rec.type == rec.type && e.rec.p[0] == rec.p[0] && e.rec.p[1] == rec.p[1] &&
+                  e.rec.p[2] == rec.p[2] && e.rec.ssr == rec.ssr && e.nverts == (verts ? verts->size() : 0);
+      if (same && verts)
+        for (size_t i = 0; i < verts->size() && same; ++i)
+          for (int k = 0; k < 3; ++k) same = same && e.verts[3 * i + k] == (*verts)[i][k];
+      if (same) return e.handle;
+      handles.erase(it);
+    }
+    Entry ent;
+    if (const std::vector<Vec3f>* v = verts) {
+      std::vector<double>& flat = ent.verts;
+      flat.resize(3 * v->size());
       for (size_t i = 0; i < v->size(); ++i)
         for (int k = 0; k < 3; ++k) flat[3 * i + k] = (*v)[i][k];
       check(hfb_geom_register_convex(ctx, flat.data(), (uint32_t)v->size(), &rec.data));
+      ent.nverts = v->size();
     }
     uint32_t h;
     check(hfb_geom_register_shapes(ctx, &rec, 1, &h));
-    handles[g] = h;
+    ent.rec = rec;
+    ent.handle = h;
+    handles[g] = ent;
     dirty = true;
     return h;
   }
@@ -357,8 +374,14 @@ class Context {
     const int rc = hfb_ctx_create(device, &ctx);
     if (rc != HFB_OK) throw std::runtime_error("hppfcl_b200: no usable CUDA device (there is no CPU fallback)");
   }
+  struct Entry {
+    hfb_shape rec{};
+    uint32_t handle = 0;
+    size_t nverts = 0;
+    std::vector<double> verts;
+  };
   hfb_ctx* ctx = nullptr;
-  std::unordered_map<const CollisionGeometry*, uint32_t> handles;
+  std::unordered_map<const CollisionGeometry*, Entry> handles;
   bool dirty = false;
 };
 

@@ -299,12 +299,16 @@ int hfb_get_stats(hfb_ctx* ctx, hfb_stats* out);
  * around every kernel launch; the reference's counterpart is request.enable_timings
  * -> result.timings, collision.cpp:196-201).  Off by default. */
 typedef struct hfb_kernel_times {
-  double pairs_ms;   /* sum over launches of the phase-1 kernels (k_pairs*) */
+  double pairs_ms;   /* sum over launches of the GJK-routed primitive-pair kernel (phase 1) */
   double epa_ms;     /* sum over launches of the EPA kernel */
   double other_ms;   /* classify / support / clear */
   uint64_t pairs_launches;
   uint64_t epa_launches;
   uint64_t other_launches;
+  double closed_ms;  /* closed-form pair kernel */
+  double convex_ms;  /* lane-group kernel for pairs touching ConvexBase / TriangleP */
+  uint64_t closed_launches;
+  uint64_t convex_launches;
 } hfb_kernel_times;
 int hfb_set_profiling(hfb_ctx* ctx, int enable);
 int hfb_get_kernel_times(hfb_ctx* ctx, hfb_kernel_times* out, int reset);

@@ -140,6 +140,21 @@ def test_convex_vs_primitives_mixed(convex_scene):
     compare_distance(ref, got, what="mixed convex/primitive")
 
 
+@pytest.mark.parametrize("g", [8, 16, 32])
+def test_lane_group_sizes(g, monkeypatch):
+    """every instantiated lanes-per-pair setting (HFB_GC / HFB_GE) gives the same bits"""
+    monkeypatch.setenv("HFB_GC", str(g))
+    monkeypatch.setenv("HFB_GE", str(g))
+    sc, w, hc, hp = _convex_scene(False)
+    n = 20000
+    rng = np.random.default_rng(g)
+    allh = np.concatenate([hc, hp])
+    h1, h2 = allh[rng.integers(0, len(allh), n)], allh[rng.integers(0, len(allh), n)]
+    ref = sc.b["oracle"].batch_collide(h1, w["tf1"][:n], h2, w["tf2"][:n], nthreads=0)
+    got = sc.b["gpu"].batch_collide(h1, w["tf1"][:n], h2, w["tf2"][:n])
+    compare_distance(ref, got, what="G=%d" % g)
+
+
 def test_convex_support_kernel(convex_scene):
     sc, w, hc, hp = convex_scene
     rng = np.random.default_rng(2)
