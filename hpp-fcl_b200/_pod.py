@@ -145,7 +145,8 @@ class KernelTimes(C.Structure):
     _fields_ = [("pairs_ms", C.c_double), ("epa_ms", C.c_double), ("other_ms", C.c_double),
                 ("pairs_launches", C.c_uint64), ("epa_launches", C.c_uint64), ("other_launches", C.c_uint64),
                 ("closed_ms", C.c_double), ("convex_ms", C.c_double),
-                ("closed_launches", C.c_uint64), ("convex_launches", C.c_uint64)]
+                ("closed_launches", C.c_uint64), ("convex_launches", C.c_uint64),
+                ("bvh_ms", C.c_double), ("bvh_launches", C.c_uint64)]
 
 
 def status_gjk(s):

@@ -23,12 +23,25 @@ struct ConvexDesc {
   double cx, cy, cz;  // aabb_local.center()
 };
 
+struct BvhDesc {  // one registered BVHModel<OBBRSS>
+  uint32_t node_off, num_nodes;  // into the node array
+  uint32_t vert_off, num_verts;  // in vertices (3 doubles each)
+  uint32_t tri_off, num_tris;    // in triangles (3 uint32 each)
+  uint32_t _r0, _r1;
+};
+
 struct ArenaView {
   const hfb_shape* shapes;
   const ConvexDesc* cvx;
   const double* pool;
   uint32_t nshapes;
   uint32_t ncvx;
+  // OBBRSS BVH models (nodes are the 256-B records of include/hppfcl_b200.h)
+  const hfb_bvh_node* bvh_nodes;
+  const double* bvh_verts;
+  const uint32_t* bvh_tris;
+  const BvhDesc* bvh_desc;
+  uint32_t nbvh;
 };
 
 template <int CAPS>
@@ -67,7 +80,41 @@ struct HostArena {
   std::vector<hfb_shape> shapes;
   std::vector<ConvexDesc> cvx;
   std::vector<double> pool;
-  bool has_convex = false, has_tri = false, has_unknown = false;
+  std::vector<hfb_bvh_node> bvh_nodes;
+  std::vector<double> bvh_verts;
+  std::vector<uint32_t> bvh_tris;
+  std::vector<BvhDesc> bvh_desc;
+  bool has_convex = false, has_tri = false, has_unknown = false, has_bvh = false;
+
+  // validates the tree (child links, leaf primitive ids, triangle vertex ids) and stores it
+  bool add_bvh(const hfb_bvh_node* nodes, uint32_t nn, const double* verts, uint32_t nv, const uint32_t* tris,
+               uint32_t nt, uint32_t* id) {
+    if (nn == 0 || nv == 0 || nt == 0) return false;
+    for (uint32_t i = 0; i < nn; ++i) {
+      const int fc = nodes[i].first_child;
+      if (fc < 0) {
+        if ((uint32_t)(-(fc + 1)) >= nt) return false;
+      } else if ((uint32_t)fc + 1 >= nn || (uint32_t)fc <= i) {
+        return false;  // children follow their parent in BVHModel::bvs (recursiveBuildTree)
+      }
+    }
+    for (uint32_t i = 0; i < 3 * nt; ++i)
+      if (tris[i] >= nv) return false;
+    BvhDesc d;
+    d.node_off = (uint32_t)bvh_nodes.size();
+    d.num_nodes = nn;
+    d.vert_off = (uint32_t)(bvh_verts.size() / 3);
+    d.num_verts = nv;
+    d.tri_off = (uint32_t)(bvh_tris.size() / 3);
+    d.num_tris = nt;
+    d._r0 = d._r1 = 0;
+    bvh_nodes.insert(bvh_nodes.end(), nodes, nodes + nn);
+    bvh_verts.insert(bvh_verts.end(), verts, verts + 3 * (size_t)nv);
+    bvh_tris.insert(bvh_tris.end(), tris, tris + 3 * (size_t)nt);
+    bvh_desc.push_back(d);
+    *id = (uint32_t)bvh_desc.size() - 1;
+    return true;
+  }
 
   uint32_t add_convex(const double* pts, uint32_t n) {
     ConvexDesc d;
@@ -95,7 +142,10 @@ struct HostArena {
   }
   // returns false on an invalid record
   bool add_shape(const hfb_shape& s, uint32_t* handle) {
-    if (s.type == HFB_GEOM_CONVEX || s.type == HFB_GEOM_TRIANGLE) {
+    if (s.type == HFB_BV_OBBRSS) {
+      if (s.data >= bvh_desc.size()) return false;
+      has_bvh = true;
+    } else if (s.type == HFB_GEOM_CONVEX || s.type == HFB_GEOM_TRIANGLE) {
       if (s.data >= cvx.size()) return false;
       if (s.type == HFB_GEOM_TRIANGLE && cvx[s.data].nv < 3) return false;
       if (s.type == HFB_GEOM_CONVEX) has_convex = true; else has_tri = true;
@@ -114,6 +164,11 @@ struct HostArena {
     v.pool = pool.data();
     v.nshapes = (uint32_t)shapes.size();
     v.ncvx = (uint32_t)cvx.size();
+    v.bvh_nodes = bvh_nodes.data();
+    v.bvh_verts = bvh_verts.data();
+    v.bvh_tris = bvh_tris.data();
+    v.bvh_desc = bvh_desc.data();
+    v.nbvh = (uint32_t)bvh_desc.size();
     return v;
   }
 };

@@ -1,0 +1,1261 @@
+// OBBRSS BVH vs shape: bounding-volume tests, the per-query shape BV and the
+// depth-first traversals, for one (mesh, shape) query.
+//
+// Replaces
+//   RSS distance / rectDistance / segCoords / inVoronoi     src/BV/RSS.cpp:67-713, 995-1005
+//   OBB SAT with squared lower bound                        src/BV/OBB.cpp:290-393, 475-483
+//   computeBV<OBBRSS,S> = fit(getBoundVertices(S, tf))      include/hpp/fcl/shape/geometric_shapes_utility.h:73-83,
+//       src/shape/geometric_shapes_utility.cpp:47-262, src/BVH/BV_fitter.cpp:49-216,
+//       src/BVH/BVH_utility.cpp:183-600, include/hpp/fcl/internal/tools.h:60-203
+//   distanceRecurse / collisionRecurse                      src/traversal/traversal_recurse.cpp:44-85, 153-203
+//   MeshShape{Distance,Collision}TraversalNodeOBBRSS        include/hpp/fcl/internal/traversal_node_bvh_shape.h:97-194, 286-478
+//
+// Design: the reference recurses; here each query walks the tree with an explicit
+// per-thread stack in the same order (nearer child first for distance, left child
+// first for collision) so pruning, witness triangle and lower bounds come out the
+// same.  Nodes are the 256-byte hfb_bvh_node records the host copies out of
+// BVHModel<OBBRSS>::bvs.
+#pragma once
+#include "hfb_arena.cuh"
+#include "hfb_pair.cuh"
+
+namespace hfb {
+
+struct RssD {
+  m3 axes;  // columns are the axes; held as rows of the 3x3 (element (r,c))
+  v3 Tr;
+  double l0, l1, radius;
+};
+struct ObbD {
+  m3 axes;
+  v3 To, extent;
+};
+
+// column-major 9 doubles -> m3 rows
+HFB_HD m3 load_colmajor(const double* p) {
+  m3 A;
+  A.r0 = mk(p[0], p[3], p[6]);
+  A.r1 = mk(p[1], p[4], p[7]);
+  A.r2 = mk(p[2], p[5], p[8]);
+  return A;
+}
+HFB_HD m3 mmulm(const m3& A, const m3& B) {  // A * B, each element left to right over k
+  m3 C;
+  const v3 b0 = mcol(B, 0), b1 = mcol(B, 1), b2 = mcol(B, 2);
+  C.r0 = mk(dot(A.r0, b0), dot(A.r0, b1), dot(A.r0, b2));
+  C.r1 = mk(dot(A.r1, b0), dot(A.r1, b1), dot(A.r1, b2));
+  C.r2 = mk(dot(A.r2, b0), dot(A.r2, b1), dot(A.r2, b2));
+  return C;
+}
+HFB_HD m3 mtrans(const m3& A) {
+  m3 T;
+  T.r0 = mcol(A, 0);
+  T.r1 = mcol(A, 1);
+  T.r2 = mcol(A, 2);
+  return T;
+}
+HFB_HD double mel(const m3& A, int r, int c) { return comp(r == 0 ? A.r0 : (r == 1 ? A.r1 : A.r2), c); }
+
+// -------------------------------------------------------------------- RSS -------
+HFB_HD void clip_range(double& val, double a, double b) {
+  if (val < a) val = a;
+  else if (val > b) val = b;
+}
+HFB_HD void seg_coords(double& t, double& u, double a, double b, double A_dot_B, double A_dot_T, double B_dot_T) {
+  const double denom = 1 - A_dot_B * A_dot_B;
+  if (denom == 0) t = 0;
+  else {
+    t = (A_dot_T - B_dot_T * A_dot_B) / denom;
+    clip_range(t, 0, a);
+  }
+  u = t * A_dot_B - B_dot_T;
+  if (u < 0) {
+    u = 0;
+    t = A_dot_T;
+    clip_range(t, 0, a);
+  } else if (u > b) {
+    u = b;
+    t = u * A_dot_B + A_dot_T;
+    clip_range(t, 0, a);
+  }
+}
+HFB_HD bool in_voronoi(double a, double b, double Anorm_dot_B, double Anorm_dot_T, double A_dot_B, double A_dot_T,
+                       double B_dot_T) {
+  if (fabs(Anorm_dot_B) < 1e-7) return false;
+  double t, u, v;
+  u = -Anorm_dot_T / Anorm_dot_B;
+  clip_range(u, 0, b);
+  t = u * A_dot_B + A_dot_T;
+  clip_range(t, 0, a);
+  v = t * A_dot_B - B_dot_T;
+  if (Anorm_dot_B > 0) {
+    if (v > (u + 1e-7)) return true;
+  } else {
+    if (v < (u - 1e-7)) return true;
+  }
+  return false;
+}
+
+// rectDistance (RSS.cpp:121-713), closest points not requested.  The sixteen edge-pair cases
+// keep the reference's expressions term for term (the association order differs between cases).
+HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1, double b0, double b1) {
+  const double R00 = Rab.r0.x, R01 = Rab.r0.y, R02 = Rab.r0.z;
+  const double R10 = Rab.r1.x, R11 = Rab.r1.y, R12 = Rab.r1.z;
+  const double R20 = Rab.r2.x, R21 = Rab.r2.y;
+  const double A0_dot_B0 = R00, A0_dot_B1 = R01, A1_dot_B0 = R10, A1_dot_B1 = R11;
+  const double aA0_dot_B0 = a0 * A0_dot_B0, aA0_dot_B1 = a0 * A0_dot_B1, aA1_dot_B0 = a1 * A1_dot_B0,
+               aA1_dot_B1 = a1 * A1_dot_B1;
+  const double bA0_dot_B0 = b0 * A0_dot_B0, bA1_dot_B0 = b0 * A1_dot_B0, bA0_dot_B1 = b1 * A0_dot_B1,
+               bA1_dot_B1 = b1 * A1_dot_B1;
+  const v3 Tba = mtmul(Rab, Tab);
+  const double Tab0 = Tab.x, Tab1 = Tab.y, Tab2 = Tab.z, Tba0 = Tba.x, Tba1 = Tba.y, Tba2 = Tba.z;
+  v3 S;
+  double t, u;
+
+  double LA1_lx, LA1_ux, UA1_lx, UA1_ux, LB1_lx, LB1_ux, UB1_lx, UB1_ux;
+  const double ALL_x = -Tba0;
+  const double ALU_x = ALL_x + aA1_dot_B0;
+  const double AUL_x = ALL_x + aA0_dot_B0;
+  const double AUU_x = ALU_x + aA0_dot_B0;
+  if (ALL_x < ALU_x) { LA1_lx = ALL_x; LA1_ux = ALU_x; UA1_lx = AUL_x; UA1_ux = AUU_x; }
+  else { LA1_lx = ALU_x; LA1_ux = ALL_x; UA1_lx = AUU_x; UA1_ux = AUL_x; }
+  const double BLL_x = Tab0;
+  const double BLU_x = BLL_x + bA0_dot_B1;
+  const double BUL_x = BLL_x + bA0_dot_B0;
+  const double BUU_x = BLU_x + bA0_dot_B0;
+  if (BLL_x < BLU_x) { LB1_lx = BLL_x; LB1_ux = BLU_x; UB1_lx = BUL_x; UB1_ux = BUU_x; }
+  else { LB1_lx = BLU_x; LB1_ux = BLL_x; UB1_lx = BUU_x; UB1_ux = BUL_x; }
+
+  // UA1, UB1
+  if ((UA1_ux > b0) && (UB1_ux > a0)) {
+    if (((UA1_lx > b0) || in_voronoi(b1, a1, A1_dot_B0, aA0_dot_B0 - b0 - Tba0, A1_dot_B1, aA0_dot_B1 - Tba1,
+                                     -Tab1 - bA1_dot_B0)) &&
+        ((UB1_lx > a0) || in_voronoi(a1, b1, A0_dot_B1, Tab0 + bA0_dot_B0 - a0, A1_dot_B1, Tab1 + bA1_dot_B0,
+                                     Tba1 - aA0_dot_B1))) {
+      seg_coords(t, u, a1, b1, A1_dot_B1, Tab1 + bA1_dot_B0, Tba1 - aA0_dot_B1);
+      S.x = Tab0 + R00 * b0 + R01 * u - a0;
+      S.y = Tab1 + R10 * b0 + R11 * u - t;
+      S.z = Tab2 + R20 * b0 + R21 * u;
+      return nrm(S);
+    }
+  }
+  // UA1, LB1
+  if ((UA1_lx < 0) && (LB1_ux > a0)) {
+    if (((UA1_ux < 0) || in_voronoi(b1, a1, -A1_dot_B0, Tba0 - aA0_dot_B0, A1_dot_B1, aA0_dot_B1 - Tba1, -Tab1)) &&
+        ((LB1_lx > a0) || in_voronoi(a1, b1, A0_dot_B1, Tab0 - a0, A1_dot_B1, Tab1, Tba1 - aA0_dot_B1))) {
+      seg_coords(t, u, a1, b1, A1_dot_B1, Tab1, Tba1 - aA0_dot_B1);
+      S.x = Tab0 + R01 * u - a0;
+      S.y = Tab1 + R11 * u - t;
+      S.z = Tab2 + R21 * u;
+      return nrm(S);
+    }
+  }
+  // LA1, UB1
+  if ((LA1_ux > b0) && (UB1_lx < 0)) {
+    if (((LA1_lx > b0) || in_voronoi(b1, a1, A1_dot_B0, -Tba0 - b0, A1_dot_B1, -Tba1, -Tab1 - bA1_dot_B0)) &&
+        ((UB1_ux < 0) || in_voronoi(a1, b1, -A0_dot_B1, -Tab0 - bA0_dot_B0, A1_dot_B1, Tab1 + bA1_dot_B0, Tba1))) {
+      seg_coords(t, u, a1, b1, A1_dot_B1, Tab1 + bA1_dot_B0, Tba1);
+      S.x = Tab0 + R00 * b0 + R01 * u;
+      S.y = Tab1 + R10 * b0 + R11 * u - t;
+      S.z = Tab2 + R20 * b0 + R21 * u;
+      return nrm(S);
+    }
+  }
+  // LA1, LB1
+  if ((LA1_lx < 0) && (LB1_lx < 0)) {
+    if (((LA1_ux < 0) || in_voronoi(b1, a1, -A1_dot_B0, Tba0, A1_dot_B1, -Tba1, -Tab1)) &&
+        ((LB1_ux < 0) || in_voronoi(a1, b1, -A0_dot_B1, -Tab0, A1_dot_B1, Tab1, Tba1))) {
+      seg_coords(t, u, a1, b1, A1_dot_B1, Tab1, Tba1);
+      S.x = Tab0 + R01 * u;
+      S.y = Tab1 + R11 * u - t;
+      S.z = Tab2 + R21 * u;
+      return nrm(S);
+    }
+  }
+
+  double LA1_ly, LA1_uy, UA1_ly, UA1_uy, LB0_lx, LB0_ux, UB0_lx, UB0_ux;
+  const double ALL_y = -Tba1;
+  const double ALU_y = ALL_y + aA1_dot_B1;
+  const double AUL_y = ALL_y + aA0_dot_B1;
+  const double AUU_y = ALU_y + aA0_dot_B1;
+  if (ALL_y < ALU_y) { LA1_ly = ALL_y; LA1_uy = ALU_y; UA1_ly = AUL_y; UA1_uy = AUU_y; }
+  else { LA1_ly = ALU_y; LA1_uy = ALL_y; UA1_ly = AUU_y; UA1_uy = AUL_y; }
+  if (BLL_x < BUL_x) { LB0_lx = BLL_x; LB0_ux = BUL_x; UB0_lx = BLU_x; UB0_ux = BUU_x; }
+  else { LB0_lx = BUL_x; LB0_ux = BLL_x; UB0_lx = BUU_x; UB0_ux = BLU_x; }
+
+  // UA1, UB0
+  if ((UA1_uy > b1) && (UB0_ux > a0)) {
+    if (((UA1_ly > b1) || in_voronoi(b0, a1, A1_dot_B1, aA0_dot_B1 - Tba1 - b1, A1_dot_B0, aA0_dot_B0 - Tba0,
+                                     -Tab1 - bA1_dot_B1)) &&
+        ((UB0_lx > a0) || in_voronoi(a1, b0, A0_dot_B0, Tab0 - a0 + bA0_dot_B1, A1_dot_B0, Tab1 + bA1_dot_B1,
+                                     Tba0 - aA0_dot_B0))) {
+      seg_coords(t, u, a1, b0, A1_dot_B0, Tab1 + bA1_dot_B1, Tba0 - aA0_dot_B0);
+      S.x = Tab0 + R01 * b1 + R00 * u - a0;
+      S.y = Tab1 + R11 * b1 + R10 * u - t;
+      S.z = Tab2 + R21 * b1 + R20 * u;
+      return nrm(S);
+    }
+  }
+  // UA1, LB0
+  if ((UA1_ly < 0) && (LB0_ux > a0)) {
+    if (((UA1_uy < 0) || in_voronoi(b0, a1, -A1_dot_B1, Tba1 - aA0_dot_B1, A1_dot_B0, aA0_dot_B0 - Tba0, -Tab1)) &&
+        ((LB0_lx > a0) || in_voronoi(a1, b0, A0_dot_B0, Tab0 - a0, A1_dot_B0, Tab1, Tba0 - aA0_dot_B0))) {
+      seg_coords(t, u, a1, b0, A1_dot_B0, Tab1, Tba0 - aA0_dot_B0);
+      S.x = Tab0 + R00 * u - a0;
+      S.y = Tab1 + R10 * u - t;
+      S.z = Tab2 + R20 * u;
+      return nrm(S);
+    }
+  }
+  // LA1, UB0
+  if ((LA1_uy > b1) && (UB0_lx < 0)) {
+    if (((LA1_ly > b1) || in_voronoi(b0, a1, A1_dot_B1, -Tba1 - b1, A1_dot_B0, -Tba0, -Tab1 - bA1_dot_B1)) &&
+        ((UB0_ux < 0) || in_voronoi(a1, b0, -A0_dot_B0, -Tab0 - bA0_dot_B1, A1_dot_B0, Tab1 + bA1_dot_B1, Tba0))) {
+      seg_coords(t, u, a1, b0, A1_dot_B0, Tab1 + bA1_dot_B1, Tba0);
+      S.x = Tab0 + R01 * b1 + R00 * u;
+      S.y = Tab1 + R11 * b1 + R10 * u - t;
+      S.z = Tab2 + R21 * b1 + R20 * u;
+      return nrm(S);
+    }
+  }
+  // LA1, LB0
+  if ((LA1_ly < 0) && (LB0_lx < 0)) {
+    if (((LA1_uy < 0) || in_voronoi(b0, a1, -A1_dot_B1, Tba1, A1_dot_B0, -Tba0, -Tab1)) &&
+        ((LB0_ux < 0) || in_voronoi(a1, b0, -A0_dot_B0, -Tab0, A1_dot_B0, Tab1, Tba0))) {
+      seg_coords(t, u, a1, b0, A1_dot_B0, Tab1, Tba0);
+      S.x = Tab0 + R00 * u;
+      S.y = Tab1 + R10 * u - t;
+      S.z = Tab2 + R20 * u;
+      return nrm(S);
+    }
+  }
+
+  double LA0_lx, LA0_ux, UA0_lx, UA0_ux, LB1_ly, LB1_uy, UB1_ly, UB1_uy;
+  const double BLL_y = Tab1;
+  const double BLU_y = BLL_y + bA1_dot_B1;
+  const double BUL_y = BLL_y + bA1_dot_B0;
+  const double BUU_y = BLU_y + bA1_dot_B0;
+  if (ALL_x < AUL_x) { LA0_lx = ALL_x; LA0_ux = AUL_x; UA0_lx = ALU_x; UA0_ux = AUU_x; }
+  else { LA0_lx = AUL_x; LA0_ux = ALL_x; UA0_lx = AUU_x; UA0_ux = ALU_x; }
+  if (BLL_y < BLU_y) { LB1_ly = BLL_y; LB1_uy = BLU_y; UB1_ly = BUL_y; UB1_uy = BUU_y; }
+  else { LB1_ly = BLU_y; LB1_uy = BLL_y; UB1_ly = BUU_y; UB1_uy = BUL_y; }
+
+  // UA0, UB1
+  if ((UA0_ux > b0) && (UB1_uy > a1)) {
+    if (((UA0_lx > b0) || in_voronoi(b1, a0, A0_dot_B0, aA1_dot_B0 - Tba0 - b0, A0_dot_B1, aA1_dot_B1 - Tba1,
+                                     -Tab0 - bA0_dot_B0)) &&
+        ((UB1_ly > a1) || in_voronoi(a0, b1, A1_dot_B1, Tab1 - a1 + bA1_dot_B0, A0_dot_B1, Tab0 + bA0_dot_B0,
+                                     Tba1 - aA1_dot_B1))) {
+      seg_coords(t, u, a0, b1, A0_dot_B1, Tab0 + bA0_dot_B0, Tba1 - aA1_dot_B1);
+      S.x = Tab0 + R00 * b0 + R01 * u - t;
+      S.y = Tab1 + R10 * b0 + R11 * u - a1;
+      S.z = Tab2 + R20 * b0 + R21 * u;
+      return nrm(S);
+    }
+  }
+  // UA0, LB1
+  if ((UA0_lx < 0) && (LB1_uy > a1)) {
+    if (((UA0_ux < 0) || in_voronoi(b1, a0, -A0_dot_B0, Tba0 - aA1_dot_B0, A0_dot_B1, aA1_dot_B1 - Tba1, -Tab0)) &&
+        ((LB1_ly > a1) || in_voronoi(a0, b1, A1_dot_B1, Tab1 - a1, A0_dot_B1, Tab0, Tba1 - aA1_dot_B1))) {
+      seg_coords(t, u, a0, b1, A0_dot_B1, Tab0, Tba1 - aA1_dot_B1);
+      S.x = Tab0 + R01 * u - t;
+      S.y = Tab1 + R11 * u - a1;
+      S.z = Tab2 + R21 * u;
+      return nrm(S);
+    }
+  }
+  // LA0, UB1
+  if ((LA0_ux > b0) && (UB1_ly < 0)) {
+    if (((LA0_lx > b0) || in_voronoi(b1, a0, A0_dot_B0, -b0 - Tba0, A0_dot_B1, -Tba1, -bA0_dot_B0 - Tab0)) &&
+        ((UB1_uy < 0) || in_voronoi(a0, b1, -A1_dot_B1, -Tab1 - bA1_dot_B0, A0_dot_B1, Tab0 + bA0_dot_B0, Tba1))) {
+      seg_coords(t, u, a0, b1, A0_dot_B1, Tab0 + bA0_dot_B0, Tba1);
+      S.x = Tab0 + R00 * b0 + R01 * u - t;
+      S.y = Tab1 + R10 * b0 + R11 * u;
+      S.z = Tab2 + R20 * b0 + R21 * u;
+      return nrm(S);
+    }
+  }
+  // LA0, LB1
+  if ((LA0_lx < 0) && (LB1_ly < 0)) {
+    if (((LA0_ux < 0) || in_voronoi(b1, a0, -A0_dot_B0, Tba0, A0_dot_B1, -Tba1, -Tab0)) &&
+        ((LB1_uy < 0) || in_voronoi(a0, b1, -A1_dot_B1, -Tab1, A0_dot_B1, Tab0, Tba1))) {
+      seg_coords(t, u, a0, b1, A0_dot_B1, Tab0, Tba1);
+      S.x = Tab0 + R01 * u - t;
+      S.y = Tab1 + R11 * u;
+      S.z = Tab2 + R21 * u;
+      return nrm(S);
+    }
+  }
+
+  double LA0_ly, LA0_uy, UA0_ly, UA0_uy, LB0_ly, LB0_uy, UB0_ly, UB0_uy;
+  if (ALL_y < AUL_y) { LA0_ly = ALL_y; LA0_uy = AUL_y; UA0_ly = ALU_y; UA0_uy = AUU_y; }
+  else { LA0_ly = AUL_y; LA0_uy = ALL_y; UA0_ly = AUU_y; UA0_uy = ALU_y; }
+  if (BLL_y < BUL_y) { LB0_ly = BLL_y; LB0_uy = BUL_y; UB0_ly = BLU_y; UB0_uy = BUU_y; }
+  else { LB0_ly = BUL_y; LB0_uy = BLL_y; UB0_ly = BUU_y; UB0_uy = BLU_y; }
+
+  // UA0, UB0
+  if ((UA0_uy > b1) && (UB0_uy > a1)) {
+    if (((UA0_ly > b1) || in_voronoi(b0, a0, A0_dot_B1, aA1_dot_B1 - Tba1 - b1, A0_dot_B0, aA1_dot_B0 - Tba0,
+                                     -Tab0 - bA0_dot_B1)) &&
+        ((UB0_ly > a1) || in_voronoi(a0, b0, A1_dot_B0, Tab1 - a1 + bA1_dot_B1, A0_dot_B0, Tab0 + bA0_dot_B1,
+                                     Tba0 - aA1_dot_B0))) {
+      seg_coords(t, u, a0, b0, A0_dot_B0, Tab0 + bA0_dot_B1, Tba0 - aA1_dot_B0);
+      S.x = Tab0 + R01 * b1 + R00 * u - t;
+      S.y = Tab1 + R11 * b1 + R10 * u - a1;
+      S.z = Tab2 + R21 * b1 + R20 * u;
+      return nrm(S);
+    }
+  }
+  // UA0, LB0
+  if ((UA0_ly < 0) && (LB0_uy > a1)) {
+    if (((UA0_uy < 0) || in_voronoi(b0, a0, -A0_dot_B1, Tba1 - aA1_dot_B1, A0_dot_B0, aA1_dot_B0 - Tba0, -Tab0)) &&
+        ((LB0_ly > a1) || in_voronoi(a0, b0, A1_dot_B0, Tab1 - a1, A0_dot_B0, Tab0, Tba0 - aA1_dot_B0))) {
+      seg_coords(t, u, a0, b0, A0_dot_B0, Tab0, Tba0 - aA1_dot_B0);
+      S.x = Tab0 + R00 * u - t;
+      S.y = Tab1 + R10 * u - a1;
+      S.z = Tab2 + R20 * u;
+      return nrm(S);
+    }
+  }
+  // LA0, UB0
+  if ((LA0_uy > b1) && (UB0_ly < 0)) {
+    if (((LA0_ly > b1) || in_voronoi(b0, a0, A0_dot_B1, -Tba1 - b1, A0_dot_B0, -Tba0, -Tab0 - bA0_dot_B1)) &&
+        ((UB0_uy < 0) || in_voronoi(a0, b0, -A1_dot_B0, -Tab1 - bA1_dot_B1, A0_dot_B0, Tab0 + bA0_dot_B1, Tba0))) {
+      seg_coords(t, u, a0, b0, A0_dot_B0, Tab0 + bA0_dot_B1, Tba0);
+      S.x = Tab0 + R01 * b1 + R00 * u - t;
+      S.y = Tab1 + R11 * b1 + R10 * u;
+      S.z = Tab2 + R21 * b1 + R20 * u;
+      return nrm(S);
+    }
+  }
+  // LA0, LB0
+  if ((LA0_ly < 0) && (LB0_ly < 0)) {
+    if (((LA0_uy < 0) || in_voronoi(b0, a0, -A0_dot_B1, Tba1, A0_dot_B0, -Tba0, -Tab0)) &&
+        ((LB0_uy < 0) || in_voronoi(a0, b0, -A1_dot_B0, -Tab1, A0_dot_B0, Tab0, Tba0))) {
+      seg_coords(t, u, a0, b0, A0_dot_B0, Tab0, Tba0);
+      S.x = Tab0 + R00 * u - t;
+      S.y = Tab1 + R10 * u;
+      S.z = Tab2 + R20 * u;
+      return nrm(S);
+    }
+  }
+
+  // no edge pair holds the closest points: separation along the face normals
+  double sep1, sep2;
+  if (Tab2 > 0.0) {
+    sep1 = Tab2;
+    if (R20 < 0.0) sep1 += b0 * R20;
+    if (R21 < 0.0) sep1 += b1 * R21;
+  } else {
+    sep1 = -Tab2;
+    if (R20 > 0.0) sep1 -= b0 * R20;
+    if (R21 > 0.0) sep1 -= b1 * R21;
+  }
+  if (Tba2 < 0) {
+    sep2 = -Tba2;
+    if (R02 < 0.0) sep2 += a0 * R02;
+    if (R12 < 0.0) sep2 += a1 * R12;
+  } else {
+    sep2 = Tba2;
+    if (R02 > 0.0) sep2 -= a0 * R02;
+    if (R12 > 0.0) sep2 -= a1 * R12;
+  }
+  const double sep = (sep1 > sep2 ? sep1 : sep2);
+  return (sep > 0 ? sep : 0);
+}
+
+// distance(R0, T0, b1, b2) (RSS.cpp:995-1005)
+HFB_HD double rss_distance(const m3& R0, v3 T0, const RssD& b1, const RssD& b2) {
+  const m3 b1t = mtrans(b1.axes);
+  const m3 R = mmulm(mmulm(b1t, R0), b2.axes);
+  const v3 Ttemp = mmul(R0, b2.Tr) + T0 - b1.Tr;
+  const v3 T = mtmul(b1.axes, Ttemp);
+  double dist = rect_distance(R, T, b1.l0, b1.l1, b2.l0, b2.l1);
+  dist -= (b1.radius + b2.radius);
+  return (dist < 0.0) ? 0.0 : dist;
+}
+
+// -------------------------------------------------------------------- OBB -------
+// obbDisjointAndLowerBoundDistance (OBB.cpp:290-393)
+HFB_HD bool obb_disjoint_lb(const m3& B, v3 T, v3 a_, v3 b_, double security_margin, double break_distance,
+                            double& sq_lb) {
+  const double bd2 = break_distance * break_distance;
+  m3 Bf;
+  Bf.r0 = mk(fabs(B.r0.x), fabs(B.r0.y), fabs(B.r0.z));
+  Bf.r1 = mk(fabs(B.r1.x), fabs(B.r1.y), fabs(B.r1.z));
+  Bf.r2 = mk(fabs(B.r2.x), fabs(B.r2.y), fabs(B.r2.z));
+  const double hm = security_margin / 2;
+  const v3 a = mk(fmax(a_.x + hm, 0.0), fmax(a_.y + hm, 0.0), fmax(a_.z + hm, 0.0));
+  const v3 b = mk(fmax(b_.x + hm, 0.0), fmax(b_.y + hm, 0.0), fmax(b_.z + hm, 0.0));
+  {
+    v3 corner = mk(fabs(T.x) - a.x, fabs(T.y) - a.y, fabs(T.z) - a.z);
+    corner = corner - mmul(Bf, b);
+    const v3 c = mk(fmax(corner.x, 0.0), fmax(corner.y, 0.0), fmax(corner.z, 0.0));
+    sq_lb = sqn(c);
+  }
+  if (sq_lb > bd2) return true;
+  {
+    double s, t = 0;
+    s = fabs(dot(mcol(B, 0), T)) - dot(mcol(Bf, 0), a) - b.x;
+    if (s > 0) t += s * s;
+    s = fabs(dot(mcol(B, 1), T)) - dot(mcol(Bf, 1), a) - b.y;
+    if (s > 0) t += s * s;
+    s = fabs(dot(mcol(B, 2), T)) - dot(mcol(Bf, 2), a) - b.z;
+    if (s > 0) t += s * s;
+    sq_lb = t;
+  }
+  if (sq_lb > bd2) return true;
+  int ja = 1, ka = 2;
+  for (int ia = 0; ia < 3; ++ia) {
+    for (int ib = 0; ib < 3; ++ib) {
+      const int jb = (ib + 1) % 3, kb = (ib + 2) % 3;
+      const double bf = mel(Bf, ia, ib);
+      const double sinus2 = 1 - bf * bf;
+      if (sinus2 < 1e-6) continue;
+      const double s = comp(T, ka) * mel(B, ja, ib) - comp(T, ja) * mel(B, ka, ib);
+      const double diff = fabs(s) - (comp(a, ja) * mel(Bf, ka, ib) + comp(a, ka) * mel(Bf, ja, ib) +
+                                     comp(b, jb) * mel(Bf, ia, kb) + comp(b, kb) * mel(Bf, ia, jb));
+      if (diff > 0) {
+        sq_lb = diff * diff / sinus2;
+        if (sq_lb > bd2) return true;
+      }
+    }
+    ja = ka;
+    ka = ia;
+  }
+  return false;
+}
+// overlap(R0, T0, b1, b2, request, sqrDistLowerBound) (OBB.cpp:475-483)
+HFB_HD bool obb_overlap(const m3& R0, v3 T0, const ObbD& b1, const ObbD& b2, double security_margin,
+                        double break_distance, double& sq_lb) {
+  const v3 Ttemp = mtmul(R0, b2.To - T0) - b1.To;
+  const v3 T = mtmul(b1.axes, Ttemp);
+  const m3 R = mmulm(mmulm(mtrans(b1.axes), mtrans(R0)), b2.axes);
+  return !obb_disjoint_lb(R, T, b1.extent, b2.extent, security_margin, break_distance, sq_lb);
+}
+
+// ------------------------------------------------------ shape bounding volume -----
+// getBoundVertices (geometric_shapes_utility.cpp:47-262): the i-th bound vertex in the shape frame
+HFB_HD int bound_vertex_count(const ShapeD& s) {
+  switch (s.type) {
+    case HFB_GEOM_BOX: return 8;
+    case HFB_GEOM_SPHERE: return 12;
+    case HFB_GEOM_ELLIPSOID: return 12;
+    case HFB_GEOM_CAPSULE: return 36;
+    case HFB_GEOM_CONE: return 7;
+    case HFB_GEOM_CYLINDER: return 12;
+    case HFB_GEOM_CONVEX: return s.nv;
+    default: return 0;
+  }
+}
+// icosahedron-like 12-point pattern used for sphere / ellipsoid / capsule caps: (0,±a,±b),(±a,±b,0),(±b,0,±a)
+HFB_HD v3 ico12(int i, double ax, double ay, double az, double bx, double by, double bz) {
+  switch (i) {
+    case 0: return mk(0, ay, bz);
+    case 1: return mk(0, -ay, bz);
+    case 2: return mk(0, ay, -bz);
+    case 3: return mk(0, -ay, -bz);
+    case 4: return mk(ax, by, 0);
+    case 5: return mk(-ax, by, 0);
+    case 6: return mk(ax, -by, 0);
+    case 7: return mk(-ax, -by, 0);
+    case 8: return mk(bx, 0, az);
+    case 9: return mk(bx, 0, -az);
+    case 10: return mk(-bx, 0, az);
+    default: return mk(-bx, 0, -az);
+  }
+}
+HFB_HD v3 hexagon(int i, double r2, double c, double d, double z) {  // (r2,0),(c,d),(-c,d),(-r2,0),(-c,-d),(c,-d)
+  switch (i) {
+    case 0: return mk(r2, 0, z);
+    case 1: return mk(c, d, z);
+    case 2: return mk(-c, d, z);
+    case 3: return mk(-r2, 0, z);
+    case 4: return mk(-c, -d, z);
+    default: return mk(c, -d, z);
+  }
+}
+HFB_HD v3 bound_vertex_local(const ShapeD& s, int i) {
+  switch (s.type) {
+    case HFB_GEOM_BOX:
+      return mk((i & 4) ? -s.p0 : s.p0, (i & 2) ? -s.p1 : s.p1, (i & 1) ? -s.p2 : s.p2);
+    case HFB_GEOM_SPHERE: {
+      const double m = (1 + sqrt(5.0)) / 2.0;
+      const double e = s.p0 * 6 / (sqrt(27.0) + sqrt(15.0));
+      const double a = e, b = m * e;
+      return ico12(i, a, a, a, b, b, b);
+    }
+    case HFB_GEOM_ELLIPSOID: {
+      const double phi = (1 + sqrt(5.0)) / 2.0;
+      const double a = sqrt(3.0) / (phi * phi);
+      const double b = phi * a;
+      return ico12(i, s.p0 * a, s.p1 * a, s.p2 * a, s.p0 * b, s.p1 * b, s.p2 * b);
+    }
+    case HFB_GEOM_CAPSULE: {
+      const double m = (1 + sqrt(5.0)) / 2.0;
+      const double hl = s.p1;
+      const double e = s.p0 * 6 / (sqrt(27.0) + sqrt(15.0));
+      const double a = e, b = m * e;
+      const double r2 = s.p0 * 2 / sqrt(3.0);
+      if (i < 24) {
+        const int k = i % 12;
+        const bool top = i < 12;
+        // z offsets: (0,±a,±b + hl) etc. -- written as in the reference: b + hl, -b + hl, a + hl, -a + hl; b - hl, ...
+        switch (k) {
+          case 0: return mk(0, a, top ? (b + hl) : (b - hl));
+          case 1: return mk(0, -a, top ? (b + hl) : (b - hl));
+          case 2: return mk(0, a, top ? (-b + hl) : (-b - hl));
+          case 3: return mk(0, -a, top ? (-b + hl) : (-b - hl));
+          case 4: return mk(a, b, top ? hl : -hl);
+          case 5: return mk(-a, b, top ? hl : -hl);
+          case 6: return mk(a, -b, top ? hl : -hl);
+          case 7: return mk(-a, -b, top ? hl : -hl);
+          case 8: return mk(b, 0, top ? (a + hl) : (a - hl));
+          case 9: return mk(b, 0, top ? (-a + hl) : (-a - hl));
+          case 10: return mk(-b, 0, top ? (a + hl) : (a - hl));
+          default: return mk(-b, 0, top ? (-a + hl) : (-a - hl));
+        }
+      }
+      const double c = 0.5 * r2, d = s.p0;
+      return hexagon((i - 24) % 6, r2, c, d, (i < 30) ? hl : -hl);
+    }
+    case HFB_GEOM_CONE: {
+      const double hl = s.p1, r2 = s.p0 * 2 / sqrt(3.0), a = 0.5 * r2, b = s.p0;
+      if (i == 6) return mk(0, 0, hl);
+      return hexagon(i, r2, a, b, -hl);
+    }
+    case HFB_GEOM_CYLINDER: {
+      const double hl = s.p1, r2 = s.p0 * 2 / sqrt(3.0), a = 0.5 * r2, b = s.p0;
+      return hexagon(i % 6, r2, a, b, (i < 6) ? -hl : hl);
+    }
+    case HFB_GEOM_CONVEX:
+      return mk(s.cx[i], s.cy[i], s.cz[i]);
+    default:
+      return mk(0, 0, 0);
+  }
+}
+
+// generateCoordinateSystem (tools.h:60-96)
+HFB_HD void gen_coord_system(v3 w, v3& u, v3& v) {
+  double inv_length;
+  if (fabs(w.x) >= fabs(w.y)) {
+    inv_length = 1.0 / sqrt(w.x * w.x + w.z * w.z);
+    u = mk(-w.z * inv_length, 0, w.x * inv_length);
+    v = mk(w.y * u.z, w.z * u.x - w.x * u.z, -w.y * u.x);
+  } else {
+    inv_length = 1.0 / sqrt(w.y * w.y + w.z * w.z);
+    u = mk(0, w.z * inv_length, -w.y * inv_length);
+    v = mk(w.y * u.z - w.z * u.y, -w.x * u.z, w.x * u.y);
+  }
+}
+
+// Jacobi eigen-decomposition (tools.h:103-203) followed by axisFromEigen (BV_fitter.cpp:49-76)
+HFB_HD_NOINLINE void fit_axes_from_covariance(const double Min[6], m3& axes) {
+  // Min = {M00, M11, M22, M01, M12, M02}
+  double R[3][3] = {{Min[0], Min[3], Min[5]}, {Min[3], Min[1], Min[4]}, {Min[5], Min[4], Min[2]}};
+  double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  double b[3], z[3], d[3];
+  double dout[3] = {0, 0, 0};
+  double vout[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  const int n = 3;
+  for (int ip = 0; ip < n; ++ip) {
+    b[ip] = d[ip] = R[ip][ip];
+    z[ip] = 0;
+  }
+  bool done = false;
+  for (int i = 0; i < 50 && !done; ++i) {
+    double sm = 0;
+    for (int ip = 0; ip < n; ++ip)
+      for (int iq = ip + 1; iq < n; ++iq) sm += fabs(R[ip][iq]);
+    if (sm == 0.0) {
+      for (int k = 0; k < 3; ++k) {
+        vout[k][0] = v[k][0];
+        vout[k][1] = v[k][1];
+        vout[k][2] = v[k][2];
+        dout[k] = d[k];
+      }
+      done = true;
+      break;
+    }
+    const double tresh = (i < 3) ? 0.2 * sm / (n * n) : 0.0;
+    for (int ip = 0; ip < n; ++ip) {
+      for (int iq = ip + 1; iq < n; ++iq) {
+        double g = 100.0 * fabs(R[ip][iq]);
+        if (i > 3 && fabs(d[ip]) + g == fabs(d[ip]) && fabs(d[iq]) + g == fabs(d[iq]))
+          R[ip][iq] = 0.0;
+        else if (fabs(R[ip][iq]) > tresh) {
+          double h = d[iq] - d[ip];
+          double t;
+          if (fabs(h) + g == fabs(h))
+            t = (R[ip][iq]) / h;
+          else {
+            const double theta = 0.5 * h / (R[ip][iq]);
+            t = 1.0 / (fabs(theta) + sqrt(1.0 + theta * theta));
+            if (theta < 0.0) t = -t;
+          }
+          const double c = 1.0 / sqrt(1 + t * t);
+          const double s = t * c;
+          const double tau = s / (1.0 + c);
+          h = t * R[ip][iq];
+          z[ip] -= h;
+          z[iq] += h;
+          d[ip] -= h;
+          d[iq] += h;
+          R[ip][iq] = 0.0;
+          for (int j = 0; j < ip; ++j) {
+            g = R[j][ip];
+            h = R[j][iq];
+            R[j][ip] = g - s * (h + g * tau);
+            R[j][iq] = h + s * (g - h * tau);
+          }
+          for (int j = ip + 1; j < iq; ++j) {
+            g = R[ip][j];
+            h = R[j][iq];
+            R[ip][j] = g - s * (h + g * tau);
+            R[j][iq] = h + s * (g - h * tau);
+          }
+          for (int j = iq + 1; j < n; ++j) {
+            g = R[ip][j];
+            h = R[iq][j];
+            R[ip][j] = g - s * (h + g * tau);
+            R[iq][j] = h + s * (g - h * tau);
+          }
+          for (int j = 0; j < n; ++j) {
+            g = v[j][ip];
+            h = v[j][iq];
+            v[j][ip] = g - s * (h + g * tau);
+            v[j][iq] = h + s * (g - h * tau);
+          }
+        }
+      }
+    }
+    for (int ip = 0; ip < n; ++ip) {
+      b[ip] += z[ip];
+      d[ip] = b[ip];
+      z[ip] = 0.0;
+    }
+  }
+  // axisFromEigen
+  int mn, mid, mx;
+  if (dout[0] > dout[1]) { mx = 0; mn = 1; } else { mn = 0; mx = 1; }
+  if (dout[2] < dout[mn]) { mid = mn; mn = 2; }
+  else if (dout[2] > dout[mx]) { mid = mx; mx = 2; }
+  else { mid = 2; }
+  const v3 c0 = mk(vout[0][mx], vout[1][mx], vout[2][mx]);
+  const v3 c1 = mk(vout[0][mid], vout[1][mid], vout[2][mid]);
+  const v3 c2 = mk(vout[1][mx] * vout[2][mid] - vout[1][mid] * vout[2][mx],
+                   vout[0][mid] * vout[2][mx] - vout[0][mx] * vout[2][mid],
+                   vout[0][mx] * vout[1][mid] - vout[0][mid] * vout[1][mx]);
+  axes.r0 = mk(c0.x, c1.x, c2.x);
+  axes.r1 = mk(c0.y, c1.y, c2.y);
+  axes.r2 = mk(c0.z, c1.z, c2.z);
+}
+
+// world-frame bound vertex i
+HFB_HD v3 bound_vertex(const ShapeD& s, const xf& tf, int i) { return xform(tf, bound_vertex_local(s, i)); }
+
+// getCovariance over the bound vertices (BVH_utility.cpp:183-259, point branch)
+HFB_HD void bound_covariance(const ShapeD& s, const xf& tf, int n, double M[6]) {
+  v3 S1 = mk(0, 0, 0);
+  double s00 = 0, s11 = 0, s22 = 0, s01 = 0, s02 = 0, s12 = 0;
+  for (int i = 0; i < n; ++i) {
+    const v3 p = bound_vertex(s, tf, i);
+    S1 = S1 + p;
+    s00 += (p.x * p.x);
+    s11 += (p.y * p.y);
+    s22 += (p.z * p.z);
+    s01 += (p.x * p.y);
+    s02 += (p.x * p.z);
+    s12 += (p.y * p.z);
+  }
+  const unsigned np = (unsigned)n;
+  M[0] = s00 - S1.x * S1.x / np;
+  M[1] = s11 - S1.y * S1.y / np;
+  M[2] = s22 - S1.z * S1.z / np;
+  M[3] = s01 - S1.x * S1.y / np;
+  M[4] = s12 - S1.y * S1.z / np;
+  M[5] = s02 - S1.x * S1.z / np;
+}
+
+// projection of bound vertex i on the three axes (P[i][k] of getRadiusAndOriginAndRectangleSize)
+HFB_HD v3 bound_proj(const ShapeD& s, const xf& tf, const m3& axes, int i) {
+  const v3 v = bound_vertex(s, tf, i);
+  return mk(dot(mcol(axes, 0), v), dot(mcol(axes, 1), v), dot(mcol(axes, 2), v));
+}
+
+// getRadiusAndOriginAndRectangleSize (BVH_utility.cpp:264-482) over the bound vertices; projections
+// are recomputed per pass instead of being stored (the reference heap-allocates P[size][3]).
+HFB_HD_NOINLINE void fit_rss_rectangle(const ShapeD& s, const xf& tf, int n, RssD& bv) {
+  const m3& axes = bv.axes;
+  v3 P0 = bound_proj(s, tf, axes, 0);
+  double minz = P0.z, maxz = P0.z;
+  for (int i = 1; i < n; ++i) {
+    const double zv = bound_proj(s, tf, axes, i).z;
+    if (zv < minz) minz = zv;
+    else if (zv > maxz) maxz = zv;
+  }
+  const double r = 0.5 * (maxz - minz);
+  const double radsqr = r * r;
+  const double cz = 0.5 * (maxz + minz);
+  double minx, maxx, miny, maxy;
+  // x
+  {
+    int minindex = 0, maxindex = 0;
+    double mintmp = P0.x, maxtmp = P0.x;
+    for (int i = 1; i < n; ++i) {
+      const double xv = bound_proj(s, tf, axes, i).x;
+      if (xv < mintmp) { minindex = i; mintmp = xv; }
+      else if (xv > maxtmp) { maxindex = i; maxtmp = xv; }
+    }
+    v3 Pm = bound_proj(s, tf, axes, minindex);
+    double dz = Pm.z - cz;
+    minx = Pm.x + sqrt(fmax(radsqr - dz * dz, 0.0));
+    Pm = bound_proj(s, tf, axes, maxindex);
+    dz = Pm.z - cz;
+    maxx = Pm.x - sqrt(fmax(radsqr - dz * dz, 0.0));
+    for (int i = 0; i < n; ++i) {
+      const v3 Pi = bound_proj(s, tf, axes, i);
+      if (Pi.x < minx) {
+        dz = Pi.z - cz;
+        const double x = Pi.x + sqrt(fmax(radsqr - dz * dz, 0.0));
+        if (x < minx) minx = x;
+      } else if (Pi.x > maxx) {
+        dz = Pi.z - cz;
+        const double x = Pi.x - sqrt(fmax(radsqr - dz * dz, 0.0));
+        if (x > maxx) maxx = x;
+      }
+    }
+  }
+  // y
+  {
+    int minindex = 0, maxindex = 0;
+    double mintmp = P0.y, maxtmp = P0.y;
+    for (int i = 1; i < n; ++i) {
+      const double yv = bound_proj(s, tf, axes, i).y;
+      if (yv < mintmp) { minindex = i; mintmp = yv; }
+      else if (yv > maxtmp) { maxindex = i; maxtmp = yv; }
+    }
+    v3 Pm = bound_proj(s, tf, axes, minindex);
+    double dz = Pm.z - cz;
+    miny = Pm.y + sqrt(fmax(radsqr - dz * dz, 0.0));
+    Pm = bound_proj(s, tf, axes, maxindex);
+    dz = Pm.z - cz;
+    maxy = Pm.y - sqrt(fmax(radsqr - dz * dz, 0.0));
+    for (int i = 0; i < n; ++i) {
+      const v3 Pi = bound_proj(s, tf, axes, i);
+      if (Pi.y < miny) {
+        dz = Pi.z - cz;
+        const double y = Pi.y + sqrt(fmax(radsqr - dz * dz, 0.0));
+        if (y < miny) miny = y;
+      } else if (Pi.y > maxy) {
+        dz = Pi.z - cz;
+        const double y = Pi.y - sqrt(fmax(radsqr - dz * dz, 0.0));
+        if (y > maxy) maxy = y;
+      }
+    }
+  }
+  // corners
+  const double a = sqrt(0.5);
+  for (int i = 0; i < n; ++i) {
+    const v3 Pi = bound_proj(s, tf, axes, i);
+    double dx, dy, u, t;
+    if (Pi.x > maxx) {
+      if (Pi.y > maxy) {
+        dx = Pi.x - maxx;
+        dy = Pi.y - maxy;
+        u = dx * a + dy * a;
+        t = (a * u - dx) * (a * u - dx) + (a * u - dy) * (a * u - dy) + (cz - Pi.z) * (cz - Pi.z);
+        u = u - sqrt(fmax(radsqr - t, 0.0));
+        if (u > 0) { maxx += u * a; maxy += u * a; }
+      } else if (Pi.y < miny) {
+        dx = Pi.x - maxx;
+        dy = Pi.y - miny;
+        u = dx * a - dy * a;
+        t = (a * u - dx) * (a * u - dx) + (-a * u - dy) * (-a * u - dy) + (cz - Pi.z) * (cz - Pi.z);
+        u = u - sqrt(fmax(radsqr - t, 0.0));
+        if (u > 0) { maxx += u * a; miny -= u * a; }
+      }
+    } else if (Pi.x < minx) {
+      if (Pi.y > maxy) {
+        dx = Pi.x - minx;
+        dy = Pi.y - maxy;
+        u = dy * a - dx * a;
+        t = (-a * u - dx) * (-a * u - dx) + (a * u - dy) * (a * u - dy) + (cz - Pi.z) * (cz - Pi.z);
+        u = u - sqrt(fmax(radsqr - t, 0.0));
+        if (u > 0) { minx -= u * a; maxy += u * a; }
+      } else if (Pi.y < miny) {
+        dx = Pi.x - minx;
+        dy = Pi.y - miny;
+        u = -dx * a - dy * a;
+        t = (-a * u - dx) * (-a * u - dx) + (-a * u - dy) * (-a * u - dy) + (cz - Pi.z) * (cz - Pi.z);
+        u = u - sqrt(fmax(radsqr - t, 0.0));
+        if (u > 0) { minx -= u * a; miny -= u * a; }
+      }
+    }
+  }
+  bv.Tr = mmul(axes, mk(minx, miny, cz));
+  bv.l0 = fmax(maxx - minx, 0.0);
+  bv.l1 = fmax(maxy - miny, 0.0);
+  bv.radius = r;
+}
+
+// getExtentAndCenter_pointcloud (BVH_utility.cpp:487-527) over the bound vertices
+HFB_HD void fit_obb_extent(const ShapeD& s, const xf& tf, int n, ObbD& bv) {
+  v3 mn = mk(DBL_MAX, DBL_MAX, DBL_MAX), mx = mk(-DBL_MAX, -DBL_MAX, -DBL_MAX);
+  for (int i = 0; i < n; ++i) {
+    const v3 proj = mtmul(bv.axes, bound_vertex(s, tf, i));
+    if (proj.x > mx.x) mx.x = proj.x;
+    if (proj.x < mn.x) mn.x = proj.x;
+    if (proj.y > mx.y) mx.y = proj.y;
+    if (proj.y < mn.y) mn.y = proj.y;
+    if (proj.z > mx.z) mx.z = proj.z;
+    if (proj.z < mn.z) mn.z = proj.z;
+  }
+  bv.To = mmul(bv.axes, mx + mn) / 2;
+  bv.extent = (mx - mn) / 2;
+}
+
+// fit(ps, n, bv) (BV_fitter.cpp:455-470): n = 1, 2, 3 special cases, else covariance fit.
+// Only ConvexBase with fewer than 4 vertices can take the special cases.
+HFB_HD void fit_axes_small(const ShapeD& s, const xf& tf, int n, m3& axes, v3& p_first, v3& p_second, double& len12) {
+  const v3 p1 = bound_vertex(s, tf, 0);
+  p_first = p1;
+  if (n == 1) {
+    axes.r0 = mk(1, 0, 0);
+    axes.r1 = mk(0, 1, 0);
+    axes.r2 = mk(0, 0, 1);
+    return;
+  }
+  const v3 p2 = bound_vertex(s, tf, 1);
+  p_second = p2;
+  if (n == 2) {
+    v3 p1p2 = p1 - p2;
+    len12 = nrm(p1p2);
+    const v3 c0 = unit(p1p2);
+    v3 u, v;
+    gen_coord_system(c0, u, v);
+    axes.r0 = mk(c0.x, u.x, v.x);
+    axes.r1 = mk(c0.y, u.y, v.y);
+    axes.r2 = mk(c0.z, u.z, v.z);
+    return;
+  }
+  const v3 p3 = bound_vertex(s, tf, 2);
+  const v3 e0 = p1 - p2, e1 = p2 - p3, e2 = p3 - p1;
+  const double l0 = sqn(e0), l1 = sqn(e1), l2 = sqn(e2);
+  int imax = 0;
+  if (l1 > l0) imax = 1;
+  if (l2 > (imax == 0 ? l0 : l1)) imax = 2;
+  const v3 c2 = unit(cross(e0, e1));
+  const v3 c0 = unit(imax == 0 ? e0 : (imax == 1 ? e1 : e2));
+  const v3 c1 = cross(c2, c0);
+  axes.r0 = mk(c0.x, c1.x, c2.x);
+  axes.r1 = mk(c0.y, c1.y, c2.y);
+  axes.r2 = mk(c0.z, c1.z, c2.z);
+}
+
+HFB_HD void compute_shape_rss(const ShapeD& s, const xf& tf, RssD& bv) {  // RSS half of computeBV<OBBRSS,S>
+  const int n = bound_vertex_count(s);
+  if (n <= 3) {
+    v3 p1, p2;
+    double len = 0;
+    if (n == 2) {
+      // RSS fit2 (:155-168) normalises with axes.col(0) /= len rather than normalize()
+      p1 = bound_vertex(s, tf, 0);
+      p2 = bound_vertex(s, tf, 1);
+      v3 c0 = p1 - p2;
+      len = nrm(c0);
+      c0 = c0 / len;
+      v3 u, v;
+      gen_coord_system(c0, u, v);
+      bv.axes.r0 = mk(c0.x, u.x, v.x);
+      bv.axes.r1 = mk(c0.y, u.y, v.y);
+      bv.axes.r2 = mk(c0.z, u.z, v.z);
+      bv.l0 = len;
+      bv.l1 = 0;
+      bv.Tr = p2;
+      bv.radius = 0;
+      return;
+    }
+    fit_axes_small(s, tf, n, bv.axes, p1, p2, len);
+    if (n == 1) {
+      bv.Tr = p1;
+      bv.l0 = bv.l1 = 0;
+      bv.radius = 0;
+      return;
+    }
+    fit_rss_rectangle(s, tf, 3, bv);
+    return;
+  }
+  double M[6];
+  bound_covariance(s, tf, n, M);
+  fit_axes_from_covariance(M, bv.axes);
+  fit_rss_rectangle(s, tf, n, bv);
+}
+
+HFB_HD void compute_shape_obb(const ShapeD& s, const xf& tf, ObbD& bv) {  // OBB half of computeBV<OBBRSS,S>
+  const int n = bound_vertex_count(s);
+  if (n <= 3) {
+    v3 p1, p2;
+    double len = 0;
+    fit_axes_small(s, tf, n, bv.axes, p1, p2, len);
+    if (n == 1) {
+      bv.To = p1;
+      bv.extent = mk(0, 0, 0);
+      return;
+    }
+    if (n == 2) {
+      bv.extent = mk(len * 0.5, 0, 0);
+      bv.To = (p1 + p2) / 2;
+      return;
+    }
+    fit_obb_extent(s, tf, 3, bv);
+    return;
+  }
+  double M[6];
+  bound_covariance(s, tf, n, M);
+  fit_axes_from_covariance(M, bv.axes);
+  fit_obb_extent(s, tf, n, bv);
+}
+
+// ----------------------------------------------------------------- node access ----
+HFB_HD RssD load_node_rss(const hfb_bvh_node& nd) {
+  RssD r;
+  r.axes = load_colmajor(nd.rss_axes);
+  r.Tr = mk(nd.rss_Tr[0], nd.rss_Tr[1], nd.rss_Tr[2]);
+  r.l0 = nd.rss_length[0];
+  r.l1 = nd.rss_length[1];
+  r.radius = nd.rss_radius;
+  return r;
+}
+HFB_HD ObbD load_node_obb(const hfb_bvh_node& nd) {
+  ObbD o;
+  o.axes = load_colmajor(nd.obb_axes);
+  o.To = mk(nd.obb_To[0], nd.obb_To[1], nd.obb_To[2]);
+  o.extent = mk(nd.obb_extent[0], nd.obb_extent[1], nd.obb_extent[2]);
+  return o;
+}
+
+#define HFB_BVH_STACK 128
+
+struct BvhQuery {  // one (mesh, shape) query after the operand swap of distance()/collide()
+  const hfb_bvh_node* nodes;
+  const double* verts;    // xyz triples
+  const uint32_t* tris;   // index triples
+  xf tf_mesh, tf_shape;
+  ShapeD shape;
+};
+
+// resolves the (BVH, shape) operands of a pair; `swapped` when the caller passed (shape, BVH)
+// (distance.cpp:74-89, collision.cpp:92-108).  Returns false for unsupported partners
+// (mesh-mesh, triangle, plane, ...).
+template <int CAPS>
+HFB_HD bool bvh_make_query(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2, const xf& tf2, BvhQuery& q,
+                           bool& swapped) {
+  const hfb_shape& r1 = A.shapes[h1];
+  const hfb_shape& r2 = A.shapes[h2];
+  swapped = r1.type != HFB_BV_OBBRSS;
+  const hfb_shape& rm = swapped ? r2 : r1;
+  const uint32_t hs = swapped ? h1 : h2;
+  const hfb_shape& rs = swapped ? r1 : r2;
+  if (rm.type != HFB_BV_OBBRSS) return false;
+  if (!(rs.type == HFB_GEOM_BOX || rs.type == HFB_GEOM_SPHERE || rs.type == HFB_GEOM_CAPSULE ||
+        rs.type == HFB_GEOM_CONE || rs.type == HFB_GEOM_CYLINDER || rs.type == HFB_GEOM_ELLIPSOID ||
+        rs.type == HFB_GEOM_CONVEX))
+    return false;
+  const BvhDesc& d = A.bvh_desc[rm.data];
+  q.nodes = A.bvh_nodes + d.node_off;
+  q.verts = A.bvh_verts + 3 * (size_t)d.vert_off;
+  q.tris = A.bvh_tris + 3 * (size_t)d.tri_off;
+  q.tf_mesh = swapped ? tf2 : tf1;
+  q.tf_shape = swapped ? tf1 : tf2;
+  q.shape = load_shape<CAPS>(A, hs);
+  return true;
+}
+
+// leaf: TriangleP(mesh triangle) vs shape, internal::ShapeShapeDistance<TriangleP,S>
+// (traversal_node_bvh_shape.h:342-364, 139-188); solver warm-start state carries from leaf to leaf.
+template <int CAPS>
+HFB_HD void bvh_leaf(const BvhQuery& q, int primitive_id, const SolverP& P, EpaWs* ws, PairIn& in, PairOut& o) {
+  const uint32_t* t = q.tris + 3 * (size_t)primitive_id;
+  const double* a = q.verts + 3 * (size_t)t[0];
+  const double* b = q.verts + 3 * (size_t)t[1];
+  const double* c = q.verts + 3 * (size_t)t[2];
+  in.s1.type = HFB_GEOM_TRIANGLE;
+  in.s1.ssr = 0;
+  in.s1.p0 = in.s1.p1 = in.s1.p2 = 0;
+  in.s1.nv = 0;
+  in.s1.cx = in.s1.cy = in.s1.cz = nullptr;
+  in.s1.center = mk(0, 0, 0);
+  in.s1.ta = mk(a[0], a[1], a[2]);
+  in.s1.tb = mk(b[0], b[1], b[2]);
+  in.s1.tc = mk(c[0], c[1], c[2]);
+  GjkState g;
+  if (pair_phase1<1, CAPS, PATH_BOTH>(in, P, o, g)) pair_phase2<1, CAPS>(in, P, g, ws, o);
+  // GJKSolver keeps cached_guess / support_func_cached_guess between calls (narrowphase.h:353-391, 625-626)
+  in.cached_guess = o.cached_guess;
+  in.hint0 = o.hint0;
+  in.hint1 = o.hint1;
+}
+
+struct BvhDistOut {
+  double min_distance;
+  v3 p1, p2, normal;
+  int b1;
+  unsigned bv_tests, leaf_tests;
+};
+
+// orientedBVHShapeDistance + distance(node) + distanceRecurse, on a fresh DistanceResult
+template <int CAPS>
+HFB_HD void bvh_shape_distance(const BvhQuery& q, const SolverP& P, double rel_err, double abs_err, EpaWs* ws,
+                               PairIn& in, BvhDistOut& out) {
+  RssD sbv;
+  compute_shape_rss(q.shape, q.tf_shape, sbv);  // traversal_node_setup.h:765
+  in.s2 = q.shape;
+  in.tf1 = q.tf_mesh;
+  in.tf2 = q.tf_shape;
+  out.min_distance = DBL_MAX;
+  out.p1 = out.p2 = out.normal = nan3();
+  out.b1 = -1;
+  out.bv_tests = out.leaf_tests = 0;
+  PairOut o;
+  // preprocess(): seed with triangle 0 (traversal_node_bvh_shape.h:457-461)
+  bvh_leaf<CAPS>(q, 0, P, ws, in, o);
+  if (out.min_distance > o.distance) {
+    out.min_distance = o.distance;
+    out.b1 = 0;
+    out.p1 = o.p1;
+    out.p2 = o.p2;
+    out.normal = o.normal;
+  }
+  // distanceRecurse (traversal_recurse.cpp:153-203) with an explicit stack.  A stack entry is a node
+  // that is still to be visited together with the lower bound that canStop() must re-check when the
+  // node is popped (the reference evaluates canStop for the second child after the first returned).
+  int stk_node[HFB_BVH_STACK];
+  double stk_d[HFB_BVH_STACK];
+  int sp = 0;
+  stk_node[0] = 0;
+  stk_d[0] = -1.0;  // root: visited unconditionally
+  sp = 1;
+  while (sp > 0) {
+    --sp;
+    const int b = stk_node[sp];
+    const double dlow = stk_d[sp];
+    if (dlow >= 0) {  // canStop(d) (:322-327)
+      if ((dlow >= out.min_distance - abs_err) && (dlow * (1 + rel_err) >= out.min_distance)) continue;
+    }
+    const hfb_bvh_node& nd = q.nodes[b];
+    if (nd.first_child < 0) {
+      const int prim = -(nd.first_child + 1);
+      bvh_leaf<CAPS>(q, prim, P, ws, in, o);
+      out.leaf_tests++;
+      if (out.min_distance > o.distance) {  // DistanceResult::update: strict '>' keeps the first minimum
+        out.min_distance = o.distance;
+        out.b1 = prim;
+        out.p1 = o.p1;
+        out.p2 = o.p2;
+        out.normal = o.normal;
+      }
+      continue;
+    }
+    const int a1 = nd.first_child, c1 = nd.first_child + 1;
+    const double d1 = rss_distance(q.tf_mesh.R, q.tf_mesh.T, sbv, load_node_rss(q.nodes[a1]));
+    const double d2 = rss_distance(q.tf_mesh.R, q.tf_mesh.T, sbv, load_node_rss(q.nodes[c1]));
+    out.bv_tests += 2;
+    // visit the nearer child first: push the farther one below it
+    if (sp + 2 > HFB_BVH_STACK) break;  // cannot happen for trees of depth < 128
+    if (d2 < d1) {
+      stk_node[sp] = a1; stk_d[sp] = d1; ++sp;
+      stk_node[sp] = c1; stk_d[sp] = d2; ++sp;
+    } else {
+      stk_node[sp] = c1; stk_d[sp] = d2; ++sp;
+      stk_node[sp] = a1; stk_d[sp] = d1; ++sp;
+    }
+  }
+}
+
+struct BvhColOut {
+  double distance_lower_bound;
+  v3 lb_p1, lb_p2, lb_normal;
+  bool has_contact;
+  int b1;
+  double distance;
+  v3 p1, p2, normal;
+  unsigned bv_tests, leaf_tests;
+};
+
+// BVHShapeCollider<OBBRSS,S>::oriented + collide(node) + collisionRecurse, num_max_contacts contacts
+// (only the first is returned), on a fresh CollisionResult
+template <int CAPS>
+HFB_HD void bvh_shape_collide(const BvhQuery& q, const SolverP& P, double security_margin, double break_distance,
+                              double collision_distance_threshold, unsigned num_max_contacts, EpaWs* ws, PairIn& in,
+                              BvhColOut& out) {
+  ObbD sbv;
+  compute_shape_obb(q.shape, q.tf_shape, sbv);  // traversal_node_setup.h:655-694
+  in.s2 = q.shape;
+  in.tf1 = q.tf_mesh;
+  in.tf2 = q.tf_shape;
+  out.distance_lower_bound = DBL_MAX;
+  out.lb_p1 = out.lb_p2 = out.lb_normal = nan3();
+  out.has_contact = false;
+  out.b1 = -1;
+  out.distance = DBL_MAX;
+  out.p1 = out.p2 = out.normal = nan3();
+  out.bv_tests = out.leaf_tests = 0;
+  unsigned ncontacts = 0;
+  PairOut o;
+  int stk[HFB_BVH_STACK];
+  int sp = 0;
+  stk[sp++] = 0;
+  while (sp > 0) {
+    const int b = stk[--sp];
+    const hfb_bvh_node& nd = q.nodes[b];
+    if (nd.first_child < 0) {  // leafCollides (traversal_node_bvh_shape.h:139-188)
+      const int prim = -(nd.first_child + 1);
+      bvh_leaf<CAPS>(q, prim, P, ws, in, o);
+      out.leaf_tests++;
+      const double d2c = o.distance - security_margin;
+      if (d2c < out.distance_lower_bound) {  // updateDistanceLowerBoundFromLeaf
+        out.distance_lower_bound = d2c;
+        out.lb_p1 = o.p1;
+        out.lb_p2 = o.p2;
+        out.lb_normal = o.normal;
+      }
+      if (d2c <= collision_distance_threshold) {
+        if (ncontacts < num_max_contacts) {
+          if (ncontacts == 0) {
+            out.has_contact = true;
+            out.b1 = prim;
+            out.distance = o.distance;
+            out.p1 = o.p1;
+            out.p2 = o.p2;
+            out.normal = o.normal;
+          }
+          ++ncontacts;
+        }
+      }
+      // canStop() after the first child returned (traversal_recurse.cpp:69): isSatisfied
+      if (ncontacts > 0 && num_max_contacts <= ncontacts) break;
+      continue;
+    }
+    double sq_lb;
+    out.bv_tests++;
+    const bool disjoint = !obb_overlap(q.tf_mesh.R, q.tf_mesh.T, load_node_obb(nd), sbv, security_margin, break_distance,
+                                       sq_lb);
+    if (disjoint) {  // updateDistanceLowerBoundFromBV (collision_data.h:1177-1184)
+      if (out.distance_lower_bound > 0) {
+        const double nd_lb = sqrt(sq_lb);
+        if (nd_lb < out.distance_lower_bound) out.distance_lower_bound = nd_lb;
+      }
+      continue;
+    }
+    if (sp + 2 > HFB_BVH_STACK) break;
+    stk[sp++] = nd.first_child + 1;  // right child visited after the left one
+    stk[sp++] = nd.first_child;
+  }
+}
+
+// ---- record writers: one (h1, tf1, h2, tf2) pair where one operand is a BVH ------------------
+HFB_HD void put3d(double* o, v3 v) {
+  o[0] = v.x;
+  o[1] = v.y;
+  o[2] = v.z;
+}
+HFB_HD void bvh_unsupported_distance(hfb_distance_result* r) {
+  r->min_distance = DBL_MAX;
+  put3d(r->p1, nan3());
+  put3d(r->p2, nan3());
+  put3d(r->normal, nan3());
+  r->b1 = r->b2 = -1;
+  r->status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
+  r->iterations = 0;
+}
+
+struct BvhReq {  // request fields the traversals need beyond SolverP
+  double rel_err, abs_err;               // DistanceRequest
+  double security_margin, break_distance, collision_distance_threshold;  // CollisionRequest
+  unsigned num_max_contacts;
+};
+
+// distance(): BVHShapeDistancer<OBBRSS,S> with the (GEOM, BVH) operand swap of distance.cpp:74-89
+// (o1/o2, nearest points and normal are swapped back; b1/b2 are not)
+template <int CAPS>
+HFB_HD void bvh_pair_distance(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2, const xf& tf2,
+                              const SolverP& P, const BvhReq& R, v3 cached_guess, int hint0, int hint1, EpaWs* ws,
+                              hfb_distance_result* r, unsigned& bv_tests, unsigned& leaf_tests) {
+  BvhQuery q;
+  bool swapped;
+  bv_tests = leaf_tests = 0;
+  if (!bvh_make_query<CAPS>(A, h1, tf1, h2, tf2, q, swapped)) {
+    bvh_unsupported_distance(r);
+    return;
+  }
+  PairIn in;
+  in.cached_guess = cached_guess;
+  in.hint0 = hint0;
+  in.hint1 = hint1;
+  BvhDistOut o;
+  bvh_shape_distance<CAPS>(q, P, R.rel_err, R.abs_err, ws, in, o);
+  r->min_distance = o.min_distance;
+  put3d(r->p1, swapped ? o.p2 : o.p1);
+  put3d(r->p2, swapped ? o.p1 : o.p2);
+  put3d(r->normal, swapped ? -o.normal : o.normal);
+  r->b1 = o.b1;
+  r->b2 = -1;
+  r->status = pack_status(0, 0, HFB_PATH_BVH);
+  r->iterations = (o.bv_tests & 0xffffu) | ((o.leaf_tests & 0xffffu) << 16);
+  bv_tests = o.bv_tests;
+  leaf_tests = o.leaf_tests;
+}
+
+// collide(): BVHShapeCollider<OBBRSS,S>::oriented with swapObjects() for (GEOM, BVH)
+// (collision.cpp:92-108): contact b1/b2, nearest points and normals are swapped back.
+template <int CAPS>
+HFB_HD void bvh_pair_collide(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2, const xf& tf2,
+                             const SolverP& P, const BvhReq& R, v3 cached_guess, int hint0, int hint1, EpaWs* ws,
+                             hfb_contact* r, unsigned& bv_tests, unsigned& leaf_tests) {
+  BvhQuery q;
+  bool swapped;
+  bv_tests = leaf_tests = 0;
+  r->distance = DBL_MAX;
+  r->distance_lower_bound = DBL_MAX;
+  put3d(r->p1, nan3());
+  put3d(r->p2, nan3());
+  put3d(r->normal, nan3());
+  put3d(r->pos, nan3());
+  r->b1 = r->b2 = -1;
+  r->num_contacts = 0;
+  r->iterations = 0;
+  r->_pad = 0;
+  // negative security margins throw for BVH models (collision_func_matrix.cpp:109-112)
+  if (R.security_margin < 0 || !bvh_make_query<CAPS>(A, h1, tf1, h2, tf2, q, swapped)) {
+    r->status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
+    return;
+  }
+  PairIn in;
+  in.cached_guess = cached_guess;
+  in.hint0 = hint0;
+  in.hint1 = hint1;
+  BvhColOut o;
+  bvh_shape_collide<CAPS>(q, P, R.security_margin, R.break_distance, R.collision_distance_threshold,
+                          R.num_max_contacts, ws, in, o);
+  r->distance_lower_bound = o.distance_lower_bound;
+  put3d(r->p1, swapped ? o.lb_p2 : o.lb_p1);
+  put3d(r->p2, swapped ? o.lb_p1 : o.lb_p2);
+  put3d(r->normal, swapped ? -o.lb_normal : o.lb_normal);
+  if (o.has_contact) {
+    r->num_contacts = 1;
+    r->distance = o.distance;
+    r->b1 = swapped ? -1 : o.b1;
+    r->b2 = swapped ? o.b1 : -1;
+    put3d(r->pos, (o.p1 + o.p2) / 2);
+    put3d(r->p1, swapped ? o.p2 : o.p1);
+    put3d(r->p2, swapped ? o.p1 : o.p2);
+    put3d(r->normal, swapped ? -o.normal : o.normal);
+  }
+  r->status = pack_status(0, 0, HFB_PATH_BVH);
+  r->iterations = (o.bv_tests & 0xffffu) | ((o.leaf_tests & 0xffffu) << 16);
+  bv_tests = o.bv_tests;
+  leaf_tests = o.leaf_tests;
+}
+
+}  // namespace hfb

@@ -24,6 +24,7 @@
 #include <vector>
 
 #include "hfb_arena.cuh"
+#include "hfb_bvh.cuh"
 #include "hfb_request.cuh"
 
 using namespace hfb;
@@ -38,10 +39,11 @@ using namespace hfb;
 // pair classes of the device-side counting sort (k_bin_*): bins [0,8) closed-form
 // combos, [8,45) GJK-routed primitive combos (+ bin 44: unknown node types, reported
 // as unsupported), bin 45: pairs touching ConvexBase / TriangleP
-#define HFB_NBINS 46
+#define HFB_NBINS 47
 #define HFB_BIN_GJK0 8
 #define HFB_BIN_UNKNOWN 44
 #define HFB_BIN_CONVEX 45
+#define HFB_BIN_BVH 46  // one operand is a BVHModel<OBBRSS>
 
 // ---------------------------------------------------------------- EPA queue --
 struct EpaItem {
@@ -72,6 +74,9 @@ struct BatchArgs {
   const unsigned* range_hi;
   SolverP P;
   CollideP C;
+  BvhReq B;                   // traversal request fields (BVH pairs)
+  EpaWs* bvh_ws;              // one EPA workspace per thread of k_bvh (global memory)
+  unsigned long long* bvh_counters;  // [0] bv tests, [1] leaf tests (running totals)
   unsigned n;
 };
 
@@ -197,6 +202,43 @@ __global__ void __launch_bounds__(4 * G) k_epa(const BatchArgs a) {
   }
 }
 
+// ----------------------------------------------------------------- BVH pairs ---
+// One thread per (mesh, shape) query: per-query shape BV, depth-first traversal with a
+// per-thread stack (RSS distance bounds / OBB SAT per node, loaded from the 256-B node
+// records), triangle-shape GJK(+EPA) at the leaves.
+template <int MODE>
+__global__ void __launch_bounds__(64) k_bvh(const BatchArgs a) {
+  const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned nthreads = gridDim.x * blockDim.x;
+  const unsigned lo = *a.range_lo, hi = *a.range_hi;
+  EpaWs* ws = a.bvh_ws + tid;
+  unsigned long long bv_total = 0, leaf_total = 0;
+  for (unsigned k = lo + tid; k < hi; k += nthreads) {
+    const unsigned i = a.index_list[k];
+    v3 guess = mk(1, 0, 0);
+    int h0 = 0, h1 = 0;
+    if (a.P.initial_guess == HFB_GUESS_CACHED) {
+      if (a.guess_in) guess = mk(a.guess_in[3 * i], a.guess_in[3 * i + 1], a.guess_in[3 * i + 2]);
+      if (a.hint_in) {
+        h0 = a.hint_in[2 * i];
+        h1 = a.hint_in[2 * i + 1];
+      }
+    }
+    unsigned bt, lt;
+    const xf t1 = load_xf(a.tf1[i].R), t2 = load_xf(a.tf2[i].R);
+    if (MODE == 0)
+      bvh_pair_distance<CAPS_ALL>(a.A, a.h1[i], t1, a.h2[i], t2, a.P, a.B, guess, h0, h1, ws,
+                                  reinterpret_cast<hfb_distance_result*>(a.out) + i, bt, lt);
+    else
+      bvh_pair_collide<CAPS_ALL>(a.A, a.h1[i], t1, a.h2[i], t2, a.P, a.B, guess, h0, h1, ws,
+                                 reinterpret_cast<hfb_contact*>(a.out) + i, bt, lt);
+    bv_total += bt;
+    leaf_total += lt;
+  }
+  if (bv_total) atomicAdd(a.bvh_counters, bv_total);
+  if (leaf_total) atomicAdd(a.bvh_counters + 1, leaf_total);
+}
+
 // --------------------------------------------------- pair-class counting sort ---
 __device__ __forceinline__ int type_index(uint32_t t) {
   switch (t) {
@@ -208,11 +250,13 @@ __device__ __forceinline__ int type_index(uint32_t t) {
     case HFB_GEOM_ELLIPSOID: return 5;
     case HFB_GEOM_CONVEX: return 6;
     case HFB_GEOM_TRIANGLE: return 7;
+    case HFB_BV_OBBRSS: return 9;
     default: return 8;
   }
 }
 __device__ __forceinline__ int pair_bin(uint32_t t1, uint32_t t2) {
   const int a = type_index(t1), b = type_index(t2);
+  if (a == 9 || b == 9) return HFB_BIN_BVH;
   if (a == 8 || b == 8) return HFB_BIN_UNKNOWN;
   if (a >= 6 || b >= 6) return HFB_BIN_CONVEX;
   if (is_closed_form((int)t1, (int)t2)) {  // same predicate the per-pair dispatch uses
@@ -337,7 +381,7 @@ constexpr size_t kChunk = 1u << 17;  // pairs per pipelined chunk of the host en
 
 struct Slot {
   cudaStream_t stream = nullptr;
-  DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists;
+  DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, bvh_ws, bvh_cnt;
 };
 
 }  // namespace
@@ -378,7 +422,7 @@ int cuda_fail(hfb_ctx* c, cudaError_t e, const char* where) {
     if (_e != cudaSuccess) return cuda_fail(ctx, _e, #call);           \
   } while (0)
 
-// kernel timing hooks: kind 0 = GJK pairs, 1 = epa, 2 = other, 3 = closed-form pairs, 4 = convex pairs
+// kernel timing hooks: kind 0 = GJK pairs, 1 = epa, 2 = other, 3 = closed-form pairs, 4 = convex pairs, 5 = bvh
 struct KTimer {
   hfb_ctx* c;
   cudaStream_t s;
@@ -494,12 +538,34 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   ag.range_lo = offsets + HFB_BIN_GJK0;
   ag.range_hi = offsets + HFB_BIN_CONVEX;
   av.range_lo = offsets + HFB_BIN_CONVEX;
-  av.range_hi = offsets + HFB_NBINS;
+  av.range_hi = offsets + HFB_BIN_BVH;
   if ((rc = launch_pairs<1, CAP_PRIM, MODE, PATH_CLOSED>(ctx, ac, n, s))) return rc;
   if ((rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE>(ctx, ag, n, s))) return rc;
   const bool mixed = ctx->arena.has_convex || ctx->arena.has_tri;
   if (mixed)
     if ((rc = launch_pairs_convex<MODE>(ctx, av, n, s))) return rc;
+  if (ctx->arena.has_bvh) {
+    const int threads = 64;
+    unsigned blocks = (n + threads - 1) / threads;
+    const unsigned cap = (unsigned)ctx->num_sms * 4u;
+    if (blocks > cap) blocks = cap;
+    CK(sl.bvh_ws.reserve((size_t)cap * threads * sizeof(EpaWs)));
+    if (!sl.bvh_cnt.p) {
+      CK(sl.bvh_cnt.reserve(2 * sizeof(unsigned long long)));
+      CK(cudaMemsetAsync(sl.bvh_cnt.p, 0, 2 * sizeof(unsigned long long), s));
+    }
+    BatchArgs ab = a;
+    ab.range_lo = offsets + HFB_BIN_BVH;
+    ab.range_hi = offsets + HFB_NBINS;
+    ab.bvh_ws = static_cast<EpaWs*>(sl.bvh_ws.p);
+    ab.bvh_counters = static_cast<unsigned long long*>(sl.bvh_cnt.p);
+    {
+      KTimer kt(ctx, s, 5);
+      k_bvh<MODE><<<blocks, threads, 0, s>>>(ab);
+    }
+    ctx->stats.kernel_launches++;
+    CK(cudaGetLastError());
+  }
   if (a.P.compute_penetration) {
     if (mixed) rc = launch_epa_g<CAPS_ALL, MODE>(ctx, a, s);
     else rc = launch_epa_g<CAP_PRIM, MODE>(ctx, a, s);
@@ -526,8 +592,8 @@ int check_handles(hfb_ctx* ctx, const uint32_t* h, size_t n) {
 
 template <int MODE, typename Req, typename OutT>
 int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
-               const hfb_transform* tf2, const Req* req, const SolverP& P, const CollideP& Cp, OutT* out,
-               const hfb_guess_out* go) {
+               const hfb_transform* tf2, const Req* req, const SolverP& P, const CollideP& Cp, const BvhReq& Bq,
+               OutT* out, const hfb_guess_out* go) {
   int rc;
   if ((rc = check_ready(ctx))) return rc;
   if (n == 0) return HFB_OK;
@@ -563,6 +629,7 @@ int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* 
     a.out = sl.out.p;
     a.P = P;
     a.C = Cp;
+    a.B = Bq;
     if (gin) {
       CK(sl.gin.reserve(m * 24));
       CK(cudaMemcpyAsync(sl.gin.p, gin + 3 * done, m * 24, cudaMemcpyHostToDevice, s));
@@ -596,8 +663,8 @@ int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* 
 
 template <int MODE, typename Req>
 int device_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
-                 const hfb_transform* tf2, const Req* req, const SolverP& P, const CollideP& Cp, void* out,
-                 const hfb_guess_out* go, void* stream) {
+                 const hfb_transform* tf2, const Req* req, const SolverP& P, const CollideP& Cp, const BvhReq& Bq,
+                 void* out, const hfb_guess_out* go, void* stream) {
   int rc;
   if ((rc = check_ready(ctx))) return rc;
   if (n == 0) return HFB_OK;
@@ -614,6 +681,7 @@ int device_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform
   a.out = out;
   a.P = P;
   a.C = Cp;
+  a.B = Bq;
   a.guess_in = cached ? req->q.cached_gjk_guess : nullptr;
   a.hint_in = cached ? req->q.cached_support_func_guess : nullptr;
   a.guess_out = go ? go->cached_gjk_guess : nullptr;
@@ -684,7 +752,7 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   auto rel = [](Slot& s) {
-    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists};
+    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.bvh_ws, &s.bvh_cnt};
     for (DevBuf* b : bs) b->release();
     if (s.stream) cudaStreamDestroy(s.stream);
   };
@@ -718,9 +786,14 @@ int hfb_geom_register_convex(hfb_ctx* ctx, const double* points, uint32_t num_po
   return HFB_OK;
 }
 
-int hfb_geom_register_bvh_obbrss(hfb_ctx* ctx, const hfb_bvh_node*, uint32_t, const double*, uint32_t,
-                                 const uint32_t*, uint32_t, uint32_t*) {
-  return fail(ctx, HFB_ERR_UNSUPPORTED_PAIR, "OBBRSS BVH traversal is not implemented in this build");
+int hfb_geom_register_bvh_obbrss(hfb_ctx* ctx, const hfb_bvh_node* nodes, uint32_t num_nodes, const double* vertices,
+                                 uint32_t num_vertices, const uint32_t* triangles, uint32_t num_triangles,
+                                 uint32_t* bvh_id) {
+  if (!ctx || !nodes || !vertices || !triangles || !bvh_id) return HFB_ERR_INVALID_ARGUMENT;
+  if (!ctx->arena.add_bvh(nodes, num_nodes, vertices, num_vertices, triangles, num_triangles, bvh_id))
+    return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "malformed OBBRSS BVH (child links / primitive ids / vertex ids)");
+  ctx->committed = false;
+  return HFB_OK;
 }
 
 int hfb_geom_commit(hfb_ctx* ctx) {
@@ -731,8 +804,12 @@ int hfb_geom_commit(hfb_ctx* ctx) {
   const size_t bs = up(A.shapes.size() * sizeof(hfb_shape));
   const size_t bc = up(A.cvx.size() * sizeof(ConvexDesc));
   const size_t bp = up(A.pool.size() * sizeof(double));
+  const size_t bn = up(A.bvh_nodes.size() * sizeof(hfb_bvh_node));
+  const size_t bv = up(A.bvh_verts.size() * sizeof(double));
+  const size_t bt = up(A.bvh_tris.size() * sizeof(uint32_t));
+  const size_t bd = up(A.bvh_desc.size() * sizeof(BvhDesc));
   CK(cudaDeviceSynchronize());
-  CK(ctx->d_arena.reserve(bs + bc + bp + 256));
+  CK(ctx->d_arena.reserve(bs + bc + bp + bn + bv + bt + bd + 256));
   unsigned char* base = static_cast<unsigned char*>(ctx->d_arena.p);
   if (!A.shapes.empty()) CK(cudaMemcpy(base, A.shapes.data(), A.shapes.size() * sizeof(hfb_shape), cudaMemcpyHostToDevice));
   if (!A.cvx.empty()) CK(cudaMemcpy(base + bs, A.cvx.data(), A.cvx.size() * sizeof(ConvexDesc), cudaMemcpyHostToDevice));
@@ -742,6 +819,18 @@ int hfb_geom_commit(hfb_ctx* ctx) {
   ctx->dview.pool = reinterpret_cast<const double*>(base + bs + bc);
   ctx->dview.nshapes = (uint32_t)A.shapes.size();
   ctx->dview.ncvx = (uint32_t)A.cvx.size();
+  unsigned char* pb = base + bs + bc + bp;
+  if (!A.bvh_nodes.empty()) {
+    CK(cudaMemcpy(pb, A.bvh_nodes.data(), A.bvh_nodes.size() * sizeof(hfb_bvh_node), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pb + bn, A.bvh_verts.data(), A.bvh_verts.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pb + bn + bv, A.bvh_tris.data(), A.bvh_tris.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(pb + bn + bv + bt, A.bvh_desc.data(), A.bvh_desc.size() * sizeof(BvhDesc), cudaMemcpyHostToDevice));
+  }
+  ctx->dview.bvh_nodes = reinterpret_cast<const hfb_bvh_node*>(pb);
+  ctx->dview.bvh_verts = reinterpret_cast<const double*>(pb + bn);
+  ctx->dview.bvh_tris = reinterpret_cast<const uint32_t*>(pb + bn + bv);
+  ctx->dview.bvh_desc = reinterpret_cast<const BvhDesc*>(pb + bn + bv + bt);
+  ctx->dview.nbvh = (uint32_t)A.bvh_desc.size();
   ctx->committed = true;
   return HFB_OK;
 }
@@ -762,7 +851,8 @@ int hfb_batch_distance(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_tra
   if (!ctx || !req) return HFB_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (int rc = validate_query(req->q)) return fail(ctx, rc, "invalid request");
-  return host_batch<0>(ctx, n, h1, tf1, h2, tf2, req, solver_from_distance_request(*req), CollideP{0, 0}, out, go);
+  return host_batch<0>(ctx, n, h1, tf1, h2, tf2, req, solver_from_distance_request(*req), CollideP{0, 0},
+                       BvhReq{req->rel_err, req->abs_err, 0, 0, 0, 1}, out, go);
 }
 
 int hfb_batch_distance_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1,
@@ -771,7 +861,8 @@ int hfb_batch_distance_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const 
   if (!ctx || !req) return HFB_ERR_INVALID_ARGUMENT;
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (int rc = validate_query(req->q)) return fail(ctx, rc, "invalid request");
-  return device_batch<0>(ctx, n, h1, tf1, h2, tf2, req, solver_from_distance_request(*req), CollideP{0, 0}, out, go, stream);
+  return device_batch<0>(ctx, n, h1, tf1, h2, tf2, req, solver_from_distance_request(*req), CollideP{0, 0},
+                         BvhReq{req->rel_err, req->abs_err, 0, 0, 0, 1}, out, go, stream);
 }
 
 static int collide_prelude(hfb_ctx* ctx, const hfb_collision_request* req, bool* minus_inf) {
@@ -813,7 +904,10 @@ int hfb_batch_collide(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_tran
     return HFB_OK;
   }
   CollideP C{req->security_margin, req->q.collision_distance_threshold};
-  return host_batch<1>(ctx, n, h1, tf1, h2, tf2, req, solver_from_collision_request(*req), C, out, go);
+  return host_batch<1>(ctx, n, h1, tf1, h2, tf2, req, solver_from_collision_request(*req), C,
+                       BvhReq{0, 0, req->security_margin, req->break_distance, req->q.collision_distance_threshold,
+                              req->num_max_contacts},
+                       out, go);
 }
 
 int hfb_batch_collide_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1,
@@ -832,7 +926,10 @@ int hfb_batch_collide_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const h
     return HFB_OK;
   }
   CollideP C{req->security_margin, req->q.collision_distance_threshold};
-  return device_batch<1>(ctx, n, h1, tf1, h2, tf2, req, solver_from_collision_request(*req), C, out, go, stream);
+  return device_batch<1>(ctx, n, h1, tf1, h2, tf2, req, solver_from_collision_request(*req), C,
+                         BvhReq{0, 0, req->security_margin, req->break_distance, req->q.collision_distance_threshold,
+                                req->num_max_contacts},
+                         out, go, stream);
 }
 
 int hfb_batch_convex_support_device(hfb_ctx* ctx, size_t n, const uint32_t* ids, const double* dirs,
@@ -898,6 +995,7 @@ int hfb_get_kernel_times(hfb_ctx* ctx, hfb_kernel_times* out, int reset) {
     else if (e.kind == 1) { ctx->ktimes.epa_ms += ms; ctx->ktimes.epa_launches++; }
     else if (e.kind == 3) { ctx->ktimes.closed_ms += ms; ctx->ktimes.closed_launches++; }
     else if (e.kind == 4) { ctx->ktimes.convex_ms += ms; ctx->ktimes.convex_launches++; }
+    else if (e.kind == 5) { ctx->ktimes.bvh_ms += ms; ctx->ktimes.bvh_launches++; }
     else { ctx->ktimes.other_ms += ms; ctx->ktimes.other_launches++; }
     cudaEventDestroy(e.a);
     cudaEventDestroy(e.b);
@@ -922,6 +1020,19 @@ int hfb_get_stats(hfb_ctx* ctx, hfb_stats* out) {
   };
   for (int k = 0; k < kSlots; ++k) CK(add(ctx->slots[k]));
   CK(add(ctx->dev_slot));
+  uint64_t bvt = 0, lft = 0;
+  auto addb = [&](Slot& s) -> cudaError_t {
+    if (!s.bvh_cnt.p) return cudaSuccess;
+    unsigned long long v[2] = {0, 0};
+    cudaError_t e = cudaMemcpy(v, s.bvh_cnt.p, sizeof(v), cudaMemcpyDeviceToHost);
+    bvt += v[0];
+    lft += v[1];
+    return e;
+  };
+  for (int k = 0; k < kSlots; ++k) CK(addb(ctx->slots[k]));
+  CK(addb(ctx->dev_slot));
+  ctx->stats.bv_tests = bvt;
+  ctx->stats.leaf_tests = lft;
   ctx->stats.epa_pairs = epa;
   *out = ctx->stats;
   return HFB_OK;

@@ -50,6 +50,7 @@ struct Coop {
 template <>
 struct Coop<1> {
   static HFB_HD int lane() { return 0; }
+  static HFB_HD unsigned mask() { return 0xffffffffu; }
   static HFB_HD void argmax(double&, int&) {}
   static HFB_HD void sync() {}
 };

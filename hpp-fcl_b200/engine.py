@@ -115,10 +115,10 @@ class Engine:
         nodes = np.ascontiguousarray(nodes, dtype=P.bvh_node_dtype)
         v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
         t = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
-        h = C.c_uint32()
+        bid = C.c_uint32()
         self._check(self.L.hfb_geom_register_bvh_obbrss(self.h, _ptr(nodes), nodes.shape[0], _ptr(v),
-                                                        v.shape[0], _ptr(t), t.shape[0], C.byref(h)))
-        return h.value
+                                                        v.shape[0], _ptr(t), t.shape[0], C.byref(bid)))
+        return bid.value  # use as `data` of a shape record of type BV_OBBRSS
 
     def commit(self):
         self._check(self.L.hfb_geom_commit(self.h))

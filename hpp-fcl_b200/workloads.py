@@ -131,3 +131,50 @@ def icosahedron_from_ellipsoid(radii):
         [11, 10, 2], [10, 7, 6], [7, 1, 8], [3, 9, 4], [3, 4, 2], [3, 2, 6], [3, 6, 8],
         [3, 8, 9], [4, 9, 5], [2, 4, 11], [6, 2, 10], [8, 6, 7], [9, 8, 1]], dtype=np.uint32)
     return pts, tris
+
+
+def sphere_mesh(radius=1.0, seg=100, ring=50, noise=0.0, rng=None):
+    """generateBVHModel(Sphere, seg, ring) (shape/geometric_shape_to_BVH_model.h:100-150):
+    2*seg*ring triangles (seg=100, ring=50 -> 10 000); optional radial noise breaks symmetric ties."""
+    pts, tris = [], []
+    phid, thetad = 2 * np.pi / seg, np.pi / (ring + 1)
+    for i in range(ring):
+        theta = thetad * (i + 1)
+        for j in range(seg):
+            phi = phid * j
+            pts.append([radius * np.sin(theta) * np.cos(phi), radius * np.sin(theta) * np.sin(phi),
+                        radius * np.cos(theta)])
+    pts.append([0, 0, radius])
+    pts.append([0, 0, -radius])
+    for i in range(ring - 1):
+        for j in range(seg):
+            a = i * seg + j
+            b = i * seg if j == seg - 1 else i * seg + j + 1
+            c = (i + 1) * seg + j
+            d = (i + 1) * seg if j == seg - 1 else (i + 1) * seg + j + 1
+            tris.append([a, c, b])
+            tris.append([b, c, d])
+    for j in range(seg):
+        a, b, c = j, (0 if j == seg - 1 else j + 1), ring * seg
+        tris.append([c, a, b])
+        a = (ring - 1) * seg + j
+        b = (ring - 1) * seg if j == seg - 1 else (ring - 1) * seg + j + 1
+        c = ring * seg + 1
+        tris.append([a, c, b])
+    pts = np.array(pts, dtype=np.float64)
+    if noise and rng is not None:
+        pts *= 1 + noise * rng.standard_normal((len(pts), 1))
+    return pts, np.array(tris, dtype=np.uint32)
+
+
+def config4_mesh_vs_capsules(n_queries, seed=0xFC1 + 4, seg=100, ring=50, pool=4096):
+    """BASELINE config 4: 10k-triangle OBBRSS mesh vs capsules, distance + nearest points."""
+    rng = np.random.default_rng(seed)
+    verts, tris = sphere_mesh(1.0, seg, ring, noise=0.01, rng=rng)
+    caps = P.make_shapes([P.GEOM_CAPSULE] * pool,
+                         np.stack([0.02 + 0.08 * rng.random(pool), (0.05 + 0.25 * rng.random(pool)) / 2,
+                                   np.zeros(pool)], axis=1))
+    hc = rng.integers(0, pool, n_queries).astype(np.uint32)
+    tf_mesh = random_transforms(rng, n_queries, (-0.2, -0.2, -0.2), (0.2, 0.2, 0.2))
+    tf_caps = random_transforms(rng, n_queries, (-2, -2, -2), (2, 2, 2))
+    return dict(verts=verts, tris=tris, capsules=caps, hc=hc, tf_mesh=tf_mesh, tf_caps=tf_caps)

@@ -233,10 +233,14 @@ typedef struct hfb_bvh_node {
   double rss_length[2]; /* RSS::length */
   double rss_radius;    /* RSS::radius */
 } hfb_bvh_node;
+/* Returns the BVH id in *bvh_id; a shape record {type = HFB_BV_OBBRSS, data = bvh id}
+ * registered with hfb_geom_register_shapes gives the handle used in batches.  Supported
+ * partners: the primitive shapes and ConvexBase (mesh-shape distance and collide,
+ * either operand order); mesh-mesh pairs are reported as unsupported. */
 int hfb_geom_register_bvh_obbrss(hfb_ctx* ctx, const hfb_bvh_node* nodes,
                                  uint32_t num_nodes, const double* vertices,
                                  uint32_t num_vertices, const uint32_t* triangles,
-                                 uint32_t num_triangles, uint32_t* handle_out);
+                                 uint32_t num_triangles, uint32_t* bvh_id);
 /* Uploads everything registered so far to the device. Must be called before
  * the first query and after any further registration. */
 int hfb_geom_commit(hfb_ctx* ctx);
@@ -309,6 +313,8 @@ typedef struct hfb_kernel_times {
   double convex_ms;  /* lane-group kernel for pairs touching ConvexBase / TriangleP */
   uint64_t closed_launches;
   uint64_t convex_launches;
+  double bvh_ms;     /* OBBRSS mesh-shape traversal kernel */
+  uint64_t bvh_launches;
 } hfb_kernel_times;
 int hfb_set_profiling(hfb_ctx* ctx, int enable);
 int hfb_get_kernel_times(hfb_ctx* ctx, hfb_kernel_times* out, int reset);

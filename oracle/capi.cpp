@@ -10,6 +10,7 @@
 #include <omp.h>
 #endif
 
+#include "bvh.hpp"
 #include "oracle.hpp"
 
 using namespace oracle;
@@ -17,7 +18,8 @@ using namespace oracle;
 namespace {
 struct Scene {
   std::vector<std::unique_ptr<Convex>> convexes;
-  std::vector<Shape> shapes;
+  std::vector<std::unique_ptr<BVHModel>> bvhs;
+  std::vector<Shape> shapes;  // type HFB_BV_OBBRSS: p[0] holds the BVH index
 };
 
 inline void put3(double* o, const V3& v) { o[0] = v.x; o[1] = v.y; o[2] = v.z; }
@@ -62,6 +64,47 @@ int oracle_register_convex(void* sc, const double* points, uint32_t n, const uin
   return (int)s->convexes.size() - 1;
 }
 
+// BVHModel<OBBRSS>: beginModel/addSubModel/endModel -> buildTree (BVH_model.cpp:860-960)
+int oracle_register_bvh(void* sc, const double* vertices, uint32_t nv, const uint32_t* tris, uint32_t nt) {
+  Scene* s = static_cast<Scene*>(sc);
+  std::unique_ptr<BVHModel> m(new BVHModel());
+  m->vertices.resize(nv);
+  for (uint32_t i = 0; i < nv; ++i) m->vertices[i] = V3(vertices[3 * i], vertices[3 * i + 1], vertices[3 * i + 2]);
+  m->tris.resize(nt);
+  for (uint32_t i = 0; i < nt; ++i)
+    for (int k = 0; k < 3; ++k) m->tris[i].v[k] = tris[3 * i + k];
+  m->build();
+  s->bvhs.push_back(std::move(m));
+  return (int)s->bvhs.size() - 1;
+}
+// exports the built tree in the product's node layout (what a binding would copy out of
+// BVHModel<OBBRSS>::bvs); returns the node count
+int oracle_bvh_export(void* sc, int id, hfb_bvh_node* out, uint32_t cap) {
+  Scene* s = static_cast<Scene*>(sc);
+  const BVHModel& m = *s->bvhs[(size_t)id];
+  if (!out) return (int)m.num_bvs;
+  for (uint32_t i = 0; i < m.num_bvs && i < cap; ++i) {
+    const BVNode& n = m.bvs[i];
+    hfb_bvh_node& o = out[i];
+    o.first_child = n.first_child;
+    o.first_primitive = n.first_primitive;
+    o.num_primitives = n.num_primitives;
+    o._pad = 0;
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r) {
+        o.obb_axes[c * 3 + r] = n.bv.obb.axes.m[r][c];
+        o.rss_axes[c * 3 + r] = n.bv.rss.axes.m[r][c];
+      }
+    put3(o.obb_To, n.bv.obb.To);
+    put3(o.obb_extent, n.bv.obb.extent);
+    put3(o.rss_Tr, n.bv.rss.Tr);
+    o.rss_length[0] = n.bv.rss.length[0];
+    o.rss_length[1] = n.bv.rss.length[1];
+    o.rss_radius = n.bv.rss.radius;
+  }
+  return (int)m.num_bvs;
+}
+
 // returns the handle of shapes[0]; handles are consecutive. -1 on error.
 int64_t oracle_register_shapes(void* sc, const hfb_shape* shapes, size_t n) {
   Scene* s = static_cast<Scene*>(sc);
@@ -73,6 +116,10 @@ int64_t oracle_register_shapes(void* sc, const hfb_shape* shapes, size_t n) {
     sh.p[1] = shapes[i].p[1];
     sh.p[2] = shapes[i].p[2];
     sh.ssr = shapes[i].ssr;
+    if (sh.type == HFB_BV_OBBRSS) {
+      if (shapes[i].data >= s->bvhs.size()) return -1;
+      sh.p[0] = (double)shapes[i].data;
+    }
     if (sh.type == HFB_GEOM_CONVEX || sh.type == HFB_GEOM_TRIANGLE) {
       if (shapes[i].data >= s->convexes.size()) return -1;
       sh.cvx = s->convexes[shapes[i].data].get();
@@ -135,6 +182,39 @@ int oracle_batch_distance(void* sc, size_t n, const uint32_t* h1, const hfb_tran
       V3 p1, p2, normal;
       double distance;
       bool closed = false;
+      if (s1.type == HFB_BV_OBBRSS || s2.type == HFB_BV_OBBRSS) {
+        // distance(): (GEOM, BVH) calls the (BVH, GEOM) entry with swapped operands and swaps
+        // o1/o2, the nearest points and the normal back -- not b1/b2 (distance.cpp:74-89)
+        const bool swap = s1.type != HFB_BV_OBBRSS;
+        const Shape& sm = swap ? s2 : s1;
+        const Shape& ss = swap ? s1 : s2;
+        if (ss.type == HFB_BV_OBBRSS || !(ss.type == HFB_GEOM_BOX || ss.type == HFB_GEOM_SPHERE ||
+            ss.type == HFB_GEOM_CAPSULE || ss.type == HFB_GEOM_CONE || ss.type == HFB_GEOM_CYLINDER ||
+            ss.type == HFB_GEOM_ELLIPSOID || ss.type == HFB_GEOM_CONVEX)) {
+          r.status = (uint32_t)HFB_PATH_UNSUPPORTED << 16;  // mesh-mesh distance etc.: not covered
+          r.iterations = 0;
+        } else {
+          BvhQueryResult q;
+          bvhShapeDistance(*s->bvhs[(size_t)sm.p[0]], swap ? T2 : T1, ss, swap ? T1 : T2, solver,
+                           req->enable_signed_distance != 0, req->rel_err, req->abs_err, q);
+          r.min_distance = q.distance;
+          put3(r.p1, swap ? q.p2 : q.p1);
+          put3(r.p2, swap ? q.p1 : q.p2);
+          put3(r.normal, swap ? -q.normal : q.normal);
+          r.b1 = q.b1;
+          r.b2 = -1;
+          r.status = (uint32_t)HFB_PATH_BVH << 16;
+          r.iterations = (uint32_t)(q.num_bv_tests & 0xffff) | ((uint32_t)(q.num_leaf_tests & 0xffff) << 16);
+        }
+        if (guess_out) {
+          if (guess_out->cached_gjk_guess) put3(guess_out->cached_gjk_guess + 3 * i, solver.cached_guess);
+          if (guess_out->cached_support_func_guess) {
+            guess_out->cached_support_func_guess[2 * i] = solver.support_func_cached_guess[0];
+            guess_out->cached_support_func_guess[2 * i + 1] = solver.support_func_cached_guess[1];
+          }
+        }
+        continue;
+      }
       bool ok = shapeShapeDistance(s1, T1, s2, T2, solver, req->enable_signed_distance != 0, distance,
                                    p1, p2, normal, closed);
       if (!ok) {
@@ -221,6 +301,41 @@ int oracle_batch_collide(void* sc, size_t n, const uint32_t* h1, const hfb_trans
       solver.gjk.iterations = 0;
       solver.epa.iterations = 0;
 
+      if (s1.type == HFB_BV_OBBRSS || s2.type == HFB_BV_OBBRSS) {
+        // collide(): (GEOM, BVH) is run as (BVH, GEOM) and swapObjects() swaps o1/o2, b1/b2, the
+        // nearest points and negates the normal of each contact and of the result (collision.cpp:92-108)
+        const bool swap = s1.type != HFB_BV_OBBRSS;
+        const Shape& sm = swap ? s2 : s1;
+        const Shape& ss = swap ? s1 : s2;
+        const bool shape_ok = ss.type == HFB_GEOM_BOX || ss.type == HFB_GEOM_SPHERE || ss.type == HFB_GEOM_CAPSULE ||
+                              ss.type == HFB_GEOM_CONE || ss.type == HFB_GEOM_CYLINDER ||
+                              ss.type == HFB_GEOM_ELLIPSOID || ss.type == HFB_GEOM_CONVEX;
+        if (!shape_ok || req->security_margin < 0) {  // negative margin throws for BVH (collision_func_matrix.cpp:109-112)
+          r.status = (uint32_t)HFB_PATH_UNSUPPORTED << 16;
+          continue;
+        }
+        BvhCollideResult q;
+        bvhShapeCollide(*s->bvhs[(size_t)sm.p[0]], swap ? T2 : T1, ss, swap ? T1 : T2, solver, *req, q);
+        r.distance_lower_bound = q.distance_lower_bound;
+        put3(r.p1, swap ? q.lb_p2 : q.lb_p1);
+        put3(r.p2, swap ? q.lb_p1 : q.lb_p2);
+        put3(r.normal, swap ? -q.lb_normal : q.lb_normal);
+        if (!q.contacts.empty()) {
+          const BvhContact& c = q.contacts[0];
+          r.num_contacts = 1;
+          r.distance = c.distance;
+          r.b1 = swap ? -1 : c.b1;
+          r.b2 = swap ? c.b1 : -1;
+          put3(r.pos, (c.p1 + c.p2) / 2);
+          // the record carries one set of witness fields: the contact's when there is a contact
+          put3(r.p1, swap ? c.p2 : c.p1);
+          put3(r.p2, swap ? c.p1 : c.p2);
+          put3(r.normal, swap ? -c.normal : c.normal);
+        }
+        r.status = (uint32_t)HFB_PATH_BVH << 16;
+        r.iterations = (uint32_t)(q.num_bv_tests & 0xffff) | ((uint32_t)(q.num_leaf_tests & 0xffff) << 16);
+        continue;
+      }
       // ShapeShapeCollider::run (shape_shape_func.h:134-163)
       const bool compute_penetration = (req->enable_contact != 0) || (req->security_margin < 0);
       V3 p1, p2, normal;

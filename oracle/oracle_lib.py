@@ -46,6 +46,10 @@ def lib():
         L.oracle_batch_convex_support_log.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
                                                       C.c_void_p]
         L.oracle_max_threads.restype = C.c_int
+        L.oracle_register_bvh.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.oracle_register_bvh.restype = C.c_int
+        L.oracle_bvh_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32]
+        L.oracle_bvh_export.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -79,6 +83,16 @@ class OracleScene:
         cid = self.L.oracle_register_convex(self.h, _ptr(pts), pts.shape[0], _ptr(t),
                                             0 if t is None else t.shape[0])
         return cid
+
+    def register_bvh(self, vertices, triangles):
+        """Builds a BVHModel<OBBRSS> with the reference's builder; returns (bvh id, exported nodes)."""
+        v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+        t = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
+        bid = self.L.oracle_register_bvh(self.h, _ptr(v), v.shape[0], _ptr(t), t.shape[0])
+        n = self.L.oracle_bvh_export(self.h, bid, None, 0)
+        nodes = np.zeros(n, dtype=self.pod.bvh_node_dtype)
+        self.L.oracle_bvh_export(self.h, bid, _ptr(nodes), n)
+        return bid, nodes
 
     def register_shapes(self, shapes):
         shapes = np.ascontiguousarray(shapes, dtype=self.pod.shape_dtype)

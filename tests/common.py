@@ -39,6 +39,8 @@ def emu_lib():
         for name in ("emu_batch_distance", "emu_batch_collide"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 7
         L.emu_batch_convex_support.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 4
+        L.emu_register_bvh.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
+                                       C.c_uint32]
         _EMU = L
     return _EMU
 
@@ -61,6 +63,14 @@ class EmuScene:
     def register_convex(self, points):
         pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
         return self.L.emu_register_convex(self.h, _ptr(pts), pts.shape[0])
+
+    def register_bvh_obbrss(self, nodes, vertices, triangles):
+        nodes = np.ascontiguousarray(nodes, dtype=P.bvh_node_dtype)
+        v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+        t = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
+        bid = self.L.emu_register_bvh(self.h, _ptr(nodes), nodes.shape[0], _ptr(v), v.shape[0], _ptr(t), t.shape[0])
+        assert bid >= 0
+        return bid
 
     def register_shapes(self, shapes):
         shapes = np.ascontiguousarray(shapes, dtype=P.shape_dtype)
@@ -122,6 +132,15 @@ class MultiScene:
                 ids.add(int(s.register_convex(points)))
         assert len(ids) == 1
         return ids.pop()
+
+    def register_bvh(self, vertices, triangles):
+        """The oracle builds the tree with the reference's builder; the other backends get the exported
+        node array through the product ABI (what a binding copies out of BVHModel<OBBRSS>::bvs)."""
+        bid, nodes = self.b["oracle"].register_bvh(vertices, triangles)
+        for name, s in self.b.items():
+            if name != "oracle":
+                assert s.register_bvh_obbrss(nodes, vertices, triangles) == bid
+        return bid, nodes
 
     def register_shapes(self, shapes):
         hs = [s.register_shapes(shapes) for s in self.b.values()]

@@ -10,6 +10,7 @@
 #include <memory>
 
 #include "../../hpp-fcl_b200/csrc/hfb_arena.cuh"
+#include "../../hpp-fcl_b200/csrc/hfb_bvh.cuh"
 #include "../../hpp-fcl_b200/csrc/hfb_request.cuh"
 
 using namespace hfb;
@@ -67,6 +68,12 @@ void emu_destroy(void* e) { delete static_cast<Emu*>(e); }
 int emu_register_convex(void* e, const double* pts, uint32_t n) {
   return (int)static_cast<Emu*>(e)->arena.add_convex(pts, n);
 }
+int emu_register_bvh(void* e, const hfb_bvh_node* nodes, uint32_t nn, const double* verts, uint32_t nv,
+                     const uint32_t* tris, uint32_t nt) {
+  uint32_t id;
+  if (!static_cast<Emu*>(e)->arena.add_bvh(nodes, nn, verts, nv, tris, nt, &id)) return -1;
+  return (int)id;
+}
 int64_t emu_register_shapes(void* e, const hfb_shape* shapes, size_t n) {
   Emu* E = static_cast<Emu*>(e);
   int64_t first = (int64_t)E->arena.shapes.size();
@@ -87,6 +94,19 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
   std::unique_ptr<EpaWs> ws(new EpaWs());
   for (size_t i = 0; i < n; ++i) {
     if (h1[i] >= A.nshapes || h2[i] >= A.nshapes) return HFB_ERR_INVALID_ARGUMENT;
+    if (A.shapes[h1[i]].type == HFB_BV_OBBRSS || A.shapes[h2[i]].type == HFB_BV_OBBRSS) {
+      BvhReq R{req->rel_err, req->abs_err, 0, 0, 0, 1};
+      unsigned bt, lt;
+      v3 guess = mk(1, 0, 0);
+      int hh0 = 0, hh1 = 0;
+      if (req->q.gjk_initial_guess == HFB_GUESS_CACHED) {
+        if (req->q.cached_gjk_guess) guess = mk(req->q.cached_gjk_guess[3 * i], req->q.cached_gjk_guess[3 * i + 1], req->q.cached_gjk_guess[3 * i + 2]);
+        if (req->q.cached_support_func_guess) { hh0 = req->q.cached_support_func_guess[2 * i]; hh1 = req->q.cached_support_func_guess[2 * i + 1]; }
+      }
+      bvh_pair_distance<CAPS_ALL>(A, h1[i], load_xf(tf1[i].R), h2[i], load_xf(tf2[i].R), P, R, guess, hh0, hh1,
+                                  ws.get(), &out[i], bt, lt);
+      continue;
+    }
     const PairIn in = load_pair(A, i, h1, tf1, h2, tf2, req->q);
     PairOut o;
     run_pair(in, P, ws.get(), o);
@@ -117,6 +137,20 @@ int emu_batch_collide(void* e, size_t n, const uint32_t* h1, const hfb_transform
       o.iterations = 0;
       write_contact(o, C, &out[i]);
       out[i].status = 0;
+      continue;
+    }
+    if (A.shapes[h1[i]].type == HFB_BV_OBBRSS || A.shapes[h2[i]].type == HFB_BV_OBBRSS) {
+      BvhReq R{0, 0, req->security_margin, req->break_distance, req->q.collision_distance_threshold,
+               req->num_max_contacts};
+      unsigned bt, lt;
+      v3 guess = mk(1, 0, 0);
+      int hh0 = 0, hh1 = 0;
+      if (req->q.gjk_initial_guess == HFB_GUESS_CACHED) {
+        if (req->q.cached_gjk_guess) guess = mk(req->q.cached_gjk_guess[3 * i], req->q.cached_gjk_guess[3 * i + 1], req->q.cached_gjk_guess[3 * i + 2]);
+        if (req->q.cached_support_func_guess) { hh0 = req->q.cached_support_func_guess[2 * i]; hh1 = req->q.cached_support_func_guess[2 * i + 1]; }
+      }
+      bvh_pair_collide<CAPS_ALL>(A, h1[i], load_xf(tf1[i].R), h2[i], load_xf(tf2[i].R), P, R, guess, hh0, hh1,
+                                 ws.get(), &out[i], bt, lt);
       continue;
     }
     const PairIn in = load_pair(A, i, h1, tf1, h2, tf2, req->q);

@@ -1,0 +1,123 @@
+"""OBBRSS BVH vs shape: oracle (reference builder, recursion) vs the emulated
+device code (explicit-stack traversal, per-query shape BV, RSS/OBB tests) on CPU, and vs the CUDA
+kernel on the GPU box.  The tree itself comes from the oracle's restatement of the reference builder
+and reaches the product through hfb_geom_register_bvh_obbrss, like a binding would pass
+BVHModel<OBBRSS>::bvs.  Bar: everything bit-identical, incl. witness triangle ids and the
+BV-test / leaf-test counters (they pin the traversal order)."""
+import numpy as np
+import pytest
+
+from tests.common import P, compare_distance, make_scenes
+from hppfcl_b200 import workloads as W
+
+SHAPES = (P.GEOM_SPHERE, P.GEOM_CAPSULE, P.GEOM_BOX, P.GEOM_CYLINDER, P.GEOM_CONE, P.GEOM_ELLIPSOID)
+
+
+def build_scene(gpu, emu, seg=24, ring=12, n=3000, seed=1):
+    sc = make_scenes(gpu=gpu, emu=emu)
+    rng = np.random.default_rng(seed)
+    verts, tris = W.sphere_mesh(1.0, seg, ring, noise=0.02, rng=rng)
+    bid, nodes = sc.register_bvh(verts, tris)
+    hb = sc.register_shapes(P.make_shapes([P.BV_OBBRSS], [[0, 0, 0]], data=[bid]))
+    prims = W.random_primitive_shapes(rng, 96, SHAPES)
+    prims["p"] *= 0.3
+    hp = sc.register_shapes(prims)
+    pts, ctris = W.icosahedron_from_ellipsoid((0.2, 0.3, 0.25))
+    cid = sc.register_convex(pts, ctris)
+    hc = sc.register_shapes(P.make_shapes([P.GEOM_CONVEX], [[0, 0, 0]], data=[cid]))
+    sc.commit()
+    allh = np.concatenate([hp, hc])
+    hs = allh[rng.integers(0, len(allh), n)]
+    tfm = W.random_transforms(rng, n, (-0.3, -0.3, -0.3), (0.3, 0.3, 0.3))
+    tfs = W.random_transforms(rng, n, (-1.6, -1.6, -1.6), (1.6, 1.6, 1.6))
+    hm = np.full(n, hb[0], dtype=np.uint32)
+    return sc, nodes, hm, tfm, hs, tfs, (verts, tris)
+
+
+def test_builder_invariants():
+    sc, nodes, hm, tfm, hs, tfs, (verts, tris) = build_scene(False, False, n=10)
+    assert len(nodes) == 2 * len(tris) - 1
+    leaf = nodes["first_child"] < 0
+    assert leaf.sum() == len(tris)
+    assert sorted(-(nodes["first_child"][leaf] + 1)) == list(range(len(tris)))  # every triangle exactly once
+    inner = nodes[~leaf]
+    assert np.all(inner["first_child"] > np.nonzero(~leaf)[0])                   # children follow the parent
+    # OBB axes orthonormal, extents >= 0, RSS contains the OBB centre roughly
+    A = nodes["obb_axes"].reshape(-1, 3, 3)
+    assert np.allclose(np.einsum("nij,nkj->nik", A, A), np.eye(3), atol=1e-9)
+    assert np.all(nodes["obb_extent"] >= 0) and np.all(nodes["rss_radius"] >= 0)
+    # root OBB contains every vertex
+    R = nodes["obb_axes"][0].reshape(3, 3).T
+    loc = (verts - nodes["obb_To"][0]) @ R
+    assert np.all(np.abs(loc) <= nodes["obb_extent"][0] + 1e-9)
+
+
+def _check(sc, backend, hm, tfm, hs, tfs):
+    o, e = sc.b["oracle"], sc.b[backend]
+    for req in (P.DistanceRequestPOD(), P.DistanceRequestPOD(enable_signed_distance=0),
+                P.DistanceRequestPOD(gjk_variant=P.NesterovAcceleration), P.DistanceRequestPOD(rel_err=0.05, abs_err=0.01)):
+        ro = o.batch_distance(hm, tfm, hs, tfs, req, nthreads=0)
+        re = e.batch_distance(hm, tfm, hs, tfs, req)
+        compare_distance(ro, re, what="bvh distance")
+        assert np.all(P.status_path(ro["status"]) == P.PATH_BVH)
+    assert (ro["min_distance"] < 0).sum() > 20 and (ro["b1"] >= 0).all()
+    # (shape, mesh) operand order: results swapped back (distance.cpp:74-89)
+    rs = o.batch_distance(hs, tfs, hm, tfm, nthreads=0)
+    compare_distance(rs, e.batch_distance(hs, tfs, hm, tfm), what="bvh distance swapped")
+    r0 = o.batch_distance(hm, tfm, hs, tfs, nthreads=0)
+    m = ~np.isnan(r0["p1"][:, 0])
+    assert np.array_equal(rs["p1"][m], r0["p2"][m]) and np.array_equal(rs["normal"][m], -r0["normal"][m])
+    for creq in (P.CollisionRequestPOD(), P.CollisionRequestPOD(security_margin=0.05),
+                 P.CollisionRequestPOD(num_max_contacts=4, enable_contact=0)):
+        co = o.batch_collide(hm, tfm, hs, tfs, creq, nthreads=0)
+        compare_distance(co, e.batch_collide(hm, tfm, hs, tfs, creq), what="bvh collide")
+        cs = o.batch_collide(hs, tfs, hm, tfm, creq, nthreads=0)
+        compare_distance(cs, e.batch_collide(hs, tfs, hm, tfm, creq), what="bvh collide swapped")
+    assert co["num_contacts"].sum() > 20
+    # negative margin is rejected for BVH models (collision_func_matrix.cpp:109-112)
+    bad = e.batch_collide(hm[:4], tfm[:4], hs[:4], tfs[:4], P.CollisionRequestPOD(security_margin=-0.01))
+    assert np.all(P.status_path(bad["status"]) == P.PATH_UNSUPPORTED)
+
+
+def test_bvh_emulated_device_code_vs_oracle():
+    sc, nodes, hm, tfm, hs, tfs, _ = build_scene(False, True)
+    _check(sc, "emu", hm, tfm, hs, tfs)
+
+
+def test_bvh_distance_is_the_true_minimum():
+    """differential check in the style of test/distance.cpp: traversal result == brute force over all triangles"""
+    sc, nodes, hm, tfm, hs, tfs, (verts, tris) = build_scene(False, False, seg=12, ring=6, n=40)
+    o = sc.b["oracle"]
+    cids = [o.register_convex(verts[t], None) for t in tris]
+    ht = o.register_shapes(P.make_shapes([P.GEOM_TRIANGLE] * len(tris), np.zeros((len(tris), 3)), data=cids))
+    r = o.batch_distance(hm, tfm, hs, tfs)
+    for q in range(len(hm)):
+        nt = len(tris)
+        rr = o.batch_distance(ht, np.repeat(tfm[q:q + 1], nt), np.full(nt, hs[q], dtype=np.uint32), np.repeat(tfs[q:q + 1], nt))
+        assert rr["min_distance"][r[q]["b1"]] == r[q]["min_distance"]
+        if rr["min_distance"].min() > 0:
+            assert r[q]["min_distance"] == rr["min_distance"].min()
+        else:  # once a penetrating triangle is found every BV lower bound (>= 0) prunes: any negative leaf
+            assert r[q]["min_distance"] <= 0
+
+
+@pytest.mark.gpu
+def test_bvh_gpu_vs_oracle():
+    sc, nodes, hm, tfm, hs, tfs, _ = build_scene(True, False, seg=40, ring=20, n=20000)
+    _check(sc, "gpu", hm, tfm, hs, tfs)
+
+
+@pytest.mark.gpu
+def test_bvh_config4_shape():
+    """config 4 geometry (10 000-triangle mesh vs capsules) on a 20k-query slice"""
+    sc = make_scenes(gpu=True, emu=False)
+    w = W.config4_mesh_vs_capsules(20000)
+    bid, nodes = sc.register_bvh(w["verts"], w["tris"])
+    assert len(w["tris"]) == 10000 and len(nodes) == 19999
+    hb = sc.register_shapes(P.make_shapes([P.BV_OBBRSS], [[0, 0, 0]], data=[bid]))
+    hc = sc.register_shapes(w["capsules"])
+    sc.commit()
+    hm = np.full(len(w["hc"]), hb[0], dtype=np.uint32)
+    ro = sc.b["oracle"].batch_distance(hm, w["tf_mesh"], hc[w["hc"]], w["tf_caps"], nthreads=0)
+    rg = sc.b["gpu"].batch_distance(hm, w["tf_mesh"], hc[w["hc"]], w["tf_caps"])
+    compare_distance(ro, rg, what="config4")
