@@ -148,6 +148,50 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def support_kernel_roofline(eng_factory, peak, n_hulls=131072, nv=64, n_queries=1 << 21):
+    """The north_star's convex-support kernel: batched ConvexBase support argmax over DISTINCT hulls
+    (201 MB of vertices > 126 MB L2), one warp per query, coalesced SoA rows.  Algorithmic bytes per
+    query: 24*nv vertices + 24 B direction + 28 B output + 4 B id (1 588 B at nv = 64)."""
+    import torch
+    from hppfcl_b200 import _pod as P
+    rng = np.random.default_rng(99)
+    eng = eng_factory(torch.cuda.current_device())
+    v = rng.normal(size=(n_hulls, nv, 3))
+    v /= np.linalg.norm(v, axis=2, keepdims=True)
+    v *= 0.05 + 0.95 * rng.random((n_hulls, 1, 3))
+    for k in range(n_hulls):
+        eng.register_convex(v[k])
+    eng.commit()
+    ids = rng.permutation(n_queries).astype(np.uint32) % n_hulls
+    dirs = rng.normal(size=(n_queries, 3))
+    d_ids = torch.from_numpy(ids).cuda()
+    d_dirs = torch.from_numpy(dirs).cuda()
+    d_idx = torch.empty(n_queries, dtype=torch.int32, device="cuda")
+    d_sup = torch.empty((n_queries, 3), dtype=torch.float64, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(3):
+        eng.batch_convex_support_device(n_queries, d_ids.data_ptr(), d_dirs.data_ptr(), d_idx.data_ptr(), d_sup.data_ptr(), stream)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        eng.batch_convex_support_device(n_queries, d_ids.data_ptr(), d_dirs.data_ptr(), d_idx.data_ptr(), d_sup.data_ptr(), stream)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    bytes_per = 24 * nv + 24 + 28 + 4
+    achieved = bytes_per * n_queries / (ms * 1e-3) / 1e9
+    # spot check against numpy
+    k = 4096
+    got = d_idx[:k].cpu().numpy()
+    want = np.argmax(np.einsum("qvc,qc->qv", v[ids[:k]], dirs[:k]), axis=1)
+    return {"kernel": "k_convex_support", "supports_per_s": n_queries / (ms * 1e-3), "kernel_ms": ms,
+            "bytes_per_support": bytes_per, "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "frac": achieved / peak, "distinct_hulls": n_hulls, "vertices": nv, "queries": n_queries,
+            "matches_numpy_argmax": bool(np.array_equal(got, want))}
+
+
 def run_ours(args):
     import torch
     import hppfcl_b200 as hf
@@ -303,6 +347,7 @@ def run_ours(args):
                         "epa_pairs_per_step": (st1["epa_pairs"] - st0["epa_pairs"]) / max(1, args.steps)},
         }
         if world == 1:
+            line["convex_support_kernel"] = support_kernel_roofline(eng_factory=hf.Engine, peak=peak)
             v, cores, ns = cpu_reference_rate(args, w, args.cpu_sample)
             v1, _, ns1 = cpu_reference_rate(args, w, min(args.cpu_sample, 100_000), threads=1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",

@@ -652,7 +652,7 @@ HFB_HD_NOINLINE void fit_axes_from_covariance(const double Min[6], m3& axes) {
 }
 
 // world-frame bound vertex i
-HFB_HD v3 bound_vertex(const ShapeD& s, const xf& tf, int i) { return xform(tf, bound_vertex_local(s, i)); }
+HFB_HD_NOINLINE v3 bound_vertex(const ShapeD& s, const xf& tf, int i) { return xform(tf, bound_vertex_local(s, i)); }
 
 // getCovariance over the bound vertices (BVH_utility.cpp:183-259, point branch)
 HFB_HD void bound_covariance(const ShapeD& s, const xf& tf, int n, double M[6]) {
@@ -1036,39 +1036,51 @@ HFB_HD void bvh_shape_distance(const BvhQuery& q, const SolverP& P, double rel_e
   stk_node[0] = 0;
   stk_d[0] = -1.0;  // root: visited unconditionally
   sp = 1;
+  // The walk alternates two phases so that the lanes of a warp (one query each) run the same code
+  // together: (A) pop / prune / expand inner nodes until the top of the stack is a leaf that survives
+  // canStop(), (B) run the triangle-shape test of that leaf.  Per query the visiting order is
+  // exactly the recursion's.
   while (sp > 0) {
-    --sp;
-    const int b = stk_node[sp];
-    const double dlow = stk_d[sp];
-    if (dlow >= 0) {  // canStop(d) (:322-327)
-      if ((dlow >= out.min_distance - abs_err) && (dlow * (1 + rel_err) >= out.min_distance)) continue;
-    }
-    const hfb_bvh_node& nd = q.nodes[b];
-    if (nd.first_child < 0) {
-      const int prim = -(nd.first_child + 1);
-      bvh_leaf<CAPS>(q, prim, P, ws, in, o);
-      out.leaf_tests++;
-      if (out.min_distance > o.distance) {  // DistanceResult::update: strict '>' keeps the first minimum
-        out.min_distance = o.distance;
-        out.b1 = prim;
-        out.p1 = o.p1;
-        out.p2 = o.p2;
-        out.normal = o.normal;
+    int leaf_prim = -1;
+    while (sp > 0) {  // phase A
+      --sp;
+      const int b = stk_node[sp];
+      const double dlow = stk_d[sp];
+      if (dlow >= 0) {  // canStop(d) (:322-327)
+        if ((dlow >= out.min_distance - abs_err) && (dlow * (1 + rel_err) >= out.min_distance)) continue;
       }
-      continue;
+      const int fc = q.nodes[b].first_child;
+      if (fc < 0) {
+        leaf_prim = -(fc + 1);
+        break;
+      }
+      const int a1 = fc, c1 = fc + 1;
+      const double d1 = rss_distance(q.tf_mesh.R, q.tf_mesh.T, sbv, load_node_rss(q.nodes[a1]));
+      const double d2 = rss_distance(q.tf_mesh.R, q.tf_mesh.T, sbv, load_node_rss(q.nodes[c1]));
+      out.bv_tests += 2;
+      if (sp + 2 > HFB_BVH_STACK) {  // cannot happen for trees of depth < 128
+        sp = 0;
+        break;
+      }
+      // visit the nearer child first: push the farther one below it
+      if (d2 < d1) {
+        stk_node[sp] = a1; stk_d[sp] = d1; ++sp;
+        stk_node[sp] = c1; stk_d[sp] = d2; ++sp;
+      } else {
+        stk_node[sp] = c1; stk_d[sp] = d2; ++sp;
+        stk_node[sp] = a1; stk_d[sp] = d1; ++sp;
+      }
     }
-    const int a1 = nd.first_child, c1 = nd.first_child + 1;
-    const double d1 = rss_distance(q.tf_mesh.R, q.tf_mesh.T, sbv, load_node_rss(q.nodes[a1]));
-    const double d2 = rss_distance(q.tf_mesh.R, q.tf_mesh.T, sbv, load_node_rss(q.nodes[c1]));
-    out.bv_tests += 2;
-    // visit the nearer child first: push the farther one below it
-    if (sp + 2 > HFB_BVH_STACK) break;  // cannot happen for trees of depth < 128
-    if (d2 < d1) {
-      stk_node[sp] = a1; stk_d[sp] = d1; ++sp;
-      stk_node[sp] = c1; stk_d[sp] = d2; ++sp;
-    } else {
-      stk_node[sp] = c1; stk_d[sp] = d2; ++sp;
-      stk_node[sp] = a1; stk_d[sp] = d1; ++sp;
+    if (leaf_prim < 0) break;
+    // phase B: leafComputeDistance
+    bvh_leaf<CAPS>(q, leaf_prim, P, ws, in, o);
+    out.leaf_tests++;
+    if (out.min_distance > o.distance) {  // DistanceResult::update: strict '>' keeps the first minimum
+      out.min_distance = o.distance;
+      out.b1 = leaf_prim;
+      out.p1 = o.p1;
+      out.p2 = o.p2;
+      out.normal = o.normal;
     }
   }
 }
@@ -1107,50 +1119,58 @@ HFB_HD void bvh_shape_collide(const BvhQuery& q, const SolverP& P, double securi
   int sp = 0;
   stk[sp++] = 0;
   while (sp > 0) {
-    const int b = stk[--sp];
-    const hfb_bvh_node& nd = q.nodes[b];
-    if (nd.first_child < 0) {  // leafCollides (traversal_node_bvh_shape.h:139-188)
-      const int prim = -(nd.first_child + 1);
-      bvh_leaf<CAPS>(q, prim, P, ws, in, o);
-      out.leaf_tests++;
-      const double d2c = o.distance - security_margin;
-      if (d2c < out.distance_lower_bound) {  // updateDistanceLowerBoundFromLeaf
-        out.distance_lower_bound = d2c;
-        out.lb_p1 = o.p1;
-        out.lb_p2 = o.p2;
-        out.lb_normal = o.normal;
+    int leaf_prim = -1;
+    while (sp > 0) {  // phase A: OBB tests down to the next leaf
+      const int b = stk[--sp];
+      const hfb_bvh_node& nd = q.nodes[b];
+      if (nd.first_child < 0) {
+        leaf_prim = -(nd.first_child + 1);
+        break;
       }
-      if (d2c <= collision_distance_threshold) {
-        if (ncontacts < num_max_contacts) {
-          if (ncontacts == 0) {
-            out.has_contact = true;
-            out.b1 = prim;
-            out.distance = o.distance;
-            out.p1 = o.p1;
-            out.p2 = o.p2;
-            out.normal = o.normal;
-          }
-          ++ncontacts;
+      double sq_lb;
+      out.bv_tests++;
+      const bool disjoint = !obb_overlap(q.tf_mesh.R, q.tf_mesh.T, load_node_obb(nd), sbv, security_margin,
+                                         break_distance, sq_lb);
+      if (disjoint) {  // updateDistanceLowerBoundFromBV (collision_data.h:1177-1184)
+        if (out.distance_lower_bound > 0) {
+          const double nd_lb = sqrt(sq_lb);
+          if (nd_lb < out.distance_lower_bound) out.distance_lower_bound = nd_lb;
         }
+        continue;
       }
-      // canStop() after the first child returned (traversal_recurse.cpp:69): isSatisfied
-      if (ncontacts > 0 && num_max_contacts <= ncontacts) break;
-      continue;
-    }
-    double sq_lb;
-    out.bv_tests++;
-    const bool disjoint = !obb_overlap(q.tf_mesh.R, q.tf_mesh.T, load_node_obb(nd), sbv, security_margin, break_distance,
-                                       sq_lb);
-    if (disjoint) {  // updateDistanceLowerBoundFromBV (collision_data.h:1177-1184)
-      if (out.distance_lower_bound > 0) {
-        const double nd_lb = sqrt(sq_lb);
-        if (nd_lb < out.distance_lower_bound) out.distance_lower_bound = nd_lb;
+      if (sp + 2 > HFB_BVH_STACK) {
+        sp = 0;
+        break;
       }
-      continue;
+      stk[sp++] = nd.first_child + 1;  // right child visited after the left one
+      stk[sp++] = nd.first_child;
     }
-    if (sp + 2 > HFB_BVH_STACK) break;
-    stk[sp++] = nd.first_child + 1;  // right child visited after the left one
-    stk[sp++] = nd.first_child;
+    if (leaf_prim < 0) break;
+    // phase B: leafCollides (traversal_node_bvh_shape.h:139-188)
+    bvh_leaf<CAPS>(q, leaf_prim, P, ws, in, o);
+    out.leaf_tests++;
+    const double d2c = o.distance - security_margin;
+    if (d2c < out.distance_lower_bound) {  // updateDistanceLowerBoundFromLeaf
+      out.distance_lower_bound = d2c;
+      out.lb_p1 = o.p1;
+      out.lb_p2 = o.p2;
+      out.lb_normal = o.normal;
+    }
+    if (d2c <= collision_distance_threshold) {
+      if (ncontacts < num_max_contacts) {
+        if (ncontacts == 0) {
+          out.has_contact = true;
+          out.b1 = leaf_prim;
+          out.distance = o.distance;
+          out.p1 = o.p1;
+          out.p2 = o.p2;
+          out.normal = o.normal;
+        }
+        ++ncontacts;
+      }
+    }
+    // canStop() (traversal_recurse.cpp:69): once the request is satisfied every frame returns
+    if (ncontacts > 0 && num_max_contacts <= ncontacts) break;
   }
 }
 

@@ -122,8 +122,8 @@ __device__ __forceinline__ void st3(double* p, v3 v) {
 __device__ __forceinline__ v3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
 
 // ------------------------------------------------------------------ phase 1 --
-template <int G, int CAPS, int MODE, int PATHS>
-__global__ void __launch_bounds__(128) k_pairs(const BatchArgs a) {
+template <int G, int CAPS, int MODE, int PATHS, int MINB>
+__global__ void __launch_bounds__(128, MINB) k_pairs(const BatchArgs a) {
   const unsigned ngroups = (gridDim.x * blockDim.x) / G;
   const unsigned gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   const unsigned lo = a.index_list ? *a.range_lo : 0u;
@@ -397,7 +397,7 @@ struct hfb_ctx {
   Slot dev_slot;  // resources of the *_device entry points (caller's stream)
   DevBuf sup_ids, sup_dirs, sup_idx, sup_out;
   hfb_stats stats{};
-  int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT;
+  int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1;
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int kind; };
   std::vector<Ev> events;
@@ -442,7 +442,7 @@ struct KTimer {
   }
 };
 
-template <int G, int CAPS, int MODE, int PATHS>
+template <int G, int CAPS, int MODE, int PATHS, int MINB = 1>
 int launch_pairs(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s) {
   if (work == 0) return HFB_OK;
   const int threads = 128;
@@ -452,7 +452,7 @@ int launch_pairs(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s
   if (blocks > cap) blocks = cap;
   {
     KTimer kt(ctx, s, (CAPS != CAP_PRIM) ? 4 : (PATHS == PATH_CLOSED ? 3 : 0));
-    k_pairs<G, CAPS, MODE, PATHS><<<blocks, threads, 0, s>>>(a);
+    k_pairs<G, CAPS, MODE, PATHS, MINB><<<blocks, threads, 0, s>>>(a);
   }
   ctx->stats.kernel_launches++;
   CK(cudaGetLastError());
@@ -540,7 +540,12 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   av.range_lo = offsets + HFB_BIN_CONVEX;
   av.range_hi = offsets + HFB_BIN_BVH;
   if ((rc = launch_pairs<1, CAP_PRIM, MODE, PATH_CLOSED>(ctx, ac, n, s))) return rc;
-  if ((rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE>(ctx, ag, n, s))) return rc;
+  switch (ctx->minb) {  // register budget of the GJK kernel: 255 / 168 / 128 registers per thread
+    case 3: rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE, 3>(ctx, ag, n, s); break;
+    case 4: rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE, 4>(ctx, ag, n, s); break;
+    default: rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE, 1>(ctx, ag, n, s);
+  }
+  if (rc) return rc;
   const bool mixed = ctx->arena.has_convex || ctx->arena.has_tri;
   if (mixed)
     if ((rc = launch_pairs_convex<MODE>(ctx, av, n, s))) return rc;
@@ -738,6 +743,7 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   };
   c->gc = env_g("HFB_GC", HFB_GC_DEFAULT);
   c->ge = env_g("HFB_GE", HFB_GE_DEFAULT);
+  if (const char* mb = getenv("HFB_MINB")) c->minb = atoi(mb);
   for (int k = 0; k < kSlots; ++k)
     if (cudaStreamCreateWithFlags(&c->slots[k].stream, cudaStreamNonBlocking) != cudaSuccess) {
       delete c;

@@ -73,36 +73,13 @@ struct ShapeD {
 // capability mask of a kernel instantiation: which shape classes it may meet
 enum { CAP_PRIM = 1, CAP_CONVEX = 2, CAP_TRI = 4 };
 
-template <int G, int CAPS>
-HFB_HD v3 shape_support(const ShapeD& s, v3 dir, int& hint) {
+// primitive supports, out of line on the device: one copy of this code serves both operands of
+// the Minkowski difference (inlined twice it dominated the GJK loop's instruction footprint and the
+// kernel stalled on instruction fetch, see profiles/r01_summary.md)
+HFB_HD_NOINLINE v3 prim_support(int type, double p0, double p1, double p2, v3 dir) {
   v3 r = mk(0, 0, 0);
-  if ((CAPS & CAP_CONVEX) && s.type == HFB_GEOM_CONVEX) {
-    // exhaustive argmax, striped over the group's lanes
-    double best = -DBL_MAX;
-    int bi = 0x7fffffff;
-    bool first = true;
-    for (int i = Coop<G>::lane(); i < s.nv; i += G) {
-      double d = (s.cx[i] * dir.x + s.cy[i] * dir.y) + s.cz[i] * dir.z;
-      if (first || d > best) {
-        best = d;
-        bi = i;
-        first = false;
-      }
-    }
-    Coop<G>::argmax(best, bi);
-    hint = bi;
-    return mk(s.cx[bi], s.cy[bi], s.cz[bi]);
-  }
-  if ((CAPS & CAP_TRI) && s.type == HFB_GEOM_TRIANGLE) {  // :111-134
-    double dota = dot(dir, s.ta), dotb = dot(dir, s.tb), dotc = dot(dir, s.tc);
-    if (dota > dotb) {
-      r = (dotc > dota) ? s.tc : s.ta;
-    } else {
-      r = (dotc > dotb) ? s.tc : s.tb;
-    }
-    return r;
-  }
-  if (CAPS & CAP_PRIM) {
+  struct { int type; double p0, p1, p2; } s = {type, p0, p1, p2};
+  {
     switch (s.type) {
       case HFB_GEOM_BOX: {  // :141-157
         r.x = ((dir.x > HFB_DUMMY_PRECISION) ? s.p0 : 0.0) +
@@ -165,6 +142,39 @@ HFB_HD v3 shape_support(const ShapeD& s, v3 dir, int& hint) {
         break;
     }
   }
+  return r;
+}
+
+template <int G, int CAPS>
+HFB_HD v3 shape_support(const ShapeD& s, v3 dir, int& hint) {
+  v3 r = mk(0, 0, 0);
+  if ((CAPS & CAP_CONVEX) && s.type == HFB_GEOM_CONVEX) {
+    // exhaustive argmax, striped over the group's lanes
+    double best = -DBL_MAX;
+    int bi = 0x7fffffff;
+    bool first = true;
+    for (int i = Coop<G>::lane(); i < s.nv; i += G) {
+      double d = (s.cx[i] * dir.x + s.cy[i] * dir.y) + s.cz[i] * dir.z;
+      if (first || d > best) {
+        best = d;
+        bi = i;
+        first = false;
+      }
+    }
+    Coop<G>::argmax(best, bi);
+    hint = bi;
+    return mk(s.cx[bi], s.cy[bi], s.cz[bi]);
+  }
+  if ((CAPS & CAP_TRI) && s.type == HFB_GEOM_TRIANGLE) {  // :111-134
+    double dota = dot(dir, s.ta), dotb = dot(dir, s.tb), dotc = dot(dir, s.tc);
+    if (dota > dotb) {
+      r = (dotc > dota) ? s.tc : s.ta;
+    } else {
+      r = (dotc > dotb) ? s.tc : s.tb;
+    }
+    return r;
+  }
+  if (CAPS & CAP_PRIM) return prim_support(s.type, s.p0, s.p1, s.p2, dir);
   return r;
 }
 
