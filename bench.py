@@ -115,7 +115,11 @@ def cpu_reference_rate(args, w, n_sample, threads=0):
     n = min(n_sample, len(w["h1"]))
     h1, h2 = hs[w["h1"][:n] % len(hs)], hs[w["h2"][:n] % len(hs)]
     req = P.DistanceRequestPOD(gjk_variant=args.variant)
-    cores = oracle_lib.lib().oracle_max_threads() if threads == 0 else threads
+    # all host cores this process may run on; torchrun exports OMP_NUM_THREADS=1, which must not
+    # shrink the CPU arm, so the count is passed explicitly
+    if threads == 0:
+        threads = len(os.sched_getaffinity(0))
+    cores = threads
     orc.batch_distance(h1[:20000], w["tf1"][:20000], h2[:20000], w["tf2"][:20000], req, nthreads=threads)
     t0 = time.perf_counter()
     orc.batch_distance(h1, w["tf1"][:n], h2, w["tf2"][:n], req, nthreads=threads)

@@ -15,6 +15,14 @@
 //  * `stock` is a LIFO of free slots (slot identity has no numerical meaning;
 //    only the count matters for OutOfFaces).
 //  * the recursive expand (:1361-1449) and encloseOrigin run on explicit stacks.
+//  * newFace is split into its two halves: the slot/topology part runs inside the
+//    horizon walk (every lane of the group executes it redundantly), the geometry
+//    part (normal, offset, ignore flag, convexity verdict) is deferred to the end of
+//    the round and spread over the group's lanes, one new face per lane.  The walk
+//    never reads the geometry of a face created in the same round unless it steps on
+//    a re-used slot; in that case the pending faces are completed on the spot, in
+//    creation order, which is the order the reference meets their verdicts in.
+//  * the closest-face scan stops at the highest slot ever handed out.
 #pragma once
 #include "hfb_gjk.cuh"
 
@@ -28,6 +36,7 @@ namespace hfb {
 struct EpaWs {
   double vw0[HFB_EPA_MAXV * 3];
   double vw1[HFB_EPA_MAXV * 3];
+  double vw[HFB_EPA_MAXV * 3];  // w0 - w1
   double fn[HFB_EPA_MAXF * 3];
   double fd[HFB_EPA_MAXF];
   uint16_t fseq[HFB_EPA_MAXF];
@@ -39,6 +48,7 @@ struct EpaWs {
   uint8_t stock[HFB_EPA_MAXF];
   uint8_t stk_f[HFB_EPA_MAXF + 4];
   uint8_t stk_s[HFB_EPA_MAXF + 4];  // e | stage << 2
+  uint8_t newf[HFB_EPA_MAXF + 4];   // faces whose geometry is pending, in creation order
 };
 
 struct EpaParams {
@@ -55,19 +65,18 @@ struct EpaState {
   int hint0, hint1;
   unsigned iterations;
   // bookkeeping
-  int num_vertices, hull_count, stock_top, seq;
+  int num_vertices, hull_count, stock_top, seq;  // stock_top: freed slots waiting in EpaWs::stock
+  int hwm;        // slots [0, hwm) have been handed out at least once
+  int n_pending;  // entries of EpaWs::newf
   unsigned nfaces_cap, nverts_cap;
 };
 
-HFB_HD v3 ws_vw(const EpaWs* ws, int i) {
-  return mk(ws->vw0[3 * i] - ws->vw1[3 * i], ws->vw0[3 * i + 1] - ws->vw1[3 * i + 1],
-            ws->vw0[3 * i + 2] - ws->vw1[3 * i + 2]);
-}
+HFB_HD v3 ws_vw(const EpaWs* ws, int i) { return mk(ws->vw[3 * i], ws->vw[3 * i + 1], ws->vw[3 * i + 2]); }
 HFB_HD SV ws_sv(const EpaWs* ws, int i) {
   SV s;
   s.w0 = mk(ws->vw0[3 * i], ws->vw0[3 * i + 1], ws->vw0[3 * i + 2]);
   s.w1 = mk(ws->vw1[3 * i], ws->vw1[3 * i + 1], ws->vw1[3 * i + 2]);
-  s.w = s.w0 - s.w1;
+  s.w = ws_vw(ws, i);
   return s;
 }
 HFB_HD void ws_put_v(EpaWs* ws, int i, const SV& s) {
@@ -77,13 +86,20 @@ HFB_HD void ws_put_v(EpaWs* ws, int i, const SV& s) {
   ws->vw1[3 * i] = s.w1.x;
   ws->vw1[3 * i + 1] = s.w1.y;
   ws->vw1[3 * i + 2] = s.w1.z;
+  ws->vw[3 * i] = s.w.x;
+  ws->vw[3 * i + 1] = s.w.y;
+  ws->vw[3 * i + 2] = s.w.z;
 }
 HFB_HD v3 ws_fn(const EpaWs* ws, int f) { return mk(ws->fn[3 * f], ws->fn[3 * f + 1], ws->fn[3 * f + 2]); }
 
+HFB_HD int ws_fedge(const EpaWs* ws, int f, int e) { return ws->fedge[3 * f + e]; }
+// plain stores only: every lane of a group writes the same topology redundantly, which is race-free
+// as long as no write is a read-modify-write of a word that another lane also updates
+HFB_HD void ws_set_fedge(EpaWs* ws, int f, int e, int v) { ws->fedge[3 * f + e] = (uint8_t)v; }
 HFB_HD void epa_bind(EpaWs* ws, int fa, int ea, int fb, int eb) {  // gjk.h:312-320
-  ws->fedge[3 * fa + ea] = (uint8_t)eb;
+  ws_set_fedge(ws, fa, ea, eb);
   ws->fadj[3 * fa + ea] = (uint8_t)fb;
-  ws->fedge[3 * fb + eb] = (uint8_t)ea;
+  ws_set_fedge(ws, fb, eb, ea);
   ws->fadj[3 * fb + eb] = (uint8_t)fa;
 }
 HFB_HD void epa_hull_remove(EpaWs* ws, EpaState& E, int f) {  // hull.remove + stock.append
@@ -92,10 +108,13 @@ HFB_HD void epa_hull_remove(EpaWs* ws, EpaState& E, int f) {  // hull.remove + s
   ws->stock[E.stock_top++] = (uint8_t)f;
 }
 
-// EPA::newFace (:1068-1138). returns slot id or HFB_EPA_NONE
-HFB_HD int epa_new_face(EpaWs* ws, EpaState& E, double tol, int ia, int ib, int ic, bool force) {
-  if (E.stock_top > 0) {
-    const int f = ws->stock[--E.stock_top];
+// EPA::newFace (:1068-1138), first half: take a slot from the stock, link it into the hull and
+// record its vertices.  Returns the slot id, or HFB_EPA_NONE with status OutOfFaces (:1131-1137).
+HFB_HD int epa_alloc_face(EpaWs* ws, EpaState& E, int ia, int ib, int ic) {
+  // the reference's stock hands out fc_store[0], [1], ... and re-uses freed faces last-in first-out
+  // (:1034-1035, gjk.h:292-298): a LIFO of freed slots on top of a counter of untouched ones
+  if (E.stock_top > 0 || E.hwm < (int)E.nfaces_cap) {
+    const int f = E.stock_top > 0 ? ws->stock[--E.stock_top] : E.hwm++;
     E.hull_count += 1;
     ws->fflag[f] = 1;
     ws->fseq[f] = (uint16_t)(E.seq++);
@@ -103,34 +122,84 @@ HFB_HD int epa_new_face(EpaWs* ws, EpaState& E, double tol, int ia, int ib, int 
     ws->fvid[3 * f] = (uint8_t)ia;
     ws->fvid[3 * f + 1] = (uint8_t)ib;
     ws->fvid[3 * f + 2] = (uint8_t)ic;
-    const v3 a = ws_vw(ws, ia), b = ws_vw(ws, ib), c = ws_vw(ws, ic);
-    v3 n = cross(b - a, c - a);
-    if (nrm(n) > DBL_EPSILON) {
-      n = unit(n);
-      ws->fn[3 * f] = n.x;
-      ws->fn[3 * f + 1] = n.y;
-      ws->fn[3 * f + 2] = n.z;
-      const double a_dot_nab = dot(a, cross(b - a, n));
-      const double b_dot_nbc = dot(b, cross(c - b, n));
-      const double c_dot_nca = dot(c, cross(a - c, n));
-      double d;
-      if (a_dot_nab >= -tol && b_dot_nbc >= -tol && c_dot_nca >= -tol) {
-        d = dot(a, n);
-      } else {
-        d = DBL_MAX;
-        ws->fflag[f] = 3;  // in hull + ignore
-      }
-      ws->fd[f] = d;
-      if (d >= -tol || force) return f;
-      E.status = HFB_EPA_NON_CONVEX;
-    } else {
-      E.status = HFB_EPA_DEGENERATED;
-    }
-    epa_hull_remove(ws, E, f);
-    return HFB_EPA_NONE;
+    ws->newf[E.n_pending++] = (uint8_t)f;
+    return f;
   }
   E.status = HFB_EPA_OUT_OF_FACES;
   return HFB_EPA_NONE;
+}
+
+// EPA::newFace, second half (:1081-1128): normal, signed offset, ignore flag.  Returns 0 when the
+// face is kept, else the status the reference sets (Degenerated / NonConvex).
+HFB_HD int epa_face_geometry(EpaWs* ws, int f, double tol, bool force) {
+  const v3 a = ws_vw(ws, ws->fvid[3 * f]), b = ws_vw(ws, ws->fvid[3 * f + 1]), c = ws_vw(ws, ws->fvid[3 * f + 2]);
+  v3 n = cross(b - a, c - a);
+  if (nrm(n) > DBL_EPSILON) {
+    n = unit(n);
+    ws->fn[3 * f] = n.x;
+    ws->fn[3 * f + 1] = n.y;
+    ws->fn[3 * f + 2] = n.z;
+    const double a_dot_nab = dot(a, cross(b - a, n));
+    const double b_dot_nbc = dot(b, cross(c - b, n));
+    const double c_dot_nca = dot(c, cross(a - c, n));
+    double d;
+    if (a_dot_nab >= -tol && b_dot_nbc >= -tol && c_dot_nca >= -tol) {
+      d = dot(a, n);
+    } else {
+      d = DBL_MAX;
+      ws->fflag[f] = 3;  // in hull + ignore
+    }
+    ws->fd[f] = d;
+    if (d >= -tol || force) return 0;
+    return HFB_EPA_NON_CONVEX;
+  }
+  return HFB_EPA_DEGENERATED;
+}
+
+// Completes the pending faces in creation order, every lane doing all of them (the rare path: the
+// horizon walk is about to read a face created in this round).  Returns false, with the status of the
+// first face the reference would have rejected, if one fails.
+HFB_HD bool epa_flush_pending_serial(EpaWs* ws, EpaState& E, double tol, bool force) {
+  const int n = E.n_pending;
+  E.n_pending = 0;
+  for (int k = 0; k < n; ++k) {
+    const int st = epa_face_geometry(ws, ws->newf[k], tol, force);
+    if (st) {
+      E.status = st;
+      return false;
+    }
+  }
+  return true;
+}
+
+// Completes the pending faces, one per lane.  Same verdict as the serial form: the first rejected
+// face in creation order decides the status.
+template <int G>
+HFB_HD bool epa_flush_pending(EpaWs* ws, EpaState& E, double tol, bool force) {
+  const int n = E.n_pending;
+  E.n_pending = 0;
+  Coop<G>::sync();  // every lane is done reading the slots' previous occupants
+  int first_bad = 0x7fffffff;  // creation index << 8 | status
+  for (int k = Coop<G>::lane(); k < n; k += G) {
+    const int st = epa_face_geometry(ws, ws->newf[k], tol, force);
+    if (st && first_bad == 0x7fffffff) first_bad = (k << 8) | st;
+  }
+#if defined(__CUDA_ARCH__)
+  if (G > 1) {
+    const unsigned m = Coop<G>::mask();
+#pragma unroll
+    for (int off = G / 2; off > 0; off >>= 1) {
+      const int o = __shfl_xor_sync(m, first_bad, off);
+      if (o < first_bad) first_bad = o;
+    }
+    __syncwarp(m);  // the other lanes' faces are read by the scan that follows
+  }
+#endif
+  if (first_bad != 0x7fffffff) {
+    E.status = first_bad & 0xff;
+    return false;
+  }
+  return true;
 }
 
 // EPA::findClosestFace (:1141-1154): argmin d^2 over non-ignored hull faces,
@@ -140,7 +209,7 @@ HFB_HD int epa_find_closest(const EpaWs* ws, const EpaState& E) {
   double best = DBL_MAX;
   int bseq = -1, bidx = HFB_EPA_NONE;
   int rseq = -1, ridx = HFB_EPA_NONE;  // newest face in the hull
-  for (int f = Coop<G>::lane(); f < (int)E.nfaces_cap; f += G) {
+  for (int f = Coop<G>::lane(); f < E.hwm; f += G) {
     const int fl = ws->fflag[f];
     if (!(fl & 1)) continue;
     const int sq = ws->fseq[f];
@@ -184,8 +253,8 @@ HFB_HD int epa_find_closest(const EpaWs* ws, const EpaState& E) {
 }
 
 // EPA::expand (:1361-1449), iterative.  Returns `valid`.
-HFB_HD bool epa_expand(EpaWs* ws, EpaState& E, double tol, int pass, v3 ww, int id_w, int f0, int e0,
-                       int& hz_first, int& hz_cur, int& hz_num) {
+HFB_HD bool epa_expand(EpaWs* ws, EpaState& E, double tol, int pass, int round_seq0, v3 ww, int id_w, int f0,
+                       int e0, int& hz_first, int& hz_cur, int& hz_num) {
   const double dummy_precision = 3 * sqrt(DBL_EPSILON);
   int sp = 0;
   ws->stk_f[0] = (uint8_t)f0;
@@ -202,10 +271,15 @@ HFB_HD bool epa_expand(EpaWs* ws, EpaState& E, double tol, int pass, v3 ww, int 
         E.status = HFB_EPA_INVALID_HULL;
         return false;
       }
+      if (E.n_pending > 0 && ws->fseq[f] >= round_seq0) {
+        // stepping on a face created in this round (a slot freed and handed out again): its geometry,
+        // and every verdict the reference reached before this point, must exist now
+        if (!epa_flush_pending_serial(ws, E, tol, false)) return false;
+      }
       const v3 vf = ws_vw(ws, ws->fvid[3 * f + e]);
       if (dot(ws_fn(ws, f), ww - vf) < dummy_precision) {
         // case 1: support point "below" f -> new face on edge e of f
-        const int nf = epa_new_face(ws, E, tol, ws->fvid[3 * f + e1], ws->fvid[3 * f + e], id_w, false);
+        const int nf = epa_alloc_face(ws, E, ws->fvid[3 * f + e1], ws->fvid[3 * f + e], id_w);
         if (nf == HFB_EPA_NONE) return false;
         epa_bind(ws, nf, 0, f, e);
         if (hz_cur != HFB_EPA_NONE) epa_bind(ws, nf, 2, hz_cur, 1);
@@ -221,7 +295,7 @@ HFB_HD bool epa_expand(EpaWs* ws, EpaState& E, double tol, int pass, v3 ww, int 
       ws->stk_s[sp] = (uint8_t)(e | (1 << 2));
       ++sp;
       ws->stk_f[sp] = ws->fadj[3 * f + e1];
-      ws->stk_s[sp] = ws->fedge[3 * f + e1];
+      ws->stk_s[sp] = (uint8_t)ws_fedge(ws, f, e1);
       continue;
     }
     if (!ret) return false;  // a failed sub-expand fails every caller (&& short-circuit)
@@ -229,7 +303,7 @@ HFB_HD bool epa_expand(EpaWs* ws, EpaState& E, double tol, int pass, v3 ww, int 
       ws->stk_s[sp] = (uint8_t)(e | (2 << 2));
       ++sp;
       ws->stk_f[sp] = ws->fadj[3 * f + e2];
-      ws->stk_s[sp] = ws->fedge[3 * f + e2];
+      ws->stk_s[sp] = (uint8_t)ws_fedge(ws, f, e2);
       continue;
     }
     // stage 2: both sub-expands succeeded
@@ -305,11 +379,9 @@ HFB_HD void epa_evaluate(const ShapeD& sa, const ShapeD& sb, const MinkD& md, co
     // reset (:1014-1037): all faces in stock, first allocation = slot 0
     E.hull_count = 0;
     E.seq = 0;
-    E.stock_top = (int)E.nfaces_cap;
-    for (int k = 0; k < (int)E.nfaces_cap; ++k) {
-      ws->stock[k] = (uint8_t)(E.nfaces_cap - 1 - k);
-      ws->fflag[k] = 0;
-    }
+    E.hwm = 0;
+    E.n_pending = 0;
+    E.stock_top = 0;
     E.status = HFB_EPA_VALID;
     E.num_vertices = 0;
     // outward orientation (:1178-1184)
@@ -323,11 +395,14 @@ HFB_HD void epa_evaluate(const ShapeD& sa, const ShapeD& sb, const MinkD& md, co
     ws_put_v(ws, 2, g.s2);
     ws_put_v(ws, 3, g.s3);
     E.num_vertices = 4;
-    const int t0 = epa_new_face(ws, E, tol, 0, 1, 2, true);
-    const int t1 = epa_new_face(ws, E, tol, 1, 0, 3, true);
-    const int t2 = epa_new_face(ws, E, tol, 2, 1, 3, true);
-    const int t3 = epa_new_face(ws, E, tol, 0, 2, 3, true);
-    if (E.hull_count == 4) {
+    Coop<G>::sync();  // vertices written above are read by other lanes below
+    const int t0 = epa_alloc_face(ws, E, 0, 1, 2);
+    const int t1 = epa_alloc_face(ws, E, 1, 0, 3);
+    const int t2 = epa_alloc_face(ws, E, 2, 1, 3);
+    const int t3 = epa_alloc_face(ws, E, 0, 2, 3);
+    // a forced face can only be rejected as Degenerated; the reference then has fewer than 4 faces in
+    // the hull and falls through to FallBack (:1196)
+    if (epa_flush_pending<G>(ws, E, tol, true)) {
       epa_bind(ws, t0, 0, t1, 0);
       epa_bind(ws, t0, 1, t2, 0);
       epa_bind(ws, t0, 2, t3, 0);
@@ -371,9 +446,12 @@ HFB_HD void epa_evaluate(const ShapeD& sa, const ShapeD& sb, const MinkD& md, co
           break;
         }
         bool valid = true;
+        const int round_seq0 = E.seq;
         for (int j = 0; (j < 3) && valid; ++j)
-          valid = valid && epa_expand(ws, E, tol, pass, w.w, id_w, ws->fadj[3 * closest + j],
-                                      ws->fedge[3 * closest + j], hz_first, hz_cur, hz_num);
+          valid = valid && epa_expand(ws, E, tol, pass, round_seq0, w.w, id_w, ws->fadj[3 * closest + j],
+                                      ws_fedge(ws, closest, j), hz_first, hz_cur, hz_num);
+        // verdicts of the faces created in this round come before whatever stopped the walk after them
+        if (!epa_flush_pending<G>(ws, E, tol, false)) valid = false;
         if (!valid || hz_num < 3) break;
         epa_bind(ws, hz_first, 2, hz_cur, 1);
         epa_hull_remove(ws, E, closest);

@@ -30,6 +30,7 @@
 using namespace hfb;
 
 #define CAPS_ALL (CAP_PRIM | CAP_CONVEX | CAP_TRI)
+#define CAPS_BVH (CAPS_ALL | CAP_INLINE_PRIM)
 // lanes per pair: pairs touching ConvexBase/TriangleP (GC) and the EPA kernel (GE).
 // Instantiated for 8 / 16 / 32; the defaults can be overridden per context with the
 // environment variables HFB_GC / HFB_GE (tuning knobs, see profiles/).
@@ -69,6 +70,10 @@ struct BatchArgs {
   void* out;                  // hfb_distance_result* or hfb_contact*
   EpaItem* queue;
   unsigned* queue_count;      // [0] = items pushed this batch, [1] = running total
+  const unsigned* epa_lo;     // k_epa: device pointers to the [lo, hi) slice of the queue this launch owns
+  const unsigned* epa_hi;
+  unsigned* epa_head;         // k_epa: work counter of this launch (items are handed out one by one)
+  unsigned sub_idx, sub_cnt;  // k_pairs: this launch takes the sub_idx-th of sub_cnt equal parts of [lo, hi)
   const uint32_t* index_list; // optional indirection: pair ids sorted by class (k_bin_scatter)
   const unsigned* range_lo;   // device pointers to the [lo, hi) slice of index_list to process
   const unsigned* range_hi;
@@ -126,8 +131,14 @@ template <int G, int CAPS, int MODE, int PATHS, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_pairs(const BatchArgs a) {
   const unsigned ngroups = (gridDim.x * blockDim.x) / G;
   const unsigned gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-  const unsigned lo = a.index_list ? *a.range_lo : 0u;
-  const unsigned hi = a.index_list ? *a.range_hi : a.n;
+  unsigned lo = a.index_list ? *a.range_lo : 0u;
+  unsigned hi = a.index_list ? *a.range_hi : a.n;
+  if (a.sub_cnt > 1) {
+    const unsigned long long len = hi - lo;
+    const unsigned l2 = lo + (unsigned)(len * a.sub_idx / a.sub_cnt);
+    hi = lo + (unsigned)(len * (a.sub_idx + 1) / a.sub_cnt);
+    lo = l2;
+  }
   for (unsigned k = lo + gid; k < hi; k += ngroups) {
     const unsigned i = a.index_list ? a.index_list[k] : k;
     const PairIn in = load_pair_in<CAPS>(a, i);
@@ -160,15 +171,24 @@ __global__ void __launch_bounds__(128, MINB) k_pairs(const BatchArgs a) {
 }
 
 // ------------------------------------------------------------------ phase 2 --
+// groups per block: as many EPA workspaces as fit next to each other in one SM's shared memory, in
+// two blocks (G = 8, 16); G = 32 is bounded by registers instead
+template <int G>
+struct EpaCfg {
+  static constexpr int GPB = (G == 32) ? 4 : 10;
+  static constexpr int THREADS = GPB * G;
+};
 template <int G, int CAPS, int MODE>
-__global__ void __launch_bounds__(4 * G) k_epa(const BatchArgs a) {
+__global__ void __launch_bounds__(EpaCfg<G>::THREADS) k_epa(const BatchArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned lg = threadIdx.x / G;  // group within block
   EpaWs* ws = reinterpret_cast<EpaWs*>(smem) + lg;
-  const unsigned ngroups = (gridDim.x * blockDim.x) / G;
-  const unsigned gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
-  const unsigned total = *a.queue_count;
-  for (unsigned k = gid; k < total; k += ngroups) {
+  const unsigned lo = *a.epa_lo, hi = *a.epa_hi;
+  for (;;) {
+    unsigned k = 0;
+    if (Coop<G>::lane() == 0) k = lo + atomicAdd(a.epa_head, 1u);
+    k = __shfl_sync(Coop<G>::mask(), k, (threadIdx.x & 31u) & ~(unsigned)(G - 1));
+    if (k >= hi) break;
     const EpaItem* it = a.queue + k;
     const unsigned i = it->pair;
     const PairIn in = load_pair_in<CAPS>(a, i);
@@ -227,10 +247,10 @@ __global__ void __launch_bounds__(64) k_bvh(const BatchArgs a) {
     unsigned bt, lt;
     const xf t1 = load_xf(a.tf1[i].R), t2 = load_xf(a.tf2[i].R);
     if (MODE == 0)
-      bvh_pair_distance<CAPS_ALL>(a.A, a.h1[i], t1, a.h2[i], t2, a.P, a.B, guess, h0, h1, ws,
+      bvh_pair_distance<CAPS_BVH>(a.A, a.h1[i], t1, a.h2[i], t2, a.P, a.B, guess, h0, h1, ws,
                                   reinterpret_cast<hfb_distance_result*>(a.out) + i, bt, lt);
     else
-      bvh_pair_collide<CAPS_ALL>(a.A, a.h1[i], t1, a.h2[i], t2, a.P, a.B, guess, h0, h1, ws,
+      bvh_pair_collide<CAPS_BVH>(a.A, a.h1[i], t1, a.h2[i], t2, a.P, a.B, guess, h0, h1, ws,
                                  reinterpret_cast<hfb_contact*>(a.out) + i, bt, lt);
     bv_total += bt;
     leaf_total += lt;
@@ -379,8 +399,13 @@ struct DevBuf {
 constexpr int kSlots = 3;
 constexpr size_t kChunk = 1u << 17;  // pairs per pipelined chunk of the host entry points
 
+constexpr int kMaxParts = 8;  // phase-1 launches per batch that may each be followed by an EPA launch
 struct Slot {
   cudaStream_t stream = nullptr;
+  // EPA of the parts of a batch that are through phase 1 runs here, next to phase 1 of the later parts
+  cudaStream_t epa_stream = nullptr;
+  cudaEvent_t ev_part[kMaxParts] = {};
+  cudaEvent_t ev_join = nullptr;
   DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, bvh_ws, bvh_cnt;
 };
 
@@ -397,7 +422,7 @@ struct hfb_ctx {
   Slot dev_slot;  // resources of the *_device entry points (caller's stream)
   DevBuf sup_ids, sup_dirs, sup_idx, sup_out;
   hfb_stats stats{};
-  int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1;
+  int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0;
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int kind; };
   std::vector<Ev> events;
@@ -461,8 +486,8 @@ int launch_pairs(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s
 
 template <int G, int CAPS, int MODE>
 int launch_epa(hfb_ctx* ctx, const BatchArgs& a, cudaStream_t s) {
-  const int threads = 4 * G;
-  const size_t smem = 4 * sizeof(EpaWs);
+  const int threads = EpaCfg<G>::THREADS;
+  const size_t smem = EpaCfg<G>::GPB * sizeof(EpaWs);
   static int per_sm = 0;
   if (per_sm == 0) {
     CK(cudaFuncSetAttribute(k_epa<G, CAPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -503,22 +528,36 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   const unsigned n = a.n;
   if (n == 0) return HFB_OK;
   CK(sl.queue.reserve((size_t)n * sizeof(EpaItem)));
-  // counters: [0] EPA queue count, [1] running EPA total, [8..8+NBINS) hist, then offsets (NBINS+1), cursor (NBINS)
-  const size_t ncnt = 8 + 3 * (HFB_NBINS + 2);
+  // counters: [0] EPA queue count, [1] running EPA total, [4..4+kMaxParts] queue marks (mark[0] = 0,
+  // mark[j+1] = queue count after part j of phase 1), [16..16+kMaxParts) EPA work counters,
+  // [32..) hist (NBINS), offsets (NBINS+1), cursor (NBINS)
+  const size_t ncnt = 32 + 3 * (HFB_NBINS + 2);
   if (!sl.counters.p) {
     CK(sl.counters.reserve(ncnt * sizeof(unsigned)));
     CK(cudaMemsetAsync(sl.counters.p, 0, ncnt * sizeof(unsigned), s));
   }
+  if (!sl.epa_stream) {
+    CK(cudaStreamCreateWithFlags(&sl.epa_stream, cudaStreamNonBlocking));
+    for (int k = 0; k < kMaxParts; ++k) CK(cudaEventCreateWithFlags(&sl.ev_part[k], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&sl.ev_join, cudaEventDisableTiming));
+  }
   CK(sl.lists.reserve((size_t)n * sizeof(uint32_t)));
   a.queue = static_cast<EpaItem*>(sl.queue.p);
   unsigned* cnt = static_cast<unsigned*>(sl.counters.p);
-  unsigned* hist = cnt + 8;
+  unsigned* mark = cnt + 4;
+  unsigned* heads = cnt + 16;
+  unsigned* hist = cnt + 32;
   unsigned* offsets = hist + HFB_NBINS + 1;
   unsigned* cursor = offsets + HFB_NBINS + 2;
   uint32_t* perm = static_cast<uint32_t*>(sl.lists.p);
   a.queue_count = cnt;
+  a.epa_lo = a.epa_hi = nullptr;
+  a.epa_head = nullptr;
+  a.sub_idx = 0;
+  a.sub_cnt = 1;
   a.A = ctx->dview;
   CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned), s));
+  CK(cudaMemsetAsync(cnt + 2, 0, 30 * sizeof(unsigned), s));
   CK(cudaMemsetAsync(hist, 0, HFB_NBINS * sizeof(unsigned), s));
   {
     KTimer kt(ctx, s, 2);
@@ -532,6 +571,35 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   CK(cudaGetLastError());
   a.index_list = perm;
   int rc;
+  const bool mixed = ctx->arena.has_convex || ctx->arena.has_tri;
+  const bool want_epa = a.P.compute_penetration;
+
+  // EPA over the queue items pushed since the previous mark.  Parts other than the last go to the
+  // side stream, where they overlap phase 1 of the parts that follow; an EPA item is long and there
+  // are few of them, so run at the end they would leave most of the GPU idle.
+  int parts_done = 0;
+  auto epa_after_part = [&](bool last) -> int {
+    if (!want_epa) return HFB_OK;
+    const int j = parts_done++;
+    if (cudaMemcpyAsync(mark + j + 1, cnt, sizeof(unsigned), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
+      return fail(ctx, HFB_ERR_CUDA, "queue mark copy failed");
+    BatchArgs ae = a;
+    ae.epa_lo = mark + j;
+    ae.epa_hi = mark + j + 1;
+    ae.epa_head = heads + j;
+    cudaStream_t es = s;
+    if (!last) {
+      es = sl.epa_stream;
+      if (cudaEventRecord(sl.ev_part[j], s) != cudaSuccess || cudaStreamWaitEvent(es, sl.ev_part[j], 0) != cudaSuccess)
+        return fail(ctx, HFB_ERR_CUDA, "event record/wait failed");
+    } else if (j > 0) {
+      // the side stream's launches finish before the caller's stream moves past this batch
+      if (cudaEventRecord(sl.ev_join, sl.epa_stream) != cudaSuccess || cudaStreamWaitEvent(s, sl.ev_join, 0) != cudaSuccess)
+        return fail(ctx, HFB_ERR_CUDA, "event record/wait failed");
+    }
+    return mixed ? launch_epa_g<CAPS_ALL, MODE>(ctx, ae, es) : launch_epa_g<CAP_PRIM, MODE>(ctx, ae, es);
+  };
+
   BatchArgs ac = a, ag = a, av = a;
   ac.range_lo = offsets + 0;
   ac.range_hi = offsets + HFB_BIN_GJK0;
@@ -540,15 +608,30 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   av.range_lo = offsets + HFB_BIN_CONVEX;
   av.range_hi = offsets + HFB_BIN_BVH;
   if ((rc = launch_pairs<1, CAP_PRIM, MODE, PATH_CLOSED>(ctx, ac, n, s))) return rc;
-  switch (ctx->minb) {  // register budget of the GJK kernel: 255 / 168 / 128 registers per thread
-    case 3: rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE, 3>(ctx, ag, n, s); break;
-    case 4: rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE, 4>(ctx, ag, n, s); break;
-    default: rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE, 1>(ctx, ag, n, s);
+  // the class populations are only known on the device, so both GJK ranges are cut the same way
+  unsigned nsub = ctx->nsub > 0 ? (unsigned)ctx->nsub : (n >= (1u << 19) ? 3u : (n >= (1u << 17) ? 2u : 1u));
+  if (!want_epa) nsub = 1;
+  if (nsub > (unsigned)(kMaxParts / 2)) nsub = kMaxParts / 2;
+  const unsigned sub_work = (n + nsub - 1) / nsub;
+  for (unsigned j = 0; j < nsub; ++j) {
+    ag.sub_idx = j;
+    ag.sub_cnt = nsub;
+    switch (ctx->minb) {  // register budget of the GJK kernel: 255 / 168 / 128 registers per thread
+      case 3: rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE, 3>(ctx, ag, sub_work, s); break;
+      case 4: rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE, 4>(ctx, ag, sub_work, s); break;
+      default: rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE, 1>(ctx, ag, sub_work, s);
+    }
+    if (rc) return rc;
+    if ((rc = epa_after_part(!mixed && j + 1 == nsub))) return rc;
   }
-  if (rc) return rc;
-  const bool mixed = ctx->arena.has_convex || ctx->arena.has_tri;
-  if (mixed)
-    if ((rc = launch_pairs_convex<MODE>(ctx, av, n, s))) return rc;
+  if (mixed) {
+    for (unsigned j = 0; j < nsub; ++j) {
+      av.sub_idx = j;
+      av.sub_cnt = nsub;
+      if ((rc = launch_pairs_convex<MODE>(ctx, av, sub_work, s))) return rc;
+      if ((rc = epa_after_part(j + 1 == nsub))) return rc;
+    }
+  }
   if (ctx->arena.has_bvh) {
     const int threads = 64;
     unsigned blocks = (n + threads - 1) / threads;
@@ -570,11 +653,6 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
     }
     ctx->stats.kernel_launches++;
     CK(cudaGetLastError());
-  }
-  if (a.P.compute_penetration) {
-    if (mixed) rc = launch_epa_g<CAPS_ALL, MODE>(ctx, a, s);
-    else rc = launch_epa_g<CAP_PRIM, MODE>(ctx, a, s);
-    if (rc) return rc;
   }
   ctx->stats.pairs_processed += n;
   return HFB_OK;
@@ -744,6 +822,7 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   c->gc = env_g("HFB_GC", HFB_GC_DEFAULT);
   c->ge = env_g("HFB_GE", HFB_GE_DEFAULT);
   if (const char* mb = getenv("HFB_MINB")) c->minb = atoi(mb);
+  if (const char* ns = getenv("HFB_NSUB")) c->nsub = atoi(ns);
   for (int k = 0; k < kSlots; ++k)
     if (cudaStreamCreateWithFlags(&c->slots[k].stream, cudaStreamNonBlocking) != cudaSuccess) {
       delete c;
@@ -761,6 +840,10 @@ void hfb_ctx_destroy(hfb_ctx* c) {
     DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.bvh_ws, &s.bvh_cnt};
     for (DevBuf* b : bs) b->release();
     if (s.stream) cudaStreamDestroy(s.stream);
+    if (s.epa_stream) cudaStreamDestroy(s.epa_stream);
+    for (cudaEvent_t e : s.ev_part)
+      if (e) cudaEventDestroy(e);
+    if (s.ev_join) cudaEventDestroy(s.ev_join);
   };
   for (int k = 0; k < kSlots; ++k) rel(c->slots[k]);
   rel(c->dev_slot);

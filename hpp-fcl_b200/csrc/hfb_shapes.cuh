@@ -71,12 +71,11 @@ struct ShapeD {
 };
 
 // capability mask of a kernel instantiation: which shape classes it may meet
-enum { CAP_PRIM = 1, CAP_CONVEX = 2, CAP_TRI = 4 };
+// CAP_INLINE_PRIM: expand the primitive supports in place (the BVH walk: a call inside the leaf test
+// costs more in spills than the duplicate code costs in instruction fetch)
+enum { CAP_PRIM = 1, CAP_CONVEX = 2, CAP_TRI = 4, CAP_INLINE_PRIM = 8 };
 
-// primitive supports, out of line on the device: one copy of this code serves both operands of
-// the Minkowski difference (inlined twice it dominated the GJK loop's instruction footprint and the
-// kernel stalled on instruction fetch, see profiles/r01_summary.md)
-HFB_HD_NOINLINE v3 prim_support(int type, double p0, double p1, double p2, v3 dir) {
+HFB_HD v3 prim_support_inl(int type, double p0, double p1, double p2, v3 dir) {
   v3 r = mk(0, 0, 0);
   struct { int type; double p0, p1, p2; } s = {type, p0, p1, p2};
   {
@@ -144,6 +143,12 @@ HFB_HD_NOINLINE v3 prim_support(int type, double p0, double p1, double p2, v3 di
   }
   return r;
 }
+// primitive supports, out of line on the device: one copy of this code serves both operands of
+// the Minkowski difference (inlined twice it dominated the GJK loop's instruction footprint and the
+// kernel stalled on instruction fetch, see profiles/r01_summary.md)
+HFB_HD_NOINLINE v3 prim_support(int type, double p0, double p1, double p2, v3 dir) {
+  return prim_support_inl(type, p0, p1, p2, dir);
+}
 
 template <int G, int CAPS>
 HFB_HD v3 shape_support(const ShapeD& s, v3 dir, int& hint) {
@@ -174,7 +179,10 @@ HFB_HD v3 shape_support(const ShapeD& s, v3 dir, int& hint) {
     }
     return r;
   }
-  if (CAPS & CAP_PRIM) return prim_support(s.type, s.p0, s.p1, s.p2, dir);
+  if (CAPS & CAP_PRIM) {
+    if (CAPS & CAP_INLINE_PRIM) return prim_support_inl(s.type, s.p0, s.p1, s.p2, dir);
+    return prim_support(s.type, s.p0, s.p1, s.p2, dir);
+  }
   return r;
 }
 
