@@ -33,23 +33,36 @@ namespace hfb {
 #define HFB_EPA_MAXF (2 * HFB_EPA_CAP_IT + 4)
 #define HFB_EPA_NONE 0xff
 
-struct EpaWs {
-  double vw0[HFB_EPA_MAXV * 3];
-  double vw1[HFB_EPA_MAXV * 3];
-  double vw[HFB_EPA_MAXV * 3];  // w0 - w1
-  double fn[HFB_EPA_MAXF * 3];
-  double fd[HFB_EPA_MAXF];
-  uint16_t fseq[HFB_EPA_MAXF];
-  uint8_t fvid[HFB_EPA_MAXF * 3];
-  uint8_t fadj[HFB_EPA_MAXF * 3];
-  uint8_t fedge[HFB_EPA_MAXF * 3];
-  uint8_t fpass[HFB_EPA_MAXF];
-  uint8_t fflag[HFB_EPA_MAXF];  // bit0: in hull, bit1: ignore
-  uint8_t stock[HFB_EPA_MAXF];
-  uint8_t stk_f[HFB_EPA_MAXF + 4];
-  uint8_t stk_s[HFB_EPA_MAXF + 4];  // e | stage << 2
-  uint8_t newf[HFB_EPA_MAXF + 4];   // faces whose geometry is pending, in creation order
+// internal verdict of a run in a workspace smaller than the request's caps: the polytope outgrew it
+// before the reference would have stopped; the pair is run again in the full-size workspace
+#define HFB_EPA_WS_OVERFLOW 0x7f
+
+template <int MAXV_, int MAXF_>
+struct EpaWsT {
+  static constexpr int MAXV = MAXV_;
+  static constexpr int MAXF = MAXF_;
+  double vw0[MAXV_ * 3];
+  double vw1[MAXV_ * 3];
+  double vw[MAXV_ * 3];  // w0 - w1
+  double fn[MAXF_ * 3];
+  double fd[MAXF_];
+  uint16_t fseq[MAXF_];
+  uint8_t fvid[MAXF_ * 3];
+  uint8_t fadj[MAXF_ * 3];
+  uint8_t fedge[MAXF_ * 3];
+  uint8_t fpass[MAXF_];
+  uint8_t fflag[MAXF_];  // bit0: in hull, bit1: ignore
+  uint8_t stock[MAXF_];
+  uint8_t stk_f[MAXF_ + 4];
+  uint8_t stk_s[MAXF_ + 4];  // e | stage << 2
+  uint8_t newf[MAXF_ + 4];   // faces whose geometry is pending, in creation order
 };
+// full size: any request up to epa_max_iterations = HFB_EPA_CAP_IT fits
+typedef EpaWsT<HFB_EPA_MAXV, HFB_EPA_MAXF> EpaWs;
+// first-try size of the EPA kernel: room for 24 iterations (99% of the penetrating pairs of the
+// benchmark workloads stop within 20), 2.4x more pairs in flight per SM than the full size
+#define HFB_EPA_SMALL_IT 24
+typedef EpaWsT<HFB_EPA_SMALL_IT + 4, 2 * HFB_EPA_SMALL_IT + 4> EpaWsSmall;
 
 struct EpaParams {
   double tolerance;
@@ -71,15 +84,18 @@ struct EpaState {
   unsigned nfaces_cap, nverts_cap;
 };
 
-HFB_HD v3 ws_vw(const EpaWs* ws, int i) { return mk(ws->vw[3 * i], ws->vw[3 * i + 1], ws->vw[3 * i + 2]); }
-HFB_HD SV ws_sv(const EpaWs* ws, int i) {
+template <class WS>
+HFB_HD v3 ws_vw(const WS* ws, int i) { return mk(ws->vw[3 * i], ws->vw[3 * i + 1], ws->vw[3 * i + 2]); }
+template <class WS>
+HFB_HD SV ws_sv(const WS* ws, int i) {
   SV s;
   s.w0 = mk(ws->vw0[3 * i], ws->vw0[3 * i + 1], ws->vw0[3 * i + 2]);
   s.w1 = mk(ws->vw1[3 * i], ws->vw1[3 * i + 1], ws->vw1[3 * i + 2]);
   s.w = ws_vw(ws, i);
   return s;
 }
-HFB_HD void ws_put_v(EpaWs* ws, int i, const SV& s) {
+template <class WS>
+HFB_HD void ws_put_v(WS* ws, int i, const SV& s) {
   ws->vw0[3 * i] = s.w0.x;
   ws->vw0[3 * i + 1] = s.w0.y;
   ws->vw0[3 * i + 2] = s.w0.z;
@@ -90,19 +106,24 @@ HFB_HD void ws_put_v(EpaWs* ws, int i, const SV& s) {
   ws->vw[3 * i + 1] = s.w.y;
   ws->vw[3 * i + 2] = s.w.z;
 }
-HFB_HD v3 ws_fn(const EpaWs* ws, int f) { return mk(ws->fn[3 * f], ws->fn[3 * f + 1], ws->fn[3 * f + 2]); }
+template <class WS>
+HFB_HD v3 ws_fn(const WS* ws, int f) { return mk(ws->fn[3 * f], ws->fn[3 * f + 1], ws->fn[3 * f + 2]); }
 
-HFB_HD int ws_fedge(const EpaWs* ws, int f, int e) { return ws->fedge[3 * f + e]; }
+template <class WS>
+HFB_HD int ws_fedge(const WS* ws, int f, int e) { return ws->fedge[3 * f + e]; }
 // plain stores only: every lane of a group writes the same topology redundantly, which is race-free
 // as long as no write is a read-modify-write of a word that another lane also updates
-HFB_HD void ws_set_fedge(EpaWs* ws, int f, int e, int v) { ws->fedge[3 * f + e] = (uint8_t)v; }
-HFB_HD void epa_bind(EpaWs* ws, int fa, int ea, int fb, int eb) {  // gjk.h:312-320
+template <class WS>
+HFB_HD void ws_set_fedge(WS* ws, int f, int e, int v) { ws->fedge[3 * f + e] = (uint8_t)v; }
+template <class WS>
+HFB_HD void epa_bind(WS* ws, int fa, int ea, int fb, int eb) {  // gjk.h:312-320
   ws_set_fedge(ws, fa, ea, eb);
   ws->fadj[3 * fa + ea] = (uint8_t)fb;
   ws_set_fedge(ws, fb, eb, ea);
   ws->fadj[3 * fb + eb] = (uint8_t)fa;
 }
-HFB_HD void epa_hull_remove(EpaWs* ws, EpaState& E, int f) {  // hull.remove + stock.append
+template <class WS>
+HFB_HD void epa_hull_remove(WS* ws, EpaState& E, int f) {  // hull.remove + stock.append
   ws->fflag[f] = 0;
   E.hull_count -= 1;
   ws->stock[E.stock_top++] = (uint8_t)f;
@@ -110,10 +131,15 @@ HFB_HD void epa_hull_remove(EpaWs* ws, EpaState& E, int f) {  // hull.remove + s
 
 // EPA::newFace (:1068-1138), first half: take a slot from the stock, link it into the hull and
 // record its vertices.  Returns the slot id, or HFB_EPA_NONE with status OutOfFaces (:1131-1137).
-HFB_HD int epa_alloc_face(EpaWs* ws, EpaState& E, int ia, int ib, int ic) {
+template <class WS>
+HFB_HD int epa_alloc_face(WS* ws, EpaState& E, int ia, int ib, int ic) {
   // the reference's stock hands out fc_store[0], [1], ... and re-uses freed faces last-in first-out
   // (:1034-1035, gjk.h:292-298): a LIFO of freed slots on top of a counter of untouched ones
   if (E.stock_top > 0 || E.hwm < (int)E.nfaces_cap) {
+    if (E.stock_top == 0 && E.hwm >= WS::MAXF) {  // the request allows more faces than this workspace holds
+      E.status = HFB_EPA_WS_OVERFLOW;
+      return HFB_EPA_NONE;
+    }
     const int f = E.stock_top > 0 ? ws->stock[--E.stock_top] : E.hwm++;
     E.hull_count += 1;
     ws->fflag[f] = 1;
@@ -131,7 +157,8 @@ HFB_HD int epa_alloc_face(EpaWs* ws, EpaState& E, int ia, int ib, int ic) {
 
 // EPA::newFace, second half (:1081-1128): normal, signed offset, ignore flag.  Returns 0 when the
 // face is kept, else the status the reference sets (Degenerated / NonConvex).
-HFB_HD int epa_face_geometry(EpaWs* ws, int f, double tol, bool force) {
+template <class WS>
+HFB_HD int epa_face_geometry(WS* ws, int f, double tol, bool force) {
   const v3 a = ws_vw(ws, ws->fvid[3 * f]), b = ws_vw(ws, ws->fvid[3 * f + 1]), c = ws_vw(ws, ws->fvid[3 * f + 2]);
   v3 n = cross(b - a, c - a);
   if (nrm(n) > DBL_EPSILON) {
@@ -159,7 +186,8 @@ HFB_HD int epa_face_geometry(EpaWs* ws, int f, double tol, bool force) {
 // Completes the pending faces in creation order, every lane doing all of them (the rare path: the
 // horizon walk is about to read a face created in this round).  Returns false, with the status of the
 // first face the reference would have rejected, if one fails.
-HFB_HD bool epa_flush_pending_serial(EpaWs* ws, EpaState& E, double tol, bool force) {
+template <class WS>
+HFB_HD bool epa_flush_pending_serial(WS* ws, EpaState& E, double tol, bool force) {
   const int n = E.n_pending;
   E.n_pending = 0;
   for (int k = 0; k < n; ++k) {
@@ -174,8 +202,8 @@ HFB_HD bool epa_flush_pending_serial(EpaWs* ws, EpaState& E, double tol, bool fo
 
 // Completes the pending faces, one per lane.  Same verdict as the serial form: the first rejected
 // face in creation order decides the status.
-template <int G>
-HFB_HD bool epa_flush_pending(EpaWs* ws, EpaState& E, double tol, bool force) {
+template <int G, class WS>
+HFB_HD bool epa_flush_pending(WS* ws, EpaState& E, double tol, bool force) {
   const int n = E.n_pending;
   E.n_pending = 0;
   Coop<G>::sync();  // every lane is done reading the slots' previous occupants
@@ -204,8 +232,8 @@ HFB_HD bool epa_flush_pending(EpaWs* ws, EpaState& E, double tol, bool force) {
 
 // EPA::findClosestFace (:1141-1154): argmin d^2 over non-ignored hull faces,
 // ties -> newest (largest seq); all ignored -> hull.root (newest face).
-template <int G>
-HFB_HD int epa_find_closest(const EpaWs* ws, const EpaState& E) {
+template <int G, class WS>
+HFB_HD int epa_find_closest(const WS* ws, const EpaState& E) {
   double best = DBL_MAX;
   int bseq = -1, bidx = HFB_EPA_NONE;
   int rseq = -1, ridx = HFB_EPA_NONE;  // newest face in the hull
@@ -253,7 +281,8 @@ HFB_HD int epa_find_closest(const EpaWs* ws, const EpaState& E) {
 }
 
 // EPA::expand (:1361-1449), iterative.  Returns `valid`.
-HFB_HD bool epa_expand(EpaWs* ws, EpaState& E, double tol, int pass, int round_seq0, v3 ww, int id_w, int f0,
+template <class WS>
+HFB_HD bool epa_expand(WS* ws, EpaState& E, double tol, int pass, int round_seq0, v3 ww, int id_w, int f0,
                        int e0, int& hz_first, int& hz_cur, int& hz_num) {
   const double dummy_precision = 3 * sqrt(DBL_EPSILON);
   int sp = 0;
@@ -362,9 +391,9 @@ HFB_HD bool gjk_enclose_origin(const ShapeD& sa, const ShapeD& sb, const MinkD& 
 }
 
 // EPA::evaluate (:1156-1316)
-template <int G, int CAPS>
+template <int G, int CAPS, class WS>
 HFB_HD void epa_evaluate(const ShapeD& sa, const ShapeD& sb, const MinkD& md, const EpaParams& P,
-                         GjkState& g, EpaWs* ws, EpaState& E) {
+                         GjkState& g, WS* ws, EpaState& E) {
   const double tol = P.tolerance;
   E.hint0 = g.hint0;
   E.hint1 = g.hint1;
@@ -422,6 +451,10 @@ HFB_HD void epa_evaluate(const ShapeD& sa, const ShapeD& sb, const MinkD& md, co
       for (; it < P.max_iterations; ++it) {
         if (E.num_vertices >= (int)E.nverts_cap) {
           E.status = HFB_EPA_OUT_OF_VERTICES;
+          break;
+        }
+        if (E.num_vertices >= WS::MAXV) {
+          E.status = HFB_EPA_WS_OVERFLOW;
           break;
         }
         int hz_first = HFB_EPA_NONE, hz_cur = HFB_EPA_NONE, hz_num = 0;

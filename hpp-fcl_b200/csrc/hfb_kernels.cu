@@ -73,6 +73,8 @@ struct BatchArgs {
   const unsigned* epa_lo;     // k_epa: device pointers to the [lo, hi) slice of the queue this launch owns
   const unsigned* epa_hi;
   unsigned* epa_head;         // k_epa: work counter of this launch (items are handed out one by one)
+  uint32_t* retry;            // queue indices of the items that outgrew the reduced-size EPA workspace
+  unsigned* retry_count;
   unsigned sub_idx, sub_cnt;  // k_pairs: this launch takes the sub_idx-th of sub_cnt equal parts of [lo, hi)
   const uint32_t* index_list; // optional indirection: pair ids sorted by class (k_bin_scatter)
   const unsigned* range_lo;   // device pointers to the [lo, hi) slice of index_list to process
@@ -171,24 +173,37 @@ __global__ void __launch_bounds__(128, MINB) k_pairs(const BatchArgs a) {
 }
 
 // ------------------------------------------------------------------ phase 2 --
-// groups per block: as many EPA workspaces as fit next to each other in one SM's shared memory, in
-// two blocks (G = 8, 16); G = 32 is bounded by registers instead
-template <int G>
+// EPA runs in two tiers.  Tier 0 gives every pair a reduced-size workspace (EpaWsSmall), so that 48
+// lane groups fit in one SM's shared memory instead of 20: the kernel is bound by the latency of one
+// pair's dependent FP64 chain, and throughput is the number of pairs in flight.  A pair whose polytope
+// outgrows it is appended to the retry list and run again by tier 1 in the full-size workspace.
+template <int G, int TIER>
 struct EpaCfg {
-  static constexpr int GPB = (G == 32) ? 4 : 10;
+  typedef EpaWs WS;
+  static constexpr int GPB = (G == 32) ? 4 : 10;  // two blocks per SM (G = 8, 16); registers bound G = 32
   static constexpr int THREADS = GPB * G;
+  static constexpr int MINB = 1;
 };
-template <int G, int CAPS, int MODE>
-__global__ void __launch_bounds__(EpaCfg<G>::THREADS) k_epa(const BatchArgs a) {
+template <int G>
+struct EpaCfg<G, 0> {
+  typedef EpaWsSmall WS;
+  static constexpr int GPB = (G == 8) ? 16 : (G == 16 ? 16 : 8);
+  static constexpr int THREADS = GPB * G;
+  static constexpr int MINB = (G == 8) ? 3 : 1;  // G = 8: 3 blocks x 16 groups per SM, 168 registers
+};
+template <int G, int CAPS, int MODE, int TIER>
+__global__ void __launch_bounds__(EpaCfg<G, TIER>::THREADS, EpaCfg<G, TIER>::MINB) k_epa(const BatchArgs a) {
+  typedef typename EpaCfg<G, TIER>::WS WS;
   extern __shared__ __align__(16) unsigned char smem[];
   const unsigned lg = threadIdx.x / G;  // group within block
-  EpaWs* ws = reinterpret_cast<EpaWs*>(smem) + lg;
-  const unsigned lo = *a.epa_lo, hi = *a.epa_hi;
+  WS* ws = reinterpret_cast<WS*>(smem) + lg;
+  const unsigned lo = TIER == 0 ? *a.epa_lo : 0u, hi = TIER == 0 ? *a.epa_hi : *a.retry_count;
   for (;;) {
     unsigned k = 0;
     if (Coop<G>::lane() == 0) k = lo + atomicAdd(a.epa_head, 1u);
     k = __shfl_sync(Coop<G>::mask(), k, (threadIdx.x & 31u) & ~(unsigned)(G - 1));
     if (k >= hi) break;
+    if (TIER == 1) k = a.retry[k];
     const EpaItem* it = a.queue + k;
     const unsigned i = it->pair;
     const PairIn in = load_pair_in<CAPS>(a, i);
@@ -216,8 +231,11 @@ __global__ void __launch_bounds__(EpaCfg<G>::THREADS) k_epa(const BatchArgs a) {
     o.cached_guess = mk(1, 0, 0);
     o.hint0 = o.hint1 = 0;
     Coop<G>::sync();
-    pair_phase2<G, CAPS>(in, a.P, g, ws, o);
-    if (Coop<G>::lane() == 0) store_result<MODE>(a, i, o);
+    const bool done = pair_phase2<G, CAPS>(in, a.P, g, ws, o);
+    if (Coop<G>::lane() == 0) {
+      if (done) store_result<MODE>(a, i, o);
+      else a.retry[atomicAdd(a.retry_count, 1u)] = k;  // TIER 0 only
+    }
     Coop<G>::sync();
   }
 }
@@ -406,7 +424,7 @@ struct Slot {
   cudaStream_t epa_stream = nullptr;
   cudaEvent_t ev_part[kMaxParts] = {};
   cudaEvent_t ev_join = nullptr;
-  DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, bvh_ws, bvh_cnt;
+  DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, retry, bvh_ws, bvh_cnt;
 };
 
 }  // namespace
@@ -484,31 +502,31 @@ int launch_pairs(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s
   return HFB_OK;
 }
 
-template <int G, int CAPS, int MODE>
+template <int G, int CAPS, int MODE, int TIER>
 int launch_epa(hfb_ctx* ctx, const BatchArgs& a, cudaStream_t s) {
-  const int threads = EpaCfg<G>::THREADS;
-  const size_t smem = EpaCfg<G>::GPB * sizeof(EpaWs);
+  const int threads = EpaCfg<G, TIER>::THREADS;
+  const size_t smem = EpaCfg<G, TIER>::GPB * sizeof(typename EpaCfg<G, TIER>::WS);
   static int per_sm = 0;
   if (per_sm == 0) {
-    CK(cudaFuncSetAttribute(k_epa<G, CAPS, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epa<G, CAPS, MODE>, threads, smem));
+    CK(cudaFuncSetAttribute(k_epa<G, CAPS, MODE, TIER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epa<G, CAPS, MODE, TIER>, threads, smem));
     if (per_sm < 1) per_sm = 1;
   }
   {
     KTimer kt(ctx, s, 1);
-    k_epa<G, CAPS, MODE><<<ctx->num_sms * per_sm, threads, smem, s>>>(a);
+    k_epa<G, CAPS, MODE, TIER><<<ctx->num_sms * per_sm, threads, smem, s>>>(a);
   }
   ctx->stats.kernel_launches++;
   CK(cudaGetLastError());
   return HFB_OK;
 }
 
-template <int CAPS, int MODE>
+template <int CAPS, int MODE, int TIER>
 int launch_epa_g(hfb_ctx* ctx, const BatchArgs& a, cudaStream_t s) {
   switch (ctx->ge) {
-    case 8: return launch_epa<8, CAPS, MODE>(ctx, a, s);
-    case 16: return launch_epa<16, CAPS, MODE>(ctx, a, s);
-    default: return launch_epa<32, CAPS, MODE>(ctx, a, s);
+    case 8: return launch_epa<8, CAPS, MODE, TIER>(ctx, a, s);
+    case 16: return launch_epa<16, CAPS, MODE, TIER>(ctx, a, s);
+    default: return launch_epa<32, CAPS, MODE, TIER>(ctx, a, s);
   }
 }
 template <int MODE>
@@ -528,7 +546,7 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   const unsigned n = a.n;
   if (n == 0) return HFB_OK;
   CK(sl.queue.reserve((size_t)n * sizeof(EpaItem)));
-  // counters: [0] EPA queue count, [1] running EPA total, [4..4+kMaxParts] queue marks (mark[0] = 0,
+  // counters: [0] EPA queue count, [1] running EPA total, [2] retry count, [3] tier-1 work counter, [4..4+kMaxParts] queue marks (mark[0] = 0,
   // mark[j+1] = queue count after part j of phase 1), [16..16+kMaxParts) EPA work counters,
   // [32..) hist (NBINS), offsets (NBINS+1), cursor (NBINS)
   const size_t ncnt = 32 + 3 * (HFB_NBINS + 2);
@@ -542,7 +560,9 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
     CK(cudaEventCreateWithFlags(&sl.ev_join, cudaEventDisableTiming));
   }
   CK(sl.lists.reserve((size_t)n * sizeof(uint32_t)));
+  CK(sl.retry.reserve((size_t)n * sizeof(uint32_t)));
   a.queue = static_cast<EpaItem*>(sl.queue.p);
+  a.retry = static_cast<uint32_t*>(sl.retry.p);
   unsigned* cnt = static_cast<unsigned*>(sl.counters.p);
   unsigned* mark = cnt + 4;
   unsigned* heads = cnt + 16;
@@ -551,6 +571,7 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   unsigned* cursor = offsets + HFB_NBINS + 2;
   uint32_t* perm = static_cast<uint32_t*>(sl.lists.p);
   a.queue_count = cnt;
+  a.retry_count = cnt + 2;
   a.epa_lo = a.epa_hi = nullptr;
   a.epa_head = nullptr;
   a.sub_idx = 0;
@@ -597,7 +618,11 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
       if (cudaEventRecord(sl.ev_join, sl.epa_stream) != cudaSuccess || cudaStreamWaitEvent(s, sl.ev_join, 0) != cudaSuccess)
         return fail(ctx, HFB_ERR_CUDA, "event record/wait failed");
     }
-    return mixed ? launch_epa_g<CAPS_ALL, MODE>(ctx, ae, es) : launch_epa_g<CAP_PRIM, MODE>(ctx, ae, es);
+    int r = mixed ? launch_epa_g<CAPS_ALL, MODE, 0>(ctx, ae, es) : launch_epa_g<CAP_PRIM, MODE, 0>(ctx, ae, es);
+    if (r || !last) return r;
+    // tier 1 over the retry list, after every tier-0 launch of this batch
+    ae.epa_head = cnt + 3;
+    return mixed ? launch_epa_g<CAPS_ALL, MODE, 1>(ctx, ae, s) : launch_epa_g<CAP_PRIM, MODE, 1>(ctx, ae, s);
   };
 
   BatchArgs ac = a, ag = a, av = a;
@@ -609,7 +634,9 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   av.range_hi = offsets + HFB_BIN_BVH;
   if ((rc = launch_pairs<1, CAP_PRIM, MODE, PATH_CLOSED>(ctx, ac, n, s))) return rc;
   // the class populations are only known on the device, so both GJK ranges are cut the same way
-  unsigned nsub = ctx->nsub > 0 ? (unsigned)ctx->nsub : (n >= (1u << 19) ? 3u : (n >= (1u << 17) ? 2u : 1u));
+  // measured on B200 (profiles/r01_summary.md): cutting phase 1 costs more in kernel tails than the overlap
+  // returns, so one part is the default; HFB_NSUB asks for more
+  unsigned nsub = ctx->nsub > 0 ? (unsigned)ctx->nsub : 1u;
   if (!want_epa) nsub = 1;
   if (nsub > (unsigned)(kMaxParts / 2)) nsub = kMaxParts / 2;
   const unsigned sub_work = (n + nsub - 1) / nsub;
@@ -837,7 +864,7 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   auto rel = [](Slot& s) {
-    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.bvh_ws, &s.bvh_cnt};
+    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt};
     for (DevBuf* b : bs) b->release();
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.epa_stream) cudaStreamDestroy(s.epa_stream);

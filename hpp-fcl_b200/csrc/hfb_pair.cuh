@@ -244,12 +244,15 @@ HFB_HD bool pair_phase1(const PairIn& in, const SolverP& P, PairOut& o, GjkState
 }
 
 // ---- phase 2: EPA + EPAExtractWitnessPointsAndNormal (narrowphase.h:514-583, 658-723)
-template <int G, int CAPS>
-HFB_HD void pair_phase2(const PairIn& in, const SolverP& P, GjkState& g, EpaWs* ws, PairOut& o) {
+// Returns false (and leaves `o` unset) only when WS is a reduced-size workspace and the polytope
+// outgrew it: the caller runs the pair again, from the queued GJK state, in the full-size one.
+template <int G, int CAPS, class WS>
+HFB_HD bool pair_phase2(const PairIn& in, const SolverP& P, GjkState& g, WS* ws, PairOut& o) {
   GjkSetup S;
   make_setup<CAPS>(in, S);
   EpaState E;
   epa_evaluate<G, CAPS>(S.a, S.b, S.md, P.epa, g, ws, E);
+  if (E.status == HFB_EPA_WS_OVERFLOW) return false;
   o.iterations = (g.iterations & 0xffffu) | ((E.iterations & 0xffffu) << 16);
   o.status = pack_status(HFB_GJK_COLLISION, E.status, HFB_PATH_GJK);
   if (E.status == HFB_EPA_FALLBACK) {  // EPAFailedExtract... :713-723
@@ -257,7 +260,7 @@ HFB_HD void pair_phase2(const PairIn& in, const SolverP& P, GjkState& g, EpaWs* 
     o.hint0 = o.hint1 = 0;
     o.distance = -DBL_MAX;
     o.p1 = o.p2 = o.normal = nan3();
-    return;
+    return true;
   }
   o.cached_guess = -(E.depth * E.normal);
   o.hint0 = E.hint0;
@@ -266,6 +269,7 @@ HFB_HD void pair_phase2(const PairIn& in, const SolverP& P, GjkState& g, EpaWs* 
   epa_witness(E, S.md, o.p1, o.p2, o.normal);
   recentre(S.tfa, o.distance, o.p1, o.p2, o.normal);
   unswap(S, o);
+  return true;
 }
 
 // ---- epilogues -----------------------------------------------------------------

@@ -40,10 +40,20 @@ inline PairIn load_pair(const ArenaView& A, size_t i, const uint32_t* h1, const 
   return in;
 }
 
+long g_retries = 0;
 inline void run_pair(const PairIn& in, const SolverP& P, EpaWs* ws, PairOut& o) {
   GjkState g;
   std::memset(&g, 0, sizeof(g));
-  if (pair_phase1<1, CAPS_ALL>(in, P, o, g)) pair_phase2<1, CAPS_ALL>(in, P, g, ws, o);
+  if (pair_phase1<1, CAPS_ALL>(in, P, o, g)) {
+    // the two tiers of k_epa: reduced-size workspace first, full size when the polytope outgrows it
+    const GjkState g0 = g;
+    EpaWsSmall small;
+    if (!pair_phase2<1, CAPS_ALL>(in, P, g, &small, o)) {
+      ++g_retries;
+      g = g0;
+      pair_phase2<1, CAPS_ALL>(in, P, g, ws, o);
+    }
+  }
 }
 
 inline void put_guess(const hfb_guess_out* go, size_t i, const PairOut& o) {
@@ -63,6 +73,7 @@ inline void put_guess(const hfb_guess_out* go, size_t i, const PairOut& o) {
 extern "C" {
 
 void* emu_create() { return new Emu(); }
+long emu_epa_retries() { return g_retries; }
 void emu_destroy(void* e) { delete static_cast<Emu*>(e); }
 
 int emu_register_convex(void* e, const double* pts, uint32_t n) {

@@ -48,6 +48,24 @@ def test_collide_request_fields(prim, kw):
     assert np.array_equal(og.view(np.uint64), eg.view(np.uint64)) and np.array_equal(oh, eh)
 
 
+def test_epa_two_tier_workspace(prim):
+    """k_epa first runs a pair in a reduced-size polytope workspace and repeats it in the full-size one
+    when the polytope outgrows it; a tight tolerance makes many curved pairs take that second path."""
+    from tests.common import emu_lib
+    L = emu_lib()
+    L.emu_epa_retries.restype = __import__("ctypes").c_long
+    sc, w = prim
+    n = 6000
+    req = P.DistanceRequestPOD(epa_tolerance=1e-12)
+    before = L.emu_epa_retries()
+    ro = sc.b["oracle"].batch_distance(w["h1"][:n], w["tf1"][:n], w["h2"][:n], w["tf2"][:n], req, nthreads=0)
+    re = sc.b["emu"].batch_distance(w["h1"][:n], w["tf1"][:n], w["h2"][:n], w["tf2"][:n], req)
+    compare_distance(ro, re, what="two-tier EPA")
+    assert L.emu_epa_retries() - before > 20
+    ep = ro["iterations"] >> 16
+    assert ep.max() > 30  # runs past the reduced workspace's 24 iterations
+
+
 def test_signed_distance_off(prim):
     sc, w = prim
     req = P.DistanceRequestPOD(enable_signed_distance=0)

@@ -34,6 +34,22 @@ def test_distance_primitives_all_types(prim_scene, variant):
     assert (ref["min_distance"] < 0).sum() > 100  # the penetrating (EPA) branch is exercised
 
 
+@pytest.mark.parametrize("nsub", ["1", "3"])
+def test_epa_two_tier_and_parts(nsub, monkeypatch):
+    """Tight EPA tolerance: many pairs outgrow the reduced-size workspace of k_epa's first tier and are
+    repeated by the second; HFB_NSUB=3 cuts phase 1 in parts whose EPA runs on the side stream."""
+    monkeypatch.setenv("HFB_NSUB", nsub)
+    sc = make_scenes(gpu=True, emu=False)
+    w = W.config2_mixed_primitives(150_000, pool=4096, types=ALL_PRIMS)
+    sc.register_shapes(w["shapes"])
+    sc.commit()
+    req = P.DistanceRequestPOD(epa_tolerance=1e-12)
+    ref = sc.b["oracle"].batch_distance(w["h1"], w["tf1"], w["h2"], w["tf2"], req, nthreads=0)
+    got = sc.b["gpu"].batch_distance(w["h1"], w["tf1"], w["h2"], w["tf2"], req)
+    compare_distance(ref, got, what="two-tier EPA nsub=%s" % nsub)
+    assert ((ref["iterations"] >> 16) > 24).sum() > 200
+
+
 @pytest.mark.parametrize("margin", [0.0, 0.05, -0.02])
 def test_collide_primitives(prim_scene, margin):
     sc, w = prim_scene
