@@ -93,13 +93,14 @@ def _default_query(q):
 
 
 class DistanceRequestPOD(C.Structure):
-    _fields_ = [("q", QueryRequest), ("enable_signed_distance", C.c_int32), ("_pad", C.c_int32),
+    _fields_ = [("q", QueryRequest), ("enable_signed_distance", C.c_int32), ("enable_nearest_points", C.c_int32),
                 ("rel_err", C.c_double), ("abs_err", C.c_double)]
 
     def __init__(self, **kw):
         super().__init__()
         _default_query(self.q)
         self.enable_signed_distance = 1
+        self.enable_nearest_points = 1
         self.rel_err = 0.0
         self.abs_err = 0.0
         _apply_kw(self, kw)

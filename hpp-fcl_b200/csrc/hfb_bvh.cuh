@@ -1174,6 +1174,392 @@ HFB_HD void bvh_shape_collide(const BvhQuery& q, const SolverP& P, double securi
   }
 }
 
+// ============================ mesh-mesh: two OBBRSS trees =========================================
+// MeshDistanceTraversalNodeOBBRSS / MeshCollisionTraversalNodeOBBRSS (traversal_node_bvhs.h:63-242, 386-536)
+// walked with distanceRecurse / collisionRecurse (traversal_recurse.cpp:44-85, 153-203).
+
+// TriangleDistance::segPoints (src/intersect.cpp:60-153)
+HFB_HD void seg_points(v3 P, v3 A, v3 Q, v3 B, v3& VEC, v3& X, v3& Y) {
+  v3 T = Q - P;
+  const double A_dot_A = dot(A, A), B_dot_B = dot(B, B), A_dot_B = dot(A, B);
+  const double A_dot_T = dot(A, T), B_dot_T = dot(B, T);
+  const double denom = A_dot_A * B_dot_B - A_dot_B * A_dot_B;
+  double t = (A_dot_T * B_dot_B - B_dot_T * A_dot_B) / denom;
+  if ((t < 0) || isnan(t)) t = 0;
+  else if (t > 1) t = 1;
+  const double u = (t * A_dot_B - B_dot_T) / B_dot_B;
+  if ((u <= 0) || isnan(u)) {
+    Y = Q;
+    t = A_dot_T / A_dot_A;
+    if ((t <= 0) || isnan(t)) {
+      X = P;
+      VEC = Q - P;
+    } else if (t >= 1) {
+      X = P + A;
+      VEC = Q - X;
+    } else {
+      X = P + A * t;
+      VEC = cross(A, cross(T, A));
+    }
+  } else if (u >= 1) {
+    Y = Q + B;
+    t = (A_dot_B + A_dot_T) / A_dot_A;
+    if ((t <= 0) || isnan(t)) {
+      X = P;
+      VEC = Y - P;
+    } else if (t >= 1) {
+      X = P + A;
+      VEC = Y - X;
+    } else {
+      X = P + A * t;
+      T = Y - P;
+      VEC = cross(A, cross(T, A));
+    }
+  } else {
+    Y = Q + B * u;
+    if ((t <= 0) || isnan(t)) {
+      X = P;
+      VEC = cross(B, cross(T, B));
+    } else if (t >= 1) {
+      X = P + A;
+      T = Q - X;
+      VEC = cross(B, cross(T, B));
+    } else {
+      X = P + A * t;
+      VEC = cross(A, B);
+      if (dot(VEC, T) < 0) VEC = VEC * (-1.0);
+    }
+  }
+}
+
+struct Tri3 {
+  v3 v[3];
+};
+
+// "vertex of one triangle over the face of the other" test of sqrTriDistance (:262-303 / :311-352):
+// F is the face triangle with edge vectors Fv, O the other triangle.  Returns the index of the vertex
+// of O whose projection falls inside F (-1: none, -2: Fn not a separating direction); `sep` reports
+// that Fn separates the triangles.
+HFB_HD int tri_vertex_over_face(const Tri3& F, const v3 Fv[3], const Tri3& O, v3& Fn, double& Fnl, double proj[3],
+                                bool& sep) {
+  sep = false;
+  Fn = cross(Fv[0], Fv[1]);
+  Fnl = dot(Fn, Fn);
+  if (!(Fnl > 1e-15)) return -2;
+  proj[0] = dot(F.v[0] - O.v[0], Fn);
+  proj[1] = dot(F.v[0] - O.v[1], Fn);
+  proj[2] = dot(F.v[0] - O.v[2], Fn);
+  int point = -1;
+  if ((proj[0] > 0) && (proj[1] > 0) && (proj[2] > 0)) {
+    point = (proj[0] < proj[1]) ? 0 : 1;
+    if (proj[2] < proj[point]) point = 2;
+  } else if ((proj[0] < 0) && (proj[1] < 0) && (proj[2] < 0)) {
+    point = (proj[0] > proj[1]) ? 0 : 1;
+    if (proj[2] > proj[point]) point = 2;
+  }
+  if (point < 0) return -2;
+  sep = true;
+  if (dot(O.v[point] - F.v[0], cross(Fn, Fv[0])) > 0 && dot(O.v[point] - F.v[1], cross(Fn, Fv[1])) > 0 &&
+      dot(O.v[point] - F.v[2], cross(Fn, Fv[2])) > 0)
+    return point;
+  return -1;
+}
+
+// TriangleDistance::sqrTriDistance (src/intersect.cpp:156-357).  P and Q are overwritten by every
+// segPoints call, so the "triangles overlap" exit (return 0) leaves the last edge pair's points in them.
+HFB_HD_NOINLINE double sqr_tri_distance(const Tri3& S, const Tri3& T, v3& P, v3& Q) {
+  v3 Sv[3], Tv[3], VEC;
+  Sv[0] = S.v[1] - S.v[0];
+  Sv[1] = S.v[2] - S.v[1];
+  Sv[2] = S.v[0] - S.v[2];
+  Tv[0] = T.v[1] - T.v[0];
+  Tv[1] = T.v[2] - T.v[1];
+  Tv[2] = T.v[0] - T.v[2];
+  v3 V, Z, minP = nan3(), minQ = nan3();
+  bool shown_disjoint = false;
+  double mindd = dot(S.v[0] - T.v[0], S.v[0] - T.v[0]) + 1;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      seg_points(S.v[i], Sv[i], T.v[j], Tv[j], VEC, P, Q);
+      V = Q - P;
+      const double dd = dot(V, V);
+      if (dd <= mindd) {
+        minP = P;
+        minQ = Q;
+        mindd = dd;
+        Z = S.v[(i + 2) % 3] - P;
+        double a = dot(Z, VEC);
+        Z = T.v[(j + 2) % 3] - Q;
+        double b = dot(Z, VEC);
+        if ((a <= 0) && (b >= 0)) return dd;
+        const double p = dot(V, VEC);
+        if (a < 0) a = 0;
+        if (b > 0) b = 0;
+        if ((p - a + b) > 0) shown_disjoint = true;
+      }
+    }
+  }
+  v3 n;
+  double nl, proj[3];
+  bool sep;
+  int point = tri_vertex_over_face(S, Sv, T, n, nl, proj, sep);
+  if (sep) shown_disjoint = true;
+  if (point >= 0) {
+    P = T.v[point] + n * (proj[point] / nl);
+    Q = T.v[point];
+    return dot(P - Q, P - Q);
+  }
+  point = tri_vertex_over_face(T, Tv, S, n, nl, proj, sep);
+  if (sep) shown_disjoint = true;
+  if (point >= 0) {
+    P = S.v[point];
+    Q = S.v[point] + n * (proj[point] / nl);
+    return dot(P - Q, P - Q);
+  }
+  if (shown_disjoint) {
+    P = minP;
+    Q = minQ;
+    return mindd;
+  }
+  return 0;
+}
+
+struct BvhMeshView {
+  const hfb_bvh_node* nodes;
+  const double* verts;
+  const uint32_t* tris;
+};
+struct BvhPairQuery {  // one (mesh, mesh) query
+  BvhMeshView m1, m2;
+  xf tf1, tf2;
+  m3 R;  // RT = tf1^-1 * tf2 (internal/tools.h:91-99, traversal_node_setup.h:561-563, 688-689)
+  v3 T;
+};
+HFB_HD BvhMeshView bvh_mesh_view(const ArenaView& A, uint32_t bvh_id) {
+  const BvhDesc& d = A.bvh_desc[bvh_id];
+  BvhMeshView m;
+  m.nodes = A.bvh_nodes + d.node_off;
+  m.verts = A.bvh_verts + 3 * (size_t)d.vert_off;
+  m.tris = A.bvh_tris + 3 * (size_t)d.tri_off;
+  return m;
+}
+HFB_HD Tri3 bvh_triangle(const BvhMeshView& m, int primitive_id) {
+  const uint32_t* t = m.tris + 3 * (size_t)primitive_id;
+  Tri3 r;
+  for (int k = 0; k < 3; ++k) {
+    const double* a = m.verts + 3 * (size_t)t[k];
+    r.v[k] = mk(a[0], a[1], a[2]);
+  }
+  return r;
+}
+// firstOverSecond (traversal_node_bvhs.h:87-98, 333-344): bv.size() of an OBBRSS is the squared norm
+// of the OBB extent (OBBRSS.h:114, OBB.h:110)
+HFB_HD bool bvh_first_over_second(const hfb_bvh_node& n1, const hfb_bvh_node& n2) {
+  const double sz1 = (n1.obb_extent[0] * n1.obb_extent[0] + n1.obb_extent[1] * n1.obb_extent[1]) +
+                     n1.obb_extent[2] * n1.obb_extent[2];
+  const double sz2 = (n2.obb_extent[0] * n2.obb_extent[0] + n2.obb_extent[1] * n2.obb_extent[1]) +
+                     n2.obb_extent[2] * n2.obb_extent[2];
+  const bool l1 = n1.first_child < 0, l2 = n2.first_child < 0;
+  return l2 || (!l1 && (sz1 > sz2));
+}
+
+struct BvhPairDistOut {
+  double min_distance;
+  v3 p1, p2;
+  int b1, b2;
+  unsigned bv_tests, leaf_tests;
+};
+
+HFB_HD void bvh_tri_pair_distance(const BvhPairQuery& q, int id1, int id2, BvhPairDistOut& out) {  // :437-470
+  const Tri3 S = bvh_triangle(q.m1, id1);
+  Tri3 Tt = bvh_triangle(q.m2, id2);
+  for (int k = 0; k < 3; ++k) Tt.v[k] = mmul(q.R, Tt.v[k]) + q.T;  // intersect.cpp:401-409
+  v3 P1 = nan3(), P2 = nan3();
+  const double d = sqrt(sqr_tri_distance(S, Tt, P1, P2));
+  if (out.min_distance > d) {  // DistanceResult::update (collision_data.h:1126-1138)
+    out.min_distance = d;
+    out.b1 = id1;
+    out.b2 = id2;
+    out.p1 = P1;
+    out.p2 = P2;
+  }
+}
+
+// orientedMeshDistance + distance(node): seed with triangles (0, 0), walk the pair tree, move the
+// nearest points to the world frame.  The reference never writes `normal` on this path.
+HFB_HD void bvh_bvh_distance(const BvhPairQuery& q, double rel_err, double abs_err, bool enable_nearest_points,
+                             BvhPairDistOut& out) {
+  out.min_distance = DBL_MAX;
+  out.p1 = out.p2 = nan3();
+  out.b1 = out.b2 = -1;
+  out.bv_tests = out.leaf_tests = 0;
+  bvh_tri_pair_distance(q, 0, 0, out);  // preprocessOrientedNode (:487-510)
+  int stk_a[HFB_BVH_STACK], stk_b[HFB_BVH_STACK];
+  double stk_d[HFB_BVH_STACK];
+  int sp = 1;
+  stk_a[0] = 0;
+  stk_b[0] = 0;
+  stk_d[0] = -1.0;
+  while (sp > 0) {
+    int leaf1 = -1, leaf2 = -1;
+    while (sp > 0) {  // phase A: BV pairs
+      --sp;
+      const int b1 = stk_a[sp], b2 = stk_b[sp];
+      const double dlow = stk_d[sp];
+      if (dlow >= 0) {  // canStop (:473-478)
+        if ((dlow >= out.min_distance - abs_err) && (dlow * (1 + rel_err) >= out.min_distance)) continue;
+      }
+      const hfb_bvh_node& n1 = q.m1.nodes[b1];
+      const hfb_bvh_node& n2 = q.m2.nodes[b2];
+      if (n1.first_child < 0 && n2.first_child < 0) {
+        leaf1 = -(n1.first_child + 1);
+        leaf2 = -(n2.first_child + 1);
+        break;
+      }
+      int a1, a2, c1, c2;
+      if (bvh_first_over_second(n1, n2)) {
+        a1 = n1.first_child;
+        a2 = b2;
+        c1 = n1.first_child + 1;
+        c2 = b2;
+      } else {
+        a1 = b1;
+        a2 = n2.first_child;
+        c1 = b1;
+        c2 = n2.first_child + 1;
+      }
+      const double d1 = rss_distance(q.R, q.T, load_node_rss(q.m1.nodes[a1]), load_node_rss(q.m2.nodes[a2]));
+      const double d2 = rss_distance(q.R, q.T, load_node_rss(q.m1.nodes[c1]), load_node_rss(q.m2.nodes[c2]));
+      out.bv_tests += 2;
+      if (sp + 2 > HFB_BVH_STACK) {  // deeper than any tree pair the arena accepts
+        sp = 0;
+        break;
+      }
+      if (d2 < d1) {
+        stk_a[sp] = a1; stk_b[sp] = a2; stk_d[sp] = d1; ++sp;
+        stk_a[sp] = c1; stk_b[sp] = c2; stk_d[sp] = d2; ++sp;
+      } else {
+        stk_a[sp] = c1; stk_b[sp] = c2; stk_d[sp] = d2; ++sp;
+        stk_a[sp] = a1; stk_b[sp] = a2; stk_d[sp] = d1; ++sp;
+      }
+    }
+    if (leaf1 < 0) break;
+    bvh_tri_pair_distance(q, leaf1, leaf2, out);  // phase B
+    out.leaf_tests++;
+  }
+  if (enable_nearest_points) {  // postprocessOrientedNode (:527-536)
+    out.p1 = xform(q.tf1, out.p1);
+    out.p2 = xform(q.tf1, out.p2);
+  }
+}
+
+struct BvhPairColOut {
+  double distance_lower_bound;
+  v3 lb_p1, lb_p2, lb_normal;
+  bool has_contact;
+  int b1, b2;
+  double distance;
+  v3 p1, p2, normal;
+  unsigned bv_tests, leaf_tests;
+};
+
+// orientedMeshCollide + collide(node).  Every leaf builds its own GJKSolver from the request
+// (traversal_node_bvhs.h:197), so the warm start `in0` is the same for all of them.
+template <int CAPS>
+HFB_HD void bvh_bvh_collide(const BvhPairQuery& q, const SolverP& P, double security_margin, double break_distance,
+                            double collision_distance_threshold, unsigned num_max_contacts, EpaWs* ws,
+                            const PairIn& in0, BvhPairColOut& out) {
+  out.distance_lower_bound = DBL_MAX;
+  out.lb_p1 = out.lb_p2 = out.lb_normal = nan3();
+  out.has_contact = false;
+  out.b1 = out.b2 = -1;
+  out.distance = DBL_MAX;
+  out.p1 = out.p2 = out.normal = nan3();
+  out.bv_tests = out.leaf_tests = 0;
+  unsigned ncontacts = 0;
+  int stk_a[HFB_BVH_STACK], stk_b[HFB_BVH_STACK];
+  int sp = 1;
+  stk_a[0] = 0;
+  stk_b[0] = 0;
+  while (sp > 0) {
+    int leaf1 = -1, leaf2 = -1;
+    while (sp > 0) {  // phase A: OBB tests
+      --sp;
+      const int b1 = stk_a[sp], b2 = stk_b[sp];
+      const hfb_bvh_node& n1 = q.m1.nodes[b1];
+      const hfb_bvh_node& n2 = q.m2.nodes[b2];
+      if (n1.first_child < 0 && n2.first_child < 0) {
+        leaf1 = -(n1.first_child + 1);
+        leaf2 = -(n2.first_child + 1);
+        break;
+      }
+      double sq_lb;
+      out.bv_tests++;
+      // operand order of the reference (:147-162): (RT, bv of model 2, bv of model 1)
+      const bool disjoint =
+          !obb_overlap(q.R, q.T, load_node_obb(n2), load_node_obb(n1), security_margin, break_distance, sq_lb);
+      if (disjoint) {  // updateDistanceLowerBoundFromBV
+        if (out.distance_lower_bound > 0) {
+          const double nd_lb = sqrt(sq_lb);
+          if (nd_lb < out.distance_lower_bound) out.distance_lower_bound = nd_lb;
+        }
+        continue;
+      }
+      if (sp + 2 > HFB_BVH_STACK) {
+        sp = 0;
+        break;
+      }
+      if (bvh_first_over_second(n1, n2)) {
+        stk_a[sp] = n1.first_child + 1; stk_b[sp] = b2; ++sp;
+        stk_a[sp] = n1.first_child; stk_b[sp] = b2; ++sp;
+      } else {
+        stk_a[sp] = b1; stk_b[sp] = n2.first_child + 1; ++sp;
+        stk_a[sp] = b1; stk_b[sp] = n2.first_child; ++sp;
+      }
+    }
+    if (leaf1 < 0) break;
+    // phase B: leafCollides (:173-232), ShapeShapeDistance<TriangleP, TriangleP> in world poses
+    PairIn in = in0;
+    const Tri3 t1 = bvh_triangle(q.m1, leaf1), t2 = bvh_triangle(q.m2, leaf2);
+    in.s1.type = in.s2.type = HFB_GEOM_TRIANGLE;
+    in.s1.ssr = in.s2.ssr = 0;
+    in.s1.p0 = in.s1.p1 = in.s1.p2 = in.s2.p0 = in.s2.p1 = in.s2.p2 = 0;
+    in.s1.nv = in.s2.nv = 0;
+    in.s1.cx = in.s1.cy = in.s1.cz = in.s2.cx = in.s2.cy = in.s2.cz = nullptr;
+    in.s1.center = in.s2.center = mk(0, 0, 0);
+    in.s1.ta = t1.v[0]; in.s1.tb = t1.v[1]; in.s1.tc = t1.v[2];
+    in.s2.ta = t2.v[0]; in.s2.tb = t2.v[1]; in.s2.tc = t2.v[2];
+    in.tf1 = q.tf1;
+    in.tf2 = q.tf2;
+    PairOut o;
+    GjkState g;
+    if (pair_phase1<1, CAPS, PATH_BOTH>(in, P, o, g)) pair_phase2<1, CAPS>(in, P, g, ws, o);
+    out.leaf_tests++;
+    const double d2c = o.distance - security_margin;
+    if (d2c < out.distance_lower_bound) {  // updateDistanceLowerBoundFromLeaf
+      out.distance_lower_bound = d2c;
+      out.lb_p1 = o.p1;
+      out.lb_p2 = o.p2;
+      out.lb_normal = o.normal;
+    }
+    if (d2c <= collision_distance_threshold) {
+      if (ncontacts < num_max_contacts) {
+        if (ncontacts == 0) {
+          out.has_contact = true;
+          out.b1 = leaf1;
+          out.b2 = leaf2;
+          out.distance = o.distance;
+          out.p1 = o.p1;
+          out.p2 = o.p2;
+          out.normal = o.normal;
+        }
+        ++ncontacts;
+      }
+    }
+    if (ncontacts > 0 && num_max_contacts <= ncontacts) break;  // canStop()
+  }
+}
+
 // ---- record writers: one (h1, tf1, h2, tf2) pair where one operand is a BVH ------------------
 HFB_HD void put3d(double* o, v3 v) {
   o[0] = v.x;
@@ -1194,6 +1580,7 @@ struct BvhReq {  // request fields the traversals need beyond SolverP
   double rel_err, abs_err;               // DistanceRequest
   double security_margin, break_distance, collision_distance_threshold;  // CollisionRequest
   unsigned num_max_contacts;
+  bool enable_nearest_points;  // DistanceRequest, mesh-mesh only
 };
 
 // distance(): BVHShapeDistancer<OBBRSS,S> with the (GEOM, BVH) operand swap of distance.cpp:74-89
@@ -1205,6 +1592,28 @@ HFB_HD void bvh_pair_distance(const ArenaView& A, uint32_t h1, const xf& tf1, ui
   BvhQuery q;
   bool swapped;
   bv_tests = leaf_tests = 0;
+  if (A.shapes[h1].type == HFB_BV_OBBRSS && A.shapes[h2].type == HFB_BV_OBBRSS) {  // BVHDistance<OBBRSS>
+    BvhPairQuery pq;
+    pq.m1 = bvh_mesh_view(A, A.shapes[h1].data);
+    pq.m2 = bvh_mesh_view(A, A.shapes[h2].data);
+    pq.tf1 = tf1;
+    pq.tf2 = tf2;
+    pq.R = mtmulm(tf1.R, tf2.R);
+    pq.T = mtmul(tf1.R, tf2.T - tf1.T);
+    BvhPairDistOut o;
+    bvh_bvh_distance(pq, R.rel_err, R.abs_err, R.enable_nearest_points, o);
+    r->min_distance = o.min_distance;
+    put3d(r->p1, o.p1);
+    put3d(r->p2, o.p2);
+    put3d(r->normal, nan3());
+    r->b1 = o.b1;
+    r->b2 = o.b2;
+    r->status = pack_status(0, 0, HFB_PATH_BVH);
+    r->iterations = (o.bv_tests & 0xffffu) | ((o.leaf_tests & 0xffffu) << 16);
+    bv_tests = o.bv_tests;
+    leaf_tests = o.leaf_tests;
+    return;
+  }
   if (!bvh_make_query<CAPS>(A, h1, tf1, h2, tf2, q, swapped)) {
     bvh_unsupported_distance(r);
     return;
@@ -1246,15 +1655,46 @@ HFB_HD void bvh_pair_collide(const ArenaView& A, uint32_t h1, const xf& tf1, uin
   r->num_contacts = 0;
   r->iterations = 0;
   r->_pad = 0;
+  PairIn in;
+  in.cached_guess = cached_guess;
+  in.hint0 = hint0;
+  in.hint1 = hint1;
+  if (A.shapes[h1].type == HFB_BV_OBBRSS && A.shapes[h2].type == HFB_BV_OBBRSS) {  // BVHCollide<OBBRSS>
+    BvhPairQuery pq;
+    pq.m1 = bvh_mesh_view(A, A.shapes[h1].data);
+    pq.m2 = bvh_mesh_view(A, A.shapes[h2].data);
+    pq.tf1 = tf1;
+    pq.tf2 = tf2;
+    pq.R = mtmulm(tf1.R, tf2.R);
+    pq.T = mtmul(tf1.R, tf2.T - tf1.T);
+    BvhPairColOut o;
+    bvh_bvh_collide<CAPS>(pq, P, R.security_margin, R.break_distance, R.collision_distance_threshold,
+                          R.num_max_contacts, ws, in, o);
+    r->distance_lower_bound = o.distance_lower_bound;
+    put3d(r->p1, o.lb_p1);
+    put3d(r->p2, o.lb_p2);
+    put3d(r->normal, o.lb_normal);
+    if (o.has_contact) {
+      r->num_contacts = 1;
+      r->distance = o.distance;
+      r->b1 = o.b1;
+      r->b2 = o.b2;
+      put3d(r->pos, (o.p1 + o.p2) / 2);
+      put3d(r->p1, o.p1);
+      put3d(r->p2, o.p2);
+      put3d(r->normal, o.normal);
+    }
+    r->status = pack_status(0, 0, HFB_PATH_BVH);
+    r->iterations = (o.bv_tests & 0xffffu) | ((o.leaf_tests & 0xffffu) << 16);
+    bv_tests = o.bv_tests;
+    leaf_tests = o.leaf_tests;
+    return;
+  }
   // negative security margins throw for BVH models (collision_func_matrix.cpp:109-112)
   if (R.security_margin < 0 || !bvh_make_query<CAPS>(A, h1, tf1, h2, tf2, q, swapped)) {
     r->status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
     return;
   }
-  PairIn in;
-  in.cached_guess = cached_guess;
-  in.hint0 = hint0;
-  in.hint1 = hint1;
   BvhColOut o;
   bvh_shape_collide<CAPS>(q, P, R.security_margin, R.break_distance, R.collision_distance_threshold,
                           R.num_max_contacts, ws, in, o);

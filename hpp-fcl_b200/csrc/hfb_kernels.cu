@@ -814,6 +814,7 @@ void hfb_default_distance_request(hfb_distance_request* r) {
   r->q.epa_tolerance = 1e-6;
   r->q.collision_distance_threshold = 1e-12;
   r->enable_signed_distance = 1;
+  r->enable_nearest_points = 1;
 }
 void hfb_default_collision_request(hfb_collision_request* r) {
   std::memset(r, 0, sizeof(*r));
@@ -968,7 +969,7 @@ int hfb_batch_distance(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_tra
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (int rc = validate_query(req->q)) return fail(ctx, rc, "invalid request");
   return host_batch<0>(ctx, n, h1, tf1, h2, tf2, req, solver_from_distance_request(*req), CollideP{0, 0},
-                       BvhReq{req->rel_err, req->abs_err, 0, 0, 0, 1}, out, go);
+                       BvhReq{req->rel_err, req->abs_err, 0, 0, 0, 1, req->enable_nearest_points != 0}, out, go);
 }
 
 int hfb_batch_distance_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1,
@@ -978,7 +979,7 @@ int hfb_batch_distance_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const 
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (int rc = validate_query(req->q)) return fail(ctx, rc, "invalid request");
   return device_batch<0>(ctx, n, h1, tf1, h2, tf2, req, solver_from_distance_request(*req), CollideP{0, 0},
-                         BvhReq{req->rel_err, req->abs_err, 0, 0, 0, 1}, out, go, stream);
+                         BvhReq{req->rel_err, req->abs_err, 0, 0, 0, 1, req->enable_nearest_points != 0}, out, go, stream);
 }
 
 static int collide_prelude(hfb_ctx* ctx, const hfb_collision_request* req, bool* minus_inf) {
@@ -1022,7 +1023,7 @@ int hfb_batch_collide(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_tran
   CollideP C{req->security_margin, req->q.collision_distance_threshold};
   return host_batch<1>(ctx, n, h1, tf1, h2, tf2, req, solver_from_collision_request(*req), C,
                        BvhReq{0, 0, req->security_margin, req->break_distance, req->q.collision_distance_threshold,
-                              req->num_max_contacts},
+                              req->num_max_contacts, true},
                        out, go);
 }
 
@@ -1044,7 +1045,7 @@ int hfb_batch_collide_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const h
   CollideP C{req->security_margin, req->q.collision_distance_threshold};
   return device_batch<1>(ctx, n, h1, tf1, h2, tf2, req, solver_from_collision_request(*req), C,
                          BvhReq{0, 0, req->security_margin, req->break_distance, req->q.collision_distance_threshold,
-                                req->num_max_contacts},
+                                req->num_max_contacts, true},
                          out, go, stream);
 }
 

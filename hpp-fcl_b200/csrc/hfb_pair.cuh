@@ -186,7 +186,15 @@ HFB_HD bool pair_phase1(const PairIn& in, const SolverP& P, PairOut& o, GjkState
     v3 guess;
     if (P.initial_guess == HFB_GUESS_CACHED) guess = in.cached_guess;
     else guess = (a.ta + a.tb + a.tc - b.ta - b.tb - b.tc) / 3;
-    gjk_evaluate<G, CAPS>(a, b, md, P.gjk, guess, 0, 0, g);
+    // this specialisation only calls gjk.reset(max_iterations, tolerance): variant, convergence
+    // criterion and early-stop bound are those of a freshly constructed GJK (gjk.cpp:51-57), not the
+    // request's (runGJKAndEPA, which copies them, is never reached)
+    GjkParams pg = P.gjk;
+    pg.distance_upper_bound = DBL_MAX;
+    pg.variant = HFB_GJK_DEFAULT;
+    pg.criterion = HFB_CRIT_DEFAULT;
+    pg.criterion_type = HFB_CRIT_RELATIVE;
+    gjk_evaluate<G, CAPS>(a, b, md, pg, guess, 0, 0, g);
     o.cached_guess = g.ray;
     o.hint0 = g.hint0;
     o.hint1 = g.hint1;

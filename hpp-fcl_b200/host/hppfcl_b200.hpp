@@ -398,7 +398,7 @@ inline void fill(const CollisionRequest& r, hfb_collision_request& q) {
 inline void fill(const DistanceRequest& r, hfb_distance_request& q) {
   r.fill(q.q);
   q.enable_signed_distance = r.enable_signed_distance;
-  q._pad = 0;
+  q.enable_nearest_points = r.enable_nearest_points;
   q.rel_err = r.rel_err;
   q.abs_err = r.abs_err;
 }

@@ -141,7 +141,8 @@ typedef struct hfb_query_request {
 typedef struct hfb_distance_request {
   hfb_query_request q;
   int32_t enable_signed_distance; /* default 1 */
-  int32_t _pad;
+  int32_t enable_nearest_points;  /* default 1; read by the mesh-mesh walk only: when 0 the nearest
+                                     points stay in the first mesh's frame (traversal_node_bvhs.h:527-536) */
   double rel_err; /* BVH traversal only */
   double abs_err; /* BVH traversal only */
 } hfb_distance_request;

@@ -1163,4 +1163,369 @@ void bvhShapeCollide(const BVHModel& m, const Tf& tf1, const Shape& s, const Tf&
   collisionRecurse(n, 0, sqrDistLowerBound);
 }
 
+
+// ===================== mesh-mesh: MeshDistanceTraversalNodeOBBRSS / MeshCollisionTraversalNodeOBBRSS ==========
+
+// TriangleDistance::segPoints (src/intersect.cpp:60-153)
+static void segPoints(const V3& P, const V3& A, const V3& Q, const V3& B, V3& VEC, V3& X, V3& Y) {
+  V3 T = Q - P;
+  const double A_dot_A = dot(A, A), B_dot_B = dot(B, B), A_dot_B = dot(A, B);
+  const double A_dot_T = dot(A, T), B_dot_T = dot(B, T);
+  const double denom = A_dot_A * B_dot_B - A_dot_B * A_dot_B;
+  double t = (A_dot_T * B_dot_B - B_dot_T * A_dot_B) / denom;
+  if ((t < 0) || std::isnan(t)) t = 0;
+  else if (t > 1) t = 1;
+  const double u = (t * A_dot_B - B_dot_T) / B_dot_B;
+  if ((u <= 0) || std::isnan(u)) {
+    Y = Q;
+    t = A_dot_T / A_dot_A;
+    if ((t <= 0) || std::isnan(t)) {
+      X = P;
+      VEC = Q - P;
+    } else if (t >= 1) {
+      X = P + A;
+      VEC = Q - X;
+    } else {
+      X = P + A * t;
+      VEC = cross(A, cross(T, A));
+    }
+  } else if (u >= 1) {
+    Y = Q + B;
+    t = (A_dot_B + A_dot_T) / A_dot_A;
+    if ((t <= 0) || std::isnan(t)) {
+      X = P;
+      VEC = Y - P;
+    } else if (t >= 1) {
+      X = P + A;
+      VEC = Y - X;
+    } else {
+      X = P + A * t;
+      T = Y - P;
+      VEC = cross(A, cross(T, A));
+    }
+  } else {
+    Y = Q + B * u;
+    if ((t <= 0) || std::isnan(t)) {
+      X = P;
+      VEC = cross(B, cross(T, B));
+    } else if (t >= 1) {
+      X = P + A;
+      T = Q - X;
+      VEC = cross(B, cross(T, B));
+    } else {
+      X = P + A * t;
+      VEC = cross(A, B);
+      if (dot(VEC, T) < 0) VEC = VEC * (-1.0);
+    }
+  }
+}
+
+// TriangleDistance::sqrTriDistance (src/intersect.cpp:156-357).  P and Q are written by every segPoints
+// call, so on the "triangles overlap" exit (return 0) they hold the last edge pair's points.
+double sqrTriDistance(const V3 S[3], const V3 T[3], V3& P, V3& Q) {
+  V3 Sv[3], Tv[3], VEC;
+  Sv[0] = S[1] - S[0];
+  Sv[1] = S[2] - S[1];
+  Sv[2] = S[0] - S[2];
+  Tv[0] = T[1] - T[0];
+  Tv[1] = T[2] - T[1];
+  Tv[2] = T[0] - T[2];
+  V3 V, Z, minP = nan3(), minQ = nan3();
+  int shown_disjoint = 0;
+  double mindd = sqnorm(S[0] - T[0]) + 1;
+  for (int i = 0; i < 3; ++i) {
+    for (int j = 0; j < 3; ++j) {
+      segPoints(S[i], Sv[i], T[j], Tv[j], VEC, P, Q);
+      V = Q - P;
+      const double dd = dot(V, V);
+      if (dd <= mindd) {
+        minP = P;
+        minQ = Q;
+        mindd = dd;
+        Z = S[(i + 2) % 3] - P;
+        double a = dot(Z, VEC);
+        Z = T[(j + 2) % 3] - Q;
+        double b = dot(Z, VEC);
+        if ((a <= 0) && (b >= 0)) return dd;
+        const double p = dot(V, VEC);
+        if (a < 0) a = 0;
+        if (b > 0) b = 0;
+        if ((p - a + b) > 0) shown_disjoint = 1;
+      }
+    }
+  }
+  const V3 Sn = cross(Sv[0], Sv[1]);
+  const double Snl = dot(Sn, Sn);
+  if (Snl > 1e-15) {
+    double Tp[3];
+    Tp[0] = dot(S[0] - T[0], Sn);
+    Tp[1] = dot(S[0] - T[1], Sn);
+    Tp[2] = dot(S[0] - T[2], Sn);
+    int point = -1;
+    if ((Tp[0] > 0) && (Tp[1] > 0) && (Tp[2] > 0)) {
+      point = (Tp[0] < Tp[1]) ? 0 : 1;
+      if (Tp[2] < Tp[point]) point = 2;
+    } else if ((Tp[0] < 0) && (Tp[1] < 0) && (Tp[2] < 0)) {
+      point = (Tp[0] > Tp[1]) ? 0 : 1;
+      if (Tp[2] > Tp[point]) point = 2;
+    }
+    if (point >= 0) {
+      shown_disjoint = 1;
+      if (dot(T[point] - S[0], cross(Sn, Sv[0])) > 0 && dot(T[point] - S[1], cross(Sn, Sv[1])) > 0 &&
+          dot(T[point] - S[2], cross(Sn, Sv[2])) > 0) {
+        P = T[point] + Sn * (Tp[point] / Snl);
+        Q = T[point];
+        return sqnorm(P - Q);
+      }
+    }
+  }
+  const V3 Tn = cross(Tv[0], Tv[1]);
+  const double Tnl = dot(Tn, Tn);
+  if (Tnl > 1e-15) {
+    double Sp[3];
+    Sp[0] = dot(T[0] - S[0], Tn);
+    Sp[1] = dot(T[0] - S[1], Tn);
+    Sp[2] = dot(T[0] - S[2], Tn);
+    int point = -1;
+    if ((Sp[0] > 0) && (Sp[1] > 0) && (Sp[2] > 0)) {
+      point = (Sp[0] < Sp[1]) ? 0 : 1;
+      if (Sp[2] < Sp[point]) point = 2;
+    } else if ((Sp[0] < 0) && (Sp[1] < 0) && (Sp[2] < 0)) {
+      point = (Sp[0] > Sp[1]) ? 0 : 1;
+      if (Sp[2] > Sp[point]) point = 2;
+    }
+    if (point >= 0) {
+      shown_disjoint = 1;
+      if (dot(S[point] - T[0], cross(Tn, Tv[0])) > 0 && dot(S[point] - T[1], cross(Tn, Tv[1])) > 0 &&
+          dot(S[point] - T[2], cross(Tn, Tv[2])) > 0) {
+        P = S[point];
+        Q = S[point] + Tn * (Sp[point] / Tnl);
+        return sqnorm(P - Q);
+      }
+    }
+  }
+  if (shown_disjoint) {
+    P = minP;
+    Q = minQ;
+    return mindd;
+  }
+  return 0;
+}
+
+struct MMDistNode {
+  const BVHModel *model1, *model2;
+  Tf tf1;
+  M3 R;  // RT: model 2 in the frame of model 1 (internal/tools.h:91-99)
+  V3 T;
+  double rel_err, abs_err;
+  double min_distance;
+  V3 p1, p2;
+  int b1, b2;
+  uint64_t num_bv_tests = 0, num_leaf_tests = 0;
+};
+static inline double obbSize(const OBBRSS& bv) { return sqnorm(bv.obb.extent); }  // OBBRSS.h:114, OBB.h:110
+// BVHDistanceTraversalNode::firstOverSecond (traversal_node_bvhs.h:333-344, same rule as :87-98)
+template <class N>
+static inline bool firstOverSecond(const N& n, unsigned b1, unsigned b2) {
+  const BVNode& n1 = n.model1->bvs[b1];
+  const BVNode& n2 = n.model2->bvs[b2];
+  const double sz1 = obbSize(n1.bv), sz2 = obbSize(n2.bv);
+  const bool l1 = n1.first_child < 0, l2 = n2.first_child < 0;
+  return l2 || (!l1 && (sz1 > sz2));
+}
+static void mmTriDistance(MMDistNode& n, int id1, int id2, bool count) {  // :437-470 (and :487-510 for the seed)
+  const Tri& t1 = n.model1->tris[id1];
+  const Tri& t2 = n.model2->tris[id2];
+  V3 S[3], Tt[3];
+  for (int k = 0; k < 3; ++k) {
+    S[k] = n.model1->vertices[t1.v[k]];
+    Tt[k] = mul(n.R, n.model2->vertices[t2.v[k]]) + n.T;  // intersect.cpp:401-409
+  }
+  V3 P1 = nan3(), P2 = nan3();
+  const double d = std::sqrt(sqrTriDistance(S, Tt, P1, P2));
+  if (count) n.num_leaf_tests++;
+  if (n.min_distance > d) {  // DistanceResult::update with b2 (collision_data.h:1126-1138)
+    n.min_distance = d;
+    n.b1 = id1;
+    n.b2 = id2;
+    n.p1 = P1;
+    n.p2 = P2;
+  }
+}
+static inline bool mmCanStop(const MMDistNode& n, double c) {  // :473-478
+  return (c >= n.min_distance - n.abs_err) && (c * (1 + n.rel_err) >= n.min_distance);
+}
+static inline double mmBvLowerBound(MMDistNode& n, unsigned b1, unsigned b2) {  // :426-434, :258-262
+  n.num_bv_tests++;
+  return rss_distance(n.R, n.T, n.model1->bvs[b1].bv.rss, n.model2->bvs[b2].bv.rss);
+}
+static void mmDistanceRecurse(MMDistNode& n, unsigned b1, unsigned b2) {  // traversal_recurse.cpp:153-203
+  const BVNode& n1 = n.model1->bvs[b1];
+  const BVNode& n2 = n.model2->bvs[b2];
+  if (n1.first_child < 0 && n2.first_child < 0) {
+    mmTriDistance(n, -(n1.first_child + 1), -(n2.first_child + 1), true);
+    return;
+  }
+  unsigned a1, a2, c1, c2;
+  if (firstOverSecond(n, b1, b2)) {
+    a1 = (unsigned)n1.first_child;
+    a2 = b2;
+    c1 = (unsigned)n1.first_child + 1;
+    c2 = b2;
+  } else {
+    a1 = b1;
+    a2 = (unsigned)n2.first_child;
+    c1 = b1;
+    c2 = (unsigned)n2.first_child + 1;
+  }
+  const double d1 = mmBvLowerBound(n, a1, a2);
+  const double d2 = mmBvLowerBound(n, c1, c2);
+  if (d2 < d1) {
+    if (!mmCanStop(n, d2)) mmDistanceRecurse(n, c1, c2);
+    if (!mmCanStop(n, d1)) mmDistanceRecurse(n, a1, a2);
+  } else {
+    if (!mmCanStop(n, d1)) mmDistanceRecurse(n, a1, a2);
+    if (!mmCanStop(n, d2)) mmDistanceRecurse(n, c1, c2);
+  }
+}
+
+// orientedMeshDistance<MeshDistanceTraversalNodeOBBRSS> (distance_func_matrix.cpp:221-239) + distance(node)
+// (collision_node.cpp:81-91) on a fresh DistanceResult.  `normal` is never written by this node
+// (leafComputeDistance passes an uninitialised Vec3f): reported as NaN here.
+void bvhBvhDistance(const BVHModel& m1, const Tf& tf1, const BVHModel& m2, const Tf& tf2, double rel_err,
+                    double abs_err, bool enable_nearest_points, BvhQueryResult& out) {
+  MMDistNode n;
+  n.model1 = &m1;
+  n.model2 = &m2;
+  n.tf1 = tf1;
+  n.R = tmul(tf1.R, tf2.R);
+  n.T = tmul(tf1.R, tf2.T - tf1.T);
+  n.rel_err = rel_err;
+  n.abs_err = abs_err;
+  n.min_distance = std::numeric_limits<double>::max();
+  n.p1 = n.p2 = nan3();
+  n.b1 = n.b2 = -1;
+  mmTriDistance(n, 0, 0, false);  // preprocessOrientedNode (:487-510)
+  mmDistanceRecurse(n, 0, 0);
+  if (enable_nearest_points) {  // postprocessOrientedNode (:527-536)
+    n.p1 = tf1.transform(n.p1);
+    n.p2 = tf1.transform(n.p2);
+  }
+  out.distance = n.min_distance;
+  out.p1 = n.p1;
+  out.p2 = n.p2;
+  out.normal = nan3();
+  out.b1 = n.b1;
+  out.b2 = n.b2;
+  out.num_bv_tests = n.num_bv_tests;
+  out.num_leaf_tests = n.num_leaf_tests;
+}
+
+struct MMColNode {
+  const BVHModel *model1, *model2;
+  Tf tf1, tf2;
+  M3 R;
+  V3 T;
+  GJKSolver* solver;
+  const hfb_collision_request* req;
+  BvhCollideResult* res;
+};
+static void mmLeafCollides(MMColNode& n, unsigned b1, unsigned b2, double& sqrDistLowerBound) {  // :173-232
+  const int id1 = -(n.model1->bvs[b1].first_child + 1), id2 = -(n.model2->bvs[b2].first_child + 1);
+  const Tri& t1 = n.model1->tris[id1];
+  const Tri& t2 = n.model2->tris[id2];
+  Shape tri1, tri2;
+  tri1.type = tri2.type = HFB_GEOM_TRIANGLE;
+  for (int k = 0; k < 3; ++k) {
+    tri1.tri[k] = n.model1->vertices[t1.v[k]];
+    tri2.tri[k] = n.model2->vertices[t2.v[k]];
+  }
+  const bool compute_penetration = n.req->enable_contact || (n.req->security_margin < 0);
+  V3 p1, p2, normal;
+  double distance;
+  bool closed;
+  GJKSolver solver = *n.solver;  // "GJKSolver solver(this->request)" (:197): a fresh one per leaf
+  shapeShapeDistance(tri1, n.tf1, tri2, n.tf2, solver, compute_penetration, distance, p1, p2, normal, closed);
+  n.res->num_leaf_tests++;
+  const double distToCollision = distance - n.req->security_margin;
+  BvhCollideResult& r = *n.res;
+  if (distToCollision < r.distance_lower_bound) {  // updateDistanceLowerBoundFromLeaf
+    r.distance_lower_bound = distToCollision;
+    r.lb_p1 = p1;
+    r.lb_p2 = p2;
+    r.lb_normal = normal;
+  }
+  if (distToCollision <= n.req->q.collision_distance_threshold) {
+    sqrDistLowerBound = 0;
+    if (r.contacts.size() < n.req->num_max_contacts) {
+      BvhContact c;
+      c.b1 = id1;
+      c.b2 = id2;
+      c.p1 = p1;
+      c.p2 = p2;
+      c.normal = normal;
+      c.distance = distance;
+      r.contacts.push_back(c);
+    }
+  } else {
+    sqrDistLowerBound = distToCollision * distToCollision;
+  }
+}
+static bool mmBvDisjoints(MMColNode& n, unsigned b1, unsigned b2, double& sqrDistLowerBound) {  // :147-162
+  n.res->num_bv_tests++;
+  // note the operand order of the reference: (RT, bv of model 2, bv of model 1)
+  const bool disjoint = !obb_overlap(n.R, n.T, n.model2->bvs[b2].bv.obb, n.model1->bvs[b1].bv.obb,
+                                     n.req->security_margin, n.req->break_distance, sqrDistLowerBound);
+  if (disjoint) {
+    BvhCollideResult& r = *n.res;
+    if (r.distance_lower_bound > 0) {
+      const double new_dlb = std::sqrt(sqrDistLowerBound);
+      if (new_dlb < r.distance_lower_bound) r.distance_lower_bound = new_dlb;
+    }
+  }
+  return disjoint;
+}
+static inline bool mmColCanStop(const MMColNode& n) {
+  return !n.res->contacts.empty() && (n.req->num_max_contacts <= n.res->contacts.size());
+}
+static void mmCollisionRecurse(MMColNode& n, unsigned b1, unsigned b2, double& sqrDistLowerBound) {  // :44-85
+  double lb1 = 0, lb2 = 0;
+  const BVNode& n1 = n.model1->bvs[b1];
+  const BVNode& n2 = n.model2->bvs[b2];
+  if (n1.first_child < 0 && n2.first_child < 0) {
+    mmLeafCollides(n, b1, b2, sqrDistLowerBound);
+    return;
+  }
+  if (mmBvDisjoints(n, b1, b2, sqrDistLowerBound)) return;
+  if (firstOverSecond(n, b1, b2)) {
+    const unsigned c1 = (unsigned)n1.first_child, c2 = c1 + 1;
+    mmCollisionRecurse(n, c1, b2, lb1);
+    if (mmColCanStop(n)) return;
+    mmCollisionRecurse(n, c2, b2, lb2);
+  } else {
+    const unsigned c1 = (unsigned)n2.first_child, c2 = c1 + 1;
+    mmCollisionRecurse(n, b1, c1, lb1);
+    if (mmColCanStop(n)) return;
+    mmCollisionRecurse(n, b1, c2, lb2);
+  }
+  sqrDistLowerBound = std::min(lb1, lb2);
+}
+
+// orientedMeshCollide<MeshCollisionTraversalNodeOBBRSS> (collision_func_matrix.cpp:187-206) on a fresh result
+void bvhBvhCollide(const BVHModel& m1, const Tf& tf1, const BVHModel& m2, const Tf& tf2, GJKSolver& solver,
+                   const hfb_collision_request& req, BvhCollideResult& out) {
+  MMColNode n;
+  n.model1 = &m1;
+  n.model2 = &m2;
+  n.tf1 = tf1;
+  n.tf2 = tf2;
+  n.R = tmul(tf1.R, tf2.R);  // traversal_node_setup.h:561-563
+  n.T = tmul(tf1.R, tf2.T - tf1.T);
+  n.solver = &solver;
+  n.req = &req;
+  n.res = &out;
+  double sqrDistLowerBound = 0;
+  mmCollisionRecurse(n, 0, 0, sqrDistLowerBound);
+}
+
 }  // namespace oracle

@@ -30,8 +30,9 @@ struct BvhQueryResult {
   V3 p1, p2, normal;
   int b1;
   uint64_t num_bv_tests, num_leaf_tests;
+  int b2 = -1;
 };
-struct BvhContact { int b1; V3 p1, p2, normal; double distance; };
+struct BvhContact { int b1; V3 p1, p2, normal; double distance; int b2 = -1; };
 struct BvhCollideResult {
   std::vector<BvhContact> contacts;
   double distance_lower_bound = std::numeric_limits<double>::max();
@@ -48,5 +49,12 @@ void bvhShapeDistance(const BVHModel& m, const Tf& tf1, const Shape& s, const Tf
                       bool signed_distance, double rel_err, double abs_err, BvhQueryResult& out);
 void bvhShapeCollide(const BVHModel& m, const Tf& tf1, const Shape& s, const Tf& tf2, GJKSolver& solver,
                      const hfb_collision_request& req, BvhCollideResult& out);
+
+// mesh-mesh (BVHModel<OBBRSS> x BVHModel<OBBRSS>)
+double sqrTriDistance(const V3 S[3], const V3 T[3], V3& P, V3& Q);
+void bvhBvhDistance(const BVHModel& m1, const Tf& tf1, const BVHModel& m2, const Tf& tf2, double rel_err,
+                    double abs_err, bool enable_nearest_points, BvhQueryResult& out);
+void bvhBvhCollide(const BVHModel& m1, const Tf& tf1, const BVHModel& m2, const Tf& tf2, GJKSolver& solver,
+                   const hfb_collision_request& req, BvhCollideResult& out);
 
 }  // namespace oracle

@@ -171,6 +171,13 @@ int oracle_batch_distance(void* sc, size_t n, const uint32_t* h1, const hfb_tran
       solver.distance_upper_bound = std::numeric_limits<double>::max();
       solver.gjk.iterations = 0;
       solver.epa.iterations = 0;
+      // the GJK object of a fresh solver carries its constructor's settings (gjk.cpp:51-57) until
+      // runGJKAndEPA overwrites them; the TriangleP-TriangleP specialisation only calls reset() and so
+      // runs with these whatever the request says (triangle_triangle.cpp:67)
+      solver.gjk.distance_upper_bound = std::numeric_limits<double>::max();
+      solver.gjk.gjk_variant = HFB_GJK_DEFAULT;
+      solver.gjk.convergence_criterion = HFB_CRIT_DEFAULT;
+      solver.gjk.convergence_criterion_type = HFB_CRIT_RELATIVE;
 
       hfb_distance_result& r = out[i];
       // DistanceResult::clear (collision_data.h:1140-1151)
@@ -188,10 +195,22 @@ int oracle_batch_distance(void* sc, size_t n, const uint32_t* h1, const hfb_tran
         const bool swap = s1.type != HFB_BV_OBBRSS;
         const Shape& sm = swap ? s2 : s1;
         const Shape& ss = swap ? s1 : s2;
-        if (ss.type == HFB_BV_OBBRSS || !(ss.type == HFB_GEOM_BOX || ss.type == HFB_GEOM_SPHERE ||
+        if (s1.type == HFB_BV_OBBRSS && s2.type == HFB_BV_OBBRSS) {  // BVHDistance<OBBRSS> (distance_func_matrix.cpp:259-268)
+          BvhQueryResult q;
+          bvhBvhDistance(*s->bvhs[(size_t)s1.p[0]], T1, *s->bvhs[(size_t)s2.p[0]], T2, req->rel_err, req->abs_err,
+                         req->enable_nearest_points != 0, q);
+          r.min_distance = q.distance;
+          put3(r.p1, q.p1);
+          put3(r.p2, q.p2);
+          put3(r.normal, nan3());
+          r.b1 = q.b1;
+          r.b2 = q.b2;
+          r.status = (uint32_t)HFB_PATH_BVH << 16;
+          r.iterations = (uint32_t)(q.num_bv_tests & 0xffff) | ((uint32_t)(q.num_leaf_tests & 0xffff) << 16);
+        } else if (ss.type == HFB_BV_OBBRSS || !(ss.type == HFB_GEOM_BOX || ss.type == HFB_GEOM_SPHERE ||
             ss.type == HFB_GEOM_CAPSULE || ss.type == HFB_GEOM_CONE || ss.type == HFB_GEOM_CYLINDER ||
             ss.type == HFB_GEOM_ELLIPSOID || ss.type == HFB_GEOM_CONVEX)) {
-          r.status = (uint32_t)HFB_PATH_UNSUPPORTED << 16;  // mesh-mesh distance etc.: not covered
+          r.status = (uint32_t)HFB_PATH_UNSUPPORTED << 16;  // plane, halfspace, triangle partners: not covered
           r.iterations = 0;
         } else {
           BvhQueryResult q;
@@ -300,6 +319,13 @@ int oracle_batch_collide(void* sc, size_t n, const uint32_t* h1, const hfb_trans
           std::max(0., std::max(req->distance_upper_bound, req->security_margin));
       solver.gjk.iterations = 0;
       solver.epa.iterations = 0;
+      // the GJK object of a fresh solver carries its constructor's settings (gjk.cpp:51-57) until
+      // runGJKAndEPA overwrites them; the TriangleP-TriangleP specialisation only calls reset() and so
+      // runs with these whatever the request says (triangle_triangle.cpp:67)
+      solver.gjk.distance_upper_bound = std::numeric_limits<double>::max();
+      solver.gjk.gjk_variant = HFB_GJK_DEFAULT;
+      solver.gjk.convergence_criterion = HFB_CRIT_DEFAULT;
+      solver.gjk.convergence_criterion_type = HFB_CRIT_RELATIVE;
 
       if (s1.type == HFB_BV_OBBRSS || s2.type == HFB_BV_OBBRSS) {
         // collide(): (GEOM, BVH) is run as (BVH, GEOM) and swapObjects() swaps o1/o2, b1/b2, the
@@ -307,6 +333,30 @@ int oracle_batch_collide(void* sc, size_t n, const uint32_t* h1, const hfb_trans
         const bool swap = s1.type != HFB_BV_OBBRSS;
         const Shape& sm = swap ? s2 : s1;
         const Shape& ss = swap ? s1 : s2;
+        if (s1.type == HFB_BV_OBBRSS && s2.type == HFB_BV_OBBRSS) {  // BVHCollide<OBBRSS> (collision_func_matrix.cpp:248-257)
+          const GJKSolver proto = solver;  // every leaf builds GJKSolver(request) (traversal_node_bvhs.h:197)
+          BvhCollideResult q;
+          GJKSolver leaf_solver = proto;
+          bvhBvhCollide(*s->bvhs[(size_t)s1.p[0]], T1, *s->bvhs[(size_t)s2.p[0]], T2, leaf_solver, *req, q);
+          r.distance_lower_bound = q.distance_lower_bound;
+          put3(r.p1, q.lb_p1);
+          put3(r.p2, q.lb_p2);
+          put3(r.normal, q.lb_normal);
+          if (!q.contacts.empty()) {
+            const BvhContact& c = q.contacts[0];
+            r.num_contacts = 1;
+            r.distance = c.distance;
+            r.b1 = c.b1;
+            r.b2 = c.b2;
+            put3(r.pos, (c.p1 + c.p2) / 2);
+            put3(r.p1, c.p1);
+            put3(r.p2, c.p2);
+            put3(r.normal, c.normal);
+          }
+          r.status = (uint32_t)HFB_PATH_BVH << 16;
+          r.iterations = (uint32_t)(q.num_bv_tests & 0xffff) | ((uint32_t)(q.num_leaf_tests & 0xffff) << 16);
+          continue;
+        }
         const bool shape_ok = ss.type == HFB_GEOM_BOX || ss.type == HFB_GEOM_SPHERE || ss.type == HFB_GEOM_CAPSULE ||
                               ss.type == HFB_GEOM_CONE || ss.type == HFB_GEOM_CYLINDER ||
                               ss.type == HFB_GEOM_ELLIPSOID || ss.type == HFB_GEOM_CONVEX;

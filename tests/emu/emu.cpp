@@ -106,7 +106,7 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
   for (size_t i = 0; i < n; ++i) {
     if (h1[i] >= A.nshapes || h2[i] >= A.nshapes) return HFB_ERR_INVALID_ARGUMENT;
     if (A.shapes[h1[i]].type == HFB_BV_OBBRSS || A.shapes[h2[i]].type == HFB_BV_OBBRSS) {
-      BvhReq R{req->rel_err, req->abs_err, 0, 0, 0, 1};
+      BvhReq R{req->rel_err, req->abs_err, 0, 0, 0, 1, req->enable_nearest_points != 0};
       unsigned bt, lt;
       v3 guess = mk(1, 0, 0);
       int hh0 = 0, hh1 = 0;
@@ -152,7 +152,7 @@ int emu_batch_collide(void* e, size_t n, const uint32_t* h1, const hfb_transform
     }
     if (A.shapes[h1[i]].type == HFB_BV_OBBRSS || A.shapes[h2[i]].type == HFB_BV_OBBRSS) {
       BvhReq R{0, 0, req->security_margin, req->break_distance, req->q.collision_distance_threshold,
-               req->num_max_contacts};
+               req->num_max_contacts, true};
       unsigned bt, lt;
       v3 guess = mk(1, 0, 0);
       int hh0 = 0, hh1 = 0;

@@ -101,6 +101,82 @@ def test_bvh_distance_is_the_true_minimum():
             assert r[q]["min_distance"] <= 0
 
 
+# ---- mesh-mesh (BVHModel<OBBRSS> x BVHModel<OBBRSS>) --------------------------------------------
+def build_mesh_pair_scene(gpu, emu, n=300, seed=5, seg=14, ring=8):
+    sc = make_scenes(gpu=gpu, emu=emu)
+    rng = np.random.default_rng(seed)
+    va, ta = W.sphere_mesh(1.0, seg, ring, noise=0.03, rng=rng)
+    vb, tb = W.sphere_mesh(0.6, seg - 4, ring - 2, noise=0.05, rng=rng)
+    vb = vb * np.array([1.0, 0.6, 1.4])
+    ia, _ = sc.register_bvh(va, ta)
+    ib, _ = sc.register_bvh(vb, tb)
+    h = sc.register_shapes(P.make_shapes([P.BV_OBBRSS, P.BV_OBBRSS], [[0, 0, 0]] * 2, data=[ia, ib]))
+    sc.commit()
+    which = rng.integers(0, 2, (n, 2))
+    h1, h2 = h[which[:, 0]], h[which[:, 1]]
+    tf1 = W.random_transforms(rng, n, (-0.2, -0.2, -0.2), (0.2, 0.2, 0.2))
+    tf2 = W.random_transforms(rng, n, (-2.2, -2.2, -2.2), (2.2, 2.2, 2.2))
+    return sc, h1, tf1, h2, tf2, ((va, ta), (vb, tb)), which
+
+
+def _check_mesh_pairs(sc, backend, h1, tf1, h2, tf2):
+    o, e = sc.b["oracle"], sc.b[backend]
+    for req in (P.DistanceRequestPOD(), P.DistanceRequestPOD(rel_err=0.05, abs_err=0.01),
+                P.DistanceRequestPOD(enable_nearest_points=0)):
+        ro = o.batch_distance(h1, tf1, h2, tf2, req, nthreads=0)
+        compare_distance(ro, e.batch_distance(h1, tf1, h2, tf2, req), what="mesh-mesh distance")
+        assert np.all(P.status_path(ro["status"]) == P.PATH_BVH)
+    ro = o.batch_distance(h1, tf1, h2, tf2, nthreads=0)
+    assert (ro["min_distance"] == 0).sum() > 10 and (ro["min_distance"] > 0).sum() > 10
+    assert np.all(ro["b1"] >= 0) and np.all(ro["b2"] >= 0) and np.all(np.isnan(ro["normal"]))
+    sep = ro["min_distance"] > 0  # nearest points are world-frame and realise the distance
+    assert np.allclose(np.linalg.norm(ro["p1"][sep] - ro["p2"][sep], axis=1), ro["min_distance"][sep], rtol=1e-9)
+    for creq in (P.CollisionRequestPOD(), P.CollisionRequestPOD(security_margin=0.05),
+                 P.CollisionRequestPOD(security_margin=-0.01), P.CollisionRequestPOD(num_max_contacts=3, enable_contact=0),
+                 P.CollisionRequestPOD(gjk_variant=P.NesterovAcceleration)):
+        co = o.batch_collide(h1, tf1, h2, tf2, creq, nthreads=0)
+        compare_distance(co, e.batch_collide(h1, tf1, h2, tf2, creq), what="mesh-mesh collide")
+    co = o.batch_collide(h1, tf1, h2, tf2, nthreads=0)
+    assert co["num_contacts"].sum() > 10 and (co["num_contacts"] == 0).sum() > 10
+    hit = co["num_contacts"] == 1
+    assert np.all(co["b1"][hit] >= 0) and np.all(co["b2"][hit] >= 0)
+    # collide and distance agree on which pairs touch
+    assert np.array_equal(hit, ro["min_distance"] <= 1e-12)
+
+
+def test_mesh_mesh_emulated_device_code_vs_oracle():
+    sc, h1, tf1, h2, tf2, _, _ = build_mesh_pair_scene(False, True)
+    _check_mesh_pairs(sc, "emu", h1, tf1, h2, tf2)
+
+
+def test_mesh_mesh_distance_is_the_true_minimum():
+    """differential check (test/distance.cpp style): BVTT walk + sqrTriDistance == brute force over all
+    triangle pairs with the GJK triangle-triangle path"""
+    sc, h1, tf1, h2, tf2, meshes, which = build_mesh_pair_scene(False, False, n=6, seg=8, ring=5)
+    o = sc.b["oracle"]
+    r = o.batch_distance(h1, tf1, h2, tf2)
+    hts = []
+    for (v, t) in meshes:
+        cids = [o.register_convex(v[tri], None) for tri in t]
+        hts.append(o.register_shapes(P.make_shapes([P.GEOM_TRIANGLE] * len(t), np.zeros((len(t), 3)), data=cids)))
+    for q in range(len(h1)):
+        ha, hb = hts[which[q, 0]], hts[which[q, 1]]
+        ia, ib = np.meshgrid(np.arange(len(ha)), np.arange(len(hb)), indexing="ij")
+        ia, ib = ia.ravel(), ib.ravel()
+        rr = o.batch_distance(ha[ia], np.repeat(tf1[q:q + 1], len(ia)), hb[ib], np.repeat(tf2[q:q + 1], len(ia)),
+                              nthreads=0)
+        brute = max(rr["min_distance"].min(), 0.0)
+        assert abs(r[q]["min_distance"] - brute) <= 1e-6 * max(1.0, brute)
+        k = np.nonzero((ia == r[q]["b1"]) & (ib == r[q]["b2"]))[0][0]
+        assert abs(max(rr["min_distance"][k], 0.0) - r[q]["min_distance"]) <= 1e-6
+
+
+@pytest.mark.gpu
+def test_mesh_mesh_gpu_vs_oracle():
+    sc, h1, tf1, h2, tf2, _, _ = build_mesh_pair_scene(True, False, n=3000, seg=24, ring=12)
+    _check_mesh_pairs(sc, "gpu", h1, tf1, h2, tf2)
+
+
 @pytest.mark.gpu
 def test_bvh_gpu_vs_oracle():
     sc, nodes, hm, tfm, hs, tfs, _ = build_scene(True, False, seg=40, ring=20, n=20000)

@@ -128,7 +128,11 @@ def test_triangles_and_unsupported():
     h1, h2 = allh[rng.integers(0, len(allh), n)], allh[rng.integers(0, len(allh), n)]
     t1 = W.random_transforms(rng, n, (0, 0, 0), (0, 0, 0))
     t2 = W.random_transforms(rng, n, (-1.5, -1.5, -1.5), (1.5, 1.5, 1.5))
-    for req in (P.DistanceRequestPOD(), P.DistanceRequestPOD(gjk_variant=P.NesterovAcceleration)):
+    # TriangleP-TriangleP ignores the request's variant / criterion (triangle_triangle.cpp:67 only resets
+    # the GJK object), every other pair of the batch honours them
+    for req in (P.DistanceRequestPOD(), P.DistanceRequestPOD(gjk_variant=P.NesterovAcceleration),
+                P.DistanceRequestPOD(gjk_variant=P.PolyakAcceleration, gjk_convergence_criterion=P.DualityGap,
+                                     gjk_convergence_criterion_type=P.Absolute)):
         ro = sc.b["oracle"].batch_distance(h1, t1, h2, t2, req, nthreads=0)
         re = sc.b["emu"].batch_distance(h1, t1, h2, t2, req)
         compare_distance(ro, re, what="triangles")
