@@ -1004,84 +1004,123 @@ struct BvhDistOut {
   unsigned bv_tests, leaf_tests;
 };
 
-// orientedBVHShapeDistance + distance(node) + distanceRecurse, on a fresh DistanceResult
+// ---- warp-scheduled walk ------------------------------------------------------------------------
+// One lane walks one query's tree, depth first, in exactly the order of the reference's recursion.
+// Left to itself every lane of a warp would be in a different piece of code (bounding-volume test,
+// GJK on a leaf, EPA, stack handling): ncu showed 2.5 of 32 lanes active per issued instruction.  So
+// the lanes vote: each is either waiting to run a bounding-volume test or a leaf test, the warp runs
+// the phase more lanes wait for, the others sit out that round.  The per-query order of events is
+// untouched -- a lane only ever delays its own next step.
+enum { BVS_ADVANCE = 0, BVS_NEED_BV = 1, BVS_NEED_LEAF = 2, BVS_DONE = 3 };
+struct WarpVote {
+  static HFB_HD unsigned ballot(bool p) {
+#if defined(__CUDA_ARCH__)
+    return __ballot_sync(0xffffffffu, p);
+#else
+    return p ? 1u : 0u;
+#endif
+  }
+  static HFB_HD int popc(unsigned m) {
+#if defined(__CUDA_ARCH__)
+    return __popc(m);
+#else
+    return __builtin_popcount(m);
+#endif
+  }
+  static HFB_HD void sync() {
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+  }
+};
+
+// orientedBVHShapeDistance + distance(node) + distanceRecurse (traversal_recurse.cpp:153-203), on a
+// fresh DistanceResult.  Every lane of the warp calls this together; `valid` is false for lanes
+// without a query.  A stack entry is a node still to be visited plus the lower bound that canStop()
+// re-checks when the node is popped (the reference evaluates canStop for the second child after the
+// first returned).
 template <int CAPS>
-HFB_HD void bvh_shape_distance(const BvhQuery& q, const SolverP& P, double rel_err, double abs_err, EpaWs* ws,
-                               PairIn& in, BvhDistOut& out) {
+HFB_HD void bvh_shape_distance(bool valid, const BvhQuery& q, const SolverP& P, double rel_err, double abs_err,
+                               EpaWs* ws, PairIn& in, BvhDistOut& out) {
   RssD sbv;
-  compute_shape_rss(q.shape, q.tf_shape, sbv);  // traversal_node_setup.h:765
-  in.s2 = q.shape;
-  in.tf1 = q.tf_mesh;
-  in.tf2 = q.tf_shape;
   out.min_distance = DBL_MAX;
   out.p1 = out.p2 = out.normal = nan3();
   out.b1 = -1;
   out.bv_tests = out.leaf_tests = 0;
-  PairOut o;
-  // preprocess(): seed with triangle 0 (traversal_node_bvh_shape.h:457-461)
-  bvh_leaf<CAPS>(q, 0, P, ws, in, o);
-  if (out.min_distance > o.distance) {
-    out.min_distance = o.distance;
-    out.b1 = 0;
-    out.p1 = o.p1;
-    out.p2 = o.p2;
-    out.normal = o.normal;
+  if (valid) {
+    compute_shape_rss(q.shape, q.tf_shape, sbv);  // traversal_node_setup.h:765
+    in.s2 = q.shape;
+    in.tf1 = q.tf_mesh;
+    in.tf2 = q.tf_shape;
   }
-  // distanceRecurse (traversal_recurse.cpp:153-203) with an explicit stack.  A stack entry is a node
-  // that is still to be visited together with the lower bound that canStop() must re-check when the
-  // node is popped (the reference evaluates canStop for the second child after the first returned).
   int stk_node[HFB_BVH_STACK];
   double stk_d[HFB_BVH_STACK];
-  int sp = 0;
+  int sp = 1;
   stk_node[0] = 0;
   stk_d[0] = -1.0;  // root: visited unconditionally
-  sp = 1;
-  // The walk alternates two phases so that the lanes of a warp (one query each) run the same code
-  // together: (A) pop / prune / expand inner nodes until the top of the stack is a leaf that survives
-  // canStop(), (B) run the triangle-shape test of that leaf.  Per query the visiting order is
-  // exactly the recursion's.
-  while (sp > 0) {
-    int leaf_prim = -1;
-    while (sp > 0) {  // phase A
-      --sp;
-      const int b = stk_node[sp];
-      const double dlow = stk_d[sp];
-      if (dlow >= 0) {  // canStop(d) (:322-327)
-        if ((dlow >= out.min_distance - abs_err) && (dlow * (1 + rel_err) >= out.min_distance)) continue;
-      }
-      const int fc = q.nodes[b].first_child;
-      if (fc < 0) {
-        leaf_prim = -(fc + 1);
+  // preprocess(): seed with triangle 0 (traversal_node_bvh_shape.h:457-461), not counted as a leaf test
+  int state = valid ? BVS_NEED_LEAF : BVS_DONE;
+  int leaf_prim = 0, first_child = 0;
+  bool seed = true;
+  for (;;) {
+    if (state == BVS_ADVANCE) {  // pop / prune down to the next node that needs work
+      state = BVS_DONE;
+      while (sp > 0) {
+        --sp;
+        const int b = stk_node[sp];
+        const double dlow = stk_d[sp];
+        if (dlow >= 0) {  // canStop(d) (:322-327)
+          if ((dlow >= out.min_distance - abs_err) && (dlow * (1 + rel_err) >= out.min_distance)) continue;
+        }
+        const int fc = q.nodes[b].first_child;
+        if (fc < 0) {
+          leaf_prim = -(fc + 1);
+          state = BVS_NEED_LEAF;
+        } else if (sp + 2 > HFB_BVH_STACK) {  // cannot happen for trees of depth < 128
+          sp = 0;
+        } else {
+          first_child = fc;
+          state = BVS_NEED_BV;
+        }
         break;
       }
-      const int a1 = fc, c1 = fc + 1;
-      const double d1 = rss_distance(q.tf_mesh.R, q.tf_mesh.T, sbv, load_node_rss(q.nodes[a1]));
-      const double d2 = rss_distance(q.tf_mesh.R, q.tf_mesh.T, sbv, load_node_rss(q.nodes[c1]));
-      out.bv_tests += 2;
-      if (sp + 2 > HFB_BVH_STACK) {  // cannot happen for trees of depth < 128
-        sp = 0;
-        break;
+    }
+    const unsigned want_leaf = WarpVote::ballot(state == BVS_NEED_LEAF);
+    const unsigned want_bv = WarpVote::ballot(state == BVS_NEED_BV);
+    if (!(want_leaf | want_bv)) break;
+    if (want_bv == 0 || WarpVote::popc(want_leaf) >= WarpVote::popc(want_bv)) {
+      if (state == BVS_NEED_LEAF) {  // leafComputeDistance
+        PairOut o;
+        bvh_leaf<CAPS>(q, leaf_prim, P, ws, in, o);
+        if (!seed) out.leaf_tests++;
+        seed = false;
+        if (out.min_distance > o.distance) {  // DistanceResult::update: strict '>' keeps the first minimum
+          out.min_distance = o.distance;
+          out.b1 = leaf_prim;
+          out.p1 = o.p1;
+          out.p2 = o.p2;
+          out.normal = o.normal;
+        }
+        state = BVS_ADVANCE;
       }
-      // visit the nearer child first: push the farther one below it
-      if (d2 < d1) {
-        stk_node[sp] = a1; stk_d[sp] = d1; ++sp;
-        stk_node[sp] = c1; stk_d[sp] = d2; ++sp;
-      } else {
-        stk_node[sp] = c1; stk_d[sp] = d2; ++sp;
-        stk_node[sp] = a1; stk_d[sp] = d1; ++sp;
+    } else {
+      if (state == BVS_NEED_BV) {  // BVDistanceLowerBound of both children (:465-469)
+        const int a1 = first_child, c1 = first_child + 1;
+        const double d1 = rss_distance(q.tf_mesh.R, q.tf_mesh.T, sbv, load_node_rss(q.nodes[a1]));
+        const double d2 = rss_distance(q.tf_mesh.R, q.tf_mesh.T, sbv, load_node_rss(q.nodes[c1]));
+        out.bv_tests += 2;
+        // visit the nearer child first: push the farther one below it
+        if (d2 < d1) {
+          stk_node[sp] = a1; stk_d[sp] = d1; ++sp;
+          stk_node[sp] = c1; stk_d[sp] = d2; ++sp;
+        } else {
+          stk_node[sp] = c1; stk_d[sp] = d2; ++sp;
+          stk_node[sp] = a1; stk_d[sp] = d1; ++sp;
+        }
+        state = BVS_ADVANCE;
       }
     }
-    if (leaf_prim < 0) break;
-    // phase B: leafComputeDistance
-    bvh_leaf<CAPS>(q, leaf_prim, P, ws, in, o);
-    out.leaf_tests++;
-    if (out.min_distance > o.distance) {  // DistanceResult::update: strict '>' keeps the first minimum
-      out.min_distance = o.distance;
-      out.b1 = leaf_prim;
-      out.p1 = o.p1;
-      out.p2 = o.p2;
-      out.normal = o.normal;
-    }
+    WarpVote::sync();
   }
 }
 
@@ -1095,17 +1134,14 @@ struct BvhColOut {
   unsigned bv_tests, leaf_tests;
 };
 
-// BVHShapeCollider<OBBRSS,S>::oriented + collide(node) + collisionRecurse, num_max_contacts contacts
-// (only the first is returned), on a fresh CollisionResult
+// BVHShapeCollider<OBBRSS,S>::oriented + collide(node) + collisionRecurse (traversal_recurse.cpp:44-85),
+// num_max_contacts contacts (only the first is returned), on a fresh CollisionResult.  Warp-scheduled
+// like bvh_shape_distance.
 template <int CAPS>
-HFB_HD void bvh_shape_collide(const BvhQuery& q, const SolverP& P, double security_margin, double break_distance,
-                              double collision_distance_threshold, unsigned num_max_contacts, EpaWs* ws, PairIn& in,
-                              BvhColOut& out) {
+HFB_HD void bvh_shape_collide(bool valid, const BvhQuery& q, const SolverP& P, double security_margin,
+                              double break_distance, double collision_distance_threshold, unsigned num_max_contacts,
+                              EpaWs* ws, PairIn& in, BvhColOut& out) {
   ObbD sbv;
-  compute_shape_obb(q.shape, q.tf_shape, sbv);  // traversal_node_setup.h:655-694
-  in.s2 = q.shape;
-  in.tf1 = q.tf_mesh;
-  in.tf2 = q.tf_shape;
   out.distance_lower_bound = DBL_MAX;
   out.lb_p1 = out.lb_p2 = out.lb_normal = nan3();
   out.has_contact = false;
@@ -1113,64 +1149,86 @@ HFB_HD void bvh_shape_collide(const BvhQuery& q, const SolverP& P, double securi
   out.distance = DBL_MAX;
   out.p1 = out.p2 = out.normal = nan3();
   out.bv_tests = out.leaf_tests = 0;
+  if (valid) {
+    compute_shape_obb(q.shape, q.tf_shape, sbv);  // traversal_node_setup.h:655-694
+    in.s2 = q.shape;
+    in.tf1 = q.tf_mesh;
+    in.tf2 = q.tf_shape;
+  }
   unsigned ncontacts = 0;
-  PairOut o;
   int stk[HFB_BVH_STACK];
-  int sp = 0;
-  stk[sp++] = 0;
-  while (sp > 0) {
-    int leaf_prim = -1;
-    while (sp > 0) {  // phase A: OBB tests down to the next leaf
-      const int b = stk[--sp];
-      const hfb_bvh_node& nd = q.nodes[b];
-      if (nd.first_child < 0) {
-        leaf_prim = -(nd.first_child + 1);
-        break;
-      }
-      double sq_lb;
-      out.bv_tests++;
-      const bool disjoint = !obb_overlap(q.tf_mesh.R, q.tf_mesh.T, load_node_obb(nd), sbv, security_margin,
-                                         break_distance, sq_lb);
-      if (disjoint) {  // updateDistanceLowerBoundFromBV (collision_data.h:1177-1184)
-        if (out.distance_lower_bound > 0) {
-          const double nd_lb = sqrt(sq_lb);
-          if (nd_lb < out.distance_lower_bound) out.distance_lower_bound = nd_lb;
+  int sp = 1;
+  stk[0] = 0;
+  int state = valid ? BVS_ADVANCE : BVS_DONE;
+  int leaf_prim = 0, node = 0;
+  for (;;) {
+    if (state == BVS_ADVANCE) {
+      state = BVS_DONE;
+      if (sp > 0) {
+        node = stk[--sp];
+        const int fc = q.nodes[node].first_child;
+        if (fc < 0) {
+          leaf_prim = -(fc + 1);
+          state = BVS_NEED_LEAF;
+        } else if (sp + 2 > HFB_BVH_STACK) {
+          sp = 0;
+        } else {
+          state = BVS_NEED_BV;
         }
-        continue;
       }
-      if (sp + 2 > HFB_BVH_STACK) {
-        sp = 0;
-        break;
-      }
-      stk[sp++] = nd.first_child + 1;  // right child visited after the left one
-      stk[sp++] = nd.first_child;
     }
-    if (leaf_prim < 0) break;
-    // phase B: leafCollides (traversal_node_bvh_shape.h:139-188)
-    bvh_leaf<CAPS>(q, leaf_prim, P, ws, in, o);
-    out.leaf_tests++;
-    const double d2c = o.distance - security_margin;
-    if (d2c < out.distance_lower_bound) {  // updateDistanceLowerBoundFromLeaf
-      out.distance_lower_bound = d2c;
-      out.lb_p1 = o.p1;
-      out.lb_p2 = o.p2;
-      out.lb_normal = o.normal;
-    }
-    if (d2c <= collision_distance_threshold) {
-      if (ncontacts < num_max_contacts) {
-        if (ncontacts == 0) {
-          out.has_contact = true;
-          out.b1 = leaf_prim;
-          out.distance = o.distance;
-          out.p1 = o.p1;
-          out.p2 = o.p2;
-          out.normal = o.normal;
+    const unsigned want_leaf = WarpVote::ballot(state == BVS_NEED_LEAF);
+    const unsigned want_bv = WarpVote::ballot(state == BVS_NEED_BV);
+    if (!(want_leaf | want_bv)) break;
+    if (want_bv == 0 || WarpVote::popc(want_leaf) >= WarpVote::popc(want_bv)) {
+      if (state == BVS_NEED_LEAF) {  // leafCollides (traversal_node_bvh_shape.h:139-188)
+        PairOut o;
+        bvh_leaf<CAPS>(q, leaf_prim, P, ws, in, o);
+        out.leaf_tests++;
+        const double d2c = o.distance - security_margin;
+        if (d2c < out.distance_lower_bound) {  // updateDistanceLowerBoundFromLeaf
+          out.distance_lower_bound = d2c;
+          out.lb_p1 = o.p1;
+          out.lb_p2 = o.p2;
+          out.lb_normal = o.normal;
         }
-        ++ncontacts;
+        if (d2c <= collision_distance_threshold) {
+          if (ncontacts < num_max_contacts) {
+            if (ncontacts == 0) {
+              out.has_contact = true;
+              out.b1 = leaf_prim;
+              out.distance = o.distance;
+              out.p1 = o.p1;
+              out.p2 = o.p2;
+              out.normal = o.normal;
+            }
+            ++ncontacts;
+          }
+        }
+        state = BVS_ADVANCE;
+        // canStop() (traversal_recurse.cpp:69): once the request is satisfied every frame returns
+        if (ncontacts > 0 && num_max_contacts <= ncontacts) sp = 0;
+      }
+    } else {
+      if (state == BVS_NEED_BV) {  // BVDisjoints (:120-136)
+        const hfb_bvh_node& nd = q.nodes[node];
+        double sq_lb;
+        out.bv_tests++;
+        const bool disjoint = !obb_overlap(q.tf_mesh.R, q.tf_mesh.T, load_node_obb(nd), sbv, security_margin,
+                                           break_distance, sq_lb);
+        if (disjoint) {  // updateDistanceLowerBoundFromBV (collision_data.h:1177-1184)
+          if (out.distance_lower_bound > 0) {
+            const double nd_lb = sqrt(sq_lb);
+            if (nd_lb < out.distance_lower_bound) out.distance_lower_bound = nd_lb;
+          }
+        } else {
+          stk[sp++] = nd.first_child + 1;  // right child visited after the left one
+          stk[sp++] = nd.first_child;
+        }
+        state = BVS_ADVANCE;
       }
     }
-    // canStop() (traversal_recurse.cpp:69): once the request is satisfied every frame returns
-    if (ncontacts > 0 && num_max_contacts <= ncontacts) break;
+    WarpVote::sync();
   }
 }
 
@@ -1585,14 +1643,19 @@ struct BvhReq {  // request fields the traversals need beyond SolverP
 
 // distance(): BVHShapeDistancer<OBBRSS,S> with the (GEOM, BVH) operand swap of distance.cpp:74-89
 // (o1/o2, nearest points and normal are swapped back; b1/b2 are not)
-template <int CAPS>
-HFB_HD void bvh_pair_distance(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2, const xf& tf2,
-                              const SolverP& P, const BvhReq& R, v3 cached_guess, int hint0, int hint1, EpaWs* ws,
-                              hfb_distance_result* r, unsigned& bv_tests, unsigned& leaf_tests) {
+// KINDS: bit 0 = (mesh, shape) pairs, bit 1 = (mesh, mesh) pairs may occur.  Every lane of a warp
+// calls this together (the mesh-shape walk is warp-scheduled); `valid` is false for idle lanes.
+enum { BVK_SHAPE = 1, BVK_MESH = 2 };
+template <int CAPS, int KINDS>
+HFB_HD void bvh_pair_distance(bool valid, const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2,
+                              const xf& tf2, const SolverP& P, const BvhReq& R, v3 cached_guess, int hint0,
+                              int hint1, EpaWs* ws, hfb_distance_result* r, unsigned& bv_tests,
+                              unsigned& leaf_tests) {
   BvhQuery q;
-  bool swapped;
+  bool swapped = false;
   bv_tests = leaf_tests = 0;
-  if (A.shapes[h1].type == HFB_BV_OBBRSS && A.shapes[h2].type == HFB_BV_OBBRSS) {  // BVHDistance<OBBRSS>
+  if ((KINDS & BVK_MESH) && valid && A.shapes[h1].type == HFB_BV_OBBRSS &&
+      A.shapes[h2].type == HFB_BV_OBBRSS) {  // BVHDistance<OBBRSS>
     BvhPairQuery pq;
     pq.m1 = bvh_mesh_view(A, A.shapes[h1].data);
     pq.m2 = bvh_mesh_view(A, A.shapes[h2].data);
@@ -1612,18 +1675,23 @@ HFB_HD void bvh_pair_distance(const ArenaView& A, uint32_t h1, const xf& tf1, ui
     r->iterations = (o.bv_tests & 0xffffu) | ((o.leaf_tests & 0xffffu) << 16);
     bv_tests = o.bv_tests;
     leaf_tests = o.leaf_tests;
+    valid = false;
+  }
+  if (!(KINDS & BVK_SHAPE)) {
+    if (valid) bvh_unsupported_distance(r);
     return;
   }
-  if (!bvh_make_query<CAPS>(A, h1, tf1, h2, tf2, q, swapped)) {
+  if (valid && !bvh_make_query<CAPS>(A, h1, tf1, h2, tf2, q, swapped)) {
     bvh_unsupported_distance(r);
-    return;
+    valid = false;
   }
   PairIn in;
   in.cached_guess = cached_guess;
   in.hint0 = hint0;
   in.hint1 = hint1;
   BvhDistOut o;
-  bvh_shape_distance<CAPS>(q, P, R.rel_err, R.abs_err, ws, in, o);
+  bvh_shape_distance<CAPS>(valid, q, P, R.rel_err, R.abs_err, ws, in, o);
+  if (!valid) return;
   r->min_distance = o.min_distance;
   put3d(r->p1, swapped ? o.p2 : o.p1);
   put3d(r->p2, swapped ? o.p1 : o.p2);
@@ -1638,13 +1706,14 @@ HFB_HD void bvh_pair_distance(const ArenaView& A, uint32_t h1, const xf& tf1, ui
 
 // collide(): BVHShapeCollider<OBBRSS,S>::oriented with swapObjects() for (GEOM, BVH)
 // (collision.cpp:92-108): contact b1/b2, nearest points and normals are swapped back.
-template <int CAPS>
-HFB_HD void bvh_pair_collide(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2, const xf& tf2,
-                             const SolverP& P, const BvhReq& R, v3 cached_guess, int hint0, int hint1, EpaWs* ws,
-                             hfb_contact* r, unsigned& bv_tests, unsigned& leaf_tests) {
+template <int CAPS, int KINDS>
+HFB_HD void bvh_pair_collide(bool valid, const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2,
+                             const xf& tf2, const SolverP& P, const BvhReq& R, v3 cached_guess, int hint0, int hint1,
+                             EpaWs* ws, hfb_contact* r, unsigned& bv_tests, unsigned& leaf_tests) {
   BvhQuery q;
-  bool swapped;
+  bool swapped = false;
   bv_tests = leaf_tests = 0;
+  if (valid) {
   r->distance = DBL_MAX;
   r->distance_lower_bound = DBL_MAX;
   put3d(r->p1, nan3());
@@ -1655,11 +1724,13 @@ HFB_HD void bvh_pair_collide(const ArenaView& A, uint32_t h1, const xf& tf1, uin
   r->num_contacts = 0;
   r->iterations = 0;
   r->_pad = 0;
+  }
   PairIn in;
   in.cached_guess = cached_guess;
   in.hint0 = hint0;
   in.hint1 = hint1;
-  if (A.shapes[h1].type == HFB_BV_OBBRSS && A.shapes[h2].type == HFB_BV_OBBRSS) {  // BVHCollide<OBBRSS>
+  if ((KINDS & BVK_MESH) && valid && A.shapes[h1].type == HFB_BV_OBBRSS &&
+      A.shapes[h2].type == HFB_BV_OBBRSS) {  // BVHCollide<OBBRSS>
     BvhPairQuery pq;
     pq.m1 = bvh_mesh_view(A, A.shapes[h1].data);
     pq.m2 = bvh_mesh_view(A, A.shapes[h2].data);
@@ -1688,16 +1759,21 @@ HFB_HD void bvh_pair_collide(const ArenaView& A, uint32_t h1, const xf& tf1, uin
     r->iterations = (o.bv_tests & 0xffffu) | ((o.leaf_tests & 0xffffu) << 16);
     bv_tests = o.bv_tests;
     leaf_tests = o.leaf_tests;
+    valid = false;
+  }
+  if (!(KINDS & BVK_SHAPE)) {
+    if (valid) r->status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
     return;
   }
   // negative security margins throw for BVH models (collision_func_matrix.cpp:109-112)
-  if (R.security_margin < 0 || !bvh_make_query<CAPS>(A, h1, tf1, h2, tf2, q, swapped)) {
+  if (valid && (R.security_margin < 0 || !bvh_make_query<CAPS>(A, h1, tf1, h2, tf2, q, swapped))) {
     r->status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
-    return;
+    valid = false;
   }
   BvhColOut o;
-  bvh_shape_collide<CAPS>(q, P, R.security_margin, R.break_distance, R.collision_distance_threshold,
+  bvh_shape_collide<CAPS>(valid, q, P, R.security_margin, R.break_distance, R.collision_distance_threshold,
                           R.num_max_contacts, ws, in, o);
+  if (!valid) return;
   r->distance_lower_bound = o.distance_lower_bound;
   put3d(r->p1, swapped ? o.lb_p2 : o.lb_p1);
   put3d(r->p2, swapped ? o.lb_p1 : o.lb_p2);

@@ -40,11 +40,12 @@ using namespace hfb;
 // pair classes of the device-side counting sort (k_bin_*): bins [0,8) closed-form
 // combos, [8,45) GJK-routed primitive combos (+ bin 44: unknown node types, reported
 // as unsupported), bin 45: pairs touching ConvexBase / TriangleP
-#define HFB_NBINS 47
+#define HFB_NBINS 48
 #define HFB_BIN_GJK0 8
 #define HFB_BIN_UNKNOWN 44
 #define HFB_BIN_CONVEX 45
-#define HFB_BIN_BVH 46  // one operand is a BVHModel<OBBRSS>
+#define HFB_BIN_BVH 46   // one operand is a BVHModel<OBBRSS>
+#define HFB_BIN_BVH2 47  // both are
 
 // ---------------------------------------------------------------- EPA queue --
 struct EpaItem {
@@ -244,18 +245,21 @@ __global__ void __launch_bounds__(EpaCfg<G, TIER>::THREADS, EpaCfg<G, TIER>::MIN
 // One thread per (mesh, shape) query: per-query shape BV, depth-first traversal with a
 // per-thread stack (RSS distance bounds / OBB SAT per node, loaded from the 256-B node
 // records), triangle-shape GJK(+EPA) at the leaves.
-template <int MODE>
+template <int MODE, int KINDS>
 __global__ void __launch_bounds__(64) k_bvh(const BatchArgs a) {
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned nthreads = gridDim.x * blockDim.x;
   const unsigned lo = *a.range_lo, hi = *a.range_hi;
   EpaWs* ws = a.bvh_ws + tid;
   unsigned long long bv_total = 0, leaf_total = 0;
-  for (unsigned k = lo + tid; k < hi; k += nthreads) {
-    const unsigned i = a.index_list[k];
+  // warp-uniform trip count: the mesh-shape walk votes across the warp, idle lanes come along
+  for (unsigned base = lo + (tid & ~31u); base < hi; base += nthreads) {
+    const unsigned k = base + (tid & 31u);
+    const bool valid = k < hi;
+    const unsigned i = valid ? a.index_list[k] : 0u;
     v3 guess = mk(1, 0, 0);
     int h0 = 0, h1 = 0;
-    if (a.P.initial_guess == HFB_GUESS_CACHED) {
+    if (valid && a.P.initial_guess == HFB_GUESS_CACHED) {
       if (a.guess_in) guess = mk(a.guess_in[3 * i], a.guess_in[3 * i + 1], a.guess_in[3 * i + 2]);
       if (a.hint_in) {
         h0 = a.hint_in[2 * i];
@@ -263,13 +267,20 @@ __global__ void __launch_bounds__(64) k_bvh(const BatchArgs a) {
       }
     }
     unsigned bt, lt;
-    const xf t1 = load_xf(a.tf1[i].R), t2 = load_xf(a.tf2[i].R);
+    xf t1, t2;
+    uint32_t g1 = 0, g2 = 0;
+    if (valid) {
+      t1 = load_xf(a.tf1[i].R);
+      t2 = load_xf(a.tf2[i].R);
+      g1 = a.h1[i];
+      g2 = a.h2[i];
+    }
     if (MODE == 0)
-      bvh_pair_distance<CAPS_BVH>(a.A, a.h1[i], t1, a.h2[i], t2, a.P, a.B, guess, h0, h1, ws,
-                                  reinterpret_cast<hfb_distance_result*>(a.out) + i, bt, lt);
+      bvh_pair_distance<CAPS_BVH, KINDS>(valid, a.A, g1, t1, g2, t2, a.P, a.B, guess, h0, h1, ws,
+                                         reinterpret_cast<hfb_distance_result*>(a.out) + i, bt, lt);
     else
-      bvh_pair_collide<CAPS_BVH>(a.A, a.h1[i], t1, a.h2[i], t2, a.P, a.B, guess, h0, h1, ws,
-                                 reinterpret_cast<hfb_contact*>(a.out) + i, bt, lt);
+      bvh_pair_collide<CAPS_BVH, KINDS>(valid, a.A, g1, t1, g2, t2, a.P, a.B, guess, h0, h1, ws,
+                                        reinterpret_cast<hfb_contact*>(a.out) + i, bt, lt);
     bv_total += bt;
     leaf_total += lt;
   }
@@ -294,6 +305,7 @@ __device__ __forceinline__ int type_index(uint32_t t) {
 }
 __device__ __forceinline__ int pair_bin(uint32_t t1, uint32_t t2) {
   const int a = type_index(t1), b = type_index(t2);
+  if (a == 9 && b == 9) return HFB_BIN_BVH2;
   if (a == 9 || b == 9) return HFB_BIN_BVH;
   if (a == 8 || b == 8) return HFB_BIN_UNKNOWN;
   if (a >= 6 || b >= 6) return HFB_BIN_CONVEX;
@@ -670,16 +682,26 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
       CK(cudaMemsetAsync(sl.bvh_cnt.p, 0, 2 * sizeof(unsigned long long), s));
     }
     BatchArgs ab = a;
-    ab.range_lo = offsets + HFB_BIN_BVH;
-    ab.range_hi = offsets + HFB_NBINS;
     ab.bvh_ws = static_cast<EpaWs*>(sl.bvh_ws.p);
     ab.bvh_counters = static_cast<unsigned long long*>(sl.bvh_cnt.p);
+    ab.range_lo = offsets + HFB_BIN_BVH;
+    ab.range_hi = offsets + HFB_BIN_BVH2;
     {
       KTimer kt(ctx, s, 5);
-      k_bvh<MODE><<<blocks, threads, 0, s>>>(ab);
+      k_bvh<MODE, BVK_SHAPE><<<blocks, threads, 0, s>>>(ab);
     }
     ctx->stats.kernel_launches++;
     CK(cudaGetLastError());
+    {  // (mesh, mesh) pairs, own instantiation: an empty range costs one launch
+      ab.range_lo = offsets + HFB_BIN_BVH2;
+      ab.range_hi = offsets + HFB_NBINS;
+      {
+        KTimer kt(ctx, s, 5);
+        k_bvh<MODE, BVK_MESH><<<blocks, threads, 0, s>>>(ab);
+      }
+      ctx->stats.kernel_launches++;
+      CK(cudaGetLastError());
+    }
   }
   ctx->stats.pairs_processed += n;
   return HFB_OK;

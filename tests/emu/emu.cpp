@@ -114,7 +114,7 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
         if (req->q.cached_gjk_guess) guess = mk(req->q.cached_gjk_guess[3 * i], req->q.cached_gjk_guess[3 * i + 1], req->q.cached_gjk_guess[3 * i + 2]);
         if (req->q.cached_support_func_guess) { hh0 = req->q.cached_support_func_guess[2 * i]; hh1 = req->q.cached_support_func_guess[2 * i + 1]; }
       }
-      bvh_pair_distance<CAPS_ALL>(A, h1[i], load_xf(tf1[i].R), h2[i], load_xf(tf2[i].R), P, R, guess, hh0, hh1,
+      bvh_pair_distance<CAPS_ALL, BVK_SHAPE | BVK_MESH>(true, A, h1[i], load_xf(tf1[i].R), h2[i], load_xf(tf2[i].R), P, R, guess, hh0, hh1,
                                   ws.get(), &out[i], bt, lt);
       continue;
     }
@@ -160,7 +160,7 @@ int emu_batch_collide(void* e, size_t n, const uint32_t* h1, const hfb_transform
         if (req->q.cached_gjk_guess) guess = mk(req->q.cached_gjk_guess[3 * i], req->q.cached_gjk_guess[3 * i + 1], req->q.cached_gjk_guess[3 * i + 2]);
         if (req->q.cached_support_func_guess) { hh0 = req->q.cached_support_func_guess[2 * i]; hh1 = req->q.cached_support_func_guess[2 * i + 1]; }
       }
-      bvh_pair_collide<CAPS_ALL>(A, h1[i], load_xf(tf1[i].R), h2[i], load_xf(tf2[i].R), P, R, guess, hh0, hh1,
+      bvh_pair_collide<CAPS_ALL, BVK_SHAPE | BVK_MESH>(true, A, h1[i], load_xf(tf1[i].R), h2[i], load_xf(tf2[i].R), P, R, guess, hh0, hh1,
                                  ws.get(), &out[i], bt, lt);
       continue;
     }
