@@ -997,21 +997,16 @@ HFB_HD void bvh_leaf(const BvhQuery& q, int primitive_id, const SolverP& P, EpaW
   in.hint1 = o.hint1;
 }
 
-struct BvhDistOut {
-  double min_distance;
-  v3 p1, p2, normal;
-  int b1;
-  unsigned bv_tests, leaf_tests;
-};
-
 // ---- warp-scheduled walk ------------------------------------------------------------------------
 // One lane walks one query's tree, depth first, in exactly the order of the reference's recursion.
 // Left to itself every lane of a warp would be in a different piece of code (bounding-volume test,
-// GJK on a leaf, EPA, stack handling): ncu showed 2.5 of 32 lanes active per issued instruction.  So
-// the lanes vote: each is either waiting to run a bounding-volume test or a leaf test, the warp runs
-// the phase more lanes wait for, the others sit out that round.  The per-query order of events is
-// untouched -- a lane only ever delays its own next step.
-enum { BVS_ADVANCE = 0, BVS_NEED_BV = 1, BVS_NEED_LEAF = 2, BVS_DONE = 3 };
+// GJK on a leaf, EPA, stack handling) and queries differ tenfold in length: ncu showed 2.5 of 32 lanes
+// active per issued instruction.  So (1) a lane that finishes a query fetches the next one itself, and
+// (2) the lanes vote: each is waiting to set up a query, to run a bounding-volume test or to run a
+// leaf test; the warp runs the phase most lanes wait for and the others sit that round out.  The order
+// of events inside a query is untouched -- a lane only ever delays its own next step.
+enum { BVS_FETCH = 0, BVS_ADVANCE = 1, BVS_NEED_INIT = 2, BVS_NEED_BV = 3, BVS_NEED_LEAF = 4, BVS_EXIT = 5 };
+#define HFB_BVH_INIT_QUORUM 6  // lanes waiting for a new query before the (long) set-up phase is run
 struct WarpVote {
   static HFB_HD unsigned ballot(bool p) {
 #if defined(__CUDA_ARCH__)
@@ -1033,38 +1028,71 @@ struct WarpVote {
 #endif
   }
 };
+// 0: set-up phase, 1: bounding-volume phase, 2: leaf phase, -1: every lane has left
+HFB_HD int bvh_vote(int state) {
+  const int ni = WarpVote::popc(WarpVote::ballot(state == BVS_NEED_INIT));
+  const int nb = WarpVote::popc(WarpVote::ballot(state == BVS_NEED_BV));
+  const int nl = WarpVote::popc(WarpVote::ballot(state == BVS_NEED_LEAF));
+  if (ni + nb + nl == 0) return -1;
+  if (ni >= HFB_BVH_INIT_QUORUM || nb + nl == 0) return 0;
+  return (nl >= nb) ? 2 : 1;
+}
 
-// orientedBVHShapeDistance + distance(node) + distanceRecurse (traversal_recurse.cpp:153-203), on a
-// fresh DistanceResult.  Every lane of the warp calls this together; `valid` is false for lanes
-// without a query.  A stack entry is a node still to be visited plus the lower bound that canStop()
-// re-checks when the node is popped (the reference evaluates canStop for the second child after the
-// first returned).
-template <int CAPS>
-HFB_HD void bvh_shape_distance(bool valid, const BvhQuery& q, const SolverP& P, double rel_err, double abs_err,
-                               EpaWs* ws, PairIn& in, BvhDistOut& out) {
+// one (mesh, shape) query handed to a lane by a source: the operands after the swap of
+// distance()/collide(), the solver warm start and the caller's result record
+struct BvhJob {
+  BvhQuery q;
+  bool swapped;
+  v3 cached_guess;
+  int hint0, hint1;
+  void* rec;
+};
+
+struct BvhDistOut {
+  double min_distance;
+  v3 p1, p2, normal;
+  int b1;
+  unsigned bv_tests, leaf_tests;
+};
+HFB_HD void put3d(double* o, v3 v) {
+  o[0] = v.x;
+  o[1] = v.y;
+  o[2] = v.z;
+}
+// distance(): the (GEOM, BVH) operand swap of distance.cpp:74-89 is undone on o1/o2, the nearest
+// points and the normal -- not on b1/b2
+HFB_HD void bvh_write_shape_distance(hfb_distance_result* r, bool swapped, const BvhDistOut& o) {
+  r->min_distance = o.min_distance;
+  put3d(r->p1, swapped ? o.p2 : o.p1);
+  put3d(r->p2, swapped ? o.p1 : o.p2);
+  put3d(r->normal, swapped ? -o.normal : o.normal);
+  r->b1 = o.b1;
+  r->b2 = -1;
+  r->status = pack_status(0, 0, HFB_PATH_BVH);
+  r->iterations = (o.bv_tests & 0xffffu) | ((o.leaf_tests & 0xffffu) << 16);
+}
+
+// orientedBVHShapeDistance + distance(node) + distanceRecurse (traversal_recurse.cpp:153-203), each
+// query on a fresh DistanceResult.  Every lane of the warp calls this together and keeps pulling
+// queries from `src` until it has none left.  A stack entry is a node still to be visited plus the
+// lower bound that canStop() re-checks when the node is popped (the reference evaluates canStop for
+// the second child after the first returned).
+template <int CAPS, class Src>
+HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err, double abs_err, EpaWs* ws,
+                                      unsigned long long& bv_total, unsigned long long& leaf_total) {
+  BvhJob job;
   RssD sbv;
-  out.min_distance = DBL_MAX;
-  out.p1 = out.p2 = out.normal = nan3();
-  out.b1 = -1;
-  out.bv_tests = out.leaf_tests = 0;
-  if (valid) {
-    compute_shape_rss(q.shape, q.tf_shape, sbv);  // traversal_node_setup.h:765
-    in.s2 = q.shape;
-    in.tf1 = q.tf_mesh;
-    in.tf2 = q.tf_shape;
-  }
+  PairIn in;
+  BvhDistOut out;
   int stk_node[HFB_BVH_STACK];
   double stk_d[HFB_BVH_STACK];
-  int sp = 1;
-  stk_node[0] = 0;
-  stk_d[0] = -1.0;  // root: visited unconditionally
-  // preprocess(): seed with triangle 0 (traversal_node_bvh_shape.h:457-461), not counted as a leaf test
-  int state = valid ? BVS_NEED_LEAF : BVS_DONE;
+  int sp = 0;
+  int state = BVS_FETCH;
   int leaf_prim = 0, first_child = 0;
   bool seed = true;
   for (;;) {
     if (state == BVS_ADVANCE) {  // pop / prune down to the next node that needs work
-      state = BVS_DONE;
+      state = BVS_FETCH;
       while (sp > 0) {
         --sp;
         const int b = stk_node[sp];
@@ -1072,7 +1100,7 @@ HFB_HD void bvh_shape_distance(bool valid, const BvhQuery& q, const SolverP& P, 
         if (dlow >= 0) {  // canStop(d) (:322-327)
           if ((dlow >= out.min_distance - abs_err) && (dlow * (1 + rel_err) >= out.min_distance)) continue;
         }
-        const int fc = q.nodes[b].first_child;
+        const int fc = job.q.nodes[b].first_child;
         if (fc < 0) {
           leaf_prim = -(fc + 1);
           state = BVS_NEED_LEAF;
@@ -1084,14 +1112,40 @@ HFB_HD void bvh_shape_distance(bool valid, const BvhQuery& q, const SolverP& P, 
         }
         break;
       }
+      if (state == BVS_FETCH) {  // walk finished
+        bvh_write_shape_distance(static_cast<hfb_distance_result*>(job.rec), job.swapped, out);
+        bv_total += out.bv_tests;
+        leaf_total += out.leaf_tests;
+      }
     }
-    const unsigned want_leaf = WarpVote::ballot(state == BVS_NEED_LEAF);
-    const unsigned want_bv = WarpVote::ballot(state == BVS_NEED_BV);
-    if (!(want_leaf | want_bv)) break;
-    if (want_bv == 0 || WarpVote::popc(want_leaf) >= WarpVote::popc(want_bv)) {
+    if (state == BVS_FETCH) state = src.next(job) ? BVS_NEED_INIT : BVS_EXIT;
+    const int phase = bvh_vote(state);
+    if (phase < 0) break;
+    if (phase == 0) {
+      if (state == BVS_NEED_INIT) {
+        compute_shape_rss(job.q.shape, job.q.tf_shape, sbv);  // traversal_node_setup.h:765
+        in.cached_guess = job.cached_guess;
+        in.hint0 = job.hint0;
+        in.hint1 = job.hint1;
+        in.s2 = job.q.shape;
+        in.tf1 = job.q.tf_mesh;
+        in.tf2 = job.q.tf_shape;
+        out.min_distance = DBL_MAX;
+        out.p1 = out.p2 = out.normal = nan3();
+        out.b1 = -1;
+        out.bv_tests = out.leaf_tests = 0;
+        sp = 1;
+        stk_node[0] = 0;
+        stk_d[0] = -1.0;  // root: visited unconditionally
+        // preprocess(): seed with triangle 0 (traversal_node_bvh_shape.h:457-461), not a counted leaf test
+        leaf_prim = 0;
+        seed = true;
+        state = BVS_NEED_LEAF;
+      }
+    } else if (phase == 2) {
       if (state == BVS_NEED_LEAF) {  // leafComputeDistance
         PairOut o;
-        bvh_leaf<CAPS>(q, leaf_prim, P, ws, in, o);
+        bvh_leaf<CAPS>(job.q, leaf_prim, P, ws, in, o);
         if (!seed) out.leaf_tests++;
         seed = false;
         if (out.min_distance > o.distance) {  // DistanceResult::update: strict '>' keeps the first minimum
@@ -1106,8 +1160,8 @@ HFB_HD void bvh_shape_distance(bool valid, const BvhQuery& q, const SolverP& P, 
     } else {
       if (state == BVS_NEED_BV) {  // BVDistanceLowerBound of both children (:465-469)
         const int a1 = first_child, c1 = first_child + 1;
-        const double d1 = rss_distance(q.tf_mesh.R, q.tf_mesh.T, sbv, load_node_rss(q.nodes[a1]));
-        const double d2 = rss_distance(q.tf_mesh.R, q.tf_mesh.T, sbv, load_node_rss(q.nodes[c1]));
+        const double d1 = rss_distance(job.q.tf_mesh.R, job.q.tf_mesh.T, sbv, load_node_rss(job.q.nodes[a1]));
+        const double d2 = rss_distance(job.q.tf_mesh.R, job.q.tf_mesh.T, sbv, load_node_rss(job.q.nodes[c1]));
         out.bv_tests += 2;
         // visit the nearer child first: push the farther one below it
         if (d2 < d1) {
@@ -1133,57 +1187,106 @@ struct BvhColOut {
   v3 p1, p2, normal;
   unsigned bv_tests, leaf_tests;
 };
+// CollisionResult::clear() as a record
+HFB_HD void bvh_init_contact(hfb_contact* r) {
+  r->distance = DBL_MAX;
+  r->distance_lower_bound = DBL_MAX;
+  put3d(r->p1, nan3());
+  put3d(r->p2, nan3());
+  put3d(r->normal, nan3());
+  put3d(r->pos, nan3());
+  r->b1 = r->b2 = -1;
+  r->num_contacts = 0;
+  r->iterations = 0;
+  r->_pad = 0;
+}
+// collide(): swapObjects() for (GEOM, BVH) (collision.cpp:92-108) swaps contact b1/b2, nearest points
+// and normals back
+HFB_HD void bvh_write_shape_collide(hfb_contact* r, bool swapped, const BvhColOut& o) {
+  bvh_init_contact(r);
+  r->distance_lower_bound = o.distance_lower_bound;
+  put3d(r->p1, swapped ? o.lb_p2 : o.lb_p1);
+  put3d(r->p2, swapped ? o.lb_p1 : o.lb_p2);
+  put3d(r->normal, swapped ? -o.lb_normal : o.lb_normal);
+  if (o.has_contact) {
+    r->num_contacts = 1;
+    r->distance = o.distance;
+    r->b1 = swapped ? -1 : o.b1;
+    r->b2 = swapped ? o.b1 : -1;
+    put3d(r->pos, (o.p1 + o.p2) / 2);
+    put3d(r->p1, swapped ? o.p2 : o.p1);
+    put3d(r->p2, swapped ? o.p1 : o.p2);
+    put3d(r->normal, swapped ? -o.normal : o.normal);
+  }
+  r->status = pack_status(0, 0, HFB_PATH_BVH);
+  r->iterations = (o.bv_tests & 0xffffu) | ((o.leaf_tests & 0xffffu) << 16);
+}
 
 // BVHShapeCollider<OBBRSS,S>::oriented + collide(node) + collisionRecurse (traversal_recurse.cpp:44-85),
-// num_max_contacts contacts (only the first is returned), on a fresh CollisionResult.  Warp-scheduled
-// like bvh_shape_distance.
-template <int CAPS>
-HFB_HD void bvh_shape_collide(bool valid, const BvhQuery& q, const SolverP& P, double security_margin,
-                              double break_distance, double collision_distance_threshold, unsigned num_max_contacts,
-                              EpaWs* ws, PairIn& in, BvhColOut& out) {
+// num_max_contacts contacts (only the first is returned), each query on a fresh CollisionResult.
+// Warp-scheduled like bvh_shape_distance_stream.
+template <int CAPS, class Src>
+HFB_HD void bvh_shape_collide_stream(Src& src, const SolverP& P, double security_margin, double break_distance,
+                                     double collision_distance_threshold, unsigned num_max_contacts, EpaWs* ws,
+                                     unsigned long long& bv_total, unsigned long long& leaf_total) {
+  BvhJob job;
   ObbD sbv;
-  out.distance_lower_bound = DBL_MAX;
-  out.lb_p1 = out.lb_p2 = out.lb_normal = nan3();
-  out.has_contact = false;
-  out.b1 = -1;
-  out.distance = DBL_MAX;
-  out.p1 = out.p2 = out.normal = nan3();
-  out.bv_tests = out.leaf_tests = 0;
-  if (valid) {
-    compute_shape_obb(q.shape, q.tf_shape, sbv);  // traversal_node_setup.h:655-694
-    in.s2 = q.shape;
-    in.tf1 = q.tf_mesh;
-    in.tf2 = q.tf_shape;
-  }
+  PairIn in;
+  BvhColOut out;
   unsigned ncontacts = 0;
   int stk[HFB_BVH_STACK];
-  int sp = 1;
-  stk[0] = 0;
-  int state = valid ? BVS_ADVANCE : BVS_DONE;
+  int sp = 0;
+  int state = BVS_FETCH;
   int leaf_prim = 0, node = 0;
   for (;;) {
     if (state == BVS_ADVANCE) {
-      state = BVS_DONE;
+      state = BVS_FETCH;
       if (sp > 0) {
         node = stk[--sp];
-        const int fc = q.nodes[node].first_child;
+        const int fc = job.q.nodes[node].first_child;
         if (fc < 0) {
           leaf_prim = -(fc + 1);
           state = BVS_NEED_LEAF;
-        } else if (sp + 2 > HFB_BVH_STACK) {
+        } else if (sp + 2 > HFB_BVH_STACK) {  // cannot happen for trees of depth < 128
           sp = 0;
         } else {
           state = BVS_NEED_BV;
         }
       }
+      if (state == BVS_FETCH) {
+        bvh_write_shape_collide(static_cast<hfb_contact*>(job.rec), job.swapped, out);
+        bv_total += out.bv_tests;
+        leaf_total += out.leaf_tests;
+      }
     }
-    const unsigned want_leaf = WarpVote::ballot(state == BVS_NEED_LEAF);
-    const unsigned want_bv = WarpVote::ballot(state == BVS_NEED_BV);
-    if (!(want_leaf | want_bv)) break;
-    if (want_bv == 0 || WarpVote::popc(want_leaf) >= WarpVote::popc(want_bv)) {
+    if (state == BVS_FETCH) state = src.next(job) ? BVS_NEED_INIT : BVS_EXIT;
+    const int phase = bvh_vote(state);
+    if (phase < 0) break;
+    if (phase == 0) {
+      if (state == BVS_NEED_INIT) {
+        compute_shape_obb(job.q.shape, job.q.tf_shape, sbv);  // traversal_node_setup.h:655-694
+        in.cached_guess = job.cached_guess;
+        in.hint0 = job.hint0;
+        in.hint1 = job.hint1;
+        in.s2 = job.q.shape;
+        in.tf1 = job.q.tf_mesh;
+        in.tf2 = job.q.tf_shape;
+        out.distance_lower_bound = DBL_MAX;
+        out.lb_p1 = out.lb_p2 = out.lb_normal = nan3();
+        out.has_contact = false;
+        out.b1 = -1;
+        out.distance = DBL_MAX;
+        out.p1 = out.p2 = out.normal = nan3();
+        out.bv_tests = out.leaf_tests = 0;
+        ncontacts = 0;
+        sp = 1;
+        stk[0] = 0;
+        state = BVS_ADVANCE;
+      }
+    } else if (phase == 2) {
       if (state == BVS_NEED_LEAF) {  // leafCollides (traversal_node_bvh_shape.h:139-188)
         PairOut o;
-        bvh_leaf<CAPS>(q, leaf_prim, P, ws, in, o);
+        bvh_leaf<CAPS>(job.q, leaf_prim, P, ws, in, o);
         out.leaf_tests++;
         const double d2c = o.distance - security_margin;
         if (d2c < out.distance_lower_bound) {  // updateDistanceLowerBoundFromLeaf
@@ -1211,11 +1314,11 @@ HFB_HD void bvh_shape_collide(bool valid, const BvhQuery& q, const SolverP& P, d
       }
     } else {
       if (state == BVS_NEED_BV) {  // BVDisjoints (:120-136)
-        const hfb_bvh_node& nd = q.nodes[node];
+        const hfb_bvh_node& nd = job.q.nodes[node];
         double sq_lb;
         out.bv_tests++;
-        const bool disjoint = !obb_overlap(q.tf_mesh.R, q.tf_mesh.T, load_node_obb(nd), sbv, security_margin,
-                                           break_distance, sq_lb);
+        const bool disjoint = !obb_overlap(job.q.tf_mesh.R, job.q.tf_mesh.T, load_node_obb(nd), sbv,
+                                           security_margin, break_distance, sq_lb);
         if (disjoint) {  // updateDistanceLowerBoundFromBV (collision_data.h:1177-1184)
           if (out.distance_lower_bound > 0) {
             const double nd_lb = sqrt(sq_lb);
@@ -1618,12 +1721,7 @@ HFB_HD void bvh_bvh_collide(const BvhPairQuery& q, const SolverP& P, double secu
   }
 }
 
-// ---- record writers: one (h1, tf1, h2, tf2) pair where one operand is a BVH ------------------
-HFB_HD void put3d(double* o, v3 v) {
-  o[0] = v.x;
-  o[1] = v.y;
-  o[2] = v.z;
-}
+// ---- one pair: classification, the (mesh, mesh) walks, and a single-query source -----------------
 HFB_HD void bvh_unsupported_distance(hfb_distance_result* r) {
   r->min_distance = DBL_MAX;
   put3d(r->p1, nan3());
@@ -1641,157 +1739,106 @@ struct BvhReq {  // request fields the traversals need beyond SolverP
   bool enable_nearest_points;  // DistanceRequest, mesh-mesh only
 };
 
-// distance(): BVHShapeDistancer<OBBRSS,S> with the (GEOM, BVH) operand swap of distance.cpp:74-89
-// (o1/o2, nearest points and normal are swapped back; b1/b2 are not)
-// KINDS: bit 0 = (mesh, shape) pairs, bit 1 = (mesh, mesh) pairs may occur.  Every lane of a warp
-// calls this together (the mesh-shape walk is warp-scheduled); `valid` is false for idle lanes.
-enum { BVK_SHAPE = 1, BVK_MESH = 2 };
-template <int CAPS, int KINDS>
-HFB_HD void bvh_pair_distance(bool valid, const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2,
-                              const xf& tf2, const SolverP& P, const BvhReq& R, v3 cached_guess, int hint0,
-                              int hint1, EpaWs* ws, hfb_distance_result* r, unsigned& bv_tests,
-                              unsigned& leaf_tests) {
-  BvhQuery q;
-  bool swapped = false;
-  bv_tests = leaf_tests = 0;
-  if ((KINDS & BVK_MESH) && valid && A.shapes[h1].type == HFB_BV_OBBRSS &&
-      A.shapes[h2].type == HFB_BV_OBBRSS) {  // BVHDistance<OBBRSS>
-    BvhPairQuery pq;
-    pq.m1 = bvh_mesh_view(A, A.shapes[h1].data);
-    pq.m2 = bvh_mesh_view(A, A.shapes[h2].data);
-    pq.tf1 = tf1;
-    pq.tf2 = tf2;
-    pq.R = mtmulm(tf1.R, tf2.R);
-    pq.T = mtmul(tf1.R, tf2.T - tf1.T);
-    BvhPairDistOut o;
-    bvh_bvh_distance(pq, R.rel_err, R.abs_err, R.enable_nearest_points, o);
-    r->min_distance = o.min_distance;
-    put3d(r->p1, o.p1);
-    put3d(r->p2, o.p2);
-    put3d(r->normal, nan3());
-    r->b1 = o.b1;
-    r->b2 = o.b2;
-    r->status = pack_status(0, 0, HFB_PATH_BVH);
-    r->iterations = (o.bv_tests & 0xffffu) | ((o.leaf_tests & 0xffffu) << 16);
-    bv_tests = o.bv_tests;
-    leaf_tests = o.leaf_tests;
-    valid = false;
-  }
-  if (!(KINDS & BVK_SHAPE)) {
-    if (valid) bvh_unsupported_distance(r);
-    return;
-  }
-  if (valid && !bvh_make_query<CAPS>(A, h1, tf1, h2, tf2, q, swapped)) {
-    bvh_unsupported_distance(r);
-    valid = false;
-  }
-  PairIn in;
-  in.cached_guess = cached_guess;
-  in.hint0 = hint0;
-  in.hint1 = hint1;
-  BvhDistOut o;
-  bvh_shape_distance<CAPS>(valid, q, P, R.rel_err, R.abs_err, ws, in, o);
-  if (!valid) return;
+HFB_HD BvhPairQuery bvh_make_pair_query(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2, const xf& tf2) {
+  BvhPairQuery pq;
+  pq.m1 = bvh_mesh_view(A, A.shapes[h1].data);
+  pq.m2 = bvh_mesh_view(A, A.shapes[h2].data);
+  pq.tf1 = tf1;
+  pq.tf2 = tf2;
+  pq.R = mtmulm(tf1.R, tf2.R);
+  pq.T = mtmul(tf1.R, tf2.T - tf1.T);
+  return pq;
+}
+
+// distance() of a (mesh, mesh) pair: BVHDistance<OBBRSS> (distance_func_matrix.cpp:259-268)
+HFB_HD void bvh_mesh_pair_distance(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2, const xf& tf2,
+                                   const BvhReq& R, hfb_distance_result* r, unsigned& bv_tests,
+                                   unsigned& leaf_tests) {
+  const BvhPairQuery pq = bvh_make_pair_query(A, h1, tf1, h2, tf2);
+  BvhPairDistOut o;
+  bvh_bvh_distance(pq, R.rel_err, R.abs_err, R.enable_nearest_points, o);
   r->min_distance = o.min_distance;
-  put3d(r->p1, swapped ? o.p2 : o.p1);
-  put3d(r->p2, swapped ? o.p1 : o.p2);
-  put3d(r->normal, swapped ? -o.normal : o.normal);
+  put3d(r->p1, o.p1);
+  put3d(r->p2, o.p2);
+  put3d(r->normal, nan3());
   r->b1 = o.b1;
-  r->b2 = -1;
+  r->b2 = o.b2;
   r->status = pack_status(0, 0, HFB_PATH_BVH);
   r->iterations = (o.bv_tests & 0xffffu) | ((o.leaf_tests & 0xffffu) << 16);
   bv_tests = o.bv_tests;
   leaf_tests = o.leaf_tests;
 }
 
-// collide(): BVHShapeCollider<OBBRSS,S>::oriented with swapObjects() for (GEOM, BVH)
-// (collision.cpp:92-108): contact b1/b2, nearest points and normals are swapped back.
-template <int CAPS, int KINDS>
-HFB_HD void bvh_pair_collide(bool valid, const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2,
-                             const xf& tf2, const SolverP& P, const BvhReq& R, v3 cached_guess, int hint0, int hint1,
-                             EpaWs* ws, hfb_contact* r, unsigned& bv_tests, unsigned& leaf_tests) {
-  BvhQuery q;
-  bool swapped = false;
-  bv_tests = leaf_tests = 0;
-  if (valid) {
-  r->distance = DBL_MAX;
-  r->distance_lower_bound = DBL_MAX;
-  put3d(r->p1, nan3());
-  put3d(r->p2, nan3());
-  put3d(r->normal, nan3());
-  put3d(r->pos, nan3());
-  r->b1 = r->b2 = -1;
-  r->num_contacts = 0;
-  r->iterations = 0;
-  r->_pad = 0;
-  }
+// collide() of a (mesh, mesh) pair: BVHCollide<OBBRSS> (collision_func_matrix.cpp:248-257)
+template <int CAPS>
+HFB_HD void bvh_mesh_pair_collide(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2, const xf& tf2,
+                                  const SolverP& P, const BvhReq& R, v3 cached_guess, int hint0, int hint1,
+                                  EpaWs* ws, hfb_contact* r, unsigned& bv_tests, unsigned& leaf_tests) {
+  const BvhPairQuery pq = bvh_make_pair_query(A, h1, tf1, h2, tf2);
   PairIn in;
   in.cached_guess = cached_guess;
   in.hint0 = hint0;
   in.hint1 = hint1;
-  if ((KINDS & BVK_MESH) && valid && A.shapes[h1].type == HFB_BV_OBBRSS &&
-      A.shapes[h2].type == HFB_BV_OBBRSS) {  // BVHCollide<OBBRSS>
-    BvhPairQuery pq;
-    pq.m1 = bvh_mesh_view(A, A.shapes[h1].data);
-    pq.m2 = bvh_mesh_view(A, A.shapes[h2].data);
-    pq.tf1 = tf1;
-    pq.tf2 = tf2;
-    pq.R = mtmulm(tf1.R, tf2.R);
-    pq.T = mtmul(tf1.R, tf2.T - tf1.T);
-    BvhPairColOut o;
-    bvh_bvh_collide<CAPS>(pq, P, R.security_margin, R.break_distance, R.collision_distance_threshold,
-                          R.num_max_contacts, ws, in, o);
-    r->distance_lower_bound = o.distance_lower_bound;
-    put3d(r->p1, o.lb_p1);
-    put3d(r->p2, o.lb_p2);
-    put3d(r->normal, o.lb_normal);
-    if (o.has_contact) {
-      r->num_contacts = 1;
-      r->distance = o.distance;
-      r->b1 = o.b1;
-      r->b2 = o.b2;
-      put3d(r->pos, (o.p1 + o.p2) / 2);
-      put3d(r->p1, o.p1);
-      put3d(r->p2, o.p2);
-      put3d(r->normal, o.normal);
-    }
-    r->status = pack_status(0, 0, HFB_PATH_BVH);
-    r->iterations = (o.bv_tests & 0xffffu) | ((o.leaf_tests & 0xffffu) << 16);
-    bv_tests = o.bv_tests;
-    leaf_tests = o.leaf_tests;
-    valid = false;
-  }
-  if (!(KINDS & BVK_SHAPE)) {
-    if (valid) r->status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
-    return;
-  }
-  // negative security margins throw for BVH models (collision_func_matrix.cpp:109-112)
-  if (valid && (R.security_margin < 0 || !bvh_make_query<CAPS>(A, h1, tf1, h2, tf2, q, swapped))) {
-    r->status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
-    valid = false;
-  }
-  BvhColOut o;
-  bvh_shape_collide<CAPS>(valid, q, P, R.security_margin, R.break_distance, R.collision_distance_threshold,
-                          R.num_max_contacts, ws, in, o);
-  if (!valid) return;
+  BvhPairColOut o;
+  bvh_bvh_collide<CAPS>(pq, P, R.security_margin, R.break_distance, R.collision_distance_threshold,
+                        R.num_max_contacts, ws, in, o);
+  bvh_init_contact(r);
   r->distance_lower_bound = o.distance_lower_bound;
-  put3d(r->p1, swapped ? o.lb_p2 : o.lb_p1);
-  put3d(r->p2, swapped ? o.lb_p1 : o.lb_p2);
-  put3d(r->normal, swapped ? -o.lb_normal : o.lb_normal);
+  put3d(r->p1, o.lb_p1);
+  put3d(r->p2, o.lb_p2);
+  put3d(r->normal, o.lb_normal);
   if (o.has_contact) {
     r->num_contacts = 1;
     r->distance = o.distance;
-    r->b1 = swapped ? -1 : o.b1;
-    r->b2 = swapped ? o.b1 : -1;
+    r->b1 = o.b1;
+    r->b2 = o.b2;
     put3d(r->pos, (o.p1 + o.p2) / 2);
-    put3d(r->p1, swapped ? o.p2 : o.p1);
-    put3d(r->p2, swapped ? o.p1 : o.p2);
-    put3d(r->normal, swapped ? -o.normal : o.normal);
+    put3d(r->p1, o.p1);
+    put3d(r->p2, o.p2);
+    put3d(r->normal, o.normal);
   }
   r->status = pack_status(0, 0, HFB_PATH_BVH);
   r->iterations = (o.bv_tests & 0xffffu) | ((o.leaf_tests & 0xffffu) << 16);
   bv_tests = o.bv_tests;
   leaf_tests = o.leaf_tests;
 }
+
+// Turns pair (h1, tf1, h2, tf2) into a (mesh, shape) job.  Returns false -- with the record already
+// written -- when there is nothing to walk: unsupported partner (the reference throws), or, for
+// collide(), a negative security margin (collision_func_matrix.cpp:109-112).
+template <int CAPS, int MODE>
+HFB_HD bool bvh_make_job(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2, const xf& tf2, const BvhReq& R,
+                         v3 cached_guess, int hint0, int hint1, void* rec, BvhJob& job) {
+  bool ok = bvh_make_query<CAPS>(A, h1, tf1, h2, tf2, job.q, job.swapped);
+  if (MODE == 1 && R.security_margin < 0) ok = false;
+  if (!ok) {
+    if (MODE == 0) {
+      bvh_unsupported_distance(static_cast<hfb_distance_result*>(rec));
+    } else {
+      bvh_init_contact(static_cast<hfb_contact*>(rec));
+      static_cast<hfb_contact*>(rec)->status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
+    }
+    return false;
+  }
+  job.cached_guess = cached_guess;
+  job.hint0 = hint0;
+  job.hint1 = hint1;
+  job.rec = rec;
+  return true;
+}
+
+// pair kinds a k_bvh instantiation serves
+enum { BVK_SHAPE = 1, BVK_MESH = 2 };
+
+struct BvhSingleSrc {  // a source holding one job (the CPU emulation of the device code, tests)
+  BvhJob job;
+  bool pending;
+  HFB_HD bool next(BvhJob& j) {
+    if (!pending) return false;
+    pending = false;
+    j = job;
+    return true;
+  }
+};
 
 }  // namespace hfb

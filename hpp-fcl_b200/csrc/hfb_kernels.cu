@@ -85,6 +85,7 @@ struct BatchArgs {
   BvhReq B;                   // traversal request fields (BVH pairs)
   EpaWs* bvh_ws;              // one EPA workspace per thread of k_bvh (global memory)
   unsigned long long* bvh_counters;  // [0] bv tests, [1] leaf tests (running totals)
+  unsigned* bvh_work;         // k_bvh: work counter of this launch
   unsigned n;
 };
 
@@ -245,44 +246,74 @@ __global__ void __launch_bounds__(EpaCfg<G, TIER>::THREADS, EpaCfg<G, TIER>::MIN
 // One thread per (mesh, shape) query: per-query shape BV, depth-first traversal with a
 // per-thread stack (RSS distance bounds / OBB SAT per node, loaded from the 256-B node
 // records), triangle-shape GJK(+EPA) at the leaves.
+// (mesh, shape) and (mesh, mesh) pairs.  Work is handed out one pair at a time from a counter: the
+// walks differ tenfold in length, a fixed assignment would leave most lanes of a warp waiting.
+__device__ __forceinline__ void bvh_load_pair(const BatchArgs& a, unsigned i, xf& t1, xf& t2, v3& guess, int& h0,
+                                              int& h1) {
+  t1 = load_xf(a.tf1[i].R);
+  t2 = load_xf(a.tf2[i].R);
+  guess = mk(1, 0, 0);
+  h0 = h1 = 0;
+  if (a.P.initial_guess == HFB_GUESS_CACHED) {
+    if (a.guess_in) guess = mk(a.guess_in[3 * i], a.guess_in[3 * i + 1], a.guess_in[3 * i + 2]);
+    if (a.hint_in) {
+      h0 = a.hint_in[2 * i];
+      h1 = a.hint_in[2 * i + 1];
+    }
+  }
+}
+template <int MODE>
+struct BvhDeviceSrc {
+  const BatchArgs& a;
+  unsigned lo, hi;
+  __device__ bool next(BvhJob& j) {
+    for (;;) {
+      const unsigned k = lo + atomicAdd(a.bvh_work, 1u);
+      if (k >= hi) return false;
+      const unsigned i = a.index_list[k];
+      xf t1, t2;
+      v3 guess;
+      int h0, h1;
+      bvh_load_pair(a, i, t1, t2, guess, h0, h1);
+      void* rec = MODE == 0 ? static_cast<void*>(reinterpret_cast<hfb_distance_result*>(a.out) + i)
+                            : static_cast<void*>(reinterpret_cast<hfb_contact*>(a.out) + i);
+      if (bvh_make_job<CAPS_BVH, MODE>(a.A, a.h1[i], t1, a.h2[i], t2, a.B, guess, h0, h1, rec, j)) return true;
+    }
+  }
+};
 template <int MODE, int KINDS>
 __global__ void __launch_bounds__(64) k_bvh(const BatchArgs a) {
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned nthreads = gridDim.x * blockDim.x;
   const unsigned lo = *a.range_lo, hi = *a.range_hi;
   EpaWs* ws = a.bvh_ws + tid;
   unsigned long long bv_total = 0, leaf_total = 0;
-  // warp-uniform trip count: the mesh-shape walk votes across the warp, idle lanes come along
-  for (unsigned base = lo + (tid & ~31u); base < hi; base += nthreads) {
-    const unsigned k = base + (tid & 31u);
-    const bool valid = k < hi;
-    const unsigned i = valid ? a.index_list[k] : 0u;
-    v3 guess = mk(1, 0, 0);
-    int h0 = 0, h1 = 0;
-    if (valid && a.P.initial_guess == HFB_GUESS_CACHED) {
-      if (a.guess_in) guess = mk(a.guess_in[3 * i], a.guess_in[3 * i + 1], a.guess_in[3 * i + 2]);
-      if (a.hint_in) {
-        h0 = a.hint_in[2 * i];
-        h1 = a.hint_in[2 * i + 1];
-      }
-    }
-    unsigned bt, lt;
-    xf t1, t2;
-    uint32_t g1 = 0, g2 = 0;
-    if (valid) {
-      t1 = load_xf(a.tf1[i].R);
-      t2 = load_xf(a.tf2[i].R);
-      g1 = a.h1[i];
-      g2 = a.h2[i];
-    }
+  if (KINDS == BVK_SHAPE) {
+    BvhDeviceSrc<MODE> src{a, lo, hi};
     if (MODE == 0)
-      bvh_pair_distance<CAPS_BVH, KINDS>(valid, a.A, g1, t1, g2, t2, a.P, a.B, guess, h0, h1, ws,
-                                         reinterpret_cast<hfb_distance_result*>(a.out) + i, bt, lt);
+      bvh_shape_distance_stream<CAPS_BVH>(src, a.P, a.B.rel_err, a.B.abs_err, ws, bv_total, leaf_total);
     else
-      bvh_pair_collide<CAPS_BVH, KINDS>(valid, a.A, g1, t1, g2, t2, a.P, a.B, guess, h0, h1, ws,
+      bvh_shape_collide_stream<CAPS_BVH>(src, a.P, a.B.security_margin, a.B.break_distance,
+                                         a.B.collision_distance_threshold, a.B.num_max_contacts, ws, bv_total,
+                                         leaf_total);
+  } else {
+    for (;;) {
+      const unsigned k = lo + atomicAdd(a.bvh_work, 1u);
+      if (k >= hi) break;
+      const unsigned i = a.index_list[k];
+      xf t1, t2;
+      v3 guess;
+      int h0, h1;
+      bvh_load_pair(a, i, t1, t2, guess, h0, h1);
+      unsigned bt, lt;
+      if (MODE == 0)
+        bvh_mesh_pair_distance(a.A, a.h1[i], t1, a.h2[i], t2, a.B, reinterpret_cast<hfb_distance_result*>(a.out) + i,
+                               bt, lt);
+      else
+        bvh_mesh_pair_collide<CAPS_BVH>(a.A, a.h1[i], t1, a.h2[i], t2, a.P, a.B, guess, h0, h1, ws,
                                         reinterpret_cast<hfb_contact*>(a.out) + i, bt, lt);
-    bv_total += bt;
-    leaf_total += lt;
+      bv_total += bt;
+      leaf_total += lt;
+    }
   }
   if (bv_total) atomicAdd(a.bvh_counters, bv_total);
   if (leaf_total) atomicAdd(a.bvh_counters + 1, leaf_total);
@@ -559,7 +590,7 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   if (n == 0) return HFB_OK;
   CK(sl.queue.reserve((size_t)n * sizeof(EpaItem)));
   // counters: [0] EPA queue count, [1] running EPA total, [2] retry count, [3] tier-1 work counter, [4..4+kMaxParts] queue marks (mark[0] = 0,
-  // mark[j+1] = queue count after part j of phase 1), [16..16+kMaxParts) EPA work counters,
+  // mark[j+1] = queue count after part j of phase 1), [16..16+kMaxParts) EPA work counters, [24], [25] k_bvh work counters,
   // [32..) hist (NBINS), offsets (NBINS+1), cursor (NBINS)
   const size_t ncnt = 32 + 3 * (HFB_NBINS + 2);
   if (!sl.counters.p) {
@@ -686,6 +717,7 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
     ab.bvh_counters = static_cast<unsigned long long*>(sl.bvh_cnt.p);
     ab.range_lo = offsets + HFB_BIN_BVH;
     ab.range_hi = offsets + HFB_BIN_BVH2;
+    ab.bvh_work = cnt + 24;
     {
       KTimer kt(ctx, s, 5);
       k_bvh<MODE, BVK_SHAPE><<<blocks, threads, 0, s>>>(ab);
@@ -695,6 +727,7 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
     {  // (mesh, mesh) pairs, own instantiation: an empty range costs one launch
       ab.range_lo = offsets + HFB_BIN_BVH2;
       ab.range_hi = offsets + HFB_NBINS;
+      ab.bvh_work = cnt + 25;
       {
         KTimer kt(ctx, s, 5);
         k_bvh<MODE, BVK_MESH><<<blocks, threads, 0, s>>>(ab);

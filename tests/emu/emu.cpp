@@ -114,8 +114,15 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
         if (req->q.cached_gjk_guess) guess = mk(req->q.cached_gjk_guess[3 * i], req->q.cached_gjk_guess[3 * i + 1], req->q.cached_gjk_guess[3 * i + 2]);
         if (req->q.cached_support_func_guess) { hh0 = req->q.cached_support_func_guess[2 * i]; hh1 = req->q.cached_support_func_guess[2 * i + 1]; }
       }
-      bvh_pair_distance<CAPS_ALL, BVK_SHAPE | BVK_MESH>(true, A, h1[i], load_xf(tf1[i].R), h2[i], load_xf(tf2[i].R), P, R, guess, hh0, hh1,
-                                  ws.get(), &out[i], bt, lt);
+      const xf t1 = load_xf(tf1[i].R), t2 = load_xf(tf2[i].R);
+      if (A.shapes[h1[i]].type == HFB_BV_OBBRSS && A.shapes[h2[i]].type == HFB_BV_OBBRSS) {
+        bvh_mesh_pair_distance(A, h1[i], t1, h2[i], t2, R, &out[i], bt, lt);
+      } else {
+        BvhSingleSrc src;
+        src.pending = bvh_make_job<CAPS_ALL, 0>(A, h1[i], t1, h2[i], t2, R, guess, hh0, hh1, &out[i], src.job);
+        unsigned long long b2 = 0, l2 = 0;
+        bvh_shape_distance_stream<CAPS_ALL>(src, P, R.rel_err, R.abs_err, ws.get(), b2, l2);
+      }
       continue;
     }
     const PairIn in = load_pair(A, i, h1, tf1, h2, tf2, req->q);
@@ -160,8 +167,16 @@ int emu_batch_collide(void* e, size_t n, const uint32_t* h1, const hfb_transform
         if (req->q.cached_gjk_guess) guess = mk(req->q.cached_gjk_guess[3 * i], req->q.cached_gjk_guess[3 * i + 1], req->q.cached_gjk_guess[3 * i + 2]);
         if (req->q.cached_support_func_guess) { hh0 = req->q.cached_support_func_guess[2 * i]; hh1 = req->q.cached_support_func_guess[2 * i + 1]; }
       }
-      bvh_pair_collide<CAPS_ALL, BVK_SHAPE | BVK_MESH>(true, A, h1[i], load_xf(tf1[i].R), h2[i], load_xf(tf2[i].R), P, R, guess, hh0, hh1,
-                                 ws.get(), &out[i], bt, lt);
+      const xf t1 = load_xf(tf1[i].R), t2 = load_xf(tf2[i].R);
+      if (A.shapes[h1[i]].type == HFB_BV_OBBRSS && A.shapes[h2[i]].type == HFB_BV_OBBRSS) {
+        bvh_mesh_pair_collide<CAPS_ALL>(A, h1[i], t1, h2[i], t2, P, R, guess, hh0, hh1, ws.get(), &out[i], bt, lt);
+      } else {
+        BvhSingleSrc src;
+        src.pending = bvh_make_job<CAPS_ALL, 1>(A, h1[i], t1, h2[i], t2, R, guess, hh0, hh1, &out[i], src.job);
+        unsigned long long b2 = 0, l2 = 0;
+        bvh_shape_collide_stream<CAPS_ALL>(src, P, R.security_margin, R.break_distance, R.collision_distance_threshold,
+                                           R.num_max_contacts, ws.get(), b2, l2);
+      }
       continue;
     }
     const PairIn in = load_pair(A, i, h1, tf1, h2, tf2, req->q);
