@@ -96,9 +96,17 @@ HFB_HD bool in_voronoi(double a, double b, double Anorm_dot_B, double Anorm_dot_
   return false;
 }
 
+// lanes that run a bounding-volume test together (a ballot of the warp-scheduled walk); 0 = alone
+#if defined(__CUDA_ARCH__)
+#define HFB_LANES_SYNC(m) do { if (m) __syncwarp(m); } while (0)
+#else
+#define HFB_LANES_SYNC(m) do { (void)(m); } while (0)
+#endif
+
 // rectDistance (RSS.cpp:121-713), closest points not requested.  The sixteen edge-pair cases
 // keep the reference's expressions term for term (the association order differs between cases).
-HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1, double b0, double b1) {
+HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1, double b0, double b1,
+                                     unsigned lanes) {
   const double R00 = Rab.r0.x, R01 = Rab.r0.y, R02 = Rab.r0.z;
   const double R10 = Rab.r1.x, R11 = Rab.r1.y, R12 = Rab.r1.z;
   const double R20 = Rab.r2.x, R21 = Rab.r2.y;
@@ -109,7 +117,7 @@ HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1
                bA1_dot_B1 = b1 * A1_dot_B1;
   const v3 Tba = mtmul(Rab, Tab);
   const double Tab0 = Tab.x, Tab1 = Tab.y, Tab2 = Tab.z, Tba0 = Tba.x, Tba1 = Tba.y, Tba2 = Tba.z;
-  v3 S;
+  v3 S = mk(0, 0, 0);
   double t, u;
 
   double LA1_lx, LA1_ux, UA1_lx, UA1_ux, LB1_lx, LB1_ux, UB1_lx, UB1_ux;
@@ -126,52 +134,6 @@ HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1
   if (BLL_x < BLU_x) { LB1_lx = BLL_x; LB1_ux = BLU_x; UB1_lx = BUL_x; UB1_ux = BUU_x; }
   else { LB1_lx = BLU_x; LB1_ux = BLL_x; UB1_lx = BUU_x; UB1_ux = BUL_x; }
 
-  // UA1, UB1
-  if ((UA1_ux > b0) && (UB1_ux > a0)) {
-    if (((UA1_lx > b0) || in_voronoi(b1, a1, A1_dot_B0, aA0_dot_B0 - b0 - Tba0, A1_dot_B1, aA0_dot_B1 - Tba1,
-                                     -Tab1 - bA1_dot_B0)) &&
-        ((UB1_lx > a0) || in_voronoi(a1, b1, A0_dot_B1, Tab0 + bA0_dot_B0 - a0, A1_dot_B1, Tab1 + bA1_dot_B0,
-                                     Tba1 - aA0_dot_B1))) {
-      seg_coords(t, u, a1, b1, A1_dot_B1, Tab1 + bA1_dot_B0, Tba1 - aA0_dot_B1);
-      S.x = Tab0 + R00 * b0 + R01 * u - a0;
-      S.y = Tab1 + R10 * b0 + R11 * u - t;
-      S.z = Tab2 + R20 * b0 + R21 * u;
-      return nrm(S);
-    }
-  }
-  // UA1, LB1
-  if ((UA1_lx < 0) && (LB1_ux > a0)) {
-    if (((UA1_ux < 0) || in_voronoi(b1, a1, -A1_dot_B0, Tba0 - aA0_dot_B0, A1_dot_B1, aA0_dot_B1 - Tba1, -Tab1)) &&
-        ((LB1_lx > a0) || in_voronoi(a1, b1, A0_dot_B1, Tab0 - a0, A1_dot_B1, Tab1, Tba1 - aA0_dot_B1))) {
-      seg_coords(t, u, a1, b1, A1_dot_B1, Tab1, Tba1 - aA0_dot_B1);
-      S.x = Tab0 + R01 * u - a0;
-      S.y = Tab1 + R11 * u - t;
-      S.z = Tab2 + R21 * u;
-      return nrm(S);
-    }
-  }
-  // LA1, UB1
-  if ((LA1_ux > b0) && (UB1_lx < 0)) {
-    if (((LA1_lx > b0) || in_voronoi(b1, a1, A1_dot_B0, -Tba0 - b0, A1_dot_B1, -Tba1, -Tab1 - bA1_dot_B0)) &&
-        ((UB1_ux < 0) || in_voronoi(a1, b1, -A0_dot_B1, -Tab0 - bA0_dot_B0, A1_dot_B1, Tab1 + bA1_dot_B0, Tba1))) {
-      seg_coords(t, u, a1, b1, A1_dot_B1, Tab1 + bA1_dot_B0, Tba1);
-      S.x = Tab0 + R00 * b0 + R01 * u;
-      S.y = Tab1 + R10 * b0 + R11 * u - t;
-      S.z = Tab2 + R20 * b0 + R21 * u;
-      return nrm(S);
-    }
-  }
-  // LA1, LB1
-  if ((LA1_lx < 0) && (LB1_lx < 0)) {
-    if (((LA1_ux < 0) || in_voronoi(b1, a1, -A1_dot_B0, Tba0, A1_dot_B1, -Tba1, -Tab1)) &&
-        ((LB1_ux < 0) || in_voronoi(a1, b1, -A0_dot_B1, -Tab0, A1_dot_B1, Tab1, Tba1))) {
-      seg_coords(t, u, a1, b1, A1_dot_B1, Tab1, Tba1);
-      S.x = Tab0 + R01 * u;
-      S.y = Tab1 + R11 * u - t;
-      S.z = Tab2 + R21 * u;
-      return nrm(S);
-    }
-  }
 
   double LA1_ly, LA1_uy, UA1_ly, UA1_uy, LB0_lx, LB0_ux, UB0_lx, UB0_ux;
   const double ALL_y = -Tba1;
@@ -183,52 +145,6 @@ HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1
   if (BLL_x < BUL_x) { LB0_lx = BLL_x; LB0_ux = BUL_x; UB0_lx = BLU_x; UB0_ux = BUU_x; }
   else { LB0_lx = BUL_x; LB0_ux = BLL_x; UB0_lx = BUU_x; UB0_ux = BLU_x; }
 
-  // UA1, UB0
-  if ((UA1_uy > b1) && (UB0_ux > a0)) {
-    if (((UA1_ly > b1) || in_voronoi(b0, a1, A1_dot_B1, aA0_dot_B1 - Tba1 - b1, A1_dot_B0, aA0_dot_B0 - Tba0,
-                                     -Tab1 - bA1_dot_B1)) &&
-        ((UB0_lx > a0) || in_voronoi(a1, b0, A0_dot_B0, Tab0 - a0 + bA0_dot_B1, A1_dot_B0, Tab1 + bA1_dot_B1,
-                                     Tba0 - aA0_dot_B0))) {
-      seg_coords(t, u, a1, b0, A1_dot_B0, Tab1 + bA1_dot_B1, Tba0 - aA0_dot_B0);
-      S.x = Tab0 + R01 * b1 + R00 * u - a0;
-      S.y = Tab1 + R11 * b1 + R10 * u - t;
-      S.z = Tab2 + R21 * b1 + R20 * u;
-      return nrm(S);
-    }
-  }
-  // UA1, LB0
-  if ((UA1_ly < 0) && (LB0_ux > a0)) {
-    if (((UA1_uy < 0) || in_voronoi(b0, a1, -A1_dot_B1, Tba1 - aA0_dot_B1, A1_dot_B0, aA0_dot_B0 - Tba0, -Tab1)) &&
-        ((LB0_lx > a0) || in_voronoi(a1, b0, A0_dot_B0, Tab0 - a0, A1_dot_B0, Tab1, Tba0 - aA0_dot_B0))) {
-      seg_coords(t, u, a1, b0, A1_dot_B0, Tab1, Tba0 - aA0_dot_B0);
-      S.x = Tab0 + R00 * u - a0;
-      S.y = Tab1 + R10 * u - t;
-      S.z = Tab2 + R20 * u;
-      return nrm(S);
-    }
-  }
-  // LA1, UB0
-  if ((LA1_uy > b1) && (UB0_lx < 0)) {
-    if (((LA1_ly > b1) || in_voronoi(b0, a1, A1_dot_B1, -Tba1 - b1, A1_dot_B0, -Tba0, -Tab1 - bA1_dot_B1)) &&
-        ((UB0_ux < 0) || in_voronoi(a1, b0, -A0_dot_B0, -Tab0 - bA0_dot_B1, A1_dot_B0, Tab1 + bA1_dot_B1, Tba0))) {
-      seg_coords(t, u, a1, b0, A1_dot_B0, Tab1 + bA1_dot_B1, Tba0);
-      S.x = Tab0 + R01 * b1 + R00 * u;
-      S.y = Tab1 + R11 * b1 + R10 * u - t;
-      S.z = Tab2 + R21 * b1 + R20 * u;
-      return nrm(S);
-    }
-  }
-  // LA1, LB0
-  if ((LA1_ly < 0) && (LB0_lx < 0)) {
-    if (((LA1_uy < 0) || in_voronoi(b0, a1, -A1_dot_B1, Tba1, A1_dot_B0, -Tba0, -Tab1)) &&
-        ((LB0_ux < 0) || in_voronoi(a1, b0, -A0_dot_B0, -Tab0, A1_dot_B0, Tab1, Tba0))) {
-      seg_coords(t, u, a1, b0, A1_dot_B0, Tab1, Tba0);
-      S.x = Tab0 + R00 * u;
-      S.y = Tab1 + R10 * u - t;
-      S.z = Tab2 + R20 * u;
-      return nrm(S);
-    }
-  }
 
   double LA0_lx, LA0_ux, UA0_lx, UA0_ux, LB1_ly, LB1_uy, UB1_ly, UB1_uy;
   const double BLL_y = Tab1;
@@ -240,52 +156,6 @@ HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1
   if (BLL_y < BLU_y) { LB1_ly = BLL_y; LB1_uy = BLU_y; UB1_ly = BUL_y; UB1_uy = BUU_y; }
   else { LB1_ly = BLU_y; LB1_uy = BLL_y; UB1_ly = BUU_y; UB1_uy = BUL_y; }
 
-  // UA0, UB1
-  if ((UA0_ux > b0) && (UB1_uy > a1)) {
-    if (((UA0_lx > b0) || in_voronoi(b1, a0, A0_dot_B0, aA1_dot_B0 - Tba0 - b0, A0_dot_B1, aA1_dot_B1 - Tba1,
-                                     -Tab0 - bA0_dot_B0)) &&
-        ((UB1_ly > a1) || in_voronoi(a0, b1, A1_dot_B1, Tab1 - a1 + bA1_dot_B0, A0_dot_B1, Tab0 + bA0_dot_B0,
-                                     Tba1 - aA1_dot_B1))) {
-      seg_coords(t, u, a0, b1, A0_dot_B1, Tab0 + bA0_dot_B0, Tba1 - aA1_dot_B1);
-      S.x = Tab0 + R00 * b0 + R01 * u - t;
-      S.y = Tab1 + R10 * b0 + R11 * u - a1;
-      S.z = Tab2 + R20 * b0 + R21 * u;
-      return nrm(S);
-    }
-  }
-  // UA0, LB1
-  if ((UA0_lx < 0) && (LB1_uy > a1)) {
-    if (((UA0_ux < 0) || in_voronoi(b1, a0, -A0_dot_B0, Tba0 - aA1_dot_B0, A0_dot_B1, aA1_dot_B1 - Tba1, -Tab0)) &&
-        ((LB1_ly > a1) || in_voronoi(a0, b1, A1_dot_B1, Tab1 - a1, A0_dot_B1, Tab0, Tba1 - aA1_dot_B1))) {
-      seg_coords(t, u, a0, b1, A0_dot_B1, Tab0, Tba1 - aA1_dot_B1);
-      S.x = Tab0 + R01 * u - t;
-      S.y = Tab1 + R11 * u - a1;
-      S.z = Tab2 + R21 * u;
-      return nrm(S);
-    }
-  }
-  // LA0, UB1
-  if ((LA0_ux > b0) && (UB1_ly < 0)) {
-    if (((LA0_lx > b0) || in_voronoi(b1, a0, A0_dot_B0, -b0 - Tba0, A0_dot_B1, -Tba1, -bA0_dot_B0 - Tab0)) &&
-        ((UB1_uy < 0) || in_voronoi(a0, b1, -A1_dot_B1, -Tab1 - bA1_dot_B0, A0_dot_B1, Tab0 + bA0_dot_B0, Tba1))) {
-      seg_coords(t, u, a0, b1, A0_dot_B1, Tab0 + bA0_dot_B0, Tba1);
-      S.x = Tab0 + R00 * b0 + R01 * u - t;
-      S.y = Tab1 + R10 * b0 + R11 * u;
-      S.z = Tab2 + R20 * b0 + R21 * u;
-      return nrm(S);
-    }
-  }
-  // LA0, LB1
-  if ((LA0_lx < 0) && (LB1_ly < 0)) {
-    if (((LA0_ux < 0) || in_voronoi(b1, a0, -A0_dot_B0, Tba0, A0_dot_B1, -Tba1, -Tab0)) &&
-        ((LB1_uy < 0) || in_voronoi(a0, b1, -A1_dot_B1, -Tab1, A0_dot_B1, Tab0, Tba1))) {
-      seg_coords(t, u, a0, b1, A0_dot_B1, Tab0, Tba1);
-      S.x = Tab0 + R01 * u - t;
-      S.y = Tab1 + R11 * u;
-      S.z = Tab2 + R21 * u;
-      return nrm(S);
-    }
-  }
 
   double LA0_ly, LA0_uy, UA0_ly, UA0_uy, LB0_ly, LB0_uy, UB0_ly, UB0_uy;
   if (ALL_y < AUL_y) { LA0_ly = ALL_y; LA0_uy = AUL_y; UA0_ly = ALU_y; UA0_uy = AUU_y; }
@@ -293,53 +163,183 @@ HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1
   if (BLL_y < BUL_y) { LB0_ly = BLL_y; LB0_uy = BUL_y; UB0_ly = BLU_y; UB0_uy = BUU_y; }
   else { LB0_ly = BUL_y; LB0_uy = BLL_y; UB0_ly = BUU_y; UB0_uy = BLU_y; }
 
-  // UA0, UB0
-  if ((UA0_uy > b1) && (UB0_uy > a1)) {
-    if (((UA0_ly > b1) || in_voronoi(b0, a0, A0_dot_B1, aA1_dot_B1 - Tba1 - b1, A0_dot_B0, aA1_dot_B0 - Tba0,
-                                     -Tab0 - bA0_dot_B1)) &&
-        ((UB0_ly > a1) || in_voronoi(a0, b0, A1_dot_B0, Tab1 - a1 + bA1_dot_B1, A0_dot_B0, Tab0 + bA0_dot_B1,
-                                     Tba0 - aA1_dot_B0))) {
-      seg_coords(t, u, a0, b0, A0_dot_B0, Tab0 + bA0_dot_B1, Tba0 - aA1_dot_B0);
-      S.x = Tab0 + R01 * b1 + R00 * u - t;
-      S.y = Tab1 + R11 * b1 + R10 * u - a1;
-      S.z = Tab2 + R21 * b1 + R20 * u;
-      return nrm(S);
-    }
-  }
-  // UA0, LB0
-  if ((UA0_ly < 0) && (LB0_uy > a1)) {
-    if (((UA0_uy < 0) || in_voronoi(b0, a0, -A0_dot_B1, Tba1 - aA1_dot_B1, A0_dot_B0, aA1_dot_B0 - Tba0, -Tab0)) &&
-        ((LB0_ly > a1) || in_voronoi(a0, b0, A1_dot_B0, Tab1 - a1, A0_dot_B0, Tab0, Tba0 - aA1_dot_B0))) {
-      seg_coords(t, u, a0, b0, A0_dot_B0, Tab0, Tba0 - aA1_dot_B0);
-      S.x = Tab0 + R00 * u - t;
-      S.y = Tab1 + R10 * u - a1;
-      S.z = Tab2 + R20 * u;
-      return nrm(S);
-    }
-  }
-  // LA0, UB0
-  if ((LA0_uy > b1) && (UB0_ly < 0)) {
-    if (((LA0_ly > b1) || in_voronoi(b0, a0, A0_dot_B1, -Tba1 - b1, A0_dot_B0, -Tba0, -Tab0 - bA0_dot_B1)) &&
-        ((UB0_uy < 0) || in_voronoi(a0, b0, -A1_dot_B0, -Tab1 - bA1_dot_B1, A0_dot_B0, Tab0 + bA0_dot_B1, Tba0))) {
-      seg_coords(t, u, a0, b0, A0_dot_B0, Tab0 + bA0_dot_B1, Tba0);
-      S.x = Tab0 + R01 * b1 + R00 * u - t;
-      S.y = Tab1 + R11 * b1 + R10 * u;
-      S.z = Tab2 + R21 * b1 + R20 * u;
-      return nrm(S);
-    }
-  }
-  // LA0, LB0
-  if ((LA0_ly < 0) && (LB0_ly < 0)) {
-    if (((LA0_uy < 0) || in_voronoi(b0, a0, -A0_dot_B1, Tba1, A0_dot_B0, -Tba0, -Tab0)) &&
-        ((LB0_uy < 0) || in_voronoi(a0, b0, -A1_dot_B0, -Tab1, A0_dot_B0, Tab0, Tba0))) {
-      seg_coords(t, u, a0, b0, A0_dot_B0, Tab0, Tba0);
-      S.x = Tab0 + R00 * u - t;
-      S.y = Tab1 + R10 * u;
-      S.z = Tab2 + R20 * u;
-      return nrm(S);
-    }
-  }
 
+  // The sixteen edge-pair cases are tried in the reference's order and the first one whose conditions
+  // hold decides.  They are a loop here, not sixteen blocks with a return each: the lanes of `lanes`
+  // (one query each) then walk the cases side by side, the expensive part of a case (two inVoronoi
+  // tests) is one copy of code, and segCoords + the distance run once, for the winning case.
+  int kwin = -1;
+#pragma unroll 1
+  for (int k = 0; k < 16; ++k) {
+    bool guard = false, ca = false, cb = false;
+    double va0 = 0, va1 = 0, va2 = 0, va3 = 0, va4 = 0, va5 = 0, va6 = 0;
+    double vb0 = 0, vb1 = 0, vb2 = 0, vb3 = 0, vb4 = 0, vb5 = 0, vb6 = 0;
+    switch (k) {
+      case 0:  // UA1, UB1
+        guard = (UA1_ux > b0) && (UB1_ux > a0);
+        ca = UA1_lx > b0;
+        va0 = b1; va1 = a1; va2 = A1_dot_B0; va3 = aA0_dot_B0 - b0 - Tba0; va4 = A1_dot_B1; va5 = aA0_dot_B1 - Tba1; va6 = -Tab1 - bA1_dot_B0;
+        cb = UB1_lx > a0;
+        vb0 = a1; vb1 = b1; vb2 = A0_dot_B1; vb3 = Tab0 + bA0_dot_B0 - a0; vb4 = A1_dot_B1; vb5 = Tab1 + bA1_dot_B0; vb6 = Tba1 - aA0_dot_B1;
+        break;
+      case 1:  // UA1, LB1
+        guard = (UA1_lx < 0) && (LB1_ux > a0);
+        ca = UA1_ux < 0;
+        va0 = b1; va1 = a1; va2 = -A1_dot_B0; va3 = Tba0 - aA0_dot_B0; va4 = A1_dot_B1; va5 = aA0_dot_B1 - Tba1; va6 = -Tab1;
+        cb = LB1_lx > a0;
+        vb0 = a1; vb1 = b1; vb2 = A0_dot_B1; vb3 = Tab0 - a0; vb4 = A1_dot_B1; vb5 = Tab1; vb6 = Tba1 - aA0_dot_B1;
+        break;
+      case 2:  // LA1, UB1
+        guard = (LA1_ux > b0) && (UB1_lx < 0);
+        ca = LA1_lx > b0;
+        va0 = b1; va1 = a1; va2 = A1_dot_B0; va3 = -Tba0 - b0; va4 = A1_dot_B1; va5 = -Tba1; va6 = -Tab1 - bA1_dot_B0;
+        cb = UB1_ux < 0;
+        vb0 = a1; vb1 = b1; vb2 = -A0_dot_B1; vb3 = -Tab0 - bA0_dot_B0; vb4 = A1_dot_B1; vb5 = Tab1 + bA1_dot_B0; vb6 = Tba1;
+        break;
+      case 3:  // LA1, LB1
+        guard = (LA1_lx < 0) && (LB1_lx < 0);
+        ca = LA1_ux < 0;
+        va0 = b1; va1 = a1; va2 = -A1_dot_B0; va3 = Tba0; va4 = A1_dot_B1; va5 = -Tba1; va6 = -Tab1;
+        cb = LB1_ux < 0;
+        vb0 = a1; vb1 = b1; vb2 = -A0_dot_B1; vb3 = -Tab0; vb4 = A1_dot_B1; vb5 = Tab1; vb6 = Tba1;
+        break;
+      case 4:  // UA1, UB0
+        guard = (UA1_uy > b1) && (UB0_ux > a0);
+        ca = UA1_ly > b1;
+        va0 = b0; va1 = a1; va2 = A1_dot_B1; va3 = aA0_dot_B1 - Tba1 - b1; va4 = A1_dot_B0; va5 = aA0_dot_B0 - Tba0; va6 = -Tab1 - bA1_dot_B1;
+        cb = UB0_lx > a0;
+        vb0 = a1; vb1 = b0; vb2 = A0_dot_B0; vb3 = Tab0 - a0 + bA0_dot_B1; vb4 = A1_dot_B0; vb5 = Tab1 + bA1_dot_B1; vb6 = Tba0 - aA0_dot_B0;
+        break;
+      case 5:  // UA1, LB0
+        guard = (UA1_ly < 0) && (LB0_ux > a0);
+        ca = UA1_uy < 0;
+        va0 = b0; va1 = a1; va2 = -A1_dot_B1; va3 = Tba1 - aA0_dot_B1; va4 = A1_dot_B0; va5 = aA0_dot_B0 - Tba0; va6 = -Tab1;
+        cb = LB0_lx > a0;
+        vb0 = a1; vb1 = b0; vb2 = A0_dot_B0; vb3 = Tab0 - a0; vb4 = A1_dot_B0; vb5 = Tab1; vb6 = Tba0 - aA0_dot_B0;
+        break;
+      case 6:  // LA1, UB0
+        guard = (LA1_uy > b1) && (UB0_lx < 0);
+        ca = LA1_ly > b1;
+        va0 = b0; va1 = a1; va2 = A1_dot_B1; va3 = -Tba1 - b1; va4 = A1_dot_B0; va5 = -Tba0; va6 = -Tab1 - bA1_dot_B1;
+        cb = UB0_ux < 0;
+        vb0 = a1; vb1 = b0; vb2 = -A0_dot_B0; vb3 = -Tab0 - bA0_dot_B1; vb4 = A1_dot_B0; vb5 = Tab1 + bA1_dot_B1; vb6 = Tba0;
+        break;
+      case 7:  // LA1, LB0
+        guard = (LA1_ly < 0) && (LB0_lx < 0);
+        ca = LA1_uy < 0;
+        va0 = b0; va1 = a1; va2 = -A1_dot_B1; va3 = Tba1; va4 = A1_dot_B0; va5 = -Tba0; va6 = -Tab1;
+        cb = LB0_ux < 0;
+        vb0 = a1; vb1 = b0; vb2 = -A0_dot_B0; vb3 = -Tab0; vb4 = A1_dot_B0; vb5 = Tab1; vb6 = Tba0;
+        break;
+      case 8:  // UA0, UB1
+        guard = (UA0_ux > b0) && (UB1_uy > a1);
+        ca = UA0_lx > b0;
+        va0 = b1; va1 = a0; va2 = A0_dot_B0; va3 = aA1_dot_B0 - Tba0 - b0; va4 = A0_dot_B1; va5 = aA1_dot_B1 - Tba1; va6 = -Tab0 - bA0_dot_B0;
+        cb = UB1_ly > a1;
+        vb0 = a0; vb1 = b1; vb2 = A1_dot_B1; vb3 = Tab1 - a1 + bA1_dot_B0; vb4 = A0_dot_B1; vb5 = Tab0 + bA0_dot_B0; vb6 = Tba1 - aA1_dot_B1;
+        break;
+      case 9:  // UA0, LB1
+        guard = (UA0_lx < 0) && (LB1_uy > a1);
+        ca = UA0_ux < 0;
+        va0 = b1; va1 = a0; va2 = -A0_dot_B0; va3 = Tba0 - aA1_dot_B0; va4 = A0_dot_B1; va5 = aA1_dot_B1 - Tba1; va6 = -Tab0;
+        cb = LB1_ly > a1;
+        vb0 = a0; vb1 = b1; vb2 = A1_dot_B1; vb3 = Tab1 - a1; vb4 = A0_dot_B1; vb5 = Tab0; vb6 = Tba1 - aA1_dot_B1;
+        break;
+      case 10:  // LA0, UB1
+        guard = (LA0_ux > b0) && (UB1_ly < 0);
+        ca = LA0_lx > b0;
+        va0 = b1; va1 = a0; va2 = A0_dot_B0; va3 = -b0 - Tba0; va4 = A0_dot_B1; va5 = -Tba1; va6 = -bA0_dot_B0 - Tab0;
+        cb = UB1_uy < 0;
+        vb0 = a0; vb1 = b1; vb2 = -A1_dot_B1; vb3 = -Tab1 - bA1_dot_B0; vb4 = A0_dot_B1; vb5 = Tab0 + bA0_dot_B0; vb6 = Tba1;
+        break;
+      case 11:  // LA0, LB1
+        guard = (LA0_lx < 0) && (LB1_ly < 0);
+        ca = LA0_ux < 0;
+        va0 = b1; va1 = a0; va2 = -A0_dot_B0; va3 = Tba0; va4 = A0_dot_B1; va5 = -Tba1; va6 = -Tab0;
+        cb = LB1_uy < 0;
+        vb0 = a0; vb1 = b1; vb2 = -A1_dot_B1; vb3 = -Tab1; vb4 = A0_dot_B1; vb5 = Tab0; vb6 = Tba1;
+        break;
+      case 12:  // UA0, UB0
+        guard = (UA0_uy > b1) && (UB0_uy > a1);
+        ca = UA0_ly > b1;
+        va0 = b0; va1 = a0; va2 = A0_dot_B1; va3 = aA1_dot_B1 - Tba1 - b1; va4 = A0_dot_B0; va5 = aA1_dot_B0 - Tba0; va6 = -Tab0 - bA0_dot_B1;
+        cb = UB0_ly > a1;
+        vb0 = a0; vb1 = b0; vb2 = A1_dot_B0; vb3 = Tab1 - a1 + bA1_dot_B1; vb4 = A0_dot_B0; vb5 = Tab0 + bA0_dot_B1; vb6 = Tba0 - aA1_dot_B0;
+        break;
+      case 13:  // UA0, LB0
+        guard = (UA0_ly < 0) && (LB0_uy > a1);
+        ca = UA0_uy < 0;
+        va0 = b0; va1 = a0; va2 = -A0_dot_B1; va3 = Tba1 - aA1_dot_B1; va4 = A0_dot_B0; va5 = aA1_dot_B0 - Tba0; va6 = -Tab0;
+        cb = LB0_ly > a1;
+        vb0 = a0; vb1 = b0; vb2 = A1_dot_B0; vb3 = Tab1 - a1; vb4 = A0_dot_B0; vb5 = Tab0; vb6 = Tba0 - aA1_dot_B0;
+        break;
+      case 14:  // LA0, UB0
+        guard = (LA0_uy > b1) && (UB0_ly < 0);
+        ca = LA0_ly > b1;
+        va0 = b0; va1 = a0; va2 = A0_dot_B1; va3 = -Tba1 - b1; va4 = A0_dot_B0; va5 = -Tba0; va6 = -Tab0 - bA0_dot_B1;
+        cb = UB0_uy < 0;
+        vb0 = a0; vb1 = b0; vb2 = -A1_dot_B0; vb3 = -Tab1 - bA1_dot_B1; vb4 = A0_dot_B0; vb5 = Tab0 + bA0_dot_B1; vb6 = Tba0;
+        break;
+      case 15:  // LA0, LB0
+        guard = (LA0_ly < 0) && (LB0_ly < 0);
+        ca = LA0_uy < 0;
+        va0 = b0; va1 = a0; va2 = -A0_dot_B1; va3 = Tba1; va4 = A0_dot_B0; va5 = -Tba0; va6 = -Tab0;
+        cb = LB0_uy < 0;
+        vb0 = a0; vb1 = b0; vb2 = -A1_dot_B0; vb3 = -Tab1; vb4 = A0_dot_B0; vb5 = Tab0; vb6 = Tba0;
+        break;
+      default:
+        break;
+    }
+    if (kwin < 0 && guard) {
+      if ((ca || in_voronoi(va0, va1, va2, va3, va4, va5, va6)) &&
+          (cb || in_voronoi(vb0, vb1, vb2, vb3, vb4, vb5, vb6)))
+        kwin = k;
+    }
+    HFB_LANES_SYNC(lanes);
+  }
+  if (kwin >= 0) {
+    double sa = 0, sb = 0, s_ab = 0, s_at = 0, s_bt = 0;
+    switch (kwin) {
+    case 0: sa = a1; sb = b1; s_ab = A1_dot_B1; s_at = Tab1 + bA1_dot_B0; s_bt = Tba1 - aA0_dot_B1; break;
+    case 1: sa = a1; sb = b1; s_ab = A1_dot_B1; s_at = Tab1; s_bt = Tba1 - aA0_dot_B1; break;
+    case 2: sa = a1; sb = b1; s_ab = A1_dot_B1; s_at = Tab1 + bA1_dot_B0; s_bt = Tba1; break;
+    case 3: sa = a1; sb = b1; s_ab = A1_dot_B1; s_at = Tab1; s_bt = Tba1; break;
+    case 4: sa = a1; sb = b0; s_ab = A1_dot_B0; s_at = Tab1 + bA1_dot_B1; s_bt = Tba0 - aA0_dot_B0; break;
+    case 5: sa = a1; sb = b0; s_ab = A1_dot_B0; s_at = Tab1; s_bt = Tba0 - aA0_dot_B0; break;
+    case 6: sa = a1; sb = b0; s_ab = A1_dot_B0; s_at = Tab1 + bA1_dot_B1; s_bt = Tba0; break;
+    case 7: sa = a1; sb = b0; s_ab = A1_dot_B0; s_at = Tab1; s_bt = Tba0; break;
+    case 8: sa = a0; sb = b1; s_ab = A0_dot_B1; s_at = Tab0 + bA0_dot_B0; s_bt = Tba1 - aA1_dot_B1; break;
+    case 9: sa = a0; sb = b1; s_ab = A0_dot_B1; s_at = Tab0; s_bt = Tba1 - aA1_dot_B1; break;
+    case 10: sa = a0; sb = b1; s_ab = A0_dot_B1; s_at = Tab0 + bA0_dot_B0; s_bt = Tba1; break;
+    case 11: sa = a0; sb = b1; s_ab = A0_dot_B1; s_at = Tab0; s_bt = Tba1; break;
+    case 12: sa = a0; sb = b0; s_ab = A0_dot_B0; s_at = Tab0 + bA0_dot_B1; s_bt = Tba0 - aA1_dot_B0; break;
+    case 13: sa = a0; sb = b0; s_ab = A0_dot_B0; s_at = Tab0; s_bt = Tba0 - aA1_dot_B0; break;
+    case 14: sa = a0; sb = b0; s_ab = A0_dot_B0; s_at = Tab0 + bA0_dot_B1; s_bt = Tba0; break;
+    case 15: sa = a0; sb = b0; s_ab = A0_dot_B0; s_at = Tab0; s_bt = Tba0; break;
+    default: break;
+    }
+    seg_coords(t, u, sa, sb, s_ab, s_at, s_bt);
+    switch (kwin) {
+    case 0: S.x = Tab0 + R00 * b0 + R01 * u - a0; S.y = Tab1 + R10 * b0 + R11 * u - t; S.z = Tab2 + R20 * b0 + R21 * u; break;
+    case 1: S.x = Tab0 + R01 * u - a0; S.y = Tab1 + R11 * u - t; S.z = Tab2 + R21 * u; break;
+    case 2: S.x = Tab0 + R00 * b0 + R01 * u; S.y = Tab1 + R10 * b0 + R11 * u - t; S.z = Tab2 + R20 * b0 + R21 * u; break;
+    case 3: S.x = Tab0 + R01 * u; S.y = Tab1 + R11 * u - t; S.z = Tab2 + R21 * u; break;
+    case 4: S.x = Tab0 + R01 * b1 + R00 * u - a0; S.y = Tab1 + R11 * b1 + R10 * u - t; S.z = Tab2 + R21 * b1 + R20 * u; break;
+    case 5: S.x = Tab0 + R00 * u - a0; S.y = Tab1 + R10 * u - t; S.z = Tab2 + R20 * u; break;
+    case 6: S.x = Tab0 + R01 * b1 + R00 * u; S.y = Tab1 + R11 * b1 + R10 * u - t; S.z = Tab2 + R21 * b1 + R20 * u; break;
+    case 7: S.x = Tab0 + R00 * u; S.y = Tab1 + R10 * u - t; S.z = Tab2 + R20 * u; break;
+    case 8: S.x = Tab0 + R00 * b0 + R01 * u - t; S.y = Tab1 + R10 * b0 + R11 * u - a1; S.z = Tab2 + R20 * b0 + R21 * u; break;
+    case 9: S.x = Tab0 + R01 * u - t; S.y = Tab1 + R11 * u - a1; S.z = Tab2 + R21 * u; break;
+    case 10: S.x = Tab0 + R00 * b0 + R01 * u - t; S.y = Tab1 + R10 * b0 + R11 * u; S.z = Tab2 + R20 * b0 + R21 * u; break;
+    case 11: S.x = Tab0 + R01 * u - t; S.y = Tab1 + R11 * u; S.z = Tab2 + R21 * u; break;
+    case 12: S.x = Tab0 + R01 * b1 + R00 * u - t; S.y = Tab1 + R11 * b1 + R10 * u - a1; S.z = Tab2 + R21 * b1 + R20 * u; break;
+    case 13: S.x = Tab0 + R00 * u - t; S.y = Tab1 + R10 * u - a1; S.z = Tab2 + R20 * u; break;
+    case 14: S.x = Tab0 + R01 * b1 + R00 * u - t; S.y = Tab1 + R11 * b1 + R10 * u; S.z = Tab2 + R21 * b1 + R20 * u; break;
+    case 15: S.x = Tab0 + R00 * u - t; S.y = Tab1 + R10 * u; S.z = Tab2 + R20 * u; break;
+    default: break;
+    }
+    return nrm(S);
+  }
   // no edge pair holds the closest points: separation along the face normals
   double sep1, sep2;
   if (Tab2 > 0.0) {
@@ -365,12 +365,12 @@ HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1
 }
 
 // distance(R0, T0, b1, b2) (RSS.cpp:995-1005)
-HFB_HD double rss_distance(const m3& R0, v3 T0, const RssD& b1, const RssD& b2) {
+HFB_HD double rss_distance(const m3& R0, v3 T0, const RssD& b1, const RssD& b2, unsigned lanes = 0) {
   const m3 b1t = mtrans(b1.axes);
   const m3 R = mmulm(mmulm(b1t, R0), b2.axes);
   const v3 Ttemp = mmul(R0, b2.Tr) + T0 - b1.Tr;
   const v3 T = mtmul(b1.axes, Ttemp);
-  double dist = rect_distance(R, T, b1.l0, b1.l1, b2.l0, b2.l1);
+  double dist = rect_distance(R, T, b1.l0, b1.l1, b2.l0, b2.l1, lanes);
   dist -= (b1.radius + b2.radius);
   return (dist < 0.0) ? 0.0 : dist;
 }
@@ -1029,12 +1029,19 @@ struct WarpVote {
   }
 };
 // 0: set-up phase, 1: bounding-volume phase, 2: leaf phase, -1: every lane has left
-HFB_HD int bvh_vote(int state) {
-  const int ni = WarpVote::popc(WarpVote::ballot(state == BVS_NEED_INIT));
-  const int nb = WarpVote::popc(WarpVote::ballot(state == BVS_NEED_BV));
-  const int nl = WarpVote::popc(WarpVote::ballot(state == BVS_NEED_LEAF));
+// `lanes`: the lanes that run the chosen phase
+HFB_HD int bvh_vote(int state, unsigned& lanes) {
+  const unsigned mi = WarpVote::ballot(state == BVS_NEED_INIT);
+  const unsigned mb = WarpVote::ballot(state == BVS_NEED_BV);
+  const unsigned ml = WarpVote::ballot(state == BVS_NEED_LEAF);
+  const int ni = WarpVote::popc(mi), nb = WarpVote::popc(mb), nl = WarpVote::popc(ml);
+  lanes = 0;
   if (ni + nb + nl == 0) return -1;
-  if (ni >= HFB_BVH_INIT_QUORUM || nb + nl == 0) return 0;
+  if (ni >= HFB_BVH_INIT_QUORUM || nb + nl == 0) {
+    lanes = mi;
+    return 0;
+  }
+  lanes = (nl >= nb) ? ml : mb;
   return (nl >= nb) ? 2 : 1;
 }
 
@@ -1119,7 +1126,8 @@ HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err
       }
     }
     if (state == BVS_FETCH) state = src.next(job) ? BVS_NEED_INIT : BVS_EXIT;
-    const int phase = bvh_vote(state);
+    unsigned lanes;
+    const int phase = bvh_vote(state, lanes);
     if (phase < 0) break;
     if (phase == 0) {
       if (state == BVS_NEED_INIT) {
@@ -1160,8 +1168,8 @@ HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err
     } else {
       if (state == BVS_NEED_BV) {  // BVDistanceLowerBound of both children (:465-469)
         const int a1 = first_child, c1 = first_child + 1;
-        const double d1 = rss_distance(job.q.tf_mesh.R, job.q.tf_mesh.T, sbv, load_node_rss(job.q.nodes[a1]));
-        const double d2 = rss_distance(job.q.tf_mesh.R, job.q.tf_mesh.T, sbv, load_node_rss(job.q.nodes[c1]));
+        const double d1 = rss_distance(job.q.tf_mesh.R, job.q.tf_mesh.T, sbv, load_node_rss(job.q.nodes[a1]), lanes);
+        const double d2 = rss_distance(job.q.tf_mesh.R, job.q.tf_mesh.T, sbv, load_node_rss(job.q.nodes[c1]), lanes);
         out.bv_tests += 2;
         // visit the nearer child first: push the farther one below it
         if (d2 < d1) {
@@ -1260,7 +1268,8 @@ HFB_HD void bvh_shape_collide_stream(Src& src, const SolverP& P, double security
       }
     }
     if (state == BVS_FETCH) state = src.next(job) ? BVS_NEED_INIT : BVS_EXIT;
-    const int phase = bvh_vote(state);
+    unsigned lanes;
+    const int phase = bvh_vote(state, lanes);
     if (phase < 0) break;
     if (phase == 0) {
       if (state == BVS_NEED_INIT) {
