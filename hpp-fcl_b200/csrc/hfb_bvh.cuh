@@ -99,8 +99,10 @@ HFB_HD bool in_voronoi(double a, double b, double Anorm_dot_B, double Anorm_dot_
 // lanes that run a bounding-volume test together (a ballot of the warp-scheduled walk); 0 = alone
 #if defined(__CUDA_ARCH__)
 #define HFB_LANES_SYNC(m) do { if (m) __syncwarp(m); } while (0)
+#define HFB_LANES_ALL(m, p) ((m) ? (__all_sync((m), (p)) != 0) : (p))
 #else
 #define HFB_LANES_SYNC(m) do { (void)(m); } while (0)
+#define HFB_LANES_ALL(m, p) (p)
 #endif
 
 // rectDistance (RSS.cpp:121-713), closest points not requested.  The sixteen edge-pair cases
@@ -295,7 +297,8 @@ HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1
           (cb || in_voronoi(vb0, vb1, vb2, vb3, vb4, vb5, vb6)))
         kwin = k;
     }
-    HFB_LANES_SYNC(lanes);
+    // every lane of the phase has its case: stop early
+    if (HFB_LANES_ALL(lanes, kwin >= 0)) break;
   }
   if (kwin >= 0) {
     double sa = 0, sb = 0, s_ab = 0, s_at = 0, s_bt = 0;

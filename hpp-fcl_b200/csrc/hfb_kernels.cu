@@ -281,8 +281,8 @@ struct BvhDeviceSrc {
     }
   }
 };
-template <int MODE, int KINDS>
-__global__ void __launch_bounds__(64) k_bvh(const BatchArgs a) {
+template <int MODE, int KINDS, int MINB>
+__global__ void __launch_bounds__(64, MINB) k_bvh(const BatchArgs a) {
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lo = *a.range_lo, hi = *a.range_hi;
   EpaWs* ws = a.bvh_ws + tid;
@@ -483,7 +483,7 @@ struct hfb_ctx {
   Slot dev_slot;  // resources of the *_device entry points (caller's stream)
   DevBuf sup_ids, sup_dirs, sup_idx, sup_out;
   hfb_stats stats{};
-  int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0;
+  int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4;
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int kind; };
   std::vector<Ev> events;
@@ -707,7 +707,7 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
     unsigned blocks = (n + threads - 1) / threads;
     const unsigned cap = (unsigned)ctx->num_sms * 4u;
     if (blocks > cap) blocks = cap;
-    CK(sl.bvh_ws.reserve((size_t)cap * threads * sizeof(EpaWs)));
+    CK(sl.bvh_ws.reserve((size_t)cap * 2 * threads * sizeof(EpaWs)));
     if (!sl.bvh_cnt.p) {
       CK(sl.bvh_cnt.reserve(2 * sizeof(unsigned long long)));
       CK(cudaMemsetAsync(sl.bvh_cnt.p, 0, 2 * sizeof(unsigned long long), s));
@@ -720,7 +720,8 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
     ab.bvh_work = cnt + 24;
     {
       KTimer kt(ctx, s, 5);
-      k_bvh<MODE, BVK_SHAPE><<<blocks, threads, 0, s>>>(ab);
+      if (ctx->bvh_minb >= 8) k_bvh<MODE, BVK_SHAPE, 8><<<blocks * 2, threads, 0, s>>>(ab);
+      else k_bvh<MODE, BVK_SHAPE, 4><<<blocks, threads, 0, s>>>(ab);
     }
     ctx->stats.kernel_launches++;
     CK(cudaGetLastError());
@@ -730,7 +731,7 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
       ab.bvh_work = cnt + 25;
       {
         KTimer kt(ctx, s, 5);
-        k_bvh<MODE, BVK_MESH><<<blocks, threads, 0, s>>>(ab);
+        k_bvh<MODE, BVK_MESH, 4><<<blocks, threads, 0, s>>>(ab);
       }
       ctx->stats.kernel_launches++;
       CK(cudaGetLastError());
@@ -906,6 +907,7 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   c->ge = env_g("HFB_GE", HFB_GE_DEFAULT);
   if (const char* mb = getenv("HFB_MINB")) c->minb = atoi(mb);
   if (const char* ns = getenv("HFB_NSUB")) c->nsub = atoi(ns);
+  if (const char* bm = getenv("HFB_BVH_MINB")) c->bvh_minb = atoi(bm);
   for (int k = 0; k < kSlots; ++k)
     if (cudaStreamCreateWithFlags(&c->slots[k].stream, cudaStreamNonBlocking) != cudaSuccess) {
       delete c;
