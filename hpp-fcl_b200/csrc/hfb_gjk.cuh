@@ -283,13 +283,21 @@ HFB_HD bool gjk_converged(const GjkParams& P, v3 ray, v3 w, double rl, double& a
 }
 
 // GJK::evaluate (:188-370)
-template <int G, int CAPS>
-HFB_HD void gjk_evaluate(const ShapeD& sa, const ShapeD& sb, const MinkD& md, const GjkParams& P,
-                         v3 guess, int hint0, int hint1, GjkState& g) {
-  double alpha = 0;
+// GJK::evaluate (gjk.cpp:188-370) as set-up + one-iteration steps, so that a kernel can interleave the
+// iterations of different pairs (a lane whose pair is done takes the next pair instead of idling until
+// the slowest pair of its warp converges).  gjk_evaluate below is the plain loop over the same pieces.
+struct GjkLoop {  // what the do-while of the reference carries from one iteration to the next
+  double alpha, rl;
+  double ssr, upper_bound;
+  int variant;
+  v3 w, dir;
+};
+
+HFB_HD void gjk_begin(const MinkD& md, const GjkParams& P, v3 guess, int hint0, int hint1, GjkState& g, GjkLoop& L) {
+  L.alpha = 0;
   g.iterations = 0;
-  const double ssr = md.ssr0 + md.ssr1;
-  const double upper_bound = P.distance_upper_bound + ssr;
+  L.ssr = md.ssr0 + md.ssr1;
+  L.upper_bound = P.distance_upper_bound + L.ssr;
   const double tol = P.tolerance;
   g.status = HFB_GJK_NO_COLLISION;
   g.distance = 0.0;
@@ -297,101 +305,115 @@ HFB_HD void gjk_evaluate(const ShapeD& sa, const ShapeD& sb, const MinkD& md, co
   g.hint0 = hint0;
   g.hint1 = hint1;
 
-  double rl = nrm(guess);
-  if (rl < tol) {
+  L.rl = nrm(guess);
+  if (L.rl < tol) {
     g.ray = mk(-1, 0, 0);
-    rl = 1;
+    L.rl = 1;
   } else {
     g.ray = guess;
   }
-  int variant = P.variant;
-  v3 w = g.ray;
-  v3 dir = g.ray;
+  L.variant = P.variant;
+  L.w = g.ray;
+  L.dir = g.ray;
+}
 
-  do {
-    // check A (:228-243)
-    if (rl < tol) {
-      g.status = HFB_GJK_COLLISION;
-      g.distance = rl;
-      break;
-    }
-    // support direction (:246-278)
-    if (variant == HFB_GJK_DEFAULT) {
-      dir = g.ray;
-    } else if (variant == HFB_GJK_NESTEROV) {
-      if (md.normalize_support_direction) {
-        const double momentum = ((double)g.iterations + 2) / ((double)g.iterations + 3);
-        const v3 y = momentum * g.ray + (1 - momentum) * w;
-        const double y_norm = nrm(y);
-        dir = momentum * dir / nrm(dir) + (1 - momentum) * y / y_norm;
-      } else {
-        const double momentum = ((double)g.iterations + 1) / ((double)g.iterations + 3);
-        const v3 y = momentum * g.ray + (1 - momentum) * w;
-        dir = momentum * dir + (1 - momentum) * y;
-      }
-    } else {  // Polyak
-      const double momentum = 1 / ((double)g.iterations + 1);
-      dir = momentum * dir + (1 - momentum) * g.ray;
-    }
-
-    // appendVertex(curr_simplex, -dir, support_hint) (:281)
-    const SV nv = gjk_support<G, CAPS>(sa, sb, md, -dir, g.hint0, g.hint1);
-    put(g, g.rank, nv);
-    g.rank += 1;
-    w = nv.w;
-
-    // check B (:288-293)
-    const double omega = dot(dir, w) / nrm(dir);
-    if (omega > upper_bound) {
-      g.distance = omega - ssr;
-      g.status = HFB_GJK_NO_COLLISION_EARLY_STOPPED;
-      break;
-    }
-
-    // drop the momentum when the Frank-Wolfe duality gap closes (:296-304)
-    if (variant != HFB_GJK_DEFAULT) {
-      const double fw_gap = 2 * dot(g.ray, g.ray - w);
-      if (fw_gap - tol <= 0) {
-        g.rank -= 1;  // removeVertex
-        variant = HFB_GJK_DEFAULT;
-        continue;     // NB: does not advance `iterations` (do-while continue)
-      }
-    }
-
-    // check C (:308-326)
-    const bool cv = gjk_converged(P, g.ray, w, rl, alpha, omega);
-    if (g.iterations > 0 && cv) {
-      g.rank -= 1;  // removeVertex
-      if (variant != HFB_GJK_DEFAULT) {
-        variant = HFB_GJK_DEFAULT;
-        continue;
-      }
-      g.distance = rl - ssr;
-      g.status = (g.distance < tol) ? HFB_GJK_COLLISION_WITH_PENETRATION : HFB_GJK_NO_COLLISION;
-      break;
-    }
-
-    // simplex sub-solve (:330-350)
-    bool inside;
-    if (g.rank == 1) {
-      g.ray = w;
-      inside = false;
-    } else if (g.rank == 2) {
-      inside = project_line(g);
-    } else if (g.rank == 3) {
-      inside = project_triangle(g);
+// one pass through the body of the do-while; returns whether the loop goes on
+template <int G, int CAPS>
+HFB_HD bool gjk_step(const ShapeD& sa, const ShapeD& sb, const MinkD& md, const GjkParams& P, GjkState& g,
+                     GjkLoop& L) {
+  const double tol = P.tolerance;
+  // check A (:228-243)
+  if (L.rl < tol) {
+    g.status = HFB_GJK_COLLISION;
+    g.distance = L.rl;
+    return false;
+  }
+  // support direction (:246-278)
+  if (L.variant == HFB_GJK_DEFAULT) {
+    L.dir = g.ray;
+  } else if (L.variant == HFB_GJK_NESTEROV) {
+    if (md.normalize_support_direction) {
+      const double momentum = ((double)g.iterations + 2) / ((double)g.iterations + 3);
+      const v3 y = momentum * g.ray + (1 - momentum) * L.w;
+      const double y_norm = nrm(y);
+      L.dir = momentum * L.dir / nrm(L.dir) + (1 - momentum) * y / y_norm;
     } else {
-      inside = project_tetra(g);
+      const double momentum = ((double)g.iterations + 1) / ((double)g.iterations + 3);
+      const v3 y = momentum * g.ray + (1 - momentum) * L.w;
+      L.dir = momentum * L.dir + (1 - momentum) * y;
     }
-    rl = nrm(g.ray);
-    if (inside || rl == 0) {
-      g.status = HFB_GJK_COLLISION;
-      g.distance = rl;
-      break;
+  } else {  // Polyak
+    const double momentum = 1 / ((double)g.iterations + 1);
+    L.dir = momentum * L.dir + (1 - momentum) * g.ray;
+  }
+
+  // appendVertex(curr_simplex, -dir, support_hint) (:281)
+  const SV nv = gjk_support<G, CAPS>(sa, sb, md, -L.dir, g.hint0, g.hint1);
+  put(g, g.rank, nv);
+  g.rank += 1;
+  L.w = nv.w;
+
+  // check B (:288-293)
+  const double omega = dot(L.dir, L.w) / nrm(L.dir);
+  if (omega > L.upper_bound) {
+    g.distance = omega - L.ssr;
+    g.status = HFB_GJK_NO_COLLISION_EARLY_STOPPED;
+    return false;
+  }
+
+  // drop the momentum when the Frank-Wolfe duality gap closes (:296-304)
+  if (L.variant != HFB_GJK_DEFAULT) {
+    const double fw_gap = 2 * dot(g.ray, g.ray - L.w);
+    if (fw_gap - tol <= 0) {
+      g.rank -= 1;  // removeVertex
+      L.variant = HFB_GJK_DEFAULT;
+      return true;  // `continue`: does not advance `iterations`
     }
-    g.iterations += 1;
-    if (!(g.iterations < P.max_iterations)) g.status = HFB_GJK_FAILED;
-  } while (g.status == HFB_GJK_NO_COLLISION);
+  }
+
+  // check C (:308-326)
+  const bool cv = gjk_converged(P, g.ray, L.w, L.rl, L.alpha, omega);
+  if (g.iterations > 0 && cv) {
+    g.rank -= 1;  // removeVertex
+    if (L.variant != HFB_GJK_DEFAULT) {
+      L.variant = HFB_GJK_DEFAULT;
+      return true;  // `continue`
+    }
+    g.distance = L.rl - L.ssr;
+    g.status = (g.distance < tol) ? HFB_GJK_COLLISION_WITH_PENETRATION : HFB_GJK_NO_COLLISION;
+    return false;
+  }
+
+  // simplex sub-solve (:330-350)
+  bool inside;
+  if (g.rank == 1) {
+    g.ray = L.w;
+    inside = false;
+  } else if (g.rank == 2) {
+    inside = project_line(g);
+  } else if (g.rank == 3) {
+    inside = project_triangle(g);
+  } else {
+    inside = project_tetra(g);
+  }
+  L.rl = nrm(g.ray);
+  if (inside || L.rl == 0) {
+    g.status = HFB_GJK_COLLISION;
+    g.distance = L.rl;
+    return false;
+  }
+  g.iterations += 1;
+  if (!(g.iterations < P.max_iterations)) g.status = HFB_GJK_FAILED;
+  return g.status == HFB_GJK_NO_COLLISION;
+}
+
+template <int G, int CAPS>
+HFB_HD void gjk_evaluate(const ShapeD& sa, const ShapeD& sb, const MinkD& md, const GjkParams& P,
+                         v3 guess, int hint0, int hint1, GjkState& g) {
+  GjkLoop L;
+  gjk_begin(md, P, guess, hint0, hint1, g, L);
+  while (gjk_step<G, CAPS>(sa, sb, md, P, g, L)) {
+  }
 }
 
 // ---- Project::*Origin (src/intersect.cpp:570-705), parameterization only ----

@@ -77,6 +77,8 @@ struct BatchArgs {
   uint32_t* retry;            // queue indices of the items that outgrew the reduced-size EPA workspace
   unsigned* retry_count;
   unsigned sub_idx, sub_cnt;  // k_pairs: this launch takes the sub_idx-th of sub_cnt equal parts of [lo, hi)
+  unsigned* gjk_work;         // k_gjk_refill: work counter of this launch
+  unsigned iter_quorum;       // k_gjk_refill: lanes that must be mid-GJK for an iteration round to run
   const uint32_t* index_list; // optional indirection: pair ids sorted by class (k_bin_scatter)
   const unsigned* range_lo;   // device pointers to the [lo, hi) slice of index_list to process
   const unsigned* range_hi;
@@ -171,6 +173,85 @@ __global__ void __launch_bounds__(128, MINB) k_pairs(const BatchArgs a) {
         store_result<MODE>(a, i, o);
       }
     }
+  }
+}
+
+// Phase 1 for the GJK-routed primitive classes with lane refill.  GJK takes 3 to 26 iterations inside
+// one class; with a pair per lane for the whole kernel a warp runs at the pace of its slowest pair
+// (ncu: 9 of 32 lanes active per instruction).  Here a lane is in one of three states -- needs a pair,
+// iterating, needs its result extracted -- and the warp alternates between an iteration round (every
+// iterating lane does one GJK iteration) and a service round (finished lanes extract + store or queue
+// for EPA, then every free lane takes the next pair and sets it up).  Results do not depend on the
+// schedule: every pair runs gjk_begin / gjk_step* / pair_gjk_end exactly as in pair_phase1.
+__device__ __forceinline__ void push_epa_item(const BatchArgs& a, unsigned i, const GjkState& g) {
+  const unsigned slot = atomicAdd(a.queue_count, 1u);
+  atomicAdd(a.queue_count + 1, 1u);
+  EpaItem* it = a.queue + slot;
+  it->pair = i;
+  it->rank = g.rank;
+  it->hint0 = g.hint0;
+  it->hint1 = g.hint1;
+  it->gjk_iterations = g.iterations;
+  st3(it->w0 + 0, g.s0.w0);
+  st3(it->w1 + 0, g.s0.w1);
+  st3(it->w0 + 3, g.s1.w0);
+  st3(it->w1 + 3, g.s1.w1);
+  st3(it->w0 + 6, g.s2.w0);
+  st3(it->w1 + 6, g.s2.w1);
+  st3(it->w0 + 9, g.s3.w0);
+  st3(it->w1 + 9, g.s3.w1);
+}
+enum { GR_FETCH = 0, GR_ITER = 1, GR_FINISH = 2, GR_EXIT = 3 };
+template <int MODE>
+__global__ void __launch_bounds__(128, 1) k_gjk_refill(const BatchArgs a) {
+  unsigned lo = *a.range_lo, hi = *a.range_hi;
+  if (a.sub_cnt > 1) {
+    const unsigned long long len = hi - lo;
+    const unsigned l2 = lo + (unsigned)(len * a.sub_idx / a.sub_cnt);
+    hi = lo + (unsigned)(len * (a.sub_idx + 1) / a.sub_cnt);
+    lo = l2;
+  }
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned lt_mask = (1u << lane) - 1u;
+  int state = GR_FETCH;
+  unsigned i = 0;
+  GjkSetup S;
+  GjkLoop L;
+  GjkState g;
+  PairOut o;
+  for (;;) {
+    const unsigned m_iter = __ballot_sync(0xffffffffu, state == GR_ITER);
+    const unsigned m_serv = __ballot_sync(0xffffffffu, state == GR_FETCH || state == GR_FINISH);
+    if (!(m_iter | m_serv)) break;
+    if (m_serv == 0 || __popc(m_iter) >= (int)a.iter_quorum) {
+      if (state == GR_ITER) {
+        if (!gjk_step<1, CAP_PRIM>(S.a, S.b, S.md, a.P.gjk, g, L)) state = GR_FINISH;
+      }
+    } else {
+      if (state == GR_FINISH) {
+        o.iterations = 0;
+        if (pair_gjk_end(a.P, S, g, o)) push_epa_item(a, i, g);
+        else store_result<MODE>(a, i, o);
+        state = GR_FETCH;
+      }
+      // every free lane takes the next pair: one counter bump per warp
+      const unsigned m_fetch = __ballot_sync(0xffffffffu, state == GR_FETCH);
+      unsigned base = 0;
+      if (lane == (unsigned)(__ffs(m_fetch) - 1)) base = atomicAdd(a.gjk_work, (unsigned)__popc(m_fetch));
+      base = __shfl_sync(0xffffffffu, base, __ffs(m_fetch) - 1);
+      if (state == GR_FETCH) {
+        const unsigned k = lo + base + (unsigned)__popc(m_fetch & lt_mask);
+        if (k < hi) {
+          i = a.index_list[k];
+          const PairIn in = load_pair_in<CAP_PRIM>(a, i);
+          pair_gjk_begin<CAP_PRIM>(in, a.P, S, L, g, o);
+          state = GR_ITER;
+        } else {
+          state = GR_EXIT;
+        }
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -483,7 +564,7 @@ struct hfb_ctx {
   Slot dev_slot;  // resources of the *_device entry points (caller's stream)
   DevBuf sup_ids, sup_dirs, sup_idx, sup_out;
   hfb_stats stats{};
-  int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4;
+  int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4, refill = 1, iter_quorum = 20;
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int kind; };
   std::vector<Ev> events;
@@ -689,7 +770,21 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
     switch (ctx->minb) {  // register budget of the GJK kernel: 255 / 168 / 128 registers per thread
       case 3: rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE, 3>(ctx, ag, sub_work, s); break;
       case 4: rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE, 4>(ctx, ag, sub_work, s); break;
-      default: rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE, 1>(ctx, ag, sub_work, s);
+      default:
+        if (ctx->refill) {
+          ag.gjk_work = cnt + 26 + j;
+          ag.iter_quorum = (unsigned)ctx->iter_quorum;
+          const unsigned blocks = (unsigned)ctx->num_sms * 2u;  // 255 registers: 2 blocks of 128 per SM
+          {
+            KTimer kt(ctx, s, 0);
+            k_gjk_refill<MODE><<<blocks, 128, 0, s>>>(ag);
+          }
+          ctx->stats.kernel_launches++;
+          if (cudaGetLastError() != cudaSuccess) return fail(ctx, HFB_ERR_CUDA, "k_gjk_refill launch failed");
+          rc = HFB_OK;
+        } else {
+          rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE, 1>(ctx, ag, sub_work, s);
+        }
     }
     if (rc) return rc;
     if ((rc = epa_after_part(!mixed && j + 1 == nsub))) return rc;
@@ -908,6 +1003,8 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   if (const char* mb = getenv("HFB_MINB")) c->minb = atoi(mb);
   if (const char* ns = getenv("HFB_NSUB")) c->nsub = atoi(ns);
   if (const char* bm = getenv("HFB_BVH_MINB")) c->bvh_minb = atoi(bm);
+  if (const char* rf = getenv("HFB_REFILL")) c->refill = atoi(rf);
+  if (const char* iq = getenv("HFB_ITER_QUORUM")) c->iter_quorum = atoi(iq);
   for (int k = 0; k < kSlots; ++k)
     if (cudaStreamCreateWithFlags(&c->slots[k].stream, cudaStreamNonBlocking) != cudaSuccess) {
       delete c;

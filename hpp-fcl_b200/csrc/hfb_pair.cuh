@@ -129,6 +129,54 @@ HFB_HD void unswap(const GjkSetup& S, PairOut& o) {  // narrowphase.h:344-346
 // so each kernel only needs its own path: smaller code, no divergence between classes)
 enum { PATH_CLOSED = 1, PATH_GJKROUTE = 2, PATH_BOTH = 3 };
 
+// the general GJK route of phase 1 in three pieces (set-up, iterations, extraction), so that the
+// primitive-pair kernel can refill lanes between iterations; pair_phase1 chains them for everybody else
+template <int CAPS>
+HFB_HD void pair_gjk_begin(const PairIn& in, const SolverP& P, GjkSetup& S, GjkLoop& L, GjkState& g, PairOut& o) {
+  o.cached_guess = (P.initial_guess == HFB_GUESS_CACHED) ? in.cached_guess : mk(1, 0, 0);
+  o.hint0 = in.hint0;
+  o.hint1 = in.hint1;
+  o.iterations = 0;
+  make_setup<CAPS>(in, S);
+  const v3 guess = initial_guess(P, in, S);
+  gjk_begin(S.md, P.gjk, guess, in.hint0, in.hint1, g, L);
+}
+// returns true when EPA must still run (g holds GJK's final simplex)
+HFB_HD bool pair_gjk_end(const SolverP& P, const GjkSetup& S, GjkState& g, PairOut& o) {
+  o.iterations = g.iterations & 0xffffu;
+  o.status = pack_status(g.status, HFB_EPA_DID_NOT_RUN, HFB_PATH_GJK);
+  switch (g.status) {
+    case HFB_GJK_FAILED:
+    case HFB_GJK_NO_COLLISION:
+    case HFB_GJK_COLLISION_WITH_PENETRATION: {  // GJKExtractWitnessPointsAndNormal :610-636
+      o.cached_guess = g.ray;
+      o.hint0 = g.hint0;
+      o.hint1 = g.hint1;
+      o.distance = g.distance;
+      gjk_witness(g, S.md, o.p1, o.p2, o.normal);
+      recentre(S.tfa, o.distance, o.p1, o.p2, o.normal);
+      unswap(S, o);
+    } break;
+    case HFB_GJK_NO_COLLISION_EARLY_STOPPED:  // :589-608
+      o.cached_guess = g.ray;
+      o.hint0 = g.hint0;
+      o.hint1 = g.hint1;
+      o.distance = g.distance;
+      o.p1 = o.p2 = o.normal = nan3();
+      break;
+    default:  // HFB_GJK_COLLISION
+      if (!P.compute_penetration) {  // :638-656
+        o.hint0 = g.hint0;
+        o.hint1 = g.hint1;
+        o.distance = g.distance;
+        o.p1 = o.p2 = o.normal = nan3();
+      } else {
+        return true;
+      }
+  }
+  return false;
+}
+
 // ---- phase 1 -----------------------------------------------------------------
 // returns true when EPA must still run (g holds GJK's final simplex).
 template <int G, int CAPS, int PATHS = PATH_BOTH>
@@ -214,41 +262,11 @@ HFB_HD bool pair_phase1(const PairIn& in, const SolverP& P, PairOut& o, GjkState
   }
 
   GjkSetup S;
-  make_setup<CAPS>(in, S);
-  const v3 guess = initial_guess(P, in, S);
-  gjk_evaluate<G, CAPS>(S.a, S.b, S.md, P.gjk, guess, in.hint0, in.hint1, g);
-  o.iterations = g.iterations & 0xffffu;
-  o.status = pack_status(g.status, HFB_EPA_DID_NOT_RUN, HFB_PATH_GJK);
-  switch (g.status) {
-    case HFB_GJK_FAILED:
-    case HFB_GJK_NO_COLLISION:
-    case HFB_GJK_COLLISION_WITH_PENETRATION: {  // GJKExtractWitnessPointsAndNormal :610-636
-      o.cached_guess = g.ray;
-      o.hint0 = g.hint0;
-      o.hint1 = g.hint1;
-      o.distance = g.distance;
-      gjk_witness(g, S.md, o.p1, o.p2, o.normal);
-      recentre(S.tfa, o.distance, o.p1, o.p2, o.normal);
-      unswap(S, o);
-    } break;
-    case HFB_GJK_NO_COLLISION_EARLY_STOPPED:  // :589-608
-      o.cached_guess = g.ray;
-      o.hint0 = g.hint0;
-      o.hint1 = g.hint1;
-      o.distance = g.distance;
-      o.p1 = o.p2 = o.normal = nan3();
-      break;
-    default:  // HFB_GJK_COLLISION
-      if (!P.compute_penetration) {  // :638-656
-        o.hint0 = g.hint0;
-        o.hint1 = g.hint1;
-        o.distance = g.distance;
-        o.p1 = o.p2 = o.normal = nan3();
-      } else {
-        return true;
-      }
+  GjkLoop L;
+  pair_gjk_begin<CAPS>(in, P, S, L, g, o);
+  while (gjk_step<G, CAPS>(S.a, S.b, S.md, P.gjk, g, L)) {
   }
-  return false;
+  return pair_gjk_end(P, S, g, o);
 }
 
 // ---- phase 2: EPA + EPAExtractWitnessPointsAndNormal (narrowphase.h:514-583, 658-723)

@@ -236,8 +236,12 @@ typedef struct hfb_bvh_node {
 } hfb_bvh_node;
 /* Returns the BVH id in *bvh_id; a shape record {type = HFB_BV_OBBRSS, data = bvh id}
  * registered with hfb_geom_register_shapes gives the handle used in batches.  Supported
- * partners: the primitive shapes and ConvexBase (mesh-shape distance and collide,
- * either operand order); mesh-mesh pairs are reported as unsupported. */
+ * partners: the primitive shapes and ConvexBase (mesh-shape distance and collide, either
+ * operand order: BVHShapeCollider / BVHShapeDistancer<OBBRSS, S>, collision_func_matrix.cpp:
+ * 97-186, distance_func_matrix.cpp:77-127) and another BVHModel<OBBRSS> (mesh-mesh:
+ * BVHCollide<OBBRSS> collision_func_matrix.cpp:248-257, BVHDistance<OBBRSS>
+ * distance_func_matrix.cpp:259-268; both contact primitive ids b1, b2 are returned, the
+ * normal of a mesh-mesh distance is NaN as the reference never writes it). */
 int hfb_geom_register_bvh_obbrss(hfb_ctx* ctx, const hfb_bvh_node* nodes,
                                  uint32_t num_nodes, const double* vertices,
                                  uint32_t num_vertices, const uint32_t* triangles,
