@@ -79,6 +79,7 @@ struct BatchArgs {
   unsigned sub_idx, sub_cnt;  // k_pairs: this launch takes the sub_idx-th of sub_cnt equal parts of [lo, hi)
   unsigned* gjk_work;         // k_gjk_refill: work counter of this launch
   unsigned iter_quorum;       // k_gjk_refill: lanes that must be mid-GJK for an iteration round to run
+  unsigned stage;             // lane-group k_pairs: TMA-stage the hulls' vertex blocks into shared memory
   const uint32_t* index_list; // optional indirection: pair ids sorted by class (k_bin_scatter)
   const unsigned* range_lo;   // device pointers to the [lo, hi) slice of index_list to process
   const unsigned* range_hi;
@@ -133,8 +134,88 @@ __device__ __forceinline__ void st3(double* p, v3 v) {
 __device__ __forceinline__ v3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
 
 // ------------------------------------------------------------------ phase 1 --
+// ---- TMA staging of ConvexBase vertex blocks (lane-group kernels) -------------------------------
+// A group's two hulls are copied once per pair from the arena into the group's shared-memory slots by
+// the copy engine (cp.async.bulk, completion on an mbarrier); the GJK loop's support argmax then reads
+// shared memory.  One SoA block x[vpad] y[vpad] z[vpad] is contiguous and 16-byte aligned in the pool
+// (hfb_arena.cuh), i.e. one bulk copy per hull.  Hulls above HFB_STAGE_MAXV vertices stay in global memory.
+#define HFB_STAGE_MAXV 64
+#define HFB_STAGE_SLOT_BYTES (3 * HFB_STAGE_MAXV * 8)
+struct __align__(16) StageGroup {  // double-buffered: the next pair's hulls land while this pair computes
+  double slot[2][2][3 * HFB_STAGE_MAXV];  // [buffer][operand]
+  unsigned long long mbar[2];
+};
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* m, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(m)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* m, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(m)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* m) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(m))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* m, unsigned parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "HFB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra HFB_DONE;\n\t"
+      "bra HFB_WAIT;\n\t"
+      "HFB_DONE:\n\t"
+      "}" ::"r"(smem_u32(m)),
+      "r"(parity)
+      : "memory");
+}
+// vertex block of shape handle h if it is a ConvexBase that fits a slot: pointer + bytes (else 0 bytes)
+__device__ __forceinline__ unsigned stage_block(const ArenaView& A, uint32_t h, const double*& src) {
+  const hfb_shape& r = A.shapes[h];
+  if (r.type != HFB_GEOM_CONVEX) return 0u;
+  const ConvexDesc& d = A.cvx[r.data];
+  const unsigned b = d.vpad * 24u;  // 3 arrays of vpad doubles
+  src = A.pool + d.off;
+  return b <= HFB_STAGE_SLOT_BYTES ? b : 0u;
+}
+// lane 0 of a group: start the copies of pair i's hulls into buffer `buf`
+__device__ __forceinline__ void stage_issue(const BatchArgs& a, unsigned i, StageGroup* sg, int buf) {
+  const double *p1 = nullptr, *p2 = nullptr;
+  const unsigned b1 = stage_block(a.A, a.h1[i], p1), b2 = stage_block(a.A, a.h2[i], p2);
+  if (b1 | b2) {
+    // the buffer was last read through the generic proxy (two pairs ago, ordered by the group sync at the
+    // end of the loop body); the copy engine writes through the async proxy
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_expect_tx(&sg->mbar[buf], b1 + b2);
+    if (b1) bulk_g2s(sg->slot[buf][0], p1, b1, &sg->mbar[buf]);
+    if (b2) bulk_g2s(sg->slot[buf][1], p2, b2, &sg->mbar[buf]);
+  }
+}
+__device__ __forceinline__ unsigned stage_bytes(const ShapeD& s) {
+  if (s.type != HFB_GEOM_CONVEX) return 0u;
+  const unsigned b = (unsigned)(s.cy - s.cx) * 24u;
+  return b <= HFB_STAGE_SLOT_BYTES ? b : 0u;
+}
+
+// ------------------------------------------------------------------ phase 1 --
 template <int G, int CAPS, int MODE, int PATHS, int MINB>
 __global__ void __launch_bounds__(128, MINB) k_pairs(const BatchArgs a) {
+  const bool STAGE = (G > 1) && (CAPS & CAP_CONVEX) && a.stage;  // uniform across the grid
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  StageGroup* sg = nullptr;
+  unsigned parity0 = 0, parity1 = 0;
+  int buf = 0;
+  if (STAGE) {
+    sg = reinterpret_cast<StageGroup*>(dyn_smem) + threadIdx.x / G;
+    if (Coop<G>::lane() == 0) {
+      mbar_init(&sg->mbar[0], 1);
+      mbar_init(&sg->mbar[1], 1);
+    }
+    Coop<G>::sync();
+  }
   const unsigned ngroups = (gridDim.x * blockDim.x) / G;
   const unsigned gid = (blockIdx.x * blockDim.x + threadIdx.x) / G;
   unsigned lo = a.index_list ? *a.range_lo : 0u;
@@ -145,9 +226,36 @@ __global__ void __launch_bounds__(128, MINB) k_pairs(const BatchArgs a) {
     hi = lo + (unsigned)(len * (a.sub_idx + 1) / a.sub_cnt);
     lo = l2;
   }
+  if (STAGE && lo + gid < hi && Coop<G>::lane() == 0)
+    stage_issue(a, a.index_list ? a.index_list[lo + gid] : lo + gid, sg, 0);
   for (unsigned k = lo + gid; k < hi; k += ngroups) {
     const unsigned i = a.index_list ? a.index_list[k] : k;
-    const PairIn in = load_pair_in<CAPS>(a, i);
+    PairIn in = load_pair_in<CAPS>(a, i);
+    if (STAGE) {
+      // next pair's hulls into the other buffer (its readers finished before the sync that ended the
+      // previous iteration)
+      if (k + ngroups < hi && Coop<G>::lane() == 0)
+        stage_issue(a, a.index_list ? a.index_list[k + ngroups] : k + ngroups, sg, buf ^ 1);
+      const unsigned b1 = stage_bytes(in.s1), b2 = stage_bytes(in.s2);
+      if (b1 | b2) {
+        mbar_wait(&sg->mbar[buf], buf ? parity1 : parity0);
+        if (buf) parity1 ^= 1u;
+        else parity0 ^= 1u;
+        if (b1) {
+          const unsigned vpad = (unsigned)(in.s1.cy - in.s1.cx);
+          in.s1.cx = sg->slot[buf][0];
+          in.s1.cy = sg->slot[buf][0] + vpad;
+          in.s1.cz = sg->slot[buf][0] + 2 * vpad;
+        }
+        if (b2) {
+          const unsigned vpad = (unsigned)(in.s2.cy - in.s2.cx);
+          in.s2.cx = sg->slot[buf][1];
+          in.s2.cy = sg->slot[buf][1] + vpad;
+          in.s2.cz = sg->slot[buf][1] + 2 * vpad;
+        }
+      }
+      buf ^= 1;
+    }
     PairOut o;
     GjkState g;
     const bool need_epa = pair_phase1<G, CAPS, PATHS>(in, a.P, o, g);
@@ -173,6 +281,7 @@ __global__ void __launch_bounds__(128, MINB) k_pairs(const BatchArgs a) {
         store_result<MODE>(a, i, o);
       }
     }
+    if (STAGE) Coop<G>::sync();  // every lane is done with the slots before the next pair's copy lands
   }
 }
 
@@ -564,7 +673,7 @@ struct hfb_ctx {
   Slot dev_slot;  // resources of the *_device entry points (caller's stream)
   DevBuf sup_ids, sup_dirs, sup_idx, sup_out;
   hfb_stats stats{};
-  int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4, refill = 1, iter_quorum = 20;
+  int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4, refill = 0, iter_quorum = 8, stage = 0;
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int kind; };
   std::vector<Ev> events;
@@ -617,9 +726,17 @@ int launch_pairs(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s
   unsigned blocks = (work + groups_per_block - 1) / groups_per_block;
   const unsigned cap = (unsigned)ctx->num_sms * 32u;  // grid-stride beyond this
   if (blocks > cap) blocks = cap;
+  const size_t smem = ((G > 1) && (CAPS & CAP_CONVEX) && a.stage) ? (size_t)groups_per_block * sizeof(StageGroup) : 0;
+  if (smem > 48 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) {
+      CK(cudaFuncSetAttribute(k_pairs<G, CAPS, MODE, PATHS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      attr_set = true;
+    }
+  }
   {
     KTimer kt(ctx, s, (CAPS != CAP_PRIM) ? 4 : (PATHS == PATH_CLOSED ? 3 : 0));
-    k_pairs<G, CAPS, MODE, PATHS, MINB><<<blocks, threads, 0, s>>>(a);
+    k_pairs<G, CAPS, MODE, PATHS, MINB><<<blocks, threads, smem, s>>>(a);
   }
   ctx->stats.kernel_launches++;
   CK(cudaGetLastError());
@@ -700,6 +817,9 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   a.epa_head = nullptr;
   a.sub_idx = 0;
   a.sub_cnt = 1;
+  a.stage = (unsigned)(ctx->stage != 0);
+  a.gjk_work = nullptr;
+  a.iter_quorum = 0;
   a.A = ctx->dview;
   CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned), s));
   CK(cudaMemsetAsync(cnt + 2, 0, 30 * sizeof(unsigned), s));
@@ -1004,6 +1124,7 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   if (const char* ns = getenv("HFB_NSUB")) c->nsub = atoi(ns);
   if (const char* bm = getenv("HFB_BVH_MINB")) c->bvh_minb = atoi(bm);
   if (const char* rf = getenv("HFB_REFILL")) c->refill = atoi(rf);
+  if (const char* st = getenv("HFB_STAGE")) c->stage = atoi(st);
   if (const char* iq = getenv("HFB_ITER_QUORUM")) c->iter_quorum = atoi(iq);
   for (int k = 0; k < kSlots; ++k)
     if (cudaStreamCreateWithFlags(&c->slots[k].stream, cudaStreamNonBlocking) != cudaSuccess) {

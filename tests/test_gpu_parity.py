@@ -171,6 +171,22 @@ def test_lane_group_sizes(g, monkeypatch):
     compare_distance(ref, got, what="G=%d" % g)
 
 
+@pytest.mark.parametrize("knob", ["HFB_STAGE", "HFB_REFILL"])
+def test_optional_kernel_paths(knob, monkeypatch):
+    """the two measured-and-kept-optional paths give the same bits: cp.async.bulk (TMA) staging of the
+    hulls' vertex blocks into shared memory, and the lane-refill GJK kernel for primitive pairs"""
+    monkeypatch.setenv(knob, "1")
+    sc, w, hc, hp = _convex_scene(False)
+    n = 40000
+    rng = np.random.default_rng(11)
+    allh = np.concatenate([hc, hp])
+    h1, h2 = allh[rng.integers(0, len(allh), n)], allh[rng.integers(0, len(allh), n)]
+    for req in (P.DistanceRequestPOD(), P.DistanceRequestPOD(gjk_variant=P.NesterovAcceleration)):
+        ref = sc.b["oracle"].batch_distance(h1, w["tf1"][:n], h2, w["tf2"][:n], req, nthreads=0)
+        got = sc.b["gpu"].batch_distance(h1, w["tf1"][:n], h2, w["tf2"][:n], req)
+        compare_distance(ref, got, what=knob)
+
+
 def test_convex_support_kernel(convex_scene):
     sc, w, hc, hp = convex_scene
     rng = np.random.default_rng(2)
