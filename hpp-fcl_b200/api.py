@@ -157,6 +157,65 @@ class TriangleP(CollisionGeometry):
         return np.stack([self.a, self.b, self.c])
 
 
+class BVHModelOBBRSS(CollisionGeometry):
+    """BVHModel<OBBRSS> (include/hpp/fcl/BVH/BVH_model.h) with the reference's build protocol; the tree is
+    built on the host by the library (hfb_bvh_build_obbrss, mean split), the queries walk it on the GPU."""
+    node_type = P.BV_OBBRSS
+
+    def __init__(self):
+        super().__init__()
+        self._verts, self._tris = [], []
+        self.vertices = self.tri_indices = self.bvs = None
+        self._begun = False
+
+    def beginModel(self, num_tris=0, num_vertices=0):
+        self._verts, self._tris = [], []
+        self.vertices = self.tri_indices = self.bvs = None
+        self._begun = True
+        return 0
+
+    def _need_begun(self):
+        if not self._begun:
+            raise ValueError("BVH construction does not follow correct sequence (beginModel first)")
+
+    def addVertex(self, p):
+        self._need_begun()
+        self._verts.append(np.asarray(p, dtype=np.float64).reshape(3))
+        return 0
+
+    def addTriangle(self, p1, p2, p3):  # BVH_model.cpp:359-414: three new vertices
+        self._need_begun()
+        o = len(self._verts)
+        for p in (p1, p2, p3):
+            self.addVertex(p)
+        self._tris.append((o, o + 1, o + 2))
+        return 0
+
+    def addSubModel(self, points, triangles):  # :470-538
+        self._need_begun()
+        o = len(self._verts)
+        for p in np.asarray(points, dtype=np.float64).reshape(-1, 3):
+            self._verts.append(p)
+        for t in np.asarray(triangles, dtype=np.int64).reshape(-1, 3):
+            self._tris.append((int(t[0]) + o, int(t[1]) + o, int(t[2]) + o))
+        return 0
+
+    def endModel(self):
+        self._need_begun()
+        if not self._tris:
+            raise ValueError("BVH construction error: empty model")
+        from .engine import build_bvh_obbrss
+        self.vertices = np.ascontiguousarray(np.stack(self._verts), dtype=np.float64)
+        self.tri_indices = np.ascontiguousarray(np.array(self._tris), dtype=np.uint32)
+        self.bvs = build_bvh_obbrss(self.vertices, self.tri_indices)
+        self.num_vertices, self.num_tris = len(self.vertices), len(self.tri_indices)
+        self._begun = False
+        return 0
+
+    def getNumBVs(self):
+        return 0 if self.bvs is None else len(self.bvs)
+
+
 # ---------------------------------------------------------- requests/results --
 class _QueryRequest:
     _pod_cls = None
@@ -262,12 +321,16 @@ class _Scene:
     def handle(self, geom):
         key = id(geom)
         ent = self._handles.get(key)
-        sig = (geom.node_type, geom._params(), geom.getSweptSphereRadius())
+        sig = (geom.node_type, geom._params(), geom.getSweptSphereRadius(), id(getattr(geom, "bvs", None)))
         if ent is not None and ent[1] == sig and ent[2] is geom:
             return ent[0]
         data = 0
         pts = geom._points()
-        if pts is not None:
+        if geom.node_type == P.BV_OBBRSS:
+            if geom.bvs is None:
+                raise ValueError("BVHModel: endModel() was not called")
+            data = self.engine.register_bvh_obbrss(geom.bvs, geom.vertices, geom.tri_indices)
+        elif pts is not None:
             data = self.engine.register_convex(pts)
         rec = P.make_shapes([geom.node_type], [geom._params()], ssr=geom.getSweptSphereRadius(), data=data)
         h = int(self.engine.register_shapes(rec)[0])

@@ -680,20 +680,38 @@ HFB_HD void bound_covariance(const ShapeD& s, const xf& tf, int n, double M[6]) 
   M[5] = s02 - S1.x * S1.z / np;
 }
 
-// projection of bound vertex i on the three axes (P[i][k] of getRadiusAndOriginAndRectangleSize)
-HFB_HD v3 bound_proj(const ShapeD& s, const xf& tf, const m3& axes, int i) {
-  const v3 v = bound_vertex(s, tf, i);
+// point sets the fitting routines run over: the bound vertices of a shape (computeBV), or the vertices
+// of a list of mesh triangles, triangle-major (BVFitter<OBBRSS>::fit, the tree builder)
+struct BoundPts {
+  const ShapeD& s;
+  const xf& tf;
+  HFB_HD v3 at(int i) const { return bound_vertex(s, tf, i); }
+};
+struct TriPts {
+  const double* verts;      // xyz triples
+  const uint32_t* tris;     // index triples
+  const uint32_t* prims;    // primitive (triangle) ids
+  HFB_HD v3 at(int i) const {
+    const double* p = verts + 3 * (size_t)tris[3 * (size_t)prims[i / 3] + (unsigned)(i % 3)];
+    return mk(p[0], p[1], p[2]);
+  }
+};
+// projection of point i on the three axes (P[i][k] of getRadiusAndOriginAndRectangleSize)
+template <class Pts>
+HFB_HD v3 pts_proj(const Pts& pts, const m3& axes, int i) {
+  const v3 v = pts.at(i);
   return mk(dot(mcol(axes, 0), v), dot(mcol(axes, 1), v), dot(mcol(axes, 2), v));
 }
 
-// getRadiusAndOriginAndRectangleSize (BVH_utility.cpp:264-482) over the bound vertices; projections
+// getRadiusAndOriginAndRectangleSize (BVH_utility.cpp:264-482) over a point set; projections
 // are recomputed per pass instead of being stored (the reference heap-allocates P[size][3]).
-HFB_HD_NOINLINE void fit_rss_rectangle(const ShapeD& s, const xf& tf, int n, RssD& bv) {
+template <class Pts>
+HFB_HD_NOINLINE void fit_rss_rectangle(const Pts& pts, int n, RssD& bv) {
   const m3& axes = bv.axes;
-  v3 P0 = bound_proj(s, tf, axes, 0);
+  v3 P0 = pts_proj(pts, axes, 0);
   double minz = P0.z, maxz = P0.z;
   for (int i = 1; i < n; ++i) {
-    const double zv = bound_proj(s, tf, axes, i).z;
+    const double zv = pts_proj(pts, axes, i).z;
     if (zv < minz) minz = zv;
     else if (zv > maxz) maxz = zv;
   }
@@ -706,18 +724,18 @@ HFB_HD_NOINLINE void fit_rss_rectangle(const ShapeD& s, const xf& tf, int n, Rss
     int minindex = 0, maxindex = 0;
     double mintmp = P0.x, maxtmp = P0.x;
     for (int i = 1; i < n; ++i) {
-      const double xv = bound_proj(s, tf, axes, i).x;
+      const double xv = pts_proj(pts, axes, i).x;
       if (xv < mintmp) { minindex = i; mintmp = xv; }
       else if (xv > maxtmp) { maxindex = i; maxtmp = xv; }
     }
-    v3 Pm = bound_proj(s, tf, axes, minindex);
+    v3 Pm = pts_proj(pts, axes, minindex);
     double dz = Pm.z - cz;
     minx = Pm.x + sqrt(fmax(radsqr - dz * dz, 0.0));
-    Pm = bound_proj(s, tf, axes, maxindex);
+    Pm = pts_proj(pts, axes, maxindex);
     dz = Pm.z - cz;
     maxx = Pm.x - sqrt(fmax(radsqr - dz * dz, 0.0));
     for (int i = 0; i < n; ++i) {
-      const v3 Pi = bound_proj(s, tf, axes, i);
+      const v3 Pi = pts_proj(pts, axes, i);
       if (Pi.x < minx) {
         dz = Pi.z - cz;
         const double x = Pi.x + sqrt(fmax(radsqr - dz * dz, 0.0));
@@ -734,18 +752,18 @@ HFB_HD_NOINLINE void fit_rss_rectangle(const ShapeD& s, const xf& tf, int n, Rss
     int minindex = 0, maxindex = 0;
     double mintmp = P0.y, maxtmp = P0.y;
     for (int i = 1; i < n; ++i) {
-      const double yv = bound_proj(s, tf, axes, i).y;
+      const double yv = pts_proj(pts, axes, i).y;
       if (yv < mintmp) { minindex = i; mintmp = yv; }
       else if (yv > maxtmp) { maxindex = i; maxtmp = yv; }
     }
-    v3 Pm = bound_proj(s, tf, axes, minindex);
+    v3 Pm = pts_proj(pts, axes, minindex);
     double dz = Pm.z - cz;
     miny = Pm.y + sqrt(fmax(radsqr - dz * dz, 0.0));
-    Pm = bound_proj(s, tf, axes, maxindex);
+    Pm = pts_proj(pts, axes, maxindex);
     dz = Pm.z - cz;
     maxy = Pm.y - sqrt(fmax(radsqr - dz * dz, 0.0));
     for (int i = 0; i < n; ++i) {
-      const v3 Pi = bound_proj(s, tf, axes, i);
+      const v3 Pi = pts_proj(pts, axes, i);
       if (Pi.y < miny) {
         dz = Pi.z - cz;
         const double y = Pi.y + sqrt(fmax(radsqr - dz * dz, 0.0));
@@ -760,7 +778,7 @@ HFB_HD_NOINLINE void fit_rss_rectangle(const ShapeD& s, const xf& tf, int n, Rss
   // corners
   const double a = sqrt(0.5);
   for (int i = 0; i < n; ++i) {
-    const v3 Pi = bound_proj(s, tf, axes, i);
+    const v3 Pi = pts_proj(pts, axes, i);
     double dx, dy, u, t;
     if (Pi.x > maxx) {
       if (Pi.y > maxy) {
@@ -886,13 +904,13 @@ HFB_HD void compute_shape_rss(const ShapeD& s, const xf& tf, RssD& bv) {  // RSS
       bv.radius = 0;
       return;
     }
-    fit_rss_rectangle(s, tf, 3, bv);
+    fit_rss_rectangle(BoundPts{s, tf}, 3, bv);
     return;
   }
   double M[6];
   bound_covariance(s, tf, n, M);
   fit_axes_from_covariance(M, bv.axes);
-  fit_rss_rectangle(s, tf, n, bv);
+  fit_rss_rectangle(BoundPts{s, tf}, n, bv);
 }
 
 HFB_HD void compute_shape_obb(const ShapeD& s, const xf& tf, ObbD& bv) {  // OBB half of computeBV<OBBRSS,S>

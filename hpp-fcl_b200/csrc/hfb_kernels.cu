@@ -25,6 +25,7 @@
 
 #include "hfb_arena.cuh"
 #include "hfb_bvh.cuh"
+#include "hfb_bvh_build.cuh"
 #include "hfb_request.cuh"
 
 using namespace hfb;
@@ -1176,6 +1177,13 @@ int hfb_geom_register_convex(hfb_ctx* ctx, const double* points, uint32_t num_po
   *convex_id = ctx->arena.add_convex(points, num_points);
   ctx->committed = false;
   return HFB_OK;
+}
+
+int hfb_bvh_build_obbrss(const double* vertices, uint32_t num_vertices, const uint32_t* triangles,
+                         uint32_t num_triangles, hfb_bvh_node* nodes_out, uint32_t nodes_capacity) {
+  if (num_triangles == 0 || nodes_capacity < 2 * num_triangles - 1) return HFB_ERR_INVALID_ARGUMENT;
+  return build_obbrss_tree(vertices, num_vertices, triangles, num_triangles, nodes_out) ? HFB_OK
+                                                                                        : HFB_ERR_INVALID_ARGUMENT;
 }
 
 int hfb_geom_register_bvh_obbrss(hfb_ctx* ctx, const hfb_bvh_node* nodes, uint32_t num_nodes, const double* vertices,

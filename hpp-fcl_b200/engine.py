@@ -43,6 +43,7 @@ def load_library(path=None):
     L.hfb_geom_register_shapes.argtypes = [vp, vp, sz, vp]
     L.hfb_geom_register_convex.argtypes = [vp, vp, u32, vp]
     L.hfb_geom_register_bvh_obbrss.argtypes = [vp, vp, u32, vp, u32, vp, u32, vp]
+    L.hfb_bvh_build_obbrss.argtypes = [vp, u32, vp, u32, vp, u32]
     L.hfb_geom_commit.argtypes = [vp]
     L.hfb_geom_device_arena.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
     L.hfb_geom_num_shapes.argtypes = [vp]
@@ -58,6 +59,19 @@ def load_library(path=None):
     if path == library_path():
         _LIB = L
     return L
+
+
+def build_bvh_obbrss(vertices, triangles):
+    """Host-side OBBRSS tree of a triangle mesh (BVHModel<OBBRSS>::endModel, mean split): the node array
+    hfb_geom_register_bvh_obbrss takes.  Needs no GPU."""
+    L = load_library()
+    v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+    t = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
+    nodes = np.zeros(max(2 * t.shape[0] - 1, 0), dtype=P.bvh_node_dtype)
+    rc = L.hfb_bvh_build_obbrss(_ptr(v), v.shape[0], _ptr(t), t.shape[0], _ptr(nodes), nodes.shape[0])
+    if rc != 0:
+        raise EngineError("hfb_bvh_build_obbrss: %s" % _ERR.get(rc, rc))
+    return nodes
 
 
 def _ptr(a):
@@ -112,6 +126,10 @@ class Engine:
         return handles
 
     def register_bvh_obbrss(self, nodes, vertices, triangles):
+        """nodes: BVHModel<OBBRSS>::bvs as hfb_bvh_node records (the reference's own tree, or
+        build_bvh_obbrss(vertices, triangles)); None builds it here."""
+        if nodes is None:
+            nodes = build_bvh_obbrss(vertices, triangles)
         nodes = np.ascontiguousarray(nodes, dtype=P.bvh_node_dtype)
         v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
         t = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)

@@ -104,7 +104,7 @@ enum NODE_TYPE {  // collision_object.h:65-89 (subset)
   GEOM_BOX = HFB_GEOM_BOX, GEOM_SPHERE = HFB_GEOM_SPHERE, GEOM_CAPSULE = HFB_GEOM_CAPSULE,
   GEOM_CONE = HFB_GEOM_CONE, GEOM_CYLINDER = HFB_GEOM_CYLINDER, GEOM_CONVEX = HFB_GEOM_CONVEX,
   GEOM_PLANE = HFB_GEOM_PLANE, GEOM_HALFSPACE = HFB_GEOM_HALFSPACE, GEOM_TRIANGLE = HFB_GEOM_TRIANGLE,
-  GEOM_ELLIPSOID = HFB_GEOM_ELLIPSOID
+  GEOM_ELLIPSOID = HFB_GEOM_ELLIPSOID, BV_OBBRSS = HFB_BV_OBBRSS
 };
 
 class CollisionGeometry {
@@ -114,6 +114,13 @@ class CollisionGeometry {
   // flattening hooks used by the arena
   virtual void params(double p[3]) const { p[0] = p[1] = p[2] = 0; }
   virtual const std::vector<Vec3f>* vertices() const { return nullptr; }
+  // triangle meshes: flattened tree + geometry (null for shapes)
+  struct MeshData {
+    const std::vector<hfb_bvh_node>* nodes;
+    const std::vector<double>* verts;
+    const std::vector<uint32_t>* tris;
+  };
+  virtual bool mesh(MeshData&) const { return false; }
 };
 
 class ShapeBase : public CollisionGeometry {  // geometric_shapes.h:59-102
@@ -181,6 +188,92 @@ class TriangleP : public ShapeBase {  // :109-162
 
  private:
   std::vector<Vec3f> abc;
+};
+// BVHModel<OBBRSS> (include/hpp/fcl/BVH/BVH_model.h): the build protocol of the reference
+// (beginModel / addVertex / addTriangle / addSubModel / endModel), triangles only, SPLIT_METHOD_MEAN.
+// endModel() builds the tree on the host (hfb_bvh_build_obbrss: bit-identical to the reference's
+// BVHModel::bvs); queries walk it on the GPU.  Other BV types are not provided.
+struct OBBRSS {};
+struct Triangle {  // data_types.h
+  size_t vids[3];
+  Triangle() : vids{0, 0, 0} {}
+  Triangle(size_t a, size_t b, size_t c) : vids{a, b, c} {}
+  size_t operator[](int i) const { return vids[i]; }
+};
+enum BVHBuildState { BVH_BUILD_STATE_EMPTY, BVH_BUILD_STATE_BEGUN, BVH_BUILD_STATE_PROCESSED };
+enum BVHReturnCode { BVH_OK = 0, BVH_ERR_BUILD_OUT_OF_SEQUENCE = -2, BVH_ERR_BUILD_EMPTY_MODEL = -3 };
+template <typename BV>
+class BVHModel;
+template <>
+class BVHModel<OBBRSS> : public CollisionGeometry {
+ public:
+  NODE_TYPE getNodeType() const override { return BV_OBBRSS; }
+  unsigned num_tris = 0, num_vertices = 0;
+  BVHBuildState build_state = BVH_BUILD_STATE_EMPTY;
+  int beginModel(unsigned num_tris_ = 0, unsigned num_vertices_ = 0) {  // BVH_model.cpp:226-263
+    if (build_state != BVH_BUILD_STATE_EMPTY) {
+      verts_.clear();
+      tris_.clear();
+      nodes_.clear();
+      num_tris = num_vertices = 0;
+    }
+    tris_.reserve(3 * (size_t)num_tris_);
+    verts_.reserve(3 * (size_t)num_vertices_);
+    build_state = BVH_BUILD_STATE_BEGUN;
+    return BVH_OK;
+  }
+  int addVertex(const Vec3f& p) {
+    if (build_state != BVH_BUILD_STATE_BEGUN) return BVH_ERR_BUILD_OUT_OF_SEQUENCE;
+    for (int k = 0; k < 3; ++k) verts_.push_back(p[k]);
+    ++num_vertices;
+    return BVH_OK;
+  }
+  int addTriangle(const Vec3f& p1, const Vec3f& p2, const Vec3f& p3) {  // :359-414: three new vertices
+    if (build_state != BVH_BUILD_STATE_BEGUN) return BVH_ERR_BUILD_OUT_OF_SEQUENCE;
+    const uint32_t offset = num_vertices;
+    addVertex(p1);
+    addVertex(p2);
+    addVertex(p3);
+    tris_.push_back(offset);
+    tris_.push_back(offset + 1);
+    tris_.push_back(offset + 2);
+    ++num_tris;
+    return BVH_OK;
+  }
+  int addSubModel(const std::vector<Vec3f>& ps, const std::vector<Triangle>& ts) {  // :470-538
+    if (build_state != BVH_BUILD_STATE_BEGUN) return BVH_ERR_BUILD_OUT_OF_SEQUENCE;
+    const uint32_t offset = num_vertices;
+    for (const Vec3f& p : ps) addVertex(p);
+    for (const Triangle& t : ts) {
+      for (int k = 0; k < 3; ++k) tris_.push_back((uint32_t)t[k] + offset);
+      ++num_tris;
+    }
+    return BVH_OK;
+  }
+  int endModel() {  // :540-586 + buildTree
+    if (build_state != BVH_BUILD_STATE_BEGUN) return BVH_ERR_BUILD_OUT_OF_SEQUENCE;
+    if (num_tris == 0) return BVH_ERR_BUILD_EMPTY_MODEL;
+    nodes_.resize(2 * (size_t)num_tris - 1);
+    if (hfb_bvh_build_obbrss(verts_.data(), num_vertices, tris_.data(), num_tris, nodes_.data(),
+                             (uint32_t)nodes_.size()) != HFB_OK)
+      throw std::invalid_argument("BVHModel: invalid triangle indices");
+    build_state = BVH_BUILD_STATE_PROCESSED;
+    return BVH_OK;
+  }
+  unsigned getNumBVs() const { return (unsigned)nodes_.size(); }
+  const hfb_bvh_node& getBV(unsigned i) const { return nodes_[i]; }
+  bool mesh(MeshData& m) const override {
+    if (build_state != BVH_BUILD_STATE_PROCESSED) throw std::invalid_argument("BVHModel: endModel() was not called");
+    m.nodes = &nodes_;
+    m.verts = &verts_;
+    m.tris = &tris_;
+    return true;
+  }
+
+ private:
+  std::vector<double> verts_;
+  std::vector<uint32_t> tris_;
+  std::vector<hfb_bvh_node> nodes_;
 };
 typedef std::shared_ptr<CollisionGeometry> CollisionGeometryPtr_t;
 
@@ -320,6 +413,8 @@ class Context {
   ~Context() { hfb_ctx_destroy(ctx); }
   hfb_ctx* raw() { return ctx; }
   uint32_t handle(const CollisionGeometry* g) {
+    CollisionGeometry::MeshData md;
+    if (g->mesh(md)) return mesh_handle(g, md);
     hfb_shape rec;
     rec.type = (uint32_t)g->getNodeType();
     rec.data = 0;
@@ -357,6 +452,28 @@ class Context {
     dirty = true;
     return h;
   }
+  uint32_t mesh_handle(const CollisionGeometry* g, const CollisionGeometry::MeshData& md) {
+    auto it = handles.find(g);
+    if (it != handles.end()) {
+      const Entry& e = it->second;
+      if (e.rec.type == HFB_BV_OBBRSS && e.verts == *md.verts && e.tris == *md.tris) return e.handle;
+      handles.erase(it);
+    }
+    Entry ent;
+    ent.rec = hfb_shape{};
+    ent.rec.type = HFB_BV_OBBRSS;
+    check(hfb_geom_register_bvh_obbrss(ctx, md.nodes->data(), (uint32_t)md.nodes->size(), md.verts->data(),
+                                       (uint32_t)(md.verts->size() / 3), md.tris->data(),
+                                       (uint32_t)(md.tris->size() / 3), &ent.rec.data));
+    uint32_t h;
+    check(hfb_geom_register_shapes(ctx, &ent.rec, 1, &h));
+    ent.handle = h;
+    ent.verts = *md.verts;
+    ent.tris = *md.tris;
+    handles[g] = ent;
+    dirty = true;
+    return h;
+  }
   void invalidate(const CollisionGeometry* g) { handles.erase(g); }
   void commit() {
     if (dirty) check(hfb_geom_commit(ctx));
@@ -379,6 +496,7 @@ class Context {
     uint32_t handle = 0;
     size_t nverts = 0;
     std::vector<double> verts;
+    std::vector<uint32_t> tris;
   };
   hfb_ctx* ctx = nullptr;
   std::unordered_map<const CollisionGeometry*, Entry> handles;

@@ -242,6 +242,14 @@ typedef struct hfb_bvh_node {
  * BVHCollide<OBBRSS> collision_func_matrix.cpp:248-257, BVHDistance<OBBRSS>
  * distance_func_matrix.cpp:259-268; both contact primitive ids b1, b2 are returned, the
  * normal of a mesh-mesh distance is NaN as the reference never writes it). */
+/* Host-side tree builder, no context or GPU involved: BVHModel<OBBRSS>::endModel() for a triangle
+ * model with the default SPLIT_METHOD_MEAN (src/BVH/BVH_model.cpp:860-960, BV_fitter.cpp:501-531,
+ * BV_splitter.cpp:80-118,242-278).  Writes 2 * num_triangles - 1 nodes, bit-identical to the
+ * reference's BVHModel::bvs for the same vertices/triangles; pass them to
+ * hfb_geom_register_bvh_obbrss.  A caller that already holds a reference BVHModel passes its bvs
+ * instead and never calls this. */
+int hfb_bvh_build_obbrss(const double* vertices, uint32_t num_vertices, const uint32_t* triangles,
+                         uint32_t num_triangles, hfb_bvh_node* nodes_out, uint32_t nodes_capacity);
 int hfb_geom_register_bvh_obbrss(hfb_ctx* ctx, const hfb_bvh_node* nodes,
                                  uint32_t num_nodes, const double* vertices,
                                  uint32_t num_vertices, const uint32_t* triangles,

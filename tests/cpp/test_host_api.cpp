@@ -122,6 +122,50 @@ int main() {
     std::vector<hfb_contact> cc = batch.collide(CollisionRequest());
     CHECK(cc[10].num_contacts == 1 && cc[90].num_contacts == 0);
   }
+  {  // BVHModel<OBBRSS>: a unit cube as 12 triangles, the build protocol of the reference
+     // (test/utility.cpp generateBVHModel(Box) style); mesh-shape and mesh-mesh queries
+    BVHModel<OBBRSS> cube;
+    std::vector<Vec3f> ps;
+    for (int i = 0; i < 8; ++i) ps.push_back(Vec3f((i & 1) ? .5 : -.5, (i & 2) ? .5 : -.5, (i & 4) ? .5 : -.5));
+    const int q[6][4] = {{0, 2, 3, 1}, {4, 5, 7, 6}, {0, 1, 5, 4}, {2, 6, 7, 3}, {0, 4, 6, 2}, {1, 3, 7, 5}};
+    std::vector<Triangle> ts;
+    for (int f = 0; f < 6; ++f) {
+      ts.push_back(Triangle(q[f][0], q[f][1], q[f][2]));
+      ts.push_back(Triangle(q[f][0], q[f][2], q[f][3]));
+    }
+    CHECK(cube.addVertex(Vec3f(0, 0, 0)) == BVH_ERR_BUILD_OUT_OF_SEQUENCE);
+    cube.beginModel();
+    cube.addSubModel(ps, ts);
+    CHECK(cube.endModel() == BVH_OK);
+    CHECK(cube.getNodeType() == BV_OBBRSS && cube.getNumBVs() == 23 && cube.num_tris == 12);
+    Sphere sph(0.25);
+    DistanceRequest dreq(true, true, 0, 0);
+    DistanceResult dres;
+    // sphere 1 away from the +x face: distance 1 - 0.5 - 0.25
+    double d = distance(&cube, Transform3f(), &sph, Transform3f(Vec3f(1, 0.1, -0.2)), dreq, dres);
+    CHECK(std::fabs(d - 0.25) < 1e-9);
+    CHECK(dres.b1 >= 0 && dres.b1 < 12 && dres.b2 == -1);
+    CHECK(std::fabs(dres.nearest_points[0][0] - 0.5) < 1e-9 && std::fabs(dres.nearest_points[1][0] - 0.75) < 1e-9);
+    // operands swapped: same distance, points swapped, triangle id still reported in b1 (distance.cpp:74-89)
+    DistanceResult dres2;
+    d = distance(&sph, Transform3f(Vec3f(1, 0.1, -0.2)), &cube, Transform3f(), dreq, dres2);
+    CHECK(std::fabs(d - 0.25) < 1e-9 && std::fabs(dres2.nearest_points[0][0] - 0.75) < 1e-9);
+    CollisionRequest creq;
+    CollisionResult cres;
+    CHECK(collide(&cube, Transform3f(), &sph, Transform3f(Vec3f(0.7, 0, 0)), creq, cres) == 1);
+    CHECK(cres.getContact(0).b1 >= 0 && cres.getContact(0).b2 == -1);
+    cres.clear();
+    CHECK(collide(&cube, Transform3f(), &sph, Transform3f(Vec3f(0.8, 0, 0)), creq, cres) == 0);
+    // mesh-mesh: two cubes, gap 0.5 along x
+    DistanceResult mm;
+    d = distance(&cube, Transform3f(), &cube, Transform3f(Vec3f(1.5, 0.2, 0.1)), dreq, mm);
+    CHECK(std::fabs(d - 0.5) < 1e-9 && mm.b1 >= 0 && mm.b2 >= 0);
+    cres.clear();
+    CHECK(collide(&cube, Transform3f(), &cube, Transform3f(Vec3f(0.9, 0.2, 0.1)), creq, cres) == 1);
+    CHECK(cres.getContact(0).b1 >= 0 && cres.getContact(0).b2 >= 0);
+    cres.clear();
+    CHECK(collide(&cube, Transform3f(), &cube, Transform3f(Vec3f(1.1, 0.2, 0.1)), creq, cres) == 0);
+  }
   std::printf(failures ? "HOST-API-FAILED %d\n" : "HOST-API-OK\n", failures);
   return failures ? 1 : 0;
 }

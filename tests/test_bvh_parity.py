@@ -52,6 +52,24 @@ def test_builder_invariants():
     assert np.all(np.abs(loc) <= nodes["obb_extent"][0] + 1e-9)
 
 
+@pytest.mark.parametrize("seg,ring,noise", [(24, 12, 0.02), (100, 50, 0.02), (8, 5, 0.0), (3, 2, 0.0)])
+def test_product_builder_matches_reference_builder(seg, ring, noise):
+    """hfb_bvh_build_obbrss (host code of the product, no GPU) against the oracle's restatement of
+    BVHModel<OBBRSS>::endModel: every node bit-identical (fit, split, numbering)."""
+    from hppfcl_b200.engine import build_bvh_obbrss
+    from oracle import oracle_lib
+    verts, tris = W.sphere_mesh(1.0, seg, ring, noise=noise, rng=np.random.default_rng(seg))
+    orc = oracle_lib.OracleScene(P)
+    _, ref = orc.register_bvh(verts, tris)
+    got = build_bvh_obbrss(verts, tris)
+    assert ref.dtype == got.dtype and len(ref) == 2 * len(tris) - 1
+    assert ref.tobytes() == got.tobytes()
+    # degenerate / invalid input is refused, not built
+    from hppfcl_b200.engine import EngineError
+    with pytest.raises(EngineError):
+        build_bvh_obbrss(verts, np.array([[0, 1, len(verts)]], dtype=np.uint32))
+
+
 def _check(sc, backend, hm, tfm, hs, tfs):
     o, e = sc.b["oracle"], sc.b[backend]
     for req in (P.DistanceRequestPOD(), P.DistanceRequestPOD(enable_signed_distance=0),
@@ -175,6 +193,32 @@ def test_mesh_mesh_distance_is_the_true_minimum():
 def test_mesh_mesh_gpu_vs_oracle():
     sc, h1, tf1, h2, tf2, _, _ = build_mesh_pair_scene(True, False, n=3000, seg=24, ring=12)
     _check_mesh_pairs(sc, "gpu", h1, tf1, h2, tf2)
+
+
+@pytest.mark.gpu
+def test_python_api_bvh_model():
+    """the Python mirror of BVHModel<OBBRSS> + distance()/collide() against the batch path"""
+    import hppfcl_b200 as hf
+    verts, tris = W.sphere_mesh(1.0, 16, 8, noise=0.0, rng=np.random.default_rng(0))
+    m = hf.BVHModelOBBRSS()
+    with pytest.raises(ValueError):
+        m.addVertex([0, 0, 0])
+    m.beginModel()
+    m.addSubModel(verts, tris)
+    m.endModel()
+    assert m.getNumBVs() == 2 * len(tris) - 1
+    s = hf.Sphere(0.2)
+    res = hf.DistanceResult()
+    d = hf.distance(m, hf.Transform3f(), s, hf.Transform3f(T=[2.0, 0.1, 0.2]), hf.DistanceRequest(), res)
+    r = np.linalg.norm([2.0, 0.1, 0.2])
+    assert abs(d - (r - 1.0 - 0.2)) < 2e-2 and res.b1 >= 0 and res.b2 == -1  # faceted sphere: within the facet sag
+    cres = hf.CollisionResult()
+    assert hf.collide(m, hf.Transform3f(), s, hf.Transform3f(T=[1.1, 0, 0]), hf.CollisionRequest(), cres) == 1
+    cres.clear()
+    assert hf.collide(m, hf.Transform3f(), m, hf.Transform3f(T=[2.5, 0, 0]), hf.CollisionRequest(), cres) == 0
+    res.clear()
+    d = hf.distance(m, hf.Transform3f(), m, hf.Transform3f(T=[2.5, 0, 0]), hf.DistanceRequest(), res)
+    assert abs(d - 0.5) < 2e-2 and res.b1 >= 0 and res.b2 >= 0
 
 
 @pytest.mark.gpu
