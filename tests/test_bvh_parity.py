@@ -211,14 +211,14 @@ def test_python_api_bvh_model():
     res = hf.DistanceResult()
     d = hf.distance(m, hf.Transform3f(), s, hf.Transform3f(T=[2.0, 0.1, 0.2]), hf.DistanceRequest(), res)
     r = np.linalg.norm([2.0, 0.1, 0.2])
-    assert abs(d - (r - 1.0 - 0.2)) < 2e-2 and res.b1 >= 0 and res.b2 == -1  # faceted sphere: within the facet sag
+    assert 0 <= d - (r - 1.0 - 0.2) < 8e-2 and res.b1 >= 0 and res.b2 == -1  # faceted sphere: inside the true one, within the facet sag
     cres = hf.CollisionResult()
     assert hf.collide(m, hf.Transform3f(), s, hf.Transform3f(T=[1.1, 0, 0]), hf.CollisionRequest(), cres) == 1
     cres.clear()
     assert hf.collide(m, hf.Transform3f(), m, hf.Transform3f(T=[2.5, 0, 0]), hf.CollisionRequest(), cres) == 0
     res.clear()
     d = hf.distance(m, hf.Transform3f(), m, hf.Transform3f(T=[2.5, 0, 0]), hf.DistanceRequest(), res)
-    assert abs(d - 0.5) < 2e-2 and res.b1 >= 0 and res.b2 >= 0
+    assert 0 <= d - 0.5 < 0.16 and res.b1 >= 0 and res.b2 >= 0
 
 
 @pytest.mark.gpu
