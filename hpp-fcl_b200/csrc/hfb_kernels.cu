@@ -648,7 +648,7 @@ struct DevBuf {
   }
 };
 
-constexpr int kSlots = 3;
+constexpr int kSlots = 4;
 constexpr size_t kChunk = 1u << 17;  // pairs per pipelined chunk of the host entry points
 
 constexpr int kMaxParts = 8;  // phase-1 launches per batch that may each be followed by an EPA launch
@@ -674,7 +674,7 @@ struct hfb_ctx {
   Slot dev_slot;  // resources of the *_device entry points (caller's stream)
   DevBuf sup_ids, sup_dirs, sup_idx, sup_out;
   hfb_stats stats{};
-  int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4, refill = 0, iter_quorum = 8, stage = 0;
+  int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4, refill = 0, iter_quorum = 8, stage = 0, chunk = 0;
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int kind; };
   std::vector<Ev> events;
@@ -980,15 +980,21 @@ int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* 
   if ((rc = check_ready(ctx))) return rc;
   if (n == 0) return HFB_OK;
   if (!h1 || !h2 || !tf1 || !tf2 || !out) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "null buffer");
-  if ((rc = check_handles(ctx, h1, n)) || (rc = check_handles(ctx, h2, n))) return rc;
   CK(cudaSetDevice(ctx->device));
   const bool cached = req->q.gjk_initial_guess == HFB_GUESS_CACHED;
   const double* gin = cached ? req->q.cached_gjk_guess : nullptr;
   const int32_t* hin = cached ? req->q.cached_support_func_guess : nullptr;
   size_t done = 0;
   int si = 0;
+  const size_t chunk = ctx->chunk > 0 ? (size_t)ctx->chunk : kChunk;
   while (done < n) {
-    const size_t m = (n - done < kChunk) ? (n - done) : kChunk;
+    const size_t m = (n - done < chunk) ? (n - done) : chunk;
+    // handles are validated chunk by chunk, while the previous chunks are in flight.  A bad handle in a
+    // later chunk therefore surfaces after earlier chunks ran; the call still fails as a whole.
+    if ((rc = check_handles(ctx, h1 + done, m)) || (rc = check_handles(ctx, h2 + done, m))) {
+      for (int k = 0; k < kSlots; ++k) cudaStreamSynchronize(ctx->slots[k].stream);
+      return rc;
+    }
     Slot& sl = ctx->slots[si];
     cudaStream_t s = sl.stream;
     // the slot's previous chunk must have drained before its buffers are reused
@@ -1126,6 +1132,7 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   if (const char* bm = getenv("HFB_BVH_MINB")) c->bvh_minb = atoi(bm);
   if (const char* rf = getenv("HFB_REFILL")) c->refill = atoi(rf);
   if (const char* st = getenv("HFB_STAGE")) c->stage = atoi(st);
+  if (const char* ch = getenv("HFB_CHUNK")) c->chunk = atoi(ch);
   if (const char* iq = getenv("HFB_ITER_QUORUM")) c->iter_quorum = atoi(iq);
   for (int k = 0; k < kSlots; ++k)
     if (cudaStreamCreateWithFlags(&c->slots[k].stream, cudaStreamNonBlocking) != cudaSuccess) {

@@ -171,6 +171,21 @@ def test_lane_group_sizes(g, monkeypatch):
     compare_distance(ref, got, what="G=%d" % g)
 
 
+def test_reference_known_answers_on_gpu():
+    """the reference's own literal known-answer cases (tests/test_oracle_golden.py: box_box_distance.cpp,
+    gjk.cpp, capsule_*.cpp, geometric_shapes.cpp, security_margin.cpp ...) with the CUDA path as the
+    backend whose numbers are asserted"""
+    import os
+    import subprocess
+    import sys
+    from tests.common import ROOT
+    env = dict(os.environ, HFB_GOLDEN_BACKEND="gpu")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_oracle_golden.py"), "-q",
+                        "-x", "-p", "no:cacheprovider"], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    assert " passed" in r.stdout
+
+
 @pytest.mark.parametrize("knob", ["HFB_STAGE", "HFB_REFILL"])
 def test_optional_kernel_paths(knob, monkeypatch):
     """the two measured-and-kept-optional paths give the same bits: cp.async.bulk (TMA) staging of the

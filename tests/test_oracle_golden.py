@@ -52,10 +52,16 @@ def cone(r, lz):
 
 
 class Q:
-    """single-pair distance()/collide() through oracle AND emulated device code."""
+    """single-pair distance()/collide() through oracle AND emulated device code.  With
+    HFB_GOLDEN_BACKEND=gpu (tests/test_gpu_parity.py::test_reference_known_answers_on_gpu re-runs this
+    file that way) the second backend is the CUDA path through the C ABI, and the record the literal
+    numbers are checked on is the GPU's."""
 
     def __init__(self):
-        self.sc = make_scenes()
+        import os
+        self.gpu = os.environ.get("HFB_GOLDEN_BACKEND") == "gpu"
+        self.other = "gpu" if self.gpu else "emu"
+        self.sc = make_scenes(gpu=self.gpu, emu=not self.gpu)
 
     def add(self, rec):
         return int(self.sc.register_shapes(rec)[0])
@@ -66,17 +72,19 @@ class Q:
 
     def distance(self, h1, t1, h2, t2, **kw):
         req = P.DistanceRequestPOD(**kw)
+        self.sc.commit()
         ro = self.sc.b["oracle"].batch_distance([h1], t1, [h2], t2, req)
-        re = self.sc.b["emu"].batch_distance([h1], t1, [h2], t2, req)
+        re = self.sc.b[self.other].batch_distance([h1], t1, [h2], t2, req)
         compare_distance(ro, re, what="golden")
-        return ro[0]
+        return re[0] if self.gpu else ro[0]
 
     def collide(self, h1, t1, h2, t2, **kw):
         req = P.CollisionRequestPOD(**kw)
+        self.sc.commit()
         ro = self.sc.b["oracle"].batch_collide([h1], t1, [h2], t2, req)
-        re = self.sc.b["emu"].batch_collide([h1], t1, [h2], t2, req)
+        re = self.sc.b[self.other].batch_collide([h1], t1, [h2], t2, req)
         compare_distance(ro, re, what="golden")
-        return ro[0]
+        return re[0] if self.gpu else ro[0]
 
 
 def close_pct(a, b, pct):  # BOOST_CHECK_CLOSE semantics (percent)
