@@ -32,10 +32,11 @@ using namespace hfb;
 
 #define CAPS_ALL (CAP_PRIM | CAP_CONVEX | CAP_TRI)
 #define CAPS_BVH (CAPS_ALL | CAP_INLINE_PRIM)
-// lanes per pair: pairs touching ConvexBase/TriangleP (GC) and the EPA kernel (GE).
-// Instantiated for 8 / 16 / 32; the defaults can be overridden per context with the
-// environment variables HFB_GC / HFB_GE (tuning knobs, see profiles/).
-#define HFB_GC_DEFAULT 8
+// lanes per pair: pairs touching ConvexBase/TriangleP (GC: 1, 2, 4, 8, 16, 32) and the EPA kernel
+// (GE: 4, 8, 16, 32).  The defaults are the measured optimum on B200 (profiles/r01_summary.md: the
+// scalar part of a GJK iteration is repeated by every lane of the group, so small groups win until
+// divergence between the pairs of a warp takes over at 1); HFB_GC / HFB_GE override them per context.
+#define HFB_GC_DEFAULT 2
 #define HFB_GE_DEFAULT 8
 
 // pair classes of the device-side counting sort (k_bin_*): bins [0,8) closed-form
@@ -202,9 +203,9 @@ __device__ __forceinline__ unsigned stage_bytes(const ShapeD& s) {
 }
 
 // ------------------------------------------------------------------ phase 1 --
-template <int G, int CAPS, int MODE, int PATHS, int MINB>
+template <int G, int CAPS, int MODE, int PATHS, int MINB, bool STAGE_>
 __global__ void __launch_bounds__(128, MINB) k_pairs(const BatchArgs a) {
-  const bool STAGE = (G > 1) && (CAPS & CAP_CONVEX) && a.stage;  // uniform across the grid
+  constexpr bool STAGE = STAGE_ && (G > 1) && (CAPS & CAP_CONVEX);
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   StageGroup* sg = nullptr;
   unsigned parity0 = 0, parity1 = 0;
@@ -373,16 +374,17 @@ __global__ void __launch_bounds__(128, 1) k_gjk_refill(const BatchArgs a) {
 template <int G, int TIER>
 struct EpaCfg {
   typedef EpaWs WS;
-  static constexpr int GPB = (G == 32) ? 4 : 10;  // two blocks per SM (G = 8, 16); registers bound G = 32
+  static constexpr int GPB = (G == 32) ? 4 : 10;  // two blocks per SM (G <= 16); registers bound G = 32
   static constexpr int THREADS = GPB * G;
   static constexpr int MINB = 1;
 };
 template <int G>
 struct EpaCfg<G, 0> {
   typedef EpaWsSmall WS;
-  static constexpr int GPB = (G == 8) ? 16 : (G == 16 ? 16 : 8);
+  static constexpr int GPB = (G == 4) ? 24 : ((G == 8) ? 16 : (G == 16 ? 16 : 8));
   static constexpr int THREADS = GPB * G;
-  static constexpr int MINB = (G == 8) ? 3 : 1;  // G = 8: 3 blocks x 16 groups per SM, 168 registers
+  // G = 8: 3 blocks x 16 groups per SM, 168 registers; G = 4: 2 blocks x 24 groups
+  static constexpr int MINB = (G == 8) ? 3 : (G == 4 ? 2 : 1);
 };
 template <int G, int CAPS, int MODE, int TIER>
 __global__ void __launch_bounds__(EpaCfg<G, TIER>::THREADS, EpaCfg<G, TIER>::MINB) k_epa(const BatchArgs a) {
@@ -719,7 +721,7 @@ struct KTimer {
   }
 };
 
-template <int G, int CAPS, int MODE, int PATHS, int MINB = 1>
+template <int G, int CAPS, int MODE, int PATHS, int MINB = 1, bool STAGE = false>
 int launch_pairs(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s) {
   if (work == 0) return HFB_OK;
   const int threads = 128;
@@ -727,17 +729,17 @@ int launch_pairs(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s
   unsigned blocks = (work + groups_per_block - 1) / groups_per_block;
   const unsigned cap = (unsigned)ctx->num_sms * 32u;  // grid-stride beyond this
   if (blocks > cap) blocks = cap;
-  const size_t smem = ((G > 1) && (CAPS & CAP_CONVEX) && a.stage) ? (size_t)groups_per_block * sizeof(StageGroup) : 0;
+  const size_t smem = (STAGE && (G > 1) && (CAPS & CAP_CONVEX)) ? (size_t)groups_per_block * sizeof(StageGroup) : 0;
   if (smem > 48 * 1024) {
     static bool attr_set = false;
     if (!attr_set) {
-      CK(cudaFuncSetAttribute(k_pairs<G, CAPS, MODE, PATHS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      CK(cudaFuncSetAttribute(k_pairs<G, CAPS, MODE, PATHS, MINB, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_set = true;
     }
   }
   {
     KTimer kt(ctx, s, (CAPS != CAP_PRIM) ? 4 : (PATHS == PATH_CLOSED ? 3 : 0));
-    k_pairs<G, CAPS, MODE, PATHS, MINB><<<blocks, threads, smem, s>>>(a);
+    k_pairs<G, CAPS, MODE, PATHS, MINB, STAGE><<<blocks, threads, smem, s>>>(a);
   }
   ctx->stats.kernel_launches++;
   CK(cudaGetLastError());
@@ -766,6 +768,7 @@ int launch_epa(hfb_ctx* ctx, const BatchArgs& a, cudaStream_t s) {
 template <int CAPS, int MODE, int TIER>
 int launch_epa_g(hfb_ctx* ctx, const BatchArgs& a, cudaStream_t s) {
   switch (ctx->ge) {
+    case 4: return launch_epa<4, CAPS, MODE, TIER>(ctx, a, s);
     case 8: return launch_epa<8, CAPS, MODE, TIER>(ctx, a, s);
     case 16: return launch_epa<16, CAPS, MODE, TIER>(ctx, a, s);
     default: return launch_epa<32, CAPS, MODE, TIER>(ctx, a, s);
@@ -774,7 +777,14 @@ int launch_epa_g(hfb_ctx* ctx, const BatchArgs& a, cudaStream_t s) {
 template <int MODE>
 int launch_pairs_convex(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s) {
   switch (ctx->gc) {
-    case 8: return launch_pairs<8, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
+    case 1: return launch_pairs<1, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
+    case 2: return launch_pairs<2, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
+    case 4:
+      if (a.stage) return launch_pairs<4, CAPS_ALL, MODE, PATH_BOTH, 1, true>(ctx, a, work, s);
+      return launch_pairs<4, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
+    case 8:
+      if (a.stage) return launch_pairs<8, CAPS_ALL, MODE, PATH_BOTH, 1, true>(ctx, a, work, s);
+      return launch_pairs<8, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
     case 16: return launch_pairs<16, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
     default: return launch_pairs<32, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
   }
@@ -1126,6 +1136,12 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
     return (g == 8 || g == 16 || g == 32) ? g : dflt;
   };
   c->gc = env_g("HFB_GC", HFB_GC_DEFAULT);
+  if (const char* v4 = getenv("HFB_GC")) {
+    const int g = atoi(v4);
+    if (g == 1 || g == 2 || g == 4) c->gc = g;  // phase 1 also comes with 1, 2, 4 lanes per pair
+  }
+  if (const char* v4 = getenv("HFB_GE"))
+    if (atoi(v4) == 4) c->ge = 4;
   c->ge = env_g("HFB_GE", HFB_GE_DEFAULT);
   if (const char* mb = getenv("HFB_MINB")) c->minb = atoi(mb);
   if (const char* ns = getenv("HFB_NSUB")) c->nsub = atoi(ns);
