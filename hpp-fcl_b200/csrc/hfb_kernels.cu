@@ -1140,9 +1140,9 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
     const int g = atoi(v4);
     if (g == 1 || g == 2 || g == 4) c->gc = g;  // phase 1 also comes with 1, 2, 4 lanes per pair
   }
+  c->ge = env_g("HFB_GE", HFB_GE_DEFAULT);
   if (const char* v4 = getenv("HFB_GE"))
     if (atoi(v4) == 4) c->ge = 4;
-  c->ge = env_g("HFB_GE", HFB_GE_DEFAULT);
   if (const char* mb = getenv("HFB_MINB")) c->minb = atoi(mb);
   if (const char* ns = getenv("HFB_NSUB")) c->nsub = atoi(ns);
   if (const char* bm = getenv("HFB_BVH_MINB")) c->bvh_minb = atoi(bm);
