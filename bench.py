@@ -372,6 +372,15 @@ def run_ours(args):
             dom, dom_ms, dom_launches = "k_pairs<G,CAPS_ALL,0,PATH_BOTH>", kt["convex_ms"], kt["convex_launches"]
             units = float(n)
             bpp = 2 * 1536 + 192 + 8 + 96
+        # DRAM bytes of the dominant kernel per full-size launch, from the committed ncu capture of this
+        # command (profiles/r01_dominant_kernel_traffic.json; a profiler run, not measured live)
+        traffic = None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic.json")))
+            if n == (100_000 if args.workload == "config4" else 1_000_000) and args.variant == 0:
+                traffic = tj[args.workload]["traffic"]
+        except Exception:
+            pass
         pairs_ms = dom_ms / max(1, dom_launches)
         achieved = bpp * units / (pairs_ms * 1e-3) / 1e9 if pairs_ms > 0 else None
         line = {
@@ -389,7 +398,8 @@ def run_ours(args):
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": dom,
                          "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/launches_r01_final_*.csv" if traffic else None,
                          "bytes_per_pair": bpp, "pairs_per_launch": units, "kernel_ms": pairs_ms,
                          "peak_source": peak_src},
             "kernels": {"gjk_pairs_ms_per_step": kt["pairs_ms"] / args.steps,
