@@ -40,9 +40,12 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1_000_000)
     ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4"])
-    ap.add_argument("--variant", type=int, default=0, help="0 DefaultGJK, 2 NesterovAcceleration")
+    ap.add_argument("--variant", type=int, default=None,
+                    help="0 DefaultGJK, 1 Polyak, 2 NesterovAcceleration (default: 0; config3: 2, as BASELINE names it)")
     ap.add_argument("--cpu-sample", type=int, default=400_000)
     a = ap.parse_args()
+    if a.variant is None:
+        a.variant = 2 if a.workload == "config3" else 0
     if a.workload == "config4" and a.pairs == 1_000_000:
         a.pairs = 100_000  # BASELINE config 4 is quoted on 100k capsules
         a.cpu_sample = min(a.cpu_sample, 20_000)
@@ -95,7 +98,7 @@ def make_workload(args, rank):
         name = "config2: %d mixed primitive pairs (sphere/capsule/box/cylinder), GJK distance + witness points" % args.pairs
     elif args.workload == "config3":
         w = W.config3_convex_pairs(args.pairs, seed=0xFC1 + 3 + 1000 * rank)
-        name = "config3: %d ConvexBase(64) x ConvexBase(64) pairs, distance + EPA" % args.pairs
+        name = "config3: %d ConvexBase(64) x ConvexBase(64) pairs, Nesterov-accelerated GJK distance + EPA penetration/contact points" % args.pairs
     else:
         c = W.config4_mesh_vs_capsules(args.pairs, seed=0xFC1 + 4 + 1000 * rank)
         # handle table: [mesh] + capsule pool; pair k = (mesh, capsule hc[k])
@@ -377,7 +380,7 @@ def run_ours(args):
         traffic = None
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic.json")))
-            if n == (100_000 if args.workload == "config4" else 1_000_000) and args.variant == 0:
+            if n == (100_000 if args.workload == "config4" else 1_000_000) and args.variant == 0:  # capture was taken with DefaultGJK
                 traffic = tj[args.workload]["traffic"]
         except Exception:
             pass
