@@ -1267,6 +1267,15 @@ int hfb_geom_device_arena(hfb_ctx* ctx, void** base, size_t* bytes) {
 }
 
 size_t hfb_geom_num_shapes(const hfb_ctx* ctx) { return ctx ? ctx->arena.shapes.size() : 0; }
+int hfb_geom_clear(hfb_ctx* ctx) {
+  if (!ctx) return HFB_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  ctx->arena = HostArena();
+  ctx->dview = ArenaView{};
+  ctx->committed = false;
+  return HFB_OK;
+}
 
 int hfb_batch_distance(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1,
                        const uint32_t* h2, const hfb_transform* tf2, const hfb_distance_request* req,

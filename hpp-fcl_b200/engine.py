@@ -48,6 +48,7 @@ def load_library(path=None):
     L.hfb_geom_device_arena.argtypes = [vp, C.POINTER(vp), C.POINTER(sz)]
     L.hfb_geom_num_shapes.argtypes = [vp]
     L.hfb_geom_num_shapes.restype = sz
+    L.hfb_geom_clear.argtypes = [vp]
     for name in ("hfb_batch_distance", "hfb_batch_collide"):
         getattr(L, name).argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
         getattr(L, name + "_device").argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -140,6 +141,10 @@ class Engine:
 
     def commit(self):
         self._check(self.L.hfb_geom_commit(self.h))
+
+    def clear_geometry(self):
+        """drops every registered shape / hull / mesh; all handles become invalid"""
+        self._check(self.L.hfb_geom_clear(self.h))
 
     def device_arena(self):
         base = C.c_void_p()

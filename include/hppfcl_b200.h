@@ -261,6 +261,10 @@ int hfb_geom_commit(hfb_ctx* ctx);
  * layer): shape table, point pool, convex descriptors. */
 int hfb_geom_device_arena(hfb_ctx* ctx, void** base, size_t* bytes);
 size_t hfb_geom_num_shapes(const hfb_ctx* ctx);
+/* Empties the arena: every shape handle, convex id and BVH id issued so far becomes invalid.  The
+ * reference has no counterpart (geometry is caller-owned and passed by pointer on every call); this
+ * is how a long-running caller of the batch ABI drops geometry it no longer queries. */
+int hfb_geom_clear(hfb_ctx* ctx);
 
 /* ---- batched distance(): n independent (o1,tf1,o2,tf2) queries --------- */
 /* HOST buffers in/out; blocking.  Mirrors distance() of src/distance.cpp:60-109

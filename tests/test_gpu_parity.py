@@ -239,6 +239,25 @@ def test_errors_and_edge_cases(prim_scene):
     compare_distance(ref, got, what="n=1")
 
 
+def test_geometry_clear_and_reuse():
+    """hfb_geom_clear drops the arena; queries need a new registration + commit, handles restart at 0"""
+    eng = hf.Engine(0)
+    h = eng.register_shapes(P.make_shapes([P.GEOM_SPHERE, P.GEOM_BOX], [[0.5, 0, 0], [0.5, 0.5, 0.5]]))
+    eng.commit()
+    tf = W.identity_transforms(1)
+    tf2 = P.make_transforms(np.eye(3)[None], np.array([[3.0, 0, 0]]))
+    r = eng.batch_distance(h[:1], tf, h[1:], tf2)
+    assert abs(r[0]["min_distance"] - 2.0) < 1e-12
+    eng.clear_geometry()
+    with pytest.raises(hf.EngineError):
+        eng.batch_distance(h[:1], tf, h[1:], tf2)  # not committed any more
+    h2 = eng.register_shapes(P.make_shapes([P.GEOM_SPHERE, P.GEOM_SPHERE], [[1.0, 0, 0], [0.25, 0, 0]]))
+    assert list(h2) == [0, 1]
+    eng.commit()
+    r = eng.batch_distance(h2[:1], tf, h2[1:], tf2)
+    assert abs(r[0]["min_distance"] - 1.75) < 1e-12
+
+
 def test_full_size_properties():
     """1M-pair batch (BASELINE config 2 size): size-independent properties instead of the oracle:
     p2 = p1 + d*n, |n| = 1, swapping the operands mirrors the result
