@@ -1138,44 +1138,7 @@ HFB_HD int bvc_item_node(const hfb_bvh_node* nodes, int fc, int i) {
   }
   return node;
 }
-// ---- look-ahead of leaf tests ------------------------------------------------------------------------
-// A leaf test (GJK/EPA of a mesh triangle against the shape) is a pure function of the query and the
-// triangle as long as the request does not carry the solver's cached guess from leaf to leaf.  One lane
-// per warp (the lowest one waiting for a leaf round) publishes its query; the lanes that sit the round
-// out run the tests of the other leaves of its cached subtree; the owner later consumes them in DFS
-// order exactly as if it had run them itself.
-struct LeafSpec {
-  int owner;      // lane whose query the entries belong to (-1: none)
-  unsigned gen;   // that lane's query counter when it published
-  int cur;        // the leaf the owner runs itself this round
-  BvhQuery q;
-  PairIn in;
-  int prim[HFB_BVC_N];
-  double dist[HFB_BVC_N];
-  double p1[HFB_BVC_N][3], p2[HFB_BVC_N][3], nrm[HFB_BVC_N][3];
-};
-HFB_HD int lsp_find(const LeafSpec& L, int prim) {
-  for (int i = 0; i < HFB_BVC_N; ++i)
-    if (L.prim[i] == prim) return i;
-  return -1;
-}
-HFB_HD void lsp_put(LeafSpec& L, int slot, int prim, const PairOut& o) {
-  L.dist[slot] = o.distance;
-  L.p1[slot][0] = o.p1.x; L.p1[slot][1] = o.p1.y; L.p1[slot][2] = o.p1.z;
-  L.p2[slot][0] = o.p2.x; L.p2[slot][1] = o.p2.y; L.p2[slot][2] = o.p2.z;
-  L.nrm[slot][0] = o.normal.x; L.nrm[slot][1] = o.normal.y; L.nrm[slot][2] = o.normal.z;
-  L.prim[slot] = prim;
-}
-// lanes that must sit a round out before they are put to work for somebody else's query
-#define HFB_BVH_MIN_HELPERS 6
-
 #if defined(__CUDA_ARCH__)
-// true when one of the lanes in `owners` is on its seed leaf (triangle 0 of a fresh query: its bound
-// cache is empty, nothing to look ahead to)
-__device__ __forceinline__ bool seed_any(unsigned owners, bool seed) {
-  (void)owners;
-  return false && seed;
-}
 __device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 __device__ __forceinline__ v3 shfl_v3(v3 v, int src) { return mk(shfl_d(v.x, src), shfl_d(v.y, src), shfl_d(v.z, src)); }
 __device__ __forceinline__ m3 shfl_m3(const m3& A, int src) {
@@ -1195,7 +1158,7 @@ __device__ __forceinline__ m3 shfl_m3(const m3& A, int src) {
 // memory on the device), indexed by lane.
 template <int CAPS, class Src>
 HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err, double abs_err, EpaWs* ws,
-                                      BvCache* caches, LeafSpec* lspec, unsigned long long& bv_total,
+                                      BvCache* caches, unsigned long long& bv_total,
                                       unsigned long long& leaf_total) {
 #if defined(__CUDA_ARCH__)
   const int lane = (int)(threadIdx.x & 31u);
@@ -1203,11 +1166,6 @@ HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err
   const int lane = 0;
 #endif
   BvCache& cache = caches[lane];
-  LeafSpec& LS = *lspec;  // one per warp
-  const bool pure_leaves = P.initial_guess != HFB_GUESS_CACHED;
-  unsigned qgen = 0;
-  if (lane == 0) LS.owner = -1;
-  WarpVote::sync();
   BvhJob job;
   RssD sbv;
   PairIn in;
@@ -1237,21 +1195,8 @@ HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err
         const int fc = job.q.nodes[b].first_child;
         if (fc < 0) {
           leaf_prim = -(fc + 1);
-          const int k = (LS.owner == lane && LS.gen == qgen) ? lsp_find(LS, leaf_prim) : -1;
-          if (k < 0) {
-            state = BVS_NEED_LEAF;
-            break;
-          }
-          // leafComputeDistance, from the look-ahead entry
-          out.leaf_tests++;
-          if (out.min_distance > LS.dist[k]) {
-            out.min_distance = LS.dist[k];
-            out.b1 = leaf_prim;
-            out.p1 = mk(LS.p1[k][0], LS.p1[k][1], LS.p1[k][2]);
-            out.p2 = mk(LS.p2[k][0], LS.p2[k][1], LS.p2[k][2]);
-            out.normal = mk(LS.nrm[k][0], LS.nrm[k][1], LS.nrm[k][2]);
-          }
-          continue;
+          state = BVS_NEED_LEAF;
+          break;
         }
         if (sp + 2 > HFB_BVH_STACK) {  // cannot happen for trees of depth < 128
           sp = 0;
@@ -1301,100 +1246,26 @@ HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err
         stk_node[0] = 0;
         stk_d[0] = -1.0;  // root: visited unconditionally
         bvc_clear(cache);
-        ++qgen;
         // preprocess(): seed with triangle 0 (traversal_node_bvh_shape.h:457-461), not a counted leaf test
         leaf_prim = 0;
         seed = true;
         state = BVS_NEED_LEAF;
       }
     } else if (phase == 2) {
-      // leaf round.  Owners: the lanes in NEED_LEAF run their own leaf.  When enough lanes sit the round
-      // out, they run other leaves of the first owner's cached subtree into the warp's look-ahead table.
-      const bool is_owner = state == BVS_NEED_LEAF;
-      bool helper = false;
-      int my_prim = leaf_prim, slot = -1;
-      PairIn hin;
-#if defined(__CUDA_ARCH__)
-      const unsigned owners = lanes;
-      const int primary = __ffs(owners) - 1;
-      const bool spec = pure_leaves && (32 - __popc(owners)) >= HFB_BVH_MIN_HELPERS && !seed_any(owners, seed);
-      if (spec) {
-        if (lane == primary) {
-          if (LS.owner != lane || LS.gen != qgen) {
-            LS.owner = lane;
-            LS.gen = qgen;
-            for (int i = 0; i < HFB_BVC_N; ++i) LS.prim[i] = -1;
-          }
-          LS.q = job.q;
-          LS.in = in;
-          LS.cur = leaf_prim;
-        }
-        __syncwarp();
-        if (!is_owner) {
-          const int r = __popc(~owners & ((1u << lane) - 1u));  // rank among the lanes sitting out
-          if (r < HFB_BVC_N) {
-            const int node = caches[primary].node[r];
-            if (node >= 0) {
-              const int fc = LS.q.nodes[node].first_child;
-              if (fc < 0) {
-                const int prim = -(fc + 1);
-                if (prim != LS.cur && lsp_find(LS, prim) < 0) {
-                  helper = true;
-                  my_prim = prim;
-                  slot = r;
-                  hin = LS.in;
-                }
-              }
-            }
-          }
-        }
-        __syncwarp();  // every lsp_find above read the table before anybody writes to it
-      }
-#else
-      const bool spec = false;
-#endif
-      if (is_owner || helper) {  // leafComputeDistance
+      if (state == BVS_NEED_LEAF) {  // leafComputeDistance
         PairOut o;
-        bvh_leaf<CAPS>(helper ? LS.q : job.q, my_prim, P, ws, helper ? hin : in, o);
-        if (helper) {
-          lsp_put(LS, slot, my_prim, o);
-        } else {
-          if (!seed) out.leaf_tests++;
-          seed = false;
-          if (out.min_distance > o.distance) {  // DistanceResult::update: strict '>' keeps the first minimum
-            out.min_distance = o.distance;
-            out.b1 = leaf_prim;
-            out.p1 = o.p1;
-            out.p2 = o.p2;
-            out.normal = o.normal;
-          }
-          state = BVS_ADVANCE;
+        bvh_leaf<CAPS>(job.q, leaf_prim, P, ws, in, o);
+        if (!seed) out.leaf_tests++;
+        seed = false;
+        if (out.min_distance > o.distance) {  // DistanceResult::update: strict '>' keeps the first minimum
+          out.min_distance = o.distance;
+          out.b1 = leaf_prim;
+          out.p1 = o.p1;
+          out.p2 = o.p2;
+          out.normal = o.normal;
         }
+        state = BVS_ADVANCE;
       }
-#if !defined(__CUDA_ARCH__)
-      // one lane (the CPU emulation): the owner runs the other leaves of its cached subtree itself, so
-      // that the replay over look-ahead entries is exercised and checked against the oracle
-      if (is_owner && pure_leaves) {
-        if (LS.owner != lane || LS.gen != qgen) {
-          LS.owner = lane;
-          LS.gen = qgen;
-          for (int i = 0; i < HFB_BVC_N; ++i) LS.prim[i] = -1;
-        }
-        for (int r = 0; r < HFB_BVC_N; ++r) {
-          const int node = cache.node[r];
-          if (node < 0) continue;
-          const int fc = job.q.nodes[node].first_child;
-          if (fc >= 0) continue;
-          const int prim = -(fc + 1);
-          if (prim == leaf_prim || lsp_find(LS, prim) >= 0) continue;
-          PairIn tmp = in;
-          PairOut o2;
-          bvh_leaf<CAPS>(job.q, prim, P, ws, tmp, o2);
-          lsp_put(LS, r, prim, o2);
-        }
-      }
-#endif
-      (void)spec;
     } else {
       // bounding-volume round.  Owners: the lanes in NEED_BV.  Every other lane of the warp helps one owner.
       const bool is_owner = state == BVS_NEED_BV;
@@ -1403,7 +1274,6 @@ HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err
       const int n_own = __popc(owners);
       int per = (32 - n_own) / n_own;  // helpers per owner
       if (per > HFB_BVC_N - 1) per = HFB_BVC_N - 1;
-      if (per < 2) per = 0;  // a crowded round: the owners do both children themselves, nobody is drafted
       int srcl = lane, item = -1;
       if (is_owner) {
         item = 0;
