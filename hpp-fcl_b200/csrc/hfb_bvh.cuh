@@ -1100,72 +1100,14 @@ HFB_HD void bvh_write_shape_distance(hfb_distance_result* r, bool swapped, const
   r->iterations = (o.bv_tests & 0xffffu) | ((o.leaf_tests & 0xffffu) << 16);
 }
 
-// ---- look-ahead of bounding-volume lower bounds ---------------------------------------------------
-// A lower bound d(node) = rss_distance(query BV, node BV) is a pure function of the query and the node.
-// When a lane (the "owner") needs the bounds of the two children of a node, the lanes of its warp that
-// have nothing to do in this round compute, with the owner's query data, the bounds of the owner's
-// grandchildren down to four levels (2 + 4 + 8 + 16 = 30 nodes) into the owner's cache.  The owner
-// then replays the reference's decisions (order of the children, canStop, counters) over cached values
-// and only asks for a new round when it steps outside the cached subtree.  Nothing about the walk
-// changes -- only who computes a bound, and when.  A long query (a capsule near the centre of a closed
-// mesh visits thousands of nodes) is what bounds the batch; this shortens its chain of rounds.
-#define HFB_BVC_N 30
-struct BvCache {
-  int node[HFB_BVC_N];
-  double d[HFB_BVC_N];
-};
-HFB_HD void bvc_clear(BvCache& c) {
-  for (int i = 0; i < HFB_BVC_N; ++i) c.node[i] = -1;
-}
-HFB_HD int bvc_find(const BvCache& c, int node) {
-  for (int i = 0; i < HFB_BVC_N; ++i)
-    if (c.node[i] == node) return i;
-  return -1;
-}
-// node of look-ahead item i below a node whose first child is fc: items 0-1 are the children, 2-5 the
-// grandchildren, 6-13 and 14-29 the next two levels; -1 when the path ends in a leaf earlier
-HFB_HD int bvc_item_node(const hfb_bvh_node* nodes, int fc, int i) {
-  int L, p;
-  if (i < 2) { L = 1; p = i; }
-  else if (i < 6) { L = 2; p = i - 2; }
-  else if (i < 14) { L = 3; p = i - 6; }
-  else { L = 4; p = i - 14; }
-  int node = fc + ((p >> (L - 1)) & 1);
-  for (int k = L - 2; k >= 0; --k) {
-    const int f = nodes[node].first_child;
-    if (f < 0) return -1;
-    node = f + ((p >> k) & 1);
-  }
-  return node;
-}
-#if defined(__CUDA_ARCH__)
-__device__ __forceinline__ double shfl_d(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
-__device__ __forceinline__ v3 shfl_v3(v3 v, int src) { return mk(shfl_d(v.x, src), shfl_d(v.y, src), shfl_d(v.z, src)); }
-__device__ __forceinline__ m3 shfl_m3(const m3& A, int src) {
-  m3 R;
-  R.r0 = shfl_v3(A.r0, src);
-  R.r1 = shfl_v3(A.r1, src);
-  R.r2 = shfl_v3(A.r2, src);
-  return R;
-}
-#endif
-
 // orientedBVHShapeDistance + distance(node) + distanceRecurse (traversal_recurse.cpp:153-203), each
 // query on a fresh DistanceResult.  Every lane of the warp calls this together and keeps pulling
 // queries from `src` until it has none left.  A stack entry is a node still to be visited plus the
 // lower bound that canStop() re-checks when the node is popped (the reference evaluates canStop for
-// the second child after the first returned).  `caches`: one BvCache per lane of the warp (shared
-// memory on the device), indexed by lane.
+// the second child after the first returned).
 template <int CAPS, class Src>
 HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err, double abs_err, EpaWs* ws,
-                                      BvCache* caches, unsigned long long& bv_total,
-                                      unsigned long long& leaf_total) {
-#if defined(__CUDA_ARCH__)
-  const int lane = (int)(threadIdx.x & 31u);
-#else
-  const int lane = 0;
-#endif
-  BvCache& cache = caches[lane];
+                                      unsigned long long& bv_total, unsigned long long& leaf_total) {
   BvhJob job;
   RssD sbv;
   PairIn in;
@@ -1176,12 +1118,6 @@ HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err
   int state = BVS_FETCH;
   int leaf_prim = 0, first_child = 0;
   bool seed = true;
-  job.q.nodes = nullptr;
-  sbv.axes.r0 = sbv.axes.r1 = sbv.axes.r2 = mk(0, 0, 0);
-  sbv.Tr = mk(0, 0, 0);
-  sbv.l0 = sbv.l1 = sbv.radius = 0;
-  job.q.tf_mesh.R = sbv.axes;
-  job.q.tf_mesh.T = mk(0, 0, 0);
   for (;;) {
     if (state == BVS_ADVANCE) {  // pop / prune down to the next node that needs work
       state = BVS_FETCH;
@@ -1196,28 +1132,13 @@ HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err
         if (fc < 0) {
           leaf_prim = -(fc + 1);
           state = BVS_NEED_LEAF;
-          break;
-        }
-        if (sp + 2 > HFB_BVH_STACK) {  // cannot happen for trees of depth < 128
+        } else if (sp + 2 > HFB_BVH_STACK) {  // cannot happen for trees of depth < 128
           sp = 0;
-          break;
-        }
-        const int i1 = bvc_find(cache, fc), i2 = bvc_find(cache, fc + 1);
-        if (i1 < 0 || i2 < 0) {
+        } else {
           first_child = fc;
           state = BVS_NEED_BV;
-          break;
         }
-        // both bounds were computed ahead: BVDistanceLowerBound of both children (:465-469), from the cache
-        const double d1 = cache.d[i1], d2 = cache.d[i2];
-        out.bv_tests += 2;
-        if (d2 < d1) {
-          stk_node[sp] = fc; stk_d[sp] = d1; ++sp;
-          stk_node[sp] = fc + 1; stk_d[sp] = d2; ++sp;
-        } else {
-          stk_node[sp] = fc + 1; stk_d[sp] = d2; ++sp;
-          stk_node[sp] = fc; stk_d[sp] = d1; ++sp;
-        }
+        break;
       }
       if (state == BVS_FETCH) {  // walk finished
         bvh_write_shape_distance(static_cast<hfb_distance_result*>(job.rec), job.swapped, out);
@@ -1245,7 +1166,6 @@ HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err
         sp = 1;
         stk_node[0] = 0;
         stk_d[0] = -1.0;  // root: visited unconditionally
-        bvc_clear(cache);
         // preprocess(): seed with triangle 0 (traversal_node_bvh_shape.h:457-461), not a counted leaf test
         leaf_prim = 0;
         seed = true;
@@ -1267,70 +1187,10 @@ HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err
         state = BVS_ADVANCE;
       }
     } else {
-      // bounding-volume round.  Owners: the lanes in NEED_BV.  Every other lane of the warp helps one owner.
-      const bool is_owner = state == BVS_NEED_BV;
-#if defined(__CUDA_ARCH__)
-      const unsigned owners = lanes;
-      const int n_own = __popc(owners);
-      int per = (32 - n_own) / n_own;  // helpers per owner
-      if (per > HFB_BVC_N - 1) per = HFB_BVC_N - 1;
-      int srcl = lane, item = -1;
-      if (is_owner) {
-        item = 0;
-      } else if (per > 0) {
-        const int r = __popc(~owners & ((1u << lane) - 1u));  // rank among the helpers
-        const int oi = r / per;
-        if (oi < n_own) {
-          srcl = (int)__fns(owners, 0, oi + 1);
-          item = 1 + r % per;
-        }
-      }
-      // the owner's query, as seen by its helpers
-      const int fc_o = __shfl_sync(0xffffffffu, first_child, srcl);
-      const unsigned long long np = __shfl_sync(0xffffffffu, (unsigned long long)job.q.nodes, srcl);
-      const hfb_bvh_node* nodes_o = reinterpret_cast<const hfb_bvh_node*>(np);
-      const m3 R_o = shfl_m3(job.q.tf_mesh.R, srcl);
-      const v3 T_o = shfl_v3(job.q.tf_mesh.T, srcl);
-      RssD sbv_o;
-      sbv_o.axes = shfl_m3(sbv.axes, srcl);
-      sbv_o.Tr = shfl_v3(sbv.Tr, srcl);
-      sbv_o.l0 = shfl_d(sbv.l0, srcl);
-      sbv_o.l1 = shfl_d(sbv.l1, srcl);
-      sbv_o.radius = shfl_d(sbv.radius, srcl);
-      if (is_owner) bvc_clear(cache);
-      __syncwarp();
-      const int node = item >= 0 ? bvc_item_node(nodes_o, fc_o, item) : -1;
-      const unsigned m1 = __ballot_sync(0xffffffffu, node >= 0);
-      double dres = 0;
-      if (node >= 0) dres = rss_distance(R_o, T_o, sbv_o, load_node_rss(nodes_o[node]), m1);
-      if (node >= 0) {
-        BvCache& oc = caches[srcl];
-        oc.node[item] = node;
-        oc.d[item] = dres;
-      }
-      const bool need2 = is_owner && per == 0;  // no helper took the second child
-      const unsigned m2 = __ballot_sync(0xffffffffu, need2);
-      if (need2) {
-        cache.node[1] = first_child + 1;
-        cache.d[1] = rss_distance(job.q.tf_mesh.R, job.q.tf_mesh.T, sbv, load_node_rss(job.q.nodes[first_child + 1]), m2);
-      }
-      __syncwarp();
-#else
-      // one lane (the CPU emulation of the device code): the owner helps itself, so that the replay
-      // over cached bounds is exercised and checked against the oracle
-      if (is_owner) {
-        bvc_clear(cache);
-        for (int item = 0; item < HFB_BVC_N; ++item) {
-          const int node = bvc_item_node(job.q.nodes, first_child, item);
-          if (node < 0) continue;
-          cache.node[item] = node;
-          cache.d[item] = rss_distance(job.q.tf_mesh.R, job.q.tf_mesh.T, sbv, load_node_rss(job.q.nodes[node]), 0u);
-        }
-      }
-#endif
-      if (is_owner) {  // BVDistanceLowerBound of both children (:465-469)
+      if (state == BVS_NEED_BV) {  // BVDistanceLowerBound of both children (:465-469)
         const int a1 = first_child, c1 = first_child + 1;
-        const double d1 = cache.d[0], d2 = cache.d[1];
+        const double d1 = rss_distance(job.q.tf_mesh.R, job.q.tf_mesh.T, sbv, load_node_rss(job.q.nodes[a1]), lanes);
+        const double d2 = rss_distance(job.q.tf_mesh.R, job.q.tf_mesh.T, sbv, load_node_rss(job.q.nodes[c1]), lanes);
         out.bv_tests += 2;
         // visit the nearer child first: push the farther one below it
         if (d2 < d1) {

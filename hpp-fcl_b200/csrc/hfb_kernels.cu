@@ -482,10 +482,8 @@ __global__ void __launch_bounds__(64, MINB) k_bvh(const BatchArgs a) {
   unsigned long long bv_total = 0, leaf_total = 0;
   if (KINDS == BVK_SHAPE) {
     BvhDeviceSrc<MODE> src{a, lo, hi};
-    __shared__ BvCache bv_caches[64];  // one per lane; written by the lane's helpers (hfb_bvh.cuh)
     if (MODE == 0)
-      bvh_shape_distance_stream<CAPS_BVH>(src, a.P, a.B.rel_err, a.B.abs_err, ws,
-                                          bv_caches + (threadIdx.x & ~31u), bv_total, leaf_total);
+      bvh_shape_distance_stream<CAPS_BVH>(src, a.P, a.B.rel_err, a.B.abs_err, ws, bv_total, leaf_total);
     else
       bvh_shape_collide_stream<CAPS_BVH>(src, a.P, a.B.security_margin, a.B.break_distance,
                                          a.B.collision_distance_threshold, a.B.num_max_contacts, ws, bv_total,

@@ -121,8 +121,7 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
         BvhSingleSrc src;
         src.pending = bvh_make_job<CAPS_ALL, 0>(A, h1[i], t1, h2[i], t2, R, guess, hh0, hh1, &out[i], src.job);
         unsigned long long b2 = 0, l2 = 0;
-        BvCache cache;
-        bvh_shape_distance_stream<CAPS_ALL>(src, P, R.rel_err, R.abs_err, ws.get(), &cache, b2, l2);
+        bvh_shape_distance_stream<CAPS_ALL>(src, P, R.rel_err, R.abs_err, ws.get(), b2, l2);
       }
       continue;
     }
