@@ -349,6 +349,22 @@ def run_ours(args):
     e2e_value = world * n * e2e_steps / dt
     clocks = sampler.summary()
     checksum = float(np.nansum(host_out["min_distance"][:: max(1, n // 4096)]))
+    # pair-type histogram, GJK-only subset and the FP64-issue view of the pair kernels
+    path = (host_out["status"] >> 16) & 0xff
+    gjk_it = (host_out["iterations"] & 0xffff)[path == 0]
+    epa_it = (host_out["iterations"] >> 16)[path == 0]
+    workload_stats = None
+    if args.workload in ("config2", "config3"):
+        workload_stats = {"gjk_routed_pairs": int((path == 0).sum()), "closed_form_pairs": int((path == 1).sum()),
+                          "gjk_iterations_mean": float(gjk_it.mean()) if len(gjk_it) else 0.0,
+                          "gjk_iterations_max": int(gjk_it.max()) if len(gjk_it) else 0,
+                          "epa_pairs": int((epa_it > 0).sum()),
+                          "epa_iterations_mean": float(epa_it[epa_it > 0].mean()) if (epa_it > 0).any() else 0.0}
+        if args.workload == "config2":
+            names = {P.GEOM_SPHERE: "sphere", P.GEOM_CAPSULE: "capsule", P.GEOM_BOX: "box", P.GEOM_CYLINDER: "cylinder"}
+            t1, t2 = w["shapes"]["type"][w["h1"]], w["shapes"]["type"][w["h2"]]
+            workload_stats["type_histogram"] = {"%s-%s" % (names[a], names[b]): int(((t1 == a) & (t2 == b)).sum())
+                                                for a in names for b in names}
 
     if rank == 0:
         peaks = {}
@@ -413,6 +429,16 @@ def run_ours(args):
                         "bvh_ms_per_step": kt["bvh_ms"] / args.steps,
                         "epa_pairs_per_step": (st1["epa_pairs"] - st0["epa_pairs"]) / max(1, args.steps)},
         }
+        if workload_stats is not None:
+            line["workload_stats"] = workload_stats
+            # secondary view: FP64 issue.  ~450 flop per GJK iteration on primitives (SURVEY 8d estimate; the
+            # convex kernels add 6 flop per hull vertex and support call); nominal B200 FP64 (non-tensor) 37 TFLOP/s
+            it_flop = 450.0 if args.workload == "config2" else 450.0 + 2 * 64 * 6
+            gsec = (kt["pairs_ms"] if args.workload == "config2" else kt["convex_ms"]) / max(1, args.steps) * 1e-3
+            if gsec > 0:
+                line["fp64_view"] = {"flop_per_gjk_iteration_estimate": it_flop,
+                                     "achieved_tflops_estimate": workload_stats["gjk_routed_pairs"] * workload_stats["gjk_iterations_mean"] * it_flop / gsec / 1e12,
+                                     "nominal_fp64_tflops": 37.0}
         if world == 1:
             line["convex_support_kernel"] = support_kernel_roofline(eng_factory=hf.Engine, peak=peak)
             v, cores, ns = cpu_reference_rate(args, w, args.cpu_sample)
