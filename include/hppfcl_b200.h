@@ -199,7 +199,13 @@ typedef struct hfb_ctx hfb_ctx;
 
 /* ---- lifetime ---------------------------------------------------------- */
 /* Creates a context bound to CUDA device `device`. Fails with
- * HFB_ERR_NO_DEVICE when there is no usable GPU: there is no CPU fallback. */
+ * HFB_ERR_NO_DEVICE when there is no usable GPU: there is no CPU fallback.
+ * Threading: a context is thread-compatible, not thread-safe -- one thread at a time per context,
+ * any number of contexts (one per GPU, or several per GPU) in a process.  The reference's collide() /
+ * distance() are re-entrant because every call builds its solver on the stack; here the per-call
+ * state (streams, scratch buffers, the EPA queue) lives in the context.  The host entry points block
+ * until the results are in the caller's buffers; the *_device entry points enqueue on the caller's
+ * stream and return, the results are ready when that stream reaches the point of the call. */
 int hfb_ctx_create(int device, hfb_ctx** out);
 void hfb_ctx_destroy(hfb_ctx* ctx);
 const char* hfb_last_error(const hfb_ctx* ctx);
