@@ -137,10 +137,22 @@ def cpu_reference_rate(args, w, n_sample, threads=0):
     n = min(n_sample, len(w["h1"]))
     h1, h2 = hs[w["h1"][:n] % len(hs)], hs[w["h2"][:n] % len(hs)]
     req = P.DistanceRequestPOD(gjk_variant=args.variant)
-    # all host cores this process may run on; torchrun exports OMP_NUM_THREADS=1, which must not
-    # shrink the CPU arm, so the count is passed explicitly
+    # "all the host threads it can use": torchrun exports OMP_NUM_THREADS=1 and the box exposes 128 logical
+    # CPUs of which oversubscribing hurts (measured: 128 threads 6e6 pairs/s, 64 threads 3.4e7), so the
+    # thread count is calibrated on a short sample among {affinity, affinity/2, OpenMP's own default}
     if threads == 0:
-        threads = len(os.sched_getaffinity(0))
+        aff = len(os.sched_getaffinity(0))
+        cands = sorted({c for c in (aff, max(1, aff // 2), max(1, aff // 4), oracle_lib.lib().oracle_max_threads()) if c >= 1})
+        m = min(n, 50000)
+        best, best_t = 1, None
+        for c in cands:
+            orc.batch_distance(h1[:m], w["tf1"][:m], h2[:m], w["tf2"][:m], req, nthreads=c)  # spin the team up
+            t0 = time.perf_counter()
+            orc.batch_distance(h1[:m], w["tf1"][:m], h2[:m], w["tf2"][:m], req, nthreads=c)
+            dtc = time.perf_counter() - t0
+            if best_t is None or dtc < best_t:
+                best, best_t = c, dtc
+        threads = best
     cores = threads
     orc.batch_distance(h1[:20000], w["tf1"][:20000], h2[:20000], w["tf2"][:20000], req, nthreads=threads)
     t0 = time.perf_counter()
