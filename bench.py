@@ -127,12 +127,17 @@ def register(eng_or_orc, w, args, oracle=False):
     return eng_or_orc.register_shapes(P.make_shapes([P.GEOM_CONVEX] * len(cids), np.zeros((len(cids), 3)), data=cids))
 
 
+def cpu_arm_kind():
+    from oracle import oracle_lib
+    return "reference" if oracle_lib.ref_available() else "port"
+
+
 def cpu_reference_rate(args, w, n_sample, threads=0):
-    """The reference's CPU path (oracle restatement: the reference itself needs Eigen+Boost and
-    cannot be built in this image) on a bounded sample of the same workload."""
+    """The reference's CPU path on a bounded sample of the same workload: oracle/_ref (the reference's own
+    sources compiled in place, see oracle/Makefile `ref`) when it was built, else the oracle's restatement."""
     from hppfcl_b200 import _pod as P
     from oracle import oracle_lib
-    orc = oracle_lib.OracleScene(P)
+    orc = oracle_lib.RefScene(P) if oracle_lib.ref_available() else oracle_lib.OracleScene(P)
     hs = register(orc, w, args, oracle=True)
     n = min(n_sample, len(w["h1"]))
     h1, h2 = hs[w["h1"][:n] % len(hs)], hs[w["h2"][:n] % len(hs)]
@@ -179,7 +184,7 @@ def run_reference(args):
             "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "impl": "reference", "config": {"workload": name, "sample_pairs_per_step": n},
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_arm_kind(),
                              "sample": "%d pairs of the same seeded workload per step, OpenMP static over pairs" % n},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -455,8 +460,10 @@ def run_ours(args):
             line["convex_support_kernel"] = support_kernel_roofline(eng_factory=hf.Engine, peak=peak)
             v, cores, ns = cpu_reference_rate(args, w, args.cpu_sample)
             v1, _, ns1 = cpu_reference_rate(args, w, min(args.cpu_sample, 100_000), threads=1)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                    "sample": "%d pairs of the same workload, oracle (CPU restatement of hpp-fcl), OpenMP over pairs" % ns,
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_arm_kind(),
+                                    "sample": "%d pairs of the same workload, %s, OpenMP over pairs" % (
+                                        ns, "hpp-fcl's own sources (oracle/_ref)" if cpu_arm_kind() == "reference"
+                                        else "oracle (CPU restatement of hpp-fcl)"),
                                     "single_thread_value": v1}
         print(json.dumps(line))
     if world > 1:

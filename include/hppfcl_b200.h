@@ -143,8 +143,12 @@ typedef struct hfb_distance_request {
   int32_t enable_signed_distance; /* default 1 */
   int32_t enable_nearest_points;  /* default 1; read by the mesh-mesh walk only: when 0 the nearest
                                      points stay in the first mesh's frame (traversal_node_bvhs.h:527-536) */
-  double rel_err; /* BVH traversal only */
-  double abs_err; /* BVH traversal only */
+  /* carried for layout parity with DistanceRequest; like in the reference they do not influence any
+   * OBBRSS walk: the mesh-shape traversal node zeroes its copies in its constructor
+   * (internal/traversal_node_bvh_shape.h:294-295), the mesh-mesh node takes them from its own default
+   * request before the caller's is stored (internal/traversal_node_bvhs.h:409-410) */
+  double rel_err;
+  double abs_err;
 } hfb_distance_request;
 
 /* ---- CollisionRequest (collision_data.h:312-383) ----------------------- */

@@ -197,7 +197,7 @@ int oracle_batch_distance(void* sc, size_t n, const uint32_t* h1, const hfb_tran
         const Shape& ss = swap ? s1 : s2;
         if (s1.type == HFB_BV_OBBRSS && s2.type == HFB_BV_OBBRSS) {  // BVHDistance<OBBRSS> (distance_func_matrix.cpp:259-268)
           BvhQueryResult q;
-          bvhBvhDistance(*s->bvhs[(size_t)s1.p[0]], T1, *s->bvhs[(size_t)s2.p[0]], T2, req->rel_err, req->abs_err,
+          bvhBvhDistance(*s->bvhs[(size_t)s1.p[0]], T1, *s->bvhs[(size_t)s2.p[0]], T2, 0.0, 0.0 /* see below */,
                          req->enable_nearest_points != 0, q);
           r.min_distance = q.distance;
           put3(r.p1, q.p1);
@@ -215,7 +215,12 @@ int oracle_batch_distance(void* sc, size_t n, const uint32_t* h1, const hfb_tran
         } else {
           BvhQueryResult q;
           bvhShapeDistance(*s->bvhs[(size_t)sm.p[0]], swap ? T2 : T1, ss, swap ? T1 : T2, solver,
-                           req->enable_signed_distance != 0, req->rel_err, req->abs_err, q);
+                           req->enable_signed_distance != 0,
+                           // rel_err / abs_err never reach the walk: the mesh-shape node zeroes its copies in
+                           // its constructor (traversal_node_bvh_shape.h:294-295) and nothing sets them; the
+                           // mesh-mesh node copies them from its own default-constructed request
+                           // (traversal_node_bvhs.h:409-410), before initialize() stores the caller's
+                           0.0, 0.0, q);
           r.min_distance = q.distance;
           put3(r.p1, swap ? q.p2 : q.p1);
           put3(r.p2, swap ? q.p1 : q.p2);

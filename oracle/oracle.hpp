@@ -6,10 +6,12 @@
 // may build, link or call anything in this directory; the product library
 // (hpp-fcl_b200/) never does.
 //
-// Parity status: PINNED against the reference's own known-answer tests
-// (tests/test_oracle_golden.py cites each test/file:line).  The reference itself
-// cannot be compiled in this image (Eigen3 + Boost are hard requirements,
-// CMakeLists.txt:121,130 -- neither is installed), so there is no oracle/_ref.
+// Parity status: PINNED (1) against the reference's own known-answer tests
+// (tests/test_oracle_golden.py cites each test/file:line) and (2) bit for bit against
+// the reference's own sources compiled in place into oracle/_ref/ (`make ref`;
+// Eigen3 and Boost, hard requirements of the reference's headers, are not installed:
+// ref_shim/ is a minimal stand-in for the fixed-size Eigen API they use) --
+// tests/test_reference_build.py.
 //
 // Floating-point convention ("Floating-point order
 // caveat"): every 3-vector reduction is evaluated left to right,

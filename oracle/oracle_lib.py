@@ -1,8 +1,12 @@
 """ORACLE -- TEST INFRASTRUCTURE ONLY.
 
 ctypes binding of oracle/liboracle.so (the CPU restatement of the hpp-fcl hot
-path).  Imported by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
---impl reference legs ONLY; the product package never imports this module.
+path) and of oracle/_ref/libhppfcl_ref.so (the reference's own sources compiled in
+place, `make -C oracle ref`).  Imported by tests/, __graft_entry__.smoke() and
+bench.py's cpu_baseline / --impl reference legs ONLY; the product package never
+imports this module.  The restatement is pinned against the reference's known-answer
+tests (tests/test_oracle_golden.py) and, bit for bit, against the reference build
+(tests/test_reference_build.py).
 """
 import ctypes as C
 import os
@@ -173,3 +177,93 @@ class OracleScene:
               4: self.L.oracle_project_tetrahedra_origin}[len(pts)]
         fn(*[_ptr(p) for p in pts], _ptr(param), C.byref(sqr), C.byref(enc))
         return param, sqr.value, enc.value
+
+
+# ---------------------------------------------------------------------------------------------------
+# The reference itself (oracle/_ref/libhppfcl_ref.so: /root/reference compiled in place, see
+# oracle/Makefile target `ref` and oracle/ref_driver.cpp).  Same interface as OracleScene.
+_REF = None
+
+
+def ref_available():
+    return os.path.exists(os.path.join(_HERE, "_ref", "libhppfcl_ref.so"))
+
+
+def build_ref():
+    """(re)builds oracle/_ref when /root/reference is present; a no-op elsewhere"""
+    subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+    return ref_available()
+
+
+def ref_lib():
+    global _REF
+    if _REF is None:
+        L = C.CDLL(os.path.join(_HERE, "_ref", "libhppfcl_ref.so"))
+        L.ref_scene_create.restype = C.c_void_p
+        L.ref_scene_destroy.argtypes = [C.c_void_p]
+        L.ref_register_convex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.ref_register_bvh.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
+        L.ref_bvh_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32]
+        L.ref_register_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.ref_register_shapes.restype = C.c_int64
+        for name in ("ref_batch_distance", "ref_batch_collide"):
+            f = getattr(L, name)
+            f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+            f.restype = C.c_int
+        L.ref_max_threads.restype = C.c_int
+        _REF = L
+    return _REF
+
+
+class RefScene(OracleScene):
+    """The reference's own collide()/distance() behind the interface of OracleScene."""
+
+    def __init__(self, pod):
+        self.pod = pod
+        self.L = ref_lib()
+        self.h = C.c_void_p(self.L.ref_scene_create())
+
+    def close(self):
+        if self.h:
+            self.L.ref_scene_destroy(self.h)
+            self.h = None
+
+    def register_convex(self, points, tris=None):
+        if tris is None:
+            raise ValueError("the reference needs the hull's triangles (Convex<Triangle>)")
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        t = np.ascontiguousarray(tris, dtype=np.uint32).reshape(-1, 3)
+        return self.L.ref_register_convex(self.h, _ptr(pts), pts.shape[0], _ptr(t), t.shape[0])
+
+    def register_points(self, points):
+        """a bare point set (TriangleP vertices)"""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        t = np.zeros((0, 3), dtype=np.uint32)
+        return self.L.ref_register_convex(self.h, _ptr(pts), pts.shape[0], _ptr(t), 0)
+
+    def register_bvh(self, vertices, triangles):
+        v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+        t = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
+        bid = self.L.ref_register_bvh(self.h, _ptr(v), v.shape[0], _ptr(t), t.shape[0])
+        n = self.L.ref_bvh_export(self.h, bid, None, 0)
+        nodes = np.zeros(n, dtype=self.pod.bvh_node_dtype)
+        self.L.ref_bvh_export(self.h, bid, _ptr(nodes), n)
+        return bid, nodes
+
+    def register_shapes(self, shapes):
+        shapes = np.ascontiguousarray(shapes, dtype=self.pod.shape_dtype)
+        first = self.L.ref_register_shapes(self.h, _ptr(shapes), shapes.shape[0])
+        if first < 0:
+            raise ValueError("ref_register_shapes failed")
+        return np.arange(first, first + shapes.shape[0], dtype=np.uint32)
+
+    def batch_distance(self, h1, tf1, h2, tf2, req=None, want_guess=False, nthreads=1):
+        req = req or self.pod.DistanceRequestPOD()
+        return self._run(self.L.ref_batch_distance, self.pod.distance_result_dtype, h1, tf1, h2, tf2,
+                         req, want_guess, nthreads)
+
+    def batch_collide(self, h1, tf1, h2, tf2, req=None, want_guess=False, nthreads=1):
+        req = req or self.pod.CollisionRequestPOD()
+        return self._run(self.L.ref_batch_collide, self.pod.contact_dtype, h1, tf1, h2, tf2, req,
+                         want_guess, nthreads)
