@@ -78,6 +78,37 @@ def test_primitives_collide(have_ref, kw):
                 orc.batch_collide(h[w["h1"]], w["tf1"], h[w["h2"]], w["tf2"], req, nthreads=0), what="collide %s" % kw)
 
 
+def test_swept_radii_guess_modes_and_request_fields(have_ref):
+    n = 20000
+    w = W.config2_mixed_primitives(n, pool=512, types=ALL, seed=11)
+    rng = np.random.default_rng(1)
+    shapes = w["shapes"].copy()
+    shapes["ssr"] = np.where(rng.random(len(shapes)) < 0.5, rng.random(len(shapes)) * 0.1, 0.0)  # swept-sphere radii
+    orc, ref = scenes()
+    h = orc.register_shapes(shapes)
+    ref.register_shapes(shapes)
+    h1, h2 = h[w["h1"]], h[w["h2"]]
+    compare_distance(ref.batch_distance(h1, w["tf1"], h2, w["tf2"], nthreads=0), orc.batch_distance(h1, w["tf1"], h2, w["tf2"], nthreads=0))
+    gg = rng.normal(size=(n, 3))
+    gg[:100] = 0  # below the tolerance: the (-1,0,0) restart of gjk.cpp:208-213
+    gh = np.zeros((n, 2), dtype=np.int32)
+    for mode in (P.CachedGuess, P.BoundingVolumeGuess):
+        dreq, creq = P.DistanceRequestPOD(gjk_initial_guess=mode), P.CollisionRequestPOD(gjk_initial_guess=mode)
+        if mode == P.CachedGuess:
+            for r in (dreq, creq):
+                r.q.cached_gjk_guess = gg.ctypes.data
+                r.q.cached_support_func_guess = gh.ctypes.data
+        compare_distance(ref.batch_distance(h1, w["tf1"], h2, w["tf2"], dreq, nthreads=0),
+                         orc.batch_distance(h1, w["tf1"], h2, w["tf2"], dreq, nthreads=0), what="guess mode %d" % mode)
+        cmp_collide(ref.batch_collide(h1, w["tf1"], h2, w["tf2"], creq, nthreads=0),
+                    orc.batch_collide(h1, w["tf1"], h2, w["tf2"], creq, nthreads=0), what="guess mode %d" % mode)
+    for kw in (dict(distance_upper_bound=0.1, security_margin=0.3), dict(num_max_contacts=5), dict(break_distance=0.5),
+               dict(gjk_variant=P.PolyakAcceleration), dict(gjk_tolerance=1e-9, epa_tolerance=1e-9)):
+        creq = P.CollisionRequestPOD(**kw)
+        cmp_collide(ref.batch_collide(h1, w["tf1"], h2, w["tf2"], creq, nthreads=0),
+                    orc.batch_collide(h1, w["tf1"], h2, w["tf2"], creq, nthreads=0), what=str(kw))
+
+
 def convex_scene(n=6000):
     c3 = W.config3_convex_pairs(n, pool=24, nv=64, seed=5)
     orc, ref = scenes()
