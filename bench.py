@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--variant", type=int, default=None,
                     help="0 DefaultGJK, 1 Polyak, 2 NesterovAcceleration (default: 0; config3: 2, as BASELINE names it)")
     ap.add_argument("--cpu-sample", type=int, default=400_000)
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads of the CPU arm (0: calibrated)")
     a = ap.parse_args()
     if a.variant is None:
         a.variant = 2 if a.workload == "config3" else 0
@@ -175,7 +176,7 @@ def run_reference(args):
     n = args.cpu_sample
     cores = 1
     for it in range(args.warmup + args.steps):
-        r, cores, n = cpu_reference_rate(args, w, args.cpu_sample)
+        r, cores, n = cpu_reference_rate(args, w, args.cpu_sample, threads=args.cpu_threads)
         if it >= args.warmup:
             rates.append(r)
     v = float(np.mean(rates))
@@ -458,8 +459,21 @@ def run_ours(args):
                                      "nominal_fp64_tflops": 37.0}
         if world == 1:
             line["convex_support_kernel"] = support_kernel_roofline(eng_factory=hf.Engine, peak=peak)
-            v, cores, ns = cpu_reference_rate(args, w, args.cpu_sample)
-            v1, _, ns1 = cpu_reference_rate(args, w, min(args.cpu_sample, 100_000), threads=1)
+            # the CPU arm runs in a process of its own: this one has torch's OpenMP runtime loaded next to the
+            # system one, and the reference's per-call heap traffic is sensitive to that (measured 4e6 vs 2e7)
+            def cpu_arm(sample, threads):
+                cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
+                       "--pairs", str(args.pairs), "--variant", str(args.variant), "--steps", "2", "--warmup", "1",
+                       "--cpu-sample", str(sample), "--cpu-threads", str(threads)]
+                env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS",)}
+                out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1200).stdout
+                for ln in out.splitlines():
+                    if ln.startswith("{"):
+                        d = json.loads(ln)
+                        return d["value"], d["cpu_baseline"]["cores"], sample
+                raise RuntimeError("CPU arm produced no line")
+            v, cores, ns = cpu_arm(args.cpu_sample, 0)
+            v1, _, ns1 = cpu_arm(min(args.cpu_sample, 100_000), 1)
             line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_arm_kind(),
                                     "sample": "%d pairs of the same workload, %s, OpenMP over pairs" % (
                                         ns, "hpp-fcl's own sources (oracle/_ref)" if cpu_arm_kind() == "reference"
