@@ -1,18 +1,19 @@
 // CUDA kernels (sm_100a) and the C-ABI of include/hppfcl_b200.h.
 //
-// Kernel inventory
-//   k_pairs<G,CAPS,MODE>   phase 1: one lane-group of G threads per shape pair:
-//                          closed form or GJK (+ witness extraction); pairs that
-//                          need EPA are compacted into a device queue.
-//   k_epa<G,CAPS,MODE>     phase 2: persistent kernel over the EPA queue, one warp
-//                          per pair, polytope in per-warp shared memory.
-//   k_bin_hist/scan/scatter  device-side counting sort of the batch by pair class
-//                          (closed-form combos | GJK-routed primitive combos |
-//                          touches ConvexBase/TriangleP) so that every warp of the
-//                          pair kernels runs one code path; k_pairs is instantiated
-//                          per class (PATHS) to keep each kernel's code small.
-//   k_convex_support       batched ConvexBase support argmax (warp per query,
-//                          coalesced streaming of the vertex block: HBM-bound).
+// Kernel inventory (DESIGN.md section 3 has the measurements)
+//   k_bin_hist/scan/scatter  device-side counting sort of the batch by pair class (closed-form combos |
+//                          GJK-routed primitive combos | touches ConvexBase/TriangleP | mesh-shape |
+//                          mesh-mesh): every warp of the kernels below meets one class
+//   k_pairs<G,CAPS,MODE,PATHS,MINB,STAGE>  phase 1, a lane group of G threads per pair: closed form, or GJK +
+//                          witness extraction; pairs that need EPA are appended to a device queue.
+//                          Instantiated per class family (PATHS) to keep each kernel's code small;
+//                          STAGE adds cp.async.bulk staging of the hulls' vertex blocks
+//   k_gjk_refill<MODE>     optional (HFB_REFILL=1): phase 1 for primitive pairs with lane refill
+//   k_epa<G,CAPS,MODE,TIER>  phase 2 over the EPA queue, polytope in shared memory; tier 0 in a
+//                          reduced-size workspace, tier 1 retries the pairs that outgrew it
+//   k_bvh<MODE,KINDS,MINB> OBBRSS tree walks: mesh-shape (warp-scheduled, exact DFS order) and mesh-mesh
+//   k_convex_support       batched ConvexBase support argmax (warp per query, coalesced streaming of the
+//                          vertex block: HBM-bound, 88 % of the measured peak)
 // MODE 0 = distance() epilogue, MODE 1 = collide() epilogue.
 #include <cuda_runtime.h>
 
