@@ -192,10 +192,12 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def support_kernel_roofline(eng_factory, peak, n_hulls=131072, nv=64, n_queries=1 << 21):
+def support_kernel_roofline(eng_factory, peak, n_hulls=786432, nv=64, n_queries=1 << 21):
     """The north_star's convex-support kernel: batched ConvexBase support argmax over DISTINCT hulls
-    (201 MB of vertices > 126 MB L2), one warp per query, coalesced SoA rows.  Algorithmic bytes per
-    query: 24*nv vertices + 24 B direction + 28 B output + 4 B id (1 588 B at nv = 64)."""
+    (1.2 GB of vertices, ten times the 126 MB L2, each hull queried 2.7 times on average, so the
+    algorithmic bytes are close to what DRAM delivers), one warp per query, coalesced SoA rows.
+    Algorithmic bytes per query: 24*nv vertices + 24 B direction + 28 B output + 4 B id (SURVEY 8d:
+    1 588 B at nv = 64)."""
     import torch
     from hppfcl_b200 import _pod as P
     rng = np.random.default_rng(99)
@@ -203,8 +205,7 @@ def support_kernel_roofline(eng_factory, peak, n_hulls=131072, nv=64, n_queries=
     v = rng.normal(size=(n_hulls, nv, 3))
     v /= np.linalg.norm(v, axis=2, keepdims=True)
     v *= 0.05 + 0.95 * rng.random((n_hulls, 1, 3))
-    for k in range(n_hulls):
-        eng.register_convex(v[k])
+    assert eng.register_convex_batch(v) == 0
     eng.commit()
     ids = rng.permutation(n_queries).astype(np.uint32) % n_hulls
     dirs = rng.normal(size=(n_queries, 3))

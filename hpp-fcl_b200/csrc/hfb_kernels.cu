@@ -1196,6 +1196,16 @@ int hfb_geom_register_shapes(hfb_ctx* ctx, const hfb_shape* shapes, size_t n, ui
   return HFB_OK;
 }
 
+int hfb_geom_register_convex_batch(hfb_ctx* ctx, const double* points, uint32_t num_points, uint32_t count,
+                                   uint32_t* first_id) {
+  if (!ctx || !points || num_points == 0 || count == 0 || !first_id) return HFB_ERR_INVALID_ARGUMENT;
+  for (uint32_t k = 0; k < count; ++k) {
+    const uint32_t id = ctx->arena.add_convex(points + 3 * (size_t)num_points * k, num_points);
+    if (k == 0) *first_id = id;
+  }
+  ctx->committed = false;
+  return HFB_OK;
+}
 int hfb_geom_register_convex(hfb_ctx* ctx, const double* points, uint32_t num_points, uint32_t* convex_id) {
   if (!ctx || !points || num_points == 0 || !convex_id) return HFB_ERR_INVALID_ARGUMENT;
   *convex_id = ctx->arena.add_convex(points, num_points);

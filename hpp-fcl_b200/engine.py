@@ -42,6 +42,7 @@ def load_library(path=None):
     L.hfb_default_collision_request.argtypes = [vp]
     L.hfb_geom_register_shapes.argtypes = [vp, vp, sz, vp]
     L.hfb_geom_register_convex.argtypes = [vp, vp, u32, vp]
+    L.hfb_geom_register_convex_batch.argtypes = [vp, vp, u32, u32, vp]
     L.hfb_geom_register_bvh_obbrss.argtypes = [vp, vp, u32, vp, u32, vp, u32, vp]
     L.hfb_bvh_build_obbrss.argtypes = [vp, u32, vp, u32, vp, u32]
     L.hfb_geom_commit.argtypes = [vp]
@@ -125,6 +126,14 @@ class Engine:
         handles = np.zeros(shapes.shape[0], dtype=np.uint32)
         self._check(self.L.hfb_geom_register_shapes(self.h, _ptr(shapes), shapes.shape[0], _ptr(handles)))
         return handles
+
+    def register_convex_batch(self, points):
+        """points: (count, nv, 3); returns the id of the first hull, the others follow"""
+        pts = np.ascontiguousarray(points, dtype=np.float64)
+        assert pts.ndim == 3 and pts.shape[2] == 3
+        first = C.c_uint32()
+        self._check(self.L.hfb_geom_register_convex_batch(self.h, _ptr(pts), pts.shape[1], pts.shape[0], C.byref(first)))
+        return first.value
 
     def register_bvh_obbrss(self, nodes, vertices, triangles):
         """nodes: BVHModel<OBBRSS>::bvs as hfb_bvh_node records (the reference's own tree, or

@@ -228,6 +228,10 @@ int hfb_geom_register_shapes(hfb_ctx* ctx, const hfb_shape* shapes, size_t n,
  * `points` = num_points x 3 doubles. Returns the convex id in *convex_id. */
 int hfb_geom_register_convex(hfb_ctx* ctx, const double* points,
                              uint32_t num_points, uint32_t* convex_id);
+/* `count` vertex sets of `num_points` vertices each, back to back in `points`; their ids are
+ * first_id, first_id + 1, ... (one call instead of `count`). */
+int hfb_geom_register_convex_batch(hfb_ctx* ctx, const double* points, uint32_t num_points,
+                                   uint32_t count, uint32_t* first_id);
 /* Registers a BVHModel<OBBRSS> (include/hpp/fcl/BVH/BVH_model.h:315-496,
  * BV/BV_node.h:52-148, BV/OBBRSS.h) built on the host: `nodes` = num_nodes
  * records of hfb_bvh_node, vertices num_vertices x 3, triangles num_tris x 3. */
