@@ -13,7 +13,7 @@
 //                          reduced-size workspace, tier 1 retries the pairs that outgrew it
 //   k_bvh<MODE,KINDS,MINB> OBBRSS tree walks: mesh-shape (warp-scheduled, exact DFS order) and mesh-mesh
 //   k_convex_support       batched ConvexBase support argmax (warp per query, coalesced streaming of the
-//                          vertex block: HBM-bound, 88 % of the measured peak)
+//                          vertex block: HBM-bound, 77 % of the measured peak over a 1.2 GB pool)
 // MODE 0 = distance() epilogue, MODE 1 = collide() epilogue.
 #include <cuda_runtime.h>
 
