@@ -983,6 +983,8 @@ HFB_HD bool bvh_make_query(const ArenaView& A, uint32_t h1, const xf& tf1, uint3
         rs.type == HFB_GEOM_CONE || rs.type == HFB_GEOM_CYLINDER || rs.type == HFB_GEOM_ELLIPSOID ||
         rs.type == HFB_GEOM_CONVEX))
     return false;
+  // computeBV<OBBRSS, S> refuses a swept-sphere radius ("not yet supported", geometric_shapes_utility.h:73-78)
+  if (rs.ssr > 0) return false;
   const BvhDesc& d = A.bvh_desc[rm.data];
   q.nodes = A.bvh_nodes + d.node_off;
   q.verts = A.bvh_verts + 3 * (size_t)d.vert_off;
@@ -1207,6 +1209,14 @@ HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err
   }
 }
 
+// GJKSolver::getGJKInitialGuess with BoundingVolumeGuess needs aabb_local of both operands
+// (narrowphase.h:368-377); the TriangleP a leaf test builds never had computeLocalAABB called, so the reference
+// throws std::logic_error at the first leaf that reaches GJK (sphere partners take the closed form,
+// details.h:286-342).  Mirrored as an unsupported query.
+HFB_HD bool bvh_leaf_guess_throws(int initial_guess, const ShapeD& partner) {
+  return initial_guess == HFB_GUESS_BOUNDING_VOLUME && partner.type != HFB_GEOM_SPHERE;
+}
+
 struct BvhColOut {
   double distance_lower_bound;
   v3 lb_p1, lb_p2, lb_normal;
@@ -1215,6 +1225,7 @@ struct BvhColOut {
   double distance;
   v3 p1, p2, normal;
   unsigned bv_tests, leaf_tests;
+  bool threw;  // bvh_leaf_guess_throws at a leaf: the query ends as unsupported
 };
 // CollisionResult::clear() as a record
 HFB_HD void bvh_init_contact(hfb_contact* r) {
@@ -1233,6 +1244,10 @@ HFB_HD void bvh_init_contact(hfb_contact* r) {
 // and normals back
 HFB_HD void bvh_write_shape_collide(hfb_contact* r, bool swapped, const BvhColOut& o) {
   bvh_init_contact(r);
+  if (o.threw) {
+    r->status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
+    return;
+  }
   r->distance_lower_bound = o.distance_lower_bound;
   put3d(r->p1, swapped ? o.lb_p2 : o.lb_p1);
   put3d(r->p2, swapped ? o.lb_p1 : o.lb_p2);
@@ -1308,13 +1323,18 @@ HFB_HD void bvh_shape_collide_stream(Src& src, const SolverP& P, double security
         out.distance = DBL_MAX;
         out.p1 = out.p2 = out.normal = nan3();
         out.bv_tests = out.leaf_tests = 0;
+        out.threw = false;
         ncontacts = 0;
         sp = 1;
         stk[0] = 0;
         state = BVS_ADVANCE;
       }
     } else if (phase == 2) {
-      if (state == BVS_NEED_LEAF) {  // leafCollides (traversal_node_bvh_shape.h:139-188)
+      if (state == BVS_NEED_LEAF && bvh_leaf_guess_throws(P.initial_guess, job.q.shape)) {
+        out.threw = true;
+        sp = 0;
+        state = BVS_ADVANCE;
+      } else if (state == BVS_NEED_LEAF) {  // leafCollides (traversal_node_bvh_shape.h:139-188)
         PairOut o;
         bvh_leaf<CAPS>(job.q, leaf_prim, P, ws, in, o);
         out.leaf_tests++;
@@ -1767,7 +1787,9 @@ struct BvhReq {  // request fields the traversals need beyond SolverP
   double security_margin, break_distance, collision_distance_threshold;  // CollisionRequest
   unsigned num_max_contacts;
   bool enable_nearest_points;  // DistanceRequest, mesh-mesh only
+  int initial_guess;           // QueryRequest::gjk_initial_guess (see bvh_leaf_guess_throws)
 };
+
 
 HFB_HD BvhPairQuery bvh_make_pair_query(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2, const xf& tf2) {
   BvhPairQuery pq;
@@ -1841,6 +1863,8 @@ HFB_HD bool bvh_make_job(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_
                          v3 cached_guess, int hint0, int hint1, void* rec, BvhJob& job) {
   bool ok = bvh_make_query<CAPS>(A, h1, tf1, h2, tf2, job.q, job.swapped);
   if (MODE == 1 && R.security_margin < 0) ok = false;
+  // distance(): preprocess() always evaluates the seed triangle, so the throw is certain
+  if (MODE == 0 && ok && bvh_leaf_guess_throws(R.initial_guess, job.q.shape)) ok = false;
   if (!ok) {
     if (MODE == 0) {
       bvh_unsupported_distance(static_cast<hfb_distance_result*>(rec));

@@ -1295,7 +1295,7 @@ int hfb_batch_distance(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_tra
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (int rc = validate_query(req->q)) return fail(ctx, rc, "invalid request");
   return host_batch<0>(ctx, n, h1, tf1, h2, tf2, req, solver_from_distance_request(*req), CollideP{0, 0},
-                       BvhReq{/* rel_err, abs_err: see hfb_distance_request */ 0, 0, 0, 0, 0, 1, req->enable_nearest_points != 0}, out, go);
+                       BvhReq{/* rel_err, abs_err: see hfb_distance_request */ 0, 0, 0, 0, 0, 1, req->enable_nearest_points != 0, req->q.gjk_initial_guess}, out, go);
 }
 
 int hfb_batch_distance_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1,
@@ -1305,7 +1305,7 @@ int hfb_batch_distance_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const 
   std::lock_guard<std::mutex> lk(ctx->mu);
   if (int rc = validate_query(req->q)) return fail(ctx, rc, "invalid request");
   return device_batch<0>(ctx, n, h1, tf1, h2, tf2, req, solver_from_distance_request(*req), CollideP{0, 0},
-                         BvhReq{/* rel_err, abs_err: see hfb_distance_request */ 0, 0, 0, 0, 0, 1, req->enable_nearest_points != 0}, out, go, stream);
+                         BvhReq{/* rel_err, abs_err: see hfb_distance_request */ 0, 0, 0, 0, 0, 1, req->enable_nearest_points != 0, req->q.gjk_initial_guess}, out, go, stream);
 }
 
 static int collide_prelude(hfb_ctx* ctx, const hfb_collision_request* req, bool* minus_inf) {
@@ -1349,7 +1349,7 @@ int hfb_batch_collide(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_tran
   CollideP C{req->security_margin, req->q.collision_distance_threshold};
   return host_batch<1>(ctx, n, h1, tf1, h2, tf2, req, solver_from_collision_request(*req), C,
                        BvhReq{0, 0, req->security_margin, req->break_distance, req->q.collision_distance_threshold,
-                              req->num_max_contacts, true},
+                              req->num_max_contacts, true, req->q.gjk_initial_guess},
                        out, go);
 }
 
@@ -1371,7 +1371,7 @@ int hfb_batch_collide_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const h
   CollideP C{req->security_margin, req->q.collision_distance_threshold};
   return device_batch<1>(ctx, n, h1, tf1, h2, tf2, req, solver_from_collision_request(*req), C,
                          BvhReq{0, 0, req->security_margin, req->break_distance, req->q.collision_distance_threshold,
-                                req->num_max_contacts, true},
+                                req->num_max_contacts, true, req->q.gjk_initial_guess},
                          out, go, stream);
 }
 

@@ -82,6 +82,12 @@ enum {
 #define HFB_STATUS_EPA(s) (((s) >> 8) & 0xffu)
 #define HFB_STATUS_PATH(s) (((s) >> 16) & 0xffu)
 enum { HFB_PATH_GJK = 0, HFB_PATH_CLOSED_FORM = 1, HFB_PATH_BVH = 2, HFB_PATH_UNSUPPORTED = 0xee };
+/* HFB_PATH_UNSUPPORTED marks a record of a pair on which the reference throws: the record is the cleared
+ * result (DistanceResult::clear / CollisionResult::clear) and a binding re-raises.  Cases: a type pair outside
+ * the function matrices covered here (collision.cpp:110-117); collide() of a mesh with a negative security
+ * margin (collision_func_matrix.cpp:109-112); a mesh-shape query whose shape has a swept-sphere radius
+ * (geometric_shapes_utility.h:73-78); BoundingVolumeGuess on a mesh-shape query that evaluates a GJK leaf --
+ * every distance(), a collide() whose walk reaches a leaf; sphere partners excepted (narrowphase.h:368-377). */
 
 /* error codes */
 enum {

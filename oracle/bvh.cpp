@@ -12,6 +12,7 @@
 //   traversal    src/traversal/traversal_recurse.cpp:44-85,153-203, src/collision_node.cpp:64-91,
 //                include/hpp/fcl/internal/traversal_node_bvh_shape.h:97-194,286-478,
 //                include/hpp/fcl/internal/traversal_node_setup.h:655-694,746-810
+#include <stdexcept>
 #include <algorithm>
 #include <cassert>
 #include <cstdio>
@@ -989,6 +990,14 @@ struct DistNode {
   bool last_closed = false;
 };
 
+// GJKSolver::getGJKInitialGuess with BoundingVolumeGuess requires aabb_local of both shapes
+// (narrowphase.h:368-377); the TriangleP a leaf builds on the fly never had computeLocalAABB called, so the
+// reference throws std::logic_error at the first leaf that reaches GJK (sphere partners use the closed form)
+static inline void leafGuessCheck(const GJKSolver& solver, const Shape& partner) {
+  if (solver.gjk_initial_guess == HFB_GUESS_BOUNDING_VOLUME && partner.type != HFB_GEOM_SPHERE)
+    throw std::logic_error("computeLocalAABB must have been called on the shapes before using BoundingVolumeGuess");
+}
+
 static void leafDistance(DistNode& n, int primitive_id) {  // traversal_node_bvh_shape.h:342-364
   const Tri& t = n.model1->tris[primitive_id];
   Shape tri;
@@ -999,6 +1008,7 @@ static void leafDistance(DistNode& n, int primitive_id) {  // traversal_node_bvh
   V3 p1, p2, normal;
   double distance;
   bool closed = false;
+  leafGuessCheck(*n.solver, *n.model2);
   shapeShapeDistance(tri, n.tf1, *n.model2, n.tf2, *n.solver, n.signed_distance, distance, p1, p2, normal, closed);
   n.num_leaf_tests++;
   if (n.min_distance > distance) {  // DistanceResult::update (collision_data.h:1111-1124)
@@ -1087,6 +1097,7 @@ static void leafCollides(ColNode& n, unsigned b1, double& sqrDistLowerBound) {  
   V3 c1, c2, normal;
   double distance;
   bool closed;
+  leafGuessCheck(*n.solver, *n.model2);
   shapeShapeDistance(tri, n.tf1, *n.model2, n.tf2, *n.solver, compute_penetration, distance, c1, c2, normal, closed);
   n.res->num_leaf_tests++;
   const double distToCollision = distance - n.req->security_margin;

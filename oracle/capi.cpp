@@ -3,6 +3,7 @@
 // same POD buffers the product C-ABI (include/hppfcl_b200.h) takes.
 // distance():  src/distance.cpp:60-109 + ShapeShapeDistancer::run (shape_shape_func.h:51-82)
 // collide():   src/collision.cpp:69-130 + ShapeShapeCollider::run (shape_shape_func.h:132-164)
+#include <stdexcept>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -209,11 +210,14 @@ int oracle_batch_distance(void* sc, size_t n, const uint32_t* h1, const hfb_tran
           r.iterations = (uint32_t)(q.num_bv_tests & 0xffff) | ((uint32_t)(q.num_leaf_tests & 0xffff) << 16);
         } else if (ss.type == HFB_BV_OBBRSS || !(ss.type == HFB_GEOM_BOX || ss.type == HFB_GEOM_SPHERE ||
             ss.type == HFB_GEOM_CAPSULE || ss.type == HFB_GEOM_CONE || ss.type == HFB_GEOM_CYLINDER ||
-            ss.type == HFB_GEOM_ELLIPSOID || ss.type == HFB_GEOM_CONVEX)) {
+            ss.type == HFB_GEOM_ELLIPSOID || ss.type == HFB_GEOM_CONVEX) ||
+            // computeBV<OBBRSS, S> throws "Swept-sphere radius not yet supported" (geometric_shapes_utility.h:73-78)
+            ss.ssr > 0) {
           r.status = (uint32_t)HFB_PATH_UNSUPPORTED << 16;  // plane, halfspace, triangle partners: not covered
           r.iterations = 0;
         } else {
           BvhQueryResult q;
+          try {
           bvhShapeDistance(*s->bvhs[(size_t)sm.p[0]], swap ? T2 : T1, ss, swap ? T1 : T2, solver,
                            req->enable_signed_distance != 0,
                            // rel_err / abs_err never reach the walk: the mesh-shape node zeroes its copies in
@@ -221,6 +225,11 @@ int oracle_batch_distance(void* sc, size_t n, const uint32_t* h1, const hfb_tran
                            // mesh-mesh node copies them from its own default-constructed request
                            // (traversal_node_bvhs.h:409-410), before initialize() stores the caller's
                            0.0, 0.0, q);
+          } catch (const std::logic_error&) {  // BoundingVolumeGuess at a mesh leaf (bvh.cpp leafGuessCheck)
+            r.status = (uint32_t)HFB_PATH_UNSUPPORTED << 16;
+            r.iterations = 0;
+            continue;
+          }
           r.min_distance = q.distance;
           put3(r.p1, swap ? q.p2 : q.p1);
           put3(r.p2, swap ? q.p1 : q.p2);
@@ -365,12 +374,18 @@ int oracle_batch_collide(void* sc, size_t n, const uint32_t* h1, const hfb_trans
         const bool shape_ok = ss.type == HFB_GEOM_BOX || ss.type == HFB_GEOM_SPHERE || ss.type == HFB_GEOM_CAPSULE ||
                               ss.type == HFB_GEOM_CONE || ss.type == HFB_GEOM_CYLINDER ||
                               ss.type == HFB_GEOM_ELLIPSOID || ss.type == HFB_GEOM_CONVEX;
-        if (!shape_ok || req->security_margin < 0) {  // negative margin throws for BVH (collision_func_matrix.cpp:109-112)
+        // a swept-sphere radius on the shape throws in computeBV (geometric_shapes_utility.h:73-78)
+        if (!shape_ok || ss.ssr > 0 || req->security_margin < 0) {  // negative margin throws for BVH (collision_func_matrix.cpp:109-112)
           r.status = (uint32_t)HFB_PATH_UNSUPPORTED << 16;
           continue;
         }
         BvhCollideResult q;
-        bvhShapeCollide(*s->bvhs[(size_t)sm.p[0]], swap ? T2 : T1, ss, swap ? T1 : T2, solver, *req, q);
+        try {
+          bvhShapeCollide(*s->bvhs[(size_t)sm.p[0]], swap ? T2 : T1, ss, swap ? T1 : T2, solver, *req, q);
+        } catch (const std::logic_error&) {  // BoundingVolumeGuess at a mesh leaf (bvh.cpp leafGuessCheck)
+          r.status = (uint32_t)HFB_PATH_UNSUPPORTED << 16;
+          continue;
+        }
         r.distance_lower_bound = q.distance_lower_bound;
         put3(r.p1, swap ? q.lb_p2 : q.lb_p1);
         put3(r.p2, swap ? q.lb_p1 : q.lb_p2);
@@ -539,6 +554,9 @@ int oracle_gjk_lowlevel(void* sc, uint32_t h0, const hfb_transform* tf0, uint32_
   out[12] = gjk.distance;
   return HFB_OK;
 }
+
+// number of Project::*Origin calls so far that the reference answers from uninitialised memory (gjk_epa.cpp)
+unsigned long long oracle_undefined_projections() { return g_undefined_projections.load(); }
 
 int oracle_max_threads() {
 #ifdef _OPENMP

@@ -1,7 +1,10 @@
 // ORACLE -- TEST INFRASTRUCTURE ONLY (see oracle.hpp).
 // Restatement of src/narrowphase/gjk.cpp (GJK :51-1010, EPA :1012-1466) and of
 // src/intersect.cpp Project::*Origin (:570-705), operation by operation.
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
+#include <atomic>
 #include <cassert>
 
 #include "oracle.hpp"
@@ -9,6 +12,12 @@
 namespace oracle {
 
 static const double kDummyPrecision = 1e-12;  // Eigen::NumTraits<double>::dummy_precision()
+
+// Project::ProjectResult's constructor leaves parameterization[4] uninitialised (internal/intersect.h:58-70), and
+// the projections return it untouched for an exactly degenerate simplex (l == 0 / vl == 0): the reference then
+// builds its witness points from stack garbage.  The restatement (and the device code) define that case as
+// all-zero weights; this counter lets the tests recognise the pairs on which the reference is undefined.
+std::atomic<unsigned long long> g_undefined_projections{0};
 
 // ======================================================= Project (intersect.cpp)
 ProjectResult projectLineOrigin(const V3& a, const V3& b) {  // :570-595
@@ -29,6 +38,8 @@ ProjectResult projectLineOrigin(const V3& a, const V3& b) {  // :570-595
       res.sqr_distance = sqnorm(a + d * res.parameterization[1]);
       res.encode = 3;
     }
+  } else {
+    g_undefined_projections.fetch_add(1, std::memory_order_relaxed);
   }
   return res;
 }
@@ -67,6 +78,8 @@ ProjectResult projectTriangleOrigin(const V3& a, const V3& b, const V3& c) {  //
       res.parameterization[2] = 1 - res.parameterization[0] - res.parameterization[1];
     }
     res.sqr_distance = mindist;
+  } else {
+    g_undefined_projections.fetch_add(1, std::memory_order_relaxed);
   }
   return res;
 }
@@ -109,6 +122,8 @@ ProjectResult projectTetrahedraOrigin(const V3& a, const V3& b, const V3& c, con
   } else if (!ng) {
     res = projectTriangleOrigin(a, b, c);
     res.parameterization[3] = 0;
+  } else {
+    g_undefined_projections.fetch_add(1, std::memory_order_relaxed);
   }
   return res;
 }
@@ -202,6 +217,14 @@ static void inflate(const MinkowskiDiff& shape, const V3& normal, V3& w0, V3& w1
 void GJK::getWitnessPointsAndNormal(const MinkowskiDiff& shape_, V3& w0, V3& w1,
                                     V3& normal) const {  // :177-186
   getClosestPoints(*simplex, w0, w1);
+  if (getenv("HFB_ORACLE_DUMP_SIMPLEX")) {  // debugging aid (single-pair runs)
+    fprintf(stderr, "oracle simplex rank %d ray %.17g %.17g %.17g\n", (int)simplex->rank, ray.x, ray.y, ray.z);
+    for (int k = 0; k < (int)simplex->rank; ++k) {
+      const SimplexV* v = simplex->vertex[k];
+      fprintf(stderr, "  w0 %.17g %.17g %.17g  w1 %.17g %.17g %.17g\n", v->w0.x, v->w0.y, v->w0.z, v->w1.x, v->w1.y, v->w1.z);
+    }
+    fprintf(stderr, "  closest w0 %.17g %.17g %.17g  w1 %.17g %.17g %.17g\n", w0.x, w0.y, w0.z, w1.x, w1.y, w1.z);
+  }
   if (norm(w1 - w0) > kDummyPrecision) {
     normal = normalized(w1 - w0);
   } else {

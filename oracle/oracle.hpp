@@ -19,6 +19,7 @@
 // x86-64 (packet of two + scalar remainder); no FMA contraction
 // (-ffp-contract=off), IEEE sqrt/div.
 #pragma once
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstddef>
@@ -288,6 +289,7 @@ bool shapeShapeDistance(const Shape& s1, const Tf& tf1, const Shape& s2, const T
 // Project (src/intersect.cpp:570-705)
 struct ProjectResult { double parameterization[4]; double sqr_distance; unsigned encode;
                        ProjectResult() : parameterization{0, 0, 0, 0}, sqr_distance(-1), encode(0) {} };
+extern std::atomic<unsigned long long> g_undefined_projections;  // see gjk_epa.cpp
 ProjectResult projectLineOrigin(const V3& a, const V3& b);
 ProjectResult projectTriangleOrigin(const V3& a, const V3& b, const V3& c);
 ProjectResult projectTetrahedraOrigin(const V3& a, const V3& b, const V3& c, const V3& d);

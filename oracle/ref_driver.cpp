@@ -12,6 +12,8 @@
 //   hpp::fcl::distance() / collide()   (src/distance.cpp:60-109, src/collision.cpp:69-130)
 // on fresh result objects; the ComputeDistance / ComputeCollision functors (the same code path with the
 // solver kept as a member) are used so that the solver's status and iteration counters can be read back.
+#include <cstdio>
+#include <cstdlib>
 #include <hpp/fcl/BVH/BVH_model.h>
 #include <hpp/fcl/collision.h>
 #include <hpp/fcl/distance.h>
@@ -236,7 +238,16 @@ int ref_batch_distance(void* p, size_t n, const uint32_t* h1, const hfb_transfor
       status = pack(f.s(), bvh, tt);
       if (!bvh && !tt && f.s().gjk.status != details::GJK::DidNotRun)
         iters = (unsigned)(f.s().gjk.getNumIterations() & 0xffff) | ((unsigned)(f.s().epa.getNumIterations() & 0xffff) << 16);
-    } catch (const std::exception&) {
+      if (getenv("HFB_REF_DUMP_SIMPLEX") && (size_t)atol(getenv("HFB_REF_DUMP_SIMPLEX")) == i) {  // debugging aid
+        const details::GJK::Simplex* sx = f.s().gjk.getSimplex();
+        fprintf(stderr, "ref simplex rank %d ray %.17g %.17g %.17g\n", (int)sx->rank, f.s().gjk.ray[0], f.s().gjk.ray[1], f.s().gjk.ray[2]);
+        for (int k = 0; k < (int)sx->rank; ++k) {
+          const details::GJK::SimplexV* v = sx->vertex[k];
+          fprintf(stderr, "  w0 %.17g %.17g %.17g  w1 %.17g %.17g %.17g\n", v->w0[0], v->w0[1], v->w0[2], v->w1[0], v->w1[1], v->w1[2]);
+        }
+      }
+    } catch (const std::exception& e) {
+      if (getenv("HFB_REF_VERBOSE")) fprintf(stderr, "reference threw (pair %zu): %s\n", i, e.what());
       res.clear();
     }
     r.min_distance = res.min_distance;
@@ -298,7 +309,8 @@ int ref_batch_collide(void* p, size_t n, const uint32_t* h1, const hfb_transform
         if (!bvh && !tt && f.s().gjk.status != details::GJK::DidNotRun)
           iters = (unsigned)(f.s().gjk.getNumIterations() & 0xffff) | ((unsigned)(f.s().epa.getNumIterations() & 0xffff) << 16);
       }
-    } catch (const std::exception&) {
+    } catch (const std::exception& e) {
+      if (getenv("HFB_REF_VERBOSE")) fprintf(stderr, "reference threw (pair %zu): %s\n", i, e.what());
       res.clear();
     }
     r.distance = std::numeric_limits<double>::max();

@@ -106,7 +106,7 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
   for (size_t i = 0; i < n; ++i) {
     if (h1[i] >= A.nshapes || h2[i] >= A.nshapes) return HFB_ERR_INVALID_ARGUMENT;
     if (A.shapes[h1[i]].type == HFB_BV_OBBRSS || A.shapes[h2[i]].type == HFB_BV_OBBRSS) {
-      BvhReq R{/* rel_err, abs_err: see hfb_distance_request */ 0, 0, 0, 0, 0, 1, req->enable_nearest_points != 0};
+      BvhReq R{/* rel_err, abs_err: see hfb_distance_request */ 0, 0, 0, 0, 0, 1, req->enable_nearest_points != 0, req->q.gjk_initial_guess};
       unsigned bt, lt;
       v3 guess = mk(1, 0, 0);
       int hh0 = 0, hh1 = 0;
@@ -159,7 +159,7 @@ int emu_batch_collide(void* e, size_t n, const uint32_t* h1, const hfb_transform
     }
     if (A.shapes[h1[i]].type == HFB_BV_OBBRSS || A.shapes[h2[i]].type == HFB_BV_OBBRSS) {
       BvhReq R{0, 0, req->security_margin, req->break_distance, req->q.collision_distance_threshold,
-               req->num_max_contacts, true};
+               req->num_max_contacts, true, req->q.gjk_initial_guess};
       unsigned bt, lt;
       v3 guess = mk(1, 0, 0);
       int hh0 = 0, hh1 = 0;
