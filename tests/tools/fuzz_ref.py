@@ -151,6 +151,22 @@ def small_hulls(rng, scale):
     return [(p * scale, t) for p, t in hulls]
 
 
+def big_hulls(rng, scale):
+    """more than 32 vertices: the reference climbs over neighbours (support_functions.cpp:324-397); lattices and
+    prisms give it plateaus and ties to walk through"""
+    hulls = [W.ellipsoid_hull(rng, nv) for nv in (33, 48, 64, 100)]
+    k = 12  # 2 x 3k-gon prism, regular: every side face is a rectangle (ties along edges)
+    ang = 2 * np.pi * np.arange(3 * k) / (3 * k)
+    ring = np.stack([np.cos(ang), np.sin(ang)], axis=1)
+    prism = np.concatenate([np.c_[ring, np.full(3 * k, -0.5)], np.c_[ring, np.full(3 * k, 0.5)]])
+    hulls.append((prism, hull_tris(prism)))
+    g = np.array(list(itertools.product((-1.0, -1 / 3, 1 / 3, 1.0), repeat=3)))
+    shell = g[np.abs(g).max(axis=1) == 1.0]  # 56 lattice points on the faces of a cube: coplanar quadruples
+    shell = shell / np.linalg.norm(shell, axis=1, keepdims=True) * (1 + 0.05 * rng.random((len(shell), 1)))
+    hulls.append((shell, hull_tris(shell)))
+    return [(np.ascontiguousarray(p * scale), t) for p, t in hulls if len(np.unique(t)) == len(p)]
+
+
 def hull_tris(pts):
     from scipy.spatial import ConvexHull
     h = ConvexHull(pts)
@@ -250,6 +266,9 @@ def build_cases(seed, n, use_ref, use_emu):
     hp = B.register_shapes(prim)
     ids = [B.register_convex(p, t) for p, t in small_hulls(rng, scale)]
     hc = B.register_shapes(P.make_shapes([P.GEOM_CONVEX] * len(ids), np.zeros((len(ids), 3)), data=ids))
+    big = big_hulls(rng, scale)
+    bids = [B.register_convex(p, t) for p, t in big]
+    hb = B.register_shapes(P.make_shapes([P.GEOM_CONVEX] * len(bids), np.zeros((len(bids), 3)), data=bids))
     mids = [B.register_bvh(v, t) for v, t in fuzz_meshes(rng, scale)]
     hm = B.register_shapes(P.make_shapes([P.BV_OBBRSS] * len(mids), np.zeros((len(mids), 3)), data=mids))
     B.commit()
@@ -264,32 +283,53 @@ def build_cases(seed, n, use_ref, use_emu):
     creq, ckw = random_request(rng, "collide")
     tag = "seed %d scale %g mode %s" % (seed, scale, mode)
     cases = [("shapes", "distance", h1, tf1, h2, tf2, dreq, dkw), ("shapes", "collide", h1, tf1, h2, tf2, creq, ckw)]
+    # CachedGuess with arbitrary guesses (some below the tolerance: the (-1,0,0) restart of gjk.cpp:208-213)
+    gg = rng.normal(size=(n, 3)) * scale
+    gg[rng.random(n) < 0.1] = 0
+    gh = np.zeros((n, 2), dtype=np.int32)
+    for kind in ("distance", "collide"):
+        req, kw = random_request(rng, kind)
+        req.q.gjk_initial_guess = P.CachedGuess
+        req.q.cached_gjk_guess = gg.ctypes.data
+        req.q.cached_support_func_guess = gh.ctypes.data
+        kw = dict(kw, gjk_initial_guess="cached")
+        cases.append(("shapes", kind, h1, tf1, h2, tf2, req, kw, (gg, gh)))  # the arrays the request points into
+    # hulls of more than 32 vertices: reference vs oracle only (the device code takes the exhaustive argmax)
+    nb = max(200, n // 4)
+    bpool = np.concatenate([hb, hb, hp])
+    b1, b2 = bpool[rng.integers(0, len(bpool), nb)], bpool[rng.integers(0, len(bpool), nb)]
+    for kind in ("distance", "collide"):
+        req, kw = random_request(rng, kind)
+        cases.append(("big-hulls", kind, b1, tf1[:nb], b2, tf2[:nb], req, kw))
     # meshes: against shapes (both operand orders) and against each other
     m = max(200, n // 8)
     mt1, mt2 = adversarial_poses(rng, m, scale, base if base != "far" else "random")
     g1 = hm[rng.integers(0, len(hm), m)]
     g2 = hm[rng.integers(0, len(hm), m)]
     q = pool[rng.integers(0, len(pool), m)]
-    mreq = P.DistanceRequestPOD()
+    _, mdkw = random_request(rng, "distance")
+    for k in ("gjk_max_iterations", "epa_max_iterations"):
+        mdkw.pop(k, None)
+    mreq = P.DistanceRequestPOD(**mdkw)
     _, mckw = random_request(rng, "collide")
     for k in ("gjk_max_iterations", "epa_max_iterations"):
         mckw.pop(k, None)
     mcreq = P.CollisionRequestPOD(**mckw)
     for name, a, b in (("mesh-shape", g1, q), ("shape-mesh", q, g1), ("mesh-mesh", g1, g2)):
-        cases.append((name, "distance", a, mt1, b, mt2, mreq, {}))
+        cases.append((name, "distance", a, mt1, b, mt2, mreq, mdkw))
         cases.append((name, "collide", a, mt1, b, mt2, mcreq, mckw))
     return B, tag, cases
 
 
 def run_case(scene, case):
-    name, kind, a, t1, b, t2, req, _ = case
+    name, kind, a, t1, b, t2, req = case[:7]
     kw = dict(nthreads=0) if isinstance(scene, oracle_lib.OracleScene) else {}
     return (scene.batch_distance if kind == "distance" else scene.batch_collide)(a, t1, b, t2, req, **kw)
 
 
 def compare_case(case, ref, got, what):
     name, kind = case[0], case[1]
-    if name == "shapes":
+    if name in ("shapes", "big-hulls"):
         if kind == "distance":
             compare_distance(ref, got, what=what)
         else:
@@ -302,7 +342,7 @@ def compare_case(case, ref, got, what):
 
 def rows_differing(case, ref, got):
     name, kind = case[0], case[1]
-    if name == "shapes":
+    if name in ("shapes", "big-hulls"):
         fields = ["status", "iterations", "b1", "b2", "p1", "p2", "normal"]
         fields += ["min_distance"] if kind == "distance" else ["distance", "pos", "distance_lower_bound", "num_contacts"]
     elif kind == "distance":
@@ -331,6 +371,12 @@ def reference_undefined(B, case, rows):
         one = list(case)
         for k in (2, 3, 4, 5):
             one[k] = case[k][r:r + 1].copy()
+        if len(case) > 8:  # per-pair cached guesses: point a copy of the request at this row's
+            gg, gh = case[8][0][r:r + 1].copy(), case[8][1][r:r + 1].copy()
+            one[6] = type(case[6]).from_buffer_copy(case[6])
+            one[6].q.cached_gjk_guess = gg.ctypes.data
+            one[6].q.cached_support_func_guess = gh.ctypes.data
+            one[8] = (gg, gh)
         before = L.oracle_undefined_projections()
         run_case(B.orc, one)
         if L.oracle_undefined_projections() == before:
@@ -359,7 +405,7 @@ def one_round(seed, n, use_ref, use_emu):
                     compare_case(case, r[keep], o[keep], "ref/oracle " + what)
                 else:
                     compare_case(case, r, o, "ref/oracle " + what)
-            if B.emu:
+            if B.emu and case[0] != "big-hulls":
                 compare_case(case, o, run_case(B.emu, case), "oracle/device code " + what)
     except AssertionError as e:
         print("MISMATCH", e, flush=True)
