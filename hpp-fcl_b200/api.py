@@ -379,7 +379,19 @@ class BatchQuery:
         return self.scene.engine.batch_collide(h1, _tf_array(tfs1), h2, _tf_array(tfs2), request._pod)
 
 
-def _unsupported(o1, o2, what):
+def _unsupported(o1, o2, what, request=None):
+    """the exception the reference throws for this pair (the record carries HFB_PATH_UNSUPPORTED)"""
+    mesh = [o for o in (o1, o2) if o.node_type == P.BV_OBBRSS]
+    shape = [o for o in (o1, o2) if o.node_type != P.BV_OBBRSS]
+    if len(mesh) == 1 and shape:
+        if what == "Collision" and request is not None and request.security_margin < 0:
+            # collision_func_matrix.cpp:109-112
+            raise ValueError("Negative security margin are not handled yet for BVHModel")
+        if getattr(shape[0], "getSweptSphereRadius", lambda: 0.0)() > 0:
+            raise RuntimeError("Swept-sphere radius not yet supported.")  # geometric_shapes_utility.h:73-78
+        if request is not None and request.gjk_initial_guess == P.BoundingVolumeGuess:
+            raise RuntimeError("computeLocalAABB must have been called on the shapes before using "
+                               "GJKInitialGuess::BoundingVolumeGuess.")  # narrowphase.h:368-377
     raise ValueError("%s function between node type %s and node type %s is not yet supported."
                      % (what, o1.node_type, o2.node_type))
 
@@ -401,7 +413,7 @@ def collide(o1, tf1, o2, tf2, request, result, device=0):
                                              want_guess=True)
     rec = out[0]
     if P.status_path(rec["status"]) == P.PATH_UNSUPPORTED:
-        _unsupported(o1, o2, "Collision")
+        _unsupported(o1, o2, "Collision", request)
     if rec["distance_lower_bound"] < result.distance_lower_bound:
         result.distance_lower_bound = float(rec["distance_lower_bound"])
         result.nearest_points = [rec["p1"].copy(), rec["p2"].copy()]
@@ -425,7 +437,7 @@ def distance(o1, tf1, o2, tf2, request, result, device=0):
                                               want_guess=True)
     rec = out[0]
     if P.status_path(rec["status"]) == P.PATH_UNSUPPORTED:
-        _unsupported(o1, o2, "Distance")
+        _unsupported(o1, o2, "Distance", request)
     d = float(rec["min_distance"])
     closed = P.status_path(rec["status"]) == P.PATH_CLOSED_FORM
     if closed or result.min_distance > d:
