@@ -420,6 +420,7 @@ def main():
     ap.add_argument("--n", type=int, default=4000)
     ap.add_argument("--no-emu", action="store_true")
     ap.add_argument("--keep-going", action="store_true")
+    ap.add_argument("--gpu", action="store_true", help="the real kernels (hppfcl_b200.Engine) instead of the host build")
     a = ap.parse_args()
     use_ref = False
     if os.path.isdir("/root/reference/src"):
@@ -427,7 +428,11 @@ def main():
     use_ref = oracle_lib.ref_available()
     t0, seed, bad = time.time(), a.seed, 0
     while time.time() - t0 < a.minutes * 60:
-        ok, tag = one_round(seed, a.n, use_ref, not a.no_emu)
+        dev = not a.no_emu
+        if a.gpu:
+            import hppfcl_b200 as hf
+            dev = hf.Engine(0)
+        ok, tag = one_round(seed, a.n, use_ref, dev)
         print("%s %s (ref %s)" % ("ok  " if ok else "FAIL", tag, use_ref), flush=True)
         bad += not ok
         if not ok and not a.keep_going:
