@@ -599,15 +599,25 @@ __global__ void __launch_bounds__(256) k_convex_support(const ConvexDesc* cvx, c
     const double* y = x + d.vpad;
     const double* z = y + d.vpad;
     const double dx = dirs[3 * q], dy = dirs[3 * q + 1], dz = dirs[3 * q + 2];
-    double best = -DBL_MAX;
+    // same NaN rules as shape_support (hfb_shapes.cuh): the answer is the serial scan's for any direction
+    double best = -(double)INFINITY;
     int bi = 0x7fffffff;
     bool first = true;
     for (unsigned i = lane; i < d.nv; i += 32) {
       const double v = (x[i] * dx + y[i] * dy) + z[i] * dz;
-      if (first || v > best) {
+      if (first) {
+        if (v == v) {
+          best = v;
+          bi = (int)i;
+          first = false;
+        } else if (i == 0) {
+          best = (double)INFINITY;
+          bi = -1;
+          first = false;
+        }
+      } else if (v > best) {
         best = v;
         bi = (int)i;
-        first = false;
       }
     }
 #pragma unroll
@@ -619,6 +629,7 @@ __global__ void __launch_bounds__(256) k_convex_support(const ConvexDesc* cvx, c
         bi = oi;
       }
     }
+    if (bi < 0) bi = 0;
     if (lane == 0) {
       idx_out[q] = bi;
       sup_out[3 * q] = x[bi];

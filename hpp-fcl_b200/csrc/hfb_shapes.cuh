@@ -154,19 +154,35 @@ template <int G, int CAPS>
 HFB_HD v3 shape_support(const ShapeD& s, v3 dir, int& hint) {
   v3 r = mk(0, 0, 0);
   if ((CAPS & CAP_CONVEX) && s.type == HFB_GEOM_CONVEX) {
-    // exhaustive argmax, striped over the group's lanes
-    double best = -DBL_MAX;
+    // exhaustive argmax, striped over the group's lanes.  It must equal the serial scan (start from vertex 0,
+    // move on strictly greater) for EVERY input, including a NaN direction -- GJK does produce one now and
+    // then (0/0 in the projection of a degenerate simplex) and carries on: the serial scan then keeps
+    // vertex 0, because vertex 0 is taken unconditionally and nothing compares greater than NaN, while
+    // elsewhere a NaN never wins.  So a NaN at index 0 is made the winner (+inf, index -1 < every index),
+    // a NaN at the head of another lane's stripe is skipped, and no NaN reaches the cross-lane reduction
+    // (where it would leave the lanes of a group with different answers).
+    double best = -(double)INFINITY;
     int bi = 0x7fffffff;
     bool first = true;
     for (int i = Coop<G>::lane(); i < s.nv; i += G) {
       double d = (s.cx[i] * dir.x + s.cy[i] * dir.y) + s.cz[i] * dir.z;
-      if (first || d > best) {
+      if (first) {
+        if (d == d) {
+          best = d;
+          bi = i;
+          first = false;
+        } else if (i == 0) {
+          best = (double)INFINITY;
+          bi = -1;
+          first = false;
+        }
+      } else if (d > best) {
         best = d;
         bi = i;
-        first = false;
       }
     }
     Coop<G>::argmax(best, bi);
+    if (bi < 0) bi = 0;
     hint = bi;
     return mk(s.cx[bi], s.cy[bi], s.cz[bi]);
   }

@@ -1,21 +1,91 @@
 // TEST HARNESS ONLY -- not part of the product and never loaded by it.
 //
 // Compiles the per-pair DEVICE code of hpp-fcl_b200/csrc/*.cuh with g++ (G = 1
-// lane per pair, HFB_HD expands to `inline`) so that the exact arithmetic the
+// lane per pair, HFB_HD expands to `inline`; lane groups only for the support argmax, see LaneSim) so that the exact arithmetic the
 // CUDA kernels execute can be checked against the oracle in the CPU-only
 // container (`-m "not gpu"` tests).  The product library has no such path: its
 // entry points fail with HFB_ERR_NO_DEVICE when there is no GPU.
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <vector>
 
 #include "../../hpp-fcl_b200/csrc/hfb_arena.cuh"
 #include "../../hpp-fcl_b200/csrc/hfb_bvh.cuh"
 #include "../../hpp-fcl_b200/csrc/hfb_request.cuh"
 
+// ---- lane groups on the host: Coop<G> for G > 1 (device-only in the product) simulated in two passes --------
+// Pass 0 runs every lane of a group up to its cross-lane argmax and records what the lane brings to it; the
+// butterfly of Coop<G>::argmax (hfb_shapes.cuh: xor-shuffle, `greater, or equal with the lower index`) is
+// then replayed on the recorded values; pass 1 runs every lane again and hands it its reduced value.  Good
+// for code with one reduction per call (shape_support): checks that every lane of a group ends with the
+// answer of the serial scan.
+namespace hfb {
+struct LaneSim {
+  static inline int lane = 0, pass = 0;
+  static inline double v[32];
+  static inline int idx[32];
+  static void reduce(int G) {
+    for (int off = G / 2; off > 0; off >>= 1) {
+      double nv[32];
+      int ni[32];
+      for (int l = 0; l < G; ++l) {
+        const double ov = v[l ^ off];
+        const int oi = idx[l ^ off];
+        nv[l] = v[l];
+        ni[l] = idx[l];
+        if (ov > v[l] || (ov == v[l] && oi < idx[l])) {
+          nv[l] = ov;
+          ni[l] = oi;
+        }
+      }
+      for (int l = 0; l < G; ++l) {
+        v[l] = nv[l];
+        idx[l] = ni[l];
+      }
+    }
+  }
+};
+#define HFB_EMU_COOP(G_)                                      \
+  template <>                                                 \
+  struct Coop<G_> {                                           \
+    static int lane() { return LaneSim::lane; }               \
+    static unsigned mask() { return 0; }                      \
+    static void argmax(double& v, int& idx) {                 \
+      if (LaneSim::pass == 0) {                               \
+        LaneSim::v[LaneSim::lane] = v;                        \
+        LaneSim::idx[LaneSim::lane] = idx;                    \
+      } else {                                                \
+        v = LaneSim::v[LaneSim::lane];                        \
+        idx = LaneSim::idx[LaneSim::lane];                    \
+      }                                                       \
+    }                                                         \
+    static void sync() {}                                     \
+  };
+HFB_EMU_COOP(2)
+HFB_EMU_COOP(4)
+HFB_EMU_COOP(8)
+HFB_EMU_COOP(16)
+HFB_EMU_COOP(32)
+}  // namespace hfb
+
 using namespace hfb;
 
 namespace {
+template <int G>
+void lane_group_support(const ShapeD& s, v3 dir, int32_t* idx_per_lane) {
+  int hint = 0;
+  for (LaneSim::pass = 0; LaneSim::pass < 2; ++LaneSim::pass) {
+    for (LaneSim::lane = 0; LaneSim::lane < G; ++LaneSim::lane) {
+      hint = -7;
+      shape_support<G, CAP_CONVEX>(s, dir, hint);
+      if (LaneSim::pass == 1) idx_per_lane[LaneSim::lane] = hint;
+    }
+    if (LaneSim::pass == 0) LaneSim::reduce(G);
+  }
+  LaneSim::lane = LaneSim::pass = 0;
+}
+
 struct Emu {
   HostArena arena;
 };
@@ -206,6 +276,37 @@ int emu_batch_convex_support(void* e, size_t n, const uint32_t* ids, const doubl
     sup[3 * i] = r.x;
     sup[3 * i + 1] = r.y;
     sup[3 * i + 2] = r.z;
+  }
+  return HFB_OK;
+}
+
+// support vertex of a point set along `dir` as each of the G lanes of a group computes it (see LaneSim)
+int emu_lane_group_support(int G, const double* points, int nv, const double* dir, int32_t* idx_per_lane) {
+  std::vector<double> x(nv), y(nv), z(nv);
+  for (int i = 0; i < nv; ++i) {
+    x[i] = points[3 * i];
+    y[i] = points[3 * i + 1];
+    z[i] = points[3 * i + 2];
+  }
+  ShapeD s;
+  s.type = HFB_GEOM_CONVEX;
+  s.cx = x.data();
+  s.cy = y.data();
+  s.cz = z.data();
+  s.nv = nv;
+  const v3 d = mk(dir[0], dir[1], dir[2]);
+  switch (G) {
+    case 1: {
+      int hint = 0;
+      shape_support<1, CAP_CONVEX>(s, d, hint);
+      idx_per_lane[0] = hint;
+    } break;
+    case 2: lane_group_support<2>(s, d, idx_per_lane); break;
+    case 4: lane_group_support<4>(s, d, idx_per_lane); break;
+    case 8: lane_group_support<8>(s, d, idx_per_lane); break;
+    case 16: lane_group_support<16>(s, d, idx_per_lane); break;
+    case 32: lane_group_support<32>(s, d, idx_per_lane); break;
+    default: return HFB_ERR_INVALID_ARGUMENT;
   }
   return HFB_OK;
 }

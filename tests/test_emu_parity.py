@@ -248,3 +248,51 @@ def test_edge_cases():
         e.batch_distance(hs[:4], t, hs[:4], t, P.DistanceRequestPOD(gjk_tolerance=0.0))
     with pytest.raises(ValueError):
         e.batch_distance(hs[:4], t, hs[:4], t, P.DistanceRequestPOD(epa_max_iterations=1000))
+
+
+def test_lane_group_argmax_equals_the_serial_scan_for_any_direction():
+    """The support argmax of a ConvexBase is split over the G lanes that own a pair.  Every lane must end with
+    the serial scan's vertex (start from vertex 0, move on strictly greater: support_functions.cpp:401-421)
+    for ANY direction -- GJK feeds it NaN now and then (0/0 in the projection of a degenerate simplex) and
+    carries on, and with NaN dots the serial scan keeps vertex 0.  Found by the GPU fuzz: the lanes of a group
+    used to disagree there.  tests/emu simulates the lane group on the host (LaneSim)."""
+    import ctypes as C
+    from tests.common import emu_lib
+    L = emu_lib()
+    L.emu_lane_group_support.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+    rng = np.random.default_rng(5)
+    special = [np.nan, np.inf, -np.inf, 0.0, -0.0, 1.0, -1.0]
+
+    def serial(pts, d):
+        best, bi = None, 0
+        for i, p in enumerate(pts):
+            with np.errstate(all="ignore"):
+                v = (p[0] * d[0] + p[1] * d[1]) + p[2] * d[2]
+            if i == 0 or v > best:
+                best, bi = v, i
+        return bi
+
+    checked = nan_cases = 0
+    for trial in range(1500):
+        nv = int(rng.choice([1, 2, 3, 5, 8, 20, 33, 64]))
+        pts = rng.normal(size=(nv, 3))
+        kind = trial % 5
+        if kind == 1:  # ties: duplicated and lattice points
+            pts = np.round(pts)
+        elif kind == 2:  # zeros in the coordinates: inf * 0 = NaN for some vertices only
+            pts[rng.random((nv, 3)) < 0.4] = 0.0
+        d = rng.normal(size=3)
+        if kind >= 2:
+            for k in range(3):
+                if rng.random() < 0.5:
+                    d[k] = special[rng.integers(0, len(special))]
+        pts = np.ascontiguousarray(pts)
+        d = np.ascontiguousarray(d)
+        want = serial(pts, d)
+        nan_cases += bool(np.isnan(d).any() or np.isinf(d).any())
+        for G in (1, 2, 4, 8, 16, 32):
+            out = np.full(G, -99, dtype=np.int32)
+            assert L.emu_lane_group_support(G, pts.ctypes.data, nv, d.ctypes.data, out.ctypes.data) == 0
+            assert np.all(out == want), "G=%d nv=%d dir=%s: lanes %s, serial scan %d" % (G, nv, d, out, want)
+            checked += 1
+    assert checked == 9000 and nan_cases > 300
