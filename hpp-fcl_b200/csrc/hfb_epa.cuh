@@ -212,17 +212,14 @@ HFB_HD bool epa_flush_pending(WS* ws, EpaState& E, double tol, bool force) {
     const int st = epa_face_geometry(ws, ws->newf[k], tol, force);
     if (st && first_bad == 0x7fffffff) first_bad = (k << 8) | st;
   }
-#if defined(__CUDA_ARCH__)
   if (G > 1) {
-    const unsigned m = Coop<G>::mask();
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) {
-      const int o = __shfl_xor_sync(m, first_bad, off);
+      const int o = Coop<G>::shfl_xor(first_bad, off);
       if (o < first_bad) first_bad = o;
     }
-    __syncwarp(m);  // the other lanes' faces are read by the scan that follows
+    Coop<G>::sync();  // the other lanes' faces are read by the scan that follows
   }
-#endif
   if (first_bad != 0x7fffffff) {
     E.status = first_bad & 0xff;
     return false;
@@ -253,16 +250,14 @@ HFB_HD int epa_find_closest(const WS* ws, const EpaState& E) {
       bidx = f;
     }
   }
-#if defined(__CUDA_ARCH__)
   if (G > 1) {
-    const unsigned m = Coop<G>::mask();
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) {
-      const double ob = __shfl_xor_sync(m, best, off);
-      const int os = __shfl_xor_sync(m, bseq, off);
-      const int oi = __shfl_xor_sync(m, bidx, off);
-      const int ors = __shfl_xor_sync(m, rseq, off);
-      const int ori = __shfl_xor_sync(m, ridx, off);
+      const double ob = Coop<G>::shfl_xor(best, off);
+      const int os = Coop<G>::shfl_xor(bseq, off);
+      const int oi = Coop<G>::shfl_xor(bidx, off);
+      const int ors = Coop<G>::shfl_xor(rseq, off);
+      const int ori = Coop<G>::shfl_xor(ridx, off);
       // candidate validity first (a lane with no candidate has bidx == NONE)
       const bool mine = bidx != HFB_EPA_NONE, theirs = oi != HFB_EPA_NONE;
       if (theirs && (!mine || ob < best || (ob == best && os > bseq))) {
@@ -276,7 +271,6 @@ HFB_HD int epa_find_closest(const WS* ws, const EpaState& E) {
       }
     }
   }
-#endif
   return bidx != HFB_EPA_NONE ? bidx : ridx;
 }
 

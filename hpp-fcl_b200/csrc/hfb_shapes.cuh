@@ -22,6 +22,18 @@ namespace hfb {
 #define HFB_INFLATE (1 + 1e-10)
 
 // ---- lane-group policy: G lanes of a warp own one pair ---------------------
+// Four primitives -- lane(), mask(), shfl_xor(), sync() -- carry everything the pair code does across lanes;
+// argmax() and the two reductions of hfb_epa.cuh are written on top of them.  On the device they are the warp
+// intrinsics.  tests/emu (HFB_LANE_SIM) supplies host versions in which the G lanes of a group are G threads
+// meeting at barriers, so that the cooperative paths run -- and race -- on the CPU as well.
+#if !defined(__CUDACC__) && defined(HFB_LANE_SIM)
+namespace lanesim {  // defined by the test harness
+int lane();
+void sync();
+double shfl_xor(double v, int off);
+int shfl_xor(int v, int off);
+}  // namespace lanesim
+#endif
 template <int G>
 struct Coop {
 #if defined(__CUDACC__)
@@ -31,26 +43,40 @@ struct Coop {
     unsigned wl = threadIdx.x & 31u;
     return (((1u << G) - 1u)) << (wl & ~(unsigned)(G - 1));
   }
+  static __device__ __forceinline__ double shfl_xor(double v, int off) { return __shfl_xor_sync(mask(), v, off); }
+  static __device__ __forceinline__ int shfl_xor(int v, int off) { return __shfl_xor_sync(mask(), v, off); }
+  static __device__ __forceinline__ void sync() { __syncwarp(mask()); }
+#define HFB_COOP_FN static __device__ __forceinline__
+#elif defined(HFB_LANE_SIM)
+  static int lane() { return lanesim::lane(); }
+  static unsigned mask() { return 0u; }
+  static double shfl_xor(double v, int off) { return lanesim::shfl_xor(v, off); }
+  static int shfl_xor(int v, int off) { return lanesim::shfl_xor(v, off); }
+  static void sync() { lanesim::sync(); }
+#define HFB_COOP_FN static inline
+#endif
+#if defined(__CUDACC__) || defined(HFB_LANE_SIM)
   // group-wide argmax; ties -> lowest index; result broadcast to every lane
-  static __device__ __forceinline__ void argmax(double& v, int& idx) {
-    const unsigned m = mask();
+  HFB_COOP_FN void argmax(double& v, int& idx) {
 #pragma unroll
     for (int off = G / 2; off > 0; off >>= 1) {
-      double ov = __shfl_xor_sync(m, v, off);
-      int oi = __shfl_xor_sync(m, idx, off);
+      double ov = shfl_xor(v, off);
+      int oi = shfl_xor(idx, off);
       if (ov > v || (ov == v && oi < idx)) {
         v = ov;
         idx = oi;
       }
     }
   }
-  static __device__ __forceinline__ void sync() { __syncwarp(mask()); }
+#undef HFB_COOP_FN
 #endif
 };
 template <>
 struct Coop<1> {
   static HFB_HD int lane() { return 0; }
   static HFB_HD unsigned mask() { return 0xffffffffu; }
+  static HFB_HD double shfl_xor(double v, int) { return v; }
+  static HFB_HD int shfl_xor(int v, int) { return v; }
   static HFB_HD void argmax(double&, int&) {}
   static HFB_HD void sync() {}
 };

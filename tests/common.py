@@ -29,7 +29,7 @@ def emu_lib():
         deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off",
-                                   "-march=x86-64-v2", "-Wno-unknown-pragmas", "-shared", "-o", so, src])
+                                   "-march=x86-64-v2", "-Wno-unknown-pragmas", "-pthread", "-shared", "-o", so, src])
         L = C.CDLL(so)
         L.emu_create.restype = C.c_void_p
         L.emu_destroy.argtypes = [C.c_void_p]
@@ -81,6 +81,8 @@ class EmuScene:
     def commit(self):
         pass
 
+    lanes = 1  # > 1: shape pairs run through lane groups of that many threads (tests/emu lanesim)
+
     def _run(self, fn, dtype, h1, tf1, h2, tf2, req, want_guess):
         h1 = np.ascontiguousarray(h1, dtype=np.uint32)
         h2 = np.ascontiguousarray(h2, dtype=np.uint32)
@@ -93,8 +95,22 @@ class EmuScene:
             gg = np.zeros((n, 3))
             gh = np.zeros((n, 2), dtype=np.int32)
             g = P.GuessOut(_ptr(gg), _ptr(gh))
-        rc = fn(self.h, n, _ptr(h1), _ptr(tf1), _ptr(h2), _ptr(tf2), C.byref(req), _ptr(out),
-                C.byref(g) if g is not None else None)
+        if self.lanes > 1:
+            lfn = self.L.emu_batch_distance_lanes if fn is self.L.emu_batch_distance else self.L.emu_batch_collide_lanes
+            lfn.restype = C.c_long
+            lfn.argtypes = [C.c_void_p, C.c_int, C.c_size_t] + [C.c_void_p] * 7
+            rc = lfn(self.h, self.lanes, n, _ptr(h1), _ptr(tf1), _ptr(h2), _ptr(tf2), C.byref(req), _ptr(out),
+                     C.byref(g) if g is not None else None)
+            if rc == -1:
+                raise RuntimeError("a lane of a group never reached a barrier (divergent control flow)")
+            if rc > 0:
+                raise RuntimeError("the lanes of a group disagreed on %d pairs" % rc)
+            if rc == -2:  # meshes in the batch (one lane per query on the device as well) or a special request
+                rc = fn(self.h, n, _ptr(h1), _ptr(tf1), _ptr(h2), _ptr(tf2), C.byref(req), _ptr(out),
+                        C.byref(g) if g is not None else None)
+        else:
+            rc = fn(self.h, n, _ptr(h1), _ptr(tf1), _ptr(h2), _ptr(tf2), C.byref(req), _ptr(out),
+                    C.byref(g) if g is not None else None)
         if rc != 0:
             raise ValueError("emu error %d" % rc)
         return (out, gg, gh) if want_guess else out

@@ -1,7 +1,7 @@
 // TEST HARNESS ONLY -- not part of the product and never loaded by it.
 //
 // Compiles the per-pair DEVICE code of hpp-fcl_b200/csrc/*.cuh with g++ (G = 1
-// lane per pair, HFB_HD expands to `inline`; lane groups only for the support argmax, see LaneSim) so that the exact arithmetic the
+// lane per pair, HFB_HD expands to `inline`; lane groups of G threads: see lanesim below) so that the exact arithmetic the
 // CUDA kernels execute can be checked against the oracle in the CPU-only
 // container (`-m "not gpu"` tests).  The product library has no such path: its
 // entry points fail with HFB_ERR_NO_DEVICE when there is no GPU.
@@ -10,80 +10,99 @@
 #include <memory>
 #include <vector>
 
+#define HFB_LANE_SIM 1  // host lane groups, see below
 #include "../../hpp-fcl_b200/csrc/hfb_arena.cuh"
 #include "../../hpp-fcl_b200/csrc/hfb_bvh.cuh"
 #include "../../hpp-fcl_b200/csrc/hfb_request.cuh"
 
-// ---- lane groups on the host: Coop<G> for G > 1 (device-only in the product) simulated in two passes --------
-// Pass 0 runs every lane of a group up to its cross-lane argmax and records what the lane brings to it; the
-// butterfly of Coop<G>::argmax (hfb_shapes.cuh: xor-shuffle, `greater, or equal with the lower index`) is
-// then replayed on the recorded values; pass 1 runs every lane again and hands it its reduced value.  Good
-// for code with one reduction per call (shape_support): checks that every lane of a group ends with the
-// answer of the serial scan.
+// ---- lane groups on the host ---------------------------------------------------------------------------
+// Coop<G> for G > 1 is warp intrinsics on the device.  Here (HFB_LANE_SIM) the G lanes of a group are G threads
+// that run the same device function and meet at a barrier wherever the device code shuffles or syncs; whatever
+// the lanes share on the device (the EPA workspace) they share here.  Between two barriers the threads interleave
+// freely, so code that only works because a warp happens to run in lock step shows up as a mismatch (or a lane
+// that never arrives: the barrier gives up after a while and the batch call reports it).
+#include <atomic>
+#include <chrono>
+#include <thread>
+
 namespace hfb {
-struct LaneSim {
-  static inline int lane = 0, pass = 0;
-  static inline double v[32];
-  static inline int idx[32];
-  static void reduce(int G) {
-    for (int off = G / 2; off > 0; off >>= 1) {
-      double nv[32];
-      int ni[32];
-      for (int l = 0; l < G; ++l) {
-        const double ov = v[l ^ off];
-        const int oi = idx[l ^ off];
-        nv[l] = v[l];
-        ni[l] = idx[l];
-        if (ov > v[l] || (ov == v[l] && oi < idx[l])) {
-          nv[l] = ov;
-          ni[l] = oi;
-        }
-      }
-      for (int l = 0; l < G; ++l) {
-        v[l] = nv[l];
-        idx[l] = ni[l];
-      }
+namespace lanesim {
+struct Group {
+  int G = 1;
+  std::atomic<int> count{0};
+  std::atomic<int> gen{0};
+  std::atomic<bool> failed{false};
+  double dv[32];
+  int iv[32];
+};
+thread_local Group* tl_group = nullptr;
+thread_local int tl_lane = 0;
+int lane() { return tl_lane; }
+void sync() {
+  Group* g = tl_group;
+  if (!g || g->G == 1 || g->failed.load(std::memory_order_relaxed)) return;
+  const int gen = g->gen.load(std::memory_order_acquire);
+  if (g->count.fetch_add(1, std::memory_order_acq_rel) + 1 == g->G) {
+    g->count.store(0, std::memory_order_relaxed);
+    g->gen.store(gen + 1, std::memory_order_release);
+    return;
+  }
+  const auto t0 = std::chrono::steady_clock::now();
+  for (unsigned spins = 0; g->gen.load(std::memory_order_acquire) == gen; ++spins) {
+    if (g->failed.load(std::memory_order_relaxed)) return;
+    if (spins > 200) std::this_thread::yield();
+    if ((spins & 0xffff) == 0xffff && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) {
+      g->failed.store(true);  // a lane took another path: on the device this is a hang
+      return;
     }
   }
-};
-#define HFB_EMU_COOP(G_)                                      \
-  template <>                                                 \
-  struct Coop<G_> {                                           \
-    static int lane() { return LaneSim::lane; }               \
-    static unsigned mask() { return 0; }                      \
-    static void argmax(double& v, int& idx) {                 \
-      if (LaneSim::pass == 0) {                               \
-        LaneSim::v[LaneSim::lane] = v;                        \
-        LaneSim::idx[LaneSim::lane] = idx;                    \
-      } else {                                                \
-        v = LaneSim::v[LaneSim::lane];                        \
-        idx = LaneSim::idx[LaneSim::lane];                    \
-      }                                                       \
-    }                                                         \
-    static void sync() {}                                     \
-  };
-HFB_EMU_COOP(2)
-HFB_EMU_COOP(4)
-HFB_EMU_COOP(8)
-HFB_EMU_COOP(16)
-HFB_EMU_COOP(32)
+}
+double shfl_xor(double v, int off) {
+  Group* g = tl_group;
+  g->dv[tl_lane] = v;
+  sync();
+  const double r = g->dv[tl_lane ^ off];
+  sync();
+  return r;
+}
+int shfl_xor(int v, int off) {
+  Group* g = tl_group;
+  g->iv[tl_lane] = v;
+  sync();
+  const int r = g->iv[tl_lane ^ off];
+  sync();
+  return r;
+}
+}  // namespace lanesim
 }  // namespace hfb
 
 using namespace hfb;
 
 namespace {
+// runs fn(lane) on G threads that form one lane group; false when a lane never arrived at a barrier
+template <class Fn>
+bool run_lane_group(int G, Fn fn) {
+  lanesim::Group grp;
+  grp.G = G;
+  std::vector<std::thread> th;
+  for (int l = 0; l < G; ++l)
+    th.emplace_back([&grp, l, &fn]() {
+      lanesim::tl_group = &grp;
+      lanesim::tl_lane = l;
+      fn(l);
+      lanesim::tl_group = nullptr;
+    });
+  for (auto& t : th) t.join();
+  return !grp.failed.load();
+}
+
 template <int G>
-void lane_group_support(const ShapeD& s, v3 dir, int32_t* idx_per_lane) {
-  int hint = 0;
-  for (LaneSim::pass = 0; LaneSim::pass < 2; ++LaneSim::pass) {
-    for (LaneSim::lane = 0; LaneSim::lane < G; ++LaneSim::lane) {
-      hint = -7;
-      shape_support<G, CAP_CONVEX>(s, dir, hint);
-      if (LaneSim::pass == 1) idx_per_lane[LaneSim::lane] = hint;
-    }
-    if (LaneSim::pass == 0) LaneSim::reduce(G);
-  }
-  LaneSim::lane = LaneSim::pass = 0;
+bool lane_group_support(const ShapeD& s, v3 dir, int32_t* idx_per_lane) {
+  return run_lane_group(G, [&](int l) {
+    int hint = -7;
+    shape_support<G, CAP_CONVEX>(s, dir, hint);
+    idx_per_lane[l] = hint;
+  });
 }
 
 struct Emu {
@@ -136,6 +155,107 @@ inline void put_guess(const hfb_guess_out* go, size_t i, const PairOut& o) {
   if (go->cached_support_func_guess) {
     go->cached_support_func_guess[2 * i] = o.hint0;
     go->cached_support_func_guess[2 * i + 1] = o.hint1;
+  }
+}
+
+// what k_pairs queues for k_epa and k_epa rebuilds (hfb_kernels.cu): rank, hints, GJK iteration count and the
+// simplex's w0 / w1, w recomputed as w0 - w1
+inline GjkState requeue(const GjkState& q) {
+  GjkState g;
+  std::memset(&g, 0, sizeof(g));
+  g.rank = q.rank;
+  g.hint0 = q.hint0;
+  g.hint1 = q.hint1;
+  g.iterations = q.iterations;
+  g.status = HFB_GJK_COLLISION;
+  g.distance = 0;
+  g.ray = mk(0, 0, 0);
+  g.s0.w0 = q.s0.w0; g.s0.w1 = q.s0.w1;
+  g.s1.w0 = q.s1.w0; g.s1.w1 = q.s1.w1;
+  g.s2.w0 = q.s2.w0; g.s2.w1 = q.s2.w1;
+  g.s3.w0 = q.s3.w0; g.s3.w1 = q.s3.w1;
+  g.s0.w = g.s0.w0 - g.s0.w1;
+  g.s1.w = g.s1.w0 - g.s1.w1;
+  g.s2.w = g.s2.w0 - g.s2.w1;
+  g.s3.w = g.s3.w0 - g.s3.w1;
+  return g;
+}
+
+// A batch of shape pairs with phase 1 (closed forms, GJK: k_pairs<G>) run by lane groups of G threads.
+// Phase 2 is left to one lane: EPA's lanes share one polytope workspace and re-execute its serial parts
+// redundantly, which is sound for the converged lanes of a warp and not for free-running threads.
+// Returns the number of pairs on which some lane's phase-1 outcome (result record or queued GJK state)
+// differed from lane 0's (must be 0), or -1 when a lane never reached a barrier.
+template <int G, int MODE>
+long batch_lanes(Emu* E, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
+                 const hfb_transform* tf2, const hfb_query_request& q, const SolverP& P, const CollideP& C, void* out,
+                 const hfb_guess_out* go) {
+  const ArenaView A = E->arena.view();
+  std::unique_ptr<EpaWs> ws(new EpaWs());
+  struct LaneOut {
+    PairOut o;
+    GjkState g;
+    bool need_epa;
+  };
+  std::vector<LaneOut> outs(G);
+  long disagree = 0;
+  const bool ok = run_lane_group(G, [&](int l) {
+    for (size_t i = 0; i < n; ++i) {
+      const PairIn in = load_pair(A, i, h1, tf1, h2, tf2, q);
+      LaneOut& mine = outs[l];
+      std::memset(&mine, 0, sizeof(mine));
+      mine.need_epa = pair_phase1<G, CAPS_ALL>(in, P, mine.o, mine.g);
+      Coop<G>::sync();
+      if (l == 0) {
+        for (int k = 1; k < G; ++k) {
+          const bool same = outs[k].need_epa == mine.need_epa &&
+                            (mine.need_epa ? std::memcmp(&outs[k].g, &mine.g, sizeof(GjkState)) == 0
+                                           : std::memcmp(&outs[k].o, &mine.o, sizeof(PairOut)) == 0);
+          if (!same) {
+            ++disagree;
+            break;
+          }
+        }
+        PairOut o = mine.o;
+        if (mine.need_epa) {  // k_epa, both tiers, one lane
+          const GjkState queued = mine.g;
+          GjkState g = requeue(queued);
+          o.cached_guess = mk(1, 0, 0);
+          o.hint0 = o.hint1 = 0;
+          EpaWsSmall small;
+          if (!pair_phase2<1, CAPS_ALL>(in, P, g, &small, o)) {
+            ++g_retries;
+            g = requeue(queued);
+            o.cached_guess = mk(1, 0, 0);
+            o.hint0 = o.hint1 = 0;
+            pair_phase2<1, CAPS_ALL>(in, P, g, ws.get(), o);
+          }
+        }
+        if (MODE == 0) write_distance(o, static_cast<hfb_distance_result*>(out) + i);
+        else write_contact(o, C, static_cast<hfb_contact*>(out) + i);
+        put_guess(go, i, o);
+      }
+      Coop<G>::sync();
+    }
+  });
+  return ok ? disagree : -1;
+}
+
+template <int MODE>
+long batch_lanes_g(int G, Emu* E, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
+                   const hfb_transform* tf2, const hfb_query_request& q, const SolverP& P, const CollideP& C, void* out,
+                   const hfb_guess_out* go) {
+  const ArenaView A = E->arena.view();
+  for (size_t i = 0; i < n; ++i) {
+    if (h1[i] >= A.nshapes || h2[i] >= A.nshapes) return -2;
+    if (A.shapes[h1[i]].type == HFB_BV_OBBRSS || A.shapes[h2[i]].type == HFB_BV_OBBRSS) return -2;  // one lane per query
+  }
+  switch (G) {
+    case 2: return batch_lanes<2, MODE>(E, n, h1, tf1, h2, tf2, q, P, C, out, go);
+    case 4: return batch_lanes<4, MODE>(E, n, h1, tf1, h2, tf2, q, P, C, out, go);
+    case 8: return batch_lanes<8, MODE>(E, n, h1, tf1, h2, tf2, q, P, C, out, go);
+    case 16: return batch_lanes<16, MODE>(E, n, h1, tf1, h2, tf2, q, P, C, out, go);
+    default: return -2;
   }
 }
 }  // namespace
@@ -257,6 +377,28 @@ int emu_batch_collide(void* e, size_t n, const uint32_t* h1, const hfb_transform
   return HFB_OK;
 }
 
+// shape pairs (no meshes) through lane groups of G threads, see batch_lanes
+long emu_batch_distance_lanes(void* e, int G, size_t n, const uint32_t* h1, const hfb_transform* tf1,
+                              const uint32_t* h2, const hfb_transform* tf2, const hfb_distance_request* req,
+                              hfb_distance_result* out, const hfb_guess_out* go) {
+  if (validate_query(req->q)) return -2;
+  CollideP C;
+  C.security_margin = 0;
+  C.collision_distance_threshold = 0;
+  return batch_lanes_g<0>(G, static_cast<Emu*>(e), n, h1, tf1, h2, tf2, req->q, solver_from_distance_request(*req), C,
+                          out, go);
+}
+long emu_batch_collide_lanes(void* e, int G, size_t n, const uint32_t* h1, const hfb_transform* tf1,
+                             const uint32_t* h2, const hfb_transform* tf2, const hfb_collision_request* req,
+                             hfb_contact* out, const hfb_guess_out* go) {
+  if (validate_query(req->q) || req->security_margin == -INFINITY || req->num_max_contacts == 0) return -2;
+  CollideP C;
+  C.security_margin = req->security_margin;
+  C.collision_distance_threshold = req->q.collision_distance_threshold;
+  return batch_lanes_g<1>(G, static_cast<Emu*>(e), n, h1, tf1, h2, tf2, req->q, solver_from_collision_request(*req), C,
+                          out, go);
+}
+
 int emu_batch_convex_support(void* e, size_t n, const uint32_t* ids, const double* dirs, int32_t* idx,
                              double* sup) {
   Emu* E = static_cast<Emu*>(e);
@@ -280,7 +422,7 @@ int emu_batch_convex_support(void* e, size_t n, const uint32_t* ids, const doubl
   return HFB_OK;
 }
 
-// support vertex of a point set along `dir` as each of the G lanes of a group computes it (see LaneSim)
+// support vertex of a point set along `dir` as each of the G lanes of a group computes it (lanesim)
 int emu_lane_group_support(int G, const double* points, int nv, const double* dir, int32_t* idx_per_lane) {
   std::vector<double> x(nv), y(nv), z(nv);
   for (int i = 0; i < nv; ++i) {
@@ -301,11 +443,11 @@ int emu_lane_group_support(int G, const double* points, int nv, const double* di
       shape_support<1, CAP_CONVEX>(s, d, hint);
       idx_per_lane[0] = hint;
     } break;
-    case 2: lane_group_support<2>(s, d, idx_per_lane); break;
-    case 4: lane_group_support<4>(s, d, idx_per_lane); break;
-    case 8: lane_group_support<8>(s, d, idx_per_lane); break;
-    case 16: lane_group_support<16>(s, d, idx_per_lane); break;
-    case 32: lane_group_support<32>(s, d, idx_per_lane); break;
+    case 2: return lane_group_support<2>(s, d, idx_per_lane) ? HFB_OK : HFB_ERR_CUDA;
+    case 4: return lane_group_support<4>(s, d, idx_per_lane) ? HFB_OK : HFB_ERR_CUDA;
+    case 8: return lane_group_support<8>(s, d, idx_per_lane) ? HFB_OK : HFB_ERR_CUDA;
+    case 16: return lane_group_support<16>(s, d, idx_per_lane) ? HFB_OK : HFB_ERR_CUDA;
+    case 32: return lane_group_support<32>(s, d, idx_per_lane) ? HFB_OK : HFB_ERR_CUDA;
     default: return HFB_ERR_INVALID_ARGUMENT;
   }
   return HFB_OK;

@@ -296,3 +296,57 @@ def test_lane_group_argmax_equals_the_serial_scan_for_any_direction():
             assert np.all(out == want), "G=%d nv=%d dir=%s: lanes %s, serial scan %d" % (G, nv, d, out, want)
             checked += 1
     assert checked == 9000 and nan_cases > 300
+
+
+@pytest.mark.parametrize("lanes", [2, 4, 8])
+def test_phase1_through_lane_groups(lanes):
+    """k_pairs<G> runs a pair on G cooperating lanes.  tests/emu runs the same device code with the G lanes of a
+    group as G host threads meeting at barriers where the device shuffles or syncs (lanesim): every lane must
+    reach the same phase-1 outcome, and the results must be the oracle's bit for bit -- hulls with few and many
+    vertices, triangles, primitives, with requests that drive GJK through NaN rays (relative duality gap on
+    exact-zero poses at scale 1000, the configuration in which the GPU fuzz found the lanes disagreeing)."""
+    from tests.common import EmuScene
+    from oracle import oracle_lib
+    import itertools
+    rng = np.random.default_rng(11)
+    orc, emu = oracle_lib.OracleScene(P), EmuScene()
+    emu.lanes = lanes
+    scale = 1000.0
+    hulls = [W.ellipsoid_hull(rng, nv) for nv in (6, 20, 32)] + [W.icosahedron_from_ellipsoid((0.3, 0.5, 0.2))]
+    cube = np.array(list(itertools.product((-1.0, 1.0), repeat=3))) * 0.4
+    ids = []
+    for pts in [h[0] for h in hulls] + [cube]:
+        a, b = orc.register_convex(pts * scale, None), emu.register_convex(pts * scale)
+        assert a == b
+        ids.append(a)
+    prim = W.random_primitive_shapes(rng, 64, ALL_PRIMS)
+    prim["p"] *= scale
+    recs = np.concatenate([P.make_shapes([P.GEOM_CONVEX] * len(ids), np.zeros((len(ids), 3)), data=ids), prim])
+    h = orc.register_shapes(recs)
+    assert np.array_equal(h, emu.register_shapes(recs))
+    n = 6000
+    h1, h2 = h[rng.integers(0, len(h), n)], h[rng.integers(0, len(h), n)]
+    h1[: n // 2] = h[rng.integers(0, len(ids), n // 2)]  # a hull in at least half of the pairs
+    tf1 = W.identity_transforms(n)
+    tf2 = W.identity_transforms(n, rng.uniform(-2, 2, (n, 3)) * (rng.random((n, 3)) < 0.5) * scale)
+    tf2[n // 2:] = W.random_transforms(rng, n - n // 2, (-2 * scale,) * 3, (2 * scale,) * 3)
+    gg = rng.normal(size=(n, 3)) * scale
+    gg[rng.random(n) < 0.3] = 0
+    gh = np.zeros((n, 2), dtype=np.int32)
+    nan_rays = 0
+    for kw in (dict(), dict(gjk_convergence_criterion=P.DualityGap),
+               dict(gjk_variant=P.PolyakAcceleration, gjk_convergence_criterion=P.DualityGap),
+               dict(gjk_variant=P.NesterovAcceleration, gjk_convergence_criterion=P.Hybrid)):
+        req = P.DistanceRequestPOD(gjk_initial_guess=P.CachedGuess, **kw)
+        req.q.cached_gjk_guess = gg.ctypes.data
+        req.q.cached_support_func_guess = gh.ctypes.data
+        ro, og, oh = orc.batch_distance(h1, tf1, h2, tf2, req, want_guess=True, nthreads=0)
+        re, eg, eh = emu.batch_distance(h1, tf1, h2, tf2, req, want_guess=True)
+        compare_distance(ro, re, what="lanes=%d %s" % (lanes, kw))
+        same = (og.view(np.uint64) == eg.view(np.uint64)) | (np.isnan(og) & np.isnan(eg))  # NaN payloads aside
+        assert same.all() and np.array_equal(oh, eh)
+        nan_rays += int(np.isnan(og).any(axis=1).sum())
+        creq = P.CollisionRequestPOD(security_margin=0.01 * scale, **kw)
+        compare_distance(orc.batch_collide(h1, tf1, h2, tf2, creq, nthreads=0), emu.batch_collide(h1, tf1, h2, tf2, creq),
+                         what="collide lanes=%d %s" % (lanes, kw))
+    assert nan_rays > 0  # the batch does contain pairs whose GJK ends on a NaN ray

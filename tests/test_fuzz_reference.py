@@ -26,6 +26,18 @@ def test_fuzz_oracle_reference_and_device_code(first):
         assert ok, tag
 
 
+@pytest.mark.parametrize("lanes,seeds", [(2, (3, 4, 5)), (8, (3, 4))])
+def test_fuzz_device_code_through_lane_groups(lanes, seeds):
+    """the rounds the GPU failed (seeds 3 and 4 at n = 4000, see below) with phase 1 run by lane groups of host
+    threads (tests/emu lanesim): fails on the code of that GPU run ("the lanes of a group disagreed"), passes now"""
+    from tests.common import EmuScene
+    for seed in seeds:
+        dev = EmuScene()
+        dev.lanes = lanes
+        ok, tag = fuzz_ref.one_round(seed, 4000, _ref(), dev)
+        assert ok, tag
+
+
 # Seeds run on a B200 in round 1 (profiles/r01_summary.md).  1, 2, 5-10 were green.  3 and 4 exposed a defect of
 # the lane-group support argmax: a NaN direction (GJK produces one from 0/0 in the projection of a degenerate
 # simplex, and carries on -- so does the reference) left the lanes of a group with different vertices.  Fixed in

@@ -421,6 +421,7 @@ def main():
     ap.add_argument("--no-emu", action="store_true")
     ap.add_argument("--keep-going", action="store_true")
     ap.add_argument("--gpu", action="store_true", help="the real kernels (hppfcl_b200.Engine) instead of the host build")
+    ap.add_argument("--lanes", type=int, default=1, help="host build: lane groups of this many threads for phase 1")
     a = ap.parse_args()
     use_ref = False
     if os.path.isdir("/root/reference/src"):
@@ -429,6 +430,9 @@ def main():
     t0, seed, bad = time.time(), a.seed, 0
     while time.time() - t0 < a.minutes * 60:
         dev = not a.no_emu
+        if dev and a.lanes > 1:
+            dev = EmuScene()
+            dev.lanes = a.lanes
         if a.gpu:
             import hppfcl_b200 as hf
             dev = hf.Engine(0)
