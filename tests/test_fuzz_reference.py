@@ -41,7 +41,8 @@ def test_fuzz_device_code_through_lane_groups(lanes, seeds):
 # Seeds run on a B200 in round 1 (profiles/r01_summary.md).  1, 2, 5-10 were green.  3 and 4 exposed a defect of
 # the lane-group support argmax: a NaN direction (GJK produces one from 0/0 in the projection of a degenerate
 # simplex, and carries on -- so does the reference) left the lanes of a group with different vertices.  Fixed in
-# hfb_shapes.cuh and pinned on the host by tests/test_emu_parity.py::test_lane_group_argmax_...; the GPU budget of
+# hfb_shapes.cuh, reproduced and pinned on the host (test_fuzz_device_code_through_lane_groups above and
+# tests/test_emu_parity.py::test_lane_group_argmax_... / test_phase1_through_lane_groups); the GPU budget of
 # the round was spent by then, so 3, 4 and the seeds never run on a GPU stay non-strict xfail until a GPU run
 # confirms them (an XPASS is the expected outcome).
 GPU_GREEN = [1, 2, 5, 6, 7, 8, 9, 10]
