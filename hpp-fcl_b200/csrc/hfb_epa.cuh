@@ -219,6 +219,23 @@ HFB_HD bool epa_flush_pending(WS* ws, EpaState& E, double tol, bool force) {
       if (o < first_bad) first_bad = o;
     }
     Coop<G>::sync();  // the other lanes' faces are read by the scan that follows
+#if !defined(__CUDACC__) && defined(HFB_LANE_SIM)
+    // host lane simulation only (tests/emu): every lane thread owns a private copy of the workspace (the
+    // redundant serial parts of an iteration are sound for converged lanes of a warp, not for free-running
+    // threads), so what the owner lanes computed above is fetched from their copies
+    for (int k = 0; k < n; ++k) {
+      const int owner = k % G;
+      if (owner == Coop<G>::lane()) continue;
+      const WS* peer = static_cast<const WS*>(lanesim::peer_workspace(owner));
+      const int f = ws->newf[k];
+      ws->fn[3 * f] = peer->fn[3 * f];
+      ws->fn[3 * f + 1] = peer->fn[3 * f + 1];
+      ws->fn[3 * f + 2] = peer->fn[3 * f + 2];
+      ws->fd[f] = peer->fd[f];
+      ws->fflag[f] = peer->fflag[f];
+    }
+    Coop<G>::sync();  // peers may move on only after everybody has read
+#endif
   }
   if (first_bad != 0x7fffffff) {
     E.status = first_bad & 0xff;

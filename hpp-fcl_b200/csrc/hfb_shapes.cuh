@@ -32,6 +32,7 @@ int lane();
 void sync();
 double shfl_xor(double v, int off);
 int shfl_xor(int v, int off);
+const void* peer_workspace(int lane);  // the EPA workspace lane `lane` of this group registered (private copies)
 }  // namespace lanesim
 #endif
 template <int G>

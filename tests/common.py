@@ -23,11 +23,12 @@ _EMU = None
 def emu_lib():
     global _EMU
     if _EMU is None:
-        so = os.path.join(EMU_DIR, "libemu.so")
+        so = os.environ.get("HFB_EMU_SO") or os.path.join(EMU_DIR, "libemu.so")  # another build under test
         src = os.path.join(EMU_DIR, "emu.cpp")
         csrc = os.path.join(ROOT, "hpp-fcl_b200", "csrc")
         deps = [src] + [os.path.join(csrc, f) for f in os.listdir(csrc) if f.endswith(".cuh")]
-        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+        if "HFB_EMU_SO" not in os.environ and (
+                not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps)):
             subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-fPIC", "-ffp-contract=off",
                                    "-march=x86-64-v2", "-Wno-unknown-pragmas", "-pthread", "-shared", "-o", so, src])
         L = C.CDLL(so)

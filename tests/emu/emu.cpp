@@ -34,6 +34,7 @@ struct Group {
   std::atomic<bool> failed{false};
   double dv[32];
   int iv[32];
+  const void* ws[32];  // the lanes' private EPA workspaces (see hfb_epa.cuh, epa_flush_pending)
 };
 thread_local Group* tl_group = nullptr;
 thread_local int tl_lane = 0;
@@ -57,6 +58,7 @@ void sync() {
     }
   }
 }
+void register_workspace(const void* p);
 double shfl_xor(double v, int off) {
   Group* g = tl_group;
   g->dv[tl_lane] = v;
@@ -72,6 +74,11 @@ int shfl_xor(int v, int off) {
   const int r = g->iv[tl_lane ^ off];
   sync();
   return r;
+}
+const void* peer_workspace(int l) { return tl_group->ws[l]; }
+void register_workspace(const void* p) {
+  tl_group->ws[tl_lane] = p;
+  sync();
 }
 }  // namespace lanesim
 }  // namespace hfb
@@ -181,17 +188,18 @@ inline GjkState requeue(const GjkState& q) {
   return g;
 }
 
-// A batch of shape pairs with phase 1 (closed forms, GJK: k_pairs<G>) run by lane groups of G threads.
-// Phase 2 is left to one lane: EPA's lanes share one polytope workspace and re-execute its serial parts
-// redundantly, which is sound for the converged lanes of a warp and not for free-running threads.
-// Returns the number of pairs on which some lane's phase-1 outcome (result record or queued GJK state)
-// differed from lane 0's (must be 0), or -1 when a lane never reached a barrier.
+// A batch of shape pairs run by lane groups of G threads: phase 1 (closed forms, GJK: k_pairs<G>) and phase 2
+// (EPA: k_epa<G>, reduced workspace first, full size when the polytope outgrows it).  In phase 2 every lane
+// works in a private copy of the polytope workspace -- EPA's lanes re-execute the serial parts of an iteration
+// redundantly on one shared workspace, which is sound for the converged lanes of a warp and not for free-running
+// threads -- and fetches the face geometry its peers computed (hfb_epa.cuh, epa_flush_pending).
+// Returns the number of pairs on which some lane's outcome differed from lane 0's (must be 0), or -1 when a
+// lane never reached a barrier.
 template <int G, int MODE>
 long batch_lanes(Emu* E, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
                  const hfb_transform* tf2, const hfb_query_request& q, const SolverP& P, const CollideP& C, void* out,
                  const hfb_guess_out* go) {
   const ArenaView A = E->arena.view();
-  std::unique_ptr<EpaWs> ws(new EpaWs());
   struct LaneOut {
     PairOut o;
     GjkState g;
@@ -200,40 +208,42 @@ long batch_lanes(Emu* E, size_t n, const uint32_t* h1, const hfb_transform* tf1,
   std::vector<LaneOut> outs(G);
   long disagree = 0;
   const bool ok = run_lane_group(G, [&](int l) {
+    std::unique_ptr<EpaWs> ws(new EpaWs());
+    std::unique_ptr<EpaWsSmall> small(new EpaWsSmall());
     for (size_t i = 0; i < n; ++i) {
       const PairIn in = load_pair(A, i, h1, tf1, h2, tf2, q);
       LaneOut& mine = outs[l];
       std::memset(&mine, 0, sizeof(mine));
       mine.need_epa = pair_phase1<G, CAPS_ALL>(in, P, mine.o, mine.g);
+      if (mine.need_epa) {  // k_epa: the queued state, tier 0, then tier 1
+        const GjkState queued = mine.g;
+        GjkState g = requeue(queued);
+        mine.o.cached_guess = mk(1, 0, 0);
+        mine.o.hint0 = mine.o.hint1 = 0;
+        lanesim::register_workspace(small.get());
+        Coop<G>::sync();
+        const bool done = pair_phase2<G, CAPS_ALL>(in, P, g, small.get(), mine.o);
+        Coop<G>::sync();
+        if (!done) {
+          if (l == 0) ++g_retries;
+          g = requeue(queued);
+          mine.o.cached_guess = mk(1, 0, 0);
+          mine.o.hint0 = mine.o.hint1 = 0;
+          lanesim::register_workspace(ws.get());
+          Coop<G>::sync();
+          pair_phase2<G, CAPS_ALL>(in, P, g, ws.get(), mine.o);
+        }
+      }
       Coop<G>::sync();
       if (l == 0) {
-        for (int k = 1; k < G; ++k) {
-          const bool same = outs[k].need_epa == mine.need_epa &&
-                            (mine.need_epa ? std::memcmp(&outs[k].g, &mine.g, sizeof(GjkState)) == 0
-                                           : std::memcmp(&outs[k].o, &mine.o, sizeof(PairOut)) == 0);
-          if (!same) {
+        for (int k = 1; k < G; ++k)
+          if (outs[k].need_epa != mine.need_epa || std::memcmp(&outs[k].o, &mine.o, sizeof(PairOut)) != 0) {
             ++disagree;
             break;
           }
-        }
-        PairOut o = mine.o;
-        if (mine.need_epa) {  // k_epa, both tiers, one lane
-          const GjkState queued = mine.g;
-          GjkState g = requeue(queued);
-          o.cached_guess = mk(1, 0, 0);
-          o.hint0 = o.hint1 = 0;
-          EpaWsSmall small;
-          if (!pair_phase2<1, CAPS_ALL>(in, P, g, &small, o)) {
-            ++g_retries;
-            g = requeue(queued);
-            o.cached_guess = mk(1, 0, 0);
-            o.hint0 = o.hint1 = 0;
-            pair_phase2<1, CAPS_ALL>(in, P, g, ws.get(), o);
-          }
-        }
-        if (MODE == 0) write_distance(o, static_cast<hfb_distance_result*>(out) + i);
-        else write_contact(o, C, static_cast<hfb_contact*>(out) + i);
-        put_guess(go, i, o);
+        if (MODE == 0) write_distance(mine.o, static_cast<hfb_distance_result*>(out) + i);
+        else write_contact(mine.o, C, static_cast<hfb_contact*>(out) + i);
+        put_guess(go, i, mine.o);
       }
       Coop<G>::sync();
     }

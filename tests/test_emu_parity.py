@@ -299,10 +299,11 @@ def test_lane_group_argmax_equals_the_serial_scan_for_any_direction():
 
 
 @pytest.mark.parametrize("lanes", [2, 4, 8])
-def test_phase1_through_lane_groups(lanes):
-    """k_pairs<G> runs a pair on G cooperating lanes.  tests/emu runs the same device code with the G lanes of a
-    group as G host threads meeting at barriers where the device shuffles or syncs (lanesim): every lane must
-    reach the same phase-1 outcome, and the results must be the oracle's bit for bit -- hulls with few and many
+def test_pairs_through_lane_groups(lanes):
+    """k_pairs<G> and k_epa<G> run a pair on G cooperating lanes.  tests/emu runs the same device code with the G
+    lanes of a group as G host threads meeting at barriers where the device shuffles or syncs (lanesim; in EPA
+    every lane works in a private copy of the polytope workspace and fetches the faces its peers computed): every
+    lane must reach the same outcome, and the results must be the oracle's bit for bit -- hulls with few and many
     vertices, triangles, primitives, with requests that drive GJK through NaN rays (relative duality gap on
     exact-zero poses at scale 1000, the configuration in which the GPU fuzz found the lanes disagreeing)."""
     from tests.common import EmuScene
