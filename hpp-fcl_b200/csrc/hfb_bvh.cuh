@@ -1054,6 +1054,9 @@ struct WarpVote {
 // 0: set-up phase, 1: bounding-volume phase, 2: leaf phase, -1: every lane has left
 // `lanes`: the lanes that run the chosen phase
 HFB_HD int bvh_vote(int state, unsigned& lanes) {
+#if !defined(__CUDACC__) && defined(HFB_LANE_SIM)
+  lanesim::trace_bvh_state(state);  // tests/tools/bvh_sched_model.py: per-query phase sequences for the offline model
+#endif
   const unsigned mi = WarpVote::ballot(state == BVS_NEED_INIT);
   const unsigned mb = WarpVote::ballot(state == BVS_NEED_BV);
   const unsigned ml = WarpVote::ballot(state == BVS_NEED_LEAF);

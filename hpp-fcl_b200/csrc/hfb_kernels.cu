@@ -689,6 +689,7 @@ struct hfb_ctx {
   DevBuf sup_ids, sup_dirs, sup_idx, sup_out;
   hfb_stats stats{};
   int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4, refill = 0, iter_quorum = 8, stage = 0, chunk = 0;
+  int bvh_bps = 4;  // k_bvh: blocks (of 2 warps) per SM the grid is capped at; HFB_BVH_BPS, see tests/tools/bvh_sched_model.py
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int kind; };
   std::vector<Ev> events;
@@ -943,9 +944,9 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   if (ctx->arena.has_bvh) {
     const int threads = 64;
     unsigned blocks = (n + threads - 1) / threads;
-    const unsigned cap = (unsigned)ctx->num_sms * 4u;
+    const unsigned cap = (unsigned)ctx->num_sms * (unsigned)ctx->bvh_bps;
     if (blocks > cap) blocks = cap;
-    CK(sl.bvh_ws.reserve((size_t)cap * 2 * threads * sizeof(EpaWs)));
+    CK(sl.bvh_ws.reserve((size_t)ctx->num_sms * 4u * 2 * threads * sizeof(EpaWs)));
     if (!sl.bvh_cnt.p) {
       CK(sl.bvh_cnt.reserve(2 * sizeof(unsigned long long)));
       CK(cudaMemsetAsync(sl.bvh_cnt.p, 0, 2 * sizeof(unsigned long long), s));
@@ -1158,6 +1159,10 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   if (const char* mb = getenv("HFB_MINB")) c->minb = atoi(mb);
   if (const char* ns = getenv("HFB_NSUB")) c->nsub = atoi(ns);
   if (const char* bm = getenv("HFB_BVH_MINB")) c->bvh_minb = atoi(bm);
+  if (const char* bp = getenv("HFB_BVH_BPS")) {
+    const int v = atoi(bp);
+    if (v >= 1 && v <= 4) c->bvh_bps = v;  // the workspace is sized for 4
+  }
   if (const char* rf = getenv("HFB_REFILL")) c->refill = atoi(rf);
   if (const char* st = getenv("HFB_STAGE")) c->stage = atoi(st);
   if (const char* ch = getenv("HFB_CHUNK")) c->chunk = atoi(ch);

@@ -33,6 +33,7 @@ void sync();
 double shfl_xor(double v, int off);
 int shfl_xor(int v, int off);
 const void* peer_workspace(int lane);  // the EPA workspace lane `lane` of this group registered (private copies)
+void trace_bvh_state(int state);       // the phase a lane of the BVH walk waits for, once per scheduling round
 }  // namespace lanesim
 #endif
 template <int G>

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <queue>
 #include <vector>
 
 #define HFB_LANE_SIM 1  // host lane groups, see below
@@ -76,6 +77,11 @@ int shfl_xor(int v, int off) {
   return r;
 }
 const void* peer_workspace(int l) { return tl_group->ws[l]; }
+// phase sequences of BVH queries for the offline scheduling model (emu_bvh_trace_distance)
+thread_local std::vector<uint8_t>* tl_trace = nullptr;
+void trace_bvh_state(int state) {
+  if (tl_trace) tl_trace->push_back((uint8_t)state);
+}
 void register_workspace(const void* p) {
   tl_group->ws[tl_lane] = p;
   sync();
@@ -384,6 +390,108 @@ int emu_batch_collide(void* e, size_t n, const uint32_t* h1, const hfb_transform
     write_contact(o, C, &out[i]);
     put_guess(go, i, o);
   }
+  return HFB_OK;
+}
+
+// The sequence of phases (BVS_NEED_INIT / BVS_NEED_BV / BVS_NEED_LEAF, one byte per scheduling round) every
+// (mesh, shape) distance query goes through, for tests/tools/bvh_sched_model.py.  offsets: n + 1 entries.
+// Returns the total length, or -1 if `cap` bytes do not hold it.
+long emu_bvh_trace_distance(void* e, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
+                            const hfb_transform* tf2, const hfb_distance_request* req, uint8_t* states, size_t cap,
+                            uint64_t* offsets) {
+  Emu* E = static_cast<Emu*>(e);
+  const SolverP P = solver_from_distance_request(*req);
+  const ArenaView A = E->arena.view();
+  std::unique_ptr<EpaWs> ws(new EpaWs());
+  std::vector<uint8_t> tr;
+  size_t total = 0;
+  BvhReq R{0, 0, 0, 0, 0, 1, req->enable_nearest_points != 0, req->q.gjk_initial_guess};
+  for (size_t i = 0; i < n; ++i) {
+    offsets[i] = total;
+    tr.clear();
+    hfb_distance_result rec;
+    BvhSingleSrc src;
+    src.pending = bvh_make_job<CAPS_ALL, 0>(A, h1[i], load_xf(tf1[i].R), h2[i], load_xf(tf2[i].R), R, mk(1, 0, 0), 0, 0,
+                                            &rec, src.job);
+    unsigned long long b2 = 0, l2 = 0;
+    lanesim::tl_trace = &tr;
+    bvh_shape_distance_stream<CAPS_ALL>(src, P, 0.0, 0.0, ws.get(), b2, l2);
+    lanesim::tl_trace = nullptr;
+    for (uint8_t st : tr)
+      if (st == BVS_NEED_INIT || st == BVS_NEED_BV || st == BVS_NEED_LEAF) {
+        if (total >= cap) return -1;
+        states[total++] = st;
+      }
+  }
+  offsets[n] = total;
+  return (long)total;
+}
+
+// Model of k_bvh's warps (see tests/tools/bvh_sched_model.py): `warps` warps of 32 lanes pull queries in `order`
+// from one counter, each lane holding up to `slots` queries at a time (1 = the kernel as built); each scheduling
+// round a warp votes like bvh_vote over the lanes that have a query waiting for a phase and runs one phase: every
+// such lane advances one of its queries by one step.  A round of phase p takes cost[p] of the warp's time.
+// policy 0: bvh_vote as built; 1: bounding volumes win ties.
+// stats: [0] makespan, [1..3] rounds per phase, [4..6] lane-steps per phase, [7] time at which the counter ran dry
+int emu_bvh_sched_sim(size_t nq, const uint8_t* states, const uint64_t* offsets, const uint32_t* order, int warps,
+                      const double* cost, int init_quorum, int policy, int slots, double* stats) {
+  struct Slot {
+    int64_t q = -1;
+    uint64_t pos = 0, end = 0;
+  };
+  if (slots < 1 || slots > 4) return HFB_ERR_INVALID_ARGUMENT;
+  std::vector<Slot> st((size_t)warps * 32 * slots);
+  size_t next = 0;
+  double dry_at = -1;
+  for (int k = 0; k < 8; ++k) stats[k] = 0;
+  typedef std::pair<double, int> Ev;
+  std::priority_queue<Ev, std::vector<Ev>, std::greater<Ev>> pq;
+  for (int w = 0; w < warps; ++w) pq.push(Ev(0.0, w));
+  while (!pq.empty()) {
+    const int w = pq.top().second;
+    const double t = pq.top().first;
+    pq.pop();
+    Slot* L = &st[(size_t)w * 32 * slots];
+    int cnt[3] = {0, 0, 0};
+    for (int l = 0; l < 32; ++l) {
+      bool want[3] = {false, false, false};
+      for (int k = 0; k < slots; ++k) {
+        Slot& s = L[l * slots + k];
+        if (s.q < 0 && next < nq) {  // FETCH
+          const uint32_t q = order ? order[next] : (uint32_t)next;
+          ++next;
+          if (next == nq) dry_at = t;
+          s.q = q;
+          s.pos = offsets[q];
+          s.end = offsets[q + 1];
+          if (s.pos == s.end) s.q = -1;
+        }
+        if (s.q >= 0) want[states[s.pos] - BVS_NEED_INIT] = true;
+      }
+      for (int p = 0; p < 3; ++p) cnt[p] += want[p];
+    }
+    const int ni = cnt[0], nb = cnt[1], nl = cnt[2];
+    if (ni + nb + nl == 0) {
+      if (t > stats[0]) stats[0] = t;
+      continue;
+    }
+    int phase;
+    if (ni >= init_quorum || nb + nl == 0) phase = 0;
+    else if (policy == 1) phase = (nb >= nl) ? 1 : 2;
+    else phase = (nl >= nb) ? 2 : 1;
+    for (int l = 0; l < 32; ++l)
+      for (int k = 0; k < slots; ++k) {
+        Slot& s = L[l * slots + k];
+        if (s.q >= 0 && states[s.pos] - BVS_NEED_INIT == phase) {
+          if (++s.pos == s.end) s.q = -1;
+          stats[4 + phase] += 1;
+          break;  // one step per lane and round
+        }
+      }
+    stats[1 + phase] += 1;
+    pq.push(Ev(t + cost[phase], w));
+  }
+  stats[7] = dry_at;
   return HFB_OK;
 }
 
