@@ -140,14 +140,47 @@ struct HostArena {
     cvx.push_back(d);
     return (uint32_t)cvx.size() - 1;
   }
+  // vertex set `id` replaced by another one of the same size (a deformed / re-scaled hull)
+  bool set_convex(uint32_t id, const double* pts, uint32_t n) {
+    if (id >= cvx.size() || cvx[id].nv != n || n == 0) return false;
+    ConvexDesc& d = cvx[id];
+    double mn[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, mx[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    for (uint32_t i = 0; i < n; ++i)
+      for (int k = 0; k < 3; ++k) {
+        const double v = pts[3 * i + k];
+        pool[d.off + (size_t)k * d.vpad + i] = v;
+        mn[k] = v < mn[k] ? v : mn[k];
+        mx[k] = v > mx[k] ? v : mx[k];
+      }
+    for (uint32_t i = n; i < d.vpad; ++i)
+      for (int k = 0; k < 3; ++k) pool[d.off + (size_t)k * d.vpad + i] = pts[k];
+    d.cx = (mn[0] + mx[0]) * 0.5;
+    d.cy = (mn[1] + mx[1]) * 0.5;
+    d.cz = (mn[2] + mx[2]) * 0.5;
+    return true;
+  }
+  // record of handle `h` replaced (same validation as add_shape); a record of type 0 retires the handle:
+  // pairs that name it come back as HFB_PATH_UNSUPPORTED
+  bool set_shape(uint32_t h, const hfb_shape& s) {
+    if (h >= shapes.size()) return false;
+    uint32_t tmp;  // run the record through add_shape's checks and flags, then move it into place
+    if (!add_shape(s, &tmp)) return false;
+    shapes[h] = shapes.back();
+    shapes.pop_back();
+    return true;
+  }
+  bool valid_shape(const hfb_shape& s) const {
+    if (s.type == HFB_BV_OBBRSS) return s.data < bvh_desc.size();
+    if (s.type == HFB_GEOM_CONVEX) return s.data < cvx.size();
+    if (s.type == HFB_GEOM_TRIANGLE) return s.data < cvx.size() && cvx[s.data].nv >= 3;
+    return true;
+  }
   // returns false on an invalid record
   bool add_shape(const hfb_shape& s, uint32_t* handle) {
+    if (!valid_shape(s)) return false;
     if (s.type == HFB_BV_OBBRSS) {
-      if (s.data >= bvh_desc.size()) return false;
       has_bvh = true;
     } else if (s.type == HFB_GEOM_CONVEX || s.type == HFB_GEOM_TRIANGLE) {
-      if (s.data >= cvx.size()) return false;
-      if (s.type == HFB_GEOM_TRIANGLE && cvx[s.data].nv < 3) return false;
       if (s.type == HFB_GEOM_CONVEX) has_convex = true; else has_tri = true;
     } else if (!(s.type == HFB_GEOM_BOX || s.type == HFB_GEOM_SPHERE || s.type == HFB_GEOM_CAPSULE ||
                  s.type == HFB_GEOM_CONE || s.type == HFB_GEOM_CYLINDER || s.type == HFB_GEOM_ELLIPSOID)) {

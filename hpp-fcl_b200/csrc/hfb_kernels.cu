@@ -1304,6 +1304,39 @@ int hfb_geom_clear(hfb_ctx* ctx) {
   return HFB_OK;
 }
 
+int hfb_geom_update_shapes(hfb_ctx* ctx, const uint32_t* handles, const hfb_shape* shapes, size_t n) {
+  if (!ctx || ((!handles || !shapes) && n)) return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  for (size_t i = 0; i < n; ++i)  // all or nothing
+    if (handles[i] >= ctx->arena.shapes.size()) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "shape handle out of range");
+  for (size_t i = 0; i < n; ++i)
+    if (!ctx->arena.valid_shape(shapes[i])) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "bad shape record");
+  for (size_t i = 0; i < n; ++i) ctx->arena.set_shape(handles[i], shapes[i]);
+  ctx->committed = false;
+  return HFB_OK;
+}
+
+int hfb_geom_update_convex(hfb_ctx* ctx, uint32_t convex_id, const double* points, uint32_t num_points) {
+  if (!ctx || !points) return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (!ctx->arena.set_convex(convex_id, points, num_points))
+    return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "unknown convex id or a different number of points");
+  ctx->committed = false;
+  return HFB_OK;
+}
+
+int hfb_geom_release_shapes(hfb_ctx* ctx, const uint32_t* handles, size_t n) {
+  if (!ctx || (!handles && n)) return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  for (size_t i = 0; i < n; ++i)
+    if (handles[i] >= ctx->arena.shapes.size()) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "shape handle out of range");
+  hfb_shape gone;
+  std::memset(&gone, 0, sizeof(gone));  // type 0: no such geometry
+  for (size_t i = 0; i < n; ++i) ctx->arena.set_shape(handles[i], gone);
+  ctx->committed = false;
+  return HFB_OK;
+}
+
 int hfb_batch_distance(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1,
                        const uint32_t* h2, const hfb_transform* tf2, const hfb_distance_request* req,
                        hfb_distance_result* out, const hfb_guess_out* go) {

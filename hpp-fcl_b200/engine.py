@@ -50,6 +50,9 @@ def load_library(path=None):
     L.hfb_geom_num_shapes.argtypes = [vp]
     L.hfb_geom_num_shapes.restype = sz
     L.hfb_geom_clear.argtypes = [vp]
+    L.hfb_geom_update_shapes.argtypes = [vp, vp, vp, C.c_size_t]
+    L.hfb_geom_update_convex.argtypes = [vp, C.c_uint32, vp, C.c_uint32]
+    L.hfb_geom_release_shapes.argtypes = [vp, vp, C.c_size_t]
     for name in ("hfb_batch_distance", "hfb_batch_collide"):
         getattr(L, name).argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
         getattr(L, name + "_device").argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
@@ -154,6 +157,23 @@ class Engine:
     def clear_geometry(self):
         """drops every registered shape / hull / mesh; all handles become invalid"""
         self._check(self.L.hfb_geom_clear(self.h))
+
+    def update_shapes(self, handles, shapes):
+        """replace the records of registered handles (e.g. new sizes); commit() before the next query"""
+        handles = np.ascontiguousarray(handles, dtype=np.uint32)
+        shapes = np.ascontiguousarray(shapes, dtype=P.shape_dtype)
+        assert handles.shape[0] == shapes.shape[0]
+        self._check(self.L.hfb_geom_update_shapes(self.h, _ptr(handles), _ptr(shapes), handles.shape[0]))
+
+    def update_convex(self, convex_id, points):
+        """replace the vertices of a registered hull by as many new ones"""
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        self._check(self.L.hfb_geom_update_convex(self.h, int(convex_id), _ptr(pts), pts.shape[0]))
+
+    def release_shapes(self, handles):
+        """retire handles: pairs that still name them come back as unsupported"""
+        handles = np.ascontiguousarray(handles, dtype=np.uint32)
+        self._check(self.L.hfb_geom_release_shapes(self.h, _ptr(handles), handles.shape[0]))
 
     def device_arena(self):
         base = C.c_void_p()

@@ -285,6 +285,16 @@ size_t hfb_geom_num_shapes(const hfb_ctx* ctx);
  * reference has no counterpart (geometry is caller-owned and passed by pointer on every call); this
  * is how a long-running caller of the batch ABI drops geometry it no longer queries. */
 int hfb_geom_clear(hfb_ctx* ctx);
+/* In-place changes of registered geometry (the reference's callers mutate the CollisionGeometry they own:
+ * Box::halfSide, Sphere::radius, ConvexBase::points, setSweptSphereRadius ... and pass it again).  Handles
+ * and ids stay valid; hfb_geom_commit must follow before the next query.
+ *   update_shapes:  the records of `handles[i]` are replaced by `shapes[i]` (validated like a registration);
+ *   update_convex:  vertex set `convex_id` replaced by `points` (same number of points);
+ *   release_shapes: the handles are retired -- a pair that still names one comes back with
+ *                   HFB_PATH_UNSUPPORTED; the storage of hulls and meshes is reclaimed by hfb_geom_clear. */
+int hfb_geom_update_shapes(hfb_ctx* ctx, const uint32_t* handles, const hfb_shape* shapes, size_t n);
+int hfb_geom_update_convex(hfb_ctx* ctx, uint32_t convex_id, const double* points, uint32_t num_points);
+int hfb_geom_release_shapes(hfb_ctx* ctx, const uint32_t* handles, size_t n);
 
 /* ---- batched distance(): n independent (o1,tf1,o2,tf2) queries --------- */
 /* HOST buffers in/out; blocking.  Mirrors distance() of src/distance.cpp:60-109

@@ -42,6 +42,8 @@ def emu_lib():
         L.emu_batch_convex_support.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 4
         L.emu_register_bvh.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                        C.c_uint32]
+        L.emu_update_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.emu_update_convex.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         _EMU = L
     return _EMU
 
@@ -81,6 +83,19 @@ class EmuScene:
 
     def commit(self):
         pass
+
+    def update_shapes(self, handles, shapes):
+        handles = np.ascontiguousarray(handles, dtype=np.uint32)
+        shapes = np.ascontiguousarray(shapes, dtype=P.shape_dtype)
+        rc = self.L.emu_update_shapes(self.h, _ptr(handles), _ptr(shapes), C.c_size_t(handles.shape[0]))
+        if rc != 0:
+            raise ValueError("emu error %d" % rc)
+
+    def update_convex(self, convex_id, points):
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        rc = self.L.emu_update_convex(self.h, C.c_uint32(int(convex_id)), _ptr(pts), C.c_uint32(pts.shape[0]))
+        if rc != 0:
+            raise ValueError("emu error %d" % rc)
 
     lanes = 1  # > 1: shape pairs run through lane groups of that many threads (tests/emu lanesim)
 

@@ -301,6 +301,17 @@ int64_t emu_register_shapes(void* e, const hfb_shape* shapes, size_t n) {
   return first;
 }
 
+int emu_update_shapes(void* e, const uint32_t* handles, const hfb_shape* shapes, size_t n) {
+  Emu* E = static_cast<Emu*>(e);
+  for (size_t i = 0; i < n; ++i)
+    if (handles[i] >= E->arena.shapes.size() || !E->arena.valid_shape(shapes[i])) return HFB_ERR_INVALID_ARGUMENT;
+  for (size_t i = 0; i < n; ++i) E->arena.set_shape(handles[i], shapes[i]);
+  return HFB_OK;
+}
+int emu_update_convex(void* e, uint32_t id, const double* pts, uint32_t n) {
+  return static_cast<Emu*>(e)->arena.set_convex(id, pts, n) ? HFB_OK : HFB_ERR_INVALID_ARGUMENT;
+}
+
 int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transform* tf1,
                        const uint32_t* h2, const hfb_transform* tf2, const hfb_distance_request* req,
                        hfb_distance_result* out, const hfb_guess_out* go) {

@@ -136,3 +136,64 @@ def test_api_objects_without_gpu():
     assert np.allclose(t.transform([1, 1, 1]), [2, 3, 4])
     with pytest.raises(ValueError):
         hf.Sphere(1).setSweptSphereRadius(-1)
+
+
+def _update_scenario(dev, fresh):
+    """register, query, change sizes / a hull / retire a handle, query again: `dev` after its updates must answer
+    like `fresh` registered with the final geometry from scratch"""
+    rng = np.random.default_rng(21)
+    ALL = (P.GEOM_SPHERE, P.GEOM_CAPSULE, P.GEOM_BOX, P.GEOM_CYLINDER, P.GEOM_CONE, P.GEOM_ELLIPSOID)
+    prim = W.random_primitive_shapes(rng, 40, ALL)
+    hull_a, _ = W.ellipsoid_hull(rng, 20)
+    hull_b = hull_a * np.array([1.5, 0.7, 1.1]) + 0.05
+    cid = dev.register_convex(hull_a)
+    rec = np.concatenate([prim, P.make_shapes([P.GEOM_CONVEX], [[0, 0, 0]], data=[cid])])
+    h = dev.register_shapes(rec)
+    dev.commit()
+    n = 3000
+    h1, h2 = h[rng.integers(0, len(h), n)], h[rng.integers(0, len(h), n)]
+    tf1 = W.random_transforms(rng, n, (-1, -1, -1), (1, 1, 1))
+    tf2 = W.random_transforms(rng, n, (-1.5, -1.5, -1.5), (1.5, 1.5, 1.5))
+    before = dev.batch_distance(h1, tf1, h2, tf2)
+    # the changes
+    rec2 = rec.copy()
+    rec2["p"][:10] *= 1.7                      # ten shapes grow
+    rec2[10] = P.make_shapes([P.GEOM_SPHERE], [[0.33, 0, 0]])[0]  # one changes its type
+    rec2["ssr"][11] = 0.05
+    dev.update_shapes(h[:12], rec2[:12])
+    dev.update_convex(cid, hull_b)
+    gone = h[12:14]
+    if hasattr(dev, "release_shapes"):
+        dev.release_shapes(gone)
+    dev.commit()
+    after = dev.batch_distance(h1, tf1, h2, tf2)
+    fid = fresh.register_convex(hull_b, None) if type(fresh).__name__ == "OracleScene" else fresh.register_convex(hull_b)
+    assert fid == cid
+    assert np.array_equal(fresh.register_shapes(rec2), h)
+    fresh.commit() if hasattr(fresh, "commit") else None
+    kw = dict(nthreads=0) if type(fresh).__name__ == "OracleScene" else {}
+    want = fresh.batch_distance(h1, tf1, h2, tf2, **kw)
+    live = ~(np.isin(h1, gone) | np.isin(h2, gone)) if hasattr(dev, "release_shapes") else np.ones(n, dtype=bool)
+    assert np.array_equal(after[live], want[live]) or all(
+        np.array_equal(after[live][f], want[live][f], equal_nan=(after.dtype[f].kind == "f")) for f in after.dtype.names if f != "_pad")
+    touched = np.isin(h1, h[:12]) | np.isin(h2, h[:12]) | (h1 == h[-1]) | (h2 == h[-1])
+    assert (before["min_distance"][touched & live] != after["min_distance"][touched & live]).mean() > 0.5
+    if hasattr(dev, "release_shapes"):
+        assert np.all(P.status_path(after["status"][~live]) == P.PATH_UNSUPPORTED)
+    # invalid updates leave everything as it was
+    with pytest.raises(Exception):
+        dev.update_convex(cid, hull_b[:5])
+    with pytest.raises(Exception):
+        dev.update_shapes([len(h) + 7], rec2[:1])
+
+
+def test_geometry_updates_in_the_arena():
+    """HostArena::set_shape / set_convex behind hfb_geom_update_* (shared by the library and tests/emu)"""
+    from tests.common import EmuScene
+    from oracle import oracle_lib
+    _update_scenario(EmuScene(), oracle_lib.OracleScene(P))
+
+
+@pytest.mark.gpu
+def test_geometry_update_and_release_on_the_gpu():
+    _update_scenario(hf.Engine(0), hf.Engine(0))
