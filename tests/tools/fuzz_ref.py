@@ -178,8 +178,14 @@ def hull_tris(pts):
     return tris
 
 
+BIG_MESHES = [False]  # --big-meshes: deeper trees (1 600 and 640 triangles) and more mesh queries per round
+
+
 def fuzz_meshes(rng, scale):
     out = []
+    if BIG_MESHES[0]:
+        out.append(W.sphere_mesh(1.0, 40, 20, noise=0.02, rng=rng))
+        out.append(W.sphere_mesh(0.7, 32, 10, noise=0.0, rng=rng))
     out.append(W.sphere_mesh(1.0, 12, 6, noise=0.05, rng=rng))
     out.append(W.sphere_mesh(0.5, 8, 4, noise=0.0, rng=rng))  # symmetric: ties in the fit and the walk
     # flat grid (rank-deficient covariance), then a soup of random triangles
@@ -302,7 +308,7 @@ def build_cases(seed, n, use_ref, use_emu):
         req, kw = random_request(rng, kind)
         cases.append(("big-hulls", kind, b1, tf1[:nb], b2, tf2[:nb], req, kw))
     # meshes: against shapes (both operand orders) and against each other
-    m = max(200, n // 8)
+    m = max(200, n // (2 if BIG_MESHES[0] else 8))
     mt1, mt2 = adversarial_poses(rng, m, scale, base if base != "far" else "random")
     g1 = hm[rng.integers(0, len(hm), m)]
     g2 = hm[rng.integers(0, len(hm), m)]
@@ -420,10 +426,12 @@ def main():
     ap.add_argument("--n", type=int, default=4000)
     ap.add_argument("--no-emu", action="store_true")
     ap.add_argument("--keep-going", action="store_true")
+    ap.add_argument("--big-meshes", action="store_true")
     ap.add_argument("--gpu", action="store_true", help="the real kernels (hppfcl_b200.Engine) instead of the host build")
     ap.add_argument("--lanes", type=int, default=1, help="host build: lane groups of this many threads for phase 1")
     a = ap.parse_args()
     use_ref = False
+    BIG_MESHES[0] = a.big_meshes
     if os.path.isdir("/root/reference/src"):
         oracle_lib.build_ref()
     use_ref = oracle_lib.ref_available()
