@@ -1071,6 +1071,15 @@ HFB_HD int bvh_vote(int state, unsigned& lanes) {
   return (nl >= nb) ? 2 : 1;
 }
 
+// Where the contacts of a mesh pair go beyond the first (hfb_batch_collide_contacts): the reference keeps up to
+// num_max_contacts of them in CollisionResult::contacts (collision_data.h:431), the batch record holds contacts[0].
+// All null / zero for the plain entry points.
+struct BvhContactSink {
+  hfb_contact* extra;  // extra[k - 1] receives contacts[k], k >= 1
+  unsigned cap;        // records available in `extra`
+  uint32_t* count;     // receives CollisionResult::numContacts()
+};
+
 // one (mesh, shape) query handed to a lane by a source: the operands after the swap of
 // distance()/collide(), the solver warm start and the caller's result record
 struct BvhJob {
@@ -1079,6 +1088,9 @@ struct BvhJob {
   v3 cached_guess;
   int hint0, hint1;
   void* rec;
+};
+struct BvhColJob : BvhJob {  // collide(): plus where contacts[1..] go
+  BvhContactSink sink = BvhContactSink{nullptr, 0, nullptr};
 };
 
 struct BvhDistOut {
@@ -1243,6 +1255,23 @@ HFB_HD void bvh_init_contact(hfb_contact* r) {
   r->iterations = 0;
   r->_pad = 0;
 }
+// contacts[k], k >= 1, of a mesh pair as a record of its own: the Contact fields (collision_data.h:59-148), after the
+// operand swap of collide() for (shape, mesh) pairs (collision.cpp:92-108)
+HFB_HD void bvh_sink_contact(const BvhContactSink& s, unsigned k, bool swapped, int b1, int b2, double distance, v3 p1,
+                             v3 p2, v3 normal) {
+  if (!s.extra || k == 0 || k - 1 >= s.cap) return;
+  hfb_contact* r = s.extra + (k - 1);
+  bvh_init_contact(r);
+  r->num_contacts = 1;
+  r->distance = distance;
+  r->b1 = swapped ? b2 : b1;
+  r->b2 = swapped ? b1 : b2;
+  put3d(r->pos, (p1 + p2) / 2);
+  put3d(r->p1, swapped ? p2 : p1);
+  put3d(r->p2, swapped ? p1 : p2);
+  put3d(r->normal, swapped ? -normal : normal);
+  r->status = pack_status(0, 0, HFB_PATH_BVH);
+}
 // collide(): swapObjects() for (GEOM, BVH) (collision.cpp:92-108) swaps contact b1/b2, nearest points
 // and normals back
 HFB_HD void bvh_write_shape_collide(hfb_contact* r, bool swapped, const BvhColOut& o) {
@@ -1276,7 +1305,7 @@ template <int CAPS, class Src>
 HFB_HD void bvh_shape_collide_stream(Src& src, const SolverP& P, double security_margin, double break_distance,
                                      double collision_distance_threshold, unsigned num_max_contacts, EpaWs* ws,
                                      unsigned long long& bv_total, unsigned long long& leaf_total) {
-  BvhJob job;
+  BvhColJob job;
   ObbD sbv;
   PairIn in;
   BvhColOut out;
@@ -1302,6 +1331,7 @@ HFB_HD void bvh_shape_collide_stream(Src& src, const SolverP& P, double security
       }
       if (state == BVS_FETCH) {
         bvh_write_shape_collide(static_cast<hfb_contact*>(job.rec), job.swapped, out);
+        if (job.sink.count) *job.sink.count = out.threw ? 0u : ncontacts;
         bv_total += out.bv_tests;
         leaf_total += out.leaf_tests;
       }
@@ -1357,6 +1387,8 @@ HFB_HD void bvh_shape_collide_stream(Src& src, const SolverP& P, double security
               out.p1 = o.p1;
               out.p2 = o.p2;
               out.normal = o.normal;
+            } else {
+              bvh_sink_contact(job.sink, ncontacts, job.swapped, leaf_prim, -1, o.distance, o.p1, o.p2, o.normal);
             }
             ++ncontacts;
           }
@@ -1682,7 +1714,7 @@ struct BvhPairColOut {
 template <int CAPS>
 HFB_HD void bvh_bvh_collide(const BvhPairQuery& q, const SolverP& P, double security_margin, double break_distance,
                             double collision_distance_threshold, unsigned num_max_contacts, EpaWs* ws,
-                            const PairIn& in0, BvhPairColOut& out) {
+                            const PairIn& in0, BvhPairColOut& out, const BvhContactSink& sink) {
   out.distance_lower_bound = DBL_MAX;
   out.lb_p1 = out.lb_p2 = out.lb_normal = nan3();
   out.has_contact = false;
@@ -1766,12 +1798,15 @@ HFB_HD void bvh_bvh_collide(const BvhPairQuery& q, const SolverP& P, double secu
           out.p1 = o.p1;
           out.p2 = o.p2;
           out.normal = o.normal;
+        } else {
+          bvh_sink_contact(sink, ncontacts, false, leaf1, leaf2, o.distance, o.p1, o.p2, o.normal);
         }
         ++ncontacts;
       }
     }
     if (ncontacts > 0 && num_max_contacts <= ncontacts) break;  // canStop()
   }
+  if (sink.count) *sink.count = ncontacts;
 }
 
 // ---- one pair: classification, the (mesh, mesh) walks, and a single-query source -----------------
@@ -1828,7 +1863,8 @@ HFB_HD void bvh_mesh_pair_distance(const ArenaView& A, uint32_t h1, const xf& tf
 template <int CAPS>
 HFB_HD void bvh_mesh_pair_collide(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2, const xf& tf2,
                                   const SolverP& P, const BvhReq& R, v3 cached_guess, int hint0, int hint1,
-                                  EpaWs* ws, hfb_contact* r, unsigned& bv_tests, unsigned& leaf_tests) {
+                                  EpaWs* ws, hfb_contact* r, unsigned& bv_tests, unsigned& leaf_tests,
+                                  BvhContactSink sink = BvhContactSink{nullptr, 0, nullptr}) {
   const BvhPairQuery pq = bvh_make_pair_query(A, h1, tf1, h2, tf2);
   PairIn in;
   in.cached_guess = cached_guess;
@@ -1836,7 +1872,7 @@ HFB_HD void bvh_mesh_pair_collide(const ArenaView& A, uint32_t h1, const xf& tf1
   in.hint1 = hint1;
   BvhPairColOut o;
   bvh_bvh_collide<CAPS>(pq, P, R.security_margin, R.break_distance, R.collision_distance_threshold,
-                        R.num_max_contacts, ws, in, o);
+                        R.num_max_contacts, ws, in, o, sink);
   bvh_init_contact(r);
   r->distance_lower_bound = o.distance_lower_bound;
   put3d(r->p1, o.lb_p1);
@@ -1887,15 +1923,18 @@ HFB_HD bool bvh_make_job(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_
 // pair kinds a k_bvh instantiation serves
 enum { BVK_SHAPE = 1, BVK_MESH = 2 };
 
-struct BvhSingleSrc {  // a source holding one job (the CPU emulation of the device code, tests)
-  BvhJob job;
+template <class Job>
+struct BvhSingleSrcT {  // a source holding one job (the CPU emulation of the device code, tests)
+  Job job;
   bool pending;
-  HFB_HD bool next(BvhJob& j) {
+  HFB_HD bool next(Job& j) {
     if (!pending) return false;
     pending = false;
     j = job;
     return true;
   }
 };
+typedef BvhSingleSrcT<BvhJob> BvhSingleSrc;
+typedef BvhSingleSrcT<BvhColJob> BvhSingleColSrc;
 
 }  // namespace hfb

@@ -93,7 +93,19 @@ struct BatchArgs {
   unsigned long long* bvh_counters;  // [0] bv tests, [1] leaf tests (running totals)
   unsigned* bvh_work;         // k_bvh: work counter of this launch
   unsigned n;
+  // hfb_batch_collide_contacts (null / 0 otherwise): contacts[1..] of mesh pairs, extra_cap records per pair, and
+  // the number of contacts of every mesh pair
+  hfb_contact* extra;
+  uint32_t* counts;
+  unsigned extra_cap;
 };
+__device__ __forceinline__ BvhContactSink contact_sink(const BatchArgs& a, unsigned i) {
+  BvhContactSink s;
+  s.extra = a.extra ? a.extra + (size_t)i * a.extra_cap : nullptr;
+  s.cap = a.extra ? a.extra_cap : 0u;
+  s.count = a.counts ? a.counts + i : nullptr;
+  return s;
+}
 
 template <int CAPS>
 __device__ __forceinline__ PairIn load_pair_in(const BatchArgs& a, unsigned i) {
@@ -456,11 +468,17 @@ __device__ __forceinline__ void bvh_load_pair(const BatchArgs& a, unsigned i, xf
     }
   }
 }
+__device__ __forceinline__ void bvh_set_sink(BvhJob&, const BatchArgs&, unsigned) {}
+__device__ __forceinline__ void bvh_set_sink(BvhColJob& j, const BatchArgs& a, unsigned i) {
+  j.sink = contact_sink(a, i);
+  if (j.sink.count) *j.sink.count = 0;  // stays 0 for a pair that is not walked
+}
 template <int MODE>
 struct BvhDeviceSrc {
   const BatchArgs& a;
   unsigned lo, hi;
-  __device__ bool next(BvhJob& j) {
+  template <class Job>
+  __device__ bool next(Job& j) {
     for (;;) {
       const unsigned k = lo + atomicAdd(a.bvh_work, 1u);
       if (k >= hi) return false;
@@ -471,6 +489,7 @@ struct BvhDeviceSrc {
       bvh_load_pair(a, i, t1, t2, guess, h0, h1);
       void* rec = MODE == 0 ? static_cast<void*>(reinterpret_cast<hfb_distance_result*>(a.out) + i)
                             : static_cast<void*>(reinterpret_cast<hfb_contact*>(a.out) + i);
+      bvh_set_sink(j, a, i);
       if (bvh_make_job<CAPS_BVH, MODE>(a.A, a.h1[i], t1, a.h2[i], t2, a.B, guess, h0, h1, rec, j)) return true;
     }
   }
@@ -504,7 +523,7 @@ __global__ void __launch_bounds__(64, MINB) k_bvh(const BatchArgs a) {
                                bt, lt);
       else
         bvh_mesh_pair_collide<CAPS_BVH>(a.A, a.h1[i], t1, a.h2[i], t2, a.P, a.B, guess, h0, h1, ws,
-                                        reinterpret_cast<hfb_contact*>(a.out) + i, bt, lt);
+                                        reinterpret_cast<hfb_contact*>(a.out) + i, bt, lt, contact_sink(a, i));
       bv_total += bt;
       leaf_total += lt;
     }
@@ -672,7 +691,7 @@ struct Slot {
   cudaStream_t epa_stream = nullptr;
   cudaEvent_t ev_part[kMaxParts] = {};
   cudaEvent_t ev_join = nullptr;
-  DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, retry, bvh_ws, bvh_cnt;
+  DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, retry, bvh_ws, bvh_cnt, extra, ccnt;
 };
 
 }  // namespace
@@ -998,7 +1017,8 @@ int check_handles(hfb_ctx* ctx, const uint32_t* h, size_t n) {
 template <int MODE, typename Req, typename OutT>
 int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
                const hfb_transform* tf2, const Req* req, const SolverP& P, const CollideP& Cp, const BvhReq& Bq,
-               OutT* out, const hfb_guess_out* go) {
+               OutT* out, const hfb_guess_out* go, hfb_contact* extra_out = nullptr, uint32_t* counts_out = nullptr,
+               unsigned extra_cap = 0) {
   int rc;
   if ((rc = check_ready(ctx))) return rc;
   if (n == 0) return HFB_OK;
@@ -1059,7 +1079,21 @@ int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* 
       CK(sl.hout.reserve(m * 8));
       a.hint_out = static_cast<int32_t*>(sl.hout.p);
     }
+    if (counts_out) {  // hfb_batch_collide_contacts
+      CK(sl.ccnt.reserve(m * sizeof(uint32_t)));
+      CK(cudaMemsetAsync(sl.ccnt.p, 0xff, m * sizeof(uint32_t), s));  // pairs no mesh kernel writes keep the mark
+      a.counts = static_cast<uint32_t*>(sl.ccnt.p);
+      if (extra_out && extra_cap) {
+        CK(sl.extra.reserve(m * (size_t)extra_cap * sizeof(hfb_contact)));
+        a.extra = static_cast<hfb_contact*>(sl.extra.p);
+        a.extra_cap = extra_cap;
+      }
+    }
     if ((rc = run_device_batch<MODE>(ctx, sl, a, s))) return rc;
+    if (a.counts) CK(cudaMemcpyAsync(counts_out + done, a.counts, m * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    if (a.extra)
+      CK(cudaMemcpyAsync(extra_out + done * extra_cap, a.extra, m * (size_t)extra_cap * sizeof(hfb_contact),
+                         cudaMemcpyDeviceToHost, s));
     CK(cudaMemcpyAsync(out + done, sl.out.p, m * sizeof(OutT), cudaMemcpyDeviceToHost, s));
     if (a.guess_out)
       CK(cudaMemcpyAsync(go->cached_gjk_guess + 3 * done, a.guess_out, m * 24, cudaMemcpyDeviceToHost, s));
@@ -1181,7 +1215,7 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   auto rel = [](Slot& s) {
-    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt};
+    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt};
     for (DevBuf* b : bs) b->release();
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.epa_stream) cudaStreamDestroy(s.epa_stream);
@@ -1400,6 +1434,34 @@ int hfb_batch_collide(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_tran
                        BvhReq{0, 0, req->security_margin, req->break_distance, req->q.collision_distance_threshold,
                               req->num_max_contacts, true, req->q.gjk_initial_guess},
                        out, go);
+}
+
+int hfb_batch_collide_contacts(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
+                               const hfb_transform* tf2, const hfb_collision_request* req, hfb_contact* out,
+                               uint32_t max_extra, hfb_contact* extra, uint32_t* counts, const hfb_guess_out* go) {
+  if (!ctx || !req || !counts || (max_extra && !extra)) return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  bool minus_inf;
+  if (int rc = collide_prelude(ctx, req, &minus_inf)) return rc;
+  if (minus_inf) {  // collision.cpp:73-76: cleared results, no contacts
+    if (int rc = check_ready(ctx)) return rc;
+    if (n && !out) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "null buffer");
+    for (size_t i = 0; i < n; ++i) {
+      bvh_init_contact(&out[i]);
+      out[i].status = 0;
+      counts[i] = 0;
+    }
+    return HFB_OK;
+  }
+  CollideP C{req->security_margin, req->q.collision_distance_threshold};
+  const int rc = host_batch<1>(ctx, n, h1, tf1, h2, tf2, req, solver_from_collision_request(*req), C,
+                               BvhReq{0, 0, req->security_margin, req->break_distance, req->q.collision_distance_threshold,
+                                      req->num_max_contacts, true, req->q.gjk_initial_guess},
+                               out, go, extra, counts, max_extra);
+  if (rc) return rc;
+  for (size_t i = 0; i < n; ++i)
+    if (counts[i] == 0xffffffffu) counts[i] = out[i].num_contacts;  // shape pairs: at most one contact
+  return HFB_OK;
 }
 
 int hfb_batch_collide_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1,

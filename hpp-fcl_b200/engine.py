@@ -56,6 +56,7 @@ def load_library(path=None):
     for name in ("hfb_batch_distance", "hfb_batch_collide"):
         getattr(L, name).argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
         getattr(L, name + "_device").argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.hfb_batch_collide_contacts.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp]
     L.hfb_batch_convex_support.argtypes = [vp, sz, vp, vp, vp, vp]
     L.hfb_batch_convex_support_device.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.hfb_get_stats.argtypes = [vp, vp]
@@ -213,6 +214,22 @@ class Engine:
         req = req or P.CollisionRequestPOD()
         return self._host_call(self.L.hfb_batch_collide, P.contact_dtype, h1, tf1, h2, tf2, req,
                                want_guess, out)
+
+    def batch_collide_contacts(self, h1, tf1, h2, tf2, req=None, max_extra=3):
+        """collide() keeping up to 1 + max_extra contacts of a mesh pair: -> (out, extra[n, max_extra], counts);
+        contacts[k] of pair i, 1 <= k < min(counts[i], max_extra + 1), is extra[i, k - 1]"""
+        req = req or P.CollisionRequestPOD()
+        h1 = np.ascontiguousarray(h1, dtype=np.uint32)
+        h2 = np.ascontiguousarray(h2, dtype=np.uint32)
+        tf1 = np.ascontiguousarray(tf1, dtype=P.transform_dtype)
+        tf2 = np.ascontiguousarray(tf2, dtype=P.transform_dtype)
+        n = h1.shape[0]
+        out = np.zeros(n, dtype=P.contact_dtype)
+        extra = np.zeros((n, max(max_extra, 1)), dtype=P.contact_dtype)
+        counts = np.zeros(n, dtype=np.uint32)
+        self._check(self.L.hfb_batch_collide_contacts(self.h, n, _ptr(h1), _ptr(tf1), _ptr(h2), _ptr(tf2), C.byref(req),
+                                                      _ptr(out), max_extra, _ptr(extra), _ptr(counts), None))
+        return out, extra[:, :max_extra], counts
 
     def batch_convex_support(self, convex_ids, dirs):
         ids = np.ascontiguousarray(convex_ids, dtype=np.uint32)

@@ -311,6 +311,15 @@ int hfb_batch_distance_device(hfb_ctx* ctx, size_t n, const uint32_t* d_h1,
                               hfb_distance_result* d_out,
                               const hfb_guess_out* d_guess_out, void* cuda_stream);
 
+/* collide() keeping every contact of a mesh pair (CollisionResult::contacts, up to request.num_max_contacts;
+ * collision_data.h:431).  `out` is what hfb_batch_collide returns (contacts[0], the lower bound, the status);
+ * counts[i] = numContacts() of pair i (0 or 1 for a shape pair); contacts[k], 1 <= k < min(counts[i], max_extra + 1),
+ * are extra[i * max_extra + k - 1]: b1, b2, normal, p1, p2, pos and distance (= Contact::penetration_depth) set,
+ * num_contacts = 1.  Contacts beyond max_extra + 1 are counted, not stored.  HOST buffers; blocking. */
+int hfb_batch_collide_contacts(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1,
+                               const uint32_t* h2, const hfb_transform* tf2,
+                               const hfb_collision_request* req, hfb_contact* out, uint32_t max_extra,
+                               hfb_contact* extra, uint32_t* counts, const hfb_guess_out* guess_out);
 /* ---- batched collide(): mirrors collide() of src/collision.cpp:69-130 --- */
 int hfb_batch_collide(hfb_ctx* ctx, size_t n, const uint32_t* h1,
                       const hfb_transform* tf1, const uint32_t* h2,

@@ -277,6 +277,31 @@ int oracle_batch_distance(void* sc, size_t n, const uint32_t* h1, const hfb_tran
   return HFB_OK;
 }
 
+// contacts[1..] and numContacts() of mesh pairs (oracle_batch_collide_contacts); unset otherwise
+static hfb_contact* g_extra = nullptr;
+static uint32_t* g_counts = nullptr;
+static uint32_t g_max_extra = 0;
+static void sink_contacts(size_t i, const std::vector<BvhContact>& cs, bool swap, bool mesh_mesh) {
+  if (g_counts) g_counts[i] = (uint32_t)cs.size();
+  if (!g_extra) return;
+  for (size_t k = 1; k < cs.size() && k - 1 < g_max_extra; ++k) {
+    const BvhContact& c = cs[k];
+    hfb_contact& r = g_extra[i * g_max_extra + (k - 1)];
+    std::memset(&r, 0, sizeof(r));
+    r.distance_lower_bound = std::numeric_limits<double>::max();
+    r.num_contacts = 1;
+    r.distance = c.distance;
+    const int cb2 = mesh_mesh ? c.b2 : -1;
+    r.b1 = swap ? cb2 : c.b1;
+    r.b2 = swap ? c.b1 : cb2;
+    put3(r.pos, (c.p1 + c.p2) / 2);
+    put3(r.p1, swap ? c.p2 : c.p1);
+    put3(r.p2, swap ? c.p1 : c.p2);
+    put3(r.normal, swap ? -c.normal : c.normal);
+    r.status = (uint32_t)HFB_PATH_BVH << 16;
+  }
+}
+
 int oracle_batch_collide(void* sc, size_t n, const uint32_t* h1, const hfb_transform* tf1,
                          const uint32_t* h2, const hfb_transform* tf2,
                          const hfb_collision_request* req, hfb_contact* out,
@@ -369,6 +394,7 @@ int oracle_batch_collide(void* sc, size_t n, const uint32_t* h1, const hfb_trans
           }
           r.status = (uint32_t)HFB_PATH_BVH << 16;
           r.iterations = (uint32_t)(q.num_bv_tests & 0xffff) | ((uint32_t)(q.num_leaf_tests & 0xffff) << 16);
+          sink_contacts(i, q.contacts, false, true);
           continue;
         }
         const bool shape_ok = ss.type == HFB_GEOM_BOX || ss.type == HFB_GEOM_SPHERE || ss.type == HFB_GEOM_CAPSULE ||
@@ -404,6 +430,7 @@ int oracle_batch_collide(void* sc, size_t n, const uint32_t* h1, const hfb_trans
         }
         r.status = (uint32_t)HFB_PATH_BVH << 16;
         r.iterations = (uint32_t)(q.num_bv_tests & 0xffff) | ((uint32_t)(q.num_leaf_tests & 0xffff) << 16);
+        sink_contacts(i, q.contacts, swap, false);
         continue;
       }
       // ShapeShapeCollider::run (shape_shape_func.h:134-163)
@@ -446,6 +473,24 @@ int oracle_batch_collide(void* sc, size_t n, const uint32_t* h1, const hfb_trans
 }
 
 // getShapeSupportLinear over registered convexes (support_functions.cpp:401-421)
+
+// oracle_batch_collide plus every contact of a mesh pair (see hfb_batch_collide_contacts in include/hppfcl_b200.h)
+int oracle_batch_collide_contacts(void* sc, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
+                                  const hfb_transform* tf2, const hfb_collision_request* req, hfb_contact* out,
+                                  uint32_t max_extra, hfb_contact* extra, uint32_t* counts, int nthreads) {
+  for (size_t i = 0; i < n; ++i) counts[i] = 0xffffffffu;
+  g_extra = max_extra ? extra : nullptr;
+  g_counts = counts;
+  g_max_extra = max_extra;
+  const int rc = oracle_batch_collide(sc, n, h1, tf1, h2, tf2, req, out, nullptr, nthreads);
+  g_extra = nullptr;
+  g_counts = nullptr;
+  if (rc) return rc;
+  for (size_t i = 0; i < n; ++i)
+    if (counts[i] == 0xffffffffu) counts[i] = out[i].num_contacts;
+  return HFB_OK;
+}
+
 int oracle_batch_convex_support(void* sc, size_t n, const uint32_t* convex_ids, const double* dirs,
                                 int32_t* index_out, double* support_out) {
   Scene* s = static_cast<Scene*>(sc);

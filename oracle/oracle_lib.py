@@ -136,6 +136,27 @@ class OracleScene:
         return self._run(self.L.oracle_batch_collide, self.pod.contact_dtype, h1, tf1, h2, tf2, req,
                          want_guess, nthreads)
 
+    _contacts_fn = "oracle_batch_collide_contacts"
+
+    def batch_collide_contacts(self, h1, tf1, h2, tf2, req=None, max_extra=3, nthreads=1):
+        """-> (out, extra[n, max_extra], counts): see hfb_batch_collide_contacts in include/hppfcl_b200.h"""
+        req = req or self.pod.CollisionRequestPOD()
+        h1 = np.ascontiguousarray(h1, dtype=np.uint32)
+        h2 = np.ascontiguousarray(h2, dtype=np.uint32)
+        tf1 = np.ascontiguousarray(tf1, dtype=self.pod.transform_dtype)
+        tf2 = np.ascontiguousarray(tf2, dtype=self.pod.transform_dtype)
+        n = h1.shape[0]
+        out = np.zeros(n, dtype=self.pod.contact_dtype)
+        extra = np.zeros((n, max(max_extra, 1)), dtype=self.pod.contact_dtype)
+        counts = np.zeros(n, dtype=np.uint32)
+        fn = getattr(self.L, self._contacts_fn)
+        fn.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 6 + [C.c_uint32, C.c_void_p, C.c_void_p, C.c_int]
+        rc = fn(self.h, n, _ptr(h1), _ptr(tf1), _ptr(h2), _ptr(tf2), C.byref(req), _ptr(out), max_extra, _ptr(extra),
+                _ptr(counts), nthreads)
+        if rc != 0:
+            raise ValueError("error code %d" % rc)
+        return out, extra[:, :max_extra], counts
+
     def batch_convex_support(self, convex_ids, dirs, log=False):
         ids = np.ascontiguousarray(convex_ids, dtype=np.uint32)
         d = np.ascontiguousarray(dirs, dtype=np.float64).reshape(-1, 3)
@@ -267,3 +288,5 @@ class RefScene(OracleScene):
         req = req or self.pod.CollisionRequestPOD()
         return self._run(self.L.ref_batch_collide, self.pod.contact_dtype, h1, tf1, h2, tf2, req,
                          want_guess, nthreads)
+
+    _contacts_fn = "ref_batch_collide_contacts"

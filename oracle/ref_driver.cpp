@@ -269,6 +269,10 @@ int ref_batch_distance(void* p, size_t n, const uint32_t* h1, const hfb_transfor
   return HFB_OK;
 }
 
+static hfb_contact* g_extra = nullptr;  // ref_batch_collide_contacts
+static uint32_t* g_counts = nullptr;
+static uint32_t g_max_extra = 0;
+
 int ref_batch_collide(void* p, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
                       const hfb_transform* tf2, const hfb_collision_request* req, hfb_contact* out,
                       const hfb_guess_out* go, int nthreads) {
@@ -334,6 +338,23 @@ int ref_batch_collide(void* p, size_t n, const uint32_t* h1, const hfb_transform
     }
     r.status = status;
     r.iterations = iters;
+    if (g_counts) g_counts[i] = (uint32_t)res.numContacts();
+    if (g_extra)
+      for (size_t k = 1; k < res.numContacts() && k - 1 < g_max_extra; ++k) {
+        const Contact& c = res.getContact(k);
+        hfb_contact& x = g_extra[i * g_max_extra + (k - 1)];
+        std::memset(&x, 0, sizeof(x));
+        x.distance_lower_bound = std::numeric_limits<double>::max();
+        x.num_contacts = 1;
+        x.distance = c.penetration_depth;
+        x.b1 = c.b1;
+        x.b2 = c.b2;
+        put3(x.pos, c.pos);
+        put3(x.p1, c.nearest_points[0]);
+        put3(x.p2, c.nearest_points[1]);
+        put3(x.normal, c.normal);
+        x.status = status;
+      }
     if (go) {
       if (go->cached_gjk_guess) put3(go->cached_gjk_guess + 3 * i, res.cached_gjk_guess);
       if (go->cached_support_func_guess) {
@@ -343,6 +364,19 @@ int ref_batch_collide(void* p, size_t n, const uint32_t* h1, const hfb_transform
     }
   }
   return HFB_OK;
+}
+
+
+int ref_batch_collide_contacts(void* p, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
+                               const hfb_transform* tf2, const hfb_collision_request* req, hfb_contact* out,
+                               uint32_t max_extra, hfb_contact* extra, uint32_t* counts, int nthreads) {
+  g_extra = max_extra ? extra : nullptr;
+  g_counts = counts;
+  g_max_extra = max_extra;
+  const int rc = ref_batch_collide(p, n, h1, tf1, h2, tf2, req, out, nullptr, nthreads);
+  g_extra = nullptr;
+  g_counts = nullptr;
+  return rc;
 }
 
 }  // extern "C"

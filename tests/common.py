@@ -139,6 +139,24 @@ class EmuScene:
         return self._run(self.L.emu_batch_collide, P.contact_dtype, h1, tf1, h2, tf2,
                          req or P.CollisionRequestPOD(), want_guess)
 
+    def batch_collide_contacts(self, h1, tf1, h2, tf2, req=None, max_extra=3):
+        req = req or P.CollisionRequestPOD()
+        h1 = np.ascontiguousarray(h1, dtype=np.uint32)
+        h2 = np.ascontiguousarray(h2, dtype=np.uint32)
+        tf1 = np.ascontiguousarray(tf1, dtype=P.transform_dtype)
+        tf2 = np.ascontiguousarray(tf2, dtype=P.transform_dtype)
+        n = h1.shape[0]
+        out = np.zeros(n, dtype=P.contact_dtype)
+        extra = np.zeros((n, max(max_extra, 1)), dtype=P.contact_dtype)
+        counts = np.zeros(n, dtype=np.uint32)
+        fn = self.L.emu_batch_collide_contacts
+        fn.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 6 + [C.c_uint32, C.c_void_p, C.c_void_p]
+        rc = fn(self.h, n, _ptr(h1), _ptr(tf1), _ptr(h2), _ptr(tf2), C.byref(req), _ptr(out), max_extra, _ptr(extra),
+                _ptr(counts))
+        if rc != 0:
+            raise ValueError("emu error %d" % rc)
+        return out, extra[:, :max_extra], counts
+
     def batch_convex_support(self, ids, dirs):
         ids = np.ascontiguousarray(ids, dtype=np.uint32)
         d = np.ascontiguousarray(dirs, dtype=np.float64).reshape(-1, 3)

@@ -351,9 +351,30 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
   return HFB_OK;
 }
 
+static int emu_collide_impl(void* e, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
+                            const hfb_transform* tf2, const hfb_collision_request* req, hfb_contact* out,
+                            const hfb_guess_out* go, uint32_t max_extra, hfb_contact* extra, uint32_t* counts);
+
 int emu_batch_collide(void* e, size_t n, const uint32_t* h1, const hfb_transform* tf1,
                       const uint32_t* h2, const hfb_transform* tf2, const hfb_collision_request* req,
                       hfb_contact* out, const hfb_guess_out* go) {
+  return emu_collide_impl(e, n, h1, tf1, h2, tf2, req, out, go, 0, nullptr, nullptr);
+}
+// hfb_batch_collide_contacts of the library on the host build of the device code
+int emu_batch_collide_contacts(void* e, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
+                               const hfb_transform* tf2, const hfb_collision_request* req, hfb_contact* out,
+                               uint32_t max_extra, hfb_contact* extra, uint32_t* counts) {
+  for (size_t i = 0; i < n; ++i) counts[i] = 0xffffffffu;
+  const int rc = emu_collide_impl(e, n, h1, tf1, h2, tf2, req, out, nullptr, max_extra, extra, counts);
+  if (rc) return rc;
+  for (size_t i = 0; i < n; ++i)
+    if (counts[i] == 0xffffffffu) counts[i] = out[i].num_contacts;
+  return HFB_OK;
+}
+
+static int emu_collide_impl(void* e, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
+                            const hfb_transform* tf2, const hfb_collision_request* req, hfb_contact* out,
+                            const hfb_guess_out* go, uint32_t max_extra, hfb_contact* extra, uint32_t* counts) {
   Emu* E = static_cast<Emu*>(e);
   if (int rc = validate_query(req->q)) return rc;
   const bool minus_inf = req->security_margin == -INFINITY;
@@ -385,10 +406,16 @@ int emu_batch_collide(void* e, size_t n, const uint32_t* h1, const hfb_transform
         if (req->q.cached_support_func_guess) { hh0 = req->q.cached_support_func_guess[2 * i]; hh1 = req->q.cached_support_func_guess[2 * i + 1]; }
       }
       const xf t1 = load_xf(tf1[i].R), t2 = load_xf(tf2[i].R);
+      BvhContactSink sink;
+      sink.extra = (extra && max_extra) ? extra + i * (size_t)max_extra : nullptr;
+      sink.cap = sink.extra ? max_extra : 0u;
+      sink.count = counts ? counts + i : nullptr;
       if (A.shapes[h1[i]].type == HFB_BV_OBBRSS && A.shapes[h2[i]].type == HFB_BV_OBBRSS) {
-        bvh_mesh_pair_collide<CAPS_ALL>(A, h1[i], t1, h2[i], t2, P, R, guess, hh0, hh1, ws.get(), &out[i], bt, lt);
+        bvh_mesh_pair_collide<CAPS_ALL>(A, h1[i], t1, h2[i], t2, P, R, guess, hh0, hh1, ws.get(), &out[i], bt, lt, sink);
       } else {
-        BvhSingleSrc src;
+        BvhSingleColSrc src;
+        src.job.sink = sink;
+        if (sink.count) *sink.count = 0;
         src.pending = bvh_make_job<CAPS_ALL, 1>(A, h1[i], t1, h2[i], t2, R, guess, hh0, hh1, &out[i], src.job);
         unsigned long long b2 = 0, l2 = 0;
         bvh_shape_collide_stream<CAPS_ALL>(src, P, R.security_margin, R.break_distance, R.collision_distance_threshold,

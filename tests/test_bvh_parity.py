@@ -241,3 +241,89 @@ def test_bvh_config4_shape():
     ro = sc.b["oracle"].batch_distance(hm, w["tf_mesh"], hc[w["hc"]], w["tf_caps"], nthreads=0)
     rg = sc.b["gpu"].batch_distance(hm, w["tf_mesh"], hc[w["hc"]], w["tf_caps"])
     compare_distance(ro, rg, what="config4")
+
+
+def _contacts_scene(backends):
+    """two meshes and a pool of shapes registered identically in every backend given (name -> scene)"""
+    rng = np.random.default_rng(5)
+    ALL = (P.GEOM_SPHERE, P.GEOM_CAPSULE, P.GEOM_BOX, P.GEOM_CYLINDER, P.GEOM_CONE, P.GEOM_ELLIPSOID)
+    meshes = [W.sphere_mesh(1.0, 20, 10, noise=0.03, rng=rng), W.sphere_mesh(0.6, 12, 6, noise=0.05, rng=rng)]
+    from oracle import oracle_lib
+    from hppfcl_b200.engine import build_bvh_obbrss
+    ids = []
+    for v, t in meshes:
+        got = set()
+        for s in backends.values():
+            if isinstance(s, oracle_lib.OracleScene):
+                got.add(int(s.register_bvh(v, t)[0]))
+            else:
+                got.add(int(s.register_bvh_obbrss(build_bvh_obbrss(v, t), v, t)))
+        assert len(got) == 1
+        ids.append(got.pop())
+    prims = W.random_primitive_shapes(rng, 32, ALL)
+    prims["p"] *= 0.4
+    rec = np.concatenate([P.make_shapes([P.BV_OBBRSS] * 2, [[0, 0, 0]] * 2, data=ids), prims])
+    hs = [s.register_shapes(rec) for s in backends.values()]
+    for s in backends.values():
+        if hasattr(s, "commit"):
+            s.commit()
+    h = hs[0]
+    n = 3000
+    pool = np.concatenate([h[:2], h[:2], h])
+    h1, h2 = pool[rng.integers(0, len(pool), n)], pool[rng.integers(0, len(pool), n)]
+    tf1 = W.random_transforms(rng, n, (-.3, -.3, -.3), (.3, .3, .3))
+    tf2 = W.random_transforms(rng, n, (-1.2, -1.2, -1.2), (1.2, 1.2, 1.2))
+    return h1, tf1, h2, tf2
+
+
+CONTACT_FIELDS = ("b1", "b2", "p1", "p2", "normal", "pos", "distance", "num_contacts")
+
+
+def _same_fields(a, b, fields):
+    for f in fields:
+        x, y = a[f], b[f]
+        ok = (x == y) | (np.isnan(x) & np.isnan(y)) if x.dtype.kind == "f" else x == y
+        assert np.all(ok), "field %s differs" % f
+
+
+def _check_contacts(backends, h1, tf1, h2, tf2, first, others):
+    """hfb_batch_collide_contacts: every contact the reference keeps in CollisionResult::contacts (mesh-shape,
+    shape-mesh with the operand swap, mesh-mesh), numContacts(), and contacts counted but not stored"""
+    from oracle import oracle_lib
+    total_extra = 0
+    for kw, mx in ((dict(num_max_contacts=6), 3), (dict(num_max_contacts=3, security_margin=0.05), 5),
+                   (dict(num_max_contacts=1), 2), (dict(num_max_contacts=50, enable_contact=0), 8)):
+        req = P.CollisionRequestPOD(**kw)
+
+        def run(s):
+            kws = dict(nthreads=0) if isinstance(s, oracle_lib.OracleScene) else {}
+            return s.batch_collide_contacts(h1, tf1, h2, tf2, req, mx, **kws)
+        fo, fe, fc = run(backends[first])
+        if isinstance(backends[first], oracle_lib.OracleScene) and not isinstance(backends[first], oracle_lib.RefScene):
+            assert fo.tobytes() == backends[first].batch_collide(h1, tf1, h2, tf2, req, nthreads=0).tobytes()
+        for name in others:
+            o, e, c = run(backends[name])
+            assert np.array_equal(fc, c), "numContacts differs (%s vs %s)" % (first, name)
+            a, b_ = fo.copy(), o.copy()
+            a["distance"][fc == 0] = 0  # the reference keeps no distance for a pair without a contact
+            b_["distance"][fc == 0] = 0
+            _same_fields(a, b_, CONTACT_FIELDS)
+            for k in range(mx):
+                m = fc > k + 1
+                _same_fields(fe[m, k], e[m, k], CONTACT_FIELDS)
+                total_extra += int(m.sum())
+        assert fc.max() == min(kw["num_max_contacts"], fc.max())
+    assert total_extra > 1000
+
+
+def test_all_contacts_of_mesh_pairs():
+    from oracle import oracle_lib
+    from tests.common import EmuScene
+    import os
+    b = {"oracle": oracle_lib.OracleScene(P), "emu": EmuScene()}
+    if os.path.isdir("/root/reference/src"):
+        oracle_lib.build_ref()
+    if oracle_lib.ref_available():
+        b["ref"] = oracle_lib.RefScene(P)
+    h1, tf1, h2, tf2 = _contacts_scene(b)
+    _check_contacts(b, h1, tf1, h2, tf2, "oracle", [k for k in b if k != "oracle"])

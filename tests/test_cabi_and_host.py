@@ -193,7 +193,3 @@ def test_geometry_updates_in_the_arena():
     from oracle import oracle_lib
     _update_scenario(EmuScene(), oracle_lib.OracleScene(P))
 
-
-@pytest.mark.gpu
-def test_geometry_update_and_release_on_the_gpu():
-    _update_scenario(hf.Engine(0), hf.Engine(0))

@@ -1,0 +1,27 @@
+"""GPU tests of entry points written after the round's GPU budget was spent: they have run against the oracle and the
+reference build on the host build of the device code only.  Non-strict xfail until a GPU run has seen them pass
+(an XPASS is the expected outcome), so that they cannot mask the confirmed suite."""
+import pytest
+
+from tests.common import P, hf
+
+UNCONFIRMED = pytest.mark.xfail(strict=False, reason="never run on a GPU yet")
+
+
+@pytest.mark.gpu
+@UNCONFIRMED
+def test_all_contacts_of_mesh_pairs_on_the_gpu():
+    from oracle import oracle_lib
+    from tests.test_bvh_parity import _check_contacts, _contacts_scene
+    b = {"oracle": oracle_lib.OracleScene(P), "gpu": hf.Engine(0)}
+    if oracle_lib.ref_available():
+        b["ref"] = oracle_lib.RefScene(P)
+    h1, tf1, h2, tf2 = _contacts_scene(b)
+    _check_contacts(b, h1, tf1, h2, tf2, "oracle", [k for k in b if k != "oracle"])
+
+
+@pytest.mark.gpu
+@UNCONFIRMED
+def test_geometry_update_and_release_on_the_gpu():
+    from tests.test_cabi_and_host import _update_scenario
+    _update_scenario(hf.Engine(0), hf.Engine(0))
