@@ -409,8 +409,16 @@ def collide(o1, tf1, o2, tf2, request, result, device=0):
     scene = bq.scene
     h1, h2 = scene.handle(o1), scene.handle(o2)
     scene.commit()
-    out, gg, gh = scene.engine.batch_collide([h1], _tf_array(tf1), [h2], _tf_array(tf2), request._pod,
-                                             want_guess=True)
+    mesh = P.BV_OBBRSS in (o1.node_type, o2.node_type)
+    more = []
+    if mesh and request.num_max_contacts > 1:  # every contact of the pair, not only contacts[0]
+        out, extra, counts = scene.engine.batch_collide_contacts([h1], _tf_array(tf1), [h2], _tf_array(tf2), request._pod,
+                                                                 max_extra=int(request.num_max_contacts) - 1)
+        more = [extra[0, k] for k in range(int(counts[0]) - 1)]
+        gg, gh = [result.cached_gjk_guess], [result.cached_support_func_guess]
+    else:
+        out, gg, gh = scene.engine.batch_collide([h1], _tf_array(tf1), [h2], _tf_array(tf2), request._pod,
+                                                 want_guess=True)
     rec = out[0]
     if P.status_path(rec["status"]) == P.PATH_UNSUPPORTED:
         _unsupported(o1, o2, "Collision", request)
@@ -420,6 +428,8 @@ def collide(o1, tf1, o2, tf2, request, result, device=0):
         result.normal = rec["normal"].copy()
     if rec["num_contacts"]:
         result.contacts.append(Contact(o1, o2, rec))
+        for x in more:
+            result.contacts.append(Contact(o1, o2, x))
     result.cached_gjk_guess = gg[0]
     result.cached_support_func_guess = gh[0]
     return result.numContacts() if rec["num_contacts"] else 0

@@ -25,3 +25,24 @@ def test_all_contacts_of_mesh_pairs_on_the_gpu():
 def test_geometry_update_and_release_on_the_gpu():
     from tests.test_cabi_and_host import _update_scenario
     _update_scenario(hf.Engine(0), hf.Engine(0))
+
+
+@pytest.mark.gpu
+@UNCONFIRMED
+def test_python_collide_keeps_every_contact_of_a_mesh_pair():
+    import numpy as np
+    from hppfcl_b200 import workloads as W
+    verts, tris = W.sphere_mesh(1.0, 16, 8, noise=0.0, rng=np.random.default_rng(0))
+    m = hf.BVHModelOBBRSS()
+    m.beginModel()
+    m.addSubModel(verts, tris)
+    m.endModel()
+    box = hf.Box(0.6, 0.6, 0.6)
+    req = hf.CollisionRequest(num_max_contacts=8)
+    res = hf.CollisionResult()
+    n = hf.collide(m, hf.Transform3f(), box, hf.Transform3f.from_quat(1, 0, 0, 0, (0.9, 0, 0)), req, res)
+    assert n == res.numContacts() and 1 < n <= 8
+    assert len({c.b1 for c in res.contacts}) == n  # distinct triangles
+    one = hf.CollisionResult()
+    hf.collide(m, hf.Transform3f(), box, hf.Transform3f.from_quat(1, 0, 0, 0, (0.9, 0, 0)), hf.CollisionRequest(), one)
+    assert one.numContacts() == 1 and one.contacts[0].b1 == res.contacts[0].b1
