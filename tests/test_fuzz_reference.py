@@ -38,6 +38,17 @@ def test_fuzz_device_code_through_lane_groups(lanes, seeds):
         assert ok, tag
 
 
+def test_fuzz_every_contact_of_mesh_pairs():
+    """the mesh collide cases of the rounds through batch_collide_contacts: numContacts() and contacts[1..]"""
+    fuzz_ref.CONTACTS[0] = True
+    try:
+        for seed in range(200, 230):
+            ok, tag = fuzz_ref.one_round(seed, 1500, _ref(), True)
+            assert ok, tag
+    finally:
+        fuzz_ref.CONTACTS[0] = False
+
+
 # Seeds run on a B200 in round 1 (profiles/r01_summary.md).  1, 2, 5-10 were green.  3 and 4 exposed a defect of
 # the lane-group support argmax: a NaN direction (GJK produces one from 0/0 in the projection of a degenerate
 # simplex, and carries on -- so does the reference) left the lanes of a group with different vertices.  Fixed in

@@ -327,14 +327,35 @@ def build_cases(seed, n, use_ref, use_emu):
     return B, tag, cases
 
 
+CONTACTS = [False]  # --contacts: mesh collide cases go through batch_collide_contacts (every contact of a pair)
+MAX_EXTRA = 4
+
+
 def run_case(scene, case):
     name, kind, a, t1, b, t2, req = case[:7]
     kw = dict(nthreads=0) if isinstance(scene, oracle_lib.OracleScene) else {}
+    if CONTACTS[0] and kind == "collide" and "mesh" in name:
+        out, extra, counts = scene.batch_collide_contacts(a, t1, b, t2, req, MAX_EXTRA, **kw)
+        # one structured array per pair: the first record, numContacts and the stored extra contacts
+        # (unused slots zeroed so that whole rows compare)
+        rec = np.zeros(len(out), dtype=[("first", out.dtype), ("count", "<u4"), ("extra", out.dtype, (MAX_EXTRA,))])
+        rec["first"], rec["count"] = out, counts
+        for k in range(MAX_EXTRA):
+            m = counts > k + 1
+            rec["extra"][m, k] = extra[m, k]
+        return rec
     return (scene.batch_distance if kind == "distance" else scene.batch_collide)(a, t1, b, t2, req, **kw)
 
 
 def compare_case(case, ref, got, what):
     name, kind = case[0], case[1]
+    if ref.dtype.names and "first" in ref.dtype.names:
+        assert np.array_equal(ref["count"], got["count"]), "%s: numContacts differs" % what
+        cmp_fields(ref["first"], got["first"], C_MESH, what)
+        for k in range(MAX_EXTRA):
+            cmp_fields(ref["extra"][:, k], got["extra"][:, k], ("p1", "p2", "normal", "pos", "b1", "b2", "distance"),
+                       what + " contacts[%d]" % (k + 1))
+        return
     if name in ("shapes", "big-hulls"):
         if kind == "distance":
             compare_distance(ref, got, what=what)
@@ -348,6 +369,14 @@ def compare_case(case, ref, got, what):
 
 def rows_differing(case, ref, got):
     name, kind = case[0], case[1]
+    if ref.dtype.names and "first" in ref.dtype.names:
+        bad = ref["count"] != got["count"]
+        for k in range(MAX_EXTRA):
+            for f in ("p1", "p2", "normal", "pos", "b1", "b2", "distance"):
+                x, y = ref["extra"][:, k][f], got["extra"][:, k][f]
+                ne = ~((x == y) | (np.isnan(x) & np.isnan(y))) if x.dtype.kind == "f" else x != y
+                bad |= ne.reshape(len(ref), -1).any(axis=1)
+        return np.union1d(np.nonzero(bad)[0], rows_differing(case, ref["first"], got["first"]))
     if name in ("shapes", "big-hulls"):
         fields = ["status", "iterations", "b1", "b2", "p1", "p2", "normal"]
         fields += ["min_distance"] if kind == "distance" else ["distance", "pos", "distance_lower_bound", "num_contacts"]
@@ -427,11 +456,13 @@ def main():
     ap.add_argument("--no-emu", action="store_true")
     ap.add_argument("--keep-going", action="store_true")
     ap.add_argument("--big-meshes", action="store_true")
+    ap.add_argument("--contacts", action="store_true", help="mesh collide cases keep every contact (batch_collide_contacts)")
     ap.add_argument("--gpu", action="store_true", help="the real kernels (hppfcl_b200.Engine) instead of the host build")
     ap.add_argument("--lanes", type=int, default=1, help="host build: lane groups of this many threads for phase 1")
     a = ap.parse_args()
     use_ref = False
     BIG_MESHES[0] = a.big_meshes
+    CONTACTS[0] = a.contacts
     if os.path.isdir("/root/reference/src"):
         oracle_lib.build_ref()
     use_ref = oracle_lib.ref_available()
