@@ -585,7 +585,18 @@ inline std::size_t collide(const CollisionGeometry* o1, const Transform3f& tf1, 
   hfb_guess_out go{gout, hout};
   hfb_contact rec;
   const hfb_transform t1 = tf1.pod(), t2 = tf2.pod();
-  C.check(hfb_batch_collide(C.raw(), 1, &h1, &t1, &h2, &t2, &q, &rec, &go));
+  // a mesh pair can have more than one contact (CollisionResult::contacts): fetch them all when asked to
+  std::vector<hfb_contact> more;
+  uint32_t count = 0;
+  const bool mesh = o1->getNodeType() == BV_OBBRSS || o2->getNodeType() == BV_OBBRSS;
+  if (mesh && request.num_max_contacts > 1) {
+    more.resize(request.num_max_contacts - 1);
+    C.check(hfb_batch_collide_contacts(C.raw(), 1, &h1, &t1, &h2, &t2, &q, &rec, (uint32_t)more.size(), more.data(),
+                                       &count, &go));
+    more.resize(count > 1 ? count - 1 : 0);
+  } else {
+    C.check(hfb_batch_collide(C.raw(), 1, &h1, &t1, &h2, &t2, &q, &rec, &go));
+  }
   if (HFB_STATUS_PATH(rec.status) == HFB_PATH_UNSUPPORTED) detail::unsupported("Collision", o1, o2);
   if (rec.distance_lower_bound < result.distance_lower_bound) {  // collision_data.h:1186-1197
     result.distance_lower_bound = rec.distance_lower_bound;
@@ -604,6 +615,19 @@ inline std::size_t collide(const CollisionGeometry* o1, const Transform3f& tf1, 
     c.pos = detail::v3(rec.pos);
     c.penetration_depth = rec.distance;
     result.addContact(c);
+    for (const hfb_contact& x : more) {
+      if (!(result.numContacts() < request.num_max_contacts)) break;
+      Contact d;
+      d.o1 = o1;
+      d.o2 = o2;
+      d.b1 = x.b1;
+      d.b2 = x.b2;
+      d.normal = detail::v3(x.normal);
+      d.nearest_points = {{detail::v3(x.p1), detail::v3(x.p2)}};
+      d.pos = detail::v3(x.pos);
+      d.penetration_depth = x.distance;
+      result.addContact(d);
+    }
     res = result.numContacts();
   }
   result.cached_gjk_guess = detail::v3(gout);  // collision.cpp:125-127
