@@ -1053,6 +1053,7 @@ struct WarpVote {
 };
 // 0: set-up phase, 1: bounding-volume phase, 2: leaf phase, -1: every lane has left
 // `lanes`: the lanes that run the chosen phase
+template <int QUORUM>
 HFB_HD int bvh_vote(int state, unsigned& lanes) {
 #if !defined(__CUDACC__) && defined(HFB_LANE_SIM)
   lanesim::trace_bvh_state(state);  // tests/tools/bvh_sched_model.py: per-query phase sequences for the offline model
@@ -1063,7 +1064,7 @@ HFB_HD int bvh_vote(int state, unsigned& lanes) {
   const int ni = WarpVote::popc(mi), nb = WarpVote::popc(mb), nl = WarpVote::popc(ml);
   lanes = 0;
   if (ni + nb + nl == 0) return -1;
-  if (ni >= HFB_BVH_INIT_QUORUM || nb + nl == 0) {
+  if (ni >= QUORUM || nb + nl == 0) {
     lanes = mi;
     return 0;
   }
@@ -1122,7 +1123,7 @@ HFB_HD void bvh_write_shape_distance(hfb_distance_result* r, bool swapped, const
 // queries from `src` until it has none left.  A stack entry is a node still to be visited plus the
 // lower bound that canStop() re-checks when the node is popped (the reference evaluates canStop for
 // the second child after the first returned).
-template <int CAPS, class Src>
+template <int CAPS, class Src, int QUORUM = HFB_BVH_INIT_QUORUM>
 HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err, double abs_err, EpaWs* ws,
                                       unsigned long long& bv_total, unsigned long long& leaf_total) {
   BvhJob job;
@@ -1165,7 +1166,7 @@ HFB_HD void bvh_shape_distance_stream(Src& src, const SolverP& P, double rel_err
     }
     if (state == BVS_FETCH) state = src.next(job) ? BVS_NEED_INIT : BVS_EXIT;
     unsigned lanes;
-    const int phase = bvh_vote(state, lanes);
+    const int phase = bvh_vote<QUORUM>(state, lanes);
     if (phase < 0) break;
     if (phase == 0) {
       if (state == BVS_NEED_INIT) {
@@ -1301,7 +1302,7 @@ HFB_HD void bvh_write_shape_collide(hfb_contact* r, bool swapped, const BvhColOu
 // BVHShapeCollider<OBBRSS,S>::oriented + collide(node) + collisionRecurse (traversal_recurse.cpp:44-85),
 // num_max_contacts contacts (only the first is returned), each query on a fresh CollisionResult.
 // Warp-scheduled like bvh_shape_distance_stream.
-template <int CAPS, class Src>
+template <int CAPS, class Src, int QUORUM = HFB_BVH_INIT_QUORUM>
 HFB_HD void bvh_shape_collide_stream(Src& src, const SolverP& P, double security_margin, double break_distance,
                                      double collision_distance_threshold, unsigned num_max_contacts, EpaWs* ws,
                                      unsigned long long& bv_total, unsigned long long& leaf_total) {
@@ -1338,7 +1339,7 @@ HFB_HD void bvh_shape_collide_stream(Src& src, const SolverP& P, double security
     }
     if (state == BVS_FETCH) state = src.next(job) ? BVS_NEED_INIT : BVS_EXIT;
     unsigned lanes;
-    const int phase = bvh_vote(state, lanes);
+    const int phase = bvh_vote<QUORUM>(state, lanes);
     if (phase < 0) break;
     if (phase == 0) {
       if (state == BVS_NEED_INIT) {

@@ -494,7 +494,7 @@ struct BvhDeviceSrc {
     }
   }
 };
-template <int MODE, int KINDS, int MINB>
+template <int MODE, int KINDS, int MINB, int QUORUM = HFB_BVH_INIT_QUORUM>
 __global__ void __launch_bounds__(64, MINB) k_bvh(const BatchArgs a) {
   const unsigned tid = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lo = *a.range_lo, hi = *a.range_hi;
@@ -503,9 +503,10 @@ __global__ void __launch_bounds__(64, MINB) k_bvh(const BatchArgs a) {
   if (KINDS == BVK_SHAPE) {
     BvhDeviceSrc<MODE> src{a, lo, hi};
     if (MODE == 0)
-      bvh_shape_distance_stream<CAPS_BVH>(src, a.P, a.B.rel_err, a.B.abs_err, ws, bv_total, leaf_total);
+      bvh_shape_distance_stream<CAPS_BVH, BvhDeviceSrc<MODE>, QUORUM>(src, a.P, a.B.rel_err, a.B.abs_err, ws, bv_total,
+                                                                      leaf_total);
     else
-      bvh_shape_collide_stream<CAPS_BVH>(src, a.P, a.B.security_margin, a.B.break_distance,
+      bvh_shape_collide_stream<CAPS_BVH, BvhDeviceSrc<MODE>, QUORUM>(src, a.P, a.B.security_margin, a.B.break_distance,
                                          a.B.collision_distance_threshold, a.B.num_max_contacts, ws, bv_total,
                                          leaf_total);
   } else {
@@ -708,6 +709,7 @@ struct hfb_ctx {
   DevBuf sup_ids, sup_dirs, sup_idx, sup_out;
   hfb_stats stats{};
   int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4, refill = 0, iter_quorum = 8, stage = 0, chunk = 0;
+  int bvh_quorum = HFB_BVH_INIT_QUORUM;  // HFB_BVH_QUORUM=1: a lane sets its next query up as soon as it is free
   int bvh_bps = 4;  // k_bvh: blocks (of 2 warps) per SM the grid is capped at; HFB_BVH_BPS, see tests/tools/bvh_sched_model.py
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int kind; };
@@ -979,6 +981,7 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
     {
       KTimer kt(ctx, s, 5);
       if (ctx->bvh_minb >= 8) k_bvh<MODE, BVK_SHAPE, 8><<<blocks * 2, threads, 0, s>>>(ab);
+      else if (ctx->bvh_quorum == 1) k_bvh<MODE, BVK_SHAPE, 4, 1><<<blocks, threads, 0, s>>>(ab);  // HFB_BVH_QUORUM=1
       else k_bvh<MODE, BVK_SHAPE, 4><<<blocks, threads, 0, s>>>(ab);
     }
     ctx->stats.kernel_launches++;
@@ -1193,6 +1196,8 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   if (const char* mb = getenv("HFB_MINB")) c->minb = atoi(mb);
   if (const char* ns = getenv("HFB_NSUB")) c->nsub = atoi(ns);
   if (const char* bm = getenv("HFB_BVH_MINB")) c->bvh_minb = atoi(bm);
+  if (const char* bq = getenv("HFB_BVH_QUORUM"))
+    if (atoi(bq) == 1) c->bvh_quorum = 1;
   if (const char* bp = getenv("HFB_BVH_BPS")) {
     const int v = atoi(bp);
     if (v >= 1 && v <= 4) c->bvh_bps = v;  // the workspace is sized for 4

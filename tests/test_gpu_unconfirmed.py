@@ -46,3 +46,37 @@ def test_python_collide_keeps_every_contact_of_a_mesh_pair():
     one = hf.CollisionResult()
     hf.collide(m, hf.Transform3f(), box, hf.Transform3f.from_quat(1, 0, 0, 0, (0.9, 0, 0)), hf.CollisionRequest(), one)
     assert one.numContacts() == 1 and one.contacts[0].b1 == res.contacts[0].b1
+
+
+@pytest.mark.gpu
+@UNCONFIRMED
+@pytest.mark.parametrize("env", [dict(HFB_BVH_QUORUM="1"), dict(HFB_BVH_BPS="2"), dict(HFB_BVH_QUORUM="1", HFB_BVH_BPS="1")])
+def test_bvh_scheduling_knobs_do_not_change_results(env, monkeypatch):
+    """k_bvh's set-up quorum and grid size only change which lane runs when (tests/tools/bvh_sched_model.py)"""
+    import numpy as np
+    from hppfcl_b200 import workloads as W
+    from oracle import oracle_lib
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    w = W.config4_mesh_vs_capsules(6000, seg=30, ring=15)
+    eng, orc = hf.Engine(0), oracle_lib.OracleScene(P)
+    bid = eng.register_bvh_obbrss(None, w["verts"], w["tris"])
+    obid, _ = orc.register_bvh(w["verts"], w["tris"])
+    assert bid == obid
+    rec = np.concatenate([P.make_shapes([P.BV_OBBRSS], [[0, 0, 0]], data=[bid]), w["capsules"]])
+    h = eng.register_shapes(rec)
+    assert np.array_equal(h, orc.register_shapes(rec))
+    eng.commit()
+    hm = np.full(len(w["hc"]), h[0], dtype=np.uint32)
+    hq = h[1:][w["hc"]]
+    got = eng.batch_distance(hm, w["tf_mesh"], hq, w["tf_caps"])
+    want = orc.batch_distance(hm, w["tf_mesh"], hq, w["tf_caps"], nthreads=0)
+    for f in ("min_distance", "p1", "p2", "normal", "b1", "iterations"):
+        assert np.array_equal(got[f], want[f], equal_nan=got[f].dtype.kind == "f"), f
+    tf_near = w["tf_caps"].copy()
+    tf_near["T"] *= 0.5
+    cg = eng.batch_collide(hm, w["tf_mesh"], hq, tf_near)
+    cw = orc.batch_collide(hm, w["tf_mesh"], hq, tf_near, nthreads=0)
+    for f in ("num_contacts", "b1", "p1", "p2", "normal", "distance_lower_bound"):
+        assert np.array_equal(cg[f], cw[f], equal_nan=cg[f].dtype.kind == "f"), f
+    assert cw["num_contacts"].sum() > 50
