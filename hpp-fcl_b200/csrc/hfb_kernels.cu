@@ -533,6 +533,65 @@ __global__ void __launch_bounds__(64, MINB) k_bvh(const BatchArgs a) {
   if (leaf_total) atomicAdd(a.bvh_counters + 1, leaf_total);
 }
 
+// ---- hand-out order of the (mesh, shape) queries (HFB_BVH_ORDER=1; tests/tools/bvh_sched_model.py) ------------
+// k_bvh is bound by its tail at BASELINE sizes: the longest walks should start first.  A walk is long when many
+// triangles are about as near as the nearest one; the key of a query is the number of HFB_ORDER_SAMPLES sampled
+// mesh vertices within 1.2 x the nearest sample's distance of the shape's centre (correlation 0.5 with the number
+// of rounds on config 4).  A counting sort by descending key rewrites the slice of the class-sorted index list;
+// results do not depend on the order.
+#define HFB_ORDER_SAMPLES 128
+__global__ void __launch_bounds__(128) k_bvh_order_keys(const BatchArgs a, const unsigned* lo_p, const unsigned* hi_p,
+                                                        unsigned char* keys, unsigned* hist) {
+  const unsigned lo = *lo_p, hi = *hi_p;
+  for (unsigned k = lo + blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += gridDim.x * blockDim.x) {
+    const unsigned i = a.index_list[k];
+    const hfb_shape& r1 = a.A.shapes[a.h1[i]];
+    const bool swapped = r1.type != HFB_BV_OBBRSS;
+    const hfb_shape& rm = swapped ? a.A.shapes[a.h2[i]] : r1;
+    const xf tm = load_xf(swapped ? a.tf2[i].R : a.tf1[i].R);
+    const xf ts = load_xf(swapped ? a.tf1[i].R : a.tf2[i].R);
+    unsigned key = 0;
+    if (rm.type == HFB_BV_OBBRSS) {
+      const BvhDesc d = a.A.bvh_desc[rm.data];
+      const double* v = a.A.bvh_verts + 3 * (size_t)d.vert_off;
+      const v3 c = mtmul(tm.R, ts.T - tm.T);  // the shape's origin in the mesh frame
+      const unsigned stride = d.num_verts > HFB_ORDER_SAMPLES ? d.num_verts / HFB_ORDER_SAMPLES : 1u;
+      double dmin = DBL_MAX;
+      for (unsigned j = 0, q = 0; j < HFB_ORDER_SAMPLES && q < d.num_verts; ++j, q += stride) {
+        const v3 e = mk(v[3 * q], v[3 * q + 1], v[3 * q + 2]) - c;
+        const double d2 = sqn(e);
+        dmin = d2 < dmin ? d2 : dmin;
+      }
+      const double lim = dmin * (1.2 * 1.2);
+      for (unsigned j = 0, q = 0; j < HFB_ORDER_SAMPLES && q < d.num_verts; ++j, q += stride) {
+        const v3 e = mk(v[3 * q], v[3 * q + 1], v[3 * q + 2]) - c;
+        key += sqn(e) <= lim ? 1u : 0u;
+      }
+    }
+    keys[k - lo] = (unsigned char)key;
+    atomicAdd(hist + key, 1u);
+  }
+}
+// descending keys: cursor[key] = number of queries with a larger key
+__global__ void k_bvh_order_scan(const unsigned* hist, unsigned* cursor) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    unsigned run = 0;
+    for (int key = HFB_ORDER_SAMPLES; key >= 0; --key) {
+      cursor[key] = run;
+      run += hist[key];
+    }
+  }
+}
+__global__ void __launch_bounds__(128) k_bvh_order_scatter(const uint32_t* index_list, const unsigned* lo_p,
+                                                           const unsigned* hi_p, const unsigned char* keys,
+                                                           unsigned* cursor, uint32_t* out_list) {
+  const unsigned lo = *lo_p, hi = *hi_p;
+  for (unsigned k = lo + blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += gridDim.x * blockDim.x) {
+    const unsigned pos = atomicAdd(cursor + keys[k - lo], 1u);
+    out_list[lo + pos] = index_list[k];
+  }
+}
+
 // --------------------------------------------------- pair-class counting sort ---
 __device__ __forceinline__ int type_index(uint32_t t) {
   switch (t) {
@@ -692,7 +751,7 @@ struct Slot {
   cudaStream_t epa_stream = nullptr;
   cudaEvent_t ev_part[kMaxParts] = {};
   cudaEvent_t ev_join = nullptr;
-  DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, retry, bvh_ws, bvh_cnt, extra, ccnt;
+  DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, retry, bvh_ws, bvh_cnt, extra, ccnt, okeys, ohist, olist;
 };
 
 }  // namespace
@@ -710,6 +769,7 @@ struct hfb_ctx {
   hfb_stats stats{};
   int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4, refill = 0, iter_quorum = 8, stage = 0, chunk = 0;
   int bvh_quorum = HFB_BVH_INIT_QUORUM;  // HFB_BVH_QUORUM=1: a lane sets its next query up as soon as it is free
+  int bvh_order = 0;  // HFB_BVH_ORDER=1: hand the (mesh, shape) queries out longest-expected first
   int bvh_bps = 4;  // k_bvh: blocks (of 2 warps) per SM the grid is capped at; HFB_BVH_BPS, see tests/tools/bvh_sched_model.py
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int kind; };
@@ -978,6 +1038,24 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
     ab.range_lo = offsets + HFB_BIN_BVH;
     ab.range_hi = offsets + HFB_BIN_BVH2;
     ab.bvh_work = cnt + 24;
+    if (ctx->bvh_order) {
+      CK(sl.okeys.reserve((size_t)n));
+      CK(sl.ohist.reserve(2 * (HFB_ORDER_SAMPLES + 1) * sizeof(unsigned)));
+      CK(sl.olist.reserve((size_t)n * sizeof(uint32_t)));
+      unsigned* ohist = static_cast<unsigned*>(sl.ohist.p);
+      unsigned* ocur = ohist + HFB_ORDER_SAMPLES + 1;
+      CK(cudaMemsetAsync(ohist, 0, 2 * (HFB_ORDER_SAMPLES + 1) * sizeof(unsigned), s));
+      const unsigned ob = (n + 127) / 128 < (unsigned)ctx->num_sms * 8u ? (n + 127) / 128 : (unsigned)ctx->num_sms * 8u;
+      KTimer kt(ctx, s, 2);
+      k_bvh_order_keys<<<ob, 128, 0, s>>>(ab, ab.range_lo, ab.range_hi, static_cast<unsigned char*>(sl.okeys.p), ohist);
+      k_bvh_order_scan<<<1, 32, 0, s>>>(ohist, ocur);
+      k_bvh_order_scatter<<<ob, 128, 0, s>>>(ab.index_list, ab.range_lo, ab.range_hi,
+                                             static_cast<const unsigned char*>(sl.okeys.p), ocur,
+                                             static_cast<uint32_t*>(sl.olist.p));
+      ctx->stats.kernel_launches += 3;
+      CK(cudaGetLastError());
+      ab.index_list = static_cast<const uint32_t*>(sl.olist.p);  // only its [lo, hi) slice is written -- and read
+    }
     {
       KTimer kt(ctx, s, 5);
       if (ctx->bvh_minb >= 8) k_bvh<MODE, BVK_SHAPE, 8><<<blocks * 2, threads, 0, s>>>(ab);
@@ -987,6 +1065,7 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
     ctx->stats.kernel_launches++;
     CK(cudaGetLastError());
     {  // (mesh, mesh) pairs, own instantiation: an empty range costs one launch
+      ab.index_list = a.index_list;  // (the reordered list holds the (mesh, shape) slice only)
       ab.range_lo = offsets + HFB_BIN_BVH2;
       ab.range_hi = offsets + HFB_NBINS;
       ab.bvh_work = cnt + 25;
@@ -1196,6 +1275,7 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   if (const char* mb = getenv("HFB_MINB")) c->minb = atoi(mb);
   if (const char* ns = getenv("HFB_NSUB")) c->nsub = atoi(ns);
   if (const char* bm = getenv("HFB_BVH_MINB")) c->bvh_minb = atoi(bm);
+  if (const char* bo = getenv("HFB_BVH_ORDER")) c->bvh_order = atoi(bo) != 0;
   if (const char* bq = getenv("HFB_BVH_QUORUM"))
     if (atoi(bq) == 1) c->bvh_quorum = 1;
   if (const char* bp = getenv("HFB_BVH_BPS")) {
@@ -1220,7 +1300,7 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   auto rel = [](Slot& s) {
-    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt};
+    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist};
     for (DevBuf* b : bs) b->release();
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.epa_stream) cudaStreamDestroy(s.epa_stream);
