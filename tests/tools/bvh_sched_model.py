@@ -66,6 +66,9 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=100000)
     a = ap.parse_args()
+    if a.n != 100000:
+        print("note: the round costs are fitted to the measurements at 100 000 and 400 000 queries; with --n %d the"
+              " milliseconds below are not predictions, only the round and lane counts are meaningful" % a.n)
     t1, t4 = traces(a.n), traces(4 * a.n)
     ln = np.diff(t1[2].astype(np.int64))
     print("rounds per query: mean %.0f, p99 %.0f, max %d; steps: %s" % (
