@@ -43,7 +43,7 @@ struct Coop {
   static __device__ __forceinline__ unsigned mask() {
     if (G == 32) return 0xffffffffu;
     unsigned wl = threadIdx.x & 31u;
-    return (((1u << G) - 1u)) << (wl & ~(unsigned)(G - 1));
+    return (((1u << (G & 31)) - 1u)) << (wl & ~(unsigned)(G - 1));  // (G & 31: no over-wide shift in the dead G == 32 copy)
   }
   static __device__ __forceinline__ double shfl_xor(double v, int off) { return __shfl_xor_sync(mask(), v, off); }
   static __device__ __forceinline__ int shfl_xor(int v, int off) { return __shfl_xor_sync(mask(), v, off); }
