@@ -191,20 +191,28 @@ HFB_HD v3 shape_support(const ShapeD& s, v3 dir, int& hint) {
     // (where it would leave the lanes of a group with different answers).
     double best = -(double)INFINITY;
     int bi = 0x7fffffff;
-    bool first = true;
-    for (int i = Coop<G>::lane(); i < s.nv; i += G) {
-      double d = (s.cx[i] * dir.x + s.cy[i] * dir.y) + s.cz[i] * dir.z;
-      if (first) {
-        if (d == d) {
-          best = d;
-          bi = i;
-          first = false;
-        } else if (i == 0) {
-          best = (double)INFINITY;
-          bi = -1;
-          first = false;
-        }
-      } else if (d > best) {
+    int i = Coop<G>::lane();
+    // head of the lane's stripe: its first dot that is a number -- or the NaN at vertex 0
+    for (; i < s.nv; i += G) {
+      const double d = (s.cx[i] * dir.x + s.cy[i] * dir.y) + s.cz[i] * dir.z;
+      if (d == d) {
+        best = d;
+        bi = i;
+        i += G;
+        break;
+      }
+      if (i == 0) {
+        best = (double)INFINITY;
+        bi = -1;
+        i += G;
+        break;
+      }
+    }
+    // the rest: a NaN never passes '>' (a plain loop the compiler unrolls, as before the NaN rule)
+#pragma unroll 4
+    for (; i < s.nv; i += G) {
+      const double d = (s.cx[i] * dir.x + s.cy[i] * dir.y) + s.cz[i] * dir.z;
+      if (d > best) {
         best = d;
         bi = i;
       }
