@@ -139,7 +139,8 @@ class GuessOut(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("pairs_processed", C.c_uint64),
-                ("epa_pairs", C.c_uint64), ("bv_tests", C.c_uint64), ("leaf_tests", C.c_uint64)]
+                ("epa_pairs", C.c_uint64), ("bv_tests", C.c_uint64), ("leaf_tests", C.c_uint64),
+                ("watchdog_trips", C.c_uint64)]
 
 
 class KernelTimes(C.Structure):

@@ -86,20 +86,54 @@ struct HostArena {
   std::vector<BvhDesc> bvh_desc;
   bool has_convex = false, has_tri = false, has_unknown = false, has_bvh = false;
 
-  // validates the tree (child links, leaf primitive ids, triangle vertex ids) and stores it
+  // validates the tree (child links, every node but the root referenced once, leaf primitive ids, triangle
+  // vertex ids, depth within the walks' stacks) and stores it.  The stored copy of a node carries in `_pad` the
+  // number of triangles below it when its descendants are ONE contiguous block of the array -- what
+  // recursiveBuildTree produces (BVH_model.cpp:860-960: the two children are allocated together, then the left
+  // subtree is built completely before the right one) -- and 0 otherwise; the walk of hfb_bvhq.cuh speculates only
+  // on such subtrees.
+  int max_bvh_depth = 0;  // deepest registered tree (root = depth 0)
   bool add_bvh(const hfb_bvh_node* nodes, uint32_t nn, const double* verts, uint32_t nv, const uint32_t* tris,
                uint32_t nt, uint32_t* id) {
     if (nn == 0 || nv == 0 || nt == 0) return false;
+    std::vector<uint8_t> refs(nn, 0);
     for (uint32_t i = 0; i < nn; ++i) {
       const int fc = nodes[i].first_child;
       if (fc < 0) {
         if ((uint32_t)(-(fc + 1)) >= nt) return false;
       } else if ((uint32_t)fc + 1 >= nn || (uint32_t)fc <= i) {
         return false;  // children follow their parent in BVHModel::bvs (recursiveBuildTree)
+      } else {
+        if (refs[fc] || refs[fc + 1]) return false;
+        refs[fc] = refs[fc + 1] = 1;
       }
     }
+    for (uint32_t i = 1; i < nn; ++i)
+      if (!refs[i]) return false;
     for (uint32_t i = 0; i < 3 * nt; ++i)
       if (tris[i] >= nv) return false;
+    // depth (parents precede their children) -- the walks keep explicit stacks of HFB_BVH_STACK = 128 entries:
+    // a mesh-shape walk needs depth + 2, a mesh-mesh walk depth1 + depth2 + 2
+    std::vector<int> depth(nn, 0);
+    int maxd = 0;
+    for (uint32_t i = 0; i < nn; ++i) {
+      const int fc = nodes[i].first_child;
+      if (fc >= 0) {
+        depth[fc] = depth[fc + 1] = depth[i] + 1;
+        if (depth[i] + 1 > maxd) maxd = depth[i] + 1;
+      }
+    }
+    if (maxd > 62) return false;
+    // leaves below every node and the last index of its subtree, children first
+    std::vector<uint32_t> leaves(nn, 1), last(nn, 0);
+    for (uint32_t k = nn; k-- > 0;) {
+      const int fc = nodes[k].first_child;
+      last[k] = k;
+      if (fc >= 0) {
+        leaves[k] = leaves[fc] + leaves[fc + 1];
+        last[k] = last[fc] > last[fc + 1] ? last[fc] : last[fc + 1];
+      }
+    }
     BvhDesc d;
     d.node_off = (uint32_t)bvh_nodes.size();
     d.num_nodes = nn;
@@ -107,8 +141,17 @@ struct HostArena {
     d.num_verts = nv;
     d.tri_off = (uint32_t)(bvh_tris.size() / 3);
     d.num_tris = nt;
-    d._r0 = d._r1 = 0;
+    d._r0 = (uint32_t)maxd;
+    d._r1 = 0;
     bvh_nodes.insert(bvh_nodes.end(), nodes, nodes + nn);
+    for (uint32_t k = 0; k < nn; ++k) {
+      const int fc = nodes[k].first_child;
+      uint32_t mark = 0;
+      if (fc < 0) mark = 1;
+      else if (last[k] - (uint32_t)fc + 1 == 2 * leaves[k] - 2) mark = leaves[k];  // exactly the block [fc, last]
+      bvh_nodes[d.node_off + k]._pad = mark;
+    }
+    if (maxd > max_bvh_depth) max_bvh_depth = maxd;
     bvh_verts.insert(bvh_verts.end(), verts, verts + 3 * (size_t)nv);
     bvh_tris.insert(bvh_tris.end(), tris, tris + 3 * (size_t)nt);
     bvh_desc.push_back(d);

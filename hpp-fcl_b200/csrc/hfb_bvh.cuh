@@ -107,8 +107,20 @@ HFB_HD bool in_voronoi(double a, double b, double Anorm_dot_B, double Anorm_dot_
 
 // rectDistance (RSS.cpp:121-713), closest points not requested.  The sixteen edge-pair cases
 // keep the reference's expressions term for term (the association order differs between cases).
-HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1, double b0, double b1,
-                                     unsigned lanes) {
+// Three pieces, so that the lanes of a group can share one rectangle pair (hfb_bvhq.cuh): the values
+// every case reads (rect_prelude), the conditions of one case (rect_case: the reference returns from
+// the first case whose conditions hold), and the distance of the winning case or, when no edge pair
+// holds the closest points, of the face-normal separation (rect_finish).  rect_distance chains them.
+struct RectPre {
+  double R00, R01, R02, R10, R11, R12, R20, R21, a0, a1, b0, b1;
+  double A0_dot_B0, A0_dot_B1, A1_dot_B0, A1_dot_B1, aA0_dot_B0, aA0_dot_B1, aA1_dot_B0, aA1_dot_B1, bA0_dot_B0, bA1_dot_B0, bA0_dot_B1, bA1_dot_B1;
+  double Tab0, Tab1, Tab2, Tba0, Tba1, Tba2;
+  double LA1_lx, LA1_ux, UA1_lx, UA1_ux, LB1_lx, LB1_ux, UB1_lx, UB1_ux;
+  double LA1_ly, LA1_uy, UA1_ly, UA1_uy, LB0_lx, LB0_ux, UB0_lx, UB0_ux;
+  double LA0_lx, LA0_ux, UA0_lx, UA0_ux, LB1_ly, LB1_uy, UB1_ly, UB1_uy;
+  double LA0_ly, LA0_uy, UA0_ly, UA0_uy, LB0_ly, LB0_uy, UB0_ly, UB0_uy;
+};
+HFB_HD void rect_prelude(const m3& Rab, v3 Tab, double a0, double a1, double b0, double b1, RectPre& p) {
   const double R00 = Rab.r0.x, R01 = Rab.r0.y, R02 = Rab.r0.z;
   const double R10 = Rab.r1.x, R11 = Rab.r1.y, R12 = Rab.r1.z;
   const double R20 = Rab.r2.x, R21 = Rab.r2.y;
@@ -119,8 +131,6 @@ HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1
                bA1_dot_B1 = b1 * A1_dot_B1;
   const v3 Tba = mtmul(Rab, Tab);
   const double Tab0 = Tab.x, Tab1 = Tab.y, Tab2 = Tab.z, Tba0 = Tba.x, Tba1 = Tba.y, Tba2 = Tba.z;
-  v3 S = mk(0, 0, 0);
-  double t, u;
 
   double LA1_lx, LA1_ux, UA1_lx, UA1_ux, LB1_lx, LB1_ux, UB1_lx, UB1_ux;
   const double ALL_x = -Tba0;
@@ -166,141 +176,267 @@ HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1
   else { LB0_ly = BUL_y; LB0_uy = BLL_y; UB0_ly = BUU_y; UB0_uy = BLU_y; }
 
 
-  // The sixteen edge-pair cases are tried in the reference's order and the first one whose conditions
-  // hold decides.  They are a loop here, not sixteen blocks with a return each: the lanes of `lanes`
-  // (one query each) then walk the cases side by side, the expensive part of a case (two inVoronoi
-  // tests) is one copy of code, and segCoords + the distance run once, for the winning case.
-  int kwin = -1;
-#pragma unroll 1
-  for (int k = 0; k < 16; ++k) {
-    bool guard = false, ca = false, cb = false;
-    double va0 = 0, va1 = 0, va2 = 0, va3 = 0, va4 = 0, va5 = 0, va6 = 0;
-    double vb0 = 0, vb1 = 0, vb2 = 0, vb3 = 0, vb4 = 0, vb5 = 0, vb6 = 0;
-    switch (k) {
-      case 0:  // UA1, UB1
-        guard = (UA1_ux > b0) && (UB1_ux > a0);
-        ca = UA1_lx > b0;
-        va0 = b1; va1 = a1; va2 = A1_dot_B0; va3 = aA0_dot_B0 - b0 - Tba0; va4 = A1_dot_B1; va5 = aA0_dot_B1 - Tba1; va6 = -Tab1 - bA1_dot_B0;
-        cb = UB1_lx > a0;
-        vb0 = a1; vb1 = b1; vb2 = A0_dot_B1; vb3 = Tab0 + bA0_dot_B0 - a0; vb4 = A1_dot_B1; vb5 = Tab1 + bA1_dot_B0; vb6 = Tba1 - aA0_dot_B1;
-        break;
-      case 1:  // UA1, LB1
-        guard = (UA1_lx < 0) && (LB1_ux > a0);
-        ca = UA1_ux < 0;
-        va0 = b1; va1 = a1; va2 = -A1_dot_B0; va3 = Tba0 - aA0_dot_B0; va4 = A1_dot_B1; va5 = aA0_dot_B1 - Tba1; va6 = -Tab1;
-        cb = LB1_lx > a0;
-        vb0 = a1; vb1 = b1; vb2 = A0_dot_B1; vb3 = Tab0 - a0; vb4 = A1_dot_B1; vb5 = Tab1; vb6 = Tba1 - aA0_dot_B1;
-        break;
-      case 2:  // LA1, UB1
-        guard = (LA1_ux > b0) && (UB1_lx < 0);
-        ca = LA1_lx > b0;
-        va0 = b1; va1 = a1; va2 = A1_dot_B0; va3 = -Tba0 - b0; va4 = A1_dot_B1; va5 = -Tba1; va6 = -Tab1 - bA1_dot_B0;
-        cb = UB1_ux < 0;
-        vb0 = a1; vb1 = b1; vb2 = -A0_dot_B1; vb3 = -Tab0 - bA0_dot_B0; vb4 = A1_dot_B1; vb5 = Tab1 + bA1_dot_B0; vb6 = Tba1;
-        break;
-      case 3:  // LA1, LB1
-        guard = (LA1_lx < 0) && (LB1_lx < 0);
-        ca = LA1_ux < 0;
-        va0 = b1; va1 = a1; va2 = -A1_dot_B0; va3 = Tba0; va4 = A1_dot_B1; va5 = -Tba1; va6 = -Tab1;
-        cb = LB1_ux < 0;
-        vb0 = a1; vb1 = b1; vb2 = -A0_dot_B1; vb3 = -Tab0; vb4 = A1_dot_B1; vb5 = Tab1; vb6 = Tba1;
-        break;
-      case 4:  // UA1, UB0
-        guard = (UA1_uy > b1) && (UB0_ux > a0);
-        ca = UA1_ly > b1;
-        va0 = b0; va1 = a1; va2 = A1_dot_B1; va3 = aA0_dot_B1 - Tba1 - b1; va4 = A1_dot_B0; va5 = aA0_dot_B0 - Tba0; va6 = -Tab1 - bA1_dot_B1;
-        cb = UB0_lx > a0;
-        vb0 = a1; vb1 = b0; vb2 = A0_dot_B0; vb3 = Tab0 - a0 + bA0_dot_B1; vb4 = A1_dot_B0; vb5 = Tab1 + bA1_dot_B1; vb6 = Tba0 - aA0_dot_B0;
-        break;
-      case 5:  // UA1, LB0
-        guard = (UA1_ly < 0) && (LB0_ux > a0);
-        ca = UA1_uy < 0;
-        va0 = b0; va1 = a1; va2 = -A1_dot_B1; va3 = Tba1 - aA0_dot_B1; va4 = A1_dot_B0; va5 = aA0_dot_B0 - Tba0; va6 = -Tab1;
-        cb = LB0_lx > a0;
-        vb0 = a1; vb1 = b0; vb2 = A0_dot_B0; vb3 = Tab0 - a0; vb4 = A1_dot_B0; vb5 = Tab1; vb6 = Tba0 - aA0_dot_B0;
-        break;
-      case 6:  // LA1, UB0
-        guard = (LA1_uy > b1) && (UB0_lx < 0);
-        ca = LA1_ly > b1;
-        va0 = b0; va1 = a1; va2 = A1_dot_B1; va3 = -Tba1 - b1; va4 = A1_dot_B0; va5 = -Tba0; va6 = -Tab1 - bA1_dot_B1;
-        cb = UB0_ux < 0;
-        vb0 = a1; vb1 = b0; vb2 = -A0_dot_B0; vb3 = -Tab0 - bA0_dot_B1; vb4 = A1_dot_B0; vb5 = Tab1 + bA1_dot_B1; vb6 = Tba0;
-        break;
-      case 7:  // LA1, LB0
-        guard = (LA1_ly < 0) && (LB0_lx < 0);
-        ca = LA1_uy < 0;
-        va0 = b0; va1 = a1; va2 = -A1_dot_B1; va3 = Tba1; va4 = A1_dot_B0; va5 = -Tba0; va6 = -Tab1;
-        cb = LB0_ux < 0;
-        vb0 = a1; vb1 = b0; vb2 = -A0_dot_B0; vb3 = -Tab0; vb4 = A1_dot_B0; vb5 = Tab1; vb6 = Tba0;
-        break;
-      case 8:  // UA0, UB1
-        guard = (UA0_ux > b0) && (UB1_uy > a1);
-        ca = UA0_lx > b0;
-        va0 = b1; va1 = a0; va2 = A0_dot_B0; va3 = aA1_dot_B0 - Tba0 - b0; va4 = A0_dot_B1; va5 = aA1_dot_B1 - Tba1; va6 = -Tab0 - bA0_dot_B0;
-        cb = UB1_ly > a1;
-        vb0 = a0; vb1 = b1; vb2 = A1_dot_B1; vb3 = Tab1 - a1 + bA1_dot_B0; vb4 = A0_dot_B1; vb5 = Tab0 + bA0_dot_B0; vb6 = Tba1 - aA1_dot_B1;
-        break;
-      case 9:  // UA0, LB1
-        guard = (UA0_lx < 0) && (LB1_uy > a1);
-        ca = UA0_ux < 0;
-        va0 = b1; va1 = a0; va2 = -A0_dot_B0; va3 = Tba0 - aA1_dot_B0; va4 = A0_dot_B1; va5 = aA1_dot_B1 - Tba1; va6 = -Tab0;
-        cb = LB1_ly > a1;
-        vb0 = a0; vb1 = b1; vb2 = A1_dot_B1; vb3 = Tab1 - a1; vb4 = A0_dot_B1; vb5 = Tab0; vb6 = Tba1 - aA1_dot_B1;
-        break;
-      case 10:  // LA0, UB1
-        guard = (LA0_ux > b0) && (UB1_ly < 0);
-        ca = LA0_lx > b0;
-        va0 = b1; va1 = a0; va2 = A0_dot_B0; va3 = -b0 - Tba0; va4 = A0_dot_B1; va5 = -Tba1; va6 = -bA0_dot_B0 - Tab0;
-        cb = UB1_uy < 0;
-        vb0 = a0; vb1 = b1; vb2 = -A1_dot_B1; vb3 = -Tab1 - bA1_dot_B0; vb4 = A0_dot_B1; vb5 = Tab0 + bA0_dot_B0; vb6 = Tba1;
-        break;
-      case 11:  // LA0, LB1
-        guard = (LA0_lx < 0) && (LB1_ly < 0);
-        ca = LA0_ux < 0;
-        va0 = b1; va1 = a0; va2 = -A0_dot_B0; va3 = Tba0; va4 = A0_dot_B1; va5 = -Tba1; va6 = -Tab0;
-        cb = LB1_uy < 0;
-        vb0 = a0; vb1 = b1; vb2 = -A1_dot_B1; vb3 = -Tab1; vb4 = A0_dot_B1; vb5 = Tab0; vb6 = Tba1;
-        break;
-      case 12:  // UA0, UB0
-        guard = (UA0_uy > b1) && (UB0_uy > a1);
-        ca = UA0_ly > b1;
-        va0 = b0; va1 = a0; va2 = A0_dot_B1; va3 = aA1_dot_B1 - Tba1 - b1; va4 = A0_dot_B0; va5 = aA1_dot_B0 - Tba0; va6 = -Tab0 - bA0_dot_B1;
-        cb = UB0_ly > a1;
-        vb0 = a0; vb1 = b0; vb2 = A1_dot_B0; vb3 = Tab1 - a1 + bA1_dot_B1; vb4 = A0_dot_B0; vb5 = Tab0 + bA0_dot_B1; vb6 = Tba0 - aA1_dot_B0;
-        break;
-      case 13:  // UA0, LB0
-        guard = (UA0_ly < 0) && (LB0_uy > a1);
-        ca = UA0_uy < 0;
-        va0 = b0; va1 = a0; va2 = -A0_dot_B1; va3 = Tba1 - aA1_dot_B1; va4 = A0_dot_B0; va5 = aA1_dot_B0 - Tba0; va6 = -Tab0;
-        cb = LB0_ly > a1;
-        vb0 = a0; vb1 = b0; vb2 = A1_dot_B0; vb3 = Tab1 - a1; vb4 = A0_dot_B0; vb5 = Tab0; vb6 = Tba0 - aA1_dot_B0;
-        break;
-      case 14:  // LA0, UB0
-        guard = (LA0_uy > b1) && (UB0_ly < 0);
-        ca = LA0_ly > b1;
-        va0 = b0; va1 = a0; va2 = A0_dot_B1; va3 = -Tba1 - b1; va4 = A0_dot_B0; va5 = -Tba0; va6 = -Tab0 - bA0_dot_B1;
-        cb = UB0_uy < 0;
-        vb0 = a0; vb1 = b0; vb2 = -A1_dot_B0; vb3 = -Tab1 - bA1_dot_B1; vb4 = A0_dot_B0; vb5 = Tab0 + bA0_dot_B1; vb6 = Tba0;
-        break;
-      case 15:  // LA0, LB0
-        guard = (LA0_ly < 0) && (LB0_ly < 0);
-        ca = LA0_uy < 0;
-        va0 = b0; va1 = a0; va2 = -A0_dot_B1; va3 = Tba1; va4 = A0_dot_B0; va5 = -Tba0; va6 = -Tab0;
-        cb = LB0_uy < 0;
-        vb0 = a0; vb1 = b0; vb2 = -A1_dot_B0; vb3 = -Tab1; vb4 = A0_dot_B0; vb5 = Tab0; vb6 = Tba0;
-        break;
-      default:
-        break;
-    }
-    if (kwin < 0 && guard) {
-      if ((ca || in_voronoi(va0, va1, va2, va3, va4, va5, va6)) &&
-          (cb || in_voronoi(vb0, vb1, vb2, vb3, vb4, vb5, vb6)))
-        kwin = k;
-    }
-    // every lane of the phase has its case: stop early
-    if (HFB_LANES_ALL(lanes, kwin >= 0)) break;
-  }
+  p.R00 = R00;
+  p.R01 = R01;
+  p.R02 = R02;
+  p.R10 = R10;
+  p.R11 = R11;
+  p.R12 = R12;
+  p.R20 = R20;
+  p.R21 = R21;
+  p.a0 = a0;
+  p.a1 = a1;
+  p.b0 = b0;
+  p.b1 = b1;
+  p.A0_dot_B0 = A0_dot_B0;
+  p.A0_dot_B1 = A0_dot_B1;
+  p.A1_dot_B0 = A1_dot_B0;
+  p.A1_dot_B1 = A1_dot_B1;
+  p.aA0_dot_B0 = aA0_dot_B0;
+  p.aA0_dot_B1 = aA0_dot_B1;
+  p.aA1_dot_B0 = aA1_dot_B0;
+  p.aA1_dot_B1 = aA1_dot_B1;
+  p.bA0_dot_B0 = bA0_dot_B0;
+  p.bA1_dot_B0 = bA1_dot_B0;
+  p.bA0_dot_B1 = bA0_dot_B1;
+  p.bA1_dot_B1 = bA1_dot_B1;
+  p.Tab0 = Tab0;
+  p.Tab1 = Tab1;
+  p.Tab2 = Tab2;
+  p.Tba0 = Tba0;
+  p.Tba1 = Tba1;
+  p.Tba2 = Tba2;
+  p.LA1_lx = LA1_lx;
+  p.LA1_ux = LA1_ux;
+  p.UA1_lx = UA1_lx;
+  p.UA1_ux = UA1_ux;
+  p.LB1_lx = LB1_lx;
+  p.LB1_ux = LB1_ux;
+  p.UB1_lx = UB1_lx;
+  p.UB1_ux = UB1_ux;
+  p.LA1_ly = LA1_ly;
+  p.LA1_uy = LA1_uy;
+  p.UA1_ly = UA1_ly;
+  p.UA1_uy = UA1_uy;
+  p.LB0_lx = LB0_lx;
+  p.LB0_ux = LB0_ux;
+  p.UB0_lx = UB0_lx;
+  p.UB0_ux = UB0_ux;
+  p.LA0_lx = LA0_lx;
+  p.LA0_ux = LA0_ux;
+  p.UA0_lx = UA0_lx;
+  p.UA0_ux = UA0_ux;
+  p.LB1_ly = LB1_ly;
+  p.LB1_uy = LB1_uy;
+  p.UB1_ly = UB1_ly;
+  p.UB1_uy = UB1_uy;
+  p.LA0_ly = LA0_ly;
+  p.LA0_uy = LA0_uy;
+  p.UA0_ly = UA0_ly;
+  p.UA0_uy = UA0_uy;
+  p.LB0_ly = LB0_ly;
+  p.LB0_uy = LB0_uy;
+  p.UB0_ly = UB0_ly;
+  p.UB0_uy = UB0_uy;
+}
+// conditions of edge-pair case k (0..15, the reference's order)
+HFB_HD bool rect_case(const RectPre& p, int k) {
+  const double R00 = p.R00;
+  const double R01 = p.R01;
+  const double R02 = p.R02;
+  const double R10 = p.R10;
+  const double R11 = p.R11;
+  const double R12 = p.R12;
+  const double R20 = p.R20;
+  const double R21 = p.R21;
+  const double a0 = p.a0;
+  const double a1 = p.a1;
+  const double b0 = p.b0;
+  const double b1 = p.b1;
+  const double A0_dot_B0 = p.A0_dot_B0;
+  const double A0_dot_B1 = p.A0_dot_B1;
+  const double A1_dot_B0 = p.A1_dot_B0;
+  const double A1_dot_B1 = p.A1_dot_B1;
+  const double aA0_dot_B0 = p.aA0_dot_B0;
+  const double aA0_dot_B1 = p.aA0_dot_B1;
+  const double aA1_dot_B0 = p.aA1_dot_B0;
+  const double aA1_dot_B1 = p.aA1_dot_B1;
+  const double bA0_dot_B0 = p.bA0_dot_B0;
+  const double bA1_dot_B0 = p.bA1_dot_B0;
+  const double bA0_dot_B1 = p.bA0_dot_B1;
+  const double bA1_dot_B1 = p.bA1_dot_B1;
+  const double Tab0 = p.Tab0;
+  const double Tab1 = p.Tab1;
+  const double Tab2 = p.Tab2;
+  const double Tba0 = p.Tba0;
+  const double Tba1 = p.Tba1;
+  const double Tba2 = p.Tba2;
+  const double LA1_lx = p.LA1_lx;
+  const double LA1_ux = p.LA1_ux;
+  const double UA1_lx = p.UA1_lx;
+  const double UA1_ux = p.UA1_ux;
+  const double LB1_lx = p.LB1_lx;
+  const double LB1_ux = p.LB1_ux;
+  const double UB1_lx = p.UB1_lx;
+  const double UB1_ux = p.UB1_ux;
+  const double LA1_ly = p.LA1_ly;
+  const double LA1_uy = p.LA1_uy;
+  const double UA1_ly = p.UA1_ly;
+  const double UA1_uy = p.UA1_uy;
+  const double LB0_lx = p.LB0_lx;
+  const double LB0_ux = p.LB0_ux;
+  const double UB0_lx = p.UB0_lx;
+  const double UB0_ux = p.UB0_ux;
+  const double LA0_lx = p.LA0_lx;
+  const double LA0_ux = p.LA0_ux;
+  const double UA0_lx = p.UA0_lx;
+  const double UA0_ux = p.UA0_ux;
+  const double LB1_ly = p.LB1_ly;
+  const double LB1_uy = p.LB1_uy;
+  const double UB1_ly = p.UB1_ly;
+  const double UB1_uy = p.UB1_uy;
+  const double LA0_ly = p.LA0_ly;
+  const double LA0_uy = p.LA0_uy;
+  const double UA0_ly = p.UA0_ly;
+  const double UA0_uy = p.UA0_uy;
+  const double LB0_ly = p.LB0_ly;
+  const double LB0_uy = p.LB0_uy;
+  const double UB0_ly = p.UB0_ly;
+  const double UB0_uy = p.UB0_uy;
+  (void)R00; (void)R01; (void)R02; (void)R10; (void)R11; (void)R12; (void)R20; (void)R21; (void)Tab2; (void)Tba2;
+  bool guard = false, ca = false, cb = false;
+  double va0 = 0, va1 = 0, va2 = 0, va3 = 0, va4 = 0, va5 = 0, va6 = 0;
+  double vb0 = 0, vb1 = 0, vb2 = 0, vb3 = 0, vb4 = 0, vb5 = 0, vb6 = 0;
+  switch (k) {
+  case 0:  // UA1, UB1
+    guard = (UA1_ux > b0) && (UB1_ux > a0);
+    ca = UA1_lx > b0;
+    va0 = b1; va1 = a1; va2 = A1_dot_B0; va3 = aA0_dot_B0 - b0 - Tba0; va4 = A1_dot_B1; va5 = aA0_dot_B1 - Tba1; va6 = -Tab1 - bA1_dot_B0;
+    cb = UB1_lx > a0;
+    vb0 = a1; vb1 = b1; vb2 = A0_dot_B1; vb3 = Tab0 + bA0_dot_B0 - a0; vb4 = A1_dot_B1; vb5 = Tab1 + bA1_dot_B0; vb6 = Tba1 - aA0_dot_B1;
+    break;
+  case 1:  // UA1, LB1
+    guard = (UA1_lx < 0) && (LB1_ux > a0);
+    ca = UA1_ux < 0;
+    va0 = b1; va1 = a1; va2 = -A1_dot_B0; va3 = Tba0 - aA0_dot_B0; va4 = A1_dot_B1; va5 = aA0_dot_B1 - Tba1; va6 = -Tab1;
+    cb = LB1_lx > a0;
+    vb0 = a1; vb1 = b1; vb2 = A0_dot_B1; vb3 = Tab0 - a0; vb4 = A1_dot_B1; vb5 = Tab1; vb6 = Tba1 - aA0_dot_B1;
+    break;
+  case 2:  // LA1, UB1
+    guard = (LA1_ux > b0) && (UB1_lx < 0);
+    ca = LA1_lx > b0;
+    va0 = b1; va1 = a1; va2 = A1_dot_B0; va3 = -Tba0 - b0; va4 = A1_dot_B1; va5 = -Tba1; va6 = -Tab1 - bA1_dot_B0;
+    cb = UB1_ux < 0;
+    vb0 = a1; vb1 = b1; vb2 = -A0_dot_B1; vb3 = -Tab0 - bA0_dot_B0; vb4 = A1_dot_B1; vb5 = Tab1 + bA1_dot_B0; vb6 = Tba1;
+    break;
+  case 3:  // LA1, LB1
+    guard = (LA1_lx < 0) && (LB1_lx < 0);
+    ca = LA1_ux < 0;
+    va0 = b1; va1 = a1; va2 = -A1_dot_B0; va3 = Tba0; va4 = A1_dot_B1; va5 = -Tba1; va6 = -Tab1;
+    cb = LB1_ux < 0;
+    vb0 = a1; vb1 = b1; vb2 = -A0_dot_B1; vb3 = -Tab0; vb4 = A1_dot_B1; vb5 = Tab1; vb6 = Tba1;
+    break;
+  case 4:  // UA1, UB0
+    guard = (UA1_uy > b1) && (UB0_ux > a0);
+    ca = UA1_ly > b1;
+    va0 = b0; va1 = a1; va2 = A1_dot_B1; va3 = aA0_dot_B1 - Tba1 - b1; va4 = A1_dot_B0; va5 = aA0_dot_B0 - Tba0; va6 = -Tab1 - bA1_dot_B1;
+    cb = UB0_lx > a0;
+    vb0 = a1; vb1 = b0; vb2 = A0_dot_B0; vb3 = Tab0 - a0 + bA0_dot_B1; vb4 = A1_dot_B0; vb5 = Tab1 + bA1_dot_B1; vb6 = Tba0 - aA0_dot_B0;
+    break;
+  case 5:  // UA1, LB0
+    guard = (UA1_ly < 0) && (LB0_ux > a0);
+    ca = UA1_uy < 0;
+    va0 = b0; va1 = a1; va2 = -A1_dot_B1; va3 = Tba1 - aA0_dot_B1; va4 = A1_dot_B0; va5 = aA0_dot_B0 - Tba0; va6 = -Tab1;
+    cb = LB0_lx > a0;
+    vb0 = a1; vb1 = b0; vb2 = A0_dot_B0; vb3 = Tab0 - a0; vb4 = A1_dot_B0; vb5 = Tab1; vb6 = Tba0 - aA0_dot_B0;
+    break;
+  case 6:  // LA1, UB0
+    guard = (LA1_uy > b1) && (UB0_lx < 0);
+    ca = LA1_ly > b1;
+    va0 = b0; va1 = a1; va2 = A1_dot_B1; va3 = -Tba1 - b1; va4 = A1_dot_B0; va5 = -Tba0; va6 = -Tab1 - bA1_dot_B1;
+    cb = UB0_ux < 0;
+    vb0 = a1; vb1 = b0; vb2 = -A0_dot_B0; vb3 = -Tab0 - bA0_dot_B1; vb4 = A1_dot_B0; vb5 = Tab1 + bA1_dot_B1; vb6 = Tba0;
+    break;
+  case 7:  // LA1, LB0
+    guard = (LA1_ly < 0) && (LB0_lx < 0);
+    ca = LA1_uy < 0;
+    va0 = b0; va1 = a1; va2 = -A1_dot_B1; va3 = Tba1; va4 = A1_dot_B0; va5 = -Tba0; va6 = -Tab1;
+    cb = LB0_ux < 0;
+    vb0 = a1; vb1 = b0; vb2 = -A0_dot_B0; vb3 = -Tab0; vb4 = A1_dot_B0; vb5 = Tab1; vb6 = Tba0;
+    break;
+  case 8:  // UA0, UB1
+    guard = (UA0_ux > b0) && (UB1_uy > a1);
+    ca = UA0_lx > b0;
+    va0 = b1; va1 = a0; va2 = A0_dot_B0; va3 = aA1_dot_B0 - Tba0 - b0; va4 = A0_dot_B1; va5 = aA1_dot_B1 - Tba1; va6 = -Tab0 - bA0_dot_B0;
+    cb = UB1_ly > a1;
+    vb0 = a0; vb1 = b1; vb2 = A1_dot_B1; vb3 = Tab1 - a1 + bA1_dot_B0; vb4 = A0_dot_B1; vb5 = Tab0 + bA0_dot_B0; vb6 = Tba1 - aA1_dot_B1;
+    break;
+  case 9:  // UA0, LB1
+    guard = (UA0_lx < 0) && (LB1_uy > a1);
+    ca = UA0_ux < 0;
+    va0 = b1; va1 = a0; va2 = -A0_dot_B0; va3 = Tba0 - aA1_dot_B0; va4 = A0_dot_B1; va5 = aA1_dot_B1 - Tba1; va6 = -Tab0;
+    cb = LB1_ly > a1;
+    vb0 = a0; vb1 = b1; vb2 = A1_dot_B1; vb3 = Tab1 - a1; vb4 = A0_dot_B1; vb5 = Tab0; vb6 = Tba1 - aA1_dot_B1;
+    break;
+  case 10:  // LA0, UB1
+    guard = (LA0_ux > b0) && (UB1_ly < 0);
+    ca = LA0_lx > b0;
+    va0 = b1; va1 = a0; va2 = A0_dot_B0; va3 = -b0 - Tba0; va4 = A0_dot_B1; va5 = -Tba1; va6 = -bA0_dot_B0 - Tab0;
+    cb = UB1_uy < 0;
+    vb0 = a0; vb1 = b1; vb2 = -A1_dot_B1; vb3 = -Tab1 - bA1_dot_B0; vb4 = A0_dot_B1; vb5 = Tab0 + bA0_dot_B0; vb6 = Tba1;
+    break;
+  case 11:  // LA0, LB1
+    guard = (LA0_lx < 0) && (LB1_ly < 0);
+    ca = LA0_ux < 0;
+    va0 = b1; va1 = a0; va2 = -A0_dot_B0; va3 = Tba0; va4 = A0_dot_B1; va5 = -Tba1; va6 = -Tab0;
+    cb = LB1_uy < 0;
+    vb0 = a0; vb1 = b1; vb2 = -A1_dot_B1; vb3 = -Tab1; vb4 = A0_dot_B1; vb5 = Tab0; vb6 = Tba1;
+    break;
+  case 12:  // UA0, UB0
+    guard = (UA0_uy > b1) && (UB0_uy > a1);
+    ca = UA0_ly > b1;
+    va0 = b0; va1 = a0; va2 = A0_dot_B1; va3 = aA1_dot_B1 - Tba1 - b1; va4 = A0_dot_B0; va5 = aA1_dot_B0 - Tba0; va6 = -Tab0 - bA0_dot_B1;
+    cb = UB0_ly > a1;
+    vb0 = a0; vb1 = b0; vb2 = A1_dot_B0; vb3 = Tab1 - a1 + bA1_dot_B1; vb4 = A0_dot_B0; vb5 = Tab0 + bA0_dot_B1; vb6 = Tba0 - aA1_dot_B0;
+    break;
+  case 13:  // UA0, LB0
+    guard = (UA0_ly < 0) && (LB0_uy > a1);
+    ca = UA0_uy < 0;
+    va0 = b0; va1 = a0; va2 = -A0_dot_B1; va3 = Tba1 - aA1_dot_B1; va4 = A0_dot_B0; va5 = aA1_dot_B0 - Tba0; va6 = -Tab0;
+    cb = LB0_ly > a1;
+    vb0 = a0; vb1 = b0; vb2 = A1_dot_B0; vb3 = Tab1 - a1; vb4 = A0_dot_B0; vb5 = Tab0; vb6 = Tba0 - aA1_dot_B0;
+    break;
+  case 14:  // LA0, UB0
+    guard = (LA0_uy > b1) && (UB0_ly < 0);
+    ca = LA0_ly > b1;
+    va0 = b0; va1 = a0; va2 = A0_dot_B1; va3 = -Tba1 - b1; va4 = A0_dot_B0; va5 = -Tba0; va6 = -Tab0 - bA0_dot_B1;
+    cb = UB0_uy < 0;
+    vb0 = a0; vb1 = b0; vb2 = -A1_dot_B0; vb3 = -Tab1 - bA1_dot_B1; vb4 = A0_dot_B0; vb5 = Tab0 + bA0_dot_B1; vb6 = Tba0;
+    break;
+  case 15:  // LA0, LB0
+    guard = (LA0_ly < 0) && (LB0_ly < 0);
+    ca = LA0_uy < 0;
+    va0 = b0; va1 = a0; va2 = -A0_dot_B1; va3 = Tba1; va4 = A0_dot_B0; va5 = -Tba0; va6 = -Tab0;
+    cb = LB0_uy < 0;
+    vb0 = a0; vb1 = b0; vb2 = -A1_dot_B0; vb3 = -Tab1; vb4 = A0_dot_B0; vb5 = Tab0; vb6 = Tba0;
+    break;
+  default:
+    break;
+}
+  if (!guard) return false;
+  return (ca || in_voronoi(va0, va1, va2, va3, va4, va5, va6)) && (cb || in_voronoi(vb0, vb1, vb2, vb3, vb4, vb5, vb6));
+}
+// kwin: the first case whose conditions hold, or -1
+HFB_HD double rect_finish(const RectPre& p, int kwin) {
+  const double R00 = p.R00, R01 = p.R01, R02 = p.R02, R10 = p.R10, R11 = p.R11, R12 = p.R12, R20 = p.R20, R21 = p.R21;
+  const double a0 = p.a0, a1 = p.a1, b0 = p.b0, b1 = p.b1;
+  const double A0_dot_B0 = p.A0_dot_B0, A0_dot_B1 = p.A0_dot_B1, A1_dot_B0 = p.A1_dot_B0, A1_dot_B1 = p.A1_dot_B1;
+  const double aA0_dot_B0 = p.aA0_dot_B0, aA0_dot_B1 = p.aA0_dot_B1, aA1_dot_B0 = p.aA1_dot_B0, aA1_dot_B1 = p.aA1_dot_B1;
+  const double bA0_dot_B0 = p.bA0_dot_B0, bA1_dot_B0 = p.bA1_dot_B0, bA0_dot_B1 = p.bA0_dot_B1, bA1_dot_B1 = p.bA1_dot_B1;
+  const double Tab0 = p.Tab0, Tab1 = p.Tab1, Tab2 = p.Tab2, Tba0 = p.Tba0, Tba1 = p.Tba1, Tba2 = p.Tba2;
   if (kwin >= 0) {
+    v3 S = mk(0, 0, 0);
+    double t, u;
     double sa = 0, sb = 0, s_ab = 0, s_at = 0, s_bt = 0;
     switch (kwin) {
     case 0: sa = a1; sb = b1; s_ab = A1_dot_B1; s_at = Tab1 + bA1_dot_B0; s_bt = Tba1 - aA0_dot_B1; break;
@@ -365,6 +501,20 @@ HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1
   }
   const double sep = (sep1 > sep2 ? sep1 : sep2);
   return (sep > 0 ? sep : 0);
+}
+HFB_HD_NOINLINE double rect_distance(const m3& Rab, v3 Tab, double a0, double a1, double b0, double b1,
+                                     unsigned lanes) {
+  RectPre p;
+  rect_prelude(Rab, Tab, a0, a1, b0, b1, p);
+  // the cases are a loop, not sixteen blocks with a return each: the lanes of `lanes` (one query each)
+  // walk them side by side and the two inVoronoi tests of a case are one copy of code
+  int kwin = -1;
+#pragma unroll 1
+  for (int k = 0; k < 16; ++k) {
+    if (kwin < 0 && rect_case(p, k)) kwin = k;
+    if (HFB_LANES_ALL(lanes, kwin >= 0)) break;  // every lane of the phase has its case
+  }
+  return rect_finish(p, kwin);
 }
 
 // distance(R0, T0, b1, b2) (RSS.cpp:995-1005)

@@ -1,0 +1,401 @@
+// Mesh-shape distance walk as a task system (kernel k_bvhq, hfb_bvhq_kernel.cuh).
+//
+// Replaces, like bvh_shape_distance_stream (hfb_bvh.cuh), for distance():
+//   distanceRecurse                                   src/traversal/traversal_recurse.cpp:153-203
+//   MeshShapeDistanceTraversalNodeOBBRSS              include/hpp/fcl/internal/traversal_node_bvh_shape.h:286-478
+//   BVDistanceLowerBound = RSS distance               src/BV/RSS.cpp:995-1005
+//
+// Why another walk.  The reference recurses one query at a time; a query is a chain of dependent steps
+// (bounding-volume test of two children -> push -> pop/prune -> ... -> triangle-shape GJK) and config 4
+// holds one query of 9 360 steps next to a mean of 246.  A lane per query (k_bvh) leaves most lanes of a
+// warp idle -- every lane is at a different step -- and is bound by that longest chain.  Here a query is a
+// small state machine whose steps are ITEMS handed to whichever warp is free:
+//   * a BV item  = the RSS distances of the two children of a node: 8 lanes, the sixteen edge-pair cases of
+//     rectDistance split four per lane (rect_case), first passing case by ballot -- the reference's
+//     first-return order;
+//   * a leaf item = one triangle-shape GJK (+EPA): one lane, 32 items of 32 different queries per warp;
+//   * the walk (pop / prune / push, canStop, both counters) runs on the lane that finished the query's
+//     last outstanding item, in exactly the recursion's order.
+// Items of one kind come from one queue, so every warp instruction works on 32 leaf tests or 4 x 8 lanes of
+// bounding-volume tests, whatever the queries' individual progress.
+//
+// Speculation for long walks.  A bounding-volume distance is a pure function of (query, node); a leaf test is
+// one too unless the request chains GJK guesses from leaf to leaf (CachedGuess).  Once a query has used
+// `spec_after` items, reaching a node with at most HFB_Q_TREELET_MAX triangles below it (a "treelet"; the
+// builder lays a subtree out as one contiguous block of node pairs, checked at registration) issues ALL the
+// subtree's BV items and leaf items at once; when the last one lands the walk replays the recursion over the
+// cached values -- same visiting order, same pruning, same counters (tests never visited are not counted) --
+// and the chain of ~2 x 62 dependent steps costs two.  Results cannot differ from the unspeculated walk;
+// tests/emu runs this file on the host with items executed in random order against the oracle.
+#pragma once
+#include "hfb_bvh.cuh"
+
+namespace hfb {
+
+#define HFB_Q_TREELET_MAX 32
+#define HFB_Q_ITEM_SPEC 0x100000u
+#define HFB_Q_ITEM_VALID 0x80000000u
+#define HFB_Q_SLOT_MASK 0xfffu
+
+struct QStackEnt {  // a node still to be visited + the lower bound canStop() re-checks at pop time
+  double dlow;
+  int fc;    // first_child of the node (< 0: leaf, primitive -(fc + 1))
+  int node;  // its index
+};
+
+struct QPrep {  // per query, written by k_bvhq_prep: the shape's RSS (computeBV) and b1^T * R0
+  double sbv[15];  // axes (rows of the m3), Tr, l0, l1, radius
+  double M[9];
+  int ok, swapped;
+};
+
+struct QTreelet {  // cached values of one speculated subtree: descendants tfc .. tfc + 2L - 3
+  double d[2 * HFB_Q_TREELET_MAX];
+  int fc[2 * HFB_Q_TREELET_MAX];
+  int leaf_of[2 * HFB_Q_TREELET_MAX];
+  int prim[HFB_Q_TREELET_MAX];
+  double leaf[HFB_Q_TREELET_MAX][10];  // distance, p1, p2, normal
+};
+
+struct QSlot {  // one query in flight (shared memory on the device; 83 eight-byte words: odd stride)
+  double tfm[12], tfs[12];
+  double sbv[15], M[9];
+  double shp[7];  // p0 p1 p2 ssr center
+  double guess[3];
+  double out[10];  // min_distance, p1, p2, normal
+  const void* ptr[6];  // nodes, verts, tris, cx, cy, cz
+  int type, nv, hint0, hint1, b1, sp, bv_tests, leaf_tests, pair, swapped, pending, rounds, tfc, tend, scr, cur;
+  int seed, _i1;
+};
+
+struct QCtx {  // uniform per launch
+  SolverP P;
+  double rel_err, abs_err;
+  int spec_after;  // items a query must have used before it may speculate; < 0: never
+};
+
+HFB_HD void q_put_m3(double* o, const m3& A) {
+  o[0] = A.r0.x; o[1] = A.r0.y; o[2] = A.r0.z;
+  o[3] = A.r1.x; o[4] = A.r1.y; o[5] = A.r1.z;
+  o[6] = A.r2.x; o[7] = A.r2.y; o[8] = A.r2.z;
+}
+HFB_HD m3 q_get_m3(const double* o) {
+  m3 A;
+  A.r0 = mk(o[0], o[1], o[2]);
+  A.r1 = mk(o[3], o[4], o[5]);
+  A.r2 = mk(o[6], o[7], o[8]);
+  return A;
+}
+HFB_HD void q_put_xf(double* o, const xf& t) {
+  q_put_m3(o, t.R);
+  o[9] = t.T.x; o[10] = t.T.y; o[11] = t.T.z;
+}
+HFB_HD xf q_get_xf(const double* o) {
+  xf t;
+  t.R = q_get_m3(o);
+  t.T = mk(o[9], o[10], o[11]);
+  return t;
+}
+HFB_HD void q_put_rss(double* o, const RssD& r) {
+  q_put_m3(o, r.axes);
+  o[9] = r.Tr.x; o[10] = r.Tr.y; o[11] = r.Tr.z;
+  o[12] = r.l0; o[13] = r.l1; o[14] = r.radius;
+}
+HFB_HD RssD q_get_rss(const double* o) {
+  RssD r;
+  r.axes = q_get_m3(o);
+  r.Tr = mk(o[9], o[10], o[11]);
+  r.l0 = o[12]; r.l1 = o[13]; r.radius = o[14];
+  return r;
+}
+
+// the per-query set-up of orientedBVHShapeDistance (traversal_node_setup.h:765): computeBV<OBBRSS>(shape)
+// and the constant factor of every RSS distance of this query
+HFB_HD void q_make_prep(const BvhQuery& q, bool swapped, QPrep& pr) {
+  RssD sbv;
+  compute_shape_rss(q.shape, q.tf_shape, sbv);
+  q_put_rss(pr.sbv, sbv);
+  q_put_m3(pr.M, mmulm(mtrans(sbv.axes), q.tf_mesh.R));
+  pr.ok = 1;
+  pr.swapped = swapped ? 1 : 0;
+}
+
+// a fresh walk: DistanceResult cleared, root on the stack, preprocess() seeds with triangle 0
+// (traversal_node_bvh_shape.h:457-461) -- the caller pushes that leaf item
+HFB_HD void q_start(QSlot& s, QStackEnt* stk, const BvhQuery& q, const QPrep& pr, unsigned pair, v3 guess, int h0,
+                    int h1) {
+  q_put_xf(s.tfm, q.tf_mesh);
+  q_put_xf(s.tfs, q.tf_shape);
+  for (int k = 0; k < 15; ++k) s.sbv[k] = pr.sbv[k];
+  for (int k = 0; k < 9; ++k) s.M[k] = pr.M[k];
+  s.shp[0] = q.shape.p0; s.shp[1] = q.shape.p1; s.shp[2] = q.shape.p2; s.shp[3] = q.shape.ssr;
+  s.shp[4] = q.shape.center.x; s.shp[5] = q.shape.center.y; s.shp[6] = q.shape.center.z;
+  s.guess[0] = guess.x; s.guess[1] = guess.y; s.guess[2] = guess.z;
+  s.out[0] = DBL_MAX;
+  for (int k = 1; k < 10; ++k) s.out[k] = nan3().x;
+  s.ptr[0] = q.nodes; s.ptr[1] = q.verts; s.ptr[2] = q.tris;
+  s.ptr[3] = q.shape.cx; s.ptr[4] = q.shape.cy; s.ptr[5] = q.shape.cz;
+  s.type = q.shape.type;
+  s.nv = q.shape.nv;
+  s.hint0 = h0; s.hint1 = h1;
+  s.b1 = -1;
+  s.bv_tests = s.leaf_tests = 0;
+  s.pair = (int)pair;
+  s.swapped = pr.swapped;
+  s.rounds = 0;
+  s.tfc = s.tend = -1;
+  s.scr = -1;
+  s.seed = 1;
+  stk[0].dlow = -1.0;  // root: visited unconditionally
+  stk[0].fc = q.nodes[0].first_child;
+  stk[0].node = 0;
+  s.sp = 1;
+  s.cur = 0;
+  s.pending = 1;
+}
+
+struct QLeafRes {
+  double distance;
+  v3 p1, p2, normal, guess;
+  int hint0, hint1;
+};
+// leafComputeDistance (traversal_node_bvh_shape.h:342-364): TriangleP(mesh triangle) vs the shape.
+// `chained`: the warm start of this query's previous leaf goes in (normal items; it only matters to
+// CachedGuess requests), otherwise the request's default.
+template <int CAPS>
+HFB_HD void q_leaf_eval(const QSlot& s, int prim, const SolverP& P, EpaWs* ws, bool chained, QLeafRes& r) {
+  PairIn in;
+  const uint32_t* t = static_cast<const uint32_t*>(s.ptr[2]) + 3 * (size_t)prim;
+  const double* verts = static_cast<const double*>(s.ptr[1]);
+  const double* a = verts + 3 * (size_t)t[0];
+  const double* b = verts + 3 * (size_t)t[1];
+  const double* c = verts + 3 * (size_t)t[2];
+  in.s1.type = HFB_GEOM_TRIANGLE;
+  in.s1.ssr = 0;
+  in.s1.p0 = in.s1.p1 = in.s1.p2 = 0;
+  in.s1.nv = 0;
+  in.s1.cx = in.s1.cy = in.s1.cz = nullptr;
+  in.s1.center = mk(0, 0, 0);
+  in.s1.ta = mk(a[0], a[1], a[2]);
+  in.s1.tb = mk(b[0], b[1], b[2]);
+  in.s1.tc = mk(c[0], c[1], c[2]);
+  in.s2.type = s.type;
+  in.s2.p0 = s.shp[0]; in.s2.p1 = s.shp[1]; in.s2.p2 = s.shp[2]; in.s2.ssr = s.shp[3];
+  in.s2.center = mk(s.shp[4], s.shp[5], s.shp[6]);
+  in.s2.cx = static_cast<const double*>(s.ptr[3]);
+  in.s2.cy = static_cast<const double*>(s.ptr[4]);
+  in.s2.cz = static_cast<const double*>(s.ptr[5]);
+  in.s2.nv = s.nv;
+  in.s2.ta = in.s2.tb = in.s2.tc = mk(0, 0, 0);
+  in.tf1 = q_get_xf(s.tfm);
+  in.tf2 = q_get_xf(s.tfs);
+  in.cached_guess = chained ? mk(s.guess[0], s.guess[1], s.guess[2]) : mk(1, 0, 0);
+  in.hint0 = chained ? s.hint0 : 0;
+  in.hint1 = chained ? s.hint1 : 0;
+  PairOut o;
+  GjkState g;
+  if (pair_phase1<1, CAPS, PATH_BOTH>(in, P, o, g)) pair_phase2<1, CAPS>(in, P, g, ws, o);
+  r.distance = o.distance;
+  r.p1 = o.p1; r.p2 = o.p2; r.normal = o.normal;
+  r.guess = o.cached_guess;
+  r.hint0 = o.hint0; r.hint1 = o.hint1;
+}
+
+// RSS distance of one node against the query's shape RSS: rss_distance (hfb_bvh.cuh) with the factor
+// b1^T * R0 taken from the slot.  The serial form (host emulation, and the reference for the lane-group form)
+HFB_HD void q_rss_operands(const QSlot& s, const hfb_bvh_node& nd, m3& R, v3& T, double& b0, double& b1, double& rad) {
+  const m3 ax2 = load_colmajor(nd.rss_axes);
+  const v3 Tr2 = mk(nd.rss_Tr[0], nd.rss_Tr[1], nd.rss_Tr[2]);
+  const m3 M = q_get_m3(s.M);
+  const m3 R0 = q_get_m3(s.tfm);
+  const v3 T0 = mk(s.tfm[9], s.tfm[10], s.tfm[11]);
+  const m3 ax1 = q_get_m3(s.sbv);
+  const v3 Tr1 = mk(s.sbv[9], s.sbv[10], s.sbv[11]);
+  R = mmulm(M, ax2);
+  const v3 Ttemp = mmul(R0, Tr2) + T0 - Tr1;
+  T = mtmul(ax1, Ttemp);
+  b0 = nd.rss_length[0];
+  b1 = nd.rss_length[1];
+  rad = s.sbv[14] + nd.rss_radius;
+}
+HFB_HD double q_rss_child(const QSlot& s, const hfb_bvh_node& nd) {
+  m3 R;
+  v3 T;
+  double b0, b1, rad;
+  q_rss_operands(s, nd, R, T, b0, b1, rad);
+  double dist = rect_distance(R, T, s.sbv[12], s.sbv[13], b0, b1, 0);
+  dist -= rad;
+  return (dist < 0.0) ? 0.0 : dist;
+}
+
+enum { Q_ISSUED = 0, Q_DONE = 1 };
+
+// pushes the two children of a node in the reference's order: the nearer one is visited first
+HFB_HD void q_push_children(QStackEnt* stk, int& sp, int base, double d1, double d2, int f1, int f2) {
+  if (d2 < d1) {
+    stk[sp].dlow = d1; stk[sp].fc = f1; stk[sp].node = base; ++sp;
+    stk[sp].dlow = d2; stk[sp].fc = f2; stk[sp].node = base + 1; ++sp;
+  } else {
+    stk[sp].dlow = d2; stk[sp].fc = f2; stk[sp].node = base + 1; ++sp;
+    stk[sp].dlow = d1; stk[sp].fc = f1; stk[sp].node = base; ++sp;
+  }
+}
+// DistanceResult::update: strict '>' keeps the first minimum
+HFB_HD void q_take_leaf(QSlot& s, int prim, const double* leaf10) {
+  if (s.out[0] > leaf10[0]) {
+    s.b1 = prim;
+    for (int k = 0; k < 10; ++k) s.out[k] = leaf10[k];
+  }
+}
+
+// The recursion, from the query's stack: pops / prunes (canStop, traversal_node_bvh_shape.h:322-327) until a
+// node needs a value that is not at hand, issues the item(s) for it and returns Q_ISSUED; Q_DONE when the
+// stack is empty.  Called by whoever completed the query's last outstanding item.
+template <class Sink>
+HFB_HD int q_advance(QSlot& s, unsigned slot_id, QStackEnt* stk, QTreelet* tls, const QCtx& c, Sink& sink) {
+  int sp = s.sp;
+  const hfb_bvh_node* nodes = static_cast<const hfb_bvh_node*>(s.ptr[0]);
+  for (;;) {
+    if (sp == 0) break;
+    const QStackEnt e = stk[--sp];
+    if (e.dlow >= 0) {
+      if ((e.dlow >= s.out[0] - c.abs_err) && (e.dlow * (1 + c.rel_err) >= s.out[0])) continue;
+    }
+    QTreelet* T = s.scr >= 0 ? tls + s.scr : nullptr;
+    if (e.fc < 0) {  // leaf
+      const int prim = -(e.fc + 1);
+      if (T && e.node >= s.tfc && e.node < s.tend) {
+        s.leaf_tests++;
+        q_take_leaf(s, prim, T->leaf[T->leaf_of[e.node - s.tfc]]);
+        continue;
+      }
+      if (T) {  // the walk has left the speculated subtree
+        sink.treelet_release(s.scr);
+        s.scr = -1;
+        s.tfc = s.tend = -1;
+      }
+      s.cur = prim;
+      s.pending = 1;
+      s.rounds++;
+      s.sp = sp;
+      sink.push_leaf(slot_id);
+      return Q_ISSUED;
+    }
+    if (T && e.fc >= s.tfc && e.fc < s.tend) {  // both children cached
+      const int k = e.fc - s.tfc;
+      s.bv_tests += 2;
+      q_push_children(stk, sp, e.fc, T->d[k], T->d[k + 1], T->fc[k], T->fc[k + 1]);
+      continue;
+    }
+    if (T) {
+      sink.treelet_release(s.scr);
+      s.scr = -1;
+      s.tfc = s.tend = -1;
+    }
+    if (c.spec_after >= 0 && s.rounds >= c.spec_after) {
+      const unsigned L = nodes[e.node]._pad;  // triangles below; 0 unless the subtree is one contiguous block
+      if (L >= 2 && L <= HFB_Q_TREELET_MAX) {
+        const int id = sink.treelet_acquire();
+        if (id >= 0) {
+          QTreelet* N = tls + id;
+          const int nd = 2 * (int)L - 2;
+          int nleaf = 0;
+          for (int k = 0; k < nd; ++k) {
+            const int f = nodes[e.fc + k].first_child;
+            N->fc[k] = f;
+            if (f < 0) {
+              N->leaf_of[k] = nleaf;
+              N->prim[nleaf] = -(f + 1);
+              ++nleaf;
+            }
+          }
+          s.scr = id;
+          s.tfc = e.fc;
+          s.tend = e.fc + nd;
+          stk[sp++] = e;  // the replay starts by popping this node again; its children are cached then
+          s.sp = sp;
+          s.pending = nd / 2 + nleaf;
+          s.rounds++;
+          for (int p = 0; p < nd / 2; ++p) sink.push_bv(slot_id | ((unsigned)p << 12) | HFB_Q_ITEM_SPEC);
+          for (int j = 0; j < nleaf; ++j) sink.push_leaf(slot_id | ((unsigned)j << 12) | HFB_Q_ITEM_SPEC);
+          return Q_ISSUED;
+        }
+      }
+    }
+    s.cur = e.fc;
+    s.pending = 1;
+    s.rounds++;
+    s.sp = sp;
+    sink.push_bv(slot_id);
+    return Q_ISSUED;
+  }
+  if (s.scr >= 0) {
+    sink.treelet_release(s.scr);
+    s.scr = -1;
+    s.tfc = s.tend = -1;
+  }
+  s.sp = 0;
+  return Q_DONE;
+}
+
+// completion of a BV item whose values are in hand (d of children base, base + 1 and their first_child)
+template <class Sink>
+HFB_HD int q_bv_done(QSlot& s, unsigned item, QStackEnt* stk, QTreelet* tls, const QCtx& c, Sink& sink, double d1,
+                     double d2, int f1, int f2) {
+  const unsigned slot_id = item & HFB_Q_SLOT_MASK;
+  if (item & HFB_Q_ITEM_SPEC) {
+    QTreelet* T = tls + s.scr;
+    const int k = 2 * (int)((item >> 12) & 0xffu);
+    T->d[k] = d1;
+    T->d[k + 1] = d2;
+    if (sink.dec_pending(s) != 1) return Q_ISSUED;
+    return q_advance(s, slot_id, stk, tls, c, sink);
+  }
+  s.bv_tests += 2;  // BVDistanceLowerBound of both children (:465-469)
+  int sp = s.sp;
+  q_push_children(stk, sp, s.cur, d1, d2, f1, f2);
+  s.sp = sp;
+  return q_advance(s, slot_id, stk, tls, c, sink);
+}
+// node pair a BV item is about
+HFB_HD int q_bv_base(const QSlot& s, unsigned item) {
+  return (item & HFB_Q_ITEM_SPEC) ? s.tfc + 2 * (int)((item >> 12) & 0xffu) : s.cur;
+}
+HFB_HD int q_leaf_prim(const QSlot& s, const QTreelet* tls, unsigned item) {
+  return (item & HFB_Q_ITEM_SPEC) ? tls[s.scr].prim[(item >> 12) & 0xffu] : s.cur;
+}
+
+template <class Sink>
+HFB_HD int q_leaf_done(QSlot& s, unsigned item, QStackEnt* stk, QTreelet* tls, const QCtx& c, Sink& sink,
+                       const QLeafRes& r) {
+  const unsigned slot_id = item & HFB_Q_SLOT_MASK;
+  double v[10] = {r.distance, r.p1.x, r.p1.y, r.p1.z, r.p2.x, r.p2.y, r.p2.z, r.normal.x, r.normal.y, r.normal.z};
+  if (item & HFB_Q_ITEM_SPEC) {
+    double* dst = tls[s.scr].leaf[(item >> 12) & 0xffu];
+    for (int k = 0; k < 10; ++k) dst[k] = v[k];
+    if (sink.dec_pending(s) != 1) return Q_ISSUED;
+    return q_advance(s, slot_id, stk, tls, c, sink);
+  }
+  if (!s.seed) s.leaf_tests++;  // the seed triangle of preprocess() is not a counted leaf test
+  s.seed = 0;
+  q_take_leaf(s, s.cur, v);
+  // GJKSolver keeps cached_guess / support_func_cached_guess between calls (narrowphase.h:353-391, 625-626)
+  s.guess[0] = r.guess.x; s.guess[1] = r.guess.y; s.guess[2] = r.guess.z;
+  s.hint0 = r.hint0;
+  s.hint1 = r.hint1;
+  return q_advance(s, slot_id, stk, tls, c, sink);
+}
+
+HFB_HD void q_write_result(const QSlot& s, hfb_distance_result* rec) {
+  BvhDistOut o;
+  o.min_distance = s.out[0];
+  o.p1 = mk(s.out[1], s.out[2], s.out[3]);
+  o.p2 = mk(s.out[4], s.out[5], s.out[6]);
+  o.normal = mk(s.out[7], s.out[8], s.out[9]);
+  o.b1 = s.b1;
+  o.bv_tests = (unsigned)s.bv_tests;
+  o.leaf_tests = (unsigned)s.leaf_tests;
+  bvh_write_shape_distance(rec, s.swapped != 0, o);
+}
+
+}  // namespace hfb

@@ -27,6 +27,7 @@
 #include "hfb_arena.cuh"
 #include "hfb_bvh.cuh"
 #include "hfb_bvh_build.cuh"
+#include "hfb_bvhq_launch.h"
 #include "hfb_request.cuh"
 
 using namespace hfb;
@@ -752,6 +753,7 @@ struct Slot {
   cudaEvent_t ev_part[kMaxParts] = {};
   cudaEvent_t ev_join = nullptr;
   DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, retry, bvh_ws, bvh_cnt, extra, ccnt, okeys, ohist, olist;
+  DevBuf qprep, qstacks, qtl, qws;  // task-system mesh-shape walk (hfb_bvhq.cu)
 };
 
 }  // namespace
@@ -770,6 +772,8 @@ struct hfb_ctx {
   int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4, refill = 0, iter_quorum = 8, stage = 0, chunk = 0;
   int bvh_quorum = HFB_BVH_INIT_QUORUM;  // HFB_BVH_QUORUM=1: a lane sets its next query up as soon as it is free
   int bvh_order = 0;  // HFB_BVH_ORDER=1: hand the (mesh, shape) queries out longest-expected first
+  int bvhq = 1;        // HFB_BVHQ=0: mesh-shape distance queries through the lane-per-query kernel k_bvh instead of the task system k_bvhq
+  int bvh_spec = 200;  // HFB_BVH_SPEC: items a query uses before it may speculate on subtrees (< 0: never)
   int bvh_bps = 4;  // k_bvh: blocks (of 2 warps) per SM the grid is capped at; HFB_BVH_BPS, see tests/tools/bvh_sched_model.py
   bool profiling = false;
   struct Ev { cudaEvent_t a, b; int kind; };
@@ -1029,8 +1033,8 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
     if (blocks > cap) blocks = cap;
     CK(sl.bvh_ws.reserve((size_t)ctx->num_sms * 4u * 2 * threads * sizeof(EpaWs)));
     if (!sl.bvh_cnt.p) {
-      CK(sl.bvh_cnt.reserve(2 * sizeof(unsigned long long)));
-      CK(cudaMemsetAsync(sl.bvh_cnt.p, 0, 2 * sizeof(unsigned long long), s));
+      CK(sl.bvh_cnt.reserve(4 * sizeof(unsigned long long)));
+      CK(cudaMemsetAsync(sl.bvh_cnt.p, 0, 4 * sizeof(unsigned long long), s));
     }
     BatchArgs ab = a;
     ab.bvh_ws = static_cast<EpaWs*>(sl.bvh_ws.p);
@@ -1056,14 +1060,50 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
       CK(cudaGetLastError());
       ab.index_list = static_cast<const uint32_t*>(sl.olist.p);  // only its [lo, hi) slice is written -- and read
     }
-    {
-      KTimer kt(ctx, s, 5);
-      if (ctx->bvh_minb >= 8) k_bvh<MODE, BVK_SHAPE, 8><<<blocks * 2, threads, 0, s>>>(ab);
-      else if (ctx->bvh_quorum == 1) k_bvh<MODE, BVK_SHAPE, 4, 1><<<blocks, threads, 0, s>>>(ab);  // HFB_BVH_QUORUM=1
-      else k_bvh<MODE, BVK_SHAPE, 4><<<blocks, threads, 0, s>>>(ab);
+    bool walked = false;
+    if constexpr (MODE == 0) {
+      if (ctx->bvhq) {  // distance(): the task-system walk
+        const unsigned qb = bvhq_blocks(ctx->num_sms, n);
+        const int cap = ctx->arena.max_bvh_depth + 3;
+        const BvhqSizes z = bvhq_sizes(qb, n, cap);
+        CK(sl.qprep.reserve(z.prep));
+        CK(sl.qstacks.reserve(z.stacks));
+        CK(sl.qtl.reserve(z.treelets));
+        CK(sl.qws.reserve(z.ws));
+        BvhqLaunch L{};
+        L.A = ab.A;
+        L.h1 = ab.h1; L.tf1 = ab.tf1; L.h2 = ab.h2; L.tf2 = ab.tf2;
+        L.guess_in = ab.guess_in; L.hint_in = ab.hint_in;
+        L.out = static_cast<hfb_distance_result*>(ab.out);
+        L.index_list = ab.index_list;
+        L.range_lo = ab.range_lo; L.range_hi = ab.range_hi;
+        L.P = ab.P; L.B = ab.B;
+        L.prep = static_cast<QPrep*>(sl.qprep.p);
+        L.stacks = static_cast<QStackEnt*>(sl.qstacks.p);
+        L.treelets = static_cast<QTreelet*>(sl.qtl.p);
+        L.ws = static_cast<EpaWs*>(sl.qws.p);
+        L.work = ab.bvh_work;
+        L.counters = ab.bvh_counters;
+        L.stack_cap = cap;
+        L.spec_after = ctx->bvh_spec;
+        {
+          KTimer kt(ctx, s, 5);
+          if (bvhq_launch(L, qb, n, s) != 0) return fail(ctx, HFB_ERR_CUDA, "k_bvhq launch failed");
+        }
+        ctx->stats.kernel_launches += 2;
+        walked = true;
+      }
     }
-    ctx->stats.kernel_launches++;
-    CK(cudaGetLastError());
+    if (!walked) {
+      {
+        KTimer kt(ctx, s, 5);
+        if (ctx->bvh_minb >= 8) k_bvh<MODE, BVK_SHAPE, 8><<<blocks * 2, threads, 0, s>>>(ab);
+        else if (ctx->bvh_quorum == 1) k_bvh<MODE, BVK_SHAPE, 4, 1><<<blocks, threads, 0, s>>>(ab);  // HFB_BVH_QUORUM=1
+        else k_bvh<MODE, BVK_SHAPE, 4><<<blocks, threads, 0, s>>>(ab);
+      }
+      ctx->stats.kernel_launches++;
+      CK(cudaGetLastError());
+    }
     {  // (mesh, mesh) pairs, own instantiation: an empty range costs one launch
       ab.index_list = a.index_list;  // (the reordered list holds the (mesh, shape) slice only)
       ab.range_lo = offsets + HFB_BIN_BVH2;
@@ -1276,6 +1316,8 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   if (const char* ns = getenv("HFB_NSUB")) c->nsub = atoi(ns);
   if (const char* bm = getenv("HFB_BVH_MINB")) c->bvh_minb = atoi(bm);
   if (const char* bo = getenv("HFB_BVH_ORDER")) c->bvh_order = atoi(bo) != 0;
+  if (const char* bq2 = getenv("HFB_BVHQ")) c->bvhq = atoi(bq2) != 0;
+  if (const char* bs = getenv("HFB_BVH_SPEC")) c->bvh_spec = atoi(bs);
   if (const char* bq = getenv("HFB_BVH_QUORUM"))
     if (atoi(bq) == 1) c->bvh_quorum = 1;
   if (const char* bp = getenv("HFB_BVH_BPS")) {
@@ -1300,7 +1342,7 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   auto rel = [](Slot& s) {
-    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist};
+    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist, &s.qprep, &s.qstacks, &s.qtl, &s.qws};
     for (DevBuf* b : bs) b->release();
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.epa_stream) cudaStreamDestroy(s.epa_stream);
@@ -1659,19 +1701,21 @@ int hfb_get_stats(hfb_ctx* ctx, hfb_stats* out) {
   };
   for (int k = 0; k < kSlots; ++k) CK(add(ctx->slots[k]));
   CK(add(ctx->dev_slot));
-  uint64_t bvt = 0, lft = 0;
+  uint64_t bvt = 0, lft = 0, wdt = 0;
   auto addb = [&](Slot& s) -> cudaError_t {
     if (!s.bvh_cnt.p) return cudaSuccess;
-    unsigned long long v[2] = {0, 0};
+    unsigned long long v[3] = {0, 0, 0};
     cudaError_t e = cudaMemcpy(v, s.bvh_cnt.p, sizeof(v), cudaMemcpyDeviceToHost);
     bvt += v[0];
     lft += v[1];
+    wdt += v[2];
     return e;
   };
   for (int k = 0; k < kSlots; ++k) CK(addb(ctx->slots[k]));
   CK(addb(ctx->dev_slot));
   ctx->stats.bv_tests = bvt;
   ctx->stats.leaf_tests = lft;
+  ctx->stats.watchdog_trips = wdt;
   ctx->stats.epa_pairs = epa;
   *out = ctx->stats;
   return HFB_OK;

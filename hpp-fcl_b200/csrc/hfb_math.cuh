@@ -15,7 +15,7 @@
 // out-of-line on the device: multi-call-site helpers that run once per pair; inlining
 // them multiplies the kernel's code size (instruction-cache misses dominated the first
 // ncu profile of k_pairs: stall_no_instruction 9.7 cycles per issue)
-#define HFB_HD_NOINLINE __host__ __device__ __noinline__
+#define HFB_HD_NOINLINE __host__ __device__ __noinline__ inline
 #else
 #define HFB_HD inline
 #define HFB_D inline

@@ -352,6 +352,7 @@ typedef struct hfb_stats {
   uint64_t epa_pairs;       /* pairs that went through the EPA kernel */
   uint64_t bv_tests;
   uint64_t leaf_tests;
+  uint64_t watchdog_trips;  /* must stay 0: a block of the mesh-shape walk gave up waiting for work (its results are incomplete) */
 } hfb_stats;
 int hfb_get_stats(hfb_ctx* ctx, hfb_stats* out);
 

@@ -5,6 +5,7 @@
 // CUDA kernels execute can be checked against the oracle in the CPU-only
 // container (`-m "not gpu"` tests).  The product library has no such path: its
 // entry points fail with HFB_ERR_NO_DEVICE when there is no GPU.
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <memory>
@@ -14,6 +15,7 @@
 #define HFB_LANE_SIM 1  // host lane groups, see below
 #include "../../hpp-fcl_b200/csrc/hfb_arena.cuh"
 #include "../../hpp-fcl_b200/csrc/hfb_bvh.cuh"
+#include "../../hpp-fcl_b200/csrc/hfb_bvhq.cuh"
 #include "../../hpp-fcl_b200/csrc/hfb_request.cuh"
 
 // ---- lane groups on the host ---------------------------------------------------------------------------
@@ -276,8 +278,115 @@ long batch_lanes_g(int G, Emu* E, size_t n, const uint32_t* h1, const hfb_transf
 }
 }  // namespace
 
+
+// ---- the task-system walk of hfb_bvhq.cuh on the host ---------------------------------------------------
+// Same functions as the kernel k_bvhq; the block's queues are two vectors here and the items -- of several
+// queries in flight, speculated subtrees included -- are executed ONE AT A TIME IN RANDOM ORDER, which is every
+// interleaving the device's warps can produce as far as the walk logic can tell.
+struct HostQSink {
+  std::vector<unsigned> leafq, bvq;
+  std::vector<int> free_tl;
+  void push_leaf(unsigned it) { leafq.push_back(it); }
+  void push_bv(unsigned it) { bvq.push_back(it); }
+  int treelet_acquire() {
+    if (free_tl.empty()) return -1;
+    const int id = free_tl.back();
+    free_tl.pop_back();
+    return id;
+  }
+  void treelet_release(int id) { free_tl.push_back(id); }
+  int dec_pending(QSlot& s) { return s.pending--; }
+};
+long g_q_spec_items = 0, g_q_items = 0;
+// every (mesh, shape) pair of `todo` through the walk; spec_after < 0: never speculate
+static void host_bvhq_distance(const ArenaView& A, const std::vector<size_t>& todo, const uint32_t* h1,
+                               const hfb_transform* tf1, const uint32_t* h2, const hfb_transform* tf2,
+                               const hfb_distance_request* req, const SolverP& P, hfb_distance_result* out,
+                               int spec_after, unsigned seed, int nslots, int ntl) {
+  BvhReq R{0, 0, 0, 0, 0, 1, req->enable_nearest_points != 0, req->q.gjk_initial_guess};
+  QCtx c;
+  c.P = P;
+  c.rel_err = R.rel_err;
+  c.abs_err = R.abs_err;
+  c.spec_after = (P.initial_guess == HFB_GUESS_CACHED) ? -1 : spec_after;
+  std::vector<QSlot> slots((size_t)nslots);
+  std::vector<QStackEnt> stacks((size_t)nslots * 64);
+  std::vector<QTreelet> tls((size_t)(ntl > 0 ? ntl : 1));
+  HostQSink sink;
+  for (int k = 0; k < ntl; ++k) sink.free_tl.push_back(k);
+  std::unique_ptr<EpaWs> ws(new EpaWs());
+  size_t next = 0;
+  int active = 0;
+  unsigned long long rng = 0x9E3779B97F4A7C15ull * (seed + 1);
+  auto rnd = [&]() {
+    rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+    return (unsigned)(rng >> 33);
+  };
+  auto fetch = [&](int sl) -> bool {
+    while (next < todo.size()) {
+      const size_t i = todo[next++];
+      v3 guess = mk(1, 0, 0);
+      int hh0 = 0, hh1 = 0;
+      if (req->q.gjk_initial_guess == HFB_GUESS_CACHED) {
+        if (req->q.cached_gjk_guess) guess = mk(req->q.cached_gjk_guess[3 * i], req->q.cached_gjk_guess[3 * i + 1], req->q.cached_gjk_guess[3 * i + 2]);
+        if (req->q.cached_support_func_guess) { hh0 = req->q.cached_support_func_guess[2 * i]; hh1 = req->q.cached_support_func_guess[2 * i + 1]; }
+      }
+      const xf t1 = load_xf(tf1[i].R), t2 = load_xf(tf2[i].R);
+      BvhJob job;
+      if (!bvh_make_job<CAPS_ALL, 0>(A, h1[i], t1, h2[i], t2, R, guess, hh0, hh1, &out[i], job)) continue;
+      QPrep pr;
+      q_make_prep(job.q, job.swapped, pr);
+      q_start(slots[sl], &stacks[(size_t)sl * 64], job.q, pr, (unsigned)i, guess, hh0, hh1);
+      sink.push_leaf((unsigned)sl);
+      return true;
+    }
+    return false;
+  };
+  for (int sl = 0; sl < nslots; ++sl)
+    if (fetch(sl)) ++active;
+  while (active > 0) {
+    const size_t nl = sink.leafq.size(), nb = sink.bvq.size();
+    if (nl + nb == 0) std::abort();  // a query in flight always has an item outstanding
+    size_t pick = rnd() % (nl + nb);
+    unsigned item;
+    int rc;
+    ++g_q_items;
+    if (pick < nl) {
+      item = sink.leafq[pick];
+      sink.leafq[pick] = sink.leafq.back();
+      sink.leafq.pop_back();
+      QSlot& s = slots[item & HFB_Q_SLOT_MASK];
+      const bool spec = (item & HFB_Q_ITEM_SPEC) != 0;
+      g_q_spec_items += spec;
+      QLeafRes r;
+      q_leaf_eval<CAPS_ALL>(s, q_leaf_prim(s, tls.data(), item), P, ws.get(), !spec, r);
+      rc = q_leaf_done(s, item, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), c, sink, r);
+    } else {
+      pick -= nl;
+      item = sink.bvq[pick];
+      sink.bvq[pick] = sink.bvq.back();
+      sink.bvq.pop_back();
+      QSlot& s = slots[item & HFB_Q_SLOT_MASK];
+      g_q_spec_items += (item & HFB_Q_ITEM_SPEC) != 0;
+      const hfb_bvh_node* nodes = static_cast<const hfb_bvh_node*>(s.ptr[0]);
+      const int base = q_bv_base(s, item);
+      const double d1 = q_rss_child(s, nodes[base]), d2 = q_rss_child(s, nodes[base + 1]);
+      rc = q_bv_done(s, item, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), c, sink, d1, d2,
+                     nodes[base].first_child, nodes[base + 1].first_child);
+    }
+    if (rc == Q_DONE) {
+      const int sl = (int)(item & HFB_Q_SLOT_MASK);
+      q_write_result(slots[sl], &out[slots[sl].pair]);
+      if (!fetch(sl)) --active;
+    }
+  }
+  if (!sink.leafq.empty() || !sink.bvq.empty() || (int)sink.free_tl.size() != ntl) std::abort();
+}
+
 extern "C" {
 
+long emu_q_spec_items() { return g_q_spec_items; }
+long emu_q_items() { return g_q_items; }
 void* emu_create() { return new Emu(); }
 long emu_epa_retries() { return g_retries; }
 void emu_destroy(void* e) { delete static_cast<Emu*>(e); }
@@ -320,8 +429,16 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
   const SolverP P = solver_from_distance_request(*req);
   const ArenaView A = E->arena.view();
   std::unique_ptr<EpaWs> ws(new EpaWs());
+  // HFB_EMU_BVHQ="spec_after[,seed[,slots[,treelets]]]": (mesh, shape) pairs through the task-system walk
+  const char* qenv = getenv("HFB_EMU_BVHQ");
+  std::vector<size_t> qtodo;
   for (size_t i = 0; i < n; ++i) {
     if (h1[i] >= A.nshapes || h2[i] >= A.nshapes) return HFB_ERR_INVALID_ARGUMENT;
+    const bool m1 = A.shapes[h1[i]].type == HFB_BV_OBBRSS, m2 = A.shapes[h2[i]].type == HFB_BV_OBBRSS;
+    if (qenv && (m1 != m2)) {
+      qtodo.push_back(i);
+      continue;
+    }
     if (A.shapes[h1[i]].type == HFB_BV_OBBRSS || A.shapes[h2[i]].type == HFB_BV_OBBRSS) {
       BvhReq R{/* rel_err, abs_err: see hfb_distance_request */ 0, 0, 0, 0, 0, 1, req->enable_nearest_points != 0, req->q.gjk_initial_guess};
       unsigned bt, lt;
@@ -347,6 +464,12 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
     run_pair(in, P, ws.get(), o);
     write_distance(o, &out[i]);
     put_guess(go, i, o);
+  }
+  if (!qtodo.empty()) {
+    int spec_after = 0, slots = 6, ntl = 2;
+    unsigned seed = 1;
+    sscanf(qenv, "%d,%u,%d,%d", &spec_after, &seed, &slots, &ntl);
+    host_bvhq_distance(A, qtodo, h1, tf1, h2, tf2, req, P, out, spec_after, seed, slots, ntl);
   }
   return HFB_OK;
 }

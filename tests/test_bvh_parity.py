@@ -102,6 +102,40 @@ def test_bvh_emulated_device_code_vs_oracle():
     _check(sc, "emu", hm, tfm, hs, tfs)
 
 
+@pytest.mark.parametrize("knobs", ["0,1,6,2", "0,2,1,1", "-1,3,5,0", "40,4,9,3", "0,5,32,1", "3,6,3,8"])
+def test_bvh_task_system_walk_vs_oracle(knobs, monkeypatch):
+    """hfb_bvhq.cuh (the walk of kernel k_bvhq) on the host: queries as state machines, their bounding-volume and
+    leaf items executed one at a time in RANDOM order, subtrees speculated after `spec_after` items
+    (knobs = spec_after, seed, slots in flight, treelet buffers).  Bit-identical to the recursion, counters included."""
+    monkeypatch.setenv("HFB_EMU_BVHQ", knobs)
+    sc, nodes, hm, tfm, hs, tfs, _ = build_scene(False, True, n=1500, seed=int(knobs.split(",")[1]))
+    o, e = sc.b["oracle"], sc.b["emu"]
+    it0, sp0 = e.L.emu_q_items(), e.L.emu_q_spec_items()
+    for req in (P.DistanceRequestPOD(), P.DistanceRequestPOD(enable_signed_distance=0),
+                P.DistanceRequestPOD(rel_err=0.05, abs_err=0.01)):
+        compare_distance(o.batch_distance(hm, tfm, hs, tfs, req, nthreads=0), e.batch_distance(hm, tfm, hs, tfs, req),
+                         what="task-system walk")
+    compare_distance(o.batch_distance(hs, tfs, hm, tfm, nthreads=0), e.batch_distance(hs, tfs, hm, tfm),
+                     what="task-system walk, swapped operands")
+    spec = e.L.emu_q_spec_items() - sp0
+    assert e.L.emu_q_items() - it0 > 10000
+    if knobs.startswith("-1") or knobs.endswith(",0"):
+        assert spec == 0
+    else:
+        assert spec > 1000  # the speculated path really ran
+    # CachedGuess chains the solver's guess from leaf to leaf: such a request must never speculate
+    n = 300
+    req = P.DistanceRequestPOD(gjk_initial_guess=P.CachedGuess)
+    g = np.tile(np.array([0.3, -0.2, 0.9]), (n, 1))
+    hint = np.zeros((n, 2), dtype=np.int32)
+    req.q.cached_gjk_guess = g.ctypes.data
+    req.q.cached_support_func_guess = hint.ctypes.data
+    sp1 = e.L.emu_q_spec_items()
+    compare_distance(o.batch_distance(hm[:n], tfm[:n], hs[:n], tfs[:n], req, nthreads=0),
+                     e.batch_distance(hm[:n], tfm[:n], hs[:n], tfs[:n], req), what="task-system walk, cached guess")
+    assert e.L.emu_q_spec_items() == sp1
+
+
 def test_bvh_distance_is_the_true_minimum():
     """differential check in the style of test/distance.cpp: traversal result == brute force over all triangles"""
     sc, nodes, hm, tfm, hs, tfs, (verts, tris) = build_scene(False, False, seg=12, ring=6, n=40)
