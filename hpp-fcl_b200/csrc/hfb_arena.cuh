@@ -47,6 +47,14 @@ struct ArenaView {
 template <int CAPS>
 HFB_HD ShapeD load_shape(const ArenaView& A, uint32_t h) {
   ShapeD s;
+  if (h >= A.nshapes) {  // a handle the arena never issued (device entry points trust their caller only this far):
+    s.type = 0;          // no such geometry -> the pair is reported as HFB_PATH_UNSUPPORTED
+    s.p0 = s.p1 = s.p2 = s.ssr = 0;
+    s.cx = s.cy = s.cz = nullptr;
+    s.nv = 0;
+    s.center = s.ta = s.tb = s.tc = mk(0, 0, 0);
+    return s;
+  }
   const hfb_shape& r = A.shapes[h];
   s.type = (int)r.type;
   s.p0 = r.p[0];

@@ -32,8 +32,12 @@ struct DevSink {
     __threadfence_block();  // the slot / stack / treelet writes of this item's producer come first
     const int pos = atomicAdd(tail, 1) & (HFB_Q_QCAP - 1);
     volatile unsigned* q = buf;
-    while (q[pos] != 0u) {
-    }  // the ring is larger than the number of items that can exist: the previous occupant was taken long ago
+    // the ring is larger than the number of items that can exist: the previous occupant was taken long ago
+    for (unsigned spins = 0; q[pos] != 0u; ++spins)
+      if (spins > (1u << 26)) {  // cannot happen; never hang the GPU over it
+        atomicExch(&sc->abort_, 1);
+        break;
+      }
     q[pos] = item | HFB_Q_ITEM_VALID;
   }
   __device__ __forceinline__ void push_leaf(unsigned it) { push(sc->leafq, &sc->ltail, it); }
@@ -56,6 +60,17 @@ struct DevSink {
     return old;
   }
 };
+
+// waits for the producer of a reserved ring entry (it stores right after reserving)
+__device__ __forceinline__ unsigned q_take(volatile unsigned* q, int pos, QSched* sc) {
+  unsigned item;
+  for (unsigned spins = 0; ((item = q[pos]) & HFB_Q_ITEM_VALID) == 0u; ++spins)
+    if (spins > (1u << 26)) {  // cannot happen; never hang the GPU over it
+      atomicExch(&sc->abort_, 1);
+      break;
+    }
+  return item;
+}
 
 // next query of the slice into slot `sl` (+ its seed leaf item); false when the slice is exhausted
 __device__ bool q_fetch(const BvhqLaunch& L, unsigned lo, unsigned hi, QSlot& s, QStackEnt* stk, unsigned sl,
@@ -212,7 +227,6 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
           __nanosleep(64);
           if (++spins > (1u << 24)) {  // watchdog: seconds without an item while queries are in flight
             atomicExch(&sc->abort_, 1);
-            atomicAdd(L.counters + 2, 1ull);
             kind = -1;
             break;
           }
@@ -227,18 +241,19 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
       if ((int)lane < cnt) {
         volatile unsigned* q = sc->leafq;
         const int pos = (base + (int)lane) & (HFB_Q_QCAP - 1);
-        unsigned item;
-        while (((item = q[pos]) & HFB_Q_ITEM_VALID) == 0u) {
-        }
+        unsigned item = q_take(q, pos, sc);
         q[pos] = 0u;
         __threadfence_block();
+        const bool valid = (item & HFB_Q_ITEM_VALID) != 0u;
         item &= ~HFB_Q_ITEM_VALID;
         const unsigned sl = item & HFB_Q_SLOT_MASK;
         QSlot& s = slots[sl];
         const bool spec = (item & HFB_Q_ITEM_SPEC) != 0u;
-        QLeafRes r;
-        q_leaf_eval<CAPS_BVHQ>(s, q_leaf_prim(s, tls, item), L.P, ws, !spec, r);
-        if (q_leaf_done(s, item, stacks + (size_t)sl * L.stack_cap, tls, c, sink, r) == Q_DONE) retire(sl);
+        if (valid) {
+          QLeafRes r;
+          q_leaf_eval<CAPS_BVHQ>(s, q_leaf_prim(s, tls, item), L.P, ws, !spec, r);
+          if (q_leaf_done(s, item, stacks + (size_t)sl * L.stack_cap, tls, c, sink, r) == Q_DONE) retire(sl);
+        }
       }
     } else {  // up to 4 bounding-volume items, 8 lanes each
       const unsigned g = lane >> 3, sub = lane & 7u;
@@ -246,22 +261,23 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
         const unsigned gbase = g * 8u, gmask = 0xffu << gbase;
         volatile unsigned* q = sc->bvq;
         const int pos = (base + (int)g) & (HFB_Q_QCAP - 1);
-        unsigned item;
-        while (((item = q[pos]) & HFB_Q_ITEM_VALID) == 0u) {
-        }
+        unsigned item = q_take(q, pos, sc);
         __syncwarp(gmask);  // every lane of the group has read the item before its leader clears the entry
+        item = __shfl_sync(gmask, item, (int)gbase);
         if (sub == 0u) q[pos] = 0u;
         __threadfence_block();
-        item &= ~HFB_Q_ITEM_VALID;
-        const unsigned sl = item & HFB_Q_SLOT_MASK;
-        QSlot& s = slots[sl];
-        const hfb_bvh_node* nodes = static_cast<const hfb_bvh_node*>(s.ptr[0]);
-        double d1, d2;
-        int f1, f2;
-        q_bv_group(s, nodes + q_bv_base(s, item), gmask, gbase, sub, d1, d2, f1, f2);
-        if (sub == 0u) {
-          if (q_bv_done(s, item, stacks + (size_t)sl * L.stack_cap, tls, c, sink, d1, d2, f1, f2) == Q_DONE)
-            retire(sl);
+        if (item & HFB_Q_ITEM_VALID) {  // (uniform over the group)
+          item &= ~HFB_Q_ITEM_VALID;
+          const unsigned sl = item & HFB_Q_SLOT_MASK;
+          QSlot& s = slots[sl];
+          const hfb_bvh_node* nodes = static_cast<const hfb_bvh_node*>(s.ptr[0]);
+          double d1, d2;
+          int f1, f2;
+          q_bv_group(s, nodes + q_bv_base(s, item), gmask, gbase, sub, d1, d2, f1, f2);
+          if (sub == 0u) {
+            if (q_bv_done(s, item, stacks + (size_t)sl * L.stack_cap, tls, c, sink, d1, d2, f1, f2) == Q_DONE)
+              retire(sl);
+          }
         }
       }
     }
@@ -269,6 +285,8 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
   }
   if (bv_total) atomicAdd(L.counters, bv_total);
   if (leaf_total) atomicAdd(L.counters + 1, leaf_total);
+  __syncthreads();
+  if (threadIdx.x == 0 && sc->abort_ && sc->active > 0) atomicAdd(L.counters + 2, 1ull);
 }
 
 static size_t bvhq_smem_bytes() { return HFB_Q_NSLOTS * sizeof(QSlot) + sizeof(QSched); }

@@ -22,6 +22,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "hfb_arena.cuh"
@@ -627,13 +628,17 @@ __device__ __forceinline__ int pair_bin(uint32_t t1, uint32_t t2) {
   return HFB_BIN_GJK0 + a * 6 + b;
 }
 
-__global__ void __launch_bounds__(256) k_bin_hist(const hfb_shape* shapes, const uint32_t* h1, const uint32_t* h2,
-                                                  unsigned n, unsigned* hist) {
+// type of a handle; 0 (no such geometry -> HFB_BIN_UNKNOWN) for one the arena never issued
+__device__ __forceinline__ uint32_t handle_type(const hfb_shape* shapes, uint32_t nshapes, uint32_t h) {
+  return h < nshapes ? shapes[h].type : 0u;
+}
+__global__ void __launch_bounds__(256) k_bin_hist(const hfb_shape* shapes, uint32_t nshapes, const uint32_t* h1,
+                                                  const uint32_t* h2, unsigned n, unsigned* hist) {
   __shared__ unsigned sh[HFB_NBINS];
   if (threadIdx.x < HFB_NBINS) sh[threadIdx.x] = 0;
   __syncthreads();
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-    atomicAdd(&sh[pair_bin(shapes[h1[i]].type, shapes[h2[i]].type)], 1u);
+    atomicAdd(&sh[pair_bin(handle_type(shapes, nshapes, h1[i]), handle_type(shapes, nshapes, h2[i]))], 1u);
   __syncthreads();
   if (threadIdx.x < HFB_NBINS && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
@@ -649,11 +654,11 @@ __global__ void k_bin_scan(const unsigned* hist, unsigned* offsets, unsigned* cu
     offsets[HFB_NBINS] = acc;
   }
 }
-__global__ void __launch_bounds__(256) k_bin_scatter(const hfb_shape* shapes, const uint32_t* h1, const uint32_t* h2,
-                                                     unsigned n, unsigned* cursor, uint32_t* perm) {
+__global__ void __launch_bounds__(256) k_bin_scatter(const hfb_shape* shapes, uint32_t nshapes, const uint32_t* h1,
+                                                     const uint32_t* h2, unsigned n, unsigned* cursor, uint32_t* perm) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < n;
-  const int key = valid ? pair_bin(shapes[h1[i]].type, shapes[h2[i]].type) : -1;
+  const int key = valid ? pair_bin(handle_type(shapes, nshapes, h1[i]), handle_type(shapes, nshapes, h2[i])) : -1;
   // warp-aggregated append per key
   const unsigned peers = __match_any_sync(0xffffffffu, key);
   const unsigned lane = threadIdx.x & 31u;
@@ -767,6 +772,11 @@ struct hfb_ctx {
   ArenaView dview{};
   Slot slots[kSlots];
   Slot dev_slot;  // resources of the *_device entry points (caller's stream)
+  // the *_device calls of a context share dev_slot's scratch: a call enqueued on another stream than the previous one
+  // first waits for it (one device call of a context in flight at a time; calls on one stream are ordered anyway)
+  cudaEvent_t dev_done = nullptr;
+  cudaStream_t dev_last_stream = nullptr;
+  bool dev_used = false;
   DevBuf sup_ids, sup_dirs, sup_idx, sup_out;
   hfb_stats stats{};
   int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4, refill = 0, iter_quorum = 8, stage = 0, chunk = 0;
@@ -779,6 +789,9 @@ struct hfb_ctx {
   struct Ev { cudaEvent_t a, b; int kind; };
   std::vector<Ev> events;
   hfb_kernel_times ktimes{};
+  // per-kernel launch configuration (dynamic shared-memory opt-in, blocks per SM): function attributes are per
+  // DEVICE, so the cache belongs to the context (one device), not to the process; guarded by `mu`
+  std::unordered_map<const void*, int> func_cfg;
   std::string err;
   std::mutex mu;
 };
@@ -829,10 +842,10 @@ int launch_pairs(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s
   if (blocks > cap) blocks = cap;
   const size_t smem = (STAGE && (G > 1) && (CAPS & CAP_CONVEX)) ? (size_t)groups_per_block * sizeof(StageGroup) : 0;
   if (smem > 48 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    const void* fn = reinterpret_cast<const void*>(&k_pairs<G, CAPS, MODE, PATHS, MINB, STAGE>);
+    if (!ctx->func_cfg.count(fn)) {
       CK(cudaFuncSetAttribute(k_pairs<G, CAPS, MODE, PATHS, MINB, STAGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      attr_set = true;
+      ctx->func_cfg[fn] = 1;
     }
   }
   {
@@ -848,11 +861,16 @@ template <int G, int CAPS, int MODE, int TIER>
 int launch_epa(hfb_ctx* ctx, const BatchArgs& a, cudaStream_t s) {
   const int threads = EpaCfg<G, TIER>::THREADS;
   const size_t smem = EpaCfg<G, TIER>::GPB * sizeof(typename EpaCfg<G, TIER>::WS);
-  static int per_sm = 0;
-  if (per_sm == 0) {
+  const void* fn = reinterpret_cast<const void*>(&k_epa<G, CAPS, MODE, TIER>);
+  int per_sm = 0;
+  auto it = ctx->func_cfg.find(fn);
+  if (it == ctx->func_cfg.end()) {
     CK(cudaFuncSetAttribute(k_epa<G, CAPS, MODE, TIER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_epa<G, CAPS, MODE, TIER>, threads, smem));
     if (per_sm < 1) per_sm = 1;
+    ctx->func_cfg[fn] = per_sm;
+  } else {
+    per_sm = it->second;
   }
   {
     KTimer kt(ctx, s, 1);
@@ -937,9 +955,9 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
     KTimer kt(ctx, s, 2);
     unsigned hb = (n + 255) / 256;
     if (hb > (unsigned)ctx->num_sms * 8u) hb = (unsigned)ctx->num_sms * 8u;
-    k_bin_hist<<<hb, 256, 0, s>>>(ctx->dview.shapes, a.h1, a.h2, n, hist);
+    k_bin_hist<<<hb, 256, 0, s>>>(ctx->dview.shapes, ctx->dview.nshapes, a.h1, a.h2, n, hist);
     k_bin_scan<<<1, 32, 0, s>>>(hist, offsets, cursor);
-    k_bin_scatter<<<(n + 255) / 256, 256, 0, s>>>(ctx->dview.shapes, a.h1, a.h2, n, cursor, perm);
+    k_bin_scatter<<<(n + 255) / 256, 256, 0, s>>>(ctx->dview.shapes, ctx->dview.nshapes, a.h1, a.h2, n, cursor, perm);
   }
   ctx->stats.kernel_launches += 3;
   CK(cudaGetLastError());
@@ -1253,7 +1271,14 @@ int device_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform
   a.hint_in = cached ? req->q.cached_support_func_guess : nullptr;
   a.guess_out = go ? go->cached_gjk_guess : nullptr;
   a.hint_out = go ? go->cached_support_func_guess : nullptr;
-  return run_device_batch<MODE>(ctx, ctx->dev_slot, a, static_cast<cudaStream_t>(stream));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!ctx->dev_done) CK(cudaEventCreateWithFlags(&ctx->dev_done, cudaEventDisableTiming));
+  if (ctx->dev_used && ctx->dev_last_stream != st) CK(cudaStreamWaitEvent(st, ctx->dev_done, 0));
+  rc = run_device_batch<MODE>(ctx, ctx->dev_slot, a, st);
+  ctx->dev_used = true;
+  ctx->dev_last_stream = st;
+  CK(cudaEventRecord(ctx->dev_done, st));
+  return rc;
 }
 
 }  // namespace
@@ -1352,6 +1377,7 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   };
   for (int k = 0; k < kSlots; ++k) rel(c->slots[k]);
   rel(c->dev_slot);
+  if (c->dev_done) cudaEventDestroy(c->dev_done);
   c->d_arena.release();
   c->sup_ids.release();
   c->sup_dirs.release();
@@ -1601,6 +1627,8 @@ int hfb_batch_collide_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const h
   if (minus_inf) {
     if (int rc = check_ready(ctx)) return rc;
     if (n == 0) return HFB_OK;
+    if (n > 0xffffffffull) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "batch too large");
+    if (!out) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "null buffer");
     k_clear_contacts<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(out, (unsigned)n);
     ctx->stats.kernel_launches++;
     CK(cudaGetLastError());

@@ -38,6 +38,7 @@ inline int validate_query(const hfb_query_request& q) {
   if (q.gjk_variant < 0 || q.gjk_variant > 2) return HFB_ERR_INVALID_ARGUMENT;
   if (q.gjk_convergence_criterion < 0 || q.gjk_convergence_criterion > 2) return HFB_ERR_INVALID_ARGUMENT;
   if (q.gjk_initial_guess < 0 || q.gjk_initial_guess > 2) return HFB_ERR_INVALID_ARGUMENT;
+  if (q.gjk_convergence_criterion_type < 0 || q.gjk_convergence_criterion_type > 1) return HFB_ERR_INVALID_ARGUMENT;
   return HFB_OK;
 }
 

@@ -215,7 +215,12 @@ typedef struct hfb_ctx hfb_ctx;
  * distance() are re-entrant because every call builds its solver on the stack; here the per-call
  * state (streams, scratch buffers, the EPA queue) lives in the context.  The host entry points block
  * until the results are in the caller's buffers; the *_device entry points enqueue on the caller's
- * stream and return, the results are ready when that stream reaches the point of the call. */
+ * stream and return, the results are ready when that stream reaches the point of the call.
+ * Streams: the *_device calls of one context share its scratch, so they run one at a time on the device -- a
+ * call enqueued on a different stream than the context's previous *_device call first waits (on the device,
+ * cudaStreamWaitEvent) for that call; use one context per stream for concurrent batches.  Device handles are
+ * trusted up to the arena size: a handle >= hfb_geom_num_shapes() is answered with HFB_PATH_UNSUPPORTED in the
+ * pair's record, never dereferenced. */
 int hfb_ctx_create(int device, hfb_ctx** out);
 void hfb_ctx_destroy(hfb_ctx* ctx);
 const char* hfb_last_error(const hfb_ctx* ctx);

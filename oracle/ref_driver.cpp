@@ -220,6 +220,10 @@ int ref_batch_distance(void* p, size_t n, const uint32_t* h1, const hfb_transfor
 #else
   nthreads = 1;
 #endif
+  // debugging aids, read once: nothing but the reference's own work runs inside the timed loop
+  const char* dump_env = getenv("HFB_REF_DUMP_SIMPLEX");
+  const long long dump_pair = dump_env ? atoll(dump_env) : -1;
+  const bool verbose = getenv("HFB_REF_VERBOSE") != nullptr;
 #pragma omp parallel for schedule(static) num_threads(nthreads)
   for (long long ii = 0; ii < (long long)n; ++ii) {
     const size_t i = (size_t)ii;
@@ -238,7 +242,7 @@ int ref_batch_distance(void* p, size_t n, const uint32_t* h1, const hfb_transfor
       status = pack(f.s(), bvh, tt);
       if (!bvh && !tt && f.s().gjk.status != details::GJK::DidNotRun)
         iters = (unsigned)(f.s().gjk.getNumIterations() & 0xffff) | ((unsigned)(f.s().epa.getNumIterations() & 0xffff) << 16);
-      if (getenv("HFB_REF_DUMP_SIMPLEX") && (size_t)atol(getenv("HFB_REF_DUMP_SIMPLEX")) == i) {  // debugging aid
+      if (dump_pair == ii) {  // debugging aid
         const details::GJK::Simplex* sx = f.s().gjk.getSimplex();
         fprintf(stderr, "ref simplex rank %d ray %.17g %.17g %.17g\n", (int)sx->rank, f.s().gjk.ray[0], f.s().gjk.ray[1], f.s().gjk.ray[2]);
         for (int k = 0; k < (int)sx->rank; ++k) {
@@ -247,7 +251,7 @@ int ref_batch_distance(void* p, size_t n, const uint32_t* h1, const hfb_transfor
         }
       }
     } catch (const std::exception& e) {
-      if (getenv("HFB_REF_VERBOSE")) fprintf(stderr, "reference threw (pair %zu): %s\n", i, e.what());
+      if (verbose) fprintf(stderr, "reference threw (pair %zu): %s\n", i, e.what());
       res.clear();
     }
     r.min_distance = res.min_distance;

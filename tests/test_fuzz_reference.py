@@ -49,31 +49,24 @@ def test_fuzz_every_contact_of_mesh_pairs():
         fuzz_ref.CONTACTS[0] = False
 
 
-# Seeds run on a B200 in round 1 (profiles/r01_summary.md).  1, 2, 5-10 were green.  3 and 4 exposed a defect of
-# the lane-group support argmax: a NaN direction (GJK produces one from 0/0 in the projection of a degenerate
-# simplex, and carries on -- so does the reference) left the lanes of a group with different vertices.  Fixed in
+# Seeds 1, 2, 5-10 were green on a B200 in round 1 (profiles/r01_summary.md).  3 and 4 exposed a defect of the
+# lane-group support argmax: a NaN direction (GJK produces one from 0/0 in the projection of a degenerate simplex,
+# and carries on -- so does the reference) left the lanes of a group with different vertices.  Fixed in
 # hfb_shapes.cuh, reproduced and pinned on the host (test_fuzz_device_code_through_lane_groups above and
-# tests/test_emu_parity.py::test_lane_group_argmax_... / test_phase1_through_lane_groups); the GPU budget of
-# the round was spent by then, so 3, 4 and the seeds never run on a GPU stay non-strict xfail until a GPU run
-# confirms them (an XPASS is the expected outcome).
-GPU_GREEN = [1, 2, 5, 6, 7, 8, 9, 10]
-GPU_UNCONFIRMED = [3, 4] + list(range(11, 25))
+# tests/test_emu_parity.py::test_lane_group_argmax_... / test_phase1_through_lane_groups); the driver's GPU run at
+# the end of round 1 passed every seed (GPUTEST_r01.json), so all of them are plain tests.
+GPU_SEEDS = list(range(1, 25))
 
 
 def _gpu_round(seed):
     import hppfcl_b200 as hf
-    ok, tag = fuzz_ref.one_round(seed, 4000, oracle_lib.ref_available(), hf.Engine(0))
+    eng = hf.Engine(0)
+    ok, tag = fuzz_ref.one_round(seed, 4000, oracle_lib.ref_available(), eng)
     assert ok, tag
+    assert eng.stats()["watchdog_trips"] == 0
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("seed", GPU_GREEN)
+@pytest.mark.parametrize("seed", GPU_SEEDS)
 def test_fuzz_on_the_gpu(seed):
-    _gpu_round(seed)
-
-
-@pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="fix made without a GPU run to confirm it; see the comment above")
-@pytest.mark.parametrize("seed", GPU_UNCONFIRMED)
-def test_fuzz_on_the_gpu_unconfirmed(seed):
     _gpu_round(seed)

@@ -1,15 +1,11 @@
-"""GPU tests of entry points written after the round's GPU budget was spent: they have run against the oracle and the
-reference build on the host build of the device code only.  Non-strict xfail until a GPU run has seen them pass
-(an XPASS is the expected outcome), so that they cannot mask the confirmed suite."""
+"""GPU tests of the entry points added late in round 1 (all contacts of a mesh pair, in-place geometry updates,
+the scheduling knobs of the mesh-shape kernels).  They passed on the driver's GPU run of round 1 and are plain
+tests since."""
 import pytest
 
 from tests.common import P, hf
 
-UNCONFIRMED = pytest.mark.xfail(strict=False, reason="never run on a GPU yet")
-
-
 @pytest.mark.gpu
-@UNCONFIRMED
 def test_all_contacts_of_mesh_pairs_on_the_gpu():
     from oracle import oracle_lib
     from tests.test_bvh_parity import _check_contacts, _contacts_scene
@@ -21,14 +17,12 @@ def test_all_contacts_of_mesh_pairs_on_the_gpu():
 
 
 @pytest.mark.gpu
-@UNCONFIRMED
 def test_geometry_update_and_release_on_the_gpu():
     from tests.test_cabi_and_host import _update_scenario
     _update_scenario(hf.Engine(0), hf.Engine(0))
 
 
 @pytest.mark.gpu
-@UNCONFIRMED
 def test_python_collide_keeps_every_contact_of_a_mesh_pair():
     import numpy as np
     from hppfcl_b200 import workloads as W
@@ -49,13 +43,17 @@ def test_python_collide_keeps_every_contact_of_a_mesh_pair():
 
 
 @pytest.mark.gpu
-@UNCONFIRMED
-@pytest.mark.parametrize("env", [dict(HFB_BVH_QUORUM="1"), dict(HFB_BVH_BPS="2"), dict(HFB_BVH_QUORUM="1", HFB_BVH_BPS="1"),
-                                 dict(HFB_BVH_ORDER="1"), dict(HFB_BVH_ORDER="1", HFB_BVH_QUORUM="1", HFB_BVH_BPS="2")])
+@pytest.mark.parametrize("env", [dict(HFB_BVHQ="0", HFB_BVH_QUORUM="1"), dict(HFB_BVHQ="0", HFB_BVH_BPS="2"),
+                                 dict(HFB_BVHQ="0", HFB_BVH_QUORUM="1", HFB_BVH_BPS="1"),
+                                 dict(HFB_BVHQ="0", HFB_BVH_ORDER="1"),
+                                 dict(HFB_BVHQ="0", HFB_BVH_ORDER="1", HFB_BVH_QUORUM="1", HFB_BVH_BPS="2"),
+                                 dict(HFB_BVH_SPEC="-1"), dict(HFB_BVH_SPEC="0"), dict(HFB_BVH_SPEC="0", HFB_BVH_ORDER="1"),
+                                 dict(HFB_BVH_SPEC="25"), dict(HFB_BVH_SPEC="200", HFB_BVH_ORDER="1")])
 def test_bvh_scheduling_knobs_do_not_change_results(env, monkeypatch):
-    """k_bvh's set-up quorum, grid size and hand-out order only change which lane runs what when
-    (tests/tools/bvh_sched_model.py); the batch also holds mesh-mesh and plain shape pairs, whose slices of the
-    class-sorted index list the reordering must leave alone"""
+    """k_bvh's set-up quorum, grid size and hand-out order (HFB_BVHQ=0: the lane-per-query kernel), and the
+    speculation threshold / hand-out order of the task-system walk k_bvhq only change which lane runs what when; the
+    batch also holds mesh-mesh and plain shape pairs, whose slices of the class-sorted index list the reordering must
+    leave alone"""
     import numpy as np
     from hppfcl_b200 import workloads as W
     from oracle import oracle_lib
@@ -91,3 +89,4 @@ def test_bvh_scheduling_knobs_do_not_change_results(env, monkeypatch):
     for f in ("num_contacts", "b1", "p1", "p2", "normal", "distance_lower_bound"):
         assert np.array_equal(cg[f], cw[f], equal_nan=cg[f].dtype.kind == "f"), f
     assert cw["num_contacts"].sum() > 50
+    assert eng.stats()["watchdog_trips"] == 0

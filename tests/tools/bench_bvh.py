@@ -75,4 +75,5 @@ print(json.dumps({"workload": "config4: 10k-tri OBBRSS mesh vs %d capsules, dist
                   "bv_tests_per_query": bv / n, "leaf_tests_per_query": lf / n,
                   "algorithmic_GBps": alg_bytes / (kt["bvh_ms"] / steps * 1e-3) / 1e9,
                   "cpu_oracle_queries_per_s": ns / t_cpu, "cpu_threads": oracle_lib.lib().oracle_max_threads(),
-                  "cpu_single_thread_queries_per_s": 2000 / t_cpu1, "bit_identical_to_oracle": same}))
+                  "cpu_single_thread_queries_per_s": 2000 / t_cpu1, "bit_identical_to_oracle": same,
+                  "watchdog_trips": s1["watchdog_trips"]}))
