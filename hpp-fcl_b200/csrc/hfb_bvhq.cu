@@ -3,10 +3,16 @@
 // One persistent block of 8 warps per SM.  Shared memory holds the block's HFB_Q_NSLOTS queries in flight
 // (QSlot: poses, the shape's RSS, result so far, counters), two item queues (rings of 32-bit items) and a
 // free mask of the treelet buffers; the traversal stacks and the treelet value caches live in global memory
-// (L1/L2-resident, written and read by the same SM).  Every warp loops: take up to 32 leaf items or up to 4
-// bounding-volume items, run them, and let the lane that completed a query's last outstanding item continue
-// that query's walk (q_advance) -- which pushes the next item(s) or retires the query and starts another.
+// (L1/L2-resident, written and read by the same SM).  The block alternates between two phases: in the
+// bounding-volume phase every warp takes BV items until their queue is empty, then -- after a block barrier -- every
+// warp takes leaf items; the lane that completes a query's last outstanding item continues that query's walk
+// (q_advance), which pushes the next item(s) or retires the query and starts another.
+// Why phases and not "any warp takes any item" (the first version, profiles/r02_k_bvhq_*): the kernel is ~18 000
+// instructions, the SM's instruction cache holds 2 000 (L1.5: 32 KB) -- with its eight warps in eight different
+// places of that code ncu showed 8.9 stall cycles per issued instruction waiting for instruction fetch.  In a
+// phase the eight warps run the same two thousand instructions at the same time.
 #include <cfloat>
+#include <type_traits>
 
 #include "hfb_bvhq_launch.h"
 
@@ -73,7 +79,7 @@ __device__ __forceinline__ unsigned q_take(volatile unsigned* q, int pos, QSched
 }
 
 // next query of the slice into slot `sl` (+ its seed leaf item); false when the slice is exhausted
-__device__ bool q_fetch(const BvhqLaunch& L, unsigned lo, unsigned hi, QSlot& s, QStackEnt* stk, unsigned sl,
+__device__ __noinline__ bool q_fetch(const BvhqLaunch& L, unsigned lo, unsigned hi, QSlot& s, QStackEnt* stk, unsigned sl,
                         DevSink& sink) {
   for (;;) {
     const unsigned k = atomicAdd(L.work, 1u);
@@ -100,13 +106,37 @@ __device__ bool q_fetch(const BvhqLaunch& L, unsigned lo, unsigned hi, QSlot& s,
   }
 }
 
-// The RSS distances of the two children `pair[0]`, `pair[1]` of a node by the 8 lanes gbase .. gbase + 7 of the
-// warp: lanes 0-3 of the group take child 0, lanes 4-7 child 1; lane u of a child evaluates the edge-pair cases
-// u, 4 + u, 8 + u, 12 + u of rectDistance in turn until one of the child's four lanes has a passing case; the
-// lowest passing case index is the reference's first return (RSS.cpp:121-713), its lane computes the distance.
+// the walk of slot `sl` continues on this lane; a finished query is written out and the slot refilled.  One copy of
+// this code for every call site (instruction-cache footprint).
+struct QBlock {
+  QSlot* slots;
+  QStackEnt* stacks;
+  QTreelet* tls;
+  QSched* sc;
+  unsigned lo, hi;
+};
+__device__ __noinline__ void q_continue(const BvhqLaunch& L, const QBlock& B, const QCtx& c, unsigned sl,
+                                        unsigned long long& bv_total, unsigned long long& leaf_total) {
+  DevSink sink{B.sc};
+  QSlot& s = B.slots[sl];
+  QStackEnt* stk = B.stacks + (size_t)sl * L.stack_cap;
+  if (q_advance(s, sl, stk, B.tls, c, sink) != Q_DONE) return;
+  q_write_result(s, L.out + s.pair);
+  bv_total += (unsigned)s.bv_tests;
+  leaf_total += (unsigned)s.leaf_tests;
+  if (!q_fetch(L, B.lo, B.hi, s, stk, sl, sink)) atomicSub(&B.sc->active, 1);
+}
+
+// The RSS distances of the two children `pair[0]`, `pair[1]` of a node by a group of G = 2 * LC lanes of the warp
+// (lanes gbase .. gbase + G - 1): the first LC lanes take child 0, the others child 1; lane u of a child evaluates
+// the edge-pair cases u, LC + u, 2 LC + u, ... of rectDistance in turn until one of the child's lanes has a passing
+// case; the lowest passing case index is the reference's first return (RSS.cpp:121-713), its lane computes the
+// distance.  LC = 1 (16 items per warp, no divergence between the lanes of a case) when the queue is long, LC = 4
+// (4 items per warp, a quarter of the dependent chain) when it is not.
+template <int LC>
 __device__ __forceinline__ void q_bv_group(const QSlot& s, const hfb_bvh_node* pair, unsigned gmask, unsigned gbase,
                                            unsigned sub, double& d1, double& d2, int& f1, int& f2) {
-  const unsigned child = sub >> 2, u = sub & 3u;
+  const unsigned child = sub / LC, u = sub % LC;
   const hfb_bvh_node& nd = pair[child];
   m3 R;
   v3 T;
@@ -117,29 +147,30 @@ __device__ __forceinline__ void q_bv_group(const QSlot& s, const hfb_bvh_node* p
   rect_prelude(R, T, s.sbv[12], s.sbv[13], b0, b1, p);
   int kmine = 16;
   bool sub_found = false;
+  const unsigned cmask = (1u << LC) - 1u;
 #pragma unroll 1
-  for (int t = 0; t < 4; ++t) {
-    if (!sub_found && rect_case(p, 4 * t + (int)u)) kmine = 4 * t + (int)u;
+  for (int t = 0; t < 16 / LC; ++t) {
+    if (!sub_found && rect_case(p, LC * t + (int)u)) kmine = LC * t + (int)u;
     const unsigned b = __ballot_sync(gmask, kmine < 16) >> gbase;
-    sub_found = ((b >> (4u * child)) & 0xfu) != 0u;
-    if ((b & 0xfu) != 0u && (b & 0xf0u) != 0u) break;  // both children have their case (uniform over the group)
+    sub_found = ((b >> (LC * child)) & cmask) != 0u;
+    if ((b & cmask) != 0u && ((b >> LC) & cmask) != 0u) break;  // both children have their case (uniform over the group)
   }
   int kwin = kmine;
-  kwin = min(kwin, __shfl_xor_sync(gmask, kwin, 1));
-  kwin = min(kwin, __shfl_xor_sync(gmask, kwin, 2));
+#pragma unroll
+  for (int off = 1; off < LC; off <<= 1) kwin = min(kwin, __shfl_xor_sync(gmask, kwin, off));
   double dist = 0;
   if (kwin < 16 ? (kmine == kwin) : (u == 0u)) {
     dist = rect_finish(p, kwin < 16 ? kwin : -1);
     dist -= rad;
     dist = (dist < 0.0) ? 0.0 : dist;
   }
-  const unsigned src0 = gbase + (kwin < 16 ? (unsigned)(kwin & 3) : 0u);
+  const unsigned src0 = gbase + (kwin < 16 ? (unsigned)(kwin % LC) : 0u);
   // every lane of a child asks its own child's winner; then the group leader collects both
-  const double dc = __shfl_sync(gmask, dist, (int)(src0 + 4u * child));
+  const double dc = __shfl_sync(gmask, dist, (int)(src0 + LC * child));
   d1 = __shfl_sync(gmask, dc, (int)gbase);
-  d2 = __shfl_sync(gmask, dc, (int)gbase + 4);
+  d2 = __shfl_sync(gmask, dc, (int)gbase + LC);
   f1 = __shfl_sync(gmask, fc, (int)gbase);
-  f2 = __shfl_sync(gmask, fc, (int)gbase + 4);
+  f2 = __shfl_sync(gmask, fc, (int)gbase + LC);
 }
 
 __global__ void __launch_bounds__(128) k_bvhq_prep(const BvhqLaunch L) {
@@ -190,98 +221,96 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
       atomicAdd(&sc->active, 1);
   }
   __syncthreads();
-  // what a lane does when q_advance / q_*_done reports the walk finished
-  auto retire = [&](unsigned sl) {
-    QSlot& s = slots[sl];
-    q_write_result(s, L.out + s.pair);
-    bv_total += (unsigned)s.bv_tests;
-    leaf_total += (unsigned)s.leaf_tests;
-    if (!q_fetch(L, lo, hi, s, stacks + (size_t)sl * L.stack_cap, sl, sink)) atomicSub(&sc->active, 1);
-  };
-  for (;;) {
-    int kind = 0, cnt = 0, base = 0;
+  const QBlock B{slots, stacks, tls, sc, lo, hi};
+  // up to `want` items of one queue for this warp; 0 when the queue is empty
+  auto pop = [&](int* head, int* tail, int want, int& base) -> int {
+    int cnt = 0;
     if (lane == 0) {
-      unsigned spins = 0;
       for (;;) {
-        const int lh = vload(&sc->lhead), lt = vload(&sc->ltail), bh = vload(&sc->bhead), bt = vload(&sc->btail);
-        const int nl = lt - lh, nb = bt - bh;
-        if (nl >= 32 || (nb <= 0 && nl > 0)) {
-          cnt = nl < 32 ? nl : 32;
-          if (atomicCAS(&sc->lhead, lh, lh + cnt) == lh) {
-            kind = 1;
-            base = lh;
-            break;
-          }
-        } else if (nb > 0) {
-          cnt = nb < 4 ? nb : 4;
-          if (atomicCAS(&sc->bhead, bh, bh + cnt) == bh) {
-            kind = 2;
-            base = bh;
-            break;
-          }
-        } else {
-          if (vload(&sc->active) <= 0 || vload(&sc->abort_)) {
-            kind = -1;
-            break;
-          }
-          __nanosleep(64);
-          if (++spins > (1u << 24)) {  // watchdog: seconds without an item while queries are in flight
-            atomicExch(&sc->abort_, 1);
-            kind = -1;
-            break;
-          }
+        const int h = vload(head), avail = vload(tail) - h;
+        if (avail <= 0) break;
+        cnt = avail < want ? avail : want;
+        if (atomicCAS(head, h, h + cnt) == h) {
+          base = h;
+          break;
         }
+        cnt = 0;
       }
     }
-    kind = __shfl_sync(0xffffffffu, kind, 0);
     cnt = __shfl_sync(0xffffffffu, cnt, 0);
     base = __shfl_sync(0xffffffffu, base, 0);
-    if (kind < 0) break;
-    if (kind == 1) {  // up to 32 leaf items, one per lane
-      if ((int)lane < cnt) {
-        volatile unsigned* q = sc->leafq;
-        const int pos = (base + (int)lane) & (HFB_Q_QCAP - 1);
-        unsigned item = q_take(q, pos, sc);
-        q[pos] = 0u;
-        __threadfence_block();
-        const bool valid = (item & HFB_Q_ITEM_VALID) != 0u;
+    return cnt;
+  };
+  // one task of G-lane groups over `cnt` BV items starting at ring position `base`
+  auto bv_task = [&](auto lc_tag, int cnt, int base) {
+    constexpr int LC = decltype(lc_tag)::value, G = 2 * LC;
+    const unsigned g = lane / G, sub = lane % G;
+    if ((int)g < cnt) {
+      const unsigned gbase = g * G, gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << gbase;
+      volatile unsigned* q = sc->bvq;
+      const int pos = (base + (int)g) & (HFB_Q_QCAP - 1);
+      unsigned item = q_take(q, pos, sc);
+      __syncwarp(gmask);  // every lane of the group has read the item before its leader clears the entry
+      item = __shfl_sync(gmask, item, (int)gbase);
+      if (sub == 0u) q[pos] = 0u;
+      __threadfence_block();
+      if (item & HFB_Q_ITEM_VALID) {  // (uniform over the group)
         item &= ~HFB_Q_ITEM_VALID;
         const unsigned sl = item & HFB_Q_SLOT_MASK;
         QSlot& s = slots[sl];
-        const bool spec = (item & HFB_Q_ITEM_SPEC) != 0u;
-        if (valid) {
-          QLeafRes r;
-          q_leaf_eval<CAPS_BVHQ>(s, q_leaf_prim(s, tls, item), L.P, ws, !spec, r);
-          if (q_leaf_done(s, item, stacks + (size_t)sl * L.stack_cap, tls, c, sink, r) == Q_DONE) retire(sl);
-        }
-      }
-    } else {  // up to 4 bounding-volume items, 8 lanes each
-      const unsigned g = lane >> 3, sub = lane & 7u;
-      if ((int)g < cnt) {
-        const unsigned gbase = g * 8u, gmask = 0xffu << gbase;
-        volatile unsigned* q = sc->bvq;
-        const int pos = (base + (int)g) & (HFB_Q_QCAP - 1);
-        unsigned item = q_take(q, pos, sc);
-        __syncwarp(gmask);  // every lane of the group has read the item before its leader clears the entry
-        item = __shfl_sync(gmask, item, (int)gbase);
-        if (sub == 0u) q[pos] = 0u;
-        __threadfence_block();
-        if (item & HFB_Q_ITEM_VALID) {  // (uniform over the group)
-          item &= ~HFB_Q_ITEM_VALID;
-          const unsigned sl = item & HFB_Q_SLOT_MASK;
-          QSlot& s = slots[sl];
-          const hfb_bvh_node* nodes = static_cast<const hfb_bvh_node*>(s.ptr[0]);
-          double d1, d2;
-          int f1, f2;
-          q_bv_group(s, nodes + q_bv_base(s, item), gmask, gbase, sub, d1, d2, f1, f2);
-          if (sub == 0u) {
-            if (q_bv_done(s, item, stacks + (size_t)sl * L.stack_cap, tls, c, sink, d1, d2, f1, f2) == Q_DONE)
-              retire(sl);
-          }
-        }
+        const hfb_bvh_node* nodes = static_cast<const hfb_bvh_node*>(s.ptr[0]);
+        double d1, d2;
+        int f1, f2;
+        q_bv_group<LC>(s, nodes + q_bv_base(s, item), gmask, gbase, sub, d1, d2, f1, f2);
+        if (sub == 0u && q_bv_store(s, item, stacks + (size_t)sl * L.stack_cap, tls, sink, d1, d2, f1, f2))
+          q_continue(L, B, c, sl, bv_total, leaf_total);
       }
     }
     __syncwarp();
+  };
+  for (;;) {
+    // ---- bounding-volume phase: until the queue is empty (items pushed meanwhile included) ----
+    {
+      const int nb0 = vload(&sc->btail) - vload(&sc->bhead);  // (stable: nothing is pushed between the barrier and here)
+      int base = 0, cnt;
+      if (nb0 >= 64) {
+        while ((cnt = pop(&sc->bhead, &sc->btail, 16, base)) > 0) bv_task(std::integral_constant<int, 1>(), cnt, base);
+      } else {
+        while ((cnt = pop(&sc->bhead, &sc->btail, 4, base)) > 0) bv_task(std::integral_constant<int, 4>(), cnt, base);
+      }
+    }
+    __syncthreads();
+    // ---- leaf phase ----
+    {
+      const int nl0 = vload(&sc->ltail) - vload(&sc->lhead);
+      int want = (nl0 + (HFB_Q_THREADS / 32) - 1) / (HFB_Q_THREADS / 32);  // spread over the warps: a task is as long as its longest GJK
+      want = want < 1 ? 1 : (want > 32 ? 32 : want);
+      int base = 0, cnt;
+      while ((cnt = pop(&sc->lhead, &sc->ltail, want, base)) > 0) {
+        if ((int)lane < cnt) {
+          volatile unsigned* q = sc->leafq;
+          const int pos = (base + (int)lane) & (HFB_Q_QCAP - 1);
+          unsigned item = q_take(q, pos, sc);
+          q[pos] = 0u;
+          __threadfence_block();
+          const bool valid = (item & HFB_Q_ITEM_VALID) != 0u;
+          item &= ~HFB_Q_ITEM_VALID;
+          const unsigned sl = item & HFB_Q_SLOT_MASK;
+          QSlot& s = slots[sl];
+          const bool spec = (item & HFB_Q_ITEM_SPEC) != 0u;
+          if (valid) {
+            QLeafRes r;
+            q_leaf_eval<CAPS_BVHQ>(s, q_leaf_prim(s, tls, item), L.P, ws, !spec, r);
+            if (q_leaf_store(s, item, tls, sink, r)) q_continue(L, B, c, sl, bv_total, leaf_total);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    const bool stop = vload(&sc->active) <= 0 || vload(&sc->abort_);
+    __syncthreads();  // nobody retires a query (changes `active`) before every thread has read it
+    if (stop) break;
   }
   if (bv_total) atomicAdd(L.counters, bv_total);
   if (leaf_total) atomicAdd(L.counters + 1, leaf_total);

@@ -338,24 +338,23 @@ HFB_HD int q_advance(QSlot& s, unsigned slot_id, QStackEnt* stk, QTreelet* tls, 
   return Q_DONE;
 }
 
-// completion of a BV item whose values are in hand (d of children base, base + 1 and their first_child)
+// completion of a BV item whose values are in hand (d of children base, base + 1 and their first_child).
+// Returns true when this was the query's last outstanding item: the caller continues the walk (q_advance).
 template <class Sink>
-HFB_HD int q_bv_done(QSlot& s, unsigned item, QStackEnt* stk, QTreelet* tls, const QCtx& c, Sink& sink, double d1,
-                     double d2, int f1, int f2) {
-  const unsigned slot_id = item & HFB_Q_SLOT_MASK;
+HFB_HD bool q_bv_store(QSlot& s, unsigned item, QStackEnt* stk, QTreelet* tls, Sink& sink, double d1, double d2, int f1,
+                       int f2) {
   if (item & HFB_Q_ITEM_SPEC) {
     QTreelet* T = tls + s.scr;
     const int k = 2 * (int)((item >> 12) & 0xffu);
     T->d[k] = d1;
     T->d[k + 1] = d2;
-    if (sink.dec_pending(s) != 1) return Q_ISSUED;
-    return q_advance(s, slot_id, stk, tls, c, sink);
+    return sink.dec_pending(s) == 1;
   }
   s.bv_tests += 2;  // BVDistanceLowerBound of both children (:465-469)
   int sp = s.sp;
   q_push_children(stk, sp, s.cur, d1, d2, f1, f2);
   s.sp = sp;
-  return q_advance(s, slot_id, stk, tls, c, sink);
+  return true;
 }
 // node pair a BV item is about
 HFB_HD int q_bv_base(const QSlot& s, unsigned item) {
@@ -365,16 +364,14 @@ HFB_HD int q_leaf_prim(const QSlot& s, const QTreelet* tls, unsigned item) {
   return (item & HFB_Q_ITEM_SPEC) ? tls[s.scr].prim[(item >> 12) & 0xffu] : s.cur;
 }
 
+// completion of a leaf item; true: the caller continues the walk
 template <class Sink>
-HFB_HD int q_leaf_done(QSlot& s, unsigned item, QStackEnt* stk, QTreelet* tls, const QCtx& c, Sink& sink,
-                       const QLeafRes& r) {
-  const unsigned slot_id = item & HFB_Q_SLOT_MASK;
+HFB_HD bool q_leaf_store(QSlot& s, unsigned item, QTreelet* tls, Sink& sink, const QLeafRes& r) {
   double v[10] = {r.distance, r.p1.x, r.p1.y, r.p1.z, r.p2.x, r.p2.y, r.p2.z, r.normal.x, r.normal.y, r.normal.z};
   if (item & HFB_Q_ITEM_SPEC) {
     double* dst = tls[s.scr].leaf[(item >> 12) & 0xffu];
     for (int k = 0; k < 10; ++k) dst[k] = v[k];
-    if (sink.dec_pending(s) != 1) return Q_ISSUED;
-    return q_advance(s, slot_id, stk, tls, c, sink);
+    return sink.dec_pending(s) == 1;
   }
   if (!s.seed) s.leaf_tests++;  // the seed triangle of preprocess() is not a counted leaf test
   s.seed = 0;
@@ -383,7 +380,7 @@ HFB_HD int q_leaf_done(QSlot& s, unsigned item, QStackEnt* stk, QTreelet* tls, c
   s.guess[0] = r.guess.x; s.guess[1] = r.guess.y; s.guess[2] = r.guess.z;
   s.hint0 = r.hint0;
   s.hint1 = r.hint1;
-  return q_advance(s, slot_id, stk, tls, c, sink);
+  return true;
 }
 
 HFB_HD void q_write_result(const QSlot& s, hfb_distance_result* rec) {

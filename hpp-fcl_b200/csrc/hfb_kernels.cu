@@ -669,6 +669,55 @@ __global__ void __launch_bounds__(256) k_bin_scatter(const hfb_shape* shapes, ui
   if (valid) perm[base + __popc(peers & ((1u << lane) - 1u))] = i;
 }
 
+
+// ------------------------------------------------------------ object-table batches ---
+// hfb_batch_*_objects: a scene is a table of objects (geometry handle + pose) and a list of index pairs, the
+// batched form of collide(const CollisionObject*, const CollisionObject*, ...) (collision.h:58-61).  The pairs are
+// expanded on the device into the (h1, tf1, h2, tf2) rows every kernel reads, so the host sends 8 B per pair and
+// 100 B per object instead of 200 B per pair.  An index past the table becomes handle 0xffffffff: the pair comes
+// back as HFB_PATH_UNSUPPORTED (see load_shape).
+__global__ void __launch_bounds__(256) k_expand_pairs(const uint32_t* obj_h, const hfb_transform* obj_tf, unsigned n_obj,
+                                                      const uint32_t* pi, const uint32_t* pj, unsigned n, uint32_t* h1,
+                                                      hfb_transform* tf1, uint32_t* h2, hfb_transform* tf2) {
+  // 12 lanes move one 96-byte pose as 8-byte words: 2 poses per pair
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  for (unsigned i = t; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t a = pi[i], b = pj[i];
+    h1[i] = a < n_obj ? obj_h[a] : 0xffffffffu;
+    h2[i] = b < n_obj ? obj_h[b] : 0xffffffffu;
+  }
+  const size_t words = (size_t)n * 24;  // doubles of tf1 and tf2 together
+  for (size_t w = t; w < words; w += (size_t)gridDim.x * blockDim.x) {
+    const unsigned i = (unsigned)(w / 24), k = (unsigned)(w % 24);
+    const uint32_t o = k < 12 ? pi[i] : pj[i];
+    const double v = o < n_obj ? reinterpret_cast<const double*>(obj_tf + o)[k % 12] : 0.0;
+    (k < 12 ? reinterpret_cast<double*>(tf1 + i) : reinterpret_cast<double*>(tf2 + i))[k % 12] = v;
+  }
+}
+// compact result modes: the distance alone (DistanceResult::min_distance) ...
+__global__ void __launch_bounds__(256) k_pick_min_distance(const hfb_distance_result* r, unsigned n, double* d) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = r[i].min_distance;
+}
+// ... and collide() as a bit per pair (isCollision()) plus the records of the colliding pairs only, appended in no
+// particular order together with their pair ids
+__global__ void __launch_bounds__(256) k_compact_contacts(const hfb_contact* r, unsigned n, unsigned base, uint32_t* flags,
+                                                          unsigned* count, uint32_t* ids, hfb_contact* recs, unsigned cap) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool hit = i < n && r[i].num_contacts > 0;
+  const unsigned m = __ballot_sync(0xffffffffu, hit);
+  const unsigned lane = threadIdx.x & 31u;
+  if (lane == 0 && i < n) flags[i >> 5] = m;  // (chunks are multiples of 32 pairs)
+  if (!m) return;
+  unsigned pos = 0;
+  if (lane == 0) pos = atomicAdd(count, (unsigned)__popc(m));
+  pos = __shfl_sync(0xffffffffu, pos, 0) + (unsigned)__popc(m & ((1u << lane) - 1u));
+  if (hit && pos < cap) {
+    ids[pos] = base + i;
+    recs[pos] = r[i];
+  }
+}
+
 // ----------------------------------------------------- convex support kernel --
 // One warp per query: streams the SoA vertex block (coalesced 256-B rows) and
 // reduces with shuffles.  Algorithmic traffic per query: 24*nv + 24 + 28 bytes.
@@ -759,6 +808,7 @@ struct Slot {
   cudaEvent_t ev_join = nullptr;
   DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, retry, bvh_ws, bvh_cnt, extra, ccnt, okeys, ohist, olist;
   DevBuf qprep, qstacks, qtl, qws;  // task-system mesh-shape walk (hfb_bvhq.cu)
+  DevBuf pi, pj, cmp;                // object-table batches: pair indices of the chunk; compact results
 };
 
 }  // namespace
@@ -778,6 +828,8 @@ struct hfb_ctx {
   cudaStream_t dev_last_stream = nullptr;
   bool dev_used = false;
   DevBuf sup_ids, sup_dirs, sup_idx, sup_out;
+  DevBuf obj_h, obj_tf, cmp_flags, cmp_count, cmp_ids, cmp_recs;  // object table of the running call; compact collide results
+  cudaEvent_t obj_ready = nullptr;
   hfb_stats stats{};
   int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4, refill = 0, iter_quorum = 8, stage = 0, chunk = 0;
   int bvh_quorum = HFB_BVH_INIT_QUORUM;  // HFB_BVH_QUORUM=1: a lane sets its next query up as soon as it is free
@@ -1154,27 +1206,68 @@ int check_handles(hfb_ctx* ctx, const uint32_t* h, size_t n) {
   return HFB_OK;
 }
 
+// what an object-table call adds to a batch: the table on the device, the pair indices on the host
+struct ObjSrc {
+  size_t n_objects;
+  const uint32_t* d_handles;
+  const hfb_transform* d_tfs;
+  const uint32_t* first;
+  const uint32_t* second;
+};
+// compact result modes of the object-table calls (null pointers: full records into `out`)
+struct OutMode {
+  double* min_out = nullptr;       // distance(): min_distance only, 8 B per pair
+  uint32_t* flags = nullptr;       // collide(): one bit per pair ...
+  uint32_t* n_hits = nullptr;      // ... and the records of the colliding pairs (at most `cap`) with their pair ids
+  uint32_t* hit_ids = nullptr;
+  hfb_contact* hit_recs = nullptr;
+  uint32_t cap = 0;
+};
+
 template <int MODE, typename Req, typename OutT>
 int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
                const hfb_transform* tf2, const Req* req, const SolverP& P, const CollideP& Cp, const BvhReq& Bq,
                OutT* out, const hfb_guess_out* go, hfb_contact* extra_out = nullptr, uint32_t* counts_out = nullptr,
-               unsigned extra_cap = 0) {
+               unsigned extra_cap = 0, const ObjSrc* obj = nullptr, const OutMode* om = nullptr) {
   int rc;
   if ((rc = check_ready(ctx))) return rc;
   if (n == 0) return HFB_OK;
-  if (!h1 || !h2 || !tf1 || !tf2 || !out) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "null buffer");
+  const bool compact = om && (om->min_out || om->flags);
+  if (obj ? (!obj->first || !obj->second) : (!h1 || !h2 || !tf1 || !tf2)) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "null buffer");
+  if (!out && !compact) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "null buffer");
   CK(cudaSetDevice(ctx->device));
   const bool cached = req->q.gjk_initial_guess == HFB_GUESS_CACHED;
   const double* gin = cached ? req->q.cached_gjk_guess : nullptr;
   const int32_t* hin = cached ? req->q.cached_support_func_guess : nullptr;
   size_t done = 0;
   int si = 0;
-  const size_t chunk = ctx->chunk > 0 ? (size_t)ctx->chunk : kChunk;
+  size_t chunk = ctx->chunk > 0 ? (size_t)ctx->chunk : kChunk;
+  chunk = (chunk + 31) & ~(size_t)31;  // the compact collide mode writes whole 32-pair flag words per chunk
+  unsigned* d_hits = nullptr;
+  if (om && om->flags) {
+    CK(ctx->cmp_flags.reserve(((n + 31) / 32) * 4));
+    CK(ctx->cmp_count.reserve(sizeof(unsigned)));
+    CK(ctx->cmp_ids.reserve((size_t)om->cap * 4 + 4));
+    CK(ctx->cmp_recs.reserve((size_t)om->cap * sizeof(hfb_contact) + 8));
+    d_hits = static_cast<unsigned*>(ctx->cmp_count.p);
+    CK(cudaMemsetAsync(d_hits, 0, sizeof(unsigned), ctx->slots[0].stream));
+  }
+  if (obj || d_hits) {  // the object table (uploaded by the caller on slot 0's stream) and the zeroed counter come first
+    if (!ctx->obj_ready) CK(cudaEventCreateWithFlags(&ctx->obj_ready, cudaEventDisableTiming));
+    CK(cudaEventRecord(ctx->obj_ready, ctx->slots[0].stream));
+    for (int k = 1; k < kSlots; ++k) CK(cudaStreamWaitEvent(ctx->slots[k].stream, ctx->obj_ready, 0));
+  }
   while (done < n) {
     const size_t m = (n - done < chunk) ? (n - done) : chunk;
     // handles are validated chunk by chunk, while the previous chunks are in flight.  A bad handle in a
     // later chunk therefore surfaces after earlier chunks ran; the call still fails as a whole.
-    if ((rc = check_handles(ctx, h1 + done, m)) || (rc = check_handles(ctx, h2 + done, m))) {
+    if (obj) {
+      for (size_t i = done; i < done + m; ++i)
+        if (obj->first[i] >= obj->n_objects || obj->second[i] >= obj->n_objects) {
+          for (int k = 0; k < kSlots; ++k) cudaStreamSynchronize(ctx->slots[k].stream);
+          return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "object index out of range");
+        }
+    } else if ((rc = check_handles(ctx, h1 + done, m)) || (rc = check_handles(ctx, h2 + done, m))) {
       for (int k = 0; k < kSlots; ++k) cudaStreamSynchronize(ctx->slots[k].stream);
       return rc;
     }
@@ -1187,10 +1280,25 @@ int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* 
     CK(sl.tf1.reserve(m * sizeof(hfb_transform)));
     CK(sl.tf2.reserve(m * sizeof(hfb_transform)));
     CK(sl.out.reserve(m * sizeof(OutT)));
-    CK(cudaMemcpyAsync(sl.h1.p, h1 + done, m * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(sl.h2.p, h2 + done, m * 4, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(sl.tf1.p, tf1 + done, m * sizeof(hfb_transform), cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(sl.tf2.p, tf2 + done, m * sizeof(hfb_transform), cudaMemcpyHostToDevice, s));
+    if (obj) {
+      CK(sl.pi.reserve(m * 4));
+      CK(sl.pj.reserve(m * 4));
+      CK(cudaMemcpyAsync(sl.pi.p, obj->first + done, m * 4, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(sl.pj.p, obj->second + done, m * 4, cudaMemcpyHostToDevice, s));
+      unsigned eb = (unsigned)((m * 24 + 255) / 256);
+      if (eb > (unsigned)ctx->num_sms * 16u) eb = (unsigned)ctx->num_sms * 16u;
+      k_expand_pairs<<<eb, 256, 0, s>>>(obj->d_handles, obj->d_tfs, (unsigned)obj->n_objects,
+                                        static_cast<const uint32_t*>(sl.pi.p), static_cast<const uint32_t*>(sl.pj.p),
+                                        (unsigned)m, static_cast<uint32_t*>(sl.h1.p), static_cast<hfb_transform*>(sl.tf1.p),
+                                        static_cast<uint32_t*>(sl.h2.p), static_cast<hfb_transform*>(sl.tf2.p));
+      ctx->stats.kernel_launches++;
+      CK(cudaGetLastError());
+    } else {
+      CK(cudaMemcpyAsync(sl.h1.p, h1 + done, m * 4, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(sl.h2.p, h2 + done, m * 4, cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(sl.tf1.p, tf1 + done, m * sizeof(hfb_transform), cudaMemcpyHostToDevice, s));
+      CK(cudaMemcpyAsync(sl.tf2.p, tf2 + done, m * sizeof(hfb_transform), cudaMemcpyHostToDevice, s));
+    }
     BatchArgs a{};
     a.n = (unsigned)m;
     a.h1 = static_cast<const uint32_t*>(sl.h1.p);
@@ -1234,7 +1342,24 @@ int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* 
     if (a.extra)
       CK(cudaMemcpyAsync(extra_out + done * extra_cap, a.extra, m * (size_t)extra_cap * sizeof(hfb_contact),
                          cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(out + done, sl.out.p, m * sizeof(OutT), cudaMemcpyDeviceToHost, s));
+    if constexpr (MODE == 0) {
+      if (om && om->min_out) {
+        CK(sl.cmp.reserve(m * 8));
+        k_pick_min_distance<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(static_cast<const hfb_distance_result*>(sl.out.p),
+                                                                         (unsigned)m, static_cast<double*>(sl.cmp.p));
+        ctx->stats.kernel_launches++;
+        CK(cudaMemcpyAsync(om->min_out + done, sl.cmp.p, m * 8, cudaMemcpyDeviceToHost, s));
+      }
+    } else {
+      if (om && om->flags) {
+        k_compact_contacts<<<(unsigned)((m + 255) / 256), 256, 0, s>>>(
+            static_cast<const hfb_contact*>(sl.out.p), (unsigned)m, (unsigned)done,
+            static_cast<uint32_t*>(ctx->cmp_flags.p) + done / 32, d_hits, static_cast<uint32_t*>(ctx->cmp_ids.p),
+            static_cast<hfb_contact*>(ctx->cmp_recs.p), om->cap);
+        ctx->stats.kernel_launches++;
+      }
+    }
+    if (out) CK(cudaMemcpyAsync(out + done, sl.out.p, m * sizeof(OutT), cudaMemcpyDeviceToHost, s));
     if (a.guess_out)
       CK(cudaMemcpyAsync(go->cached_gjk_guess + 3 * done, a.guess_out, m * 24, cudaMemcpyDeviceToHost, s));
     if (a.hint_out)
@@ -1243,6 +1368,15 @@ int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* 
     si = (si + 1) % kSlots;
   }
   for (int k = 0; k < kSlots; ++k) CK(cudaStreamSynchronize(ctx->slots[k].stream));
+  if (om && om->flags) {
+    unsigned hits = 0;
+    CK(cudaMemcpy(&hits, d_hits, sizeof(unsigned), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(om->flags, ctx->cmp_flags.p, ((n + 31) / 32) * 4, cudaMemcpyDeviceToHost));
+    if (om->n_hits) *om->n_hits = hits;
+    const unsigned kept = hits < om->cap ? hits : om->cap;
+    if (kept && om->hit_ids) CK(cudaMemcpy(om->hit_ids, ctx->cmp_ids.p, (size_t)kept * 4, cudaMemcpyDeviceToHost));
+    if (kept && om->hit_recs) CK(cudaMemcpy(om->hit_recs, ctx->cmp_recs.p, (size_t)kept * sizeof(hfb_contact), cudaMemcpyDeviceToHost));
+  }
   return HFB_OK;
 }
 
@@ -1367,7 +1501,7 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   auto rel = [](Slot& s) {
-    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist, &s.qprep, &s.qstacks, &s.qtl, &s.qws};
+    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist, &s.qprep, &s.qstacks, &s.qtl, &s.qws, &s.pi, &s.pj, &s.cmp};
     for (DevBuf* b : bs) b->release();
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.epa_stream) cudaStreamDestroy(s.epa_stream);
@@ -1383,6 +1517,13 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   c->sup_dirs.release();
   c->sup_idx.release();
   c->sup_out.release();
+  c->obj_h.release();
+  c->obj_tf.release();
+  c->cmp_flags.release();
+  c->cmp_count.release();
+  c->cmp_ids.release();
+  c->cmp_recs.release();
+  if (c->obj_ready) cudaEventDestroy(c->obj_ready);
   delete c;
 }
 
@@ -1639,6 +1780,151 @@ int hfb_batch_collide_device(hfb_ctx* ctx, size_t n, const uint32_t* h1, const h
                          BvhReq{0, 0, req->security_margin, req->break_distance, req->q.collision_distance_threshold,
                                 req->num_max_contacts, true, req->q.gjk_initial_guess},
                          out, go, stream);
+}
+
+
+// ---- object-table entry points ------------------------------------------------------------------------
+static int upload_objects(hfb_ctx* ctx, const hfb_object_pairs* sc, ObjSrc* o) {
+  if (!sc) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "null scene");
+  if (int rc = check_ready(ctx)) return rc;
+  if (sc->n_pairs > 0xffffffffull || sc->n_objects > 0xffffffffull) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "batch too large");
+  if (sc->n_objects && (!sc->object_handles || !sc->object_tfs)) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "null buffer");
+  if (int rc = check_handles(ctx, sc->object_handles, sc->n_objects)) return rc;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s0 = ctx->slots[0].stream;
+  CK(ctx->obj_h.reserve(sc->n_objects * 4 + 4));
+  CK(ctx->obj_tf.reserve(sc->n_objects * sizeof(hfb_transform) + 8));
+  if (sc->n_objects) {
+    CK(cudaMemcpyAsync(ctx->obj_h.p, sc->object_handles, sc->n_objects * 4, cudaMemcpyHostToDevice, s0));
+    CK(cudaMemcpyAsync(ctx->obj_tf.p, sc->object_tfs, sc->n_objects * sizeof(hfb_transform), cudaMemcpyHostToDevice, s0));
+  }
+  o->n_objects = sc->n_objects;
+  o->d_handles = static_cast<const uint32_t*>(ctx->obj_h.p);
+  o->d_tfs = static_cast<const hfb_transform*>(ctx->obj_tf.p);
+  o->first = sc->first;
+  o->second = sc->second;
+  return HFB_OK;
+}
+static BvhReq bvh_req_of_distance(const hfb_distance_request* req) {
+  return BvhReq{/* rel_err, abs_err: see hfb_distance_request */ 0, 0, 0, 0, 0, 1, req->enable_nearest_points != 0, req->q.gjk_initial_guess};
+}
+static BvhReq bvh_req_of_collision(const hfb_collision_request* req) {
+  return BvhReq{0, 0, req->security_margin, req->break_distance, req->q.collision_distance_threshold, req->num_max_contacts, true,
+                req->q.gjk_initial_guess};
+}
+
+int hfb_batch_distance_objects(hfb_ctx* ctx, const hfb_object_pairs* scene, const hfb_distance_request* req,
+                               hfb_distance_result* out, double* min_distance_out, const hfb_guess_out* go) {
+  if (!ctx || !req) return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (int rc = validate_query(req->q)) return fail(ctx, rc, "invalid request");
+  ObjSrc o;
+  if (int rc = upload_objects(ctx, scene, &o)) return rc;
+  OutMode om;
+  om.min_out = min_distance_out;
+  return host_batch<0>(ctx, scene->n_pairs, nullptr, nullptr, nullptr, nullptr, req, solver_from_distance_request(*req),
+                       CollideP{0, 0}, bvh_req_of_distance(req), out, go, nullptr, nullptr, 0, &o, &om);
+}
+
+int hfb_batch_collide_objects(hfb_ctx* ctx, const hfb_object_pairs* scene, const hfb_collision_request* req,
+                              hfb_contact* out, const hfb_compact_contacts* compact, const hfb_guess_out* go) {
+  if (!ctx || !req) return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  bool minus_inf;
+  if (int rc = collide_prelude(ctx, req, &minus_inf)) return rc;
+  if (compact && (!compact->flags || (compact->capacity && (!compact->pair_ids || !compact->contacts))))
+    return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "null buffer");
+  ObjSrc o;
+  if (int rc = upload_objects(ctx, scene, &o)) return rc;
+  const size_t n = scene->n_pairs;
+  if (minus_inf) {  // collision.cpp:73-76: cleared results, no contacts
+    if (n && !out && !compact) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "null buffer");
+    CK(cudaStreamSynchronize(ctx->slots[0].stream));
+    for (size_t i = 0; out && i < n; ++i) {
+      bvh_init_contact(&out[i]);
+      out[i].status = 0;
+    }
+    if (compact) {
+      std::memset(compact->flags, 0, ((n + 31) / 32) * 4);
+      if (compact->n_colliding) *compact->n_colliding = 0;
+    }
+    return HFB_OK;
+  }
+  OutMode om;
+  if (compact) {
+    om.flags = compact->flags;
+    om.n_hits = compact->n_colliding;
+    om.hit_ids = compact->pair_ids;
+    om.hit_recs = compact->contacts;
+    om.cap = compact->capacity;
+  }
+  CollideP C{req->security_margin, req->q.collision_distance_threshold};
+  return host_batch<1>(ctx, n, nullptr, nullptr, nullptr, nullptr, req, solver_from_collision_request(*req), C,
+                       bvh_req_of_collision(req), out, go, nullptr, nullptr, 0, &o, &om);
+}
+
+}  // extern "C"
+// device-resident scene: the pairs are expanded into the context's scratch rows, then the batch runs as
+// hfb_batch_*_device does
+template <int MODE, typename Req>
+static int objects_device(hfb_ctx* ctx, const hfb_object_pairs* sc, const Req* req, const SolverP& P, const CollideP& Cp,
+                          const BvhReq& Bq, void* out, const hfb_guess_out* go, void* stream) {
+  if (!sc) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "null scene");
+  if (int rc = check_ready(ctx)) return rc;
+  const size_t n = sc->n_pairs;
+  if (n == 0) return HFB_OK;
+  if (n > 0xffffffffull || sc->n_objects > 0xffffffffull) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "batch too large");
+  if (!sc->object_handles || !sc->object_tfs || !sc->first || !sc->second || !out) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "null buffer");
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!ctx->dev_done) CK(cudaEventCreateWithFlags(&ctx->dev_done, cudaEventDisableTiming));
+  if (ctx->dev_used && ctx->dev_last_stream != st) CK(cudaStreamWaitEvent(st, ctx->dev_done, 0));
+  ctx->dev_used = true;  // (the expansion below already writes the shared scratch)
+  ctx->dev_last_stream = st;
+  Slot& sl = ctx->dev_slot;
+  CK(sl.h1.reserve(n * 4));
+  CK(sl.h2.reserve(n * 4));
+  CK(sl.tf1.reserve(n * sizeof(hfb_transform)));
+  CK(sl.tf2.reserve(n * sizeof(hfb_transform)));
+  unsigned eb = (unsigned)((n * 24 + 255) / 256);
+  if (eb > (unsigned)ctx->num_sms * 16u) eb = (unsigned)ctx->num_sms * 16u;
+  k_expand_pairs<<<eb, 256, 0, st>>>(sc->object_handles, sc->object_tfs, (unsigned)sc->n_objects, sc->first, sc->second,
+                                     (unsigned)n, static_cast<uint32_t*>(sl.h1.p), static_cast<hfb_transform*>(sl.tf1.p),
+                                     static_cast<uint32_t*>(sl.h2.p), static_cast<hfb_transform*>(sl.tf2.p));
+  ctx->stats.kernel_launches++;
+  CK(cudaGetLastError());
+  return device_batch<MODE>(ctx, n, static_cast<const uint32_t*>(sl.h1.p), static_cast<const hfb_transform*>(sl.tf1.p),
+                            static_cast<const uint32_t*>(sl.h2.p), static_cast<const hfb_transform*>(sl.tf2.p), req, P, Cp,
+                            Bq, out, go, stream);
+}
+extern "C" {
+
+int hfb_batch_distance_objects_device(hfb_ctx* ctx, const hfb_object_pairs* d_scene, const hfb_distance_request* req,
+                                      hfb_distance_result* d_out, const hfb_guess_out* d_go, void* stream) {
+  if (!ctx || !req) return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (int rc = validate_query(req->q)) return fail(ctx, rc, "invalid request");
+  return objects_device<0>(ctx, d_scene, req, solver_from_distance_request(*req), CollideP{0, 0}, bvh_req_of_distance(req), d_out,
+                           d_go, stream);
+}
+
+int hfb_batch_collide_objects_device(hfb_ctx* ctx, const hfb_object_pairs* d_scene, const hfb_collision_request* req,
+                                     hfb_contact* d_out, const hfb_guess_out* d_go, void* stream) {
+  if (!ctx || !req) return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  bool minus_inf;
+  if (int rc = collide_prelude(ctx, req, &minus_inf)) return rc;
+  if (minus_inf) {
+    if (int rc = check_ready(ctx)) return rc;
+    if (!d_scene || d_scene->n_pairs == 0) return HFB_OK;
+    if (d_scene->n_pairs > 0xffffffffull || !d_out) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "bad buffer");
+    k_clear_contacts<<<(unsigned)((d_scene->n_pairs + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_out, (unsigned)d_scene->n_pairs);
+    ctx->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    return HFB_OK;
+  }
+  CollideP C{req->security_margin, req->q.collision_distance_threshold};
+  return objects_device<1>(ctx, d_scene, req, solver_from_collision_request(*req), C, bvh_req_of_collision(req), d_out, d_go, stream);
 }
 
 int hfb_batch_convex_support_device(hfb_ctx* ctx, size_t n, const uint32_t* ids, const double* dirs,

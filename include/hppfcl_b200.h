@@ -336,6 +336,46 @@ int hfb_batch_collide_device(hfb_ctx* ctx, size_t n, const uint32_t* d_h1,
                              const hfb_collision_request* req, hfb_contact* d_out,
                              const hfb_guess_out* d_guess_out, void* cuda_stream);
 
+/* ---- object-table batches: the batched form of the CollisionObject overloads --------------------------
+ * collide(const CollisionObject* o1, const CollisionObject* o2, ...) / distance(...) (include/hpp/fcl/collision.h:
+ * 58-61, distance.h:53-56) take their geometry and pose from the objects.  A scene here is a table of objects
+ * (geometry handle + pose, the two things a CollisionObject holds: collision_object.h:214-330) and a list of
+ * pairs of table indices -- what a broadphase manager's collide()/distance() callback receives
+ * (broadphase/default_broadphase_callbacks.h:224-252).  The host sends 100 B per object and 8 B per pair instead
+ * of 200 B per pair; the pairs are expanded on the device.  Results are those of hfb_batch_distance /
+ * hfb_batch_collide on the expanded rows, bit for bit.  An object index >= n_objects is an invalid argument. */
+typedef struct hfb_object_pairs {
+  size_t n_objects;
+  const uint32_t* object_handles;   /* n_objects shape handles */
+  const hfb_transform* object_tfs;  /* n_objects poses */
+  size_t n_pairs;
+  const uint32_t* first;   /* n_pairs indices into the object table: o1 of pair k */
+  const uint32_t* second;  /*                                         o2 of pair k */
+} hfb_object_pairs;
+/* HOST buffers; blocking.  `out` (full 96-byte records) and `min_distance_out` (DistanceResult::min_distance only,
+ * 8 bytes per pair back over PCIe) may each be null, not both. */
+int hfb_batch_distance_objects(hfb_ctx* ctx, const hfb_object_pairs* scene, const hfb_distance_request* req,
+                               hfb_distance_result* out, double* min_distance_out, const hfb_guess_out* guess_out);
+/* compact collide() results: bit k of flags[k / 32] = CollisionResult::isCollision() of pair k; the records of the
+ * colliding pairs (as hfb_batch_collide writes them) are appended to `contacts`, their pair indices to `pair_ids`,
+ * in no particular order, at most `capacity` of them; *n_colliding counts all of them. */
+typedef struct hfb_compact_contacts {
+  uint32_t* flags;       /* (n_pairs + 31) / 32 words */
+  uint32_t* n_colliding;
+  uint32_t* pair_ids;    /* capacity */
+  hfb_contact* contacts; /* capacity */
+  uint32_t capacity;
+} hfb_compact_contacts;
+/* `out` (full records) and `compact` may each be null, not both. */
+int hfb_batch_collide_objects(hfb_ctx* ctx, const hfb_object_pairs* scene, const hfb_collision_request* req,
+                              hfb_contact* out, const hfb_compact_contacts* compact, const hfb_guess_out* guess_out);
+/* every pointer inside *d_scene, d_out and d_guess_out are DEVICE pointers (the struct itself is read on the host);
+ * asynchronous on `cuda_stream`.  Indices are not validated: one past the table gives HFB_PATH_UNSUPPORTED. */
+int hfb_batch_distance_objects_device(hfb_ctx* ctx, const hfb_object_pairs* d_scene, const hfb_distance_request* req,
+                                      hfb_distance_result* d_out, const hfb_guess_out* d_guess_out, void* cuda_stream);
+int hfb_batch_collide_objects_device(hfb_ctx* ctx, const hfb_object_pairs* d_scene, const hfb_collision_request* req,
+                                     hfb_contact* d_out, const hfb_guess_out* d_guess_out, void* cuda_stream);
+
 /* ---- batched ConvexBase support function (the convex-support kernel):
  *      for each query i: argmax_v <dir_i, v> over the vertices of convex
  *      convex_ids[i]  (getShapeSupportLinear, support_functions.cpp:401-421;

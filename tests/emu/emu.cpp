@@ -360,7 +360,9 @@ static void host_bvhq_distance(const ArenaView& A, const std::vector<size_t>& to
       g_q_spec_items += spec;
       QLeafRes r;
       q_leaf_eval<CAPS_ALL>(s, q_leaf_prim(s, tls.data(), item), P, ws.get(), !spec, r);
-      rc = q_leaf_done(s, item, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), c, sink, r);
+      rc = Q_ISSUED;
+      if (q_leaf_store(s, item, tls.data(), sink, r))
+        rc = q_advance(s, item & HFB_Q_SLOT_MASK, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), c, sink);
     } else {
       pick -= nl;
       item = sink.bvq[pick];
@@ -371,8 +373,10 @@ static void host_bvhq_distance(const ArenaView& A, const std::vector<size_t>& to
       const hfb_bvh_node* nodes = static_cast<const hfb_bvh_node*>(s.ptr[0]);
       const int base = q_bv_base(s, item);
       const double d1 = q_rss_child(s, nodes[base]), d2 = q_rss_child(s, nodes[base + 1]);
-      rc = q_bv_done(s, item, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), c, sink, d1, d2,
-                     nodes[base].first_child, nodes[base + 1].first_child);
+      rc = Q_ISSUED;
+      if (q_bv_store(s, item, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), sink, d1, d2,
+                     nodes[base].first_child, nodes[base + 1].first_child))
+        rc = q_advance(s, item & HFB_Q_SLOT_MASK, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), c, sink);
     }
     if (rc == Q_DONE) {
       const int sl = (int)(item & HFB_Q_SLOT_MASK);
