@@ -137,6 +137,17 @@ class GuessOut(C.Structure):
     _fields_ = [("cached_gjk_guess", C.c_void_p), ("cached_support_func_guess", C.c_void_p)]
 
 
+class ObjectPairs(C.Structure):
+    """hfb_object_pairs: an object table (handle + pose) and index pairs into it"""
+    _fields_ = [("n_objects", C.c_size_t), ("object_handles", C.c_void_p), ("object_tfs", C.c_void_p),
+                ("n_pairs", C.c_size_t), ("first", C.c_void_p), ("second", C.c_void_p)]
+
+
+class CompactContacts(C.Structure):
+    _fields_ = [("flags", C.c_void_p), ("n_colliding", C.c_void_p), ("pair_ids", C.c_void_p),
+                ("contacts", C.c_void_p), ("capacity", C.c_uint32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("pairs_processed", C.c_uint64),
                 ("epa_pairs", C.c_uint64), ("bv_tests", C.c_uint64), ("leaf_tests", C.c_uint64),

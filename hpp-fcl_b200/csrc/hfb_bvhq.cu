@@ -21,13 +21,15 @@ namespace hfb {
 #define CAPS_BVHQ (CAP_PRIM | CAP_CONVEX | CAP_TRI | CAP_INLINE_PRIM)
 
 struct QSched {
-  int lhead, ltail, bhead, btail;
+  int lhead, ltail, bhead, btail, ehead, etail;
   int active;          // queries in flight in this block
   unsigned tl_free;    // free treelet buffers
   int abort_;
-  int _pad;
+  int lsnap;           // leaf phase: items queued before this ring position belong to the phase
+  int do_epa, stop;    // decisions of the cycle, taken by thread 0 between two barriers
   unsigned leafq[HFB_Q_QCAP];
   unsigned bvq[HFB_Q_QCAP];
+  unsigned epaq[HFB_Q_QCAP];
 };
 
 __device__ __forceinline__ int vload(const int* p) { return *reinterpret_cast<const volatile int*>(p); }
@@ -48,6 +50,7 @@ struct DevSink {
   }
   __device__ __forceinline__ void push_leaf(unsigned it) { push(sc->leafq, &sc->ltail, it); }
   __device__ __forceinline__ void push_bv(unsigned it) { push(sc->bvq, &sc->btail, it); }
+  __device__ __forceinline__ void push_epa(unsigned it) { push(sc->epaq, &sc->etail, it); }
   __device__ __forceinline__ int treelet_acquire() {
     unsigned m = *reinterpret_cast<volatile unsigned*>(&sc->tl_free);
     while (m) {
@@ -195,7 +198,8 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
   const unsigned lo = *L.range_lo, hi = *L.range_hi;
   const unsigned lane = threadIdx.x & 31u;
   if (threadIdx.x == 0) {
-    sc->lhead = sc->ltail = sc->bhead = sc->btail = 0;
+    sc->lhead = sc->ltail = sc->bhead = sc->btail = sc->ehead = sc->etail = 0;
+    sc->lsnap = sc->do_epa = sc->stop = 0;
     sc->active = 0;
     sc->tl_free = (1u << HFB_Q_NTREELETS) - 1u;
     sc->abort_ = 0;
@@ -203,11 +207,13 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
   for (unsigned k = threadIdx.x; k < HFB_Q_QCAP; k += blockDim.x) {
     sc->leafq[k] = 0u;
     sc->bvq[k] = 0u;
+    sc->epaq[k] = 0u;
   }
   __syncthreads();
   QStackEnt* stacks = L.stacks + (size_t)blockIdx.x * HFB_Q_NSLOTS * (size_t)L.stack_cap;
   QTreelet* tls = L.treelets + (size_t)blockIdx.x * HFB_Q_NTREELETS;
   EpaWs* ws = L.ws + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  QLeafSave* saves = L.saves + (size_t)blockIdx.x * (HFB_Q_NSLOTS + HFB_Q_TREELET_MAX * HFB_Q_NTREELETS);
   DevSink sink{sc};
   QCtx c;
   c.P = L.P;
@@ -223,11 +229,13 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
   __syncthreads();
   const QBlock B{slots, stacks, tls, sc, lo, hi};
   // up to `want` items of one queue for this warp; 0 when the queue is empty
-  auto pop = [&](int* head, int* tail, int want, int& base) -> int {
+  auto pop = [&](int* head, int* tail, int want, int& base, const int* limit = nullptr) -> int {
     int cnt = 0;
     if (lane == 0) {
       for (;;) {
-        const int h = vload(head), avail = vload(tail) - h;
+        const int h = vload(head);
+        int avail = vload(tail) - h;
+        if (limit && vload(limit) - h < avail) avail = vload(limit) - h;
         if (avail <= 0) break;
         cnt = avail < want ? avail : want;
         if (atomicCAS(head, h, h + cnt) == h) {
@@ -268,6 +276,12 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
     }
     __syncwarp();
   };
+  long long t_prev = clock64(), t_bv = 0, t_leaf = 0, t_epa = 0, n_cycles = 0, n_epa = 0;
+  auto lap = [&](long long& acc) {
+    const long long t = clock64();
+    acc += t - t_prev;
+    t_prev = t;
+  };
   for (;;) {
     // ---- bounding-volume phase: until the queue is empty (items pushed meanwhile included) ----
     {
@@ -280,13 +294,21 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
       }
     }
     __syncthreads();
-    // ---- leaf phase ----
+    if (threadIdx.x == 0) {
+      lap(t_bv);
+      const int nl = vload(&sc->ltail) - vload(&sc->lhead), ne = vload(&sc->etail) - vload(&sc->ehead);
+      sc->lsnap = vload(&sc->ltail);
+      // EPA items are rare and long: they wait until there are enough of them to fill lanes, or nothing else is left
+      sc->do_epa = (ne >= 32 || (ne > 0 && nl == 0)) ? 1 : 0;
+    }
+    __syncthreads();
+    // ---- leaf phase: the items queued before it started; each runs at most gjk_chunk GJK iterations ----
     {
-      const int nl0 = vload(&sc->ltail) - vload(&sc->lhead);
-      int want = (nl0 + (HFB_Q_THREADS / 32) - 1) / (HFB_Q_THREADS / 32);  // spread over the warps: a task is as long as its longest GJK
+      const int nl0 = vload(&sc->lsnap) - vload(&sc->lhead);
+      int want = (nl0 + (HFB_Q_THREADS / 32) - 1) / (HFB_Q_THREADS / 32);  // spread over the warps: a task is as long as its longest item
       want = want < 1 ? 1 : (want > 32 ? 32 : want);
       int base = 0, cnt;
-      while ((cnt = pop(&sc->lhead, &sc->ltail, want, base)) > 0) {
+      while ((cnt = pop(&sc->lhead, &sc->ltail, want, base, &sc->lsnap)) > 0) {
         if ((int)lane < cnt) {
           volatile unsigned* q = sc->leafq;
           const int pos = (base + (int)lane) & (HFB_Q_QCAP - 1);
@@ -300,22 +322,69 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
           const bool spec = (item & HFB_Q_ITEM_SPEC) != 0u;
           if (valid) {
             QLeafRes r;
-            q_leaf_eval<CAPS_BVHQ>(s, q_leaf_prim(s, tls, item), L.P, ws, !spec, r);
-            if (q_leaf_store(s, item, tls, sink, r)) q_continue(L, B, c, sl, bv_total, leaf_total);
+            QLeafSave& sv = saves[q_save_index(s, item, HFB_Q_NSLOTS)];
+            const int st = q_leaf_gjk<CAPS_BVHQ>(s, q_leaf_prim(s, tls, item), L.P, !spec, (item & HFB_Q_ITEM_RESUME) != 0u,
+                                                 L.gjk_chunk, sv, r);
+            if (st == QL_SUSPENDED) sink.push_leaf(item | HFB_Q_ITEM_RESUME);
+            else if (st == QL_NEED_EPA) sink.push_epa(item & ~HFB_Q_ITEM_RESUME);
+            else if (q_leaf_store(s, item, tls, sink, r)) q_continue(L, B, c, sl, bv_total, leaf_total);
           }
         }
         __syncwarp();
       }
     }
     __syncthreads();
-    const bool stop = vload(&sc->active) <= 0 || vload(&sc->abort_);
-    __syncthreads();  // nobody retires a query (changes `active`) before every thread has read it
-    if (stop) break;
+    if (threadIdx.x == 0) lap(t_leaf);
+    // ---- EPA phase (some cycles only) ----
+    if (vload(&sc->do_epa)) {
+      const int ne0 = vload(&sc->etail) - vload(&sc->ehead);
+      int want = (ne0 + (HFB_Q_THREADS / 32) - 1) / (HFB_Q_THREADS / 32);
+      want = want < 1 ? 1 : (want > 32 ? 32 : want);
+      int base = 0, cnt;
+      while ((cnt = pop(&sc->ehead, &sc->etail, want, base)) > 0) {
+        if ((int)lane < cnt) {
+          volatile unsigned* q = sc->epaq;
+          const int pos = (base + (int)lane) & (HFB_Q_QCAP - 1);
+          unsigned item = q_take(q, pos, sc);
+          q[pos] = 0u;
+          __threadfence_block();
+          const bool valid = (item & HFB_Q_ITEM_VALID) != 0u;
+          item &= ~HFB_Q_ITEM_VALID;
+          const unsigned sl = item & HFB_Q_SLOT_MASK;
+          QSlot& s = slots[sl];
+          const bool spec = (item & HFB_Q_ITEM_SPEC) != 0u;
+          if (valid) {
+            QLeafRes r;
+            q_leaf_epa<CAPS_BVHQ>(s, q_leaf_prim(s, tls, item), L.P, !spec, ws, saves[q_save_index(s, item, HFB_Q_NSLOTS)], r);
+            if (q_leaf_store(s, item, tls, sink, r)) q_continue(L, B, c, sl, bv_total, leaf_total);
+          }
+        }
+        __syncwarp();
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        lap(t_epa);
+        ++n_epa;
+      }
+    }
+    if (threadIdx.x == 0) {
+      ++n_cycles;
+      sc->stop = (vload(&sc->active) <= 0 || vload(&sc->abort_)) ? 1 : 0;
+    }
+    __syncthreads();  // nobody retires a query (changes `active`) between thread 0's read and this barrier
+    if (vload(&sc->stop)) break;
   }
   if (bv_total) atomicAdd(L.counters, bv_total);
   if (leaf_total) atomicAdd(L.counters + 1, leaf_total);
   __syncthreads();
   if (threadIdx.x == 0 && sc->abort_ && sc->active > 0) atomicAdd(L.counters + 2, 1ull);
+  if (threadIdx.x == 0) {  // phase profile (clock cycles summed over the blocks; hfb_debug_bvh_profile)
+    atomicAdd(L.counters + 3, (unsigned long long)t_bv);
+    atomicAdd(L.counters + 4, (unsigned long long)t_leaf);
+    atomicAdd(L.counters + 5, (unsigned long long)t_epa);
+    atomicAdd(L.counters + 6, (unsigned long long)n_cycles);
+    atomicAdd(L.counters + 7, (unsigned long long)n_epa);
+  }
 }
 
 static size_t bvhq_smem_bytes() { return HFB_Q_NSLOTS * sizeof(QSlot) + sizeof(QSched); }
@@ -333,12 +402,13 @@ BvhqSizes bvhq_sizes(unsigned blocks, size_t n, int stack_cap) {
   z.stacks = (size_t)blocks * HFB_Q_NSLOTS * (size_t)stack_cap * sizeof(QStackEnt);
   z.treelets = (size_t)blocks * HFB_Q_NTREELETS * sizeof(QTreelet);
   z.ws = (size_t)blocks * HFB_Q_THREADS * sizeof(EpaWs);
+  z.saves = (size_t)blocks * (HFB_Q_NSLOTS + HFB_Q_TREELET_MAX * HFB_Q_NTREELETS) * sizeof(QLeafSave);
   return z;
 }
 
 int bvhq_launch(const BvhqLaunch& L, unsigned blocks, size_t n, cudaStream_t s) {
   static_assert(HFB_Q_NSLOTS <= HFB_Q_THREADS, "thread t fills slot t");
-  static_assert(HFB_Q_NSLOTS + 32 * HFB_Q_NTREELETS <= HFB_Q_QCAP, "item rings hold every item that can exist");
+  static_assert(HFB_Q_NSLOTS + HFB_Q_TREELET_MAX * HFB_Q_NTREELETS <= HFB_Q_QCAP, "item rings hold every item that can exist");
   static_assert(sizeof(QSlot) % 16 == 8, "odd stride in 8-byte words: lanes reading one field of 32 slots spread over the banks");
   const size_t smem = bvhq_smem_bytes();
   cudaError_t e = cudaFuncSetAttribute(k_bvhq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -34,6 +34,7 @@ namespace hfb {
 
 #define HFB_Q_TREELET_MAX 32
 #define HFB_Q_ITEM_SPEC 0x100000u
+#define HFB_Q_ITEM_RESUME 0x200000u  // leaf item: the solver state is parked, continue from it
 #define HFB_Q_ITEM_VALID 0x80000000u
 #define HFB_Q_SLOT_MASK 0xfffu
 
@@ -159,12 +160,10 @@ struct QLeafRes {
   v3 p1, p2, normal, guess;
   int hint0, hint1;
 };
-// leafComputeDistance (traversal_node_bvh_shape.h:342-364): TriangleP(mesh triangle) vs the shape.
+// operands of leafComputeDistance (traversal_node_bvh_shape.h:342-364): TriangleP(mesh triangle) vs the shape.
 // `chained`: the warm start of this query's previous leaf goes in (normal items; it only matters to
 // CachedGuess requests), otherwise the request's default.
-template <int CAPS>
-HFB_HD void q_leaf_eval(const QSlot& s, int prim, const SolverP& P, EpaWs* ws, bool chained, QLeafRes& r) {
-  PairIn in;
+HFB_HD void q_leaf_inputs(const QSlot& s, int prim, bool chained, PairIn& in) {
   const uint32_t* t = static_cast<const uint32_t*>(s.ptr[2]) + 3 * (size_t)prim;
   const double* verts = static_cast<const double*>(s.ptr[1]);
   const double* a = verts + 3 * (size_t)t[0];
@@ -192,13 +191,90 @@ HFB_HD void q_leaf_eval(const QSlot& s, int prim, const SolverP& P, EpaWs* ws, b
   in.cached_guess = chained ? mk(s.guess[0], s.guess[1], s.guess[2]) : mk(1, 0, 0);
   in.hint0 = chained ? s.hint0 : 0;
   in.hint1 = chained ? s.hint1 : 0;
-  PairOut o;
-  GjkState g;
-  if (pair_phase1<1, CAPS, PATH_BOTH>(in, P, o, g)) pair_phase2<1, CAPS>(in, P, g, ws, o);
+}
+HFB_HD void q_leaf_result(const PairOut& o, QLeafRes& r) {
   r.distance = o.distance;
   r.p1 = o.p1; r.p2 = o.p2; r.normal = o.normal;
   r.guess = o.cached_guess;
   r.hint0 = o.hint0; r.hint1 = o.hint1;
+}
+// the whole leaf test in one go (host emulation of an unsuspended item; the device splits it, see q_leaf_gjk)
+template <int CAPS>
+HFB_HD void q_leaf_eval(const QSlot& s, int prim, const SolverP& P, EpaWs* ws, bool chained, QLeafRes& r) {
+  PairIn in;
+  q_leaf_inputs(s, prim, chained, in);
+  PairOut o;
+  GjkState g;
+  if (pair_phase1<1, CAPS, PATH_BOTH>(in, P, o, g)) pair_phase2<1, CAPS>(in, P, g, ws, o);
+  q_leaf_result(o, r);
+}
+
+// A leaf test in pieces.  GJK takes 3 to 26 iterations on a triangle-capsule pair, and the block runs its leaf
+// items in a phase that lasts as long as its longest item: a leaf item therefore runs at most `max_steps` GJK
+// iterations, then parks the solver state (QLeafSave, global memory) and queues itself again (QL_SUSPENDED);
+// EPA -- rare, up to 64 long iterations -- is an item kind of its own (QL_NEED_EPA, q_leaf_epa).  The pieces
+// are pair_phase1 / pair_phase2 of hfb_pair.cuh cut at their loop boundaries: same operations in the same order.
+struct QLeafSave {
+  GjkState g;
+  GjkLoop L;
+};
+enum { QL_DONE = 0, QL_SUSPENDED = 1, QL_NEED_EPA = 2 };
+template <int CAPS>
+HFB_HD int q_leaf_gjk(const QSlot& s, int prim, const SolverP& P, bool chained, bool resume, int max_steps,
+                      QLeafSave& sv, QLeafRes& r) {
+  PairIn in;
+  q_leaf_inputs(s, prim, chained, in);
+  PairOut o;
+  GjkState g;
+  if (is_closed_form(HFB_GEOM_TRIANGLE, in.s2.type)) {  // sphere partner: details.h:286-342, no solver
+    pair_phase1<1, CAPS, PATH_BOTH>(in, P, o, g);
+    q_leaf_result(o, r);
+    return QL_DONE;
+  }
+  GjkSetup S;
+  GjkLoop L;
+  if (!resume) {
+    pair_gjk_begin<CAPS>(in, P, S, L, g, o);
+  } else {
+    o.cached_guess = (P.initial_guess == HFB_GUESS_CACHED) ? in.cached_guess : mk(1, 0, 0);
+    o.hint0 = in.hint0;
+    o.hint1 = in.hint1;
+    o.iterations = 0;
+    make_setup<CAPS>(in, S);
+    g = sv.g;
+    L = sv.L;
+  }
+  bool more = true;
+  for (int k = 0; k < max_steps && more; ++k) more = gjk_step<1, CAPS>(S.a, S.b, S.md, P.gjk, g, L);
+  if (more) {
+    sv.g = g;
+    sv.L = L;
+    return QL_SUSPENDED;
+  }
+  if (pair_gjk_end(P, S, g, o)) {
+    sv.g = g;
+    return QL_NEED_EPA;
+  }
+  q_leaf_result(o, r);
+  return QL_DONE;
+}
+template <int CAPS>
+HFB_HD void q_leaf_epa(const QSlot& s, int prim, const SolverP& P, bool chained, EpaWs* ws, const QLeafSave& sv,
+                       QLeafRes& r) {
+  PairIn in;
+  q_leaf_inputs(s, prim, chained, in);
+  PairOut o;
+  o.cached_guess = mk(1, 0, 0);
+  o.hint0 = o.hint1 = 0;
+  GjkState g = sv.g;
+  pair_phase2<1, CAPS>(in, P, g, ws, o);
+  q_leaf_result(o, r);
+}
+// where the parked state of an item lives: one entry per slot (its one unspeculated leaf) and one per leaf of every
+// treelet buffer
+HFB_HD unsigned q_save_index(const QSlot& s, unsigned item, unsigned nslots) {
+  return (item & HFB_Q_ITEM_SPEC) ? nslots + (unsigned)s.scr * HFB_Q_TREELET_MAX + ((item >> 12) & 0xffu)
+                                  : (item & HFB_Q_SLOT_MASK);
 }
 
 // RSS distance of one node against the query's shape RSS: rss_distance (hfb_bvh.cuh) with the factor

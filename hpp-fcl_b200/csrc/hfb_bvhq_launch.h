@@ -29,15 +29,17 @@ struct BvhqLaunch {
   QStackEnt* stacks;     // blocks x NSLOTS x stack_cap
   QTreelet* treelets;    // blocks x NTREELETS
   EpaWs* ws;             // one per thread
+  QLeafSave* saves;      // blocks x (NSLOTS + 32 * NTREELETS): parked solver state of suspended leaf items
   unsigned* work;        // hand-out counter of this launch (zeroed by the caller)
   unsigned long long* counters;  // [0] bv tests, [1] leaf tests, [2] watchdog trips (running totals)
   int stack_cap;
   int spec_after;
+  int gjk_chunk;         // GJK iterations a leaf item runs before it parks its state and queues itself again
 };
 
 // scratch the launch needs for `blocks` blocks and up to n queries
 struct BvhqSizes {
-  size_t prep, stacks, treelets, ws;
+  size_t prep, stacks, treelets, ws, saves;
 };
 BvhqSizes bvhq_sizes(unsigned blocks, size_t n, int stack_cap);
 unsigned bvhq_blocks(int num_sms, size_t n);

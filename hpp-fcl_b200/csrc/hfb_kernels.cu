@@ -807,7 +807,7 @@ struct Slot {
   cudaEvent_t ev_part[kMaxParts] = {};
   cudaEvent_t ev_join = nullptr;
   DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, retry, bvh_ws, bvh_cnt, extra, ccnt, okeys, ohist, olist;
-  DevBuf qprep, qstacks, qtl, qws;  // task-system mesh-shape walk (hfb_bvhq.cu)
+  DevBuf qprep, qstacks, qtl, qws, qsv;  // task-system mesh-shape walk (hfb_bvhq.cu)
   DevBuf pi, pj, cmp;                // object-table batches: pair indices of the chunk; compact results
 };
 
@@ -835,6 +835,7 @@ struct hfb_ctx {
   int bvh_quorum = HFB_BVH_INIT_QUORUM;  // HFB_BVH_QUORUM=1: a lane sets its next query up as soon as it is free
   int bvh_order = 0;  // HFB_BVH_ORDER=1: hand the (mesh, shape) queries out longest-expected first
   int bvhq = 1;        // HFB_BVHQ=0: mesh-shape distance queries through the lane-per-query kernel k_bvh instead of the task system k_bvhq
+  int bvh_chunk = 6;   // HFB_BVH_GJK_CHUNK: GJK iterations a leaf item runs before it parks its state
   int bvh_spec = 200;  // HFB_BVH_SPEC: items a query uses before it may speculate on subtrees (< 0: never)
   int bvh_bps = 4;  // k_bvh: blocks (of 2 warps) per SM the grid is capped at; HFB_BVH_BPS, see tests/tools/bvh_sched_model.py
   bool profiling = false;
@@ -1103,8 +1104,8 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
     if (blocks > cap) blocks = cap;
     CK(sl.bvh_ws.reserve((size_t)ctx->num_sms * 4u * 2 * threads * sizeof(EpaWs)));
     if (!sl.bvh_cnt.p) {
-      CK(sl.bvh_cnt.reserve(4 * sizeof(unsigned long long)));
-      CK(cudaMemsetAsync(sl.bvh_cnt.p, 0, 4 * sizeof(unsigned long long), s));
+      CK(sl.bvh_cnt.reserve(8 * sizeof(unsigned long long)));
+      CK(cudaMemsetAsync(sl.bvh_cnt.p, 0, 8 * sizeof(unsigned long long), s));
     }
     BatchArgs ab = a;
     ab.bvh_ws = static_cast<EpaWs*>(sl.bvh_ws.p);
@@ -1140,6 +1141,7 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
         CK(sl.qstacks.reserve(z.stacks));
         CK(sl.qtl.reserve(z.treelets));
         CK(sl.qws.reserve(z.ws));
+        CK(sl.qsv.reserve(z.saves));
         BvhqLaunch L{};
         L.A = ab.A;
         L.h1 = ab.h1; L.tf1 = ab.tf1; L.h2 = ab.h2; L.tf2 = ab.tf2;
@@ -1152,6 +1154,8 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
         L.stacks = static_cast<QStackEnt*>(sl.qstacks.p);
         L.treelets = static_cast<QTreelet*>(sl.qtl.p);
         L.ws = static_cast<EpaWs*>(sl.qws.p);
+        L.saves = static_cast<QLeafSave*>(sl.qsv.p);
+        L.gjk_chunk = ctx->bvh_chunk;
         L.work = ab.bvh_work;
         L.counters = ab.bvh_counters;
         L.stack_cap = cap;
@@ -1477,6 +1481,7 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   if (const char* bo = getenv("HFB_BVH_ORDER")) c->bvh_order = atoi(bo) != 0;
   if (const char* bq2 = getenv("HFB_BVHQ")) c->bvhq = atoi(bq2) != 0;
   if (const char* bs = getenv("HFB_BVH_SPEC")) c->bvh_spec = atoi(bs);
+  if (const char* bc = getenv("HFB_BVH_GJK_CHUNK")) c->bvh_chunk = atoi(bc) > 0 ? atoi(bc) : 1;
   if (const char* bq = getenv("HFB_BVH_QUORUM"))
     if (atoi(bq) == 1) c->bvh_quorum = 1;
   if (const char* bp = getenv("HFB_BVH_BPS")) {
@@ -1501,7 +1506,7 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   auto rel = [](Slot& s) {
-    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist, &s.qprep, &s.qstacks, &s.qtl, &s.qws, &s.pi, &s.pj, &s.cmp};
+    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist, &s.qprep, &s.qstacks, &s.qtl, &s.qws, &s.qsv, &s.pi, &s.pj, &s.cmp};
     for (DevBuf* b : bs) b->release();
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.epa_stream) cudaStreamDestroy(s.epa_stream);
@@ -1970,6 +1975,18 @@ int hfb_batch_convex_support(hfb_ctx* ctx, size_t n, const uint32_t* ids, const 
   CK(cudaMemcpyAsync(idx, ctx->sup_idx.p, n * 4, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(sup, ctx->sup_out.p, n * 24, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return HFB_OK;
+}
+
+// development aid (not in the header): phase profile of k_bvhq of the *_device entry points since the context was
+// created -- clock cycles of thread 0 summed over the blocks in the BV / leaf / EPA phases, cycles, EPA phases
+int hfb_debug_bvh_profile(hfb_ctx* ctx, unsigned long long out[5]) {
+  if (!ctx || !out) return HFB_ERR_INVALID_ARGUMENT;
+  CK(cudaSetDevice(ctx->device));
+  CK(cudaDeviceSynchronize());
+  unsigned long long v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (ctx->dev_slot.bvh_cnt.p) CK(cudaMemcpy(v, ctx->dev_slot.bvh_cnt.p, sizeof(v), cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 5; ++k) out[k] = v[3 + k];
   return HFB_OK;
 }
 

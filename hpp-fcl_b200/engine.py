@@ -57,6 +57,10 @@ def load_library(path=None):
         getattr(L, name).argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
         getattr(L, name + "_device").argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
     L.hfb_batch_collide_contacts.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp]
+    L.hfb_batch_distance_objects.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.hfb_batch_collide_objects.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.hfb_batch_distance_objects_device.argtypes = [vp, vp, vp, vp, vp, vp]
+    L.hfb_batch_collide_objects_device.argtypes = [vp, vp, vp, vp, vp, vp]
     L.hfb_batch_convex_support.argtypes = [vp, sz, vp, vp, vp, vp]
     L.hfb_batch_convex_support_device.argtypes = [vp, sz, vp, vp, vp, vp, vp]
     L.hfb_get_stats.argtypes = [vp, vp]
@@ -230,6 +234,68 @@ class Engine:
         self._check(self.L.hfb_batch_collide_contacts(self.h, n, _ptr(h1), _ptr(tf1), _ptr(h2), _ptr(tf2), C.byref(req),
                                                       _ptr(out), max_extra, _ptr(extra), _ptr(counts), None))
         return out, extra[:, :max_extra], counts
+
+    # -- object-table queries: the batched form of the CollisionObject overloads (collision.h:58-61) -----
+    @staticmethod
+    def _scene(obj_handles, obj_tfs, first, second):
+        oh = np.ascontiguousarray(obj_handles, dtype=np.uint32)
+        ot = np.ascontiguousarray(obj_tfs, dtype=P.transform_dtype)
+        pi = np.ascontiguousarray(first, dtype=np.uint32)
+        pj = np.ascontiguousarray(second, dtype=np.uint32)
+        if oh.shape[0] != ot.shape[0] or pi.shape[0] != pj.shape[0]:
+            raise ValueError("object table / pair list arrays must have equal length")
+        sc = P.ObjectPairs(oh.shape[0], oh.ctypes.data, ot.ctypes.data, pi.shape[0], pi.ctypes.data, pj.ctypes.data)
+        return sc, (oh, ot, pi, pj)
+
+    def batch_distance_objects(self, obj_handles, obj_tfs, first, second, req=None, out=None, min_only=False):
+        """distance() of the object pairs (first[k], second[k]).  min_only: only DistanceResult::min_distance
+        comes back (8 B per pair over PCIe instead of 96)"""
+        req = req or P.DistanceRequestPOD()
+        sc, keep = self._scene(obj_handles, obj_tfs, first, second)
+        n = sc.n_pairs
+        if min_only:
+            d = np.empty(n, dtype=np.float64) if out is None else out
+            self._check(self.L.hfb_batch_distance_objects(self.h, C.byref(sc), C.byref(req), None, _ptr(d), None))
+            return d
+        if out is None:
+            out = np.empty(n, dtype=P.distance_result_dtype)
+        self._check(self.L.hfb_batch_distance_objects(self.h, C.byref(sc), C.byref(req), _ptr(out), None, None))
+        return out
+
+    def batch_collide_objects(self, obj_handles, obj_tfs, first, second, req=None, out=None, compact_capacity=None):
+        """collide() of the object pairs.  compact_capacity = c: -> (flags bit per pair, n_colliding, pair_ids,
+        contacts) with the records of at most c colliding pairs, in no particular order; else full records"""
+        req = req or P.CollisionRequestPOD()
+        sc, keep = self._scene(obj_handles, obj_tfs, first, second)
+        n = sc.n_pairs
+        if compact_capacity is not None:
+            cap = int(compact_capacity)
+            flags = np.zeros((n + 31) // 32, dtype=np.uint32)
+            nhit = np.zeros(1, dtype=np.uint32)
+            ids = np.zeros(max(cap, 1), dtype=np.uint32)
+            recs = np.zeros(max(cap, 1), dtype=P.contact_dtype)
+            cc = P.CompactContacts(flags.ctypes.data, nhit.ctypes.data, ids.ctypes.data, recs.ctypes.data, cap)
+            self._check(self.L.hfb_batch_collide_objects(self.h, C.byref(sc), C.byref(req), None, C.byref(cc), None))
+            k = min(int(nhit[0]), cap)
+            return flags, int(nhit[0]), ids[:k], recs[:k]
+        if out is None:
+            out = np.empty(n, dtype=P.contact_dtype)
+        self._check(self.L.hfb_batch_collide_objects(self.h, C.byref(sc), C.byref(req), _ptr(out), None, None))
+        return out
+
+    def batch_distance_objects_device(self, n_objects, d_handles, d_tfs, n_pairs, d_first, d_second, d_out, req=None,
+                                      stream=0):
+        req = req or P.DistanceRequestPOD()
+        sc = P.ObjectPairs(n_objects, d_handles, d_tfs, n_pairs, d_first, d_second)
+        self._check(self.L.hfb_batch_distance_objects_device(self.h, C.byref(sc), C.byref(req), _ptr(d_out), None,
+                                                             _ptr(stream)))
+
+    def batch_collide_objects_device(self, n_objects, d_handles, d_tfs, n_pairs, d_first, d_second, d_out, req=None,
+                                     stream=0):
+        req = req or P.CollisionRequestPOD()
+        sc = P.ObjectPairs(n_objects, d_handles, d_tfs, n_pairs, d_first, d_second)
+        self._check(self.L.hfb_batch_collide_objects_device(self.h, C.byref(sc), C.byref(req), _ptr(d_out), None,
+                                                            _ptr(stream)))
 
     def batch_convex_support(self, convex_ids, dirs):
         ids = np.ascontiguousarray(convex_ids, dtype=np.uint32)

@@ -284,7 +284,8 @@ long batch_lanes_g(int G, Emu* E, size_t n, const uint32_t* h1, const hfb_transf
 // queries in flight, speculated subtrees included -- are executed ONE AT A TIME IN RANDOM ORDER, which is every
 // interleaving the device's warps can produce as far as the walk logic can tell.
 struct HostQSink {
-  std::vector<unsigned> leafq, bvq;
+  std::vector<unsigned> leafq, bvq, epaq;
+  void push_epa(unsigned it) { epaq.push_back(it); }
   std::vector<int> free_tl;
   void push_leaf(unsigned it) { leafq.push_back(it); }
   void push_bv(unsigned it) { bvq.push_back(it); }
@@ -302,7 +303,7 @@ long g_q_spec_items = 0, g_q_items = 0;
 static void host_bvhq_distance(const ArenaView& A, const std::vector<size_t>& todo, const uint32_t* h1,
                                const hfb_transform* tf1, const uint32_t* h2, const hfb_transform* tf2,
                                const hfb_distance_request* req, const SolverP& P, hfb_distance_result* out,
-                               int spec_after, unsigned seed, int nslots, int ntl) {
+                               int spec_after, unsigned seed, int nslots, int ntl, int gjk_chunk) {
   BvhReq R{0, 0, 0, 0, 0, 1, req->enable_nearest_points != 0, req->q.gjk_initial_guess};
   QCtx c;
   c.P = P;
@@ -312,6 +313,7 @@ static void host_bvhq_distance(const ArenaView& A, const std::vector<size_t>& to
   std::vector<QSlot> slots((size_t)nslots);
   std::vector<QStackEnt> stacks((size_t)nslots * 64);
   std::vector<QTreelet> tls((size_t)(ntl > 0 ? ntl : 1));
+  std::vector<QLeafSave> saves((size_t)nslots + (size_t)(ntl > 0 ? ntl : 1) * HFB_Q_TREELET_MAX);
   HostQSink sink;
   for (int k = 0; k < ntl; ++k) sink.free_tl.push_back(k);
   std::unique_ptr<EpaWs> ws(new EpaWs());
@@ -345,26 +347,35 @@ static void host_bvhq_distance(const ArenaView& A, const std::vector<size_t>& to
   for (int sl = 0; sl < nslots; ++sl)
     if (fetch(sl)) ++active;
   while (active > 0) {
-    const size_t nl = sink.leafq.size(), nb = sink.bvq.size();
-    if (nl + nb == 0) std::abort();  // a query in flight always has an item outstanding
-    size_t pick = rnd() % (nl + nb);
+    const size_t nl = sink.leafq.size(), nb = sink.bvq.size(), ne = sink.epaq.size();
+    if (nl + nb + ne == 0) std::abort();  // a query in flight always has an item outstanding
+    size_t pick = rnd() % (nl + nb + ne);
     unsigned item;
-    int rc;
+    int rc = Q_ISSUED;
     ++g_q_items;
-    if (pick < nl) {
-      item = sink.leafq[pick];
-      sink.leafq[pick] = sink.leafq.back();
-      sink.leafq.pop_back();
-      QSlot& s = slots[item & HFB_Q_SLOT_MASK];
+    if (pick < nl + ne) {
+      const bool epa = pick >= nl;
+      std::vector<unsigned>& qv = epa ? sink.epaq : sink.leafq;
+      if (epa) pick -= nl;
+      item = qv[pick];
+      qv[pick] = qv.back();
+      qv.pop_back();
+      const unsigned sl = item & HFB_Q_SLOT_MASK;
+      QSlot& s = slots[sl];
       const bool spec = (item & HFB_Q_ITEM_SPEC) != 0;
       g_q_spec_items += spec;
       QLeafRes r;
-      q_leaf_eval<CAPS_ALL>(s, q_leaf_prim(s, tls.data(), item), P, ws.get(), !spec, r);
-      rc = Q_ISSUED;
-      if (q_leaf_store(s, item, tls.data(), sink, r))
-        rc = q_advance(s, item & HFB_Q_SLOT_MASK, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), c, sink);
+      QLeafSave& sv = saves[q_save_index(s, item, (unsigned)nslots)];
+      const int prim = q_leaf_prim(s, tls.data(), item);
+      int st = QL_DONE;
+      if (epa) q_leaf_epa<CAPS_ALL>(s, prim, P, !spec, ws.get(), sv, r);
+      else st = q_leaf_gjk<CAPS_ALL>(s, prim, P, !spec, (item & HFB_Q_ITEM_RESUME) != 0, gjk_chunk, sv, r);
+      if (st == QL_SUSPENDED) sink.push_leaf(item | HFB_Q_ITEM_RESUME);
+      else if (st == QL_NEED_EPA) sink.push_epa(item & ~HFB_Q_ITEM_RESUME);
+      else if (q_leaf_store(s, item, tls.data(), sink, r))
+        rc = q_advance(s, sl, &stacks[(size_t)sl * 64], tls.data(), c, sink);
     } else {
-      pick -= nl;
+      pick -= nl + ne;
       item = sink.bvq[pick];
       sink.bvq[pick] = sink.bvq.back();
       sink.bvq.pop_back();
@@ -373,7 +384,6 @@ static void host_bvhq_distance(const ArenaView& A, const std::vector<size_t>& to
       const hfb_bvh_node* nodes = static_cast<const hfb_bvh_node*>(s.ptr[0]);
       const int base = q_bv_base(s, item);
       const double d1 = q_rss_child(s, nodes[base]), d2 = q_rss_child(s, nodes[base + 1]);
-      rc = Q_ISSUED;
       if (q_bv_store(s, item, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), sink, d1, d2,
                      nodes[base].first_child, nodes[base + 1].first_child))
         rc = q_advance(s, item & HFB_Q_SLOT_MASK, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), c, sink);
@@ -384,7 +394,7 @@ static void host_bvhq_distance(const ArenaView& A, const std::vector<size_t>& to
       if (!fetch(sl)) --active;
     }
   }
-  if (!sink.leafq.empty() || !sink.bvq.empty() || (int)sink.free_tl.size() != ntl) std::abort();
+  if (!sink.leafq.empty() || !sink.bvq.empty() || !sink.epaq.empty() || (int)sink.free_tl.size() != ntl) std::abort();
 }
 
 extern "C" {
@@ -433,7 +443,7 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
   const SolverP P = solver_from_distance_request(*req);
   const ArenaView A = E->arena.view();
   std::unique_ptr<EpaWs> ws(new EpaWs());
-  // HFB_EMU_BVHQ="spec_after[,seed[,slots[,treelets]]]": (mesh, shape) pairs through the task-system walk
+  // HFB_EMU_BVHQ="spec_after[,seed[,slots[,treelets[,GJK iterations per leaf item]]]]": (mesh, shape) pairs through the task-system walk
   const char* qenv = getenv("HFB_EMU_BVHQ");
   std::vector<size_t> qtodo;
   for (size_t i = 0; i < n; ++i) {
@@ -470,10 +480,10 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
     put_guess(go, i, o);
   }
   if (!qtodo.empty()) {
-    int spec_after = 0, slots = 6, ntl = 2;
+    int spec_after = 0, slots = 6, ntl = 2, chunk = 3;
     unsigned seed = 1;
-    sscanf(qenv, "%d,%u,%d,%d", &spec_after, &seed, &slots, &ntl);
-    host_bvhq_distance(A, qtodo, h1, tf1, h2, tf2, req, P, out, spec_after, seed, slots, ntl);
+    sscanf(qenv, "%d,%u,%d,%d,%d", &spec_after, &seed, &slots, &ntl, &chunk);
+    host_bvhq_distance(A, qtodo, h1, tf1, h2, tf2, req, P, out, spec_after, seed, slots, ntl, chunk);
   }
   return HFB_OK;
 }

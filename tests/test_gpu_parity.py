@@ -283,3 +283,67 @@ def test_full_size_properties():
     r2 = eng.batch_distance(w["h2"][s], w["tf2"][s], w["h1"][s], w["tf1"][s])
     m = ~np.isnan(ref["p1"][:, 0]) & ~np.isnan(r2["p1"][:, 0])
     assert np.allclose(ref["min_distance"][m], r2["min_distance"][m], atol=5e-4)
+
+
+def test_object_table_calls_equal_the_pair_calls():
+    """hfb_batch_{distance,collide}_objects: an object table (handle + pose) and index pairs, expanded on the device.
+    The records must equal, bit for bit, those of the pair calls on the expanded rows -- shape pairs, convex pairs and
+    mesh pairs alike -- and the compact result modes must be projections of the full records."""
+    import torch
+    rng = np.random.default_rng(11)
+    eng = hf.Engine(0)
+    w = W.config2_mixed_primitives(1000, pool=512, types=ALL_PRIMS, seed=3)
+    hp = eng.register_shapes(w["shapes"])
+    pts, _ = W.ellipsoid_hull(rng, 40)
+    cid = eng.register_convex(pts)
+    hc = eng.register_shapes(P.make_shapes([P.GEOM_CONVEX], [[0, 0, 0]], data=[cid]))
+    verts, tris = W.sphere_mesh(0.6, 12, 6, noise=0.02, rng=rng)
+    bid = eng.register_bvh_obbrss(None, verts, tris)
+    hm = eng.register_shapes(P.make_shapes([P.BV_OBBRSS], [[0, 0, 0]], data=[bid]))
+    eng.commit()
+    n_obj, n_pairs = 20_000, 300_000
+    allh = np.concatenate([hp, np.repeat(hc, 40), np.repeat(hm, 10)])
+    oh = allh[rng.integers(0, len(allh), n_obj)].astype(np.uint32)
+    otf = W.random_transforms(rng, n_obj, (-2, -2, -2), (2, 2, 2))
+    pi = rng.integers(0, n_obj, n_pairs).astype(np.uint32)
+    pj = rng.integers(0, n_obj, n_pairs).astype(np.uint32)
+    full = eng.batch_distance(oh[pi], otf[pi], oh[pj], otf[pj])
+    obj = eng.batch_distance_objects(oh, otf, pi, pj)
+    assert full.tobytes() == obj.tobytes()
+    dmin = eng.batch_distance_objects(oh, otf, pi, pj, min_only=True)
+    assert dmin.tobytes() == np.ascontiguousarray(full["min_distance"]).tobytes()
+    req = P.CollisionRequestPOD(security_margin=0.01)
+    cfull = eng.batch_collide(oh[pi], otf[pi], oh[pj], otf[pj], req)
+    cobj = eng.batch_collide_objects(oh, otf, pi, pj, req)
+    assert cfull.tobytes() == cobj.tobytes()
+    hits = np.nonzero(cfull["num_contacts"] > 0)[0]
+    assert len(hits) > 500
+    flags, nh, ids, recs = eng.batch_collide_objects(oh, otf, pi, pj, req, compact_capacity=len(hits) + 7)
+    bits = np.unpackbits(flags.view(np.uint8), bitorder="little")[:n_pairs].astype(bool)
+    assert np.array_equal(np.nonzero(bits)[0], hits) and nh == len(hits)
+    order = np.argsort(ids)
+    assert np.array_equal(ids[order], hits) and recs[order].tobytes() == cfull[hits].tobytes()
+    # capacity below the number of colliding pairs: all counted, `capacity` kept
+    _, nh2, ids2, recs2 = eng.batch_collide_objects(oh, otf, pi, pj, req, compact_capacity=100)
+    assert nh2 == len(hits) and len(ids2) == 100 and np.all(np.isin(ids2, hits))
+    assert all(recs2[k].tobytes() == cfull[ids2[k]].tobytes() for k in range(100))
+    # device-resident scene
+    def dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
+    d = [dev(oh), dev(otf), dev(pi), dev(pj)]
+    d_out = torch.empty(n_pairs * P.distance_result_dtype.itemsize, dtype=torch.uint8, device="cuda")
+    eng.batch_distance_objects_device(n_obj, d[0].data_ptr(), d[1].data_ptr(), n_pairs, d[2].data_ptr(), d[3].data_ptr(),
+                                      d_out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert d_out.cpu().numpy().tobytes() == full.tobytes()
+    d_c = torch.empty(n_pairs * P.contact_dtype.itemsize, dtype=torch.uint8, device="cuda")
+    eng.batch_collide_objects_device(n_obj, d[0].data_ptr(), d[1].data_ptr(), n_pairs, d[2].data_ptr(), d[3].data_ptr(),
+                                     d_c.data_ptr(), req, stream=torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    assert d_c.cpu().numpy().tobytes() == cfull.tobytes()
+    # an index past the table: invalid argument on the host path
+    bad = pi.copy()
+    bad[5] = n_obj
+    with pytest.raises(hf.EngineError):
+        eng.batch_distance_objects(oh, otf, bad, pj)
+    assert eng.stats()["watchdog_trips"] == 0

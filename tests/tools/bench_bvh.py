@@ -70,7 +70,16 @@ same = bool(np.array_equal(ref["min_distance"], got["min_distance"][:ns]) and np
 bv = (s1["bv_tests"] - s0["bv_tests"]) / steps
 lf = (s1["leaf_tests"] - s0["leaf_tests"]) / steps
 alg_bytes = 136 * bv + 96 * lf + (136 + 96) * n  # RSS half of the node + header, leaf triangle, capsule+pose, result
-print(json.dumps({"workload": "config4: 10k-tri OBBRSS mesh vs %d capsules, distance" % n, "queries_per_s": n / (ms * 1e-3),
+import ctypes as _C
+_prof = (_C.c_ulonglong * 5)()
+eng.L.hfb_debug_bvh_profile.argtypes = [_C.c_void_p, _C.c_void_p]
+eng.L.hfb_debug_bvh_profile(eng.h, _prof)
+_calls = steps + 3
+_nb = min(148, (n + 63) // 64)
+phase = {"bv_us_per_block": _prof[0] / 1.9e3 / _nb / _calls, "leaf_us_per_block": _prof[1] / 1.9e3 / _nb / _calls,
+         "epa_us_per_block": _prof[2] / 1.9e3 / _nb / _calls, "cycles_per_block": _prof[3] / _nb / _calls,
+         "epa_phases_per_block": _prof[4] / _nb / _calls}
+print(json.dumps({"phase_profile": phase, "workload": "config4: 10k-tri OBBRSS mesh vs %d capsules, distance" % n, "queries_per_s": n / (ms * 1e-3),
                   "ms_per_batch": ms, "k_bvh_ms": kt["bvh_ms"] / steps, "host_api_queries_per_s": n / t_host,
                   "bv_tests_per_query": bv / n, "leaf_tests_per_query": lf / n,
                   "algorithmic_GBps": alg_bytes / (kt["bvh_ms"] / steps * 1e-3) / 1e9,
