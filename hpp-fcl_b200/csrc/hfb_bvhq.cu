@@ -27,6 +27,7 @@ struct QSched {
   int abort_;
   int lsnap;           // leaf phase: items queued before this ring position belong to the phase
   int do_epa, stop;    // decisions of the cycle, taken by thread 0 between two barriers
+  int bn0;             // BV items of the generation that is starting
   unsigned leafq[HFB_Q_QCAP];
   unsigned bvq[HFB_Q_QCAP];
   unsigned epaq[HFB_Q_QCAP];
@@ -119,11 +120,12 @@ struct QBlock {
   unsigned lo, hi;
 };
 __device__ __noinline__ void q_continue(const BvhqLaunch& L, const QBlock& B, const QCtx& c, unsigned sl,
-                                        unsigned long long& bv_total, unsigned long long& leaf_total) {
+                                        unsigned long long& bv_total, unsigned long long& leaf_total, bool have,
+                                        QStackEnt near) {
   DevSink sink{B.sc};
   QSlot& s = B.slots[sl];
   QStackEnt* stk = B.stacks + (size_t)sl * L.stack_cap;
-  if (q_advance(s, sl, stk, B.tls, c, sink) != Q_DONE) return;
+  if (q_advance(s, sl, stk, B.tls, c, sink, have, near) != Q_DONE) return;
   q_write_result(s, L.out + s.pair);
   bv_total += (unsigned)s.bv_tests;
   leaf_total += (unsigned)s.leaf_tests;
@@ -220,6 +222,7 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
   c.rel_err = L.B.rel_err;
   c.abs_err = L.B.abs_err;
   c.spec_after = (L.P.initial_guess == HFB_GUESS_CACHED) ? -1 : L.spec_after;
+  c.spec_big_after = L.spec_big_after;
   unsigned long long bv_total = 0, leaf_total = 0;
   {  // thread t fills slot t
     const unsigned sl = threadIdx.x;
@@ -270,8 +273,10 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
         double d1, d2;
         int f1, f2;
         q_bv_group<LC>(s, nodes + q_bv_base(s, item), gmask, gbase, sub, d1, d2, f1, f2);
-        if (sub == 0u && q_bv_store(s, item, stacks + (size_t)sl * L.stack_cap, tls, sink, d1, d2, f1, f2))
-          q_continue(L, B, c, sl, bv_total, leaf_total);
+        bool have;
+        QStackEnt near;
+        if (sub == 0u && q_bv_store(s, item, stacks + (size_t)sl * L.stack_cap, tls, sink, d1, d2, f1, f2, have, near))
+          q_continue(L, B, c, sl, bv_total, leaf_total, have, near);
       }
     }
     __syncwarp();
@@ -283,14 +288,28 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
     t_prev = t;
   };
   for (;;) {
-    // ---- bounding-volume phase: until the queue is empty (items pushed meanwhile included) ----
-    {
-      const int nb0 = vload(&sc->btail) - vload(&sc->bhead);  // (stable: nothing is pushed between the barrier and here)
+    // ---- bounding-volume phase: bv_gens generations of items.  A generation is what was queued when it started;
+    // the items it pushes (a walk going down a level) are the next generation.  Running "until the queue is empty"
+    // instead made every cycle wait for its deepest descent with a handful of lanes busy
+    // (profiles/r02_k_bvhq_phases.md: 66 us of BV phase per cycle against 10 us of leaf phase). ----
+    for (int gen = 0; gen < L.bv_gens; ++gen) {
+      if (gen > 0) __syncthreads();
+      if (threadIdx.x == 0) {
+        sc->lsnap = vload(&sc->btail);
+        sc->bn0 = sc->lsnap - vload(&sc->bhead);
+      }
+      __syncthreads();
+      const int nb0 = vload(&sc->bn0);
+      if (nb0 <= 0) break;  // (uniform: written by thread 0 before the barrier, by nobody after it)
+      const int ipw = (nb0 + (HFB_Q_THREADS / 32) - 1) / (HFB_Q_THREADS / 32);  // items per warp
       int base = 0, cnt;
-      if (nb0 >= 64) {
-        while ((cnt = pop(&sc->bhead, &sc->btail, 16, base)) > 0) bv_task(std::integral_constant<int, 1>(), cnt, base);
+      // lanes per child: the fewer items, the more lanes share one (shorter dependent chain per task)
+      if (ipw > 8) {
+        while ((cnt = pop(&sc->bhead, &sc->btail, 16, base, &sc->lsnap)) > 0) bv_task(std::integral_constant<int, 1>(), cnt, base);
+      } else if (ipw > 4) {
+        while ((cnt = pop(&sc->bhead, &sc->btail, 8, base, &sc->lsnap)) > 0) bv_task(std::integral_constant<int, 2>(), cnt, base);
       } else {
-        while ((cnt = pop(&sc->bhead, &sc->btail, 4, base)) > 0) bv_task(std::integral_constant<int, 4>(), cnt, base);
+        while ((cnt = pop(&sc->bhead, &sc->btail, 4, base, &sc->lsnap)) > 0) bv_task(std::integral_constant<int, 4>(), cnt, base);
       }
     }
     __syncthreads();
@@ -327,7 +346,7 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
                                                  L.gjk_chunk, sv, r);
             if (st == QL_SUSPENDED) sink.push_leaf(item | HFB_Q_ITEM_RESUME);
             else if (st == QL_NEED_EPA) sink.push_epa(item & ~HFB_Q_ITEM_RESUME);
-            else if (q_leaf_store(s, item, tls, sink, r)) q_continue(L, B, c, sl, bv_total, leaf_total);
+            else if (q_leaf_store(s, item, tls, sink, r)) q_continue(L, B, c, sl, bv_total, leaf_total, false, QStackEnt());
           }
         }
         __syncwarp();
@@ -356,7 +375,7 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
           if (valid) {
             QLeafRes r;
             q_leaf_epa<CAPS_BVHQ>(s, q_leaf_prim(s, tls, item), L.P, !spec, ws, saves[q_save_index(s, item, HFB_Q_NSLOTS)], r);
-            if (q_leaf_store(s, item, tls, sink, r)) q_continue(L, B, c, sl, bv_total, leaf_total);
+            if (q_leaf_store(s, item, tls, sink, r)) q_continue(L, B, c, sl, bv_total, leaf_total, false, QStackEnt());
           }
         }
         __syncwarp();

@@ -32,7 +32,8 @@
 
 namespace hfb {
 
-#define HFB_Q_TREELET_MAX 32
+#define HFB_Q_TREELET_MAX 128   // triangles of the largest subtree a walk speculates on
+#define HFB_Q_TREELET_SMALL 32  // ... before it has used spec_big_after items
 #define HFB_Q_ITEM_SPEC 0x100000u
 #define HFB_Q_ITEM_RESUME 0x200000u  // leaf item: the solver state is parked, continue from it
 #define HFB_Q_ITEM_VALID 0x80000000u
@@ -66,13 +67,15 @@ struct QSlot {  // one query in flight (shared memory on the device; 83 eight-by
   double out[10];  // min_distance, p1, p2, normal
   const void* ptr[6];  // nodes, verts, tris, cx, cy, cz
   int type, nv, hint0, hint1, b1, sp, bv_tests, leaf_tests, pair, swapped, pending, rounds, tfc, tend, scr, cur;
-  int seed, _i1;
+  int seed, tbase;
 };
 
 struct QCtx {  // uniform per launch
   SolverP P;
   double rel_err, abs_err;
-  int spec_after;  // items a query must have used before it may speculate; < 0: never
+  int spec_after;      // items a query must have used before it may speculate (subtrees of up to HFB_Q_TREELET_SMALL
+                       // triangles); < 0: never
+  int spec_big_after;  // ... before it speculates on subtrees of up to HFB_Q_TREELET_MAX triangles
 };
 
 HFB_HD void q_put_m3(double* o, const m3& A) {
@@ -145,6 +148,7 @@ HFB_HD void q_start(QSlot& s, QStackEnt* stk, const BvhQuery& q, const QPrep& pr
   s.swapped = pr.swapped;
   s.rounds = 0;
   s.tfc = s.tend = -1;
+  s.tbase = 0;
   s.scr = -1;
   s.seed = 1;
   stk[0].dlow = -1.0;  // root: visited unconditionally
@@ -306,15 +310,18 @@ HFB_HD double q_rss_child(const QSlot& s, const hfb_bvh_node& nd) {
 
 enum { Q_ISSUED = 0, Q_DONE = 1 };
 
-// pushes the two children of a node in the reference's order: the nearer one is visited first
-HFB_HD void q_push_children(QStackEnt* stk, int& sp, int base, double d1, double d2, int f1, int f2) {
+// the two children of a node in the reference's order: the farther one goes on the stack, the nearer one is
+// visited next (returned; the recursion would push it and pop it again at once)
+HFB_HD QStackEnt q_push_children(QStackEnt* stk, int& sp, int base, double d1, double d2, int f1, int f2) {
+  QStackEnt a, c;
+  a.dlow = d1; a.fc = f1; a.node = base;
+  c.dlow = d2; c.fc = f2; c.node = base + 1;
   if (d2 < d1) {
-    stk[sp].dlow = d1; stk[sp].fc = f1; stk[sp].node = base; ++sp;
-    stk[sp].dlow = d2; stk[sp].fc = f2; stk[sp].node = base + 1; ++sp;
-  } else {
-    stk[sp].dlow = d2; stk[sp].fc = f2; stk[sp].node = base + 1; ++sp;
-    stk[sp].dlow = d1; stk[sp].fc = f1; stk[sp].node = base; ++sp;
+    stk[sp++] = a;
+    return c;
   }
+  stk[sp++] = c;
+  return a;
 }
 // DistanceResult::update: strict '>' keeps the first minimum
 HFB_HD void q_take_leaf(QSlot& s, int prim, const double* leaf10) {
@@ -326,21 +333,29 @@ HFB_HD void q_take_leaf(QSlot& s, int prim, const double* leaf10) {
 
 // The recursion, from the query's stack: pops / prunes (canStop, traversal_node_bvh_shape.h:322-327) until a
 // node needs a value that is not at hand, issues the item(s) for it and returns Q_ISSUED; Q_DONE when the
-// stack is empty.  Called by whoever completed the query's last outstanding item.
+// stack is empty.  Called by whoever completed the query's last outstanding item; `e0` (when `have`) is the node
+// to visit before anything is popped -- the nearer child of the node a BV item just finished.
+// While a speculated subtree is being replayed, `s.tbase` is the stack height below which the entries belong to the
+// walk outside it: the subtree's root sits at index tbase, everything above was pushed by the replay.
 template <class Sink>
-HFB_HD int q_advance(QSlot& s, unsigned slot_id, QStackEnt* stk, QTreelet* tls, const QCtx& c, Sink& sink) {
+HFB_HD int q_advance(QSlot& s, unsigned slot_id, QStackEnt* stk, QTreelet* tls, const QCtx& c, Sink& sink, bool have,
+                     QStackEnt e) {
   int sp = s.sp;
   const hfb_bvh_node* nodes = static_cast<const hfb_bvh_node*>(s.ptr[0]);
   for (;;) {
-    if (sp == 0) break;
-    const QStackEnt e = stk[--sp];
+    if (!have) {
+      if (sp == 0) break;
+      e = stk[--sp];
+    }
+    have = false;
     if (e.dlow >= 0) {
       if ((e.dlow >= s.out[0] - c.abs_err) && (e.dlow * (1 + c.rel_err) >= s.out[0])) continue;
     }
     QTreelet* T = s.scr >= 0 ? tls + s.scr : nullptr;
+    const bool inside = T && sp >= s.tbase;  // (the entry just taken sat at index sp or is a child of one that did)
     if (e.fc < 0) {  // leaf
       const int prim = -(e.fc + 1);
-      if (T && e.node >= s.tfc && e.node < s.tend) {
+      if (inside) {
         s.leaf_tests++;
         q_take_leaf(s, prim, T->leaf[T->leaf_of[e.node - s.tfc]]);
         continue;
@@ -348,7 +363,6 @@ HFB_HD int q_advance(QSlot& s, unsigned slot_id, QStackEnt* stk, QTreelet* tls, 
       if (T) {  // the walk has left the speculated subtree
         sink.treelet_release(s.scr);
         s.scr = -1;
-        s.tfc = s.tend = -1;
       }
       s.cur = prim;
       s.pending = 1;
@@ -357,20 +371,21 @@ HFB_HD int q_advance(QSlot& s, unsigned slot_id, QStackEnt* stk, QTreelet* tls, 
       sink.push_leaf(slot_id);
       return Q_ISSUED;
     }
-    if (T && e.fc >= s.tfc && e.fc < s.tend) {  // both children cached
+    if (inside) {  // both children cached
       const int k = e.fc - s.tfc;
       s.bv_tests += 2;
-      q_push_children(stk, sp, e.fc, T->d[k], T->d[k + 1], T->fc[k], T->fc[k + 1]);
+      e = q_push_children(stk, sp, e.fc, T->d[k], T->d[k + 1], T->fc[k], T->fc[k + 1]);
+      have = true;
       continue;
     }
     if (T) {
       sink.treelet_release(s.scr);
       s.scr = -1;
-      s.tfc = s.tend = -1;
     }
     if (c.spec_after >= 0 && s.rounds >= c.spec_after) {
       const unsigned L = nodes[e.node]._pad;  // triangles below; 0 unless the subtree is one contiguous block
-      if (L >= 2 && L <= HFB_Q_TREELET_MAX) {
+      const unsigned lmax = s.rounds >= c.spec_big_after ? HFB_Q_TREELET_MAX : HFB_Q_TREELET_SMALL;
+      if (L >= 2 && L <= lmax) {
         const int id = sink.treelet_acquire();
         if (id >= 0) {
           QTreelet* N = tls + id;
@@ -387,7 +402,8 @@ HFB_HD int q_advance(QSlot& s, unsigned slot_id, QStackEnt* stk, QTreelet* tls, 
           }
           s.scr = id;
           s.tfc = e.fc;
-          s.tend = e.fc + nd;
+          s.tbase = sp;
+          e.dlow = -1.0;  // (it passed canStop just now, and nothing changes the minimum before the replay)
           stk[sp++] = e;  // the replay starts by popping this node again; its children are cached then
           s.sp = sp;
           s.pending = nd / 2 + nleaf;
@@ -408,17 +424,18 @@ HFB_HD int q_advance(QSlot& s, unsigned slot_id, QStackEnt* stk, QTreelet* tls, 
   if (s.scr >= 0) {
     sink.treelet_release(s.scr);
     s.scr = -1;
-    s.tfc = s.tend = -1;
   }
   s.sp = 0;
   return Q_DONE;
 }
 
 // completion of a BV item whose values are in hand (d of children base, base + 1 and their first_child).
-// Returns true when this was the query's last outstanding item: the caller continues the walk (q_advance).
+// Returns true when this was the query's last outstanding item: the caller continues the walk (q_advance) with
+// `near` (if `have`) as the node to visit first.
 template <class Sink>
 HFB_HD bool q_bv_store(QSlot& s, unsigned item, QStackEnt* stk, QTreelet* tls, Sink& sink, double d1, double d2, int f1,
-                       int f2) {
+                       int f2, bool& have, QStackEnt& near) {
+  have = false;
   if (item & HFB_Q_ITEM_SPEC) {
     QTreelet* T = tls + s.scr;
     const int k = 2 * (int)((item >> 12) & 0xffu);
@@ -428,8 +445,9 @@ HFB_HD bool q_bv_store(QSlot& s, unsigned item, QStackEnt* stk, QTreelet* tls, S
   }
   s.bv_tests += 2;  // BVDistanceLowerBound of both children (:465-469)
   int sp = s.sp;
-  q_push_children(stk, sp, s.cur, d1, d2, f1, f2);
+  near = q_push_children(stk, sp, s.cur, d1, d2, f1, f2);
   s.sp = sp;
+  have = true;
   return true;
 }
 // node pair a BV item is about

@@ -8,8 +8,8 @@ namespace hfb {
 
 #define HFB_Q_THREADS 256    // 8 warps per block, one block per SM
 #define HFB_Q_NSLOTS 256     // queries in flight per block
-#define HFB_Q_NTREELETS 12   // speculated subtrees in flight per block
-#define HFB_Q_QCAP 1024      // ring size of each item queue (>= NSLOTS + 32 * NTREELETS)
+#define HFB_Q_NTREELETS 8    // speculated subtrees in flight per block
+#define HFB_Q_QCAP 2048      // ring size of each item queue (>= NSLOTS + HFB_Q_TREELET_MAX * NTREELETS)
 
 struct BvhqLaunch {
   ArenaView A;
@@ -33,7 +33,9 @@ struct BvhqLaunch {
   unsigned* work;        // hand-out counter of this launch (zeroed by the caller)
   unsigned long long* counters;  // [0] bv tests, [1] leaf tests, [2] watchdog trips (running totals)
   int stack_cap;
-  int spec_after;
+  int spec_after;        // QCtx::spec_after / spec_big_after
+  int spec_big_after;
+  int bv_gens;           // generations of BV items a cycle runs before its leaf phase
   int gjk_chunk;         // GJK iterations a leaf item runs before it parks its state and queues itself again
 };
 

@@ -835,6 +835,8 @@ struct hfb_ctx {
   int bvh_quorum = HFB_BVH_INIT_QUORUM;  // HFB_BVH_QUORUM=1: a lane sets its next query up as soon as it is free
   int bvh_order = 0;  // HFB_BVH_ORDER=1: hand the (mesh, shape) queries out longest-expected first
   int bvhq = 1;        // HFB_BVHQ=0: mesh-shape distance queries through the lane-per-query kernel k_bvh instead of the task system k_bvhq
+  int bvh_gens = 2;    // HFB_BVH_GENS: generations of BV items per cycle of k_bvhq
+  int bvh_spec_big = 300;  // HFB_BVH_SPEC_BIG: items more before subtrees of up to 128 triangles are speculated
   int bvh_chunk = 6;   // HFB_BVH_GJK_CHUNK: GJK iterations a leaf item runs before it parks its state
   int bvh_spec = 200;  // HFB_BVH_SPEC: items a query uses before it may speculate on subtrees (< 0: never)
   int bvh_bps = 4;  // k_bvh: blocks (of 2 warps) per SM the grid is capped at; HFB_BVH_BPS, see tests/tools/bvh_sched_model.py
@@ -1160,6 +1162,8 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
         L.counters = ab.bvh_counters;
         L.stack_cap = cap;
         L.spec_after = ctx->bvh_spec;
+        L.spec_big_after = ctx->bvh_spec < 0 ? 0x7fffffff : ctx->bvh_spec + ctx->bvh_spec_big;
+        L.bv_gens = ctx->bvh_gens;
         {
           KTimer kt(ctx, s, 5);
           if (bvhq_launch(L, qb, n, s) != 0) return fail(ctx, HFB_ERR_CUDA, "k_bvhq launch failed");
@@ -1482,6 +1486,8 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   if (const char* bq2 = getenv("HFB_BVHQ")) c->bvhq = atoi(bq2) != 0;
   if (const char* bs = getenv("HFB_BVH_SPEC")) c->bvh_spec = atoi(bs);
   if (const char* bc = getenv("HFB_BVH_GJK_CHUNK")) c->bvh_chunk = atoi(bc) > 0 ? atoi(bc) : 1;
+  if (const char* bg = getenv("HFB_BVH_GENS")) c->bvh_gens = atoi(bg) > 0 ? atoi(bg) : 1;
+  if (const char* bb = getenv("HFB_BVH_SPEC_BIG")) c->bvh_spec_big = atoi(bb) >= 0 ? atoi(bb) : 0;
   if (const char* bq = getenv("HFB_BVH_QUORUM"))
     if (atoi(bq) == 1) c->bvh_quorum = 1;
   if (const char* bp = getenv("HFB_BVH_BPS")) {

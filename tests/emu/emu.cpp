@@ -303,13 +303,14 @@ long g_q_spec_items = 0, g_q_items = 0;
 static void host_bvhq_distance(const ArenaView& A, const std::vector<size_t>& todo, const uint32_t* h1,
                                const hfb_transform* tf1, const uint32_t* h2, const hfb_transform* tf2,
                                const hfb_distance_request* req, const SolverP& P, hfb_distance_result* out,
-                               int spec_after, unsigned seed, int nslots, int ntl, int gjk_chunk) {
+                               int spec_after, unsigned seed, int nslots, int ntl, int gjk_chunk, int big_after) {
   BvhReq R{0, 0, 0, 0, 0, 1, req->enable_nearest_points != 0, req->q.gjk_initial_guess};
   QCtx c;
   c.P = P;
   c.rel_err = R.rel_err;
   c.abs_err = R.abs_err;
   c.spec_after = (P.initial_guess == HFB_GUESS_CACHED) ? -1 : spec_after;
+  c.spec_big_after = spec_after + big_after;
   std::vector<QSlot> slots((size_t)nslots);
   std::vector<QStackEnt> stacks((size_t)nslots * 64);
   std::vector<QTreelet> tls((size_t)(ntl > 0 ? ntl : 1));
@@ -373,7 +374,7 @@ static void host_bvhq_distance(const ArenaView& A, const std::vector<size_t>& to
       if (st == QL_SUSPENDED) sink.push_leaf(item | HFB_Q_ITEM_RESUME);
       else if (st == QL_NEED_EPA) sink.push_epa(item & ~HFB_Q_ITEM_RESUME);
       else if (q_leaf_store(s, item, tls.data(), sink, r))
-        rc = q_advance(s, sl, &stacks[(size_t)sl * 64], tls.data(), c, sink);
+        rc = q_advance(s, sl, &stacks[(size_t)sl * 64], tls.data(), c, sink, false, QStackEnt());
     } else {
       pick -= nl + ne;
       item = sink.bvq[pick];
@@ -384,9 +385,11 @@ static void host_bvhq_distance(const ArenaView& A, const std::vector<size_t>& to
       const hfb_bvh_node* nodes = static_cast<const hfb_bvh_node*>(s.ptr[0]);
       const int base = q_bv_base(s, item);
       const double d1 = q_rss_child(s, nodes[base]), d2 = q_rss_child(s, nodes[base + 1]);
+      bool have;
+      QStackEnt near;
       if (q_bv_store(s, item, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), sink, d1, d2,
-                     nodes[base].first_child, nodes[base + 1].first_child))
-        rc = q_advance(s, item & HFB_Q_SLOT_MASK, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), c, sink);
+                     nodes[base].first_child, nodes[base + 1].first_child, have, near))
+        rc = q_advance(s, item & HFB_Q_SLOT_MASK, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), c, sink, have, near);
     }
     if (rc == Q_DONE) {
       const int sl = (int)(item & HFB_Q_SLOT_MASK);
@@ -443,7 +446,7 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
   const SolverP P = solver_from_distance_request(*req);
   const ArenaView A = E->arena.view();
   std::unique_ptr<EpaWs> ws(new EpaWs());
-  // HFB_EMU_BVHQ="spec_after[,seed[,slots[,treelets[,GJK iterations per leaf item]]]]": (mesh, shape) pairs through the task-system walk
+  // HFB_EMU_BVHQ="spec_after[,seed[,slots[,treelets[,GJK iterations per leaf item[,items more before big subtrees]]]]]": (mesh, shape) pairs through the task-system walk
   const char* qenv = getenv("HFB_EMU_BVHQ");
   std::vector<size_t> qtodo;
   for (size_t i = 0; i < n; ++i) {
@@ -480,10 +483,10 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
     put_guess(go, i, o);
   }
   if (!qtodo.empty()) {
-    int spec_after = 0, slots = 6, ntl = 2, chunk = 3;
+    int spec_after = 0, slots = 6, ntl = 2, chunk = 3, big_after = 30;
     unsigned seed = 1;
-    sscanf(qenv, "%d,%u,%d,%d,%d", &spec_after, &seed, &slots, &ntl, &chunk);
-    host_bvhq_distance(A, qtodo, h1, tf1, h2, tf2, req, P, out, spec_after, seed, slots, ntl, chunk);
+    sscanf(qenv, "%d,%u,%d,%d,%d,%d", &spec_after, &seed, &slots, &ntl, &chunk, &big_after);
+    host_bvhq_distance(A, qtodo, h1, tf1, h2, tf2, req, P, out, spec_after, seed, slots, ntl, chunk, big_after);
   }
   return HFB_OK;
 }

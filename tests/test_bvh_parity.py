@@ -102,12 +102,13 @@ def test_bvh_emulated_device_code_vs_oracle():
     _check(sc, "emu", hm, tfm, hs, tfs)
 
 
-@pytest.mark.parametrize("knobs", ["0,1,6,2,3", "0,2,1,1,1", "-1,3,5,0,2", "40,4,9,3,100", "0,5,32,1,4", "3,6,3,8,1"])
+@pytest.mark.parametrize("knobs", ["0,1,6,2,3,30", "0,2,1,1,1,0", "-1,3,5,0,2,0", "40,4,9,3,100,10", "0,5,32,1,4,1000000", "3,6,3,8,1,5"])
 def test_bvh_task_system_walk_vs_oracle(knobs, monkeypatch):
     """hfb_bvhq.cuh (the walk of kernel k_bvhq) on the host: queries as state machines, their bounding-volume and
     leaf items executed one at a time in RANDOM order, subtrees speculated after `spec_after` items
     (knobs = spec_after, seed, slots in flight, treelet buffers, GJK iterations a leaf item runs before it parks its
-    solver state and queues itself again; EPA is an item of its own).  Bit-identical to the recursion, counters
+    solver state and queues itself again -- EPA is an item of its own --, items more before subtrees of up to 128
+    triangles are speculated instead of 32).  Bit-identical to the recursion, counters
     included."""
     monkeypatch.setenv("HFB_EMU_BVHQ", knobs)
     sc, nodes, hm, tfm, hs, tfs, _ = build_scene(False, True, n=1500, seed=int(knobs.split(",")[1]))
