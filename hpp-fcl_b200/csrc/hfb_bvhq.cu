@@ -139,9 +139,14 @@ __device__ __noinline__ void q_continue(const BvhqLaunch& L, const QBlock& B, co
 // distance.  LC = 1 (16 items per warp, no divergence between the lanes of a case) when the queue is long, LC = 4
 // (4 items per warp, a quarter of the dependent chain) when it is not.
 template <int LC>
-__device__ __forceinline__ void q_bv_group(const QSlot& s, const hfb_bvh_node* pair, unsigned gmask, unsigned gbase,
+__device__ __forceinline__ void q_bv_group(bool active, const QSlot& s, const hfb_bvh_node* pair, unsigned gbase,
                                            unsigned sub, double& d1, double& d2, int& f1, int& f2) {
+  // every lane of the warp comes here (votes and shuffles are warp-wide: a vote over part of a warp is executed
+  // once per distinct mask, which cost a fifth of the kernel's instructions in the first version); lanes of a group
+  // without an item are passengers
+  constexpr unsigned FULL = 0xffffffffu;
   const unsigned child = sub / LC, u = sub % LC;
+  // (passenger lanes run the same arithmetic on slot 0 and the root's children -- valid memory, values unused)
   const hfb_bvh_node& nd = pair[child];
   m3 R;
   v3 T;
@@ -155,14 +160,15 @@ __device__ __forceinline__ void q_bv_group(const QSlot& s, const hfb_bvh_node* p
   const unsigned cmask = (1u << LC) - 1u;
 #pragma unroll 1
   for (int t = 0; t < 16 / LC; ++t) {
-    if (!sub_found && rect_case(p, LC * t + (int)u)) kmine = LC * t + (int)u;
-    const unsigned b = __ballot_sync(gmask, kmine < 16) >> gbase;
+    if (active && !sub_found && rect_case(p, LC * t + (int)u)) kmine = LC * t + (int)u;
+    const unsigned b = __ballot_sync(FULL, kmine < 16) >> gbase;
     sub_found = ((b >> (LC * child)) & cmask) != 0u;
-    if ((b & cmask) != 0u && ((b >> LC) & cmask) != 0u) break;  // both children have their case (uniform over the group)
+    const bool group_done = !active || ((b & cmask) != 0u && ((b >> LC) & cmask) != 0u);  // both children have their case
+    if (__all_sync(FULL, group_done)) break;
   }
   int kwin = kmine;
 #pragma unroll
-  for (int off = 1; off < LC; off <<= 1) kwin = min(kwin, __shfl_xor_sync(gmask, kwin, off));
+  for (int off = 1; off < LC; off <<= 1) kwin = min(kwin, __shfl_xor_sync(FULL, kwin, off));
   double dist = 0;
   if (kwin < 16 ? (kmine == kwin) : (u == 0u)) {
     dist = rect_finish(p, kwin < 16 ? kwin : -1);
@@ -171,11 +177,11 @@ __device__ __forceinline__ void q_bv_group(const QSlot& s, const hfb_bvh_node* p
   }
   const unsigned src0 = gbase + (kwin < 16 ? (unsigned)(kwin % LC) : 0u);
   // every lane of a child asks its own child's winner; then the group leader collects both
-  const double dc = __shfl_sync(gmask, dist, (int)(src0 + LC * child));
-  d1 = __shfl_sync(gmask, dc, (int)gbase);
-  d2 = __shfl_sync(gmask, dc, (int)gbase + LC);
-  f1 = __shfl_sync(gmask, fc, (int)gbase);
-  f2 = __shfl_sync(gmask, fc, (int)gbase + LC);
+  const double dc = __shfl_sync(FULL, dist, (int)(src0 + LC * child));
+  d1 = __shfl_sync(FULL, dc, (int)gbase);
+  d2 = __shfl_sync(FULL, dc, (int)gbase + LC);
+  f1 = __shfl_sync(FULL, fc, (int)gbase);
+  f2 = __shfl_sync(FULL, fc, (int)gbase + LC);
 }
 
 __global__ void __launch_bounds__(128) k_bvhq_prep(const BvhqLaunch L) {
@@ -193,7 +199,8 @@ __global__ void __launch_bounds__(128) k_bvhq_prep(const BvhqLaunch L) {
   }
 }
 
-__global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 1) k_bvhq(const BvhqLaunch L) {
   extern __shared__ __align__(16) unsigned char q_smem[];
   QSlot* slots = reinterpret_cast<QSlot*>(q_smem);
   QSched* sc = reinterpret_cast<QSched*>(q_smem + HFB_Q_NSLOTS * sizeof(QSlot));
@@ -255,30 +262,29 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
   // one task of G-lane groups over `cnt` BV items starting at ring position `base`
   auto bv_task = [&](auto lc_tag, int cnt, int base) {
     constexpr int LC = decltype(lc_tag)::value, G = 2 * LC;
-    const unsigned g = lane / G, sub = lane % G;
-    if ((int)g < cnt) {
-      const unsigned gbase = g * G, gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1u)) << gbase;
-      volatile unsigned* q = sc->bvq;
-      const int pos = (base + (int)g) & (HFB_Q_QCAP - 1);
-      unsigned item = q_take(q, pos, sc);
-      __syncwarp(gmask);  // every lane of the group has read the item before its leader clears the entry
-      item = __shfl_sync(gmask, item, (int)gbase);
-      if (sub == 0u) q[pos] = 0u;
-      __threadfence_block();
-      if (item & HFB_Q_ITEM_VALID) {  // (uniform over the group)
-        item &= ~HFB_Q_ITEM_VALID;
-        const unsigned sl = item & HFB_Q_SLOT_MASK;
-        QSlot& s = slots[sl];
-        const hfb_bvh_node* nodes = static_cast<const hfb_bvh_node*>(s.ptr[0]);
-        double d1, d2;
-        int f1, f2;
-        q_bv_group<LC>(s, nodes + q_bv_base(s, item), gmask, gbase, sub, d1, d2, f1, f2);
-        bool have;
-        QStackEnt near;
-        if (sub == 0u && q_bv_store(s, item, stacks + (size_t)sl * L.stack_cap, tls, sink, d1, d2, f1, f2, have, near))
-          q_continue(L, B, c, sl, bv_total, leaf_total, have, near);
-      }
+    const unsigned g = lane / G, sub = lane % G, gbase = g * G;
+    const bool mine = (int)g < cnt;
+    volatile unsigned* q = sc->bvq;
+    const int pos = (base + (int)g) & (HFB_Q_QCAP - 1);
+    unsigned item = 0;
+    if (mine && sub == 0u) {
+      item = q_take(q, pos, sc);
+      q[pos] = 0u;
     }
+    item = __shfl_sync(0xffffffffu, item, (int)gbase);
+    __threadfence_block();
+    const bool active = mine && (item & HFB_Q_ITEM_VALID) != 0u;
+    item &= ~HFB_Q_ITEM_VALID;
+    const unsigned sl = active ? (item & HFB_Q_SLOT_MASK) : 0u;
+    QSlot& s = slots[sl];
+    const hfb_bvh_node* nodes = static_cast<const hfb_bvh_node*>(s.ptr[0]);
+    double d1, d2;
+    int f1, f2;
+    q_bv_group<LC>(active, s, nodes + (active ? q_bv_base(s, item) : 1), gbase, sub, d1, d2, f1, f2);
+    bool have;
+    QStackEnt near;
+    if (active && sub == 0u && q_bv_store(s, item, stacks + (size_t)sl * L.stack_cap, tls, sink, d1, d2, f1, f2, have, near))
+      q_continue(L, B, c, sl, bv_total, leaf_total, have, near);
     __syncwarp();
   };
   long long t_prev = clock64(), t_bv = 0, t_leaf = 0, t_epa = 0, n_cycles = 0, n_epa = 0;
@@ -301,7 +307,7 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
       __syncthreads();
       const int nb0 = vload(&sc->bn0);
       if (nb0 <= 0) break;  // (uniform: written by thread 0 before the barrier, by nobody after it)
-      const int ipw = (nb0 + (HFB_Q_THREADS / 32) - 1) / (HFB_Q_THREADS / 32);  // items per warp
+      const int ipw = (nb0 + (THREADS / 32) - 1) / (THREADS / 32);  // items per warp
       int base = 0, cnt;
       // lanes per child: the fewer items, the more lanes share one (shorter dependent chain per task)
       if (ipw > 8) {
@@ -324,7 +330,7 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
     // ---- leaf phase: the items queued before it started; each runs at most gjk_chunk GJK iterations ----
     {
       const int nl0 = vload(&sc->lsnap) - vload(&sc->lhead);
-      int want = (nl0 + (HFB_Q_THREADS / 32) - 1) / (HFB_Q_THREADS / 32);  // spread over the warps: a task is as long as its longest item
+      int want = (nl0 + (THREADS / 32) - 1) / (THREADS / 32);  // spread over the warps: a task is as long as its longest item
       want = want < 1 ? 1 : (want > 32 ? 32 : want);
       int base = 0, cnt;
       while ((cnt = pop(&sc->lhead, &sc->ltail, want, base, &sc->lsnap)) > 0) {
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(HFB_Q_THREADS, 1) k_bvhq(const BvhqLaunch L) {
     // ---- EPA phase (some cycles only) ----
     if (vload(&sc->do_epa)) {
       const int ne0 = vload(&sc->etail) - vload(&sc->ehead);
-      int want = (ne0 + (HFB_Q_THREADS / 32) - 1) / (HFB_Q_THREADS / 32);
+      int want = (ne0 + (THREADS / 32) - 1) / (THREADS / 32);
       want = want < 1 ? 1 : (want > 32 ? 32 : want);
       int base = 0, cnt;
       while ((cnt = pop(&sc->ehead, &sc->etail, want, base)) > 0) {
@@ -420,23 +426,26 @@ BvhqSizes bvhq_sizes(unsigned blocks, size_t n, int stack_cap) {
   z.prep = n * sizeof(QPrep);
   z.stacks = (size_t)blocks * HFB_Q_NSLOTS * (size_t)stack_cap * sizeof(QStackEnt);
   z.treelets = (size_t)blocks * HFB_Q_NTREELETS * sizeof(QTreelet);
-  z.ws = (size_t)blocks * HFB_Q_THREADS * sizeof(EpaWs);
+  z.ws = (size_t)blocks * HFB_Q_MAX_THREADS * sizeof(EpaWs);
   z.saves = (size_t)blocks * (HFB_Q_NSLOTS + HFB_Q_TREELET_MAX * HFB_Q_NTREELETS) * sizeof(QLeafSave);
   return z;
 }
 
 int bvhq_launch(const BvhqLaunch& L, unsigned blocks, size_t n, cudaStream_t s) {
-  static_assert(HFB_Q_NSLOTS <= HFB_Q_THREADS, "thread t fills slot t");
+  static_assert(HFB_Q_NSLOTS <= 256, "thread t fills slot t");
   static_assert(HFB_Q_NSLOTS + HFB_Q_TREELET_MAX * HFB_Q_NTREELETS <= HFB_Q_QCAP, "item rings hold every item that can exist");
   static_assert(sizeof(QSlot) % 16 == 8, "odd stride in 8-byte words: lanes reading one field of 32 slots spread over the banks");
   const size_t smem = bvhq_smem_bytes();
-  cudaError_t e = cudaFuncSetAttribute(k_bvhq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool wide = L.warps >= 16;
+  cudaError_t e = wide ? cudaFuncSetAttribute(k_bvhq<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                       : cudaFuncSetAttribute(k_bvhq<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   unsigned pb = (unsigned)((n + 127) / 128);
   if (pb > blocks * 16u) pb = blocks * 16u;
   if (pb == 0) pb = 1;
   k_bvhq_prep<<<pb, 128, 0, s>>>(L);
-  k_bvhq<<<blocks, HFB_Q_THREADS, smem, s>>>(L);
+  if (wide) k_bvhq<512><<<blocks, 512, smem, s>>>(L);
+  else k_bvhq<256><<<blocks, 256, smem, s>>>(L);
   return (int)cudaGetLastError();
 }
 

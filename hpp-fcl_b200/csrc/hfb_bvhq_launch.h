@@ -6,7 +6,7 @@
 
 namespace hfb {
 
-#define HFB_Q_THREADS 256    // 8 warps per block, one block per SM
+#define HFB_Q_MAX_THREADS 512  // the kernel comes with 8 warps per block (255 registers per thread) and with 16 (128)
 #define HFB_Q_NSLOTS 256     // queries in flight per block
 #define HFB_Q_NTREELETS 8    // speculated subtrees in flight per block
 #define HFB_Q_QCAP 2048      // ring size of each item queue (>= NSLOTS + HFB_Q_TREELET_MAX * NTREELETS)
@@ -36,6 +36,7 @@ struct BvhqLaunch {
   int spec_after;        // QCtx::spec_after / spec_big_after
   int spec_big_after;
   int bv_gens;           // generations of BV items a cycle runs before its leaf phase
+  int warps;             // 8 or 16 warps per block
   int gjk_chunk;         // GJK iterations a leaf item runs before it parks its state and queues itself again
 };
 

@@ -25,16 +25,11 @@
 #include <unordered_map>
 #include <vector>
 
-#include "hfb_arena.cuh"
-#include "hfb_bvh.cuh"
+#include "hfb_batch.cuh"
 #include "hfb_bvh_build.cuh"
 #include "hfb_bvhq_launch.h"
-#include "hfb_request.cuh"
+#include "hfb_gjkpass.h"
 
-using namespace hfb;
-
-#define CAPS_ALL (CAP_PRIM | CAP_CONVEX | CAP_TRI)
-#define CAPS_BVH (CAPS_ALL | CAP_INLINE_PRIM)
 // lanes per pair: pairs touching ConvexBase/TriangleP (GC: 1, 2, 4, 8, 16, 32) and the EPA kernel
 // (GE: 4, 8, 16, 32).  The defaults are the measured optimum on B200 (profiles/r01_summary.md: the
 // scalar part of a GJK iteration is repeated by every lane of the group, so small groups win until
@@ -51,104 +46,6 @@ using namespace hfb;
 #define HFB_BIN_CONVEX 45
 #define HFB_BIN_BVH 46   // one operand is a BVHModel<OBBRSS>
 #define HFB_BIN_BVH2 47  // both are
-
-// ---------------------------------------------------------------- EPA queue --
-struct EpaItem {
-  uint32_t pair;
-  int32_t rank;
-  int32_t hint0, hint1;
-  uint32_t gjk_iterations;
-  uint32_t _pad;
-  double w0[12];
-  double w1[12];
-};
-
-struct BatchArgs {
-  ArenaView A;
-  const uint32_t* h1;
-  const hfb_transform* tf1;
-  const uint32_t* h2;
-  const hfb_transform* tf2;
-  const double* guess_in;     // n x 3 or null
-  const int32_t* hint_in;     // n x 2 or null
-  double* guess_out;          // n x 3 or null
-  int32_t* hint_out;          // n x 2 or null
-  void* out;                  // hfb_distance_result* or hfb_contact*
-  EpaItem* queue;
-  unsigned* queue_count;      // [0] = items pushed this batch, [1] = running total
-  const unsigned* epa_lo;     // k_epa: device pointers to the [lo, hi) slice of the queue this launch owns
-  const unsigned* epa_hi;
-  unsigned* epa_head;         // k_epa: work counter of this launch (items are handed out one by one)
-  uint32_t* retry;            // queue indices of the items that outgrew the reduced-size EPA workspace
-  unsigned* retry_count;
-  unsigned sub_idx, sub_cnt;  // k_pairs: this launch takes the sub_idx-th of sub_cnt equal parts of [lo, hi)
-  unsigned* gjk_work;         // k_gjk_refill: work counter of this launch
-  unsigned iter_quorum;       // k_gjk_refill: lanes that must be mid-GJK for an iteration round to run
-  unsigned stage;             // lane-group k_pairs: TMA-stage the hulls' vertex blocks into shared memory
-  const uint32_t* index_list; // optional indirection: pair ids sorted by class (k_bin_scatter)
-  const unsigned* range_lo;   // device pointers to the [lo, hi) slice of index_list to process
-  const unsigned* range_hi;
-  SolverP P;
-  CollideP C;
-  BvhReq B;                   // traversal request fields (BVH pairs)
-  EpaWs* bvh_ws;              // one EPA workspace per thread of k_bvh (global memory)
-  unsigned long long* bvh_counters;  // [0] bv tests, [1] leaf tests (running totals)
-  unsigned* bvh_work;         // k_bvh: work counter of this launch
-  unsigned n;
-  // hfb_batch_collide_contacts (null / 0 otherwise): contacts[1..] of mesh pairs, extra_cap records per pair, and
-  // the number of contacts of every mesh pair
-  hfb_contact* extra;
-  uint32_t* counts;
-  unsigned extra_cap;
-};
-__device__ __forceinline__ BvhContactSink contact_sink(const BatchArgs& a, unsigned i) {
-  BvhContactSink s;
-  s.extra = a.extra ? a.extra + (size_t)i * a.extra_cap : nullptr;
-  s.cap = a.extra ? a.extra_cap : 0u;
-  s.count = a.counts ? a.counts + i : nullptr;
-  return s;
-}
-
-template <int CAPS>
-__device__ __forceinline__ PairIn load_pair_in(const BatchArgs& a, unsigned i) {
-  PairIn in;
-  in.s1 = load_shape<CAPS>(a.A, a.h1[i]);
-  in.s2 = load_shape<CAPS>(a.A, a.h2[i]);
-  in.tf1 = load_xf(a.tf1[i].R);
-  in.tf2 = load_xf(a.tf2[i].R);
-  in.cached_guess = mk(1, 0, 0);
-  in.hint0 = in.hint1 = 0;
-  if (a.P.initial_guess == HFB_GUESS_CACHED) {
-    if (a.guess_in) in.cached_guess = mk(a.guess_in[3 * i], a.guess_in[3 * i + 1], a.guess_in[3 * i + 2]);
-    if (a.hint_in) {
-      in.hint0 = a.hint_in[2 * i];
-      in.hint1 = a.hint_in[2 * i + 1];
-    }
-  }
-  return in;
-}
-
-template <int MODE>
-__device__ __forceinline__ void store_result(const BatchArgs& a, unsigned i, const PairOut& o) {
-  if (MODE == 0) write_distance(o, reinterpret_cast<hfb_distance_result*>(a.out) + i);
-  else write_contact(o, a.C, reinterpret_cast<hfb_contact*>(a.out) + i);
-  if (a.guess_out) {
-    a.guess_out[3 * i] = o.cached_guess.x;
-    a.guess_out[3 * i + 1] = o.cached_guess.y;
-    a.guess_out[3 * i + 2] = o.cached_guess.z;
-  }
-  if (a.hint_out) {
-    a.hint_out[2 * i] = o.hint0;
-    a.hint_out[2 * i + 1] = o.hint1;
-  }
-}
-
-__device__ __forceinline__ void st3(double* p, v3 v) {
-  p[0] = v.x;
-  p[1] = v.y;
-  p[2] = v.z;
-}
-__device__ __forceinline__ v3 ld3(const double* p) { return mk(p[0], p[1], p[2]); }
 
 // ------------------------------------------------------------------ phase 1 --
 // ---- TMA staging of ConvexBase vertex blocks (lane-group kernels) -------------------------------
@@ -309,24 +206,6 @@ __global__ void __launch_bounds__(128, MINB) k_pairs(const BatchArgs a) {
 // iterating lane does one GJK iteration) and a service round (finished lanes extract + store or queue
 // for EPA, then every free lane takes the next pair and sets it up).  Results do not depend on the
 // schedule: every pair runs gjk_begin / gjk_step* / pair_gjk_end exactly as in pair_phase1.
-__device__ __forceinline__ void push_epa_item(const BatchArgs& a, unsigned i, const GjkState& g) {
-  const unsigned slot = atomicAdd(a.queue_count, 1u);
-  atomicAdd(a.queue_count + 1, 1u);
-  EpaItem* it = a.queue + slot;
-  it->pair = i;
-  it->rank = g.rank;
-  it->hint0 = g.hint0;
-  it->hint1 = g.hint1;
-  it->gjk_iterations = g.iterations;
-  st3(it->w0 + 0, g.s0.w0);
-  st3(it->w1 + 0, g.s0.w1);
-  st3(it->w0 + 3, g.s1.w0);
-  st3(it->w1 + 3, g.s1.w1);
-  st3(it->w0 + 6, g.s2.w0);
-  st3(it->w1 + 6, g.s2.w1);
-  st3(it->w0 + 9, g.s3.w0);
-  st3(it->w1 + 9, g.s3.w1);
-}
 enum { GR_FETCH = 0, GR_ITER = 1, GR_FINISH = 2, GR_EXIT = 3 };
 template <int MODE>
 __global__ void __launch_bounds__(128, 1) k_gjk_refill(const BatchArgs a) {
@@ -808,6 +687,7 @@ struct Slot {
   cudaEvent_t ev_join = nullptr;
   DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, retry, bvh_ws, bvh_cnt, extra, ccnt, okeys, ohist, olist;
   DevBuf qprep, qstacks, qtl, qws, qsv;  // task-system mesh-shape walk (hfb_bvhq.cu)
+  DevBuf gstate, glist, gcnt;        // GJK passes (hfb_gjkpass.cu): solver state, two lists of running pairs, counts
   DevBuf pi, pj, cmp;                // object-table batches: pair indices of the chunk; compact results
 };
 
@@ -835,6 +715,11 @@ struct hfb_ctx {
   int bvh_quorum = HFB_BVH_INIT_QUORUM;  // HFB_BVH_QUORUM=1: a lane sets its next query up as soon as it is free
   int bvh_order = 0;  // HFB_BVH_ORDER=1: hand the (mesh, shape) queries out longest-expected first
   int bvhq = 1;        // HFB_BVHQ=0: mesh-shape distance queries through the lane-per-query kernel k_bvh instead of the task system k_bvhq
+  // HFB_GJK_PASSES="3,3,4": iterations of the first passes of the primitive-pair GJK (one more pass runs to
+  // convergence); "0": the single kernel k_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE>
+  int gjk_steps[8] = {3, 3, 4, 0, 0, 0, 0, 0};
+  int gjk_npass = 4;
+  int bvh_warps = 8;   // HFB_BVH_WARPS: 8 (255 registers per thread) or 16 (128) warps per block of k_bvhq
   int bvh_gens = 2;    // HFB_BVH_GENS: generations of BV items per cycle of k_bvhq
   int bvh_spec_big = 300;  // HFB_BVH_SPEC_BIG: items more before subtrees of up to 128 triangles are speculated
   int bvh_chunk = 6;   // HFB_BVH_GJK_CHUNK: GJK iterations a leaf item runs before it parks its state
@@ -1084,6 +969,20 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
           ctx->stats.kernel_launches++;
           if (cudaGetLastError() != cudaSuccess) return fail(ctx, HFB_ERR_CUDA, "k_gjk_refill launch failed");
           rc = HFB_OK;
+        } else if (ctx->gjk_npass > 0 && nsub == 1) {
+          CK(sl.gstate.reserve(gjk_pass_state_bytes(n)));
+          CK(sl.glist.reserve(2 * (size_t)n * sizeof(uint32_t)));
+          CK(sl.gcnt.reserve(8 * sizeof(unsigned)));
+          int nl = 0;
+          {
+            KTimer kt(ctx, s, 0);
+            if (gjk_passes_launch(ag, MODE, n, sl.gstate.p, static_cast<uint32_t*>(sl.glist.p),
+                                  static_cast<uint32_t*>(sl.glist.p) + n, static_cast<unsigned*>(sl.gcnt.p), ctx->gjk_steps,
+                                  ctx->gjk_npass, ctx->num_sms, s, &nl) != 0)
+              return fail(ctx, HFB_ERR_CUDA, "GJK pass launch failed");
+          }
+          ctx->stats.kernel_launches += (uint64_t)nl;
+          rc = HFB_OK;
         } else {
           rc = launch_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE, 1>(ctx, ag, sub_work, s);
         }
@@ -1164,6 +1063,7 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
         L.spec_after = ctx->bvh_spec;
         L.spec_big_after = ctx->bvh_spec < 0 ? 0x7fffffff : ctx->bvh_spec + ctx->bvh_spec_big;
         L.bv_gens = ctx->bvh_gens;
+        L.warps = ctx->bvh_warps;
         {
           KTimer kt(ctx, s, 5);
           if (bvhq_launch(L, qb, n, s) != 0) return fail(ctx, HFB_ERR_CUDA, "k_bvhq launch failed");
@@ -1486,6 +1386,18 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   if (const char* bq2 = getenv("HFB_BVHQ")) c->bvhq = atoi(bq2) != 0;
   if (const char* bs = getenv("HFB_BVH_SPEC")) c->bvh_spec = atoi(bs);
   if (const char* bc = getenv("HFB_BVH_GJK_CHUNK")) c->bvh_chunk = atoi(bc) > 0 ? atoi(bc) : 1;
+  if (const char* gp = getenv("HFB_GJK_PASSES")) {
+    c->gjk_npass = 0;
+    int k = 0;
+    for (const char* q = gp; *q && k < 7;) {
+      const int v = atoi(q);
+      if (v > 0) c->gjk_steps[k++] = v;
+      while (*q && *q != ',') ++q;
+      if (*q == ',') ++q;
+    }
+    c->gjk_npass = k > 0 ? k + 1 : 0;
+  }
+  if (const char* bw = getenv("HFB_BVH_WARPS")) c->bvh_warps = atoi(bw) >= 16 ? 16 : 8;
   if (const char* bg = getenv("HFB_BVH_GENS")) c->bvh_gens = atoi(bg) > 0 ? atoi(bg) : 1;
   if (const char* bb = getenv("HFB_BVH_SPEC_BIG")) c->bvh_spec_big = atoi(bb) >= 0 ? atoi(bb) : 0;
   if (const char* bq = getenv("HFB_BVH_QUORUM"))
@@ -1512,7 +1424,7 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   auto rel = [](Slot& s) {
-    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist, &s.qprep, &s.qstacks, &s.qtl, &s.qws, &s.qsv, &s.pi, &s.pj, &s.cmp};
+    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist, &s.qprep, &s.qstacks, &s.qtl, &s.qws, &s.qsv, &s.gstate, &s.glist, &s.gcnt, &s.pi, &s.pj, &s.cmp};
     for (DevBuf* b : bs) b->release();
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.epa_stream) cudaStreamDestroy(s.epa_stream);
