@@ -146,7 +146,7 @@ __device__ __forceinline__ void q_bv_group(bool active, const QSlot& s, const hf
   // without an item are passengers
   constexpr unsigned FULL = 0xffffffffu;
   const unsigned child = sub / LC, u = sub % LC;
-  // (passenger lanes run the same arithmetic on slot 0 and the root's children -- valid memory, values unused)
+  // (passenger lanes run the same arithmetic on the first group's item -- valid memory, values unused)
   const hfb_bvh_node& nd = pair[child];
   m3 R;
   v3 T;
@@ -275,12 +275,15 @@ __global__ void __launch_bounds__(THREADS, 1) k_bvhq(const BvhqLaunch L) {
     __threadfence_block();
     const bool active = mine && (item & HFB_Q_ITEM_VALID) != 0u;
     item &= ~HFB_Q_ITEM_VALID;
-    const unsigned sl = active ? (item & HFB_Q_SLOT_MASK) : 0u;
+    // passenger lanes (groups without an item) run the arithmetic of group 0's item: valid memory, results unused
+    const unsigned item0 = __shfl_sync(0xffffffffu, item, 0);  // (every lane takes part in the shuffle)
+    const unsigned item_x = active ? item : item0;
+    const unsigned sl = item_x & HFB_Q_SLOT_MASK;
     QSlot& s = slots[sl];
     const hfb_bvh_node* nodes = static_cast<const hfb_bvh_node*>(s.ptr[0]);
     double d1, d2;
     int f1, f2;
-    q_bv_group<LC>(active, s, nodes + (active ? q_bv_base(s, item) : 1), gbase, sub, d1, d2, f1, f2);
+    q_bv_group<LC>(active, s, nodes + q_bv_base(s, item_x), gbase, sub, d1, d2, f1, f2);
     bool have;
     QStackEnt near;
     if (active && sub == 0u && q_bv_store(s, item, stacks + (size_t)sl * L.stack_cap, tls, sink, d1, d2, f1, f2, have, near))

@@ -715,10 +715,10 @@ struct hfb_ctx {
   int bvh_quorum = HFB_BVH_INIT_QUORUM;  // HFB_BVH_QUORUM=1: a lane sets its next query up as soon as it is free
   int bvh_order = 0;  // HFB_BVH_ORDER=1: hand the (mesh, shape) queries out longest-expected first
   int bvhq = 1;        // HFB_BVHQ=0: mesh-shape distance queries through the lane-per-query kernel k_bvh instead of the task system k_bvhq
-  // HFB_GJK_PASSES="3,3,4": iterations of the first passes of the primitive-pair GJK (one more pass runs to
+  // HFB_GJK_PASSES="6" (default) or e.g. "3,3,4": iterations of the first passes of the primitive-pair GJK (one more pass runs to
   // convergence); "0": the single kernel k_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE>
-  int gjk_steps[8] = {3, 3, 4, 0, 0, 0, 0, 0};
-  int gjk_npass = 4;
+  int gjk_steps[8] = {6, 0, 0, 0, 0, 0, 0, 0};  // measured on config 2 (profiles/r02_summary.md): "6" 1.00 ms, "4,4" 1.05, "3,3,4" 1.12, single kernel 1.16
+  int gjk_npass = 2;
   int bvh_warps = 8;   // HFB_BVH_WARPS: 8 (255 registers per thread) or 16 (128) warps per block of k_bvhq
   int bvh_gens = 2;    // HFB_BVH_GENS: generations of BV items per cycle of k_bvhq
   int bvh_spec_big = 300;  // HFB_BVH_SPEC_BIG: items more before subtrees of up to 128 triangles are speculated

@@ -81,6 +81,34 @@ def config2_mixed_primitives(n_pairs, seed=0xFC1 + 2, pool=65536,
     return dict(shapes=shapes, h1=h1, tf1=tf1, h2=h2, tf2=tf2)
 
 
+def config2_scene(n_objects=100_000, n_pairs=1_000_000, seed=0xFC1 + 2, pool=65536,
+                  types=(P.GEOM_SPHERE, P.GEOM_CAPSULE, P.GEOM_BOX, P.GEOM_CYLINDER)):
+    """BASELINE config 2 as a SCENE: n_objects mixed primitives (sphere/capsule/box/cylinder, sizes as in
+    config2_mixed_primitives) with random poses in a cube, and the n_pairs object pairs a broadphase would hand to the
+    narrow phase -- every ordered pair (i, j) whose relative translation lies in [-3,3]^2 x [0,3], the box
+    test/accelerated_gjk.cpp:122 draws relative translations from, so the pairs have config 2's statistics (uniform
+    relative translation in that box, independent uniform rotations) while 1 M pairs share 100 k objects, as pairs do
+    in a real scene.  -> shapes (the pool), obj_h (pool index per object), obj_tf, first, second."""
+    from scipy.spatial import cKDTree
+    rng = np.random.default_rng(seed)
+    shapes = random_primitive_shapes(rng, pool, types)
+    obj_h = rng.integers(0, pool, n_objects).astype(np.uint32)
+    # expected pairs = N^2 / 2 * 6^3 / side^3; aim 8 % above n_pairs, then cut
+    side = (0.5 * n_objects * n_objects * 216.0 / (1.08 * n_pairs)) ** (1.0 / 3.0)
+    for _ in range(6):
+        tf = random_transforms(rng, n_objects, (0, 0, 0), (side, side, side))
+        pr = cKDTree(tf["T"]).query_pairs(3.0, p=np.inf, output_type="ndarray")
+        if len(pr) >= n_pairs:
+            break
+        side *= 0.96
+    assert len(pr) >= n_pairs, "scene too sparse"
+    pr = pr[rng.permutation(len(pr))[:n_pairs]]
+    dz = tf["T"][pr[:, 1], 2] - tf["T"][pr[:, 0], 2]
+    first = np.where(dz >= 0, pr[:, 0], pr[:, 1]).astype(np.uint32)
+    second = np.where(dz >= 0, pr[:, 1], pr[:, 0]).astype(np.uint32)
+    return dict(shapes=shapes, obj_h=obj_h, obj_tf=tf, first=first, second=second)
+
+
 def ellipsoid_hull(rng, nv=64, radii=None):
     """nv points on a random ellipsoid (all are hull vertices) + triangulated hull faces."""
     from scipy.spatial import ConvexHull
