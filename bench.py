@@ -7,10 +7,14 @@
 One "step" = one pass of the hot path (distance(): closed form / GJK / EPA + witness
 points) over one batch of synthetic pairs.  Workload at every N: BASELINE config 2,
 `--pairs` (default 1M) mixed primitive pairs PER GPU (weak scaling), distinct
-seeds per rank.  `value` = pairs/s with inputs resident in HBM; `e2e` = the same
-through the host C-ABI call (hfb_batch_distance) with pinned HOST buffers, H2D and
-D2H inside the timed region.  For N>1 geometry is broadcast once over NCCL and the
-per-rank result buffers are all-gathered inside the timed step.
+seeds per rank, as a scene: 100 k objects and the 1 M object pairs whose relative
+pose falls in config 2's box.  `value` = pairs/s with the expanded pair rows resident
+in HBM; `e2e` = the same pairs through the host C-ABI call of the scene form
+(hfb_batch_distance_objects) with pinned HOST buffers, H2D and D2H inside the timed
+region.  For N>1 geometry is broadcast once over NCCL and the per-rank result buffers
+are all-gathered inside the timed step.  At N=1 the line also carries, under
+`workloads`, BASELINE configs 3 and 4 at their own sizes (value / e2e / roofline /
+cpu_baseline each) and the convex-support kernel's roofline.
 """
 import argparse
 import json
@@ -49,7 +53,8 @@ def parse():
         a.variant = 2 if a.workload == "config3" else 0
     if a.workload == "config4" and a.pairs == 1_000_000:
         a.pairs = 100_000  # BASELINE config 4 is quoted on 100k capsules
-        a.cpu_sample = min(a.cpu_sample, 20_000)
+    if a.cpu_sample == 400_000:
+        a.cpu_sample = {"config2": 400_000, "config3": 100_000, "config4": 20_000}[a.workload]
     return a
 
 
@@ -92,29 +97,50 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-def make_workload(args, rank):
+def make_workload(args, rank, workload=None, pairs=None):
+    """-> (w, name): w holds the geometry to register and the batch in POOL indices: rows h1/tf1/h2/tf2 (every
+    workload) and, for config 2, the scene they were expanded from (obj_h, obj_tf, first, second)."""
     from hppfcl_b200 import workloads as W
-    if args.workload == "config2":
-        w = W.config2_mixed_primitives(args.pairs, seed=0xFC1 + 2 + 1000 * rank)
-        name = "config2: %d mixed primitive pairs (sphere/capsule/box/cylinder), GJK distance + witness points" % args.pairs
-    elif args.workload == "config3":
-        w = W.config3_convex_pairs(args.pairs, seed=0xFC1 + 3 + 1000 * rank)
-        name = "config3: %d ConvexBase(64) x ConvexBase(64) pairs, Nesterov-accelerated GJK distance + EPA penetration/contact points" % args.pairs
+    workload = workload or args.workload
+    pairs = pairs or args.pairs
+    if workload == "config2":
+        # BASELINE config 2 as a scene: 1 M pairs over pairs / 10 objects, relative poses with config 2's statistics
+        s = W.config2_scene(max(pairs // 10, 2000), pairs, seed=0xFC1 + 2 + 1000 * rank)
+        w = dict(shapes=s["shapes"], obj_h=s["obj_h"], obj_tf=s["obj_tf"], first=s["first"], second=s["second"],
+                 h1=s["obj_h"][s["first"]], h2=s["obj_h"][s["second"]],
+                 tf1=np.ascontiguousarray(s["obj_tf"][s["first"]]), tf2=np.ascontiguousarray(s["obj_tf"][s["second"]]))
+        name = ("config2: %d mixed primitive pairs (sphere/capsule/box/cylinder) of a %d-object scene, GJK distance + "
+                "witness points" % (pairs, len(s["obj_h"])))
+    elif workload == "config3":
+        w = W.config3_convex_pairs(pairs, seed=0xFC1 + 3 + 1000 * rank)
+        name = "config3: %d ConvexBase(64) x ConvexBase(64) pairs, %s GJK distance + EPA penetration/contact points" % (
+            pairs, {0: "default", 1: "Polyak-accelerated", 2: "Nesterov-accelerated"}[variant_of(args, workload)])
     else:
-        c = W.config4_mesh_vs_capsules(args.pairs, seed=0xFC1 + 4 + 1000 * rank)
+        c = W.config4_mesh_vs_capsules(pairs, seed=0xFC1 + 4 + 1000 * rank)
         # handle table: [mesh] + capsule pool; pair k = (mesh, capsule hc[k])
         w = dict(verts=c["verts"], tris=c["tris"], capsules=c["capsules"],
-                 h1=np.zeros(args.pairs, dtype=np.uint32), h2=(1 + c["hc"]).astype(np.uint32),
+                 h1=np.zeros(pairs, dtype=np.uint32), h2=(1 + c["hc"]).astype(np.uint32),
                  tf1=c["tf_mesh"], tf2=c["tf_caps"])
-        name = "config4: %d-triangle OBBRSS BVH mesh vs %d capsules, distance + nearest points" % (len(c["tris"]), args.pairs)
+        name = "config4: %d-triangle OBBRSS BVH mesh vs %d capsules, distance + nearest points" % (len(c["tris"]), pairs)
     return w, name
 
 
-def register(eng_or_orc, w, args, oracle=False):
+def variant_of(args, workload):
+    """GJK variant of a workload: --variant for the main one; BASELINE names Nesterov for config 3"""
+    if workload == args.workload and args.variant is not None:
+        return args.variant
+    return 2 if workload == "config3" else 0
+
+
+DEFAULT_PAIRS = {"config2": 1_000_000, "config3": 1_000_000, "config4": 100_000}
+CPU_SAMPLE = {"config2": 400_000, "config3": 100_000, "config4": 20_000}
+
+
+def register(eng_or_orc, w, workload, oracle=False):
     from hppfcl_b200 import _pod as P
-    if args.workload == "config2":
+    if workload == "config2":
         return eng_or_orc.register_shapes(w["shapes"])
-    if args.workload == "config4":
+    if workload == "config4":
         if oracle:  # the oracle builds the tree with its restatement of the reference builder
             bid, _ = eng_or_orc.register_bvh(w["verts"], w["tris"])
         else:       # the product builds it with its own host builder (hfb_bvh_build_obbrss)
@@ -133,23 +159,31 @@ def cpu_arm_kind():
     return "reference" if oracle_lib.ref_available() else "port"
 
 
-def cpu_reference_rate(args, w, n_sample, threads=0):
+_CAL = {}  # thread count of the CPU arm, calibrated once per (workload, variant) and process
+
+
+def cpu_reference_rate(args, w, workload, n_sample, threads=0):
     """The reference's CPU path on a bounded sample of the same workload: oracle/_ref (the reference's own
     sources compiled in place, see oracle/Makefile `ref`) when it was built, else the oracle's restatement."""
     from hppfcl_b200 import _pod as P
     from oracle import oracle_lib
-    orc = oracle_lib.RefScene(P) if oracle_lib.ref_available() else oracle_lib.OracleScene(P)
-    hs = register(orc, w, args, oracle=True)
+    key = (workload, variant_of(args, workload))
+    if "scene" not in _CAL.setdefault(key, {}):
+        orc = oracle_lib.RefScene(P) if oracle_lib.ref_available() else oracle_lib.OracleScene(P)
+        _CAL[key]["scene"] = (orc, register(orc, w, workload, oracle=True))
+    orc, hs = _CAL[key]["scene"]
     n = min(n_sample, len(w["h1"]))
     h1, h2 = hs[w["h1"][:n] % len(hs)], hs[w["h2"][:n] % len(hs)]
-    req = P.DistanceRequestPOD(gjk_variant=args.variant)
+    req = P.DistanceRequestPOD(gjk_variant=variant_of(args, workload))
     # "all the host threads it can use": torchrun exports OMP_NUM_THREADS=1 and the box exposes 128 logical
     # CPUs of which oversubscribing hurts (measured: 128 threads 6e6 pairs/s, 64 threads 3.4e7), so the
-    # thread count is calibrated on a short sample among {affinity, affinity/2, OpenMP's own default}
+    # thread count is calibrated ONCE on a short sample among {affinity, affinity/2, affinity/4, OpenMP's default}
+    if threads == 0:
+        threads = _CAL[key].get("threads", 0)
     if threads == 0:
         aff = len(os.sched_getaffinity(0))
         cands = sorted({c for c in (aff, max(1, aff // 2), max(1, aff // 4), oracle_lib.lib().oracle_max_threads()) if c >= 1})
-        m = min(n, 50000)
+        m = min(n, 50000 if workload != "config4" else 4000)
         best, best_t = 1, None
         for c in cands:
             orc.batch_distance(h1[:m], w["tf1"][:m], h2[:m], w["tf2"][:m], req, nthreads=c)  # spin the team up
@@ -158,13 +192,11 @@ def cpu_reference_rate(args, w, n_sample, threads=0):
             dtc = time.perf_counter() - t0
             if best_t is None or dtc < best_t:
                 best, best_t = c, dtc
-        threads = best
-    cores = threads
-    orc.batch_distance(h1[:20000], w["tf1"][:20000], h2[:20000], w["tf2"][:20000], req, nthreads=threads)
+        threads = _CAL[key]["threads"] = best
     t0 = time.perf_counter()
     orc.batch_distance(h1, w["tf1"][:n], h2, w["tf2"][:n], req, nthreads=threads)
     dt = time.perf_counter() - t0
-    return n / dt, cores, n
+    return n / dt, threads, n
 
 
 def run_reference(args):
@@ -176,7 +208,7 @@ def run_reference(args):
     n = args.cpu_sample
     cores = 1
     for it in range(args.warmup + args.steps):
-        r, cores, n = cpu_reference_rate(args, w, args.cpu_sample, threads=args.cpu_threads)
+        r, cores, n = cpu_reference_rate(args, w, args.workload, args.cpu_sample, threads=args.cpu_threads)
         if it >= args.warmup:
             rates.append(r)
     v = float(np.mean(rates))
@@ -184,7 +216,8 @@ def run_reference(args):
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "impl": "reference", "config": {"workload": name, "sample_pairs_per_step": n},
+            "impl": "reference", "config": {"workload": name, "sample_pairs_per_step": n,
+                                            "gjk_variant": variant_of(args, args.workload)},
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_arm_kind(),
                              "sample": "%d pairs of the same seeded workload per step, OpenMP static over pairs" % n},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -237,41 +270,50 @@ def support_kernel_roofline(eng_factory, peak, n_hulls=786432, nv=64, n_queries=
             "matches_numpy_argmax": bool(np.array_equal(got, want))}
 
 
-def run_ours(args):
+def _peak():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
+    return peak, src
+
+
+def _traffic(workload, n, variant):
+    """DRAM bytes of the dominant kernel per full-size launch, from the committed ncu capture of this command
+    (profiles/r02_dominant_kernel_traffic.json; a profiler run, not measured live)"""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_dominant_kernel_traffic.json")))
+        e = tj[workload]
+        if n == e.get("pairs") and variant == e.get("variant", variant):
+            return e["traffic"], e.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
+def measure(args, workload, rank, local, world, dist, steps, warmup, clocks=False):
+    """One workload on this rank's GPU: device-resident rate (`value`), end-to-end rate through the host C-ABI with
+    pinned host buffers (`e2e`), the per-kernel times of a SEPARATE profiled pass, roofline of the dominant kernel."""
     import torch
     import hppfcl_b200 as hf
     from hppfcl_b200 import _pod as P
 
-    rank, local, world = env_rank()
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
-    torch.cuda.set_device(local)
-    dist = None
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    hf.build_extension()
-    w, name = make_workload(args, rank)
-    n = args.pairs
-
-    # ---- geometry: rank 0's arena is broadcast once over NCCL, every rank registers it ------
-    if world > 1 and args.workload == "config2":
+    n = args.pairs if workload == args.workload else DEFAULT_PAIRS[workload]
+    variant = variant_of(args, workload)
+    w, name = make_workload(args, rank, workload, n)
+    if world > 1 and workload == "config2":  # geometry: rank 0's arena is broadcast once over NCCL
         g = torch.from_numpy(w["shapes"].view(np.uint8).copy()).cuda()
         dist.broadcast(g, 0)
         w["shapes"] = g.cpu().numpy().view(P.shape_dtype)
     eng = hf.Engine(local)
-    hs = register(eng, w, args)
+    hs = register(eng, w, workload)
     eng.commit()
     h1 = hs[w["h1"] % len(hs)].astype(np.uint32)
     h2 = hs[w["h2"] % len(hs)].astype(np.uint32)
-    req = P.DistanceRequestPOD(gjk_variant=args.variant)
-    st_gjk_pairs = n
-    if args.workload == "config2":  # pairs the GJK kernel actually processes (the rest are closed form)
-        t1, t2 = w["shapes"]["type"][w["h1"]], w["shapes"]["type"][w["h2"]]
-        sph, cap = P.GEOM_SPHERE, P.GEOM_CAPSULE
-        closed = (t1 == sph) | (t2 == sph) | ((t1 == cap) & (t2 == cap))
-        st_gjk_pairs = int((~closed).sum())
+    req = P.DistanceRequestPOD(gjk_variant=variant)
 
     def dev(a):
         return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
@@ -281,13 +323,11 @@ def run_ours(args):
     # two result buffers per rank: the all-gather of step k runs on NCCL's stream while step k+1 computes
     d_outs = [torch.empty(out_bytes, dtype=torch.uint8, device="cuda") for _ in range(2 if world > 1 else 1)]
     d_alls = [torch.empty(out_bytes * world, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
-    d_out = d_outs[0]
     gathers = [None, None]
     step_no = [0]
     stream = torch.cuda.current_stream().cuda_stream
-
     # config 4's working set (34 MB) fits the 126 MB L2: flush it between steps by overwriting 256 MB
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if args.workload == "config4" else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if workload == "config4" else None
 
     def step():
         if flush is not None:
@@ -312,174 +352,252 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(warmup, 3)):
         step()
     barrier()
     st0 = eng.stats()
-    eng.set_profiling(True)
-    eng.kernel_times(reset=True)
-    sampler = ClockSampler(local)
-    sampler.start()
+    sampler = ClockSampler(local) if clocks else None
+    if sampler:
+        sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         step()
     if world > 1:
         drain()  # the timed region ends when the last all-gather has landed
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
-    kt = eng.kernel_times(reset=True)
-    eng.set_profiling(False)
     st1 = eng.stats()
     if world > 1:
         t = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    value = world * n * args.steps / (ms * 1e-3)
+    value = world * n * steps / (ms * 1e-3)
 
-    # ---- e2e: host C-ABI call with pinned host buffers, H2D + D2H inside --------------------
+    # ---- per-kernel times: a separate pass with the event hooks on (they are off in the timed region) ----
+    prof_steps = 3
+    eng.set_profiling(True)
+    eng.kernel_times(reset=True)
+    sp0 = eng.stats()
+    for _ in range(prof_steps):
+        step()
+    barrier()
+    kt = eng.kernel_times(reset=True)
+    eng.set_profiling(False)
+    sp1 = eng.stats()
+
+    # ---- e2e: the host C-ABI call with pinned host buffers, H2D + D2H inside the timed region ----
     def pinned(a):
         t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
         return t, t.numpy().view(a.dtype).reshape(a.shape)
 
     keep = []
-    ph = []
-    for a in (h1, w["tf1"], h2, w["tf2"]):
-        t, v = pinned(a)
-        keep.append(t)
-        ph.append(v)
     t_out = torch.empty(out_bytes, dtype=torch.uint8).pin_memory()
     host_out = t_out.numpy().view(P.distance_result_dtype)
-    e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(2):
-        eng.batch_distance(ph[0], ph[1], ph[2], ph[3], req, out=host_out)
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        eng.batch_distance(ph[0], ph[1], ph[2], ph[3], req, out=host_out)
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = float(t.item())
-    e2e_value = world * n * e2e_steps / dt
-    clocks = sampler.summary()
+    if workload == "config2":
+        # the scene form (hfb_batch_distance_objects): object table + index pairs in, full result records out
+        ph = []
+        for a in (hs[w["obj_h"] % len(hs)].astype(np.uint32), w["obj_tf"], w["first"], w["second"]):
+            t, v = pinned(a)
+            keep.append(t)
+            ph.append(v)
+        h2d = int(ph[0].nbytes + ph[1].nbytes + ph[2].nbytes + ph[3].nbytes)
+        api = "hfb_batch_distance_objects (object table + index pairs; full 96-byte records back)"
+
+        def e2e_call():
+            eng.batch_distance_objects(ph[0], ph[1], ph[2], ph[3], req, out=host_out)
+    else:
+        ph = []
+        for a in (h1, w["tf1"], h2, w["tf2"]):
+            t, v = pinned(a)
+            keep.append(t)
+            ph.append(v)
+        h2d = int(n * 200)
+        api = "hfb_batch_distance (pair rows)"
+
+        def e2e_call():
+            eng.batch_distance(ph[0], ph[1], ph[2], ph[3], req, out=host_out)
+
+    def time_e2e(call, k):
+        for _ in range(2):
+            call()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(k):
+            call()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        return world * n * k / dt
+
+    e2e_steps = max(3, min(steps, 10))
+    e2e_value = time_e2e(e2e_call, e2e_steps)
     checksum = float(np.nansum(host_out["min_distance"][:: max(1, n // 4096)]))
-    # pair-type histogram, GJK-only subset and the FP64-issue view of the pair kernels
+    res = {"workload": workload, "name": name, "n": n, "variant": variant, "value": value, "ms_per_step": ms / steps,
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(out_bytes),
+                   "steps": e2e_steps, "checksum": checksum, "api": api},
+           "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
+           "watchdog_trips": int(st1["watchdog_trips"])}
+    if workload == "config2":
+        # secondary e2e figures: the pair-row form of round 1 (200 B per pair up), and distances only (8 B per pair down)
+        ph2 = []
+        for a in (h1, w["tf1"], h2, w["tf2"]):
+            t, v = pinned(a)
+            keep.append(t)
+            ph2.append(v)
+        res["e2e_pair_rows"] = {"value": time_e2e(lambda: eng.batch_distance(ph2[0], ph2[1], ph2[2], ph2[3], req, out=host_out), 3),
+                                "unit": UNIT, "h2d_bytes_per_step": int(n * 200), "d2h_bytes_per_step": int(out_bytes),
+                                "api": "hfb_batch_distance (pair rows)"}
+        t_min = torch.empty(n, dtype=torch.float64).pin_memory()
+        res["e2e_min_distance_only"] = {
+            "value": time_e2e(lambda: eng.batch_distance_objects(ph[0], ph[1], ph[2], ph[3], req, out=t_min.numpy(), min_only=True), 3),
+            "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(8 * n),
+            "api": "hfb_batch_distance_objects, min_distance_out (8 bytes per pair back)"}
+    if sampler:
+        res["clocks"] = sampler.summary()
+
+    # ---- workload statistics + roofline of the dominant kernel ----
     path = (host_out["status"] >> 16) & 0xff
     gjk_it = (host_out["iterations"] & 0xffff)[path == 0]
     epa_it = (host_out["iterations"] >> 16)[path == 0]
-    workload_stats = None
-    if args.workload in ("config2", "config3"):
-        workload_stats = {"gjk_routed_pairs": int((path == 0).sum()), "closed_form_pairs": int((path == 1).sum()),
-                          "gjk_iterations_mean": float(gjk_it.mean()) if len(gjk_it) else 0.0,
-                          "gjk_iterations_max": int(gjk_it.max()) if len(gjk_it) else 0,
-                          "epa_pairs": int((epa_it > 0).sum()),
-                          "epa_iterations_mean": float(epa_it[epa_it > 0].mean()) if (epa_it > 0).any() else 0.0}
-        if args.workload == "config2":
-            names = {P.GEOM_SPHERE: "sphere", P.GEOM_CAPSULE: "capsule", P.GEOM_BOX: "box", P.GEOM_CYLINDER: "cylinder"}
-            t1, t2 = w["shapes"]["type"][w["h1"]], w["shapes"]["type"][w["h2"]]
-            workload_stats["type_histogram"] = {"%s-%s" % (names[a], names[b]): int(((t1 == a) & (t2 == b)).sum())
-                                                for a in names for b in names}
+    peak, peak_src = _peak()
+    if workload in ("config2", "config3"):
+        ws = {"gjk_routed_pairs": int((path == 0).sum()), "closed_form_pairs": int((path == 1).sum()),
+              "gjk_iterations_mean": float(gjk_it.mean()) if len(gjk_it) else 0.0,
+              "gjk_iterations_max": int(gjk_it.max()) if len(gjk_it) else 0,
+              "epa_pairs": int((epa_it > 0).sum()),
+              "epa_iterations_mean": float(epa_it[epa_it > 0].mean()) if (epa_it > 0).any() else 0.0}
+        res["workload_stats"] = ws
+    if workload == "config2":
+        dom, dom_ms, dom_launches = "GJK passes k_gjk_first/_more/_end (primitive pairs)", kt["pairs_ms"], kt["pairs_launches"]
+        units = float((path == 0).sum())
+        bpp = BYTES_PER_PAIR
+    elif workload == "config4":
+        # 136 B per BV test (node header + RSS half), 96 B per leaf test (indices + vertices),
+        # 232 B per query (capsule record + poses + result); counts from the device counters
+        bv = (sp1["bv_tests"] - sp0["bv_tests"]) / prof_steps
+        lf = (sp1["leaf_tests"] - sp0["leaf_tests"]) / prof_steps
+        dom, dom_ms, dom_launches = "k_bvhq (+ k_bvhq_prep)", kt["bvh_ms"], max(1, kt["bvh_launches"] // 2)
+        units = float(n)
+        bpp = (136 * bv + 96 * lf) / n + 232
+        res["workload_stats"] = {"bv_tests_per_query": bv / n, "leaf_tests_per_query": lf / n}
+    else:
+        dom, dom_ms, dom_launches = "k_pairs<G,CAPS_ALL,0,PATH_BOTH>", kt["convex_ms"], kt["convex_launches"]
+        units = float(n)
+        bpp = 2 * 1536 + 192 + 8 + 96
+    k_ms = dom_ms / max(1, dom_launches)
+    achieved = bpp * units / (k_ms * 1e-3) / 1e9 if k_ms > 0 else None
+    traffic, tsrc = _traffic(workload, n, variant)
+    res["roofline"] = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                       "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": tsrc,
+                       "bytes_per_pair": bpp, "pairs_per_launch": units, "kernel_ms": k_ms, "peak_source": peak_src,
+                       "timing": "CUDA events around the kernel's launches on the launching stream, in a separate pass "
+                                 "of %d steps after the timed region" % prof_steps}
+    res["kernels"] = {"gjk_pairs_ms_per_step": kt["pairs_ms"] / prof_steps,
+                      "closed_pairs_ms_per_step": kt["closed_ms"] / prof_steps,
+                      "convex_pairs_ms_per_step": kt["convex_ms"] / prof_steps,
+                      "bin_sort_ms_per_step": kt["other_ms"] / prof_steps,
+                      "epa_ms_per_step": kt["epa_ms"] / prof_steps,
+                      "bvh_ms_per_step": kt["bvh_ms"] / prof_steps,
+                      "epa_pairs_per_step": (sp1["epa_pairs"] - sp0["epa_pairs"]) / prof_steps}
+    if workload in ("config2", "config3") and res["kernels"]["gjk_pairs_ms_per_step" if workload == "config2" else "convex_pairs_ms_per_step"] > 0:
+        # secondary view: FP64 issue.  ~450 flop per GJK iteration on primitives (SURVEY 8d estimate; the
+        # convex kernels add 6 flop per hull vertex and support call); nominal B200 FP64 (non-tensor) 37 TFLOP/s
+        it_flop = 450.0 if workload == "config2" else 450.0 + 2 * 64 * 6
+        gsec = res["kernels"]["gjk_pairs_ms_per_step" if workload == "config2" else "convex_pairs_ms_per_step"] * 1e-3
+        res["fp64_view"] = {"flop_per_gjk_iteration_estimate": it_flop,
+                            "achieved_tflops_estimate": res["workload_stats"]["gjk_routed_pairs"] * res["workload_stats"]["gjk_iterations_mean"] * it_flop / gsec / 1e12,
+                            "nominal_fp64_tflops": 37.0}
+    if workload == "config2":
+        names = {P.GEOM_SPHERE: "sphere", P.GEOM_CAPSULE: "capsule", P.GEOM_BOX: "box", P.GEOM_CYLINDER: "cylinder"}
+        t1, t2 = w["shapes"]["type"][w["h1"]], w["shapes"]["type"][w["h2"]]
+        res["workload_stats"]["type_histogram"] = {"%s-%s" % (names[a], names[b]): int(((t1 == a) & (t2 == b)).sum())
+                                                   for a in names for b in names}
+    res["l2"] = ("L2 flushed between steps (256 MB overwrite inside the timed region)" if flush is not None else
+                 "inputs+outputs per step (%d MB) exceed the 126 MB L2; no explicit flush" % ((n * (BYTES_PER_PAIR - 80)) >> 20))
+    del eng
+    return res
 
+
+def cpu_arm(args, workload, sample, threads):
+    """the CPU arm in a process of its own: this one has torch's OpenMP runtime loaded next to the system one, and
+    the reference's per-call heap traffic is sensitive to that (measured 4e6 vs 2e7)"""
+    n = args.pairs if workload == args.workload else DEFAULT_PAIRS[workload]
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload,
+           "--pairs", str(n), "--variant", str(variant_of(args, workload)), "--steps", "2", "--warmup", "1",
+           "--cpu-sample", str(sample), "--cpu-threads", str(threads)]
+    env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS",)}
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1200).stdout
+    for ln in out.splitlines():
+        if ln.startswith("{"):
+            d = json.loads(ln)
+            return d["value"], d["cpu_baseline"]["cores"], sample
+    raise RuntimeError("CPU arm produced no line")
+
+
+def cpu_baseline_block(args, workload):
+    sample = min(args.cpu_sample, CPU_SAMPLE[workload]) if workload != args.workload else args.cpu_sample
+    v, cores, ns = cpu_arm(args, workload, sample, 0)
+    v1, _, _ = cpu_arm(args, workload, max(1000, sample // 8), 1)
+    return {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_arm_kind(),
+            "sample": "%d pairs of the same workload, %s, OpenMP over pairs" % (
+                ns, "hpp-fcl's own sources (oracle/_ref)" if cpu_arm_kind() == "reference"
+                else "oracle (CPU restatement of hpp-fcl)"),
+            "single_thread_value": v1}
+
+
+def run_ours(args):
+    import torch
+    import hppfcl_b200 as hf
+
+    rank, local, world = env_rank()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hf.build_extension()
+    m = measure(args, args.workload, rank, local, world, dist, args.steps, max(args.warmup, 3), clocks=True)
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        peak_src = "MEASURED_PEAKS.json hbm_gbs (measured)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s (B200_PROFILING.md)"
-        # dominant kernel: the GJK-routed pair kernel for config 2, the lane-group kernel for config 3
-        if args.workload == "config2":
-            dom, dom_ms, dom_launches = "k_pairs<1,CAP_PRIM,0,PATH_GJKROUTE>", kt["pairs_ms"], kt["pairs_launches"]
-            units = float(st_gjk_pairs)
-            bpp = BYTES_PER_PAIR
-        elif args.workload == "config4":
-            # 136 B per BV test (node header + RSS half), 96 B per leaf test (indices + vertices),
-            # 232 B per query (capsule record + poses + result); counts from the device counters
-            bv = (st1["bv_tests"] - st0["bv_tests"]) / args.steps
-            lf = (st1["leaf_tests"] - st0["leaf_tests"]) / args.steps
-            dom, dom_ms, dom_launches = "k_bvh<0,BVK_SHAPE>", kt["bvh_ms"], max(1, kt["bvh_launches"] // 2)
-            units = float(n)
-            bpp = (136 * bv + 96 * lf) / n + 232
-        else:
-            dom, dom_ms, dom_launches = "k_pairs<G,CAPS_ALL,0,PATH_BOTH>", kt["convex_ms"], kt["convex_launches"]
-            units = float(n)
-            bpp = 2 * 1536 + 192 + 8 + 96
-        # DRAM bytes of the dominant kernel per full-size launch, from the committed ncu capture of this
-        # command (profiles/r01_dominant_kernel_traffic.json; a profiler run, not measured live)
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01_dominant_kernel_traffic.json")))
-            if n == (100_000 if args.workload == "config4" else 1_000_000) and args.variant == 0:  # capture was taken with DefaultGJK
-                traffic = tj[args.workload]["traffic"]
-        except Exception:
-            pass
-        pairs_ms = dom_ms / max(1, dom_launches)
-        achieved = bpp * units / (pairs_ms * 1e-3) / 1e9 if pairs_ms > 0 else None
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": name, "pairs_per_gpu": n, "gjk_variant": args.variant,
-                       "l2": ("L2 flushed between steps (256 MB overwrite inside the timed region)" if flush is not None else
-                              "inputs+outputs per step (%d MB) exceed the 126 MB L2; no explicit flush"
-                              % ((n * (BYTES_PER_PAIR - 80)) >> 20)),
+            "config": {"workload": m["name"], "pairs_per_gpu": m["n"], "gjk_variant": m["variant"], "l2": m["l2"],
                        "parallelism": "pairs sharded over %d rank(s); geometry broadcast once; results all-gathered per step (NCCL, overlapped with the next step's kernels)" % world},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(n * 200),
-                    "d2h_bytes_per_step": int(out_bytes), "steps": e2e_steps, "checksum": checksum},
-            "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": dom,
-                         "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                         "traffic_source": "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, profiles/launches_r01_final_*.csv" if traffic else None,
-                         "bytes_per_pair": bpp, "pairs_per_launch": units, "kernel_ms": pairs_ms,
-                         "peak_source": peak_src},
-            "kernels": {"gjk_pairs_ms_per_step": kt["pairs_ms"] / args.steps,
-                        "closed_pairs_ms_per_step": kt["closed_ms"] / args.steps,
-                        "convex_pairs_ms_per_step": kt["convex_ms"] / args.steps,
-                        "bin_sort_ms_per_step": kt["other_ms"] / args.steps,
-                        "epa_ms_per_step": kt["epa_ms"] / args.steps,
-                        "bvh_ms_per_step": kt["bvh_ms"] / args.steps,
-                        "epa_pairs_per_step": (st1["epa_pairs"] - st0["epa_pairs"]) / max(1, args.steps)},
+            "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "clocks": m.get("clocks"),
+            "roofline": m["roofline"], "kernels": m["kernels"],
         }
-        if workload_stats is not None:
-            line["workload_stats"] = workload_stats
-            # secondary view: FP64 issue.  ~450 flop per GJK iteration on primitives (SURVEY 8d estimate; the
-            # convex kernels add 6 flop per hull vertex and support call); nominal B200 FP64 (non-tensor) 37 TFLOP/s
-            it_flop = 450.0 if args.workload == "config2" else 450.0 + 2 * 64 * 6
-            gsec = (kt["pairs_ms"] if args.workload == "config2" else kt["convex_ms"]) / max(1, args.steps) * 1e-3
-            if gsec > 0:
-                line["fp64_view"] = {"flop_per_gjk_iteration_estimate": it_flop,
-                                     "achieved_tflops_estimate": workload_stats["gjk_routed_pairs"] * workload_stats["gjk_iterations_mean"] * it_flop / gsec / 1e12,
-                                     "nominal_fp64_tflops": 37.0}
+        for k in ("e2e_pair_rows", "e2e_min_distance_only", "workload_stats", "fp64_view", "watchdog_trips"):
+            if k in m:
+                line[k] = m[k]
         if world == 1:
+            line["cpu_baseline"] = cpu_baseline_block(args, args.workload)
+            # the other BASELINE configurations that fit one GPU, at their BASELINE sizes, each with its own
+            # value / e2e / roofline / cpu_baseline (fewer steps: they are reported, not the headline)
+            others = {}
+            for wl in ("config3", "config4"):
+                if wl == args.workload:
+                    continue
+                try:
+                    o = measure(args, wl, rank, local, world, dist, 5, 3)
+                    o["cpu_baseline"] = cpu_baseline_block(args, wl)
+                    o["config"] = {"workload": o.pop("name"), "pairs": o.pop("n"), "gjk_variant": o.pop("variant"), "l2": o.pop("l2")}
+                    o.pop("workload", None)
+                    o["metric"], o["unit"], o["steps"], o["warmup"] = METRIC, UNIT, 5, 3
+                    others[wl] = o
+                except Exception as ex:  # a failing side workload must not take the headline line with it
+                    others[wl] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+            line["workloads"] = others
+            peak, _ = _peak()
             line["convex_support_kernel"] = support_kernel_roofline(eng_factory=hf.Engine, peak=peak)
-            # the CPU arm runs in a process of its own: this one has torch's OpenMP runtime loaded next to the
-            # system one, and the reference's per-call heap traffic is sensitive to that (measured 4e6 vs 2e7)
-            def cpu_arm(sample, threads):
-                cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", args.workload,
-                       "--pairs", str(args.pairs), "--variant", str(args.variant), "--steps", "2", "--warmup", "1",
-                       "--cpu-sample", str(sample), "--cpu-threads", str(threads)]
-                env = {k: v for k, v in os.environ.items() if k not in ("OMP_NUM_THREADS",)}
-                out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=1200).stdout
-                for ln in out.splitlines():
-                    if ln.startswith("{"):
-                        d = json.loads(ln)
-                        return d["value"], d["cpu_baseline"]["cores"], sample
-                raise RuntimeError("CPU arm produced no line")
-            v, cores, ns = cpu_arm(args.cpu_sample, 0)
-            v1, _, ns1 = cpu_arm(min(args.cpu_sample, 100_000), 1)
-            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": cpu_arm_kind(),
-                                    "sample": "%d pairs of the same workload, %s, OpenMP over pairs" % (
-                                        ns, "hpp-fcl's own sources (oracle/_ref)" if cpu_arm_kind() == "reference"
-                                        else "oracle (CPU restatement of hpp-fcl)"),
-                                    "single_thread_value": v1}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
