@@ -9,7 +9,7 @@ raises if the extension or a GPU is missing.
 from . import _pod  # noqa: F401
 from ._pod import *  # noqa: F401,F403
 from .build import build_extension, library_path  # noqa: F401
-from .engine import Engine, EngineError, build_bvh_obbrss, load_library  # noqa: F401
+from .engine import Engine, EngineError, broadphase_pairs, build_bvh_obbrss, load_library  # noqa: F401
 from .api import (  # noqa: F401
     BVHModelOBBRSS, Box, Capsule, CollisionRequest, CollisionResult, Cone, Contact, Convex, Cylinder,
     DistanceRequest, DistanceResult, Ellipsoid, Sphere, Transform3f, TriangleP,

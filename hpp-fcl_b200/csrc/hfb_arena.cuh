@@ -42,6 +42,8 @@ struct ArenaView {
   const uint32_t* bvh_tris;
   const BvhDesc* bvh_desc;
   uint32_t nbvh;
+  // aabb_local of every shape handle (min xyz, max xyz; NaN for node types without one): the broadphase feed
+  const double* local_aabbs;
 };
 
 template <int CAPS>
@@ -253,6 +255,7 @@ struct HostArena {
     v.bvh_tris = bvh_tris.data();
     v.bvh_desc = bvh_desc.data();
     v.nbvh = (uint32_t)bvh_desc.size();
+    v.local_aabbs = nullptr;
     return v;
   }
 };

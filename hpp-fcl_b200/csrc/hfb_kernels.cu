@@ -29,6 +29,8 @@
 #include "hfb_bvh_build.cuh"
 #include "hfb_bvhq_launch.h"
 #include "hfb_gjkpass.h"
+#include "hfb_broadphase.cuh"
+#include "hfb_broadphase.h"
 
 // lanes per pair: pairs touching ConvexBase/TriangleP (GC: 1, 2, 4, 8, 16, 32) and the EPA kernel
 // (GE: 4, 8, 16, 32).  The defaults are the measured optimum on B200 (profiles/r01_summary.md: the
@@ -732,6 +734,8 @@ struct hfb_ctx {
   // per-kernel launch configuration (dynamic shared-memory opt-in, blocks per SM): function attributes are per
   // DEVICE, so the cache belongs to the context (one device), not to the process; guarded by `mu`
   std::unordered_map<const void*, int> func_cfg;
+  std::vector<double> local_aabbs;  // aabb_local per shape handle, as committed (host copy)
+  DevBuf bp_scratch;                // device broadphase
   std::string err;
   std::mutex mu;
 };
@@ -1441,6 +1445,7 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   c->sup_idx.release();
   c->sup_out.release();
   c->obj_h.release();
+  c->bp_scratch.release();
   c->obj_tf.release();
   c->cmp_flags.release();
   c->cmp_count.release();
@@ -1509,8 +1514,18 @@ int hfb_geom_commit(hfb_ctx* ctx) {
   const size_t bv = up(A.bvh_verts.size() * sizeof(double));
   const size_t bt = up(A.bvh_tris.size() * sizeof(uint32_t));
   const size_t bd = up(A.bvh_desc.size() * sizeof(BvhDesc));
+  const size_t bl = up(A.shapes.size() * 6 * sizeof(double));
+  ctx->local_aabbs.assign(A.shapes.size() * 6, NAN);
+  for (size_t i = 0; i < A.shapes.size(); ++i) {
+    LocalAabb b;
+    if (shape_local_aabb(A, A.shapes[i], b))
+      for (int k = 0; k < 3; ++k) {
+        ctx->local_aabbs[6 * i + k] = b.mn[k];
+        ctx->local_aabbs[6 * i + 3 + k] = b.mx[k];
+      }
+  }
   CK(cudaDeviceSynchronize());
-  CK(ctx->d_arena.reserve(bs + bc + bp + bn + bv + bt + bd + 256));
+  CK(ctx->d_arena.reserve(bs + bc + bp + bn + bv + bt + bd + bl + 256));
   unsigned char* base = static_cast<unsigned char*>(ctx->d_arena.p);
   if (!A.shapes.empty()) CK(cudaMemcpy(base, A.shapes.data(), A.shapes.size() * sizeof(hfb_shape), cudaMemcpyHostToDevice));
   if (!A.cvx.empty()) CK(cudaMemcpy(base + bs, A.cvx.data(), A.cvx.size() * sizeof(ConvexDesc), cudaMemcpyHostToDevice));
@@ -1532,6 +1547,12 @@ int hfb_geom_commit(hfb_ctx* ctx) {
   ctx->dview.bvh_tris = reinterpret_cast<const uint32_t*>(pb + bn + bv);
   ctx->dview.bvh_desc = reinterpret_cast<const BvhDesc*>(pb + bn + bv + bt);
   ctx->dview.nbvh = (uint32_t)A.bvh_desc.size();
+  {
+    unsigned char* pl = base + bs + bc + bp + bn + bv + bt + bd;
+    if (!ctx->local_aabbs.empty())
+      CK(cudaMemcpy(pl, ctx->local_aabbs.data(), ctx->local_aabbs.size() * sizeof(double), cudaMemcpyHostToDevice));
+    ctx->dview.local_aabbs = reinterpret_cast<const double*>(pl);
+  }
   ctx->committed = true;
   return HFB_OK;
 }
@@ -1848,6 +1869,57 @@ int hfb_batch_collide_objects_device(hfb_ctx* ctx, const hfb_object_pairs* d_sce
   }
   CollideP C{req->security_margin, req->q.collision_distance_threshold};
   return objects_device<1>(ctx, d_scene, req, solver_from_collision_request(*req), C, bvh_req_of_collision(req), d_out, d_go, stream);
+}
+
+
+// ---- broadphase feed (hfb_broadphase.cuh) -----------------------------------------------------------------
+int hfb_scene_aabbs(hfb_ctx* ctx, size_t n, const uint32_t* handles, const hfb_transform* tfs, double* aabbs) {
+  if (!ctx || (n && (!handles || !tfs || !aabbs))) return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (int rc = check_ready(ctx)) return rc;
+  if (int rc = check_handles(ctx, handles, n)) return rc;
+  for (size_t i = 0; i < n; ++i) {
+    const double* l = ctx->local_aabbs.data() + 6 * (size_t)handles[i];
+    if (!(l[0] <= l[3])) return fail(ctx, HFB_ERR_UNSUPPORTED_PAIR, "node type without a local AABB");
+    object_aabb(l, l + 3, tfs[i], aabbs + 6 * i);
+  }
+  return HFB_OK;
+}
+
+int hfb_broadphase_pairs(size_t n, const double* aabbs, uint32_t* first, uint32_t* second, size_t capacity,
+                         size_t* n_pairs) {
+  if ((n && !aabbs) || !n_pairs || (capacity && (!first || !second)) || n > 0xffffffffull) return HFB_ERR_INVALID_ARGUMENT;
+  *n_pairs = broadphase_pairs_host(n, aabbs, first, second, capacity);
+  return HFB_OK;
+}
+
+int hfb_scene_aabbs_device(hfb_ctx* ctx, size_t n, const uint32_t* d_handles, const hfb_transform* d_tfs, double* d_aabbs,
+                           void* stream) {
+  if (!ctx || (n && (!d_handles || !d_tfs || !d_aabbs)) || n > 0xffffffffull) return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  if (int rc = check_ready(ctx)) return rc;
+  CK(cudaSetDevice(ctx->device));
+  if (bp_scene_aabbs_launch(ctx->dview.local_aabbs, ctx->dview.nshapes, n, d_handles, d_tfs, d_aabbs,
+                            static_cast<cudaStream_t>(stream)) != 0)
+    return fail(ctx, HFB_ERR_CUDA, "k_scene_aabbs launch failed");
+  ctx->stats.kernel_launches += n ? 1 : 0;
+  return HFB_OK;
+}
+
+int hfb_broadphase_pairs_device(hfb_ctx* ctx, size_t n, const double* d_aabbs, size_t first_object, size_t num_first_objects,
+                                uint32_t* d_first, uint32_t* d_second, size_t capacity, uint32_t* d_n_pairs, void* stream) {
+  if (!ctx || (n && !d_aabbs) || !d_n_pairs || (capacity && (!d_first || !d_second)) || n > 0xffffffffull)
+    return HFB_ERR_INVALID_ARGUMENT;
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  CK(cudaSetDevice(ctx->device));
+  CK(ctx->bp_scratch.reserve(bp_scratch_bytes(n)));
+  int nl = 0;
+  if (bp_pairs_launch(n, d_aabbs, first_object, first_object + (num_first_objects < n ? num_first_objects : n), d_first, d_second,
+                      capacity, d_n_pairs, ctx->bp_scratch.p, ctx->num_sms,
+                      static_cast<cudaStream_t>(stream), &nl) != 0)
+    return fail(ctx, HFB_ERR_CUDA, "broadphase launch failed");
+  ctx->stats.kernel_launches += (uint64_t)nl;
+  return HFB_OK;
 }
 
 int hfb_batch_convex_support_device(hfb_ctx* ctx, size_t n, const uint32_t* ids, const double* dirs,

@@ -57,6 +57,10 @@ def load_library(path=None):
         getattr(L, name).argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
         getattr(L, name + "_device").argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp, vp]
     L.hfb_batch_collide_contacts.argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, u32, vp, vp, vp]
+    L.hfb_scene_aabbs.argtypes = [vp, sz, vp, vp, vp]
+    L.hfb_broadphase_pairs.argtypes = [sz, vp, vp, vp, sz, vp]
+    L.hfb_scene_aabbs_device.argtypes = [vp, sz, vp, vp, vp, vp]
+    L.hfb_broadphase_pairs_device.argtypes = [vp, sz, vp, sz, sz, vp, vp, sz, vp, vp]
     L.hfb_batch_distance_objects.argtypes = [vp, vp, vp, vp, vp, vp]
     L.hfb_batch_collide_objects.argtypes = [vp, vp, vp, vp, vp, vp]
     L.hfb_batch_distance_objects_device.argtypes = [vp, vp, vp, vp, vp, vp]
@@ -82,6 +86,26 @@ def build_bvh_obbrss(vertices, triangles):
     if rc != 0:
         raise EngineError("hfb_bvh_build_obbrss: %s" % _ERR.get(rc, rc))
     return nodes
+
+
+def broadphase_pairs(aabbs, capacity=None):
+    """every pair i < j of overlapping boxes (n x 6: min xyz, max xyz), in no particular order -> (first, second).
+    Host function of the library: needs neither a context nor a GPU."""
+    L = load_library()
+    bb = np.ascontiguousarray(aabbs, dtype=np.float64).reshape(-1, 6)
+    n = bb.shape[0]
+    cap = int(capacity) if capacity is not None else max(16 * n, 1024)
+    while True:
+        first = np.empty(cap, dtype=np.uint32)
+        second = np.empty(cap, dtype=np.uint32)
+        cnt = C.c_size_t(0)
+        rc = L.hfb_broadphase_pairs(n, _ptr(bb), _ptr(first), _ptr(second), cap, C.byref(cnt))
+        if rc != 0:
+            raise EngineError("hfb_broadphase_pairs: %s" % _ERR.get(rc, rc))
+        if cnt.value <= cap or capacity is not None:
+            k = min(cnt.value, cap)
+            return first[:k], second[:k]
+        cap = cnt.value
 
 
 def _ptr(a):
@@ -234,6 +258,25 @@ class Engine:
         self._check(self.L.hfb_batch_collide_contacts(self.h, n, _ptr(h1), _ptr(tf1), _ptr(h2), _ptr(tf2), C.byref(req),
                                                       _ptr(out), max_extra, _ptr(extra), _ptr(counts), None))
         return out, extra[:, :max_extra], counts
+
+    # -- broadphase feed ---------------------------------------------------------------------------------
+    def scene_aabbs(self, obj_handles, obj_tfs):
+        """CollisionObject::computeAABB of every object -> n x 6 (min xyz, max xyz); host function"""
+        oh = np.ascontiguousarray(obj_handles, dtype=np.uint32)
+        ot = np.ascontiguousarray(obj_tfs, dtype=P.transform_dtype)
+        bb = np.empty((oh.shape[0], 6), dtype=np.float64)
+        self._check(self.L.hfb_scene_aabbs(self.h, oh.shape[0], _ptr(oh), _ptr(ot), _ptr(bb)))
+        return bb
+
+    def scene_aabbs_device(self, n, d_handles, d_tfs, d_aabbs, stream=0):
+        self._check(self.L.hfb_scene_aabbs_device(self.h, n, _ptr(d_handles), _ptr(d_tfs), _ptr(d_aabbs), _ptr(stream)))
+
+    def broadphase_pairs_device(self, n, d_aabbs, d_first, d_second, capacity, d_n_pairs, stream=0, first_object=0,
+                                num_first_objects=None):
+        """pairs (i, j), i < j, with i in [first_object, first_object + num_first_objects) (default: all)"""
+        self._check(self.L.hfb_broadphase_pairs_device(self.h, n, _ptr(d_aabbs), first_object,
+                                                       n if num_first_objects is None else num_first_objects, _ptr(d_first),
+                                                       _ptr(d_second), capacity, _ptr(d_n_pairs), _ptr(stream)))
 
     # -- object-table queries: the batched form of the CollisionObject overloads (collision.h:58-61) -----
     @staticmethod

@@ -14,6 +14,7 @@
 // throw std::invalid_argument like HPP_FCL_THROW_PRETTY does (fwd.hh:63-72).
 #pragma once
 #include <array>
+#include <algorithm>
 #include <cmath>
 #include <limits>
 #include <memory>
@@ -277,16 +278,30 @@ class BVHModel<OBBRSS> : public CollisionGeometry {
 };
 typedef std::shared_ptr<CollisionGeometry> CollisionGeometryPtr_t;
 
+struct AABB {  // BV/AABB.h
+  Vec3f min_, max_;
+  bool overlap(const AABB& o) const {  // :111-118, closed intervals
+    for (int k = 0; k < 3; ++k)
+      if (min_[k] > o.max_[k] || max_[k] < o.min_[k]) return false;
+    return true;
+  }
+};
+
 class CollisionObject {  // collision_object.h
  public:
   CollisionObject(const CollisionGeometryPtr_t& g, const Transform3f& tf) : geom(g), t(tf) {}
   const CollisionGeometry* collisionGeometryPtr() const { return geom.get(); }
+  const CollisionGeometryPtr_t& collisionGeometry() const { return geom; }
   const Transform3f& getTransform() const { return t; }
   void setTransform(const Transform3f& tf) { t = tf; }
+  /// world-space box (:258-278); filled by the broadphase manager's setup() / update() for all its objects at once
+  const AABB& getAABB() const { return aabb; }
+  AABB& getAABB() { return aabb; }
 
  private:
   CollisionGeometryPtr_t geom;
   Transform3f t;
+  AABB aabb;
 };
 
 // -------------------------------------------------------------- requests ------
@@ -560,6 +575,142 @@ struct BatchNarrowPhase {
   std::vector<uint32_t> h1, h2;
   std::vector<hfb_transform> t1, t2;
 };
+
+// ------------------------------------------------------------ broadphase feed ----
+// The seam BASELINE config 5 goes through: a broadphase manager hands candidate pairs to a callback
+// (broadphase/broadphase_callbacks.h:54-75); the collecting callback (default_broadphase_callbacks.h:224-252,
+// src/broadphase/default_broadphase_callbacks.cpp:43-60... CollisionCallBackCollect) keeps them, and the batch then
+// goes to the narrow phase in ONE call (hfb_batch_collide_objects) instead of one collide() per callback.
+struct CollisionCallBackBase {
+  virtual void init() {}
+  virtual bool collide(CollisionObject* o1, CollisionObject* o2) = 0;  // true: stop the broadphase
+  virtual bool operator()(CollisionObject* o1, CollisionObject* o2) { return collide(o1, o2); }
+  virtual ~CollisionCallBackBase() {}
+};
+struct CollisionCallBackCollect : CollisionCallBackBase {
+  typedef std::pair<CollisionObject*, CollisionObject*> CollisionPair;
+  explicit CollisionCallBackCollect(size_t max_size_) : max_size(max_size_) { collision_pairs.resize(max_size); }
+  bool collide(CollisionObject* o1, CollisionObject* o2) override {
+    collision_pairs.push_back(std::make_pair(o1, o2));
+    return false;
+  }
+  size_t numCollisionPairs() const { return collision_pairs.size(); }
+  const std::vector<CollisionPair>& getCollisionPairs() const { return collision_pairs; }
+  void init() override { collision_pairs.clear(); }
+  bool exist(const CollisionPair& pair) const {
+    return std::find(collision_pairs.begin(), collision_pairs.end(), pair) != collision_pairs.end();
+  }
+  bool exist(CollisionObject* o1, CollisionObject* o2) const { return exist(std::make_pair(o1, o2)); }
+
+ protected:
+  std::vector<CollisionPair> collision_pairs;
+  size_t max_size;
+};
+
+// The manager: BroadPhaseCollisionManager's interface (broadphase/broadphase_collision_manager.h:56-134) for the
+// self-collision query of config 5.  setup() / update() compute every object's box (CollisionObject::computeAABB)
+// and collide(callback) reports every pair of objects with overlapping boxes exactly once -- the set the reference's
+// DynamicAABBTreeCollisionManager reports (broadphase_dynamic_AABB_tree.cpp:336-407,716-721); the order is each
+// manager's own.  No tree is kept: a uniform grid is rebuilt per query (hfb_broadphase.cuh), so update() costs a
+// re-computation of the boxes and nothing else.
+class DynamicAABBTreeCollisionManager {
+ public:
+  explicit DynamicAABBTreeCollisionManager(int device = 0) : C(Context::instance(device)) {}
+  void registerObjects(const std::vector<CollisionObject*>& other_objs) {
+    objs.insert(objs.end(), other_objs.begin(), other_objs.end());
+    stale = true;
+  }
+  void registerObject(CollisionObject* obj) {
+    objs.push_back(obj);
+    stale = true;
+  }
+  void unregisterObject(CollisionObject* obj) {
+    objs.erase(std::remove(objs.begin(), objs.end(), obj), objs.end());
+    stale = true;
+  }
+  void clear() {
+    objs.clear();
+    stale = true;
+  }
+  size_t size() const { return objs.size(); }
+  bool empty() const { return objs.empty(); }
+  void getObjects(std::vector<CollisionObject*>& out) const { out = objs; }
+  void setup() { refresh(); }
+  void update() { refresh(); }
+  /// self collision: callback(o1, o2) for every pair with overlapping boxes until it returns true
+  void collide(CollisionCallBackBase* callback) {
+    callback->init();
+    if (stale) refresh();
+    std::vector<uint32_t> first, second;
+    pairs(first, second);
+    for (size_t k = 0; k < first.size(); ++k)
+      if ((*callback)(objs[first[k]], objs[second[k]])) return;
+  }
+  /// the candidate pairs as object indices (what collide(callback) iterates over)
+  void pairs(std::vector<uint32_t>& first, std::vector<uint32_t>& second) {
+    if (stale) refresh();
+    size_t cap = std::max<size_t>(16 * objs.size(), 1024), cnt = 0;
+    for (;;) {
+      first.resize(cap);
+      second.resize(cap);
+      C.check(hfb_broadphase_pairs(objs.size(), boxes.data(), first.data(), second.data(), cap, &cnt));
+      if (cnt <= cap) break;
+      cap = cnt;
+    }
+    first.resize(cnt);
+    second.resize(cnt);
+  }
+  /// the object table of the scene in the form hfb_batch_*_objects takes
+  const std::vector<uint32_t>& handles() const { return hs; }
+  const std::vector<hfb_transform>& transforms() const { return tfs; }
+  Context& context() { return C; }
+
+ private:
+  void refresh() {
+    hs.resize(objs.size());
+    tfs.resize(objs.size());
+    for (size_t i = 0; i < objs.size(); ++i) {
+      hs[i] = C.handle(objs[i]->collisionGeometryPtr());
+      tfs[i] = objs[i]->getTransform().pod();
+    }
+    C.commit();
+    boxes.resize(6 * objs.size());
+    C.check(hfb_scene_aabbs(C.raw(), objs.size(), hs.data(), tfs.data(), boxes.data()));
+    for (size_t i = 0; i < objs.size(); ++i) {
+      AABB& b = objs[i]->getAABB();
+      b.min_ = Vec3f(boxes[6 * i], boxes[6 * i + 1], boxes[6 * i + 2]);
+      b.max_ = Vec3f(boxes[6 * i + 3], boxes[6 * i + 4], boxes[6 * i + 5]);
+    }
+    stale = false;
+  }
+  Context& C;
+  std::vector<CollisionObject*> objs;
+  std::vector<uint32_t> hs;
+  std::vector<hfb_transform> tfs;
+  std::vector<double> boxes;
+  bool stale = true;
+};
+
+/// config 5 in one call: the manager's candidate pairs through the batched narrow phase.  Returns, per candidate
+/// pair, the record hfb_batch_collide writes (first / second: object indices in registration order).
+inline std::vector<hfb_contact> collide(DynamicAABBTreeCollisionManager& manager, const CollisionRequest& request,
+                                        std::vector<uint32_t>& first, std::vector<uint32_t>& second) {
+  if (request.num_max_contacts == 0 && request.security_margin != -std::numeric_limits<FCL_REAL>::infinity())
+    throw std::invalid_argument("Invalid number of max contacts (current value is 0).");
+  manager.pairs(first, second);
+  hfb_collision_request q;
+  detail::fill(request, q);
+  hfb_object_pairs sc;
+  sc.n_objects = manager.handles().size();
+  sc.object_handles = manager.handles().data();
+  sc.object_tfs = manager.transforms().data();
+  sc.n_pairs = first.size();
+  sc.first = first.data();
+  sc.second = second.data();
+  std::vector<hfb_contact> out(first.size());
+  manager.context().check(hfb_batch_collide_objects(manager.context().raw(), &sc, &q, out.data(), nullptr, nullptr));
+  return out;
+}
 
 // ---------------------------------------------------------------- free functions
 // collide(): src/collision.cpp:69-130 (results accumulate; callers clear()).

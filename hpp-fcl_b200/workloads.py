@@ -206,3 +206,38 @@ def config4_mesh_vs_capsules(n_queries, seed=0xFC1 + 4, seg=100, ring=50, pool=4
     tf_mesh = random_transforms(rng, n_queries, (-0.2, -0.2, -0.2), (0.2, 0.2, 0.2))
     tf_caps = random_transforms(rng, n_queries, (-2, -2, -2), (2, 2, 2))
     return dict(verts=verts, tris=tris, capsules=caps, hc=hc, tf_mesh=tf_mesh, tf_caps=tf_caps)
+
+
+def config5_moving_boxes(n_objects=100_000, env_scale=None, seed=0xFC1 + 5, target_pairs=1_000_000):
+    """BASELINE config 5: n Box(5, 10, 20) objects (generateEnvironments, test/utility.cpp:392-404) with random poses in
+    [-env_scale, env_scale]^3; `step(k)` moves every object by a small random delta (generateRandomTransforms with
+    delta_trans / delta_rot, utility.cpp:249-...).  env_scale defaults to the value that gives about `target_pairs`
+    overlapping AABB pairs (the reference's 2000 for 1000 objects would give ~50 pairs for 100 k)."""
+    rng = np.random.default_rng(seed)
+    shapes = P.make_shapes([P.GEOM_BOX], [[2.5, 5.0, 10.0]])  # half sides of Box(5, 10, 20)
+    if env_scale is None:
+        # a rotated box's AABB has a mean side of about 16.5; two cubes of side s overlap with probability (2 s / L)^3
+        s = 16.5
+        env_scale = 0.5 * 2 * s / (2.0 * target_pairs / (float(n_objects) ** 2)) ** (1.0 / 3.0)
+    tf = random_transforms(rng, n_objects, (-env_scale,) * 3, (env_scale,) * 3)
+    obj_h = np.zeros(n_objects, dtype=np.uint32)
+
+    def step(k, delta_trans=1.0, delta_rot=0.05):
+        """poses of step k: the base poses moved by a seeded random delta"""
+        r = np.random.default_rng(seed + 7919 * (k + 1))
+        out = tf.copy()
+        out["T"] += delta_trans * (2 * r.random((n_objects, 3)) - 1)
+        # small rotation about a random axis, applied on the left: R' = dR * R
+        ax = r.standard_normal((n_objects, 3))
+        ax /= np.linalg.norm(ax, axis=1, keepdims=True)
+        ang = delta_rot * (2 * r.random(n_objects) - 1)
+        K = np.zeros((n_objects, 3, 3))
+        K[:, 0, 1], K[:, 0, 2], K[:, 1, 0] = -ax[:, 2], ax[:, 1], ax[:, 2]
+        K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -ax[:, 0], -ax[:, 1], ax[:, 0]
+        dR = np.eye(3)[None] + np.sin(ang)[:, None, None] * K + (1 - np.cos(ang))[:, None, None] * (K @ K)
+        R = out["R"].reshape(n_objects, 3, 3).transpose(0, 2, 1)  # stored column-major
+        Rn = dR @ R
+        out["R"] = Rn.transpose(0, 2, 1).reshape(out["R"].shape)
+        return out
+
+    return dict(shapes=shapes, obj_h=obj_h, obj_tf=tf, env_scale=env_scale, step=step)

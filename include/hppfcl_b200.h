@@ -336,6 +336,28 @@ int hfb_batch_collide_device(hfb_ctx* ctx, size_t n, const uint32_t* d_h1,
                              const hfb_collision_request* req, hfb_contact* d_out,
                              const hfb_guess_out* d_guess_out, void* cuda_stream);
 
+/* ---- broadphase feed: scene boxes and the overlapping pairs (BASELINE config 5) -------------------------
+ * hfb_scene_aabbs: CollisionObject::computeAABB (include/hpp/fcl/collision_object.h:258-278) of n objects over
+ * the aabb_local of their geometry (computeLocalAABB: src/shape/geometric_shapes.cpp:145-260, BVH_model.cpp);
+ * aabbs: 6 doubles per object (min xyz, max xyz).
+ * hfb_broadphase_pairs: every pair i < j whose boxes overlap (AABB::overlap, closed intervals: BV/AABB.h:111-118)
+ * -- the set of pairs BroadPhaseCollisionManager::collide(callback) hands to its callback
+ * (src/broadphase/broadphase_dynamic_AABB_tree.cpp:336-407,716-721), in no particular order; all of them are
+ * counted in *n_pairs, at most `capacity` stored.  The pair list is what hfb_batch_*_objects takes.
+ * The first two are HOST functions (no GPU work; hfb_broadphase_pairs needs no context at all); the _device forms
+ * take and leave everything on the device, asynchronous on `cuda_stream` (the count is a device word). */
+int hfb_scene_aabbs(hfb_ctx* ctx, size_t n_objects, const uint32_t* handles, const hfb_transform* tfs, double* aabbs);
+int hfb_broadphase_pairs(size_t n_objects, const double* aabbs, uint32_t* first, uint32_t* second, size_t capacity,
+                         size_t* n_pairs);
+int hfb_scene_aabbs_device(hfb_ctx* ctx, size_t n_objects, const uint32_t* d_handles, const hfb_transform* d_tfs,
+                           double* d_aabbs, void* cuda_stream);
+/* [first_object, first_object + num_first_objects): the pairs (i, j), i < j, whose SMALLER index i lies in this
+ * range (pass 0 and n_objects for all of them) -- the way a scene is cut over several GPUs: every rank holds all the
+ * boxes and reports the pairs of its own range of objects. */
+int hfb_broadphase_pairs_device(hfb_ctx* ctx, size_t n_objects, const double* d_aabbs, size_t first_object,
+                                size_t num_first_objects, uint32_t* d_first, uint32_t* d_second, size_t capacity,
+                                uint32_t* d_n_pairs, void* cuda_stream);
+
 /* ---- object-table batches: the batched form of the CollisionObject overloads --------------------------
  * collide(const CollisionObject* o1, const CollisionObject* o2, ...) / distance(...) (include/hpp/fcl/collision.h:
  * 58-61, distance.h:53-56) take their geometry and pose from the objects.  A scene here is a table of objects

@@ -4,6 +4,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <memory>
+#include <vector>
 
 #include "../../hpp-fcl_b200/host/hppfcl_b200.hpp"
 
@@ -165,6 +167,62 @@ int main() {
     CHECK(cres.getContact(0).b1 >= 0 && cres.getContact(0).b2 >= 0);
     cres.clear();
     CHECK(collide(&cube, Transform3f(), &cube, Transform3f(Vec3f(1.1, 0.2, 0.1)), creq, cres) == 0);
+  }
+  {  // the broadphase seam of BASELINE config 5 (compare test/broadphase_collision_1.cpp: a manager, a collecting
+     // callback, and the narrow phase over what it collected): boxes as generateEnvironments makes them
+    std::vector<std::unique_ptr<CollisionObject>> own;
+    std::vector<CollisionObject*> env;
+    CollisionGeometryPtr_t box(new Box(5, 10, 20));
+    unsigned long long rng = 12345;
+    auto rnd = [&]() {
+      rng = rng * 6364136223846793005ull + 1442695040888963407ull;
+      return (double)(rng >> 11) / 9007199254740992.0;
+    };
+    const int n = 3000;
+    for (int i = 0; i < n; ++i) {
+      const double a = 6.28 * rnd(), b = 6.28 * rnd();
+      Quatf q = makeQuat(std::cos(a / 2), std::sin(a / 2) * std::cos(b), std::sin(a / 2) * std::sin(b), 0);
+      own.emplace_back(new CollisionObject(box, Transform3f(q.toRotationMatrix(), Vec3f(120 * rnd(), 120 * rnd(), 120 * rnd()))));
+      env.push_back(own.back().get());
+    }
+    DynamicAABBTreeCollisionManager manager;
+    manager.registerObjects(env);
+    manager.setup();
+    CollisionCallBackCollect collect(0);
+    manager.collide(&collect);
+    // brute force over the boxes the manager computed: the same set of pairs
+    size_t brute = 0;
+    for (int i = 0; i < n; ++i)
+      for (int j = i + 1; j < n; ++j)
+        if (env[i]->getAABB().overlap(env[j]->getAABB())) {
+          ++brute;
+          CHECK(collect.exist(env[i], env[j]) || collect.exist(env[j], env[i]));
+        }
+    CHECK(brute == collect.numCollisionPairs() && brute > 1000);
+    // every box of a rotated Box(5, 10, 20) holds the object: |extent| >= the half diagonal's projection
+    CHECK(env[0]->getAABB().max_[0] - env[0]->getAABB().min_[0] >= 5 - 1e-9);
+    // the batch: the candidate pairs through the narrow phase in one call == collide() pair by pair
+    std::vector<uint32_t> first, second;
+    CollisionRequest creq;
+    std::vector<hfb_contact> recs = collide(manager, creq, first, second);
+    CHECK(recs.size() == brute);
+    size_t hits = 0, agree = 0;
+    for (size_t k = 0; k < recs.size(); k += 7) {
+      CollisionResult one;
+      const size_t nc = collide(env[first[k]], env[second[k]], creq, one);
+      agree += (nc > 0) == (recs[k].num_contacts > 0);
+      hits += nc > 0;
+      if (nc > 0) CHECK(one.getContact(0).penetration_depth == recs[k].distance);
+    }
+    CHECK(agree == (recs.size() + 6) / 7 && hits > 10);
+    // moving one object and update(): its box follows
+    env[5]->setTransform(Transform3f(Vec3f(-500, -500, -500)));
+    manager.update();
+    CHECK(env[5]->getAABB().min_[0] == -502.5 && env[5]->getAABB().max_[2] == -490);  // identity rotation: translate(aabb_local)
+    collect.init();
+    manager.collide(&collect);
+    for (size_t k = 0; k < collect.numCollisionPairs(); ++k)
+      CHECK(collect.getCollisionPairs()[k].first != env[5] && collect.getCollisionPairs()[k].second != env[5]);
   }
   std::printf(failures ? "HOST-API-FAILED %d\n" : "HOST-API-OK\n", failures);
   return failures ? 1 : 0;

@@ -1,0 +1,136 @@
+"""Broadphase feed of the batched narrow phase (BASELINE config 5): scene boxes and overlapping pairs.
+oracle/_ref cannot build hpp-fcl's broadphase managers (boost::function), so the checks are the definitions
+themselves: CollisionObject::computeAABB restated in numpy (include/hpp/fcl/collision_object.h:258-278) and the
+brute-force O(n^2) AABB::overlap test (BV/AABB.h:111-118) -- the set of pairs ANY of the reference's managers
+reports to its collision callback."""
+import numpy as np
+import pytest
+
+from tests.common import P, hf
+from hppfcl_b200 import workloads as W
+
+
+def brute_pairs(bb):
+    n = len(bb)
+    lo, hi = bb[:, None, :3], bb[:, None, 3:]
+    ov = np.all((lo <= hi.transpose(1, 0, 2)) & (hi >= lo.transpose(1, 0, 2)), axis=2)
+    i, j = np.nonzero(np.triu(ov, 1))
+    return set(zip(i.tolist(), j.tolist()))
+
+
+def ref_aabbs(local, tf):
+    """computeAABB: the box around the rotated local box (rotation not the identity)"""
+    R = tf["R"].reshape(-1, 3, 3).transpose(0, 2, 1)
+    lo = R * local[None, None, :3]
+    hi = R * local[None, None, 3:]
+    mn = np.minimum(lo, hi)
+    mx = np.maximum(lo, hi)
+    out = np.empty((len(tf), 6))
+    out[:, :3] = tf["T"] + ((mn[:, :, 0] + mn[:, :, 1]) + mn[:, :, 2])
+    out[:, 3:] = tf["T"] + ((mx[:, :, 0] + mx[:, :, 1]) + mx[:, :, 2])
+    return out
+
+
+@pytest.mark.parametrize("n,scale", [(1, 10.0), (2, 1.0), (400, 40.0), (3000, 120.0), (3000, 30.0)])
+def test_host_pair_finder_equals_brute_force(n, scale):
+    rng = np.random.default_rng(n)
+    c = scale * (2 * rng.random((n, 3)) - 1)
+    e = 0.5 + 8 * rng.random((n, 3)) * (rng.random((n, 1)) < 0.9) + 60 * (rng.random((n, 1)) < 0.02)  # a few huge boxes
+    bb = np.concatenate([c - e, c + e], axis=1)
+    if n > 2:
+        bb[1, :3] = bb[0, 3:]  # touching boxes overlap (closed intervals)
+    f, s = hf.broadphase_pairs(bb)
+    got = set(zip(f.tolist(), s.tolist()))
+    assert len(got) == len(f) and all(a < b for a, b in got)
+    assert got == brute_pairs(bb)
+    # a capacity below the count: everything counted, `capacity` stored
+    if len(f) > 5:
+        f2, s2 = hf.broadphase_pairs(bb, capacity=5)
+        assert len(f2) == 5 and set(zip(f2.tolist(), s2.tolist())) <= got
+
+
+def test_config5_scene_has_the_intended_density():
+    w = W.config5_moving_boxes(20_000, target_pairs=100_000)
+    local = np.array([-2.5, -5, -10, 2.5, 5, 10.0])
+    bb = ref_aabbs(local, w["obj_tf"])
+    f, s = hf.broadphase_pairs(bb)
+    assert 50_000 < len(f) < 200_000
+    moved = w["step"](3)
+    assert np.abs(moved["T"] - w["obj_tf"]["T"]).max() <= 1.0
+    R = moved["R"].reshape(-1, 3, 3)
+    assert np.allclose(R @ R.transpose(0, 2, 1), np.eye(3), atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_scene_aabbs_and_device_broadphase():
+    """scene boxes (host and device) against the numpy restatement; the device pair finder against the host one;
+    and the whole feed: boxes -> pairs -> hfb_batch_collide_objects_device against the pair-row call"""
+    import torch
+    rng = np.random.default_rng(5)
+    eng = hf.Engine(0)
+    prims = W.random_primitive_shapes(rng, 64, (P.GEOM_BOX, P.GEOM_SPHERE, P.GEOM_CAPSULE, P.GEOM_CYLINDER, P.GEOM_CONE,
+                                                P.GEOM_ELLIPSOID))
+    hp = eng.register_shapes(prims)
+    pts, _ = W.ellipsoid_hull(rng, 24)
+    hc = eng.register_shapes(P.make_shapes([P.GEOM_CONVEX], [[0, 0, 0]], data=[eng.register_convex(pts)]))
+    eng.commit()
+    n = 30_000
+    oh = np.concatenate([hp, hc])[rng.integers(0, 65, n)].astype(np.uint32)
+    tf = W.random_transforms(rng, n, (-14, -14, -14), (14, 14, 14))
+    tf[:50] = W.identity_transforms(50, T=tf["T"][:50])  # the isIdentity() branch of computeAABB
+    bb = eng.scene_aabbs(oh, tf)
+    # numpy restatement for the box objects
+    for h in hp[:8]:
+        m = (oh == h) & (np.arange(n) >= 50)
+        rec = prims[h - hp[0]]
+        if rec["type"] != P.GEOM_BOX or not m.any():
+            continue
+        local = np.concatenate([-rec["p"], rec["p"]])
+        assert np.array_equal(bb[m], ref_aabbs(local, tf[m]))
+    box0 = prims["type"][oh[:50] - hp[0]] == P.GEOM_BOX if (oh[:50] < hc[0]).all() else None
+
+    def dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
+
+    stream = torch.cuda.current_stream().cuda_stream
+    d_h, d_tf = dev(oh), dev(tf)
+    d_bb = torch.empty(n * 6, dtype=torch.float64, device="cuda")
+    eng.scene_aabbs_device(n, d_h.data_ptr(), d_tf.data_ptr(), d_bb.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_bb.cpu().numpy().reshape(n, 6), bb)
+    f, s = hf.broadphase_pairs(bb)
+    want = set(zip(f.tolist(), s.tolist()))
+    assert len(want) > 20_000
+    cap = len(want) + 1000
+    d_f = torch.empty(cap, dtype=torch.int32, device="cuda")
+    d_s = torch.empty(cap, dtype=torch.int32, device="cuda")
+    d_n = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for _ in range(2):  # twice: the scratch is reused
+        eng.broadphase_pairs_device(n, d_bb.data_ptr(), d_f.data_ptr(), d_s.data_ptr(), cap, d_n.data_ptr(), stream)
+    torch.cuda.synchronize()
+    k = int(d_n.item())
+    gf, gs = d_f[:k].cpu().numpy().astype(np.uint32), d_s[:k].cpu().numpy().astype(np.uint32)
+    assert k == len(want) and set(zip(gf.tolist(), gs.tolist())) == want
+    # the feed end to end: device pairs -> collide of the object pairs == collide of the expanded rows
+    d_out = torch.empty(k * P.contact_dtype.itemsize, dtype=torch.uint8, device="cuda")
+    eng.batch_collide_objects_device(n, d_h.data_ptr(), d_tf.data_ptr(), k, d_f.data_ptr(), d_s.data_ptr(), d_out.data_ptr(),
+                                     stream=stream)
+    torch.cuda.synchronize()
+    rows = eng.batch_collide(oh[gf], tf[gf], oh[gs], tf[gs])
+    assert d_out.cpu().numpy().tobytes() == rows.tobytes()
+    assert rows["num_contacts"].sum() > 1000
+    # a capacity below the count: everything counted
+    eng.broadphase_pairs_device(n, d_bb.data_ptr(), d_f.data_ptr(), d_s.data_ptr(), 100, d_n.data_ptr(), stream)
+    torch.cuda.synchronize()
+    assert int(d_n.item()) == len(want)
+    # the scene cut in three ranges of objects (three GPUs): the union of the ranges' pairs is the whole set
+    got = set()
+    for lo, cnt in ((0, 10_000), (10_000, 7_777), (17_777, n)):
+        eng.broadphase_pairs_device(n, d_bb.data_ptr(), d_f.data_ptr(), d_s.data_ptr(), cap, d_n.data_ptr(), stream,
+                                    first_object=lo, num_first_objects=cnt)
+        torch.cuda.synchronize()
+        kk = int(d_n.item())
+        part = set(zip(d_f[:kk].cpu().numpy().tolist(), d_s[:kk].cpu().numpy().tolist()))
+        assert len(part) == kk and all(lo <= a < lo + cnt for a, _ in part) and not (part & got)
+        got |= part
+    assert got == want
