@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1_000_000)
-    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4"])
+    ap.add_argument("--workload", default="config2", choices=["config2", "config3", "config4", "config5"])
     ap.add_argument("--variant", type=int, default=None,
                     help="0 DefaultGJK, 1 Polyak, 2 NesterovAcceleration (default: 0; config3: 2, as BASELINE names it)")
     ap.add_argument("--cpu-sample", type=int, default=400_000)
@@ -53,8 +53,10 @@ def parse():
         a.variant = 2 if a.workload == "config3" else 0
     if a.workload == "config4" and a.pairs == 1_000_000:
         a.pairs = 100_000  # BASELINE config 4 is quoted on 100k capsules
+    if a.workload == "config5" and a.pairs == 1_000_000:
+        a.pairs = 100_000  # BASELINE config 5: 100 k moving boxes (objects; about 1 M candidate pairs)
     if a.cpu_sample == 400_000:
-        a.cpu_sample = {"config2": 400_000, "config3": 100_000, "config4": 20_000}[a.workload]
+        a.cpu_sample = {"config2": 400_000, "config3": 100_000, "config4": 20_000, "config5": 200_000}[a.workload]
     return a
 
 
@@ -202,6 +204,16 @@ def cpu_reference_rate(args, w, workload, n_sample, threads=0):
 def run_reference(args):
     rank, local, world = env_rank()
     if rank != 0:
+        return
+    if args.workload == "config5":
+        c = cpu_config5(args, args.pairs, args.cpu_sample)
+        line = {"metric": METRIC, "value": c["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+                "config": {"workload": "config5: %d moving boxes, broadphase -> narrow phase (collide)" % args.pairs},
+                "cpu_baseline": c, "e2e": {"value": c["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
         return
     w, name = make_workload(args, 0)
     rates = []
@@ -524,6 +536,179 @@ def measure(args, workload, rank, local, world, dist, steps, warmup, clocks=Fals
     return res
 
 
+def measure_config5(args, rank, local, world, dist, steps, warmup, n_objects=None):
+    """BASELINE config 5: 100 k moving boxes, broadphase -> batched narrow phase (collide()).  One scene cut over the
+    ranks by ranges of objects (STRONG scaling): every rank holds all the poses, computes the boxes and the grid, sweeps
+    the candidate pairs of its own objects and runs collide() on them.  value: candidate pairs/s with the poses
+    resident in HBM (boxes + grid + sweep + narrow phase inside the timed region); e2e: hfb_scene_collide with pinned
+    host poses in, the colliding pairs' records out."""
+    import torch
+    import hppfcl_b200 as hf
+    from hppfcl_b200 import _pod as P, workloads as W
+    n = n_objects or args.pairs
+    w = W.config5_moving_boxes(n, seed=0xFC1 + 5)
+    eng = hf.Engine(local)
+    hb = eng.register_shapes(w["shapes"])
+    eng.commit()
+    oh = hb[w["obj_h"]].astype(np.uint32)
+    nposes = 4
+    poses = [w["step"](k) for k in range(nposes)]
+    lo, cnt = (n * rank) // world, (n * (rank + 1)) // world - (n * rank) // world
+    req = P.CollisionRequestPOD()
+
+    def dev(a):
+        return torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).cuda()
+
+    d_h = dev(oh)
+    d_tf = [dev(p) for p in poses]
+    d_bb = torch.empty(n * 6, dtype=torch.float64, device="cuda")
+    cap = int(2.0 * 1_000_000 * (n / 100_000.0) / world) + 65536
+    d_f = torch.empty(cap, dtype=torch.int32, device="cuda")
+    d_s = torch.empty(cap, dtype=torch.int32, device="cuda")
+    d_n = torch.zeros(1, dtype=torch.int32, device="cuda")
+    d_out = torch.empty(cap * P.contact_dtype.itemsize, dtype=torch.uint8, device="cuda")
+    h_n = torch.zeros(1, dtype=torch.int32).pin_memory()
+    stream = torch.cuda.current_stream().cuda_stream
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    acc = {"pairs": 0, "bp_ms": 0.0, "np_ms": 0.0}
+
+    def step(k, timed=False):
+        t = d_tf[k % nposes]
+        if timed:
+            ev[0].record()
+        eng.scene_aabbs_device(n, d_h.data_ptr(), t.data_ptr(), d_bb.data_ptr(), stream)
+        eng.broadphase_pairs_device(n, d_bb.data_ptr(), d_f.data_ptr(), d_s.data_ptr(), cap, d_n.data_ptr(), stream,
+                                    first_object=lo, num_first_objects=cnt)
+        h_n.copy_(d_n, non_blocking=True)
+        if timed:
+            ev[1].record()
+        torch.cuda.current_stream().synchronize()  # the narrow phase is launched for the number of candidates found
+        k_pairs = int(h_n.item())
+        assert k_pairs <= cap, "candidate buffer too small"
+        eng.batch_collide_objects_device(n, d_h.data_ptr(), t.data_ptr(), k_pairs, d_f.data_ptr(), d_s.data_ptr(),
+                                         d_out.data_ptr(), req, stream=stream)
+        if timed:
+            ev[2].record()
+            torch.cuda.synchronize()
+            acc["bp_ms"] += ev[0].elapsed_time(ev[1])
+            acc["np_ms"] += ev[1].elapsed_time(ev[2])
+        return k_pairs
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for k in range(max(warmup, 3)):
+        step(k)
+    barrier()
+    st0 = eng.stats()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for k in range(steps):
+        acc["pairs"] += step(k)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    st1 = eng.stats()
+    pairs = acc["pairs"]
+    if world > 1:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        t = torch.tensor([float(pairs)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        pairs = int(t.item())
+    value = pairs / (ms * 1e-3)
+    for k in range(3):  # broadphase / narrow phase split, separate pass
+        step(k, timed=True)
+    # ---- e2e: hfb_scene_collide, pinned host poses in, colliding pairs out ----
+    pin = [torch.from_numpy(np.ascontiguousarray(p).view(np.uint8).reshape(-1)).pin_memory() for p in poses]
+    hp = [t.numpy().view(P.transform_dtype) for t in pin]
+    ccap = 4 * n
+    bufs = tuple(torch.empty(ccap * it, dtype=torch.uint8).pin_memory().numpy().view(dt) for it, dt in
+                 ((4, np.uint32), (4, np.uint32), (P.contact_dtype.itemsize, P.contact_dtype)))
+    tot = {"cand": 0, "hit": 0}
+
+    def e2e_step(k):
+        f, s2, rec, ncand, nhit = eng.scene_collide(oh, hp[k % nposes], req, capacity=ccap, first_object=lo, num_first_objects=cnt,
+                                                    bufs=bufs)
+        tot["cand"] += ncand
+        tot["hit"] += nhit
+
+    for k in range(2):
+        e2e_step(k)
+    barrier()
+    tot["cand"] = tot["hit"] = 0
+    e2e_steps = max(3, min(steps, 10))
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        e2e_step(k)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    cand = tot["cand"]
+    if world > 1:
+        t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = float(t.item())
+        t = torch.tensor([float(cand)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        cand = int(t.item())
+    hits_per_step = tot["hit"] / e2e_steps
+    res = {"workload": "config5", "n": n,
+           "name": "config5: %d moving Box(5,10,20) objects, uniform-grid broadphase on the device -> batched narrow phase "
+                   "(collide), about %d candidate pairs per step" % (n, pairs // max(1, steps)),
+           "value": value, "ms_per_step": ms / steps, "candidate_pairs_per_step": pairs / steps,
+           "e2e": {"value": cand / dt, "unit": UNIT, "h2d_bytes_per_step": int(n * 100), "steps": e2e_steps,
+                   "d2h_bytes_per_step": int(hits_per_step * (8 + P.contact_dtype.itemsize) / max(1, world)),
+                   "api": "hfb_scene_collide (poses in; colliding pairs + contact records out)",
+                   "colliding_pairs_per_step": hits_per_step * (world if world > 1 else 1)},
+           "split_ms_per_step": {"boxes_grid_sweep": acc["bp_ms"] / 3, "narrow_phase": acc["np_ms"] / 3},
+           "gpu_launches": int(st1["kernel_launches"] - st0["kernel_launches"]),
+           "scaling": "strong", "env_scale": w["env_scale"]}
+    del eng
+    return res
+
+
+def cpu_config5(args, n_objects, sample_pairs):
+    """CPU arm of config 5 (rank 0): the product's HOST pair finder on one thread (hpp-fcl's managers do not build
+    here: boost::function) + the reference's collide() over a bounded sample of the candidates, all cores"""
+    import hppfcl_b200 as hf
+    from hppfcl_b200 import _pod as P, workloads as W
+    from oracle import oracle_lib
+    w = W.config5_moving_boxes(n_objects, seed=0xFC1 + 5)
+    tf = w["step"](0)
+    local = np.array([-2.5, -5, -10, 2.5, 5, 10.0])
+    R = tf["R"].reshape(-1, 3, 3).transpose(0, 2, 1)
+    mn = np.minimum(R * local[None, None, :3], R * local[None, None, 3:]).sum(axis=2)
+    mx = np.maximum(R * local[None, None, :3], R * local[None, None, 3:]).sum(axis=2)
+    bb = np.concatenate([tf["T"] + mn, tf["T"] + mx], axis=1)
+    t0 = time.perf_counter()
+    f, s2 = hf.broadphase_pairs(bb)
+    t_bp = time.perf_counter() - t0
+    orc = oracle_lib.RefScene(P) if oracle_lib.ref_available() else oracle_lib.OracleScene(P)
+    hb = orc.register_shapes(w["shapes"])
+    m = min(sample_pairs, len(f))
+    h1 = np.full(m, hb[0], dtype=np.uint32)
+    req = P.CollisionRequestPOD()
+    aff = len(os.sched_getaffinity(0))
+    best = None
+    for c in sorted({aff, max(1, aff // 2), max(1, aff // 4)}):
+        orc.batch_collide(h1[:20000], tf[f[:20000]], h1[:20000], tf[s2[:20000]], req, nthreads=c)
+        t0 = time.perf_counter()
+        orc.batch_collide(h1, tf[f[:m]], h1, tf[s2[:m]], req, nthreads=c)
+        dtc = time.perf_counter() - t0
+        if best is None or dtc < best[0]:
+            best = (dtc, c)
+    rate_np = m / best[0]
+    total = t_bp + len(f) / rate_np
+    return {"value": len(f) / total, "unit": UNIT, "cores": best[1], "kind": cpu_arm_kind(),
+            "sample": "host pair finder of the product on 1 thread over %d objects (%.1f ms, %d candidates) + the "
+                      "reference's collide() on %d of them, %d threads" % (n_objects, 1e3 * t_bp, len(f), m, best[1]),
+            "narrow_phase_only_value": rate_np, "broadphase_ms": 1e3 * t_bp}
+
+
 def cpu_arm(args, workload, sample, threads):
     """the CPU arm in a process of its own: this one has torch's OpenMP runtime loaded next to the system one, and
     the reference's per-call heap traffic is sensitive to that (measured 4e6 vs 2e7)"""
@@ -564,6 +749,24 @@ def run_ours(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     hf.build_extension()
+    if args.workload == "config5":
+        m = measure_config5(args, rank, local, world, dist, args.steps, max(args.warmup, 3))
+        if rank == 0:
+            line = {"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                    "warmup": max(args.warmup, 3), "ms_per_step": m["ms_per_step"], "higher_is_better": True,
+                    "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": {"workload": m["name"], "objects": m["n"], "env_scale": m["env_scale"],
+                               "l2": "poses, boxes, pairs and records of a step (%d MB) exceed the 126 MB L2" % (
+                                   (m["n"] * 150 + int(m["candidate_pairs_per_step"]) * 350) >> 20),
+                               "parallelism": "one scene over %d rank(s): every rank sweeps and collides the pairs of its own range of objects" % world},
+                    "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "split_ms_per_step": m["split_ms_per_step"],
+                    "candidate_pairs_per_step": m["candidate_pairs_per_step"]}
+            if world == 1:
+                line["cpu_baseline"] = cpu_config5(args, args.pairs, args.cpu_sample)
+            print(json.dumps(line))
+        if world > 1:
+            dist.destroy_process_group()
+        return
     m = measure(args, args.workload, rank, local, world, dist, args.steps, max(args.warmup, 3), clocks=True)
     if rank == 0:
         line = {
@@ -595,6 +798,14 @@ def run_ours(args):
                     others[wl] = o
                 except Exception as ex:  # a failing side workload must not take the headline line with it
                     others[wl] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+            try:  # config 5 at one GPU (its own line at 1 -> 8 GPUs: --workload config5)
+                o = measure_config5(args, rank, local, world, dist, 5, 3, n_objects=100_000)
+                o["cpu_baseline"] = cpu_config5(args, 100_000, 200_000)
+                o["config"] = {"workload": o.pop("name"), "objects": o.pop("n"), "env_scale": o.pop("env_scale")}
+                o["metric"], o["unit"], o["steps"], o["warmup"] = METRIC, UNIT, 5, 3
+                others["config5"] = o
+            except Exception as ex:
+                others["config5"] = {"error": "%s: %s" % (type(ex).__name__, ex)}
             line["workloads"] = others
             peak, _ = _peak()
             line["convex_support_kernel"] = support_kernel_roofline(eng_factory=hf.Engine, peak=peak)

@@ -148,6 +148,11 @@ class CompactContacts(C.Structure):
                 ("contacts", C.c_void_p), ("capacity", C.c_uint32)]
 
 
+class SceneContacts(C.Structure):
+    _fields_ = [("first", C.c_void_p), ("second", C.c_void_p), ("contacts", C.c_void_p), ("capacity", C.c_uint32),
+                ("n_colliding", C.c_void_p), ("n_candidates", C.c_void_p)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("pairs_processed", C.c_uint64),
                 ("epa_pairs", C.c_uint64), ("bv_tests", C.c_uint64), ("leaf_tests", C.c_uint64),

@@ -599,6 +599,26 @@ __global__ void __launch_bounds__(256) k_compact_contacts(const hfb_contact* r, 
   }
 }
 
+// hfb_scene_collide: the colliding pairs of a scene -- object indices and contact record -- appended in no
+// particular order
+__global__ void __launch_bounds__(256) k_compact_scene(const hfb_contact* r, const uint32_t* pf, const uint32_t* ps, unsigned n,
+                                                       unsigned* count, uint32_t* first, uint32_t* second, hfb_contact* recs,
+                                                       unsigned cap) {
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool hit = i < n && r[i].num_contacts > 0;
+  const unsigned m = __ballot_sync(0xffffffffu, hit);
+  if (!m) return;
+  const unsigned lane = threadIdx.x & 31u;
+  unsigned pos = 0;
+  if (lane == 0) pos = atomicAdd(count, (unsigned)__popc(m));
+  pos = __shfl_sync(0xffffffffu, pos, 0) + (unsigned)__popc(m & ((1u << lane) - 1u));
+  if (hit && pos < cap) {
+    first[pos] = pf[i];
+    second[pos] = ps[i];
+    recs[pos] = r[i];
+  }
+}
+
 // ----------------------------------------------------- convex support kernel --
 // One warp per query: streams the SoA vertex block (coalesced 256-B rows) and
 // reduces with shuffles.  Algorithmic traffic per query: 24*nv + 24 + 28 bytes.
@@ -736,6 +756,7 @@ struct hfb_ctx {
   std::unordered_map<const void*, int> func_cfg;
   std::vector<double> local_aabbs;  // aabb_local per shape handle, as committed (host copy)
   DevBuf bp_scratch;                // device broadphase
+  DevBuf sc_bb, sc_pf, sc_ps, sc_cnt, sc_out, sc_f, sc_s, sc_rec;  // hfb_scene_collide
   std::string err;
   std::mutex mu;
 };
@@ -1446,6 +1467,7 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   c->sup_out.release();
   c->obj_h.release();
   c->bp_scratch.release();
+  for (DevBuf* b : {&c->sc_bb, &c->sc_pf, &c->sc_ps, &c->sc_cnt, &c->sc_out, &c->sc_f, &c->sc_s, &c->sc_rec}) b->release();
   c->obj_tf.release();
   c->cmp_flags.release();
   c->cmp_count.release();
@@ -1919,6 +1941,95 @@ int hfb_broadphase_pairs_device(hfb_ctx* ctx, size_t n, const double* d_aabbs, s
                       static_cast<cudaStream_t>(stream), &nl) != 0)
     return fail(ctx, HFB_ERR_CUDA, "broadphase launch failed");
   ctx->stats.kernel_launches += (uint64_t)nl;
+  return HFB_OK;
+}
+
+// Broadphase + narrow phase of a scene in one call, everything on the device between the upload of the poses and the
+// download of the colliding pairs: the batched form of BroadPhaseCollisionManager::collide(callback) with the default
+// collision callback (broadphase/default_broadphase_callbacks.h:69-130: collide() of every candidate pair, contacts
+// collected).
+int hfb_scene_collide(hfb_ctx* ctx, size_t n, const uint32_t* handles, const hfb_transform* tfs, size_t first_object,
+                      size_t num_first_objects, const hfb_collision_request* req, const hfb_scene_contacts* out) {
+  if (!ctx || !req || !out || (n && (!handles || !tfs))) return HFB_ERR_INVALID_ARGUMENT;
+  if (out->capacity && (!out->first || !out->second || !out->contacts)) return HFB_ERR_INVALID_ARGUMENT;
+  std::unique_lock<std::mutex> lk(ctx->mu);
+  bool minus_inf;
+  if (int rc = collide_prelude(ctx, req, &minus_inf)) return rc;
+  if (int rc = check_ready(ctx)) return rc;
+  if (n > 0xffffffffull) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "scene too large");
+  if (int rc = check_handles(ctx, handles, n)) return rc;
+  if (out->n_candidates) *out->n_candidates = 0;
+  if (out->n_colliding) *out->n_colliding = 0;
+  if (n < 2) return HFB_OK;
+  CK(cudaSetDevice(ctx->device));
+  cudaStream_t s = ctx->slots[0].stream;
+  CK(ctx->obj_h.reserve(n * 4 + 4));
+  CK(ctx->obj_tf.reserve(n * sizeof(hfb_transform) + 8));
+  CK(ctx->sc_bb.reserve(n * 48));
+  CK(ctx->sc_cnt.reserve(16));
+  CK(ctx->bp_scratch.reserve(bp_scratch_bytes(n)));
+  CK(cudaMemcpyAsync(ctx->obj_h.p, handles, n * 4, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ctx->obj_tf.p, tfs, n * sizeof(hfb_transform), cudaMemcpyHostToDevice, s));
+  const uint32_t* d_h = static_cast<const uint32_t*>(ctx->obj_h.p);
+  const hfb_transform* d_tf = static_cast<const hfb_transform*>(ctx->obj_tf.p);
+  double* d_bb = static_cast<double*>(ctx->sc_bb.p);
+  unsigned* d_cnt = static_cast<unsigned*>(ctx->sc_cnt.p);
+  if (bp_scene_aabbs_launch(ctx->dview.local_aabbs, ctx->dview.nshapes, n, d_h, d_tf, d_bb, s) != 0)
+    return fail(ctx, HFB_ERR_CUDA, "k_scene_aabbs launch failed");
+  ctx->stats.kernel_launches++;
+  // the number of candidate pairs is not known in advance: a first sweep counts, a second one (if the buffers were too
+  // small) stores
+  const size_t i_hi = first_object + (num_first_objects < n ? num_first_objects : n);
+  size_t cap = ctx->sc_pf.cap / 4;
+  unsigned cand = 0;
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    int nl = 0;
+    if (bp_pairs_launch(n, d_bb, first_object, i_hi, static_cast<uint32_t*>(ctx->sc_pf.p), static_cast<uint32_t*>(ctx->sc_ps.p),
+                        cap, d_cnt, ctx->bp_scratch.p, ctx->num_sms, s, &nl) != 0)
+      return fail(ctx, HFB_ERR_CUDA, "broadphase launch failed");
+    ctx->stats.kernel_launches += (uint64_t)nl;
+    CK(cudaMemcpyAsync(&cand, d_cnt, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (cand <= cap) break;
+    cap = (size_t)cand + cand / 8 + 1024;
+    CK(ctx->sc_pf.reserve(cap * 4));
+    CK(ctx->sc_ps.reserve(cap * 4));
+    cap = ctx->sc_pf.cap / 4 < ctx->sc_ps.cap / 4 ? ctx->sc_pf.cap / 4 : ctx->sc_ps.cap / 4;
+  }
+  if (out->n_candidates) *out->n_candidates = cand;
+  if (cand == 0 || minus_inf) return HFB_OK;  // collision.cpp:73-76: no contacts under security_margin == -inf
+  CK(ctx->sc_out.reserve((size_t)cand * sizeof(hfb_contact)));
+  CK(ctx->sc_f.reserve((size_t)out->capacity * 4 + 4));
+  CK(ctx->sc_s.reserve((size_t)out->capacity * 4 + 4));
+  CK(ctx->sc_rec.reserve((size_t)out->capacity * sizeof(hfb_contact) + 8));
+  hfb_object_pairs sc;
+  sc.n_objects = n;
+  sc.object_handles = d_h;
+  sc.object_tfs = d_tf;
+  sc.n_pairs = cand;
+  sc.first = static_cast<const uint32_t*>(ctx->sc_pf.p);
+  sc.second = static_cast<const uint32_t*>(ctx->sc_ps.p);
+  CollideP C{req->security_margin, req->q.collision_distance_threshold};
+  if (int rc = objects_device<1>(ctx, &sc, req, solver_from_collision_request(*req), C, bvh_req_of_collision(req), ctx->sc_out.p,
+                                 nullptr, s))
+    return rc;
+  CK(cudaMemsetAsync(d_cnt + 1, 0, sizeof(unsigned), s));
+  k_compact_scene<<<(cand + 255) / 256, 256, 0, s>>>(static_cast<const hfb_contact*>(ctx->sc_out.p), sc.first, sc.second, cand,
+                                                      d_cnt + 1, static_cast<uint32_t*>(ctx->sc_f.p),
+                                                      static_cast<uint32_t*>(ctx->sc_s.p), static_cast<hfb_contact*>(ctx->sc_rec.p),
+                                                      out->capacity);
+  ctx->stats.kernel_launches++;
+  unsigned hits = 0;
+  CK(cudaMemcpyAsync(&hits, d_cnt + 1, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (out->n_colliding) *out->n_colliding = hits;
+  const unsigned kept = hits < out->capacity ? hits : out->capacity;
+  if (kept) {
+    CK(cudaMemcpyAsync(out->first, ctx->sc_f.p, (size_t)kept * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->second, ctx->sc_s.p, (size_t)kept * 4, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(out->contacts, ctx->sc_rec.p, (size_t)kept * sizeof(hfb_contact), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
   return HFB_OK;
 }
 

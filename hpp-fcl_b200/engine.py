@@ -61,6 +61,7 @@ def load_library(path=None):
     L.hfb_broadphase_pairs.argtypes = [sz, vp, vp, vp, sz, vp]
     L.hfb_scene_aabbs_device.argtypes = [vp, sz, vp, vp, vp, vp]
     L.hfb_broadphase_pairs_device.argtypes = [vp, sz, vp, sz, sz, vp, vp, sz, vp, vp]
+    L.hfb_scene_collide.argtypes = [vp, sz, vp, vp, sz, sz, vp, vp]
     L.hfb_batch_distance_objects.argtypes = [vp, vp, vp, vp, vp, vp]
     L.hfb_batch_collide_objects.argtypes = [vp, vp, vp, vp, vp, vp]
     L.hfb_batch_distance_objects_device.argtypes = [vp, vp, vp, vp, vp, vp]
@@ -277,6 +278,24 @@ class Engine:
         self._check(self.L.hfb_broadphase_pairs_device(self.h, n, _ptr(d_aabbs), first_object,
                                                        n if num_first_objects is None else num_first_objects, _ptr(d_first),
                                                        _ptr(d_second), capacity, _ptr(d_n_pairs), _ptr(stream)))
+
+    def scene_collide(self, obj_handles, obj_tfs, req=None, capacity=None, first_object=0, num_first_objects=None, bufs=None):
+        """broadphase + narrow phase of a scene in one call (hfb_scene_collide)
+        -> (first, second, contacts, n_candidates, n_colliding): the colliding pairs, in no particular order"""
+        req = req or P.CollisionRequestPOD()
+        oh = np.ascontiguousarray(obj_handles, dtype=np.uint32)
+        ot = np.ascontiguousarray(obj_tfs, dtype=P.transform_dtype)
+        n = oh.shape[0]
+        cap = int(capacity) if capacity is not None else max(4 * n, 1024)
+        if bufs is None:
+            bufs = (np.empty(cap, dtype=np.uint32), np.empty(cap, dtype=np.uint32), np.empty(cap, dtype=P.contact_dtype))
+        f, s2, rec = bufs
+        nc = np.zeros(2, dtype=np.uint32)
+        out = P.SceneContacts(f.ctypes.data, s2.ctypes.data, rec.ctypes.data, cap, nc[0:1].ctypes.data, nc[1:2].ctypes.data)
+        self._check(self.L.hfb_scene_collide(self.h, n, _ptr(oh), _ptr(ot), first_object,
+                                             n if num_first_objects is None else num_first_objects, C.byref(req), C.byref(out)))
+        k = min(int(nc[0]), cap)
+        return f[:k], s2[:k], rec[:k], int(nc[1]), int(nc[0])
 
     # -- object-table queries: the batched form of the CollisionObject overloads (collision.h:58-61) -----
     @staticmethod

@@ -358,6 +358,26 @@ int hfb_broadphase_pairs_device(hfb_ctx* ctx, size_t n_objects, const double* d_
                                 size_t num_first_objects, uint32_t* d_first, uint32_t* d_second, size_t capacity,
                                 uint32_t* d_n_pairs, void* cuda_stream);
 
+/* Broadphase and narrow phase of a scene in ONE call: the batched form of BroadPhaseCollisionManager::collide(callback)
+ * with the default collision callback (broadphase/default_broadphase_callbacks.h:69-130 -- collide() of every candidate
+ * pair, contacts collected).  HOST buffers; blocking.  Between the upload of the poses and the download of the
+ * colliding pairs everything happens on the device: boxes, grid + sweep, collide() of the candidates (as
+ * hfb_batch_collide_objects), compaction.  The colliding pairs (object indices, first < second) and their records
+ * come back in no particular order, at most `capacity` of them; *n_candidates = pairs with overlapping boxes,
+ * *n_colliding = pairs with a contact.  [first_object, first_object + num_first_objects) as in
+ * hfb_broadphase_pairs_device: the candidates whose smaller index lies there (one GPU's share of the scene). */
+typedef struct hfb_scene_contacts {
+  uint32_t* first;
+  uint32_t* second;
+  hfb_contact* contacts;
+  uint32_t capacity;
+  uint32_t* n_colliding;
+  uint32_t* n_candidates;
+} hfb_scene_contacts;
+int hfb_scene_collide(hfb_ctx* ctx, size_t n_objects, const uint32_t* object_handles, const hfb_transform* object_tfs,
+                      size_t first_object, size_t num_first_objects, const hfb_collision_request* req,
+                      const hfb_scene_contacts* out);
+
 /* ---- object-table batches: the batched form of the CollisionObject overloads --------------------------
  * collide(const CollisionObject* o1, const CollisionObject* o2, ...) / distance(...) (include/hpp/fcl/collision.h:
  * 58-61, distance.h:53-56) take their geometry and pose from the objects.  A scene here is a table of objects

@@ -134,3 +134,32 @@ def test_scene_aabbs_and_device_broadphase():
         assert len(part) == kk and all(lo <= a < lo + cnt for a, _ in part) and not (part & got)
         got |= part
     assert got == want
+
+
+@pytest.mark.gpu
+def test_scene_collide_in_one_call():
+    """hfb_scene_collide (boxes, broadphase, collide of the candidates, compaction -- all on the device) against the
+    pieces: host pair finder + pair-row collide; whole scene and cut in two ranges of objects"""
+    w = W.config5_moving_boxes(20_000, target_pairs=150_000)
+    eng = hf.Engine(0)
+    hb = eng.register_shapes(w["shapes"])
+    eng.commit()
+    oh = hb[w["obj_h"]]
+    for k in (0, 1):
+        tf = w["step"](k)
+        f, s, rec, ncand, nhit = eng.scene_collide(oh, tf)
+        pf, ps = hf.broadphase_pairs(eng.scene_aabbs(oh, tf))
+        assert ncand == len(pf) and ncand > 50_000
+        rows = eng.batch_collide(oh[pf], tf[pf], oh[ps], tf[ps])
+        hit = rows["num_contacts"] > 0
+        assert nhit == int(hit.sum()) == len(f) and nhit > 1000
+        want = {(int(a), int(b)): rows[i].tobytes() for i, (a, b) in enumerate(zip(pf, ps)) if hit[i]}
+        got = {(int(a), int(b)): rec[i].tobytes() for i, (a, b) in enumerate(zip(f, s))}
+        assert got == want
+    half = len(oh) // 2
+    f1, s1, _, c1, h1 = eng.scene_collide(oh, tf, first_object=0, num_first_objects=half)
+    f2, s2, _, c2, h2 = eng.scene_collide(oh, tf, first_object=half, num_first_objects=len(oh))
+    assert c1 + c2 == ncand and h1 + h2 == nhit and (f1 < half).all() and (f2 >= half).all()
+    # capacity below the number of colliding pairs: all counted
+    f3, _, _, _, h3 = eng.scene_collide(oh, tf, capacity=50)
+    assert h3 == nhit and len(f3) == 50
