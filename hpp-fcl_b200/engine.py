@@ -62,6 +62,13 @@ def load_library(path=None):
     L.hfb_scene_aabbs_device.argtypes = [vp, sz, vp, vp, vp, vp]
     L.hfb_broadphase_pairs_device.argtypes = [vp, sz, vp, sz, sz, vp, vp, sz, vp, vp]
     L.hfb_scene_collide.argtypes = [vp, sz, vp, vp, sz, sz, vp, vp]
+    L.hfb_comm_unique_id.argtypes = [vp]
+    L.hfb_comm_init.argtypes = [vp, vp, C.c_int, C.c_int]
+    L.hfb_comm_destroy.argtypes = [vp]
+    L.hfb_geom_broadcast.argtypes = [vp, C.c_int]
+    L.hfb_comm_wait.argtypes = [vp, vp]
+    for name in ("hfb_batch_distance_sharded_device", "hfb_batch_collide_sharded_device"):
+        getattr(L, name).argtypes = [vp, sz, vp, vp, vp, vp, vp, vp, vp]
     L.hfb_batch_distance_objects.argtypes = [vp, vp, vp, vp, vp, vp]
     L.hfb_batch_collide_objects.argtypes = [vp, vp, vp, vp, vp, vp]
     L.hfb_batch_distance_objects_device.argtypes = [vp, vp, vp, vp, vp, vp]
@@ -386,6 +393,45 @@ class Engine:
     def batch_convex_support_device(self, n, d_ids, d_dirs, d_idx, d_sup, stream=0):
         self._check(self.L.hfb_batch_convex_support_device(self.h, n, _ptr(d_ids), _ptr(d_dirs),
                                                            _ptr(d_idx), _ptr(d_sup), _ptr(stream)))
+
+    # -- multi-GPU: one context per rank (hfb_comm_*), NCCL behind the C-ABI -----------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes rank 0 creates and hands to every rank (ncclGetUniqueId)"""
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        rc = L.hfb_comm_unique_id(buf)
+        if rc != 0:
+            raise EngineError("hfb_comm_unique_id: %s" % _ERR.get(rc, rc))
+        return buf.raw
+
+    def comm_init(self, comm_id, rank, nranks):
+        self._check(self.L.hfb_comm_init(self.h, C.create_string_buffer(bytes(comm_id), 128), int(rank), int(nranks)))
+
+    def comm_destroy(self):
+        self._check(self.L.hfb_comm_destroy(self.h))
+
+    def geom_broadcast(self, root=0):
+        """the geometry registered on `root` replaces this context's, on every rank, committed"""
+        self._check(self.L.hfb_geom_broadcast(self.h, int(root)))
+
+    def batch_distance_sharded_device(self, n_local, d_h1, d_tf1, d_h2, d_tf2, req=None, stream=0):
+        """-> device pointer of the records of all ranks' pairs (rank-major); complete after comm_wait(stream)"""
+        req = req or P.DistanceRequestPOD()
+        out = C.c_void_p()
+        self._check(self.L.hfb_batch_distance_sharded_device(self.h, n_local, _ptr(d_h1), _ptr(d_tf1), _ptr(d_h2), _ptr(d_tf2),
+                                                             C.byref(req), C.byref(out), _ptr(stream)))
+        return out.value
+
+    def batch_collide_sharded_device(self, n_local, d_h1, d_tf1, d_h2, d_tf2, req=None, stream=0):
+        req = req or P.CollisionRequestPOD()
+        out = C.c_void_p()
+        self._check(self.L.hfb_batch_collide_sharded_device(self.h, n_local, _ptr(d_h1), _ptr(d_tf1), _ptr(d_h2), _ptr(d_tf2),
+                                                            C.byref(req), C.byref(out), _ptr(stream)))
+        return out.value
+
+    def comm_wait(self, stream=0):
+        self._check(self.L.hfb_comm_wait(self.h, _ptr(stream)))
 
     def set_profiling(self, on=True):
         self._check(self.L.hfb_set_profiling(self.h, int(on)))

@@ -78,3 +78,21 @@ def sharded_batch(compute, n, dtype, device=None):
     full = all_gather_records(local, per, per * world, dtype, device)
     # ranks hold [r*per, r*per + len_r): with contiguous equal ranges this is already pair order
     return full[:n]
+
+
+# ---- GPU path: the product's own communicator (hfb_comm_*, NCCL behind the C-ABI) --------------------------
+# torch.distributed is only the launcher here (rank numbers and the exchange of the 128-byte communicator id);
+# geometry broadcast and result all-gather are the library's, and nothing below touches host memory.
+
+def init_engine_comm(eng):
+    """hfb_comm_init of `eng` over the torch.distributed world: rank 0 creates the id, everybody receives it"""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    ids = [eng.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    eng.comm_init(ids[0], rank, world)
+
+
+def sharded_distance_device(eng, n_local, d_h1, d_tf1, d_h2, d_tf2, req=None, stream=0):
+    """this rank's device rows -> device pointer of all ranks' records (rank-major), all-gathered by the library on
+    its own stream (overlapping the caller's next batch); eng.comm_wait(stream) before reading it"""
+    return eng.batch_distance_sharded_device(n_local, d_h1, d_tf1, d_h2, d_tf2, req, stream)

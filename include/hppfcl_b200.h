@@ -431,6 +431,33 @@ int hfb_batch_convex_support_device(hfb_ctx* ctx, size_t n,
                                     const double* d_dirs, int32_t* d_index_out,
                                     double* d_support_out, void* cuda_stream);
 
+/* ---- multi-GPU: one context per GPU, pairs sharded over the ranks ---------------------------------------------
+ * The path shards trivially (independent pairs): there are exactly two collectives -- one broadcast of
+ * the geometry arena per scene and one all-gather of the result records per batch -- and both live here, behind
+ * the C-ABI, so that a C++ caller (hpp-fcl itself) can use a whole 8-GPU box.  NCCL is loaded with dlopen at the
+ * first hfb_comm_* call (no link-time dependency).
+ *   rank 0:      hfb_comm_unique_id(&id); hand `id` (128 bytes) to the other ranks by any means (MPI, a file, ...)
+ *   every rank:  hfb_ctx_create(gpu, &ctx); hfb_comm_init(ctx, &id, rank, nranks);
+ *   rank 0:      registers the geometry;      every rank: hfb_geom_broadcast(ctx, 0)   (commits on every rank)
+ *   every rank:  hfb_batch_distance_sharded_device(ctx, n_local, rows of ITS pairs..., &d_all, stream)
+ * d_all: the records of all ranks' pairs, rank-major (nranks * n_local), in one of two buffers the context owns;
+ * the all-gather runs on the communicator's own stream and overlaps the next call's kernels; the buffer is complete
+ * when `stream` has passed hfb_comm_wait(ctx, stream), and is reused by the next call but one. */
+typedef struct hfb_comm_id {
+  char bytes[128];
+} hfb_comm_id;
+int hfb_comm_unique_id(hfb_comm_id* id);
+int hfb_comm_init(hfb_ctx* ctx, const hfb_comm_id* id, int rank, int nranks);
+int hfb_comm_destroy(hfb_ctx* ctx);
+int hfb_geom_broadcast(hfb_ctx* ctx, int root);
+int hfb_batch_distance_sharded_device(hfb_ctx* ctx, size_t n_local, const uint32_t* d_h1, const hfb_transform* d_tf1,
+                                      const uint32_t* d_h2, const hfb_transform* d_tf2, const hfb_distance_request* req,
+                                      hfb_distance_result** d_all, void* cuda_stream);
+int hfb_batch_collide_sharded_device(hfb_ctx* ctx, size_t n_local, const uint32_t* d_h1, const hfb_transform* d_tf1,
+                                     const uint32_t* d_h2, const hfb_transform* d_tf2, const hfb_collision_request* req,
+                                     hfb_contact** d_all, void* cuda_stream);
+int hfb_comm_wait(hfb_ctx* ctx, void* cuda_stream);
+
 /* ---- counters (mirror enable_statistics num_bv_tests / num_leaf_tests,
  *      traversal_node_bvh_shape.h:91-93) and launch accounting ------------ */
 typedef struct hfb_stats {
