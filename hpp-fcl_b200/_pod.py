@@ -10,6 +10,7 @@ import ctypes as C
 import numpy as np
 
 # NODE_TYPE values (collision_object.h:65-89)
+BV_OBB = 2
 BV_OBBRSS = 5
 GEOM_BOX = 9
 GEOM_SPHERE = 10

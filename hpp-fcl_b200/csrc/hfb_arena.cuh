@@ -27,7 +27,7 @@ struct BvhDesc {  // one registered BVHModel<OBBRSS>
   uint32_t node_off, num_nodes;  // into the node array
   uint32_t vert_off, num_verts;  // in vertices (3 doubles each)
   uint32_t tri_off, num_tris;    // in triangles (3 uint32 each)
-  uint32_t _r0, _r1;
+  uint32_t _r0, _r1;  // depth of the tree; 0: BVHModel<OBBRSS>, 1: BVHModel<OBB> (RSS half of the nodes unused)
 };
 
 struct ArenaView {
@@ -104,7 +104,7 @@ struct HostArena {
   // on such subtrees.
   int max_bvh_depth = 0;  // deepest registered tree (root = depth 0)
   bool add_bvh(const hfb_bvh_node* nodes, uint32_t nn, const double* verts, uint32_t nv, const uint32_t* tris,
-               uint32_t nt, uint32_t* id) {
+               uint32_t nt, uint32_t* id, uint32_t kind = 0 /* 0: BVHModel<OBBRSS>, 1: BVHModel<OBB> */) {
     if (nn == 0 || nv == 0 || nt == 0) return false;
     std::vector<uint8_t> refs(nn, 0);
     for (uint32_t i = 0; i < nn; ++i) {
@@ -152,7 +152,7 @@ struct HostArena {
     d.tri_off = (uint32_t)(bvh_tris.size() / 3);
     d.num_tris = nt;
     d._r0 = (uint32_t)maxd;
-    d._r1 = 0;
+    d._r1 = kind;
     bvh_nodes.insert(bvh_nodes.end(), nodes, nodes + nn);
     for (uint32_t k = 0; k < nn; ++k) {
       const int fc = nodes[k].first_child;
@@ -223,7 +223,8 @@ struct HostArena {
     return true;
   }
   bool valid_shape(const hfb_shape& s) const {
-    if (s.type == HFB_BV_OBBRSS) return s.data < bvh_desc.size();
+    if (s.type == HFB_BV_OBBRSS) return s.data < bvh_desc.size() && bvh_desc[s.data]._r1 == 0;
+    if (s.type == HFB_BV_OBB) return s.data < bvh_desc.size() && bvh_desc[s.data]._r1 == 1;
     if (s.type == HFB_GEOM_CONVEX) return s.data < cvx.size();
     if (s.type == HFB_GEOM_TRIANGLE) return s.data < cvx.size() && cvx[s.data].nv >= 3;
     return true;
@@ -231,7 +232,7 @@ struct HostArena {
   // returns false on an invalid record
   bool add_shape(const hfb_shape& s, uint32_t* handle) {
     if (!valid_shape(s)) return false;
-    if (s.type == HFB_BV_OBBRSS) {
+    if (s.type == HFB_BV_OBBRSS || s.type == HFB_BV_OBB) {
       has_bvh = true;
     } else if (s.type == HFB_GEOM_CONVEX || s.type == HFB_GEOM_TRIANGLE) {
       if (s.type == HFB_GEOM_CONVEX) has_convex = true; else has_tri = true;

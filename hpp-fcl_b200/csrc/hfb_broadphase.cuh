@@ -52,6 +52,7 @@ inline bool shape_local_aabb(const HostArena& A, const hfb_shape& s, LocalAabb& 
       }
       h[0] = -1;
     } break;
+    case HFB_BV_OBB:
     case HFB_BV_OBBRSS: {
       if (s.data >= A.bvh_desc.size()) return false;
       const BvhDesc& d = A.bvh_desc[s.data];

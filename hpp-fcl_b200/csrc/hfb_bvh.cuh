@@ -1088,6 +1088,50 @@ HFB_HD void compute_shape_obb(const ShapeD& s, const xf& tf, ObbD& bv) {  // OBB
   fit_obb_extent(s, tf, n, bv);
 }
 
+// computeBV<OBB, S>, the specialisations a plain BVHModel<OBB> walk uses for the shape's box
+// (geometric_shapes_utility.cpp:458-545): pose and half sizes for Box / Sphere / Capsule / Cone / Cylinder, the fit
+// of the local vertices moved by the pose for ConvexBase; Ellipsoid has no specialisation and takes the generic fit
+HFB_HD void compute_shape_obb_plain(const ShapeD& s, const xf& tf, ObbD& bv) {
+  switch (s.type) {
+    case HFB_GEOM_BOX:
+      bv.To = tf.T;
+      bv.axes = tf.R;
+      bv.extent = mk(s.p0, s.p1, s.p2);
+      return;
+    case HFB_GEOM_SPHERE:
+      bv.To = tf.T;
+      bv.axes.r0 = mk(1, 0, 0);
+      bv.axes.r1 = mk(0, 1, 0);
+      bv.axes.r2 = mk(0, 0, 1);
+      bv.extent = mk(s.p0, s.p0, s.p0);
+      return;
+    case HFB_GEOM_CAPSULE:
+      bv.To = tf.T;
+      bv.axes = tf.R;
+      bv.extent = mk(s.p0, s.p0, s.p1 + s.p0);
+      return;
+    case HFB_GEOM_CONE:
+    case HFB_GEOM_CYLINDER:
+      bv.To = tf.T;
+      bv.axes = tf.R;
+      bv.extent = mk(s.p0, s.p0, s.p1);
+      return;
+    case HFB_GEOM_CONVEX: {
+      xf id;
+      id.R.r0 = mk(1, 0, 0);
+      id.R.r1 = mk(0, 1, 0);
+      id.R.r2 = mk(0, 0, 1);
+      id.T = mk(0, 0, 0);
+      compute_shape_obb(s, id, bv);  // fit(points, n, bv) in the shape frame
+      bv.axes = mmulm(tf.R, bv.axes);
+      bv.To = mmul(tf.R, bv.To) + tf.T;
+      return;
+    }
+    default:
+      compute_shape_obb(s, tf, bv);
+  }
+}
+
 // ----------------------------------------------------------------- node access ----
 HFB_HD RssD load_node_rss(const hfb_bvh_node& nd) {
   RssD r;
@@ -1108,7 +1152,10 @@ HFB_HD ObbD load_node_obb(const hfb_bvh_node& nd) {
 
 #define HFB_BVH_STACK 128
 
+HFB_HD bool is_bvh_type(uint32_t t) { return t == HFB_BV_OBBRSS || t == HFB_BV_OBB; }
+
 struct BvhQuery {  // one (mesh, shape) query after the operand swap of distance()/collide()
+  bool plain_obb;  // BVHModel<OBB>: collide() only (see hfb_geom_register_bvh_obb)
   const hfb_bvh_node* nodes;
   const double* verts;    // xyz triples
   const uint32_t* tris;   // index triples
@@ -1124,11 +1171,12 @@ HFB_HD bool bvh_make_query(const ArenaView& A, uint32_t h1, const xf& tf1, uint3
                            bool& swapped) {
   const hfb_shape& r1 = A.shapes[h1];
   const hfb_shape& r2 = A.shapes[h2];
-  swapped = r1.type != HFB_BV_OBBRSS;
+  swapped = !is_bvh_type(r1.type);
   const hfb_shape& rm = swapped ? r2 : r1;
   const uint32_t hs = swapped ? h1 : h2;
   const hfb_shape& rs = swapped ? r1 : r2;
-  if (rm.type != HFB_BV_OBBRSS) return false;
+  if (!is_bvh_type(rm.type)) return false;
+  q.plain_obb = rm.type == HFB_BV_OBB;
   if (!(rs.type == HFB_GEOM_BOX || rs.type == HFB_GEOM_SPHERE || rs.type == HFB_GEOM_CAPSULE ||
         rs.type == HFB_GEOM_CONE || rs.type == HFB_GEOM_CYLINDER || rs.type == HFB_GEOM_ELLIPSOID ||
         rs.type == HFB_GEOM_CONVEX))
@@ -1493,7 +1541,8 @@ HFB_HD void bvh_shape_collide_stream(Src& src, const SolverP& P, double security
     if (phase < 0) break;
     if (phase == 0) {
       if (state == BVS_NEED_INIT) {
-        compute_shape_obb(job.q.shape, job.q.tf_shape, sbv);  // traversal_node_setup.h:655-694
+        if (job.q.plain_obb) compute_shape_obb_plain(job.q.shape, job.q.tf_shape, sbv);  // computeBV<OBB, S>
+        else compute_shape_obb(job.q.shape, job.q.tf_shape, sbv);  // traversal_node_setup.h:655-694
         in.cached_guess = job.cached_guess;
         in.hint0 = job.hint0;
         in.hint1 = job.hint1;
@@ -1995,6 +2044,11 @@ HFB_HD BvhPairQuery bvh_make_pair_query(const ArenaView& A, uint32_t h1, const x
 HFB_HD void bvh_mesh_pair_distance(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_t h2, const xf& tf2,
                                    const BvhReq& R, hfb_distance_result* r, unsigned& bv_tests,
                                    unsigned& leaf_tests) {
+  if (A.shapes[h1].type != HFB_BV_OBBRSS || A.shapes[h2].type != HFB_BV_OBBRSS) {  // plain OBB models: collide() only
+    bvh_unsupported_distance(r);
+    bv_tests = leaf_tests = 0;
+    return;
+  }
   const BvhPairQuery pq = bvh_make_pair_query(A, h1, tf1, h2, tf2);
   BvhPairDistOut o;
   bvh_bvh_distance(pq, R.rel_err, R.abs_err, R.enable_nearest_points, o);
@@ -2016,6 +2070,13 @@ HFB_HD void bvh_mesh_pair_collide(const ArenaView& A, uint32_t h1, const xf& tf1
                                   const SolverP& P, const BvhReq& R, v3 cached_guess, int hint0, int hint1,
                                   EpaWs* ws, hfb_contact* r, unsigned& bv_tests, unsigned& leaf_tests,
                                   BvhContactSink sink = BvhContactSink{nullptr, 0, nullptr}) {
+  if (A.shapes[h1].type != A.shapes[h2].type) {  // collision_matrix has no [BV_OBB][BV_OBBRSS] entry
+    bvh_init_contact(r);
+    r->status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
+    if (sink.count) *sink.count = 0;
+    bv_tests = leaf_tests = 0;
+    return;
+  }
   const BvhPairQuery pq = bvh_make_pair_query(A, h1, tf1, h2, tf2);
   PairIn in;
   in.cached_guess = cached_guess;
@@ -2053,6 +2114,7 @@ HFB_HD bool bvh_make_job(const ArenaView& A, uint32_t h1, const xf& tf1, uint32_
                          v3 cached_guess, int hint0, int hint1, void* rec, BvhJob& job) {
   bool ok = bvh_make_query<CAPS>(A, h1, tf1, h2, tf2, job.q, job.swapped);
   if (MODE == 1 && R.security_margin < 0) ok = false;
+  if (MODE == 0 && ok && job.q.plain_obb) ok = false;  // no distance() on a plain OBB model
   // distance(): preprocess() always evaluates the seed triangle, so the throw is certain
   if (MODE == 0 && ok && bvh_leaf_guess_throws(R.initial_guess, job.q.shape)) ok = false;
   if (!ok) {

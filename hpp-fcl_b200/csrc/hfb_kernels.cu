@@ -430,12 +430,12 @@ __global__ void __launch_bounds__(128) k_bvh_order_keys(const BatchArgs a, const
   for (unsigned k = lo + blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += gridDim.x * blockDim.x) {
     const unsigned i = a.index_list[k];
     const hfb_shape& r1 = a.A.shapes[a.h1[i]];
-    const bool swapped = r1.type != HFB_BV_OBBRSS;
+    const bool swapped = !is_bvh_type(r1.type);
     const hfb_shape& rm = swapped ? a.A.shapes[a.h2[i]] : r1;
     const xf tm = load_xf(swapped ? a.tf2[i].R : a.tf1[i].R);
     const xf ts = load_xf(swapped ? a.tf1[i].R : a.tf2[i].R);
     unsigned key = 0;
-    if (rm.type == HFB_BV_OBBRSS) {
+    if (is_bvh_type(rm.type)) {
       const BvhDesc d = a.A.bvh_desc[rm.data];
       const double* v = a.A.bvh_verts + 3 * (size_t)d.vert_off;
       const v3 c = mtmul(tm.R, ts.T - tm.T);  // the shape's origin in the mesh frame
@@ -487,6 +487,7 @@ __device__ __forceinline__ int type_index(uint32_t t) {
     case HFB_GEOM_ELLIPSOID: return 5;
     case HFB_GEOM_CONVEX: return 6;
     case HFB_GEOM_TRIANGLE: return 7;
+    case HFB_BV_OBB:
     case HFB_BV_OBBRSS: return 9;
     default: return 8;
   }
@@ -1535,6 +1536,15 @@ int hfb_geom_register_bvh_obbrss(hfb_ctx* ctx, const hfb_bvh_node* nodes, uint32
   if (!ctx || !nodes || !vertices || !triangles || !bvh_id) return HFB_ERR_INVALID_ARGUMENT;
   if (!ctx->arena.add_bvh(nodes, num_nodes, vertices, num_vertices, triangles, num_triangles, bvh_id))
     return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "malformed OBBRSS BVH (child links / primitive ids / vertex ids)");
+  ctx->committed = false;
+  return HFB_OK;
+}
+
+int hfb_geom_register_bvh_obb(hfb_ctx* ctx, const hfb_bvh_node* nodes, uint32_t num_nodes, const double* vertices,
+                              uint32_t num_vertices, const uint32_t* triangles, uint32_t num_triangles, uint32_t* bvh_id) {
+  if (!ctx || !nodes || !vertices || !triangles || !bvh_id) return HFB_ERR_INVALID_ARGUMENT;
+  if (!ctx->arena.add_bvh(nodes, num_nodes, vertices, num_vertices, triangles, num_triangles, bvh_id, 1))
+    return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "malformed OBB BVH (child links / primitive ids / vertex ids / depth)");
   ctx->committed = false;
   return HFB_OK;
 }

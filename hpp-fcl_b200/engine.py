@@ -188,6 +188,19 @@ class Engine:
                                                         v.shape[0], _ptr(t), t.shape[0], C.byref(bid)))
         return bid.value  # use as `data` of a shape record of type BV_OBBRSS
 
+    def register_bvh_obb(self, nodes, vertices, triangles):
+        """a plain BVHModel<OBB> (collide() only): the same node records, RSS half ignored -- the OBB tree of a mesh is the
+        OBB half of its OBBRSS tree, so build_bvh_obbrss serves both; use as `data` of a shape record of type BV_OBB"""
+        if nodes is None:
+            nodes = build_bvh_obbrss(vertices, triangles)
+        nodes = np.ascontiguousarray(nodes, dtype=P.bvh_node_dtype)
+        v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+        t = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
+        bid = C.c_uint32()
+        self._check(self.L.hfb_geom_register_bvh_obb(self.h, _ptr(nodes), nodes.shape[0], _ptr(v), v.shape[0], _ptr(t),
+                                                     t.shape[0], C.byref(bid)))
+        return bid.value
+
     def commit(self):
         self._check(self.L.hfb_geom_commit(self.h))
 

@@ -35,6 +35,7 @@ extern "C" {
 /* ---- node types: numeric values mirror hpp::fcl::NODE_TYPE
  *      (include/hpp/fcl/collision_object.h:65-89) ------------------------- */
 enum {
+  HFB_BV_OBB = 2,    /* BVHModel<OBB>: collide() only, see hfb_geom_register_bvh_obb */
   HFB_BV_OBBRSS = 5,
   HFB_GEOM_BOX = 9,
   HFB_GEOM_SPHERE = 10,
@@ -279,6 +280,18 @@ int hfb_geom_register_bvh_obbrss(hfb_ctx* ctx, const hfb_bvh_node* nodes,
                                  uint32_t num_nodes, const double* vertices,
                                  uint32_t num_vertices, const uint32_t* triangles,
                                  uint32_t num_triangles, uint32_t* bvh_id);
+/* A plain BVHModel<OBB> (collision_func_matrix.cpp:488-501, 652: BVHShapeCollider<OBB, S>, BVHCollide<OBB>): the same
+ * node records with the RSS half ignored -- BVFitter<OBB>::fit and the mean splitter over OBB::axes.col(0)
+ * (BV_fitter.cpp:480-499, BV_splitter.cpp:44-46,163-170) produce exactly the OBB half of the OBBRSS tree of the same
+ * mesh, so hfb_bvh_build_obbrss serves both.  A shape record {type = HFB_BV_OBB, data = bvh id} gives the handle.
+ * collide(): mesh-shape and mesh-mesh (both operands plain OBB models), the OBB tests and the leaf tests of the
+ * OBBRSS walks.  distance() on a BVHModel<OBB> is NOT offered (HFB_PATH_UNSUPPORTED): the reference has no OBB
+ * distance (OBB::distance prints "OBB distance not implemented" and returns 0, BV/OBB.cpp), so its generic walk
+ * visits every triangle of a tree it first REBUILDS from the transformed vertices on every call
+ * (traversal_node_setup.h:709-723) -- not a path to accelerate; use the OBBRSS model for distances. */
+int hfb_geom_register_bvh_obb(hfb_ctx* ctx, const hfb_bvh_node* nodes, uint32_t num_nodes, const double* vertices,
+                              uint32_t num_vertices, const uint32_t* triangles, uint32_t num_triangles,
+                              uint32_t* bvh_id);
 /* Uploads everything registered so far to the device. Must be called before
  * the first query and after any further registration. */
 int hfb_geom_commit(hfb_ctx* ctx);

@@ -512,6 +512,51 @@ void computeBV_OBBRSS(const Shape& s, const Tf& tf, OBBRSS& bv) {  // geometric_
   fit_points_rss(v.data(), (unsigned)v.size(), bv.rss);
 }
 
+// computeBV<OBB, S>: the specialisations the plain BVHModel<OBB> walks use for the shape's box
+// (geometric_shapes_utility.cpp:458-545); Ellipsoid has none and takes the generic fit of the bound vertices
+void computeBV_OBB(const Shape& s, const Tf& tf, OBB& bv) {
+  M3 I;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) I.m[r][c] = r == c ? 1.0 : 0.0;
+  switch (s.type) {
+    case HFB_GEOM_BOX:
+      bv.To = tf.T;
+      bv.axes = tf.R;
+      bv.extent = V3(s.p[0], s.p[1], s.p[2]);
+      return;
+    case HFB_GEOM_SPHERE:
+      bv.To = tf.T;
+      bv.axes = I;
+      bv.extent = V3(s.p[0], s.p[0], s.p[0]);
+      return;
+    case HFB_GEOM_CAPSULE:
+      bv.To = tf.T;
+      bv.axes = tf.R;
+      bv.extent = V3(s.p[0], s.p[0], s.p[1] + s.p[0]);
+      return;
+    case HFB_GEOM_CONE:
+    case HFB_GEOM_CYLINDER:
+      bv.To = tf.T;
+      bv.axes = tf.R;
+      bv.extent = V3(s.p[0], s.p[0], s.p[1]);
+      return;
+    case HFB_GEOM_CONVEX: {
+      fit_points_obb(s.cvx->points.data(), (unsigned)s.cvx->points.size(), bv);
+      M3 A;  // bv.axes.applyOnTheLeft(R)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 3; ++c)
+          A.m[r][c] = (tf.R.m[r][0] * bv.axes.m[0][c] + tf.R.m[r][1] * bv.axes.m[1][c]) + tf.R.m[r][2] * bv.axes.m[2][c];
+      bv.axes = A;
+      bv.To = mul(tf.R, bv.To) + tf.T;
+      return;
+    }
+    default: {
+      std::vector<V3> v = getBoundVertices(s, tf);
+      fit_points_obb(v.data(), (unsigned)v.size(), bv);
+    }
+  }
+}
+
 // BVFitter<OBBRSS>::fit (BV_fitter.cpp:501-531): one eigen decomposition shared by both halves
 static OBBRSS fit_primitives(const BVHModel& m, const unsigned* prim, unsigned n) {
   OBBRSS bv;
@@ -1160,7 +1205,7 @@ static void collisionRecurse(ColNode& n, unsigned b1, double& sqrDistLowerBound)
 // BVHShapeCollider<OBBRSS,S>::oriented (collision_func_matrix.cpp:141-155) + collide(node)
 // (collision_node.cpp:64-79) on a fresh CollisionResult
 void bvhShapeCollide(const BVHModel& m, const Tf& tf1, const Shape& s, const Tf& tf2, GJKSolver& solver,
-                     const hfb_collision_request& req, BvhCollideResult& out) {
+                     const hfb_collision_request& req, BvhCollideResult& out, bool plain_obb) {
   ColNode n;
   n.model1 = &m;
   n.model2 = &s;
@@ -1169,7 +1214,8 @@ void bvhShapeCollide(const BVHModel& m, const Tf& tf1, const Shape& s, const Tf&
   n.solver = &solver;
   n.req = &req;
   n.res = &out;
-  computeBV_OBBRSS(s, tf2, n.model2_bv);  // traversal_node_setup.h:655-694
+  if (plain_obb) computeBV_OBB(s, tf2, n.model2_bv.obb);  // MeshShapeCollisionTraversalNodeOBB: computeBV<OBB, S>
+  else computeBV_OBBRSS(s, tf2, n.model2_bv);  // traversal_node_setup.h:655-694
   double sqrDistLowerBound = 0;
   collisionRecurse(n, 0, sqrDistLowerBound);
 }

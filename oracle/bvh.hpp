@@ -48,7 +48,8 @@ bool obb_overlap(const M3& R0, const V3& T0, const OBB& b1, const OBB& b2, doubl
 void bvhShapeDistance(const BVHModel& m, const Tf& tf1, const Shape& s, const Tf& tf2, GJKSolver& solver,
                       bool signed_distance, double rel_err, double abs_err, BvhQueryResult& out);
 void bvhShapeCollide(const BVHModel& m, const Tf& tf1, const Shape& s, const Tf& tf2, GJKSolver& solver,
-                     const hfb_collision_request& req, BvhCollideResult& out);
+                     const hfb_collision_request& req, BvhCollideResult& out, bool plain_obb = false);
+void computeBV_OBB(const Shape& s, const Tf& tf, OBB& bv);
 
 // mesh-mesh (BVHModel<OBBRSS> x BVHModel<OBBRSS>)
 double sqrTriDistance(const V3 S[3], const V3 T[3], V3& P, V3& Q);

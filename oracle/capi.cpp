@@ -117,7 +117,7 @@ int64_t oracle_register_shapes(void* sc, const hfb_shape* shapes, size_t n) {
     sh.p[1] = shapes[i].p[1];
     sh.p[2] = shapes[i].p[2];
     sh.ssr = shapes[i].ssr;
-    if (sh.type == HFB_BV_OBBRSS) {
+    if (sh.type == HFB_BV_OBBRSS || sh.type == HFB_BV_OBB) {  // (a model serves both kinds: the plain OBB tree is the OBB half)
       if (shapes[i].data >= s->bvhs.size()) return -1;
       sh.p[0] = (double)shapes[i].data;
     }
@@ -190,6 +190,13 @@ int oracle_batch_distance(void* sc, size_t n, const uint32_t* h1, const hfb_tran
       V3 p1, p2, normal;
       double distance;
       bool closed = false;
+      if (s1.type == HFB_BV_OBB || s2.type == HFB_BV_OBB) {
+        // BVHModel<OBB>: distance() is not restated (the reference rebuilds the tree from the transformed vertices on
+        // every call and walks all of it, OBB::distance being unimplemented: traversal_node_setup.h:709-723, BV/OBB.cpp)
+        r.status = (uint32_t)HFB_PATH_UNSUPPORTED << 16;
+        r.iterations = 0;
+        continue;
+      }
       if (s1.type == HFB_BV_OBBRSS || s2.type == HFB_BV_OBBRSS) {
         // distance(): (GEOM, BVH) calls the (BVH, GEOM) entry with swapped operands and swaps
         // o1/o2, the nearest points and the normal back -- not b1/b2 (distance.cpp:74-89)
@@ -366,13 +373,21 @@ int oracle_batch_collide(void* sc, size_t n, const uint32_t* h1, const hfb_trans
       solver.gjk.convergence_criterion = HFB_CRIT_DEFAULT;
       solver.gjk.convergence_criterion_type = HFB_CRIT_RELATIVE;
 
-      if (s1.type == HFB_BV_OBBRSS || s2.type == HFB_BV_OBBRSS) {
+      // BVHModel<OBB> collides through the same walks: MeshShapeCollisionTraversalNodeOBB / MeshCollisionTraversalNodeOBB
+      // test OBBs exactly as the OBBRSS nodes do (collision_func_matrix.cpp:141-166, 236-246)
+      const bool bv1 = s1.type == HFB_BV_OBBRSS || s1.type == HFB_BV_OBB, bv2 = s2.type == HFB_BV_OBBRSS || s2.type == HFB_BV_OBB;
+      if (bv1 && bv2 && s1.type != s2.type) {  // no collision_matrix[BV_OBB][BV_OBBRSS]
+        r.status = (uint32_t)HFB_PATH_UNSUPPORTED << 16;
+        r.iterations = 0;
+        continue;
+      }
+      if (bv1 || bv2) {
         // collide(): (GEOM, BVH) is run as (BVH, GEOM) and swapObjects() swaps o1/o2, b1/b2, the
         // nearest points and negates the normal of each contact and of the result (collision.cpp:92-108)
-        const bool swap = s1.type != HFB_BV_OBBRSS;
+        const bool swap = !bv1;
         const Shape& sm = swap ? s2 : s1;
         const Shape& ss = swap ? s1 : s2;
-        if (s1.type == HFB_BV_OBBRSS && s2.type == HFB_BV_OBBRSS) {  // BVHCollide<OBBRSS> (collision_func_matrix.cpp:248-257)
+        if (bv1 && bv2) {  // BVHCollide<OBBRSS> (collision_func_matrix.cpp:248-257)
           const GJKSolver proto = solver;  // every leaf builds GJKSolver(request) (traversal_node_bvhs.h:197)
           BvhCollideResult q;
           GJKSolver leaf_solver = proto;
@@ -407,7 +422,7 @@ int oracle_batch_collide(void* sc, size_t n, const uint32_t* h1, const hfb_trans
         }
         BvhCollideResult q;
         try {
-          bvhShapeCollide(*s->bvhs[(size_t)sm.p[0]], swap ? T2 : T1, ss, swap ? T1 : T2, solver, *req, q);
+          bvhShapeCollide(*s->bvhs[(size_t)sm.p[0]], swap ? T2 : T1, ss, swap ? T1 : T2, solver, *req, q, sm.type == HFB_BV_OBB);
         } catch (const std::logic_error&) {  // BoundingVolumeGuess at a mesh leaf (bvh.cpp leafGuessCheck)
           r.status = (uint32_t)HFB_PATH_UNSUPPORTED << 16;
           continue;

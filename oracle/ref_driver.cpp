@@ -36,6 +36,7 @@ struct Scene {
   std::vector<std::shared_ptr<std::vector<Vec3f>>> cvx_points;
   std::vector<std::shared_ptr<std::vector<Triangle>>> cvx_tris;
   std::vector<std::shared_ptr<BVHModel<OBBRSS>>> bvhs;
+  std::vector<std::shared_ptr<BVHModel<OBB>>> bvhs_obb;  // the same meshes as plain OBB models (same ids)
   std::vector<std::shared_ptr<CollisionGeometry>> geoms;
 };
 struct PeekDistance : ComputeDistance {
@@ -130,7 +131,30 @@ int ref_register_bvh(void* p, const double* verts, uint32_t nv, const uint32_t* 
   m->addSubModel(V, T);
   m->endModel();
   s->bvhs.push_back(m);
+  auto mo = std::make_shared<BVHModel<OBB>>();
+  mo->beginModel();
+  mo->addSubModel(V, T);
+  mo->endModel();
+  s->bvhs_obb.push_back(mo);
   return (int)s->bvhs.size() - 1;
+}
+
+// 1 when the plain BVHModel<OBB> of mesh `id` equals, node for node and bit for bit, the OBB half of its
+// BVHModel<OBBRSS> (what lets one node array serve both kinds in the product)
+int ref_bvh_obb_is_obbrss_half(void* p, int id) {
+  Scene* s = static_cast<Scene*>(p);
+  const BVHModel<OBBRSS>& a = *s->bvhs[(size_t)id];
+  const BVHModel<OBB>& b = *s->bvhs_obb[(size_t)id];
+  if (a.getNumBVs() != b.getNumBVs()) return 0;
+  for (unsigned i = 0; i < a.getNumBVs(); ++i) {
+    const BVNode<OBBRSS>& x = a.getBV(i);
+    const BVNode<OBB>& y = b.getBV(i);
+    if (x.first_child != y.first_child || x.first_primitive != y.first_primitive || x.num_primitives != y.num_primitives) return 0;
+    if (std::memcmp(x.bv.obb.axes.data(), y.bv.axes.data(), 9 * sizeof(double)) != 0) return 0;
+    for (int k = 0; k < 3; ++k)
+      if (x.bv.obb.To[k] != y.bv.To[k] || x.bv.obb.extent[k] != y.bv.extent[k]) return 0;
+  }
+  return 1;
 }
 
 // BVHModel<OBBRSS>::bvs as hfb_bvh_node records; returns the node count
@@ -191,11 +215,15 @@ int64_t ref_register_shapes(void* p, const hfb_shape* recs, size_t n) {
         if (r.data >= s->bvhs.size()) return -1;
         g = s->bvhs[r.data];
         break;
+      case HFB_BV_OBB:
+        if (r.data >= s->bvhs_obb.size()) return -1;
+        g = s->bvhs_obb[r.data];
+        break;
       default: return -1;
     }
     if (ShapeBase* sb = dynamic_cast<ShapeBase*>(g.get()))
       if (r.ssr > 0) sb->setSweptSphereRadius(r.ssr);
-    if (r.type != HFB_BV_OBBRSS) g->computeLocalAABB();
+    if (r.type != HFB_BV_OBBRSS && r.type != HFB_BV_OBB) g->computeLocalAABB();
     s->geoms.push_back(g);
   }
   return first;

@@ -42,6 +42,7 @@ def emu_lib():
         L.emu_batch_convex_support.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 4
         L.emu_register_bvh.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p,
                                        C.c_uint32]
+        L.emu_register_bvh_obb.argtypes = L.emu_register_bvh.argtypes
         L.emu_update_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.emu_update_convex.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32]
         _EMU = L
@@ -72,6 +73,14 @@ class EmuScene:
         v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
         t = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
         bid = self.L.emu_register_bvh(self.h, _ptr(nodes), nodes.shape[0], _ptr(v), v.shape[0], _ptr(t), t.shape[0])
+        assert bid >= 0
+        return bid
+
+    def register_bvh_obb(self, nodes, vertices, triangles):
+        nodes = np.ascontiguousarray(nodes, dtype=P.bvh_node_dtype)
+        v = np.ascontiguousarray(vertices, dtype=np.float64).reshape(-1, 3)
+        t = np.ascontiguousarray(triangles, dtype=np.uint32).reshape(-1, 3)
+        bid = self.L.emu_register_bvh_obb(self.h, _ptr(nodes), nodes.shape[0], _ptr(v), v.shape[0], _ptr(t), t.shape[0])
         assert bid >= 0
         return bid
 
@@ -190,6 +199,17 @@ class MultiScene:
         for name, s in self.b.items():
             if name != "oracle":
                 assert s.register_bvh_obbrss(nodes, vertices, triangles) == bid
+        return bid, nodes
+
+    def register_bvh_obb(self, vertices, triangles):
+        """a plain BVHModel<OBB> of the mesh: in the oracle and the reference build a model serves both kinds (its id
+        is shared), the product registers the node array a second time as an OBB model"""
+        bid, nodes = self.b["oracle"].register_bvh(vertices, triangles)
+        for name, s in self.b.items():
+            if name == "ref":
+                assert s.register_bvh(vertices, triangles)[0] == bid
+            elif name != "oracle":
+                assert s.register_bvh_obb(nodes, vertices, triangles) == bid
         return bid, nodes
 
     def register_shapes(self, shapes):

@@ -266,7 +266,7 @@ long batch_lanes_g(int G, Emu* E, size_t n, const uint32_t* h1, const hfb_transf
   const ArenaView A = E->arena.view();
   for (size_t i = 0; i < n; ++i) {
     if (h1[i] >= A.nshapes || h2[i] >= A.nshapes) return -2;
-    if (A.shapes[h1[i]].type == HFB_BV_OBBRSS || A.shapes[h2[i]].type == HFB_BV_OBBRSS) return -2;  // one lane per query
+    if (is_bvh_type(A.shapes[h1[i]].type) || is_bvh_type(A.shapes[h2[i]].type)) return -2;  // one lane per query
   }
   switch (G) {
     case 2: return batch_lanes<2, MODE>(E, n, h1, tf1, h2, tf2, q, P, C, out, go);
@@ -417,6 +417,12 @@ int emu_register_bvh(void* e, const hfb_bvh_node* nodes, uint32_t nn, const doub
   if (!static_cast<Emu*>(e)->arena.add_bvh(nodes, nn, verts, nv, tris, nt, &id)) return -1;
   return (int)id;
 }
+int emu_register_bvh_obb(void* e, const hfb_bvh_node* nodes, uint32_t nn, const double* verts, uint32_t nv,
+                         const uint32_t* tris, uint32_t nt) {
+  uint32_t id;
+  if (!static_cast<Emu*>(e)->arena.add_bvh(nodes, nn, verts, nv, tris, nt, &id, 1)) return -1;
+  return (int)id;
+}
 int64_t emu_register_shapes(void* e, const hfb_shape* shapes, size_t n) {
   Emu* E = static_cast<Emu*>(e);
   int64_t first = (int64_t)E->arena.shapes.size();
@@ -451,12 +457,12 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
   std::vector<size_t> qtodo;
   for (size_t i = 0; i < n; ++i) {
     if (h1[i] >= A.nshapes || h2[i] >= A.nshapes) return HFB_ERR_INVALID_ARGUMENT;
-    const bool m1 = A.shapes[h1[i]].type == HFB_BV_OBBRSS, m2 = A.shapes[h2[i]].type == HFB_BV_OBBRSS;
+    const bool m1 = is_bvh_type(A.shapes[h1[i]].type), m2 = is_bvh_type(A.shapes[h2[i]].type);
     if (qenv && (m1 != m2)) {
       qtodo.push_back(i);
       continue;
     }
-    if (A.shapes[h1[i]].type == HFB_BV_OBBRSS || A.shapes[h2[i]].type == HFB_BV_OBBRSS) {
+    if (is_bvh_type(A.shapes[h1[i]].type) || is_bvh_type(A.shapes[h2[i]].type)) {
       BvhReq R{/* rel_err, abs_err: see hfb_distance_request */ 0, 0, 0, 0, 0, 1, req->enable_nearest_points != 0, req->q.gjk_initial_guess};
       unsigned bt, lt;
       v3 guess = mk(1, 0, 0);
@@ -466,7 +472,7 @@ int emu_batch_distance(void* e, size_t n, const uint32_t* h1, const hfb_transfor
         if (req->q.cached_support_func_guess) { hh0 = req->q.cached_support_func_guess[2 * i]; hh1 = req->q.cached_support_func_guess[2 * i + 1]; }
       }
       const xf t1 = load_xf(tf1[i].R), t2 = load_xf(tf2[i].R);
-      if (A.shapes[h1[i]].type == HFB_BV_OBBRSS && A.shapes[h2[i]].type == HFB_BV_OBBRSS) {
+      if (is_bvh_type(A.shapes[h1[i]].type) && is_bvh_type(A.shapes[h2[i]].type)) {
         bvh_mesh_pair_distance(A, h1[i], t1, h2[i], t2, R, &out[i], bt, lt);
       } else {
         BvhSingleSrc src;
@@ -535,7 +541,7 @@ static int emu_collide_impl(void* e, size_t n, const uint32_t* h1, const hfb_tra
       out[i].status = 0;
       continue;
     }
-    if (A.shapes[h1[i]].type == HFB_BV_OBBRSS || A.shapes[h2[i]].type == HFB_BV_OBBRSS) {
+    if (is_bvh_type(A.shapes[h1[i]].type) || is_bvh_type(A.shapes[h2[i]].type)) {
       BvhReq R{0, 0, req->security_margin, req->break_distance, req->q.collision_distance_threshold,
                req->num_max_contacts, true, req->q.gjk_initial_guess};
       unsigned bt, lt;
@@ -550,7 +556,7 @@ static int emu_collide_impl(void* e, size_t n, const uint32_t* h1, const hfb_tra
       sink.extra = (extra && max_extra) ? extra + i * (size_t)max_extra : nullptr;
       sink.cap = sink.extra ? max_extra : 0u;
       sink.count = counts ? counts + i : nullptr;
-      if (A.shapes[h1[i]].type == HFB_BV_OBBRSS && A.shapes[h2[i]].type == HFB_BV_OBBRSS) {
+      if (is_bvh_type(A.shapes[h1[i]].type) && is_bvh_type(A.shapes[h2[i]].type)) {
         bvh_mesh_pair_collide<CAPS_ALL>(A, h1[i], t1, h2[i], t2, P, R, guess, hh0, hh1, ws.get(), &out[i], bt, lt, sink);
       } else {
         BvhSingleColSrc src;

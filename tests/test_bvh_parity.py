@@ -364,3 +364,41 @@ def test_all_contacts_of_mesh_pairs():
         b["ref"] = oracle_lib.RefScene(P)
     h1, tf1, h2, tf2 = _contacts_scene(b)
     _check_contacts(b, h1, tf1, h2, tf2, "oracle", [k for k in b if k != "oracle"])
+
+
+@pytest.mark.gpu
+def test_plain_obb_models_gpu_vs_oracle():
+    """BVHModel<OBB> (row X1): collide() of (OBB mesh, shape), (shape, OBB mesh) and (OBB mesh, OBB mesh) on the GPU
+    against the oracle (which tests/test_reference_build.py::test_plain_obb_models pins to the reference build);
+    distance() on a plain OBB model and mixed OBB / OBBRSS mesh pairs come back unsupported"""
+    sc = make_scenes(gpu=True, emu=False)
+    rng = np.random.default_rng(3)
+    va, ta = W.sphere_mesh(1.0, 30, 15, noise=0.02, rng=rng)
+    vb, tb = W.sphere_mesh(0.5, 12, 6, noise=0.04, rng=rng)
+    b0, _ = sc.register_bvh(va, ta)
+    b1, _ = sc.register_bvh_obb(va, ta)
+    b2, _ = sc.register_bvh_obb(vb, tb)
+    hm = sc.register_shapes(P.make_shapes([P.BV_OBBRSS, P.BV_OBB, P.BV_OBB], [[0, 0, 0]] * 3, data=[b0, b1, b2]))
+    prims = W.random_primitive_shapes(rng, 64, SHAPES)
+    prims["p"] *= 0.3
+    hp = sc.register_shapes(prims)
+    pts, ctris = W.icosahedron_from_ellipsoid((0.2, 0.3, 0.25))
+    hc = sc.register_shapes(P.make_shapes([P.GEOM_CONVEX], [[0, 0, 0]], data=[sc.register_convex(pts, ctris)]))
+    sc.commit()
+    n = 20000
+    tf1 = W.random_transforms(rng, n, (-.2, -.2, -.2), (.2, .2, .2))
+    tf2 = W.random_transforms(rng, n, (-1.4, -1.4, -1.4), (1.4, 1.4, 1.4))
+    hq = np.concatenate([hp, hc])[rng.integers(0, 65, n)]
+    ho = hm[1:][rng.integers(0, 2, n)]
+    ho2 = hm[1:][rng.integers(0, 2, n)]
+    o, g = sc.b["oracle"], sc.b["gpu"]
+    for req in (P.CollisionRequestPOD(), P.CollisionRequestPOD(security_margin=0.03, num_max_contacts=3)):
+        for a1, t1, a2, t2 in ((ho, tf1, hq, tf2), (hq, tf2, ho, tf1), (ho[:4000], tf1[:4000], ho2[:4000], tf2[:4000])):
+            want = o.batch_collide(a1, t1, a2, t2, req, nthreads=0)
+            compare_distance(want, g.batch_collide(a1, t1, a2, t2, req), what="plain OBB collide")
+    assert want["num_contacts"].sum() > 50
+    for a2 in (hq[:64], ho2[:64], hm[:1].repeat(64)):
+        d = g.batch_distance(ho[:64], tf1[:64], a2, tf2[:64])
+        assert np.all(P.status_path(d["status"]) == P.PATH_UNSUPPORTED)
+    c = g.batch_collide(ho[:64], tf1[:64], hm[:1].repeat(64), tf2[:64])
+    assert np.all(P.status_path(c["status"]) == P.PATH_UNSUPPORTED)

@@ -240,3 +240,59 @@ def test_gpu_against_the_reference_build(have_ref):
     k = 2000
     cmp_fields(ref2.batch_distance(hmm[:k], tf1[:k], hmm[:k], tf2[:k], nthreads=0), eng2.batch_distance(hmm[:k], tf1[:k], hmm[:k], tf2[:k]),
                ("min_distance", "p1", "p2", "b1", "b2"))
+
+
+def test_plain_obb_models(have_ref):
+    """BVHModel<OBB> (row X1): the reference's plain OBB tree of a mesh IS the OBB half of its OBBRSS tree, and collide()
+    on it -- mesh-shape with computeBV<OBB, S>'s boxes, mesh-mesh -- is reproduced bit for bit by the oracle and by the
+    host build of the device code.  distance() on a plain OBB model is not offered (unsupported records)."""
+    from tests.common import EmuScene
+    orc, ref, hm, hp, rng, (na, rna, nb, rnb), ((va, ta), (vb, tb)) = mesh_scene()
+    L = oracle_lib.ref_lib()
+    L.ref_bvh_obb_is_obbrss_half.argtypes = [__import__("ctypes").c_void_p, __import__("ctypes").c_int]
+    assert L.ref_bvh_obb_is_obbrss_half(ref.h, 0) == 1 and L.ref_bvh_obb_is_obbrss_half(ref.h, 1) == 1
+    emu = EmuScene()
+    assert emu.register_bvh_obbrss(na, va, ta) == 0 and emu.register_bvh_obbrss(nb, vb, tb) == 1
+    # the same two meshes once more, as plain OBB models (ids 2 and 3 in every backend)
+    for sc in (orc, ref):
+        assert sc.register_bvh(va, ta)[0] == 2 and sc.register_bvh(vb, tb)[0] == 3
+    assert emu.register_bvh_obb(na, va, ta) == 2 and emu.register_bvh_obb(nb, vb, tb) == 3
+    rec0 = P.make_shapes([P.BV_OBBRSS] * 2, [[0, 0, 0]] * 2, data=[0, 1])
+    rec = P.make_shapes([P.BV_OBB] * 2, [[0, 0, 0]] * 2, data=[2, 3])
+    ho = orc.register_shapes(rec)
+    assert np.array_equal(ref.register_shapes(rec), ho)
+    # the emu scene: same handle numbering as the other two (mesh_scene drew its primitives from its own generator
+    # after the two meshes: the same draws again)
+    assert np.array_equal(emu.register_shapes(rec0), hm)
+    rng2 = np.random.default_rng(7)
+    W.sphere_mesh(1.0, 20, 10, noise=0.03, rng=rng2)
+    W.sphere_mesh(0.6, 12, 6, noise=0.05, rng=rng2)
+    prims = W.random_primitive_shapes(rng2, 48, ALL)
+    prims["p"] *= 0.3
+    assert np.array_equal(emu.register_shapes(prims), hp)
+    assert np.array_equal(emu.register_shapes(rec), ho)
+    m = 2500
+    tf1 = W.random_transforms(rng, m, (-.2, -.2, -.2), (.2, .2, .2))
+    tf2 = W.random_transforms(rng, m, (-1.5, -1.5, -1.5), (1.5, 1.5, 1.5))
+    hq = hp[rng.integers(0, len(hp), m)]
+    h1 = ho[rng.integers(0, 2, m)]
+    h2 = ho[rng.integers(0, 2, m)]
+    Cf = ("p1", "p2", "normal", "pos", "distance_lower_bound", "b1", "b2", "num_contacts")
+    for kw in (dict(), dict(security_margin=0.05), dict(num_max_contacts=4, enable_contact=0)):
+        req = P.CollisionRequestPOD(**kw)
+        for a1, t1, a2, t2 in ((h1, tf1, hq, tf2), (hq, tf2, h1, tf1), (h1, tf1, h2, tf2)):
+            want = ref.batch_collide(a1, t1, a2, t2, req, nthreads=0)
+            got = orc.batch_collide(a1, t1, a2, t2, req, nthreads=0)
+            cmp_fields(want, got, Cf)
+            dev = emu.batch_collide(a1, t1, a2, t2, req)
+            cmp_fields(got, dev, Cf + ("iterations", "status"))
+    assert want["num_contacts"].sum() > 20
+    # mixed kinds and distance(): unsupported in the product and the oracle alike
+    mix = orc.batch_collide(h1[:8], tf1[:8], hm[:1].repeat(8), tf2[:8], nthreads=0)
+    assert np.all(P.status_path(mix["status"]) == P.PATH_UNSUPPORTED)
+    assert np.all(P.status_path(emu.batch_collide(h1[:8], tf1[:8], hm[:1].repeat(8), tf2[:8])["status"]) == P.PATH_UNSUPPORTED)
+    for sc in (orc, emu):
+        d = sc.batch_distance(h1[:8], tf1[:8], hq[:8], tf2[:8], **({"nthreads": 0} if sc is orc else {}))
+        assert np.all(P.status_path(d["status"]) == P.PATH_UNSUPPORTED)
+        d = sc.batch_distance(h1[:8], tf1[:8], h2[:8], tf2[:8], **({"nthreads": 0} if sc is orc else {}))
+        assert np.all(P.status_path(d["status"]) == P.PATH_UNSUPPORTED)
