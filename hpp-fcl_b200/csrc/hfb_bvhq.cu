@@ -116,6 +116,7 @@ struct QBlock {
   QSlot* slots;
   QStackEnt* stacks;
   QTreelet* tls;
+  QTreeletHot* hot;
   QSched* sc;
   unsigned lo, hi;
 };
@@ -125,7 +126,7 @@ __device__ __noinline__ void q_continue(const BvhqLaunch& L, const QBlock& B, co
   DevSink sink{B.sc};
   QSlot& s = B.slots[sl];
   QStackEnt* stk = B.stacks + (size_t)sl * L.stack_cap;
-  if (q_advance(s, sl, stk, B.tls, c, sink, have, near) != Q_DONE) return;
+  if (q_advance(s, sl, stk, B.tls, B.hot, c, sink, have, near) != Q_DONE) return;
   q_write_result(s, L.out + s.pair);
   bv_total += (unsigned)s.bv_tests;
   leaf_total += (unsigned)s.leaf_tests;
@@ -203,7 +204,8 @@ template <int THREADS>
 __global__ void __launch_bounds__(THREADS, 1) k_bvhq(const BvhqLaunch L) {
   extern __shared__ __align__(16) unsigned char q_smem[];
   QSlot* slots = reinterpret_cast<QSlot*>(q_smem);
-  QSched* sc = reinterpret_cast<QSched*>(q_smem + HFB_Q_NSLOTS * sizeof(QSlot));
+  QTreeletHot* hot = reinterpret_cast<QTreeletHot*>(q_smem + HFB_Q_NSLOTS * sizeof(QSlot));
+  QSched* sc = reinterpret_cast<QSched*>(q_smem + HFB_Q_NSLOTS * sizeof(QSlot) + HFB_Q_NTREELETS * sizeof(QTreeletHot));
   const unsigned lo = *L.range_lo, hi = *L.range_hi;
   const unsigned lane = threadIdx.x & 31u;
   if (threadIdx.x == 0) {
@@ -222,7 +224,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_bvhq(const BvhqLaunch L) {
   QStackEnt* stacks = L.stacks + (size_t)blockIdx.x * HFB_Q_NSLOTS * (size_t)L.stack_cap;
   QTreelet* tls = L.treelets + (size_t)blockIdx.x * HFB_Q_NTREELETS;
   EpaWs* ws = L.ws + (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  QLeafSave* saves = L.saves + (size_t)blockIdx.x * (HFB_Q_NSLOTS + HFB_Q_TREELET_MAX * HFB_Q_NTREELETS);
+  QLeafSave* saves = L.saves + (size_t)blockIdx.x * (HFB_Q_NSLOTS + 2 * HFB_Q_TREELET_MAX * HFB_Q_NTREELETS);
   DevSink sink{sc};
   QCtx c;
   c.P = L.P;
@@ -237,7 +239,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_bvhq(const BvhqLaunch L) {
       atomicAdd(&sc->active, 1);
   }
   __syncthreads();
-  const QBlock B{slots, stacks, tls, sc, lo, hi};
+  const QBlock B{slots, stacks, tls, hot, sc, lo, hi};
   // up to `want` items of one queue for this warp; 0 when the queue is empty
   auto pop = [&](int* head, int* tail, int want, int& base, const int* limit = nullptr) -> int {
     int cnt = 0;
@@ -286,7 +288,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_bvhq(const BvhqLaunch L) {
     q_bv_group<LC>(active, s, nodes + q_bv_base(s, item_x), gbase, sub, d1, d2, f1, f2);
     bool have;
     QStackEnt near;
-    if (active && sub == 0u && q_bv_store(s, item, stacks + (size_t)sl * L.stack_cap, tls, sink, d1, d2, f1, f2, have, near))
+    if (active && sub == 0u && q_bv_store(s, item, stacks + (size_t)sl * L.stack_cap, hot, sink, d1, d2, f1, f2, have, near))
       q_continue(L, B, c, sl, bv_total, leaf_total, have, near);
     __syncwarp();
   };
@@ -351,11 +353,11 @@ __global__ void __launch_bounds__(THREADS, 1) k_bvhq(const BvhqLaunch L) {
           if (valid) {
             QLeafRes r;
             QLeafSave& sv = saves[q_save_index(s, item, HFB_Q_NSLOTS)];
-            const int st = q_leaf_gjk<CAPS_BVHQ>(s, q_leaf_prim(s, tls, item), L.P, !spec, (item & HFB_Q_ITEM_RESUME) != 0u,
+            const int st = q_leaf_gjk<CAPS_BVHQ>(s, q_leaf_prim(s, hot, item), L.P, !spec, (item & HFB_Q_ITEM_RESUME) != 0u,
                                                  L.gjk_chunk, sv, r);
             if (st == QL_SUSPENDED) sink.push_leaf(item | HFB_Q_ITEM_RESUME);
             else if (st == QL_NEED_EPA) sink.push_epa(item & ~HFB_Q_ITEM_RESUME);
-            else if (q_leaf_store(s, item, tls, sink, r)) q_continue(L, B, c, sl, bv_total, leaf_total, false, QStackEnt());
+            else if (q_leaf_store(s, item, tls, hot, sink, r)) q_continue(L, B, c, sl, bv_total, leaf_total, false, QStackEnt());
           }
         }
         __syncwarp();
@@ -383,8 +385,8 @@ __global__ void __launch_bounds__(THREADS, 1) k_bvhq(const BvhqLaunch L) {
           const bool spec = (item & HFB_Q_ITEM_SPEC) != 0u;
           if (valid) {
             QLeafRes r;
-            q_leaf_epa<CAPS_BVHQ>(s, q_leaf_prim(s, tls, item), L.P, !spec, ws, saves[q_save_index(s, item, HFB_Q_NSLOTS)], r);
-            if (q_leaf_store(s, item, tls, sink, r)) q_continue(L, B, c, sl, bv_total, leaf_total, false, QStackEnt());
+            q_leaf_epa<CAPS_BVHQ>(s, q_leaf_prim(s, hot, item), L.P, !spec, ws, saves[q_save_index(s, item, HFB_Q_NSLOTS)], r);
+            if (q_leaf_store(s, item, tls, hot, sink, r)) q_continue(L, B, c, sl, bv_total, leaf_total, false, QStackEnt());
           }
         }
         __syncwarp();
@@ -415,7 +417,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_bvhq(const BvhqLaunch L) {
   }
 }
 
-static size_t bvhq_smem_bytes() { return HFB_Q_NSLOTS * sizeof(QSlot) + sizeof(QSched); }
+static size_t bvhq_smem_bytes() { return HFB_Q_NSLOTS * sizeof(QSlot) + HFB_Q_NTREELETS * sizeof(QTreeletHot) + sizeof(QSched); }
 
 unsigned bvhq_blocks(int num_sms, size_t n) {
   // a block is worth launching for every 64 queries; never more than one per SM (persistent)
@@ -430,13 +432,13 @@ BvhqSizes bvhq_sizes(unsigned blocks, size_t n, int stack_cap) {
   z.stacks = (size_t)blocks * HFB_Q_NSLOTS * (size_t)stack_cap * sizeof(QStackEnt);
   z.treelets = (size_t)blocks * HFB_Q_NTREELETS * sizeof(QTreelet);
   z.ws = (size_t)blocks * HFB_Q_MAX_THREADS * sizeof(EpaWs);
-  z.saves = (size_t)blocks * (HFB_Q_NSLOTS + HFB_Q_TREELET_MAX * HFB_Q_NTREELETS) * sizeof(QLeafSave);
+  z.saves = (size_t)blocks * (HFB_Q_NSLOTS + 2 * HFB_Q_TREELET_MAX * HFB_Q_NTREELETS) * sizeof(QLeafSave);
   return z;
 }
 
 int bvhq_launch(const BvhqLaunch& L, unsigned blocks, size_t n, cudaStream_t s) {
   static_assert(HFB_Q_NSLOTS <= 256, "thread t fills slot t");
-  static_assert(HFB_Q_NSLOTS + HFB_Q_TREELET_MAX * HFB_Q_NTREELETS <= HFB_Q_QCAP, "item rings hold every item that can exist");
+  static_assert(HFB_Q_NSLOTS + HFB_Q_TREELET_MAX * HFB_Q_NTREELETS <= HFB_Q_QCAP, "each ring holds every item of its kind that can exist");
   static_assert(sizeof(QSlot) % 16 == 8, "odd stride in 8-byte words: lanes reading one field of 32 slots spread over the banks");
   const size_t smem = bvhq_smem_bytes();
   const bool wide = L.warps >= 16;

@@ -51,12 +51,14 @@ struct QPrep {  // per query, written by k_bvhq_prep: the shape's RSS (computeBV
   int ok, swapped;
 };
 
-struct QTreelet {  // cached values of one speculated subtree: descendants tfc .. tfc + 2L - 3
-  double d[2 * HFB_Q_TREELET_MAX];
-  int fc[2 * HFB_Q_TREELET_MAX];
-  int leaf_of[2 * HFB_Q_TREELET_MAX];
-  int prim[HFB_Q_TREELET_MAX];
-  double leaf[HFB_Q_TREELET_MAX][10];  // distance, p1, p2, normal
+// cached values of one speculated subtree; entry k belongs to descendant node tfc + k (k < 2 L - 2)
+struct QTreeletHot {  // what the replay reads at every step: shared memory on the device
+  double d[2 * HFB_Q_TREELET_MAX];      // RSS distance of the node (as a child of its parent)
+  double leafd[2 * HFB_Q_TREELET_MAX];  // leaf nodes: distance of the triangle
+  int fc[2 * HFB_Q_TREELET_MAX];        // first_child
+};
+struct QTreelet {  // read only for a leaf that improves the minimum: global memory
+  double wit[2 * HFB_Q_TREELET_MAX][9];  // p1, p2, normal of the leaf tests
 };
 
 struct QSlot {  // one query in flight (shared memory on the device; 83 eight-byte words: odd stride)
@@ -274,10 +276,10 @@ HFB_HD void q_leaf_epa(const QSlot& s, int prim, const SolverP& P, bool chained,
   pair_phase2<1, CAPS>(in, P, g, ws, o);
   q_leaf_result(o, r);
 }
-// where the parked state of an item lives: one entry per slot (its one unspeculated leaf) and one per leaf of every
+// where the parked state of an item lives: one entry per slot (its one unspeculated leaf) and one per node of every
 // treelet buffer
 HFB_HD unsigned q_save_index(const QSlot& s, unsigned item, unsigned nslots) {
-  return (item & HFB_Q_ITEM_SPEC) ? nslots + (unsigned)s.scr * HFB_Q_TREELET_MAX + ((item >> 12) & 0xffu)
+  return (item & HFB_Q_ITEM_SPEC) ? nslots + (unsigned)s.scr * 2 * HFB_Q_TREELET_MAX + ((item >> 12) & 0xffu)
                                   : (item & HFB_Q_SLOT_MASK);
 }
 
@@ -335,34 +337,50 @@ HFB_HD void q_take_leaf(QSlot& s, int prim, const double* leaf10) {
 // node needs a value that is not at hand, issues the item(s) for it and returns Q_ISSUED; Q_DONE when the
 // stack is empty.  Called by whoever completed the query's last outstanding item; `e0` (when `have`) is the node
 // to visit before anything is popped -- the nearer child of the node a BV item just finished.
-// While a speculated subtree is being replayed, `s.tbase` is the stack height below which the entries belong to the
-// walk outside it: the subtree's root sits at index tbase, everything above was pushed by the replay.
+// Replay of a speculated subtree: its root sits on the query's stack at index s.tbase (re-pushed by the set-up);
+// everything the replay pushes goes to a stack of its own (`lstk`, thread-local: the subtree is finished before this
+// call returns, and the query's stack lives in global memory), every value it needs comes from `hot`.
+#define HFB_Q_LOCAL_STACK 64
 template <class Sink>
-HFB_HD int q_advance(QSlot& s, unsigned slot_id, QStackEnt* stk, QTreelet* tls, const QCtx& c, Sink& sink, bool have,
-                     QStackEnt e) {
+HFB_HD int q_advance(QSlot& s, unsigned slot_id, QStackEnt* stk, QTreelet* tls, QTreeletHot* hot, const QCtx& c,
+                     Sink& sink, bool have, QStackEnt e) {
   int sp = s.sp;
   const hfb_bvh_node* nodes = static_cast<const hfb_bvh_node*>(s.ptr[0]);
+  QStackEnt lstk[HFB_Q_LOCAL_STACK];
+  int lsp = 0;
+  bool inside = false;  // (of the entry in `e`)
   for (;;) {
     if (!have) {
-      if (sp == 0) break;
-      e = stk[--sp];
+      if (lsp > 0) {
+        e = lstk[--lsp];
+        inside = true;
+      } else {
+        if (sp == 0) break;
+        e = stk[--sp];
+        inside = s.scr >= 0 && sp == s.tbase;  // the speculated subtree's root
+      }
     }
     have = false;
     if (e.dlow >= 0) {
       if ((e.dlow >= s.out[0] - c.abs_err) && (e.dlow * (1 + c.rel_err) >= s.out[0])) continue;
     }
-    QTreelet* T = s.scr >= 0 ? tls + s.scr : nullptr;
-    const bool inside = T && sp >= s.tbase;  // (the entry just taken sat at index sp or is a child of one that did)
+    if (s.scr >= 0 && !inside) {  // the walk has left the speculated subtree
+      sink.treelet_release(s.scr);
+      s.scr = -1;
+    }
     if (e.fc < 0) {  // leaf
       const int prim = -(e.fc + 1);
       if (inside) {
+        const int k = e.node - s.tfc;
         s.leaf_tests++;
-        q_take_leaf(s, prim, T->leaf[T->leaf_of[e.node - s.tfc]]);
+        const QTreeletHot& H = hot[s.scr];
+        if (s.out[0] > H.leafd[k]) {  // DistanceResult::update
+          s.b1 = prim;
+          s.out[0] = H.leafd[k];
+          const double* wv = tls[s.scr].wit[k];
+          for (int q = 0; q < 9; ++q) s.out[1 + q] = wv[q];
+        }
         continue;
-      }
-      if (T) {  // the walk has left the speculated subtree
-        sink.treelet_release(s.scr);
-        s.scr = -1;
       }
       s.cur = prim;
       s.pending = 1;
@@ -373,14 +391,21 @@ HFB_HD int q_advance(QSlot& s, unsigned slot_id, QStackEnt* stk, QTreelet* tls, 
     }
     if (inside) {  // both children cached
       const int k = e.fc - s.tfc;
+      const QTreeletHot& H = hot[s.scr];
       s.bv_tests += 2;
-      e = q_push_children(stk, sp, e.fc, T->d[k], T->d[k + 1], T->fc[k], T->fc[k + 1]);
+      QStackEnt a, b;
+      a.dlow = H.d[k]; a.fc = H.fc[k]; a.node = e.fc;
+      b.dlow = H.d[k + 1]; b.fc = H.fc[k + 1]; b.node = e.fc + 1;
+      if (b.dlow < a.dlow) {  // the nearer child is visited first
+        lstk[lsp++] = a;
+        e = b;
+      } else {
+        lstk[lsp++] = b;
+        e = a;
+      }
       have = true;
+      inside = true;
       continue;
-    }
-    if (T) {
-      sink.treelet_release(s.scr);
-      s.scr = -1;
     }
     if (c.spec_after >= 0 && s.rounds >= c.spec_after) {
       const unsigned L = nodes[e.node]._pad;  // triangles below; 0 unless the subtree is one contiguous block
@@ -388,28 +413,17 @@ HFB_HD int q_advance(QSlot& s, unsigned slot_id, QStackEnt* stk, QTreelet* tls, 
       if (L >= 2 && L <= lmax) {
         const int id = sink.treelet_acquire();
         if (id >= 0) {
-          QTreelet* N = tls + id;
           const int nd = 2 * (int)L - 2;
-          int nleaf = 0;
-          for (int k = 0; k < nd; ++k) {
-            const int f = nodes[e.fc + k].first_child;
-            N->fc[k] = f;
-            if (f < 0) {
-              N->leaf_of[k] = nleaf;
-              N->prim[nleaf] = -(f + 1);
-              ++nleaf;
-            }
-          }
           s.scr = id;
           s.tfc = e.fc;
           s.tbase = sp;
           e.dlow = -1.0;  // (it passed canStop just now, and nothing changes the minimum before the replay)
           stk[sp++] = e;  // the replay starts by popping this node again; its children are cached then
           s.sp = sp;
-          s.pending = nd / 2 + nleaf;
+          // one BV item per pair of descendants; each spawns the leaf items of its own leaves (q_bv_store)
+          s.pending = nd / 2 + (int)L;
           s.rounds++;
-          for (int p = 0; p < nd / 2; ++p) sink.push_bv(slot_id | ((unsigned)p << 12) | HFB_Q_ITEM_SPEC);
-          for (int j = 0; j < nleaf; ++j) sink.push_leaf(slot_id | ((unsigned)j << 12) | HFB_Q_ITEM_SPEC);
+          for (int p = 0; p < nd / 2; ++p) sink.push_bv(slot_id | ((unsigned)(2 * p) << 12) | HFB_Q_ITEM_SPEC);
           return Q_ISSUED;
         }
       }
@@ -431,16 +445,22 @@ HFB_HD int q_advance(QSlot& s, unsigned slot_id, QStackEnt* stk, QTreelet* tls, 
 
 // completion of a BV item whose values are in hand (d of children base, base + 1 and their first_child).
 // Returns true when this was the query's last outstanding item: the caller continues the walk (q_advance) with
-// `near` (if `have`) as the node to visit first.
+// `near` (if `have`) as the node to visit first.  A speculated item stores its values and queues the leaf tests of
+// the children that are leaves.
 template <class Sink>
-HFB_HD bool q_bv_store(QSlot& s, unsigned item, QStackEnt* stk, QTreelet* tls, Sink& sink, double d1, double d2, int f1,
+HFB_HD bool q_bv_store(QSlot& s, unsigned item, QStackEnt* stk, QTreeletHot* hot, Sink& sink, double d1, double d2, int f1,
                        int f2, bool& have, QStackEnt& near) {
   have = false;
   if (item & HFB_Q_ITEM_SPEC) {
-    QTreelet* T = tls + s.scr;
-    const int k = 2 * (int)((item >> 12) & 0xffu);
-    T->d[k] = d1;
-    T->d[k + 1] = d2;
+    QTreeletHot& H = hot[s.scr];
+    const unsigned k = (item >> 12) & 0xffu;
+    H.d[k] = d1;
+    H.d[k + 1] = d2;
+    H.fc[k] = f1;
+    H.fc[k + 1] = f2;
+    const unsigned slot_id = item & HFB_Q_SLOT_MASK;
+    if (f1 < 0) sink.push_leaf(slot_id | (k << 12) | HFB_Q_ITEM_SPEC);
+    if (f2 < 0) sink.push_leaf(slot_id | ((k + 1) << 12) | HFB_Q_ITEM_SPEC);
     return sink.dec_pending(s) == 1;
   }
   s.bv_tests += 2;  // BVDistanceLowerBound of both children (:465-469)
@@ -452,21 +472,25 @@ HFB_HD bool q_bv_store(QSlot& s, unsigned item, QStackEnt* stk, QTreelet* tls, S
 }
 // node pair a BV item is about
 HFB_HD int q_bv_base(const QSlot& s, unsigned item) {
-  return (item & HFB_Q_ITEM_SPEC) ? s.tfc + 2 * (int)((item >> 12) & 0xffu) : s.cur;
+  return (item & HFB_Q_ITEM_SPEC) ? s.tfc + (int)((item >> 12) & 0xffu) : s.cur;
 }
-HFB_HD int q_leaf_prim(const QSlot& s, const QTreelet* tls, unsigned item) {
-  return (item & HFB_Q_ITEM_SPEC) ? tls[s.scr].prim[(item >> 12) & 0xffu] : s.cur;
+HFB_HD int q_leaf_prim(const QSlot& s, const QTreeletHot* hot, unsigned item) {
+  return (item & HFB_Q_ITEM_SPEC) ? -(hot[s.scr].fc[(item >> 12) & 0xffu] + 1) : s.cur;
 }
 
 // completion of a leaf item; true: the caller continues the walk
 template <class Sink>
-HFB_HD bool q_leaf_store(QSlot& s, unsigned item, QTreelet* tls, Sink& sink, const QLeafRes& r) {
-  double v[10] = {r.distance, r.p1.x, r.p1.y, r.p1.z, r.p2.x, r.p2.y, r.p2.z, r.normal.x, r.normal.y, r.normal.z};
+HFB_HD bool q_leaf_store(QSlot& s, unsigned item, QTreelet* tls, QTreeletHot* hot, Sink& sink, const QLeafRes& r) {
   if (item & HFB_Q_ITEM_SPEC) {
-    double* dst = tls[s.scr].leaf[(item >> 12) & 0xffu];
-    for (int k = 0; k < 10; ++k) dst[k] = v[k];
+    const unsigned k = (item >> 12) & 0xffu;
+    double* wv = tls[s.scr].wit[k];
+    wv[0] = r.p1.x; wv[1] = r.p1.y; wv[2] = r.p1.z;
+    wv[3] = r.p2.x; wv[4] = r.p2.y; wv[5] = r.p2.z;
+    wv[6] = r.normal.x; wv[7] = r.normal.y; wv[8] = r.normal.z;
+    hot[s.scr].leafd[k] = r.distance;
     return sink.dec_pending(s) == 1;
   }
+  double v[10] = {r.distance, r.p1.x, r.p1.y, r.p1.z, r.p2.x, r.p2.y, r.p2.z, r.normal.x, r.normal.y, r.normal.z};
   if (!s.seed) s.leaf_tests++;  // the seed triangle of preprocess() is not a counted leaf test
   s.seed = 0;
   q_take_leaf(s, s.cur, v);

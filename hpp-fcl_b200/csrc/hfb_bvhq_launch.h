@@ -7,9 +7,9 @@
 namespace hfb {
 
 #define HFB_Q_MAX_THREADS 512  // the kernel comes with 8 warps per block (255 registers per thread) and with 16 (128)
-#define HFB_Q_NSLOTS 256     // queries in flight per block
+#define HFB_Q_NSLOTS 224     // queries in flight per block (shared memory: 224 slots + the treelets' hot values + the rings)
 #define HFB_Q_NTREELETS 8    // speculated subtrees in flight per block
-#define HFB_Q_QCAP 2048      // ring size of each item queue (>= NSLOTS + HFB_Q_TREELET_MAX * NTREELETS)
+#define HFB_Q_QCAP 2048      // ring size of each item queue (>= NSLOTS + 2 * HFB_Q_TREELET_MAX * NTREELETS)
 
 struct BvhqLaunch {
   ArenaView A;
@@ -29,7 +29,7 @@ struct BvhqLaunch {
   QStackEnt* stacks;     // blocks x NSLOTS x stack_cap
   QTreelet* treelets;    // blocks x NTREELETS
   EpaWs* ws;             // one per thread
-  QLeafSave* saves;      // blocks x (NSLOTS + 32 * NTREELETS): parked solver state of suspended leaf items
+  QLeafSave* saves;      // blocks x (NSLOTS + 2 * TREELET_MAX * NTREELETS): parked solver state of suspended leaf items
   unsigned* work;        // hand-out counter of this launch (zeroed by the caller)
   unsigned long long* counters;  // [0] bv tests, [1] leaf tests, [2] watchdog trips (running totals)
   int stack_cap;

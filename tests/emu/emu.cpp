@@ -314,7 +314,8 @@ static void host_bvhq_distance(const ArenaView& A, const std::vector<size_t>& to
   std::vector<QSlot> slots((size_t)nslots);
   std::vector<QStackEnt> stacks((size_t)nslots * 64);
   std::vector<QTreelet> tls((size_t)(ntl > 0 ? ntl : 1));
-  std::vector<QLeafSave> saves((size_t)nslots + (size_t)(ntl > 0 ? ntl : 1) * HFB_Q_TREELET_MAX);
+  std::vector<QTreeletHot> hot((size_t)(ntl > 0 ? ntl : 1));
+  std::vector<QLeafSave> saves((size_t)nslots + (size_t)(ntl > 0 ? ntl : 1) * 2 * HFB_Q_TREELET_MAX);
   HostQSink sink;
   for (int k = 0; k < ntl; ++k) sink.free_tl.push_back(k);
   std::unique_ptr<EpaWs> ws(new EpaWs());
@@ -367,14 +368,14 @@ static void host_bvhq_distance(const ArenaView& A, const std::vector<size_t>& to
       g_q_spec_items += spec;
       QLeafRes r;
       QLeafSave& sv = saves[q_save_index(s, item, (unsigned)nslots)];
-      const int prim = q_leaf_prim(s, tls.data(), item);
+      const int prim = q_leaf_prim(s, hot.data(), item);
       int st = QL_DONE;
       if (epa) q_leaf_epa<CAPS_ALL>(s, prim, P, !spec, ws.get(), sv, r);
       else st = q_leaf_gjk<CAPS_ALL>(s, prim, P, !spec, (item & HFB_Q_ITEM_RESUME) != 0, gjk_chunk, sv, r);
       if (st == QL_SUSPENDED) sink.push_leaf(item | HFB_Q_ITEM_RESUME);
       else if (st == QL_NEED_EPA) sink.push_epa(item & ~HFB_Q_ITEM_RESUME);
-      else if (q_leaf_store(s, item, tls.data(), sink, r))
-        rc = q_advance(s, sl, &stacks[(size_t)sl * 64], tls.data(), c, sink, false, QStackEnt());
+      else if (q_leaf_store(s, item, tls.data(), hot.data(), sink, r))
+        rc = q_advance(s, sl, &stacks[(size_t)sl * 64], tls.data(), hot.data(), c, sink, false, QStackEnt());
     } else {
       pick -= nl + ne;
       item = sink.bvq[pick];
@@ -387,9 +388,9 @@ static void host_bvhq_distance(const ArenaView& A, const std::vector<size_t>& to
       const double d1 = q_rss_child(s, nodes[base]), d2 = q_rss_child(s, nodes[base + 1]);
       bool have;
       QStackEnt near;
-      if (q_bv_store(s, item, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), sink, d1, d2,
+      if (q_bv_store(s, item, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], hot.data(), sink, d1, d2,
                      nodes[base].first_child, nodes[base + 1].first_child, have, near))
-        rc = q_advance(s, item & HFB_Q_SLOT_MASK, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), c, sink, have, near);
+        rc = q_advance(s, item & HFB_Q_SLOT_MASK, &stacks[(size_t)(item & HFB_Q_SLOT_MASK) * 64], tls.data(), hot.data(), c, sink, have, near);
     }
     if (rc == Q_DONE) {
       const int sl = (int)(item & HFB_Q_SLOT_MASK);
