@@ -20,6 +20,8 @@ namespace {
 struct GjkSaved {
   GjkState g;
   GjkLoop L;
+  int done;  // 1: converged in the first pass (extracted early, so that its EPA can start), 2: in a later pass, 0: running
+  int _pad;
 };
 #define HFB_GJK_UNKNOWN_TYPES (-99)  // status of a pair whose node types no kernel knows (reported as unsupported)
 
@@ -30,6 +32,7 @@ struct PassArgs {
   uint32_t* out_list;        // positions still running after this pass (null: last pass)
   unsigned* out_count;
   int steps;
+  int which;  // k_gjk_end: the pairs with this `done` value
 };
 
 __device__ __forceinline__ void append_running(const PassArgs& p, bool more, unsigned pos) {
@@ -52,6 +55,7 @@ __global__ void __launch_bounds__(128) k_gjk_first(const BatchArgs a, const Pass
       const unsigned i = a.index_list[k];
       const PairIn in = load_pair_in<CAP_PRIM>(a, i);
       GjkSaved sv;
+      sv._pad = 0;
       if (!type_known(in.s1.type) || !type_known(in.s2.type)) {
         sv.g.status = HFB_GJK_UNKNOWN_TYPES;
       } else {
@@ -61,6 +65,7 @@ __global__ void __launch_bounds__(128) k_gjk_first(const BatchArgs a, const Pass
         more = true;
         for (int s = 0; s < p.steps && more; ++s) more = gjk_step<1, CAP_PRIM>(S.a, S.b, S.md, a.P.gjk, sv.g, sv.L);
       }
+      sv.done = more ? 0 : 1;
       p.state[k - lo] = sv;
     }
     if (p.out_list) append_running(p, more, k - lo);
@@ -84,6 +89,7 @@ __global__ void __launch_bounds__(128) k_gjk_more(const BatchArgs a, const PassA
       GjkSaved sv = p.state[pos];
       more = true;
       for (int s = 0; s < p.steps && more; ++s) more = gjk_step<1, CAP_PRIM>(S.a, S.b, S.md, a.P.gjk, sv.g, sv.L);
+      sv.done = more ? 0 : 2;
       p.state[pos] = sv;
     }
     if (p.out_list) append_running(p, more, pos);
@@ -94,6 +100,7 @@ template <int MODE>
 __global__ void __launch_bounds__(128) k_gjk_end(const BatchArgs a, const PassArgs p) {
   const unsigned lo = *a.range_lo, hi = *a.range_hi;
   for (unsigned k = lo + blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += gridDim.x * blockDim.x) {
+    if (p.state[k - lo].done != p.which) continue;
     const unsigned i = a.index_list[k];
     const PairIn in = load_pair_in<CAP_PRIM>(a, i);
     GjkState g = p.state[k - lo].g;
@@ -119,16 +126,26 @@ __global__ void __launch_bounds__(128) k_gjk_end(const BatchArgs a, const PassAr
 
 size_t gjk_pass_state_bytes(size_t n) { return n * sizeof(GjkSaved); }
 
-int gjk_passes_launch(const BatchArgs& a, int mode, unsigned n, void* state, uint32_t* list_a, uint32_t* list_b,
-                      unsigned* counts, const int* steps, int npass, int num_sms, cudaStream_t s, int* launches) {
-  // counts: npass words, zeroed here
-  if (npass < 1) return (int)cudaErrorInvalidValue;
-  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)npass * sizeof(unsigned), s);
-  if (e != cudaSuccess) return (int)e;
+static unsigned pass_blocks(unsigned n, int num_sms) {
   unsigned blocks = (n + 127) / 128;
   const unsigned cap = (unsigned)num_sms * 32u;
   if (blocks > cap) blocks = cap;
-  if (blocks == 0) blocks = 1;
+  return blocks ? blocks : 1u;
+}
+static void launch_end(const BatchArgs& a, int mode, PassArgs p, int which, unsigned blocks, cudaStream_t s) {
+  p.which = which;
+  if (mode == 0) k_gjk_end<0><<<blocks, 128, 0, s>>>(a, p);
+  else k_gjk_end<1><<<blocks, 128, 0, s>>>(a, p);
+}
+
+// first pass + extraction of the pairs it finished (their EPA items are in the queue when this returns, so that the
+// caller can start EPA on a side stream next to the remaining passes)
+int gjk_passes_first(const BatchArgs& a, int mode, unsigned n, void* state, uint32_t* list_a, unsigned* counts,
+                     const int* steps, int npass, int num_sms, cudaStream_t s, int* launches) {
+  if (npass < 1) return (int)cudaErrorInvalidValue;
+  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)npass * sizeof(unsigned), s);
+  if (e != cudaSuccess) return (int)e;
+  const unsigned blocks = pass_blocks(n, num_sms);
   PassArgs p;
   p.state = static_cast<GjkSaved*>(state);
   p.in_list = nullptr;
@@ -136,8 +153,21 @@ int gjk_passes_launch(const BatchArgs& a, int mode, unsigned n, void* state, uin
   p.out_list = npass > 1 ? list_a : nullptr;
   p.out_count = counts;
   p.steps = npass > 1 ? steps[0] : 0x7fffffff;
+  p.which = 0;
   k_gjk_first<<<blocks, 128, 0, s>>>(a, p);
-  ++*launches;
+  launch_end(a, mode, p, 1, blocks, s);
+  *launches += 2;
+  return (int)cudaGetLastError();
+}
+
+// the remaining passes + extraction of the pairs they finished
+int gjk_passes_rest(const BatchArgs& a, int mode, unsigned n, void* state, uint32_t* list_a, uint32_t* list_b,
+                    unsigned* counts, const int* steps, int npass, int num_sms, cudaStream_t s, int* launches) {
+  if (npass < 2) return 0;
+  const unsigned blocks = pass_blocks(n, num_sms);
+  PassArgs p;
+  p.state = static_cast<GjkSaved*>(state);
+  p.which = 0;
   for (int k = 1; k < npass; ++k) {
     const bool last = k + 1 == npass;
     p.in_list = (k & 1) ? list_a : list_b;
@@ -152,8 +182,7 @@ int gjk_passes_launch(const BatchArgs& a, int mode, unsigned n, void* state, uin
     k_gjk_more<<<b, 128, 0, s>>>(a, p);
     ++*launches;
   }
-  if (mode == 0) k_gjk_end<0><<<blocks, 128, 0, s>>>(a, p);
-  else k_gjk_end<1><<<blocks, 128, 0, s>>>(a, p);
+  launch_end(a, mode, p, 2, blocks, s);
   ++*launches;
   return (int)cudaGetLastError();
 }

@@ -747,6 +747,7 @@ struct hfb_ctx {
   // convergence); "0": the single kernel k_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE>
   int gjk_steps[8] = {6, 0, 0, 0, 0, 0, 0, 0};  // measured on config 2 (profiles/r02_summary.md): "6" 1.00 ms, "4,4" 1.05, "3,3,4" 1.12, single kernel 1.16
   int gjk_npass = 2;
+  int epa_overlap = 1;  // HFB_EPA_OVERLAP=0: EPA only after the last GJK pass
   int bvh_warps = 8;   // HFB_BVH_WARPS: 8 (255 registers per thread) or 16 (128) warps per block of k_bvhq
   int bvh_gens = 2;    // HFB_BVH_GENS: generations of BV items per cycle of k_bvhq
   int bvh_spec_big = 300;  // HFB_BVH_SPEC_BIG: items more before subtrees of up to 128 triangles are speculated
@@ -1012,11 +1013,20 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
           CK(sl.glist.reserve(2 * (size_t)n * sizeof(uint32_t)));
           CK(sl.gcnt.reserve(8 * sizeof(unsigned)));
           int nl = 0;
+          uint32_t* la = static_cast<uint32_t*>(sl.glist.p);
           {
             KTimer kt(ctx, s, 0);
-            if (gjk_passes_launch(ag, MODE, n, sl.gstate.p, static_cast<uint32_t*>(sl.glist.p),
-                                  static_cast<uint32_t*>(sl.glist.p) + n, static_cast<unsigned*>(sl.gcnt.p), ctx->gjk_steps,
-                                  ctx->gjk_npass, ctx->num_sms, s, &nl) != 0)
+            if (gjk_passes_first(ag, MODE, n, sl.gstate.p, la, static_cast<unsigned*>(sl.gcnt.p), ctx->gjk_steps, ctx->gjk_npass,
+                                 ctx->num_sms, s, &nl) != 0)
+              return fail(ctx, HFB_ERR_CUDA, "GJK pass launch failed");
+          }
+          // EPA of the pairs the first pass finished starts on the side stream, next to the remaining passes (which
+          // only keep a fraction of the GPU busy)
+          if (ctx->gjk_npass > 1 && ctx->epa_overlap && want_epa && (rc = epa_after_part(false))) return rc;
+          {
+            KTimer kt(ctx, s, 0);
+            if (gjk_passes_rest(ag, MODE, n, sl.gstate.p, la, la + n, static_cast<unsigned*>(sl.gcnt.p), ctx->gjk_steps,
+                                ctx->gjk_npass, ctx->num_sms, s, &nl) != 0)
               return fail(ctx, HFB_ERR_CUDA, "GJK pass launch failed");
           }
           ctx->stats.kernel_launches += (uint64_t)nl;
@@ -1438,6 +1448,7 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
     c->gjk_npass = k > 0 ? k + 1 : 0;
   }
   if (const char* bw = getenv("HFB_BVH_WARPS")) c->bvh_warps = atoi(bw) >= 16 ? 16 : 8;
+  if (const char* eo = getenv("HFB_EPA_OVERLAP")) c->epa_overlap = atoi(eo) != 0;
   if (const char* bg = getenv("HFB_BVH_GENS")) c->bvh_gens = atoi(bg) > 0 ? atoi(bg) : 1;
   if (const char* bb = getenv("HFB_BVH_SPEC_BIG")) c->bvh_spec_big = atoi(bb) >= 0 ? atoi(bb) : 0;
   if (const char* bq = getenv("HFB_BVH_QUORUM"))
