@@ -318,12 +318,41 @@ class _Scene:
         self._handles = {}
         self._dirty = False
 
+    @staticmethod
+    def _content(geom):
+        """what the arena holds for `geom` beyond its record: the vertices of a hull / triangle, the mesh of a model"""
+        pts = geom._points()
+        if geom.node_type == P.BV_OBBRSS:
+            return (np.ascontiguousarray(geom.bvs).tobytes() if geom.bvs is not None else None,
+                    np.ascontiguousarray(geom.vertices, dtype=np.float64).tobytes(),
+                    np.ascontiguousarray(geom.tri_indices, dtype=np.uint32).tobytes())
+        return np.ascontiguousarray(pts, dtype=np.float64).tobytes() if pts is not None else None
+
     def handle(self, geom):
+        """the arena handle of `geom`, registered on first use.  A geometry changed in place since (new sizes, new
+        swept-sphere radius, moved hull vertices) keeps its handle: the record / vertex set is updated
+        (hfb_geom_update_shapes / hfb_geom_update_convex); only a change the arena cannot absorb -- another number of
+        vertices, another mesh -- retires the handle and registers a new one."""
         key = id(geom)
         ent = self._handles.get(key)
-        sig = (geom.node_type, geom._params(), geom.getSweptSphereRadius(), id(getattr(geom, "bvs", None)))
-        if ent is not None and ent[1] == sig and ent[2] is geom:
-            return ent[0]
+        sig = (geom.node_type, tuple(np.asarray(geom._params(), dtype=np.float64).tolist()), geom.getSweptSphereRadius())
+        content = self._content(geom)
+        if ent is not None and ent[2] is geom:
+            h, old_sig, _, old_content, data = ent
+            if old_sig == sig and old_content == content:
+                return h
+            same_kind = old_sig[0] == sig[0]
+            pts = geom._points()
+            if same_kind and geom.node_type != P.BV_OBBRSS and (
+                    old_content == content or (pts is not None and old_content is not None and len(old_content) == len(content))):
+                if old_content != content:
+                    self.engine.update_convex(data, pts)
+                rec = P.make_shapes([geom.node_type], [geom._params()], ssr=geom.getSweptSphereRadius(), data=data)
+                self.engine.update_shapes([h], rec)
+                self._handles[key] = (h, sig, geom, content, data)
+                self._dirty = True
+                return h
+            self.engine.release_shapes([h])  # the storage of its vertices / mesh stays until hfb_geom_clear
         data = 0
         pts = geom._points()
         if geom.node_type == P.BV_OBBRSS:
@@ -334,7 +363,7 @@ class _Scene:
             data = self.engine.register_convex(pts)
         rec = P.make_shapes([geom.node_type], [geom._params()], ssr=geom.getSweptSphereRadius(), data=data)
         h = int(self.engine.register_shapes(rec)[0])
-        self._handles[key] = (h, sig, geom)
+        self._handles[key] = (h, sig, geom, content, data)
         self._dirty = True
         return h
 

@@ -448,6 +448,22 @@ class Context {
         for (size_t i = 0; i < verts->size() && same; ++i)
           for (int k = 0; k < 3; ++k) same = same && e.verts[3 * i + k] == (*verts)[i][k];
       if (same) return e.handle;
+      // changed in place: the handle stays when the arena can absorb the change (same node type, same number of
+      // vertices) -- record and vertex set are updated; otherwise it is retired and a new one registered
+      if (e.rec.type == rec.type && e.nverts == (verts ? verts->size() : 0)) {
+        Entry& m = it->second;
+        rec.data = m.rec.data;
+        if (verts) {
+          for (size_t i = 0; i < verts->size(); ++i)
+            for (int k = 0; k < 3; ++k) m.verts[3 * i + k] = (*verts)[i][k];
+          check(hfb_geom_update_convex(ctx, rec.data, m.verts.data(), (uint32_t)verts->size()));
+        }
+        check(hfb_geom_update_shapes(ctx, &m.handle, &rec, 1));
+        m.rec = rec;
+        dirty = true;
+        return m.handle;
+      }
+      check(hfb_geom_release_shapes(ctx, &e.handle, 1));
       handles.erase(it);
     }
     Entry ent;
@@ -472,6 +488,7 @@ class Context {
     if (it != handles.end()) {
       const Entry& e = it->second;
       if (e.rec.type == HFB_BV_OBBRSS && e.verts == *md.verts && e.tris == *md.tris) return e.handle;
+      check(hfb_geom_release_shapes(ctx, &e.handle, 1));  // a rebuilt model: the old handle is retired
       handles.erase(it);
     }
     Entry ent;

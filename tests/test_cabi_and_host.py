@@ -193,3 +193,59 @@ def test_geometry_updates_in_the_arena():
     from oracle import oracle_lib
     _update_scenario(EmuScene(), oracle_lib.OracleScene(P))
 
+
+
+def test_python_handle_cache_follows_in_place_changes():
+    """api._Scene.handle: a geometry mutated in place keeps its handle and gets its record / vertices UPDATED (no
+    stale answers for hulls and triangles, no handle leaked per change); only another vertex count re-registers"""
+    from hppfcl_b200 import api
+
+    class FakeEngine:
+        def __init__(self):
+            self.log, self.nshape, self.ncvx = [], 0, 0
+
+        def register_convex(self, pts):
+            self.log.append(("convex", len(pts)))
+            self.ncvx += 1
+            return self.ncvx - 1
+
+        def register_shapes(self, rec):
+            self.log.append(("shape", int(rec["type"][0])))
+            self.nshape += 1
+            return np.array([self.nshape - 1], dtype=np.uint32)
+
+        def update_shapes(self, handles, rec):
+            self.log.append(("update_shape", int(handles[0]), tuple(rec["p"][0].tolist()), float(rec["ssr"][0])))
+
+        def update_convex(self, cid, pts):
+            self.log.append(("update_convex", int(cid), len(pts)))
+
+        def release_shapes(self, handles):
+            self.log.append(("release", int(handles[0])))
+
+        def commit(self):
+            self.log.append(("commit",))
+
+    e = FakeEngine()
+    sc = api._Scene(e)
+    box = hf.Box(2, 4, 6)
+    h = sc.handle(box)
+    assert sc.handle(box) == h and e.log == [("shape", P.GEOM_BOX)]
+    box.halfSide[0] = 5.0  # in place
+    assert sc.handle(box) == h and e.log[-1] == ("update_shape", h, (5.0, 2.0, 3.0), 0.0)
+    box.setSweptSphereRadius(0.25)
+    assert sc.handle(box) == h and e.log[-1][0] == "update_shape" and e.log[-1][3] == 0.25
+    pts = np.random.default_rng(0).normal(size=(12, 3))
+    cvx = hf.Convex(pts.copy())
+    hc = sc.handle(cvx)
+    n0 = len(e.log)
+    assert sc.handle(cvx) == hc and len(e.log) == n0
+    cvx.points[3] += 0.5  # a moved vertex: same handle, vertices updated
+    assert sc.handle(cvx) == hc and ("update_convex", 0, 12) in e.log[n0:]
+    assert sc.handle(cvx) == hc and e.log[-1][0] == "update_shape"
+    n1 = len(e.log)
+    assert sc.handle(cvx) == hc and len(e.log) == n1  # unchanged since: nothing to do
+    tri = hf.TriangleP([0, 0, 0], [1, 0, 0], [0, 1, 0])
+    ht = sc.handle(tri)
+    tri.b[0] = 2.0
+    assert sc.handle(tri) == ht and any(x[0] == "update_convex" and x[2] == 3 for x in e.log[n1:])
