@@ -37,9 +37,17 @@ __device__ __forceinline__ int vload(const int* p) { return *reinterpret_cast<co
 
 struct DevSink {
   QSched* sc;
+  // the lanes of the warp that push to this ring at the same instruction share one bump of its tail (the tail is one
+  // shared-memory word all eight warps hammer: a bump per lane serialised them)
   __device__ __forceinline__ void push(unsigned* buf, int* tail, unsigned item) {
     __threadfence_block();  // the slot / stack / treelet writes of this item's producer come first
-    const int pos = atomicAdd(tail, 1) & (HFB_Q_QCAP - 1);
+    const unsigned act = __activemask();
+    const unsigned lane = threadIdx.x & 31u;
+    const int leader = __ffs(act) - 1;
+    int base = 0;
+    if ((int)lane == leader) base = atomicAdd(tail, __popc(act));
+    base = __shfl_sync(act, base, leader);
+    const int pos = (base + __popc(act & ((1u << lane) - 1u))) & (HFB_Q_QCAP - 1);
     volatile unsigned* q = buf;
     // the ring is larger than the number of items that can exist: the previous occupant was taken long ago
     for (unsigned spins = 0; q[pos] != 0u; ++spins)
@@ -48,6 +56,21 @@ struct DevSink {
         break;
       }
     q[pos] = item | HFB_Q_ITEM_VALID;
+  }
+  // `count` speculated BV items of one slot (pairs 0, 2, 4, ... of its subtree): one bump, then plain stores
+  __device__ __forceinline__ void push_bv_pairs(unsigned slot_id, int count) {
+    __threadfence_block();
+    const int base = atomicAdd(&sc->btail, count);
+    volatile unsigned* q = sc->bvq;
+    for (int p = 0; p < count; ++p) {
+      const int pos = (base + p) & (HFB_Q_QCAP - 1);
+      for (unsigned spins = 0; q[pos] != 0u; ++spins)
+        if (spins > (1u << 26)) {
+          atomicExch(&sc->abort_, 1);
+          break;
+        }
+      q[pos] = slot_id | ((unsigned)(2 * p) << 12) | HFB_Q_ITEM_SPEC | HFB_Q_ITEM_VALID;
+    }
   }
   __device__ __forceinline__ void push_leaf(unsigned it) { push(sc->leafq, &sc->ltail, it); }
   __device__ __forceinline__ void push_bv(unsigned it) { push(sc->bvq, &sc->btail, it); }

@@ -423,7 +423,7 @@ HFB_HD int q_advance(QSlot& s, unsigned slot_id, QStackEnt* stk, QTreelet* tls, 
           // one BV item per pair of descendants; each spawns the leaf items of its own leaves (q_bv_store)
           s.pending = nd / 2 + (int)L;
           s.rounds++;
-          for (int p = 0; p < nd / 2; ++p) sink.push_bv(slot_id | ((unsigned)(2 * p) << 12) | HFB_Q_ITEM_SPEC);
+          sink.push_bv_pairs(slot_id, nd / 2);
           return Q_ISSUED;
         }
       }

@@ -747,7 +747,9 @@ struct hfb_ctx {
   // convergence); "0": the single kernel k_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE>
   int gjk_steps[8] = {6, 0, 0, 0, 0, 0, 0, 0};  // measured on config 2 (profiles/r02_summary.md): "6" 1.00 ms, "4,4" 1.05, "3,3,4" 1.12, single kernel 1.16
   int gjk_npass = 2;
-  int epa_overlap = 1;  // HFB_EPA_OVERLAP=0: EPA only after the last GJK pass
+  // HFB_EPA_OVERLAP=1: EPA of the pairs the first GJK pass finished starts on a side stream next to the remaining passes;
+  // measured slower on config 2 (2.11 vs 2.00 ms per step: the two kernels take each other's SMs), so off
+  int epa_overlap = 0;
   int bvh_warps = 8;   // HFB_BVH_WARPS: 8 (255 registers per thread) or 16 (128) warps per block of k_bvhq
   int bvh_gens = 2;    // HFB_BVH_GENS: generations of BV items per cycle of k_bvhq
   int bvh_spec_big = 300;  // HFB_BVH_SPEC_BIG: items more before subtrees of up to 128 triangles are speculated

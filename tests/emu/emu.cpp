@@ -286,6 +286,9 @@ long batch_lanes_g(int G, Emu* E, size_t n, const uint32_t* h1, const hfb_transf
 struct HostQSink {
   std::vector<unsigned> leafq, bvq, epaq;
   void push_epa(unsigned it) { epaq.push_back(it); }
+  void push_bv_pairs(unsigned slot_id, int count) {
+    for (int p = 0; p < count; ++p) bvq.push_back(slot_id | ((unsigned)(2 * p) << 12) | HFB_Q_ITEM_SPEC);
+  }
   std::vector<int> free_tl;
   void push_leaf(unsigned it) { leafq.push_back(it); }
   void push_bv(unsigned it) { bvq.push_back(it); }
