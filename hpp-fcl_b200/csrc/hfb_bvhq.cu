@@ -464,15 +464,17 @@ int bvhq_launch(const BvhqLaunch& L, unsigned blocks, size_t n, cudaStream_t s) 
   static_assert(HFB_Q_NSLOTS + HFB_Q_TREELET_MAX * HFB_Q_NTREELETS <= HFB_Q_QCAP, "each ring holds every item of its kind that can exist");
   static_assert(sizeof(QSlot) % 16 == 8, "odd stride in 8-byte words: lanes reading one field of 32 slots spread over the banks");
   const size_t smem = bvhq_smem_bytes();
-  const bool wide = L.warps >= 16;
-  cudaError_t e = wide ? cudaFuncSetAttribute(k_bvhq<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-                       : cudaFuncSetAttribute(k_bvhq<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const int threads = L.warps >= 16 ? 512 : (L.warps >= 12 ? 384 : 256);
+  cudaError_t e = threads == 512   ? cudaFuncSetAttribute(k_bvhq<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                  : threads == 384 ? cudaFuncSetAttribute(k_bvhq<384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                                   : cudaFuncSetAttribute(k_bvhq<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return (int)e;
   unsigned pb = (unsigned)((n + 127) / 128);
   if (pb > blocks * 16u) pb = blocks * 16u;
   if (pb == 0) pb = 1;
   k_bvhq_prep<<<pb, 128, 0, s>>>(L);
-  if (wide) k_bvhq<512><<<blocks, 512, smem, s>>>(L);
+  if (threads == 512) k_bvhq<512><<<blocks, 512, smem, s>>>(L);
+  else if (threads == 384) k_bvhq<384><<<blocks, 384, smem, s>>>(L);
   else k_bvhq<256><<<blocks, 256, smem, s>>>(L);
   return (int)cudaGetLastError();
 }
