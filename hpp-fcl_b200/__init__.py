@@ -12,6 +12,6 @@ from .build import build_extension, library_path  # noqa: F401
 from .engine import Engine, EngineError, broadphase_pairs, build_bvh_obbrss, load_library  # noqa: F401
 from .api import (  # noqa: F401
     BVHModelOBBRSS, Box, Capsule, CollisionRequest, CollisionResult, Cone, Contact, Convex, Cylinder,
-    DistanceRequest, DistanceResult, Ellipsoid, Sphere, Transform3f, TriangleP,
+    DistanceRequest, DistanceResult, Ellipsoid, Halfspace, Plane, Sphere, Transform3f, TriangleP,
     collide, distance, ComputeCollision, ComputeDistance, BatchQuery,
 )

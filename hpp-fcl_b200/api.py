@@ -132,6 +132,42 @@ class Cylinder(_RadiusLength):
     node_type = P.GEOM_CYLINDER
 
 
+class _PlaneBase(CollisionGeometry):
+    """n . x <= d (Halfspace) or n . x = d (Plane); the constructor normalises (n, d) (unitNormalTest,
+    src/shape/geometric_shapes.cpp:121-143)."""
+
+    def __init__(self, a, b=None, c=None, d=None):  # (n, d) or (a, b, c, d): geometric_shapes.h:887-896, 979-988
+        super().__init__()
+        if c is None:
+            n, off = np.asarray(a, dtype=np.float64).reshape(3).copy(), float(0.0 if b is None else b)
+        else:
+            n, off = np.array([a, b, c], dtype=np.float64), float(d)
+        l = float(np.sqrt((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]))
+        if l > 0:
+            inv_l = 1.0 / l
+            n, off = n * inv_l, off * inv_l
+        else:
+            n, off = np.array([1.0, 0.0, 0.0]), 0.0
+        self.n, self.d = n, off
+
+    def _params(self):
+        return tuple(self.n)
+
+    def _plane(self):
+        return np.array([self.n[0], self.n[1], self.n[2], self.d], dtype=np.float64)
+
+
+class Halfspace(_PlaneBase):  # geometric_shapes.h:885-961
+    node_type = P.GEOM_HALFSPACE
+
+    def signedDistance(self, p):
+        return float(np.dot(self.n, p) - (self.d + self._ssr))
+
+
+class Plane(_PlaneBase):  # geometric_shapes.h:977-1050
+    node_type = P.GEOM_PLANE
+
+
 class Convex(CollisionGeometry):
     """ConvexBase / Convex<Triangle> (geometric_shapes.h:638-872, shape/convex.h)."""
     node_type = P.GEOM_CONVEX
@@ -335,6 +371,17 @@ class _Scene:
         vertices, another mesh -- retires the handle and registers a new one."""
         key = id(geom)
         ent = self._handles.get(key)
+        if geom.node_type in (P.GEOM_PLANE, P.GEOM_HALFSPACE):
+            # (n, d) live outside the 40-byte record: a plane changed in place is registered anew
+            sig = (geom.node_type, tuple(geom._plane().tolist()), geom.getSweptSphereRadius())
+            if ent is not None and ent[2] is geom:
+                if ent[1] == sig:
+                    return ent[0]
+                self.engine.release_shapes([ent[0]])
+            h = int(self.engine.register_halfspaces(geom.node_type, geom._plane(), [geom.getSweptSphereRadius()])[0])
+            self._handles[key] = (h, sig, geom, None, 0)
+            self._dirty = True
+            return h
         sig = (geom.node_type, tuple(np.asarray(geom._params(), dtype=np.float64).tolist()), geom.getSweptSphereRadius())
         content = self._content(geom)
         if ent is not None and ent[2] is geom:

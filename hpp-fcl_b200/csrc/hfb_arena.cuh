@@ -67,6 +67,9 @@ HFB_HD ShapeD load_shape(const ArenaView& A, uint32_t h) {
   s.nv = 0;
   s.center = mk(0, 0, 0);
   s.ta = s.tb = s.tc = mk(0, 0, 0);
+  if ((CAPS & CAP_PLANE) && (s.type == HFB_GEOM_PLANE || s.type == HFB_GEOM_HALFSPACE)) {
+    s.center.x = A.pool[r.data];  // the offset d (the record's p holds the unit normal): HostArena::add_halfspace
+  }
   if ((CAPS & (CAP_CONVEX | CAP_TRI)) && (s.type == HFB_GEOM_CONVEX || s.type == HFB_GEOM_TRIANGLE)) {
     const ConvexDesc& d = A.cvx[r.data];
     const double* b = A.pool + d.off;
@@ -227,7 +230,34 @@ struct HostArena {
     if (s.type == HFB_BV_OBB) return s.data < bvh_desc.size() && bvh_desc[s.data]._r1 == 1;
     if (s.type == HFB_GEOM_CONVEX) return s.data < cvx.size();
     if (s.type == HFB_GEOM_TRIANGLE) return s.data < cvx.size() && cvx[s.data].nv >= 3;
+    if (s.type == HFB_GEOM_PLANE || s.type == HFB_GEOM_HALFSPACE) return s.data < pool.size();  // (only add_halfspace makes these)
     return true;
+  }
+  // Halfspace(n, d) / Plane(n, d) (geometric_shapes.h:885-1031): the constructors normalise (n, d)
+  // (unitNormalTest, geometric_shapes.cpp:121-143); the record keeps the unit normal in p and the offset in the pool
+  bool add_halfspace(uint32_t type, const double* n_in, double d, double ssr, uint32_t* handle) {
+    if (type != HFB_GEOM_PLANE && type != HFB_GEOM_HALFSPACE) return false;
+    double n[3] = {n_in[0], n_in[1], n_in[2]};
+    const double l = sqrt((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
+    if (l > 0) {
+      const double inv_l = 1.0 / l;
+      for (int k = 0; k < 3; ++k) n[k] *= inv_l;
+      d *= inv_l;
+    } else {
+      n[0] = 1;
+      n[1] = n[2] = 0;
+      d = 0;
+    }
+    hfb_shape s;
+    s.type = type;
+    s.data = (uint32_t)pool.size();
+    pool.push_back(d);
+    pool.push_back(0.0);  // (the pool stays a whole number of 16-byte units: the hull blocks are copied in bulk)
+    s.p[0] = n[0];
+    s.p[1] = n[1];
+    s.p[2] = n[2];
+    s.ssr = ssr;
+    return add_shape(s, handle);
   }
   // returns false on an invalid record
   bool add_shape(const hfb_shape& s, uint32_t* handle) {
@@ -237,8 +267,9 @@ struct HostArena {
     } else if (s.type == HFB_GEOM_CONVEX || s.type == HFB_GEOM_TRIANGLE) {
       if (s.type == HFB_GEOM_CONVEX) has_convex = true; else has_tri = true;
     } else if (!(s.type == HFB_GEOM_BOX || s.type == HFB_GEOM_SPHERE || s.type == HFB_GEOM_CAPSULE ||
-                 s.type == HFB_GEOM_CONE || s.type == HFB_GEOM_CYLINDER || s.type == HFB_GEOM_ELLIPSOID)) {
-      has_unknown = true;  // plane / halfspace / ...: reported per pair as unsupported
+                 s.type == HFB_GEOM_CONE || s.type == HFB_GEOM_CYLINDER || s.type == HFB_GEOM_ELLIPSOID ||
+                 s.type == HFB_GEOM_PLANE || s.type == HFB_GEOM_HALFSPACE)) {
+      has_unknown = true;  // octree / height field / ...: reported per pair as unsupported
     }
     shapes.push_back(s);
     *handle = (uint32_t)shapes.size() - 1;

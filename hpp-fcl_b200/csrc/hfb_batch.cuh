@@ -8,6 +8,7 @@
 using namespace hfb;
 
 #define CAPS_ALL (CAP_PRIM | CAP_CONVEX | CAP_TRI)
+#define CAPS_ALLP (CAPS_ALL | CAP_PLANE)  // phase 1 of the hull / triangle class, which also takes their plane pairs
 #define CAPS_BVH (CAPS_ALL | CAP_INLINE_PRIM)
 
 // ---------------------------------------------------------------- EPA queue --

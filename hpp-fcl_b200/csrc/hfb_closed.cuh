@@ -315,4 +315,171 @@ HFB_HD Wit sphere_triangle(const ShapeD& s, const xf& tf1, const ShapeD& tri, co
   return r;
 }
 
+// ---- Plane / Halfspace family (src/narrowphase/details.h:343-693; the ShapeShapeDistance<S, Halfspace / Plane>
+// specialisations of src/distance/*_halfspace.cpp and *_plane.cpp).  Record: p0..p2 = unit normal,
+// center.x = offset d (hfb_geom_register_halfspaces normalises like the constructors' unitNormalTest).
+HFB_HD bool is_plane_type(int t) { return t == HFB_GEOM_PLANE || t == HFB_GEOM_HALFSPACE; }
+
+// getSupport<WithSweptSphere> (support_functions.cpp:51-91) with hint 0 and a fresh ShapeSupportData: the support
+// of the shape proper, plus (radius of a sphere / capsule +) swept-sphere radius along dir.normalized().
+// Box: `inflate` of this instantiation is a function-local static of the reference, fixed by the first direction
+// the process asks for (:146); 1 + 1e-10 here, its value once that direction had a zero component (a floor).
+template <int G, int CAPS>
+HFB_HD v3 support_swept(const ShapeD& s, v3 dir) {
+  if (s.type == HFB_GEOM_SPHERE) return (s.p0 + s.ssr) * unit(dir);  // :164-176 (assigned, not added to zero)
+  int hint = 0;
+  const v3 sup = shape_support<G, CAPS>(s, dir, hint);
+  const double r = (s.type == HFB_GEOM_CAPSULE) ? (s.p0 + s.ssr) : s.ssr;  // :206-222
+  return sup + r * unit(dir);
+}
+
+struct PlaneW {  // Halfspace / Plane in the world frame
+  v3 n;
+  double d;
+};
+// transform(Halfspace / Plane, tf) (geometric_shapes_utility.cpp:249-290): n' = R n, d' = d + n'.T, and the
+// constructor normalises (n', d') once more (unitNormalTest, geometric_shapes.cpp:121-143)
+HFB_HD PlaneW plane_world(const ShapeD& h, const xf& tf, bool negate) {
+  v3 n = mmul(tf.R, mk(h.p0, h.p1, h.p2));
+  double d = h.center.x + dot(n, tf.T);
+  if (negate) {  // the second halfspace of a plane: Halfspace(-n, -d)
+    n = -n;
+    d = -d;
+  }
+  PlaneW w;
+  const double l = nrm(n);
+  if (l > 0) {
+    const double inv_l = 1.0 / l;
+    w.n = n * inv_l;
+    w.d = d * inv_l;
+  } else {
+    w.n = mk(1, 0, 0);
+    w.d = 0;
+  }
+  return w;
+}
+
+// details.h:347-375: h halfspace (frame tf1), s any other shape (frame tf2); p1 on the halfspace, p2 on the shape
+template <int G, int CAPS>
+HFB_HD Wit halfspace_shape(const ShapeD& h, const xf& tf1, const ShapeD& s, const xf& tf2) {
+  Wit r;
+  const PlaneW w = plane_world(h, tf1, false);
+  const v3 n_2 = mtmul(tf2.R, w.n);
+  const v3 p2 = xform(tf2, support_swept<G, CAPS>(s, -n_2));
+  const double dist = dot(w.n, p2) - (w.d + h.ssr);  // Halfspace::signedDistance
+  r.d = dist;
+  r.p2 = p2;
+  r.p1 = p2 - dist * w.n;
+  r.n = w.n;
+  return r;
+}
+// details.h:381-428: the plane as two halfspaces, the larger signed distance wins (the first on a tie)
+template <int G, int CAPS>
+HFB_HD Wit plane_shape(const ShapeD& pl, const xf& tf1, const ShapeD& s, const xf& tf2) {
+  Wit r;
+  const PlaneW h0 = plane_world(pl, tf1, false), h1 = plane_world(pl, tf1, true);
+  const v3 p2h1 = xform(tf2, support_swept<G, CAPS>(s, -mtmul(tf2.R, h0.n)));
+  const v3 p2h2 = xform(tf2, support_swept<G, CAPS>(s, -mtmul(tf2.R, h1.n)));
+  const double dist1 = dot(h0.n, p2h1) - (h0.d + pl.ssr);
+  const double dist2 = dot(h1.n, p2h2) - (h1.d + pl.ssr);
+  const bool first = dist1 >= dist2;
+  r.d = first ? dist1 : dist2;
+  r.p2 = first ? p2h1 : p2h2;
+  r.n = first ? h0.n : h1.n;
+  r.p1 = r.p2 - r.d * r.n;
+  return r;
+}
+// the non-parallel branch of the three pairs below: infinite penetration, both points on the intersection line,
+// "normal" its direction (details.h:546-560, 607-621, 671-685)
+HFB_HD void plane_line(const PlaneW& a, const PlaneW& b, v3 dir, double dir_sq_norm, Wit& r) {
+  r.d = -DBL_MAX;
+  r.n = dir;
+  r.p1 = r.p2 = cross(b.n * a.d - a.n * b.d, dir) / dir_sq_norm;
+}
+HFB_HD void plane_swept(const ShapeD& s1, const ShapeD& s2, Wit& r) {
+  if (s1.ssr > 0 || s2.ssr > 0) {
+    r.p1 = r.p1 + s1.ssr * r.n;
+    r.p2 = r.p2 - s2.ssr * r.n;
+    r.d -= (s1.ssr + s2.ssr);
+  }
+}
+// details.h:509-571
+HFB_HD Wit halfspace_halfspace(const ShapeD& s1, const xf& tf1, const ShapeD& s2, const xf& tf2) {
+  Wit r;
+  const PlaneW a = plane_world(s1, tf1, false), b = plane_world(s2, tf2, false);
+  const v3 dir = cross(a.n, b.n);
+  const double dir_sq_norm = sqn(dir);
+  if (dir_sq_norm < DBL_EPSILON) {
+    if (dot(a.n, b.n) > 0) {  // same normal: one inside the other
+      r.d = -DBL_MAX;
+      if (a.d <= b.d) {
+        r.n = a.n;
+        r.p1 = r.n * r.d;
+        r.p2 = b.n * b.d;
+      } else {
+        r.n = -a.n;
+        r.p1 = a.n * a.d;
+        r.p2 = -(r.n * r.d);
+      }
+    } else {
+      r.d = -(a.d + b.d);
+      r.n = a.n;
+      r.p1 = a.n * a.d;
+      r.p2 = b.n * b.d;
+    }
+  } else {
+    plane_line(a, b, dir, dir_sq_norm, r);
+  }
+  plane_swept(s1, s2, r);
+  return r;
+}
+// details.h:585-632 (s1 halfspace, s2 plane)
+HFB_HD Wit halfspace_plane(const ShapeD& s1, const xf& tf1, const ShapeD& s2, const xf& tf2) {
+  Wit r;
+  const PlaneW a = plane_world(s1, tf1, false), b = plane_world(s2, tf2, false);
+  const v3 dir = cross(a.n, b.n);
+  const double dir_sq_norm = sqn(dir);
+  if (dir_sq_norm < DBL_EPSILON) {
+    r.n = a.n;
+    r.d = dot(a.n, b.n) > 0 ? (b.d - a.d) : -(a.d + b.d);
+    r.p1 = a.n * a.d;
+    r.p2 = b.n * b.d;
+  } else {
+    plane_line(a, b, dir, dir_sq_norm, r);
+  }
+  plane_swept(s1, s2, r);
+  return r;
+}
+// details.h:646-693
+HFB_HD Wit plane_plane(const ShapeD& s1, const xf& tf1, const ShapeD& s2, const xf& tf2) {
+  Wit r;
+  const PlaneW a = plane_world(s1, tf1, false), b = plane_world(s2, tf2, false);
+  const v3 dir = cross(a.n, b.n);
+  const double dir_sq_norm = sqn(dir);
+  if (dir_sq_norm < DBL_EPSILON) {
+    r.p1 = a.n * a.d;
+    r.p2 = b.n * b.d;
+    r.d = nrm(r.p1 - r.p2);
+    r.n = (r.d > HFB_DUMMY_PRECISION) ? unit(r.p2 - r.p1) : a.n;
+  } else {
+    plane_line(a, b, dir, dir_sq_norm, r);
+  }
+  plane_swept(s1, s2, r);
+  return r;
+}
+// dispatch of a pair with a plane or halfspace on either side
+template <int G, int CAPS>
+HFB_HD Wit plane_family(const ShapeD& s1, const xf& tf1, const ShapeD& s2, const xf& tf2) {
+  const bool h1 = s1.type == HFB_GEOM_HALFSPACE, h2 = s2.type == HFB_GEOM_HALFSPACE;
+  const bool q1 = s1.type == HFB_GEOM_PLANE, q2 = s2.type == HFB_GEOM_PLANE;
+  if (h1 && h2) return halfspace_halfspace(s1, tf1, s2, tf2);
+  if (q1 && q2) return plane_plane(s1, tf1, s2, tf2);
+  if (h1 && q2) return halfspace_plane(s1, tf1, s2, tf2);
+  if (q1 && h2) return flip(halfspace_plane(s2, tf2, s1, tf1));
+  if (h1) return halfspace_shape<G, CAPS>(s1, tf1, s2, tf2);
+  if (q1) return plane_shape<G, CAPS>(s1, tf1, s2, tf2);
+  if (h2) return flip(halfspace_shape<G, CAPS>(s2, tf2, s1, tf1));
+  return flip(plane_shape<G, CAPS>(s2, tf2, s1, tf1));
+}
+
 }  // namespace hfb

@@ -40,15 +40,17 @@
 #define HFB_GC_DEFAULT 2
 #define HFB_GE_DEFAULT 8
 
-// pair classes of the device-side counting sort (k_bin_*): bins [0,8) closed-form
-// combos, [8,45) GJK-routed primitive combos (+ bin 44: unknown node types, reported
-// as unsupported), bin 45: pairs touching ConvexBase / TriangleP
-#define HFB_NBINS 48
-#define HFB_BIN_GJK0 8
-#define HFB_BIN_UNKNOWN 44
-#define HFB_BIN_CONVEX 45
-#define HFB_BIN_BVH 46   // one operand is a BVHModel<OBBRSS>
-#define HFB_BIN_BVH2 47  // both are
+// pair classes of the device-side counting sort (k_bin_*): bins [0,9) closed-form
+// combos (bin 8: a plane or halfspace against a primitive or another plane), [9,45) GJK-routed
+// primitive combos, bin 45: unknown node types (reported as unsupported), bin 46: pairs touching
+// ConvexBase / TriangleP
+#define HFB_NBINS 49
+#define HFB_BIN_PLANE 8
+#define HFB_BIN_GJK0 9
+#define HFB_BIN_UNKNOWN 45
+#define HFB_BIN_CONVEX 46
+#define HFB_BIN_BVH 47   // one operand is a BVHModel<OBBRSS>
+#define HFB_BIN_BVH2 48  // both are
 
 // ------------------------------------------------------------------ phase 1 --
 // ---- TMA staging of ConvexBase vertex blocks (lane-group kernels) -------------------------------
@@ -489,6 +491,8 @@ __device__ __forceinline__ int type_index(uint32_t t) {
     case HFB_GEOM_TRIANGLE: return 7;
     case HFB_BV_OBB:
     case HFB_BV_OBBRSS: return 9;
+    case HFB_GEOM_PLANE:
+    case HFB_GEOM_HALFSPACE: return 10;
     default: return 8;
   }
 }
@@ -497,6 +501,10 @@ __device__ __forceinline__ int pair_bin(uint32_t t1, uint32_t t2) {
   if (a == 9 && b == 9) return HFB_BIN_BVH2;
   if (a == 9 || b == 9) return HFB_BIN_BVH;
   if (a == 8 || b == 8) return HFB_BIN_UNKNOWN;
+  if (a == 10 || b == 10) {  // the plane family is closed-form against everything (src/distance/*_plane.cpp, *_halfspace.cpp)
+    const int o = a == 10 ? b : a;
+    return (o == 6 || o == 7) ? HFB_BIN_CONVEX : HFB_BIN_PLANE;  // hull / triangle partners need the vertex-set supports
+  }
   if (a >= 6 || b >= 6) return HFB_BIN_CONVEX;
   if (is_closed_form((int)t1, (int)t2)) {  // same predicate the per-pair dispatch uses
     if (a == 1 && b == 1) return 0;
@@ -830,7 +838,7 @@ int launch_pairs(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s
     }
   }
   {
-    KTimer kt(ctx, s, (CAPS != CAP_PRIM) ? 4 : (PATHS == PATH_CLOSED ? 3 : 0));
+    KTimer kt(ctx, s, (CAPS & CAP_CONVEX) ? 4 : (PATHS == PATH_CLOSED ? 3 : 0));
     k_pairs<G, CAPS, MODE, PATHS, MINB, STAGE><<<blocks, threads, smem, s>>>(a);
   }
   ctx->stats.kernel_launches++;
@@ -874,16 +882,16 @@ int launch_epa_g(hfb_ctx* ctx, const BatchArgs& a, cudaStream_t s) {
 template <int MODE>
 int launch_pairs_convex(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStream_t s) {
   switch (ctx->gc) {
-    case 1: return launch_pairs<1, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
-    case 2: return launch_pairs<2, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
+    case 1: return launch_pairs<1, CAPS_ALLP, MODE, PATH_BOTH>(ctx, a, work, s);
+    case 2: return launch_pairs<2, CAPS_ALLP, MODE, PATH_BOTH>(ctx, a, work, s);
     case 4:
-      if (a.stage) return launch_pairs<4, CAPS_ALL, MODE, PATH_BOTH, 1, true>(ctx, a, work, s);
-      return launch_pairs<4, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
+      if (a.stage) return launch_pairs<4, CAPS_ALLP, MODE, PATH_BOTH, 1, true>(ctx, a, work, s);
+      return launch_pairs<4, CAPS_ALLP, MODE, PATH_BOTH>(ctx, a, work, s);
     case 8:
-      if (a.stage) return launch_pairs<8, CAPS_ALL, MODE, PATH_BOTH, 1, true>(ctx, a, work, s);
-      return launch_pairs<8, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
-    case 16: return launch_pairs<16, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
-    default: return launch_pairs<32, CAPS_ALL, MODE, PATH_BOTH>(ctx, a, work, s);
+      if (a.stage) return launch_pairs<8, CAPS_ALLP, MODE, PATH_BOTH, 1, true>(ctx, a, work, s);
+      return launch_pairs<8, CAPS_ALLP, MODE, PATH_BOTH>(ctx, a, work, s);
+    case 16: return launch_pairs<16, CAPS_ALLP, MODE, PATH_BOTH>(ctx, a, work, s);
+    default: return launch_pairs<32, CAPS_ALLP, MODE, PATH_BOTH>(ctx, a, work, s);
   }
 }
 
@@ -984,7 +992,7 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   ag.range_hi = offsets + HFB_BIN_CONVEX;
   av.range_lo = offsets + HFB_BIN_CONVEX;
   av.range_hi = offsets + HFB_BIN_BVH;
-  if ((rc = launch_pairs<1, CAP_PRIM, MODE, PATH_CLOSED>(ctx, ac, n, s))) return rc;
+  if ((rc = launch_pairs<1, CAP_PRIM | CAP_PLANE, MODE, PATH_CLOSED>(ctx, ac, n, s))) return rc;
   // the class populations are only known on the device, so both GJK ranges are cut the same way
   // measured on B200 (profiles/r01_summary.md): cutting phase 1 costs more in kernel tails than the overlap
   // returns, so one part is the default; HFB_NSUB asks for more
@@ -1512,7 +1520,23 @@ int hfb_geom_register_shapes(hfb_ctx* ctx, const hfb_shape* shapes, size_t n, ui
   if (!ctx || (!shapes && n)) return HFB_ERR_INVALID_ARGUMENT;
   for (size_t i = 0; i < n; ++i) {
     uint32_t h;
+    if (shapes[i].type == HFB_GEOM_PLANE || shapes[i].type == HFB_GEOM_HALFSPACE)  // (a 40-byte record has no room for n and d)
+      return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "planes and halfspaces are registered with hfb_geom_register_halfspaces");
     if (!ctx->arena.add_shape(shapes[i], &h)) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "bad convex id in shape record");
+    if (handles_out) handles_out[i] = h;
+  }
+  ctx->committed = false;
+  return HFB_OK;
+}
+
+int hfb_geom_register_halfspaces(hfb_ctx* ctx, uint32_t type, const double* n_d, const double* ssr, size_t count,
+                                 uint32_t* handles_out) {
+  if (!ctx || (!n_d && count) || (type != HFB_GEOM_PLANE && type != HFB_GEOM_HALFSPACE))
+    return HFB_ERR_INVALID_ARGUMENT;
+  for (size_t i = 0; i < count; ++i) {
+    uint32_t h;
+    if (!ctx->arena.add_halfspace(type, n_d + 4 * i, n_d[4 * i + 3], ssr ? ssr[i] : 0.0, &h))
+      return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "bad plane record");
     if (handles_out) handles_out[i] = h;
   }
   ctx->committed = false;
@@ -1641,8 +1665,11 @@ int hfb_geom_update_shapes(hfb_ctx* ctx, const uint32_t* handles, const hfb_shap
   std::lock_guard<std::mutex> lk(ctx->mu);
   for (size_t i = 0; i < n; ++i)  // all or nothing
     if (handles[i] >= ctx->arena.shapes.size()) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "shape handle out of range");
-  for (size_t i = 0; i < n; ++i)
+  for (size_t i = 0; i < n; ++i) {
+    if (shapes[i].type == HFB_GEOM_PLANE || shapes[i].type == HFB_GEOM_HALFSPACE)  // (no room for n and d in a record)
+      return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "a plane is moved by its pose, or registered anew (hfb_geom_register_halfspaces)");
     if (!ctx->arena.valid_shape(shapes[i])) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "bad shape record");
+  }
   for (size_t i = 0; i < n; ++i) ctx->arena.set_shape(handles[i], shapes[i]);
   ctx->committed = false;
   return HFB_OK;

@@ -42,11 +42,12 @@ struct PairOut {
 HFB_HD bool type_known(int t) {
   return t == HFB_GEOM_BOX || t == HFB_GEOM_SPHERE || t == HFB_GEOM_CAPSULE || t == HFB_GEOM_CONE ||
          t == HFB_GEOM_CYLINDER || t == HFB_GEOM_CONVEX || t == HFB_GEOM_TRIANGLE ||
-         t == HFB_GEOM_ELLIPSOID;
+         t == HFB_GEOM_ELLIPSOID || t == HFB_GEOM_PLANE || t == HFB_GEOM_HALFSPACE;
 }
 
 // the closed-form specialisation table (shape_shape_func.h:281-306)
 HFB_HD bool is_closed_form(int t1, int t2) {
+  if (is_plane_type(t1) || is_plane_type(t2)) return true;  // src/distance/*_halfspace.cpp, *_plane.cpp
   if (t1 == HFB_GEOM_SPHERE)
     return t2 == HFB_GEOM_SPHERE || t2 == HFB_GEOM_CAPSULE || t2 == HFB_GEOM_CYLINDER ||
            t2 == HFB_GEOM_BOX || t2 == HFB_GEOM_TRIANGLE;
@@ -190,6 +191,23 @@ HFB_HD bool pair_phase1(const PairIn& in, const SolverP& P, PairOut& o, GjkState
     o.distance = DBL_MAX;
     o.p1 = o.p2 = o.normal = nan3();
     o.status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
+    return false;
+  }
+  if (is_plane_type(t1) || is_plane_type(t2)) {
+    // only the kernels the plane classes are binned to carry this code (CAP_PLANE); elsewhere such a pair cannot
+    // arrive (k_bin_*; the mesh walks refuse plane partners in bvh_make_query)
+    if ((CAPS & CAP_PLANE) && (PATHS & PATH_CLOSED)) {
+      const Wit w = plane_family<G, CAPS>(in.s1, in.tf1, in.s2, in.tf2);
+      o.distance = w.d;
+      o.p1 = w.p1;
+      o.p2 = w.p2;
+      o.normal = w.n;
+      o.status = pack_status(HFB_GJK_DID_NOT_RUN, HFB_EPA_DID_NOT_RUN, HFB_PATH_CLOSED_FORM);
+    } else {
+      o.distance = DBL_MAX;
+      o.p1 = o.p2 = o.normal = nan3();
+      o.status = pack_status(0, 0, HFB_PATH_UNSUPPORTED);
+    }
     return false;
   }
   if ((PATHS & PATH_CLOSED) && (CAPS & CAP_PRIM) && is_closed_form(t1, t2)) {

@@ -101,7 +101,8 @@ struct ShapeD {
 // capability mask of a kernel instantiation: which shape classes it may meet
 // CAP_INLINE_PRIM: expand the primitive supports in place (the BVH walk: a call inside the leaf test
 // costs more in spills than the duplicate code costs in instruction fetch)
-enum { CAP_PRIM = 1, CAP_CONVEX = 2, CAP_TRI = 4, CAP_INLINE_PRIM = 8 };
+// CAP_PLANE: the Plane / Halfspace closed forms (only the kernels their pair classes are binned to)
+enum { CAP_PRIM = 1, CAP_CONVEX = 2, CAP_TRI = 4, CAP_INLINE_PRIM = 8, CAP_PLANE = 16 };
 
 HFB_HD v3 prim_support_inl(int type, double p0, double p1, double p2, v3 dir) {
   v3 r = mk(0, 0, 0);

@@ -41,6 +41,7 @@ def load_library(path=None):
     L.hfb_default_distance_request.argtypes = [vp]
     L.hfb_default_collision_request.argtypes = [vp]
     L.hfb_geom_register_shapes.argtypes = [vp, vp, sz, vp]
+    L.hfb_geom_register_halfspaces.argtypes = [vp, C.c_uint32, vp, vp, sz, vp]
     L.hfb_geom_register_convex.argtypes = [vp, vp, u32, vp]
     L.hfb_geom_register_convex_batch.argtypes = [vp, vp, u32, u32, vp]
     L.hfb_geom_register_bvh_obbrss.argtypes = [vp, vp, u32, vp, u32, vp, u32, vp]
@@ -165,6 +166,18 @@ class Engine:
         shapes = np.ascontiguousarray(shapes, dtype=P.shape_dtype)
         handles = np.zeros(shapes.shape[0], dtype=np.uint32)
         self._check(self.L.hfb_geom_register_shapes(self.h, _ptr(shapes), shapes.shape[0], _ptr(handles)))
+        return handles
+
+    def register_halfspaces(self, kind, n_d, ssr=None):
+        """Halfspace (kind = GEOM_HALFSPACE) or Plane (GEOM_PLANE) geometries: n_d is (count, 4) rows
+        (n.x, n.y, n.z, d), normalised by the library; ssr: count swept-sphere radii or None.  Returns the handles."""
+        nd = np.ascontiguousarray(n_d, dtype=np.float64).reshape(-1, 4)
+        r = None if ssr is None else np.ascontiguousarray(ssr, dtype=np.float64).reshape(-1)
+        if r is not None and r.shape[0] != nd.shape[0]:
+            raise ValueError("one swept-sphere radius per plane")
+        handles = np.zeros(nd.shape[0], dtype=np.uint32)
+        self._check(self.L.hfb_geom_register_halfspaces(self.h, int(kind), _ptr(nd), None if r is None else _ptr(r),
+                                                        nd.shape[0], _ptr(handles)))
         return handles
 
     def register_convex_batch(self, points):

@@ -122,6 +122,8 @@ class CollisionGeometry {
     const std::vector<uint32_t>* tris;
   };
   virtual bool mesh(MeshData&) const { return false; }
+  // Plane / Halfspace: unit normal and offset (the 40-byte record has no room for them)
+  virtual bool plane(double /*n_d*/[4]) const { return false; }
 };
 
 class ShapeBase : public CollisionGeometry {  // geometric_shapes.h:59-102
@@ -169,6 +171,40 @@ HFB_RADIUS_LENGTH_SHAPE(Capsule, GEOM_CAPSULE)    // :381-463
 HFB_RADIUS_LENGTH_SHAPE(Cone, GEOM_CONE)          // :465-553
 HFB_RADIUS_LENGTH_SHAPE(Cylinder, GEOM_CYLINDER)  // :555-634
 #undef HFB_RADIUS_LENGTH_SHAPE
+
+// Halfspace n . x <= d (:885-961) and Plane n . x = d (:977-1050); the constructors normalise (n, d) like the
+// reference's unitNormalTest (src/shape/geometric_shapes.cpp:121-143)
+#define HFB_PLANE_SHAPE(Name, Type)                                                        \
+  class Name : public ShapeBase {                                                          \
+   public:                                                                                 \
+    Name(const Vec3f& n_, FCL_REAL d_) : n(n_), d(d_) { unitNormalTest(); }                \
+    Name(FCL_REAL a, FCL_REAL b, FCL_REAL c, FCL_REAL d_) : n(a, b, c), d(d_) { unitNormalTest(); } \
+    Name() : n(1, 0, 0), d(0) {}                                                           \
+    Vec3f n;                                                                               \
+    FCL_REAL d;                                                                            \
+    NODE_TYPE getNodeType() const override { return Type; }                                \
+    void params(double p[3]) const override { p[0] = n[0]; p[1] = n[1]; p[2] = n[2]; }     \
+    bool plane(double nd[4]) const override {                                              \
+      nd[0] = n[0]; nd[1] = n[1]; nd[2] = n[2]; nd[3] = d;                                 \
+      return true;                                                                         \
+    }                                                                                      \
+                                                                                           \
+   protected:                                                                              \
+    void unitNormalTest() {                                                                \
+      const FCL_REAL l = std::sqrt((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);             \
+      if (l > 0) {                                                                         \
+        const FCL_REAL inv_l = 1.0 / l;                                                    \
+        n = Vec3f(n[0] * inv_l, n[1] * inv_l, n[2] * inv_l);                               \
+        d *= inv_l;                                                                        \
+      } else {                                                                             \
+        n = Vec3f(1, 0, 0);                                                                \
+        d = 0;                                                                             \
+      }                                                                                    \
+    }                                                                                      \
+  };
+HFB_PLANE_SHAPE(Halfspace, GEOM_HALFSPACE)
+HFB_PLANE_SHAPE(Plane, GEOM_PLANE)
+#undef HFB_PLANE_SHAPE
 
 class ConvexBase : public ShapeBase {  // :638-872 (vertex set; faces/neighbours are not needed on the device)
  public:
@@ -430,6 +466,8 @@ class Context {
   uint32_t handle(const CollisionGeometry* g) {
     CollisionGeometry::MeshData md;
     if (g->mesh(md)) return mesh_handle(g, md);
+    double nd[4];
+    if (g->plane(nd)) return plane_handle(g, nd);
     hfb_shape rec;
     rec.type = (uint32_t)g->getNodeType();
     rec.data = 0;
@@ -478,6 +516,31 @@ class Context {
     uint32_t h;
     check(hfb_geom_register_shapes(ctx, &rec, 1, &h));
     ent.rec = rec;
+    ent.handle = h;
+    handles[g] = ent;
+    dirty = true;
+    return h;
+  }
+  // Plane / Halfspace: (n, d) live outside the record, so one changed in place is registered anew
+  uint32_t plane_handle(const CollisionGeometry* g, const double nd[4]) {
+    const uint32_t type = (uint32_t)g->getNodeType();
+    const double ssr = static_cast<const ShapeBase*>(g)->getSweptSphereRadius();
+    auto it = handles.find(g);
+    if (it != handles.end()) {
+      const Entry& e = it->second;
+      if (e.rec.type == type && e.rec.ssr == ssr && e.verts.size() == 4 && e.verts[0] == nd[0] && e.verts[1] == nd[1] &&
+          e.verts[2] == nd[2] && e.verts[3] == nd[3])
+        return e.handle;
+      check(hfb_geom_release_shapes(ctx, &e.handle, 1));
+      handles.erase(it);
+    }
+    Entry ent;
+    ent.rec = hfb_shape{};
+    ent.rec.type = type;
+    ent.rec.ssr = ssr;
+    ent.verts.assign(nd, nd + 4);
+    uint32_t h;
+    check(hfb_geom_register_halfspaces(ctx, type, nd, &ssr, 1, &h));
     ent.handle = h;
     handles[g] = ent;
     dirty = true;

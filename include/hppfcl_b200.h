@@ -43,8 +43,8 @@ enum {
   HFB_GEOM_CONE = 12,
   HFB_GEOM_CYLINDER = 13,
   HFB_GEOM_CONVEX = 14,
-  HFB_GEOM_PLANE = 15,     /* not supported by the batch path (yet) */
-  HFB_GEOM_HALFSPACE = 16, /* not supported by the batch path (yet) */
+  HFB_GEOM_PLANE = 15,     /* registered with hfb_geom_register_halfspaces */
+  HFB_GEOM_HALFSPACE = 16, /* registered with hfb_geom_register_halfspaces */
   HFB_GEOM_TRIANGLE = 17,
   HFB_GEOM_ELLIPSOID = 19
 };
@@ -236,6 +236,21 @@ void hfb_default_collision_request(hfb_collision_request* r);
  * hfb_geom_register_convex. */
 int hfb_geom_register_shapes(hfb_ctx* ctx, const hfb_shape* shapes, size_t n,
                              uint32_t* handles_out);
+/* Registers `count` Halfspace (type = HFB_GEOM_HALFSPACE: the points with n.x <= d) or Plane
+ * (HFB_GEOM_PLANE: n.x = d) geometries (geometric_shapes.h:885-1031).  n_d = count x 4 doubles
+ * (n.x, n.y, n.z, d), normalised here as the reference's constructors do (unitNormalTest,
+ * geometric_shapes.cpp:121-143); ssr = count swept-sphere radii or NULL.  handles_out[i] is the handle
+ * of record i.  Such a geometry is closed-form against every primitive, ConvexBase, TriangleP and
+ * another plane or halfspace, in either operand order (details::halfspaceDistance / planeDistance /
+ * halfspaceHalfspaceDistance / halfspacePlaneDistance / planePlaneDistance, src/narrowphase/details.h:
+ * 343-693, through the ShapeShapeDistance specialisations of src/distance/<shape>_halfspace.cpp and
+ * <shape>_plane.cpp); against a BVH model the pair comes back as HFB_PATH_UNSUPPORTED.  Box partners: the
+ * reference's box support has a process-wide `inflate` static fixed by the first direction ever asked for
+ * (support_functions.cpp:146); this library computes with 1 + 1e-10, its value whenever that first
+ * direction had a zero component (a floor).  hfb_geom_register_shapes refuses these two types (a 40-byte
+ * record has no room for n and d). */
+int hfb_geom_register_halfspaces(hfb_ctx* ctx, uint32_t type, const double* n_d, const double* ssr,
+                                 size_t count, uint32_t* handles_out);
 /* Registers the vertex set of a ConvexBase (geometric_shapes.h:638-872):
  * `points` = num_points x 3 doubles. Returns the convex id in *convex_id. */
 int hfb_geom_register_convex(hfb_ctx* ctx, const double* points,

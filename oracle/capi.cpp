@@ -106,6 +106,36 @@ int oracle_bvh_export(void* sc, int id, hfb_bvh_node* out, uint32_t cap) {
   return (int)m.num_bvs;
 }
 
+// Halfspace(n, d) / Plane(n, d) (geometric_shapes.h:885-1031): `nd` holds count x (n.x, n.y, n.z, d), normalised here
+// as the constructors' unitNormalTest does (geometric_shapes.cpp:121-143); ssr may be NULL.  Returns the first handle.
+int64_t oracle_register_halfspaces(void* sc, uint32_t type, const double* nd, const double* ssr, size_t count) {
+  Scene* s = static_cast<Scene*>(sc);
+  if (type != HFB_GEOM_PLANE && type != HFB_GEOM_HALFSPACE) return -1;
+  const size_t first = s->shapes.size();
+  for (size_t i = 0; i < count; ++i) {
+    Shape sh;
+    sh.type = (int)type;
+    V3 n(nd[4 * i], nd[4 * i + 1], nd[4 * i + 2]);
+    double d = nd[4 * i + 3];
+    const double l = norm(n);
+    if (l > 0) {
+      const double inv_l = 1.0 / l;
+      n *= inv_l;
+      d *= inv_l;
+    } else {
+      n = V3(1, 0, 0);
+      d = 0;
+    }
+    sh.p[0] = n.x;
+    sh.p[1] = n.y;
+    sh.p[2] = n.z;
+    sh.d = d;
+    sh.ssr = ssr ? ssr[i] : 0.0;
+    s->shapes.push_back(sh);
+  }
+  return (int64_t)first;
+}
+
 // returns the handle of shapes[0]; handles are consecutive. -1 on error.
 int64_t oracle_register_shapes(void* sc, const hfb_shape* shapes, size_t n) {
   Scene* s = static_cast<Scene*>(sc);

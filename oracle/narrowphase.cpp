@@ -804,6 +804,194 @@ static double triangleTriangleDistance(const Shape& s1, const Tf& tf1, const Sha
 }
 
 // ------------------------------------------------------------- dispatch ----
+// ---- Plane / Halfspace family (src/narrowphase/details.h:343-693, src/distance/*_halfspace.cpp, *_plane.cpp) ----
+// getSupport<WithSweptSphere> (support_functions.cpp:51-91): the support of the shape proper plus
+// (radius of a sphere / capsule +) swept-sphere radius along dir.normalized(); a fresh ShapeSupportData and hint 0.
+// Box: the `inflate` factor of this instantiation is a function-local static fixed by the first direction the
+// process asks for (:146) -- 1 + 1e-10 when that direction has a zero component (a floor with an axis-aligned
+// normal), which is the value restated here; tests prime the reference the same way.
+static V3 supportWithSweptSphere(const Shape& s, const V3& dir) {
+  V3 support;
+  int hint = 0;
+  SupportData sd;
+  sd.last_dir = V3(0, 0, 0);
+  switch (s.type) {
+    case HFB_GEOM_SPHERE: return (s.p[0] + s.ssr) * normalized(dir);  // :164-176
+    case HFB_GEOM_CAPSULE:                                            // :206-222
+      getShapeSupport(&s, dir, support, hint, sd);
+      support += (s.p[0] + s.ssr) * normalized(dir);
+      return support;
+    case HFB_GEOM_TRIANGLE:
+    case HFB_GEOM_BOX:
+    case HFB_GEOM_ELLIPSOID:
+    case HFB_GEOM_CONE:
+    case HFB_GEOM_CYLINDER:
+    case HFB_GEOM_CONVEX:
+      getShapeSupport(&s, dir, support, hint, sd);
+      support += s.ssr * normalized(dir);
+      return support;
+    default: return V3(0, 0, 0);  // GEOM_PLANE, GEOM_HALFSPACE, ...: support.setZero() (:82-86)
+  }
+}
+// transform(Halfspace / Plane, tf) (geometric_shapes_utility.cpp:249-277): n' = R n, d' = d + n'.T, then the
+// constructor's unitNormalTest (geometric_shapes.cpp:121-143) normalises (n', d') once more
+struct WorldPlane { V3 n; double d; };
+static WorldPlane unitNormal(V3 n, double d) {
+  WorldPlane w;
+  const double l = norm(n);
+  if (l > 0) {
+    const double inv_l = 1.0 / l;
+    w.n = n * inv_l;
+    w.d = d * inv_l;
+  } else {
+    w.n = V3(1, 0, 0);
+    w.d = 0;
+  }
+  return w;
+}
+static WorldPlane transformPlane(const Shape& h, const Tf& tf, bool negate = false) {
+  const V3 n = mul(tf.R, V3(h.p[0], h.p[1], h.p[2]));
+  const double d = h.d + dot(n, tf.T);
+  return negate ? unitNormal(-n, -d) : unitNormal(n, d);  // transformToHalfspaces :279-290
+}
+// details.h:347-375 (h halfspace, s any other shape)
+static double halfspaceDistance(const Shape& h, const Tf& tf1, const Shape& s, const Tf& tf2, V3& p1, V3& p2, V3& normal) {
+  const WorldPlane new_h = transformPlane(h, tf1);
+  const V3 n_2 = tmul(tf2.R, new_h.n);
+  p2 = supportWithSweptSphere(s, -n_2);
+  p2 = tf2.transform(p2);
+  const double dist = dot(new_h.n, p2) - (new_h.d + h.ssr);  // Halfspace::signedDistance :913-915
+  p1 = p2 - dist * new_h.n;
+  normal = new_h.n;
+  return dist;
+}
+// details.h:381-428 (plane, s any other shape)
+static double planeDistance(const Shape& plane, const Tf& tf1, const Shape& s, const Tf& tf2, V3& p1, V3& p2, V3& normal) {
+  const WorldPlane h0 = transformPlane(plane, tf1), h1 = transformPlane(plane, tf1, true);
+  const V3 n_h1 = tmul(tf2.R, h0.n), n_h2 = tmul(tf2.R, h1.n);
+  V3 p2h1 = supportWithSweptSphere(s, -n_h1);
+  p2h1 = tf2.transform(p2h1);
+  V3 p2h2 = supportWithSweptSphere(s, -n_h2);
+  p2h2 = tf2.transform(p2h2);
+  const double dist1 = dot(h0.n, p2h1) - (h0.d + plane.ssr);
+  const double dist2 = dot(h1.n, p2h2) - (h1.d + plane.ssr);
+  double dist;
+  if (dist1 >= dist2) {
+    dist = dist1;
+    p2 = p2h1;
+    p1 = p2 - dist * h0.n;
+    normal = h0.n;
+  } else {
+    dist = dist2;
+    p2 = p2h2;
+    p1 = p2 - dist * h1.n;
+    normal = h1.n;
+  }
+  return dist;
+}
+// the non-parallel branch the three pairs below share (details.h:546-560, 607-621, 671-685)
+static double intersectionLine(const WorldPlane& a, const WorldPlane& b, const V3& dir, double dir_sq_norm, V3& p1, V3& p2,
+                               V3& normal) {
+  normal = dir;
+  p1 = p2 = cross(b.n * a.d - a.n * b.d, dir) / dir_sq_norm;
+  return -(std::numeric_limits<double>::max)();
+}
+static void planeSweptSpheres(const Shape& s1, const Shape& s2, double& distance, V3& p1, V3& p2, const V3& normal) {
+  if (s1.ssr > 0 || s2.ssr > 0) {  // :562-568 etc.
+    p1 += s1.ssr * normal;
+    p2 -= s2.ssr * normal;
+    distance -= (s1.ssr + s2.ssr);
+  }
+}
+// details.h:509-571
+static double halfspaceHalfspaceDistance(const Shape& s1, const Tf& tf1, const Shape& s2, const Tf& tf2, V3& p1, V3& p2,
+                                         V3& normal) {
+  const WorldPlane a = transformPlane(s1, tf1), b = transformPlane(s2, tf2);
+  double distance;
+  const V3 dir = cross(a.n, b.n);
+  const double dir_sq_norm = sqnorm(dir);
+  if (dir_sq_norm < std::numeric_limits<double>::epsilon()) {
+    if (dot(a.n, b.n) > 0) {
+      distance = -(std::numeric_limits<double>::max)();
+      if (a.d <= b.d) {
+        normal = a.n;
+        p1 = normal * distance;
+        p2 = b.n * b.d;
+      } else {
+        normal = -a.n;
+        p1 = a.n * a.d;
+        p2 = -(normal * distance);
+      }
+    } else {
+      distance = -(a.d + b.d);
+      normal = a.n;
+      p1 = a.n * a.d;
+      p2 = b.n * b.d;
+    }
+  } else {
+    distance = intersectionLine(a, b, dir, dir_sq_norm, p1, p2, normal);
+  }
+  planeSweptSpheres(s1, s2, distance, p1, p2, normal);
+  return distance;
+}
+// details.h:585-632 (s1 halfspace, s2 plane)
+static double halfspacePlaneDistance(const Shape& s1, const Tf& tf1, const Shape& s2, const Tf& tf2, V3& p1, V3& p2,
+                                     V3& normal) {
+  const WorldPlane a = transformPlane(s1, tf1), b = transformPlane(s2, tf2);
+  double distance;
+  const V3 dir = cross(a.n, b.n);
+  const double dir_sq_norm = sqnorm(dir);
+  if (dir_sq_norm < std::numeric_limits<double>::epsilon()) {
+    normal = a.n;
+    distance = dot(a.n, b.n) > 0 ? (b.d - a.d) : -(a.d + b.d);
+    p1 = a.n * a.d;
+    p2 = b.n * b.d;
+  } else {
+    distance = intersectionLine(a, b, dir, dir_sq_norm, p1, p2, normal);
+  }
+  planeSweptSpheres(s1, s2, distance, p1, p2, normal);
+  return distance;
+}
+// details.h:646-693
+static double planePlaneDistance(const Shape& s1, const Tf& tf1, const Shape& s2, const Tf& tf2, V3& p1, V3& p2, V3& normal) {
+  const WorldPlane a = transformPlane(s1, tf1), b = transformPlane(s2, tf2);
+  double distance;
+  const V3 dir = cross(a.n, b.n);
+  const double dir_sq_norm = sqnorm(dir);
+  if (dir_sq_norm < std::numeric_limits<double>::epsilon()) {
+    p1 = a.n * a.d;
+    p2 = b.n * b.d;
+    distance = norm(p1 - p2);
+    if (distance > kDummyPrecision) normal = normalized(p2 - p1);
+    else normal = a.n;
+  } else {
+    distance = intersectionLine(a, b, dir, dir_sq_norm, p1, p2, normal);
+  }
+  planeSweptSpheres(s1, s2, distance, p1, p2, normal);
+  return distance;
+}
+// the ShapeShapeDistance<S, Halfspace / Plane> specialisations (src/distance/*_halfspace.cpp, *_plane.cpp)
+static double planeFamilyDistance(const Shape& s1, const Tf& tf1, const Shape& s2, const Tf& tf2, V3& p1, V3& p2, V3& normal) {
+  const int t1 = s1.type, t2 = s2.type;
+  const bool h1 = t1 == HFB_GEOM_HALFSPACE, h2 = t2 == HFB_GEOM_HALFSPACE;
+  const bool q1 = t1 == HFB_GEOM_PLANE, q2 = t2 == HFB_GEOM_PLANE;
+  double distance;
+  if (h1 && h2) return halfspaceHalfspaceDistance(s1, tf1, s2, tf2, p1, p2, normal);
+  if (q1 && q2) return planePlaneDistance(s1, tf1, s2, tf2, p1, p2, normal);
+  if (h1 && q2) return halfspacePlaneDistance(s1, tf1, s2, tf2, p1, p2, normal);
+  if (q1 && h2) {
+    distance = halfspacePlaneDistance(s2, tf2, s1, tf1, p2, p1, normal);
+    normal = -normal;
+    return distance;
+  }
+  if (h1) return halfspaceDistance(s1, tf1, s2, tf2, p1, p2, normal);
+  if (q1) return planeDistance(s1, tf1, s2, tf2, p1, p2, normal);
+  if (h2) distance = halfspaceDistance(s2, tf2, s1, tf1, p2, p1, normal);
+  else distance = planeDistance(s2, tf2, s1, tf1, p2, p1, normal);
+  normal = -normal;
+  return distance;
+}
+
 bool shapeShapeDistance(const Shape& s1, const Tf& tf1, const Shape& s2, const Tf& tf2,
                         GJKSolver& solver, bool compute_signed_distance, double& distance, V3& p1,
                         V3& p2, V3& normal, bool& closed_form) {
@@ -811,10 +999,14 @@ bool shapeShapeDistance(const Shape& s1, const Tf& tf1, const Shape& s2, const T
   auto known = [](int t) {
     return t == HFB_GEOM_BOX || t == HFB_GEOM_SPHERE || t == HFB_GEOM_CAPSULE || t == HFB_GEOM_CONE ||
            t == HFB_GEOM_CYLINDER || t == HFB_GEOM_CONVEX || t == HFB_GEOM_TRIANGLE ||
-           t == HFB_GEOM_ELLIPSOID;
+           t == HFB_GEOM_ELLIPSOID || t == HFB_GEOM_PLANE || t == HFB_GEOM_HALFSPACE;
   };
   if (!known(t1) || !known(t2)) return false;
   closed_form = true;
+  if (t1 == HFB_GEOM_PLANE || t1 == HFB_GEOM_HALFSPACE || t2 == HFB_GEOM_PLANE || t2 == HFB_GEOM_HALFSPACE) {
+    distance = planeFamilyDistance(s1, tf1, s2, tf2, p1, p2, normal);
+    return true;
+  }
   // specialisations listed in shape_shape_func.h:281-306
   if (t1 == HFB_GEOM_SPHERE && t2 == HFB_GEOM_SPHERE) {
     distance = sphereSphereDistance(s1, tf1, s2, tf2, p1, p2, normal);  // sphere_sphere.cpp

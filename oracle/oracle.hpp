@@ -151,7 +151,8 @@ struct Shape {
   double ssr;     // swept sphere radius
   const Convex* cvx;  // CONVEX: vertex set; TRIANGLE: cvx->points[0..2] = a,b,c
   V3 tri[3];      // TRIANGLE by value (used for transformed copies)
-  Shape() : type(0), p{0, 0, 0}, ssr(0), cvx(nullptr) {}
+  double d;       // PLANE / HALFSPACE: offset (p = unit normal), geometric_shapes.h:885-1031
+  Shape() : type(0), p{0, 0, 0}, ssr(0), cvx(nullptr), d(0) {}
 };
 
 // ShapeSupportData (include/hpp/fcl/narrowphase/support_functions.h:75-94)

@@ -40,6 +40,8 @@ def lib():
         L.oracle_register_convex.restype = C.c_int
         L.oracle_register_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.oracle_register_shapes.restype = C.c_int64
+        L.oracle_register_halfspaces.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.oracle_register_halfspaces.restype = C.c_int64
         for name in ("oracle_batch_distance", "oracle_batch_collide"):
             f = getattr(L, name)
             f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -104,6 +106,18 @@ class OracleScene:
         if first < 0:
             raise ValueError("oracle_register_shapes failed")
         return np.arange(first, first + shapes.shape[0], dtype=np.uint32)
+
+    _halfspaces_fn = "oracle_register_halfspaces"
+
+    def register_halfspaces(self, kind, n_d, ssr=None):
+        """kind: GEOM_PLANE or GEOM_HALFSPACE; n_d: (count, 4) rows (n.x, n.y, n.z, d); ssr: count radii or None"""
+        nd = np.ascontiguousarray(n_d, dtype=np.float64).reshape(-1, 4)
+        r = None if ssr is None else np.ascontiguousarray(ssr, dtype=np.float64).reshape(-1)
+        assert r is None or r.shape[0] == nd.shape[0]
+        first = getattr(self.L, self._halfspaces_fn)(self.h, int(kind), _ptr(nd), None if r is None else _ptr(r), nd.shape[0])
+        if first < 0:
+            raise ValueError(self._halfspaces_fn + " failed")
+        return np.arange(first, first + nd.shape[0], dtype=np.uint32)
 
     def _run(self, fn, out_dtype, h1, tf1, h2, tf2, req, want_guess, nthreads):
         h1 = np.ascontiguousarray(h1, dtype=np.uint32)
@@ -227,6 +241,8 @@ def ref_lib():
         L.ref_bvh_export.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32]
         L.ref_register_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.ref_register_shapes.restype = C.c_int64
+        L.ref_register_halfspaces.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.ref_register_halfspaces.restype = C.c_int64
         for name in ("ref_batch_distance", "ref_batch_collide"):
             f = getattr(L, name)
             f.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -290,3 +306,4 @@ class RefScene(OracleScene):
                          want_guess, nthreads)
 
     _contacts_fn = "ref_batch_collide_contacts"
+    _halfspaces_fn = "ref_register_halfspaces"

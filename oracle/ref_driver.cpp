@@ -229,6 +229,32 @@ int64_t ref_register_shapes(void* p, const hfb_shape* recs, size_t n) {
   return first;
 }
 
+// Halfspace(n, d) / Plane(n, d); the first call also fixes the `inflate` static of the box support's
+// WithSweptSphere instantiation (support_functions.cpp:146) with an axis-aligned direction, the case the product
+// computes with (include/hppfcl_b200.h, hfb_geom_register_halfspaces)
+int64_t ref_register_halfspaces(void* p, uint32_t type, const double* nd, const double* ssr, size_t count) {
+  Scene* s = static_cast<Scene*>(p);
+  if (type != HFB_GEOM_PLANE && type != HFB_GEOM_HALFSPACE) return -1;
+  static bool primed = false;
+  if (!primed) {
+    primed = true;
+    Box b(1, 1, 1);
+    int hint = 0;
+    (void)details::getSupport<details::SupportOptions::WithSweptSphere>(&b, Vec3f(0, 0, -1), hint);
+  }
+  const int64_t first = (int64_t)s->geoms.size();
+  for (size_t i = 0; i < count; ++i) {
+    const Vec3f n(nd[4 * i], nd[4 * i + 1], nd[4 * i + 2]);
+    std::shared_ptr<CollisionGeometry> g;
+    if (type == HFB_GEOM_PLANE) g.reset(new Plane(n, nd[4 * i + 3]));
+    else g.reset(new Halfspace(n, nd[4 * i + 3]));
+    if (ssr && ssr[i] > 0) static_cast<ShapeBase*>(g.get())->setSweptSphereRadius(ssr[i]);
+    g->computeLocalAABB();
+    s->geoms.push_back(g);
+  }
+  return first;
+}
+
 int ref_max_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -37,6 +37,8 @@ def emu_lib():
         L.emu_register_convex.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.emu_register_shapes.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.emu_register_shapes.restype = C.c_int64
+        L.emu_register_halfspaces.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.emu_register_halfspaces.restype = C.c_int64
         for name in ("emu_batch_distance", "emu_batch_collide"):
             getattr(L, name).argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 7
         L.emu_batch_convex_support.argtypes = [C.c_void_p, C.c_size_t] + [C.c_void_p] * 4
@@ -89,6 +91,13 @@ class EmuScene:
         first = self.L.emu_register_shapes(self.h, _ptr(shapes), shapes.shape[0])
         assert first >= 0
         return np.arange(first, first + shapes.shape[0], dtype=np.uint32)
+
+    def register_halfspaces(self, kind, n_d, ssr=None):
+        nd = np.ascontiguousarray(n_d, dtype=np.float64).reshape(-1, 4)
+        r = None if ssr is None else np.ascontiguousarray(ssr, dtype=np.float64).reshape(-1)
+        first = self.L.emu_register_halfspaces(self.h, int(kind), _ptr(nd), None if r is None else _ptr(r), nd.shape[0])
+        assert first >= 0
+        return np.arange(first, first + nd.shape[0], dtype=np.uint32)
 
     def commit(self):
         pass
@@ -214,6 +223,12 @@ class MultiScene:
 
     def register_shapes(self, shapes):
         hs = [s.register_shapes(shapes) for s in self.b.values()]
+        for h in hs[1:]:
+            assert np.array_equal(h, hs[0])
+        return hs[0]
+
+    def register_halfspaces(self, kind, n_d, ssr=None):
+        hs = [s.register_halfspaces(kind, n_d, ssr) for s in self.b.values()]
         for h in hs[1:]:
             assert np.array_equal(h, hs[0])
         return hs[0]

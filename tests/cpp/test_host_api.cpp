@@ -19,6 +19,29 @@ static int failures = 0;
 #define CHECK_CLOSE(a, b, pct) CHECK(std::fabs((a) - (b)) <= (pct) / 100.0 * std::fmin(std::fabs(a), std::fabs(b)))
 
 int main() {
+  {  // a Halfspace floor and a Plane against a sphere (details::halfspaceDistance / planeDistance, details.h:347-428)
+    Halfspace floor(Vec3f(0, 0, 2), 1.0);  // normalised: n = (0, 0, 1), d = 0.5
+    CHECK(floor.n[2] == 1.0 && floor.d == 0.5);
+    Sphere ball(0.25);
+    DistanceRequest req(true, true, 0, 0);
+    DistanceResult res;
+    distance(&floor, Transform3f(), &ball, Transform3f(Vec3f(0.3, -0.2, 1.5)), req, res);
+    CHECK_CLOSE(res.min_distance, 1.5 - 0.25 - 0.5, 1e-12);
+    CHECK_CLOSE(res.nearest_points[1][2], 1.25, 1e-12);
+    CHECK(res.normal[2] == 1.0);
+    Plane wall(1, 0, 0, 2.0);
+    DistanceResult r2;
+    distance(&ball, Transform3f(Vec3f(5, 0, 0)), &wall, Transform3f(), req, r2);
+    CHECK_CLOSE(r2.min_distance, 3 - 0.25, 1e-12);
+    CHECK(r2.normal[0] == -1.0);  // from the sphere towards the wall
+    CollisionRequest creq;
+    CollisionResult cres;
+    CHECK(collide(&ball, Transform3f(Vec3f(2.1, 0, 0)), &wall, Transform3f(), creq, cres) == 1);
+    floor.d = 1.3;  // changed in place: registered anew
+    DistanceResult r3;
+    distance(&floor, Transform3f(), &ball, Transform3f(Vec3f(0.3, -0.2, 1.5)), req, r3);
+    CHECK_CLOSE(r3.min_distance, 1.5 - 0.25 - 1.3, 1e-12);
+  }
   {  // distance_box_box_1 (box_box_distance.cpp:62-101)
     CollisionGeometryPtr_t s1(new Box(6, 10, 2));
     CollisionGeometryPtr_t s2(new Box(2, 2, 2));

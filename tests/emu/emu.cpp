@@ -124,12 +124,13 @@ struct Emu {
   HostArena arena;
 };
 constexpr int CAPS_ALL = CAP_PRIM | CAP_CONVEX | CAP_TRI;
+constexpr int CAPS_ALLP = CAPS_ALL | CAP_PLANE;  // phase 1 of the shape-pair kernels (hfb_batch.cuh)
 
 inline PairIn load_pair(const ArenaView& A, size_t i, const uint32_t* h1, const hfb_transform* tf1,
                         const uint32_t* h2, const hfb_transform* tf2, const hfb_query_request& q) {
   PairIn in;
-  in.s1 = load_shape<CAPS_ALL>(A, h1[i]);
-  in.s2 = load_shape<CAPS_ALL>(A, h2[i]);
+  in.s1 = load_shape<CAPS_ALLP>(A, h1[i]);
+  in.s2 = load_shape<CAPS_ALLP>(A, h2[i]);
   in.tf1 = load_xf(tf1[i].R);
   in.tf2 = load_xf(tf2[i].R);
   in.cached_guess = mk(1, 0, 0);
@@ -148,7 +149,7 @@ long g_retries = 0;
 inline void run_pair(const PairIn& in, const SolverP& P, EpaWs* ws, PairOut& o) {
   GjkState g;
   std::memset(&g, 0, sizeof(g));
-  if (pair_phase1<1, CAPS_ALL>(in, P, o, g)) {
+  if (pair_phase1<1, CAPS_ALLP>(in, P, o, g)) {
     // the two tiers of k_epa: reduced-size workspace first, full size when the polytope outgrows it
     const GjkState g0 = g;
     EpaWsSmall small;
@@ -222,7 +223,7 @@ long batch_lanes(Emu* E, size_t n, const uint32_t* h1, const hfb_transform* tf1,
       const PairIn in = load_pair(A, i, h1, tf1, h2, tf2, q);
       LaneOut& mine = outs[l];
       std::memset(&mine, 0, sizeof(mine));
-      mine.need_epa = pair_phase1<G, CAPS_ALL>(in, P, mine.o, mine.g);
+      mine.need_epa = pair_phase1<G, CAPS_ALLP>(in, P, mine.o, mine.g);
       if (mine.need_epa) {  // k_epa: the queued state, tier 0, then tier 1
         const GjkState queued = mine.g;
         GjkState g = requeue(queued);
@@ -433,6 +434,16 @@ int64_t emu_register_shapes(void* e, const hfb_shape* shapes, size_t n) {
   for (size_t i = 0; i < n; ++i) {
     uint32_t h;
     if (!E->arena.add_shape(shapes[i], &h)) return -1;
+  }
+  return first;
+}
+
+int64_t emu_register_halfspaces(void* e, uint32_t type, const double* nd, const double* ssr, size_t count) {
+  Emu* E = static_cast<Emu*>(e);
+  int64_t first = (int64_t)E->arena.shapes.size();
+  for (size_t i = 0; i < count; ++i) {
+    uint32_t h;
+    if (!E->arena.add_halfspace(type, nd + 4 * i, nd[4 * i + 3], ssr ? ssr[i] : 0.0, &h)) return -1;
   }
   return first;
 }

@@ -136,6 +136,11 @@ def test_api_objects_without_gpu():
     assert np.allclose(t.transform([1, 1, 1]), [2, 3, 4])
     with pytest.raises(ValueError):
         hf.Sphere(1).setSweptSphereRadius(-1)
+    h = hf.Halfspace([0, 0, 2.0], 3.0)                                               # :887-890 + unitNormalTest
+    assert np.allclose(h.n, [0, 0, 1]) and h.d == 1.5 and h.getNodeType() == P.GEOM_HALFSPACE
+    assert h.signedDistance([0, 0, 2.0]) == 0.5
+    pl = hf.Plane(0, 0, 0, 1.0)                                                      # zero normal -> (1, 0, 0), 0
+    assert np.allclose(pl.n, [1, 0, 0]) and pl.d == 0 and pl.getNodeType() == P.GEOM_PLANE
 
 
 def _update_scenario(dev, fresh):
