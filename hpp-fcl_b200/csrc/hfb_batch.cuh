@@ -22,6 +22,14 @@ struct EpaItem {
   double w1[12];
 };
 
+// k_epa, tier 0 -> tier 1: a run that filled the reduced-size workspace at the top of an iteration leaves its state
+// here (slot = its position in the retry list) and tier 1 carries on from it in the full-size workspace instead of
+// starting the pair over
+struct EpaCont {
+  EpaResume rs;
+  EpaWsSmall ws;
+};
+
 struct BatchArgs {
   ArenaView A;
   const uint32_t* h1;
@@ -40,6 +48,8 @@ struct BatchArgs {
   unsigned* epa_head;         // k_epa: work counter of this launch (items are handed out one by one)
   uint32_t* retry;            // queue indices of the items that outgrew the reduced-size EPA workspace
   unsigned* retry_count;
+  EpaCont* cont;              // continuation records of the first cont_cap retry positions (null: every retry starts over)
+  unsigned cont_cap;
   unsigned sub_idx, sub_cnt;  // k_pairs: this launch takes the sub_idx-th of sub_cnt equal parts of [lo, hi)
   unsigned* gjk_work;         // k_gjk_refill: work counter of this launch
   unsigned iter_quorum;       // k_gjk_refill: lanes that must be mid-GJK for an iteration round to run

@@ -87,7 +87,7 @@ __global__ void __launch_bounds__(256) k_bounds_partial(const double* bb, unsign
   Bounds v = bounds_empty();
   for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const double* b = bb + 6 * (size_t)i;
-    if (!(b[0] <= b[3])) continue;  // empty box
+    if (aabb_empty(b) || aabb_unbounded(b)) continue;  // no box / a halfspace or plane: not in the grid
     Bounds o;
     for (int k = 0; k < 3; ++k) {
       o.lo[k] = o.hi[k] = 0.5 * (b[k] + b[3 + k]);
@@ -100,7 +100,8 @@ __global__ void __launch_bounds__(256) k_bounds_partial(const double* bb, unsign
   if (threadIdx.x == 0) part[blockIdx.x] = v;
 }
 // one block: final merge, then the grid (make_grid of hfb_broadphase.cuh) and the zeroed pair counter
-__global__ void __launch_bounds__(256) k_make_grid(const Bounds* part, unsigned nparts, BroadGrid* grid, unsigned* n_pairs) {
+__global__ void __launch_bounds__(256) k_make_grid(const Bounds* part, unsigned nparts, BroadGrid* grid, unsigned* n_pairs,
+                                                   unsigned* n_unbounded) {
   Bounds v = bounds_empty();
   for (unsigned i = threadIdx.x; i < nparts; i += blockDim.x) bounds_merge(v, part[i]);
   v = block_bounds(v);
@@ -125,15 +126,22 @@ __global__ void __launch_bounds__(256) k_make_grid(const Bounds* part, unsigned 
     g.inv_cell = 1.0 / cell;
     *grid = g;
     *n_pairs = 0u;
+    *n_unbounded = 0u;
   }
 }
+// cell of every object; the unbounded ones (cell 0xfffffffe) are listed from the END of `order` backwards
 __global__ void __launch_bounds__(256) k_cell_hist(const double* bb, unsigned n, const BroadGrid* grid, unsigned* cell,
-                                                   unsigned* count) {
+                                                   unsigned* count, unsigned* order, unsigned* n_unbounded) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double* b = bb + 6 * (size_t)i;
-  if (!(b[0] <= b[3])) {
+  if (aabb_empty(b)) {
     cell[i] = 0xffffffffu;  // empty box: in no cell
+    return;
+  }
+  if (aabb_unbounded(b)) {
+    cell[i] = 0xfffffffeu;
+    order[n - 1u - atomicAdd(n_unbounded, 1u)] = i;
     return;
   }
   const unsigned c = grid_cell(*grid, b);
@@ -143,7 +151,7 @@ __global__ void __launch_bounds__(256) k_cell_hist(const double* bb, unsigned n,
 __global__ void __launch_bounds__(256) k_cell_scatter(const unsigned* cell, unsigned n, const unsigned* start,
                                                       unsigned* cursor, unsigned* order) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n || cell[i] == 0xffffffffu) return;
+  if (i >= n || cell[i] >= 0xfffffffeu) return;
   order[start[cell[i]] + atomicAdd(cursor + cell[i], 1u)] = i;
 }
 // one object per thread: the 27 cells around its own, partners with a larger index
@@ -154,7 +162,7 @@ __global__ void __launch_bounds__(128) k_sweep(const double* bb, unsigned n, uns
   const unsigned i = i_lo + blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned lane = threadIdx.x & 31u;
   const BroadGrid g = *grid;
-  const bool live = i < n && cell[i] != 0xffffffffu;
+  const bool live = i < n && cell[i] < 0xfffffffeu;
   double mine[6] = {0, 0, 0, 0, 0, 0};
   int cx = 0, cy = 0, cz = 0;
   if (live) {
@@ -197,10 +205,47 @@ __global__ void __launch_bounds__(128) k_sweep(const double* bb, unsigned n, uns
   }
 }
 
+// the unbounded objects (halfspaces, planes) against every object: thread per object j, loop over the few unbounded u;
+// the pair is this launch's when its smaller index lies in [i_lo, i_hi), a pair of two unbounded objects is reported
+// from its smaller index only
+__global__ void __launch_bounds__(128) k_sweep_unbounded(const double* bb, unsigned n, unsigned i_lo, unsigned i_hi,
+                                                         const unsigned* cell, const unsigned* order, const unsigned* n_unbounded,
+                                                         uint32_t* first, uint32_t* second, unsigned capacity, unsigned* n_pairs) {
+  const unsigned nu = *n_unbounded;
+  if (nu == 0) return;
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned j0 = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned jend = (n + 31u) & ~31u;  // (warp-uniform trip count for the ballots)
+  for (unsigned j = j0; j < jend; j += gridDim.x * blockDim.x) {
+    const bool jl = j < n && cell[j] != 0xffffffffu;
+    double mine[6] = {0, 0, 0, 0, 0, 0};
+    if (jl)
+      for (int k = 0; k < 6; ++k) mine[k] = bb[6 * (size_t)j + k];
+    for (unsigned q = 0; q < nu; ++q) {
+      const unsigned u = order[n - 1u - q];
+      const unsigned lo = u < j ? u : j, hi = u < j ? j : u;
+      const bool hit = jl && j != u && !(cell[j] == 0xfffffffeu && j < u) && lo >= i_lo && lo < i_hi &&
+                       aabb_overlap(mine, bb + 6 * (size_t)u);
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (m) {
+        unsigned base = 0;
+        if (lane == (unsigned)(__ffs(m) - 1)) base = atomicAdd(n_pairs, (unsigned)__popc(m));
+        base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+        const unsigned pos = base + (unsigned)__popc(m & ((1u << lane) - 1u));
+        if (hit && pos < capacity) {
+          first[pos] = lo;
+          second[pos] = hi;
+        }
+      }
+    }
+  }
+}
+
 size_t up256(size_t b) { return (b + 255) & ~(size_t)255; }
 struct Scratch {
   Bounds* part;
   BroadGrid* grid;
+  unsigned* n_unbounded;
   unsigned* cell;
   unsigned* order;
   unsigned* count;   // kMaxCells + 1 (count, then exclusive scan in place via `start`)
@@ -220,6 +265,7 @@ Scratch carve(void* p, size_t n) {
   Scratch s;
   s.part = reinterpret_cast<Bounds*>(c); c += up256(kParts * sizeof(Bounds));
   s.grid = reinterpret_cast<BroadGrid*>(c); c += up256(sizeof(BroadGrid));
+  s.n_unbounded = reinterpret_cast<unsigned*>(c); c += 256;
   s.cell = reinterpret_cast<unsigned*>(c); c += up256(n * 4);
   s.order = reinterpret_cast<unsigned*>(c); c += up256(n * 4);
   s.count = reinterpret_cast<unsigned*>(c); c += up256((size_t)(kMaxCells + 1) * 4);
@@ -240,13 +286,13 @@ int bp_scene_aabbs_launch(const double* d_local_aabbs, uint32_t nshapes, size_t 
 }
 
 size_t bp_scratch_bytes(size_t n) {
-  return up256(kParts * sizeof(Bounds)) + up256(sizeof(BroadGrid)) + 2 * up256(n * 4) +
+  return up256(kParts * sizeof(Bounds)) + up256(sizeof(BroadGrid)) + 256 + 2 * up256(n * 4) +
          2 * up256((size_t)(kMaxCells + 1) * 4) + up256((size_t)kMaxCells * 4) + up256(cub_scan_bytes()) + 256;
 }
 
 int bp_pairs_launch(size_t n, const double* d_aabbs, size_t i_lo, size_t i_hi, uint32_t* d_first, uint32_t* d_second,
                     size_t capacity, unsigned* d_n_pairs, void* scratch, int num_sms, cudaStream_t s, int* launches) {
-  (void)num_sms;
+  if (num_sms < 1) num_sms = 1;
   Scratch w = carve(scratch, n);
   const unsigned nn = (unsigned)n;
   unsigned pb = (nn + 255) / 256;
@@ -254,13 +300,13 @@ int bp_pairs_launch(size_t n, const double* d_aabbs, size_t i_lo, size_t i_hi, u
   if (pb == 0) pb = 1;
   cudaError_t e;
   k_bounds_partial<<<pb, 256, 0, s>>>(d_aabbs, nn, w.part);
-  k_make_grid<<<1, 256, 0, s>>>(w.part, pb, w.grid, d_n_pairs);
+  k_make_grid<<<1, 256, 0, s>>>(w.part, pb, w.grid, d_n_pairs, w.n_unbounded);
   *launches += 2;
   if (n < 2) return (int)cudaGetLastError();
   // the number of cells is only known on the device: counters are cleared and scanned for the maximum
   if ((e = cudaMemsetAsync(w.count, 0, (size_t)(kMaxCells + 1) * 4, s)) != cudaSuccess) return (int)e;
   if ((e = cudaMemsetAsync(w.cursor, 0, (size_t)kMaxCells * 4, s)) != cudaSuccess) return (int)e;
-  k_cell_hist<<<(nn + 255) / 256, 256, 0, s>>>(d_aabbs, nn, w.grid, w.cell, w.count);
+  k_cell_hist<<<(nn + 255) / 256, 256, 0, s>>>(d_aabbs, nn, w.grid, w.cell, w.count, w.order, w.n_unbounded);
   size_t tb = w.cub_bytes;
   if ((e = cub::DeviceScan::ExclusiveSum(w.cub_tmp, tb, w.count, w.start, (int)(kMaxCells + 1), s)) != cudaSuccess) return (int)e;
   k_cell_scatter<<<(nn + 255) / 256, 256, 0, s>>>(w.cell, nn, w.start, w.cursor, w.order);
@@ -270,7 +316,13 @@ int bp_pairs_launch(size_t n, const double* d_aabbs, size_t i_lo, size_t i_hi, u
                                                                  w.order, d_first, d_second,
                                                                  (unsigned)(capacity > 0xffffffffull ? 0xffffffffull : capacity),
                                                                  d_n_pairs);
-  *launches += 4;
+  if (i_lo < i_hi) {
+    unsigned ub = (nn + 127) / 128;
+    if (ub > (unsigned)num_sms * 8u) ub = (unsigned)num_sms * 8u;
+    k_sweep_unbounded<<<ub ? ub : 1u, 128, 0, s>>>(d_aabbs, nn, (unsigned)i_lo, (unsigned)i_hi, w.cell, w.order, w.n_unbounded, d_first,
+                                                   d_second, (unsigned)(capacity > 0xffffffffull ? 0xffffffffull : capacity), d_n_pairs);
+  }
+  *launches += 5;
   return (int)cudaGetLastError();
 }
 

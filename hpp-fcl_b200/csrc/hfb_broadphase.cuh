@@ -68,6 +68,43 @@ inline bool shape_local_aabb(const HostArena& A, const hfb_shape& s, LocalAabb& 
         }
       h[0] = -1;
     } break;
+    case HFB_GEOM_PLANE:
+    case HFB_GEOM_HALFSPACE: {
+      // computeBV<AABB, Halfspace / Plane> with the identity pose (geometric_shapes_utility.cpp:391-456): everything,
+      // except along an axis the normal is exactly aligned with.  transform() builds a new Halfspace / Plane, whose
+      // constructor normalises (n, d) once more (unitNormalTest)
+      if (s.data >= A.pool.size()) return false;
+      double n[3] = {s.p[0], s.p[1], s.p[2]};
+      double d = A.pool[s.data] + ((n[0] * 0.0 + n[1] * 0.0) + n[2] * 0.0);
+      const double l = sqrt((n[0] * n[0] + n[1] * n[1]) + n[2] * n[2]);
+      if (l > 0) {
+        const double inv_l = 1.0 / l;
+        for (int k = 0; k < 3; ++k) n[k] *= inv_l;
+        d *= inv_l;
+      } else {
+        n[0] = 1;
+        n[1] = n[2] = 0;
+        d = 0;
+      }
+      for (int k = 0; k < 3; ++k) {
+        b.mn[k] = -DBL_MAX;
+        b.mx[k] = DBL_MAX;
+      }
+      int axis = -1;
+      if (n[1] == 0.0 && n[2] == 0.0) axis = 0;
+      else if (n[0] == 0.0 && n[2] == 0.0) axis = 1;
+      else if (n[0] == 0.0 && n[1] == 0.0) axis = 2;
+      if (axis >= 0) {
+        if (s.type == HFB_GEOM_HALFSPACE) {
+          if (n[axis] < 0) b.mn[axis] = -d;
+          else if (n[axis] > 0) b.mx[axis] = d;
+        } else {
+          if (n[axis] < 0) b.mn[axis] = b.mx[axis] = -d;
+          else if (n[axis] > 0) b.mn[axis] = b.mx[axis] = d;
+        }
+      }
+      h[0] = -1;
+    } break;
     default: return false;
   }
   if (h[0] >= 0)
@@ -118,6 +155,17 @@ HFB_HD bool aabb_overlap(const double* a, const double* b) {  // AABB::overlap: 
   return true;
 }
 
+// A box that reaches past this (a Halfspace or Plane: +-DBL_MAX, or +-inf once rotated) is "unbounded": it takes no part
+// in the grid -- a cell as large as the largest box would be the whole scene -- and is tested against every object.
+#define HFB_BP_UNBOUNDED 1e300
+HFB_HD bool aabb_unbounded(const double* b) {
+  for (int k = 0; k < 6; ++k)
+    if (!(b[k] > -HFB_BP_UNBOUNDED && b[k] < HFB_BP_UNBOUNDED)) return true;
+  return false;
+}
+// the marker hfb_scene_aabbs writes for an object without a box (no such geometry, node type without aabb_local)
+HFB_HD bool aabb_empty(const double* b) { return b[0] == DBL_MAX && b[3] == -DBL_MAX; }
+
 // grid geometry shared by the host and device pair finders
 struct BroadGrid {
   double origin[3];
@@ -137,13 +185,16 @@ HFB_HD unsigned grid_cell(const BroadGrid& g, const double* bb) {
 inline BroadGrid make_grid(size_t n, const double* bb) {
   BroadGrid g;
   double lo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, hi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX}, ext = 0;
-  for (size_t i = 0; i < n; ++i)
+  for (size_t i = 0; i < n; ++i) {
+    if (aabb_empty(bb + 6 * i) || aabb_unbounded(bb + 6 * i)) continue;
     for (int k = 0; k < 3; ++k) {
       const double c = 0.5 * (bb[6 * i + k] + bb[6 * i + 3 + k]), e = bb[6 * i + 3 + k] - bb[6 * i + k];
       lo[k] = c < lo[k] ? c : lo[k];
       hi[k] = c > hi[k] ? c : hi[k];
       ext = e > ext ? e : ext;
     }
+  }
+  if (!(lo[0] <= hi[0])) lo[0] = lo[1] = lo[2] = hi[0] = hi[1] = hi[2] = 0;  // nothing bounded
   double cell = ext > 0 ? ext : 1.0;
   for (;;) {
     double cells = 1;
@@ -165,18 +216,38 @@ inline size_t broadphase_pairs_host(size_t n, const double* bb, uint32_t* first,
   if (n < 2) return 0;
   const BroadGrid g = make_grid(n, bb);
   const size_t ncell = (size_t)g.dim[0] * g.dim[1] * g.dim[2];
-  std::vector<uint32_t> cell(n), start(ncell + 1, 0), order(n);
+  std::vector<uint32_t> cell(n), start(ncell + 1, 0), order(n), unbounded;
   for (size_t i = 0; i < n; ++i) {
-    cell[i] = grid_cell(g, bb + 6 * i);
-    ++start[cell[i] + 1];
+    if (aabb_empty(bb + 6 * i)) {
+      cell[i] = 0xffffffffu;
+    } else if (aabb_unbounded(bb + 6 * i)) {
+      cell[i] = 0xfffffffeu;
+      unbounded.push_back((uint32_t)i);
+    } else {
+      cell[i] = grid_cell(g, bb + 6 * i);
+      ++start[cell[i] + 1];
+    }
   }
   for (size_t c = 0; c < ncell; ++c) start[c + 1] += start[c];
   {
     std::vector<uint32_t> cur(start.begin(), start.end() - 1);
-    for (size_t i = 0; i < n; ++i) order[cur[cell[i]]++] = (uint32_t)i;
+    for (size_t i = 0; i < n; ++i)
+      if (cell[i] < 0xfffffffeu) order[cur[cell[i]]++] = (uint32_t)i;
   }
   size_t count = 0;
+  // the unbounded objects against everything (a pair of two of them once)
+  for (uint32_t u : unbounded)
+    for (size_t j = 0; j < n; ++j) {
+      if (j == u || cell[j] == 0xffffffffu || (cell[j] == 0xfffffffeu && j < u)) continue;
+      if (!aabb_overlap(bb + 6 * (size_t)u, bb + 6 * j)) continue;
+      if (count < capacity) {
+        first[count] = u < j ? u : (uint32_t)j;
+        second[count] = u < j ? (uint32_t)j : u;
+      }
+      ++count;
+    }
   for (size_t i = 0; i < n; ++i) {
+    if (cell[i] >= 0xfffffffeu) continue;
     const unsigned c = cell[i];
     const int cx = (int)(c % (unsigned)g.dim[0]), cy = (int)((c / (unsigned)g.dim[0]) % (unsigned)g.dim[1]),
               cz = (int)(c / ((unsigned)g.dim[0] * (unsigned)g.dim[1]));

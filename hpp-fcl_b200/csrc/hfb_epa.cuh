@@ -36,6 +36,10 @@ namespace hfb {
 // internal verdict of a run in a workspace smaller than the request's caps: the polytope outgrew it
 // before the reference would have stopped; the pair is run again in the full-size workspace
 #define HFB_EPA_WS_OVERFLOW 0x7f
+// free face slots a reduced-size workspace wants at the top of an iteration (a round makes one face per horizon edge)
+#ifndef HFB_EPA_ROUND_FACES
+#define HFB_EPA_ROUND_FACES 6
+#endif
 
 template <int MAXV_, int MAXF_>
 struct EpaWsT {
@@ -402,9 +406,24 @@ HFB_HD bool gjk_enclose_origin(const ShapeD& sa, const ShapeD& sb, const MinkD& 
 }
 
 // EPA::evaluate (:1156-1316)
+// what the expansion loop of EPA::evaluate carries from one iteration to the next, besides EpaState and the workspace
+struct EpaLoop {
+  unsigned it;
+  int pass;
+  int closest;
+  v3 outer_n;  // `outer` is a COPY of the last good closest face (:1208,1284)
+  double outer_d;
+  int ov0, ov1, ov2;
+  int resumable;  // the loop stopped at the top of an iteration because the workspace is full: it can go on, from
+                  // exactly this state, in a larger one (epa_ws_grow)
+};
+
+// EPA::evaluate (:1156-1316) in three parts, so that a run which outgrows a reduced-size workspace can continue in the
+// full-size one instead of starting over (k_epa, tier 0 -> tier 1).
+// part 1: encloseOrigin, the initial tetrahedron and its four faces.  False: FallBack (E is final).
 template <int G, int CAPS, class WS>
-HFB_HD void epa_evaluate(const ShapeD& sa, const ShapeD& sb, const MinkD& md, const EpaParams& P,
-                         GjkState& g, WS* ws, EpaState& E) {
+HFB_HD bool epa_begin(const ShapeD& sa, const ShapeD& sb, const MinkD& md, const EpaParams& P, GjkState& g, WS* ws,
+                      EpaState& E, EpaLoop& L) {
   const double tol = P.tolerance;
   E.hint0 = g.hint0;
   E.hint1 = g.hint1;
@@ -413,6 +432,9 @@ HFB_HD void epa_evaluate(const ShapeD& sa, const ShapeD& sb, const MinkD& md, co
   E.normal = mk(0, 0, 0);
   E.nverts_cap = P.max_iterations + 4;
   E.nfaces_cap = 2 * P.max_iterations + 4;
+  L.it = 0;
+  L.pass = 0;
+  L.resumable = 0;
 
   const bool enclosed = gjk_enclose_origin<G, CAPS>(sa, sb, md, g);
   if (g.rank > 1 && enclosed) {
@@ -449,72 +471,14 @@ HFB_HD void epa_evaluate(const ShapeD& sa, const ShapeD& sb, const MinkD& md, co
       epa_bind(ws, t1, 1, t3, 2);
       epa_bind(ws, t1, 2, t2, 1);
       epa_bind(ws, t2, 2, t3, 1);
-
-      int closest = epa_find_closest<G>(ws, E);
-      // `outer` is a COPY of the last good closest face (:1208,1284)
-      v3 outer_n = ws_fn(ws, closest);
-      double outer_d = ws->fd[closest];
-      int ov0 = ws->fvid[3 * closest], ov1 = ws->fvid[3 * closest + 1], ov2 = ws->fvid[3 * closest + 2];
-
+      L.closest = epa_find_closest<G>(ws, E);
+      L.outer_n = ws_fn(ws, L.closest);
+      L.outer_d = ws->fd[L.closest];
+      L.ov0 = ws->fvid[3 * L.closest];
+      L.ov1 = ws->fvid[3 * L.closest + 1];
+      L.ov2 = ws->fvid[3 * L.closest + 2];
       E.status = HFB_EPA_VALID;
-      unsigned it = 0;
-      int pass = 0;
-      for (; it < P.max_iterations; ++it) {
-        if (E.num_vertices >= (int)E.nverts_cap) {
-          E.status = HFB_EPA_OUT_OF_VERTICES;
-          break;
-        }
-        if (E.num_vertices >= WS::MAXV) {
-          E.status = HFB_EPA_WS_OVERFLOW;
-          break;
-        }
-        int hz_first = HFB_EPA_NONE, hz_cur = HFB_EPA_NONE, hz_num = 0;
-        const int id_w = E.num_vertices++;
-        ws->fpass[closest] = (uint8_t)(++pass);
-        const v3 cn = ws_fn(ws, closest);
-        const SV w = gjk_support<G, CAPS>(sa, sb, md, cn, E.hint0, E.hint1);
-        ws_put_v(ws, id_w, w);
-
-        const v3 vf1 = ws_vw(ws, ws->fvid[3 * closest]);
-        const v3 vf2 = ws_vw(ws, ws->fvid[3 * closest + 1]);
-        const v3 vf3 = ws_vw(ws, ws->fvid[3 * closest + 2]);
-        const double fdist = dot(cn, w.w - vf1);
-        const double wnorm = nrm(w.w);
-        if (fdist <= tol + tol * wnorm) {
-          E.status = HFB_EPA_ACCURACY_REACHED;
-          break;
-        }
-        if (nrm(w.w - vf1) <= tol + tol * wnorm || nrm(w.w - vf2) <= tol + tol * wnorm ||
-            nrm(w.w - vf3) <= tol + tol * wnorm) {
-          E.status = HFB_EPA_ACCURACY_REACHED;
-          break;
-        }
-        bool valid = true;
-        const int round_seq0 = E.seq;
-        for (int j = 0; (j < 3) && valid; ++j)
-          valid = valid && epa_expand(ws, E, tol, pass, round_seq0, w.w, id_w, ws->fadj[3 * closest + j],
-                                      ws_fedge(ws, closest, j), hz_first, hz_cur, hz_num);
-        // verdicts of the faces created in this round come before whatever stopped the walk after them
-        if (!epa_flush_pending<G>(ws, E, tol, false)) valid = false;
-        if (!valid || hz_num < 3) break;
-        epa_bind(ws, hz_first, 2, hz_cur, 1);
-        epa_hull_remove(ws, E, closest);
-        closest = epa_find_closest<G>(ws, E);
-        outer_n = ws_fn(ws, closest);
-        outer_d = ws->fd[closest];
-        ov0 = ws->fvid[3 * closest];
-        ov1 = ws->fvid[3 * closest + 1];
-        ov2 = ws->fvid[3 * closest + 2];
-      }
-      E.iterations = it;
-      if (!(it < P.max_iterations)) E.status = HFB_EPA_FAILED;
-      E.normal = outer_n;
-      E.depth = outer_d + (md.ssr0 + md.ssr1);
-      E.rank = 3;
-      E.r0 = ws_sv(ws, ov0);
-      E.r1 = ws_sv(ws, ov1);
-      E.r2 = ws_sv(ws, ov2);
-      return;
+      return true;
     }
   }
   // FallBack (:1299-1315); the solver maps it to EPAFailedExtract... (narrowphase.h:574-582)
@@ -522,6 +486,130 @@ HFB_HD void epa_evaluate(const ShapeD& sa, const ShapeD& sb, const MinkD& md, co
   E.depth = 0;
   E.rank = 1;
   E.r0 = g.s0;
+  return false;
+}
+
+// part 2: the expansion loop (:1209-1290), from the state (E, L, *ws) -- that of epa_begin, or of an earlier epa_run
+// that stopped with L.resumable set
+template <int G, int CAPS, class WS>
+HFB_HD void epa_run(const ShapeD& sa, const ShapeD& sb, const MinkD& md, const EpaParams& P, WS* ws, EpaState& E,
+                    EpaLoop& L) {
+  const double tol = P.tolerance;
+  unsigned it = L.it;
+  int pass = L.pass;
+  int closest = L.closest;
+  L.resumable = 0;
+  E.status = HFB_EPA_VALID;
+  for (; it < P.max_iterations; ++it) {
+    if (E.num_vertices >= (int)E.nverts_cap) {
+      E.status = HFB_EPA_OUT_OF_VERTICES;
+      break;
+    }
+    // a reduced-size workspace (the request allows more than it holds) stops HERE, where the run can be handed over
+    // to the full-size one, when it is out of vertices -- or so short of face slots that this iteration might not
+    // fit: a round that runs out half-way (epa_alloc_face) cannot be continued, only started over
+    if (E.num_vertices >= WS::MAXV ||
+        (WS::MAXF < (int)E.nfaces_cap && (WS::MAXF - E.hwm) + E.stock_top < HFB_EPA_ROUND_FACES)) {
+      E.status = HFB_EPA_WS_OVERFLOW;
+      L.resumable = 1;  // nothing of this iteration has happened yet
+      break;
+    }
+    int hz_first = HFB_EPA_NONE, hz_cur = HFB_EPA_NONE, hz_num = 0;
+    const int id_w = E.num_vertices++;
+    ws->fpass[closest] = (uint8_t)(++pass);
+    const v3 cn = ws_fn(ws, closest);
+    const SV w = gjk_support<G, CAPS>(sa, sb, md, cn, E.hint0, E.hint1);
+    ws_put_v(ws, id_w, w);
+
+    const v3 vf1 = ws_vw(ws, ws->fvid[3 * closest]);
+    const v3 vf2 = ws_vw(ws, ws->fvid[3 * closest + 1]);
+    const v3 vf3 = ws_vw(ws, ws->fvid[3 * closest + 2]);
+    const double fdist = dot(cn, w.w - vf1);
+    const double wnorm = nrm(w.w);
+    if (fdist <= tol + tol * wnorm) {
+      E.status = HFB_EPA_ACCURACY_REACHED;
+      break;
+    }
+    if (nrm(w.w - vf1) <= tol + tol * wnorm || nrm(w.w - vf2) <= tol + tol * wnorm ||
+        nrm(w.w - vf3) <= tol + tol * wnorm) {
+      E.status = HFB_EPA_ACCURACY_REACHED;
+      break;
+    }
+    bool valid = true;
+    const int round_seq0 = E.seq;
+    for (int j = 0; (j < 3) && valid; ++j)
+      valid = valid && epa_expand(ws, E, tol, pass, round_seq0, w.w, id_w, ws->fadj[3 * closest + j],
+                                  ws_fedge(ws, closest, j), hz_first, hz_cur, hz_num);
+    // verdicts of the faces created in this round come before whatever stopped the walk after them
+    if (!epa_flush_pending<G>(ws, E, tol, false)) valid = false;
+    if (!valid || hz_num < 3) break;
+    epa_bind(ws, hz_first, 2, hz_cur, 1);
+    epa_hull_remove(ws, E, closest);
+    closest = epa_find_closest<G>(ws, E);
+    L.outer_n = ws_fn(ws, closest);
+    L.outer_d = ws->fd[closest];
+    L.ov0 = ws->fvid[3 * closest];
+    L.ov1 = ws->fvid[3 * closest + 1];
+    L.ov2 = ws->fvid[3 * closest + 2];
+  }
+  L.it = it;
+  L.pass = pass;
+  L.closest = closest;
+}
+
+// part 3: the result (:1291-1298)
+template <class WS>
+HFB_HD void epa_finish(const MinkD& md, const EpaParams& P, const WS* ws, EpaState& E, const EpaLoop& L) {
+  E.iterations = L.it;
+  if (!(L.it < P.max_iterations)) E.status = HFB_EPA_FAILED;
+  E.normal = L.outer_n;
+  E.depth = L.outer_d + (md.ssr0 + md.ssr1);
+  E.rank = 3;
+  E.r0 = ws_sv(ws, L.ov0);
+  E.r1 = ws_sv(ws, L.ov1);
+  E.r2 = ws_sv(ws, L.ov2);
+}
+
+template <int G, int CAPS, class WS>
+HFB_HD void epa_evaluate(const ShapeD& sa, const ShapeD& sb, const MinkD& md, const EpaParams& P, GjkState& g, WS* ws,
+                         EpaState& E, EpaLoop* Lout = nullptr) {
+  EpaLoop L;
+  if (epa_begin<G, CAPS>(sa, sb, md, P, g, ws, E, L)) {
+    epa_run<G, CAPS>(sa, sb, md, P, ws, E, L);
+    if (!(E.status == HFB_EPA_WS_OVERFLOW && L.resumable)) epa_finish(md, P, ws, E, L);
+  }
+  if (Lout) *Lout = L;
+}
+
+// the live part of a workspace copied into a larger one (same slot and vertex numbers), by the G lanes of the group:
+// vertices [0, num_vertices), face slots [0, hwm), the stock of freed slots.  The per-iteration scratch (walk stack,
+// pending faces) is empty at the top of an iteration, which is the only place a run is resumed from.
+template <int G, class WSA, class WSB>
+HFB_HD void epa_ws_grow(const WSA* a, WSB* b, const EpaState& E) {
+#if !defined(__CUDACC__) && defined(HFB_LANE_SIM)
+  const int l = 0, G_ = 1;  // host lane simulation: every lane thread owns private copies of both workspaces
+#else
+  const int l = Coop<G>::lane(), G_ = G;
+#endif
+  for (int i = l; i < 3 * E.num_vertices; i += G_) {
+    b->vw0[i] = a->vw0[i];
+    b->vw1[i] = a->vw1[i];
+    b->vw[i] = a->vw[i];
+  }
+  for (int i = l; i < 3 * E.hwm; i += G_) {
+    b->fn[i] = a->fn[i];
+    b->fvid[i] = a->fvid[i];
+    b->fadj[i] = a->fadj[i];
+    b->fedge[i] = a->fedge[i];
+  }
+  for (int i = l; i < E.hwm; i += G_) {
+    b->fd[i] = a->fd[i];
+    b->fseq[i] = a->fseq[i];
+    b->fpass[i] = a->fpass[i];
+    b->fflag[i] = a->fflag[i];
+  }
+  for (int i = l; i < E.stock_top; i += G_) b->stock[i] = a->stock[i];
+  Coop<G>::sync();
 }
 
 // EPA::getWitnessPointsAndNormal (:1451-1466)

@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(EpaCfg<G, TIER>::THREADS, EpaCfg<G, TIER>::MIN
     if (Coop<G>::lane() == 0) k = lo + atomicAdd(a.epa_head, 1u);
     k = __shfl_sync(Coop<G>::mask(), k, (threadIdx.x & 31u) & ~(unsigned)(G - 1));
     if (k >= hi) break;
+    const unsigned k_pos = k;  // (tier 1: position in the retry list = slot of the continuation record)
     if (TIER == 1) k = a.retry[k];
     const EpaItem* it = a.queue + k;
     const unsigned i = it->pair;
@@ -325,10 +326,36 @@ __global__ void __launch_bounds__(EpaCfg<G, TIER>::THREADS, EpaCfg<G, TIER>::MIN
     o.cached_guess = mk(1, 0, 0);
     o.hint0 = o.hint1 = 0;
     Coop<G>::sync();
-    const bool done = pair_phase2<G, CAPS>(in, a.P, g, ws, o);
-    if (Coop<G>::lane() == 0) {
-      if (done) store_result<MODE>(a, i, o);
-      else a.retry[atomicAdd(a.retry_count, 1u)] = k;  // TIER 0 only
+    if (TIER == 0) {
+      EpaResume rs;
+      rs.L.resumable = 0;
+      const bool done = pair_phase2<G, CAPS>(in, a.P, g, ws, o, &rs);
+      if (done) {
+        if (Coop<G>::lane() == 0) store_result<MODE>(a, i, o);
+      } else {
+        unsigned r = 0;
+        if (Coop<G>::lane() == 0) {
+          r = atomicAdd(a.retry_count, 1u);
+          a.retry[r] = k;
+        }
+        r = __shfl_sync(Coop<G>::mask(), r, (threadIdx.x & 31u) & ~(unsigned)(G - 1));
+        if (a.cont && r < a.cont_cap) {  // (the group's lanes hold the same rs)
+          EpaCont* c = a.cont + r;
+          if (rs.L.resumable) epa_ws_grow<G>(ws, &c->ws, rs.E);
+          if (Coop<G>::lane() == 0) c->rs = rs;
+        }
+      }
+    } else {
+      const unsigned kk = k_pos;
+      bool done = false;
+      if (a.cont && kk < a.cont_cap && a.cont[kk].rs.L.resumable) {
+        EpaResume rs = a.cont[kk].rs;
+        epa_ws_grow<G>(&a.cont[kk].ws, ws, rs.E);
+        done = pair_phase2_resume<G, CAPS>(in, a.P, g, ws, rs, o);
+      } else {
+        done = pair_phase2<G, CAPS>(in, a.P, g, ws, o);
+      }
+      if (done && Coop<G>::lane() == 0) store_result<MODE>(a, i, o);
     }
     Coop<G>::sync();
   }
@@ -721,6 +748,7 @@ struct Slot {
   cudaStream_t epa_stream = nullptr;
   cudaEvent_t ev_part[kMaxParts] = {};
   cudaEvent_t ev_join = nullptr;
+  DevBuf cont;  // EpaCont records (k_epa tier 0 -> tier 1)
   DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, retry, bvh_ws, bvh_cnt, extra, ccnt, okeys, ohist, olist;
   DevBuf qprep, qstacks, qtl, qws, qsv;  // task-system mesh-shape walk (hfb_bvhq.cu)
   DevBuf gstate, glist, gcnt;        // GJK passes (hfb_gjkpass.cu): solver state, two lists of running pairs, counts
@@ -761,6 +789,7 @@ struct hfb_ctx {
   int bvh_warps = 8;   // HFB_BVH_WARPS: 8 (255 registers per thread) or 16 (128) warps per block of k_bvhq
   int bvh_gens = 2;    // HFB_BVH_GENS: generations of BV items per cycle of k_bvhq
   int bvh_spec_big = 300;  // HFB_BVH_SPEC_BIG: items more before subtrees of up to 128 triangles are speculated
+  int epa_resume = 8192;  // HFB_EPA_RESUME: retries per batch that continue from the state tier 0 reached (5 KB each)
   int bvh_chunk = 6;   // HFB_BVH_GJK_CHUNK: GJK iterations a leaf item runs before it parks its state
   int bvh_spec = 200;  // HFB_BVH_SPEC: items a query uses before it may speculate on subtrees (< 0: never)
   int bvh_bps = 4;  // k_bvh: blocks (of 2 warps) per SM the grid is capped at; HFB_BVH_BPS, see tests/tools/bvh_sched_model.py
@@ -920,6 +949,14 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   CK(sl.retry.reserve((size_t)n * sizeof(uint32_t)));
   a.queue = static_cast<EpaItem*>(sl.queue.p);
   a.retry = static_cast<uint32_t*>(sl.retry.p);
+  a.cont = nullptr;
+  a.cont_cap = 0;
+  if (ctx->epa_resume > 0) {  // HFB_EPA_RESUME: continuation records for that many retries per batch (0: retries start over)
+    const size_t cap = (size_t)ctx->epa_resume < (size_t)n ? (size_t)ctx->epa_resume : (size_t)n;
+    CK(sl.cont.reserve(cap * sizeof(EpaCont)));
+    a.cont = static_cast<EpaCont*>(sl.cont.p);
+    a.cont_cap = (unsigned)cap;
+  }
   unsigned* cnt = static_cast<unsigned*>(sl.counters.p);
   unsigned* mark = cnt + 4;
   unsigned* heads = cnt + 16;
@@ -1446,6 +1483,7 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   if (const char* bq2 = getenv("HFB_BVHQ")) c->bvhq = atoi(bq2) != 0;
   if (const char* bs = getenv("HFB_BVH_SPEC")) c->bvh_spec = atoi(bs);
   if (const char* bc = getenv("HFB_BVH_GJK_CHUNK")) c->bvh_chunk = atoi(bc) > 0 ? atoi(bc) : 1;
+  if (const char* er = getenv("HFB_EPA_RESUME")) c->epa_resume = atoi(er) > 0 ? atoi(er) : 0;
   if (const char* gp = getenv("HFB_GJK_PASSES")) {
     c->gjk_npass = 0;
     int k = 0;
@@ -1457,7 +1495,7 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
     }
     c->gjk_npass = k > 0 ? k + 1 : 0;
   }
-  if (const char* bw = getenv("HFB_BVH_WARPS")) c->bvh_warps = atoi(bw) >= 16 ? 16 : 8;
+  if (const char* bw = getenv("HFB_BVH_WARPS")) c->bvh_warps = atoi(bw) >= 16 ? 16 : (atoi(bw) >= 12 ? 12 : 8);
   if (const char* eo = getenv("HFB_EPA_OVERLAP")) c->epa_overlap = atoi(eo) != 0;
   if (const char* bg = getenv("HFB_BVH_GENS")) c->bvh_gens = atoi(bg) > 0 ? atoi(bg) : 1;
   if (const char* bb = getenv("HFB_BVH_SPEC_BIG")) c->bvh_spec_big = atoi(bb) >= 0 ? atoi(bb) : 0;
@@ -1486,7 +1524,7 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   cudaDeviceSynchronize();
   hfb_comm_destroy(c);
   auto rel = [](Slot& s) {
-    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist, &s.qprep, &s.qstacks, &s.qtl, &s.qws, &s.qsv, &s.gstate, &s.glist, &s.gcnt, &s.pi, &s.pj, &s.cmp};
+    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist, &s.qprep, &s.qstacks, &s.qtl, &s.qws, &s.qsv, &s.gstate, &s.glist, &s.gcnt, &s.pi, &s.pj, &s.cmp, &s.cont};
     for (DevBuf* b : bs) b->release();
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.epa_stream) cudaStreamDestroy(s.epa_stream);

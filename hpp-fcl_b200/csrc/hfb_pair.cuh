@@ -288,15 +288,8 @@ HFB_HD bool pair_phase1(const PairIn& in, const SolverP& P, PairOut& o, GjkState
 }
 
 // ---- phase 2: EPA + EPAExtractWitnessPointsAndNormal (narrowphase.h:514-583, 658-723)
-// Returns false (and leaves `o` unset) only when WS is a reduced-size workspace and the polytope
-// outgrew it: the caller runs the pair again, from the queued GJK state, in the full-size one.
-template <int G, int CAPS, class WS>
-HFB_HD bool pair_phase2(const PairIn& in, const SolverP& P, GjkState& g, WS* ws, PairOut& o) {
-  GjkSetup S;
-  make_setup<CAPS>(in, S);
-  EpaState E;
-  epa_evaluate<G, CAPS>(S.a, S.b, S.md, P.epa, g, ws, E);
-  if (E.status == HFB_EPA_WS_OVERFLOW) return false;
+// the result record of a finished EPA run
+HFB_HD void pair_epa_result(const GjkSetup& S, const GjkState& g, const EpaState& E, PairOut& o) {
   o.iterations = (g.iterations & 0xffffu) | ((E.iterations & 0xffffu) << 16);
   o.status = pack_status(HFB_GJK_COLLISION, E.status, HFB_PATH_GJK);
   if (E.status == HFB_EPA_FALLBACK) {  // EPAFailedExtract... :713-723
@@ -304,7 +297,7 @@ HFB_HD bool pair_phase2(const PairIn& in, const SolverP& P, GjkState& g, WS* ws,
     o.hint0 = o.hint1 = 0;
     o.distance = -DBL_MAX;
     o.p1 = o.p2 = o.normal = nan3();
-    return true;
+    return;
   }
   o.cached_guess = -(E.depth * E.normal);
   o.hint0 = E.hint0;
@@ -313,6 +306,44 @@ HFB_HD bool pair_phase2(const PairIn& in, const SolverP& P, GjkState& g, WS* ws,
   epa_witness(E, S.md, o.p1, o.p2, o.normal);
   recentre(S.tfa, o.distance, o.p1, o.p2, o.normal);
   unswap(S, o);
+}
+// what a run that outgrew a reduced-size workspace hands to its continuation in the full-size one
+struct EpaResume {
+  EpaState E;
+  EpaLoop L;
+};
+// Returns false (and leaves `o` unset) only when WS is a reduced-size workspace and the polytope outgrew it.  With
+// `rs` given and rs->L.resumable set on return, (rs, *ws) is the state at the top of the iteration that did not fit:
+// pair_phase2_resume continues from a copy of it (epa_ws_grow); otherwise the caller runs the pair again, from the
+// queued GJK state, in the full-size workspace.
+template <int G, int CAPS, class WS>
+HFB_HD bool pair_phase2(const PairIn& in, const SolverP& P, GjkState& g, WS* ws, PairOut& o, EpaResume* rs = nullptr) {
+  GjkSetup S;
+  make_setup<CAPS>(in, S);
+  EpaState E;
+  EpaLoop L;
+  epa_evaluate<G, CAPS>(S.a, S.b, S.md, P.epa, g, ws, E, &L);
+  if (E.status == HFB_EPA_WS_OVERFLOW) {
+    if (rs) {
+      rs->E = E;
+      rs->L = L;
+    }
+    return false;
+  }
+  pair_epa_result(S, g, E, o);
+  return true;
+}
+// the rest of a run that stopped with rs.L.resumable set; `ws` holds the grown copy of its workspace and `g` the GJK
+// iteration count of the pair (all the result record takes from it)
+template <int G, int CAPS, class WS>
+HFB_HD bool pair_phase2_resume(const PairIn& in, const SolverP& P, const GjkState& g, WS* ws, EpaResume& rs, PairOut& o) {
+  GjkSetup S;
+  make_setup<CAPS>(in, S);
+  epa_run<G, CAPS>(S.a, S.b, S.md, P.epa, ws, rs.E, rs.L);
+  if (rs.E.status == HFB_EPA_WS_OVERFLOW && rs.L.resumable) return false;  // (cannot happen in the full-size workspace)
+  epa_finish(S.md, P.epa, ws, rs.E, rs.L);
+  if (rs.E.status == HFB_EPA_WS_OVERFLOW) return false;
+  pair_epa_result(S, g, rs.E, o);
   return true;
 }
 

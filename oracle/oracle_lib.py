@@ -305,5 +305,15 @@ class RefScene(OracleScene):
         return self._run(self.L.ref_batch_collide, self.pod.contact_dtype, h1, tf1, h2, tf2, req,
                          want_guess, nthreads)
 
+    def object_aabbs(self, handles, tfs):
+        """CollisionObject(geometry, pose).getAABB() of the reference: (n, 6) rows min xyz, max xyz"""
+        h = np.ascontiguousarray(handles, dtype=np.uint32)
+        tf = np.ascontiguousarray(tfs, dtype=self.pod.transform_dtype)
+        out = np.zeros((len(h), 6))
+        self.L.ref_object_aabbs.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        if self.L.ref_object_aabbs(self.h, len(h), _ptr(h), _ptr(tf), _ptr(out)) != 0:
+            raise ValueError("ref_object_aabbs failed")
+        return out
+
     _contacts_fn = "ref_batch_collide_contacts"
     _halfspaces_fn = "ref_register_halfspaces"

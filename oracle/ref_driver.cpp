@@ -255,6 +255,21 @@ int64_t ref_register_halfspaces(void* p, uint32_t type, const double* nd, const 
   return first;
 }
 
+// CollisionObject::computeAABB (collision_object.h:258-278) of geometry h[i] at pose tf[i]: min xyz, max xyz
+int ref_object_aabbs(void* p, size_t n, const uint32_t* h, const hfb_transform* tf, double* out) {
+  Scene* s = static_cast<Scene*>(p);
+  for (size_t i = 0; i < n; ++i) {
+    if (h[i] >= s->geoms.size()) return HFB_ERR_INVALID_ARGUMENT;
+    CollisionObject o(s->geoms[h[i]], to_tf(tf[i]));
+    const AABB& a = o.getAABB();
+    for (int k = 0; k < 3; ++k) {
+      out[6 * i + k] = a.min_[k];
+      out[6 * i + 3 + k] = a.max_[k];
+    }
+  }
+  return HFB_OK;
+}
+
 int ref_max_threads() {
 #ifdef _OPENMP
   return omp_get_max_threads();

@@ -99,6 +99,14 @@ class EmuScene:
         assert first >= 0
         return np.arange(first, first + nd.shape[0], dtype=np.uint32)
 
+    def scene_aabbs(self, handles, tfs):
+        h = np.ascontiguousarray(handles, dtype=np.uint32)
+        tf = np.ascontiguousarray(tfs, dtype=P.transform_dtype)
+        out = np.zeros((len(h), 6))
+        self.L.emu_scene_aabbs.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p]
+        assert self.L.emu_scene_aabbs(self.h, len(h), _ptr(h), _ptr(tf), _ptr(out)) == 0
+        return out
+
     def commit(self):
         pass
 

@@ -17,6 +17,7 @@
 #include "../../hpp-fcl_b200/csrc/hfb_bvh.cuh"
 #include "../../hpp-fcl_b200/csrc/hfb_bvhq.cuh"
 #include "../../hpp-fcl_b200/csrc/hfb_request.cuh"
+#include "../../hpp-fcl_b200/csrc/hfb_broadphase.cuh"
 
 // ---- lane groups on the host ---------------------------------------------------------------------------
 // Coop<G> for G > 1 is warp intrinsics on the device.  Here (HFB_LANE_SIM) the G lanes of a group are G threads
@@ -145,18 +146,28 @@ inline PairIn load_pair(const ArenaView& A, size_t i, const uint32_t* h1, const 
   return in;
 }
 
-long g_retries = 0;
+long g_retries = 0, g_resumed = 0;
+bool g_no_resume = false;  // HFB_EMU_NO_RESUME: tier 1 always starts over (the two must agree bit for bit)
 inline void run_pair(const PairIn& in, const SolverP& P, EpaWs* ws, PairOut& o) {
   GjkState g;
   std::memset(&g, 0, sizeof(g));
   if (pair_phase1<1, CAPS_ALLP>(in, P, o, g)) {
     // the two tiers of k_epa: reduced-size workspace first, full size when the polytope outgrows it
+    // (tier 1 continues from the state tier 0 reached when it stopped at the top of an iteration, else starts over)
     const GjkState g0 = g;
     EpaWsSmall small;
-    if (!pair_phase2<1, CAPS_ALL>(in, P, g, &small, o)) {
+    EpaResume rs;
+    rs.L.resumable = 0;
+    if (!pair_phase2<1, CAPS_ALL>(in, P, g, &small, o, &rs)) {
       ++g_retries;
-      g = g0;
-      pair_phase2<1, CAPS_ALL>(in, P, g, ws, o);
+      if (rs.L.resumable && !g_no_resume) {
+        ++g_resumed;
+        epa_ws_grow<1>(&small, ws, rs.E);
+        pair_phase2_resume<1, CAPS_ALL>(in, P, g0, ws, rs, o);
+      } else {
+        g = g0;
+        pair_phase2<1, CAPS_ALL>(in, P, g, ws, o);
+      }
     }
   }
 }
@@ -231,16 +242,26 @@ long batch_lanes(Emu* E, size_t n, const uint32_t* h1, const hfb_transform* tf1,
         mine.o.hint0 = mine.o.hint1 = 0;
         lanesim::register_workspace(small.get());
         Coop<G>::sync();
-        const bool done = pair_phase2<G, CAPS_ALL>(in, P, g, small.get(), mine.o);
+        EpaResume rs;
+        rs.L.resumable = 0;
+        const bool done = pair_phase2<G, CAPS_ALL>(in, P, g, small.get(), mine.o, &rs);
         Coop<G>::sync();
         if (!done) {
           if (l == 0) ++g_retries;
-          g = requeue(queued);
           mine.o.cached_guess = mk(1, 0, 0);
           mine.o.hint0 = mine.o.hint1 = 0;
-          lanesim::register_workspace(ws.get());
-          Coop<G>::sync();
-          pair_phase2<G, CAPS_ALL>(in, P, g, ws.get(), mine.o);
+          if (rs.L.resumable && !g_no_resume) {
+            if (l == 0) ++g_resumed;
+            epa_ws_grow<G>(small.get(), ws.get(), rs.E);
+            lanesim::register_workspace(ws.get());
+            Coop<G>::sync();
+            pair_phase2_resume<G, CAPS_ALL>(in, P, requeue(queued), ws.get(), rs, mine.o);
+          } else {
+            g = requeue(queued);
+            lanesim::register_workspace(ws.get());
+            Coop<G>::sync();
+            pair_phase2<G, CAPS_ALL>(in, P, g, ws.get(), mine.o);
+          }
         }
       }
       Coop<G>::sync();
@@ -411,6 +432,8 @@ long emu_q_spec_items() { return g_q_spec_items; }
 long emu_q_items() { return g_q_items; }
 void* emu_create() { return new Emu(); }
 long emu_epa_retries() { return g_retries; }
+long emu_epa_resumed() { return g_resumed; }
+void emu_set_epa_resume(int on) { g_no_resume = on == 0; }
 void emu_destroy(void* e) { delete static_cast<Emu*>(e); }
 
 int emu_register_convex(void* e, const double* pts, uint32_t n) {
@@ -446,6 +469,23 @@ int64_t emu_register_halfspaces(void* e, uint32_t type, const double* nd, const 
     if (!E->arena.add_halfspace(type, nd + 4 * i, nd[4 * i + 3], ssr ? ssr[i] : 0.0, &h)) return -1;
   }
   return first;
+}
+
+// hfb_scene_aabbs on the host: aabb_local of the shape records (what hfb_geom_commit tabulates) + object_aabb
+int emu_scene_aabbs(void* e, size_t n, const uint32_t* handles, const hfb_transform* tfs, double* out) {
+  Emu* E = static_cast<Emu*>(e);
+  for (size_t i = 0; i < n; ++i) {
+    LocalAabb b;
+    if (handles[i] >= E->arena.shapes.size() || !shape_local_aabb(E->arena, E->arena.shapes[handles[i]], b)) {
+      for (int k = 0; k < 3; ++k) {
+        out[6 * i + k] = DBL_MAX;
+        out[6 * i + 3 + k] = -DBL_MAX;
+      }
+      continue;
+    }
+    object_aabb(b.mn, b.mx, tfs[i], out + 6 * i);
+  }
+  return HFB_OK;
 }
 
 int emu_update_shapes(void* e, const uint32_t* handles, const hfb_shape* shapes, size_t n) {

@@ -49,6 +49,68 @@ def test_host_pair_finder_equals_brute_force(n, scale):
         assert len(f2) == 5 and set(zip(f2.tolist(), s2.tolist())) <= got
 
 
+def test_unbounded_boxes_pair_with_everything_they_touch():
+    """a Halfspace / Plane object has a box that is all of space on two or three axes: it stays out of the grid and is
+    tested against every object (and against the other unbounded ones once)"""
+    rng = np.random.default_rng(3)
+    n = 1500
+    c = 30 * (2 * rng.random((n, 3)) - 1)
+    e = 0.5 + 3 * rng.random((n, 3))
+    bb = np.concatenate([c - e, c + e], axis=1)
+    big = np.finfo(np.float64).max
+    bb[7] = [-big, -big, -big, big, big, 0.0]       # a floor: z <= 0
+    bb[400] = [-np.inf, -np.inf, -np.inf, np.inf, np.inf, np.inf]   # a tilted halfspace: everything
+    bb[1499] = [5.0, -big, -big, 5.0, big, big]     # a plane x = 5
+    bb[3, :3], bb[3, 3:] = big, -big                 # an object without a box
+    f, s = hf.broadphase_pairs(bb)
+    got = set(zip(f.tolist(), s.tolist()))
+    assert len(got) == len(f) and all(a < b for a, b in got)
+    assert got == {p for p in brute_pairs(bb) if 3 not in p}  # (the boxless marker would "overlap" an infinite box)
+    assert (7, 400) in got and (400, 1499) in got and (7, 1499) in got and not any(3 in p for p in got)
+    assert sum(1 for p in got if 400 in p) == n - 2  # everything but itself and the boxless object
+
+
+def test_scene_boxes_equal_the_reference():
+    """aabb_local of every shape type (computeLocalAABB, Halfspace and Plane included) and CollisionObject::computeAABB,
+    against the reference build itself: the host build of the product code (tests/emu) must give the same boxes bit for
+    bit, poses with and without rotation"""
+    import os
+    from oracle import oracle_lib
+    from tests.common import EmuScene
+    if os.path.isdir("/root/reference/src"):
+        oracle_lib.build_ref()
+    if not oracle_lib.ref_available():
+        pytest.skip("oracle/_ref is not built (needs /root/reference)")
+    rng = np.random.default_rng(12)
+    ref, emu = oracle_lib.RefScene(P), EmuScene()
+    prims = W.random_primitive_shapes(rng, 48, (P.GEOM_BOX, P.GEOM_SPHERE, P.GEOM_CAPSULE, P.GEOM_CYLINDER, P.GEOM_CONE,
+                                                P.GEOM_ELLIPSOID))
+    prims["ssr"] = np.where(rng.random(48) < 0.3, 0.05, 0.0)
+    nd = np.concatenate([rng.normal(size=(12, 3)), rng.uniform(-2, 2, (12, 1))], axis=1)
+    nd[:6] = [[0, 0, 1, 0.5], [0, 0, -3, 1.0], [2, 0, 0, -1.0], [0, -1, 0, 0.25], [0, 1, 0, 0], [-1, 0, 0, 2.0]]
+    ssr = np.array([0.0, 0.1] * 6)
+    pts, tris = W.ellipsoid_hull(rng, 24)
+    hs = []
+    for sc, name in ((ref, "ref"), (emu, "emu")):
+        h = [sc.register_shapes(prims), sc.register_halfspaces(P.GEOM_HALFSPACE, nd, ssr),
+             sc.register_halfspaces(P.GEOM_PLANE, nd, ssr)]
+        cid = sc.register_convex(pts, tris) if name == "ref" else sc.register_convex(pts)
+        h.append(sc.register_shapes(P.make_shapes([P.GEOM_CONVEX], [[0, 0, 0]], data=[cid])))
+        hs.append(np.concatenate(h))
+    assert np.array_equal(hs[0], hs[1])
+    n = 4000
+    oh = hs[0][rng.integers(0, len(hs[0]), n)]
+    tf = W.random_transforms(rng, n, (-5, -5, -5), (5, 5, 5))
+    tf[:1500] = W.identity_transforms(1500, T=tf["T"][:1500])
+    a, b = ref.object_aabbs(oh, tf), emu.scene_aabbs(oh, tf)
+    same = (a == b) | (np.isnan(a) & np.isnan(b))
+    assert same.all(), "boxes differ at rows %s" % np.unique(np.nonzero(~same)[0])[:10]
+    assert np.isinf(a).any() and (np.abs(a) == np.finfo(np.float64).max).any()  # rotated and unrotated halfspaces
+    # and the pairs these boxes give are the brute-force set
+    f, s = hf.broadphase_pairs(b[:800])
+    assert set(zip(f.tolist(), s.tolist())) == brute_pairs(b[:800])
+
+
 def test_config5_scene_has_the_intended_density():
     w = W.config5_moving_boxes(20_000, target_pairs=100_000)
     local = np.array([-2.5, -5, -10, 2.5, 5, 10.0])
@@ -134,6 +196,49 @@ def test_scene_aabbs_and_device_broadphase():
         assert len(part) == kk and all(lo <= a < lo + cnt for a, _ in part) and not (part & got)
         got |= part
     assert got == want
+
+
+@pytest.mark.gpu
+def test_scene_with_a_floor_and_a_wall():
+    """a Halfspace floor and a Plane wall among ten thousand shapes: boxes against the reference build, the device pair
+    finder against the host one and brute force, hfb_scene_collide against the oracle on exactly those pairs"""
+    from oracle import oracle_lib
+    rng = np.random.default_rng(17)
+    eng, orc = hf.Engine(0), oracle_lib.OracleScene(P)
+    prims = W.random_primitive_shapes(rng, 32, (P.GEOM_BOX, P.GEOM_SPHERE, P.GEOM_CAPSULE, P.GEOM_CYLINDER))
+    nd_floor, nd_wall = [[0, 0, 1, 0.0]], [[1, 0, 0, 6.0]]
+    hs = []
+    for sc in (eng, orc):
+        hs.append(np.concatenate([sc.register_shapes(prims), sc.register_halfspaces(P.GEOM_HALFSPACE, nd_floor),
+                                  sc.register_halfspaces(P.GEOM_PLANE, nd_wall)]))
+    eng.commit()
+    assert np.array_equal(hs[0], hs[1])
+    n = 10_000
+    oh = hs[0][rng.integers(0, 32, n)].astype(np.uint32)
+    tf = W.random_transforms(rng, n, (-10, -10, 0.2), (10, 10, 6))
+    oh[0], oh[n - 1] = hs[0][32], hs[0][33]  # the floor first, the wall last
+    tf[0] = W.identity_transforms(1)[0]
+    tf[n - 1] = W.identity_transforms(1)[0]
+    tf["T"][:400, 2] = rng.uniform(-0.3, 0.6, 400)  # four hundred objects on or in the floor
+    tf["T"][0] = 0
+    bb = eng.scene_aabbs(oh, tf)
+    if oracle_lib.ref_available():
+        ref = oracle_lib.RefScene(P)
+        assert np.array_equal(np.concatenate([ref.register_shapes(prims), ref.register_halfspaces(P.GEOM_HALFSPACE, nd_floor),
+                                              ref.register_halfspaces(P.GEOM_PLANE, nd_wall)]), hs[0])
+        assert np.array_equal(ref.object_aabbs(oh, tf), bb)
+    f, s = hf.broadphase_pairs(bb)
+    want = set(zip(f.tolist(), s.tolist()))
+    assert sum(1 for a, b in want if a == 0) > 150 and sum(1 for a, b in want if b == n - 1) > 20
+    assert want == brute_pairs(bb[:1500]) | {p for p in want if p[1] >= 1500}  # brute force on a prefix
+    fo, so, rec, ncand, nhit = eng.scene_collide(oh, tf, capacity=len(want) + 100)
+    assert set(zip(fo.tolist(), so.tolist())) <= want and ncand == len(want) and nhit == len(fo)
+    ro = orc.batch_collide(oh[f], tf[f], oh[s], tf[s], nthreads=0)
+    hit = {(int(a), int(b)) for a, b, c in zip(f, s, ro["num_contacts"]) if c}
+    assert hit == set(zip(fo.tolist(), so.tolist())) and len(hit) > 100
+    key = {p: k for k, p in enumerate(zip(f.tolist(), s.tolist()))}
+    order = np.array([key[p] for p in zip(fo.tolist(), so.tolist())])
+    assert rec.tobytes() == ro[order].tobytes()
 
 
 @pytest.mark.gpu

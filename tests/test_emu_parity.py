@@ -64,6 +64,39 @@ def test_epa_two_tier_workspace(prim):
     assert L.emu_epa_retries() - before > 20
     ep = ro["iterations"] >> 16
     assert ep.max() > 30  # runs past the reduced workspace's 24 iterations
+    # tier 1 continues from the state tier 0 reached (epa_ws_grow + pair_phase2_resume); starting the pair over instead
+    # must give the same bits, and so must the lane-group form (8 lanes per pair, as k_epa runs it)
+    L.emu_epa_resumed.restype = __import__("ctypes").c_long
+    assert L.emu_epa_resumed() > 20
+    r0 = L.emu_epa_resumed()
+    L.emu_set_epa_resume(0)
+    try:
+        re2 = sc.b["emu"].batch_distance(w["h1"][:n], w["tf1"][:n], w["h2"][:n], w["tf2"][:n], req)
+    finally:
+        L.emu_set_epa_resume(1)
+    assert L.emu_epa_resumed() == r0
+    compare_distance(ro, re2, what="two-tier EPA, tier 1 starting over")
+
+
+def test_lane_group_epa_continues_in_the_full_workspace(prim):
+    """the same hand-over as k_epa<8> does it: eight lanes copy the reduced workspace into the full one (every lane
+    its share on the device, every lane thread its private copy here) and carry on"""
+    from tests.common import emu_lib
+    L = emu_lib()
+    L.emu_epa_resumed.restype = __import__("ctypes").c_long
+    sc, w = prim
+    n = 2500
+    req = P.DistanceRequestPOD(epa_tolerance=1e-12)
+    emu = sc.b["emu"]
+    before = L.emu_epa_resumed()
+    emu.lanes = 8
+    try:
+        re = emu.batch_distance(w["h1"][:n], w["tf1"][:n], w["h2"][:n], w["tf2"][:n], req)
+    finally:
+        emu.lanes = 1
+    ro = sc.b["oracle"].batch_distance(w["h1"][:n], w["tf1"][:n], w["h2"][:n], w["tf2"][:n], req, nthreads=0)
+    compare_distance(ro, re, what="two-tier EPA, 8 lanes")
+    assert L.emu_epa_resumed() - before > 5
 
 
 def test_signed_distance_off(prim):
