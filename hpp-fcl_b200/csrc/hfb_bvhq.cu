@@ -325,7 +325,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_bvhq(const BvhqLaunch L) {
     // ---- bounding-volume phase: bv_gens generations of items.  A generation is what was queued when it started;
     // the items it pushes (a walk going down a level) are the next generation.  Running "until the queue is empty"
     // instead made every cycle wait for its deepest descent with a handful of lanes busy
-    // (profiles/r02_k_bvhq_phases.md: 66 us of BV phase per cycle against 10 us of leaf phase). ----
+    // (profiles/r02_summary.md: 66 us of BV phase per cycle against 10 us of leaf phase). ----
     for (int gen = 0; gen < L.bv_gens; ++gen) {
       if (gen > 0) __syncthreads();
       if (threadIdx.x == 0) {

@@ -143,6 +143,7 @@ int64_t oracle_register_shapes(void* sc, const hfb_shape* shapes, size_t n) {
   for (size_t i = 0; i < n; ++i) {
     Shape sh;
     sh.type = (int)shapes[i].type;
+    if (sh.type == HFB_GEOM_PLANE || sh.type == HFB_GEOM_HALFSPACE) return -1;  // oracle_register_halfspaces (n and d)
     sh.p[0] = shapes[i].p[0];
     sh.p[1] = shapes[i].p[1];
     sh.p[2] = shapes[i].p[2];

@@ -456,6 +456,7 @@ int64_t emu_register_shapes(void* e, const hfb_shape* shapes, size_t n) {
   int64_t first = (int64_t)E->arena.shapes.size();
   for (size_t i = 0; i < n; ++i) {
     uint32_t h;
+    if (shapes[i].type == HFB_GEOM_PLANE || shapes[i].type == HFB_GEOM_HALFSPACE) return -1;  // as hfb_geom_register_shapes
     if (!E->arena.add_shape(shapes[i], &h)) return -1;
   }
   return first;

@@ -155,7 +155,7 @@ def test_triangles_and_unsupported():
         tris.append(cid)
     ht = sc.register_shapes(P.make_shapes([P.GEOM_TRIANGLE] * 32, np.zeros((32, 3)), data=tris))
     hp = sc.register_shapes(W.random_primitive_shapes(rng, 64, ALL_PRIMS))
-    hx = sc.register_shapes(P.make_shapes([P.GEOM_PLANE, P.GEOM_HALFSPACE], np.zeros((2, 3))))
+    hx = sc.register_shapes(P.make_shapes([18, 20], np.zeros((2, 3))))  # GEOM_OCTREE, HF_AABB (collision_object.h:65-89)
     allh = np.concatenate([ht, hp])
     n = 20000
     h1, h2 = allh[rng.integers(0, len(allh), n)], allh[rng.integers(0, len(allh), n)]
@@ -172,7 +172,7 @@ def test_triangles_and_unsupported():
     rc = sc.b["oracle"].batch_collide(h1, t1, h2, t2, nthreads=0)
     compare_distance(rc, sc.b["emu"].batch_collide(h1, t1, h2, t2), what="triangles collide")
     assert rc["num_contacts"].sum() > 500
-    # plane / halfspace pairs are reported per pair as unsupported (collision.cpp:110-117)
+    # node types outside the path are reported per pair as unsupported (collision.cpp:110-117)
     h1[:10] = hx[0]
     h2[10:20] = hx[1]
     ro = sc.b["oracle"].batch_distance(h1[:40], t1[:40], h2[:40], t2[:40])
