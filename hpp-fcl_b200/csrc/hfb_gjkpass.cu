@@ -15,6 +15,8 @@
 // and pass of HBM traffic (0.5 M pairs: 0.2 GB, 0.04 ms at the measured bandwidth).
 #include "hfb_gjkpass.h"
 
+#include <cub/cub.cuh>
+
 namespace {
 
 struct GjkSaved {
@@ -33,6 +35,7 @@ struct PassArgs {
   unsigned* out_count;
   int steps;
   int which;  // k_gjk_end: the pairs with this `done` value
+  unsigned char* flags;  // k_gjk_first: 1 per position still running, for the ordered compaction (null: append by atomics)
 };
 
 __device__ __forceinline__ void append_running(const PassArgs& p, bool more, unsigned pos) {
@@ -67,8 +70,9 @@ __global__ void __launch_bounds__(128) k_gjk_first(const BatchArgs a, const Pass
       }
       sv.done = more ? 0 : 1;
       p.state[k - lo] = sv;
+      if (p.flags) p.flags[k - lo] = more ? 1 : 0;
     }
-    if (p.out_list) append_running(p, more, k - lo);
+    if (p.out_list && !p.flags) append_running(p, more, k - lo);
   }
 }
 
@@ -125,6 +129,13 @@ __global__ void __launch_bounds__(128) k_gjk_end(const BatchArgs a, const PassAr
 }  // namespace
 
 size_t gjk_pass_state_bytes(size_t n) { return n * sizeof(GjkSaved); }
+// flags (n bytes, rounded) + the temporary storage of the ordered compaction
+size_t gjk_pass_select_bytes(size_t n) {
+  size_t tmp = 0;
+  cub::DeviceSelect::Flagged(nullptr, tmp, cub::CountingInputIterator<uint32_t>(0), (const unsigned char*)nullptr, (uint32_t*)nullptr,
+                             (unsigned*)nullptr, (int)n);
+  return ((n + 255) & ~(size_t)255) + tmp + 256;
+}
 
 static unsigned pass_blocks(unsigned n, int num_sms) {
   unsigned blocks = (n + 127) / 128;
@@ -141,10 +152,15 @@ static void launch_end(const BatchArgs& a, int mode, PassArgs p, int which, unsi
 // first pass + extraction of the pairs it finished (their EPA items are in the queue when this returns, so that the
 // caller can start EPA on a side stream next to the remaining passes)
 int gjk_passes_first(const BatchArgs& a, int mode, unsigned n, void* state, uint32_t* list_a, unsigned* counts,
-                     const int* steps, int npass, int num_sms, cudaStream_t s, int* launches) {
+                     const int* steps, int npass, int num_sms, cudaStream_t s, int* launches, void* select_ws) {
   if (npass < 1) return (int)cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)npass * sizeof(unsigned), s);
   if (e != cudaSuccess) return (int)e;
+  // the survivors of the first pass in CLASS ORDER (a stable compaction of the class-sorted range) rather than in the
+  // order the warps happen to finish: the second pass then meets one pair class per warp, as the first did
+  unsigned char* flags = (select_ws && npass > 1) ? static_cast<unsigned char*>(select_ws) : nullptr;
+  const size_t flag_bytes = ((size_t)n + 255) & ~(size_t)255;
+  if (flags && (e = cudaMemsetAsync(flags, 0, flag_bytes, s)) != cudaSuccess) return (int)e;
   const unsigned blocks = pass_blocks(n, num_sms);
   PassArgs p;
   p.state = static_cast<GjkSaved*>(state);
@@ -154,7 +170,15 @@ int gjk_passes_first(const BatchArgs& a, int mode, unsigned n, void* state, uint
   p.out_count = counts;
   p.steps = npass > 1 ? steps[0] : 0x7fffffff;
   p.which = 0;
+  p.flags = flags;
   k_gjk_first<<<blocks, 128, 0, s>>>(a, p);
+  if (flags) {
+    size_t tmp = gjk_pass_select_bytes(n) - flag_bytes - 256;
+    if ((e = cub::DeviceSelect::Flagged(flags + flag_bytes, tmp, cub::CountingInputIterator<uint32_t>(0), flags, list_a, counts, (int)n,
+                                        s)) != cudaSuccess)
+      return (int)e;
+    *launches += 2;  // (the select is two kernels)
+  }
   launch_end(a, mode, p, 1, blocks, s);
   *launches += 2;
   return (int)cudaGetLastError();
@@ -168,6 +192,7 @@ int gjk_passes_rest(const BatchArgs& a, int mode, unsigned n, void* state, uint3
   PassArgs p;
   p.state = static_cast<GjkSaved*>(state);
   p.which = 0;
+  p.flags = nullptr;
   for (int k = 1; k < npass; ++k) {
     const bool last = k + 1 == npass;
     p.in_list = (k & 1) ? list_a : list_b;

@@ -751,6 +751,7 @@ struct Slot {
   DevBuf cont;  // EpaCont records (k_epa tier 0 -> tier 1)
   DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, retry, bvh_ws, bvh_cnt, extra, ccnt, okeys, ohist, olist;
   DevBuf qprep, qstacks, qtl, qws, qsv;  // task-system mesh-shape walk (hfb_bvhq.cu)
+  DevBuf gsel;                       // GJK passes: flags + scratch of the ordered compaction
   DevBuf gstate, glist, gcnt;        // GJK passes (hfb_gjkpass.cu): solver state, two lists of running pairs, counts
   DevBuf pi, pj, cmp;                // object-table batches: pair indices of the chunk; compact results
 };
@@ -781,7 +782,9 @@ struct hfb_ctx {
   int bvhq = 1;        // HFB_BVHQ=0: mesh-shape distance queries through the lane-per-query kernel k_bvh instead of the task system k_bvhq
   // HFB_GJK_PASSES="6" (default) or e.g. "3,3,4": iterations of the first passes of the primitive-pair GJK (one more pass runs to
   // convergence); "0": the single kernel k_pairs<1, CAP_PRIM, MODE, PATH_GJKROUTE>
-  int gjk_steps[8] = {6, 0, 0, 0, 0, 0, 0, 0};  // measured on config 2 (profiles/r02_summary.md): "6" 1.00 ms, "4,4" 1.05, "3,3,4" 1.12, single kernel 1.16
+  // iterations of the first pass; measured on config 2 (profiles/r02_summary.md), GJK kernels per 498 k pairs:
+  // "6" 1.10 ms, "8" 1.01, "9" 0.99, "10" 0.97, "12" 0.98, "16" 1.06, "10,10" 0.99, "4,4" 1.15; single kernel 1.16
+  int gjk_steps[8] = {10, 0, 0, 0, 0, 0, 0, 0};
   int gjk_npass = 2;
   // HFB_EPA_OVERLAP=1: EPA of the pairs the first GJK pass finished starts on a side stream next to the remaining passes;
   // measured slower on config 2 (2.11 vs 2.00 ms per step: the two kernels take each other's SMs), so off
@@ -789,6 +792,7 @@ struct hfb_ctx {
   int bvh_warps = 8;   // HFB_BVH_WARPS: 8 (255 registers per thread) or 16 (128) warps per block of k_bvhq
   int bvh_gens = 2;    // HFB_BVH_GENS: generations of BV items per cycle of k_bvhq
   int bvh_spec_big = 300;  // HFB_BVH_SPEC_BIG: items more before subtrees of up to 128 triangles are speculated
+  int gjk_ordered = 0;    // HFB_GJK_ORDERED=1: the second GJK pass takes the survivors of the first in class order (measured: no gain)
   int epa_resume = 8192;  // HFB_EPA_RESUME: retries per batch that continue from the state tier 0 reached (5 KB each)
   int bvh_chunk = 6;   // HFB_BVH_GJK_CHUNK: GJK iterations a leaf item runs before it parks its state
   int bvh_spec = 200;  // HFB_BVH_SPEC: items a query uses before it may speculate on subtrees (< 0: never)
@@ -1059,12 +1063,13 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
           CK(sl.gstate.reserve(gjk_pass_state_bytes(n)));
           CK(sl.glist.reserve(2 * (size_t)n * sizeof(uint32_t)));
           CK(sl.gcnt.reserve(8 * sizeof(unsigned)));
+          if (ctx->gjk_ordered) CK(sl.gsel.reserve(gjk_pass_select_bytes(n)));
           int nl = 0;
           uint32_t* la = static_cast<uint32_t*>(sl.glist.p);
           {
             KTimer kt(ctx, s, 0);
             if (gjk_passes_first(ag, MODE, n, sl.gstate.p, la, static_cast<unsigned*>(sl.gcnt.p), ctx->gjk_steps, ctx->gjk_npass,
-                                 ctx->num_sms, s, &nl) != 0)
+                                 ctx->num_sms, s, &nl, ctx->gjk_ordered ? sl.gsel.p : nullptr) != 0)
               return fail(ctx, HFB_ERR_CUDA, "GJK pass launch failed");
           }
           // EPA of the pairs the first pass finished starts on the side stream, next to the remaining passes (which
@@ -1483,6 +1488,7 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   if (const char* bq2 = getenv("HFB_BVHQ")) c->bvhq = atoi(bq2) != 0;
   if (const char* bs = getenv("HFB_BVH_SPEC")) c->bvh_spec = atoi(bs);
   if (const char* bc = getenv("HFB_BVH_GJK_CHUNK")) c->bvh_chunk = atoi(bc) > 0 ? atoi(bc) : 1;
+  if (const char* go = getenv("HFB_GJK_ORDERED")) c->gjk_ordered = atoi(go) != 0;
   if (const char* er = getenv("HFB_EPA_RESUME")) c->epa_resume = atoi(er) > 0 ? atoi(er) : 0;
   if (const char* gp = getenv("HFB_GJK_PASSES")) {
     c->gjk_npass = 0;
@@ -1524,7 +1530,7 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   cudaDeviceSynchronize();
   hfb_comm_destroy(c);
   auto rel = [](Slot& s) {
-    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist, &s.qprep, &s.qstacks, &s.qtl, &s.qws, &s.qsv, &s.gstate, &s.glist, &s.gcnt, &s.pi, &s.pj, &s.cmp, &s.cont};
+    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist, &s.qprep, &s.qstacks, &s.qtl, &s.qws, &s.qsv, &s.gstate, &s.glist, &s.gcnt, &s.pi, &s.pj, &s.cmp, &s.cont, &s.gsel};
     for (DevBuf* b : bs) b->release();
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.epa_stream) cudaStreamDestroy(s.epa_stream);
