@@ -480,7 +480,8 @@ def measure(args, workload, rank, local, world, dist, steps, warmup, clocks=Fals
               "epa_iterations_mean": float(epa_it[epa_it > 0].mean()) if (epa_it > 0).any() else 0.0}
         res["workload_stats"] = ws
     if workload == "config2":
-        dom, dom_ms, dom_launches = "GJK passes k_gjk_first/_more/_end (primitive pairs)", kt["pairs_ms"], kt["pairs_launches"]
+        # the passes are ONE unit of work over the GJK-routed pairs (several launches, timed in two scopes): per step
+        dom, dom_ms, dom_launches = "GJK passes k_gjk_first/_more/_end (primitive pairs)", kt["pairs_ms"], prof_steps
         units = float((path == 0).sum())
         bpp = BYTES_PER_PAIR
     elif workload == "config4":

@@ -104,7 +104,7 @@ template <int MODE>
 __global__ void __launch_bounds__(128) k_gjk_end(const BatchArgs a, const PassArgs p) {
   const unsigned lo = *a.range_lo, hi = *a.range_hi;
   for (unsigned k = lo + blockIdx.x * blockDim.x + threadIdx.x; k < hi; k += gridDim.x * blockDim.x) {
-    if (p.state[k - lo].done != p.which) continue;
+    if (p.which >= 0 && p.state[k - lo].done != p.which) continue;  // (which < 0: every pair, one launch after the last pass)
     const unsigned i = a.index_list[k];
     const PairIn in = load_pair_in<CAP_PRIM>(a, i);
     GjkState g = p.state[k - lo].g;
@@ -152,7 +152,8 @@ static void launch_end(const BatchArgs& a, int mode, PassArgs p, int which, unsi
 // first pass + extraction of the pairs it finished (their EPA items are in the queue when this returns, so that the
 // caller can start EPA on a side stream next to the remaining passes)
 int gjk_passes_first(const BatchArgs& a, int mode, unsigned n, void* state, uint32_t* list_a, unsigned* counts,
-                     const int* steps, int npass, int num_sms, cudaStream_t s, int* launches, void* select_ws) {
+                     const int* steps, int npass, int num_sms, cudaStream_t s, int* launches, void* select_ws,
+                     bool extract_now) {
   if (npass < 1) return (int)cudaErrorInvalidValue;
   cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)npass * sizeof(unsigned), s);
   if (e != cudaSuccess) return (int)e;
@@ -179,14 +180,21 @@ int gjk_passes_first(const BatchArgs& a, int mode, unsigned n, void* state, uint
       return (int)e;
     *launches += 2;  // (the select is two kernels)
   }
-  launch_end(a, mode, p, 1, blocks, s);
-  *launches += 2;
+  // the pairs this pass finished are extracted now only when somebody waits for their EPA items (EPA on a side
+  // stream next to the remaining passes); otherwise one extraction launch after the last pass takes every pair, with
+  // full warps
+  if (extract_now || npass < 2) {
+    launch_end(a, mode, p, npass < 2 ? -1 : 1, blocks, s);
+    *launches += 1;
+  }
+  *launches += 1;
   return (int)cudaGetLastError();
 }
 
 // the remaining passes + extraction of the pairs they finished
 int gjk_passes_rest(const BatchArgs& a, int mode, unsigned n, void* state, uint32_t* list_a, uint32_t* list_b,
-                    unsigned* counts, const int* steps, int npass, int num_sms, cudaStream_t s, int* launches) {
+                    unsigned* counts, const int* steps, int npass, int num_sms, cudaStream_t s, int* launches,
+                    bool first_extracted) {
   if (npass < 2) return 0;
   const unsigned blocks = pass_blocks(n, num_sms);
   PassArgs p;
@@ -207,7 +215,7 @@ int gjk_passes_rest(const BatchArgs& a, int mode, unsigned n, void* state, uint3
     k_gjk_more<<<b, 128, 0, s>>>(a, p);
     ++*launches;
   }
-  launch_end(a, mode, p, 2, blocks, s);
+  launch_end(a, mode, p, first_extracted ? 2 : -1, blocks, s);
   ++*launches;
   return (int)cudaGetLastError();
 }

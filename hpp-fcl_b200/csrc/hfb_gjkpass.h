@@ -14,6 +14,8 @@ size_t gjk_pass_select_bytes(size_t n);
 // the extraction of theirs.  Between the two the caller may start EPA over the queue so far on a side stream.
 // `counts`: npass words.  Return a cudaError_t as int.
 int gjk_passes_first(const BatchArgs& a, int mode, unsigned n, void* state, uint32_t* list_a, unsigned* counts,
-                     const int* steps, int npass, int num_sms, cudaStream_t s, int* launches, void* select_ws);
+                     const int* steps, int npass, int num_sms, cudaStream_t s, int* launches, void* select_ws,
+                     bool extract_now);
 int gjk_passes_rest(const BatchArgs& a, int mode, unsigned n, void* state, uint32_t* list_a, uint32_t* list_b,
-                    unsigned* counts, const int* steps, int npass, int num_sms, cudaStream_t s, int* launches);
+                    unsigned* counts, const int* steps, int npass, int num_sms, cudaStream_t s, int* launches,
+                    bool first_extracted);

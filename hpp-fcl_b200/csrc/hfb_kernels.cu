@@ -30,6 +30,7 @@
 #include "hfb_bvh_build.cuh"
 #include "hfb_bvhq_launch.h"
 #include "hfb_gjkpass.h"
+#include "hfb_hullsort.h"
 #include "hfb_broadphase.cuh"
 #include "hfb_broadphase.h"
 
@@ -751,6 +752,7 @@ struct Slot {
   DevBuf cont;  // EpaCont records (k_epa tier 0 -> tier 1)
   DevBuf h1, h2, tf1, tf2, out, gin, hin, gout, hout, queue, counters, lists, retry, bvh_ws, bvh_cnt, extra, ccnt, okeys, ohist, olist;
   DevBuf qprep, qstacks, qtl, qws, qsv;  // task-system mesh-shape walk (hfb_bvhq.cu)
+  DevBuf hsort;                      // hfb_hullsort.cu scratch
   DevBuf gsel;                       // GJK passes: flags + scratch of the ordered compaction
   DevBuf gstate, glist, gcnt;        // GJK passes (hfb_gjkpass.cu): solver state, two lists of running pairs, counts
   DevBuf pi, pj, cmp;                // object-table batches: pair indices of the chunk; compact results
@@ -792,6 +794,7 @@ struct hfb_ctx {
   int bvh_warps = 8;   // HFB_BVH_WARPS: 8 (255 registers per thread) or 16 (128) warps per block of k_bvhq
   int bvh_gens = 2;    // HFB_BVH_GENS: generations of BV items per cycle of k_bvhq
   int bvh_spec_big = 300;  // HFB_BVH_SPEC_BIG: items more before subtrees of up to 128 triangles are speculated
+  int hull_sort = 1;      // HFB_HULL_SORT: second sort key (first operand's handle) inside the hull / triangle class
   int gjk_ordered = 0;    // HFB_GJK_ORDERED=1: the second GJK pass takes the survivors of the first in class order (measured: no gain)
   int epa_resume = 8192;  // HFB_EPA_RESUME: retries per batch that continue from the state tier 0 reached (5 KB each)
   int bvh_chunk = 6;   // HFB_BVH_GJK_CHUNK: GJK iterations a leaf item runs before it parks its state
@@ -994,6 +997,18 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   a.index_list = perm;
   int rc;
   const bool mixed = ctx->arena.has_convex || ctx->arena.has_tri;
+  if (mixed && ctx->hull_sort) {  // HFB_HULL_SORT: the hull / triangle class ordered by the handle of its first operand
+    CK(sl.hsort.reserve(hull_sort_bytes(n)));
+    const uint32_t* sorted = nullptr;
+    int nl = 0;
+    {
+      KTimer kt(ctx, s, 2);
+      if (hull_sort_launch(a.h1, n, perm, offsets, HFB_BIN_CONVEX, sl.hsort.p, &sorted, s, &nl) != 0)
+        return fail(ctx, HFB_ERR_CUDA, "hull sort launch failed");
+    }
+    ctx->stats.kernel_launches += (uint64_t)nl;
+    a.index_list = sorted;
+  }
   const bool want_epa = a.P.compute_penetration;
 
   // EPA over the queue items pushed since the previous mark.  Parts other than the last go to the
@@ -1066,19 +1081,20 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
           if (ctx->gjk_ordered) CK(sl.gsel.reserve(gjk_pass_select_bytes(n)));
           int nl = 0;
           uint32_t* la = static_cast<uint32_t*>(sl.glist.p);
+          const bool early_epa = ctx->gjk_npass > 1 && ctx->epa_overlap && want_epa;
           {
             KTimer kt(ctx, s, 0);
             if (gjk_passes_first(ag, MODE, n, sl.gstate.p, la, static_cast<unsigned*>(sl.gcnt.p), ctx->gjk_steps, ctx->gjk_npass,
-                                 ctx->num_sms, s, &nl, ctx->gjk_ordered ? sl.gsel.p : nullptr) != 0)
+                                 ctx->num_sms, s, &nl, ctx->gjk_ordered ? sl.gsel.p : nullptr, early_epa) != 0)
               return fail(ctx, HFB_ERR_CUDA, "GJK pass launch failed");
           }
           // EPA of the pairs the first pass finished starts on the side stream, next to the remaining passes (which
           // only keep a fraction of the GPU busy)
-          if (ctx->gjk_npass > 1 && ctx->epa_overlap && want_epa && (rc = epa_after_part(false))) return rc;
+          if (early_epa && (rc = epa_after_part(false))) return rc;
           {
             KTimer kt(ctx, s, 0);
             if (gjk_passes_rest(ag, MODE, n, sl.gstate.p, la, la + n, static_cast<unsigned*>(sl.gcnt.p), ctx->gjk_steps,
-                                ctx->gjk_npass, ctx->num_sms, s, &nl) != 0)
+                                ctx->gjk_npass, ctx->num_sms, s, &nl, early_epa) != 0)
               return fail(ctx, HFB_ERR_CUDA, "GJK pass launch failed");
           }
           ctx->stats.kernel_launches += (uint64_t)nl;
@@ -1488,6 +1504,7 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   if (const char* bq2 = getenv("HFB_BVHQ")) c->bvhq = atoi(bq2) != 0;
   if (const char* bs = getenv("HFB_BVH_SPEC")) c->bvh_spec = atoi(bs);
   if (const char* bc = getenv("HFB_BVH_GJK_CHUNK")) c->bvh_chunk = atoi(bc) > 0 ? atoi(bc) : 1;
+  if (const char* hs = getenv("HFB_HULL_SORT")) c->hull_sort = atoi(hs) != 0;
   if (const char* go = getenv("HFB_GJK_ORDERED")) c->gjk_ordered = atoi(go) != 0;
   if (const char* er = getenv("HFB_EPA_RESUME")) c->epa_resume = atoi(er) > 0 ? atoi(er) : 0;
   if (const char* gp = getenv("HFB_GJK_PASSES")) {
@@ -1530,7 +1547,7 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   cudaDeviceSynchronize();
   hfb_comm_destroy(c);
   auto rel = [](Slot& s) {
-    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist, &s.qprep, &s.qstacks, &s.qtl, &s.qws, &s.qsv, &s.gstate, &s.glist, &s.gcnt, &s.pi, &s.pj, &s.cmp, &s.cont, &s.gsel};
+    DevBuf* bs[] = {&s.h1, &s.h2, &s.tf1, &s.tf2, &s.out, &s.gin, &s.hin, &s.gout, &s.hout, &s.queue, &s.counters, &s.lists, &s.retry, &s.bvh_ws, &s.bvh_cnt, &s.extra, &s.ccnt, &s.okeys, &s.ohist, &s.olist, &s.qprep, &s.qstacks, &s.qtl, &s.qws, &s.qsv, &s.gstate, &s.glist, &s.gcnt, &s.pi, &s.pj, &s.cmp, &s.cont, &s.gsel, &s.hsort};
     for (DevBuf* b : bs) b->release();
     if (s.stream) cudaStreamDestroy(s.stream);
     if (s.epa_stream) cudaStreamDestroy(s.epa_stream);
