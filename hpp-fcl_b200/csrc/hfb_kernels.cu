@@ -1244,8 +1244,10 @@ int check_ready(hfb_ctx* ctx) {
 // bad handle is an invalid argument, never a device fault)
 int check_handles(hfb_ctx* ctx, const uint32_t* h, size_t n) {
   const uint32_t ns = (uint32_t)ctx->arena.shapes.size();
-  for (size_t i = 0; i < n; ++i)
-    if (h[i] >= ns) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "shape handle out of range");
+  // (branch-free so that the host compiler vectorises it: this loop sits in front of every chunk's uploads)
+  uint32_t bad = 0;
+  for (size_t i = 0; i < n; ++i) bad |= (uint32_t)(h[i] >= ns);
+  if (bad) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "shape handle out of range");
   return HFB_OK;
 }
 
@@ -1307,11 +1309,13 @@ int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* 
     // handles are validated chunk by chunk, while the previous chunks are in flight.  A bad handle in a
     // later chunk therefore surfaces after earlier chunks ran; the call still fails as a whole.
     if (obj) {
-      for (size_t i = done; i < done + m; ++i)
-        if (obj->first[i] >= obj->n_objects || obj->second[i] >= obj->n_objects) {
-          for (int k = 0; k < kSlots; ++k) cudaStreamSynchronize(ctx->slots[k].stream);
-          return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "object index out of range");
-        }
+      const uint32_t no = (uint32_t)(obj->n_objects > 0xffffffffull ? 0xffffffffull : obj->n_objects);
+      uint32_t bad = 0;  // (branch-free: vectorised by the host compiler)
+      for (size_t i = done; i < done + m; ++i) bad |= (uint32_t)(obj->first[i] >= no) | (uint32_t)(obj->second[i] >= no);
+      if (bad) {
+        for (int k = 0; k < kSlots; ++k) cudaStreamSynchronize(ctx->slots[k].stream);
+        return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "object index out of range");
+      }
     } else if ((rc = check_handles(ctx, h1 + done, m)) || (rc = check_handles(ctx, h2 + done, m))) {
       for (int k = 0; k < kSlots; ++k) cudaStreamSynchronize(ctx->slots[k].stream);
       return rc;
