@@ -11,7 +11,7 @@ from ._pod import *  # noqa: F401,F403
 from .build import build_extension, library_path  # noqa: F401
 from .engine import Engine, EngineError, broadphase_pairs, build_bvh_obbrss, load_library  # noqa: F401
 from .api import (  # noqa: F401
-    BVHModelOBBRSS, Box, Capsule, CollisionRequest, CollisionResult, Cone, Contact, Convex, Cylinder,
+    BVHModelOBB, BVHModelOBBRSS, Box, Capsule, CollisionRequest, CollisionResult, Cone, Contact, Convex, Cylinder,
     DistanceRequest, DistanceResult, Ellipsoid, Halfspace, Plane, Sphere, Transform3f, TriangleP,
     collide, distance, ComputeCollision, ComputeDistance, BatchQuery,
 )

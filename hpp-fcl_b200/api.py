@@ -252,6 +252,15 @@ class BVHModelOBBRSS(CollisionGeometry):
         return 0 if self.bvs is None else len(self.bvs)
 
 
+class BVHModelOBB(BVHModelOBBRSS):
+    """BVHModel<OBB>: collide() only, as in the library (distance() on a plain OBB model is not offered, see
+    hfb_geom_register_bvh_obb).  The plain OBB tree of a mesh is the OBB half of its OBBRSS tree, so the builder is shared."""
+    node_type = P.BV_OBB
+
+
+_MESH_TYPES = (P.BV_OBBRSS, P.BV_OBB)
+
+
 # ---------------------------------------------------------- requests/results --
 class _QueryRequest:
     _pod_cls = None
@@ -358,7 +367,7 @@ class _Scene:
     def _content(geom):
         """what the arena holds for `geom` beyond its record: the vertices of a hull / triangle, the mesh of a model"""
         pts = geom._points()
-        if geom.node_type == P.BV_OBBRSS:
+        if geom.node_type in _MESH_TYPES:
             return (np.ascontiguousarray(geom.bvs).tobytes() if geom.bvs is not None else None,
                     np.ascontiguousarray(geom.vertices, dtype=np.float64).tobytes(),
                     np.ascontiguousarray(geom.tri_indices, dtype=np.uint32).tobytes())
@@ -390,7 +399,7 @@ class _Scene:
                 return h
             same_kind = old_sig[0] == sig[0]
             pts = geom._points()
-            if same_kind and geom.node_type != P.BV_OBBRSS and (
+            if same_kind and geom.node_type not in _MESH_TYPES and (
                     old_content == content or (pts is not None and old_content is not None and len(old_content) == len(content))):
                 if old_content != content:
                     self.engine.update_convex(data, pts)
@@ -402,10 +411,11 @@ class _Scene:
             self.engine.release_shapes([h])  # the storage of its vertices / mesh stays until hfb_geom_clear
         data = 0
         pts = geom._points()
-        if geom.node_type == P.BV_OBBRSS:
+        if geom.node_type in _MESH_TYPES:
             if geom.bvs is None:
                 raise ValueError("BVHModel: endModel() was not called")
-            data = self.engine.register_bvh_obbrss(geom.bvs, geom.vertices, geom.tri_indices)
+            reg = self.engine.register_bvh_obb if geom.node_type == P.BV_OBB else self.engine.register_bvh_obbrss
+            data = reg(geom.bvs, geom.vertices, geom.tri_indices)
         elif pts is not None:
             data = self.engine.register_convex(pts)
         rec = P.make_shapes([geom.node_type], [geom._params()], ssr=geom.getSweptSphereRadius(), data=data)
@@ -457,8 +467,8 @@ class BatchQuery:
 
 def _unsupported(o1, o2, what, request=None):
     """the exception the reference throws for this pair (the record carries HFB_PATH_UNSUPPORTED)"""
-    mesh = [o for o in (o1, o2) if o.node_type == P.BV_OBBRSS]
-    shape = [o for o in (o1, o2) if o.node_type != P.BV_OBBRSS]
+    mesh = [o for o in (o1, o2) if o.node_type in _MESH_TYPES]
+    shape = [o for o in (o1, o2) if o.node_type not in _MESH_TYPES]
     if len(mesh) == 1 and shape:
         if what == "Collision" and request is not None and request.security_margin < 0:
             # collision_func_matrix.cpp:109-112
@@ -485,7 +495,7 @@ def collide(o1, tf1, o2, tf2, request, result, device=0):
     scene = bq.scene
     h1, h2 = scene.handle(o1), scene.handle(o2)
     scene.commit()
-    mesh = P.BV_OBBRSS in (o1.node_type, o2.node_type)
+    mesh = o1.node_type in _MESH_TYPES or o2.node_type in _MESH_TYPES
     more = []
     if mesh and request.num_max_contacts > 1:  # every contact of the pair, not only contacts[0]
         out, extra, counts = scene.engine.batch_collide_contacts([h1], _tf_array(tf1), [h2], _tf_array(tf2), request._pod,

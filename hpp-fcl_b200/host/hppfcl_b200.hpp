@@ -105,7 +105,7 @@ enum NODE_TYPE {  // collision_object.h:65-89 (subset)
   GEOM_BOX = HFB_GEOM_BOX, GEOM_SPHERE = HFB_GEOM_SPHERE, GEOM_CAPSULE = HFB_GEOM_CAPSULE,
   GEOM_CONE = HFB_GEOM_CONE, GEOM_CYLINDER = HFB_GEOM_CYLINDER, GEOM_CONVEX = HFB_GEOM_CONVEX,
   GEOM_PLANE = HFB_GEOM_PLANE, GEOM_HALFSPACE = HFB_GEOM_HALFSPACE, GEOM_TRIANGLE = HFB_GEOM_TRIANGLE,
-  GEOM_ELLIPSOID = HFB_GEOM_ELLIPSOID, BV_OBBRSS = HFB_BV_OBBRSS
+  GEOM_ELLIPSOID = HFB_GEOM_ELLIPSOID, BV_OBB = HFB_BV_OBB, BV_OBBRSS = HFB_BV_OBBRSS
 };
 
 class CollisionGeometry {
@@ -229,8 +229,11 @@ class TriangleP : public ShapeBase {  // :109-162
 // BVHModel<OBBRSS> (include/hpp/fcl/BVH/BVH_model.h): the build protocol of the reference
 // (beginModel / addVertex / addTriangle / addSubModel / endModel), triangles only, SPLIT_METHOD_MEAN.
 // endModel() builds the tree on the host (hfb_bvh_build_obbrss: bit-identical to the reference's
-// BVHModel::bvs); queries walk it on the GPU.  Other BV types are not provided.
+// BVHModel::bvs); queries walk it on the GPU.  BVHModel<OBB> (collide() only, as in the library) shares the builder:
+// the plain OBB tree of a mesh is the OBB half of its OBBRSS tree (oracle/ref_driver.cpp: ref_bvh_obb_is_obbrss_half).
+// Other BV types are not provided.
 struct OBBRSS {};
+struct OBB {};
 struct Triangle {  // data_types.h
   size_t vids[3];
   Triangle() : vids{0, 0, 0} {}
@@ -239,12 +242,8 @@ struct Triangle {  // data_types.h
 };
 enum BVHBuildState { BVH_BUILD_STATE_EMPTY, BVH_BUILD_STATE_BEGUN, BVH_BUILD_STATE_PROCESSED };
 enum BVHReturnCode { BVH_OK = 0, BVH_ERR_BUILD_OUT_OF_SEQUENCE = -2, BVH_ERR_BUILD_EMPTY_MODEL = -3 };
-template <typename BV>
-class BVHModel;
-template <>
-class BVHModel<OBBRSS> : public CollisionGeometry {
+class BVHModelTriangles : public CollisionGeometry {  // what the two models share (BVHModelBase + the tree)
  public:
-  NODE_TYPE getNodeType() const override { return BV_OBBRSS; }
   unsigned num_tris = 0, num_vertices = 0;
   BVHBuildState build_state = BVH_BUILD_STATE_EMPTY;
   int beginModel(unsigned num_tris_ = 0, unsigned num_vertices_ = 0) {  // BVH_model.cpp:226-263
@@ -312,6 +311,19 @@ class BVHModel<OBBRSS> : public CollisionGeometry {
   std::vector<uint32_t> tris_;
   std::vector<hfb_bvh_node> nodes_;
 };
+template <typename BV>
+class BVHModel;
+template <>
+class BVHModel<OBBRSS> : public BVHModelTriangles {
+ public:
+  NODE_TYPE getNodeType() const override { return BV_OBBRSS; }
+};
+template <>
+class BVHModel<OBB> : public BVHModelTriangles {
+ public:
+  NODE_TYPE getNodeType() const override { return BV_OBB; }
+};
+inline bool isMeshType(NODE_TYPE t) { return t == BV_OBBRSS || t == BV_OBB; }
 typedef std::shared_ptr<CollisionGeometry> CollisionGeometryPtr_t;
 
 struct AABB {  // BV/AABB.h
@@ -550,16 +562,16 @@ class Context {
     auto it = handles.find(g);
     if (it != handles.end()) {
       const Entry& e = it->second;
-      if (e.rec.type == HFB_BV_OBBRSS && e.verts == *md.verts && e.tris == *md.tris) return e.handle;
+      if (e.rec.type == (uint32_t)g->getNodeType() && e.verts == *md.verts && e.tris == *md.tris) return e.handle;
       check(hfb_geom_release_shapes(ctx, &e.handle, 1));  // a rebuilt model: the old handle is retired
       handles.erase(it);
     }
     Entry ent;
     ent.rec = hfb_shape{};
-    ent.rec.type = HFB_BV_OBBRSS;
-    check(hfb_geom_register_bvh_obbrss(ctx, md.nodes->data(), (uint32_t)md.nodes->size(), md.verts->data(),
-                                       (uint32_t)(md.verts->size() / 3), md.tris->data(),
-                                       (uint32_t)(md.tris->size() / 3), &ent.rec.data));
+    ent.rec.type = (uint32_t)g->getNodeType();
+    check((ent.rec.type == HFB_BV_OBB ? hfb_geom_register_bvh_obb : hfb_geom_register_bvh_obbrss)(
+        ctx, md.nodes->data(), (uint32_t)md.nodes->size(), md.verts->data(), (uint32_t)(md.verts->size() / 3), md.tris->data(),
+        (uint32_t)(md.tris->size() / 3), &ent.rec.data));
     uint32_t h;
     check(hfb_geom_register_shapes(ctx, &ent.rec, 1, &h));
     ent.handle = h;
@@ -819,7 +831,7 @@ inline std::size_t collide(const CollisionGeometry* o1, const Transform3f& tf1, 
   // a mesh pair can have more than one contact (CollisionResult::contacts): fetch them all when asked to
   std::vector<hfb_contact> more;
   uint32_t count = 0;
-  const bool mesh = o1->getNodeType() == BV_OBBRSS || o2->getNodeType() == BV_OBBRSS;
+  const bool mesh = isMeshType(o1->getNodeType()) || isMeshType(o2->getNodeType());
   if (mesh && request.num_max_contacts > 1) {
     more.resize(request.num_max_contacts - 1);
     C.check(hfb_batch_collide_contacts(C.raw(), 1, &h1, &t1, &h2, &t2, &q, &rec, (uint32_t)more.size(), more.data(),

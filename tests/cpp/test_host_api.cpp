@@ -19,6 +19,26 @@ static int failures = 0;
 #define CHECK_CLOSE(a, b, pct) CHECK(std::fabs((a) - (b)) <= (pct) / 100.0 * std::fmin(std::fabs(a), std::fabs(b)))
 
 int main() {
+  {  // BVHModel<OBB>: the same builder, collide() only (collision_func_matrix.cpp:141-166, 488-501)
+    BVHModel<OBB> mo;
+    BVHModel<OBBRSS> mr;
+    const Vec3f v[4] = {Vec3f(0, 0, 0), Vec3f(1, 0, 0), Vec3f(0, 1, 0), Vec3f(0, 0, 1)};
+    const int f[4][3] = {{0, 2, 1}, {0, 1, 3}, {0, 3, 2}, {1, 2, 3}};
+    for (BVHModelTriangles* m : {static_cast<BVHModelTriangles*>(&mo), static_cast<BVHModelTriangles*>(&mr)}) {
+      m->beginModel();
+      for (int k = 0; k < 4; ++k) m->addTriangle(v[f[k][0]], v[f[k][1]], v[f[k][2]]);
+      CHECK(m->endModel() == BVH_OK);
+    }
+    CHECK(mo.getNodeType() == BV_OBB && mo.getNumBVs() == 7);
+    Sphere ball(0.2);
+    CollisionRequest creq;
+    CollisionResult ra, rb;
+    const Transform3f tfs(Vec3f(0.3, 0.3, 0.45));
+    CHECK(collide(&mo, Transform3f(), &ball, tfs, creq, ra) == collide(&mr, Transform3f(), &ball, tfs, creq, rb));
+    CHECK(ra.numContacts() == 1 && ra.getContact(0).b1 == rb.getContact(0).b1);
+    CollisionResult rc;
+    CHECK(collide(&mo, Transform3f(), &ball, Transform3f(Vec3f(3, 3, 3)), creq, rc) == 0);
+  }
   {  // a Halfspace floor and a Plane against a sphere (details::halfspaceDistance / planeDistance, details.h:347-428)
     Halfspace floor(Vec3f(0, 0, 2), 1.0);  // normalised: n = (0, 0, 1), d = 0.5
     CHECK(floor.n[2] == 1.0 && floor.d == 0.5);

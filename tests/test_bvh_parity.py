@@ -256,6 +256,25 @@ def test_python_api_bvh_model():
     res.clear()
     d = hf.distance(m, hf.Transform3f(), m, hf.Transform3f(T=[2.5, 0, 0]), hf.DistanceRequest(), res)
     assert 0 <= d - 0.5 < 0.16 and res.b1 >= 0 and res.b2 >= 0
+    # BVHModel<OBB>: collide() gives the OBBRSS model's contact (the plain OBB tree is its OBB half; for a primitive
+    # partner the two models fit different boxes around it, but both are exact at the leaves); distance() is not offered
+    mo = hf.BVHModelOBB()
+    mo.beginModel()
+    mo.addSubModel(verts, tris)
+    mo.endModel()
+    assert mo.getNodeType() == P.BV_OBB and mo.getNumBVs() == m.getNumBVs()
+    box = hf.Box(0.4, 0.3, 0.5)
+    tfb = hf.Transform3f.from_quat(0.9238795325112867, 0, 0.3826834323650898, 0, (1.05, 0.1, -0.2))
+    ca, cb = hf.CollisionResult(), hf.CollisionResult()
+    req = hf.CollisionRequest()
+    req.num_max_contacts = 8
+    na, nb = hf.collide(mo, hf.Transform3f(), box, tfb, req, ca), hf.collide(m, hf.Transform3f(), box, tfb, req, cb)
+    assert na == nb and na >= 1
+    assert sorted(c.b1 for c in ca.contacts) == sorted(c.b1 for c in cb.contacts)
+    cm = hf.CollisionResult()
+    assert hf.collide(mo, hf.Transform3f(), mo, hf.Transform3f(T=[1.9, 0, 0]), hf.CollisionRequest(), cm) == 1
+    with pytest.raises(ValueError):
+        hf.distance(mo, hf.Transform3f(), box, tfb, hf.DistanceRequest(), hf.DistanceResult())
 
 
 @pytest.mark.gpu
