@@ -50,6 +50,8 @@ struct BatchArgs {
   unsigned* retry_count;
   EpaCont* cont;              // continuation records of the first cont_cap retry positions (null: every retry starts over)
   unsigned cont_cap;
+  unsigned pair_base;         // added to the pair index of an EPA queue item: the host pipeline runs phase 1 chunk by chunk
+                              // (pointers offset to the chunk) and EPA once, over the whole batch (base pointers)
   unsigned sub_idx, sub_cnt;  // k_pairs: this launch takes the sub_idx-th of sub_cnt equal parts of [lo, hi)
   unsigned* gjk_work;         // k_gjk_refill: work counter of this launch
   unsigned iter_quorum;       // k_gjk_refill: lanes that must be mid-GJK for an iteration round to run
@@ -123,7 +125,7 @@ __device__ __forceinline__ void push_epa_item(const BatchArgs& a, unsigned i, co
   const unsigned slot = atomicAdd(a.queue_count, 1u);
   atomicAdd(a.queue_count + 1, 1u);
   EpaItem* it = a.queue + slot;
-  it->pair = i;
+  it->pair = i + a.pair_base;
   it->rank = g.rank;
   it->hint0 = g.hint0;
   it->hint1 = g.hint1;

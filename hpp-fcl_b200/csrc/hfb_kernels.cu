@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <chrono>
+
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(128, MINB) k_pairs(const BatchArgs a) {
         const unsigned slot = atomicAdd(a.queue_count, 1u);
         atomicAdd(a.queue_count + 1, 1u);
         EpaItem* it = a.queue + slot;
-        it->pair = i;
+        it->pair = i + a.pair_base;
         it->rank = g.rank;
         it->hint0 = g.hint0;
         it->hint1 = g.hint1;
@@ -632,6 +634,18 @@ __global__ void __launch_bounds__(256) k_expand_pairs(const uint32_t* obj_h, con
     (k < 12 ? reinterpret_cast<double*>(tf1 + i) : reinterpret_cast<double*>(tf2 + i))[k % 12] = v;
   }
 }
+// host pipeline (host_batch_pipelined): the records of the EPA pairs of a batch, compacted with their pair ids -- the
+// chunks' rows went to the host before EPA ran
+template <class OutT>
+__global__ void __launch_bounds__(256) k_gather_epa_rows(const EpaItem* queue, const unsigned* count, const OutT* out,
+                                                         uint32_t* ids, OutT* rows) {
+  const unsigned n = *count;
+  for (unsigned k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const unsigned i = queue[k].pair;
+    ids[k] = i;
+    rows[k] = out[i];
+  }
+}
 // compact result modes: the distance alone (DistanceResult::min_distance) ...
 __global__ void __launch_bounds__(256) k_pick_min_distance(const hfb_distance_result* r, unsigned n, double* d) {
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -795,6 +809,12 @@ struct hfb_ctx {
   bool dev_used = false;
   DevBuf sup_ids, sup_dirs, sup_idx, sup_out;
   DevBuf obj_h, obj_tf, cmp_flags, cmp_count, cmp_ids, cmp_recs;  // object table of the running call; compact collide results
+  // host pipeline (host_batch_pipelined): the whole batch on the device, EPA fix-up rows, their pinned landing zone
+  DevBuf big_h1, big_h2, big_tf1, big_tf2, big_out, big_pi, big_pj, big_min, fix_ids, fix_rows;
+  void* pin_fix = nullptr;
+  size_t pin_fix_cap = 0;
+  std::vector<cudaEvent_t> pipe_events;
+  int host_pipe = 1;  // HFB_HOST_PIPE=0: the rotating-slot pipeline of round 1 for every host call
   cudaEvent_t obj_ready = nullptr;
   hfb_stats stats{};
   int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4, refill = 0, iter_quorum = 8, stage = 0, chunk = 0;
@@ -954,7 +974,9 @@ int launch_pairs_convex(hfb_ctx* ctx, const BatchArgs& a, unsigned work, cudaStr
 //   counting sort of the pairs by class -> closed-form kernel, GJK kernel (thread per pair),
 //   convex/triangle kernel (lane group per pair) -> EPA kernel over the queue
 template <int MODE>
-int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
+int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s, int epa_mode = 0) {
+  // epa_mode 0: the whole batch; 1 / 2: phase 1 only (first / a later chunk of a host batch), the EPA items stay in the
+  // queue for run_deferred_epa
   const unsigned n = a.n;
   if (n == 0) return HFB_OK;
   CK(sl.queue.reserve((size_t)n * sizeof(EpaItem)));
@@ -1000,7 +1022,7 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   a.gjk_work = nullptr;
   a.iter_quorum = 0;
   a.A = ctx->dview;
-  CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned), s));
+  if (epa_mode != 2) CK(cudaMemsetAsync(cnt, 0, sizeof(unsigned), s));  // (a later chunk appends to the queue)
   CK(cudaMemsetAsync(cnt + 2, 0, 30 * sizeof(unsigned), s));
   CK(cudaMemsetAsync(hist, 0, HFB_NBINS * sizeof(unsigned), s));
   {
@@ -1035,7 +1057,7 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   // are few of them, so run at the end they would leave most of the GPU idle.
   int parts_done = 0;
   auto epa_after_part = [&](bool last) -> int {
-    if (!want_epa) return HFB_OK;
+    if (!want_epa || epa_mode) return HFB_OK;
     const int j = parts_done++;
     if (cudaMemcpyAsync(mark + j + 1, cnt, sizeof(unsigned), cudaMemcpyDeviceToDevice, s) != cudaSuccess)
       return fail(ctx, HFB_ERR_CUDA, "queue mark copy failed");
@@ -1234,6 +1256,36 @@ int run_device_batch(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
   return HFB_OK;
 }
 
+// EPA over everything the chunks of a host batch queued (run_device_batch with epa_mode 1 / 2), with the batch's base
+// pointers: one tier-0 and one tier-1 launch for the whole batch instead of one EPA tail per chunk
+template <int MODE>
+int run_deferred_epa(hfb_ctx* ctx, Slot& sl, BatchArgs a, cudaStream_t s) {
+  if (!a.P.compute_penetration) return HFB_OK;
+  unsigned* cnt = static_cast<unsigned*>(sl.counters.p);
+  unsigned* mark = cnt + 4;
+  unsigned* heads = cnt + 16;
+  a.queue = static_cast<EpaItem*>(sl.queue.p);
+  a.retry = static_cast<uint32_t*>(sl.retry.p);
+  a.queue_count = cnt;
+  a.retry_count = cnt + 2;
+  a.cont = static_cast<EpaCont*>(sl.cont.p);
+  a.cont_cap = a.cont ? (unsigned)(((size_t)ctx->epa_resume < (size_t)a.n ? (size_t)ctx->epa_resume : (size_t)a.n)) : 0u;
+  if (a.cont && sl.cont.cap < (size_t)a.cont_cap * sizeof(EpaCont)) a.cont_cap = (unsigned)(sl.cont.cap / sizeof(EpaCont));
+  a.A = ctx->dview;
+  a.index_list = nullptr;
+  a.pair_base = 0;
+  CK(cudaMemsetAsync(cnt + 2, 0, 30 * sizeof(unsigned), s));  // retry count, tier-1 counter, marks (mark[0] = 0), heads
+  CK(cudaMemcpyAsync(mark + 1, cnt, sizeof(unsigned), cudaMemcpyDeviceToDevice, s));
+  a.epa_lo = mark;
+  a.epa_hi = mark + 1;
+  a.epa_head = heads;
+  const bool mixed = ctx->arena.has_convex || ctx->arena.has_tri;
+  int r = mixed ? launch_epa_g<CAPS_ALL, MODE, 0>(ctx, a, s) : launch_epa_g<CAP_PRIM, MODE, 0>(ctx, a, s);
+  if (r) return r;
+  a.epa_head = cnt + 3;
+  return mixed ? launch_epa_g<CAPS_ALL, MODE, 1>(ctx, a, s) : launch_epa_g<CAP_PRIM, MODE, 1>(ctx, a, s);
+}
+
 int check_ready(hfb_ctx* ctx) {
   if (!ctx) return HFB_ERR_INVALID_ARGUMENT;
   if (!ctx->committed) return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "geometry not committed (hfb_geom_commit)");
@@ -1269,6 +1321,210 @@ struct OutMode {
   uint32_t cap = 0;
 };
 
+// ---- the host pipeline of large batches -----------------------------------------------------------------------------
+// The rotating-slot pipeline below (host_batch) runs every chunk to the end, EPA included, before its rows go back:
+// with the kernels of round 2 a chunk of 256 Ki pairs is a third sort + GJK and two thirds EPA tail -- the latency of
+// its longest pair with the GPU nearly empty -- and four chunks pay four tails.  Here the whole batch lives on the
+// device: phase 1 (class sort, closed forms, GJK) runs chunk by chunk as the uploads arrive and each chunk's rows start
+// their way back at once; EPA runs ONCE over the items of all chunks (run_deferred_epa); the records of the EPA pairs
+// (1.2 % of config 2) follow compacted, and the host puts them in place.  Three streams: uploads, kernels, downloads.
+template <int MODE, typename OutT>
+int host_batch_pipelined(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
+                         const hfb_transform* tf2, const SolverP& P, const CollideP& Cp, const BvhReq& Bq, OutT* out,
+                         const ObjSrc* obj, double* min_out) {
+  int rc;
+  Slot& sl = ctx->slots[0];
+  cudaStream_t sC = sl.stream, sU = ctx->slots[1].stream, sD = ctx->slots[2].stream;
+  static const bool trace = getenv("HFB_PIPE_TRACE") != nullptr;  // debugging aid: host clock at the milestones of a call
+  const auto t0 = std::chrono::steady_clock::now();
+  auto stamp = [&](const char* what) {
+    if (trace) fprintf(stderr, "[hfb pipe] %-28s %8.3f ms\n", what, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  };
+  // How many chunks: a chunk's phase 1 has a floor of ~0.25 ms whatever its size (the serial iteration chains of the
+  // longest pairs in the GJK passes), so chunks are only worth their overlap: about one per 0.6 ms of PCIe time
+  // (uploads and downloads share the link, ~57 GB/s measured), at least 128 Ki pairs each.  1 M pairs: a scene +
+  // distances only (16 B per pair) -> 1 chunk; a scene + full rows (104 B) -> 3; pair rows + full rows (296 B) -> 8.
+  size_t chunk;
+  if (ctx->chunk > 0) {
+    chunk = (size_t)ctx->chunk;
+  } else {
+    const double bytes_per_pair = (obj ? 8.0 : 200.0) + (min_out ? 8.0 : (double)sizeof(OutT));
+    const double pcie_ms = (double)n * bytes_per_pair / 57e6;
+    size_t want = (size_t)(pcie_ms / 0.6 + 0.5);
+    const size_t most = n / kChunk ? n / kChunk : 1;
+    if (want < 1) want = 1;
+    if (want > most) want = most;
+    chunk = (n + want - 1) / want;
+  }
+  chunk = (chunk + 31) & ~(size_t)31;
+  const size_t nchunks = (n + chunk - 1) / chunk;
+  while (ctx->pipe_events.size() < 2 * nchunks + 2) {
+    cudaEvent_t e;
+    CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->pipe_events.push_back(e);
+  }
+  CK(ctx->big_h1.reserve(n * 4));
+  CK(ctx->big_h2.reserve(n * 4));
+  CK(ctx->big_tf1.reserve(n * sizeof(hfb_transform)));
+  CK(ctx->big_tf2.reserve(n * sizeof(hfb_transform)));
+  CK(ctx->big_out.reserve(n * sizeof(OutT)));
+  if (obj) {
+    CK(ctx->big_pi.reserve(n * 4));
+    CK(ctx->big_pj.reserve(n * 4));
+  }
+  if (min_out) CK(ctx->big_min.reserve(n * 8));
+  // the queue and the retry list take the EPA items of every chunk (run_device_batch asks for a chunk's worth: no
+  // reallocation once they hold the batch's)
+  CK(sl.queue.reserve(n * sizeof(EpaItem)));
+  CK(sl.retry.reserve(n * sizeof(uint32_t)));
+  uint32_t* d_h1 = static_cast<uint32_t*>(ctx->big_h1.p);
+  uint32_t* d_h2 = static_cast<uint32_t*>(ctx->big_h2.p);
+  hfb_transform* d_tf1 = static_cast<hfb_transform*>(ctx->big_tf1.p);
+  hfb_transform* d_tf2 = static_cast<hfb_transform*>(ctx->big_tf2.p);
+  OutT* d_out = static_cast<OutT*>(ctx->big_out.p);
+  auto drain = [&]() {
+    for (int k = 0; k < kSlots; ++k) cudaStreamSynchronize(ctx->slots[k].stream);
+  };
+  if (obj) {  // the object table was uploaded on slot 0's stream = sC: in order with the expansion kernels
+  }
+  size_t done = 0;
+  for (size_t c = 0; c < nchunks; ++c) {
+    const size_t m = (n - done < chunk) ? (n - done) : chunk;
+    cudaEvent_t ev_up = ctx->pipe_events[2 * c], ev_ph = ctx->pipe_events[2 * c + 1];
+    if (obj) {
+      CK(cudaMemcpyAsync(static_cast<uint32_t*>(ctx->big_pi.p) + done, obj->first + done, m * 4, cudaMemcpyHostToDevice, sU));
+      CK(cudaMemcpyAsync(static_cast<uint32_t*>(ctx->big_pj.p) + done, obj->second + done, m * 4, cudaMemcpyHostToDevice, sU));
+    } else {
+      CK(cudaMemcpyAsync(d_h1 + done, h1 + done, m * 4, cudaMemcpyHostToDevice, sU));
+      CK(cudaMemcpyAsync(d_h2 + done, h2 + done, m * 4, cudaMemcpyHostToDevice, sU));
+      CK(cudaMemcpyAsync(d_tf1 + done, tf1 + done, m * sizeof(hfb_transform), cudaMemcpyHostToDevice, sU));
+      CK(cudaMemcpyAsync(d_tf2 + done, tf2 + done, m * sizeof(hfb_transform), cudaMemcpyHostToDevice, sU));
+    }
+    CK(cudaEventRecord(ev_up, sU));
+    CK(cudaStreamWaitEvent(sC, ev_up, 0));
+    if (obj) {
+      unsigned eb = (unsigned)((m * 24 + 255) / 256);
+      if (eb > (unsigned)ctx->num_sms * 16u) eb = (unsigned)ctx->num_sms * 16u;
+      k_expand_pairs<<<eb, 256, 0, sC>>>(obj->d_handles, obj->d_tfs, (unsigned)obj->n_objects,
+                                         static_cast<const uint32_t*>(ctx->big_pi.p) + done,
+                                         static_cast<const uint32_t*>(ctx->big_pj.p) + done, (unsigned)m, d_h1 + done, d_tf1 + done,
+                                         d_h2 + done, d_tf2 + done);
+      ctx->stats.kernel_launches++;
+      CK(cudaGetLastError());
+    }
+    BatchArgs a{};
+    a.n = (unsigned)m;
+    a.h1 = d_h1 + done;
+    a.h2 = d_h2 + done;
+    a.tf1 = d_tf1 + done;
+    a.tf2 = d_tf2 + done;
+    a.out = d_out + done;
+    a.P = P;
+    a.C = Cp;
+    a.B = Bq;
+    a.pair_base = (unsigned)done;
+    if ((rc = run_device_batch<MODE>(ctx, sl, a, sC, c == 0 ? 1 : 2))) {
+      drain();
+      return rc;
+    }
+    if constexpr (MODE == 0) {
+      if (min_out) {
+        k_pick_min_distance<<<(unsigned)((m + 255) / 256), 256, 0, sC>>>(d_out + done, (unsigned)m,
+                                                                          static_cast<double*>(ctx->big_min.p) + done);
+        ctx->stats.kernel_launches++;
+      }
+    }
+    CK(cudaEventRecord(ev_ph, sC));
+    CK(cudaStreamWaitEvent(sD, ev_ph, 0));
+    if (min_out) CK(cudaMemcpyAsync(min_out + done, static_cast<double*>(ctx->big_min.p) + done, m * 8, cudaMemcpyDeviceToHost, sD));
+    else CK(cudaMemcpyAsync(out + done, d_out + done, m * sizeof(OutT), cudaMemcpyDeviceToHost, sD));
+    // the chunk's handles / object indices are validated AFTER its work is enqueued, while the GPU is busy with it (8 MB
+    // of host reads per 1 M pairs: 0.4 ms in front of a single-chunk call otherwise).  The device side is safe against
+    // a bad value (k_expand_pairs, handle_type, load_shape: such a pair comes back unsupported); the call fails.
+    if (obj) {
+      const uint32_t no = (uint32_t)(obj->n_objects > 0xffffffffull ? 0xffffffffull : obj->n_objects);
+      uint32_t bad = 0;
+      for (size_t i = done; i < done + m; ++i) bad |= (uint32_t)(obj->first[i] >= no) | (uint32_t)(obj->second[i] >= no);
+      if (bad) {
+        drain();
+        return fail(ctx, HFB_ERR_INVALID_ARGUMENT, "object index out of range");
+      }
+    } else if ((rc = check_handles(ctx, h1 + done, m)) || (rc = check_handles(ctx, h2 + done, m))) {
+      drain();
+      return rc;
+    }
+    done += m;
+  }
+  stamp("chunks enqueued");
+  if (trace) {
+    cudaStreamSynchronize(sC);
+    stamp("phase 1 of all chunks done");
+  }
+  // EPA of the whole batch, then the records it produced, compacted
+  BatchArgs ag{};
+  ag.n = (unsigned)n;
+  ag.h1 = d_h1;
+  ag.h2 = d_h2;
+  ag.tf1 = d_tf1;
+  ag.tf2 = d_tf2;
+  ag.out = d_out;
+  ag.P = P;
+  ag.C = Cp;
+  ag.B = Bq;
+  unsigned epa_pairs = 0;
+  if (P.compute_penetration) {
+    if ((rc = run_deferred_epa<MODE>(ctx, sl, ag, sC))) {
+      drain();
+      return rc;
+    }
+    CK(ctx->fix_ids.reserve(n * 4));
+    CK(ctx->fix_rows.reserve(n * sizeof(OutT)));
+    const unsigned* d_cnt = static_cast<const unsigned*>(sl.counters.p);
+    k_gather_epa_rows<OutT><<<(unsigned)ctx->num_sms * 2u, 256, 0, sC>>>(static_cast<const EpaItem*>(sl.queue.p), d_cnt, d_out,
+                                                                         static_cast<uint32_t*>(ctx->fix_ids.p),
+                                                                         static_cast<OutT*>(ctx->fix_rows.p));
+    ctx->stats.kernel_launches++;
+    CK(cudaGetLastError());
+    cudaEvent_t ev_epa = ctx->pipe_events[2 * nchunks];
+    CK(cudaEventRecord(ev_epa, sC));
+    CK(cudaStreamWaitEvent(sD, ev_epa, 0));
+    CK(cudaMemcpyAsync(&epa_pairs, d_cnt, sizeof(unsigned), cudaMemcpyDeviceToHost, sD));
+    if (trace) {
+      cudaStreamSynchronize(sC);
+      stamp("EPA + gather done");
+    }
+    CK(cudaStreamSynchronize(sD));  // every chunk's rows are on the host now, and the count
+    stamp("rows + count on the host");
+    if (epa_pairs) {
+      const size_t need = (size_t)epa_pairs * (4 + sizeof(OutT)) + 64;
+      if (ctx->pin_fix_cap < need) {
+        if (ctx->pin_fix) cudaFreeHost(ctx->pin_fix);
+        ctx->pin_fix = nullptr;
+        ctx->pin_fix_cap = 0;
+        CK(cudaHostAlloc(&ctx->pin_fix, need + need / 2, cudaHostAllocDefault));
+        ctx->pin_fix_cap = need + need / 2;
+      }
+      OutT* hrows = static_cast<OutT*>(ctx->pin_fix);
+      uint32_t* hids = reinterpret_cast<uint32_t*>(static_cast<unsigned char*>(ctx->pin_fix) + (size_t)epa_pairs * sizeof(OutT));
+      CK(cudaMemcpyAsync(hrows, ctx->fix_rows.p, (size_t)epa_pairs * sizeof(OutT), cudaMemcpyDeviceToHost, sD));
+      CK(cudaMemcpyAsync(hids, ctx->fix_ids.p, (size_t)epa_pairs * 4, cudaMemcpyDeviceToHost, sD));
+      CK(cudaStreamSynchronize(sD));
+      if constexpr (MODE == 0) {
+        if (min_out) {
+          for (unsigned k = 0; k < epa_pairs; ++k) min_out[hids[k]] = hrows[k].min_distance;
+        } else {
+          for (unsigned k = 0; k < epa_pairs; ++k) out[hids[k]] = hrows[k];
+        }
+      } else {
+        for (unsigned k = 0; k < epa_pairs; ++k) out[hids[k]] = hrows[k];
+      }
+    }
+  }
+  for (int k = 0; k < kSlots; ++k) CK(cudaStreamSynchronize(ctx->slots[k].stream));
+  stamp("done");
+  return HFB_OK;
+}
+
 template <int MODE, typename Req, typename OutT>
 int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* tf1, const uint32_t* h2,
                const hfb_transform* tf2, const Req* req, const SolverP& P, const CollideP& Cp, const BvhReq& Bq,
@@ -1284,6 +1540,18 @@ int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* 
   const bool cached = req->q.gjk_initial_guess == HFB_GUESS_CACHED;
   const double* gin = cached ? req->q.cached_gjk_guess : nullptr;
   const int32_t* hin = cached ? req->q.cached_support_func_guess : nullptr;
+  {  // large plain batches: phase 1 chunk by chunk, EPA once (host_batch_pipelined)
+    const bool plain = !go && !extra_out && !counts_out && !(om && om->flags) && !gin && !hin;
+    // (full records only: with 8 bytes per pair down there is nothing to overlap and the rotating slots are as fast --
+    // measured 4.2e8 against 4.4e8 pairs/s; HFB_HOST_PIPE=2 sends those calls here as well)
+    const bool min_only = om && om->min_out;
+    if (ctx->host_pipe && plain && n >= kChunk && n <= (size_t)16 << 20 && (min_only ? ctx->host_pipe > 1 : out != nullptr)) {
+      if constexpr (MODE == 0)
+        return host_batch_pipelined<MODE, OutT>(ctx, n, h1, tf1, h2, tf2, P, Cp, Bq, out, obj, om ? om->min_out : nullptr);
+      else
+        return host_batch_pipelined<MODE, OutT>(ctx, n, h1, tf1, h2, tf2, P, Cp, Bq, out, obj, nullptr);
+    }
+  }
   size_t done = 0;
   int si = 0;
   // object-table calls send 8 B per pair up: fewer, larger chunks (measured: 256 Ki pairs 2.57 ms per 1 M pairs with
@@ -1528,6 +1796,7 @@ int hfb_ctx_create(int device, hfb_ctx** out) {
   if (const char* bs = getenv("HFB_BVH_SPEC")) c->bvh_spec = atoi(bs);
   if (const char* bc = getenv("HFB_BVH_GJK_CHUNK")) c->bvh_chunk = atoi(bc) > 0 ? atoi(bc) : 1;
   if (const char* hs = getenv("HFB_HULL_SORT")) c->hull_sort = atoi(hs) != 0;
+  if (const char* hp = getenv("HFB_HOST_PIPE")) c->host_pipe = atoi(hp) < 0 ? 0 : atoi(hp);
   if (const char* go = getenv("HFB_GJK_ORDERED")) c->gjk_ordered = atoi(go) != 0;
   if (const char* er = getenv("HFB_EPA_RESUME")) c->epa_resume = atoi(er) > 0 ? atoi(er) : 0;
   if (const char* gp = getenv("HFB_GJK_PASSES")) {
@@ -1587,6 +1856,10 @@ void hfb_ctx_destroy(hfb_ctx* c) {
   c->sup_idx.release();
   c->sup_out.release();
   c->obj_h.release();
+  for (DevBuf* b : {&c->big_h1, &c->big_h2, &c->big_tf1, &c->big_tf2, &c->big_out, &c->big_pi, &c->big_pj, &c->big_min, &c->fix_ids, &c->fix_rows})
+    b->release();
+  if (c->pin_fix) cudaFreeHost(c->pin_fix);
+  for (cudaEvent_t e : c->pipe_events) cudaEventDestroy(e);
   c->bp_scratch.release();
   for (DevBuf* b : {&c->sc_bb, &c->sc_pf, &c->sc_ps, &c->sc_cnt, &c->sc_out, &c->sc_f, &c->sc_s, &c->sc_rec}) b->release();
   c->obj_tf.release();

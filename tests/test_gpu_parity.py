@@ -347,3 +347,71 @@ def test_object_table_calls_equal_the_pair_calls():
     with pytest.raises(hf.EngineError):
         eng.batch_distance_objects(oh, otf, bad, pj)
     assert eng.stats()["watchdog_trips"] == 0
+
+
+@pytest.mark.gpu
+def test_host_pipeline_with_one_epa_pass_equals_the_chunk_by_chunk_one():
+    """large host batches run phase 1 chunk by chunk and EPA once over the whole batch, the EPA pairs' records
+    following compacted (host_batch_pipelined); HFB_HOST_PIPE=0 keeps the chunk-by-chunk pipeline.  Same bits, for
+    rows, distances only, collide, object tables -- with many small chunks -- and the oracle's on a sample."""
+    import os
+    from oracle import oracle_lib
+    rng = np.random.default_rng(23)
+    n = 200_000
+    w = W.config2_mixed_primitives(n, pool=2048, types=ALL_PRIMS, seed=5)
+    pts, _ = W.ellipsoid_hull(rng, 24)
+    n_obj = 5000
+    pi, pj = rng.integers(0, n_obj, n).astype(np.uint32), rng.integers(0, n_obj, n).astype(np.uint32)
+    otf = W.random_transforms(rng, n_obj, (-1.5, -1.5, -1.5), (1.5, 1.5, 1.5))
+    out = {}
+    for pipe in ("1", "0"):
+        old = {k: os.environ.get(k) for k in ("HFB_HOST_PIPE", "HFB_CHUNK")}
+        os.environ["HFB_HOST_PIPE"], os.environ["HFB_CHUNK"] = ("2" if pipe == "1" else "0"), "24576"
+        try:
+            eng = hf.Engine(0)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        hp = eng.register_shapes(w["shapes"])
+        hc = eng.register_shapes(P.make_shapes([P.GEOM_CONVEX], [[0, 0, 0]], data=[eng.register_convex(pts)]))
+        eng.commit()
+        h1, h2 = hp[w["h1"] % len(hp)].copy(), hp[w["h2"] % len(hp)].copy()
+        h1[::17] = hc[0]  # hull pairs in every chunk
+        oh = np.concatenate([hp, hc])[rng.integers(0, len(hp) + 1, n_obj)].astype(np.uint32) if pipe == "1" else out["oh"]
+        res = dict(oh=oh,
+                   rows=eng.batch_distance(h1, w["tf1"], h2, w["tf2"]),
+                   col=eng.batch_collide(h1, w["tf1"], h2, w["tf2"], P.CollisionRequestPOD(security_margin=0.02)),
+                   obj=eng.batch_distance_objects(oh, otf, pi, pj),
+                   omin=eng.batch_distance_objects(oh, otf, pi, pj, min_only=True),
+                   launches=eng.stats()["kernel_launches"])
+        if pipe == "1":
+            out = res
+            first = (h1, h2)
+        else:
+            for k in ("rows", "col", "obj", "omin"):
+                assert out[k].tobytes() == res[k].tobytes(), k
+            assert out["launches"] < res["launches"]  # one EPA pass instead of one per chunk
+    epa = (out["rows"]["iterations"] >> 16) > 0
+    assert epa.sum() > 1000 and (out["col"]["num_contacts"] > 0).sum() > 5000
+    # a bad handle / object index in a late chunk fails the call (it is looked at while the GPU already works on the
+    # chunk: the device side treats such a pair as unsupported, nothing faults)
+    bad_h = first[0].copy()
+    bad_h[-5] = 0xfffffff0
+    with pytest.raises(hf.EngineError):
+        eng.batch_distance(bad_h, w["tf1"], first[1], w["tf2"])
+    bad_i = pi.copy()
+    bad_i[n // 2] = n_obj
+    with pytest.raises(hf.EngineError):
+        eng.batch_distance_objects(out["oh"], otf, bad_i, pj)
+    assert eng.batch_distance(first[0], w["tf1"], first[1], w["tf2"]).tobytes() == out["rows"].tobytes()  # and the context lives on
+    assert out["omin"].tobytes() == np.ascontiguousarray(out["obj"]["min_distance"]).tobytes()
+    orc = oracle_lib.OracleScene(P)
+    orc.register_shapes(w["shapes"])  # (same handle numbering as the engines: the primitives, then the hull)
+    orc.register_shapes(P.make_shapes([P.GEOM_CONVEX], [[0, 0, 0]], data=[orc.register_convex(pts, None)]))
+    m = 30_000
+    sel = np.sort(rng.choice(n, m, replace=False))
+    compare_distance(orc.batch_distance(first[0][sel], w["tf1"][sel], first[1][sel], w["tf2"][sel], nthreads=0), out["rows"][sel],
+                     what="pipelined host batch vs oracle")
