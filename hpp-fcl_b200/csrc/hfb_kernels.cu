@@ -815,6 +815,11 @@ struct hfb_ctx {
   size_t pin_fix_cap = 0;
   std::vector<cudaEvent_t> pipe_events;
   int host_pipe = 1;  // HFB_HOST_PIPE=0: the rotating-slot pipeline of round 1 for every host call
+  // share of EPA pairs in the last pipelined call: a batch whose EPA is throughput-bound (config 3: half of the pairs)
+  // gains nothing from one EPA pass -- the rotating slots overlap the EPA of a chunk with phase 1 of the next -- so
+  // such a context goes back to them, and looks again every 16th call
+  double pipe_epa_frac = 0.0;
+  unsigned pipe_skipped = 0;
   cudaEvent_t obj_ready = nullptr;
   hfb_stats stats{};
   int gc = HFB_GC_DEFAULT, ge = HFB_GE_DEFAULT, minb = 1, nsub = 0, bvh_minb = 4, refill = 0, iter_quorum = 8, stage = 0, chunk = 0;
@@ -1495,7 +1500,19 @@ int host_batch_pipelined(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_t
     }
     CK(cudaStreamSynchronize(sD));  // every chunk's rows are on the host now, and the count
     stamp("rows + count on the host");
-    if (epa_pairs) {
+    ctx->pipe_epa_frac = (double)epa_pairs / (double)n;
+    if (epa_pairs > n / 16) {
+      // many EPA pairs (half of the hull pairs of config 3): placing their records one by one costs the host more than
+      // taking every record again (25 ns per scattered row against 1.7 ns per row of a plain copy)
+      if (min_out) {
+        k_pick_min_distance<<<(unsigned)((n + 255) / 256), 256, 0, sD>>>(reinterpret_cast<const hfb_distance_result*>(d_out), (unsigned)n,
+                                                                          static_cast<double*>(ctx->big_min.p));
+        CK(cudaMemcpyAsync(min_out, ctx->big_min.p, n * 8, cudaMemcpyDeviceToHost, sD));
+      } else {
+        CK(cudaMemcpyAsync(out, d_out, n * sizeof(OutT), cudaMemcpyDeviceToHost, sD));
+      }
+      CK(cudaStreamSynchronize(sD));
+    } else if (epa_pairs) {
       const size_t need = (size_t)epa_pairs * (4 + sizeof(OutT)) + 64;
       if (ctx->pin_fix_cap < need) {
         if (ctx->pin_fix) cudaFreeHost(ctx->pin_fix);
@@ -1545,7 +1562,9 @@ int host_batch(hfb_ctx* ctx, size_t n, const uint32_t* h1, const hfb_transform* 
     // (full records only: with 8 bytes per pair down there is nothing to overlap and the rotating slots are as fast --
     // measured 4.2e8 against 4.4e8 pairs/s; HFB_HOST_PIPE=2 sends those calls here as well)
     const bool min_only = om && om->min_out;
-    if (ctx->host_pipe && plain && n >= kChunk && n <= (size_t)16 << 20 && (min_only ? ctx->host_pipe > 1 : out != nullptr)) {
+    bool take = ctx->host_pipe && plain && n >= kChunk && n <= (size_t)16 << 20 && (min_only ? ctx->host_pipe > 1 : out != nullptr);
+    if (take && ctx->host_pipe < 2 && ctx->pipe_epa_frac > 1.0 / 16 && ++ctx->pipe_skipped % 16 != 0) take = false;
+    if (take) {
       if constexpr (MODE == 0)
         return host_batch_pipelined<MODE, OutT>(ctx, n, h1, tf1, h2, tf2, P, Cp, Bq, out, obj, om ? om->min_out : nullptr);
       else

@@ -331,7 +331,13 @@ int hfb_geom_release_shapes(hfb_ctx* ctx, const uint32_t* handles, size_t n);
 
 /* ---- batched distance(): n independent (o1,tf1,o2,tf2) queries --------- */
 /* HOST buffers in/out; blocking.  Mirrors distance() of src/distance.cpp:60-109
- * applied to each pair with a fresh DistanceResult. */
+ * applied to each pair with a fresh DistanceResult.  Pinned host buffers make the
+ * copies asynchronous.  A batch is pipelined: uploads, kernels and downloads of its
+ * chunks overlap (large plain calls: the whole batch on the device, EPA once for all
+ * chunks; calls with warm-start or all-contacts outputs and the compact modes: every
+ * chunk run to the end on one of four streams).  Handles are validated on the host
+ * while the GPU already works: a bad one fails the call (the results are then
+ * undefined), never the device. */
 int hfb_batch_distance(hfb_ctx* ctx, size_t n, const uint32_t* h1,
                        const hfb_transform* tf1, const uint32_t* h2,
                        const hfb_transform* tf2, const hfb_distance_request* req,
