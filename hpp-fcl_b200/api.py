@@ -465,6 +465,136 @@ class BatchQuery:
         return self.scene.engine.batch_collide(h1, _tf_array(tfs1), h2, _tf_array(tfs2), request._pod)
 
 
+# ------------------------------------------------------------- broadphase seam --
+class AABB:  # BV/AABB.h
+    def __init__(self, min_=None, max_=None):
+        self.min_ = np.full(3, np.inf) if min_ is None else np.asarray(min_, dtype=np.float64)
+        self.max_ = np.full(3, -np.inf) if max_ is None else np.asarray(max_, dtype=np.float64)
+
+    def overlap(self, other):  # :111-118, closed intervals
+        return bool(np.all(self.min_ <= other.max_) and np.all(self.max_ >= other.min_))
+
+
+class CollisionObject:  # collision_object.h:214-330 (geometry + pose + world-space box)
+    def __init__(self, geom, tf=None):
+        self.geom = geom
+        self.tf = tf if tf is not None else Transform3f()
+        self.aabb = AABB()
+
+    def collisionGeometry(self):
+        return self.geom
+
+    def getTransform(self):
+        return self.tf
+
+    def setTransform(self, tf):
+        self.tf = tf
+
+    def getAABB(self):
+        return self.aabb
+
+
+class CollisionCallBackCollect:  # broadphase/default_broadphase_callbacks.h:224-252, .cpp:95-120
+    def __init__(self, max_size=0):
+        self.max_size = max_size
+        self.collision_pairs = []
+
+    def init(self):
+        self.collision_pairs = []
+
+    def collide(self, o1, o2):
+        self.collision_pairs.append((o1, o2))
+        return False
+
+    __call__ = collide
+
+    def numCollisionPairs(self):
+        return len(self.collision_pairs)
+
+    def getCollisionPairs(self):
+        return self.collision_pairs
+
+    def exist(self, o1, o2):
+        return any(a is o1 and b is o2 for a, b in self.collision_pairs)
+
+
+class DynamicAABBTreeCollisionManager:
+    """BroadPhaseCollisionManager's interface (broadphase/broadphase_collision_manager.h:56-134) for the self-collision
+    query: setup() / update() compute every object's box (CollisionObject::computeAABB, on the device), collide(callback)
+    reports every pair of objects with overlapping boxes once -- the SET the reference's managers report
+    (broadphase_dynamic_AABB_tree.cpp:336-407,716-721); the order is each manager's own.  No tree is kept: a uniform grid
+    is rebuilt per query.  collide_batch() is what the seam is for: candidates + batched narrow phase in one go."""
+
+    def __init__(self, device=0):
+        self.scene = default_engine(device)
+        self.objs = []
+        self._stale = True
+        self._handles = self._tfs = self._boxes = None
+
+    def registerObject(self, obj):
+        self.objs.append(obj)
+        self._stale = True
+
+    def registerObjects(self, objs):
+        self.objs.extend(objs)
+        self._stale = True
+
+    def unregisterObject(self, obj):
+        self.objs = [o for o in self.objs if o is not obj]
+        self._stale = True
+
+    def clear(self):
+        self.objs = []
+        self._stale = True
+
+    def size(self):
+        return len(self.objs)
+
+    def empty(self):
+        return not self.objs
+
+    def getObjects(self):
+        return list(self.objs)
+
+    def _refresh(self):
+        self._handles = np.array([self.scene.handle(o.geom) for o in self.objs], dtype=np.uint32)
+        self.scene.commit()
+        self._tfs = _tf_array([o.tf for o in self.objs]) if self.objs else np.zeros(0, dtype=P.transform_dtype)
+        self._boxes = self.scene.engine.scene_aabbs(self._handles, self._tfs) if self.objs else np.zeros((0, 6))
+        for o, b in zip(self.objs, self._boxes):
+            o.aabb = AABB(b[:3].copy(), b[3:].copy())
+        self._stale = False
+
+    def setup(self):
+        self._refresh()
+
+    def update(self):
+        self._refresh()
+
+    def pairs(self):
+        """the candidate pairs as object indices (first < second)"""
+        if self._stale:
+            self._refresh()
+        from .engine import broadphase_pairs
+        return broadphase_pairs(self._boxes)
+
+    def collide(self, callback):
+        callback.init()
+        first, second = self.pairs()
+        for a, b in zip(first.tolist(), second.tolist()):
+            if callback(self.objs[a], self.objs[b]):
+                return
+
+    def collide_batch(self, request=None):
+        """-> (first, second, contact records) of ALL candidate pairs: one hfb_batch_collide_objects call"""
+        request = request or CollisionRequest()
+        if request.num_max_contacts == 0:
+            raise ValueError("Invalid number of max contacts (current value is 0).")
+        first, second = self.pairs()
+        rec = self.scene.engine.batch_collide_objects(self._handles, self._tfs, first, second, request._pod)
+        return first, second, rec
+
+
 def _unsupported(o1, o2, what, request=None):
     """the exception the reference throws for this pair (the record carries HFB_PATH_UNSUPPORTED)"""
     mesh = [o for o in (o1, o2) if o.node_type in _MESH_TYPES]

@@ -268,3 +268,39 @@ def test_scene_collide_in_one_call():
     # capacity below the number of colliding pairs: all counted
     f3, _, _, _, h3 = eng.scene_collide(oh, tf, capacity=50)
     assert h3 == nhit and len(f3) == 50
+
+
+@pytest.mark.gpu
+def test_python_manager_mirror():
+    """DynamicAABBTreeCollisionManager / CollisionObject / CollisionCallBackCollect of the Python mirror: the pairs the
+    callback sees are the brute-force set of overlapping boxes, collide_batch() agrees with collide() pair by pair, a
+    floor Halfspace takes part, update() follows moved objects"""
+    rng = np.random.default_rng(31)
+    geoms = [hf.Box(*(0.2 + rng.random(3))) for _ in range(6)] + [hf.Sphere(0.3), hf.Capsule(0.2, 0.6), hf.Cylinder(0.25, 0.5)]
+    objs = [hf.CollisionObject(geoms[rng.integers(0, len(geoms))],
+                               hf.Transform3f.from_quat(*(lambda q: q / np.linalg.norm(q))(rng.normal(size=4)), rng.uniform(-3, 3, 3)))
+            for _ in range(400)]
+    floor = hf.CollisionObject(hf.Halfspace([0, 0, 1], -2.5))
+    mgr = hf.DynamicAABBTreeCollisionManager()
+    mgr.registerObjects(objs)
+    mgr.registerObject(floor)
+    mgr.setup()
+    assert mgr.size() == 401 and not mgr.empty()
+    bb = np.array([np.concatenate([o.getAABB().min_, o.getAABB().max_]) for o in mgr.getObjects()])
+    cb = hf.CollisionCallBackCollect(100000)
+    mgr.collide(cb)
+    idx = {id(o): k for k, o in enumerate(mgr.getObjects())}
+    got = {tuple(sorted((idx[id(a)], idx[id(b)]))) for a, b in cb.getCollisionPairs()}
+    assert got == brute_pairs(bb) and len(got) == cb.numCollisionPairs() and any(400 in p for p in got)
+    first, second, rec = mgr.collide_batch()
+    assert {(int(a), int(b)) for a, b in zip(first, second)} == got
+    req = hf.CollisionRequest()
+    for k in rng.choice(len(first), 40, replace=False):
+        a, b = mgr.getObjects()[first[k]], mgr.getObjects()[second[k]]
+        res = hf.CollisionResult()
+        assert hf.collide(a.geom, a.tf, b.geom, b.tf, req, res) == int(rec["num_contacts"][k])
+    assert rec["num_contacts"].sum() > 10
+    objs[0].setTransform(hf.Transform3f(T=[50.0, 50.0, 50.0]))  # far away from everything (and above the floor)
+    mgr.update()
+    f2, s2 = mgr.pairs()
+    assert not np.any(f2 == 0) and not np.any(s2 == 0)

@@ -136,6 +136,13 @@ def test_api_objects_without_gpu():
     assert np.allclose(t.transform([1, 1, 1]), [2, 3, 4])
     with pytest.raises(ValueError):
         hf.Sphere(1).setSweptSphereRadius(-1)
+    cb = hf.CollisionCallBackCollect(10)                                             # default_broadphase_callbacks.cpp:95-120
+    oa, ob = hf.CollisionObject(hf.Box(1, 1, 1)), hf.CollisionObject(hf.Sphere(1), hf.Transform3f(T=[1, 0, 0]))
+    assert cb(oa, ob) is False and cb.numCollisionPairs() == 1 and cb.exist(oa, ob) and not cb.exist(ob, oa)
+    cb.init()
+    assert cb.numCollisionPairs() == 0
+    assert hf.AABB([0, 0, 0], [1, 1, 1]).overlap(hf.AABB([1, 1, 1], [2, 2, 2]))     # closed intervals (AABB.h:111-118)
+    assert not hf.AABB([0, 0, 0], [1, 1, 1]).overlap(hf.AABB([1.1, 0, 0], [2, 1, 1]))
     h = hf.Halfspace([0, 0, 2.0], 3.0)                                               # :887-890 + unitNormalTest
     assert np.allclose(h.n, [0, 0, 1]) and h.d == 1.5 and h.getNodeType() == P.GEOM_HALFSPACE
     assert h.signedDistance([0, 0, 2.0]) == 0.5
