@@ -19,7 +19,8 @@
 
 namespace {
 
-struct GjkSaved {
+// (16-byte aligned: 432 B = 27 x 16, so that the copies to and from HBM can move 16 bytes per instruction)
+struct __align__(16) GjkSaved {
   GjkState g;
   GjkLoop L;
   int done;  // 1: converged in the first pass (extracted early, so that its EPA can start), 2: in a later pass, 0: running
