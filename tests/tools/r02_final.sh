@@ -6,7 +6,7 @@ out=gpurun_out/r02_final
 mkdir -p "$out"
 nvidia-smi --query-gpu=pcie.link.gen.current,pcie.link.width.current,clocks.sm --format=csv,noheader
 timeout 120 python tests/tools/probe_pcie_numa.py | cut -c1-400
-for hs in 1 0 1 0; do HFB_HULL_SORT=$hs timeout 120 python tests/tools/bench_pairs.py config3 1000000 2>&1 | tail -1 | cut -c1-330 | sed "s/^/HULL_SORT=$hs /"; done
+for hs in 1 0; do HFB_HULL_SORT=$hs timeout 120 python tests/tools/bench_pairs.py config3 1000000 2>&1 | tail -1 | cut -c1-330 | sed "s/^/HULL_SORT=$hs /"; done
 timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -6 > "$out/pytest.txt"; cat "$out/pytest.txt"
 timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
 timeout 900 python bench.py > "$out/bench.json" 2> "$out/bench.err"; tail -c 600 "$out/bench.json"; echo
