@@ -49,6 +49,19 @@ def test_fuzz_every_contact_of_mesh_pairs():
         fuzz_ref.CONTACTS[0] = False
 
 
+def test_fuzz_plane_family():
+    """the rounds with Halfspace / Plane geometries added (axis-aligned, tilted, parallel and mirrored planes against
+    every shape, hull and each other): reference build, oracle and the host build of the device code.  (On the GPU the
+    family is covered by tests/test_plane_halfspace.py; the GPU fuzz below keeps the rounds it was confirmed on.)"""
+    fuzz_ref.PLANES[0] = True
+    try:
+        for seed in range(300, 340):
+            ok, tag = fuzz_ref.one_round(seed, 1500, _ref(), True)
+            assert ok, tag
+    finally:
+        fuzz_ref.PLANES[0] = False
+
+
 # Seeds 1, 2, 5-10 were green on a B200 in round 1 (profiles/r01_summary.md).  3 and 4 exposed a defect of the
 # lane-group support argmax: a NaN direction (GJK produces one from 0/0 in the projection of a degenerate simplex,
 # and carries on -- so does the reference) left the lanes of a group with different vertices.  Fixed in

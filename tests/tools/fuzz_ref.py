@@ -229,6 +229,14 @@ class Backends:
             assert self.emu.register_convex(pts) == i
         return i
 
+    def register_halfspaces(self, kind, nd, ssr):
+        h = self.orc.register_halfspaces(kind, nd, ssr)
+        if self.ref:
+            assert np.array_equal(h, self.ref.register_halfspaces(kind, nd, ssr))
+        if self.emu:
+            assert np.array_equal(h, self.emu.register_halfspaces(kind, nd, ssr))
+        return h
+
     def register_bvh(self, v, t):
         i, nodes = self.orc.register_bvh(v, t)
         if self.ref:
@@ -277,6 +285,22 @@ def build_cases(seed, n, use_ref, use_emu):
     hb = B.register_shapes(P.make_shapes([P.GEOM_CONVEX] * len(bids), np.zeros((len(bids), 3)), data=bids))
     mids = [B.register_bvh(v, t) for v, t in fuzz_meshes(rng, scale)]
     hm = B.register_shapes(P.make_shapes([P.BV_OBBRSS] * len(mids), np.zeros((len(mids), 3)), data=mids))
+    # Plane / Halfspace geometries (--planes; their own generator, so that the other cases of a seed do not change):
+    # axis-aligned and tilted normals of any length, the same plane twice and mirrored (parallel / anti-parallel pairs),
+    # offsets at the scene's scale, some with a swept-sphere radius
+    hh = hq = None
+    if PLANES[0]:
+        prng = np.random.default_rng([seed, 0x9E3779B9])
+        npl = 24
+        nd = np.concatenate([prng.normal(size=(npl, 3)) * prng.uniform(0.1, 10, (npl, 1)), prng.uniform(-1.5, 1.5, (npl, 1)) * scale], axis=1)
+        for k, ax in enumerate(((1, 0, 0), (-1, 0, 0), (0, 1, 0), (0, -1, 0), (0, 0, 1), (0, 0, -1), (0, 0, 1), (0, 0, 0))):
+            nd[k, :3] = np.asarray(ax, dtype=np.float64) * prng.uniform(0.5, 2.0)  # (the last: the degenerate normal -> (1, 0, 0), 0)
+        nd[8] = nd[9] * 3.0
+        nd[10, :3] = -nd[9, :3]
+        nd[11, 3] = 0.0
+        pssr = np.where(prng.random(npl) < 0.3, prng.uniform(0.0, 0.2, npl) * scale, 0.0)
+        hh = B.register_halfspaces(P.GEOM_HALFSPACE, nd, pssr)
+        hq = B.register_halfspaces(P.GEOM_PLANE, nd, pssr)
     B.commit()
     mode = str(rng.choice(["random", "axis", "coincident", "identity", "far", "touch", "touch"]))
     base = "random" if mode == "touch" else mode
@@ -300,6 +324,20 @@ def build_cases(seed, n, use_ref, use_emu):
         req.q.cached_support_func_guess = gh.ctypes.data
         kw = dict(kw, gjk_initial_guess="cached")
         cases.append(("shapes", kind, h1, tf1, h2, tf2, req, kw, (gg, gh)))  # the arrays the request points into
+    # the plane family against everything (and itself), either operand order
+    if PLANES[0]:
+        npf = max(200, n // 3)
+        fam = np.concatenate([hh, hq])
+        pa = fam[prng.integers(0, len(fam), npf)]
+        pb = np.where(prng.random(npf) < 0.15, fam[prng.integers(0, len(fam), npf)], pool[prng.integers(0, len(pool), npf)])
+        sw = prng.random(npf) < 0.5
+        p1, p2 = np.where(sw, pb, pa).astype(np.uint32), np.where(sw, pa, pb).astype(np.uint32)
+        pt1, pt2 = tf1[:npf].copy(), tf2[:npf].copy()
+        same = prng.random(npf) < 0.3  # (parallel planes stay parallel under a common rotation)
+        pt2["R"][same] = pt1["R"][same]
+        for kind in ("distance", "collide"):
+            req, kw = random_request(prng, kind)
+            cases.append(("planes", kind, p1, pt1, p2, pt2, req, kw))
     # hulls of more than 32 vertices: reference vs oracle only (the device code takes the exhaustive argmax)
     nb = max(200, n // 4)
     bpool = np.concatenate([hb, hb, hp])
@@ -327,6 +365,7 @@ def build_cases(seed, n, use_ref, use_emu):
     return B, tag, cases
 
 
+PLANES = [False]  # --planes: Plane / Halfspace geometries against everything (and each other)
 CONTACTS = [False]  # --contacts: mesh collide cases go through batch_collide_contacts (every contact of a pair)
 MAX_EXTRA = 4
 
@@ -356,7 +395,7 @@ def compare_case(case, ref, got, what):
             cmp_fields(ref["extra"][:, k], got["extra"][:, k], ("p1", "p2", "normal", "pos", "b1", "b2", "distance"),
                        what + " contacts[%d]" % (k + 1))
         return
-    if name in ("shapes", "big-hulls"):
+    if name in ("shapes", "big-hulls", "planes"):
         if kind == "distance":
             compare_distance(ref, got, what=what)
         else:
@@ -377,7 +416,7 @@ def rows_differing(case, ref, got):
                 ne = ~((x == y) | (np.isnan(x) & np.isnan(y))) if x.dtype.kind == "f" else x != y
                 bad |= ne.reshape(len(ref), -1).any(axis=1)
         return np.union1d(np.nonzero(bad)[0], rows_differing(case, ref["first"], got["first"]))
-    if name in ("shapes", "big-hulls"):
+    if name in ("shapes", "big-hulls", "planes"):
         fields = ["status", "iterations", "b1", "b2", "p1", "p2", "normal"]
         fields += ["min_distance"] if kind == "distance" else ["distance", "pos", "distance_lower_bound", "num_contacts"]
     elif kind == "distance":
@@ -457,12 +496,14 @@ def main():
     ap.add_argument("--keep-going", action="store_true")
     ap.add_argument("--big-meshes", action="store_true")
     ap.add_argument("--contacts", action="store_true", help="mesh collide cases keep every contact (batch_collide_contacts)")
+    ap.add_argument("--planes", action="store_true", help="add the Plane / Halfspace family to every round")
     ap.add_argument("--gpu", action="store_true", help="the real kernels (hppfcl_b200.Engine) instead of the host build")
     ap.add_argument("--lanes", type=int, default=1, help="host build: lane groups of this many threads for phase 1")
     a = ap.parse_args()
     use_ref = False
     BIG_MESHES[0] = a.big_meshes
     CONTACTS[0] = a.contacts
+    PLANES[0] = a.planes
     if os.path.isdir("/root/reference/src"):
         oracle_lib.build_ref()
     use_ref = oracle_lib.ref_available()
