@@ -133,7 +133,9 @@ typedef struct hfb_query_request {
   int32_t gjk_convergence_criterion;      /* HFB_CRIT_*             default DEFAULT */
   int32_t gjk_convergence_criterion_type; /* HFB_CRIT_RELATIVE/ABS  default RELATIVE */
   uint32_t gjk_max_iterations;            /* 128 */
-  uint32_t epa_max_iterations;            /* 64  */
+  uint32_t epa_max_iterations;            /* 64; more is refused with HFB_ERR_INVALID_ARGUMENT: the EPA polytope lives
+                                           * in shared memory, sized for the reference's default of 64 iterations
+                                           * (68 vertices, 132 faces) */
   double gjk_tolerance;                   /* 1e-6 */
   double epa_tolerance;                   /* 1e-6 */
   double collision_distance_threshold;    /* 1e-12 (Eigen dummy_precision) */
