@@ -204,6 +204,8 @@ class MultiScene:
         for name, s in self.b.items():
             if name == "oracle":
                 ids.add(int(s.register_convex(points, tris)))
+            elif name == "ref":  # Convex<Triangle> needs its faces; a TriangleP's vertex set is a bare point set
+                ids.add(int(s.register_points(points) if tris is None else s.register_convex(points, tris)))
             else:
                 ids.add(int(s.register_convex(points)))
         assert len(ids) == 1
@@ -214,7 +216,9 @@ class MultiScene:
         node array through the product ABI (what a binding copies out of BVHModel<OBBRSS>::bvs)."""
         bid, nodes = self.b["oracle"].register_bvh(vertices, triangles)
         for name, s in self.b.items():
-            if name != "oracle":
+            if name == "ref":  # (builds its own tree: the reference's builder, which the oracle's restates)
+                assert s.register_bvh(vertices, triangles)[0] == bid
+            elif name != "oracle":
                 assert s.register_bvh_obbrss(nodes, vertices, triangles) == bid
         return bid, nodes
 
@@ -247,8 +251,12 @@ class MultiScene:
                 s.commit()
 
 
-def make_scenes(gpu=False, emu=True):
+def make_scenes(gpu=False, emu=True, ref=False):
+    """ref=True adds the reference build (oracle/_ref) where it exists: the known-answer tests then check their
+    literal numbers on records the reference's own code agrees with bit for bit"""
     b = {"oracle": oracle_lib.OracleScene(P)}
+    if ref and oracle_lib.ref_available():
+        b["ref"] = oracle_lib.RefScene(P)
     if emu:
         b["emu"] = EmuScene()
     if gpu:
@@ -286,6 +294,27 @@ def compare_distance(ref, got, rtol=1e-6, exact=True, what=""):
             assert np.all(np.abs(a[m] - b[m]) <= rtol * scale), "%s: %s exceeds rtol" % (what, f)
     if "num_contacts" in ref.dtype.names:
         assert np.array_equal(ref["num_contacts"], got["num_contacts"]), "%s: collide flags differ" % what
+
+
+def ref_agrees(sc, fn, ro, args, what, fields=None):
+    """where oracle/_ref exists: the reference build returns the same bits (it leaves `distance` of a collide()
+    without a contact unset).  `fields`: compare only these (mesh queries: the BV / leaf test counters and the path
+    byte of the record are the oracle's own, and the reference writes no normal on the mesh-mesh distance path)"""
+    if "ref" not in sc.b:
+        return
+    rr = getattr(sc.b["ref"], fn)(*args)
+    if fields is not None:
+        for f in fields:
+            x, y = rr[f], ro[f]
+            ok = (x == y) | (np.isnan(x) & np.isnan(y)) if x.dtype.kind == "f" else x == y
+            assert np.all(ok), "%s (reference build): field %s differs at rows %s" % (what, f, np.unique(np.nonzero(~ok)[0])[:8])
+        return
+    a, b = rr.copy(), ro.copy()
+    if "num_contacts" in a.dtype.names:
+        nc = a["num_contacts"] == 0
+        a["distance"][nc] = 0
+        b["distance"][nc] = 0
+    compare_distance(a, b, what=what + " (reference build)")
 
 
 def compare_hill_climb(ref, got):

@@ -10,13 +10,14 @@ pair type of the suite, 10 random shape draws x POSES random poses of the second
               dist * normal + 0.01 * normal is closer than before, and if it collides the contact is consistent
 
 with the tolerances of the reference (BOOST_CHECK_CLOSE is in percent; isApprox is relative to the smaller norm).
-Run on the oracle; the host build of the device code must return the same bits (compare_distance).  CPU only; on the
+Run on the oracle; the host build of the device code and, where oracle/_ref exists, the reference build must return
+the same bits (compare_distance).  CPU only; on the
 GPU the same properties are asserted on a 1 M pair batch (tests/test_gpu_parity.py::test_full_size_properties).
 """
 import numpy as np
 import pytest
 
-from tests.common import P, compare_distance, make_scenes
+from tests.common import P, compare_distance, make_scenes, ref_agrees
 from hppfcl_b200 import workloads as W
 
 POSES = 400  # (1000 in the reference's release build, 10 in its debug build)
@@ -132,6 +133,7 @@ def both(sc, fn, h1, t1, h2, t2, req, what):
     ro = getattr(sc.b["oracle"], fn)(h1, t1, h2, t2, req)
     re = getattr(sc.b["emu"], fn)(h1, t1, h2, t2, req)
     compare_distance(ro, re, what=what)
+    ref_agrees(sc, fn, ro, (h1, t1, h2, t2, req), what)
     return ro
 
 
@@ -219,7 +221,7 @@ def run_suite(sc, h1, h2, gjk_tol, epa_it, epa_tol, rng, what):
 def test_normal_and_nearest_points(case):
     a, b, swap, gjk_tol, epa_it, epa_tol = case
     rng = np.random.default_rng(1000 + CASES.index(case))
-    sc = make_scenes()
+    sc = make_scenes(ref=True)
     mk = Maker(sc, rng)
     ha = np.repeat([getattr(mk, a)() for _ in range(DRAWS)], POSES).astype(np.uint32)
     hb = np.repeat([getattr(mk, b)() for _ in range(DRAWS)], POSES).astype(np.uint32)

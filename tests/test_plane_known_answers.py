@@ -3,7 +3,8 @@
 1e-9 unless the case says otherwise): every case once with the poses of the test and once under a common rigid
 transform, as the reference does (its transform is random; a fixed one is used here).
 
-Checked on the oracle's records; the host build of the device code (tests/emu) must return the same bits.  CPU only:
+Checked on the oracle's records; the host build of the device code (tests/emu) and, where oracle/_ref exists, the
+reference build must return the same bits.  CPU only:
 the CUDA kernels are compared with the oracle on the plane family by tests/test_plane_halfspace.py.
 """
 import numpy as np
@@ -36,7 +37,7 @@ def apply(t, v):
 
 class World:
     def __init__(self):
-        self.sc = make_scenes()
+        self.sc = make_scenes(ref=True)
         self.g = tf(*GLOBAL)
 
     def shape(self, kind, *p):
@@ -62,7 +63,14 @@ class World:
         self.sc.commit()
         ro = self.sc.b["oracle"].batch_collide([h1], t1, [h2], t2, req)
         re = self.sc.b["emu"].batch_collide([h1], t1, [h2], t2, req)
-        compare_distance(ro, re, what="plane known answers")
+        compare_distance(ro, re, what="known answers, host build of the device code")
+        if "ref" in self.sc.b:  # the reference build: the same bits (it leaves `distance` unset without a contact)
+            rr = self.sc.b["ref"].batch_collide([h1], t1, [h2], t2, req)
+            a, b = rr.copy(), ro.copy()
+            nc = a["num_contacts"] == 0
+            a["distance"][nc] = 0
+            b["distance"][nc] = 0
+            compare_distance(a, b, what="known answers, reference build")
         return ro[0]
 
     def check(self, h1, t1, h2, t2, expect, point=None, depth=None, normal=None, opposite=False, tol=1e-9,

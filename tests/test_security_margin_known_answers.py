@@ -1,12 +1,13 @@
 """collide() with a security margin: the reference's known answers
 (/root/reference/test/security_margin.cpp:182-506 -- sphere-sphere, capsule-capsule, box-box, and box / box-as-convex-
 hull against a sphere), every block with its own tolerances (BOOST_CHECK_CLOSE is in percent, BOOST_CHECK_SMALL
-absolute).  Checked on the oracle; the host build of the device code must return the same bits.  CPU only.
+absolute).  Checked on the oracle; the host build of the device code and, where oracle/_ref exists, the reference build must
+return the same bits.  CPU only.
 """
 import numpy as np
 import pytest
 
-from tests.common import P
+from tests.common import P, compare_distance
 from tests.test_plane_known_answers import World, tf
 
 
@@ -21,6 +22,13 @@ def collide(w, h1, h2, T, margin=0.0):
     ro = w.sc.b["oracle"].batch_collide([h1], tf(), [h2], tf(T), req)
     re = w.sc.b["emu"].batch_collide([h1], tf(), [h2], tf(T), req)
     assert ro.tobytes() == re.tobytes()
+    if "ref" in w.sc.b:  # the reference build (it leaves `distance` unset without a contact)
+        rr = w.sc.b["ref"].batch_collide([h1], tf(), [h2], tf(T), req)
+        a, b = rr.copy(), ro.copy()
+        nc = a["num_contacts"] == 0
+        a["distance"][nc] = 0
+        b["distance"][nc] = 0
+        compare_distance(a, b, what="security margin, reference build")
     return ro[0]
 
 

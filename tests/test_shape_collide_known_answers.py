@@ -3,7 +3,8 @@
 computation, and where the reference gives them the normal (to 1e-9, 1e-8 or tol_gjk = 0.01 as there) -- every case
 in the frame of the test and under a common rigid transform (random in the reference, fixed here).
 
-Checked on the oracle's records; the host build of the device code (tests/emu) must return the same bits.  CPU only:
+Checked on the oracle's records; the host build of the device code (tests/emu) and, where oracle/_ref exists, the
+reference build must return the same bits.  CPU only:
 tests/test_gpu_parity.py compares the CUDA kernels with the oracle on all of these pair types.
 """
 import numpy as np
@@ -148,8 +149,8 @@ def test_flat_faces_overlap_without_contact_computation():
     (narrowphase.h:638-656), which collide() compares with collision_distance_threshold = 1e-12
     (shape_shape_func.h:148-152): 1.4e-12 > 1e-12, *no collision* -- for shapes 0.1 inside each other.  With
     enable_contact = true EPA runs and the contact is reported.  The reference compiled in place (oracle/_ref)
-    returns the same bits (tests/test_reference_build.py covers the pair types; this case was checked by hand),
-    the oracle restates it, and so do the kernels: a drop-in answers like the library, quirks included."""
+    returns the same bits (World.collide asserts it), the oracle restates it, and so do the kernels: a drop-in
+    answers like the library, quirks included."""
     w = World()
     s1, s2 = w.shape("cylinder", 5, 10), w.shape("cone", 5, 10)
     t1, t2 = w.g, compose(w.g, tf((0, 0, 9.9)))

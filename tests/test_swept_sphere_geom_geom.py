@@ -5,12 +5,13 @@ capsule, cone, cylinder, convex hull, plane, halfspace} (no two of the plane fam
 always carries witness points; the contact of the swept shapes must be the contact of the bare shapes moved by the
 radii -- depth - (r1 + r2), the same normal, p1 + r1 n, p2 - r2 n -- to 3 sqrt(tol) + max(r1, r2) / 100.
 
-Checked on the oracle; the host build of the device code must return the same bits.  CPU only.
+Checked on the oracle; the host build of the device code and, where oracle/_ref exists, the reference build must
+return the same bits.  CPU only.
 """
 import numpy as np
 import pytest
 
-from tests.common import P, compare_distance, make_scenes
+from tests.common import P, compare_distance, make_scenes, ref_agrees
 from hppfcl_b200 import workloads as W
 
 RADII = (0.0, 0.1, 1.0, 10.0)
@@ -46,7 +47,7 @@ def draw(sc, rng, kind):
 @pytest.mark.parametrize("k1", KINDS)
 def test_swept_sphere_radius_through_collide(k1):
     rng = np.random.default_rng(300 + KINDS.index(k1))
-    sc = make_scenes()
+    sc = make_scenes(ref=True)
     rows = []  # (bare 1, bare 2, swept 1, swept 2, r1, r2)
     for k2 in KINDS:
         if k1 in ("plane", "halfspace") and k2 in ("plane", "halfspace"):
@@ -67,6 +68,7 @@ def test_swept_sphere_radius_through_collide(k1):
         ro = sc.b["oracle"].batch_collide(h1, t1, h2, t2, req)
         re = sc.b["emu"].batch_collide(h1, t1, h2, t2, req)
         compare_distance(ro, re, what="%s-* %s" % (k1, "swept" if c1 else "bare"))
+        ref_agrees(sc, "batch_collide", ro, (h1, t1, h2, t2, req), "%s-* %s" % (k1, "swept" if c1 else "bare"))
         out.append(ro)
     bare, swept = out
     r1, r2 = rows[:, 4], rows[:, 5]

@@ -68,7 +68,7 @@ def kkt_check(Pw, Qw, p1, p2, what):
 @pytest.mark.parametrize("variant", [P.DefaultGJK, P.NesterovAcceleration])
 def test_triangle_triangle_distance_is_optimal(variant):
     rng = np.random.default_rng(11 + variant)
-    sc = make_scenes()
+    sc = make_scenes()  # (TriangleP operands are not in the reference's public distance table: no reference build here)
     Ps = rng.uniform(-1, 1, (N, 3, 3))
     Qs = rng.uniform(-1, 1, (N, 3, 3))
     R1 = np.eye(3)[None].repeat(N, 0)
