@@ -338,6 +338,37 @@ def build_cases(seed, n, use_ref, use_emu):
         for kind in ("distance", "collide"):
             req, kw = random_request(prng, kind)
             cases.append(("planes", kind, p1, pt1, p2, pt2, req, kw))
+    # --drift: poses as they come out of files and long products -- quaternions rounded to 8 ... 14 digits and not
+    # normalised again, or matrices with a relative error of 1e-14 ... 1e-9 --, the same rotation for both operands,
+    # the second one on an axis of the first and slid until the surfaces (almost) touch: GJK then ends with the
+    # origin on its last simplex up to rounding and the answers sit next to tolerance and threshold (found by the
+    # reference's collide_conecylinder case, tests/test_shape_collide_known_answers.py)
+    if DRIFT[0]:
+        drng = np.random.default_rng([seed, 0x51ED270B])
+        nd_ = max(200, n // 3)
+        q = drng.normal(size=(nd_, 4))
+        q /= np.linalg.norm(q, axis=1)[:, None]
+        digits = drng.integers(8, 15, nd_)
+        q = np.where((drng.random(nd_) < 0.7)[:, None], np.round(q * 10.0 ** digits[:, None]) / 10.0 ** digits[:, None], q)
+        Rd = W.quat_to_rot(q[:, 0], q[:, 1], q[:, 2], q[:, 3])
+        warp = drng.random(nd_) < 0.3
+        Rd[warp] = Rd[warp] @ (np.eye(3) + drng.normal(size=(int(warp.sum()), 3, 3)) * 10.0 ** drng.uniform(-14, -9, (int(warp.sum()), 1, 1)))
+        Td = drng.uniform(-1, 1, (nd_, 3)) * scale
+        ax = drng.integers(0, 3, nd_)
+        sign = drng.choice([-1.0, 1.0], nd_)
+        axis_w = Rd[np.arange(nd_), :, ax] * sign[:, None]  # a body axis of operand 1 in the world
+        dt1 = P.make_transforms(Rd, Td)
+        dt2 = P.make_transforms(Rd, Td + axis_w * 4.0 * scale)
+        d1, d2 = pool[drng.integers(0, len(pool), nd_)], pool[drng.integers(0, len(pool), nd_)]
+        dt2 = touching(B.orc, d1, dt1, d2, dt2, drng)
+        deep = drng.random(nd_) < 0.3  # a third of them overlapping by a visible amount
+        dt2["T"][deep] -= axis_w[deep] * (drng.uniform(0.01, 0.2, (int(deep.sum()), 1)) * scale)
+        for kind in ("distance", "collide", "collide"):
+            req, kw = random_request(drng, kind)
+            if kind == "collide" and drng.random() < 0.5:
+                req.enable_contact = 0
+                kw = dict(kw, enable_contact=0)
+            cases.append(("drift", kind, d1, dt1, d2, dt2, req, kw))
     # hulls of more than 32 vertices: reference vs oracle only (the device code takes the exhaustive argmax)
     nb = max(200, n // 4)
     bpool = np.concatenate([hb, hb, hp])
@@ -366,6 +397,7 @@ def build_cases(seed, n, use_ref, use_emu):
 
 
 PLANES = [False]  # --planes: Plane / Halfspace geometries against everything (and each other)
+DRIFT = [False]  # --drift: rotations that are orthonormal only to 1e-14 ... 1e-8, shared by coaxial, nearly touching shapes
 CONTACTS = [False]  # --contacts: mesh collide cases go through batch_collide_contacts (every contact of a pair)
 MAX_EXTRA = 4
 
@@ -395,7 +427,7 @@ def compare_case(case, ref, got, what):
             cmp_fields(ref["extra"][:, k], got["extra"][:, k], ("p1", "p2", "normal", "pos", "b1", "b2", "distance"),
                        what + " contacts[%d]" % (k + 1))
         return
-    if name in ("shapes", "big-hulls", "planes"):
+    if name in ("shapes", "big-hulls", "planes", "drift"):
         if kind == "distance":
             compare_distance(ref, got, what=what)
         else:
@@ -416,7 +448,7 @@ def rows_differing(case, ref, got):
                 ne = ~((x == y) | (np.isnan(x) & np.isnan(y))) if x.dtype.kind == "f" else x != y
                 bad |= ne.reshape(len(ref), -1).any(axis=1)
         return np.union1d(np.nonzero(bad)[0], rows_differing(case, ref["first"], got["first"]))
-    if name in ("shapes", "big-hulls", "planes"):
+    if name in ("shapes", "big-hulls", "planes", "drift"):
         fields = ["status", "iterations", "b1", "b2", "p1", "p2", "normal"]
         fields += ["min_distance"] if kind == "distance" else ["distance", "pos", "distance_lower_bound", "num_contacts"]
     elif kind == "distance":
@@ -497,6 +529,8 @@ def main():
     ap.add_argument("--big-meshes", action="store_true")
     ap.add_argument("--contacts", action="store_true", help="mesh collide cases keep every contact (batch_collide_contacts)")
     ap.add_argument("--planes", action="store_true", help="add the Plane / Halfspace family to every round")
+    ap.add_argument("--drift", action="store_true",
+                    help="add coaxial, nearly touching pairs under rotations that are not quite orthonormal to every round")
     ap.add_argument("--gpu", action="store_true", help="the real kernels (hppfcl_b200.Engine) instead of the host build")
     ap.add_argument("--lanes", type=int, default=1, help="host build: lane groups of this many threads for phase 1")
     a = ap.parse_args()
@@ -504,6 +538,7 @@ def main():
     BIG_MESHES[0] = a.big_meshes
     CONTACTS[0] = a.contacts
     PLANES[0] = a.planes
+    DRIFT[0] = a.drift
     if os.path.isdir("/root/reference/src"):
         oracle_lib.build_ref()
     use_ref = oracle_lib.ref_available()
