@@ -62,6 +62,18 @@ def test_fuzz_plane_family():
         fuzz_ref.PLANES[0] = False
 
 
+def test_fuzz_drifted_rotations():
+    """the rounds with coaxial, nearly touching pairs under rotations that are orthonormal only to 1e-14 ... 1e-8
+    (fuzz_ref --drift): reference build, oracle and the host build of the device code"""
+    fuzz_ref.DRIFT[0] = True
+    try:
+        for seed in range(400, 425):
+            ok, tag = fuzz_ref.one_round(seed, 1500, _ref(), True)
+            assert ok, tag
+    finally:
+        fuzz_ref.DRIFT[0] = False
+
+
 # Seeds 1, 2, 5-10 were green on a B200 in round 1 (profiles/r01_summary.md).  3 and 4 exposed a defect of the
 # lane-group support argmax: a NaN direction (GJK produces one from 0/0 in the projection of a degenerate simplex,
 # and carries on -- so does the reference) left the lanes of a group with different vertices.  Fixed in
