@@ -393,6 +393,23 @@ def build_cases(seed, n, use_ref, use_emu):
     for name, a, b in (("mesh-shape", g1, q), ("shape-mesh", q, g1), ("mesh-mesh", g1, g2)):
         cases.append((name, "distance", a, mt1, b, mt2, mreq, mdkw))
         cases.append((name, "collide", a, mt1, b, mt2, mcreq, mckw))
+    if DRIFT[0]:  # the mesh walks under drifted rotations (the BV tests multiply them like any other matrix)
+        mrng = np.random.default_rng([seed, 0x51ED270C])
+        md = max(100, m // 2)
+
+        def drifted(k):
+            qq = mrng.normal(size=(k, 4))
+            qq /= np.linalg.norm(qq, axis=1)[:, None]
+            dg = 10.0 ** mrng.integers(8, 15, (k, 1))
+            qq = np.round(qq * dg) / dg
+            return W.quat_to_rot(qq[:, 0], qq[:, 1], qq[:, 2], qq[:, 3])
+        dm1 = P.make_transforms(drifted(md), mt1["T"][:md])
+        dm2 = P.make_transforms(drifted(md), mt2["T"][:md])
+        same = mrng.random(md) < 0.3
+        dm2["R"][same] = dm1["R"][same]
+        for name, a, b in (("mesh-shape", g1[:md], q[:md]), ("mesh-mesh", g1[:md], g2[:md])):
+            cases.append((name, "distance", a, dm1, b, dm2, mreq, dict(mdkw, drift=1)))
+            cases.append((name, "collide", a, dm1, b, dm2, mcreq, dict(mckw, drift=1)))
     return B, tag, cases
 
 
