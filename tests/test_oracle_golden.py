@@ -6,7 +6,7 @@ citing its source.  The same cases are also run through the CPU emulation of the
 import numpy as np
 import pytest
 
-from tests.common import P, compare_distance, make_scenes
+from tests.common import P, compare_distance, make_scenes, ref_agrees
 from hppfcl_b200 import workloads as W
 
 SQ2 = np.sqrt(2.0)
@@ -61,14 +61,22 @@ class Q:
         import os
         self.gpu = os.environ.get("HFB_GOLDEN_BACKEND") == "gpu"
         self.other = "gpu" if self.gpu else "emu"
-        self.sc = make_scenes(gpu=self.gpu, emu=not self.gpu)
+        # (on the CPU the reference build, where it exists, is a third backend that must return the same bits)
+        self.sc = make_scenes(gpu=self.gpu, emu=not self.gpu, ref=not self.gpu)
+        self.tris = set()  # TriangleP operands are not in the reference's public dispatch tables
 
     def add(self, rec):
         return int(self.sc.register_shapes(rec)[0])
 
     def add_tri(self, a, b, c):
         cid = self.sc.register_convex(np.array([a, b, c], dtype=float), None)
-        return int(self.sc.register_shapes(P.make_shapes([P.GEOM_TRIANGLE], [[0, 0, 0]], data=[cid]))[0])
+        h = int(self.sc.register_shapes(P.make_shapes([P.GEOM_TRIANGLE], [[0, 0, 0]], data=[cid]))[0])
+        self.tris.add(h)
+        return h
+
+    def _ref(self, fn, ro, h1, t1, h2, t2, req):
+        if "ref" in self.sc.b and h1 not in self.tris and h2 not in self.tris:
+            ref_agrees(self.sc, fn, ro, ([h1], t1, [h2], t2, req), "golden")
 
     def distance(self, h1, t1, h2, t2, **kw):
         req = P.DistanceRequestPOD(**kw)
@@ -76,6 +84,7 @@ class Q:
         ro = self.sc.b["oracle"].batch_distance([h1], t1, [h2], t2, req)
         re = self.sc.b[self.other].batch_distance([h1], t1, [h2], t2, req)
         compare_distance(ro, re, what="golden")
+        self._ref("batch_distance", ro, h1, t1, h2, t2, req)
         return re[0] if self.gpu else ro[0]
 
     def collide(self, h1, t1, h2, t2, **kw):
@@ -84,6 +93,7 @@ class Q:
         ro = self.sc.b["oracle"].batch_collide([h1], t1, [h2], t2, req)
         re = self.sc.b[self.other].batch_collide([h1], t1, [h2], t2, req)
         compare_distance(ro, re, what="golden")
+        self._ref("batch_collide", ro, h1, t1, h2, t2, req)
         return re[0] if self.gpu else ro[0]
 
 
