@@ -109,6 +109,43 @@ def test_degenerate_sizes():
         ref_agrees(sc, fn, ro, (h1, t1, h2, t2, req), fn + ", degenerate sizes")
 
 
+def test_extreme_request_fields():
+    """request fields at and beyond the ends of their ranges (no iterations at all, tolerances of 1 and of 1e-300,
+    margins of +-DBL_MAX and infinity, a negative upper bound, negative and huge collision thresholds, ...): none of
+    them is refused by the reference, all of them must give the same records in the reference build, the oracle and
+    the host build of the device code"""
+    import numpy as np
+    from tests.common import P, compare_distance, make_scenes, ref_agrees
+    from hppfcl_b200 import workloads as W
+    _ref()
+    rng = np.random.default_rng(6)
+    sc = make_scenes(ref=True)
+    h = sc.register_shapes(W.random_primitive_shapes(rng, 64, (P.GEOM_SPHERE, P.GEOM_CAPSULE, P.GEOM_BOX, P.GEOM_CYLINDER,
+                                                              P.GEOM_CONE, P.GEOM_ELLIPSOID)))
+    pts, tris = W.icosahedron_from_ellipsoid((0.3, 0.4, 0.5))
+    cid = sc.register_convex(pts, tris)
+    h = np.concatenate([h, sc.register_shapes(P.make_shapes([P.GEOM_CONVEX], [[0, 0, 0]], data=[cid]))])
+    sc.commit()
+    n = 6000
+    h1, h2 = h[rng.integers(0, len(h), n)], h[rng.integers(0, len(h), n)]
+    t1 = W.random_transforms(rng, n, (-1, -1, -1), (1, 1, 1))
+    t2 = W.random_transforms(rng, n, (-1, -1, -1), (1, 1, 1))
+    cases = [("batch_distance", dict(gjk_max_iterations=0)), ("batch_distance", dict(epa_max_iterations=0)),
+             ("batch_distance", dict(gjk_tolerance=1.0)), ("batch_distance", dict(epa_tolerance=1.0)),
+             ("batch_distance", dict(gjk_tolerance=1e-300)), ("batch_distance", dict(gjk_max_iterations=1, epa_max_iterations=1)),
+             ("batch_distance", dict(gjk_max_iterations=100000)), ("batch_distance", dict(enable_nearest_points=0)),
+             ("batch_collide", dict(security_margin=P.DBL_MAX)), ("batch_collide", dict(security_margin=-P.DBL_MAX)),
+             ("batch_collide", dict(security_margin=float("inf"))), ("batch_collide", dict(distance_upper_bound=-1.0)),
+             ("batch_collide", dict(collision_distance_threshold=-1.0)), ("batch_collide", dict(collision_distance_threshold=10.0)),
+             ("batch_collide", dict(num_max_contacts=1000)), ("batch_collide", dict(break_distance=-1.0)),
+             ("batch_collide", dict(gjk_max_iterations=0, enable_contact=0))]
+    for fn, kw in cases:
+        req = (P.DistanceRequestPOD if fn == "batch_distance" else P.CollisionRequestPOD)(**kw)
+        ro = getattr(sc.b["oracle"], fn)(h1, t1, h2, t2, req, nthreads=0)
+        compare_distance(ro, getattr(sc.b["emu"], fn)(h1, t1, h2, t2, req), what="%s %s" % (fn, kw))
+        ref_agrees(sc, fn, ro, (h1, t1, h2, t2, req), "%s %s" % (fn, kw))
+
+
 # Seeds 1, 2, 5-10 were green on a B200 in round 1 (profiles/r01_summary.md).  3 and 4 exposed a defect of the
 # lane-group support argmax: a NaN direction (GJK produces one from 0/0 in the projection of a degenerate simplex,
 # and carries on -- so does the reference) left the lanes of a group with different vertices.  Fixed in
