@@ -183,6 +183,38 @@ def test_huge_translations():
         ref_agrees(sc, "batch_distance", ro, a, "mesh-shape at %g" % mag, fields=("min_distance", "p1", "p2", "normal", "b1", "b2"))
 
 
+def test_hulls_at_the_linear_scan_threshold():
+    """hulls of 31 and 32 vertices: the last sizes the reference scans linearly (support_functions.cpp:429,
+    num_vertices_large_convex_threshold = 32; above it climbs hills) -- here the device code's exhaustive argmax must
+    be index-exact: status words, iteration counts, support hints' consequences, every double, three-way"""
+    import numpy as np
+    from tests.common import P, compare_distance, make_scenes, ref_agrees
+    from hppfcl_b200 import workloads as W
+    _ref()
+    rng = np.random.default_rng(12)
+    sc = make_scenes(ref=True)
+    hs = []
+    for nv in (31, 32, 32, 32):
+        pts, tris = W.ellipsoid_hull(rng, nv)
+        assert len(pts) == nv
+        cid = sc.register_convex(pts, tris)
+        hs.append(int(sc.register_shapes(P.make_shapes([P.GEOM_CONVEX], [[0, 0, 0]], data=[cid]))[0]))
+    hp = sc.register_shapes(W.random_primitive_shapes(rng, 16, (P.GEOM_BOX, P.GEOM_CAPSULE, P.GEOM_SPHERE)))
+    sc.commit()
+    hs = np.array(hs, dtype=np.uint32)
+    pool = np.concatenate([hs, hp])
+    n = 8000
+    h1, h2 = hs[rng.integers(0, 4, n)], pool[rng.integers(0, len(pool), n)]
+    t1 = W.random_transforms(rng, n, (-.6, -.6, -.6), (.6, .6, .6))
+    t2 = W.random_transforms(rng, n, (-.6, -.6, -.6), (.6, .6, .6))
+    for fn, req in (("batch_distance", P.DistanceRequestPOD()),
+                    ("batch_distance", P.DistanceRequestPOD(gjk_variant=P.NesterovAcceleration)),
+                    ("batch_collide", P.CollisionRequestPOD())):
+        ro = getattr(sc.b["oracle"], fn)(h1, t1, h2, t2, req, nthreads=0)
+        compare_distance(ro, getattr(sc.b["emu"], fn)(h1, t1, h2, t2, req), what=fn + ", 32-vertex hulls")
+        ref_agrees(sc, fn, ro, (h1, t1, h2, t2, req), fn + ", 32-vertex hulls")
+
+
 @pytest.mark.timeout(300)
 def test_non_finite_poses_terminate():
     """NaN and +-Inf in a translation or rotation entry of half of the pairs: nothing is refused (the reference does
